@@ -1,0 +1,254 @@
+"""ctypes binder for a flat "network likelihood" C-ABI.
+
+The product's host library (libnetrax_b200.so, prefix ``nrxh_``, declared in include/netrax_b200.h)
+exports the NetRAX likelihood API (computeLoglikelihood, computeLoglikelihoodBrlenOpt,
+computePartitionSumtables, computeLoglikelihoodDerivatives, ...) as plain-C entry points.  The test
+oracle exports the same function set under the prefix ``orc_`` so parity tests can run identical call
+sequences against both; this module knows nothing about either implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .network_io import NetworkDesc
+
+AVERAGE, BEST = 0, 1                 # LikelihoodVariant (src/likelihood/LikelihoodVariant.hpp)
+LINKED, SCALED, UNLINKED = 0, 1, 2   # PLLMOD_COMMON_BRLEN_*
+
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+class LikelihoodError(RuntimeError):
+    """Mirrors the std::runtime_error the reference throws from its likelihood layer."""
+
+
+def _as(a, dt):
+    return np.ascontiguousarray(np.asarray(a, dtype=dt))
+
+
+class FlatAPI:
+    def __init__(self, lib: C.CDLL, prefix: str):
+        self.lib, self.prefix = lib, prefix
+        g = self._fn
+        g("last_error", C.c_char_p)
+        g("new", C.c_void_p, C.c_char_p)
+        g("free", None, C.c_void_p)
+        g("set_network", C.c_int, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, _u32p, _u32p, _f64p, _f64p,
+          C.c_uint, _u32p, _u32p, _u32p)
+        g("add_partition", C.c_int, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, _u32p, C.c_void_p, _f64p, _f64p, _f64p, _f64p)
+        g("set_options", C.c_int, C.c_void_p, C.c_int, C.c_int)
+        g("set_partition_brlens", C.c_int, C.c_void_p, C.c_uint, _f64p)
+        g("init", C.c_int, C.c_void_p)
+        g("compute_loglikelihood", C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double))
+        g("num_partitions", C.c_uint, C.c_void_p)
+        g("root", C.c_uint, C.c_void_p)
+        g("num_nodes", C.c_uint, C.c_void_p)
+        g("num_trees", C.c_int, C.c_void_p, C.c_uint)
+        g("tree_config", C.c_int, C.c_void_p, C.c_uint, C.c_uint, C.c_char_p, C.c_uint)
+        g("tree_info", C.c_int, C.c_void_p, C.c_uint, C.c_uint, C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_int))
+        g("read_clv", C.c_int, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, _f64p)
+        g("read_scaler", C.c_int, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, _u32p)
+        g("partition_loglh", C.c_int, C.c_void_p, _f64p)
+        g("set_branch_length", C.c_int, C.c_void_p, C.c_int, C.c_uint, C.c_double)
+        g("set_reticulation_prob", C.c_int, C.c_void_p, C.c_uint, C.c_double)
+        g("set_model", C.c_int, C.c_void_p, C.c_uint, _f64p, _f64p, _f64p, _f64p)
+        g("get_eigen", C.c_int, C.c_void_p, C.c_uint, _f64p, _f64p, _f64p)
+        g("get_pmatrix", C.c_int, C.c_void_p, C.c_uint, C.c_uint, _f64p)
+        g("brlen_prepare", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
+        g("brlen_logl", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
+        g("brlen_sumtables", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_uint))
+        g("brlen_read_sumtable", C.c_int, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.POINTER(C.c_double),
+          C.POINTER(C.c_uint), C.POINTER(C.c_uint))
+        g("brlen_set_length", C.c_int, C.c_void_p, C.c_int, C.c_uint, C.c_double)
+        g("brlen_derivatives", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double), C.POINTER(C.c_double),
+          C.c_void_p, C.c_void_p, C.c_void_p)
+        g("brlen_finish", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
+        g("clv_update_count", C.c_ulonglong, C.c_void_p)
+        g("reset_counters", None, C.c_void_p)
+        g("gamma_rates", C.c_int, C.c_double, C.c_uint, C.c_int, _f64p)
+
+    def _fn(self, name, restype, *argtypes):
+        f = getattr(self.lib, self.prefix + name)
+        f.restype, f.argtypes = restype, list(argtypes)
+        setattr(self, "_" + name, f)
+        return f
+
+    def has(self, name: str) -> bool:
+        return hasattr(self.lib, self.prefix + name)
+
+    def check(self, ok):
+        if not ok:
+            raise LikelihoodError(self._last_error().decode())
+
+    def gamma_rates(self, alpha: float, cats: int, mode: int = 0) -> np.ndarray:
+        out = np.zeros(cats)
+        self.check(self._gamma_rates(alpha, cats, mode, out))
+        return out
+
+
+class Partition:
+    """Inputs of one alignment partition: what create_pll_partition (src/RaxmlWrapper.cpp:686-760) sets."""
+
+    def __init__(self, states: int, rate_cats: int, tip_masks: np.ndarray, freqs, subst, rates, rate_weights=None,
+                 pattern_weights=None):
+        self.states, self.rate_cats = int(states), int(rate_cats)
+        self.tip_masks = _as(tip_masks, np.uint32)          # [tips, patterns]
+        self.sites = int(self.tip_masks.shape[1])
+        self.freqs, self.subst = _as(freqs, np.float64), _as(subst, np.float64)
+        self.rates = _as(rates, np.float64)
+        self.rate_weights = _as(rate_weights if rate_weights is not None else np.full(rate_cats, 1.0 / rate_cats), np.float64)
+        self.pattern_weights = None if pattern_weights is None else _as(pattern_weights, np.uint32)
+
+    def slice(self, lo: int, hi: int) -> "Partition":
+        """Contiguous pattern range [lo, hi): one rank's share under site sharding."""
+        pw = None if self.pattern_weights is None else self.pattern_weights[lo:hi]
+        return Partition(self.states, self.rate_cats, self.tip_masks[:, lo:hi], self.freqs, self.subst, self.rates,
+                         self.rate_weights, pw)
+
+
+class LikelihoodEngine:
+    """One AnnotatedNetwork + its likelihood state behind a FlatAPI (product or oracle)."""
+
+    def __init__(self, api: FlatAPI, net: NetworkDesc, partitions: Sequence[Partition], variant: int = AVERAGE,
+                 linkage: int = LINKED, backend: str = "", partition_brlens: Optional[Sequence[np.ndarray]] = None):
+        self.api, self.net, self.partitions = api, net, list(partitions)
+        self.h = api._new(backend.encode())
+        if not self.h:
+            raise LikelihoodError(api._last_error().decode())
+        a = api
+        a.check(a._set_network(self.h, net.num_tips, net.num_nodes, net.root, net.num_edges, _as(net.edge_source, np.uint32),
+                               _as(net.edge_target, np.uint32), _as(net.edge_length, np.float64), _as(net.edge_prob, np.float64),
+                               net.num_reticulations, _as(net.ret_node, np.uint32), _as(net.ret_first_edge, np.uint32),
+                               _as(net.ret_second_edge, np.uint32)))
+        for p in self.partitions:
+            pw = None if p.pattern_weights is None else p.pattern_weights.ctypes.data_as(C.c_void_p)
+            a.check(a._add_partition(self.h, p.states, p.rate_cats, p.sites, p.tip_masks.reshape(-1), pw, p.freqs, p.subst,
+                                     p.rates, p.rate_weights))
+        a.check(a._set_options(self.h, variant, linkage))
+        if partition_brlens is not None:
+            for i, b in enumerate(partition_brlens):
+                a.check(a._set_partition_brlens(self.h, i, _as(b, np.float64)))
+        a.check(a._init(self.h))
+        self.P = len(self.partitions)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.api._free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- src/likelihood/LikelihoodComputation.hpp:17-18 ----
+    def computeLoglikelihood(self, incremental: int = 1, update_pmatrices: int = 1) -> float:
+        out = C.c_double()
+        self.api.check(self.api._compute_loglikelihood(self.h, incremental, update_pmatrices, C.byref(out)))
+        return out.value
+
+    def partition_loglh(self) -> np.ndarray:
+        out = np.zeros(self.P)
+        self.api.check(self.api._partition_loglh(self.h, out))
+        return out
+
+    def num_trees(self, node: int) -> int:
+        return self.api._num_trees(self.h, node)
+
+    def tree_config(self, node: int, tree: int) -> str:
+        buf = C.create_string_buffer(1 << 16)
+        self.api.check(self.api._tree_config(self.h, node, tree, buf, len(buf)))
+        return buf.value.decode()
+
+    def tree_info(self, node: int, tree: int) -> Tuple[float, np.ndarray, int]:
+        lp, fl = C.c_double(), C.c_int()
+        pl = np.zeros(self.P)
+        self.api.check(self.api._tree_info(self.h, node, tree, C.byref(lp), pl.ctypes.data_as(C.c_void_p), C.byref(fl)))
+        return lp.value, pl, fl.value
+
+    def clv_entries(self, p: int) -> int:
+        part = self.partitions[p]
+        return part.sites * part.rate_cats * ((part.states + 3) & ~3)
+
+    def read_clv(self, node: int, tree: int, p: int = 0) -> np.ndarray:
+        out = np.zeros(self.clv_entries(p))
+        self.api.check(self.api._read_clv(self.h, node, tree, p, out))
+        return out
+
+    def read_scaler(self, node: int, tree: int, p: int = 0) -> np.ndarray:
+        out = np.zeros(self.partitions[p].sites, np.uint32)
+        self.api.check(self.api._read_scaler(self.h, node, tree, p, out))
+        return out
+
+    def set_branch_length(self, edge: int, value: float, partition: int = -1):
+        self.api.check(self.api._set_branch_length(self.h, partition, edge, value))
+
+    def set_reticulation_prob(self, r: int, prob: float):
+        self.api.check(self.api._set_reticulation_prob(self.h, r, prob))
+
+    def set_model(self, p: int, freqs, subst, rates, rate_weights):
+        self.api.check(self.api._set_model(self.h, p, _as(freqs, np.float64), _as(subst, np.float64), _as(rates, np.float64),
+                                           _as(rate_weights, np.float64)))
+
+    def get_eigen(self, p: int = 0):
+        part = self.partitions[p]
+        sp = (part.states + 3) & ~3
+        ev, iev, evals = np.zeros(part.states * sp), np.zeros(part.states * sp), np.zeros(sp)
+        self.api.check(self.api._get_eigen(self.h, p, ev, iev, evals))
+        return ev, iev, evals
+
+    def get_pmatrix(self, edge: int, p: int = 0) -> np.ndarray:
+        part = self.partitions[p]
+        out = np.zeros(part.rate_cats * part.states * ((part.states + 3) & ~3))
+        self.api.check(self.api._get_pmatrix(self.h, p, edge, out))
+        return out
+
+    # ---- branch-length optimisation flow (src/optimization/BranchLengthOptimization.cpp:345-420) ----
+    def brlen_prepare(self, edge: int) -> float:
+        out = C.c_double()
+        self.api.check(self.api._brlen_prepare(self.h, edge, C.byref(out)))
+        return out.value
+
+    def computeLoglikelihoodBrlenOpt(self, edge: int) -> float:
+        out = C.c_double()
+        self.api.check(self.api._brlen_logl(self.h, edge, C.byref(out)))
+        return out.value
+
+    def computePartitionSumtables(self, edge: int) -> int:
+        n = C.c_uint()
+        self.api.check(self.api._brlen_sumtables(self.h, edge, C.byref(n)))
+        self._n_sumtables = n.value
+        return n.value
+
+    def read_sumtable(self, p: int, idx: int):
+        out = np.zeros(self.clv_entries(p))
+        prob, lt, rt = C.c_double(), C.c_uint(), C.c_uint()
+        self.api.check(self.api._brlen_read_sumtable(self.h, p, idx, out.ctypes.data_as(C.c_void_p), C.byref(prob), C.byref(lt), C.byref(rt)))
+        return out, prob.value, lt.value, rt.value
+
+    def brlen_set_length(self, edge: int, value: float, partition: int = -1):
+        self.api.check(self.api._brlen_set_length(self.h, partition, edge, value))
+
+    def computeLoglikelihoodDerivatives(self, edge: int):
+        d1, d2 = C.c_double(), C.c_double()
+        pd1, pd2 = np.zeros(self.P), np.zeros(self.P)
+        raw = np.zeros(self.P * 3 * max(1, getattr(self, "_n_sumtables", 1)))
+        self.api.check(self.api._brlen_derivatives(self.h, edge, C.byref(d1), C.byref(d2), pd1.ctypes.data_as(C.c_void_p),
+                                                   pd2.ctypes.data_as(C.c_void_p), raw.ctypes.data_as(C.c_void_p)))
+        return d1.value, d2.value, pd1, pd2, raw.reshape(self.P, -1, 3)
+
+    def brlen_finish(self, edge: int) -> float:
+        out = C.c_double()
+        self.api.check(self.api._brlen_finish(self.h, edge, C.byref(out)))
+        return out.value
+
+    def clv_update_count(self) -> int:
+        return int(self.api._clv_update_count(self.h))
+
+    def reset_counters(self):
+        self.api._reset_counters(self.h)

@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Regenerates everything under tests/golden/ — run HERE (container with /root/reference), never on the GPU box.
+
+1. copies the reference's own likelihood-test fixtures (test/sample_networks/*.nw + *_alignment.txt: DATA, not
+   source) into tests/golden/fixtures/;
+2. parses the golden stdout of libpll's regression suite (LIBPLL/../test/out/derivatives.out, pinv = 0 blocks;
+   inline data of test/src/derivatives.c:60-150) into libpll_derivatives_golden.json;
+3. runs the REAL forked libpll (oracle/_ref, kind "reference") under the restated NetRAX layer on every
+   fixture pairing of test/src/LikelihoodTest.cpp:282-360 and stores network lnL, per-displayed-tree lnL /
+   log-prob, scaler sums and CLV checksums into netrax_fixtures_golden.json.
+"""
+import json, os, re, shutil, sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+REF = "/root/reference"
+LIBPLL_TEST = REF + "/libs/raxml-ng/libs/pll-modules/libs/libpll/test"
+
+import numpy as np
+from helpers import FIXTURE_PAIRS, load_fixture, fixture_summary  # noqa: E402
+from oracle import oracle  # noqa: E402
+
+
+def copy_fixtures():
+    src = REF + "/test/sample_networks"
+    for f in sorted(os.listdir(src)):
+        shutil.copy(os.path.join(src, f), os.path.join(HERE, "fixtures", f))
+
+
+def parse_libpll_golden():
+    blocks, cur = [], None
+    for line in open(LIBPLL_TEST + "/out/derivatives.out"):
+        m = re.match(r"\s*TEST alpha\(ncats\) =\s*([\d.]+)\(\s*(\d+)\) ; pinv = ([\d.]+)", line)
+        if m:
+            cur = {"alpha": float(m.group(1)), "ncats": int(m.group(2)), "pinv": float(m.group(3)), "inner": [], "tip": []}
+            blocks.append(cur)
+            continue
+        m = re.match(r"Branch(\(Tip\))?\s+([\d.]+) :\s+(\S+)\s+(\S+)\s+(\S+)", line)
+        if m and cur is not None:
+            cur["tip" if m.group(1) else "inner"].append([float(m.group(2)), float(m.group(3)), float(m.group(4)), float(m.group(5))])
+    blocks = [b for b in blocks if b["pinv"] == 0.0]
+    json.dump({"source": "libpll test/out/derivatives.out (pinv=0 blocks); columns: branch, edge lnL, d(-lnL)/dt, d2(-lnL)/dt2",
+               "tips": ["WAACTCGCTA--ATTCTAAT", "CACCATGCTA--ATTGTCTT", "AG-C-TGCAG--CTTCTACT", "CGTCTTGCAA--AT-C-AAG", "CGACTTGCCA--AT-T-AAG"],
+               "freqs": [0.3, 0.4, 0.1, 0.2], "subst": [1, 2.5, 1, 1, 2.5, 1], "branch_lengths": [0.1, 0.2],
+               "blocks": blocks}, open(os.path.join(HERE, "libpll_derivatives_golden.json"), "w"), indent=1)
+    return len(blocks)
+
+
+def netrax_golden():
+    out = {}
+    for name, (nw, aln) in FIXTURE_PAIRS.items():
+        for variant in (0, 1):
+            net, part = load_fixture(nw, aln)
+            eng = oracle.make_engine("ref", net, [part], variant=variant)
+            out[f"{name}/{'AVERAGE' if variant == 0 else 'BEST'}"] = fixture_summary(eng)
+    json.dump({"generator": "tests/golden/make_golden.py with oracle kind=reference (real forked libpll AVX2+PATTERN_TIP)",
+               "model": "GTR(1,2.5,0.8,1.2,3,1) pi=(.3,.2,.2,.3) G4 alpha=0.5", "cases": out},
+              open(os.path.join(HERE, "netrax_fixtures_golden.json"), "w"), indent=1)
+    return len(out)
+
+
+if __name__ == "__main__":
+    copy_fixtures()
+    print("libpll golden blocks:", parse_libpll_golden())
+    print("netrax golden cases:", netrax_golden())

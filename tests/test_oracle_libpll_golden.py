@@ -1,0 +1,54 @@
+"""Pins the oracle (both kinds) to the golden numbers of libpll's own regression suite
+(LIBPLL/../test/out/derivatives.out, inline data of test/src/derivatives.c).  The golden test computes an
+edge lnL and d/dt, d2/dt2 of -lnL on the inner edge (clv6,clv7) and on the tip edge (tip4,clv7) of a
+5-taxon unrooted tree; here the same tree is rooted ON that edge (t split in two halves), so the network
+lnL equals the golden edge lnL and the NetRAX branch-length derivative of the half edge equals the golden
+derivative.  Golden precision: 6 decimals (lnL), 5 significant digits (derivatives)."""
+import numpy as np
+import pytest
+
+from helpers import load_golden
+from netrax_b200._capi import Partition
+from netrax_b200.network_io import encode_dna, parse_extended_newick
+from oracle import oracle
+
+G = load_golden("libpll_derivatives_golden.json")
+KINDS = ["port"] + (["ref"] if oracle.have_ref() else [])
+
+
+def _engine(kind, block, t, tip_edge):
+    b0, b1 = G["branch_lengths"]
+    h = t / 2
+    if not tip_edge:  # clv6=((t0,t1):b0,t2) | clv7=(t3,t4), joined by matrix 0 at length t
+        nw = f"(((T0:{b1},T1:{b1}):{b0},T2:{b1})X6:{h},(T3:{b1},T4:{b1})X7:{h});"
+    else:             # after operation 3: clv7=(clv6:b0, t3:b0), joined with tip4 by matrix 1 at length t
+        nw = f"(T4:{h},(((T0:{b1},T1:{b1}):{b0},T2:{b1}):{b0},T3:{b0})X7:{h});"
+    net = parse_extended_newick(nw)
+    order = [int(l[1:]) for l in net.tip_labels]
+    masks = np.stack([encode_dna(G["tips"][i]) for i in order])
+    rates = oracle.api("port").gamma_rates(block["alpha"], block["ncats"]) if block["ncats"] > 1 else np.ones(1)
+    part = Partition(4, block["ncats"], masks, G["freqs"], G["subst"], rates)
+    return net, oracle.make_engine(kind, net, [part])
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("bi", range(len(G["blocks"])))
+@pytest.mark.parametrize("tip_edge", [False, True])
+def test_libpll_golden_edge_lnl_and_derivatives(kind, bi, tip_edge):
+    block = G["blocks"][bi]
+    for t, f, d1, d2 in block["tip" if tip_edge else "inner"]:
+        if t > 10:  # golden derivatives there are 1e-15 noise; P-matrix saturates
+            continue
+        net, eng = _engine(kind, block, t, tip_edge)
+        lnl = eng.computeLoglikelihood(0, 1)
+        assert abs(lnl - f) < 2e-6, (t, lnl, f)
+        # the edge whose child is X7 (inner case: X6's sibling) — any of the two root edges works
+        edge = [e for e in range(net.num_edges) if net.edge_source[e] == net.root][0]
+        eng.brlen_prepare(edge)
+        assert abs(eng.computeLoglikelihoodBrlenOpt(edge) - lnl) < 1e-9
+        assert eng.computePartitionSumtables(edge) == 1
+        g1, g2, *_ = eng.computeLoglikelihoodDerivatives(edge)
+        assert g1 == pytest.approx(d1, rel=2e-4, abs=1e-9), (t, g1, d1)
+        assert g2 == pytest.approx(d2, rel=2e-4, abs=1e-9), (t, g2, d2)
+        assert abs(eng.brlen_finish(edge) - lnl) < 1e-9
+        eng.close()

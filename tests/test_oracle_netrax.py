@@ -1,0 +1,208 @@
+"""Oracle self-checks at the NetRAX layer (CPU only).
+
+* port restatement vs golden files generated with the REAL forked libpll underneath (kind "reference");
+* the reference's own invariants: improved == naive per-displayed-tree evaluation
+  (test/src/LikelihoodTest.cpp:204-255), full == incremental (:257-279), virtual re-rooting preserves lnL
+  on every edge (test/src/BrlenOptTest.cpp:297-367), changing + restoring a branch restores lnL;
+* derivatives vs central finite differences of the edge-rooted lnL (sign convention Q6).
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+from helpers import FIXTURE_PAIRS, fixture_summary, load_fixture, load_golden
+from netrax_b200._capi import AVERAGE, BEST, LINKED, UNLINKED, Partition
+from netrax_b200.synth import DNA_FREQS, GAMMA4_ALPHA05, GTR_RATES, caterpillar_network, random_network, simulate_alignment
+from oracle import oracle
+
+GOLD = load_golden("netrax_fixtures_golden.json")["cases"]
+KINDS = ["port"] + (["ref"] if oracle.have_ref() else [])
+SMALL = [k for k in FIXTURE_PAIRS if not k.startswith("celine")]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("name", list(FIXTURE_PAIRS))
+@pytest.mark.parametrize("variant", [AVERAGE, BEST])
+def test_fixture_matches_reference_golden(kind, name, variant):
+    net, part = load_fixture(*FIXTURE_PAIRS[name])
+    eng = oracle.make_engine(kind, net, [part], variant=variant)
+    got = fixture_summary(eng)
+    exp = GOLD[f"{name}/{'AVERAGE' if variant == AVERAGE else 'BEST'}"]
+    assert got["lnl"] == pytest.approx(exp["lnl"], rel=1e-12)
+    assert [t["config"] for t in got["root_trees"]] == [t["config"] for t in exp["root_trees"]]
+    for a, b in zip(got["root_trees"], exp["root_trees"]):
+        assert a["logprob"] == pytest.approx(b["logprob"], rel=1e-14, abs=1e-300)
+        assert a["partition_logl"] == pytest.approx(b["partition_logl"], rel=1e-12)
+    assert got["nodes"].keys() == exp["nodes"].keys()
+    for k in got["nodes"]:
+        assert got["nodes"][k]["scaler_sum"] == exp["nodes"][k]["scaler_sum"]          # bit-exact integers
+        assert got["nodes"][k]["clv_sha"] == exp["nodes"][k]["clv_sha"], k            # DNA CLVs: bit-exact
+    eng.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("name", SMALL + ["celine_smaller_1"])
+def test_improved_equals_naive(kind, name):
+    net, part = load_fixture(*FIXTURE_PAIRS[name])
+    for variant in (AVERAGE, BEST):
+        eng = oracle.make_engine(kind, net, [part], variant=variant)
+        l = eng.computeLoglikelihood(0, 1)
+        ln, tl, lp = oracle.naive_loglikelihood(eng)
+        assert l == pytest.approx(ln, rel=1e-13)
+        eng.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_incremental_equals_full_and_branch_restore(kind):
+    net, part = load_fixture(*FIXTURE_PAIRS["three_reticulations"])
+    eng = oracle.make_engine(kind, net, [part])
+    l0 = eng.computeLoglikelihood(0, 1)
+    assert eng.computeLoglikelihood(1, 1) == l0
+    for e in range(net.num_edges):
+        old = float(net.edge_length[e])
+        eng.set_branch_length(e, old * 3 + 0.01)
+        l1 = eng.computeLoglikelihood(1, 1)
+        assert l1 == eng.computeLoglikelihood(0, 1)
+        eng.set_branch_length(e, old)
+        assert eng.computeLoglikelihood(1, 1) == pytest.approx(l0, rel=1e-14)
+    eng.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("name", SMALL)
+@pytest.mark.parametrize("variant", [AVERAGE, BEST])
+def test_rerooting_preserves_lnl_on_every_edge(kind, name, variant):
+    net, part = load_fixture(*FIXTURE_PAIRS[name])
+    eng = oracle.make_engine(kind, net, [part], variant=variant)
+    l0 = eng.computeLoglikelihood(0, 1)
+    for e in range(net.num_edges):
+        eng.brlen_prepare(e)
+        assert eng.computeLoglikelihoodBrlenOpt(e) == pytest.approx(l0, rel=1e-12), e
+        assert eng.brlen_finish(e) == pytest.approx(l0, rel=1e-13)
+    eng.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_derivatives_match_finite_differences_single_tree(kind):
+    net, part = load_fixture(*FIXTURE_PAIRS["tree"])
+    eng = oracle.make_engine(kind, net, [part])
+    eng.computeLoglikelihood(0, 1)
+    for e in range(net.num_edges):
+        t = float(net.edge_length[e])
+        eng.brlen_prepare(e)
+        eng.computePartitionSumtables(e)
+        d1, d2, *_ = eng.computeLoglikelihoodDerivatives(e)
+        if t < 0.01:  # clamped 1e-6 branches: a central second difference is pure rounding noise
+            eng.brlen_finish(e)
+            continue
+        h = 1e-4 * t
+        vals = []
+        for tt in (t - h, t, t + h):
+            eng.brlen_set_length(e, tt)
+            vals.append(eng.computeLoglikelihoodBrlenOpt(e))
+        eng.brlen_set_length(e, t)
+        fd1 = -(vals[2] - vals[0]) / (2 * h)          # libpll returns derivatives of MINUS lnL (Q6)
+        fd2 = -(vals[2] - 2 * vals[1] + vals[0]) / (h * h)
+        assert d1 == pytest.approx(fd1, rel=1e-4, abs=1e-5), e
+        assert d2 == pytest.approx(fd2, rel=1e-3, abs=1e-3), e
+        eng.brlen_finish(e)
+    eng.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("variant", [AVERAGE, BEST])
+def test_derivative_mixing_matches_mpfr_semantics(kind, variant):
+    """K7 for derivatives (LH/LikelihoodDerivatives.cpp:13-23,147-180): recompute the AVERAGE quotient rule /
+    BEST pick (quirks Q2, Q6) from the raw per-sumtable (f, d1, d2) with mpmath at 53 bits, i.e. what
+    mpfr::mpreal does in the reference."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.prec = 53
+    net = random_network(9, 2, seed=4)
+    m, w = simulate_alignment(net, 120, seed=2)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    eng = oracle.make_engine(kind, net, [part], variant=variant)
+    eng.computeLoglikelihood(0, 1)
+    checked = 0
+    for e in range(net.num_edges):
+        eng.brlen_prepare(e)
+        n = eng.computePartitionSumtables(e)
+        if n == 0:
+            eng.brlen_finish(e)
+            continue
+        d1, d2, pd1, pd2, raw = eng.computeLoglikelihoodDerivatives(e)
+        probs = [eng.read_sumtable(0, i)[1] for i in range(n)]
+        if n == 1:
+            assert (d1, d2) == (raw[0, 0, 1], raw[0, 0, 2])
+        elif variant == AVERAGE:
+            S = S1 = S2 = mp.mpf(0)
+            for (f, a, b), pr in zip(raw[0], probs):
+                lh = mp.exp(mp.mpf(float(f)))
+                lhp = lh * float(a)
+                lhpp = lhp * float(a) + lh * float(b)
+                S += lh * pr; S1 += lhp * pr; S2 += lhpp * pr
+            assert d1 == pytest.approx(float(S1 / S), rel=1e-13)
+            assert d2 == pytest.approx(float((S2 * S - S1 * S1) / (S * S)), rel=1e-11)
+            checked += 1
+        else:
+            best = max(range(n), key=lambda i: (raw[0, i, 0] * probs[i], -i))
+            assert (d1, d2) == (raw[0, best, 1], raw[0, best, 2])
+            checked += 1
+        eng.brlen_finish(e)
+    assert checked > 0
+    eng.close()
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("cfg", [(12, 2, 300, 5), (25, 3, 200, 6), (40, 5, 120, 7)])
+def test_port_equals_reference_on_synthetic(cfg):
+    n, r, pat, seed = cfg
+    net = random_network(n, r, seed=seed)
+    m, w = simulate_alignment(net, pat, seed=seed)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    a, b = oracle.make_engine("port", net, [part]), oracle.make_engine("ref", net, [part])
+    la, lb = a.computeLoglikelihood(0, 1), b.computeLoglikelihood(0, 1)
+    assert la == pytest.approx(lb, rel=1e-13)
+    for e in range(net.num_edges):
+        assert np.array_equal(a.get_pmatrix(e), b.get_pmatrix(e))
+    for v in range(net.num_tips, net.num_nodes):
+        assert a.num_trees(v) == b.num_trees(v)
+        for t in range(a.num_trees(v)):
+            assert np.array_equal(a.read_scaler(v, t), b.read_scaler(v, t))
+            assert np.array_equal(a.read_clv(v, t), b.read_clv(v, t))   # DNA: op order mirrored -> bit-exact
+    e = int(net.ret_first_edge[0])
+    for eng in (a, b):
+        eng.brlen_prepare(e)
+        eng.computePartitionSumtables(e)
+    da, db = a.computeLoglikelihoodDerivatives(e), b.computeLoglikelihoodDerivatives(e)
+    assert da[0] == pytest.approx(db[0], rel=1e-10) and da[1] == pytest.approx(db[1], rel=1e-10)
+    assert a.computeLoglikelihoodBrlenOpt(e) == pytest.approx(b.computeLoglikelihoodBrlenOpt(e), rel=1e-13)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_scaler_stress_caterpillar(kind):
+    net = caterpillar_network(400)
+    m, w = simulate_alignment(net, 200, seed=11, random_cells=True)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    eng = oracle.make_engine(kind, net, [part])
+    l = eng.computeLoglikelihood(0, 1)
+    assert np.isfinite(l) and l < 0
+    mx = max(int(eng.read_scaler(net.root, t).max()) for t in range(eng.num_trees(net.root)))
+    assert mx >= 2
+    ln, _, _ = oracle.naive_loglikelihood(eng)
+    assert l == pytest.approx(ln, rel=1e-13)
+
+
+def test_multi_partition_unlinked_best():
+    net = random_network(10, 2, seed=3)
+    parts, brl = [], []
+    rng = np.random.default_rng(0)
+    for p in range(3):
+        m, w = simulate_alignment(net, 150, seed=20 + p)
+        parts.append(Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w))
+        brl.append(net.edge_length * rng.uniform(0.5, 2, net.num_edges))
+    eng = oracle.make_engine("port", net, parts, variant=BEST, linkage=UNLINKED, partition_brlens=brl)
+    l = eng.computeLoglikelihood(0, 1)
+    ln, _, _ = oracle.naive_loglikelihood(eng)
+    assert l == pytest.approx(ln, rel=1e-13)
+    assert l == pytest.approx(eng.partition_loglh().sum(), rel=1e-14)

@@ -1,0 +1,81 @@
+/*
+ * netrax_b200.h — host-level C-ABI of the B200 network-likelihood engine: NetRAX's likelihood API
+ * (netrax_b200/csrc/host/netrax_likelihood_api.hpp, same names as the reference) flattened to plain C so that
+ * any FFI (ctypes in this repo's tests / bench; a C++ NetRAX build links the C++ header directly) can drive it.
+ * Every function returns 1 on success, 0 on failure (message in nrxh_last_error(), the text of the
+ * std::runtime_error the reference would have thrown).
+ *
+ *   nrxh_compute_loglikelihood   <- netrax::computeLoglikelihood            src/likelihood/LikelihoodComputation.hpp:17
+ *   nrxh_brlen_prepare           <- extractOldTrees + getRestrictionsActiveAliveBranch + updateCLVsVirtualRerootTrees
+ *                                   (optimize_branch step 1, src/optimization/BranchLengthOptimization.cpp:355-373)
+ *   nrxh_brlen_logl              <- netrax::computeLoglikelihoodBrlenOpt    src/likelihood/VirtualRerooting.hpp:8
+ *   nrxh_brlen_sumtables         <- netrax::computePartitionSumtables       src/likelihood/LikelihoodDerivatives.hpp:86
+ *   nrxh_brlen_set_length        <- network_derivative_func_multi's proposal step (BranchLengthOptimization.cpp:176-187)
+ *   nrxh_brlen_derivatives       <- netrax::computeLoglikelihoodDerivatives src/likelihood/LikelihoodDerivatives.hpp:82
+ *   nrxh_brlen_finish            <- invalidatePmatrixIndex + computeLoglikelihood (BranchLengthOptimization.cpp:413-419)
+ *   nrxh_set_branch_length / nrxh_set_reticulation_prob / nrxh_set_model
+ *                                <- what optimize_branch / setReticulationProb / pll_set_* + invalidate do to the state
+ *   nrxh_set_reduce_callback     <- fake_treeinfo->parallel_reduce_cb        src/RaxmlWrapper.cpp:717-718
+ */
+#ifndef NETRAX_B200_H
+#define NETRAX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void (*nrxh_reduce_cb)(void *context, double *data, size_t count, int op /* 0 = SUM */);
+
+const char *nrxh_last_error(void);
+void *nrxh_new(const char *options /* "device=N;plan_cache=0|1" or NULL */);
+void nrxh_free(void *h);
+int nrxh_set_network(void *h, unsigned num_tips, unsigned num_nodes, unsigned root, unsigned num_edges, const unsigned *edge_source,
+                     const unsigned *edge_target, const double *edge_length, const double *edge_prob, unsigned num_reticulations,
+                     const unsigned *ret_node, const unsigned *ret_first_edge, const unsigned *ret_second_edge);
+int nrxh_add_partition(void *h, unsigned states, unsigned rate_cats, unsigned sites, const uint32_t *tip_masks,
+                       const unsigned *pattern_weights, const double *freqs, const double *subst_params, const double *rates,
+                       const double *rate_weights);
+int nrxh_set_options(void *h, int likelihood_variant /* 0 AVERAGE, 1 BEST */, int brlen_linkage /* 0 linked, 2 unlinked */);
+int nrxh_set_partition_brlens(void *h, unsigned p, const double *brlens);
+int nrxh_set_reduce_callback(void *h, nrxh_reduce_cb cb, void *context);
+int nrxh_init(void *h);
+int nrxh_compute_loglikelihood(void *h, int incremental, int update_pmatrices, double *out);
+unsigned nrxh_num_partitions(void *h);
+unsigned nrxh_root(void *h);
+unsigned nrxh_num_nodes(void *h);
+int nrxh_num_trees(void *h, unsigned node);
+int nrxh_tree_config(void *h, unsigned node, unsigned tree, char *buf, unsigned buflen);
+int nrxh_tree_info(void *h, unsigned node, unsigned tree, double *logprob, double *partition_logl, int *flags);
+int nrxh_read_clv(void *h, unsigned node, unsigned tree, unsigned p, double *out);
+int nrxh_read_scaler(void *h, unsigned node, unsigned tree, unsigned p, unsigned *out);
+int nrxh_partition_loglh(void *h, double *out);
+int nrxh_set_branch_length(void *h, int partition, unsigned edge, double value);
+int nrxh_set_reticulation_prob(void *h, unsigned r, double prob);
+int nrxh_set_model(void *h, unsigned p, const double *freqs, const double *subst_params, const double *rates, const double *rate_weights);
+int nrxh_get_eigen(void *h, unsigned p, double *eigenvecs, double *inv_eigenvecs, double *eigenvals);
+int nrxh_set_eigen(void *h, unsigned p, const double *eigenvecs, const double *inv_eigenvecs, const double *eigenvals);
+int nrxh_get_pmatrix(void *h, unsigned p, unsigned edge, double *out);
+int nrxh_brlen_prepare(void *h, unsigned edge, double *old_logl);
+int nrxh_brlen_logl(void *h, unsigned edge, double *out);
+int nrxh_brlen_sumtables(void *h, unsigned edge, unsigned *count);
+int nrxh_brlen_read_sumtable(void *h, unsigned p, unsigned idx, double *out, double *tree_prob, unsigned *left_tree, unsigned *right_tree);
+int nrxh_brlen_set_length(void *h, int partition, unsigned edge, double value);
+int nrxh_brlen_derivatives(void *h, unsigned edge, double *d1, double *d2, double *part_d1, double *part_d2, double *raw);
+int nrxh_brlen_finish(void *h, unsigned edge, double *final_logl);
+unsigned long long nrxh_clv_update_count(void *h);
+void nrxh_reset_counters(void *h);
+int nrxh_gamma_rates(double alpha, unsigned cats, int mode, double *out);
+/* bench / profiling hooks */
+unsigned long long nrxh_launch_count(void *h);
+unsigned nrxh_num_slots(void *h);
+int nrxh_profile_enable(void *h, int on);
+int nrxh_profile_read(void *h, double *clv_ms, unsigned long long *launches, unsigned long long *site_updates, unsigned long long *bytes);
+int nrxh_persite_lnl(void *h, unsigned tree, double *out /* [nparts][max_sites] */, unsigned stride);
+void *nrxh_engine(void *h); /* the underlying nrx_engine* */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,131 @@
+/*
+ * nrx_engine.h — C-ABI of the B200 (sm_100a) device engine for NetRAX's network-likelihood hot path.
+ *
+ * This is the lower seam of the drop-in: the entry points below replace, for ALL displayed
+ * trees of a network node at once, the seven explicit-pointer libpll calls NetRAX issues once per displayed
+ * tree, per node, per partition (LIBPLL = libs/raxml-ng/libs/pll-modules/libs/libpll/src in the reference):
+ *
+ *   nrx_update_pmatrices  <- pll_update_prob_matrices            LIBPLL/pll.h:731-735, models.c:412-443
+ *   nrx_update_clvs       <- pll_update_partials_single          LIBPLL/pll.h:798-806, partials.c:196-240
+ *   nrx_tree_lnl          <- pll_compute_root_loglikelihood      LIBPLL/pll.h:752-757, likelihood.c:122-184
+ *   nrx_edge_lnl          <- pll_compute_edge_loglikelihood      LIBPLL/pll.h:759-768, likelihood.c:555-615
+ *   nrx_sumtables         <- pll_update_sumtable                 LIBPLL/pll.h:815-823, derivatives.c:246-326
+ *   nrx_derivatives       <- pll_compute_diagptable + pll_compute_loglikelihood_derivatives
+ *                                                                LIBPLL/pll.h:830-842, core_derivatives.c:696-959
+ *   nrx_engine_create / nrx_set_tips / nrx_set_pattern_weights / nrx_set_model
+ *                         <- pll_partition_create, pll_set_tip_states, pll_set_pattern_weights and the
+ *                            model fields of pll_partition_t after pll_update_eigen (LIBPLL/pll.h:230-277,606-632)
+ *
+ * Conventions: plain C, no torch / C++ types; every call returns 1 on success and 0 on failure
+ * (PLL_SUCCESS / PLL_FAILURE, LIBPLL/pll.h:75-76) with a thread-local message in nrx_last_error()
+ * (mirrors __thread pll_errmsg, LIBPLL/pll.c:24-25).  A handle is single-threaded and stream-ordered;
+ * host pointers are borrowed for the duration of the call only; the engine owns all device memory.
+ * There is NO CPU fallback: every entry point fails if no CUDA device is usable.
+ *
+ * Data layout in HBM (per partition p):  CLV slot  = double[patterns][rate_cats][states_padded]
+ * (states_padded = (states+3)&~3, the libpll AVX layout: DNA+G4 = 128 B per pattern), scaler slot =
+ * uint32[patterns] (per-site scalers; PLL_ATTRIB_RATE_SCALERS is off in NetRAX, src/RaxmlWrapper.cpp:336),
+ * tips = uint8 codes [tips][patterns] (PATTERN_TIP), P-matrices = double[edges][cats][states][states_padded].
+ * A "slot" index addresses the same displayed-tree CLV in every partition, like the per-partition
+ * clv_vector[] of the reference's DisplayedTreeData (src/graph/DisplayedTreeData.hpp:18-42).
+ */
+#ifndef NRX_ENGINE_H
+#define NRX_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nrx_engine nrx_engine;
+
+typedef struct nrx_partition_desc {
+  uint32_t states;    /* 4 (DNA) or 20 (protein); anything <= 32 runs on the generic kernels */
+  uint32_t rate_cats; /* 1..16 */
+  uint32_t patterns;  /* LOCAL pattern count: this rank's slice of the partition (may be 0) */
+  uint32_t tips;
+  uint32_t edges;     /* number of P-matrices INCLUDING the fake zero-length one (network edges + 1) */
+} nrx_partition_desc;
+
+enum { NRX_CLV = 0, NRX_TIP = 1, NRX_NONE = 2 };
+
+/* One CLV update = one pll_operation_t (LIBPLL/pll.h:314-324) as built by src/likelihood/Operation.cpp:7-35,
+ * with the output / input CLVs named by slot instead of by host pointer.  kind NRX_NONE is the reference's
+ * "fake" all-ones CLV behind the fake identity P-matrix (ImprovedLoglikelihood.cpp:122,138-139). */
+typedef struct nrx_op {
+  uint32_t parent_slot;
+  uint32_t left_kind, left_idx, left_edge;    /* idx: slot (NRX_CLV) or tip number (NRX_TIP) */
+  uint32_t right_kind, right_idx, right_edge;
+  uint32_t reserved;
+} nrx_op;
+
+/* An (a, b) operand pair on one edge: (source-tree, target-tree) of computeLoglikelihoodBrlenOpt /
+ * computePartitionSumtables (src/likelihood/VirtualRerooting.cpp:403-439, LikelihoodDerivatives.cpp:312-341). */
+typedef struct nrx_pair {
+  uint32_t a_kind, a_idx, b_kind, b_idx;
+} nrx_pair;
+
+const char *nrx_last_error(void);
+int nrx_device_count(void);
+
+nrx_engine *nrx_engine_create(const nrx_partition_desc *parts, uint32_t nparts, int device);
+void nrx_engine_destroy(nrx_engine *e);
+
+/* tip_masks: [tips][patterns] state bit masks (bit k = state k; DNA 1..15).  Re-coded to uint8 on upload. */
+int nrx_set_tips(nrx_engine *e, uint32_t p, const uint32_t *tip_masks);
+int nrx_set_pattern_weights(nrx_engine *e, uint32_t p, const uint32_t *weights);
+/* eigenvecs / inv_eigenvecs: [states][states_padded]; eigenvals, freqs: [states_padded] (padding ignored);
+ * prop_invar must be 0 (+I partitions are rejected). */
+int nrx_set_model(nrx_engine *e, uint32_t p, const double *freqs, const double *eigenvecs,
+                  const double *inv_eigenvecs, const double *eigenvals, const double *rates,
+                  const double *rate_weights, double prop_invar);
+/* K1: P(t) for n edges of partition p in one launch. */
+int nrx_update_pmatrices(nrx_engine *e, uint32_t p, uint32_t n, const uint32_t *edge_idx, const double *brlen);
+int nrx_get_pmatrix(nrx_engine *e, uint32_t p, uint32_t edge, double *out);
+int nrx_set_pmatrix(nrx_engine *e, uint32_t p, uint32_t edge, const double *in); /* test hook */
+
+/* CLV / scaler slot pool (all partitions): makes slots [0, nslots) exist. */
+int nrx_reserve_slots(nrx_engine *e, uint32_t nslots);
+uint32_t nrx_num_slots(nrx_engine *e);
+int nrx_copy_slot(nrx_engine *e, uint32_t dst, uint32_t src); /* device-side deep copy (extractOldTrees etc.) */
+
+/* K2: ONE launch per same-shape partition group updating `nops` CLVs (all displayed trees of a node —
+ * or of several independent nodes — x patterns x rate categories).  The ops must be mutually independent. */
+int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops);
+
+/* K3: per-tree per-partition root lnL, out[n][nparts] (LOCAL sums: the caller all-reduces across ranks).
+ * persite (optional): [n] pointers-free layout out_persite[(i * nparts + p) * max_patterns + site]. */
+int nrx_tree_lnl(nrx_engine *e, const uint32_t *slots, uint32_t n, double *out, double *persite,
+                 size_t persite_stride);
+/* K4: edge lnL for n operand pairs over P-matrix `edge`, out[n][nparts]. */
+int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n, double *out);
+/* K5: sumtables for n pairs into sumtable slots [0, n) (pool grows on demand). */
+int nrx_sumtables(nrx_engine *e, const nrx_pair *pairs, uint32_t n);
+/* K6: for sumtable slots [0, n): out[n][nparts][3] = (f, d(-lnL)/dt, d2(-lnL)/dt2) at brlen[p]
+ * (f = sum w log lk0 without scaler term, the reference's AVX2 behaviour). */
+int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen_per_partition, double *out);
+
+/* parity/debug read-back */
+int nrx_read_clv(nrx_engine *e, uint32_t p, uint32_t slot, double *out);
+int nrx_read_scaler(nrx_engine *e, uint32_t p, uint32_t slot, uint32_t *out);
+int nrx_read_sumtable(nrx_engine *e, uint32_t p, uint32_t st_slot, double *out);
+int nrx_sync(nrx_engine *e);
+
+/* device-side access for callers that keep data on the GPU (NCCL all-reduce of the [n][nparts] results):
+ * the last nrx_tree_lnl / nrx_edge_lnl / nrx_derivatives result also stays in this device buffer. */
+void *nrx_result_device_ptr(nrx_engine *e);
+void *nrx_stream(nrx_engine *e); /* cudaStream_t */
+/* number of kernels launched by this engine so far (bench.py "gpu_launches") */
+unsigned long long nrx_launch_count(nrx_engine *e);
+/* device time (ms) spent in K2 launches since the last reset, measured with CUDA events on the engine
+ * stream when profiling is enabled (bench roofline) */
+int nrx_profile_enable(nrx_engine *e, int on);
+int nrx_profile_read(nrx_engine *e, double *clv_ms, unsigned long long *clv_launches, unsigned long long *clv_site_updates,
+                     unsigned long long *clv_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

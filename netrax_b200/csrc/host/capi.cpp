@@ -1,0 +1,357 @@
+/* capi.cpp — include/netrax_b200.h over netrax_likelihood_api.hpp (exceptions -> status + message). */
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../../include/netrax_b200.h"
+#include "host_internal.hpp"
+
+using namespace netrax;
+
+namespace {
+thread_local std::string g_err;
+
+struct Handle {
+  AnnotatedNetwork ann;
+  std::vector<PartitionInput> inputs;
+  std::vector<std::vector<uint32_t>> masks, weights;
+  std::vector<std::vector<double>> part_brlens;
+  int device = 0;
+  bool net_set = false, inited = false;
+  std::vector<DisplayedTreeData> oldTrees;
+  std::vector<std::vector<SumtableInfo>> sumtables;
+};
+
+template <class F> int guarded(F &&f) {
+  try { f(); return 1; }
+  catch (const std::exception &e) { g_err = e.what(); return 0; }
+  catch (...) { g_err = "unknown error"; return 0; }
+}
+Handle *H(void *h) { return static_cast<Handle *>(h); }
+}  // namespace
+
+extern "C" {
+
+const char *nrxh_last_error(void) { return g_err.c_str(); }
+
+void *nrxh_new(const char *options) {
+  Handle *h = new Handle();
+  if (options) {
+    std::string o(options);
+    size_t p = o.find("device=");
+    if (p != std::string::npos) h->device = std::atoi(o.c_str() + p + 7);
+    p = o.find("plan_cache=");
+    if (p != std::string::npos) h->ann.use_plan_cache = std::atoi(o.c_str() + p + 11) != 0;
+  }
+  return h;
+}
+
+void nrxh_free(void *h) { delete H(h); }
+
+int nrxh_set_network(void *hv, unsigned num_tips, unsigned num_nodes, unsigned root, unsigned num_edges, const unsigned *src,
+                     const unsigned *tgt, const double *len, const double *prob, unsigned num_ret, const unsigned *ret_node,
+                     const unsigned *ret_first, const unsigned *ret_second) {
+  return guarded([&] {
+    std::vector<Edge> edges(num_edges);
+    for (unsigned e = 0; e < num_edges; ++e) { edges[e].source = src[e]; edges[e].target = tgt[e]; edges[e].length = len[e]; edges[e].prob = prob ? prob[e] : 1.0; }
+    std::vector<size_t> rn(ret_node, ret_node + num_ret), rf(ret_first, ret_first + num_ret), rs(ret_second, ret_second + num_ret);
+    H(hv)->ann.network = buildNetwork(num_tips, num_nodes, root, edges, rn, rf, rs);
+    // nodes_by_index etc. point into the moved-from vectors' storage: rebuild the pointer tables
+    Network &nw = H(hv)->ann.network;
+    for (size_t i = 0; i < nw.nodes.size(); ++i) nw.nodes_by_index[i] = &nw.nodes[i];
+    for (size_t i = 0; i < nw.edges.size(); ++i) nw.edges_by_index[i] = &nw.edges[i];
+    for (size_t i = 0; i < nw.reticulations.size(); ++i) nw.reticulation_nodes[i] = &nw.nodes[nw.reticulations[i].node];
+    nw.root = &nw.nodes[root];
+    H(hv)->net_set = true;
+  });
+}
+
+int nrxh_add_partition(void *hv, unsigned states, unsigned rate_cats, unsigned sites, const uint32_t *tip_masks, const unsigned *pw,
+                       const double *freqs, const double *subst, const double *rates, const double *rate_weights) {
+  return guarded([&] {
+    Handle *h = H(hv);
+    if (!h->net_set) throw std::runtime_error("set the network first");
+    PartitionInput in;
+    in.model.states = states; in.model.rate_cats = rate_cats; in.model.sites = sites;
+    in.model.frequencies.assign(freqs, freqs + states);
+    in.model.subst_params.assign(subst, subst + states * (states - 1) / 2);
+    in.model.rates.assign(rates, rates + rate_cats);
+    in.model.rate_weights.assign(rate_weights, rate_weights + rate_cats);
+    h->masks.emplace_back(tip_masks, tip_masks + (size_t)h->ann.network.num_tips() * sites);
+    h->weights.emplace_back(pw ? std::vector<uint32_t>(pw, pw + sites) : std::vector<uint32_t>());
+    h->inputs.push_back(in);
+  });
+}
+
+int nrxh_set_options(void *hv, int variant, int linkage) {
+  H(hv)->ann.options.likelihood_variant = variant ? LikelihoodVariant::BEST_DISPLAYED_TREE : LikelihoodVariant::AVERAGE_DISPLAYED_TREES;
+  H(hv)->ann.options.brlen_linkage = linkage;
+  return 1;
+}
+
+int nrxh_set_partition_brlens(void *hv, unsigned p, const double *brlens) {
+  return guarded([&] {
+    Handle *h = H(hv);
+    const size_t E = h->ann.network.num_branches();
+    if (h->part_brlens.size() <= p) h->part_brlens.resize(p + 1);
+    h->part_brlens[p].assign(brlens, brlens + E);
+    h->part_brlens[p].push_back(0.0);
+    if (h->inited) {
+      h->ann.fake_treeinfo->branch_lengths[p] = h->part_brlens[p];
+      for (size_t e = 0; e < E; ++e) h->ann.fake_treeinfo->pmatrix_valid[p][e] = 0;
+      invalidateAllCLVs(h->ann);
+    }
+  });
+}
+
+int nrxh_set_reduce_callback(void *hv, nrxh_reduce_cb cb, void *ctx) {
+  H(hv)->ann.fake_treeinfo->parallel_reduce_cb = cb;
+  H(hv)->ann.fake_treeinfo->parallel_context = ctx;
+  return 1;
+}
+
+int nrxh_init(void *hv) {
+  return guarded([&] {
+    Handle *h = H(hv);
+    for (size_t p = 0; p < h->inputs.size(); ++p) {
+      h->inputs[p].tip_masks = h->masks[p].data();
+      h->inputs[p].pattern_weights = h->weights[p].empty() ? nullptr : h->weights[p].data();
+    }
+    if (!h->part_brlens.empty()) {
+      std::vector<double> linked(h->ann.network.num_branches() + 1, 0.0);
+      for (size_t e = 0; e < h->ann.network.num_branches(); ++e) linked[e] = h->ann.network.edges[e].length;
+      h->ann.fake_treeinfo->branch_lengths.assign(h->inputs.size(), linked);
+      for (size_t p = 0; p < h->part_brlens.size() && p < h->inputs.size(); ++p)
+        if (!h->part_brlens[p].empty()) h->ann.fake_treeinfo->branch_lengths[p] = h->part_brlens[p];
+    }
+    init_annotated_network(h->ann, h->inputs, h->device);
+    h->masks.clear(); h->masks.shrink_to_fit();
+    h->inited = true;
+  });
+}
+
+int nrxh_compute_loglikelihood(void *hv, int incremental, int update_pmatrices, double *out) {
+  return guarded([&] { *out = computeLoglikelihood(H(hv)->ann, incremental, update_pmatrices); });
+}
+
+unsigned nrxh_num_partitions(void *hv) { return H(hv)->ann.fake_treeinfo->partition_count; }
+unsigned nrxh_root(void *hv) { return (unsigned)H(hv)->ann.network.root->clv_index; }
+unsigned nrxh_num_nodes(void *hv) { return (unsigned)H(hv)->ann.network.num_nodes(); }
+int nrxh_num_trees(void *hv, unsigned node) { return (int)H(hv)->ann.pernode_displayed_tree_data[node].num_active_displayed_trees; }
+
+int nrxh_tree_config(void *hv, unsigned node, unsigned tree, char *buf, unsigned buflen) {
+  return guarded([&] {
+    std::string s = toString(H(hv)->ann.pernode_displayed_tree_data[node].displayed_trees.at(tree).treeLoglData.reticulationChoices, H(hv)->ann.network.num_reticulations());
+    std::snprintf(buf, buflen, "%s", s.c_str());
+  });
+}
+
+int nrxh_tree_info(void *hv, unsigned node, unsigned tree, double *logprob, double *partition_logl, int *flags) {
+  return guarded([&] {
+    const DisplayedTreeData &d = H(hv)->ann.pernode_displayed_tree_data[node].displayed_trees.at(tree);
+    if (logprob) *logprob = d.treeLoglData.tree_logprob;
+    if (partition_logl) std::copy(d.treeLoglData.tree_partition_logl.begin(), d.treeLoglData.tree_partition_logl.end(), partition_logl);
+    if (flags) *flags = (d.clv_valid ? 1 : 0) | (d.treeLoglData.tree_logl_valid ? 2 : 0) | (d.treeLoglData.tree_logprob_valid ? 4 : 0);
+  });
+}
+
+int nrxh_read_clv(void *hv, unsigned node, unsigned tree, unsigned p, double *out) {
+  return guarded([&] {
+    detail::flushPendingOps(H(hv)->ann);
+    const DisplayedTreeData &d = H(hv)->ann.pernode_displayed_tree_data[node].displayed_trees.at(tree);
+    if (d.isTip) throw std::runtime_error("tips have no CLV (PATTERN_TIP)");
+    detail::engineCheck(nrx_read_clv(H(hv)->ann.engine, p, d.slot, out), "nrx_read_clv");
+  });
+}
+
+int nrxh_read_scaler(void *hv, unsigned node, unsigned tree, unsigned p, unsigned *out) {
+  return guarded([&] {
+    detail::flushPendingOps(H(hv)->ann);
+    const DisplayedTreeData &d = H(hv)->ann.pernode_displayed_tree_data[node].displayed_trees.at(tree);
+    if (d.isTip) throw std::runtime_error("tips have no scaler");
+    detail::engineCheck(nrx_read_scaler(H(hv)->ann.engine, p, d.slot, out), "nrx_read_scaler");
+  });
+}
+
+int nrxh_partition_loglh(void *hv, double *out) {
+  const auto &v = H(hv)->ann.fake_treeinfo->partition_loglh;
+  std::copy(v.begin(), v.end(), out);
+  return 1;
+}
+
+static void setBranchLength(AnnotatedNetwork &ann, int partition, unsigned edge, double value) {
+  FakeTreeinfo &ti = *ann.fake_treeinfo;
+  if (partition < 0) {
+    ti.linked_branch_lengths[edge] = value;
+    for (auto &b : ti.branch_lengths) b[edge] = value;
+  } else {
+    ti.branch_lengths.at(partition)[edge] = value;
+  }
+}
+
+int nrxh_set_branch_length(void *hv, int partition, unsigned edge, double value) {
+  return guarded([&] { setBranchLength(H(hv)->ann, partition, edge, value); invalidatePmatrixIndex(H(hv)->ann, edge); });
+}
+
+int nrxh_set_reticulation_prob(void *hv, unsigned r, double prob) {
+  return guarded([&] { setReticulationProb(H(hv)->ann, r, prob); });
+}
+
+static void pushModel(AnnotatedNetwork &ann, unsigned p) {
+  PartitionModel &m = ann.fake_treeinfo->partitions.at(p);
+  if (!m.eigen_decomp_valid) update_eigen(m);
+  std::vector<double> freqs(m.states_padded, 0.0);
+  std::copy(m.frequencies.begin(), m.frequencies.begin() + m.states, freqs.begin());
+  detail::engineCheck(nrx_set_model(ann.engine, p, freqs.data(), m.eigenvecs.data(), m.inv_eigenvecs.data(), m.eigenvals.data(), m.rates.data(), m.rate_weights.data(), 0.0), "nrx_set_model");
+  for (auto &v : ann.fake_treeinfo->pmatrix_valid[p]) v = 0;
+  invalidateAllCLVs(ann);
+}
+
+int nrxh_set_model(void *hv, unsigned p, const double *freqs, const double *subst, const double *rates, const double *rw) {
+  return guarded([&] {
+    AnnotatedNetwork &ann = H(hv)->ann;
+    PartitionModel &m = ann.fake_treeinfo->partitions.at(p);
+    m.frequencies.assign(freqs, freqs + m.states);
+    m.subst_params.assign(subst, subst + m.states * (m.states - 1) / 2);
+    m.rates.assign(rates, rates + m.rate_cats);
+    m.rate_weights.assign(rw, rw + m.rate_cats);
+    m.eigen_decomp_valid = false;  // pll_set_* clear eigen_decomp_valid; recomputed before the next P-matrix update
+    pushModel(ann, p);
+  });
+}
+
+int nrxh_get_eigen(void *hv, unsigned p, double *ev, double *iev, double *evals) {
+  return guarded([&] {
+    const PartitionModel &m = H(hv)->ann.fake_treeinfo->partitions.at(p);
+    std::copy(m.eigenvecs.begin(), m.eigenvecs.end(), ev);
+    std::copy(m.inv_eigenvecs.begin(), m.inv_eigenvecs.end(), iev);
+    std::copy(m.eigenvals.begin(), m.eigenvals.end(), evals);
+  });
+}
+
+int nrxh_set_eigen(void *hv, unsigned p, const double *ev, const double *iev, const double *evals) {
+  return guarded([&] {
+    AnnotatedNetwork &ann = H(hv)->ann;
+    PartitionModel &m = ann.fake_treeinfo->partitions.at(p);
+    m.eigenvecs.assign(ev, ev + (size_t)m.states * m.states_padded);
+    m.inv_eigenvecs.assign(iev, iev + (size_t)m.states * m.states_padded);
+    m.eigenvals.assign(evals, evals + m.states_padded);
+    m.eigen_decomp_valid = true;
+    pushModel(ann, p);
+  });
+}
+
+int nrxh_get_pmatrix(void *hv, unsigned p, unsigned edge, double *out) {
+  return guarded([&] { detail::engineCheck(nrx_get_pmatrix(H(hv)->ann.engine, p, edge, out), "nrx_get_pmatrix"); });
+}
+
+int nrxh_brlen_prepare(void *hv, unsigned edge, double *old_logl) {
+  return guarded([&] {
+    Handle *h = H(hv);
+    AnnotatedNetwork &ann = h->ann;
+    const double l = computeLoglikelihood(ann, 1, 1);
+    if (old_logl) *old_logl = l;
+    h->oldTrees = extractOldTrees(ann, ann.network.root);
+    ReticulationConfigSet restrictions = getRestrictionsActiveAliveBranch(ann, edge);
+    updateCLVsVirtualRerootTrees(ann, ann.network.root, &ann.network.nodes[ann.network.edges.at(edge).source],
+                                 &ann.network.nodes[ann.network.edges.at(edge).target], restrictions);
+    ann.cached_logl_valid = false;
+  });
+}
+
+int nrxh_brlen_logl(void *hv, unsigned edge, double *out) {
+  return guarded([&] {
+    H(hv)->ann.cached_logl_valid = false;
+    *out = computeLoglikelihoodBrlenOpt(H(hv)->ann, H(hv)->oldTrees, edge, 1);
+  });
+}
+
+int nrxh_brlen_sumtables(void *hv, unsigned edge, unsigned *count) {
+  return guarded([&] {
+    H(hv)->sumtables = computePartitionSumtables(H(hv)->ann, edge);
+    if (count) *count = H(hv)->sumtables.empty() ? 0 : (unsigned)H(hv)->sumtables[0].size();
+  });
+}
+
+int nrxh_brlen_read_sumtable(void *hv, unsigned p, unsigned idx, double *out, double *tree_prob, unsigned *lt, unsigned *rt) {
+  return guarded([&] {
+    const SumtableInfo &s = H(hv)->sumtables.at(p).at(idx);
+    if (out) detail::engineCheck(nrx_read_sumtable(H(hv)->ann.engine, p, s.index, out), "nrx_read_sumtable");
+    if (tree_prob) *tree_prob = s.tree_prob;
+    if (lt) *lt = (unsigned)s.left_tree_idx;
+    if (rt) *rt = (unsigned)s.right_tree_idx;
+  });
+}
+
+int nrxh_brlen_set_length(void *hv, int partition, unsigned edge, double value) {
+  return guarded([&] {
+    AnnotatedNetwork &ann = H(hv)->ann;
+    if (ann.options.brlen_linkage == PLLMOD_COMMON_BRLEN_UNLINKED && partition >= 0) ann.fake_treeinfo->branch_lengths.at(partition)[edge] = value;
+    else setBranchLength(ann, -1, edge, value);
+    invalidPmatrixIndexOnly(ann, edge);
+  });
+}
+
+int nrxh_brlen_derivatives(void *hv, unsigned edge, double *d1, double *d2, double *pd1, double *pd2, double *raw) {
+  return guarded([&] {
+    Handle *h = H(hv);
+    const LoglDerivatives r = computeLoglikelihoodDerivatives(h->ann, h->sumtables, edge);
+    if (d1) *d1 = r.logl_prime;
+    if (d2) *d2 = r.logl_prime_prime;
+    if (pd1) std::copy(r.partition_logl_prime.begin(), r.partition_logl_prime.end(), pd1);
+    if (pd2) std::copy(r.partition_logl_prime_prime.begin(), r.partition_logl_prime_prime.end(), pd2);
+    if (raw) {
+      const size_t n = h->sumtables.empty() ? 0 : h->sumtables[0].size();
+      for (size_t p = 0; p < r.raw.size(); ++p)
+        for (size_t k = 0; k < r.raw[p].size(); ++k) raw[p * 3 * n + k] = r.raw[p][k];
+    }
+  });
+}
+
+int nrxh_brlen_finish(void *hv, unsigned edge, double *final_logl) {
+  return guarded([&] {
+    Handle *h = H(hv);
+    h->sumtables.clear();
+    h->oldTrees.clear();
+    invalidatePmatrixIndex(h->ann, edge);
+    const double l = computeLoglikelihood(h->ann, 1, 1);
+    if (final_logl) *final_logl = l;
+  });
+}
+
+unsigned long long nrxh_clv_update_count(void *hv) { return H(hv)->ann.clv_site_updates; }
+void nrxh_reset_counters(void *hv) { H(hv)->ann.clv_site_updates = 0; }
+int nrxh_gamma_rates(double alpha, unsigned cats, int mode, double *out) {
+  if (!compute_gamma_cats(alpha, cats, out, mode)) { g_err = "Invalid alpha value / GAMMA discretization mode"; return 0; }
+  return 1;
+}
+unsigned long long nrxh_launch_count(void *hv) { return nrx_launch_count(H(hv)->ann.engine); }
+unsigned nrxh_num_slots(void *hv) { return H(hv)->ann.next_slot; }
+int nrxh_profile_enable(void *hv, int on) { return nrx_profile_enable(H(hv)->ann.engine, on); }
+int nrxh_profile_read(void *hv, double *ms, unsigned long long *l, unsigned long long *u, unsigned long long *b) {
+  if (!nrx_profile_read(H(hv)->ann.engine, ms, l, u, b)) { g_err = nrx_last_error(); return 0; }
+  return 1;
+}
+int nrxh_persite_lnl(void *hv, unsigned tree, double *out, unsigned stride) {
+  return guarded([&] {
+    AnnotatedNetwork &ann = H(hv)->ann;
+    detail::flushPendingOps(ann);
+    NodeDisplayedTreeData &rd = ann.pernode_displayed_tree_data[ann.network.root->clv_index];
+    DisplayedTreeData &t = rd.displayed_trees.at(tree);
+    detail::setReticulationParents(ann.network, t.treeLoglData.reticulationChoices.configs[0]);
+    size_t dtr = ann.network.root->clv_index;
+    detail::collect_dead_nodes(ann.network, dtr, &dtr);
+    NodeDisplayedTreeData &dd = ann.pernode_displayed_tree_data[dtr];
+    uint32_t slot = UINT32_MAX;
+    for (size_t k = 0; k < dd.num_active_displayed_trees; ++k)
+      if (reticulationConfigsCompatible(t.treeLoglData.reticulationChoices, dd.displayed_trees[k].treeLoglData.reticulationChoices)) slot = dd.displayed_trees[k].slot;
+    if (slot == UINT32_MAX) throw std::runtime_error("Found no suitable displayed tree");
+    std::vector<double> tmp(ann.fake_treeinfo->partition_count);
+    detail::engineCheck(nrx_tree_lnl(ann.engine, &slot, 1, tmp.data(), out, stride), "nrx_tree_lnl");
+  });
+}
+void *nrxh_engine(void *hv) { return H(hv)->ann.engine; }
+
+}  // extern "C"

@@ -1,0 +1,29 @@
+/* host_internal.hpp — helpers shared by the host translation units (not part of the public API). */
+#pragma once
+#include "netrax_likelihood_api.hpp"
+
+namespace netrax {
+namespace detail {
+size_t edgeBetween(const Network &nw, size_t a, size_t b);
+size_t activeParent(const Network &nw, size_t n);
+std::vector<size_t> activeAliveChildren(const Network &nw, const std::vector<char> &dead, size_t n);
+std::vector<size_t> activeNeighbors(const Network &nw, size_t n);
+std::vector<char> collect_dead_nodes(const Network &nw, size_t megablobRoot, size_t *displayed_tree_root);
+void setReticulationParents(Network &nw, const ReticulationConfig &c);
+
+ReticulationConfigSet getRestrictionsToTakeNeighbor(AnnotatedNetwork &ann, size_t node, size_t neighbor);
+ReticulationConfigSet getRestrictionsToDismissNeighbor(AnnotatedNetwork &ann, size_t node, size_t neighbor);
+ReticulationConfigSet getTreeConfig(AnnotatedNetwork &ann, size_t tree_idx);
+bool isActiveBranch(AnnotatedNetwork &ann, const ReticulationConfigSet &rc, size_t pmatrix_index);
+bool isActiveAliveBranch(AnnotatedNetwork &ann, const ReticulationConfigSet &rc, size_t pmatrix_index);
+bool clvValidCheck(AnnotatedNetwork &ann, size_t virtual_root, bool care_about_trees = true);
+void flushPendingOps(AnnotatedNetwork &ann);
+void engineCheck(int ok, const char *what);
+uint32_t allocSlot(AnnotatedNetwork &ann);
+void releaseSlot(AnnotatedNetwork &ann, uint32_t slot);
+nrx_pair makePair(const DisplayedTreeData &a, const DisplayedTreeData &b);
+void reduceSum(AnnotatedNetwork &ann, double *data, size_t count);
+/* log(sum_t exp(a_t)) and friends without leaving double range (stands in for mpfr::mpreal) */
+double logSumExp(const std::vector<double> &a);
+}  // namespace detail
+}  // namespace netrax

@@ -1,0 +1,251 @@
+/*
+ * netrax_likelihood_api.hpp — the UPPER SEAM of the drop-in: NetRAX's likelihood API with the
+ * reference's own names, argument meaning and error behaviour (std::runtime_error), re-implemented on top of
+ * the B200 device engine (include/nrx_engine.h).  Callers in src/optimization, src/search and pll-modules'
+ * optimisers (through likelihood_target_function) use exactly these entry points:
+ *
+ *   computeLoglikelihood            src/likelihood/LikelihoodComputation.hpp:17-18
+ *   computeLoglikelihoodBrlenOpt    src/likelihood/VirtualRerooting.hpp:8-12
+ *   updateCLVsVirtualRerootTrees    src/likelihood/VirtualRerooting.hpp:13-16
+ *   computePartitionSumtables       src/likelihood/LikelihoodDerivatives.hpp:86-87
+ *   computeLoglikelihoodDerivatives src/likelihood/LikelihoodDerivatives.hpp:82-85
+ *   evaluateTreesPartition          src/likelihood/ImprovedLoglikelihood.hpp:10-14
+ *   invalidate* / allClvsValid      src/helper/Helper.hpp (InvalidationHelper.cpp)
+ *
+ * What differs from the reference, by design:
+ *   - a displayed tree's CLV / scaler live in a device SLOT (all partitions), not in host vectors;
+ *   - the (child-tree, child-tree) enumeration of processNodeImproved emits nrx_op records and ONE launch
+ *     covers all displayed trees of a node (independent nodes are batched into the same launch);
+ *   - per-tree root / edge lnLs of ALL trees are reduced in one kernel + one parallel_reduce_cb call instead
+ *     of one call per tree;
+ *   - reticulation configurations are (care, value) bit masks instead of enum vectors;
+ *   - mpfr::mpreal (53 bit) is replaced by max-shifted double arithmetic.
+ * Topology surgery (moves), I/O, search and the optimisers themselves are callers and out of scope.
+ */
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/nrx_engine.h"
+
+namespace netrax {
+
+/* ---- src/graph/ReticulationConfigSet.hpp --------------------------------------------------------- */
+enum class ReticulationState { DONT_CARE = 0, TAKE_FIRST_PARENT = 1, TAKE_SECOND_PARENT = 2, INVALID = 3 };
+
+struct ReticulationConfig {  // one vector<ReticulationState> of the reference, as bit masks
+  uint32_t care = 0;         // bit i set: reticulation i is fixed
+  uint32_t second = 0;       // bit i set (only where care): TAKE_SECOND_PARENT, else TAKE_FIRST_PARENT
+  bool operator==(const ReticulationConfig &o) const { return care == o.care && second == o.second; }
+  ReticulationState operator[](size_t i) const {
+    return !((care >> i) & 1) ? ReticulationState::DONT_CARE
+                              : (((second >> i) & 1) ? ReticulationState::TAKE_SECOND_PARENT : ReticulationState::TAKE_FIRST_PARENT);
+  }
+};
+
+struct ReticulationConfigSet {  // a big OR of configurations
+  std::vector<ReticulationConfig> configs;
+  size_t max_reticulations = 0;
+  ReticulationConfigSet() = default;
+  explicit ReticulationConfigSet(size_t m) : max_reticulations(m) {}
+  bool empty() const { return configs.empty(); }
+  bool operator==(const ReticulationConfigSet &o) const;
+};
+
+double computeReticulationConfigProb(const ReticulationConfigSet &c, const std::vector<double> &first, const std::vector<double> &second);
+double computeReticulationConfigLogProb(const ReticulationConfigSet &c, const std::vector<double> &first, const std::vector<double> &second);
+bool reticulationConfigsCompatible(const ReticulationConfigSet &l, const ReticulationConfigSet &r);
+ReticulationConfigSet combineReticulationChoices(const ReticulationConfigSet &l, const ReticulationConfigSet &r);
+void simplifyReticulationChoices(ReticulationConfigSet &res);
+std::string toString(const ReticulationConfigSet &c, size_t n_reticulations);
+
+/* ---- src/graph/{Node,Edge,Network}.hpp: the fields the likelihood layer reads ------------------------ */
+enum class NodeType { BASIC_NODE = 0, RETICULATION_NODE = 1 };
+
+struct Node {
+  size_t clv_index = 0;
+  NodeType type = NodeType::BASIC_NODE;
+  size_t reticulation_index = 0;          // getReticulationData()->reticulation_index
+  std::vector<size_t> parents;            // clv indices; reticulation: {first, second}
+  std::vector<size_t> children;           // by ascending pmatrix index
+  std::vector<size_t> neighbors;          // parents first, then children (the reference's link order)
+  NodeType getType() const { return type; }
+};
+
+struct Edge {
+  size_t pmatrix_index = 0;
+  size_t source = 0, target = 0;  // getSource / getTarget
+  double length = 0.0, prob = 1.0;
+};
+
+struct ReticulationInfo { size_t node, first_parent, second_parent, child, first_edge, second_edge; };
+
+struct Network {
+  std::vector<Node> nodes;
+  std::vector<Edge> edges;
+  std::vector<Node *> nodes_by_index;
+  std::vector<Edge *> edges_by_index;
+  std::vector<Node *> reticulation_nodes;
+  std::vector<ReticulationInfo> reticulations;
+  std::vector<unsigned char> active_parent_toggle;  // ReticulationData::active_parent_toggle (stateful)
+  Node *root = nullptr;
+  size_t tipCount = 0;
+  size_t num_tips() const { return tipCount; }
+  size_t num_nodes() const { return nodes.size(); }
+  size_t num_branches() const { return edges.size(); }
+  size_t num_reticulations() const { return reticulations.size(); }
+};
+
+Network buildNetwork(size_t num_tips, size_t num_nodes, size_t root, const std::vector<Edge> &edges,
+                     const std::vector<size_t> &ret_node, const std::vector<size_t> &ret_first_edge,
+                     const std::vector<size_t> &ret_second_edge);
+std::vector<Node *> reversed_topological_sort(Network &network);  // src/helper/NetworkFunctions.cpp:542-598
+
+/* ---- src/likelihood/LikelihoodVariant.hpp, src/NetraxOptions.hpp ---------------------------------------- */
+enum class LikelihoodVariant { AVERAGE_DISPLAYED_TREES = 0, BEST_DISPLAYED_TREE = 1, SARAH_PSEUDO = 2 };
+enum { PLLMOD_COMMON_BRLEN_LINKED = 0, PLLMOD_COMMON_BRLEN_SCALED = 1, PLLMOD_COMMON_BRLEN_UNLINKED = 2 };
+enum { PLLMOD_COMMON_REDUCE_SUM = 0, PLLMOD_COMMON_REDUCE_MAX = 1, PLLMOD_COMMON_REDUCE_MIN = 2 };
+
+struct NetraxOptions {
+  LikelihoodVariant likelihood_variant = LikelihoodVariant::AVERAGE_DISPLAYED_TREES;
+  int brlen_linkage = PLLMOD_COMMON_BRLEN_LINKED;
+  size_t max_reticulations = 32;
+  double min_interesting_tree_logprob = -13.815510557964274;  // log(1e-6), NetraxOptions.hpp:108
+  double brlen_min = 1e-6, brlen_max = 100.0;
+  bool save_memory = false;
+};
+
+/* ---- per-partition model: the fields of pll_partition_t the path reads -------------------------------- */
+struct PartitionModel {
+  unsigned states = 4, states_padded = 4, rate_cats = 4, sites = 0;
+  std::vector<double> frequencies, subst_params, rates, rate_weights;
+  std::vector<double> eigenvecs, inv_eigenvecs, eigenvals;  // filled by update_eigen (own Jacobi solver) or set explicitly
+  bool eigen_decomp_valid = false;
+};
+void update_eigen(PartitionModel &m);                                                 // role of pll_update_eigen
+bool compute_gamma_cats(double alpha, unsigned cats, double *out_rates, int mode);    // role of pll_compute_gamma_cats
+
+/* ---- the "fake treeinfo": the fields of pllmod_treeinfo_t (PLLMOD/tree/pll_tree.h:208-279) in use ------ */
+struct FakeTreeinfo {
+  unsigned partition_count = 0;
+  std::vector<PartitionModel> partitions;
+  std::vector<std::vector<double>> branch_lengths;   // [partition][edge + 1 fake]
+  std::vector<double> linked_branch_lengths;         // [edge + 1 fake]
+  int brlen_linkage = PLLMOD_COMMON_BRLEN_LINKED;
+  std::vector<double> partition_loglh;
+  std::vector<std::vector<char>> clv_valid;          // [partition][node]
+  std::vector<std::vector<char>> pmatrix_valid;      // [partition][edge + 1 fake]
+  /* pllmod's reduction hook (PLLMOD/tree/pll_tree.h:262-266): SUM over all site shards (ranks). */
+  void (*parallel_reduce_cb)(void *context, double *data, size_t count, int op) = nullptr;
+  void *parallel_context = nullptr;
+};
+
+/* ---- src/graph/{TreeLoglData,DisplayedTreeData,NodeDisplayedTreeData}.hpp ------------------------------ */
+struct TreeLoglData {
+  ReticulationConfigSet reticulationChoices;
+  double tree_logprob = 0.0;
+  bool tree_logprob_valid = false;
+  std::vector<double> tree_partition_logl;
+  bool tree_logl_valid = false;
+  TreeLoglData() = default;
+  TreeLoglData(size_t n_partitions, size_t max_reticulations) : reticulationChoices(max_reticulations), tree_partition_logl(n_partitions, 0.0) {}
+};
+
+struct DisplayedTreeData {
+  TreeLoglData treeLoglData;
+  uint32_t slot = UINT32_MAX;  // device CLV + scaler slot (replaces clv_vector / scale_buffer host pointers)
+  bool clv_valid = false;
+  bool isTip = false;
+  uint32_t tip = 0;
+};
+
+struct NodeDisplayedTreeData {
+  std::vector<DisplayedTreeData> displayed_trees;
+  size_t num_active_displayed_trees = 0;
+};
+
+struct SumtableInfo {  // src/likelihood/LikelihoodDerivatives.hpp:9-74; the table itself is device sumtable slot `index`
+  double tree_prob = 0.0;
+  uint32_t index = 0;
+  size_t left_tree_idx = 0, right_tree_idx = 0;
+};
+
+struct LoglDerivatives {
+  double logl_prime = std::numeric_limits<double>::infinity();
+  double logl_prime_prime = std::numeric_limits<double>::infinity();
+  std::vector<double> partition_logl_prime, partition_logl_prime_prime;
+  std::vector<std::vector<double>> raw;  // [partition][3 * sumtable]: (f, d1, d2) per displayed-tree pair
+};
+
+struct PlanCache;  // cached evaluation plan (ops per launch) for unchanged topology
+
+struct AnnotatedNetwork {  // src/graph/AnnotatedNetwork.hpp:42-89
+  NetraxOptions options;
+  Network network;
+  FakeTreeinfo fake_treeinfo_storage;
+  FakeTreeinfo *fake_treeinfo = &fake_treeinfo_storage;
+  std::vector<double> reticulation_probs, first_parent_logprobs, second_parent_logprobs;
+  std::vector<NodeDisplayedTreeData> pernode_displayed_tree_data;
+  std::vector<Node *> travbuffer;
+  double cached_logl = 0.0;
+  bool cached_logl_valid = false;
+
+  /* device side */
+  nrx_engine *engine = nullptr;
+  uint32_t next_slot = 0;
+  std::vector<uint32_t> free_slots;
+  std::vector<nrx_op> pending_ops;            // ops of the launch being assembled
+  std::vector<char> pending_parent;           // [node] 1 if the node's trees are outputs of pending_ops
+  PlanCache *plan = nullptr;
+  bool use_plan_cache = true;
+  uint64_t clv_site_updates = 0;              // Σ trees × local patterns actually launched
+  ~AnnotatedNetwork();
+  AnnotatedNetwork() = default;
+  AnnotatedNetwork(const AnnotatedNetwork &) = delete;
+  AnnotatedNetwork &operator=(const AnnotatedNetwork &) = delete;
+};
+
+/* set-up: role of init_annotated_network (src/graph/AnnotatedNetwork.cpp:80-185) + createNetworkPllTreeinfo */
+struct PartitionInput {
+  PartitionModel model;
+  const uint32_t *tip_masks = nullptr;        // [tips][sites]
+  const uint32_t *pattern_weights = nullptr;  // [sites] or null
+};
+void init_annotated_network(AnnotatedNetwork &ann, const std::vector<PartitionInput> &parts, int device);
+void topology_changed(AnnotatedNetwork &ann);  // callers that edit the topology must call this (drops the plan cache)
+
+/* ---- the likelihood API --------------------------------------------------------------------------------- */
+double computeLoglikelihood(AnnotatedNetwork &ann_network, int incremental = 1, int update_pmatrices = 1);
+double computeLoglikelihoodImproved(AnnotatedNetwork &ann_network, int incremental, int update_pmatrices);
+void processNodeImproved(AnnotatedNetwork &ann_network, int incremental, Node *node, std::vector<Node *> &children,
+                         const ReticulationConfigSet &extraRestrictions, bool append = false);
+double evaluateTreesPartition(AnnotatedNetwork &ann_network, size_t partition_idx, std::vector<TreeLoglData> &treeLoglData);
+int pllmod_treeinfo_update_prob_matrices(AnnotatedNetwork &ann_network, int update_all);  // PLLMOD/tree/treeinfo.c:842-880
+
+std::vector<DisplayedTreeData> extractOldTrees(AnnotatedNetwork &ann_network, Node *virtual_root);
+ReticulationConfigSet getRestrictionsActiveAliveBranch(AnnotatedNetwork &ann_network, size_t pmatrix_index);
+void updateCLVsVirtualRerootTrees(AnnotatedNetwork &ann_network, Node *old_virtual_root, Node *new_virtual_root,
+                                  Node *new_virtual_root_back, ReticulationConfigSet &restrictions);
+double computeLoglikelihoodBrlenOpt(AnnotatedNetwork &ann_network, const std::vector<DisplayedTreeData> &oldTrees,
+                                    unsigned int pmatrix_index, int update_pmatrices = 1, bool print_extra_debug_info = false);
+std::vector<std::vector<SumtableInfo>> computePartitionSumtables(AnnotatedNetwork &ann_network, unsigned int pmatrix_index);
+LoglDerivatives computeLoglikelihoodDerivatives(AnnotatedNetwork &ann_network,
+                                                const std::vector<std::vector<SumtableInfo>> &sumtables,
+                                                unsigned int pmatrix_index);
+
+/* ---- src/helper/InvalidationHelper.cpp -------------------------------------------------------------------- */
+void invalidateSingleClv(AnnotatedNetwork &ann_network, unsigned int clv_index);
+void invalidateHigherCLVs(AnnotatedNetwork &ann_network, const Node *node, bool invalidate_myself);
+void invalidatePmatrixIndex(AnnotatedNetwork &ann_network, size_t pmatrix_index);
+void invalidPmatrixIndexOnly(AnnotatedNetwork &ann_network, size_t pmatrix_index);
+void invalidateAllCLVs(AnnotatedNetwork &ann_network);
+void invalidateTreeLogprobs(AnnotatedNetwork &ann_network);
+bool allClvsValid(AnnotatedNetwork &ann_network, size_t clv_index);
+void setReticulationProb(AnnotatedNetwork &ann_network, size_t reticulation_idx, double prob);
+
+}  // namespace netrax

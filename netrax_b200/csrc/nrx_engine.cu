@@ -1,0 +1,696 @@
+/*
+ * nrx_engine.cu — C-ABI (include/nrx_engine.h) over the sm_100a kernels in nrx_kernels.cuh.
+ * Device memory pool (CLV / scaler / sumtable slots), per-partition model + P-matrix storage, launch
+ * geometry, deterministic two-stage reductions.  One handle = one GPU = one stream.
+ */
+#include "nrx_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace nrx;
+
+namespace {
+thread_local std::string g_err;
+
+bool cuda_ok(cudaError_t e, const char *what) {
+  if (e == cudaSuccess) return true;
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return false;
+}
+#define CK(call) do { if (!cuda_ok((call), #call)) return 0; } while (0)
+
+struct Part {
+  nrx_partition_desc d{};
+  uint32_t sp = 0;
+  size_t clv_entries = 0, pmat_entries = 0;
+  double *pmat = nullptr;
+  uint8_t *tipchars = nullptr;
+  uint32_t *tipmap = nullptr, *weights = nullptr;
+  double *model = nullptr;  // freqs | eigenvecs | inv_eigenvecs | eigenvals | rates | rate_weights | diagp
+  double *freqs = nullptr, *eigenvecs = nullptr, *inv_eigenvecs = nullptr, *eigenvals = nullptr, *rates = nullptr, *rate_weights = nullptr, *diagp = nullptr;
+  std::vector<double> h_eigenvals, h_rates;
+  std::vector<void *> slot_mem;       // one allocation per slot: [clv | scaler]
+  std::vector<double *> h_clv;
+  std::vector<uint32_t *> h_scaler;
+  std::vector<double *> h_sumtable;
+  double **d_clv = nullptr;
+  uint32_t **d_scaler = nullptr;
+  double **d_sumtable = nullptr;
+  uint32_t table_cap = 0, st_cap = 0;
+  bool model_set = false, tips_set = false;
+};
+
+struct ShapeClass {
+  uint32_t states, cats;
+  std::vector<uint32_t> parts;     // partition indices
+  PartView *d_views = nullptr;     // device array, same order
+  uint32_t max_patterns = 0;
+};
+}  // namespace
+
+struct nrx_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<Part> parts;
+  std::vector<ShapeClass> classes;
+  uint32_t nslots = 0, nsumtables = 0;
+  uint32_t max_patterns = 0;
+  // staging
+  void *h_stage = nullptr;      // pinned
+  void *d_stage = nullptr;
+  size_t stage_cap = 0, stage_off = 0;
+  double *d_partial = nullptr;
+  size_t partial_cap = 0;
+  double *d_result = nullptr, *h_result = nullptr;
+  size_t result_cap = 0;
+  double *d_persite = nullptr;
+  size_t persite_cap = 0;
+  unsigned long long launches = 0;
+  bool views_dirty = true;
+  // profiling of K2
+  bool prof = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  double prof_ms = 0;
+  unsigned long long prof_launches = 0, prof_updates = 0, prof_bytes = 0;
+};
+
+namespace {
+
+/* Pinned host / device staging ring: small host->device payloads (ops, slot lists, branch lengths) are
+ * bump-allocated so consecutive launches never wait for each other; the stream is synchronised only when
+ * the ring wraps. */
+int stage_alloc(nrx_engine *e, size_t bytes, void **hptr, void **dptr) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (bytes > e->stage_cap) {
+    size_t cap = std::max<size_t>(bytes * 2, 8 << 20);
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->h_stage) cudaFreeHost(e->h_stage);
+    if (e->d_stage) cudaFree(e->d_stage);
+    e->h_stage = e->d_stage = nullptr;
+    e->stage_cap = 0;
+    CK(cudaMallocHost(&e->h_stage, cap));
+    CK(cudaMalloc(&e->d_stage, cap));
+    e->stage_cap = cap;
+    e->stage_off = 0;
+  }
+  if (e->stage_off + bytes > e->stage_cap) {
+    CK(cudaStreamSynchronize(e->stream));
+    e->stage_off = 0;
+  }
+  *hptr = (char *)e->h_stage + e->stage_off;
+  *dptr = (char *)e->d_stage + e->stage_off;
+  e->stage_off += bytes;
+  return 1;
+}
+
+int ensure_result(nrx_engine *e, size_t n_doubles, size_t n_partial) {
+  if (n_doubles > e->result_cap) {
+    if (e->d_result) cudaFree(e->d_result);
+    if (e->h_result) cudaFreeHost(e->h_result);
+    size_t cap = std::max<size_t>(n_doubles, 4096);
+    CK(cudaMalloc((void **)&e->d_result, cap * sizeof(double)));
+    CK(cudaMallocHost((void **)&e->h_result, cap * sizeof(double)));
+    e->result_cap = cap;
+  }
+  if (n_partial > e->partial_cap) {
+    if (e->d_partial) cudaFree(e->d_partial);
+    size_t cap = std::max<size_t>(n_partial, 1 << 16);
+    CK(cudaMalloc((void **)&e->d_partial, cap * sizeof(double)));
+    e->partial_cap = cap;
+  }
+  return 1;
+}
+
+/* stage host bytes -> device on the engine stream; returns the device pointer */
+template <class T> int upload(nrx_engine *e, const T *src, size_t n, T **dev) {
+  void *h, *d;
+  if (!stage_alloc(e, n * sizeof(T), &h, &d)) return 0;
+  std::memcpy(h, src, n * sizeof(T));
+  CK(cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+  *dev = (T *)d;
+  return 1;
+}
+
+PartView make_view(const Part &p, uint32_t index) {
+  PartView v{};
+  v.states = p.d.states; v.sp = p.sp; v.cats = p.d.rate_cats; v.patterns = p.d.patterns; v.tips = p.d.tips; v.edges = p.d.edges;
+  v.part_index = index;
+  v.pmat = p.pmat; v.tipchars = p.tipchars; v.tipmap = p.tipmap; v.weights = p.weights;
+  v.freqs = p.freqs; v.eigenvecs = p.eigenvecs; v.inv_eigenvecs = p.inv_eigenvecs; v.eigenvals = p.eigenvals;
+  v.rates = p.rates; v.rate_weights = p.rate_weights;
+  v.clv = p.d_clv; v.scaler = p.d_scaler; v.sumtable = p.d_sumtable; v.diagp = p.diagp;
+  return v;
+}
+
+int refresh_views(nrx_engine *e) {
+  if (!e->views_dirty) return 1;
+  for (ShapeClass &c : e->classes) {
+    std::vector<PartView> hv;
+    for (uint32_t pi : c.parts) hv.push_back(make_view(e->parts[pi], pi));
+    if (!c.d_views) CK(cudaMalloc((void **)&c.d_views, hv.size() * sizeof(PartView)));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(c.d_views, hv.data(), hv.size() * sizeof(PartView), cudaMemcpyHostToDevice));
+  }
+  e->views_dirty = false;
+  return 1;
+}
+
+int check_part(nrx_engine *e, uint32_t p) {
+  if (!e) { g_err = "null engine"; return 0; }
+  if (p >= e->parts.size()) { g_err = "partition index out of range"; return 0; }
+  return 1;
+}
+
+uint32_t tiles_for(uint64_t items, uint32_t per_block, uint32_t other_dims) {
+  // enough blocks for >= ~8 waves over 148 SMs when the launch is big, one tile per block when it is small
+  uint64_t full = (items + per_block - 1) / per_block;
+  if (full == 0) full = 1;
+  uint64_t want = full;
+  const uint64_t target_blocks = 148ull * 8 * 8;
+  if (full * other_dims > target_blocks) {
+    want = std::max<uint64_t>(1, target_blocks / std::max<uint32_t>(1, other_dims));
+    want = std::min<uint64_t>(want, full);
+    // never give a block more than 16 tiles: keeps the tail short
+    want = std::max<uint64_t>(want, (full + 15) / 16);
+  }
+  return (uint32_t)std::min<uint64_t>(want, 65535ull * 32);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *nrx_last_error(void) { return g_err.c_str(); }
+
+int nrx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, int device) {
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0) {
+    g_err = std::string("nrx_engine_create: no usable CUDA device (") + cudaGetErrorString(err) + "); this engine has no CPU fallback";
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev) { g_err = "nrx_engine_create: bad device index"; return nullptr; }
+  if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return nullptr;
+  nrx_engine *e = new nrx_engine();
+  e->device = device;
+  if (!cuda_ok(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete e; return nullptr; }
+  e->parts.resize(nparts);
+  for (uint32_t i = 0; i < nparts; ++i) {
+    Part &p = e->parts[i];
+    p.d = descs[i];
+    if (p.d.states < 2 || p.d.states > 32 || p.d.rate_cats < 1 || p.d.rate_cats > 16) { g_err = "unsupported states / rate_cats"; nrx_engine_destroy(e); return nullptr; }
+    p.sp = (p.d.states + 3) & ~3u;
+    p.clv_entries = (size_t)p.d.patterns * p.d.rate_cats * p.sp;
+    p.pmat_entries = (size_t)p.d.rate_cats * p.d.states * p.sp;
+    e->max_patterns = std::max(e->max_patterns, p.d.patterns);
+    const size_t S = p.d.states, SP = p.sp, C = p.d.rate_cats;
+    const size_t model_doubles = SP + 2 * S * SP + SP + 2 * C + C * S * 4;
+    bool ok = cuda_ok(cudaMalloc((void **)&p.pmat, std::max<size_t>(1, p.d.edges * p.pmat_entries) * sizeof(double)), "cudaMalloc pmat") &&
+              cuda_ok(cudaMalloc((void **)&p.tipchars, std::max<size_t>(1, (size_t)p.d.tips * p.d.patterns)), "cudaMalloc tipchars") &&
+              cuda_ok(cudaMalloc((void **)&p.tipmap, 256 * sizeof(uint32_t)), "cudaMalloc tipmap") &&
+              cuda_ok(cudaMalloc((void **)&p.weights, std::max<size_t>(1, p.d.patterns) * sizeof(uint32_t)), "cudaMalloc weights") &&
+              cuda_ok(cudaMalloc((void **)&p.model, model_doubles * sizeof(double)), "cudaMalloc model");
+    if (!ok) { nrx_engine_destroy(e); return nullptr; }
+    p.freqs = p.model; p.eigenvecs = p.freqs + SP; p.inv_eigenvecs = p.eigenvecs + S * SP; p.eigenvals = p.inv_eigenvecs + S * SP;
+    p.rates = p.eigenvals + SP; p.rate_weights = p.rates + C; p.diagp = p.rate_weights + C;
+    std::vector<uint32_t> ones(std::max<uint32_t>(1, p.d.patterns), 1);
+    cudaMemcpy(p.weights, ones.data(), ones.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    cudaMemset(p.pmat, 0, std::max<size_t>(1, p.d.edges * p.pmat_entries) * sizeof(double));
+    // group by kernel shape
+    bool found = false;
+    for (ShapeClass &c : e->classes)
+      if (c.states == p.d.states && c.cats == p.d.rate_cats) { c.parts.push_back(i); c.max_patterns = std::max(c.max_patterns, p.d.patterns); found = true; }
+    if (!found) { ShapeClass c; c.states = p.d.states; c.cats = p.d.rate_cats; c.parts = {i}; c.max_patterns = p.d.patterns; e->classes.push_back(c); }
+  }
+  return e;
+}
+
+void nrx_engine_destroy(nrx_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (Part &p : e->parts) {
+    cudaFree(p.pmat); cudaFree(p.tipchars); cudaFree(p.tipmap); cudaFree(p.weights); cudaFree(p.model);
+    for (void *m : p.slot_mem) cudaFree(m);
+    for (double *m : p.h_sumtable) cudaFree(m);
+    cudaFree(p.d_clv); cudaFree(p.d_scaler); cudaFree(p.d_sumtable);
+  }
+  for (ShapeClass &c : e->classes) cudaFree(c.d_views);
+  for (auto &ev : e->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  if (e->h_stage) cudaFreeHost(e->h_stage);
+  cudaFree(e->d_stage); cudaFree(e->d_partial); cudaFree(e->d_result); cudaFree(e->d_persite);
+  if (e->h_result) cudaFreeHost(e->h_result);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int nrx_set_tips(nrx_engine *e, uint32_t pi, const uint32_t *tip_masks) {
+  if (!check_part(e, pi)) return 0;
+  CK(cudaSetDevice(e->device));
+  Part &p = e->parts[pi];
+  const size_t n = (size_t)p.d.tips * p.d.patterns;
+  std::vector<uint8_t> codes(std::max<size_t>(1, n));
+  std::vector<uint32_t> tipmap(256, 0);
+  const uint32_t full = (p.d.states >= 32) ? 0xffffffffu : ((1u << p.d.states) - 1);
+  if (p.d.states == 4) {  // the code IS the mask (set_tipchars_4x4, LIBPLL/pll.c:875-900)
+    for (uint32_t i = 0; i < 16; ++i) tipmap[i] = i;
+    for (size_t i = 0; i < n; ++i) {
+      if (tip_masks[i] == 0 || tip_masks[i] > 15) { g_err = "Illegal state code in tip"; return 0; }
+      codes[i] = (uint8_t)tip_masks[i];
+    }
+  } else {
+    std::map<uint32_t, uint32_t> code;
+    for (size_t i = 0; i < n; ++i) {
+      const uint32_t m = tip_masks[i];
+      if (m == 0 || (m & ~full)) { g_err = "Illegal state code in tip"; return 0; }
+      auto it = code.find(m);
+      if (it == code.end()) {
+        if (code.size() >= 256) { g_err = "more than 256 distinct tip states"; return 0; }
+        const uint32_t c = (uint32_t)code.size();
+        it = code.emplace(m, c).first;
+        tipmap[c] = m;
+      }
+      codes[i] = (uint8_t)it->second;
+    }
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(p.tipchars, codes.data(), std::max<size_t>(1, n), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(p.tipmap, tipmap.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  p.tips_set = true;
+  return 1;
+}
+
+int nrx_set_pattern_weights(nrx_engine *e, uint32_t pi, const uint32_t *w) {
+  if (!check_part(e, pi)) return 0;
+  CK(cudaSetDevice(e->device));
+  Part &p = e->parts[pi];
+  CK(cudaStreamSynchronize(e->stream));
+  if (p.d.patterns) CK(cudaMemcpy(p.weights, w, (size_t)p.d.patterns * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  return 1;
+}
+
+int nrx_set_model(nrx_engine *e, uint32_t pi, const double *freqs, const double *eigenvecs, const double *inv_eigenvecs,
+                  const double *eigenvals, const double *rates, const double *rate_weights, double prop_invar) {
+  if (!check_part(e, pi)) return 0;
+  if (prop_invar != 0.0) { g_err = "proportion of invariant sites (+I) is not supported by this engine"; return 0; }
+  CK(cudaSetDevice(e->device));
+  Part &p = e->parts[pi];
+  const size_t S = p.d.states, SP = p.sp, C = p.d.rate_cats;
+  std::vector<double> h(SP + 2 * S * SP + SP + 2 * C, 0.0);
+  double *q = h.data();
+  std::memcpy(q, freqs, S * sizeof(double)); q += SP;
+  std::memcpy(q, eigenvecs, S * SP * sizeof(double)); q += S * SP;
+  std::memcpy(q, inv_eigenvecs, S * SP * sizeof(double)); q += S * SP;
+  std::memcpy(q, eigenvals, S * sizeof(double)); q += SP;
+  std::memcpy(q, rates, C * sizeof(double)); q += C;
+  std::memcpy(q, rate_weights, C * sizeof(double));
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(p.model, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+  p.h_eigenvals.assign(eigenvals, eigenvals + S);
+  p.h_rates.assign(rates, rates + C);
+  p.model_set = true;
+  return 1;
+}
+
+int nrx_update_pmatrices(nrx_engine *e, uint32_t pi, uint32_t n, const uint32_t *edge_idx, const double *brlen) {
+  if (!check_part(e, pi)) return 0;
+  if (n == 0) return 1;
+  CK(cudaSetDevice(e->device));
+  Part &p = e->parts[pi];
+  if (!p.model_set) { g_err = "nrx_update_pmatrices: model not set"; return 0; }
+  for (uint32_t i = 0; i < n; ++i) {
+    if (edge_idx[i] >= p.d.edges) { g_err = "nrx_update_pmatrices: edge index out of range"; return 0; }
+    if (!(brlen[i] >= 0.0)) { g_err = "nrx_update_pmatrices: negative branch length"; return 0; }
+  }
+  uint32_t *d_idx; double *d_len;
+  if (!upload(e, edge_idx, n, &d_idx) || !upload(e, brlen, n, &d_len)) return 0;
+  PartView v = make_view(p, pi);
+  k_pmatrix<<<n, 128, p.d.rate_cats * p.d.states * sizeof(double), e->stream>>>(v, p.pmat, d_idx, d_len);
+  e->launches++;
+  CK(cudaGetLastError());
+  return 1;
+}
+
+int nrx_get_pmatrix(nrx_engine *e, uint32_t pi, uint32_t edge, double *out) {
+  if (!check_part(e, pi)) return 0;
+  CK(cudaSetDevice(e->device));
+  Part &p = e->parts[pi];
+  if (edge >= p.d.edges) { g_err = "edge index out of range"; return 0; }
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(out, p.pmat + (size_t)edge * p.pmat_entries, p.pmat_entries * sizeof(double), cudaMemcpyDeviceToHost));
+  return 1;
+}
+
+int nrx_set_pmatrix(nrx_engine *e, uint32_t pi, uint32_t edge, const double *in) {
+  if (!check_part(e, pi)) return 0;
+  CK(cudaSetDevice(e->device));
+  Part &p = e->parts[pi];
+  if (edge >= p.d.edges) { g_err = "edge index out of range"; return 0; }
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(p.pmat + (size_t)edge * p.pmat_entries, in, p.pmat_entries * sizeof(double), cudaMemcpyHostToDevice));
+  return 1;
+}
+
+uint32_t nrx_num_slots(nrx_engine *e) { return e ? e->nslots : 0; }
+
+int nrx_reserve_slots(nrx_engine *e, uint32_t nslots) {
+  if (!e) { g_err = "null engine"; return 0; }
+  if (nslots <= e->nslots) return 1;
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  for (Part &p : e->parts) {
+    const size_t clv_bytes = (p.clv_entries * sizeof(double) + 255) & ~(size_t)255;
+    const size_t sc_bytes = ((size_t)p.d.patterns * sizeof(uint32_t) + 255) & ~(size_t)255;
+    for (uint32_t s = (uint32_t)p.slot_mem.size(); s < nslots; ++s) {
+      void *m = nullptr;
+      cudaError_t err = cudaMalloc(&m, std::max<size_t>(256, clv_bytes + sc_bytes));
+      if (err != cudaSuccess) {
+        g_err = std::string("nrx_reserve_slots: out of device memory at slot ") + std::to_string(s) + " (" + cudaGetErrorString(err) + ")";
+        cudaGetLastError();
+        return 0;
+      }
+      cudaMemsetAsync(m, 0, std::max<size_t>(256, clv_bytes + sc_bytes), e->stream);
+      p.slot_mem.push_back(m);
+      p.h_clv.push_back((double *)m);
+      p.h_scaler.push_back((uint32_t *)((char *)m + clv_bytes));
+    }
+    if (nslots > p.table_cap) {
+      uint32_t cap = std::max<uint32_t>(nslots, p.table_cap * 2 + 64);
+      cudaFree(p.d_clv); cudaFree(p.d_scaler);
+      CK(cudaMalloc((void **)&p.d_clv, cap * sizeof(double *)));
+      CK(cudaMalloc((void **)&p.d_scaler, cap * sizeof(uint32_t *)));
+      p.table_cap = cap;
+      e->views_dirty = true;
+    }
+    CK(cudaMemcpy(p.d_clv, p.h_clv.data(), p.h_clv.size() * sizeof(double *), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p.d_scaler, p.h_scaler.data(), p.h_scaler.size() * sizeof(uint32_t *), cudaMemcpyHostToDevice));
+  }
+  e->nslots = nslots;
+  return 1;
+}
+
+static int reserve_sumtables(nrx_engine *e, uint32_t n) {
+  if (n <= e->nsumtables) return 1;
+  CK(cudaStreamSynchronize(e->stream));
+  for (Part &p : e->parts) {
+    for (uint32_t s = (uint32_t)p.h_sumtable.size(); s < n; ++s) {
+      double *m = nullptr;
+      cudaError_t err = cudaMalloc((void **)&m, std::max<size_t>(256, p.clv_entries * sizeof(double)));
+      if (err != cudaSuccess) { g_err = std::string("sumtable pool: ") + cudaGetErrorString(err); cudaGetLastError(); return 0; }
+      p.h_sumtable.push_back(m);
+    }
+    if (n > p.st_cap) {
+      uint32_t cap = std::max<uint32_t>(n, p.st_cap * 2 + 16);
+      cudaFree(p.d_sumtable);
+      CK(cudaMalloc((void **)&p.d_sumtable, cap * sizeof(double *)));
+      p.st_cap = cap;
+      e->views_dirty = true;
+    }
+    CK(cudaMemcpy(p.d_sumtable, p.h_sumtable.data(), p.h_sumtable.size() * sizeof(double *), cudaMemcpyHostToDevice));
+  }
+  e->nsumtables = n;
+  return 1;
+}
+
+int nrx_copy_slot(nrx_engine *e, uint32_t dst, uint32_t src) {
+  if (!e) { g_err = "null engine"; return 0; }
+  if (dst >= e->nslots || src >= e->nslots) { g_err = "nrx_copy_slot: slot out of range"; return 0; }
+  CK(cudaSetDevice(e->device));
+  for (Part &p : e->parts) {
+    CK(cudaMemcpyAsync(p.h_clv[dst], p.h_clv[src], p.clv_entries * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(p.h_scaler[dst], p.h_scaler[src], (size_t)p.d.patterns * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
+  }
+  return 1;
+}
+
+int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops) {
+  if (!e) { g_err = "null engine"; return 0; }
+  if (nops == 0) return 1;
+  CK(cudaSetDevice(e->device));
+  unsigned long long updates = 0, bytes = 0;
+  for (uint32_t i = 0; i < nops; ++i) {
+    const nrx_op &o = ops[i];
+    if (o.parent_slot >= e->nslots) { g_err = "nrx_update_clvs: parent slot out of range"; return 0; }
+    const uint32_t kinds[2] = {o.left_kind, o.right_kind}, idx[2] = {o.left_idx, o.right_idx}, edges[2] = {o.left_edge, o.right_edge};
+    for (int s = 0; s < 2; ++s) {
+      if (kinds[s] == NRX_CLV && idx[s] >= e->nslots) { g_err = "nrx_update_clvs: child slot out of range"; return 0; }
+      if (kinds[s] > NRX_NONE) { g_err = "nrx_update_clvs: bad operand kind"; return 0; }
+      for (const Part &p : e->parts) {
+        if (kinds[s] == NRX_TIP && idx[s] >= p.d.tips) { g_err = "nrx_update_clvs: tip index out of range"; return 0; }
+        if (kinds[s] != NRX_NONE && edges[s] >= p.d.edges) { g_err = "nrx_update_clvs: edge index out of range"; return 0; }
+      }
+    }
+    if (o.left_kind == NRX_NONE && o.right_kind == NRX_NONE) { g_err = "nrx_update_clvs: both operands absent"; return 0; }
+    for (const Part &p : e->parts) {  // algorithmic bytes, SURVEY §8d table
+      const unsigned long long Cb = (unsigned long long)p.d.rate_cats * p.sp * 8;
+      unsigned long long b = Cb + 4;
+      for (int s = 0; s < 2; ++s) b += (kinds[s] == NRX_CLV) ? Cb + 4 : (kinds[s] == NRX_TIP ? 1 : 0);
+      if (o.left_kind == NRX_TIP && o.right_kind == NRX_TIP) b = Cb + 2 + 4;
+      bytes += b * p.d.patterns;
+      updates += p.d.patterns;
+    }
+  }
+  if (!refresh_views(e)) return 0;
+  nrx_op *d_ops;
+  if (!upload(e, ops, nops, &d_ops)) return 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (e->prof) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, e->stream); }
+  for (const ShapeClass &c : e->classes) {
+    if (c.max_patterns == 0) continue;
+    const uint32_t z = (uint32_t)c.parts.size();
+    if (c.states == 4 && c.cats == 4) {
+      constexpr int U = 2;
+      dim3 grid(tiles_for((uint64_t)c.max_patterns * 4, BLOCK * U, nops * z), nops, z);
+      k_clv_dna4<U><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops);
+    } else {
+      dim3 grid(tiles_for(c.max_patterns, BLOCK, nops * z), nops, z);
+      k_clv_generic<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops, nullptr);
+    }
+    e->launches++;
+    CK(cudaGetLastError());
+  }
+  if (e->prof) {
+    cudaEventRecord(ev1, e->stream);
+    e->prof_events.emplace_back(ev0, ev1);
+    e->prof_launches += e->classes.size();
+    e->prof_updates += updates;
+    e->prof_bytes += bytes;
+  }
+  return 1;
+}
+
+static int finish_reduction(nrx_engine *e, uint32_t total, uint32_t nblk, double *out) {
+  k_reduce_partials<<<(total + 127) / 128, 128, 0, e->stream>>>(e->d_partial, e->d_result, nblk, total);
+  e->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(e->h_result, e->d_result, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (out) std::memcpy(out, e->h_result, (size_t)total * sizeof(double));
+  return 1;
+}
+
+int nrx_tree_lnl(nrx_engine *e, const uint32_t *slots, uint32_t n, double *out, double *persite, size_t persite_stride) {
+  if (!e) { g_err = "null engine"; return 0; }
+  if (n == 0) return 1;
+  CK(cudaSetDevice(e->device));
+  for (uint32_t i = 0; i < n; ++i) if (slots[i] >= e->nslots) { g_err = "nrx_tree_lnl: slot out of range"; return 0; }
+  const uint32_t P = (uint32_t)e->parts.size();
+  const uint32_t nblk = std::max<uint32_t>(1, std::min<uint32_t>((e->max_patterns + BLOCK - 1) / BLOCK, std::max<uint32_t>(1, 148 * 8 / std::max<uint32_t>(1, n * P))));
+  if (!ensure_result(e, (size_t)n * P, (size_t)n * P * nblk) || !refresh_views(e)) return 0;
+  uint32_t *d_slots;
+  if (!upload(e, slots, n, &d_slots)) return 0;
+  double *d_ps = nullptr;
+  if (persite) {
+    const size_t need = (size_t)n * P * persite_stride;
+    if (need > e->persite_cap) { cudaFree(e->d_persite); CK(cudaMalloc((void **)&e->d_persite, need * sizeof(double))); e->persite_cap = need; }
+    CK(cudaMemsetAsync(e->d_persite, 0, need * sizeof(double), e->stream));
+    d_ps = e->d_persite;
+  }
+  CK(cudaMemsetAsync(e->d_partial, 0, (size_t)n * P * nblk * sizeof(double), e->stream));
+  const double log_thresh = std::log(SCALE_THRESHOLD);
+  for (const ShapeClass &c : e->classes) {
+    dim3 grid(nblk, n, (uint32_t)c.parts.size());
+    k_tree_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
+    e->launches++;
+    CK(cudaGetLastError());
+  }
+  if (!finish_reduction(e, n * P, nblk, out)) return 0;
+  if (persite) CK(cudaMemcpy(persite, e->d_persite, (size_t)n * P * persite_stride * sizeof(double), cudaMemcpyDeviceToHost));
+  return 1;
+}
+
+static int check_pairs(nrx_engine *e, const nrx_pair *pairs, uint32_t n, const char *who) {
+  for (uint32_t i = 0; i < n; ++i) {
+    const nrx_pair &q = pairs[i];
+    if (q.a_kind == NRX_TIP && q.b_kind == NRX_TIP) { g_err = std::string(who) + " was called for the tip-tip case!"; return 0; }
+    const uint32_t kinds[2] = {q.a_kind, q.b_kind}, idx[2] = {q.a_idx, q.b_idx};
+    for (int s = 0; s < 2; ++s) {
+      if (kinds[s] == NRX_CLV) { if (idx[s] >= e->nslots) { g_err = std::string(who) + ": slot out of range"; return 0; } }
+      else if (kinds[s] == NRX_TIP) { for (const Part &p : e->parts) if (idx[s] >= p.d.tips) { g_err = std::string(who) + ": tip out of range"; return 0; } }
+      else { g_err = std::string(who) + ": operand must be a CLV slot or a tip"; return 0; }
+    }
+  }
+  return 1;
+}
+
+int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n, double *out) {
+  if (!e) { g_err = "null engine"; return 0; }
+  if (n == 0) return 1;
+  CK(cudaSetDevice(e->device));
+  if (!check_pairs(e, pairs, n, "nrx_edge_lnl")) return 0;
+  for (const Part &p : e->parts) if (edge >= p.d.edges) { g_err = "nrx_edge_lnl: edge out of range"; return 0; }
+  const uint32_t P = (uint32_t)e->parts.size();
+  const uint32_t nblk = std::max<uint32_t>(1, std::min<uint32_t>((e->max_patterns + BLOCK - 1) / BLOCK, std::max<uint32_t>(1, 148 * 8 / std::max<uint32_t>(1, n * P))));
+  if (!ensure_result(e, (size_t)n * P, (size_t)n * P * nblk) || !refresh_views(e)) return 0;
+  nrx_pair *d_pairs;
+  if (!upload(e, pairs, n, &d_pairs)) return 0;
+  CK(cudaMemsetAsync(e->d_partial, 0, (size_t)n * P * nblk * sizeof(double), e->stream));
+  const double log_thresh = std::log(SCALE_THRESHOLD);
+  for (const ShapeClass &c : e->classes) {
+    dim3 grid(nblk, n, (uint32_t)c.parts.size());
+    k_edge_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh);
+    e->launches++;
+    CK(cudaGetLastError());
+  }
+  return finish_reduction(e, n * P, nblk, out);
+}
+
+int nrx_sumtables(nrx_engine *e, const nrx_pair *pairs, uint32_t n) {
+  if (!e) { g_err = "null engine"; return 0; }
+  if (n == 0) return 1;
+  CK(cudaSetDevice(e->device));
+  if (!check_pairs(e, pairs, n, "pll_update_sumtable()")) return 0;
+  if (!reserve_sumtables(e, n) || !refresh_views(e)) return 0;
+  nrx_pair *d_pairs;
+  if (!upload(e, pairs, n, &d_pairs)) return 0;
+  for (const ShapeClass &c : e->classes) {
+    if (c.max_patterns == 0) continue;
+    const uint32_t z = (uint32_t)c.parts.size();
+    dim3 grid(tiles_for((uint64_t)c.max_patterns * c.cats, BLOCK, n * z), n, z);
+    k_sumtable<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs);
+    e->launches++;
+    CK(cudaGetLastError());
+  }
+  return 1;
+}
+
+int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen, double *out) {
+  if (!e) { g_err = "null engine"; return 0; }
+  if (n == 0) return 1;
+  CK(cudaSetDevice(e->device));
+  if (n > e->nsumtables) { g_err = "nrx_derivatives: sumtables not computed"; return 0; }
+  const uint32_t P = (uint32_t)e->parts.size();
+  const uint32_t nblk = std::max<uint32_t>(1, std::min<uint32_t>((e->max_patterns + BLOCK - 1) / BLOCK, std::max<uint32_t>(1, 148 * 8 / std::max<uint32_t>(1, n * P))));
+  if (!ensure_result(e, (size_t)n * P * 3, (size_t)n * P * 3 * nblk) || !refresh_views(e)) return 0;
+  // diagptable on the host with libm exp, exactly pll_compute_diagptable (LIBPLL/core_derivatives.c:711-726)
+  for (uint32_t pi = 0; pi < P; ++pi) {
+    Part &p = e->parts[pi];
+    const uint32_t S = p.d.states, C = p.d.rate_cats;
+    std::vector<double> diag((size_t)C * S * 4);
+    double *dp = diag.data();
+    for (uint32_t i = 0; i < C; ++i) {
+      const double ki = p.h_rates[i] / (1.0 - 0.0);
+      for (uint32_t j = 0; j < S; ++j) {
+        dp[0] = std::exp(p.h_eigenvals[j] * ki * brlen[pi]);
+        dp[1] = p.h_eigenvals[j] * ki * dp[0];
+        dp[2] = p.h_eigenvals[j] * ki * p.h_eigenvals[j] * ki * dp[0];
+        dp[3] = 0;
+        dp += 4;
+      }
+    }
+    double *d_tmp;
+    if (!upload(e, diag.data(), diag.size(), &d_tmp)) return 0;
+    CK(cudaMemcpyAsync(p.diagp, d_tmp, diag.size() * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+  }
+  CK(cudaMemsetAsync(e->d_partial, 0, (size_t)n * P * 3 * nblk * sizeof(double), e->stream));
+  for (const ShapeClass &c : e->classes) {
+    dim3 grid(nblk, n, (uint32_t)c.parts.size());
+    k_derivatives<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P);
+    e->launches++;
+    CK(cudaGetLastError());
+  }
+  return finish_reduction(e, n * P * 3, nblk, out);
+}
+
+int nrx_read_clv(nrx_engine *e, uint32_t pi, uint32_t slot, double *out) {
+  if (!check_part(e, pi)) return 0;
+  if (slot >= e->nslots) { g_err = "slot out of range"; return 0; }
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  Part &p = e->parts[pi];
+  if (p.clv_entries) CK(cudaMemcpy(out, p.h_clv[slot], p.clv_entries * sizeof(double), cudaMemcpyDeviceToHost));
+  return 1;
+}
+
+int nrx_read_scaler(nrx_engine *e, uint32_t pi, uint32_t slot, uint32_t *out) {
+  if (!check_part(e, pi)) return 0;
+  if (slot >= e->nslots) { g_err = "slot out of range"; return 0; }
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  Part &p = e->parts[pi];
+  if (p.d.patterns) CK(cudaMemcpy(out, p.h_scaler[slot], (size_t)p.d.patterns * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return 1;
+}
+
+int nrx_read_sumtable(nrx_engine *e, uint32_t pi, uint32_t st, double *out) {
+  if (!check_part(e, pi)) return 0;
+  if (st >= e->nsumtables) { g_err = "sumtable slot out of range"; return 0; }
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  Part &p = e->parts[pi];
+  if (p.clv_entries) CK(cudaMemcpy(out, p.h_sumtable[st], p.clv_entries * sizeof(double), cudaMemcpyDeviceToHost));
+  return 1;
+}
+
+int nrx_sync(nrx_engine *e) {
+  if (!e) { g_err = "null engine"; return 0; }
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  return 1;
+}
+
+void *nrx_result_device_ptr(nrx_engine *e) { return e ? e->d_result : nullptr; }
+void *nrx_stream(nrx_engine *e) { return e ? (void *)e->stream : nullptr; }
+unsigned long long nrx_launch_count(nrx_engine *e) { return e ? e->launches : 0; }
+
+int nrx_profile_enable(nrx_engine *e, int on) {
+  if (!e) { g_err = "null engine"; return 0; }
+  e->prof = on != 0;
+  for (auto &ev : e->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  e->prof_events.clear();
+  e->prof_ms = 0; e->prof_launches = e->prof_updates = e->prof_bytes = 0;
+  return 1;
+}
+
+int nrx_profile_read(nrx_engine *e, double *clv_ms, unsigned long long *clv_launches, unsigned long long *clv_site_updates, unsigned long long *clv_bytes) {
+  if (!e) { g_err = "null engine"; return 0; }
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  for (auto &ev : e->prof_events) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev.first, ev.second);
+    e->prof_ms += ms;
+    cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
+  }
+  e->prof_events.clear();
+  if (clv_ms) *clv_ms = e->prof_ms;
+  if (clv_launches) *clv_launches = e->prof_launches;
+  if (clv_site_updates) *clv_site_updates = e->prof_updates;
+  if (clv_bytes) *clv_bytes = e->prof_bytes;
+  return 1;
+}
+
+}  // extern "C"

@@ -1,0 +1,465 @@
+/*
+ * nrx_kernels.cuh — hand-written sm_100a kernels of the NetRAX network-likelihood hot path.
+ *
+ * All kernels are FP64, HBM-streaming ("stencil over CLVs"): one thread owns one
+ * (pattern, rate category) pair = `states_padded` consecutive doubles, so a warp reads/writes 1 KB of
+ * contiguous CLV per 256-bit LDG/STG (LDG.E.256 on sm_100a) — fully coalesced, no shared-memory staging
+ * of CLV data needed because there is no reuse.  Per-edge P-matrix rows live in registers (DNA) and tip
+ * lookup tables in shared memory.  Scaler decisions use warp ballots over the rate-category group.
+ *
+ * DNA (4 states) arithmetic mirrors the ORDER of the reference's AVX 4x4 kernels exactly —
+ * separate multiply and add (__dmul_rn/__dadd_rn, never contracted into FMA) and pairwise sums
+ * (p0+p1)+(p2+p3) — so CLVs and scaler counts are bit-identical to libpll given identical P-matrices
+ * (LIBPLL/core_partials_avx.c:402-565,1310-1500,255-395,992-1030).
+ */
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/nrx_engine.h"
+
+namespace nrx {
+
+constexpr double SCALE_FACTOR = 115792089237316195423570985008687907853269984665640564039457584007913129639936.0;  // 2^256
+constexpr double SCALE_THRESHOLD = 1.0 / SCALE_FACTOR;
+constexpr int BLOCK = 256;
+
+/* Device view of one partition (array of these lives in HBM; blockIdx.z selects). */
+struct PartView {
+  uint32_t states, sp, cats, patterns, tips, edges;
+  uint32_t part_index, pad_;
+  const double *pmat;        // [edges][cats][states][sp]
+  const uint8_t *tipchars;   // [tips][patterns]
+  const uint32_t *tipmap;    // [256] code -> state mask
+  const uint32_t *weights;   // [patterns]
+  const double *freqs, *eigenvecs, *inv_eigenvecs, *eigenvals, *rates, *rate_weights;
+  double *const *clv;        // [nslots] -> CLV
+  uint32_t *const *scaler;   // [nslots] -> scaler
+  double *const *sumtable;   // [nsumtables]
+  const double *diagp;       // [cats][states][4] for the current derivative call
+};
+
+__device__ __forceinline__ double tree4(double a, double b, double c, double d) {
+  return __dadd_rn(__dadd_rn(a, b), __dadd_rn(c, d));
+}
+
+struct D4 { double x, y, z, w; };
+
+__device__ __forceinline__ D4 ldg256(const double *p) {
+  D4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg256(double *p, const D4 &v) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  P(t) = I + V^-1 diag(expm1(lambda r_c t)) V      (LIBPLL/core_pmatrix.c:24-244, core_pmatrix_avx.c:42)
+ * grid.x = edges to update, block = 128 threads looping over the cats*states*states outputs.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void k_pmatrix(PartView pv, double *pmat_out, const uint32_t *edge_idx, const double *brlen) {
+  extern __shared__ double expd[];  // [cats][states]
+  const uint32_t S = pv.states, SP = pv.sp, C = pv.cats;
+  const uint32_t edge = edge_idx[blockIdx.x];
+  const double t = brlen[blockIdx.x];
+  double *out = pmat_out + (size_t)edge * C * S * SP;
+  for (uint32_t i = threadIdx.x; i < C * S; i += blockDim.x) {
+    const uint32_t c = i / S, m = i % S;
+    // (eval*rate)*t exactly as core_pmatrix_avx.c:104-108 (pinv == 0)
+    expd[i] = expm1(__dmul_rn(__dmul_rn(pv.eigenvals[m], pv.rates[c]), t));
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < C * S * SP; i += blockDim.x) {
+    const uint32_t c = i / (S * SP), j = (i / SP) % S, k = i % SP;
+    double v = 0.0;
+    if (k < S) {
+      if (t > 0.0) {
+        const double *ex = expd + c * S;
+        if (S == 4) {  // tree sum, identity added last (core_pmatrix_avx.c:127-258)
+          double p0 = __dmul_rn(__dmul_rn(pv.inv_eigenvecs[j * SP + 0], ex[0]), pv.eigenvecs[0 * SP + k]);
+          double p1 = __dmul_rn(__dmul_rn(pv.inv_eigenvecs[j * SP + 1], ex[1]), pv.eigenvecs[1 * SP + k]);
+          double p2 = __dmul_rn(__dmul_rn(pv.inv_eigenvecs[j * SP + 2], ex[2]), pv.eigenvecs[2 * SP + k]);
+          double p3 = __dmul_rn(__dmul_rn(pv.inv_eigenvecs[j * SP + 3], ex[3]), pv.eigenvecs[3 * SP + k]);
+          v = __dadd_rn(tree4(p0, p1, p2, p3), (j == k) ? 1.0 : 0.0);
+        } else {       // identity first, serial accumulation (core_pmatrix.c:205-217)
+          v = (j == k) ? 1.0 : 0.0;
+          for (uint32_t m = 0; m < S; ++m)
+            v = __dadd_rn(v, __dmul_rn(__dmul_rn(pv.inv_eigenvecs[j * SP + m], ex[m]), pv.eigenvecs[m * SP + k]));
+        }
+      } else {
+        v = (j == k) ? 1.0 : 0.0;  // zero branch length: identity (core_pmatrix.c:220-226)
+      }
+    }
+    out[i] = v;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  CLV update, DNA (4 states) x 4 rate categories fast path.
+ * grid = (pattern tiles, ops, partitions of this shape); thread = one (pattern, category).
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void build_tip_lut4(double *lut /*[16][4][4]*/, const double *pm /*[4][4][4] of the edge*/, int tid) {
+  for (int idx = tid; idx < 256; idx += BLOCK) {
+    const int mask = idx >> 4, c = (idx >> 2) & 3, i = idx & 3;
+    const double *row = pm + (c * 4 + i) * 4;
+    // masked load + tree sum (core_partials_avx.c:1372-1400)
+    lut[idx] = tree4((mask & 1) ? row[0] : 0.0, (mask & 2) ? row[1] : 0.0, (mask & 4) ? row[2] : 0.0, (mask & 8) ? row[3] : 0.0);
+  }
+}
+
+/* P-matrix rows come from shared memory: [cat][row][col] with the category stride padded to 18 doubles so
+ * the four categories of a warp hit disjoint banks (each LDS.128 is then a single conflict-free wavefront
+ * with 8-lane broadcast).  Keeping the 2x16 doubles per thread in registers instead costs 64 registers and
+ * halves occupancy — measured worse for an HBM-bound kernel. */
+constexpr int PCAT = 18;  // padded doubles per category block (16 + 2)
+
+__device__ __forceinline__ D4 matvec4(const double *__restrict__ P /* smem, this thread's category */, const D4 &v) {
+  D4 r;
+  const double2 *q = reinterpret_cast<const double2 *>(P);
+  double2 a, b;
+  a = q[0]; b = q[1]; r.x = tree4(__dmul_rn(a.x, v.x), __dmul_rn(a.y, v.y), __dmul_rn(b.x, v.z), __dmul_rn(b.y, v.w));
+  a = q[2]; b = q[3]; r.y = tree4(__dmul_rn(a.x, v.x), __dmul_rn(a.y, v.y), __dmul_rn(b.x, v.z), __dmul_rn(b.y, v.w));
+  a = q[4]; b = q[5]; r.z = tree4(__dmul_rn(a.x, v.x), __dmul_rn(a.y, v.y), __dmul_rn(b.x, v.z), __dmul_rn(b.y, v.w));
+  a = q[6]; b = q[7]; r.w = tree4(__dmul_rn(a.x, v.x), __dmul_rn(a.y, v.y), __dmul_rn(b.x, v.z), __dmul_rn(b.y, v.w));
+  return r;
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(BLOCK) k_clv_dna4(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops) {
+  const PartView &pv = parts[blockIdx.z];
+  const nrx_op op = ops[blockIdx.y];
+  const int tid = threadIdx.x, cat = tid & 3, lane = tid & 31;
+  const uint64_t n_items = (uint64_t)pv.patterns * 4;
+  if ((uint64_t)blockIdx.x * BLOCK * UNROLL >= n_items) return;
+
+  __shared__ __align__(32) double lutL[256];
+  __shared__ __align__(32) double lutR[256];
+  __shared__ __align__(16) double sPL[4 * PCAT];
+  __shared__ __align__(16) double sPR[4 * PCAT];
+  const int lk = op.left_kind, rk = op.right_kind;
+  if (lk == NRX_CLV) {
+    if (tid < 64) sPL[(tid >> 4) * PCAT + (tid & 15)] = pv.pmat[(size_t)op.left_edge * 64 + tid];
+  } else if (lk == NRX_TIP) {
+    build_tip_lut4(lutL, pv.pmat + (size_t)op.left_edge * 64, tid);
+  }
+  if (rk == NRX_CLV) {
+    if (tid >= 64 && tid < 128) sPR[((tid - 64) >> 4) * PCAT + (tid & 15)] = pv.pmat[(size_t)op.right_edge * 64 + tid - 64];
+  } else if (rk == NRX_TIP) {
+    build_tip_lut4(lutR, pv.pmat + (size_t)op.right_edge * 64, tid);
+  }
+  __syncthreads();
+  const double *PL = sPL + cat * PCAT, *PR = sPR + cat * PCAT;
+
+  const double *clvL = (lk == NRX_CLV) ? pv.clv[op.left_idx] : nullptr;
+  const double *clvR = (rk == NRX_CLV) ? pv.clv[op.right_idx] : nullptr;
+  const uint32_t *scL = (lk == NRX_CLV) ? pv.scaler[op.left_idx] : nullptr;
+  const uint32_t *scR = (rk == NRX_CLV) ? pv.scaler[op.right_idx] : nullptr;
+  const uint8_t *tipL = (lk == NRX_TIP) ? pv.tipchars + (size_t)op.left_idx * pv.patterns : nullptr;
+  const uint8_t *tipR = (rk == NRX_TIP) ? pv.tipchars + (size_t)op.right_idx * pv.patterns : nullptr;
+  double *par = pv.clv[op.parent_slot];
+  uint32_t *psc = pv.scaler[op.parent_slot];
+  const bool tiptip = (lk == NRX_TIP && rk == NRX_TIP);  // scaler := 0, no scaling test (core_partials_avx.c:1003-1009)
+  const unsigned quad = 0xFu << (lane & ~3);
+
+  for (uint64_t base = (uint64_t)blockIdx.x * BLOCK * UNROLL; base < n_items; base += (uint64_t)gridDim.x * BLOCK * UNROLL) {
+    D4 l[UNROLL], r[UNROLL];
+    bool act[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {  // issue all loads first (memory-level parallelism)
+      const uint64_t g = base + (uint64_t)u * BLOCK + tid;
+      act[u] = g < n_items;
+      if (act[u]) {
+        if (lk == NRX_CLV) l[u] = ldg256(clvL + g * 4);
+        if (rk == NRX_CLV) r[u] = ldg256(clvR + g * 4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const uint64_t g = base + (uint64_t)u * BLOCK + tid;
+      const uint64_t site = g >> 2;
+      D4 x, y, p;
+      bool small = false;
+      if (act[u]) {
+        if (lk == NRX_CLV) x = matvec4(PL, l[u]);
+        else if (lk == NRX_TIP) x = *reinterpret_cast<const D4 *>(lutL + ((tipL[site] & 15) * 4 + cat) * 4);
+        if (rk == NRX_CLV) y = matvec4(PR, r[u]);
+        else if (rk == NRX_TIP) y = *reinterpret_cast<const D4 *>(lutR + ((tipR[site] & 15) * 4 + cat) * 4);
+        if (rk == NRX_NONE) p = x;        // x * 1.0 (fake all-ones CLV through identity P) is x, exactly
+        else if (lk == NRX_NONE) p = y;
+        else { p.x = __dmul_rn(x.x, y.x); p.y = __dmul_rn(x.y, y.y); p.z = __dmul_rn(x.z, y.z); p.w = __dmul_rn(x.w, y.w); }
+        small = (p.x < SCALE_THRESHOLD) & (p.y < SCALE_THRESHOLD) & (p.z < SCALE_THRESHOLD) & (p.w < SCALE_THRESHOLD);
+      }
+      // per-site scaling: all 16 entries of the site below 2^-256 (core_partials_avx.c:531-563)
+      const unsigned b = __ballot_sync(0xffffffffu, small);
+      const bool scale = !tiptip && ((b & quad) == quad);
+      if (act[u]) {
+        if (scale) { p.x = __dmul_rn(p.x, SCALE_FACTOR); p.y = __dmul_rn(p.y, SCALE_FACTOR); p.z = __dmul_rn(p.z, SCALE_FACTOR); p.w = __dmul_rn(p.w, SCALE_FACTOR); }
+        stg256(par + g * 4, p);
+        if (cat == 0) {
+          uint32_t s = 0;
+          if (!tiptip) {
+            if (scL) s += scL[site];
+            if (scR) s += scR[site];
+            s += scale ? 1u : 0u;
+          }
+          psc[site] = s;
+        }
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K2 generic (any states <= 32, any cats): one thread per (pattern, category), P rows from L1/L2.
+ * Used for protein data until the DMMA kernel takes over, and for unusual category counts.
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ double masked_rowsum(const double *row, uint32_t S, uint32_t mask) {
+  if (S == 4) return tree4((mask & 1) ? row[0] : 0.0, (mask & 2) ? row[1] : 0.0, (mask & 4) ? row[2] : 0.0, (mask & 8) ? row[3] : 0.0);
+  double s = 0.0;
+  for (uint32_t j = 0; j < S; ++j) if ((mask >> j) & 1) s = __dadd_rn(s, row[j]);
+  return s;
+}
+__device__ __forceinline__ double row_dot(const double *row, const double *v, uint32_t S) {
+  if (S == 4) return tree4(__dmul_rn(row[0], v[0]), __dmul_rn(row[1], v[1]), __dmul_rn(row[2], v[2]), __dmul_rn(row[3], v[3]));
+  double s = 0.0;
+  for (uint32_t j = 0; j < S; ++j) s = __dadd_rn(s, __dmul_rn(row[j], v[j]));
+  return s;
+}
+
+__global__ void __launch_bounds__(BLOCK) k_clv_generic(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops,
+                                                        uint32_t *__restrict__ flags /* per-site "not all small" scratch */) {
+  // Two-phase per pattern: (1) every (pattern,cat) thread writes its category block and atomically ANDs the
+  // "all small" predicate into a per-pattern word; (2) handled by k_clv_generic_scale.  To stay simple and
+  // correct for any category count, this kernel instead lets ONE thread own a whole pattern.
+  const PartView &pv = parts[blockIdx.z];
+  const nrx_op op = ops[blockIdx.y];
+  const uint32_t S = pv.states, SP = pv.sp, C = pv.cats;
+  const int lk = op.left_kind, rk = op.right_kind;
+  const bool tiptip = (lk == NRX_TIP && rk == NRX_TIP);
+  const double *pmL = pv.pmat + (size_t)op.left_edge * C * S * SP;
+  const double *pmR = pv.pmat + (size_t)op.right_edge * C * S * SP;
+  double *par = pv.clv[op.parent_slot];
+  uint32_t *psc = pv.scaler[op.parent_slot];
+  (void)flags;
+  for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
+    const uint32_t mL = (lk == NRX_TIP) ? pv.tipmap[pv.tipchars[(size_t)op.left_idx * pv.patterns + n]] : 0;
+    const uint32_t mR = (rk == NRX_TIP) ? pv.tipmap[pv.tipchars[(size_t)op.right_idx * pv.patterns + n]] : 0;
+    const double *cl = (lk == NRX_CLV) ? pv.clv[op.left_idx] + n * C * SP : nullptr;
+    const double *cr = (rk == NRX_CLV) ? pv.clv[op.right_idx] + n * C * SP : nullptr;
+    double *out = par + n * C * SP;
+    bool all_small = true;
+    for (uint32_t c = 0; c < C; ++c) {
+      for (uint32_t i = 0; i < S; ++i) {
+        const double *lrow = pmL + ((size_t)c * S + i) * SP, *rrow = pmR + ((size_t)c * S + i) * SP;
+        double x = 1.0, y = 1.0;
+        if (lk == NRX_CLV) x = row_dot(lrow, cl + c * SP, S); else if (lk == NRX_TIP) x = masked_rowsum(lrow, S, mL);
+        if (rk == NRX_CLV) y = row_dot(rrow, cr + c * SP, S); else if (rk == NRX_TIP) y = masked_rowsum(rrow, S, mR);
+        const double v = __dmul_rn(x, y);
+        out[c * SP + i] = v;
+        all_small &= (v < SCALE_THRESHOLD);
+      }
+      for (uint32_t i = S; i < SP; ++i) out[c * SP + i] = 0.0;
+    }
+    uint32_t s = 0;
+    if (!tiptip) {
+      if (lk == NRX_CLV) s += pv.scaler[op.left_idx][n];
+      if (rk == NRX_CLV) s += pv.scaler[op.right_idx][n];
+      if (all_small) {
+        for (uint32_t i = 0; i < C * SP; ++i) out[i] = __dmul_rn(out[i], SCALE_FACTOR);
+        s += 1;
+      }
+    }
+    psc[n] = s;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Block-level deterministic sum of up to 3 values; result valid in thread 0.
+ * ---------------------------------------------------------------------------------------------- */
+template <int N>
+__device__ __forceinline__ void block_sum(double (&v)[N], double *smem /* [N][BLOCK/32] */) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0)
+    for (int k = 0; k < N; ++k) smem[k * (BLOCK / 32) + warp] = v[k];
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int k = 0; k < N; ++k) {
+      double s = 0.0;
+      for (int w = 0; w < BLOCK / 32; ++w) s += smem[k * (BLOCK / 32) + w];
+      v[k] = s;
+    }
+}
+
+/* second stage: out[item][part][k] = sum over blocks of partial[((item*nparts+part)*N + k)*nblk + b], fixed order */
+__global__ void k_reduce_partials(const double *__restrict__ partial, double *__restrict__ out, uint32_t nblk, uint32_t total) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const double *p = partial + (size_t)i * nblk;
+  double s = 0.0;
+  for (uint32_t b = 0; b < nblk; ++b) s += p[b];
+  out[i] = s;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K3  root lnL (LIBPLL/core_likelihood.c:25-209, 4x4: core_likelihood_avx.c:206-282).
+ * K4  edge lnL (LIBPLL/core_likelihood.c:1191-1496 ii, :351-922 ti).
+ * Generic over states/cats: one thread per pattern (these kernels read each CLV once; the log and the
+ * reduction dominate).  grid = (tiles, items, partitions), partial sums per block, fixed-order stage 2.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(BLOCK) k_tree_lnl(const PartView *__restrict__ parts, const uint32_t *__restrict__ slots,
+                                                     double *__restrict__ partial, uint32_t nparts_total, double log_thresh,
+                                                     double *__restrict__ persite, size_t persite_stride) {
+  __shared__ double red[BLOCK / 32];
+  const PartView &pv = parts[blockIdx.z];
+  const uint32_t S = pv.states, SP = pv.sp, C = pv.cats;
+  const uint32_t slot = slots[blockIdx.y];
+  const double *clv = pv.clv[slot];
+  const uint32_t *sc = pv.scaler[slot];
+  double acc[1] = {0.0};
+  for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
+    const double *c = clv + n * C * SP;
+    double term = 0.0;
+    for (uint32_t j = 0; j < C; ++j) {
+      double term_r;
+      if (S == 4) {
+        const D4 v = ldg256(c + j * 4);
+        term_r = tree4(__dmul_rn(pv.freqs[0], v.x), __dmul_rn(pv.freqs[1], v.y), __dmul_rn(pv.freqs[2], v.z), __dmul_rn(pv.freqs[3], v.w));
+      } else {
+        term_r = 0.0;
+        for (uint32_t k = 0; k < S; ++k) term_r = __dadd_rn(term_r, __dmul_rn(c[j * SP + k], pv.freqs[k]));
+      }
+      term = __dadd_rn(term, __dmul_rn(term_r, pv.rate_weights[j]));
+    }
+    double lk = log(term);
+    const uint32_t s = sc[n];
+    if (s) lk = __dadd_rn(lk, __dmul_rn((double)s, log_thresh));
+    lk = __dmul_rn(lk, (double)pv.weights[n]);
+    if (persite) persite[((size_t)blockIdx.y * nparts_total + pv.part_index) * persite_stride + n] = lk;
+    acc[0] += lk;
+  }
+  block_sum<1>(acc, red);
+  if (threadIdx.x == 0) partial[((size_t)blockIdx.y * nparts_total + pv.part_index) * gridDim.x + blockIdx.x] = acc[0];
+}
+
+__global__ void __launch_bounds__(BLOCK) k_edge_lnl(const PartView *__restrict__ parts, const nrx_pair *__restrict__ pairs,
+                                                     uint32_t edge, double *__restrict__ partial, uint32_t nparts_total,
+                                                     double log_thresh) {
+  __shared__ double red[BLOCK / 32];
+  const PartView &pv = parts[blockIdx.z];
+  const uint32_t S = pv.states, SP = pv.sp, C = pv.cats;
+  nrx_pair pr = pairs[blockIdx.y];
+  // the tip, if any, plays "child" (LIBPLL/likelihood.c:586-601)
+  if (pr.a_kind == NRX_TIP) { nrx_pair t = pr; pr.a_kind = t.b_kind; pr.a_idx = t.b_idx; pr.b_kind = t.a_kind; pr.b_idx = t.a_idx; }
+  const double *clvp = pv.clv[pr.a_idx];
+  const uint32_t *scp = pv.scaler[pr.a_idx];
+  const double *clvc = (pr.b_kind == NRX_CLV) ? pv.clv[pr.b_idx] : nullptr;
+  const uint32_t *scc = (pr.b_kind == NRX_CLV) ? pv.scaler[pr.b_idx] : nullptr;
+  const uint8_t *tip = (pr.b_kind == NRX_TIP) ? pv.tipchars + (size_t)pr.b_idx * pv.patterns : nullptr;
+  const double *pm = pv.pmat + (size_t)edge * C * S * SP;
+  double acc[1] = {0.0};
+  for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
+    const uint32_t mask = tip ? pv.tipmap[tip[n]] : 0;
+    double terma = 0.0;
+    for (uint32_t i = 0; i < C; ++i) {
+      const double *cp = clvp + (n * C + i) * SP;
+      const double *cc = clvc ? clvc + (n * C + i) * SP : nullptr;
+      double terma_r = 0.0;
+      for (uint32_t j = 0; j < S; ++j) {
+        const double *row = pm + ((size_t)i * S + j) * SP;
+        const double termb = tip ? masked_rowsum(row, S, mask) : row_dot(row, cc, S);
+        terma_r = __dadd_rn(terma_r, __dmul_rn(__dmul_rn(cp[j], pv.freqs[j]), termb));
+      }
+      terma = __dadd_rn(terma, __dmul_rn(terma_r, pv.rate_weights[i]));
+    }
+    double lk = log(terma);
+    const uint32_t s = scp[n] + (scc ? scc[n] : 0u);
+    if (s) lk = __dadd_rn(lk, __dmul_rn((double)s, log_thresh));
+    acc[0] += __dmul_rn(lk, (double)pv.weights[n]);
+  }
+  block_sum<1>(acc, red);
+  if (threadIdx.x == 0) partial[((size_t)blockIdx.y * nparts_total + pv.part_index) * gridDim.x + blockIdx.x] = acc[0];
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K5  sumtable (LIBPLL/core_derivatives.c:321-471 ii, :473-641 ti): thread per (pattern, category).
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(BLOCK) k_sumtable(const PartView *__restrict__ parts, const nrx_pair *__restrict__ pairs) {
+  const PartView &pv = parts[blockIdx.z];
+  const uint32_t S = pv.states, SP = pv.sp, C = pv.cats;
+  nrx_pair pr = pairs[blockIdx.y];
+  // tip-inner: the TIP is the "left" operand of the core kernel (LIBPLL/derivatives.c:70-98)
+  if (pr.b_kind == NRX_TIP) { nrx_pair t = pr; pr.a_kind = t.b_kind; pr.a_idx = t.b_idx; pr.b_kind = t.a_kind; pr.b_idx = t.a_idx; }
+  const double *clvl = (pr.a_kind == NRX_CLV) ? pv.clv[pr.a_idx] : nullptr;
+  const uint8_t *tip = (pr.a_kind == NRX_TIP) ? pv.tipchars + (size_t)pr.a_idx * pv.patterns : nullptr;
+  const double *clvr = pv.clv[pr.b_idx];
+  double *out = pv.sumtable[blockIdx.y];
+  const uint64_t n_items = (uint64_t)pv.patterns * C;
+  for (uint64_t g = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; g < n_items; g += (uint64_t)gridDim.x * BLOCK) {
+    const uint64_t n = g / C;
+    const double *cr = clvr + g * SP;
+    const double *cl = clvl ? clvl + g * SP : nullptr;
+    const uint32_t mask = tip ? pv.tipmap[tip[n]] : 0;
+    for (uint32_t j = 0; j < S; ++j) {
+      double lefterm = 0.0, righterm = 0.0;
+      for (uint32_t k = 0; k < S; ++k) {
+        const double lv = tip ? (double)((mask >> k) & 1u) : cl[k];
+        lefterm = __dadd_rn(lefterm, __dmul_rn(__dmul_rn(lv, pv.freqs[k]), pv.inv_eigenvecs[k * SP + j]));
+        righterm = __dadd_rn(righterm, __dmul_rn(pv.eigenvecs[j * SP + k], cr[k]));
+      }
+      out[g * SP + j] = __dmul_rn(lefterm, righterm);
+    }
+    for (uint32_t j = S; j < SP; ++j) out[g * SP + j] = 0.0;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K6  first/second derivative + f per sumtable (LIBPLL/core_derivatives.c:643-694,840-867;
+ * f as in core_derivatives_avx2.c:1788-1874: no scaler term).  thread per pattern.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(BLOCK) k_derivatives(const PartView *__restrict__ parts, double *__restrict__ partial,
+                                                        uint32_t nparts_total) {
+  __shared__ double red[3 * (BLOCK / 32)];
+  const PartView &pv = parts[blockIdx.z];
+  const uint32_t S = pv.states, SP = pv.sp, C = pv.cats;
+  const double *st = pv.sumtable[blockIdx.y];
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
+    const double *sum = st + n * C * SP;
+    double lk0 = 0.0, lk1 = 0.0, lk2 = 0.0;
+    for (uint32_t i = 0; i < C; ++i) {
+      double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+      const double *dg = pv.diagp + (size_t)i * S * 4;
+      for (uint32_t j = 0; j < S; ++j) {
+        const double v = sum[i * SP + j];
+        c0 = __dadd_rn(c0, __dmul_rn(v, dg[j * 4 + 0]));
+        c1 = __dadd_rn(c1, __dmul_rn(v, dg[j * 4 + 1]));
+        c2 = __dadd_rn(c2, __dmul_rn(v, dg[j * 4 + 2]));
+      }
+      const double w = pv.rate_weights[i];
+      lk0 = __dadd_rn(lk0, __dmul_rn(c0, w));
+      lk1 = __dadd_rn(lk1, __dmul_rn(c1, w));
+      lk2 = __dadd_rn(lk2, __dmul_rn(c2, w));
+    }
+    const double pw = (double)pv.weights[n];
+    const double d1 = -lk1 / lk0;
+    const double d2 = d1 * d1 - lk2 / lk0;
+    acc[0] += pw * log(lk0);
+    acc[1] += pw * d1;
+    acc[2] += pw * d2;
+  }
+  block_sum<3>(acc, red);
+  if (threadIdx.x == 0) {
+    double *p = partial + ((size_t)blockIdx.y * nparts_total + pv.part_index) * 3 * gridDim.x;
+    p[0 * gridDim.x + blockIdx.x] = acc[0];
+    p[1 * gridDim.x + blockIdx.x] = acc[1];
+    p[2 * gridDim.x + blockIdx.x] = acc[2];
+  }
+}
+
+}  // namespace nrx

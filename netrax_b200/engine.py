@@ -1,0 +1,107 @@
+"""Python binding of the product: libnetrax_b200.so (C++ host mirror of NetRAX's likelihood API) on top of
+libnrx_engine.so (sm_100a CUDA kernels).  There is no CPU fallback: importing works anywhere, but creating an
+engine without the compiled extension or without a CUDA device raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from ._capi import AVERAGE, BEST, LINKED, UNLINKED, FlatAPI, LikelihoodEngine, LikelihoodError, Partition
+from .network_io import NetworkDesc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_SO = os.path.join(HERE, "libnetrax_b200.so")
+ENGINE_SO = os.path.join(HERE, "libnrx_engine.so")
+
+_api: Optional[FlatAPI] = None
+REDUCE_CB = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.c_size_t, C.c_int)
+
+
+def load() -> FlatAPI:
+    """Load the CUDA extension.  Fails loudly when it has not been built (run __graft_entry__.build())."""
+    global _api
+    if _api is None:
+        for so in (ENGINE_SO, HOST_SO):
+            if not os.path.exists(so):
+                raise ImportError(f"netrax_b200: compiled extension {so} is missing — build it with "
+                                  f"`make -C netrax_b200/csrc` (python -c 'import __graft_entry__ as g; g.build()'); "
+                                  f"there is no CPU fallback")
+        C.CDLL(ENGINE_SO, mode=C.RTLD_GLOBAL)
+        lib = C.CDLL(HOST_SO)
+        a = FlatAPI(lib, "nrxh_")
+        lib.nrxh_set_eigen.restype = C.c_int
+        lib.nrxh_set_eigen.argtypes = [C.c_void_p, C.c_uint] + [np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")] * 3
+        lib.nrxh_set_reduce_callback.restype = C.c_int
+        lib.nrxh_set_reduce_callback.argtypes = [C.c_void_p, REDUCE_CB, C.c_void_p]
+        lib.nrxh_launch_count.restype = C.c_ulonglong
+        lib.nrxh_launch_count.argtypes = [C.c_void_p]
+        lib.nrxh_num_slots.restype = C.c_uint
+        lib.nrxh_num_slots.argtypes = [C.c_void_p]
+        lib.nrxh_profile_enable.restype = C.c_int
+        lib.nrxh_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        lib.nrxh_profile_read.restype = C.c_int
+        lib.nrxh_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double)] + [C.POINTER(C.c_ulonglong)] * 3
+        lib.nrxh_persite_lnl.restype = C.c_int
+        lib.nrxh_persite_lnl.argtypes = [C.c_void_p, C.c_uint, np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), C.c_uint]
+        lib.nrxh_engine.restype = C.c_void_p
+        lib.nrxh_engine.argtypes = [C.c_void_p]
+        _api = a
+    return _api
+
+
+def device_count() -> int:
+    lib = C.CDLL(ENGINE_SO, mode=C.RTLD_GLOBAL)
+    lib.nrx_device_count.restype = C.c_int
+    return lib.nrx_device_count()
+
+
+class NetraxB200(LikelihoodEngine):
+    """AnnotatedNetwork + likelihood state on one B200.  `reduce` (optional) is the parallel_reduce_cb of the
+    reference: a callable that sums a float64 numpy array in place across all site shards (ranks)."""
+
+    def __init__(self, net: NetworkDesc, partitions: Sequence[Partition], variant: int = AVERAGE, linkage: int = LINKED,
+                 device: int = 0, plan_cache: bool = True, partition_brlens=None,
+                 reduce: Optional[Callable[[np.ndarray], None]] = None):
+        api = load()
+        self._reduce = reduce
+        self._cb = None
+        self._pre_init_hook = None
+        if reduce is not None:
+            def _cb(ctx, data, count, op):
+                arr = np.ctypeslib.as_array(data, shape=(count,))
+                reduce(arr)
+            self._cb = REDUCE_CB(_cb)
+        # LikelihoodEngine.__init__ runs nrxh_init; the callback must be installed before the first evaluation only
+        super().__init__(api, net, partitions, variant=variant, linkage=linkage,
+                         backend=f"device={device};plan_cache={1 if plan_cache else 0}", partition_brlens=partition_brlens)
+        if self._cb is not None:
+            api.check(api.lib.nrxh_set_reduce_callback(self.h, self._cb, None))
+
+    def set_eigen(self, p: int, eigenvecs, inv_eigenvecs, eigenvals):
+        """Test hook: inject an eigen-decomposition (e.g. the reference's) instead of the host Jacobi solver's."""
+        self.api.check(self.api.lib.nrxh_set_eigen(self.h, p, np.ascontiguousarray(eigenvecs), np.ascontiguousarray(inv_eigenvecs),
+                                                   np.ascontiguousarray(eigenvals)))
+
+    def launch_count(self) -> int:
+        return int(self.api.lib.nrxh_launch_count(self.h))
+
+    def num_slots(self) -> int:
+        return int(self.api.lib.nrxh_num_slots(self.h))
+
+    def profile_enable(self, on: bool = True):
+        self.api.check(self.api.lib.nrxh_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        ms = C.c_double()
+        l, u, b = C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong()
+        self.api.check(self.api.lib.nrxh_profile_read(self.h, C.byref(ms), C.byref(l), C.byref(u), C.byref(b)))
+        return {"clv_ms": ms.value, "clv_launches": l.value, "clv_site_updates": u.value, "clv_bytes": b.value}
+
+    def persite_lnl(self, tree: int) -> np.ndarray:
+        stride = max(p.sites for p in self.partitions)
+        out = np.zeros((self.P, stride))
+        self.api.check(self.api.lib.nrxh_persite_lnl(self.h, tree, out.reshape(-1), stride))
+        return out

@@ -1,0 +1,251 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C-ABI, against the oracle on the same
+seeded inputs.  Bars (BASELINE.json north_star): lnL within 1e-10 relative, derivatives within 1e-8 relative,
+scaler counts and BEST-tree selection bit-exact.  DNA CLVs are additionally required to be BIT-IDENTICAL when the
+engine is fed the oracle's eigen-decomposition (the kernels mirror the reference's operation order)."""
+import numpy as np
+import pytest
+
+from helpers import FIXTURE_PAIRS, fixture_summary, load_fixture, load_golden
+from netrax_b200._capi import AVERAGE, BEST, LINKED, UNLINKED, Partition
+from netrax_b200.synth import DNA_FREQS, GAMMA4_ALPHA05, GTR_RATES, caterpillar_network, random_network, simulate_alignment
+
+pytestmark = pytest.mark.gpu
+
+LNL_RTOL = 1e-10     # north_star: per-site and total lnL within 1e-10 relative
+DERIV_RTOL = 1e-8    # north_star: derivatives within 1e-8 relative
+
+
+def _gpu(net, parts, **kw):
+    from netrax_b200.engine import NetraxB200
+    return NetraxB200(net, parts, **kw)
+
+
+def _oracle(net, parts, **kw):
+    from oracle import oracle
+    return oracle.make_engine("ref" if oracle.have_ref() else "port", net, parts, **kw)
+
+
+def _inject_eigen(g, o):
+    for p in range(g.P):
+        g.set_eigen(p, *o.get_eigen(p))
+
+
+def _compare_all_clvs(g, o, exact):
+    net = g.net
+    for v in range(net.num_tips, net.num_nodes):
+        assert g.num_trees(v) == o.num_trees(v), v
+        for t in range(g.num_trees(v)):
+            assert g.tree_config(v, t) == o.tree_config(v, t)
+            for p in range(g.P):
+                assert np.array_equal(g.read_scaler(v, t, p), o.read_scaler(v, t, p)), (v, t, p)   # bit-exact integers
+                a, b = g.read_clv(v, t, p), o.read_clv(v, t, p)
+                if exact:
+                    assert np.array_equal(a, b), (v, t, p, np.abs(a - b).max())
+                else:
+                    np.testing.assert_allclose(a, b, rtol=1e-12, atol=0)
+
+
+GOLD = load_golden("netrax_fixtures_golden.json")["cases"]
+
+
+@pytest.mark.parametrize("name", list(FIXTURE_PAIRS))
+@pytest.mark.parametrize("variant", [AVERAGE, BEST])
+def test_reference_fixtures_match_golden(name, variant):
+    """The committed golden files were produced by the reference's real libpll (oracle kind 'reference')."""
+    net, part = load_fixture(*FIXTURE_PAIRS[name])
+    g = _gpu(net, [part], variant=variant)
+    got = fixture_summary(g)
+    exp = GOLD[f"{name}/{'AVERAGE' if variant == AVERAGE else 'BEST'}"]
+    assert got["lnl"] == pytest.approx(exp["lnl"], rel=LNL_RTOL)
+    assert [t["config"] for t in got["root_trees"]] == [t["config"] for t in exp["root_trees"]]
+    for a, b in zip(got["root_trees"], exp["root_trees"]):
+        assert a["logprob"] == pytest.approx(b["logprob"], rel=1e-13, abs=1e-300)
+        assert a["partition_logl"] == pytest.approx(b["partition_logl"], rel=LNL_RTOL)
+    assert got["nodes"].keys() == exp["nodes"].keys()
+    for k in got["nodes"]:
+        assert got["nodes"][k]["scaler_sum"] == exp["nodes"][k]["scaler_sum"], k
+        assert got["nodes"][k]["clv_sum"] == pytest.approx(exp["nodes"][k]["clv_sum"], rel=1e-11), k
+    g.close()
+
+
+@pytest.mark.parametrize("cfg", [(8, 1, 257, 1), (20, 1, 1000, 2), (25, 3, 333, 3), (40, 5, 150, 4), (12, 0, 64, 5)])
+@pytest.mark.parametrize("variant", [AVERAGE, BEST])
+def test_full_evaluation_bitexact_clvs(cfg, variant):
+    n, r, pat, seed = cfg
+    net = random_network(n, r, seed=seed)
+    m, w = simulate_alignment(net, pat, seed=seed)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    o = _oracle(net, [part], variant=variant)
+    g = _gpu(net, [part], variant=variant)
+    # (1) own eigen-decomposition + device P-matrices: tolerance-level agreement
+    lo, lg = o.computeLoglikelihood(0, 1), g.computeLoglikelihood(0, 1)
+    assert lg == pytest.approx(lo, rel=LNL_RTOL)
+    for e in range(net.num_edges + 1):
+        np.testing.assert_allclose(g.get_pmatrix(e), o.get_pmatrix(e), rtol=1e-12, atol=1e-15)
+    _compare_all_clvs(g, o, exact=False)
+    # (2) the oracle's eigen-decomposition injected: P-matrices within 1 ulp-ish, CLVs bit-identical whenever P is
+    _inject_eigen(g, o)
+    lg = g.computeLoglikelihood(0, 1)
+    assert lg == pytest.approx(lo, rel=1e-13)
+    same_p = all(np.array_equal(g.get_pmatrix(e), o.get_pmatrix(e)) for e in range(net.num_edges + 1))
+    _compare_all_clvs(g, o, exact=same_p)
+    root = net.root
+    for t in range(g.num_trees(root)):
+        assert g.tree_info(root, t)[1] == pytest.approx(o.tree_info(root, t)[1], rel=LNL_RTOL)
+    if variant == BEST:  # BEST-tree selection bit-exact
+        best_g = max(range(g.num_trees(root)), key=lambda t: (g.tree_info(root, t)[0] + g.tree_info(root, t)[1][0], -t))
+        best_o = max(range(o.num_trees(root)), key=lambda t: (o.tree_info(root, t)[0] + o.tree_info(root, t)[1][0], -t))
+        assert best_g == best_o
+    # second full evaluation goes through the cached plan: identical result
+    assert g.computeLoglikelihood(0, 1) == lg
+    g.close()
+
+
+def test_persite_lnl_matches_oracle():
+    from oracle import oracle
+    net = random_network(10, 1, seed=9)
+    m, w = simulate_alignment(net, 300, seed=9)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    g = _gpu(net, [part])
+    o = _oracle(net, [part])
+    g.computeLoglikelihood(0, 1); o.computeLoglikelihood(0, 1)
+    for t in range(g.num_trees(net.root)):
+        ps = g.persite_lnl(t)[0]
+        assert ps.sum() == pytest.approx(o.tree_info(net.root, t)[1][0], rel=LNL_RTOL)
+        assert np.all(ps < 0)
+
+
+def test_incremental_and_cached_semantics():
+    net, part = load_fixture(*FIXTURE_PAIRS["three_reticulations"])
+    g, o = _gpu(net, [part]), _oracle(net, [part])
+    l0 = g.computeLoglikelihood(0, 1)
+    assert l0 == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
+    n0 = g.launch_count()
+    assert g.computeLoglikelihood(1, 1) == l0 and g.launch_count() == n0      # cached: nothing launched
+    for e in range(net.num_edges):
+        old = float(net.edge_length[e])
+        for eng in (g, o):
+            eng.set_branch_length(e, old * 3 + 0.01)
+        l1 = g.computeLoglikelihood(1, 1)
+        assert l1 == pytest.approx(o.computeLoglikelihood(1, 1), rel=LNL_RTOL)
+        assert l1 == pytest.approx(g.computeLoglikelihood(0, 1), rel=1e-14)    # incremental == full
+        for eng in (g, o):
+            eng.set_branch_length(e, old)
+        assert g.computeLoglikelihood(1, 1) == pytest.approx(l0, rel=1e-14)
+        o.computeLoglikelihood(1, 1)
+    # reticulation probability change re-mixes cached per-tree lnLs without touching CLVs
+    n1 = g.launch_count()
+    for eng in (g, o):
+        eng.set_reticulation_prob(0, 0.31)
+    assert g.computeLoglikelihood(1, 1) == pytest.approx(o.computeLoglikelihood(1, 1), rel=LNL_RTOL)
+    assert g.launch_count() == n1
+    g.close()
+
+
+@pytest.mark.parametrize("name", ["small", "clv_averaging", "two_reticulations", "three_reticulations", "interleaved_reticulations",
+                                  "reticulation_in_reticulation", "tree"])
+@pytest.mark.parametrize("variant", [AVERAGE, BEST])
+def test_brlen_flow_every_edge(name, variant):
+    """optimize_branch's likelihood calls on every edge: re-rooting preserves lnL (BrlenOptTest.cpp:297-367),
+    edge-rooted lnL, sumtables and derivatives match the oracle at several proposal lengths."""
+    net, part = load_fixture(*FIXTURE_PAIRS[name])
+    g, o = _gpu(net, [part], variant=variant), _oracle(net, [part], variant=variant)
+    _inject_eigen(g, o)
+    l0 = g.computeLoglikelihood(0, 1)
+    assert l0 == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
+    for e in range(net.num_edges):
+        assert g.brlen_prepare(e) == pytest.approx(o.brlen_prepare(e), rel=LNL_RTOL)
+        lb = g.computeLoglikelihoodBrlenOpt(e)
+        assert lb == pytest.approx(l0, rel=1e-11), e
+        assert lb == pytest.approx(o.computeLoglikelihoodBrlenOpt(e), rel=LNL_RTOL)
+        ng, no = g.computePartitionSumtables(e), o.computePartitionSumtables(e)
+        assert ng == no
+        for i in range(ng):
+            sg, pg, lg_, rg = g.read_sumtable(0, i)
+            so, po, lo_, ro = o.read_sumtable(0, i)
+            assert (lg_, rg) == (lo_, ro) and pg == pytest.approx(po, rel=1e-14)
+            np.testing.assert_allclose(sg, so, rtol=1e-10, atol=1e-300)
+        if ng:
+            t0 = float(net.edge_length[e])
+            for t in (t0, 0.05, 0.7):
+                for eng in (g, o):
+                    eng.brlen_set_length(e, t)
+                dg, do = g.computeLoglikelihoodDerivatives(e), o.computeLoglikelihoodDerivatives(e)
+                np.testing.assert_allclose(dg[4], do[4], rtol=DERIV_RTOL, atol=1e-9)      # raw (f, d1, d2) per tree pair
+                assert dg[0] == pytest.approx(do[0], rel=DERIV_RTOL, abs=1e-7)
+                assert dg[1] == pytest.approx(do[1], rel=DERIV_RTOL, abs=1e-7)
+                assert g.computeLoglikelihoodBrlenOpt(e) == pytest.approx(o.computeLoglikelihoodBrlenOpt(e), rel=LNL_RTOL)
+            for eng in (g, o):
+                eng.brlen_set_length(e, t0)
+        assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL)
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(l0, rel=1e-13)
+    g.close()
+
+
+def test_scaler_stress_caterpillar_bitexact_scalers():
+    net = caterpillar_network(400)
+    m, w = simulate_alignment(net, 1000, seed=11, random_cells=True)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    g, o = _gpu(net, [part]), _oracle(net, [part])
+    _inject_eigen(g, o)
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
+    root = net.root
+    mx = 0
+    for t in range(g.num_trees(root)):
+        sg, so = g.read_scaler(root, t), o.read_scaler(root, t)
+        assert np.array_equal(sg, so)
+        mx = max(mx, int(sg.max()))
+    assert mx >= 2
+    g.close()
+
+
+def test_multi_partition_unlinked_best():
+    net = random_network(14, 3, seed=21)
+    rng = np.random.default_rng(0)
+    parts, brl = [], []
+    for p, pat in enumerate((500, 333, 1, 777)):   # ragged partition sizes incl. a single-pattern one
+        m, w = simulate_alignment(net, pat, seed=30 + p)
+        parts.append(Partition(4, 4, m, DNA_FREQS * 0 + [0.25 + 0.02 * p, 0.25 - 0.02 * p, 0.25, 0.25], GTR_RATES * (1 + 0.1 * p), GAMMA4_ALPHA05, pattern_weights=w))
+        brl.append(net.edge_length * rng.uniform(0.5, 2, net.num_edges))
+    for variant in (BEST, AVERAGE):
+        g = _gpu(net, parts, variant=variant, linkage=UNLINKED, partition_brlens=brl)
+        o = _oracle(net, parts, variant=variant, linkage=UNLINKED, partition_brlens=brl)
+        assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
+        np.testing.assert_allclose(g.partition_loglh(), o.partition_loglh(), rtol=LNL_RTOL)
+        e = int(net.ret_first_edge[1])
+        for eng in (g, o):
+            eng.brlen_prepare(e)
+            eng.computePartitionSumtables(e)
+        dg, do = g.computeLoglikelihoodDerivatives(e), o.computeLoglikelihoodDerivatives(e)
+        np.testing.assert_allclose(dg[2], do[2], rtol=DERIV_RTOL, atol=1e-7)
+        np.testing.assert_allclose(dg[3], do[3], rtol=DERIV_RTOL, atol=1e-7)
+        assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL)
+        g.close()
+
+
+def test_model_change_full_reevaluation():
+    from oracle import oracle
+    net = random_network(9, 2, seed=5)
+    m, w = simulate_alignment(net, 400, seed=5)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    g, o = _gpu(net, [part]), _oracle(net, [part])
+    for alpha in (0.3, 1.2):
+        rates = oracle.api("port").gamma_rates(alpha, 4)
+        for eng in (g, o):
+            eng.set_model(0, [0.2, 0.3, 0.1, 0.4], [0.5, 2.0, 1.5, 0.7, 4.0, 1.0], rates, [0.25] * 4)
+        assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
+    g.close()
+
+
+def test_error_behaviour_mirrors_reference():
+    from netrax_b200._capi import LikelihoodError
+    net = random_network(6, 1, seed=2)
+    m, w = simulate_alignment(net, 40, seed=2)
+    bad = m.copy(); bad[0, 0] = 0   # illegal state code (pll_set_tip_states fails with "Illegal state code in tip")
+    with pytest.raises(LikelihoodError, match="Illegal state code"):
+        _gpu(net, [Partition(4, 4, bad, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05)])
+    g = _gpu(net, [Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)])
+    g.computeLoglikelihood(0, 1)
+    tip_edge = 0   # edge into tip 0: source inner, target tip -> fine; a tip-tip pair cannot occur in a network
+    g.brlen_prepare(tip_edge); g.computePartitionSumtables(tip_edge); g.brlen_finish(tip_edge)
+    g.close()

@@ -74,6 +74,10 @@ int nrxh_profile_enable(void *h, int on);
 int nrxh_profile_read(void *h, double *clv_ms, unsigned long long *launches, unsigned long long *site_updates, unsigned long long *bytes);
 int nrxh_persite_lnl(void *h, unsigned tree, double *out /* [nparts][max_sites] */, unsigned stride);
 void *nrxh_engine(void *h); /* the underlying nrx_engine* */
+/* re-upload one partition's alignment slice from HOST buffers (tipchars: 1 byte per cell, DNA) + pattern weights */
+int nrxh_upload_alignment_u8(void *h, unsigned p, const uint8_t *tipchars, const unsigned *pattern_weights);
+int nrxh_timer_start(void *h);
+int nrxh_timer_stop(void *h, double *elapsed_ms);
 
 #ifdef __cplusplus
 }

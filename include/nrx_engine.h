@@ -75,6 +75,8 @@ void nrx_engine_destroy(nrx_engine *e);
 
 /* tip_masks: [tips][patterns] state bit masks (bit k = state k; DNA 1..15).  Re-coded to uint8 on upload. */
 int nrx_set_tips(nrx_engine *e, uint32_t p, const uint32_t *tip_masks);
+/* Same, for callers that already hold libpll-style tipchars (1 byte per cell; DNA: the 4-bit mask itself). */
+int nrx_set_tipchars_u8(nrx_engine *e, uint32_t p, const uint8_t *codes);
 int nrx_set_pattern_weights(nrx_engine *e, uint32_t p, const uint32_t *weights);
 /* eigenvecs / inv_eigenvecs: [states][states_padded]; eigenvals, freqs: [states_padded] (padding ignored);
  * prop_invar must be 0 (+I partitions are rejected). */
@@ -117,6 +119,9 @@ int nrx_sync(nrx_engine *e);
  * the last nrx_tree_lnl / nrx_edge_lnl / nrx_derivatives result also stays in this device buffer. */
 void *nrx_result_device_ptr(nrx_engine *e);
 void *nrx_stream(nrx_engine *e); /* cudaStream_t */
+/* CUDA-event stopwatch on the engine's own stream (torch.cuda.Event cannot see this stream). */
+int nrx_timer_start(nrx_engine *e);
+int nrx_timer_stop(nrx_engine *e, double *elapsed_ms);
 /* number of kernels launched by this engine so far (bench.py "gpu_launches") */
 unsigned long long nrx_launch_count(nrx_engine *e);
 /* device time (ms) spent in K2 launches since the last reset, measured with CUDA events on the engine

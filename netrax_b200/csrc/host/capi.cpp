@@ -353,5 +353,15 @@ int nrxh_persite_lnl(void *hv, unsigned tree, double *out, unsigned stride) {
   });
 }
 void *nrxh_engine(void *hv) { return H(hv)->ann.engine; }
+int nrxh_upload_alignment_u8(void *hv, unsigned p, const uint8_t *tipchars, const unsigned *pw) {
+  return guarded([&] {
+    AnnotatedNetwork &ann = H(hv)->ann;
+    detail::engineCheck(nrx_set_tipchars_u8(ann.engine, p, tipchars), "nrx_set_tipchars_u8");
+    if (pw) detail::engineCheck(nrx_set_pattern_weights(ann.engine, p, pw), "nrx_set_pattern_weights");
+    invalidateAllCLVs(ann);
+  });
+}
+int nrxh_timer_start(void *hv) { if (!nrx_timer_start(H(hv)->ann.engine)) { g_err = nrx_last_error(); return 0; } return 1; }
+int nrxh_timer_stop(void *hv, double *ms) { if (!nrx_timer_stop(H(hv)->ann.engine, ms)) { g_err = nrx_last_error(); return 0; } return 1; }
 
 }  // extern "C"

@@ -72,6 +72,7 @@ struct nrx_engine {
   double *d_persite = nullptr;
   size_t persite_cap = 0;
   unsigned long long launches = 0;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
   bool views_dirty = true;
   // profiling of K2
   bool prof = false;
@@ -289,6 +290,21 @@ int nrx_set_tips(nrx_engine *e, uint32_t pi, const uint32_t *tip_masks) {
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaMemcpy(p.tipchars, codes.data(), std::max<size_t>(1, n), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(p.tipmap, tipmap.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  p.tips_set = true;
+  return 1;
+}
+
+int nrx_set_tipchars_u8(nrx_engine *e, uint32_t pi, const uint8_t *codes) {
+  if (!check_part(e, pi)) return 0;
+  CK(cudaSetDevice(e->device));
+  Part &p = e->parts[pi];
+  if (p.d.states != 4) { g_err = "nrx_set_tipchars_u8: only 4-state partitions store the mask as the code"; return 0; }
+  const size_t n = (size_t)p.d.tips * p.d.patterns;
+  std::vector<uint32_t> tipmap(256, 0);
+  for (uint32_t i = 0; i < 16; ++i) tipmap[i] = i;
+  CK(cudaMemcpyAsync(p.tipchars, codes, n, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(p.tipmap, tipmap.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
   p.tips_set = true;
   return 1;
 }
@@ -665,6 +681,25 @@ int nrx_sync(nrx_engine *e) {
 void *nrx_result_device_ptr(nrx_engine *e) { return e ? e->d_result : nullptr; }
 void *nrx_stream(nrx_engine *e) { return e ? (void *)e->stream : nullptr; }
 unsigned long long nrx_launch_count(nrx_engine *e) { return e ? e->launches : 0; }
+
+int nrx_timer_start(nrx_engine *e) {
+  if (!e) { g_err = "null engine"; return 0; }
+  CK(cudaSetDevice(e->device));
+  if (!e->t0) { CK(cudaEventCreate(&e->t0)); CK(cudaEventCreate(&e->t1)); }
+  CK(cudaEventRecord(e->t0, e->stream));
+  return 1;
+}
+
+int nrx_timer_stop(nrx_engine *e, double *elapsed_ms) {
+  if (!e || !e->t0) { g_err = "timer not started"; return 0; }
+  CK(cudaSetDevice(e->device));
+  CK(cudaEventRecord(e->t1, e->stream));
+  CK(cudaEventSynchronize(e->t1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e->t0, e->t1));
+  if (elapsed_ms) *elapsed_ms = ms;
+  return 1;
+}
 
 int nrx_profile_enable(nrx_engine *e, int on) {
   if (!e) { g_err = "null engine"; return 0; }

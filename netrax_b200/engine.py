@@ -48,6 +48,12 @@ def load() -> FlatAPI:
         lib.nrxh_persite_lnl.argtypes = [C.c_void_p, C.c_uint, np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), C.c_uint]
         lib.nrxh_engine.restype = C.c_void_p
         lib.nrxh_engine.argtypes = [C.c_void_p]
+        lib.nrxh_upload_alignment_u8.restype = C.c_int
+        lib.nrxh_upload_alignment_u8.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p]
+        lib.nrxh_timer_start.restype = C.c_int
+        lib.nrxh_timer_start.argtypes = [C.c_void_p]
+        lib.nrxh_timer_stop.restype = C.c_int
+        lib.nrxh_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         _api = a
     return _api
 
@@ -105,3 +111,15 @@ class NetraxB200(LikelihoodEngine):
         out = np.zeros((self.P, stride))
         self.api.check(self.api.lib.nrxh_persite_lnl(self.h, tree, out.reshape(-1), stride))
         return out
+
+    def upload_alignment_u8(self, p: int, tipchars_ptr: int, weights_ptr: int = 0):
+        """Host -> device re-upload of one partition's alignment slice (pointers to pinned or pageable host memory)."""
+        self.api.check(self.api.lib.nrxh_upload_alignment_u8(self.h, p, C.c_void_p(tipchars_ptr), C.c_void_p(weights_ptr) if weights_ptr else None))
+
+    def timer_start(self):
+        self.api.check(self.api.lib.nrxh_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self.api.check(self.api.lib.nrxh_timer_stop(self.h, C.byref(ms)))
+        return ms.value

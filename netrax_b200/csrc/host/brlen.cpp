@@ -338,7 +338,8 @@ LoglDerivatives computeLoglikelihoodDerivatives(AnnotatedNetwork &ann, const std
   for (unsigned p = 0; p < P; ++p) {
     const bool single_tree_mode = (n == 1);
     double res_prime = 0.0, res_prime_prime = 0.0;
-    for (size_t i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) out.raw[p].push_back(vals[(i * P + p) * 3 + k]);
+    // single-tree mode: the reference passes f = nullptr to libpll (LikelihoodDerivatives.cpp:104), so no f exists
+    for (size_t i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) out.raw[p].push_back((single_tree_mode && k == 0) ? 0.0 : vals[(i * P + p) * 3 + k]);
     if (single_tree_mode) {
       res_prime = vals[p * 3 + 1];
       res_prime_prime = vals[p * 3 + 2];

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -27,7 +28,7 @@ bool cuda_ok(cudaError_t e, const char *what) {
 
 struct Part {
   nrx_partition_desc d{};
-  uint32_t sp = 0;
+  uint32_t sp = 0, pat_pad = 0;  // pat_pad: patterns rounded up to a whole K2 tile (bulk copies always move full tiles)
   size_t clv_entries = 0, pmat_entries = 0;
   double *pmat = nullptr;
   uint8_t *tipchars = nullptr;
@@ -72,6 +73,8 @@ struct nrx_engine {
   double *d_persite = nullptr;
   size_t persite_cap = 0;
   unsigned long long launches = 0;
+  int k2_variant = 0;       // 0: k_clv_dna4_pipe (production); UM: k_clv_dna4<U, MINB> (A/B experiments, env NRX_K2=UM)
+  uint32_t k2_blocks = 296; // resident-block target of the pipelined kernel (2 per SM x 148 SMs)
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   bool views_dirty = true;
   // profiling of K2
@@ -141,7 +144,7 @@ template <class T> int upload(nrx_engine *e, const T *src, size_t n, T **dev) {
 PartView make_view(const Part &p, uint32_t index) {
   PartView v{};
   v.states = p.d.states; v.sp = p.sp; v.cats = p.d.rate_cats; v.patterns = p.d.patterns; v.tips = p.d.tips; v.edges = p.d.edges;
-  v.part_index = index;
+  v.part_index = index; v.tip_pitch = p.pat_pad;
   v.pmat = p.pmat; v.tipchars = p.tipchars; v.tipmap = p.tipmap; v.weights = p.weights;
   v.freqs = p.freqs; v.eigenvecs = p.eigenvecs; v.inv_eigenvecs = p.inv_eigenvecs; v.eigenvals = p.eigenvals;
   v.rates = p.rates; v.rate_weights = p.rate_weights;
@@ -209,18 +212,27 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
   e->device = device;
   if (!cuda_ok(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete e; return nullptr; }
   e->parts.resize(nparts);
+  if (const char *v = std::getenv("NRX_K2")) e->k2_variant = std::atoi(v);
+  if (const char *v = std::getenv("NRX_K2_BLOCKS")) e->k2_blocks = (uint32_t)std::max(1, std::atoi(v));
+  {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (!std::getenv("NRX_K2_BLOCKS")) e->k2_blocks = 2u * (uint32_t)sms;
+    if (!cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClvPipeSmem)), "cudaFuncSetAttribute")) { delete e; return nullptr; }
+  }
   for (uint32_t i = 0; i < nparts; ++i) {
     Part &p = e->parts[i];
     p.d = descs[i];
     if (p.d.states < 2 || p.d.states > 32 || p.d.rate_cats < 1 || p.d.rate_cats > 16) { g_err = "unsupported states / rate_cats"; nrx_engine_destroy(e); return nullptr; }
     p.sp = (p.d.states + 3) & ~3u;
+    p.pat_pad = (p.d.patterns + TP - 1) / TP * TP;
     p.clv_entries = (size_t)p.d.patterns * p.d.rate_cats * p.sp;
     p.pmat_entries = (size_t)p.d.rate_cats * p.d.states * p.sp;
     e->max_patterns = std::max(e->max_patterns, p.d.patterns);
     const size_t S = p.d.states, SP = p.sp, C = p.d.rate_cats;
     const size_t model_doubles = SP + 2 * S * SP + SP + 2 * C + C * S * 4;
     bool ok = cuda_ok(cudaMalloc((void **)&p.pmat, std::max<size_t>(1, p.d.edges * p.pmat_entries) * sizeof(double)), "cudaMalloc pmat") &&
-              cuda_ok(cudaMalloc((void **)&p.tipchars, std::max<size_t>(1, (size_t)p.d.tips * p.d.patterns)), "cudaMalloc tipchars") &&
+              cuda_ok(cudaMalloc((void **)&p.tipchars, std::max<size_t>(1, (size_t)p.d.tips * p.pat_pad)), "cudaMalloc tipchars") &&
               cuda_ok(cudaMalloc((void **)&p.tipmap, 256 * sizeof(uint32_t)), "cudaMalloc tipmap") &&
               cuda_ok(cudaMalloc((void **)&p.weights, std::max<size_t>(1, p.d.patterns) * sizeof(uint32_t)), "cudaMalloc weights") &&
               cuda_ok(cudaMalloc((void **)&p.model, model_doubles * sizeof(double)), "cudaMalloc model");
@@ -230,6 +242,7 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
     std::vector<uint32_t> ones(std::max<uint32_t>(1, p.d.patterns), 1);
     cudaMemcpy(p.weights, ones.data(), ones.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
     cudaMemset(p.pmat, 0, std::max<size_t>(1, p.d.edges * p.pmat_entries) * sizeof(double));
+    cudaMemset(p.tipchars, 0, std::max<size_t>(1, (size_t)p.d.tips * p.pat_pad));
     // group by kernel shape
     bool found = false;
     for (ShapeClass &c : e->classes)
@@ -288,7 +301,7 @@ int nrx_set_tips(nrx_engine *e, uint32_t pi, const uint32_t *tip_masks) {
     }
   }
   CK(cudaStreamSynchronize(e->stream));
-  CK(cudaMemcpy(p.tipchars, codes.data(), std::max<size_t>(1, n), cudaMemcpyHostToDevice));
+  if (n) CK(cudaMemcpy2D(p.tipchars, p.pat_pad, codes.data(), p.d.patterns, p.d.patterns, p.d.tips, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(p.tipmap, tipmap.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice));
   p.tips_set = true;
   return 1;
@@ -302,7 +315,7 @@ int nrx_set_tipchars_u8(nrx_engine *e, uint32_t pi, const uint8_t *codes) {
   const size_t n = (size_t)p.d.tips * p.d.patterns;
   std::vector<uint32_t> tipmap(256, 0);
   for (uint32_t i = 0; i < 16; ++i) tipmap[i] = i;
-  CK(cudaMemcpyAsync(p.tipchars, codes, n, cudaMemcpyHostToDevice, e->stream));
+  if (n) CK(cudaMemcpy2DAsync(p.tipchars, p.pat_pad, codes, p.d.patterns, p.d.patterns, p.d.tips, cudaMemcpyHostToDevice, e->stream));
   CK(cudaMemcpyAsync(p.tipmap, tipmap.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   p.tips_set = true;
@@ -388,8 +401,8 @@ int nrx_reserve_slots(nrx_engine *e, uint32_t nslots) {
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
   for (Part &p : e->parts) {
-    const size_t clv_bytes = (p.clv_entries * sizeof(double) + 255) & ~(size_t)255;
-    const size_t sc_bytes = ((size_t)p.d.patterns * sizeof(uint32_t) + 255) & ~(size_t)255;
+    const size_t clv_bytes = ((size_t)p.pat_pad * p.d.rate_cats * p.sp * sizeof(double) + 255) & ~(size_t)255;
+    const size_t sc_bytes = ((size_t)p.pat_pad * sizeof(uint32_t) + 255) & ~(size_t)255;
     for (uint32_t s = (uint32_t)p.slot_mem.size(); s < nslots; ++s) {
       void *m = nullptr;
       cudaError_t err = cudaMalloc(&m, std::max<size_t>(256, clv_bytes + sc_bytes));
@@ -488,9 +501,22 @@ int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops) {
     if (c.max_patterns == 0) continue;
     const uint32_t z = (uint32_t)c.parts.size();
     if (c.states == 4 && c.cats == 4) {
-      constexpr int U = 2;
-      dim3 grid(tiles_for((uint64_t)c.max_patterns * 4, BLOCK * U, nops * z), nops, z);
-      k_clv_dna4<U><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops);
+      if (e->k2_variant == 0) {
+        // bulk-async pipeline: ~2 resident blocks per SM; block b = (op b % nops, tile group b / nops)
+        const uint32_t ntiles = (c.max_patterns + TP - 1) / TP;
+        uint32_t groups = std::max<uint32_t>(1, (e->k2_blocks + nops * z - 1) / (nops * z));
+        groups = std::min(groups, ntiles);
+        dim3 grid(nops * groups, 1, z);
+        k_clv_dna4_pipe<<<grid, BLOCK, sizeof(ClvPipeSmem), e->stream>>>(c.d_views, d_ops, nops, groups);
+      } else {
+        const uint32_t U = e->k2_variant / 10, MB = e->k2_variant % 10;
+        dim3 grid(tiles_for((uint64_t)c.max_patterns * 4, BLOCK * U, nops * z), nops, z);
+        if (U == 2 && MB == 2) k_clv_dna4<2, 2><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops);
+        else if (U == 2 && MB == 4) k_clv_dna4<2, 4><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops);
+        else if (U == 1 && MB == 5) k_clv_dna4<1, 5><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops);
+        else if (U == 4 && MB == 2) k_clv_dna4<4, 2><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops);
+        else { g_err = "NRX_K2: unknown register-kernel variant"; return 0; }
+      }
     } else {
       dim3 grid(tiles_for(c.max_patterns, BLOCK, nops * z), nops, z);
       k_clv_generic<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops, nullptr);

@@ -27,7 +27,7 @@ constexpr int BLOCK = 256;
 /* Device view of one partition (array of these lives in HBM; blockIdx.z selects). */
 struct PartView {
   uint32_t states, sp, cats, patterns, tips, edges;
-  uint32_t part_index, pad_;
+  uint32_t part_index, tip_pitch;  // tip_pitch: row pitch of tipchars (patterns rounded up to a tile multiple)
   const double *pmat;        // [edges][cats][states][sp]
   const uint8_t *tipchars;   // [tips][patterns]
   const uint32_t *tipmap;    // [256] code -> state mask
@@ -125,8 +125,8 @@ __device__ __forceinline__ D4 matvec4(const double *__restrict__ P /* smem, this
   return r;
 }
 
-template <int UNROLL>
-__global__ void __launch_bounds__(BLOCK) k_clv_dna4(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops) {
+template <int UNROLL, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_clv_dna4(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops) {
   const PartView &pv = parts[blockIdx.z];
   const nrx_op op = ops[blockIdx.y];
   const int tid = threadIdx.x, cat = tid & 3, lane = tid & 31;
@@ -155,8 +155,8 @@ __global__ void __launch_bounds__(BLOCK) k_clv_dna4(const PartView *__restrict__
   const double *clvR = (rk == NRX_CLV) ? pv.clv[op.right_idx] : nullptr;
   const uint32_t *scL = (lk == NRX_CLV) ? pv.scaler[op.left_idx] : nullptr;
   const uint32_t *scR = (rk == NRX_CLV) ? pv.scaler[op.right_idx] : nullptr;
-  const uint8_t *tipL = (lk == NRX_TIP) ? pv.tipchars + (size_t)op.left_idx * pv.patterns : nullptr;
-  const uint8_t *tipR = (rk == NRX_TIP) ? pv.tipchars + (size_t)op.right_idx * pv.patterns : nullptr;
+  const uint8_t *tipL = (lk == NRX_TIP) ? pv.tipchars + (size_t)op.left_idx * pv.tip_pitch : nullptr;
+  const uint8_t *tipR = (rk == NRX_TIP) ? pv.tipchars + (size_t)op.right_idx * pv.tip_pitch : nullptr;
   double *par = pv.clv[op.parent_slot];
   uint32_t *psc = pv.scaler[op.parent_slot];
   const bool tiptip = (lk == NRX_TIP && rk == NRX_TIP);  // scaler := 0, no scaling test (core_partials_avx.c:1003-1009)
@@ -211,6 +211,165 @@ __global__ void __launch_bounds__(BLOCK) k_clv_dna4(const PartView *__restrict__
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * K2, DNA 4x4, bulk-async pipelined version (the production kernel).
+ *
+ * HBM-bound streaming needs many bytes in flight per SM; holding them in registers caps occupancy.  Here a
+ * block owns one op and walks pattern tiles (TP patterns = 8 KB per CLV operand); one elected thread keeps
+ * NSTAGE tiles of BOTH operands (+ their scalers / tip codes) in flight with cp.async.bulk (the TMA engine's
+ * 1-D bulk copy: SASS UBLKCP) into a shared-memory ring, completion signalled on one mbarrier per stage.
+ * All 256 threads consume: thread = (pattern, category), 32 B of each operand from the ring, P-matrix rows of
+ * its category in REGISTERS (loaded once per block: the op is fixed), result written straight to HBM as one
+ * 256-bit store (a warp writes 1 KB contiguous).  Blocks are numbered op-fastest so that the ops of a node
+ * that share a child CLV touch the same tile at about the same time and the re-read hits the 126 MB L2.
+ * Arithmetic order is identical to k_clv_dna4 (and to the reference's AVX kernel).
+ * ---------------------------------------------------------------------------------------------- */
+constexpr int TP = 64;        // patterns per tile (one (pattern, cat) item per thread)
+constexpr int NSTAGE = 6;     // tiles in flight per block: 6 x 17 KB = 102 KB -> 2 blocks per SM
+
+struct __align__(128) ClvStage {
+  double l[TP * 16];
+  double r[TP * 16];
+  uint32_t scl[TP];
+  uint32_t scr[TP];
+  uint8_t tl[TP];
+  uint8_t tr[TP];
+};
+struct __align__(128) ClvPipeSmem {
+  ClvStage st[NSTAGE];
+  double lutL[256];
+  double lutR[256];
+  unsigned long long full[NSTAGE];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ D4 matvec4_reg(const double (&P)[16], const D4 &v) {
+  D4 r;
+  r.x = tree4(__dmul_rn(P[0], v.x), __dmul_rn(P[1], v.y), __dmul_rn(P[2], v.z), __dmul_rn(P[3], v.w));
+  r.y = tree4(__dmul_rn(P[4], v.x), __dmul_rn(P[5], v.y), __dmul_rn(P[6], v.z), __dmul_rn(P[7], v.w));
+  r.z = tree4(__dmul_rn(P[8], v.x), __dmul_rn(P[9], v.y), __dmul_rn(P[10], v.z), __dmul_rn(P[11], v.w));
+  r.w = tree4(__dmul_rn(P[12], v.x), __dmul_rn(P[13], v.y), __dmul_rn(P[14], v.z), __dmul_rn(P[15], v.w));
+  return r;
+}
+
+/* grid = (nops * groups, 1, partitions of this shape); block b: op = b % nops, tile group = b / nops */
+__global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops,
+                                                             uint32_t nops, uint32_t groups) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ClvPipeSmem &sm = *reinterpret_cast<ClvPipeSmem *>(smem_raw);
+  const PartView &pv = parts[blockIdx.z];
+  const nrx_op op = ops[blockIdx.x % nops];
+  const uint32_t grp = blockIdx.x / nops;
+  const int tid = threadIdx.x, cat = tid & 3, lane = tid & 31;
+  const uint32_t ntiles = (pv.patterns + TP - 1) / TP;
+  if (grp >= ntiles) return;
+  const uint32_t count = (ntiles - grp + groups - 1) / groups;  // my tiles: grp, grp + groups, ...
+  const int lk = op.left_kind, rk = op.right_kind;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) mbar_init(&sm.full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (lk == NRX_TIP) build_tip_lut4(sm.lutL, pv.pmat + (size_t)op.left_edge * 64, tid);
+  if (rk == NRX_TIP) build_tip_lut4(sm.lutR, pv.pmat + (size_t)op.right_edge * 64, tid);
+  double PL[16], PR[16];
+  if (lk == NRX_CLV) {
+    const double *src = pv.pmat + (size_t)op.left_edge * 64 + cat * 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) PL[i] = src[i];
+  }
+  if (rk == NRX_CLV) {
+    const double *src = pv.pmat + (size_t)op.right_edge * 64 + cat * 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) PR[i] = src[i];
+  }
+  __syncthreads();
+
+  const double *clvL = (lk == NRX_CLV) ? pv.clv[op.left_idx] : nullptr;
+  const double *clvR = (rk == NRX_CLV) ? pv.clv[op.right_idx] : nullptr;
+  const uint32_t *scL = (lk == NRX_CLV) ? pv.scaler[op.left_idx] : nullptr;
+  const uint32_t *scR = (rk == NRX_CLV) ? pv.scaler[op.right_idx] : nullptr;
+  const uint8_t *tipL = (lk == NRX_TIP) ? pv.tipchars + (size_t)op.left_idx * pv.tip_pitch : nullptr;
+  const uint8_t *tipR = (rk == NRX_TIP) ? pv.tipchars + (size_t)op.right_idx * pv.tip_pitch : nullptr;
+  double *par = pv.clv[op.parent_slot];
+  uint32_t *psc = pv.scaler[op.parent_slot];
+  const bool tiptip = (lk == NRX_TIP && rk == NRX_TIP);
+  const unsigned quad = 0xFu << (lane & ~3);
+  const uint32_t tx_bytes = ((lk == NRX_CLV) ? TP * 128u + TP * 4u : (lk == NRX_TIP ? (uint32_t)TP : 0u)) +
+                            ((rk == NRX_CLV) ? TP * 128u + TP * 4u : (rk == NRX_TIP ? (uint32_t)TP : 0u));
+
+  // every buffer is padded to a whole number of tiles by the engine, so full-tile copies never run off the end
+  auto issue = [&](uint32_t k) {
+    ClvStage &st = sm.st[k % NSTAGE];
+    unsigned long long *bar = &sm.full[k % NSTAGE];
+    const size_t p0 = (size_t)(grp + (size_t)k * groups) * TP;
+    mbar_expect_tx(bar, tx_bytes);
+    if (lk == NRX_CLV) { bulk_g2s(st.l, clvL + p0 * 16, TP * 128u, bar); bulk_g2s(st.scl, scL + p0, TP * 4u, bar); }
+    else if (lk == NRX_TIP) bulk_g2s(st.tl, tipL + p0, TP, bar);
+    if (rk == NRX_CLV) { bulk_g2s(st.r, clvR + p0 * 16, TP * 128u, bar); bulk_g2s(st.scr, scR + p0, TP * 4u, bar); }
+    else if (rk == NRX_TIP) bulk_g2s(st.tr, tipR + p0, TP, bar);
+  };
+  if (tid == 0) {
+    const uint32_t pre = count < (uint32_t)NSTAGE ? count : (uint32_t)NSTAGE;
+    for (uint32_t k = 0; k < pre; ++k) issue(k);
+  }
+
+  const int pl = tid >> 2;  // pattern within the tile
+  for (uint32_t k = 0; k < count; ++k) {
+    const ClvStage &st = sm.st[k % NSTAGE];
+    mbar_wait(&sm.full[k % NSTAGE], (k / NSTAGE) & 1u);
+    const size_t site = (size_t)(grp + (size_t)k * groups) * TP + pl;
+    const bool act = site < pv.patterns;
+    D4 x, y, p;
+    if (lk == NRX_CLV) x = matvec4_reg(PL, *reinterpret_cast<const D4 *>(st.l + tid * 4));
+    else if (lk == NRX_TIP) x = *reinterpret_cast<const D4 *>(sm.lutL + ((st.tl[pl] & 15) * 4 + cat) * 4);
+    if (rk == NRX_CLV) y = matvec4_reg(PR, *reinterpret_cast<const D4 *>(st.r + tid * 4));
+    else if (rk == NRX_TIP) y = *reinterpret_cast<const D4 *>(sm.lutR + ((st.tr[pl] & 15) * 4 + cat) * 4);
+    if (rk == NRX_NONE) p = x;
+    else if (lk == NRX_NONE) p = y;
+    else { p.x = __dmul_rn(x.x, y.x); p.y = __dmul_rn(x.y, y.y); p.z = __dmul_rn(x.z, y.z); p.w = __dmul_rn(x.w, y.w); }
+    const bool small = act & (p.x < SCALE_THRESHOLD) & (p.y < SCALE_THRESHOLD) & (p.z < SCALE_THRESHOLD) & (p.w < SCALE_THRESHOLD);
+    const unsigned b = __ballot_sync(0xffffffffu, small);
+    const bool scale = !tiptip && ((b & quad) == quad);
+    uint32_t s = 0;
+    if (!tiptip) {
+      if (lk == NRX_CLV) s += st.scl[pl];
+      if (rk == NRX_CLV) s += st.scr[pl];
+      s += scale ? 1u : 0u;
+    }
+    if (act) {
+      if (scale) { p.x = __dmul_rn(p.x, SCALE_FACTOR); p.y = __dmul_rn(p.y, SCALE_FACTOR); p.z = __dmul_rn(p.z, SCALE_FACTOR); p.w = __dmul_rn(p.w, SCALE_FACTOR); }
+      stg256(par + (site * 4 + cat) * 4, p);
+      if (cat == 0) psc[site] = s;
+    }
+    __syncthreads();  // everyone is done with this stage: refill it
+    if (tid == 0 && k + NSTAGE < count) issue(k + NSTAGE);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * K2 generic (any states <= 32, any cats): one thread per (pattern, category), P rows from L1/L2.
  * Used for protein data until the DMMA kernel takes over, and for unusual category counts.
  * ---------------------------------------------------------------------------------------------- */
@@ -243,8 +402,8 @@ __global__ void __launch_bounds__(BLOCK) k_clv_generic(const PartView *__restric
   uint32_t *psc = pv.scaler[op.parent_slot];
   (void)flags;
   for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
-    const uint32_t mL = (lk == NRX_TIP) ? pv.tipmap[pv.tipchars[(size_t)op.left_idx * pv.patterns + n]] : 0;
-    const uint32_t mR = (rk == NRX_TIP) ? pv.tipmap[pv.tipchars[(size_t)op.right_idx * pv.patterns + n]] : 0;
+    const uint32_t mL = (lk == NRX_TIP) ? pv.tipmap[pv.tipchars[(size_t)op.left_idx * pv.tip_pitch + n]] : 0;
+    const uint32_t mR = (rk == NRX_TIP) ? pv.tipmap[pv.tipchars[(size_t)op.right_idx * pv.tip_pitch + n]] : 0;
     const double *cl = (lk == NRX_CLV) ? pv.clv[op.left_idx] + n * C * SP : nullptr;
     const double *cr = (rk == NRX_CLV) ? pv.clv[op.right_idx] + n * C * SP : nullptr;
     double *out = par + n * C * SP;
@@ -360,7 +519,7 @@ __global__ void __launch_bounds__(BLOCK) k_edge_lnl(const PartView *__restrict__
   const uint32_t *scp = pv.scaler[pr.a_idx];
   const double *clvc = (pr.b_kind == NRX_CLV) ? pv.clv[pr.b_idx] : nullptr;
   const uint32_t *scc = (pr.b_kind == NRX_CLV) ? pv.scaler[pr.b_idx] : nullptr;
-  const uint8_t *tip = (pr.b_kind == NRX_TIP) ? pv.tipchars + (size_t)pr.b_idx * pv.patterns : nullptr;
+  const uint8_t *tip = (pr.b_kind == NRX_TIP) ? pv.tipchars + (size_t)pr.b_idx * pv.tip_pitch : nullptr;
   const double *pm = pv.pmat + (size_t)edge * C * S * SP;
   double acc[1] = {0.0};
   for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
@@ -396,7 +555,7 @@ __global__ void __launch_bounds__(BLOCK) k_sumtable(const PartView *__restrict__
   // tip-inner: the TIP is the "left" operand of the core kernel (LIBPLL/derivatives.c:70-98)
   if (pr.b_kind == NRX_TIP) { nrx_pair t = pr; pr.a_kind = t.b_kind; pr.a_idx = t.b_idx; pr.b_kind = t.a_kind; pr.b_idx = t.a_idx; }
   const double *clvl = (pr.a_kind == NRX_CLV) ? pv.clv[pr.a_idx] : nullptr;
-  const uint8_t *tip = (pr.a_kind == NRX_TIP) ? pv.tipchars + (size_t)pr.a_idx * pv.patterns : nullptr;
+  const uint8_t *tip = (pr.a_kind == NRX_TIP) ? pv.tipchars + (size_t)pr.a_idx * pv.tip_pitch : nullptr;
   const double *clvr = pv.clv[pr.b_idx];
   double *out = pv.sumtable[blockIdx.y];
   const uint64_t n_items = (uint64_t)pv.patterns * C;

@@ -5,9 +5,10 @@ A "step" = ONE full network lnL evaluation, computeLoglikelihood(ann, incrementa
 P-matrices for every edge + every CLV of every displayed tree at every node + per-tree root lnL + the
 cross-rank reduction + AVERAGE/BEST mixing (BASELINE.md §4 "What is timed").
 
-Workload (default): BASELINE.json configs[4] — DNA GTR+G4, 100 taxa, 8 reticulations, 1M site patterns sharded
-across the GPUs — run as WEAK scaling with 125 000 patterns per GPU, so that N=8 is exactly that config and N=1
-is one GPU's shard of it.  `--config 2` (50 taxa / 4 reticulations / 100 k patterns) etc. select the others.
+Workload (default): BASELINE.json configs[4], the configuration the metric is quoted on — DNA GTR+G4, 100 taxa,
+8 reticulations, 1M site patterns sharded across 1/2/4/8 B200 (STRONG scaling: the 1M patterns are split evenly
+over the ranks; at N=1 all 776 CLV slots x 1M patterns = 102 GB live on one GPU).  `--config 2` (50 taxa /
+4 reticulations / 100 k patterns) etc. select the others; `--patterns N` overrides the global pattern count.
 
 metric  = CLV site-updates/s (sum over nodes of displayed trees(node) x patterns, per second, whole job);
           lnl_evals_per_sec is reported beside it.
@@ -41,7 +42,7 @@ CONFIGS = {
     1: dict(name="config1: DNA GTR+G4, 20 taxa, 1 reticulation, 10k patterns, AVERAGE", taxa=20, ret=1, patterns=10_000, parts=1, variant=AVERAGE, linkage=LINKED),
     2: dict(name="config2: DNA GTR+G4, 50 taxa, 4 reticulations, 100k patterns, AVERAGE", taxa=50, ret=4, patterns=100_000, parts=1, variant=AVERAGE, linkage=LINKED),
     3: dict(name="config3: DNA 10 partitions x 50k patterns, unlinked brlens, 3 reticulations, BEST", taxa=50, ret=3, patterns=50_000, parts=10, variant=BEST, linkage=UNLINKED),
-    5: dict(name="config5: DNA GTR+G4, 100 taxa, 8 reticulations, 125k patterns per GPU (N=8 = 1M patterns)", taxa=100, ret=8, patterns=125_000, parts=1, variant=AVERAGE, linkage=LINKED),
+    5: dict(name="config5: DNA GTR+G4, 100 taxa, 8 reticulations, 1M site patterns sharded across the GPUs", taxa=100, ret=8, patterns=1_000_000, parts=1, variant=AVERAGE, linkage=LINKED),
 }
 
 
@@ -104,7 +105,7 @@ class ClockSampler:
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -127,30 +128,33 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="netrax_b200", choices=["netrax_b200", "reference"])
     ap.add_argument("--config", type=int, default=5, choices=sorted(CONFIGS))
-    ap.add_argument("--patterns-per-gpu", type=int, default=0)
+    ap.add_argument("--patterns", type=int, default=0, help="global pattern count per partition (default: the config's)")
     ap.add_argument("--cpu-patterns-per-core", type=int, default=0, help="0: the arm's global pattern count / host cores, capped at 16000")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     cfg = dict(CONFIGS[args.config])
-    if args.patterns_per_gpu:
-        cfg["patterns"] = args.patterns_per_gpu
+    if args.patterns:
+        cfg["patterns"] = args.patterns
     if not args.cpu_patterns_per_core:
-        args.cpu_patterns_per_core = min(16000, max(64, -(-cfg["patterns"] * max(1, args.gpus) // host_cores())))
+        args.cpu_patterns_per_core = min(16000, max(64, -(-cfg["patterns"] // host_cores())))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # strong scaling: rank r owns the contiguous slice [r*G/N, (r+1)*G/N) of every partition (reference: C1 site sharding)
+    G = cfg["patterns"]
+    local_patterns = (rank + 1) * G // world - rank * G // world
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    config = {"workload": cfg["name"], "patterns_per_gpu": cfg["patterns"], "partitions": cfg["parts"],
+    config = {"workload": cfg["name"], "global_patterns": cfg["patterns"], "patterns_per_gpu": -(-cfg["patterns"] // world), "partitions": cfg["parts"],
               "lh_model": "AVERAGE" if cfg["variant"] == AVERAGE else "BEST", "parallelism": f"site-sharding x{world}",
               "l2": "per-step working set (all CLV slots) is GBs >> 126 MB L2: inputs larger than L2, no flush needed"}
 
@@ -164,7 +168,7 @@ def main():
         ms = 1e3 * float(np.mean(st))
         v = r["site_updates_per_step"] / (ms / 1e3)
         line = {"impl": "reference", "metric": "clv_site_updates_per_sec", "value": v, "unit": "site-updates/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "lnl_evals_per_sec_on_sample": 1e3 / ms,
                 "cpu_baseline": {"value": v, "unit": "site-updates/s", "cores": cores, "kind": r["kind"], "sample": r["sample"]},
@@ -181,19 +185,19 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from netrax_b200.engine import NetraxB200
 
-    net, parts, brl = make_inputs(cfg, cfg["patterns"], rank)
-    reduce_fn = None
+    net, parts, brl = make_inputs(cfg, local_patterns, rank)
+    comm = None
     if world > 1:
-        dev_buf = torch.zeros(1 << 16, dtype=torch.float64, device=f"cuda:{local_rank}")
+        # the reference's parallel_reduce_cb (MPI_Allreduce SUM) -> ONE ncclAllReduce inside the engine per evaluation;
+        # torch.distributed only carries the 128-byte NCCL unique id to the ranks (and the timing max-reduce below)
+        from netrax_b200.engine import comm_unique_id
+        uid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        comm = (bytes(uid.cpu().numpy().tobytes()), rank, world)
 
-        def reduce_fn(arr):  # the reference's parallel_reduce_cb (MPI_Allreduce SUM) -> NCCL all-reduce over NVLink
-            n = arr.shape[0]
-            t = dev_buf[:n]
-            t.copy_(torch.from_numpy(arr))
-            dist.all_reduce(t)
-            arr[:] = t.cpu().numpy()
-
-    eng = NetraxB200(net, parts, variant=cfg["variant"], linkage=cfg["linkage"], device=local_rank, partition_brlens=brl, reduce=reduce_fn)
+    eng = NetraxB200(net, parts, variant=cfg["variant"], linkage=cfg["linkage"], device=local_rank, partition_brlens=brl, comm=comm)
 
     def barrier():
         eng.api.check(1)
@@ -260,7 +264,7 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = prof["clv_bytes"] / (prof["clv_ms"] / 1e3) / 1e9 if prof["clv_ms"] > 0 else 0.0
         line = {"metric": "clv_site_updates_per_sec", "value": value, "unit": "site-updates/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config,
                 "lnl_evals_per_sec": 1e3 / ms_step, "lnl": lnl, "sum_trees_per_node": slots_sum, "root_trees": eng.num_trees(net.root),
                 "wall_ms_per_step": ms_wall / args.steps,

@@ -16,6 +16,7 @@
  *   nrxh_set_branch_length / nrxh_set_reticulation_prob / nrxh_set_model
  *                                <- what optimize_branch / setReticulationProb / pll_set_* + invalidate do to the state
  *   nrxh_set_reduce_callback     <- fake_treeinfo->parallel_reduce_cb        src/RaxmlWrapper.cpp:717-718
+ *   nrxh_comm_init               <- ParallelContext::init_mpi + mpi_allreduce libs/raxml-ng/src/ParallelContext.cpp:56-70,452-487
  */
 #ifndef NETRAX_B200_H
 #define NETRAX_B200_H
@@ -41,6 +42,11 @@ int nrxh_set_options(void *h, int likelihood_variant /* 0 AVERAGE, 1 BEST */, in
 int nrxh_set_partition_brlens(void *h, unsigned p, const double *brlens);
 int nrxh_set_reduce_callback(void *h, nrxh_reduce_cb cb, void *context);
 int nrxh_init(void *h);
+/* site-shard communicator (after nrxh_init): NCCL all-reduce of the per-tree / per-pair partition sums inside the
+ * engine, the role of ParallelContext::parallel_reduce_cb + MPI_Allreduce (libs/raxml-ng/src/ParallelContext.cpp:425-487).
+ * With a communicator attached the reduce callback is not called. */
+int nrxh_comm_get_unique_id(uint8_t *id128);
+int nrxh_comm_init(void *h, const uint8_t *id128, int rank, int nranks);
 int nrxh_compute_loglikelihood(void *h, int incremental, int update_pmatrices, double *out);
 unsigned nrxh_num_partitions(void *h);
 unsigned nrxh_root(void *h);

@@ -115,6 +115,19 @@ int nrx_read_scaler(nrx_engine *e, uint32_t p, uint32_t slot, uint32_t *out);
 int nrx_read_sumtable(nrx_engine *e, uint32_t p, uint32_t st_slot, double *out);
 int nrx_sync(nrx_engine *e);
 
+/* C2-C4: site-shard communicator.  Replaces the reference's MPI_Allreduce(MPI_IN_PLACE, MPI_DOUBLE, SUM) behind
+ * parallel_reduce_cb (libs/raxml-ng/src/ParallelContext.cpp:425-487, installed at src/RaxmlWrapper.cpp:717-718):
+ * once a communicator is attached, nrx_tree_lnl / nrx_edge_lnl / nrx_derivatives all-reduce their [n][nparts](x3)
+ * result ON THE DEVICE with ONE ncclAllReduce (NVLink 5 / NVSwitch) on the engine's stream before the single
+ * device->host copy, so every rank returns the global sums.  rank 0 obtains the 128-byte NCCL unique id and hands
+ * it to the other ranks by any out-of-band channel (the launcher's store; MPI_Bcast in a NetRAX build).
+ * libnccl.so.2 is resolved at run time (dlopen): the engine has no link-time NCCL dependency. */
+int nrx_comm_get_unique_id(uint8_t *id128);
+int nrx_comm_init(nrx_engine *e, const uint8_t *id128, int rank, int nranks);
+int nrx_comm_size(nrx_engine *e); /* 1 when no communicator is attached */
+/* SUM all-reduce of n host doubles across the ranks (staged through the device; for callers' own scalars) */
+int nrx_comm_allreduce_sum(nrx_engine *e, double *host_inout, size_t n);
+
 /* device-side access for callers that keep data on the GPU (NCCL all-reduce of the [n][nparts] results):
  * the last nrx_tree_lnl / nrx_edge_lnl / nrx_derivatives result also stays in this device buffer. */
 void *nrx_result_device_ptr(nrx_engine *e);

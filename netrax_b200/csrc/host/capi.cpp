@@ -112,6 +112,20 @@ int nrxh_set_reduce_callback(void *hv, nrxh_reduce_cb cb, void *ctx) {
   return 1;
 }
 
+int nrxh_comm_get_unique_id(uint8_t *id128) {
+  if (nrx_comm_get_unique_id(id128)) return 1;
+  g_err = nrx_last_error();
+  return 0;
+}
+
+int nrxh_comm_init(void *hv, const uint8_t *id128, int rank, int nranks) {
+  return guarded([&] {
+    Handle *h = H(hv);
+    if (!h->ann.engine) throw std::runtime_error("nrxh_comm_init: call nrxh_init first");
+    netrax::detail::engineCheck(nrx_comm_init(h->ann.engine, id128, rank, nranks), "nrx_comm_init");
+  });
+}
+
 int nrxh_init(void *hv) {
   return guarded([&] {
     Handle *h = H(hv);

@@ -61,6 +61,8 @@ void flushPendingOps(AnnotatedNetwork &ann) {
 }
 
 void reduceSum(AnnotatedNetwork &ann, double *data, size_t count) {
+  // with an NCCL communicator attached the engine has already all-reduced its result on the device (C2-C4)
+  if (ann.engine && nrx_comm_size(ann.engine) > 1) return;
   if (ann.fake_treeinfo->parallel_reduce_cb)
     ann.fake_treeinfo->parallel_reduce_cb(ann.fake_treeinfo->parallel_context, data, count, PLLMOD_COMMON_REDUCE_SUM);
 }

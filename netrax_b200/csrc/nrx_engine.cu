@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <map>
 #include <string>
 #include <vector>
@@ -55,8 +56,42 @@ struct ShapeClass {
 };
 }  // namespace
 
+/* ---- NCCL, resolved at run time ------------------------------------------------------------------------ */
+namespace {
+struct NcclApi {
+  typedef struct { char internal[128]; } UniqueId;
+  int (*GetUniqueId)(UniqueId *) = nullptr;
+  int (*CommInitRank)(void **comm, int nranks, UniqueId id, int rank) = nullptr;
+  int (*AllReduce)(const void *send, void *recv, size_t count, int dtype, int op, void *comm, cudaStream_t s) = nullptr;
+  int (*CommDestroy)(void *comm) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi &nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+      api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+    }
+  }
+  return api;
+}
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;  // ncclDataType_t / ncclRedOp_t values (nccl.h)
+}  // namespace
+
 struct nrx_engine {
   int device = 0;
+  void *comm = nullptr;  // ncclComm_t
+  int comm_rank = 0, comm_size = 1;
   cudaStream_t stream = nullptr;
   std::vector<Part> parts;
   std::vector<ShapeClass> classes;
@@ -74,7 +109,7 @@ struct nrx_engine {
   size_t persite_cap = 0;
   unsigned long long launches = 0;
   int k2_variant = 0;       // 0: k_clv_dna4_pipe (production); UM: k_clv_dna4<U, MINB> (A/B experiments, env NRX_K2=UM)
-  uint32_t k2_blocks = 296; // resident-block target of the pipelined kernel (2 per SM x 148 SMs)
+  uint32_t k2_blocks = 2368; // block-count target of the pipelined kernel: 8 waves of 2 resident blocks per SM (measured best, profiles/)
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   bool views_dirty = true;
   // profiling of K2
@@ -217,7 +252,7 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
   {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (!std::getenv("NRX_K2_BLOCKS")) e->k2_blocks = 2u * (uint32_t)sms;
+    if (!std::getenv("NRX_K2_BLOCKS")) e->k2_blocks = 16u * (uint32_t)sms;
     if (!cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClvPipeSmem)), "cudaFuncSetAttribute")) { delete e; return nullptr; }
   }
   for (uint32_t i = 0; i < nparts; ++i) {
@@ -256,6 +291,7 @@ void nrx_engine_destroy(nrx_engine *e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->comm && nccl().ok) nccl().CommDestroy(e->comm);
   for (Part &p : e->parts) {
     cudaFree(p.pmat); cudaFree(p.tipchars); cudaFree(p.tipmap); cudaFree(p.weights); cudaFree(p.model);
     for (void *m : p.slot_mem) cudaFree(m);
@@ -505,7 +541,7 @@ int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops) {
         // bulk-async pipeline: ~2 resident blocks per SM; block b = (op b % nops, tile group b / nops)
         const uint32_t ntiles = (c.max_patterns + TP - 1) / TP;
         uint32_t groups = std::max<uint32_t>(1, (e->k2_blocks + nops * z - 1) / (nops * z));
-        groups = std::min(groups, ntiles);
+        groups = std::min(groups, std::max<uint32_t>(1, ntiles / 4));  // >= 4 tiles per block: amortise the pipeline fill
         dim3 grid(nops * groups, 1, z);
         k_clv_dna4_pipe<<<grid, BLOCK, sizeof(ClvPipeSmem), e->stream>>>(c.d_views, d_ops, nops, groups);
       } else {
@@ -538,6 +574,10 @@ static int finish_reduction(nrx_engine *e, uint32_t total, uint32_t nblk, double
   k_reduce_partials<<<(total + 127) / 128, 128, 0, e->stream>>>(e->d_partial, e->d_result, nblk, total);
   e->launches++;
   CK(cudaGetLastError());
+  if (e->comm) {  // C2-C4: one all-reduce over NVLink for all trees / pairs x partitions
+    const int rc = nccl().AllReduce(e->d_result, e->d_result, total, NCCL_FLOAT64, NCCL_SUM, e->comm, e->stream);
+    if (rc != 0) { g_err = std::string("ncclAllReduce: ") + nccl().GetErrorString(rc); return 0; }
+  }
   CK(cudaMemcpyAsync(e->h_result, e->d_result, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   if (out) std::memcpy(out, e->h_result, (size_t)total * sizeof(double));
@@ -701,6 +741,47 @@ int nrx_sync(nrx_engine *e) {
   if (!e) { g_err = "null engine"; return 0; }
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
+  return 1;
+}
+
+int nrx_comm_get_unique_id(uint8_t *id128) {
+  if (!nccl().ok) { g_err = "libnccl.so.2 could not be loaded"; return 0; }
+  NcclApi::UniqueId id;
+  const int rc = nccl().GetUniqueId(&id);
+  if (rc != 0) { g_err = std::string("ncclGetUniqueId: ") + nccl().GetErrorString(rc); return 0; }
+  std::memcpy(id128, id.internal, 128);
+  return 1;
+}
+
+int nrx_comm_init(nrx_engine *e, const uint8_t *id128, int rank, int nranks) {
+  if (!e) { g_err = "null engine"; return 0; }
+  if (nranks < 1 || rank < 0 || rank >= nranks) { g_err = "nrx_comm_init: bad rank / nranks"; return 0; }
+  if (e->comm) { g_err = "nrx_comm_init: communicator already attached"; return 0; }
+  if (nranks == 1) { e->comm_rank = 0; e->comm_size = 1; return 1; }
+  if (!nccl().ok) { g_err = "libnccl.so.2 could not be loaded"; return 0; }
+  CK(cudaSetDevice(e->device));
+  NcclApi::UniqueId id;
+  std::memcpy(id.internal, id128, 128);
+  const int rc = nccl().CommInitRank(&e->comm, nranks, id, rank);
+  if (rc != 0) { e->comm = nullptr; g_err = std::string("ncclCommInitRank: ") + nccl().GetErrorString(rc); return 0; }
+  e->comm_rank = rank; e->comm_size = nranks;
+  return 1;
+}
+
+int nrx_comm_size(nrx_engine *e) { return e ? e->comm_size : 1; }
+
+int nrx_comm_allreduce_sum(nrx_engine *e, double *host_inout, size_t n) {
+  if (!e) { g_err = "null engine"; return 0; }
+  if (!e->comm || n == 0) return 1;
+  CK(cudaSetDevice(e->device));
+  if (!ensure_result(e, n, 0)) return 0;
+  std::memcpy(e->h_result, host_inout, n * sizeof(double));
+  CK(cudaMemcpyAsync(e->d_result, e->h_result, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  const int rc = nccl().AllReduce(e->d_result, e->d_result, n, NCCL_FLOAT64, NCCL_SUM, e->comm, e->stream);
+  if (rc != 0) { g_err = std::string("ncclAllReduce: ") + nccl().GetErrorString(rc); return 0; }
+  CK(cudaMemcpyAsync(e->h_result, e->d_result, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  std::memcpy(host_inout, e->h_result, n * sizeof(double));
   return 1;
 }
 

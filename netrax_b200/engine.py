@@ -36,6 +36,10 @@ def load() -> FlatAPI:
         lib.nrxh_set_eigen.argtypes = [C.c_void_p, C.c_uint] + [np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")] * 3
         lib.nrxh_set_reduce_callback.restype = C.c_int
         lib.nrxh_set_reduce_callback.argtypes = [C.c_void_p, REDUCE_CB, C.c_void_p]
+        lib.nrxh_comm_get_unique_id.restype = C.c_int
+        lib.nrxh_comm_get_unique_id.argtypes = [C.c_char_p]
+        lib.nrxh_comm_init.restype = C.c_int
+        lib.nrxh_comm_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
         lib.nrxh_launch_count.restype = C.c_ulonglong
         lib.nrxh_launch_count.argtypes = [C.c_void_p]
         lib.nrxh_num_slots.restype = C.c_uint
@@ -58,6 +62,14 @@ def load() -> FlatAPI:
     return _api
 
 
+def comm_unique_id() -> bytes:
+    """128-byte NCCL unique id (call on rank 0, hand to the other ranks through the launcher's store)."""
+    api = load()
+    buf = C.create_string_buffer(128)
+    api.check(api.lib.nrxh_comm_get_unique_id(buf))
+    return buf.raw
+
+
 def device_count() -> int:
     lib = C.CDLL(ENGINE_SO, mode=C.RTLD_GLOBAL)
     lib.nrx_device_count.restype = C.c_int
@@ -70,7 +82,9 @@ class NetraxB200(LikelihoodEngine):
 
     def __init__(self, net: NetworkDesc, partitions: Sequence[Partition], variant: int = AVERAGE, linkage: int = LINKED,
                  device: int = 0, plan_cache: bool = True, partition_brlens=None,
-                 reduce: Optional[Callable[[np.ndarray], None]] = None):
+                 reduce: Optional[Callable[[np.ndarray], None]] = None, comm: Optional[tuple] = None):
+        """`comm` = (unique_id_bytes, rank, nranks): attach an NCCL communicator so that the engine all-reduces its
+        per-tree / per-pair partition sums on the device (site sharding across GPUs); `reduce` is then unused."""
         api = load()
         self._reduce = reduce
         self._cb = None
@@ -85,6 +99,9 @@ class NetraxB200(LikelihoodEngine):
                          backend=f"device={device};plan_cache={1 if plan_cache else 0}", partition_brlens=partition_brlens)
         if self._cb is not None:
             api.check(api.lib.nrxh_set_reduce_callback(self.h, self._cb, None))
+        if comm is not None:
+            uid, rank, nranks = comm
+            api.check(api.lib.nrxh_comm_init(self.h, bytes(uid), int(rank), int(nranks)))
 
     def set_eigen(self, p: int, eigenvecs, inv_eigenvecs, eigenvals):
         """Test hook: inject an eigen-decomposition (e.g. the reference's) instead of the host Jacobi solver's."""

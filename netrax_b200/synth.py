@@ -191,14 +191,10 @@ def simulate_alignment(net: NetworkDesc, patterns: int, seed: int = 1, states: i
                     st[v] = sv
                     continue
                 for c, t in kids.get(v, []):
-                    sc = np.zeros(n, np.int64)
-                    for ci, r in enumerate(cat_rates):
-                        m = cat == ci
-                        if not m.any():
-                            continue
-                        cum = np.cumsum(_pmat(q, t * r), axis=1)
-                        u = rng.random(int(m.sum()))
-                        sc[m] = np.minimum((u[:, None] > cum[sv[m]]).sum(1), states - 1)
+                    # one pass per edge: cumulative rows of P(t * r_cat) gathered per column by (category, parent state)
+                    cum = np.stack([np.cumsum(_pmat(q, t * r), axis=1) for r in cat_rates]).astype(np.float32)
+                    u = rng.random(n, dtype=np.float32)
+                    sc = np.minimum((u[:, None] > cum[cat, sv]).sum(1), states - 1)
                     st_all[c] = sc
                     stack.append(c)
         masks = (1 << st).astype(np.uint32)

@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check (run under torchrun, one rank per GPU): the pattern-sharded engine with the NCCL
+communicator attached must reproduce the single-GPU result on the same alignment — network lnL, every per-tree
+partition lnL, and the branch-length derivatives — to the all-reduce's rounding (<= 1e-12 relative), and BEST-tree
+selection must be identical.  Rank 0 prints one JSON line."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from netrax_b200._capi import AVERAGE, BEST, LINKED, UNLINKED, Partition  # noqa: E402
+from netrax_b200.engine import NetraxB200, comm_unique_id  # noqa: E402
+from netrax_b200.synth import DNA_FREQS, GAMMA4_ALPHA05, GTR_RATES, random_network, simulate_alignment  # noqa: E402
+
+
+def main():
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+
+    def fresh_uid():  # one NCCL unique id per communicator (an id must not be reused)
+        uid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{lr}")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        return uid.cpu().numpy().tobytes()
+
+    report = {"world": world, "cases": []}
+    for variant, linkage, nparts in ((AVERAGE, LINKED, 1), (BEST, UNLINKED, 3)):
+        net = random_network(24, 3, seed=77)
+        rng = np.random.default_rng(3)
+        full, brl = [], []
+        for p in range(nparts):
+            m, w = simulate_alignment(net, 3001 + 517 * p, seed=50 + p)   # odd sizes: ragged shards
+            full.append(Partition(4, 4, m, DNA_FREQS, GTR_RATES * (1 + 0.1 * p), GAMMA4_ALPHA05, pattern_weights=w))
+            brl.append(net.edge_length * rng.uniform(0.5, 2.0, net.num_edges))
+        brl = brl if linkage == UNLINKED else None
+        shard = [q.slice(rank * q.sites // world, (rank + 1) * q.sites // world) for q in full]
+        g = NetraxB200(net, shard, variant=variant, linkage=linkage, device=lr, partition_brlens=brl, comm=(fresh_uid(), rank, world))
+        lnl = g.computeLoglikelihood(0, 1)
+        trees = np.array([g.tree_info(net.root, t)[1] for t in range(g.num_trees(net.root))])
+        e = int(net.ret_first_edge[0])
+        g.brlen_prepare(e)
+        lb = g.computeLoglikelihoodBrlenOpt(e)
+        g.computePartitionSumtables(e)
+        d = g.computeLoglikelihoodDerivatives(e)
+        lf = g.brlen_finish(e)
+        case = {"variant": int(variant), "lnl": lnl}
+        if rank == 0:
+            s = NetraxB200(net, full, variant=variant, linkage=linkage, device=lr, partition_brlens=brl)
+            lnl1 = s.computeLoglikelihood(0, 1)
+            trees1 = np.array([s.tree_info(net.root, t)[1] for t in range(s.num_trees(net.root))])
+            s.brlen_prepare(e)
+            lb1 = s.computeLoglikelihoodBrlenOpt(e)
+            s.computePartitionSumtables(e)
+            d1 = s.computeLoglikelihoodDerivatives(e)
+            lf1 = s.brlen_finish(e)
+            assert abs(lnl - lnl1) <= 1e-12 * abs(lnl1), (lnl, lnl1)
+            np.testing.assert_allclose(trees, trees1, rtol=1e-12)
+            assert abs(lb - lb1) <= 1e-12 * abs(lb1) and abs(lf - lf1) <= 1e-12 * abs(lf1)
+            np.testing.assert_allclose(d[2], d1[2], rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(d[3], d1[3], rtol=1e-9, atol=1e-9)
+            if variant == BEST:
+                assert [int(np.argmax(trees[:, p])) for p in range(nparts)] == [int(np.argmax(trees1[:, p])) for p in range(nparts)]
+            case.update({"lnl_single_gpu": lnl1, "rel_diff": abs(lnl - lnl1) / abs(lnl1), "d1": d[0], "d1_single_gpu": d1[0]})
+            s.close()
+        # every rank must hold the same global value (the all-reduce is in-engine)
+        t = torch.tensor([lnl, -lnl], dtype=torch.float64, device=f"cuda:{lr}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert float(t[0]) == lnl and float(-t[1]) == lnl, "ranks disagree on the network lnL"
+        g.close()
+        report["cases"].append(case)
+    if rank == 0:
+        report["ok"] = True
+        print(json.dumps(report))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

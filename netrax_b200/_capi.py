@@ -135,6 +135,20 @@ class LikelihoodEngine:
         a.check(a._init(self.h))
         self.P = len(self.partitions)
 
+    def set_reduce(self, reduce):
+        """Install the reference's parallel_reduce_cb (src/RaxmlWrapper.cpp:717-718): `reduce(arr)` must SUM the float64
+        numpy array `arr` in place across all site shards (ranks).  All ranks then issue identical call sequences."""
+        cb_t = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.c_size_t, C.c_int)
+
+        def _cb(ctx, data, count, op):
+            reduce(np.ctypeslib.as_array(data, shape=(count,)))
+
+        self._reduce_cb = cb_t(_cb)   # keep alive
+        fn = getattr(self.api.lib, self.api.prefix + "set_reduce_callback")
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, cb_t, C.c_void_p]
+        self.api.check(fn(self.h, self._reduce_cb, None))
+
     def close(self):
         if getattr(self, "h", None):
             self.api._free(self.h)

@@ -17,7 +17,6 @@ HOST_SO = os.path.join(HERE, "libnetrax_b200.so")
 ENGINE_SO = os.path.join(HERE, "libnrx_engine.so")
 
 _api: Optional[FlatAPI] = None
-REDUCE_CB = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.c_size_t, C.c_int)
 
 
 def load() -> FlatAPI:
@@ -34,8 +33,6 @@ def load() -> FlatAPI:
         a = FlatAPI(lib, "nrxh_")
         lib.nrxh_set_eigen.restype = C.c_int
         lib.nrxh_set_eigen.argtypes = [C.c_void_p, C.c_uint] + [np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")] * 3
-        lib.nrxh_set_reduce_callback.restype = C.c_int
-        lib.nrxh_set_reduce_callback.argtypes = [C.c_void_p, REDUCE_CB, C.c_void_p]
         lib.nrxh_comm_get_unique_id.restype = C.c_int
         lib.nrxh_comm_get_unique_id.argtypes = [C.c_char_p]
         lib.nrxh_comm_init.restype = C.c_int
@@ -86,19 +83,11 @@ class NetraxB200(LikelihoodEngine):
         """`comm` = (unique_id_bytes, rank, nranks): attach an NCCL communicator so that the engine all-reduces its
         per-tree / per-pair partition sums on the device (site sharding across GPUs); `reduce` is then unused."""
         api = load()
-        self._reduce = reduce
-        self._cb = None
-        self._pre_init_hook = None
-        if reduce is not None:
-            def _cb(ctx, data, count, op):
-                arr = np.ctypeslib.as_array(data, shape=(count,))
-                reduce(arr)
-            self._cb = REDUCE_CB(_cb)
         # LikelihoodEngine.__init__ runs nrxh_init; the callback must be installed before the first evaluation only
         super().__init__(api, net, partitions, variant=variant, linkage=linkage,
                          backend=f"device={device};plan_cache={1 if plan_cache else 0}", partition_brlens=partition_brlens)
-        if self._cb is not None:
-            api.check(api.lib.nrxh_set_reduce_callback(self.h, self._cb, None))
+        if reduce is not None:
+            self.set_reduce(reduce)
         if comm is not None:
             uid, rank, nranks = comm
             api.check(api.lib.nrxh_comm_init(self.h, bytes(uid), int(rank), int(nranks)))

@@ -774,7 +774,8 @@ static void computeDisplayedTreeLoglikelihood(AnnotatedNetwork &ann, DisplayedTr
     double tl = ann.backend->rootLogl(p, t.clv_vector[p].p, t.scale_buffer[p].p, persite.data());
     treeAtRoot.treeLoglData.tree_partition_logl[p] = tl;
   }
-  /* parallel_reduce_cb: single process in the oracle (site sharding is exercised by the bench harness) */
+  if (ann.parallel_reduce_cb)  // LH/ImprovedLoglikelihood.cpp:472-483 (one reduce per displayed tree)
+    ann.parallel_reduce_cb(ann.parallel_context, treeAtRoot.treeLoglData.tree_partition_logl.data(), ann.partitionCount(), 0);
   treeAtRoot.treeLoglData.tree_logl_valid = true;
 }
 
@@ -1049,6 +1050,8 @@ static void recomputeTreeData(AnnotatedNetwork &ann, size_t pmatrix_index, Displ
     Operand a = makeOperand(src, p, (unsigned)pmatrix_index), b = makeOperand(tgt, p, (unsigned)pmatrix_index);
     c.tree_partition_logl[p] = ann.backend->edgeLogl(p, a, b, (unsigned)pmatrix_index, nullptr);
   }
+  if (ann.parallel_reduce_cb)  // LH/VirtualRerooting.cpp:326-344
+    ann.parallel_reduce_cb(ann.parallel_context, c.tree_partition_logl.data(), ann.partitionCount(), 0);
   c.tree_logl_valid = true;
 }
 
@@ -1165,6 +1168,11 @@ LoglDerivatives computeLoglikelihoodDerivatives(AnnotatedNetwork &ann, const std
     for (size_t i = 0; i < st.size(); ++i) {
       double f = 0.0, d1 = 0.0, d2 = 0.0;
       ann.backend->derivatives(p, st[i].sumtable.p, branch_length, !single_tree_mode, &f, &d1, &d2);
+      if (ann.parallel_reduce_cb) {  // LH/LikelihoodDerivatives.cpp:108-143 (per-partition values of a linked run are reduced one at a time here)
+        double v[3] = {f, d1, d2};
+        ann.parallel_reduce_cb(ann.parallel_context, v, 3, 0);
+        f = v[0]; d1 = v[1]; d2 = v[2];
+      }
       out.raw[p].push_back(f); out.raw[p].push_back(d1); out.raw[p].push_back(d2);
       if (single_tree_mode) { res_prime = d1; res_prime_prime = d2; done = true; break; }
       if (ann.options.likelihood_variant == LikelihoodVariant::AVERAGE_DISPLAYED_TREES) {

@@ -213,6 +213,9 @@ struct AnnotatedNetwork {  // SRC/graph/AnnotatedNetwork.hpp:42-89 (fields the p
   bool cached_logl_valid = false;
   // statistics for the benchmark metric (Σ trees(node) × patterns)
   uint64_t n_clv_updates = 0;
+  // fake_treeinfo->parallel_reduce_cb / parallel_context (SRC/RaxmlWrapper.cpp:717-718): SUM over site shards; null = single process
+  void (*parallel_reduce_cb)(void *context, double *data, size_t count, int op) = nullptr;
+  void *parallel_context = nullptr;
   unsigned partitionCount() const { return backend->partitionCount(); }
   unsigned fakePmatrixIndex() const { return (unsigned)network.edges.size(); }
 };

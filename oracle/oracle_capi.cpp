@@ -113,6 +113,13 @@ int orc_set_partition_brlens(void *hv, unsigned p, const double *brlens) {
   });
 }
 
+int orc_set_reduce_callback(void *hv, void (*cb)(void *, double *, size_t, int), void *ctx) {
+  Handle *h = static_cast<Handle *>(hv);
+  h->ann.parallel_reduce_cb = cb;
+  h->ann.parallel_context = ctx;
+  return 1;
+}
+
 int orc_init(void *hv) {
   Handle *h = static_cast<Handle *>(hv);
   return guarded([&] {

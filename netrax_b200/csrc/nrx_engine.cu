@@ -570,6 +570,13 @@ int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops) {
   return 1;
 }
 
+/* blocks along x for the reduction kernels (one value per call: the partial-sum layout uses gridDim.x as its stride) */
+static uint32_t reduce_blocks(const nrx_engine *e, uint32_t items) {
+  const uint64_t full = std::max<uint64_t>(1, ((uint64_t)e->max_patterns + BLOCK - 1) / BLOCK);
+  const uint64_t want = std::max<uint64_t>(1, (148ull * 32) / std::max<uint32_t>(1, items));  // ~32 blocks per SM in total
+  return (uint32_t)std::min<uint64_t>(full, want);
+}
+
 static int finish_reduction(nrx_engine *e, uint32_t total, uint32_t nblk, double *out) {
   k_reduce_partials<<<(total + 127) / 128, 128, 0, e->stream>>>(e->d_partial, e->d_result, nblk, total);
   e->launches++;
@@ -590,7 +597,7 @@ int nrx_tree_lnl(nrx_engine *e, const uint32_t *slots, uint32_t n, double *out, 
   CK(cudaSetDevice(e->device));
   for (uint32_t i = 0; i < n; ++i) if (slots[i] >= e->nslots) { g_err = "nrx_tree_lnl: slot out of range"; return 0; }
   const uint32_t P = (uint32_t)e->parts.size();
-  const uint32_t nblk = std::max<uint32_t>(1, std::min<uint32_t>((e->max_patterns + BLOCK - 1) / BLOCK, std::max<uint32_t>(1, 148 * 8 / std::max<uint32_t>(1, n * P))));
+  const uint32_t nblk = reduce_blocks(e, n * P);
   if (!ensure_result(e, (size_t)n * P, (size_t)n * P * nblk) || !refresh_views(e)) return 0;
   uint32_t *d_slots;
   if (!upload(e, slots, n, &d_slots)) return 0;
@@ -605,7 +612,8 @@ int nrx_tree_lnl(nrx_engine *e, const uint32_t *slots, uint32_t n, double *out, 
   const double log_thresh = std::log(SCALE_THRESHOLD);
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
-    k_tree_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
+    if (c.states == 4 && c.cats == 4) k_tree_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
+    else k_tree_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
     e->launches++;
     CK(cudaGetLastError());
   }
@@ -635,7 +643,7 @@ int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n
   if (!check_pairs(e, pairs, n, "nrx_edge_lnl")) return 0;
   for (const Part &p : e->parts) if (edge >= p.d.edges) { g_err = "nrx_edge_lnl: edge out of range"; return 0; }
   const uint32_t P = (uint32_t)e->parts.size();
-  const uint32_t nblk = std::max<uint32_t>(1, std::min<uint32_t>((e->max_patterns + BLOCK - 1) / BLOCK, std::max<uint32_t>(1, 148 * 8 / std::max<uint32_t>(1, n * P))));
+  const uint32_t nblk = reduce_blocks(e, n * P);
   if (!ensure_result(e, (size_t)n * P, (size_t)n * P * nblk) || !refresh_views(e)) return 0;
   nrx_pair *d_pairs;
   if (!upload(e, pairs, n, &d_pairs)) return 0;
@@ -643,7 +651,8 @@ int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n
   const double log_thresh = std::log(SCALE_THRESHOLD);
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
-    k_edge_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh);
+    if (c.states == 4 && c.cats == 4) k_edge_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh);
+    else k_edge_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh);
     e->launches++;
     CK(cudaGetLastError());
   }
@@ -661,8 +670,13 @@ int nrx_sumtables(nrx_engine *e, const nrx_pair *pairs, uint32_t n) {
   for (const ShapeClass &c : e->classes) {
     if (c.max_patterns == 0) continue;
     const uint32_t z = (uint32_t)c.parts.size();
-    dim3 grid(tiles_for((uint64_t)c.max_patterns * c.cats, BLOCK, n * z), n, z);
-    k_sumtable<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs);
+    if (c.states == 4 && c.cats == 4) {
+      dim3 grid(tiles_for((uint64_t)c.max_patterns * 4, BLOCK * RU, n * z), n, z);
+      k_sumtable_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs);
+    } else {
+      dim3 grid(tiles_for((uint64_t)c.max_patterns * c.cats, BLOCK, n * z), n, z);
+      k_sumtable<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs);
+    }
     e->launches++;
     CK(cudaGetLastError());
   }
@@ -675,7 +689,7 @@ int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen, double *out)
   CK(cudaSetDevice(e->device));
   if (n > e->nsumtables) { g_err = "nrx_derivatives: sumtables not computed"; return 0; }
   const uint32_t P = (uint32_t)e->parts.size();
-  const uint32_t nblk = std::max<uint32_t>(1, std::min<uint32_t>((e->max_patterns + BLOCK - 1) / BLOCK, std::max<uint32_t>(1, 148 * 8 / std::max<uint32_t>(1, n * P))));
+  const uint32_t nblk = reduce_blocks(e, n * P);
   if (!ensure_result(e, (size_t)n * P * 3, (size_t)n * P * 3 * nblk) || !refresh_views(e)) return 0;
   // diagptable on the host with libm exp, exactly pll_compute_diagptable (LIBPLL/core_derivatives.c:711-726)
   for (uint32_t pi = 0; pi < P; ++pi) {
@@ -700,7 +714,8 @@ int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen, double *out)
   CK(cudaMemsetAsync(e->d_partial, 0, (size_t)n * P * 3 * nblk * sizeof(double), e->stream));
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
-    k_derivatives<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P);
+    if (c.states == 4 && c.cats == 4) k_derivatives_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P);
+    else k_derivatives<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P);
     e->launches++;
     CK(cudaGetLastError());
   }

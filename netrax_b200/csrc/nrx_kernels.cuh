@@ -621,4 +621,200 @@ __global__ void __launch_bounds__(BLOCK) k_derivatives(const PartView *__restric
   }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * K3-K6, DNA 4x4 specialisations.  Same arithmetic as the generic kernels above (same summation order), but
+ * thread = (pattern, rate category) like K2: a warp reads 1 KB of contiguous CLV per 256-bit load, UNROLL
+ * independent loads are issued before the first use, the four categories of a pattern are combined with quad
+ * shuffles, and the small per-partition constants (frequencies, eigenvectors, P rows, diag table) sit in
+ * shared memory.  grid = (tiles, items, partitions of this shape); per-block partial sums, fixed-order stage 2.
+ * ---------------------------------------------------------------------------------------------- */
+constexpr int RU = 4;  // k_sumtable_dna4: independent 256-bit loads in flight per operand per thread
+
+/* K3 / K4 / K6 reduce over patterns and end in a log or a division per PATTERN, so here thread = pattern (all 32
+ * lanes do the transcendental part) with the four category blocks of the pattern read as four independent 256-bit
+ * loads (every 32-byte sector fetched is fully used). */
+__global__ void __launch_bounds__(BLOCK) k_tree_lnl_dna4(const PartView *__restrict__ parts, const uint32_t *__restrict__ slots,
+                                                          double *__restrict__ partial, uint32_t nparts_total, double log_thresh,
+                                                          double *__restrict__ persite, size_t persite_stride) {
+  __shared__ double red[BLOCK / 32];
+  const PartView &pv = parts[blockIdx.z];
+  const uint32_t slot = slots[blockIdx.y];
+  const double *clv = pv.clv[slot];
+  const uint32_t *sc = pv.scaler[slot];
+  const double f0 = pv.freqs[0], f1 = pv.freqs[1], f2 = pv.freqs[2], f3 = pv.freqs[3];
+  const double w0 = pv.rate_weights[0], w1 = pv.rate_weights[1], w2 = pv.rate_weights[2], w3 = pv.rate_weights[3];
+  double acc[1] = {0.0};
+  for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
+    const double *c = clv + n * 16;
+    const D4 v0 = ldg256(c), v1 = ldg256(c + 4), v2 = ldg256(c + 8), v3 = ldg256(c + 12);
+    const uint32_t s = sc[n];
+    const double pw = (double)pv.weights[n];
+    double term = __dmul_rn(tree4(__dmul_rn(f0, v0.x), __dmul_rn(f1, v0.y), __dmul_rn(f2, v0.z), __dmul_rn(f3, v0.w)), w0);
+    term = __dadd_rn(term, __dmul_rn(tree4(__dmul_rn(f0, v1.x), __dmul_rn(f1, v1.y), __dmul_rn(f2, v1.z), __dmul_rn(f3, v1.w)), w1));
+    term = __dadd_rn(term, __dmul_rn(tree4(__dmul_rn(f0, v2.x), __dmul_rn(f1, v2.y), __dmul_rn(f2, v2.z), __dmul_rn(f3, v2.w)), w2));
+    term = __dadd_rn(term, __dmul_rn(tree4(__dmul_rn(f0, v3.x), __dmul_rn(f1, v3.y), __dmul_rn(f2, v3.z), __dmul_rn(f3, v3.w)), w3));
+    double lk = log(term);
+    if (s) lk = __dadd_rn(lk, __dmul_rn((double)s, log_thresh));
+    lk = __dmul_rn(lk, pw);
+    if (persite) persite[((size_t)blockIdx.y * nparts_total + pv.part_index) * persite_stride + n] = lk;
+    acc[0] += lk;
+  }
+  block_sum<1>(acc, red);
+  if (threadIdx.x == 0) partial[((size_t)blockIdx.y * nparts_total + pv.part_index) * gridDim.x + blockIdx.x] = acc[0];
+}
+
+__device__ __forceinline__ double edge_cat_term(const D4 &a, const D4 &y, double f0, double f1, double f2, double f3) {
+  double r = __dmul_rn(__dmul_rn(a.x, f0), y.x);
+  r = __dadd_rn(r, __dmul_rn(__dmul_rn(a.y, f1), y.y));
+  r = __dadd_rn(r, __dmul_rn(__dmul_rn(a.z, f2), y.z));
+  return __dadd_rn(r, __dmul_rn(__dmul_rn(a.w, f3), y.w));
+}
+
+__global__ void __launch_bounds__(BLOCK) k_edge_lnl_dna4(const PartView *__restrict__ parts, const nrx_pair *__restrict__ pairs,
+                                                          uint32_t edge, double *__restrict__ partial, uint32_t nparts_total,
+                                                          double log_thresh) {
+  __shared__ double red[BLOCK / 32];
+  __shared__ __align__(32) double lut[256];
+  __shared__ __align__(16) double sP[64];
+  const PartView &pv = parts[blockIdx.z];
+  nrx_pair pr = pairs[blockIdx.y];
+  if (pr.a_kind == NRX_TIP) { nrx_pair t = pr; pr.a_kind = t.b_kind; pr.a_idx = t.b_idx; pr.b_kind = t.a_kind; pr.b_idx = t.a_idx; }
+  const int tid = threadIdx.x;
+  const bool tipc = pr.b_kind == NRX_TIP;
+  if (tipc) build_tip_lut4(lut, pv.pmat + (size_t)edge * 64, tid);
+  else if (tid < 64) sP[tid] = pv.pmat[(size_t)edge * 64 + tid];   // all lanes read the same row: broadcast, no conflicts
+  __syncthreads();
+  const double *clvp = pv.clv[pr.a_idx];
+  const uint32_t *scp = pv.scaler[pr.a_idx];
+  const double *clvc = tipc ? nullptr : pv.clv[pr.b_idx];
+  const uint32_t *scc = tipc ? nullptr : pv.scaler[pr.b_idx];
+  const uint8_t *tip = tipc ? pv.tipchars + (size_t)pr.b_idx * pv.tip_pitch : nullptr;
+  const double f0 = pv.freqs[0], f1 = pv.freqs[1], f2 = pv.freqs[2], f3 = pv.freqs[3];
+  const double w0 = pv.rate_weights[0], w1 = pv.rate_weights[1], w2 = pv.rate_weights[2], w3 = pv.rate_weights[3];
+  double acc[1] = {0.0};
+  for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
+    const double *cp = clvp + n * 16;
+    const D4 a0 = ldg256(cp), a1 = ldg256(cp + 4), a2 = ldg256(cp + 8), a3 = ldg256(cp + 12);
+    D4 y0, y1, y2, y3;
+    uint32_t s = scp[n];
+    if (tipc) {
+      const double *l = lut + (tip[n] & 15) * 16;
+      y0 = *reinterpret_cast<const D4 *>(l); y1 = *reinterpret_cast<const D4 *>(l + 4);
+      y2 = *reinterpret_cast<const D4 *>(l + 8); y3 = *reinterpret_cast<const D4 *>(l + 12);
+    } else {
+      const double *cc = clvc + n * 16;
+      const D4 b0 = ldg256(cc), b1 = ldg256(cc + 4), b2 = ldg256(cc + 8), b3 = ldg256(cc + 12);
+      s += scc[n];
+      y0 = matvec4(sP, b0); y1 = matvec4(sP + 16, b1); y2 = matvec4(sP + 32, b2); y3 = matvec4(sP + 48, b3);
+    }
+    const double pw = (double)pv.weights[n];
+    double term = __dmul_rn(edge_cat_term(a0, y0, f0, f1, f2, f3), w0);
+    term = __dadd_rn(term, __dmul_rn(edge_cat_term(a1, y1, f0, f1, f2, f3), w1));
+    term = __dadd_rn(term, __dmul_rn(edge_cat_term(a2, y2, f0, f1, f2, f3), w2));
+    term = __dadd_rn(term, __dmul_rn(edge_cat_term(a3, y3, f0, f1, f2, f3), w3));
+    double lk = log(term);
+    if (s) lk = __dadd_rn(lk, __dmul_rn((double)s, log_thresh));
+    acc[0] += __dmul_rn(lk, pw);
+  }
+  block_sum<1>(acc, red);
+  if (threadIdx.x == 0) partial[((size_t)blockIdx.y * nparts_total + pv.part_index) * gridDim.x + blockIdx.x] = acc[0];
+}
+
+__global__ void __launch_bounds__(BLOCK) k_sumtable_dna4(const PartView *__restrict__ parts, const nrx_pair *__restrict__ pairs) {
+  __shared__ double sV[16], sIV[16], sF[4];   // eigenvecs [j][k], inv_eigenvecs [k][j], freqs
+  const PartView &pv = parts[blockIdx.z];
+  nrx_pair pr = pairs[blockIdx.y];
+  if (pr.b_kind == NRX_TIP) { nrx_pair t = pr; pr.a_kind = t.b_kind; pr.a_idx = t.b_idx; pr.b_kind = t.a_kind; pr.b_idx = t.a_idx; }
+  const int tid = threadIdx.x;
+  if (tid < 16) { sV[tid] = pv.eigenvecs[tid]; sIV[tid] = pv.inv_eigenvecs[tid]; }
+  if (tid < 4) sF[tid] = pv.freqs[tid];
+  __syncthreads();
+  const bool tipl = pr.a_kind == NRX_TIP;
+  const double *clvl = tipl ? nullptr : pv.clv[pr.a_idx];
+  const uint8_t *tip = tipl ? pv.tipchars + (size_t)pr.a_idx * pv.tip_pitch : nullptr;
+  const double *clvr = pv.clv[pr.b_idx];
+  double *out = pv.sumtable[blockIdx.y];
+  const uint64_t n_items = (uint64_t)pv.patterns * 4;
+  for (uint64_t base = (uint64_t)blockIdx.x * BLOCK * RU; base < n_items; base += (uint64_t)gridDim.x * BLOCK * RU) {
+    D4 a[RU], b[RU];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const uint64_t g = base + (uint64_t)u * BLOCK + tid;
+      if (g < n_items) {
+        b[u] = ldg256(clvr + g * 4);
+        if (!tipl) a[u] = ldg256(clvl + g * 4);
+        else { const uint32_t m = tip[g >> 2] & 15; a[u].x = (double)(m & 1u); a[u].y = (double)((m >> 1) & 1u); a[u].z = (double)((m >> 2) & 1u); a[u].w = (double)((m >> 3) & 1u); }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const uint64_t g = base + (uint64_t)u * BLOCK + tid;
+      if (g >= n_items) continue;
+      const double lf[4] = {__dmul_rn(a[u].x, sF[0]), __dmul_rn(a[u].y, sF[1]), __dmul_rn(a[u].z, sF[2]), __dmul_rn(a[u].w, sF[3])};
+      const double rv[4] = {b[u].x, b[u].y, b[u].z, b[u].w};
+      double o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double le = 0.0, ri = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          le = __dadd_rn(le, __dmul_rn(lf[k], sIV[k * 4 + j]));
+          ri = __dadd_rn(ri, __dmul_rn(sV[j * 4 + k], rv[k]));
+        }
+        o[j] = __dmul_rn(le, ri);
+      }
+      D4 ov; ov.x = o[0]; ov.y = o[1]; ov.z = o[2]; ov.w = o[3];
+      stg256(out + g * 4, ov);
+    }
+  }
+}
+
+__device__ __forceinline__ void deriv_cat(const D4 &v, const double *dg, double w, double &lk0, double &lk1, double &lk2, bool first) {
+  const double sv[4] = {v.x, v.y, v.z, v.w};
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    c0 = __dadd_rn(c0, __dmul_rn(sv[j], dg[j * 4 + 0]));
+    c1 = __dadd_rn(c1, __dmul_rn(sv[j], dg[j * 4 + 1]));
+    c2 = __dadd_rn(c2, __dmul_rn(sv[j], dg[j * 4 + 2]));
+  }
+  if (first) { lk0 = __dmul_rn(c0, w); lk1 = __dmul_rn(c1, w); lk2 = __dmul_rn(c2, w); }
+  else { lk0 = __dadd_rn(lk0, __dmul_rn(c0, w)); lk1 = __dadd_rn(lk1, __dmul_rn(c1, w)); lk2 = __dadd_rn(lk2, __dmul_rn(c2, w)); }
+}
+
+__global__ void __launch_bounds__(BLOCK) k_derivatives_dna4(const PartView *__restrict__ parts, double *__restrict__ partial,
+                                                             uint32_t nparts_total) {
+  __shared__ double red[3 * (BLOCK / 32)];
+  __shared__ double sD[64];   // diag table [cat][state][4]: every lane reads the same entry (broadcast)
+  const PartView &pv = parts[blockIdx.z];
+  const int tid = threadIdx.x;
+  if (tid < 64) sD[tid] = pv.diagp[tid];
+  __syncthreads();
+  const double *st = pv.sumtable[blockIdx.y];
+  const double w0 = pv.rate_weights[0], w1 = pv.rate_weights[1], w2 = pv.rate_weights[2], w3 = pv.rate_weights[3];
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
+    const double *c = st + n * 16;
+    const D4 v0 = ldg256(c), v1 = ldg256(c + 4), v2 = ldg256(c + 8), v3 = ldg256(c + 12);
+    const double pw = (double)pv.weights[n];
+    double lk0, lk1, lk2;
+    deriv_cat(v0, sD, w0, lk0, lk1, lk2, true);
+    deriv_cat(v1, sD + 16, w1, lk0, lk1, lk2, false);
+    deriv_cat(v2, sD + 32, w2, lk0, lk1, lk2, false);
+    deriv_cat(v3, sD + 48, w3, lk0, lk1, lk2, false);
+    const double d1 = -lk1 / lk0;
+    const double d2 = d1 * d1 - lk2 / lk0;
+    acc[0] += pw * log(lk0);
+    acc[1] += pw * d1;
+    acc[2] += pw * d2;
+  }
+  block_sum<3>(acc, red);
+  if (threadIdx.x == 0) {
+    double *p = partial + ((size_t)blockIdx.y * nparts_total + pv.part_index) * 3 * gridDim.x;
+    p[0 * gridDim.x + blockIdx.x] = acc[0];
+    p[1 * gridDim.x + blockIdx.x] = acc[1];
+    p[2 * gridDim.x + blockIdx.x] = acc[2];
+  }
+}
+
 }  // namespace nrx

@@ -1,0 +1,122 @@
+#!/usr/bin/env python
+"""Measure every BASELINE.json config on one B200 next to the CPU reference arm (real libpll AVX2 under the restated
+NetRAX driver, all host cores, bounded sample).  bench.py stays the driver's contract (config 5); this script fills
+profiles/ with the other configs' numbers.  Usage: python scripts/bench_configs.py [--configs 1,2,3] [--out file.json]
+
+Per config it reports: full network lnL evaluations/s + CLV site-updates/s, and for config 2 the branch-length
+derivative sweep (for EVERY edge: virtual re-rooting, edge-rooted lnL, sumtables, 3 Newton-iterate derivative
+evaluations, restore) in sweeps/s and edges/s."""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from netrax_b200._capi import UNLINKED  # noqa: E402
+
+
+def derivative_sweep(eng, net, iters=3):
+    for e in range(net.num_edges):
+        t0 = float(net.edge_length[e])
+        eng.brlen_prepare(e)
+        eng.computeLoglikelihoodBrlenOpt(e)
+        if eng.computePartitionSumtables(e):
+            for k in range(iters):
+                eng.brlen_set_length(e, t0 * (1.0 + 0.1 * (k + 1)))
+                eng.computeLoglikelihoodDerivatives(e)
+            eng.brlen_set_length(e, t0)
+        eng.brlen_finish(e)
+
+
+def _cpu_worker(args):
+    kind, cfg, patterns, widx, reps, sweep = args
+    from oracle import oracle
+    net, parts, brl = bench.make_inputs(cfg, patterns, 100 + widx)
+    eng = oracle.make_engine(kind, net, parts, variant=cfg["variant"], linkage=cfg["linkage"], partition_brlens=brl)
+    eng.computeLoglikelihood(0, 1)
+    out = {"lnl": [], "sweep": []}
+    eng.reset_counters()
+    for _ in range(reps):
+        t = time.perf_counter(); eng.computeLoglikelihood(0, 1); out["lnl"].append(time.perf_counter() - t)
+    out["updates"] = eng.clv_update_count() // reps
+    if sweep:
+        t = time.perf_counter(); derivative_sweep(eng, net); out["sweep"].append(time.perf_counter() - t)
+    return out
+
+
+def cpu_arm(cfg, cores, patterns_per_core, reps, sweep):
+    from oracle import oracle
+    kind = "ref" if oracle.have_ref() else "port"
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(kind, cfg, patterns_per_core, i, reps, sweep) for i in range(cores)])
+    lnl_t = float(np.median([max(r["lnl"][k] for r in res) for k in range(reps)]))
+    out = {"kind": "reference" if kind == "ref" else "port", "cores": cores, "patterns_per_core": patterns_per_core,
+           "lnl_eval_s_on_sample": lnl_t, "site_updates_per_s": sum(r["updates"] for r in res) / lnl_t}
+    if sweep:
+        out["sweep_s_on_sample"] = max(r["sweep"][0] for r in res)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1,2,3")
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--out", default="")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    from netrax_b200.engine import NetraxB200
+    results = {}
+    for c in [int(x) for x in args.configs.split(",")]:
+        cfg = dict(bench.CONFIGS[c])
+        net, parts, brl = bench.make_inputs(cfg, cfg["patterns"], 0)
+        eng = NetraxB200(net, parts, variant=cfg["variant"], linkage=cfg["linkage"], partition_brlens=brl)
+        for _ in range(3):
+            eng.computeLoglikelihood(0, 1)
+        slots = sum(eng.num_trees(v) for v in range(net.num_tips, net.num_nodes))
+        updates = slots * sum(p.sites for p in parts)
+        l0 = eng.launch_count()
+        eng.api.check(1)
+        eng.timer_start()
+        for _ in range(args.reps):
+            eng.computeLoglikelihood(0, 1)
+        ms = eng.timer_stop() / args.reps
+        r = {"workload": cfg["name"], "sum_trees_per_node": slots, "root_trees": eng.num_trees(net.root),
+             "gpu": {"ms_per_lnl_eval": ms, "lnl_evals_per_s": 1e3 / ms, "site_updates_per_s": updates / (ms / 1e3),
+                     "launches_per_eval": (eng.launch_count() - l0) / args.reps}}
+        sweep = (c == 2)
+        if sweep:
+            derivative_sweep(eng, net)  # warm-up (allocates re-rooting slots and sumtables)
+            l0 = eng.launch_count()
+            t = time.perf_counter()
+            eng.timer_start()
+            derivative_sweep(eng, net)
+            ms_s = eng.timer_stop()
+            wall = time.perf_counter() - t
+            r["gpu"].update({"ms_per_derivative_sweep": ms_s, "wall_ms_per_derivative_sweep": 1e3 * wall, "edges": net.num_edges,
+                             "edges_per_s": net.num_edges / (ms_s / 1e3), "launches_per_sweep": eng.launch_count() - l0})
+        eng.close()
+        if not args.no_cpu:
+            cores = bench.host_cores()
+            ppc = min(4000 if sweep else 16000, max(64, -(-cfg["patterns"] // cores)))
+            cpu = cpu_arm(cfg, cores, ppc, 3, sweep)
+            scale = cfg["patterns"] / (ppc * cores)   # the sample covers ppc*cores patterns of the config's total
+            cpu["lnl_evals_per_s_full_config_est"] = 1.0 / (cpu["lnl_eval_s_on_sample"] * scale)
+            r["cpu"] = cpu
+            r["speedup_site_updates"] = r["gpu"]["site_updates_per_s"] / cpu["site_updates_per_s"]
+            if sweep:
+                cpu["sweep_s_full_config_est"] = cpu["sweep_s_on_sample"] * scale
+                r["speedup_derivative_sweep"] = cpu["sweep_s_full_config_est"] / (r["gpu"]["ms_per_derivative_sweep"] / 1e3)
+        results[f"config{c}"] = r
+        print(json.dumps({f"config{c}": r}), flush=True)
+    if args.out:
+        json.dump(results, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

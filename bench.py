@@ -36,12 +36,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from netrax_b200._capi import AVERAGE, BEST, LINKED, UNLINKED, Partition  # noqa: E402
-from netrax_b200.synth import DNA_FREQS, GAMMA4_ALPHA05, GTR_RATES, random_network, simulate_alignment  # noqa: E402
+from netrax_b200.synth import DNA_FREQS, GAMMA4_ALPHA05, GTR_RATES, lg_model, random_network, simulate_alignment  # noqa: E402
 
 CONFIGS = {
     1: dict(name="config1: DNA GTR+G4, 20 taxa, 1 reticulation, 10k patterns, AVERAGE", taxa=20, ret=1, patterns=10_000, parts=1, variant=AVERAGE, linkage=LINKED),
     2: dict(name="config2: DNA GTR+G4, 50 taxa, 4 reticulations, 100k patterns, AVERAGE", taxa=50, ret=4, patterns=100_000, parts=1, variant=AVERAGE, linkage=LINKED),
     3: dict(name="config3: DNA 10 partitions x 50k patterns, unlinked brlens, 3 reticulations, BEST", taxa=50, ret=3, patterns=50_000, parts=10, variant=BEST, linkage=UNLINKED),
+    4: dict(name="config4: Protein LG+G4, 30 taxa, 2 reticulations, 20k patterns, AVERAGE", taxa=30, ret=2, patterns=20_000, parts=1, variant=AVERAGE, linkage=LINKED, states=20),
     5: dict(name="config5: DNA GTR+G4, 100 taxa, 8 reticulations, 1M site patterns sharded across the GPUs", taxa=100, ret=8, patterns=1_000_000, parts=1, variant=AVERAGE, linkage=LINKED),
 }
 
@@ -53,6 +54,11 @@ def make_inputs(cfg, patterns_local, rank):
     parts, brl = [], []
     rng = np.random.default_rng(5)
     for p in range(cfg["parts"]):
+        if cfg.get("states", 4) == 20:
+            rates, freqs = lg_model()
+            m, w = simulate_alignment(net, patterns_local, seed=1000 * (rank + 1) + p, dedup=False, states=20, rates=rates, freqs=freqs)
+            parts.append(Partition(20, 4, m, freqs, rates, GAMMA4_ALPHA05, pattern_weights=w))
+            continue
         m, w = simulate_alignment(net, patterns_local, seed=1000 * (rank + 1) + p, dedup=False)
         parts.append(Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w))
         brl.append(net.edge_length * rng.uniform(0.5, 2.0, net.num_edges))

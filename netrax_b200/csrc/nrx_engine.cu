@@ -46,6 +46,7 @@ struct Part {
   double **d_sumtable = nullptr;
   uint32_t table_cap = 0, st_cap = 0;
   bool model_set = false, tips_set = false;
+  uint32_t tip_codes = 0;  // distinct tip codes in use
 };
 
 struct ShapeClass {
@@ -109,6 +110,8 @@ struct nrx_engine {
   size_t persite_cap = 0;
   unsigned long long launches = 0;
   int k2_variant = 0;       // 0: k_clv_dna4_pipe (production); UM: k_clv_dna4<U, MINB> (A/B experiments, env NRX_K2=UM)
+  bool aa_generic = false;  // env NRX_AA=generic: force the scalar kernel for 20-state partitions (A/B)
+  uint32_t aa_blocks = 148 * 3 * 6;  // block-count target of the DMMA kernel
   uint32_t k2_blocks = 2368; // block-count target of the pipelined kernel: 8 waves of 2 resident blocks per SM (measured best, profiles/)
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   bool views_dirty = true;
@@ -179,7 +182,7 @@ template <class T> int upload(nrx_engine *e, const T *src, size_t n, T **dev) {
 PartView make_view(const Part &p, uint32_t index) {
   PartView v{};
   v.states = p.d.states; v.sp = p.sp; v.cats = p.d.rate_cats; v.patterns = p.d.patterns; v.tips = p.d.tips; v.edges = p.d.edges;
-  v.part_index = index; v.tip_pitch = p.pat_pad;
+  v.part_index = index; v.tip_pitch = p.pat_pad; v.tip_codes = p.tip_codes;
   v.pmat = p.pmat; v.tipchars = p.tipchars; v.tipmap = p.tipmap; v.weights = p.weights;
   v.freqs = p.freqs; v.eigenvecs = p.eigenvecs; v.inv_eigenvecs = p.inv_eigenvecs; v.eigenvals = p.eigenvals;
   v.rates = p.rates; v.rate_weights = p.rate_weights;
@@ -206,6 +209,7 @@ int check_part(nrx_engine *e, uint32_t p) {
   return 1;
 }
 
+uint32_t class_tip_codes(const nrx_engine *e, const ShapeClass &c);
 uint32_t tiles_for(uint64_t items, uint32_t per_block, uint32_t other_dims) {
   // enough blocks for >= ~8 waves over 148 SMs when the launch is big, one tile per block when it is small
   uint64_t full = (items + per_block - 1) / per_block;
@@ -221,6 +225,14 @@ uint32_t tiles_for(uint64_t items, uint32_t per_block, uint32_t other_dims) {
   return (uint32_t)std::min<uint64_t>(want, 65535ull * 32);
 }
 
+}  // namespace
+
+namespace {
+uint32_t class_tip_codes(const nrx_engine *e, const ShapeClass &c) {
+  uint32_t m = 0;
+  for (uint32_t pi : c.parts) m = std::max(m, e->parts[pi].tip_codes);
+  return m;
+}
 }  // namespace
 
 extern "C" {
@@ -248,11 +260,14 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
   if (!cuda_ok(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete e; return nullptr; }
   e->parts.resize(nparts);
   if (const char *v = std::getenv("NRX_K2")) e->k2_variant = std::atoi(v);
+  if (const char *v = std::getenv("NRX_AA")) e->aa_generic = std::string(v) == "generic";
+  if (const char *v = std::getenv("NRX_AA_BLOCKS")) e->aa_blocks = (uint32_t)std::max(1, std::atoi(v));
   if (const char *v = std::getenv("NRX_K2_BLOCKS")) e->k2_blocks = (uint32_t)std::max(1, std::atoi(v));
   {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (!std::getenv("NRX_K2_BLOCKS")) e->k2_blocks = 16u * (uint32_t)sms;
+    if (!cuda_ok(cudaFuncSetAttribute(k_clv_aa20_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(AaSmem) + 2 * AA_LUT_CODES * 80 * sizeof(double))), "cudaFuncSetAttribute")) { delete e; return nullptr; }
     if (!cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClvPipeSmem)), "cudaFuncSetAttribute")) { delete e; return nullptr; }
   }
   for (uint32_t i = 0; i < nparts; ++i) {
@@ -339,7 +354,10 @@ int nrx_set_tips(nrx_engine *e, uint32_t pi, const uint32_t *tip_masks) {
   CK(cudaStreamSynchronize(e->stream));
   if (n) CK(cudaMemcpy2D(p.tipchars, p.pat_pad, codes.data(), p.d.patterns, p.d.patterns, p.d.tips, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(p.tipmap, tipmap.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  p.tip_codes = 0;
+  for (uint32_t i = 0; i < 256; ++i) if (tipmap[i]) p.tip_codes = i + 1;
   p.tips_set = true;
+  e->views_dirty = true;
   return 1;
 }
 
@@ -355,6 +373,7 @@ int nrx_set_tipchars_u8(nrx_engine *e, uint32_t pi, const uint8_t *codes) {
   CK(cudaMemcpyAsync(p.tipmap, tipmap.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   p.tips_set = true;
+  if (p.tip_codes != 16) { p.tip_codes = 16; e->views_dirty = true; }
   return 1;
 }
 
@@ -553,6 +572,16 @@ int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops) {
         else if (U == 4 && MB == 2) k_clv_dna4<4, 2><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops);
         else { g_err = "NRX_K2: unknown register-kernel variant"; return 0; }
       }
+    } else if (c.states == 20 && c.cats == 4 && !e->aa_generic && class_tip_codes(e, c) <= (uint32_t)AA_LUT_CODES) {
+      // protein: FP64 tensor cores (DMMA); 3 resident blocks of 4+1 warps per SM, 8-pattern tiles
+      bool with_lut = false;
+      for (uint32_t i = 0; i < nops; ++i) with_lut |= (ops[i].left_kind == NRX_TIP || ops[i].right_kind == NRX_TIP);
+      const uint32_t ntiles = (c.max_patterns + AA_TP - 1) / AA_TP;
+      uint32_t groups = std::max<uint32_t>(1, (e->aa_blocks + nops * z - 1) / (nops * z));
+      groups = std::min(groups, std::max<uint32_t>(1, ntiles / 8));
+      dim3 grid(nops * groups, 1, z);
+      const size_t smem = sizeof(AaSmem) + (with_lut ? 2 * AA_LUT_CODES * 80 * sizeof(double) : 0);
+      k_clv_aa20_dmma<<<grid, AA_THREADS, smem, e->stream>>>(c.d_views, d_ops, nops, groups, with_lut ? 1 : 0);
     } else {
       dim3 grid(tiles_for(c.max_patterns, BLOCK, nops * z), nops, z);
       k_clv_generic<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops, nullptr);

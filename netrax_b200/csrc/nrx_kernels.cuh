@@ -28,6 +28,7 @@ constexpr int BLOCK = 256;
 struct PartView {
   uint32_t states, sp, cats, patterns, tips, edges;
   uint32_t part_index, tip_pitch;  // tip_pitch: row pitch of tipchars (patterns rounded up to a tile multiple)
+  uint32_t tip_codes, pad_;        // number of distinct tip codes in use (entries of tipmap)
   const double *pmat;        // [edges][cats][states][sp]
   const uint8_t *tipchars;   // [tips][patterns]
   const uint32_t *tipmap;    // [256] code -> state mask
@@ -366,6 +367,224 @@ __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe(const PartView *__re
     }
     __syncthreads();  // everyone is done with this stage: refill it
     if (tid == 0 && k + NSTAGE < count) issue(k + NSTAGE);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K2, protein: 20 states x 4 rate categories on the FP64 tensor cores (DMMA, mma.sync m8n8k4 f64).
+ *
+ * Here the per-node update IS a dense contraction: x[item][i] = sum_j P_c[i][j] * clv[item][j] with a 20x20
+ * matrix per category (AI 3.3 flop/B, reference body LIBPLL/core_partials_avx2.c:630-818).  Per category:
+ * D[8 items x 8 states] += A[8 items x 4] * B[4 x 8] with A = the CLV rows as they lie in memory (row-major),
+ * B = P_c as it lies in memory ("col" layout) — 3 n-tiles (20 states padded to 24, padding rows of P are zero)
+ * x 5 k-steps = 15 DMMAs per operand per 8 items.  A warp owns ONE category for the whole block, so its 2 x 15
+ * B fragments (both child edges) stay in registers; the four category warps of a block share 8-pattern tiles.
+ * A producer warp streams the tiles with per-row cp.async.bulk copies (640 B per pattern, destination pitch
+ * 672 B so that the 8 rows of an A fragment fall into different banks) through an NSTAGE_AA-deep ring with
+ * full/empty mbarriers; consumers pull their 10 A-fragment values + scalers into registers and release the
+ * stage before the math.  Tip operands use a per-block table lut[code][cat][state] = sum_{j in mask} P[i][j]
+ * (the reference's tip-inner precomputation, core_partials_avx2.c:344-420).  Scaling: all 80 entries of a
+ * pattern < 2^-256 (core_partials.c:727-757) — AND over the quad, then over the 4 category warps through
+ * shared flags and a 128-thread named barrier.
+ * ---------------------------------------------------------------------------------------------- */
+constexpr int AA_TP = 8;            // patterns per tile
+constexpr int AA_PITCH = 84;        // doubles per staged row (80 + 4 padding)
+constexpr int NSTAGE_AA = 4;
+constexpr int AA_LUT_CODES = 32;    // tip table capacity (more distinct codes -> generic kernel)
+constexpr int AA_THREADS = 160;     // 4 consumer warps (one per category) + 1 producer warp
+
+struct __align__(128) AaStage {
+  double l[AA_TP * AA_PITCH];
+  double r[AA_TP * AA_PITCH];
+  uint32_t scl[AA_TP];
+  uint32_t scr[AA_TP];
+  uint8_t tl[16];
+  uint8_t tr[16];
+};
+struct __align__(128) AaSmem {
+  AaStage st[NSTAGE_AA];
+  unsigned long long full[NSTAGE_AA];
+  unsigned long long empty[NSTAGE_AA];
+  uint32_t flags[2][4][AA_TP];
+  // followed by double lutL[AA_LUT_CODES*80], lutR[AA_LUT_CODES*80] when the launch has tip operands
+};
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void build_tip_lut20(double *lut, const double *pm /* [4][20][20] */, const uint32_t *tipmap, uint32_t ncodes, int tid, int nthreads) {
+  for (uint32_t idx = tid; idx < ncodes * 80; idx += nthreads) {
+    const uint32_t code = idx / 80, ci = idx % 80;   // ci = cat * 20 + i
+    const uint32_t mask = tipmap[code];
+    const double *row = pm + (size_t)ci * 20;
+    double sum = 0.0;
+    for (int j = 0; j < 20; ++j) if ((mask >> j) & 1u) sum = __dadd_rn(sum, row[j]);
+    lut[idx] = sum;
+  }
+}
+
+__global__ void __launch_bounds__(AA_THREADS, 3) k_clv_aa20_dmma(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops,
+                                                                  uint32_t nops, uint32_t groups, int with_lut) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  AaSmem &sm = *reinterpret_cast<AaSmem *>(smem_raw);
+  double *lutL = reinterpret_cast<double *>(smem_raw + sizeof(AaSmem));
+  double *lutR = lutL + AA_LUT_CODES * 80;
+  const PartView &pv = parts[blockIdx.z];
+  const nrx_op op = ops[blockIdx.x % nops];
+  const uint32_t grp = blockIdx.x / nops;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t ntiles = (pv.patterns + AA_TP - 1) / AA_TP;
+  if (grp >= ntiles) return;
+  const uint32_t count = (ntiles - grp + groups - 1) / groups;
+  const int lk = op.left_kind, rk = op.right_kind;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE_AA; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (with_lut) {
+    if (lk == NRX_TIP) build_tip_lut20(lutL, pv.pmat + (size_t)op.left_edge * 1600, pv.tipmap, pv.tip_codes, tid, AA_THREADS);
+    if (rk == NRX_TIP) build_tip_lut20(lutR, pv.pmat + (size_t)op.right_edge * 1600, pv.tipmap, pv.tip_codes, tid, AA_THREADS);
+  }
+  __syncthreads();
+
+  if (warp == 4) {
+    /* ---------------- producer warp ---------------- */
+    const double *clvL = (lk == NRX_CLV) ? pv.clv[op.left_idx] : nullptr;
+    const double *clvR = (rk == NRX_CLV) ? pv.clv[op.right_idx] : nullptr;
+    const uint32_t *scL = (lk == NRX_CLV) ? pv.scaler[op.left_idx] : nullptr;
+    const uint32_t *scR = (rk == NRX_CLV) ? pv.scaler[op.right_idx] : nullptr;
+    const uint8_t *tipL = (lk == NRX_TIP) ? pv.tipchars + (size_t)op.left_idx * pv.tip_pitch : nullptr;
+    const uint8_t *tipR = (rk == NRX_TIP) ? pv.tipchars + (size_t)op.right_idx * pv.tip_pitch : nullptr;
+    const uint32_t tx_bytes = ((lk == NRX_CLV) ? AA_TP * 640u + AA_TP * 4u : (lk == NRX_TIP ? 16u : 0u)) +
+                              ((rk == NRX_CLV) ? AA_TP * 640u + AA_TP * 4u : (rk == NRX_TIP ? 16u : 0u));
+    for (uint32_t k = 0; k < count; ++k) {
+      const uint32_t s = k % NSTAGE_AA;
+      if (k >= (uint32_t)NSTAGE_AA) mbar_wait(&sm.empty[s], ((k / NSTAGE_AA) - 1) & 1u);
+      AaStage &st = sm.st[s];
+      unsigned long long *bar = &sm.full[s];
+      const size_t p0 = (size_t)(grp + (size_t)k * groups) * AA_TP;
+      if (lane == 0) mbar_expect_tx(bar, tx_bytes);
+      __syncwarp();
+      if (lane < AA_TP) {           // lanes 0..7: left rows
+        if (lk == NRX_CLV) bulk_g2s(st.l + lane * AA_PITCH, clvL + (p0 + lane) * 80, 640u, bar);
+      } else if (lane < 2 * AA_TP) {  // lanes 8..15: right rows
+        if (rk == NRX_CLV) bulk_g2s(st.r + (lane - AA_TP) * AA_PITCH, clvR + (p0 + lane - AA_TP) * 80, 640u, bar);
+      } else if (lane == 16) {
+        if (lk == NRX_CLV) bulk_g2s(st.scl, scL + p0, AA_TP * 4u, bar);
+        else if (lk == NRX_TIP) bulk_g2s(st.tl, tipL + (p0 & ~(size_t)15), 16u, bar);
+      } else if (lane == 17) {
+        if (rk == NRX_CLV) bulk_g2s(st.scr, scR + p0, AA_TP * 4u, bar);
+        else if (rk == NRX_TIP) bulk_g2s(st.tr, tipR + (p0 & ~(size_t)15), 16u, bar);
+      }
+    }
+    return;
+  }
+
+  /* ---------------- consumer warps: warp = rate category ---------------- */
+  const int cat = warp, item = lane >> 2, q = lane & 3;
+  double BL[15], BR[15];   // B fragments: [ntile * 5 + kstep] = P_c[8*ntile + lane/4][4*kstep + lane%4]
+  {
+    const int i_base = lane >> 2, j_base = lane & 3;
+#pragma unroll
+    for (int n = 0; n < 3; ++n)
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int i = 8 * n + i_base, j = 4 * k + j_base;
+        BL[n * 5 + k] = (lk == NRX_CLV && i < 20) ? pv.pmat[(size_t)op.left_edge * 1600 + (cat * 20 + i) * 20 + j] : 0.0;
+        BR[n * 5 + k] = (rk == NRX_CLV && i < 20) ? pv.pmat[(size_t)op.right_edge * 1600 + (cat * 20 + i) * 20 + j] : 0.0;
+      }
+  }
+  double *par = pv.clv[op.parent_slot];
+  uint32_t *psc = pv.scaler[op.parent_slot];
+  const bool tiptip = (lk == NRX_TIP && rk == NRX_TIP);
+
+  for (uint32_t k = 0; k < count; ++k) {
+    const uint32_t s = k % NSTAGE_AA;
+    const AaStage &st = sm.st[s];
+    mbar_wait(&sm.full[s], (k / NSTAGE_AA) & 1u);
+    const size_t p0 = (size_t)(grp + (size_t)k * groups) * AA_TP;
+    const size_t site = p0 + item;
+    const bool act = site < pv.patterns;
+    // pull this warp's operands out of the stage, then release it
+    double aL[5], aR[5];
+    uint32_t codeL = 0, codeR = 0, sc = 0;
+    if (lk == NRX_CLV) {
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) aL[kk] = st.l[item * AA_PITCH + cat * 20 + 4 * kk + q];
+      sc += st.scl[item];
+    } else if (lk == NRX_TIP) codeL = st.tl[(p0 & 15) + item];
+    if (rk == NRX_CLV) {
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) aR[kk] = st.r[item * AA_PITCH + cat * 20 + 4 * kk + q];
+      sc += st.scr[item];
+    } else if (rk == NRX_TIP) codeR = st.tr[(p0 & 15) + item];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty[s]);
+
+    double x[6], y[6];
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+      const int i0 = 8 * n + 2 * q;   // this thread's two output states of n-tile n
+      if (lk == NRX_CLV) {
+        x[2 * n] = 0.0; x[2 * n + 1] = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 5; ++kk) dmma884(x[2 * n], x[2 * n + 1], aL[kk], BL[n * 5 + kk]);
+      } else if (lk == NRX_TIP) {
+        if (i0 < 20) { const double2 v = *reinterpret_cast<const double2 *>(lutL + (codeL * 4 + cat) * 20 + i0); x[2 * n] = v.x; x[2 * n + 1] = v.y; }
+        else { x[2 * n] = 0.0; x[2 * n + 1] = 0.0; }
+      }
+      if (rk == NRX_CLV) {
+        y[2 * n] = 0.0; y[2 * n + 1] = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 5; ++kk) dmma884(y[2 * n], y[2 * n + 1], aR[kk], BR[n * 5 + kk]);
+      } else if (rk == NRX_TIP) {
+        if (i0 < 20) { const double2 v = *reinterpret_cast<const double2 *>(lutR + (codeR * 4 + cat) * 20 + i0); y[2 * n] = v.x; y[2 * n + 1] = v.y; }
+        else { y[2 * n] = 0.0; y[2 * n + 1] = 0.0; }
+      }
+    }
+    double pz[6];
+    bool small = true;
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+      const int i0 = 8 * n + 2 * q;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double v;
+        if (rk == NRX_NONE) v = x[2 * n + h];
+        else if (lk == NRX_NONE) v = y[2 * n + h];
+        else v = __dmul_rn(x[2 * n + h], y[2 * n + h]);
+        pz[2 * n + h] = v;
+        if (i0 < 20) small &= (v < SCALE_THRESHOLD);
+      }
+    }
+    // all 20 states of (pattern, cat): AND over the quad; all 4 cats: shared flags + named barrier over the 4 consumer warps
+    unsigned b = __ballot_sync(0xffffffffu, small);
+    const bool cat_small = ((b >> (lane & ~3)) & 0xFu) == 0xFu;
+    bool scale = false;
+    if (!tiptip) {
+      if (q == 0) sm.flags[k & 1][cat][item] = cat_small ? 1u : 0u;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      scale = (sm.flags[k & 1][0][item] & sm.flags[k & 1][1][item] & sm.flags[k & 1][2][item] & sm.flags[k & 1][3][item]) != 0u;
+    }
+    if (act) {
+      double *dst = par + site * 80 + cat * 20;
+#pragma unroll
+      for (int n = 0; n < 3; ++n) {
+        const int i0 = 8 * n + 2 * q;
+        if (i0 < 20) {
+          double v0 = pz[2 * n], v1 = pz[2 * n + 1];
+          if (scale) { v0 = __dmul_rn(v0, SCALE_FACTOR); v1 = __dmul_rn(v1, SCALE_FACTOR); }
+          asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(dst + i0), "d"(v0), "d"(v1) : "memory");
+        }
+      }
+      if (cat == 0 && q == 0) psc[site] = tiptip ? 0u : sc + (scale ? 1u : 0u);
+    }
   }
 }
 

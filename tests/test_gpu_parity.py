@@ -249,3 +249,74 @@ def test_error_behaviour_mirrors_reference():
     tip_edge = 0   # edge into tip 0: source inner, target tip -> fine; a tip-tip pair cannot occur in a network
     g.brlen_prepare(tip_edge); g.computePartitionSumtables(tip_edge); g.brlen_finish(tip_edge)
     g.close()
+
+
+# ---------------------------------------------------------------------------------------------- protein (20 states)
+def _protein_case(n, r, pat, seed, random_cells=False, net=None):
+    from netrax_b200.synth import lg_model
+    rates, freqs = lg_model()
+    net = net or random_network(n, r, seed=seed)
+    m, w = simulate_alignment(net, pat, seed=seed, states=20, rates=rates, freqs=freqs, random_cells=random_cells)
+    return net, Partition(20, 4, m, freqs, rates, GAMMA4_ALPHA05, pattern_weights=w)
+
+
+@pytest.mark.parametrize("cfg", [(12, 2, 300, 1), (30, 2, 1001, 2), (9, 0, 77, 3)])
+@pytest.mark.parametrize("variant", [AVERAGE, BEST])
+def test_protein_lg_g4_matches_oracle(cfg, variant):
+    """BASELINE config 4 shape (LG+G4): the DMMA (FP64 tensor core) CLV kernel against the reference's AVX2 kernels.
+    20-state sums are ordered differently (tensor-core k-steps vs AVX2 FMA lanes), so CLVs agree to rounding, not
+    bit-for-bit; scaler counts must still be identical and lnL within 1e-10 (north_star)."""
+    net, part = _protein_case(*cfg)
+    g, o = _gpu(net, [part], variant=variant), _oracle(net, [part], variant=variant)
+    _inject_eigen(g, o)
+    lo, lg = o.computeLoglikelihood(0, 1), g.computeLoglikelihood(0, 1)
+    assert lg == pytest.approx(lo, rel=LNL_RTOL)
+    for v in range(net.num_tips, net.num_nodes):
+        assert g.num_trees(v) == o.num_trees(v)
+        for t in range(g.num_trees(v)):
+            assert np.array_equal(g.read_scaler(v, t), o.read_scaler(v, t)), (v, t)
+            np.testing.assert_allclose(g.read_clv(v, t), o.read_clv(v, t), rtol=1e-11, atol=1e-300)
+    root = net.root
+    for t in range(g.num_trees(root)):
+        assert g.tree_info(root, t)[1] == pytest.approx(o.tree_info(root, t)[1], rel=LNL_RTOL)
+    # branch-length flow on a reticulation edge and a tip edge
+    edges = [0] + ([int(net.ret_first_edge[0])] if net.num_reticulations else [])
+    for e in edges:
+        assert g.brlen_prepare(e) == pytest.approx(o.brlen_prepare(e), rel=LNL_RTOL)
+        assert g.computeLoglikelihoodBrlenOpt(e) == pytest.approx(o.computeLoglikelihoodBrlenOpt(e), rel=LNL_RTOL)
+        assert g.computePartitionSumtables(e) == o.computePartitionSumtables(e)
+        dg, do = g.computeLoglikelihoodDerivatives(e), o.computeLoglikelihoodDerivatives(e)
+        assert dg[0] == pytest.approx(do[0], rel=DERIV_RTOL, abs=1e-7)
+        assert dg[1] == pytest.approx(do[1], rel=DERIV_RTOL, abs=1e-7)
+        assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL)
+    g.close()
+
+
+def test_protein_scaler_stress_bitexact_scalers():
+    net, part = _protein_case(0, 0, 500, 13, random_cells=True, net=caterpillar_network(150))
+    g, o = _gpu(net, [part]), _oracle(net, [part])
+    _inject_eigen(g, o)
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
+    mx = 0
+    for t in range(g.num_trees(net.root)):
+        sg, so = g.read_scaler(net.root, t), o.read_scaler(net.root, t)
+        assert np.array_equal(sg, so)
+        mx = max(mx, int(sg.max()))
+    assert mx >= 2
+    g.close()
+
+
+def test_protein_dmma_equals_scalar_kernel(monkeypatch):
+    """The tensor-core kernel against this repo's own scalar 20-state kernel (NRX_AA=generic): same scalers, CLVs to rounding."""
+    net, part = _protein_case(15, 2, 513, 4)
+    g = _gpu(net, [part])
+    l1 = g.computeLoglikelihood(0, 1)
+    monkeypatch.setenv("NRX_AA", "generic")
+    s = _gpu(net, [part])
+    l2 = s.computeLoglikelihood(0, 1)
+    assert l1 == pytest.approx(l2, rel=1e-12)
+    for v in range(net.num_tips, net.num_nodes):
+        for t in range(g.num_trees(v)):
+            assert np.array_equal(g.read_scaler(v, t), s.read_scaler(v, t))
+            np.testing.assert_allclose(g.read_clv(v, t), s.read_clv(v, t), rtol=1e-12, atol=1e-300)
+    g.close(); s.close()

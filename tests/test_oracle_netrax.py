@@ -206,3 +206,26 @@ def test_multi_partition_unlinked_best():
     ln, _, _ = oracle.naive_loglikelihood(eng)
     assert l == pytest.approx(ln, rel=1e-13)
     assert l == pytest.approx(eng.partition_loglh().sum(), rel=1e-14)
+
+
+def test_protein_port_equals_reference():
+    """20 states (BASELINE config 4 shape, LG+G4): scalar restatement vs the reference's AVX2 kernels."""
+    from netrax_b200.synth import lg_model
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rates, freqs = lg_model()
+    net = random_network(12, 2, seed=1)
+    m, w = simulate_alignment(net, 300, seed=1, states=20, rates=rates, freqs=freqs)
+    part = Partition(20, 4, m, freqs, rates, GAMMA4_ALPHA05, pattern_weights=w)
+    a, b = oracle.make_engine("port", net, [part]), oracle.make_engine("ref", net, [part])
+    la, lb = a.computeLoglikelihood(0, 1), b.computeLoglikelihood(0, 1)
+    assert la == pytest.approx(lb, rel=1e-12)
+    for v in range(net.num_tips, net.num_nodes):
+        for t in range(a.num_trees(v)):
+            assert np.array_equal(a.read_scaler(v, t), b.read_scaler(v, t))
+            np.testing.assert_allclose(a.read_clv(v, t), b.read_clv(v, t), rtol=1e-11, atol=1e-300)
+    e = int(net.ret_first_edge[0])
+    for eng in (a, b):
+        eng.brlen_prepare(e); eng.computePartitionSumtables(e)
+    da, db = a.computeLoglikelihoodDerivatives(e), b.computeLoglikelihoodDerivatives(e)
+    assert da[0] == pytest.approx(db[0], rel=1e-9) and da[1] == pytest.approx(db[1], rel=1e-9)

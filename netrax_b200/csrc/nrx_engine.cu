@@ -32,6 +32,7 @@ struct Part {
   uint32_t sp = 0, pat_pad = 0;  // pat_pad: patterns rounded up to a whole K2 tile (bulk copies always move full tiles)
   size_t clv_entries = 0, pmat_entries = 0;
   double *pmat = nullptr;
+  double *tiplut = nullptr;  // 20-state partitions only
   uint8_t *tipchars = nullptr;
   uint32_t *tipmap = nullptr, *weights = nullptr;
   double *model = nullptr;  // freqs | eigenvecs | inv_eigenvecs | eigenvals | rates | rate_weights | diagp
@@ -111,7 +112,7 @@ struct nrx_engine {
   unsigned long long launches = 0;
   int k2_variant = 0;       // 0: k_clv_dna4_pipe (production); UM: k_clv_dna4<U, MINB> (A/B experiments, env NRX_K2=UM)
   bool aa_generic = false;  // env NRX_AA=generic: force the scalar kernel for 20-state partitions (A/B)
-  uint32_t aa_blocks = 148 * 3 * 6;  // block-count target of the DMMA kernel
+  uint32_t aa_blocks = 148 * 3 * 4;  // block-count target of the DMMA kernel
   uint32_t k2_blocks = 2368; // block-count target of the pipelined kernel: 8 waves of 2 resident blocks per SM (measured best, profiles/)
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   bool views_dirty = true;
@@ -186,7 +187,7 @@ PartView make_view(const Part &p, uint32_t index) {
   v.pmat = p.pmat; v.tipchars = p.tipchars; v.tipmap = p.tipmap; v.weights = p.weights;
   v.freqs = p.freqs; v.eigenvecs = p.eigenvecs; v.inv_eigenvecs = p.inv_eigenvecs; v.eigenvals = p.eigenvals;
   v.rates = p.rates; v.rate_weights = p.rate_weights;
-  v.clv = p.d_clv; v.scaler = p.d_scaler; v.sumtable = p.d_sumtable; v.diagp = p.diagp;
+  v.clv = p.d_clv; v.scaler = p.d_scaler; v.sumtable = p.d_sumtable; v.diagp = p.diagp; v.tiplut = p.tiplut;
   return v;
 }
 
@@ -210,6 +211,21 @@ int check_part(nrx_engine *e, uint32_t p) {
 }
 
 uint32_t class_tip_codes(const nrx_engine *e, const ShapeClass &c);
+
+/* K1b for a list of edges (nullptr = all edges) of a 20-state partition */
+int refresh_tiplut(nrx_engine *e, uint32_t pi, const uint32_t *edges, uint32_t n) {
+  Part &p = e->parts[pi];
+  if (!p.tiplut || p.tip_codes > (uint32_t)AA_LUT_CODES) return 1;
+  std::vector<uint32_t> all;
+  if (!edges) { all.resize(p.d.edges); for (uint32_t i = 0; i < p.d.edges; ++i) all[i] = i; edges = all.data(); n = p.d.edges; }
+  if (n == 0) return 1;
+  uint32_t *d_idx;
+  if (!upload(e, edges, n, &d_idx)) return 0;
+  k_tip_lut20<<<n, 256, 0, e->stream>>>(make_view(p, pi), p.tiplut, d_idx);
+  e->launches++;
+  CK(cudaGetLastError());
+  return 1;
+}
 uint32_t tiles_for(uint64_t items, uint32_t per_block, uint32_t other_dims) {
   // enough blocks for >= ~8 waves over 148 SMs when the launch is big, one tile per block when it is small
   uint64_t full = (items + per_block - 1) / per_block;
@@ -286,6 +302,8 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
               cuda_ok(cudaMalloc((void **)&p.tipmap, 256 * sizeof(uint32_t)), "cudaMalloc tipmap") &&
               cuda_ok(cudaMalloc((void **)&p.weights, std::max<size_t>(1, p.d.patterns) * sizeof(uint32_t)), "cudaMalloc weights") &&
               cuda_ok(cudaMalloc((void **)&p.model, model_doubles * sizeof(double)), "cudaMalloc model");
+    if (ok && p.d.states == 20 && p.d.rate_cats == 4)
+      ok = cuda_ok(cudaMalloc((void **)&p.tiplut, (size_t)p.d.edges * AA_LUT_CODES * 80 * sizeof(double)), "cudaMalloc tiplut");
     if (!ok) { nrx_engine_destroy(e); return nullptr; }
     p.freqs = p.model; p.eigenvecs = p.freqs + SP; p.inv_eigenvecs = p.eigenvecs + S * SP; p.eigenvals = p.inv_eigenvecs + S * SP;
     p.rates = p.eigenvals + SP; p.rate_weights = p.rates + C; p.diagp = p.rate_weights + C;
@@ -308,7 +326,7 @@ void nrx_engine_destroy(nrx_engine *e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->comm && nccl().ok) nccl().CommDestroy(e->comm);
   for (Part &p : e->parts) {
-    cudaFree(p.pmat); cudaFree(p.tipchars); cudaFree(p.tipmap); cudaFree(p.weights); cudaFree(p.model);
+    cudaFree(p.pmat); cudaFree(p.tiplut); cudaFree(p.tipchars); cudaFree(p.tipmap); cudaFree(p.weights); cudaFree(p.model);
     for (void *m : p.slot_mem) cudaFree(m);
     for (double *m : p.h_sumtable) cudaFree(m);
     cudaFree(p.d_clv); cudaFree(p.d_scaler); cudaFree(p.d_sumtable);
@@ -358,6 +376,7 @@ int nrx_set_tips(nrx_engine *e, uint32_t pi, const uint32_t *tip_masks) {
   for (uint32_t i = 0; i < 256; ++i) if (tipmap[i]) p.tip_codes = i + 1;
   p.tips_set = true;
   e->views_dirty = true;
+  if (p.model_set && !refresh_tiplut(e, pi, nullptr, 0)) return 0;  // the code -> state-set map may have changed
   return 1;
 }
 
@@ -425,6 +444,7 @@ int nrx_update_pmatrices(nrx_engine *e, uint32_t pi, uint32_t n, const uint32_t 
   k_pmatrix<<<n, 128, p.d.rate_cats * p.d.states * sizeof(double), e->stream>>>(v, p.pmat, d_idx, d_len);
   e->launches++;
   CK(cudaGetLastError());
+  if (!refresh_tiplut(e, pi, edge_idx, n)) return 0;  // K1b: tip tables of the updated edges for the DMMA kernel
   return 1;
 }
 
@@ -445,7 +465,7 @@ int nrx_set_pmatrix(nrx_engine *e, uint32_t pi, uint32_t edge, const double *in)
   if (edge >= p.d.edges) { g_err = "edge index out of range"; return 0; }
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaMemcpy(p.pmat + (size_t)edge * p.pmat_entries, in, p.pmat_entries * sizeof(double), cudaMemcpyHostToDevice));
-  return 1;
+  return refresh_tiplut(e, pi, &edge, 1);
 }
 
 uint32_t nrx_num_slots(nrx_engine *e) { return e ? e->nslots : 0; }

@@ -38,6 +38,7 @@ struct PartView {
   uint32_t *const *scaler;   // [nslots] -> scaler
   double *const *sumtable;   // [nsumtables]
   const double *diagp;       // [cats][states][4] for the current derivative call
+  const double *tiplut;      // 20-state partitions: [edges][AA_LUT_CODES][cats*20] sums of P rows over each tip code's states (K1b)
 };
 
 __device__ __forceinline__ double tree4(double a, double b, double c, double d) {
@@ -405,6 +406,7 @@ struct __align__(128) AaSmem {
   AaStage st[NSTAGE_AA];
   unsigned long long full[NSTAGE_AA];
   unsigned long long empty[NSTAGE_AA];
+  unsigned long long lutbar;
   uint32_t flags[2][4][AA_TP];
   // followed by double lutL[AA_LUT_CODES*80], lutR[AA_LUT_CODES*80] when the launch has tip operands
 };
@@ -416,13 +418,20 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ void build_tip_lut20(double *lut, const double *pm /* [4][20][20] */, const uint32_t *tipmap, uint32_t ncodes, int tid, int nthreads) {
-  for (uint32_t idx = tid; idx < ncodes * 80; idx += nthreads) {
-    const uint32_t code = idx / 80, ci = idx % 80;   // ci = cat * 20 + i
-    const uint32_t mask = tipmap[code];
-    const double *row = pm + (size_t)ci * 20;
+/* K1b: tip tables of the edges whose P-matrix was just updated (grid.x = edges, one block each):
+ * lut[edge][code][cat*20 + i] = sum_{j in states(code)} P_cat[i][j], serial order as core_partials.c:404-420. */
+__global__ void k_tip_lut20(PartView pv, double *lut_out, const uint32_t *edge_idx) {
+  const uint32_t edge = edge_idx[blockIdx.x];
+  const double *pm = pv.pmat + (size_t)edge * 1600;
+  double *lut = lut_out + (size_t)edge * AA_LUT_CODES * 80;
+  for (uint32_t idx = threadIdx.x; idx < AA_LUT_CODES * 80; idx += blockDim.x) {
+    const uint32_t code = idx / 80, ci = idx % 80;
     double sum = 0.0;
-    for (int j = 0; j < 20; ++j) if ((mask >> j) & 1u) sum = __dadd_rn(sum, row[j]);
+    if (code < pv.tip_codes) {
+      const uint32_t mask = pv.tipmap[code];
+      const double *row = pm + (size_t)ci * 20;
+      for (int j = 0; j < 20; ++j) if ((mask >> j) & 1u) sum = __dadd_rn(sum, row[j]);
+    }
     lut[idx] = sum;
   }
 }
@@ -445,13 +454,20 @@ __global__ void __launch_bounds__(AA_THREADS, 3) k_clv_aa20_dmma(const PartView 
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < NSTAGE_AA; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 4); }
+    mbar_init(&sm.lutbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (with_lut) {
-    if (lk == NRX_TIP) build_tip_lut20(lutL, pv.pmat + (size_t)op.left_edge * 1600, pv.tipmap, pv.tip_codes, tid, AA_THREADS);
-    if (rk == NRX_TIP) build_tip_lut20(lutR, pv.pmat + (size_t)op.right_edge * 1600, pv.tipmap, pv.tip_codes, tid, AA_THREADS);
-  }
   __syncthreads();
+  if (with_lut && tid == 0) {  // tip tables of the two child edges (precomputed by k_tip_lut20): one bulk copy each
+    const uint32_t bytes = pv.tip_codes * 640u;
+    const uint32_t tx = (lk == NRX_TIP ? bytes : 0u) + (rk == NRX_TIP ? bytes : 0u);
+    if (tx) {
+      mbar_expect_tx(&sm.lutbar, tx);
+      if (lk == NRX_TIP) bulk_g2s(lutL, pv.tiplut + (size_t)op.left_edge * AA_LUT_CODES * 80, bytes, &sm.lutbar);
+      if (rk == NRX_TIP) bulk_g2s(lutR, pv.tiplut + (size_t)op.right_edge * AA_LUT_CODES * 80, bytes, &sm.lutbar);
+    }
+  }
+  const bool wait_lut = with_lut && (lk == NRX_TIP || rk == NRX_TIP);
 
   if (warp == 4) {
     /* ---------------- producer warp ---------------- */
@@ -503,6 +519,7 @@ __global__ void __launch_bounds__(AA_THREADS, 3) k_clv_aa20_dmma(const PartView 
   double *par = pv.clv[op.parent_slot];
   uint32_t *psc = pv.scaler[op.parent_slot];
   const bool tiptip = (lk == NRX_TIP && rk == NRX_TIP);
+  if (wait_lut) mbar_wait(&sm.lutbar, 0);
 
   for (uint32_t k = 0; k < count; ++k) {
     const uint32_t s = k % NSTAGE_AA;
@@ -529,24 +546,21 @@ __global__ void __launch_bounds__(AA_THREADS, 3) k_clv_aa20_dmma(const PartView 
 
     double x[6], y[6];
 #pragma unroll
+    for (int i = 0; i < 6; ++i) { x[i] = 0.0; y[i] = 0.0; }
+    // k-step outermost: the (up to) six accumulator chains advance together, so consecutive DMMAs are independent
+#pragma unroll
+    for (int kk = 0; kk < 5; ++kk) {
+#pragma unroll
+      for (int n = 0; n < 3; ++n) {
+        if (lk == NRX_CLV) dmma884(x[2 * n], x[2 * n + 1], aL[kk], BL[n * 5 + kk]);
+        if (rk == NRX_CLV) dmma884(y[2 * n], y[2 * n + 1], aR[kk], BR[n * 5 + kk]);
+      }
+    }
+#pragma unroll
     for (int n = 0; n < 3; ++n) {
       const int i0 = 8 * n + 2 * q;   // this thread's two output states of n-tile n
-      if (lk == NRX_CLV) {
-        x[2 * n] = 0.0; x[2 * n + 1] = 0.0;
-#pragma unroll
-        for (int kk = 0; kk < 5; ++kk) dmma884(x[2 * n], x[2 * n + 1], aL[kk], BL[n * 5 + kk]);
-      } else if (lk == NRX_TIP) {
-        if (i0 < 20) { const double2 v = *reinterpret_cast<const double2 *>(lutL + (codeL * 4 + cat) * 20 + i0); x[2 * n] = v.x; x[2 * n + 1] = v.y; }
-        else { x[2 * n] = 0.0; x[2 * n + 1] = 0.0; }
-      }
-      if (rk == NRX_CLV) {
-        y[2 * n] = 0.0; y[2 * n + 1] = 0.0;
-#pragma unroll
-        for (int kk = 0; kk < 5; ++kk) dmma884(y[2 * n], y[2 * n + 1], aR[kk], BR[n * 5 + kk]);
-      } else if (rk == NRX_TIP) {
-        if (i0 < 20) { const double2 v = *reinterpret_cast<const double2 *>(lutR + (codeR * 4 + cat) * 20 + i0); y[2 * n] = v.x; y[2 * n + 1] = v.y; }
-        else { y[2 * n] = 0.0; y[2 * n + 1] = 0.0; }
-      }
+      if (lk == NRX_TIP && i0 < 20) { const double2 v = *reinterpret_cast<const double2 *>(lutL + (codeL * 4 + cat) * 20 + i0); x[2 * n] = v.x; x[2 * n + 1] = v.y; }
+      if (rk == NRX_TIP && i0 < 20) { const double2 v = *reinterpret_cast<const double2 *>(lutR + (codeR * 4 + cat) * 20 + i0); y[2 * n] = v.x; y[2 * n + 1] = v.y; }
     }
     double pz[6];
     bool small = true;

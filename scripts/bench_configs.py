@@ -69,11 +69,15 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--out", default="")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--patterns", type=int, default=0, help="override the config's pattern count")
     args = ap.parse_args()
     from netrax_b200.engine import NetraxB200
     results = {}
     for c in [int(x) for x in args.configs.split(",")]:
         cfg = dict(bench.CONFIGS[c])
+        if args.patterns:
+            cfg["patterns"] = args.patterns
+            cfg["name"] += f" [patterns overridden: {args.patterns}]"
         net, parts, brl = bench.make_inputs(cfg, cfg["patterns"], 0)
         eng = NetraxB200(net, parts, variant=cfg["variant"], linkage=cfg["linkage"], partition_brlens=brl)
         for _ in range(3):
@@ -81,14 +85,20 @@ def main():
         slots = sum(eng.num_trees(v) for v in range(net.num_tips, net.num_nodes))
         updates = slots * sum(p.sites for p in parts)
         l0 = eng.launch_count()
-        eng.api.check(1)
+        eng.profile_enable(True)
         eng.timer_start()
         for _ in range(args.reps):
             eng.computeLoglikelihood(0, 1)
         ms = eng.timer_stop() / args.reps
+        prof = eng.profile_read()
+        eng.profile_enable(False)
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        k2_gbs = prof["clv_bytes"] / (prof["clv_ms"] / 1e3) / 1e9
         r = {"workload": cfg["name"], "sum_trees_per_node": slots, "root_trees": eng.num_trees(net.root),
              "gpu": {"ms_per_lnl_eval": ms, "lnl_evals_per_s": 1e3 / ms, "site_updates_per_s": updates / (ms / 1e3),
-                     "launches_per_eval": (eng.launch_count() - l0) / args.reps}}
+                     "launches_per_eval": (eng.launch_count() - l0) / args.reps,
+                     "k2_roofline": {"achieved_GBps": k2_gbs, "peak_GBps": peak, "frac": k2_gbs / peak, "share_of_eval": prof["clv_ms"] / (ms * args.reps),
+                                     "site_updates_per_s_in_kernel": prof["clv_site_updates"] / (prof["clv_ms"] / 1e3)}}}
         sweep = (c == 2)
         if sweep:
             derivative_sweep(eng, net)  # warm-up (allocates re-rooting slots and sumtables)

@@ -109,7 +109,7 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -124,6 +124,9 @@ class ClockSampler:
     def stop(self):
         if self.proc:
             self.proc.terminate()
+        busy = [r for r in self.rows if len(r) >= 8 and r[7].strip().isdigit() and int(r[7]) >= 50]
+        if busy:   # "under load": samples taken while the GPU was busy (the sampler also spans the gaps between the timed regions)
+            self.rows = busy
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -216,6 +219,9 @@ def main():
     tip_u8 = [torch.from_numpy(p.tip_masks.astype(np.uint8)).pin_memory() for p in parts]
     w_u32 = [torch.from_numpy((p.pattern_weights if p.pattern_weights is not None else np.ones(p.sites, np.uint32)).astype(np.int32)).pin_memory() for p in parts]
 
+    # clocks are sampled from the warm-up to the end of the e2e region (every part of it is the same step under load)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     lnl = None
     for _ in range(args.warmup):
         lnl = eng.computeLoglikelihood(0, 1)
@@ -223,11 +229,9 @@ def main():
     updates_per_step_local = slots_sum * sum(p.sites for p in parts)
 
     # ---- timed region 1: device-resident inputs ----
-    sampler = ClockSampler(local_rank)
     eng.profile_enable(True)
     l0 = eng.launch_count()
     barrier()
-    sampler.start()
     eng.timer_start()
     t_wall = time.perf_counter()
     for _ in range(args.steps):
@@ -235,7 +239,6 @@ def main():
     ms_dev = eng.timer_stop()
     barrier()
     ms_wall = 1e3 * (time.perf_counter() - t_wall)
-    clocks = sampler.stop()
     launches = eng.launch_count() - l0
     prof = eng.profile_read()
     eng.profile_enable(False)
@@ -249,6 +252,7 @@ def main():
         lnl_e2e = eng.computeLoglikelihood(0, 1)
     ms_e2e = eng.timer_stop()
     barrier()
+    clocks = sampler.stop()
     assert abs(lnl_e2e - lnl) <= 1e-9 * abs(lnl)
     h2d = sum(int(t.numel()) for t in tip_u8) + sum(4 * int(t.numel()) for t in w_u32) + 8 * (net.num_edges + 1) * len(parts)
     d2h = 8 * eng.num_trees(net.root) * len(parts) + 8

@@ -97,6 +97,14 @@ int nrx_copy_slot(nrx_engine *e, uint32_t dst, uint32_t src); /* device-side dee
  * or of several independent nodes — x patterns x rate categories).  The ops must be mutually independent. */
 int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops);
 
+/* Evaluation plan: the K2 batches of one whole traversal (the enumeration of displayed trees depends only on the
+ * topology).  The ops stay resident on the device and nrx_plan_run replays all batches as ONE
+ * CUDA graph launch (captured on first use) — small alignments are launch-latency-bound, not HBM-bound.
+ * ops = the batches back to back, batch_sizes[nbatches]; batch b may depend on batches < b only. */
+int nrx_plan_create(nrx_engine *e, const nrx_op *ops, const uint32_t *batch_sizes, uint32_t nbatches, uint32_t *plan_id);
+int nrx_plan_run(nrx_engine *e, uint32_t plan_id);
+int nrx_plan_destroy(nrx_engine *e, uint32_t plan_id);
+
 /* K3: per-tree per-partition root lnL, out[n][nparts] (LOCAL sums: the caller all-reduces across ranks).
  * persite (optional): [n] pointers-free layout out_persite[(i * nparts + p) * max_patterns + site]. */
 int nrx_tree_lnl(nrx_engine *e, const uint32_t *slots, uint32_t n, double *out, double *persite,

@@ -24,9 +24,12 @@ struct PlanCache {
   struct NodeSnap { std::vector<ReticulationConfigSet> configs; std::vector<uint32_t> slots; };
   std::vector<NodeSnap> nodes;
   uint64_t site_updates = 0;
+  bool on_device = false;   // the batches live on the device as an engine plan (one CUDA-graph launch per replay)
+  uint32_t engine_plan = 0;
 };
 
 AnnotatedNetwork::~AnnotatedNetwork() {
+  if (plan && plan->on_device && engine) nrx_plan_destroy(engine, plan->engine_plan);
   delete plan;
   if (engine) nrx_engine_destroy(engine);
 }
@@ -243,8 +246,12 @@ void setReticulationProb(AnnotatedNetwork &ann, size_t r, double prob) {  // src
   invalidateTreeLogprobs(ann);
 }
 
+static void dropEnginePlan(AnnotatedNetwork &ann) {
+  if (ann.plan && ann.plan->on_device) { nrx_plan_destroy(ann.engine, ann.plan->engine_plan); ann.plan->on_device = false; }
+}
+
 void topology_changed(AnnotatedNetwork &ann) {
-  if (ann.plan) ann.plan->valid = false;
+  if (ann.plan) { ann.plan->valid = false; dropEnginePlan(ann); }
   ann.travbuffer = reversed_topological_sort(ann.network);
 }
 
@@ -533,6 +540,13 @@ static void snapshotPlan(AnnotatedNetwork &ann) {
       pc.nodes[v].slots.push_back(nd.displayed_trees[i].slot);
     }
   }
+  // hand the recorded batches to the engine: ops stay resident on the device, replay = one CUDA graph launch
+  dropEnginePlan(ann);
+  std::vector<nrx_op> flat;
+  std::vector<uint32_t> sizes;
+  for (const std::vector<nrx_op> &b : pc.batches) { flat.insert(flat.end(), b.begin(), b.end()); sizes.push_back((uint32_t)b.size()); }
+  engineCheck(nrx_plan_create(ann.engine, flat.data(), sizes.data(), (uint32_t)sizes.size(), &pc.engine_plan), "nrx_plan_create");
+  pc.on_device = true;
   pc.valid = true;
 }
 
@@ -553,8 +567,9 @@ static void replayPlan(AnnotatedNetwork &ann) {
   }
   uint64_t local_sites = 0;
   for (const PartitionModel &m : ann.fake_treeinfo->partitions) local_sites += m.sites;
+  if (pc.on_device) engineCheck(nrx_plan_run(ann.engine, pc.engine_plan), "nrx_plan_run");
   for (const std::vector<nrx_op> &b : pc.batches) {
-    engineCheck(nrx_update_clvs(ann.engine, b.data(), (uint32_t)b.size()), "nrx_update_clvs");
+    if (!pc.on_device) engineCheck(nrx_update_clvs(ann.engine, b.data(), (uint32_t)b.size()), "nrx_update_clvs");
     ann.clv_site_updates += local_sites * b.size();
   }
 }
@@ -565,7 +580,7 @@ static void processPartitionsImproved(AnnotatedNetwork &ann, int incremental) { 
     replayPlan(ann);
   } else {
     const bool record = !incremental && ann.use_plan_cache;
-    if (record) { pc.batches.clear(); pc.site_updates = 0; pc.recording = true; pc.valid = false; }
+    if (record) { pc.batches.clear(); pc.site_updates = 0; pc.recording = true; pc.valid = false; dropEnginePlan(ann); }
     for (Node *n : ann.travbuffer) {
       std::vector<Node *> children;
       for (size_t c : n->children) children.push_back(&ann.network.nodes[c]);

@@ -90,8 +90,20 @@ NcclApi &nccl() {
 constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;  // ncclDataType_t / ncclRedOp_t values (nccl.h)
 }  // namespace
 
+struct EnginePlan {
+  bool alive = false;
+  nrx_op *d_ops = nullptr;
+  std::vector<size_t> offsets;
+  std::vector<uint32_t> sizes;
+  std::vector<char> tips;
+  cudaGraphExec_t exec = nullptr;
+  unsigned long long updates = 0, bytes = 0;
+};
+
 struct nrx_engine {
   int device = 0;
+  std::vector<EnginePlan> plans;
+  bool use_graphs = true;  // env NRX_GRAPH=0: replay plans as individual launches
   void *comm = nullptr;  // ncclComm_t
   int comm_rank = 0, comm_size = 1;
   cudaStream_t stream = nullptr;
@@ -276,6 +288,7 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
   if (!cuda_ok(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete e; return nullptr; }
   e->parts.resize(nparts);
   if (const char *v = std::getenv("NRX_K2")) e->k2_variant = std::atoi(v);
+  if (const char *v = std::getenv("NRX_GRAPH")) e->use_graphs = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_AA")) e->aa_generic = std::string(v) == "generic";
   if (const char *v = std::getenv("NRX_AA_BLOCKS")) e->aa_blocks = (uint32_t)std::max(1, std::atoi(v));
   if (const char *v = std::getenv("NRX_K2_BLOCKS")) e->k2_blocks = (uint32_t)std::max(1, std::atoi(v));
@@ -325,6 +338,7 @@ void nrx_engine_destroy(nrx_engine *e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->comm && nccl().ok) nccl().CommDestroy(e->comm);
+  for (EnginePlan &pl : e->plans) { if (pl.exec) cudaGraphExecDestroy(pl.exec); cudaFree(pl.d_ops); }
   for (Part &p : e->parts) {
     cudaFree(p.pmat); cudaFree(p.tiplut); cudaFree(p.tipchars); cudaFree(p.tipmap); cudaFree(p.weights); cudaFree(p.model);
     for (void *m : p.slot_mem) cudaFree(m);
@@ -540,11 +554,8 @@ int nrx_copy_slot(nrx_engine *e, uint32_t dst, uint32_t src) {
   return 1;
 }
 
-int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops) {
-  if (!e) { g_err = "null engine"; return 0; }
-  if (nops == 0) return 1;
-  CK(cudaSetDevice(e->device));
-  unsigned long long updates = 0, bytes = 0;
+/* validation + algorithmic-byte accounting of a batch of CLV updates */
+static int check_ops(nrx_engine *e, const nrx_op *ops, uint32_t nops, unsigned long long *updates, unsigned long long *bytes) {
   for (uint32_t i = 0; i < nops; ++i) {
     const nrx_op &o = ops[i];
     if (o.parent_slot >= e->nslots) { g_err = "nrx_update_clvs: parent slot out of range"; return 0; }
@@ -558,26 +569,26 @@ int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops) {
       }
     }
     if (o.left_kind == NRX_NONE && o.right_kind == NRX_NONE) { g_err = "nrx_update_clvs: both operands absent"; return 0; }
-    for (const Part &p : e->parts) {  // algorithmic bytes, SURVEY §8d table
+    for (const Part &p : e->parts) {
       const unsigned long long Cb = (unsigned long long)p.d.rate_cats * p.sp * 8;
       unsigned long long b = Cb + 4;
       for (int s = 0; s < 2; ++s) b += (kinds[s] == NRX_CLV) ? Cb + 4 : (kinds[s] == NRX_TIP ? 1 : 0);
       if (o.left_kind == NRX_TIP && o.right_kind == NRX_TIP) b = Cb + 2 + 4;
-      bytes += b * p.d.patterns;
-      updates += p.d.patterns;
+      *bytes += b * p.d.patterns;
+      *updates += p.d.patterns;
     }
   }
-  if (!refresh_views(e)) return 0;
-  nrx_op *d_ops;
-  if (!upload(e, ops, nops, &d_ops)) return 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  if (e->prof) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, e->stream); }
+  return 1;
+}
+
+/* K2 launches (one per partition shape class) for `nops` device-resident ops; `with_tips`: some op has a tip operand */
+static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, bool with_tips) {
   for (const ShapeClass &c : e->classes) {
     if (c.max_patterns == 0) continue;
     const uint32_t z = (uint32_t)c.parts.size();
     if (c.states == 4 && c.cats == 4) {
       if (e->k2_variant == 0) {
-        // bulk-async pipeline: ~2 resident blocks per SM; block b = (op b % nops, tile group b / nops)
+        // bulk-async pipeline: 2 resident blocks per SM; block b = (op b % nops, tile group b / nops)
         const uint32_t ntiles = (c.max_patterns + TP - 1) / TP;
         uint32_t groups = std::max<uint32_t>(1, (e->k2_blocks + nops * z - 1) / (nops * z));
         groups = std::min(groups, std::max<uint32_t>(1, ntiles / 4));  // >= 4 tiles per block: amortise the pipeline fill
@@ -594,14 +605,12 @@ int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops) {
       }
     } else if (c.states == 20 && c.cats == 4 && !e->aa_generic && class_tip_codes(e, c) <= (uint32_t)AA_LUT_CODES) {
       // protein: FP64 tensor cores (DMMA); 3 resident blocks of 4+1 warps per SM, 8-pattern tiles
-      bool with_lut = false;
-      for (uint32_t i = 0; i < nops; ++i) with_lut |= (ops[i].left_kind == NRX_TIP || ops[i].right_kind == NRX_TIP);
       const uint32_t ntiles = (c.max_patterns + AA_TP - 1) / AA_TP;
       uint32_t groups = std::max<uint32_t>(1, (e->aa_blocks + nops * z - 1) / (nops * z));
       groups = std::min(groups, std::max<uint32_t>(1, ntiles / 8));
       dim3 grid(nops * groups, 1, z);
-      const size_t smem = sizeof(AaSmem) + (with_lut ? 2 * AA_LUT_CODES * 80 * sizeof(double) : 0);
-      k_clv_aa20_dmma<<<grid, AA_THREADS, smem, e->stream>>>(c.d_views, d_ops, nops, groups, with_lut ? 1 : 0);
+      const size_t smem = sizeof(AaSmem) + (with_tips ? 2 * AA_LUT_CODES * 80 * sizeof(double) : 0);
+      k_clv_aa20_dmma<<<grid, AA_THREADS, smem, e->stream>>>(c.d_views, d_ops, nops, groups, with_tips ? 1 : 0);
     } else {
       dim3 grid(tiles_for(c.max_patterns, BLOCK, nops * z), nops, z);
       k_clv_generic<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops, nullptr);
@@ -609,13 +618,110 @@ int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops) {
     e->launches++;
     CK(cudaGetLastError());
   }
-  if (e->prof) {
-    cudaEventRecord(ev1, e->stream);
-    e->prof_events.emplace_back(ev0, ev1);
-    e->prof_launches += e->classes.size();
-    e->prof_updates += updates;
-    e->prof_bytes += bytes;
+  return 1;
+}
+
+static bool any_tip(const nrx_op *ops, uint32_t nops) {
+  for (uint32_t i = 0; i < nops; ++i) if (ops[i].left_kind == NRX_TIP || ops[i].right_kind == NRX_TIP) return true;
+  return false;
+}
+
+static void prof_begin(nrx_engine *e, cudaEvent_t *ev0, cudaEvent_t *ev1) {
+  *ev0 = *ev1 = nullptr;
+  if (e->prof) { cudaEventCreate(ev0); cudaEventCreate(ev1); cudaEventRecord(*ev0, e->stream); }
+}
+static void prof_end(nrx_engine *e, cudaEvent_t ev0, cudaEvent_t ev1, unsigned long long launches, unsigned long long updates, unsigned long long bytes) {
+  if (!e->prof) return;
+  cudaEventRecord(ev1, e->stream);
+  e->prof_events.emplace_back(ev0, ev1);
+  e->prof_launches += launches;
+  e->prof_updates += updates;
+  e->prof_bytes += bytes;
+}
+
+int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops) {
+  if (!e) { g_err = "null engine"; return 0; }
+  if (nops == 0) return 1;
+  CK(cudaSetDevice(e->device));
+  unsigned long long updates = 0, bytes = 0;
+  if (!check_ops(e, ops, nops, &updates, &bytes)) return 0;
+  if (!refresh_views(e)) return 0;
+  nrx_op *d_ops;
+  if (!upload(e, ops, nops, &d_ops)) return 0;
+  cudaEvent_t ev0, ev1;
+  prof_begin(e, &ev0, &ev1);
+  if (!launch_clv_batch(e, d_ops, nops, any_tip(ops, nops))) return 0;
+  prof_end(e, ev0, ev1, e->classes.size(), updates, bytes);
+  return 1;
+}
+
+/* ---- evaluation plans: the K2 launches of a whole traversal, ops resident on the device, replayed as ONE CUDA graph ---- */
+int nrx_plan_create(nrx_engine *e, const nrx_op *ops, const uint32_t *batch_sizes, uint32_t nbatches, uint32_t *plan_id) {
+  if (!e) { g_err = "null engine"; return 0; }
+  CK(cudaSetDevice(e->device));
+  EnginePlan pl;
+  size_t total = 0;
+  for (uint32_t b = 0; b < nbatches; ++b) {
+    if (batch_sizes[b] == 0) { g_err = "nrx_plan_create: empty batch"; return 0; }
+    if (!check_ops(e, ops + total, batch_sizes[b], &pl.updates, &pl.bytes)) return 0;
+    pl.offsets.push_back(total);
+    pl.sizes.push_back(batch_sizes[b]);
+    pl.tips.push_back(any_tip(ops + total, batch_sizes[b]));
+    total += batch_sizes[b];
   }
+  if (total) {
+    CK(cudaMalloc((void **)&pl.d_ops, total * sizeof(nrx_op)));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(pl.d_ops, ops, total * sizeof(nrx_op), cudaMemcpyHostToDevice));
+  }
+  pl.alive = true;
+  e->plans.push_back(pl);
+  *plan_id = (uint32_t)e->plans.size() - 1;
+  return 1;
+}
+
+int nrx_plan_run(nrx_engine *e, uint32_t plan_id) {
+  if (!e || plan_id >= e->plans.size() || !e->plans[plan_id].alive) { g_err = "nrx_plan_run: no such plan"; return 0; }
+  CK(cudaSetDevice(e->device));
+  EnginePlan &pl = e->plans[plan_id];
+  if (pl.sizes.empty()) return 1;
+  if (!refresh_views(e)) return 0;
+  cudaEvent_t ev0, ev1;
+  prof_begin(e, &ev0, &ev1);
+  const unsigned long long per_run = pl.sizes.size() * e->classes.size();
+  if (e->use_graphs && !pl.exec) {  // capture the launches once; kernel arguments (views, resident ops, geometry) never change
+    const unsigned long long l0 = e->launches;
+    CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    int ok = 1;
+    for (size_t b = 0; b < pl.sizes.size() && ok; ++b) ok = launch_clv_batch(e, pl.d_ops + pl.offsets[b], pl.sizes[b], pl.tips[b]);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+    e->launches = l0;
+    if (!ok || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); if (ok) cuda_ok(ce, "cudaStreamEndCapture"); cudaGetLastError(); return 0; }
+    const cudaError_t ie = cudaGraphInstantiate(&pl.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (!cuda_ok(ie, "cudaGraphInstantiate")) return 0;
+  }
+  if (pl.exec) {
+    CK(cudaGraphLaunch(pl.exec, e->stream));
+    e->launches += per_run;
+  } else {
+    for (size_t b = 0; b < pl.sizes.size(); ++b)
+      if (!launch_clv_batch(e, pl.d_ops + pl.offsets[b], pl.sizes[b], pl.tips[b])) return 0;
+  }
+  prof_end(e, ev0, ev1, per_run, pl.updates, pl.bytes);
+  return 1;
+}
+
+int nrx_plan_destroy(nrx_engine *e, uint32_t plan_id) {
+  if (!e || plan_id >= e->plans.size()) { g_err = "nrx_plan_destroy: no such plan"; return 0; }
+  CK(cudaSetDevice(e->device));
+  EnginePlan &pl = e->plans[plan_id];
+  if (!pl.alive) return 1;
+  CK(cudaStreamSynchronize(e->stream));
+  if (pl.exec) cudaGraphExecDestroy(pl.exec);
+  cudaFree(pl.d_ops);
+  pl = EnginePlan();
   return 1;
 }
 

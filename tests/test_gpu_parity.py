@@ -320,3 +320,29 @@ def test_protein_dmma_equals_scalar_kernel(monkeypatch):
             assert np.array_equal(g.read_scaler(v, t), s.read_scaler(v, t))
             np.testing.assert_allclose(g.read_clv(v, t), s.read_clv(v, t), rtol=1e-12, atol=1e-300)
     g.close(); s.close()
+
+
+def test_empty_partition_slice_is_skipped():
+    """A site shard may own NO pattern of a partition (reference: partitions[p] == NULL, 'skip remote partitions',
+    LH/ImprovedLoglikelihood.cpp:128-131): the engine must accept patterns = 0 and contribute exactly 0 to that partition."""
+    net = random_network(10, 2, seed=8)
+    m, w = simulate_alignment(net, 200, seed=8)
+    full = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    empty = full.slice(0, 0)
+    g = _gpu(net, [full, empty], variant=BEST, linkage=UNLINKED, partition_brlens=[net.edge_length, net.edge_length])
+    o = _oracle(net, [full])
+    lg, lo = g.computeLoglikelihood(0, 1), o.computeLoglikelihood(0, 1)
+    pl = g.partition_loglh()
+    assert pl[0] == pytest.approx(o.partition_loglh()[0], rel=LNL_RTOL)
+    # the empty slice adds only the tree log-prior of the best tree (0 site terms)
+    best_prior = max(g.tree_info(net.root, t)[0] for t in range(g.num_trees(net.root)))
+    assert pl[1] == pytest.approx(best_prior, abs=1e-12)
+    # (a partition that is empty on EVERY rank is rejected by the edge-rooted evaluation exactly as in the reference:
+    #  "bad partition logl", LH/VirtualRerooting.cpp:339-341; locally-empty slices under sharding are covered by
+    #  scripts/check_multi_gpu.py, where the all-reduced sum is non-zero)
+    from netrax_b200._capi import LikelihoodError
+    e = int(net.ret_first_edge[0])
+    g.brlen_prepare(e)
+    with pytest.raises(LikelihoodError, match="bad partition logl"):
+        g.computeLoglikelihoodBrlenOpt(e)
+    g.close()

@@ -58,7 +58,8 @@ typedef struct nrx_op {
   uint32_t parent_slot;
   uint32_t left_kind, left_idx, left_edge;    /* idx: slot (NRX_CLV) or tip number (NRX_TIP) */
   uint32_t right_kind, right_idx, right_edge;
-  uint32_t reserved;
+  uint32_t lnl_item; /* 0: none.  k+1: this CLV is root displayed tree k of the traversal — the kernel also emits its
+                      * per-site likelihood term (first half of K3 fused into K2's epilogue; see nrx_plan_create / nrx_tree_lnl_fused) */
 } nrx_op;
 
 /* An (a, b) operand pair on one edge: (source-tree, target-tree) of computeLoglikelihoodBrlenOpt /
@@ -103,6 +104,12 @@ int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops);
  * ops = the batches back to back, batch_sizes[nbatches]; batch b may depend on batches < b only. */
 int nrx_plan_create(nrx_engine *e, const nrx_op *ops, const uint32_t *batch_sizes, uint32_t nbatches, uint32_t *plan_id);
 int nrx_plan_run(nrx_engine *e, uint32_t plan_id);
+/* 1 when plans may carry lnl_item marks (every partition runs on the pipelined 4-state kernel) */
+int nrx_supports_fused_lnl(nrx_engine *e);
+/* K3 for the n marked trees (slots[k] = the CLV slot of mark k+1) of the plan that has just run: log / scaler /
+ * pattern weight and the sum over the per-site likelihood terms the K2 epilogue wrote (16 B per site read instead of
+ * the whole CLV) -> out[n][nparts], bit-identical to nrx_tree_lnl on the same slots. */
+int nrx_tree_lnl_fused(nrx_engine *e, uint32_t plan_id, const uint32_t *slots, uint32_t n, double *out);
 int nrx_plan_destroy(nrx_engine *e, uint32_t plan_id);
 
 /* K3: per-tree per-partition root lnL, out[n][nparts] (LOCAL sums: the caller all-reduces across ranks).

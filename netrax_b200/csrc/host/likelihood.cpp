@@ -26,6 +26,9 @@ struct PlanCache {
   uint64_t site_updates = 0;
   bool on_device = false;   // the batches live on the device as an engine plan (one CUDA-graph launch per replay)
   uint32_t engine_plan = 0;
+  // fused K3: the root displayed trees' slots at recording time; their producing ops carry lnl_item = index + 1
+  bool fused = false;
+  std::vector<uint32_t> lnl_slots;
 };
 
 AnnotatedNetwork::~AnnotatedNetwork() {
@@ -492,7 +495,7 @@ void processNodeImproved(AnnotatedNetwork &ann, int incremental, Node *node, std
 }
 
 /* computeDisplayedTreeLoglikelihood (:410-486) for ALL root trees: one K3 launch, one reduction */
-static void computeDisplayedTreeLoglikelihoods(AnnotatedNetwork &ann, Node *actRoot) {
+static void computeDisplayedTreeLoglikelihoods(AnnotatedNetwork &ann, Node *actRoot, bool replayed, std::vector<uint32_t> *slots_out) {
   NodeDisplayedTreeData &rd = ann.pernode_displayed_tree_data[actRoot->clv_index];
   const unsigned P = ann.fake_treeinfo->partition_count;
   std::vector<uint32_t> slots;
@@ -517,7 +520,14 @@ static void computeDisplayedTreeLoglikelihoods(AnnotatedNetwork &ann, Node *actR
   }
   flushPendingOps(ann);
   std::vector<double> out(slots.size() * P, 0.0);
-  if (!slots.empty()) engineCheck(nrx_tree_lnl(ann.engine, slots.data(), (uint32_t)slots.size(), out.data(), nullptr, 0), "nrx_tree_lnl");
+  if (slots_out) *slots_out = slots;
+  if (!slots.empty()) {
+    // after a plan replay whose ops carried lnl marks for exactly these trees, K2 has already written the per-site lnLs
+    if (replayed && ann.plan->fused && ann.plan->on_device && slots == ann.plan->lnl_slots)
+      engineCheck(nrx_tree_lnl_fused(ann.engine, ann.plan->engine_plan, slots.data(), (uint32_t)slots.size(), out.data()), "nrx_tree_lnl_fused");
+    else
+      engineCheck(nrx_tree_lnl(ann.engine, slots.data(), (uint32_t)slots.size(), out.data(), nullptr, 0), "nrx_tree_lnl");
+  }
   reduceSum(ann, out.data(), out.size());  // C2: one reduction for all trees (reference: one per tree)
   for (size_t k = 0; k < which.size(); ++k) {
     TreeLoglData &t = rd.displayed_trees[which[k]].treeLoglData;
@@ -540,14 +550,36 @@ static void snapshotPlan(AnnotatedNetwork &ann) {
       pc.nodes[v].slots.push_back(nd.displayed_trees[i].slot);
     }
   }
-  // hand the recorded batches to the engine: ops stay resident on the device, replay = one CUDA graph launch
+  pc.valid = true;
+}
+
+/* hand the recorded batches to the engine: ops stay resident on the device, replay = one CUDA graph launch; the ops
+ * that produce the root displayed trees' CLVs are marked so that K2 also emits their per-site lnL (fused K3) */
+static void createEnginePlan(AnnotatedNetwork &ann, const std::vector<uint32_t> &root_slots) {
+  PlanCache &pc = *ann.plan;
   dropEnginePlan(ann);
   std::vector<nrx_op> flat;
   std::vector<uint32_t> sizes;
   for (const std::vector<nrx_op> &b : pc.batches) { flat.insert(flat.end(), b.begin(), b.end()); sizes.push_back((uint32_t)b.size()); }
+  pc.lnl_slots = root_slots;
+  pc.fused = !root_slots.empty() && nrx_supports_fused_lnl(ann.engine);
+  if (pc.fused) {
+    std::vector<uint32_t> sorted = root_slots;
+    std::sort(sorted.begin(), sorted.end());
+    if (std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end()) pc.fused = false;  // two root trees share a CLV: keep K3 separate
+  }
+  if (pc.fused) {
+    size_t marked = 0;
+    for (nrx_op &op : flat)
+      for (size_t k = 0; k < root_slots.size(); ++k)
+        if (op.parent_slot == root_slots[k]) { op.lnl_item = (uint32_t)k + 1; ++marked; }
+    if (marked != root_slots.size()) {  // a root tree's CLV is not produced by this traversal (cannot happen for a full one)
+      for (nrx_op &op : flat) op.lnl_item = 0;
+      pc.fused = false;
+    }
+  }
   engineCheck(nrx_plan_create(ann.engine, flat.data(), sizes.data(), (uint32_t)sizes.size(), &pc.engine_plan), "nrx_plan_create");
   pc.on_device = true;
-  pc.valid = true;
 }
 
 static void replayPlan(AnnotatedNetwork &ann) {
@@ -587,9 +619,18 @@ static void processPartitionsImproved(AnnotatedNetwork &ann, int incremental) { 
       processNodeImproved(ann, incremental, n, children, ReticulationConfigSet());
     }
     flushPendingOps(ann);
-    if (record) { pc.recording = false; snapshotPlan(ann); }
+    if (record) {
+      pc.recording = false;
+      snapshotPlan(ann);
+      std::vector<uint32_t> root_slots;
+      computeDisplayedTreeLoglikelihoods(ann, ann.network.root, false, &root_slots);
+      createEnginePlan(ann, root_slots);
+      return;
+    }
+    computeDisplayedTreeLoglikelihoods(ann, ann.network.root, false, nullptr);
+    return;
   }
-  computeDisplayedTreeLoglikelihoods(ann, ann.network.root);
+  computeDisplayedTreeLoglikelihoods(ann, ann.network.root, true, nullptr);
 }
 
 double evaluateTreesPartition(AnnotatedNetwork &ann, size_t p, std::vector<TreeLoglData> &trees) {  // :521-604

@@ -98,11 +98,14 @@ struct EnginePlan {
   std::vector<char> tips;
   cudaGraphExec_t exec = nullptr;
   unsigned long long updates = 0, bytes = 0;
+  uint32_t lnl_items = 0;    // number of ops carrying an lnl_item mark (fused K3)
 };
 
 struct nrx_engine {
   int device = 0;
   std::vector<EnginePlan> plans;
+  double *d_fused = nullptr;   // per-site lnLs written by K2's fused epilogue: [items][nparts][max_patterns]
+  size_t fused_cap = 0;
   bool use_graphs = true;  // env NRX_GRAPH=0: replay plans as individual launches
   void *comm = nullptr;  // ncclComm_t
   int comm_rank = 0, comm_size = 1;
@@ -313,14 +316,14 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
     bool ok = cuda_ok(cudaMalloc((void **)&p.pmat, std::max<size_t>(1, p.d.edges * p.pmat_entries) * sizeof(double)), "cudaMalloc pmat") &&
               cuda_ok(cudaMalloc((void **)&p.tipchars, std::max<size_t>(1, (size_t)p.d.tips * p.pat_pad)), "cudaMalloc tipchars") &&
               cuda_ok(cudaMalloc((void **)&p.tipmap, 256 * sizeof(uint32_t)), "cudaMalloc tipmap") &&
-              cuda_ok(cudaMalloc((void **)&p.weights, std::max<size_t>(1, p.d.patterns) * sizeof(uint32_t)), "cudaMalloc weights") &&
+              cuda_ok(cudaMalloc((void **)&p.weights, std::max<size_t>(1, p.pat_pad) * sizeof(uint32_t)), "cudaMalloc weights") &&
               cuda_ok(cudaMalloc((void **)&p.model, model_doubles * sizeof(double)), "cudaMalloc model");
     if (ok && p.d.states == 20 && p.d.rate_cats == 4)
       ok = cuda_ok(cudaMalloc((void **)&p.tiplut, (size_t)p.d.edges * AA_LUT_CODES * 80 * sizeof(double)), "cudaMalloc tiplut");
     if (!ok) { nrx_engine_destroy(e); return nullptr; }
     p.freqs = p.model; p.eigenvecs = p.freqs + SP; p.inv_eigenvecs = p.eigenvecs + S * SP; p.eigenvals = p.inv_eigenvecs + S * SP;
     p.rates = p.eigenvals + SP; p.rate_weights = p.rates + C; p.diagp = p.rate_weights + C;
-    std::vector<uint32_t> ones(std::max<uint32_t>(1, p.d.patterns), 1);
+    std::vector<uint32_t> ones(std::max<uint32_t>(1, p.pat_pad), 1);
     cudaMemcpy(p.weights, ones.data(), ones.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
     cudaMemset(p.pmat, 0, std::max<size_t>(1, p.d.edges * p.pmat_entries) * sizeof(double));
     cudaMemset(p.tipchars, 0, std::max<size_t>(1, (size_t)p.d.tips * p.pat_pad));
@@ -348,6 +351,7 @@ void nrx_engine_destroy(nrx_engine *e) {
   for (ShapeClass &c : e->classes) cudaFree(c.d_views);
   for (auto &ev : e->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (e->h_stage) cudaFreeHost(e->h_stage);
+  cudaFree(e->d_fused);
   cudaFree(e->d_stage); cudaFree(e->d_partial); cudaFree(e->d_result); cudaFree(e->d_persite);
   if (e->h_result) cudaFreeHost(e->h_result);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -582,7 +586,7 @@ static int check_ops(nrx_engine *e, const nrx_op *ops, uint32_t nops, unsigned l
 }
 
 /* K2 launches (one per partition shape class) for `nops` device-resident ops; `with_tips`: some op has a tip operand */
-static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, bool with_tips) {
+static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, bool with_tips, bool fused = false) {
   for (const ShapeClass &c : e->classes) {
     if (c.max_patterns == 0) continue;
     const uint32_t z = (uint32_t)c.parts.size();
@@ -593,7 +597,8 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
         uint32_t groups = std::max<uint32_t>(1, (e->k2_blocks + nops * z - 1) / (nops * z));
         groups = std::min(groups, std::max<uint32_t>(1, ntiles / 4));  // >= 4 tiles per block: amortise the pipeline fill
         dim3 grid(nops * groups, 1, z);
-        k_clv_dna4_pipe<<<grid, BLOCK, sizeof(ClvPipeSmem), e->stream>>>(c.d_views, d_ops, nops, groups);
+        k_clv_dna4_pipe<<<grid, BLOCK, sizeof(ClvPipeSmem), e->stream>>>(c.d_views, d_ops, nops, groups, fused ? e->d_fused : nullptr,
+                                                                         (size_t)e->max_patterns, (uint32_t)e->parts.size());
       } else {
         const uint32_t U = e->k2_variant / 10, MB = e->k2_variant % 10;
         dim3 grid(tiles_for((uint64_t)c.max_patterns * 4, BLOCK * U, nops * z), nops, z);
@@ -674,6 +679,19 @@ int nrx_plan_create(nrx_engine *e, const nrx_op *ops, const uint32_t *batch_size
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaMemcpy(pl.d_ops, ops, total * sizeof(nrx_op), cudaMemcpyHostToDevice));
   }
+  for (size_t i = 0; i < total; ++i) pl.lnl_items = std::max(pl.lnl_items, ops[i].lnl_item);
+  if (pl.lnl_items) {
+    if (!nrx_supports_fused_lnl(e)) { cudaFree(pl.d_ops); g_err = "nrx_plan_create: lnl_item marks need every partition on the pipelined 4-state kernel"; return 0; }
+    const size_t need = (size_t)pl.lnl_items * e->parts.size() * std::max<uint32_t>(1, e->max_patterns);
+    if (need > e->fused_cap) {  // the buffer address is baked into captured graphs: re-capture them
+      CK(cudaStreamSynchronize(e->stream));
+      cudaFree(e->d_fused);
+      e->d_fused = nullptr; e->fused_cap = 0;
+      CK(cudaMalloc((void **)&e->d_fused, need * sizeof(double)));
+      e->fused_cap = need;
+      for (EnginePlan &o : e->plans) if (o.exec) { cudaGraphExecDestroy(o.exec); o.exec = nullptr; }
+    }
+  }
   pl.alive = true;
   e->plans.push_back(pl);
   *plan_id = (uint32_t)e->plans.size() - 1;
@@ -693,7 +711,7 @@ int nrx_plan_run(nrx_engine *e, uint32_t plan_id) {
     const unsigned long long l0 = e->launches;
     CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
     int ok = 1;
-    for (size_t b = 0; b < pl.sizes.size() && ok; ++b) ok = launch_clv_batch(e, pl.d_ops + pl.offsets[b], pl.sizes[b], pl.tips[b]);
+    for (size_t b = 0; b < pl.sizes.size() && ok; ++b) ok = launch_clv_batch(e, pl.d_ops + pl.offsets[b], pl.sizes[b], pl.tips[b], pl.lnl_items != 0);
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
     e->launches = l0;
@@ -707,9 +725,15 @@ int nrx_plan_run(nrx_engine *e, uint32_t plan_id) {
     e->launches += per_run;
   } else {
     for (size_t b = 0; b < pl.sizes.size(); ++b)
-      if (!launch_clv_batch(e, pl.d_ops + pl.offsets[b], pl.sizes[b], pl.tips[b])) return 0;
+      if (!launch_clv_batch(e, pl.d_ops + pl.offsets[b], pl.sizes[b], pl.tips[b], pl.lnl_items != 0)) return 0;
   }
   prof_end(e, ev0, ev1, per_run, pl.updates, pl.bytes);
+  return 1;
+}
+
+int nrx_supports_fused_lnl(nrx_engine *e) {
+  if (!e || e->k2_variant != 0 || std::getenv("NRX_NO_FUSED_LNL")) return 0;
+  for (const ShapeClass &c : e->classes) if (!(c.states == 4 && c.cats == 4)) return 0;
   return 1;
 }
 
@@ -775,6 +799,27 @@ int nrx_tree_lnl(nrx_engine *e, const uint32_t *slots, uint32_t n, double *out, 
   if (!finish_reduction(e, n * P, nblk, out)) return 0;
   if (persite) CK(cudaMemcpy(persite, e->d_persite, (size_t)n * P * persite_stride * sizeof(double), cudaMemcpyDeviceToHost));
   return 1;
+}
+
+int nrx_tree_lnl_fused(nrx_engine *e, uint32_t plan_id, const uint32_t *slots, uint32_t n, double *out) {
+  if (!e || plan_id >= e->plans.size() || !e->plans[plan_id].alive) { g_err = "nrx_tree_lnl_fused: no such plan"; return 0; }
+  if (n == 0) return 1;
+  if (n > e->plans[plan_id].lnl_items || !e->d_fused) { g_err = "nrx_tree_lnl_fused: the plan carries fewer lnl marks"; return 0; }
+  CK(cudaSetDevice(e->device));
+  const uint32_t P = (uint32_t)e->parts.size();
+  const uint32_t nblk = reduce_blocks(e, n * P);   // same geometry as nrx_tree_lnl on n trees -> bit-identical sums
+  if (!ensure_result(e, (size_t)n * P, (size_t)n * P * nblk) || !refresh_views(e)) return 0;
+  for (uint32_t i = 0; i < n; ++i) if (slots[i] >= e->nslots) { g_err = "nrx_tree_lnl_fused: slot out of range"; return 0; }
+  uint32_t *d_slots;
+  if (!upload(e, slots, n, &d_slots)) return 0;
+  CK(cudaMemsetAsync(e->d_partial, 0, (size_t)n * P * nblk * sizeof(double), e->stream));
+  for (const ShapeClass &c : e->classes) {
+    dim3 grid(nblk, n, (uint32_t)c.parts.size());
+    k_term_lnl_sum<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_fused, (size_t)e->max_patterns, e->d_partial, P, std::log(SCALE_THRESHOLD));
+    e->launches++;
+    CK(cudaGetLastError());
+  }
+  return finish_reduction(e, n * P, nblk, out);
 }
 
 static int check_pairs(nrx_engine *e, const nrx_pair *pairs, uint32_t n, const char *who) {

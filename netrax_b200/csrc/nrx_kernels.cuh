@@ -250,6 +250,9 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t coun
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
   uint32_t done;
   do {
@@ -276,8 +279,14 @@ __device__ __forceinline__ D4 matvec4_reg(const double (&P)[16], const D4 &v) {
 }
 
 /* grid = (nops * groups, 1, partitions of this shape); block b: op = b % nops, tile group = b / nops */
+/* Fused K3 (ops with lnl_item != 0, i.e. root displayed trees of a full traversal): the epilogue also computes the
+ * tree's per-site likelihood term from the values it is about to store — same arithmetic and order as
+ * k_tree_lnl_dna4 — and writes it to persite[(item * nparts_total + part) * persite_stride + site]; k_term_lnl_sum
+ * then does the log / scaler / weight part densely from 16 B per site instead of K3 re-reading the 128 B CLV.
+ * (Doing the log here as well was measured: it runs on 1 lane in 4 and lengthens every tile's critical path.) */
 __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops,
-                                                             uint32_t nops, uint32_t groups) {
+                                                             uint32_t nops, uint32_t groups, double *__restrict__ persite,
+                                                             size_t persite_stride, uint32_t nparts_total) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ClvPipeSmem &sm = *reinterpret_cast<ClvPipeSmem *>(smem_raw);
   const PartView &pv = parts[blockIdx.z];
@@ -319,8 +328,15 @@ __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe(const PartView *__re
   uint32_t *psc = pv.scaler[op.parent_slot];
   const bool tiptip = (lk == NRX_TIP && rk == NRX_TIP);
   const unsigned quad = 0xFu << (lane & ~3);
+  const bool emit = op.lnl_item != 0 && persite != nullptr;
   const uint32_t tx_bytes = ((lk == NRX_CLV) ? TP * 128u + TP * 4u : (lk == NRX_TIP ? (uint32_t)TP : 0u)) +
                             ((rk == NRX_CLV) ? TP * 128u + TP * 4u : (rk == NRX_TIP ? (uint32_t)TP : 0u));
+  double f0 = 0, f1 = 0, f2 = 0, f3 = 0, wcat = 0;
+  double *ps_out = nullptr;
+  if (emit) {
+    f0 = pv.freqs[0]; f1 = pv.freqs[1]; f2 = pv.freqs[2]; f3 = pv.freqs[3]; wcat = pv.rate_weights[cat];
+    ps_out = persite + ((size_t)(op.lnl_item - 1) * nparts_total + pv.part_index) * persite_stride;
+  }
 
   // every buffer is padded to a whole number of tiles by the engine, so full-tile copies never run off the end
   auto issue = [&](uint32_t k) {
@@ -366,7 +382,16 @@ __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe(const PartView *__re
       stg256(par + (site * 4 + cat) * 4, p);
       if (cat == 0) psc[site] = s;
     }
-    __syncthreads();  // everyone is done with this stage: refill it
+    if (emit) {  // warp-uniform (the op is fixed per block): per-site likelihood sum_c w_c sum_i pi_i clv[c][i], before the log
+      double t = 0.0;
+      if (act) t = __dmul_rn(tree4(__dmul_rn(f0, p.x), __dmul_rn(f1, p.y), __dmul_rn(f2, p.z), __dmul_rn(f3, p.w)), wcat);
+      const double t1 = __shfl_down_sync(0xffffffffu, t, 1), t2 = __shfl_down_sync(0xffffffffu, t, 2), t3 = __shfl_down_sync(0xffffffffu, t, 3);
+      if (act && cat == 0) ps_out[site] = __dadd_rn(__dadd_rn(__dadd_rn(t, t1), t2), t3);
+    }
+    // Block-wide barrier, then refill.  (Measured: releasing stages per warp through "empty" mbarriers instead, so that
+    // warps run ahead independently, is 18 % SLOWER on config 5 — the lock-step keeps a block's 8 KB of stores and the
+    // co-scheduled ops' reads of a shared child tile together in time.)
+    __syncthreads();
     if (tid == 0 && k + NSTAGE < count) issue(k + NSTAGE);
   }
 }
@@ -411,9 +436,6 @@ struct __align__(128) AaSmem {
   // followed by double lutL[AA_LUT_CODES*80], lutR[AA_LUT_CODES*80] when the launch has tip operands
 };
 
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
@@ -891,6 +913,26 @@ __global__ void __launch_bounds__(BLOCK) k_tree_lnl_dna4(const PartView *__restr
     lk = __dmul_rn(lk, pw);
     if (persite) persite[((size_t)blockIdx.y * nparts_total + pv.part_index) * persite_stride + n] = lk;
     acc[0] += lk;
+  }
+  block_sum<1>(acc, red);
+  if (threadIdx.x == 0) partial[((size_t)blockIdx.y * nparts_total + pv.part_index) * gridDim.x + blockIdx.x] = acc[0];
+}
+
+/* second half of the fused K3: log, scaler term and pattern weight on the per-site terms K2 wrote — same traversal and
+ * accumulation order as k_tree_lnl_dna4, hence bit-identical partial sums */
+__global__ void __launch_bounds__(BLOCK) k_term_lnl_sum(const PartView *__restrict__ parts, const uint32_t *__restrict__ slots,
+                                                         const double *__restrict__ terms, size_t persite_stride,
+                                                         double *__restrict__ partial, uint32_t nparts_total, double log_thresh) {
+  __shared__ double red[BLOCK / 32];
+  const PartView &pv = parts[blockIdx.z];
+  const double *ps = terms + ((size_t)blockIdx.y * nparts_total + pv.part_index) * persite_stride;
+  const uint32_t *sc = pv.scaler[slots[blockIdx.y]];
+  double acc[1] = {0.0};
+  for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
+    double lk = log(ps[n]);
+    const uint32_t s = sc[n];
+    if (s) lk = __dadd_rn(lk, __dmul_rn((double)s, log_thresh));
+    acc[0] += __dmul_rn(lk, (double)pv.weights[n]);
   }
   block_sum<1>(acc, red);
   if (threadIdx.x == 0) partial[((size_t)blockIdx.y * nparts_total + pv.part_index) * gridDim.x + blockIdx.x] = acc[0];

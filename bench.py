@@ -273,6 +273,17 @@ def main():
         e2e_value = updates_per_step / (ms_e2e / args.steps / 1e3)
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = prof["clv_bytes"] / (prof["clv_ms"] / 1e3) / 1e9 if prof["clv_ms"] > 0 else 0.0
+        # DRAM traffic of K2 from the committed ncu --set full capture (profiles/k2_traffic.json): the ratio measured
+        # traffic / algorithmic bytes of one evaluation step is a property of the plan (which ops share children),
+        # independent of the pattern count, so it scales the per-launch algorithmic bytes of THIS run.
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "k2_traffic.json")))
+            if args.config == 5:
+                traffic = tr["traffic_over_algorithmic"] * prof["clv_bytes"] / max(1, prof["clv_launches"])
+                traffic_src = tr["source"]
+        except Exception:
+            pass
         line = {"metric": "clv_site_updates_per_sec", "value": value, "unit": "site-updates/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config,
@@ -283,7 +294,8 @@ def main():
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "roofline": {"kernel": "k_clv_dna4 (K2, CLV update)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak if peak else None, "traffic": None,
+                             "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
+                             "dram_frac": (traffic / (prof["clv_ms"] / max(1, prof["clv_launches"]) / 1e3) / 1e9 / peak) if traffic and peak and prof["clv_ms"] > 0 else None,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                              "launches": int(prof["clv_launches"]), "avg_launch_ms": prof["clv_ms"] / max(1, prof["clv_launches"]),
                              "algorithmic_bytes_per_launch": prof["clv_bytes"] / max(1, prof["clv_launches"]),

@@ -29,6 +29,7 @@
 #include <limits>
 #include <stdexcept>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "../../../include/nrx_engine.h"
@@ -110,13 +111,17 @@ std::vector<Node *> reversed_topological_sort(Network &network);  // src/helper/
 enum class LikelihoodVariant { AVERAGE_DISPLAYED_TREES = 0, BEST_DISPLAYED_TREE = 1, SARAH_PSEUDO = 2 };
 enum { PLLMOD_COMMON_BRLEN_LINKED = 0, PLLMOD_COMMON_BRLEN_SCALED = 1, PLLMOD_COMMON_BRLEN_UNLINKED = 2 };
 enum { PLLMOD_COMMON_REDUCE_SUM = 0, PLLMOD_COMMON_REDUCE_MAX = 1, PLLMOD_COMMON_REDUCE_MIN = 2 };
+enum class BrlenOptMethod { BRENT_NORMAL = 0, BRENT_REROOT = 1, NEWTON_RAPHSON = 2 };  // src/NetraxOptions.hpp:17-21
 
 struct NetraxOptions {
   LikelihoodVariant likelihood_variant = LikelihoodVariant::AVERAGE_DISPLAYED_TREES;
   int brlen_linkage = PLLMOD_COMMON_BRLEN_LINKED;
   size_t max_reticulations = 32;
   double min_interesting_tree_logprob = -13.815510557964274;  // log(1e-6), NetraxOptions.hpp:108
-  double brlen_min = 1e-6, brlen_max = 100.0;
+  double brlen_min = 1e-6, brlen_max = 100.0;               // RAXML_BRLEN_MIN / MAX (RAXML/constants.hpp:14-15)
+  double brprob_min = 1e-6, brprob_max = 1.0 - 1e-6;        // NetraxOptions.hpp:102-103
+  double lh_epsilon = 0.1, tolerance = 0.1;                 // DEF_LH_EPSILON (NetraxOptions.hpp:104-105)
+  BrlenOptMethod brlenOptMethod = BrlenOptMethod::NEWTON_RAPHSON;  // NetraxOptions.hpp:124-125
   bool save_memory = false;
 };
 
@@ -237,6 +242,18 @@ std::vector<std::vector<SumtableInfo>> computePartitionSumtables(AnnotatedNetwor
 LoglDerivatives computeLoglikelihoodDerivatives(AnnotatedNetwork &ann_network,
                                                 const std::vector<std::vector<SumtableInfo>> &sumtables,
                                                 unsigned int pmatrix_index);
+
+/* ---- the immediate callers: src/optimization/BranchLengthOptimization.hpp:12-32,
+ *      ReticulationOptimization.hpp:16-18.  Same names and argument meaning; the 1-D minimisers they drive
+ *      (pll-modules' Newton-Raphson and Brent, PLLMOD/optimize/opt_algorithms.c:133-261,1043-1254,1404-1429) are restated
+ *      in host/optimize.cpp. ------------------------------------------------------------------------------- */
+double optimize_branch(AnnotatedNetwork &ann_network, size_t pmatrix_index, BrlenOptMethod brlenOptMethod, unsigned int max_iters);
+double optimize_branches(AnnotatedNetwork &ann_network, int max_iters, int max_iters_outside, int radius,
+                         std::unordered_set<size_t> candidates, bool restricted_total_iters = false);
+double optimize_branches(AnnotatedNetwork &ann_network, int max_iters, int max_iters_outside, int radius,
+                         bool restricted_total_iters = false);
+double optimize_reticulation(AnnotatedNetwork &ann_network, size_t reticulation_index);
+double optimize_reticulations(AnnotatedNetwork &ann_network, int max_iters);
 
 /* ---- src/helper/InvalidationHelper.cpp -------------------------------------------------------------------- */
 void invalidateSingleClv(AnnotatedNetwork &ann_network, unsigned int clv_index);

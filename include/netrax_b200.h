@@ -70,6 +70,16 @@ int nrxh_brlen_read_sumtable(void *h, unsigned p, unsigned idx, double *out, dou
 int nrxh_brlen_set_length(void *h, int partition, unsigned edge, double value);
 int nrxh_brlen_derivatives(void *h, unsigned edge, double *d1, double *d2, double *part_d1, double *part_d2, double *raw);
 int nrxh_brlen_finish(void *h, unsigned edge, double *final_logl);
+/* The immediate callers of the path, same control flow as the reference:
+ *   nrxh_optimize_branch(es)      <- netrax::optimize_branch / optimize_branches  src/optimization/BranchLengthOptimization.cpp:345-421,423-476,567-576
+ *   nrxh_optimize_reticulation(s) <- netrax::optimize_reticulation(s)             src/optimization/ReticulationOptimization.cpp:68-117
+ * method: 0 BRENT_NORMAL, 1 BRENT_REROOT, 2 NEWTON_RAPHSON (src/NetraxOptions.hpp:17-21; the reference's default is 2). */
+int nrxh_optimize_branch(void *h, unsigned edge, int method, unsigned max_iters, double *final_logl);
+int nrxh_optimize_branches(void *h, int max_iters, int max_iters_outside, int radius, int method, double *final_logl);
+int nrxh_optimize_reticulation(void *h, unsigned r, double *final_logl);
+int nrxh_optimize_reticulations(void *h, int max_iters, double *final_logl);
+int nrxh_get_branch_lengths(void *h, int partition /* -1: linked */, double *out /* [edges] */);
+int nrxh_get_reticulation_probs(void *h, double *out /* [reticulations] */);
 unsigned long long nrxh_clv_update_count(void *h);
 void nrxh_reset_counters(void *h);
 int nrxh_gamma_rates(double alpha, unsigned cats, int mode, double *out);

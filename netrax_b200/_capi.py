@@ -16,6 +16,7 @@ import numpy as np
 from .network_io import NetworkDesc
 
 AVERAGE, BEST = 0, 1                 # LikelihoodVariant (src/likelihood/LikelihoodVariant.hpp)
+BRENT_NORMAL, BRENT_REROOT, NEWTON_RAPHSON = 0, 1, 2   # BrlenOptMethod (src/NetraxOptions.hpp:17-21)
 LINKED, SCALED, UNLINKED = 0, 1, 2   # PLLMOD_COMMON_BRLEN_*
 
 _u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
@@ -67,6 +68,12 @@ class FlatAPI:
         g("brlen_derivatives", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double), C.POINTER(C.c_double),
           C.c_void_p, C.c_void_p, C.c_void_p)
         g("brlen_finish", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
+        g("optimize_branch", C.c_int, C.c_void_p, C.c_uint, C.c_int, C.c_uint, C.POINTER(C.c_double))
+        g("optimize_branches", C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double))
+        g("optimize_reticulation", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
+        g("optimize_reticulations", C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double))
+        g("get_branch_lengths", C.c_int, C.c_void_p, C.c_int, _f64p)
+        g("get_reticulation_probs", C.c_int, C.c_void_p, _f64p)
         g("clv_update_count", C.c_ulonglong, C.c_void_p)
         g("reset_counters", None, C.c_void_p)
         g("gamma_rates", C.c_int, C.c_double, C.c_uint, C.c_int, _f64p)
@@ -260,6 +267,39 @@ class LikelihoodEngine:
         out = C.c_double()
         self.api.check(self.api._brlen_finish(self.h, edge, C.byref(out)))
         return out.value
+
+    # ---- the immediate callers (src/optimization/BranchLengthOptimization.cpp, ReticulationOptimization.cpp) ----
+    def optimize_branch(self, edge: int, method: int = NEWTON_RAPHSON, max_iters: int = 32) -> float:
+        out = C.c_double()
+        self.api.check(self.api._optimize_branch(self.h, edge, method, max_iters, C.byref(out)))
+        return out.value
+
+    def optimize_branches(self, max_iters: int = 32, max_iters_outside: int = 32, radius: int = -1, method: int = NEWTON_RAPHSON) -> float:
+        """optimizeBranches (src/optimization/Optimization.cpp:17-38): max_iters = brlen_smooth_factor * RAXML_BRLEN_SMOOTHINGS (32),
+        radius = PLLMOD_OPT_BRLEN_OPTIMIZE_ALL (-1)."""
+        out = C.c_double()
+        self.api.check(self.api._optimize_branches(self.h, max_iters, max_iters_outside, radius, method, C.byref(out)))
+        return out.value
+
+    def optimize_reticulation(self, r: int) -> float:
+        out = C.c_double()
+        self.api.check(self.api._optimize_reticulation(self.h, r, C.byref(out)))
+        return out.value
+
+    def optimize_reticulations(self, max_iters: int = 10) -> float:
+        out = C.c_double()
+        self.api.check(self.api._optimize_reticulations(self.h, max_iters, C.byref(out)))
+        return out.value
+
+    def branch_lengths(self, partition: int = -1) -> np.ndarray:
+        out = np.zeros(self.net.num_edges)
+        self.api.check(self.api._get_branch_lengths(self.h, partition, out))
+        return out
+
+    def reticulation_probs(self) -> np.ndarray:
+        out = np.zeros(max(1, self.net.num_reticulations))
+        self.api.check(self.api._get_reticulation_probs(self.h, out))
+        return out[: self.net.num_reticulations]
 
     def clv_update_count(self) -> int:
         return int(self.api._clv_update_count(self.h))

@@ -335,6 +335,52 @@ int nrxh_brlen_finish(void *hv, unsigned edge, double *final_logl) {
   });
 }
 
+/* ---- the immediate callers: src/optimization/{BranchLengthOptimization,ReticulationOptimization}.cpp ---- */
+int nrxh_optimize_branch(void *hv, unsigned edge, int method, unsigned max_iters, double *final_logl) {
+  return guarded([&] {
+    const double l = optimize_branch(H(hv)->ann, edge, (BrlenOptMethod)method, max_iters);
+    if (final_logl) *final_logl = l;
+  });
+}
+
+int nrxh_optimize_branches(void *hv, int max_iters, int max_iters_outside, int radius, int method, double *final_logl) {
+  return guarded([&] {
+    AnnotatedNetwork &ann = H(hv)->ann;
+    ann.options.brlenOptMethod = (BrlenOptMethod)method;
+    const double l = optimize_branches(ann, max_iters, max_iters_outside, radius);
+    if (final_logl) *final_logl = l;
+  });
+}
+
+int nrxh_optimize_reticulation(void *hv, unsigned r, double *final_logl) {
+  return guarded([&] {
+    const double l = optimize_reticulation(H(hv)->ann, r);
+    if (final_logl) *final_logl = l;
+  });
+}
+
+int nrxh_optimize_reticulations(void *hv, int max_iters, double *final_logl) {
+  return guarded([&] {
+    const double l = optimize_reticulations(H(hv)->ann, max_iters);
+    if (final_logl) *final_logl = l;
+  });
+}
+
+int nrxh_get_branch_lengths(void *hv, int partition, double *out) {
+  return guarded([&] {
+    const FakeTreeinfo &ti = *H(hv)->ann.fake_treeinfo;
+    const std::vector<double> &b = (partition < 0 || ti.brlen_linkage != PLLMOD_COMMON_BRLEN_UNLINKED) ? ti.linked_branch_lengths : ti.branch_lengths.at(partition);
+    std::copy(b.begin(), b.begin() + H(hv)->ann.network.num_branches(), out);
+  });
+}
+
+int nrxh_get_reticulation_probs(void *hv, double *out) {
+  return guarded([&] {
+    const AnnotatedNetwork &ann = H(hv)->ann;
+    std::copy(ann.reticulation_probs.begin(), ann.reticulation_probs.begin() + ann.network.num_reticulations(), out);
+  });
+}
+
 unsigned long long nrxh_clv_update_count(void *hv) { return H(hv)->ann.clv_site_updates; }
 void nrxh_reset_counters(void *hv) { H(hv)->ann.clv_site_updates = 0; }
 int nrxh_gamma_rates(double alpha, unsigned cats, int mode, double *out) {

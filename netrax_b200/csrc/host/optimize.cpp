@@ -1,0 +1,312 @@
+/*
+ * optimize.cpp — the immediate callers of the likelihood path: branch-length
+ * optimisation (Newton-Raphson on the sumtable derivatives, or Brent on the edge-rooted / full lnL) and
+ * reticulation-probability optimisation (Brent on the re-mixed cached per-tree lnLs).
+ *
+ * Control flow follows src/optimization/BranchLengthOptimization.cpp and ReticulationOptimization.cpp of the
+ * reference (cited per function) and keeps its observable quirks; the two 1-D minimisers are restatements of
+ * pll-modules' algorithms (PLLMOD/optimize/opt_algorithms.c), written as small state machines:
+ *   newtonMulti  <- pllmod_opt_minimize_newton_multi  (:133-261)
+ *   brentSingle  <- pllmod_opt_minimize_brent -> brent_opt_alt / brent_opt_init / brent_opt_post_loop (:859-1254,1404-1429)
+ *
+ * One deviation and one reproduced quirk:
+ *   D1  Brent: pllmod's single-variable wrapper never sets the "all converged" flag, so brent_opt_alt keeps calling
+ *       the target with the last proposal until 101 loop iterations have passed.  Those calls do not change the
+ *       optimiser state nor (the proposal being unchanged) the network state, so we stop at convergence.
+ *   Q7  Newton-Raphson with UNLINKED branch lengths: the reference's derivative callback writes partition_count
+ *       values into the solver's arrays of size 1 (BranchLengthOptimization.cpp:190-195; a heap overflow beyond three
+ *       partitions) and the solver reads element 0, i.e. PARTITION 0's derivatives whatever partition is being
+ *       optimised; the "reload the old length if the lnL got worse" guard (:318-331) then filters the result.  We
+ *       reproduce the defined part of that behaviour (element 0) without the out-of-bounds writes.
+ */
+#include <cmath>
+#include <functional>
+
+#include "host_internal.hpp"
+
+namespace netrax {
+using namespace detail;
+
+namespace {
+
+/* ---- pllmod_opt_minimize_newton_multi for xnum functions (opt_algorithms.c:133-261) ---------------------------- */
+bool newtonMulti(unsigned xnum, double xmin, double *x, double xmax, double tolerance, unsigned max_iters,
+                 const std::function<void(double *x, double *f, double *df)> &deriv) {
+  const double dxmax = xmax / max_iters;
+  std::vector<double> lo(xnum, xmin), hi(xnum, xmax), f(xnum, 0.0), df(xnum, 0.0);
+  std::vector<char> done(xnum, 0);
+  for (unsigned i = 0; i < xnum; ++i) x[i] = std::max(std::min(x[i], xmax), xmin);
+  unsigned iter = 0;
+  bool all = false;
+  while (!all) {
+    if (iter++ > max_iters) return false;  // "Exceeded maximum number of iterations"
+    deriv(x, f.data(), df.data());
+    all = true;
+    for (unsigned i = 0; i < xnum; ++i) {
+      if (done[i]) continue;
+      if (!std::isfinite(f[i]) || !std::isfinite(df[i])) return false;  // "Wrong likelihood derivatives"
+      double dx;
+      if (df[i] > 0.0) {
+        if (std::fabs(f[i]) < tolerance) { done[i] = 1; continue; }
+        if (f[i] < 0.0) lo[i] = x[i]; else hi[i] = x[i];
+        dx = -1 * f[i] / df[i];
+      } else {
+        dx = -1 * f[i] / std::fabs(df[i]);
+      }
+      dx = std::max(std::min(dx, dxmax), -dxmax);
+      if (x[i] + dx < lo[i]) dx = lo[i] - x[i];
+      if (x[i] + dx > hi[i]) dx = hi[i] - x[i];
+      if (std::fabs(dx) < tolerance) { done[i] = 1; continue; }
+      x[i] += dx;
+      x[i] = std::max(std::min(x[i], xmax), xmin);
+      all = all && done[i];
+    }
+  }
+  return true;
+}
+
+/* ---- Brent's method, single variable, as pll-modules runs it (opt_algorithms.c:859-1254) ------------------------ */
+struct BrentState {
+  static constexpr double kGold = 0.3819660, kZeps = 1.0e-7;
+  static constexpr int kItmax = 100;
+  double tol = 0, a = 0, b = 0, d = 0, e = 0, u = 0, v = 0, w = 0, x = 0, fv = 0, fw = 0, fx = 0, startx = 0, fstartx = 0;
+  static double sign(double mag, double s) { return s >= 0.0 ? std::fabs(mag) : -std::fabs(mag); }
+
+  /* the part of an iteration before the target is evaluated: convergence test + next proposal u; false = converged */
+  bool propose() {
+    const double xm = 0.5 * (a + b);
+    const double tol1 = tol * std::fabs(x) + kZeps, tol2 = 2.0 * tol1;
+    if (std::fabs(x - xm) <= (tol2 - 0.5 * (b - a))) return false;
+    if (std::fabs(e) > tol1) {
+      double r = (x - w) * (fx - fv);
+      double q = (x - v) * (fx - fw);
+      double p = (x - v) * q - (x - w) * r;
+      q = 2.0 * (q - r);
+      if (q > 0.0) p = -p;
+      q = std::fabs(q);
+      const double etemp = e;
+      e = d;
+      if (std::fabs(p) >= std::fabs(0.5 * q * etemp) || p <= q * (a - x) || p >= q * (b - x)) {
+        e = (x >= xm ? a - x : b - x);
+        d = kGold * e;
+      } else {
+        d = p / q;
+        const double t = x + d;
+        if (t - a < tol2 || b - t < tol2) d = sign(tol1, xm - x);
+      }
+    } else {
+      e = (x >= xm ? a - x : b - x);
+      d = kGold * e;
+    }
+    u = (std::fabs(d) >= tol1 ? x + d : x + sign(tol1, d));
+    return true;
+  }
+
+  bool init(double ax, double bx, double cx, double tol_, double fax, double fbx, double fcx) {
+    tol = tol_;
+    a = (ax < cx ? ax : cx);
+    b = (ax > cx ? ax : cx);
+    startx = x = bx;
+    fstartx = fx = fbx;
+    if (fax < fcx) { w = ax; fw = fax; v = cx; fv = fcx; }
+    else { w = cx; fw = fcx; v = ax; fv = fax; }
+    return propose();
+  }
+
+  bool absorb(double fu) {  // the part after the evaluation, then the next proposal
+    if (fu <= fx) {
+      if (u >= x) a = x; else b = x;
+      v = w; w = x; x = u;
+      fv = fw; fw = fx; fx = fu;
+    } else {
+      if (u < x) a = u; else b = u;
+      if (fu <= fw || w == x) { v = w; w = u; fv = fw; fw = fu; }
+      else if (fu <= fv || v == x || v == w) { v = u; fv = fu; }
+    }
+    return propose();
+  }
+};
+
+double brentSingle(double xmin, double xguess, double xmax, double xtol, const std::function<double(double)> &target) {
+  if (xguess < xmin) xguess = xmin;
+  if (xguess > xmax) xguess = xmax;
+  const double eps = xguess > 0 ? xguess * xtol * 50.0 : 2. * xtol;  // bracketing heuristic (:1138-1148)
+  double ax = xguess - eps, cx = xguess + eps;
+  if (ax < xmin) ax = xmin;
+  if (cx > xmax) cx = xmax;
+  double fa = target(ax);
+  const double fb = target(xguess);
+  double fc = target(cx);
+  const double fmin = target(xmin), fmax = target(xmax);
+  if (fa < fb || fc < fb) { fa = fmin; fc = fmax; ax = xmin; cx = xmax; }
+  BrentState s;
+  bool running = s.init(ax, xguess, cx, xtol, fa, fb, fc);
+  for (int it = 0; running && it <= BrentState::kItmax; ++it) running = s.absorb(target(s.u));  // deviation D1: stop at convergence
+  const double xopt = (s.fx > s.fstartx) ? s.startx : s.x;  // if the new score is worse, return the initial value
+  target(xopt);
+  return xopt;
+}
+
+double &brlenRef(AnnotatedNetwork &ann, size_t partition_index, size_t pmatrix_index) {
+  FakeTreeinfo &ti = *ann.fake_treeinfo;
+  return ti.brlen_linkage == PLLMOD_COMMON_BRLEN_UNLINKED ? ti.branch_lengths[partition_index][pmatrix_index]
+                                                          : ti.linked_branch_lengths[pmatrix_index];
+}
+
+/* In the reference the linked length is the only storage a linked/scaled analysis reads; our FakeTreeinfo keeps the
+ * per-partition copies in sync (what pllmod_treeinfo_set_branch_length does, PLLMOD/tree/treeinfo.c:507-539). */
+void storeBrlen(AnnotatedNetwork &ann, size_t partition_index, size_t pmatrix_index, double value) {
+  FakeTreeinfo &ti = *ann.fake_treeinfo;
+  if (ti.brlen_linkage == PLLMOD_COMMON_BRLEN_UNLINKED) ti.branch_lengths[partition_index][pmatrix_index] = value;
+  else {
+    ti.linked_branch_lengths[pmatrix_index] = value;
+    for (auto &b : ti.branch_lengths) b[pmatrix_index] = value;
+  }
+}
+
+/* optimize_branch_brent + brent_target_networks (BranchLengthOptimization.cpp:63-156) */
+void optimizeBranchBrent(AnnotatedNetwork &ann, std::vector<DisplayedTreeData> &oldTrees, size_t pmatrix_index, size_t partition_index,
+                         BrlenOptMethod method) {
+  const double old_brlen = brlenRef(ann, partition_index, pmatrix_index);
+  auto target = [&](double x) -> double {
+    if (brlenRef(ann, partition_index, pmatrix_index) == x)
+      return method == BrlenOptMethod::BRENT_REROOT ? -1 * computeLoglikelihoodBrlenOpt(ann, oldTrees, (unsigned)pmatrix_index, 1)
+                                                    : -1 * computeLoglikelihood(ann);
+    storeBrlen(ann, partition_index, pmatrix_index, x);
+    if (method != BrlenOptMethod::BRENT_NORMAL) invalidPmatrixIndexOnly(ann, pmatrix_index);
+    else invalidatePmatrixIndex(ann, pmatrix_index);
+    return method == BrlenOptMethod::BRENT_REROOT ? -1 * computeLoglikelihoodBrlenOpt(ann, oldTrees, (unsigned)pmatrix_index, 1)
+                                                  : -1 * computeLoglikelihood(ann, 1, 1);
+  };
+  const double new_brlen = brentSingle(ann.options.brlen_min, old_brlen, ann.options.brlen_max, ann.options.tolerance, target);
+  storeBrlen(ann, partition_index, pmatrix_index, new_brlen);
+  invalidatePmatrixIndex(ann, pmatrix_index);
+}
+
+/* optimize_branch_newton_raphson + network_derivative_func_multi (:165-241) */
+void optimizeBranchNewtonRaphson(AnnotatedNetwork &ann, std::vector<std::vector<SumtableInfo>> &sumtables, size_t pmatrix_index,
+                                 size_t partition_index, unsigned max_iters) {
+  const double tolerance = ann.options.brlen_min > 0 ? ann.options.brlen_min / 10.0 : 1.0e-4 /* PLLMOD_OPT_TOL_BRANCH_LEN */;
+  double new_brlen = brlenRef(ann, partition_index, pmatrix_index);
+  const bool unlinked = ann.fake_treeinfo->brlen_linkage == PLLMOD_COMMON_BRLEN_UNLINKED;
+  auto deriv = [&](double *x, double *df, double *ddf) {
+    storeBrlen(ann, partition_index, pmatrix_index, x[0]);
+    invalidPmatrixIndexOnly(ann, pmatrix_index);
+    const LoglDerivatives d = computeLoglikelihoodDerivatives(ann, sumtables, (unsigned)pmatrix_index);
+    if (unlinked) { df[0] = d.partition_logl_prime[0]; ddf[0] = d.partition_logl_prime_prime[0]; }  // quirk Q7
+    else { df[0] = d.logl_prime; ddf[0] = d.logl_prime_prime; }
+  };
+  newtonMulti(1, ann.options.brlen_min, &new_brlen, ann.options.brlen_max, tolerance, max_iters, deriv);
+  // the reference ignores the solver's status (libpll_reset_error) and keeps whatever length the last iterate stored
+}
+
+/* optimize_branch for one partition (:285-343) */
+double optimizeBranchPartition(AnnotatedNetwork &ann, std::vector<DisplayedTreeData> &oldTrees, std::vector<std::vector<SumtableInfo>> &sumtables,
+                               size_t pmatrix_index, size_t partition_index, BrlenOptMethod method, unsigned max_iters) {
+  ann.cached_logl_valid = false;
+  auto score = [&] { return method != BrlenOptMethod::BRENT_NORMAL ? computeLoglikelihoodBrlenOpt(ann, oldTrees, (unsigned)pmatrix_index, 1) : computeLoglikelihood(ann); };
+  const double start_logl = score();
+  if (method == BrlenOptMethod::BRENT_NORMAL || method == BrlenOptMethod::BRENT_REROOT) {
+    optimizeBranchBrent(ann, oldTrees, pmatrix_index, partition_index, method);
+  } else {
+    const double old_brlen = brlenRef(ann, partition_index, pmatrix_index);
+    optimizeBranchNewtonRaphson(ann, sumtables, pmatrix_index, partition_index, max_iters);
+    const double new_logl = computeLoglikelihoodBrlenOpt(ann, oldTrees, (unsigned)pmatrix_index, 1);
+    if (new_logl < start_logl) {  // NR did not converge: reload the old branch length
+      storeBrlen(ann, partition_index, pmatrix_index, old_brlen);
+      invalidPmatrixIndexOnly(ann, pmatrix_index);
+    }
+  }
+  return score();
+}
+
+}  // namespace
+
+/* optimize_branch (BranchLengthOptimization.cpp:345-421) */
+double optimize_branch(AnnotatedNetwork &ann, size_t pmatrix_index, BrlenOptMethod method, unsigned int max_iters) {
+  if (pmatrix_index >= ann.network.num_branches()) throw std::runtime_error("optimize_branch: pmatrix index out of range");
+  const double old_logl = computeLoglikelihood(ann);
+  std::vector<DisplayedTreeData> oldTrees;
+  std::vector<std::vector<SumtableInfo>> sumtables;
+  if (method != BrlenOptMethod::BRENT_NORMAL) {  // step 1: the virtual re-rooting
+    oldTrees = extractOldTrees(ann, ann.network.root);
+    Node *new_virtual_root = &ann.network.nodes[ann.network.edges[pmatrix_index].source];
+    Node *new_virtual_root_back = &ann.network.nodes[ann.network.edges[pmatrix_index].target];
+    ReticulationConfigSet restrictions = getRestrictionsActiveAliveBranch(ann, pmatrix_index);
+    updateCLVsVirtualRerootTrees(ann, ann.network.root, new_virtual_root, new_virtual_root_back, restrictions);
+    ann.cached_logl_valid = false;
+    const double brlenopt_logl = computeLoglikelihoodBrlenOpt(ann, oldTrees, (unsigned)pmatrix_index);
+    if (old_logl - brlenopt_logl >= 1E-3)  // the reference's `fabs(old_logl - brlenopt_logl >= 1E-3)` (:377): one-sided
+      throw std::runtime_error("Something went wrong when rerooting CLVs during brlen optimization");
+    if (method == BrlenOptMethod::NEWTON_RAPHSON) sumtables = computePartitionSumtables(ann, (unsigned)pmatrix_index);
+  }
+  if (ann.fake_treeinfo->brlen_linkage == PLLMOD_COMMON_BRLEN_UNLINKED) {
+    for (size_t p = 0; p < ann.fake_treeinfo->partition_count; ++p)
+      optimizeBranchPartition(ann, oldTrees, sumtables, pmatrix_index, p, method, max_iters);
+  } else {
+    optimizeBranchPartition(ann, oldTrees, sumtables, pmatrix_index, 0, method, max_iters);
+  }
+  if (method != BrlenOptMethod::BRENT_NORMAL) invalidatePmatrixIndex(ann, pmatrix_index);  // restore the network root
+  return computeLoglikelihood(ann);
+}
+
+/* optimize_branches_internal (:423-476); `radius` is unused there as well (the neighbour re-queueing is commented out).
+ * The candidate set is a std::unordered_set<size_t> visited from begin(), exactly as in the reference, so the visiting
+ * order is libstdc++'s — the same library a NetRAX build on this machine uses. */
+double optimize_branches(AnnotatedNetwork &ann, int max_iters, int max_iters_outside, int radius, std::unordered_set<size_t> candidates,
+                         bool restricted_total_iters) {
+  (void)radius;
+  for (size_t idx : candidates)
+    if (idx >= ann.network.num_branches()) throw std::runtime_error("optimize_branches: candidate pmatrix index out of range");
+  double old_logl = computeLoglikelihood(ann, 1, 1);
+  const double start_logl = old_logl;
+  std::vector<size_t> act_iters(ann.network.num_branches(), 0);
+  const BrlenOptMethod method = ann.options.brlenOptMethod;
+  size_t total_iters = 0;
+  while (!candidates.empty()) {
+    const size_t pmatrix_index = *candidates.begin();
+    candidates.erase(candidates.begin());
+    total_iters++;
+    if (restricted_total_iters && total_iters >= (size_t)max_iters_outside) continue;
+    if (act_iters[pmatrix_index] >= (size_t)max_iters_outside) continue;
+    act_iters[pmatrix_index]++;
+    old_logl = optimize_branch(ann, pmatrix_index, method, (unsigned)max_iters);
+  }
+  if (old_logl < start_logl && std::fabs(old_logl - start_logl) >= 1E-3) throw std::runtime_error("Overall loglikelihood got worse");
+  return old_logl;
+}
+
+double optimize_branches(AnnotatedNetwork &ann, int max_iters, int max_iters_outside, int radius, bool restricted_total_iters) {  // :567-576
+  std::unordered_set<size_t> candidates;
+  for (size_t i = 0; i < ann.network.num_branches(); ++i) candidates.emplace(i);
+  return optimize_branches(ann, max_iters, max_iters_outside, radius, candidates, restricted_total_iters);
+}
+
+/* optimize_reticulation (ReticulationOptimization.cpp:68-100): every Brent evaluation is setReticulationProb +
+ * computeLoglikelihood(1, 1) — no CLV is invalid, so it re-mixes the cached per-tree lnLs on the host (row f2: 0 launches). */
+double optimize_reticulation(AnnotatedNetwork &ann, size_t reticulation_index) {
+  if (reticulation_index >= ann.network.num_reticulations()) throw std::runtime_error("optimize_reticulation: index out of range");
+  computeLoglikelihood(ann, 1, 1);
+  const double old_brprob = ann.reticulation_probs[reticulation_index];
+  setReticulationProb(ann, reticulation_index, 0.5);  // "just for debug" in the reference; kept, it is part of the call sequence
+  const double new_brprob = brentSingle(ann.options.brprob_min, old_brprob, ann.options.brprob_max, ann.options.tolerance, [&](double x) {
+    setReticulationProb(ann, reticulation_index, x);
+    return -1 * computeLoglikelihood(ann, 1, 1);
+  });
+  setReticulationProb(ann, reticulation_index, new_brprob);
+  return computeLoglikelihood(ann, 1, 1);
+}
+
+double optimize_reticulations(AnnotatedNetwork &ann, int max_iters) {  // :102-117
+  double act_logl = computeLoglikelihood(ann, 1, 1);
+  for (int act_iters = 0; act_iters < max_iters;) {
+    double loop_logl = act_logl;
+    for (size_t i = 0; i < ann.network.num_reticulations(); ++i) loop_logl = optimize_reticulation(ann, i);
+    act_iters++;
+    if (loop_logl == act_logl) break;
+    act_logl = loop_logl;
+  }
+  return act_logl;
+}
+
+}  // namespace netrax

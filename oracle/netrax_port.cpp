@@ -513,6 +513,7 @@ void invalidateTreeLogprobs(AnnotatedNetwork &ann) {  // :273-308 (every reticul
 }
 
 void setReticulationProb(AnnotatedNetwork &ann, size_t r, double prob) {  // SRC/optimization/ReticulationOptimization.cpp:25-38
+  if (ann.reticulation_probs[r] == prob) return;
   ann.reticulation_probs[r] = prob;
   ann.first_parent_logprobs[r] = std::log(prob);
   ann.second_parent_logprobs[r] = std::log(1.0 - prob);

@@ -183,6 +183,11 @@ struct Options {  // SRC/NetraxOptions.hpp
   double min_interesting_tree_logprob = -13.815510557964274;  // log(1e-6), NetraxOptions.hpp:108
 };
 
+struct OptOptions {  // SRC/NetraxOptions.hpp:100-105 — what the optimisers read
+  double brlen_min = 1e-6, brlen_max = 100.0, brprob_min = 1e-6, brprob_max = 1.0 - 1e-6, tolerance = 0.1;
+};
+enum { OPT_BRENT_NORMAL = 0, OPT_BRENT_REROOT = 1, OPT_NEWTON_RAPHSON = 2 };  // BrlenOptMethod, SRC/NetraxOptions.hpp:17-21
+
 struct SumtableInfo {  // LH/LikelihoodDerivatives.hpp:9-74
   double tree_prob = 0.0;
   ABuf<double> sumtable;
@@ -199,6 +204,7 @@ struct LoglDerivatives {  // LH/LikelihoodDerivatives.hpp:76-81
 
 struct AnnotatedNetwork {  // SRC/graph/AnnotatedNetwork.hpp:42-89 (fields the path reads)
   Options options;
+  OptOptions opt;
   Network network;
   std::unique_ptr<Backend> backend;
   std::vector<double> reticulation_probs, first_parent_logprobs, second_parent_logprobs;
@@ -245,5 +251,11 @@ std::vector<std::vector<SumtableInfo>> computePartitionSumtables(AnnotatedNetwor
 LoglDerivatives computeLoglikelihoodDerivatives(AnnotatedNetwork &ann,
                                                 const std::vector<std::vector<SumtableInfo>> &sumtables,
                                                 unsigned pmatrix_index);
+
+/* the immediate callers (optimize_port.cpp) */
+double optimize_branch(AnnotatedNetwork &ann, size_t pmatrix_index, int method, unsigned max_iters);
+double optimize_branches(AnnotatedNetwork &ann, int max_iters, int max_iters_outside, int radius, int method, bool restricted_total_iters = false);
+double optimize_reticulation(AnnotatedNetwork &ann, size_t reticulation_index);
+double optimize_reticulations(AnnotatedNetwork &ann, int max_iters);
 
 }  // namespace orc

@@ -320,6 +320,62 @@ int orc_brlen_finish(void *hv, unsigned edge, double *final_logl) {
   });
 }
 
+/* ---- the immediate callers (optimize_port.cpp) -------------------------------------------------------- */
+int orc_optimize_branch(void *hv, unsigned edge, int method, unsigned max_iters, double *final_logl) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] { double l = optimize_branch(h->ann, edge, method, max_iters); if (final_logl) *final_logl = l; });
+}
+int orc_optimize_branches(void *hv, int max_iters, int max_iters_outside, int radius, int method, double *final_logl) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] { double l = optimize_branches(h->ann, max_iters, max_iters_outside, radius, method); if (final_logl) *final_logl = l; });
+}
+int orc_optimize_reticulation(void *hv, unsigned r, double *final_logl) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] { double l = optimize_reticulation(h->ann, r); if (final_logl) *final_logl = l; });
+}
+int orc_optimize_reticulations(void *hv, int max_iters, double *final_logl) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] { double l = optimize_reticulations(h->ann, max_iters); if (final_logl) *final_logl = l; });
+}
+int orc_get_branch_lengths(void *hv, int partition, double *out) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] {
+    const AnnotatedNetwork &ann = h->ann;
+    const std::vector<double> &b = (partition < 0 || ann.options.brlen_linkage != BRLEN_UNLINKED) ? ann.linked_branch_lengths : ann.branch_lengths.at(partition);
+    std::copy(b.begin(), b.begin() + ann.network.num_branches(), out);
+  });
+}
+int orc_get_reticulation_probs(void *hv, double *out) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] { std::copy(h->ann.reticulation_probs.begin(), h->ann.reticulation_probs.begin() + h->ann.network.num_reticulations(), out); });
+}
+/* direct access to the two 1-D minimisers on a test function (pins opt_port.c against the reference's opt_algorithms.c) */
+extern "C" {
+#ifdef ORC_HAVE_REF
+int pllmod_opt_minimize_newton_multi(unsigned int, double, double *, double, double, unsigned int, int *, void *, void(deriv_func)(void *, double *, double *, double *));
+double pllmod_opt_minimize_brent(double, double, double, double, double *, double *, void *, double (*)(void *, double));
+#endif
+int orcopt_newton_multi(unsigned int, double, double *, double, double, unsigned int, int *, void *, void (*)(void *, double *, double *, double *));
+double orcopt_brent(double, double, double, double, double *, double *, void *, double (*)(void *, double));
+}
+int orc_test_brent(int use_ref, double xmin, double xguess, double xmax, double xtol, double (*target)(void *, double), double *xopt) {
+  double fx = 0, f2x = 0;
+#ifdef ORC_HAVE_REF
+  if (use_ref) { *xopt = pllmod_opt_minimize_brent(xmin, xguess, xmax, xtol, &fx, &f2x, nullptr, target); return 1; }
+#endif
+  if (use_ref) return 0;
+  *xopt = orcopt_brent(xmin, xguess, xmax, xtol, &fx, &f2x, nullptr, target);
+  return 1;
+}
+int orc_test_newton(int use_ref, double xmin, double *x, double xmax, double tol, unsigned max_iters, void (*deriv)(void *, double *, double *, double *), int *status) {
+#ifdef ORC_HAVE_REF
+  if (use_ref) { *status = pllmod_opt_minimize_newton_multi(1, xmin, x, xmax, tol, max_iters, nullptr, nullptr, deriv); return 1; }
+#endif
+  if (use_ref) return 0;
+  *status = orcopt_newton_multi(1, xmin, x, xmax, tol, max_iters, nullptr, nullptr, deriv);
+  return 1;
+}
+
 unsigned long long orc_clv_update_count(void *hv) { return static_cast<Handle *>(hv)->ann.n_clv_updates; }
 void orc_reset_counters(void *hv) { static_cast<Handle *>(hv)->ann.n_clv_updates = 0; }
 

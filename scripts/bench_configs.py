@@ -34,6 +34,16 @@ def derivative_sweep(eng, net, iters=3):
         eng.brlen_finish(e)
 
 
+def optimisation_round(eng):
+    """One optimizeBranches + optimizeReticulationProbs round as optimizeAllNonTopology issues them
+    (src/optimization/Optimization.cpp:17-38,88-106): Newton-Raphson over every branch (max_iters = 32), then Brent over
+    every reticulation probability (<= 10 rounds).  Returns wall seconds and the lnL trajectory."""
+    l0 = eng.computeLoglikelihood(0, 1)
+    t = time.perf_counter(); l1 = eng.optimize_branches(); tb = time.perf_counter() - t
+    t = time.perf_counter(); l2 = eng.optimize_reticulations(); tr = time.perf_counter() - t
+    return {"brlen_round_s": tb, "retprob_round_s": tr, "lnl_start": l0, "lnl_after_brlen": l1, "lnl_after_retprob": l2}
+
+
 def _cpu_worker(args):
     kind, cfg, patterns, widx, reps, sweep = args
     from oracle import oracle
@@ -47,6 +57,7 @@ def _cpu_worker(args):
     out["updates"] = eng.clv_update_count() // reps
     if sweep:
         t = time.perf_counter(); derivative_sweep(eng, net); out["sweep"].append(time.perf_counter() - t)
+        out["opt"] = optimisation_round(eng)
     return out
 
 
@@ -60,6 +71,8 @@ def cpu_arm(cfg, cores, patterns_per_core, reps, sweep):
            "lnl_eval_s_on_sample": lnl_t, "site_updates_per_s": sum(r["updates"] for r in res) / lnl_t}
     if sweep:
         out["sweep_s_on_sample"] = max(r["sweep"][0] for r in res)
+        out["brlen_round_s_on_sample"] = max(r["opt"]["brlen_round_s"] for r in res)
+        out["retprob_round_s_on_sample"] = max(r["opt"]["retprob_round_s"] for r in res)
     return out
 
 
@@ -110,6 +123,9 @@ def main():
             wall = time.perf_counter() - t
             r["gpu"].update({"ms_per_derivative_sweep": ms_s, "wall_ms_per_derivative_sweep": 1e3 * wall, "edges": net.num_edges,
                              "edges_per_s": net.num_edges / (ms_s / 1e3), "launches_per_sweep": eng.launch_count() - l0})
+            l0 = eng.launch_count()
+            r["gpu"]["optimisation_round"] = optimisation_round(eng)
+            r["gpu"]["optimisation_round"]["launches"] = eng.launch_count() - l0
         eng.close()
         if not args.no_cpu:
             cores = bench.host_cores()
@@ -121,6 +137,8 @@ def main():
             r["speedup_site_updates"] = r["gpu"]["site_updates_per_s"] / cpu["site_updates_per_s"]
             if sweep:
                 cpu["sweep_s_full_config_est"] = cpu["sweep_s_on_sample"] * scale
+                cpu["brlen_round_s_full_config_est"] = cpu["brlen_round_s_on_sample"] * scale
+                r["speedup_brlen_round"] = cpu["brlen_round_s_full_config_est"] / r["gpu"]["optimisation_round"]["brlen_round_s"]
                 r["speedup_derivative_sweep"] = cpu["sweep_s_full_config_est"] / (r["gpu"]["ms_per_derivative_sweep"] / 1e3)
         results[f"config{c}"] = r
         print(json.dumps({f"config{c}": r}), flush=True)

@@ -1,0 +1,88 @@
+"""GPU parity (-m gpu) for the immediate callers of the path: branch-length optimisation (Newton-Raphson on the
+device sumtable/derivative kernels, Brent on the full lnL) and reticulation-probability optimisation (Brent over the
+re-mixed cached per-tree lnLs), product vs oracle on the same inputs.  The optimisers amplify nothing: every iterate
+is a function of lnL / derivative values that already agree to 1e-10 / 1e-8, so final lnLs must agree to 1e-9 relative
+and the optimised parameters to the solvers' own tolerance."""
+import numpy as np
+import pytest
+
+from helpers import FIXTURE_PAIRS, load_fixture
+from netrax_b200._capi import AVERAGE, BEST, BRENT_NORMAL, BRENT_REROOT, NEWTON_RAPHSON, UNLINKED, LikelihoodError, Partition
+from netrax_b200.synth import DNA_FREQS, GAMMA4_ALPHA05, GTR_RATES, random_network, simulate_alignment
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu(net, parts, **kw):
+    from netrax_b200.engine import NetraxB200
+    return NetraxB200(net, parts, **kw)
+
+
+def _oracle(net, parts, **kw):
+    from oracle import oracle
+    return oracle.make_engine("ref" if oracle.have_ref() else "port", net, parts, **kw)
+
+
+def _pair(net, parts, **kw):
+    g, o = _gpu(net, parts, **kw), _oracle(net, parts, **kw)
+    for p in range(g.P):
+        g.set_eigen(p, *o.get_eigen(p))
+    return g, o
+
+
+@pytest.mark.parametrize("name", ["small", "two_reticulations", "three_reticulations", "interleaved_reticulations", "celine"])
+@pytest.mark.parametrize("variant", [AVERAGE, BEST])
+def test_optimize_branch_every_edge_matches_oracle(name, variant):
+    net, part = load_fixture(*FIXTURE_PAIRS[name])
+    g, o = _pair(net, [part], variant=variant)
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=1e-10)
+    for e in range(net.num_edges):
+        lg, lo = g.optimize_branch(e), o.optimize_branch(e)
+        assert lg == pytest.approx(lo, rel=1e-9), e
+        assert g.branch_lengths()[e] == pytest.approx(o.branch_lengths()[e], rel=1e-5, abs=2e-7), e
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=1e-10)
+
+
+@pytest.mark.parametrize("method", [NEWTON_RAPHSON, BRENT_NORMAL])
+@pytest.mark.parametrize("variant", [AVERAGE, BEST])
+def test_optimize_branches_and_reticulations_match_oracle(method, variant):
+    net = random_network(16, 3, seed=5)
+    m, w = simulate_alignment(net, 800, seed=5)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    g, o = _pair(net, [part], variant=variant)
+    l0 = g.computeLoglikelihood(0, 1)
+    lg, lo = g.optimize_branches(method=method), o.optimize_branches(method=method)
+    assert lg >= l0 - 1e-3
+    assert lg == pytest.approx(lo, rel=1e-9)
+    np.testing.assert_allclose(g.branch_lengths(), o.branch_lengths(), rtol=1e-5, atol=2e-7)
+    launches = g.launch_count()
+    rg, ro = g.optimize_reticulations(), o.optimize_reticulations()
+    assert rg == pytest.approx(ro, rel=1e-9) and rg >= lg - 1e-3
+    np.testing.assert_allclose(g.reticulation_probs(), o.reticulation_probs(), rtol=1e-7)
+    # row f2: reticulation-probability optimisation re-mixes cached per-tree lnLs on the host — not one kernel launch
+    assert g.launch_count() == launches
+    assert rg == pytest.approx(g.computeLoglikelihood(0, 1), rel=1e-12)
+
+
+def test_optimize_branches_unlinked_partitions_match_oracle():
+    net = random_network(10, 2, seed=9)
+    parts, brl = [], []
+    rng = np.random.default_rng(2)
+    for p in range(3):
+        m, w = simulate_alignment(net, 300, seed=30 + p)
+        parts.append(Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w))
+        brl.append(net.edge_length * rng.uniform(0.5, 2.0, net.num_edges))
+    g, o = _pair(net, parts, linkage=UNLINKED, partition_brlens=brl)
+    lg, lo = g.optimize_branches(), o.optimize_branches()
+    assert lg == pytest.approx(lo, rel=1e-9)
+    for p in range(3):
+        np.testing.assert_allclose(g.branch_lengths(p), o.branch_lengths(p), rtol=1e-5, atol=2e-7)
+
+
+def test_brent_reroot_raises_the_reference_error():
+    net, part = load_fixture(*FIXTURE_PAIRS["small"])
+    g = _gpu(net, [part])
+    with pytest.raises(LikelihoodError, match="Cannot reuse old displayed trees"):
+        g.optimize_branch(0, method=BRENT_REROOT)
+    # the engine stays usable: a full re-evaluation recovers
+    assert np.isfinite(g.computeLoglikelihood(0, 1))

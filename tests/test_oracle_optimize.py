@@ -1,0 +1,157 @@
+"""Oracle tests for the immediate callers of the path (optimize_branch(es), optimize_reticulation(s)).
+
+Pins: (i) the C restatement of pll-modules' Newton-Raphson / Brent (oracle/opt_port.c) against the REFERENCE's
+own opt_algorithms.c compiled into oracle/_ref, on analytic targets — same optimum AND same evaluation sequence;
+(ii) the restated NetRAX optimiser loops over the scalar port against the same loops over the real libpll + real
+pll-modules minimisers; (iii) the invariants of the reference's tests: a branch-length optimisation never makes the
+lnL worse (test/src/BrlenOptTest.cpp:95-120 `ASSERT_GE(new_logl, old_logl)`), optimising reticulation probabilities
+never makes it worse (src/optimization/Optimization.cpp:93-106)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from helpers import FIXTURE_PAIRS, load_fixture
+from netrax_b200._capi import AVERAGE, BEST, BRENT_NORMAL, BRENT_REROOT, NEWTON_RAPHSON, UNLINKED, LikelihoodError, Partition
+from netrax_b200.synth import DNA_FREQS, GAMMA4_ALPHA05, GTR_RATES, random_network, simulate_alignment
+from oracle import oracle
+
+needs_ref = pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (needs /root/reference at build time)")
+TARGET_T = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_double)
+DERIV_T = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double))
+
+
+def _minimisers(kind):
+    lib = oracle.api(kind).lib
+    lib.orc_test_brent.restype = C.c_int
+    lib.orc_test_brent.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, TARGET_T, C.POINTER(C.c_double)]
+    lib.orc_test_newton.restype = C.c_int
+    lib.orc_test_newton.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_uint, DERIV_T, C.POINTER(C.c_int)]
+    return lib
+
+
+BRENT_CASES = [
+    (lambda x: (x - 0.3) ** 2, 1e-6, 0.5, 1 - 1e-6, 0.1),
+    (lambda x: (x - 0.3) ** 2, 1e-6, 0.5, 1 - 1e-6, 1e-4),
+    (lambda x: -math.log(0.2 * x + 0.5 * (1 - x)), 1e-6, 0.7, 1 - 1e-6, 0.1),          # monotone: optimum at a bound
+    (lambda x: math.cosh(3 * (x - 2.5)) + 0.1 * x, 1e-6, 0.1, 100.0, 0.1),
+    (lambda x: abs(x - 1e-3) ** 1.5, 1e-6, 1e-6, 100.0, 1e-3),
+    (lambda x: 1.0, 0.0, 0.0, 1.0, 0.1),                                                 # flat, xguess == 0 branch of the bracketing
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("case", range(len(BRENT_CASES)))
+def test_brent_restatement_equals_reference(case):
+    f, lo, guess, hi, tol = BRENT_CASES[case]
+    lib = _minimisers("ref")
+    seqs = []
+    for use_ref in (1, 0):
+        calls = []
+
+        def target(_, x):
+            calls.append(x)
+            return f(x)
+        out = C.c_double()
+        assert lib.orc_test_brent(use_ref, lo, guess, hi, tol, TARGET_T(target), C.byref(out))
+        seqs.append((out.value, calls))
+    assert seqs[0][0] == seqs[1][0]
+    assert seqs[0][1] == seqs[1][1]          # identical evaluation sequence, including the post-convergence repeats
+    assert len(seqs[0][1]) == 5 + 101 + 1    # the reference always spends 107 target evaluations
+
+
+NEWTON_CASES = [
+    (lambda x: (2 * (x - 0.37), 2.0), 1e-6, 0.1, 100.0, 1e-7, 32),
+    (lambda x: (math.exp(x) - 3.0, math.exp(x)), 1e-6, 5.0, 100.0, 1e-7, 32),
+    (lambda x: (-1.0 / x + 0.5, 1.0 / (x * x)), 1e-6, 0.1, 100.0, 1e-7, 32),
+    (lambda x: (1.0, -1.0), 1e-6, 0.5, 100.0, 1e-7, 8),     # negative curvature: marches to the lower bound
+    (lambda x: (math.sin(5 * x), 5 * math.cos(5 * x)), 1e-6, 1.0, 100.0, 1e-7, 4),   # hits the iteration limit
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("case", range(len(NEWTON_CASES)))
+def test_newton_restatement_equals_reference(case):
+    f, lo, guess, hi, tol, iters = NEWTON_CASES[case]
+    lib = _minimisers("ref")
+    res = []
+    for use_ref in (1, 0):
+        calls = []
+
+        def deriv(_, x, d1, d2):
+            calls.append(x[0])
+            d1[0], d2[0] = f(x[0])
+        x, st = C.c_double(guess), C.c_int()
+        assert lib.orc_test_newton(use_ref, lo, C.byref(x), hi, tol, iters, DERIV_T(deriv), C.byref(st))
+        res.append((x.value, st.value, calls))
+    assert res[0] == res[1]
+
+
+def _small_case(seed=3, taxa=12, ret=2, sites=500):
+    net = random_network(taxa, ret, seed=seed)
+    m, w = simulate_alignment(net, sites, seed=seed)
+    return net, Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+
+
+@needs_ref
+@pytest.mark.parametrize("method", [NEWTON_RAPHSON, BRENT_NORMAL])
+@pytest.mark.parametrize("variant", [AVERAGE, BEST])
+def test_optimisers_port_equals_reference_libraries(method, variant):
+    net, part = _small_case()
+    out = []
+    for kind in ("port", "ref"):
+        e = oracle.make_engine(kind, net, [part], variant=variant)
+        l0 = e.computeLoglikelihood(0, 1)
+        l1 = e.optimize_branches(method=method)
+        l2 = e.optimize_reticulations()
+        assert l1 >= l0 - 1e-3 and l2 >= l1 - 1e-3
+        assert l2 == pytest.approx(e.computeLoglikelihood(0, 1), rel=1e-12)   # incremental state == full re-evaluation
+        out.append((l1, l2, e.branch_lengths(), e.reticulation_probs()))
+    assert out[0][0] == pytest.approx(out[1][0], rel=1e-11)
+    assert out[0][1] == pytest.approx(out[1][1], rel=1e-11)
+    np.testing.assert_allclose(out[0][2], out[1][2], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(out[0][3], out[1][3], rtol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["small", "two_reticulations", "three_reticulations", "celine"])
+def test_optimize_branch_never_worse_on_reference_fixtures(name):
+    """BrlenOptTest.cpp:95-120: after optimising the branches the lnL is not worse; every single optimize_branch call
+    also returns a value equal to a full re-evaluation of the updated network."""
+    net, part = load_fixture(*FIXTURE_PAIRS[name])
+    e = oracle.make_engine("ref" if oracle.have_ref() else "port", net, [part])
+    prev = e.computeLoglikelihood(0, 1)
+    for edge in range(net.num_edges):
+        l = e.optimize_branch(edge)
+        assert l >= prev - 1e-6, (edge, l, prev)
+        prev = l
+    assert prev == pytest.approx(e.computeLoglikelihood(0, 1), rel=1e-12)
+    lens = e.branch_lengths()
+    assert lens.min() >= 1e-6 and lens.max() <= 100.0
+
+
+def test_brent_reroot_throws_like_the_reference():
+    """optimize_branch_brent ends with invalidatePmatrixIndex (BranchLengthOptimization.cpp:153), which invalidates the
+    root CLVs; the following computeLoglikelihoodBrlenOpt refuses them (VirtualRerooting.cpp:370-379).  BRENT_REROOT
+    is therefore unusable in the reference as shipped, and the restatement reproduces the same exception."""
+    net, part = _small_case()
+    e = oracle.make_engine("port", net, [part])
+    with pytest.raises(LikelihoodError, match="Cannot reuse old displayed trees"):
+        e.optimize_branch(0, method=BRENT_REROOT)
+
+
+def test_unlinked_newton_uses_partition_zero_derivative():
+    """Quirk Q7 (BranchLengthOptimization.cpp:190-195): with unlinked branch lengths every partition's Newton-Raphson run
+    is driven by partition 0's derivatives; the lnL guard keeps the result from getting worse."""
+    net = random_network(8, 1, seed=11)
+    parts, brl = [], []
+    rng = np.random.default_rng(1)
+    for p in range(3):
+        m, w = simulate_alignment(net, 200, seed=20 + p)
+        parts.append(Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w))
+        brl.append(net.edge_length * rng.uniform(0.5, 2.0, net.num_edges))
+    e = oracle.make_engine("port", net, parts, linkage=UNLINKED, partition_brlens=brl)
+    l0 = e.computeLoglikelihood(0, 1)
+    l1 = e.optimize_branch(2)
+    assert l1 >= l0 - 1e-9
+    assert l1 == pytest.approx(e.computeLoglikelihood(0, 1), rel=1e-12)

@@ -157,6 +157,23 @@ unsigned long long nrx_launch_count(nrx_engine *e);
 int nrx_profile_enable(nrx_engine *e, int on);
 int nrx_profile_read(nrx_engine *e, double *clv_ms, unsigned long long *clv_launches, unsigned long long *clv_site_updates,
                      unsigned long long *clv_bytes);
+/* the same per kernel family: device ms (CUDA events around the family's launches), launches, units of work
+ * (edges for K1, site-updates for K2, (item, pattern) pairs for K3-K6, outputs for the reduction) and
+ * ALGORITHMIC bytes (§8d table) — the per-kernel roofline table of scripts/kernel_rooflines.py */
+enum {
+  NRX_PROF_K2 = 0,      /* CLV update (k_clv_*) */
+  NRX_PROF_K1 = 1,      /* P-matrices (+ protein tip tables) */
+  NRX_PROF_K3 = 2,      /* root lnL per tree (k_tree_lnl*) */
+  NRX_PROF_K3F = 3,     /* second stage of the fused root lnL (k_term_lnl_sum) */
+  NRX_PROF_K4 = 4,      /* edge lnL per pair */
+  NRX_PROF_K5 = 5,      /* sumtables */
+  NRX_PROF_K6 = 6,      /* derivatives per sumtable and Newton iterate */
+  NRX_PROF_REDUCE = 7,  /* second-stage reduction of the per-block partial sums */
+  NRX_PROF_COPY = 8,    /* slot copies of the virtual re-rooting save/restore */
+  NRX_PROF_KINDS = 9
+};
+int nrx_profile_read_kind(nrx_engine *e, int kind, double *ms, unsigned long long *launches, unsigned long long *units,
+                          unsigned long long *bytes);
 
 #ifdef __cplusplus
 }

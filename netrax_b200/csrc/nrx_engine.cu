@@ -33,6 +33,9 @@ struct Part {
   size_t clv_entries = 0, pmat_entries = 0;
   double *pmat = nullptr;
   double *tiplut = nullptr;  // 20-state partitions only
+  double *summat = nullptr, *sumlut = nullptr;  // 20-state partitions only: K5 operand matrices / tip table (PartView)
+  std::vector<uint32_t> h_tipmap;               // code -> state mask, host copy
+  std::vector<double> h_freqs, h_inv_eigenvecs, h_eigenvecs;
   uint8_t *tipchars = nullptr;
   uint32_t *tipmap = nullptr, *weights = nullptr;
   double *model = nullptr;  // freqs | eigenvecs | inv_eigenvecs | eigenvals | rates | rate_weights | diagp
@@ -133,9 +136,12 @@ struct nrx_engine {
   bool views_dirty = true;
   // profiling of K2
   bool prof = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
-  double prof_ms = 0;
-  unsigned long long prof_launches = 0, prof_updates = 0, prof_bytes = 0;
+  struct ProfKind {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+    double ms = 0;
+    unsigned long long launches = 0, units = 0, bytes = 0;
+  };
+  ProfKind profk[NRX_PROF_KINDS];  // per kernel family (nrx_engine.h: NRX_PROF_K2 ...), CUDA events on the engine stream
 };
 
 namespace {
@@ -195,6 +201,30 @@ template <class T> int upload(nrx_engine *e, const T *src, size_t n, T **dev) {
   return 1;
 }
 
+static void prof_begin(nrx_engine *e, cudaEvent_t *ev0, cudaEvent_t *ev1) {
+  *ev0 = *ev1 = nullptr;
+  if (e->prof) { cudaEventCreate(ev0); cudaEventCreate(ev1); cudaEventRecord(*ev0, e->stream); }
+}
+static void prof_end(nrx_engine *e, cudaEvent_t ev0, cudaEvent_t ev1, unsigned long long launches, unsigned long long updates, unsigned long long bytes,
+                     int kind = NRX_PROF_K2) {
+  if (!e->prof) return;
+  cudaEventRecord(ev1, e->stream);
+  nrx_engine::ProfKind &k = e->profk[kind];
+  k.events.emplace_back(ev0, ev1);
+  k.launches += launches;
+  k.units += updates;
+  k.bytes += bytes;
+}
+/* algorithmic bytes of the pattern-streaming kernels K3-K6: per (item, pattern) `clvs` CLV-sized streams + `extra` bytes */
+static unsigned long long stream_bytes(const nrx_engine *e, unsigned long long items, unsigned clvs, unsigned extra, unsigned long long *units) {
+  unsigned long long b = 0;
+  for (const Part &p : e->parts) {
+    b += items * p.d.patterns * ((unsigned long long)clvs * p.d.rate_cats * p.sp * 8 + extra);
+    *units += items * p.d.patterns;
+  }
+  return b;
+}
+
 PartView make_view(const Part &p, uint32_t index) {
   PartView v{};
   v.states = p.d.states; v.sp = p.sp; v.cats = p.d.rate_cats; v.patterns = p.d.patterns; v.tips = p.d.tips; v.edges = p.d.edges;
@@ -203,6 +233,7 @@ PartView make_view(const Part &p, uint32_t index) {
   v.freqs = p.freqs; v.eigenvecs = p.eigenvecs; v.inv_eigenvecs = p.inv_eigenvecs; v.eigenvals = p.eigenvals;
   v.rates = p.rates; v.rate_weights = p.rate_weights;
   v.clv = p.d_clv; v.scaler = p.d_scaler; v.sumtable = p.d_sumtable; v.diagp = p.diagp; v.tiplut = p.tiplut;
+  v.summat = p.summat; v.sumlut = p.sumlut;
   return v;
 }
 
@@ -239,6 +270,30 @@ int refresh_tiplut(nrx_engine *e, uint32_t pi, const uint32_t *edges, uint32_t n
   k_tip_lut20<<<n, 256, 0, e->stream>>>(make_view(p, pi), p.tiplut, d_idx);
   e->launches++;
   CK(cudaGetLastError());
+  return 1;
+}
+/* K5 operands of a 20-state partition: A_L[j][k] = pi_k Vinv[k][j], A_R[j][k] = V[j][k] and the tip table
+ * sum_{k in code} pi_k Vinv[k][j] (serial k order as the reference's tip-inner sumtable loop, LIBPLL/core_derivatives.c:473-641) */
+int refresh_summat(nrx_engine *e, uint32_t pi) {
+  Part &p = e->parts[pi];
+  if (!p.summat || !p.model_set) return 1;
+  const uint32_t S = 20, SP = p.sp;
+  std::vector<double> m(800, 0.0), lut((size_t)AA_LUT_CODES * 80, 0.0);
+  for (uint32_t j = 0; j < S; ++j)
+    for (uint32_t k = 0; k < S; ++k) {
+      m[j * 20 + k] = p.h_freqs[k] * p.h_inv_eigenvecs[k * SP + j];
+      m[400 + j * 20 + k] = p.h_eigenvecs[j * SP + k];
+    }
+  if (p.tips_set && p.tip_codes <= (uint32_t)AA_LUT_CODES)
+    for (uint32_t code = 0; code < p.tip_codes; ++code)
+      for (uint32_t j = 0; j < S; ++j) {
+        double sum = 0.0;
+        for (uint32_t k = 0; k < S; ++k) if ((p.h_tipmap[code] >> k) & 1u) sum += p.h_freqs[k] * p.h_inv_eigenvecs[k * SP + j];
+        for (uint32_t c = 0; c < 4; ++c) lut[(size_t)code * 80 + c * 20 + j] = sum;
+      }
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(p.summat, m.data(), m.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(p.sumlut, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice));
   return 1;
 }
 uint32_t tiles_for(uint64_t items, uint32_t per_block, uint32_t other_dims) {
@@ -299,7 +354,10 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (!std::getenv("NRX_K2_BLOCKS")) e->k2_blocks = 16u * (uint32_t)sms;
-    if (!cuda_ok(cudaFuncSetAttribute(k_clv_aa20_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(AaSmem) + 2 * AA_LUT_CODES * 80 * sizeof(double))), "cudaFuncSetAttribute")) { delete e; return nullptr; }
+    const int aa_smem = (int)(sizeof(AaSmem) + 2 * AA_LUT_CODES * 80 * sizeof(double));
+    if (!cuda_ok(cudaFuncSetAttribute(k_aa20_dmma<AA_CLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa_smem), "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(k_aa20_dmma<AA_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa_smem), "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(k_aa20_dmma<AA_EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa_smem), "cudaFuncSetAttribute")) { delete e; return nullptr; }
     if (!cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClvPipeSmem)), "cudaFuncSetAttribute")) { delete e; return nullptr; }
   }
   for (uint32_t i = 0; i < nparts; ++i) {
@@ -319,7 +377,9 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
               cuda_ok(cudaMalloc((void **)&p.weights, std::max<size_t>(1, p.pat_pad) * sizeof(uint32_t)), "cudaMalloc weights") &&
               cuda_ok(cudaMalloc((void **)&p.model, model_doubles * sizeof(double)), "cudaMalloc model");
     if (ok && p.d.states == 20 && p.d.rate_cats == 4)
-      ok = cuda_ok(cudaMalloc((void **)&p.tiplut, (size_t)p.d.edges * AA_LUT_CODES * 80 * sizeof(double)), "cudaMalloc tiplut");
+      ok = cuda_ok(cudaMalloc((void **)&p.tiplut, (size_t)p.d.edges * AA_LUT_CODES * 80 * sizeof(double)), "cudaMalloc tiplut") &&
+           cuda_ok(cudaMalloc((void **)&p.summat, 800 * sizeof(double)), "cudaMalloc summat") &&
+           cuda_ok(cudaMalloc((void **)&p.sumlut, (size_t)AA_LUT_CODES * 80 * sizeof(double)), "cudaMalloc sumlut");
     if (!ok) { nrx_engine_destroy(e); return nullptr; }
     p.freqs = p.model; p.eigenvecs = p.freqs + SP; p.inv_eigenvecs = p.eigenvecs + S * SP; p.eigenvals = p.inv_eigenvecs + S * SP;
     p.rates = p.eigenvals + SP; p.rate_weights = p.rates + C; p.diagp = p.rate_weights + C;
@@ -343,13 +403,13 @@ void nrx_engine_destroy(nrx_engine *e) {
   if (e->comm && nccl().ok) nccl().CommDestroy(e->comm);
   for (EnginePlan &pl : e->plans) { if (pl.exec) cudaGraphExecDestroy(pl.exec); cudaFree(pl.d_ops); }
   for (Part &p : e->parts) {
-    cudaFree(p.pmat); cudaFree(p.tiplut); cudaFree(p.tipchars); cudaFree(p.tipmap); cudaFree(p.weights); cudaFree(p.model);
+    cudaFree(p.pmat); cudaFree(p.tiplut); cudaFree(p.summat); cudaFree(p.sumlut); cudaFree(p.tipchars); cudaFree(p.tipmap); cudaFree(p.weights); cudaFree(p.model);
     for (void *m : p.slot_mem) cudaFree(m);
     for (double *m : p.h_sumtable) cudaFree(m);
     cudaFree(p.d_clv); cudaFree(p.d_scaler); cudaFree(p.d_sumtable);
   }
   for (ShapeClass &c : e->classes) cudaFree(c.d_views);
-  for (auto &ev : e->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  for (nrx_engine::ProfKind &k : e->profk) for (auto &ev : k.events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (e->h_stage) cudaFreeHost(e->h_stage);
   cudaFree(e->d_fused);
   cudaFree(e->d_stage); cudaFree(e->d_partial); cudaFree(e->d_result); cudaFree(e->d_persite);
@@ -393,8 +453,9 @@ int nrx_set_tips(nrx_engine *e, uint32_t pi, const uint32_t *tip_masks) {
   p.tip_codes = 0;
   for (uint32_t i = 0; i < 256; ++i) if (tipmap[i]) p.tip_codes = i + 1;
   p.tips_set = true;
+  p.h_tipmap = tipmap;
   e->views_dirty = true;
-  if (p.model_set && !refresh_tiplut(e, pi, nullptr, 0)) return 0;  // the code -> state-set map may have changed
+  if (p.model_set && (!refresh_tiplut(e, pi, nullptr, 0) || !refresh_summat(e, pi))) return 0;  // the code -> state-set map may have changed
   return 1;
 }
 
@@ -442,8 +503,11 @@ int nrx_set_model(nrx_engine *e, uint32_t pi, const double *freqs, const double 
   CK(cudaMemcpy(p.model, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
   p.h_eigenvals.assign(eigenvals, eigenvals + S);
   p.h_rates.assign(rates, rates + C);
+  p.h_freqs.assign(freqs, freqs + S);
+  p.h_eigenvecs.assign(eigenvecs, eigenvecs + S * SP);
+  p.h_inv_eigenvecs.assign(inv_eigenvecs, inv_eigenvecs + S * SP);
   p.model_set = true;
-  return 1;
+  return refresh_summat(e, pi);
 }
 
 int nrx_update_pmatrices(nrx_engine *e, uint32_t pi, uint32_t n, const uint32_t *edge_idx, const double *brlen) {
@@ -459,10 +523,13 @@ int nrx_update_pmatrices(nrx_engine *e, uint32_t pi, uint32_t n, const uint32_t 
   uint32_t *d_idx; double *d_len;
   if (!upload(e, edge_idx, n, &d_idx) || !upload(e, brlen, n, &d_len)) return 0;
   PartView v = make_view(p, pi);
+  cudaEvent_t ev0, ev1;
+  prof_begin(e, &ev0, &ev1);
   k_pmatrix<<<n, 128, p.d.rate_cats * p.d.states * sizeof(double), e->stream>>>(v, p.pmat, d_idx, d_len);
   e->launches++;
   CK(cudaGetLastError());
   if (!refresh_tiplut(e, pi, edge_idx, n)) return 0;  // K1b: tip tables of the updated edges for the DMMA kernel
+  prof_end(e, ev0, ev1, 1, n, (unsigned long long)n * p.pmat_entries * 8, NRX_PROF_K1);
   return 1;
 }
 
@@ -551,10 +618,15 @@ int nrx_copy_slot(nrx_engine *e, uint32_t dst, uint32_t src) {
   if (!e) { g_err = "null engine"; return 0; }
   if (dst >= e->nslots || src >= e->nslots) { g_err = "nrx_copy_slot: slot out of range"; return 0; }
   CK(cudaSetDevice(e->device));
+  cudaEvent_t ev0, ev1;
+  prof_begin(e, &ev0, &ev1);
+  unsigned long long bytes = 0;
   for (Part &p : e->parts) {
     CK(cudaMemcpyAsync(p.h_clv[dst], p.h_clv[src], p.clv_entries * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
     CK(cudaMemcpyAsync(p.h_scaler[dst], p.h_scaler[src], (size_t)p.d.patterns * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
+    bytes += 2 * (p.clv_entries * sizeof(double) + (size_t)p.d.patterns * sizeof(uint32_t));
   }
+  prof_end(e, ev0, ev1, 2 * e->parts.size(), 1, bytes, NRX_PROF_COPY);
   return 1;
 }
 
@@ -615,7 +687,7 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
       groups = std::min(groups, std::max<uint32_t>(1, ntiles / 8));
       dim3 grid(nops * groups, 1, z);
       const size_t smem = sizeof(AaSmem) + (with_tips ? 2 * AA_LUT_CODES * 80 * sizeof(double) : 0);
-      k_clv_aa20_dmma<<<grid, AA_THREADS, smem, e->stream>>>(c.d_views, d_ops, nops, groups, with_tips ? 1 : 0);
+      k_aa20_dmma<AA_CLV><<<grid, AA_THREADS, smem, e->stream>>>(c.d_views, d_ops, nops, groups, with_tips ? 1 : 0, nullptr, 0, 0.0);
     } else {
       dim3 grid(tiles_for(c.max_patterns, BLOCK, nops * z), nops, z);
       k_clv_generic<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops, nullptr);
@@ -629,19 +701,6 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
 static bool any_tip(const nrx_op *ops, uint32_t nops) {
   for (uint32_t i = 0; i < nops; ++i) if (ops[i].left_kind == NRX_TIP || ops[i].right_kind == NRX_TIP) return true;
   return false;
-}
-
-static void prof_begin(nrx_engine *e, cudaEvent_t *ev0, cudaEvent_t *ev1) {
-  *ev0 = *ev1 = nullptr;
-  if (e->prof) { cudaEventCreate(ev0); cudaEventCreate(ev1); cudaEventRecord(*ev0, e->stream); }
-}
-static void prof_end(nrx_engine *e, cudaEvent_t ev0, cudaEvent_t ev1, unsigned long long launches, unsigned long long updates, unsigned long long bytes) {
-  if (!e->prof) return;
-  cudaEventRecord(ev1, e->stream);
-  e->prof_events.emplace_back(ev0, ev1);
-  e->prof_launches += launches;
-  e->prof_updates += updates;
-  e->prof_bytes += bytes;
 }
 
 int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops) {
@@ -757,9 +816,12 @@ static uint32_t reduce_blocks(const nrx_engine *e, uint32_t items) {
 }
 
 static int finish_reduction(nrx_engine *e, uint32_t total, uint32_t nblk, double *out) {
-  k_reduce_partials<<<(total + 127) / 128, 128, 0, e->stream>>>(e->d_partial, e->d_result, nblk, total);
+  cudaEvent_t ev0, ev1;
+  prof_begin(e, &ev0, &ev1);
+  k_reduce_partials<<<(total + 3) / 4, 128, 0, e->stream>>>(e->d_partial, e->d_result, nblk, total);
   e->launches++;
   CK(cudaGetLastError());
+  prof_end(e, ev0, ev1, 1, total, (unsigned long long)total * nblk * 8, NRX_PROF_REDUCE);
   if (e->comm) {  // C2-C4: one all-reduce over NVLink for all trees / pairs x partitions
     const int rc = nccl().AllReduce(e->d_result, e->d_result, total, NCCL_FLOAT64, NCCL_SUM, e->comm, e->stream);
     if (rc != 0) { g_err = std::string("ncclAllReduce: ") + nccl().GetErrorString(rc); return 0; }
@@ -789,6 +851,8 @@ int nrx_tree_lnl(nrx_engine *e, const uint32_t *slots, uint32_t n, double *out, 
   }
   CK(cudaMemsetAsync(e->d_partial, 0, (size_t)n * P * nblk * sizeof(double), e->stream));
   const double log_thresh = std::log(SCALE_THRESHOLD);
+  cudaEvent_t ev0, ev1;
+  prof_begin(e, &ev0, &ev1);
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
     if (c.states == 4 && c.cats == 4) k_tree_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
@@ -796,6 +860,7 @@ int nrx_tree_lnl(nrx_engine *e, const uint32_t *slots, uint32_t n, double *out, 
     e->launches++;
     CK(cudaGetLastError());
   }
+  { unsigned long long u = 0; const unsigned long long b = stream_bytes(e, n, 1, persite ? 16 : 8, &u); prof_end(e, ev0, ev1, e->classes.size(), u, b, NRX_PROF_K3); }
   if (!finish_reduction(e, n * P, nblk, out)) return 0;
   if (persite) CK(cudaMemcpy(persite, e->d_persite, (size_t)n * P * persite_stride * sizeof(double), cudaMemcpyDeviceToHost));
   return 1;
@@ -813,12 +878,15 @@ int nrx_tree_lnl_fused(nrx_engine *e, uint32_t plan_id, const uint32_t *slots, u
   uint32_t *d_slots;
   if (!upload(e, slots, n, &d_slots)) return 0;
   CK(cudaMemsetAsync(e->d_partial, 0, (size_t)n * P * nblk * sizeof(double), e->stream));
+  cudaEvent_t ev0, ev1;
+  prof_begin(e, &ev0, &ev1);
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
     k_term_lnl_sum<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_fused, (size_t)e->max_patterns, e->d_partial, P, std::log(SCALE_THRESHOLD));
     e->launches++;
     CK(cudaGetLastError());
   }
+  { unsigned long long u = 0; const unsigned long long b = stream_bytes(e, n, 0, 16, &u); prof_end(e, ev0, ev1, e->classes.size(), u, b, NRX_PROF_K3F); }
   return finish_reduction(e, n * P, nblk, out);
 }
 
@@ -836,6 +904,29 @@ static int check_pairs(nrx_engine *e, const nrx_pair *pairs, uint32_t n, const c
   return 1;
 }
 
+/* 20-state pairs as pseudo-ops of the DMMA kernel.  K4 (edge lnL): left = the parent CLV as it lies, right = the child
+ * (CLV or tip, the tip always plays child: LIBPLL/likelihood.c:586-601) through P(edge).  K5 (sumtable): left = the
+ * tip if there is one (LIBPLL/derivatives.c:70-98), parent_slot = sumtable index. */
+static bool aa_dmma_class(const nrx_engine *e, const ShapeClass &c) {
+  return c.states == 20 && c.cats == 4 && !e->aa_generic && class_tip_codes(e, c) <= (uint32_t)AA_LUT_CODES;
+}
+static std::vector<nrx_op> pairs_to_ops(const nrx_pair *pairs, uint32_t n, uint32_t edge, bool tip_left, bool *any_tip_out) {
+  std::vector<nrx_op> ops(n);
+  *any_tip_out = false;
+  for (uint32_t i = 0; i < n; ++i) {
+    nrx_pair q = pairs[i];
+    const bool swap = tip_left ? (q.b_kind == NRX_TIP) : (q.a_kind == NRX_TIP);
+    if (swap) { std::swap(q.a_kind, q.b_kind); std::swap(q.a_idx, q.b_idx); }
+    nrx_op o{};
+    o.parent_slot = i;
+    o.left_kind = q.a_kind; o.left_idx = q.a_idx; o.left_edge = edge;
+    o.right_kind = q.b_kind; o.right_idx = q.b_idx; o.right_edge = edge;
+    ops[i] = o;
+    *any_tip_out |= (q.a_kind == NRX_TIP || q.b_kind == NRX_TIP);
+  }
+  return ops;
+}
+
 int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n, double *out) {
   if (!e) { g_err = "null engine"; return 0; }
   if (n == 0) return 1;
@@ -849,13 +940,24 @@ int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n
   if (!upload(e, pairs, n, &d_pairs)) return 0;
   CK(cudaMemsetAsync(e->d_partial, 0, (size_t)n * P * nblk * sizeof(double), e->stream));
   const double log_thresh = std::log(SCALE_THRESHOLD);
+  cudaEvent_t ev0, ev1;
+  prof_begin(e, &ev0, &ev1);
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
     if (c.states == 4 && c.cats == 4) k_edge_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh);
+    else if (aa_dmma_class(e, c)) {  // FP64 tensor cores: block b = (pair b % n, tile group b / n), one partial per (pair, group)
+      bool tips;
+      const std::vector<nrx_op> ops = pairs_to_ops(pairs, n, edge, false, &tips);
+      nrx_op *d_ops;
+      if (!upload(e, ops.data(), ops.size(), &d_ops)) return 0;
+      const size_t smem = sizeof(AaSmem) + (tips ? 2 * AA_LUT_CODES * 80 * sizeof(double) : 0);
+      k_aa20_dmma<AA_EDGE><<<dim3(n * nblk, 1, (uint32_t)c.parts.size()), AA_THREADS, smem, e->stream>>>(c.d_views, d_ops, n, nblk, tips ? 1 : 0, e->d_partial, P, log_thresh);
+    }
     else k_edge_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh);
     e->launches++;
     CK(cudaGetLastError());
   }
+  { unsigned long long u = 0; const unsigned long long b = stream_bytes(e, n, 2, 12, &u); prof_end(e, ev0, ev1, e->classes.size(), u, b, NRX_PROF_K4); }
   return finish_reduction(e, n * P, nblk, out);
 }
 
@@ -867,12 +969,24 @@ int nrx_sumtables(nrx_engine *e, const nrx_pair *pairs, uint32_t n) {
   if (!reserve_sumtables(e, n) || !refresh_views(e)) return 0;
   nrx_pair *d_pairs;
   if (!upload(e, pairs, n, &d_pairs)) return 0;
+  cudaEvent_t ev0, ev1;
+  prof_begin(e, &ev0, &ev1);
   for (const ShapeClass &c : e->classes) {
     if (c.max_patterns == 0) continue;
     const uint32_t z = (uint32_t)c.parts.size();
     if (c.states == 4 && c.cats == 4) {
       dim3 grid(tiles_for((uint64_t)c.max_patterns * 4, BLOCK * RU, n * z), n, z);
       k_sumtable_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs);
+    } else if (aa_dmma_class(e, c)) {
+      bool tips;
+      const std::vector<nrx_op> ops = pairs_to_ops(pairs, n, 0, true, &tips);
+      nrx_op *d_ops;
+      if (!upload(e, ops.data(), ops.size(), &d_ops)) return 0;
+      const uint32_t ntiles = (c.max_patterns + AA_TP - 1) / AA_TP;
+      uint32_t groups = std::max<uint32_t>(1, (e->aa_blocks + n * z - 1) / (n * z));
+      groups = std::min(groups, std::max<uint32_t>(1, ntiles / 8));
+      const size_t smem = sizeof(AaSmem) + (tips ? 2 * AA_LUT_CODES * 80 * sizeof(double) : 0);
+      k_aa20_dmma<AA_SUM><<<dim3(n * groups, 1, z), AA_THREADS, smem, e->stream>>>(c.d_views, d_ops, n, groups, tips ? 1 : 0, nullptr, 0, 0.0);
     } else {
       dim3 grid(tiles_for((uint64_t)c.max_patterns * c.cats, BLOCK, n * z), n, z);
       k_sumtable<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs);
@@ -880,6 +994,7 @@ int nrx_sumtables(nrx_engine *e, const nrx_pair *pairs, uint32_t n) {
     e->launches++;
     CK(cudaGetLastError());
   }
+  { unsigned long long u = 0; const unsigned long long b = stream_bytes(e, n, 3, 0, &u); prof_end(e, ev0, ev1, e->classes.size(), u, b, NRX_PROF_K5); }
   return 1;
 }
 
@@ -912,6 +1027,8 @@ int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen, double *out)
     CK(cudaMemcpyAsync(p.diagp, d_tmp, diag.size() * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
   }
   CK(cudaMemsetAsync(e->d_partial, 0, (size_t)n * P * 3 * nblk * sizeof(double), e->stream));
+  cudaEvent_t ev0, ev1;
+  prof_begin(e, &ev0, &ev1);
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
     if (c.states == 4 && c.cats == 4) k_derivatives_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P);
@@ -919,6 +1036,7 @@ int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen, double *out)
     e->launches++;
     CK(cudaGetLastError());
   }
+  { unsigned long long u = 0; const unsigned long long b = stream_bytes(e, n, 1, 4, &u); prof_end(e, ev0, ev1, e->classes.size(), u, b, NRX_PROF_K6); }
   return finish_reduction(e, n * P * 3, nblk, out);
 }
 
@@ -1026,28 +1144,35 @@ int nrx_timer_stop(nrx_engine *e, double *elapsed_ms) {
 int nrx_profile_enable(nrx_engine *e, int on) {
   if (!e) { g_err = "null engine"; return 0; }
   e->prof = on != 0;
-  for (auto &ev : e->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
-  e->prof_events.clear();
-  e->prof_ms = 0; e->prof_launches = e->prof_updates = e->prof_bytes = 0;
+  for (nrx_engine::ProfKind &k : e->profk) {
+    for (auto &ev : k.events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    k = nrx_engine::ProfKind();
+  }
+  return 1;
+}
+
+int nrx_profile_read_kind(nrx_engine *e, int kind, double *ms, unsigned long long *launches, unsigned long long *units, unsigned long long *bytes) {
+  if (!e) { g_err = "null engine"; return 0; }
+  if (kind < 0 || kind >= NRX_PROF_KINDS) { g_err = "nrx_profile_read_kind: bad kind"; return 0; }
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  nrx_engine::ProfKind &k = e->profk[kind];
+  for (auto &ev : k.events) {
+    float t = 0;
+    cudaEventElapsedTime(&t, ev.first, ev.second);
+    k.ms += t;
+    cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
+  }
+  k.events.clear();
+  if (ms) *ms = k.ms;
+  if (launches) *launches = k.launches;
+  if (units) *units = k.units;
+  if (bytes) *bytes = k.bytes;
   return 1;
 }
 
 int nrx_profile_read(nrx_engine *e, double *clv_ms, unsigned long long *clv_launches, unsigned long long *clv_site_updates, unsigned long long *clv_bytes) {
-  if (!e) { g_err = "null engine"; return 0; }
-  CK(cudaSetDevice(e->device));
-  CK(cudaStreamSynchronize(e->stream));
-  for (auto &ev : e->prof_events) {
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ev.first, ev.second);
-    e->prof_ms += ms;
-    cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
-  }
-  e->prof_events.clear();
-  if (clv_ms) *clv_ms = e->prof_ms;
-  if (clv_launches) *clv_launches = e->prof_launches;
-  if (clv_site_updates) *clv_site_updates = e->prof_updates;
-  if (clv_bytes) *clv_bytes = e->prof_bytes;
-  return 1;
+  return nrx_profile_read_kind(e, NRX_PROF_K2, clv_ms, clv_launches, clv_site_updates, clv_bytes);
 }
 
 }  // extern "C"

@@ -39,6 +39,8 @@ struct PartView {
   double *const *sumtable;   // [nsumtables]
   const double *diagp;       // [cats][states][4] for the current derivative call
   const double *tiplut;      // 20-state partitions: [edges][AA_LUT_CODES][cats*20] sums of P rows over each tip code's states (K1b)
+  const double *summat;      // 20-state partitions: K5 operand matrices [2][20][20]: A_L[j][k] = pi_k Vinv[k][j], A_R[j][k] = V[j][k]
+  const double *sumlut;      // 20-state partitions: K5 tip table [AA_LUT_CODES][cats*20]: sum_{k in code} pi_k Vinv[k][j], replicated per category
 };
 
 __device__ __forceinline__ double tree4(double a, double b, double c, double d) {
@@ -433,6 +435,7 @@ struct __align__(128) AaSmem {
   unsigned long long empty[NSTAGE_AA];
   unsigned long long lutbar;
   uint32_t flags[2][4][AA_TP];
+  double exch[2][4][AA_TP];   // AA_EDGE: per (category, pattern) weighted site-likelihood terms
   // followed by double lutL[AA_LUT_CODES*80], lutR[AA_LUT_CODES*80] when the launch has tip operands
 };
 
@@ -458,8 +461,20 @@ __global__ void k_tip_lut20(PartView pv, double *lut_out, const uint32_t *edge_i
   }
 }
 
-__global__ void __launch_bounds__(AA_THREADS, 3) k_clv_aa20_dmma(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops,
-                                                                  uint32_t nops, uint32_t groups, int with_lut) {
+/* The same pipeline serves all three 20-state contractions (MODE):
+ *   AA_CLV  (K2): parent = (P_l . left) * (P_r . right), scaled, stored as a CLV slot.
+ *   AA_SUM  (K5): sumtable = (A_L . left) * (A_R . right) with the category-independent eigen matrices of PartView::summat
+ *                 (LIBPLL/core_derivatives.c:321-471 ii, :473-641 ti: the tip is the left operand), no scaling, stored
+ *                 to sumtable slot op.parent_slot.
+ *   AA_EDGE (K4): per pattern log( sum_c w_c sum_i pi_i left[c][i] (P_edge . right)[c][i] ) + scalers, times the pattern
+ *                 weight, summed per block into partial[] (LIBPLL/core_likelihood.c:1191-1496 ii, :351-922 ti: the tip is
+ *                 the child = right operand; the parent CLV = left operand is used as it lies, no matrix). */
+enum { AA_CLV = 0, AA_SUM = 1, AA_EDGE = 2 };
+
+template <int MODE>
+__global__ void __launch_bounds__(AA_THREADS, 3) k_aa20_dmma(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops,
+                                                              uint32_t nops, uint32_t groups, int with_lut,
+                                                              double *__restrict__ partial, uint32_t nparts_total, double log_thresh) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   AaSmem &sm = *reinterpret_cast<AaSmem *>(smem_raw);
   double *lutL = reinterpret_cast<double *>(smem_raw + sizeof(AaSmem));
@@ -485,7 +500,7 @@ __global__ void __launch_bounds__(AA_THREADS, 3) k_clv_aa20_dmma(const PartView 
     const uint32_t tx = (lk == NRX_TIP ? bytes : 0u) + (rk == NRX_TIP ? bytes : 0u);
     if (tx) {
       mbar_expect_tx(&sm.lutbar, tx);
-      if (lk == NRX_TIP) bulk_g2s(lutL, pv.tiplut + (size_t)op.left_edge * AA_LUT_CODES * 80, bytes, &sm.lutbar);
+      if (lk == NRX_TIP) bulk_g2s(lutL, MODE == AA_SUM ? pv.sumlut : pv.tiplut + (size_t)op.left_edge * AA_LUT_CODES * 80, bytes, &sm.lutbar);
       if (rk == NRX_TIP) bulk_g2s(lutR, pv.tiplut + (size_t)op.right_edge * AA_LUT_CODES * 80, bytes, &sm.lutbar);
     }
   }
@@ -499,8 +514,9 @@ __global__ void __launch_bounds__(AA_THREADS, 3) k_clv_aa20_dmma(const PartView 
     const uint32_t *scR = (rk == NRX_CLV) ? pv.scaler[op.right_idx] : nullptr;
     const uint8_t *tipL = (lk == NRX_TIP) ? pv.tipchars + (size_t)op.left_idx * pv.tip_pitch : nullptr;
     const uint8_t *tipR = (rk == NRX_TIP) ? pv.tipchars + (size_t)op.right_idx * pv.tip_pitch : nullptr;
-    const uint32_t tx_bytes = ((lk == NRX_CLV) ? AA_TP * 640u + AA_TP * 4u : (lk == NRX_TIP ? 16u : 0u)) +
-                              ((rk == NRX_CLV) ? AA_TP * 640u + AA_TP * 4u : (rk == NRX_TIP ? 16u : 0u));
+    const uint32_t sc_bytes = (MODE == AA_SUM) ? 0u : AA_TP * 4u;   // sumtables ignore the scalers
+    const uint32_t tx_bytes = ((lk == NRX_CLV) ? AA_TP * 640u + sc_bytes : (lk == NRX_TIP ? 16u : 0u)) +
+                              ((rk == NRX_CLV) ? AA_TP * 640u + sc_bytes : (rk == NRX_TIP ? 16u : 0u));
     for (uint32_t k = 0; k < count; ++k) {
       const uint32_t s = k % NSTAGE_AA;
       if (k >= (uint32_t)NSTAGE_AA) mbar_wait(&sm.empty[s], ((k / NSTAGE_AA) - 1) & 1u);
@@ -514,10 +530,10 @@ __global__ void __launch_bounds__(AA_THREADS, 3) k_clv_aa20_dmma(const PartView 
       } else if (lane < 2 * AA_TP) {  // lanes 8..15: right rows
         if (rk == NRX_CLV) bulk_g2s(st.r + (lane - AA_TP) * AA_PITCH, clvR + (p0 + lane - AA_TP) * 80, 640u, bar);
       } else if (lane == 16) {
-        if (lk == NRX_CLV) bulk_g2s(st.scl, scL + p0, AA_TP * 4u, bar);
+        if (lk == NRX_CLV) { if (MODE != AA_SUM) bulk_g2s(st.scl, scL + p0, AA_TP * 4u, bar); }
         else if (lk == NRX_TIP) bulk_g2s(st.tl, tipL + (p0 & ~(size_t)15), 16u, bar);
       } else if (lane == 17) {
-        if (rk == NRX_CLV) bulk_g2s(st.scr, scR + p0, AA_TP * 4u, bar);
+        if (rk == NRX_CLV) { if (MODE != AA_SUM) bulk_g2s(st.scr, scR + p0, AA_TP * 4u, bar); }
         else if (rk == NRX_TIP) bulk_g2s(st.tr, tipR + (p0 & ~(size_t)15), 16u, bar);
       }
     }
@@ -534,14 +550,27 @@ __global__ void __launch_bounds__(AA_THREADS, 3) k_clv_aa20_dmma(const PartView 
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
         const int i = 8 * n + i_base, j = 4 * k + j_base;
-        BL[n * 5 + k] = (lk == NRX_CLV && i < 20) ? pv.pmat[(size_t)op.left_edge * 1600 + (cat * 20 + i) * 20 + j] : 0.0;
-        BR[n * 5 + k] = (rk == NRX_CLV && i < 20) ? pv.pmat[(size_t)op.right_edge * 1600 + (cat * 20 + i) * 20 + j] : 0.0;
+        if (MODE == AA_SUM) {
+          BL[n * 5 + k] = (lk == NRX_CLV && i < 20) ? pv.summat[i * 20 + j] : 0.0;
+          BR[n * 5 + k] = (rk == NRX_CLV && i < 20) ? pv.summat[400 + i * 20 + j] : 0.0;
+        } else {
+          BL[n * 5 + k] = (MODE == AA_CLV && lk == NRX_CLV && i < 20) ? pv.pmat[(size_t)op.left_edge * 1600 + (cat * 20 + i) * 20 + j] : 0.0;
+          BR[n * 5 + k] = (rk == NRX_CLV && i < 20) ? pv.pmat[(size_t)op.right_edge * 1600 + (cat * 20 + i) * 20 + j] : 0.0;
+        }
       }
   }
-  double *par = pv.clv[op.parent_slot];
-  uint32_t *psc = pv.scaler[op.parent_slot];
+  double *par = (MODE == AA_SUM) ? pv.sumtable[op.parent_slot] : (MODE == AA_CLV ? pv.clv[op.parent_slot] : nullptr);
+  uint32_t *psc = (MODE == AA_CLV) ? pv.scaler[op.parent_slot] : nullptr;
   const bool tiptip = (lk == NRX_TIP && rk == NRX_TIP);
   if (wait_lut) mbar_wait(&sm.lutbar, 0);
+  double fr[6], wcat = 0.0, acc = 0.0;   // AA_EDGE: pi of this thread's six output states, rate weight of its category
+  if (MODE == AA_EDGE) {
+    wcat = pv.rate_weights[cat];
+#pragma unroll
+    for (int n = 0; n < 3; ++n)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) { const int i = 8 * n + 2 * (lane & 3) + h; fr[2 * n + h] = (i < 20) ? pv.freqs[i] : 0.0; }
+  }
 
   for (uint32_t k = 0; k < count; ++k) {
     const uint32_t s = k % NSTAGE_AA;
@@ -553,35 +582,45 @@ __global__ void __launch_bounds__(AA_THREADS, 3) k_clv_aa20_dmma(const PartView 
     // pull this warp's operands out of the stage, then release it
     double aL[5], aR[5];
     uint32_t codeL = 0, codeR = 0, sc = 0;
-    if (lk == NRX_CLV) {
+    double x[6], y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { x[i] = 0.0; y[i] = 0.0; }
+    if (MODE == AA_EDGE) {   // the parent CLV enters as it lies: this thread's six output states, times pi
+#pragma unroll
+      for (int n = 0; n < 3; ++n) {
+        const int i0 = 8 * n + 2 * q;
+        if (i0 < 20) {
+          const double2 v = *reinterpret_cast<const double2 *>(st.l + item * AA_PITCH + cat * 20 + i0);
+          x[2 * n] = __dmul_rn(v.x, fr[2 * n]); x[2 * n + 1] = __dmul_rn(v.y, fr[2 * n + 1]);
+        }
+      }
+      sc += st.scl[item];
+    } else if (lk == NRX_CLV) {
 #pragma unroll
       for (int kk = 0; kk < 5; ++kk) aL[kk] = st.l[item * AA_PITCH + cat * 20 + 4 * kk + q];
-      sc += st.scl[item];
+      if (MODE == AA_CLV) sc += st.scl[item];
     } else if (lk == NRX_TIP) codeL = st.tl[(p0 & 15) + item];
     if (rk == NRX_CLV) {
 #pragma unroll
       for (int kk = 0; kk < 5; ++kk) aR[kk] = st.r[item * AA_PITCH + cat * 20 + 4 * kk + q];
-      sc += st.scr[item];
+      if (MODE != AA_SUM) sc += st.scr[item];
     } else if (rk == NRX_TIP) codeR = st.tr[(p0 & 15) + item];
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[s]);
 
-    double x[6], y[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { x[i] = 0.0; y[i] = 0.0; }
     // k-step outermost: the (up to) six accumulator chains advance together, so consecutive DMMAs are independent
 #pragma unroll
     for (int kk = 0; kk < 5; ++kk) {
 #pragma unroll
       for (int n = 0; n < 3; ++n) {
-        if (lk == NRX_CLV) dmma884(x[2 * n], x[2 * n + 1], aL[kk], BL[n * 5 + kk]);
+        if (MODE != AA_EDGE && lk == NRX_CLV) dmma884(x[2 * n], x[2 * n + 1], aL[kk], BL[n * 5 + kk]);
         if (rk == NRX_CLV) dmma884(y[2 * n], y[2 * n + 1], aR[kk], BR[n * 5 + kk]);
       }
     }
 #pragma unroll
     for (int n = 0; n < 3; ++n) {
       const int i0 = 8 * n + 2 * q;   // this thread's two output states of n-tile n
-      if (lk == NRX_TIP && i0 < 20) { const double2 v = *reinterpret_cast<const double2 *>(lutL + (codeL * 4 + cat) * 20 + i0); x[2 * n] = v.x; x[2 * n + 1] = v.y; }
+      if (MODE != AA_EDGE && lk == NRX_TIP && i0 < 20) { const double2 v = *reinterpret_cast<const double2 *>(lutL + (codeL * 4 + cat) * 20 + i0); x[2 * n] = v.x; x[2 * n + 1] = v.y; }
       if (rk == NRX_TIP && i0 < 20) { const double2 v = *reinterpret_cast<const double2 *>(lutR + (codeR * 4 + cat) * 20 + i0); y[2 * n] = v.x; y[2 * n + 1] = v.y; }
     }
     double pz[6];
@@ -598,6 +637,35 @@ __global__ void __launch_bounds__(AA_THREADS, 3) k_clv_aa20_dmma(const PartView 
         pz[2 * n + h] = v;
         if (i0 < 20) small &= (v < SCALE_THRESHOLD);
       }
+    }
+    if (MODE == AA_EDGE) {
+      // sum over this (pattern, category)'s 20 states: six per thread in state order, then the quad; weighted terms of
+      // the four categories meet in shared memory (named barrier over the consumer warps), category order 0..3
+      double t = 0.0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) t = __dadd_rn(t, pz[i]);   // padding states carry pi = 0
+      t = __dadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 1));
+      t = __dadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 2));
+      if (q == 0) sm.exch[k & 1][cat][item] = __dmul_rn(t, wcat);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (cat == 0 && q == 0 && act) {
+        const double term = __dadd_rn(__dadd_rn(__dadd_rn(sm.exch[k & 1][0][item], sm.exch[k & 1][1][item]), sm.exch[k & 1][2][item]), sm.exch[k & 1][3][item]);
+        double lkv = log(term);
+        if (sc) lkv = __dadd_rn(lkv, __dmul_rn((double)sc, log_thresh));
+        acc += __dmul_rn(lkv, (double)pv.weights[site]);
+      }
+      continue;
+    }
+    if (MODE == AA_SUM) {
+      if (act) {
+        double *dst = par + site * 80 + cat * 20;
+#pragma unroll
+        for (int n = 0; n < 3; ++n) {
+          const int i0 = 8 * n + 2 * q;
+          if (i0 < 20) asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(dst + i0), "d"(pz[2 * n]), "d"(pz[2 * n + 1]) : "memory");
+        }
+      }
+      continue;
     }
     // all 20 states of (pattern, cat): AND over the quad; all 4 cats: shared flags + named barrier over the 4 consumer warps
     unsigned b = __ballot_sync(0xffffffffu, small);
@@ -621,6 +689,11 @@ __global__ void __launch_bounds__(AA_THREADS, 3) k_clv_aa20_dmma(const PartView 
       }
       if (cat == 0 && q == 0) psc[site] = tiptip ? 0u : sc + (scale ? 1u : 0u);
     }
+  }
+  if (MODE == AA_EDGE && cat == 0) {   // the eight q == 0 lanes of the category-0 warp hold the block's sum
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+    if (lane == 0) partial[((size_t)(blockIdx.x % nops) * nparts_total + pv.part_index) * groups + grp] = acc;
   }
 }
 
@@ -710,14 +783,18 @@ __device__ __forceinline__ void block_sum(double (&v)[N], double *smem /* [N][BL
     }
 }
 
-/* second stage: out[item][part][k] = sum over blocks of partial[((item*nparts+part)*N + k)*nblk + b], fixed order */
-__global__ void k_reduce_partials(const double *__restrict__ partial, double *__restrict__ out, uint32_t nblk, uint32_t total) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+/* second stage: out[item][part][k] = sum over blocks of partial[((item*nparts+part)*N + k)*nblk + b].  One WARP per
+ * output: lane l accumulates b = l, l+32, ... in order, then a fixed shuffle tree — deterministic for a given nblk, and
+ * 32 independent load chains instead of one thread walking nblk (up to 4736) values serially (was 20 us per call). */
+__global__ void __launch_bounds__(128) k_reduce_partials(const double *__restrict__ partial, double *__restrict__ out, uint32_t nblk, uint32_t total) {
+  const uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= total) return;
   const double *p = partial + (size_t)i * nblk;
   double s = 0.0;
-  for (uint32_t b = 0; b < nblk; ++b) s += p[b];
-  out[i] = s;
+  for (uint32_t b = lane; b < nblk; b += 32) s += p[b];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+  if (lane == 0) out[i] = s;
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -45,6 +45,8 @@ def load() -> FlatAPI:
         lib.nrxh_profile_enable.argtypes = [C.c_void_p, C.c_int]
         lib.nrxh_profile_read.restype = C.c_int
         lib.nrxh_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double)] + [C.POINTER(C.c_ulonglong)] * 3
+        lib.nrxh_profile_read_kind.restype = C.c_int
+        lib.nrxh_profile_read_kind.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)] + [C.POINTER(C.c_ulonglong)] * 3
         lib.nrxh_persite_lnl.restype = C.c_int
         lib.nrxh_persite_lnl.argtypes = [C.c_void_p, C.c_uint, np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), C.c_uint]
         lib.nrxh_engine.restype = C.c_void_p
@@ -111,6 +113,19 @@ class NetraxB200(LikelihoodEngine):
         l, u, b = C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong()
         self.api.check(self.api.lib.nrxh_profile_read(self.h, C.byref(ms), C.byref(l), C.byref(u), C.byref(b)))
         return {"clv_ms": ms.value, "clv_launches": l.value, "clv_site_updates": u.value, "clv_bytes": b.value}
+
+    PROF_KINDS = ("K2_clv_update", "K1_pmatrix", "K3_tree_lnl", "K3F_term_lnl_sum", "K4_edge_lnl", "K5_sumtable", "K6_derivatives",
+                  "reduce_partials", "slot_copy")  # NRX_PROF_* of include/nrx_engine.h
+
+    def profile_read_all(self):
+        """{kernel family: {ms, launches, units, bytes}} since profile_enable(True) (CUDA events on the engine stream)."""
+        out = {}
+        for kind, name in enumerate(self.PROF_KINDS):
+            ms = C.c_double()
+            l, u, b = C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong()
+            self.api.check(self.api.lib.nrxh_profile_read_kind(self.h, kind, C.byref(ms), C.byref(l), C.byref(u), C.byref(b)))
+            out[name] = {"ms": ms.value, "launches": l.value, "units": u.value, "bytes": b.value}
+        return out
 
     def persite_lnl(self, tree: int) -> np.ndarray:
         stride = max(p.sites for p in self.partitions)

@@ -322,6 +322,82 @@ def test_protein_dmma_equals_scalar_kernel(monkeypatch):
     g.close(); s.close()
 
 
+def test_protein_brlen_flow_every_edge_tensor_core_kernels():
+    """K4 (edge lnL) and K5 (sumtables) of 20-state partitions run on the FP64 tensor cores (k_aa20_dmma<AA_EDGE/AA_SUM>):
+    on EVERY edge (inner-inner and tip-inner pairs, reticulation edges) the edge-rooted lnL, every sumtable entry and the
+    derivatives at several proposal lengths must match the reference's AVX2 kernels under the oracle driver."""
+    net, part = _protein_case(14, 2, 301, 21)
+    g, o = _gpu(net, [part]), _oracle(net, [part])
+    _inject_eigen(g, o)
+    l0 = g.computeLoglikelihood(0, 1)
+    assert l0 == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
+    for e in range(net.num_edges):
+        assert g.brlen_prepare(e) == pytest.approx(o.brlen_prepare(e), rel=LNL_RTOL)
+        lb = g.computeLoglikelihoodBrlenOpt(e)
+        assert lb == pytest.approx(l0, rel=1e-11), e
+        assert lb == pytest.approx(o.computeLoglikelihoodBrlenOpt(e), rel=LNL_RTOL)
+        ng, no = g.computePartitionSumtables(e), o.computePartitionSumtables(e)
+        assert ng == no
+        for i in range(ng):
+            sg, so = g.read_sumtable(0, i)[0], o.read_sumtable(0, i)[0]
+            np.testing.assert_allclose(sg, so, rtol=1e-9, atol=1e-13 * np.abs(so).max())  # eigenvector sums cancel
+        if ng:
+            t0 = float(net.edge_length[e])
+            for t in (t0, 0.03, 0.9):
+                for eng in (g, o):
+                    eng.brlen_set_length(e, t)
+                dg, do = g.computeLoglikelihoodDerivatives(e), o.computeLoglikelihoodDerivatives(e)
+                np.testing.assert_allclose(dg[4], do[4], rtol=DERIV_RTOL, atol=1e-9)
+                assert dg[0] == pytest.approx(do[0], rel=DERIV_RTOL, abs=1e-7)
+                assert dg[1] == pytest.approx(do[1], rel=DERIV_RTOL, abs=1e-7)
+                assert g.computeLoglikelihoodBrlenOpt(e) == pytest.approx(o.computeLoglikelihoodBrlenOpt(e), rel=LNL_RTOL)
+            for eng in (g, o):
+                eng.brlen_set_length(e, t0)
+        assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL)
+    g.close()
+
+
+def test_protein_dmma_k4_k5_equal_scalar_kernels(monkeypatch):
+    """Tensor-core K4/K5 against this repo's own scalar 20-state kernels (NRX_AA=generic) incl. a ragged last tile."""
+    net, part = _protein_case(12, 1, 203, 9)
+    g = _gpu(net, [part])
+    monkeypatch.setenv("NRX_AA", "generic")
+    s = _gpu(net, [part])
+    g.computeLoglikelihood(0, 1); s.computeLoglikelihood(0, 1)
+    for e in (0, int(net.ret_first_edge[0]), net.num_edges - 1):
+        assert g.brlen_prepare(e) == pytest.approx(s.brlen_prepare(e), rel=1e-12)
+        assert g.computeLoglikelihoodBrlenOpt(e) == pytest.approx(s.computeLoglikelihoodBrlenOpt(e), rel=1e-12)
+        n = g.computePartitionSumtables(e)
+        assert n == s.computePartitionSumtables(e)
+        for i in range(n):
+            a, b = g.read_sumtable(0, i)[0], s.read_sumtable(0, i)[0]
+            np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-13 * np.abs(b).max())
+        g.brlen_finish(e); s.brlen_finish(e)
+    g.close(); s.close()
+
+
+def test_mixed_dna_and_protein_partitions():
+    """Two shape classes in one engine (4-state pipelined kernels + 20-state tensor-core kernels share the partial-sum
+    layout of every reduction): full lnL and one branch's flow against the oracle."""
+    net = random_network(12, 2, seed=31)
+    md, wd = simulate_alignment(net, 410, seed=31)
+    dna = Partition(4, 4, md, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=wd)
+    _, aa = _protein_case(12, 2, 150, 31, net=net)
+    g, o = _gpu(net, [dna, aa]), _oracle(net, [dna, aa])
+    _inject_eigen(g, o)
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
+    np.testing.assert_allclose(g.partition_loglh(), o.partition_loglh(), rtol=LNL_RTOL)
+    for e in (1, int(net.ret_first_edge[1])):
+        assert g.brlen_prepare(e) == pytest.approx(o.brlen_prepare(e), rel=LNL_RTOL)
+        assert g.computeLoglikelihoodBrlenOpt(e) == pytest.approx(o.computeLoglikelihoodBrlenOpt(e), rel=LNL_RTOL)
+        assert g.computePartitionSumtables(e) == o.computePartitionSumtables(e)
+        dg, do = g.computeLoglikelihoodDerivatives(e), o.computeLoglikelihoodDerivatives(e)
+        assert dg[0] == pytest.approx(do[0], rel=DERIV_RTOL, abs=1e-7)
+        assert dg[1] == pytest.approx(do[1], rel=DERIV_RTOL, abs=1e-7)
+        assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL)
+    g.close()
+
+
 def test_empty_partition_slice_is_skipped():
     """A site shard may own NO pattern of a partition (reference: partitions[p] == NULL, 'skip remote partitions',
     LH/ImprovedLoglikelihood.cpp:128-131): the engine must accept patterns = 0 and contribute exactly 0 to that partition."""

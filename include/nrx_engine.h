@@ -93,6 +93,8 @@ int nrx_set_pmatrix(nrx_engine *e, uint32_t p, uint32_t edge, const double *in);
 int nrx_reserve_slots(nrx_engine *e, uint32_t nslots);
 uint32_t nrx_num_slots(nrx_engine *e);
 int nrx_copy_slot(nrx_engine *e, uint32_t dst, uint32_t src); /* device-side deep copy (extractOldTrees etc.) */
+/* n copies dst[i] <- src[i] (all partitions) in one launch per partition shape */
+int nrx_copy_slots(nrx_engine *e, const uint32_t *dst, const uint32_t *src, uint32_t n);
 
 /* K2: ONE launch per same-shape partition group updating `nops` CLVs (all displayed trees of a node —
  * or of several independent nodes — x patterns x rate categories).  The ops must be mutually independent. */

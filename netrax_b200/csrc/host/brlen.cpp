@@ -129,7 +129,16 @@ NodeSaveInformation computeNodeSaveInformation(const std::vector<PathToVirtualRo
  * NodeDisplayedTreeData, i.e. memcpy's CLVs on the host: VirtualRerooting.cpp:211-220,234-238) */
 struct SavedNode { std::vector<DisplayedTreeData> trees; size_t num_active = 0; };
 
-SavedNode saveNode(AnnotatedNetwork &ann, size_t v) {
+struct SlotCopies {  // (dst, src) pairs of one save / restore step, issued as ONE device launch
+  std::vector<uint32_t> dst, src;
+  void add(uint32_t d, uint32_t s) { dst.push_back(d); src.push_back(s); }
+  void run(AnnotatedNetwork &ann) {
+    if (!dst.empty()) engineCheck(nrx_copy_slots(ann.engine, dst.data(), src.data(), (uint32_t)dst.size()), "nrx_copy_slots");
+    dst.clear(); src.clear();
+  }
+};
+
+SavedNode saveNode(AnnotatedNetwork &ann, size_t v, SlotCopies &copies) {
   SavedNode s;
   NodeDisplayedTreeData &nd = ann.pernode_displayed_tree_data[v];
   s.num_active = nd.num_active_displayed_trees;
@@ -137,14 +146,14 @@ SavedNode saveNode(AnnotatedNetwork &ann, size_t v) {
     DisplayedTreeData d = nd.displayed_trees[i];
     if (!d.isTip) {
       d.slot = allocSlot(ann);
-      engineCheck(nrx_copy_slot(ann.engine, d.slot, nd.displayed_trees[i].slot), "nrx_copy_slot");
+      copies.add(d.slot, nd.displayed_trees[i].slot);
     }
     s.trees.push_back(d);
   }
   return s;
 }
 
-void restoreNode(AnnotatedNetwork &ann, size_t v, const SavedNode &s) {
+void restoreNode(AnnotatedNetwork &ann, size_t v, const SavedNode &s, SlotCopies &copies) {
   NodeDisplayedTreeData &nd = ann.pernode_displayed_tree_data[v];
   if (v < ann.network.num_tips()) return;  // tips are immutable
   for (size_t i = 0; i < s.trees.size(); ++i) {
@@ -156,7 +165,7 @@ void restoreNode(AnnotatedNetwork &ann, size_t v, const SavedNode &s) {
     const uint32_t own = nd.displayed_trees[i].slot;
     nd.displayed_trees[i] = s.trees[i];
     nd.displayed_trees[i].slot = own;  // entries keep their own slot; only the contents come back
-    engineCheck(nrx_copy_slot(ann.engine, own, s.trees[i].slot), "nrx_copy_slot");
+    copies.add(own, s.trees[i].slot);
   }
   nd.num_active_displayed_trees = s.num_active;
 }
@@ -170,11 +179,14 @@ void updateCLVsVirtualRerootTrees(AnnotatedNetwork &ann, Node *old_virtual_root,
   const std::vector<PathToVirtualRoot> paths = getPathsToVirtualRoot(ann, old_vr, new_vr, back);
   const NodeSaveInformation info = computeNodeSaveInformation(paths);
   std::vector<SavedNode> buffered(ann.network.num_nodes());
-  for (size_t n : info.nodesInDanger) buffered[n] = saveNode(ann, n);
+  SlotCopies copies;
+  for (size_t n : info.nodesInDanger) buffered[n] = saveNode(ann, n, copies);
+  copies.run(ann);
   for (size_t p = 0; p < paths.size(); ++p) {
     if (!reticulationConfigsCompatible(paths[p].reticulationChoices, restrictions)) continue;
     if (!info.pathNodesToRestore[p].empty()) flushPendingOps(ann);
-    for (size_t n : info.pathNodesToRestore[p]) restoreNode(ann, n, buffered[n]);
+    for (size_t n : info.pathNodesToRestore[p]) restoreNode(ann, n, buffered[n], copies);
+    copies.run(ann);
     for (size_t i = 0; i < paths[p].path.size(); ++i) {
       const bool appendMode = (p > 0) && (paths[p].path[i] == new_vr);
       std::vector<Node *> children;

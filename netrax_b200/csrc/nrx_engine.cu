@@ -99,6 +99,7 @@ struct EnginePlan {
   std::vector<size_t> offsets;
   std::vector<uint32_t> sizes;
   std::vector<char> tips;
+  std::vector<uint32_t> ntt;   // leading tip-tip ops of each batch (20-state engines order them first)
   cudaGraphExec_t exec = nullptr;
   unsigned long long updates = 0, bytes = 0;
   uint32_t lnl_items = 0;    // number of ops carrying an lnl_item mark (fused K3)
@@ -630,6 +631,36 @@ int nrx_copy_slot(nrx_engine *e, uint32_t dst, uint32_t src) {
   return 1;
 }
 
+int nrx_copy_slots(nrx_engine *e, const uint32_t *dst, const uint32_t *src, uint32_t n) {
+  if (!e) { g_err = "null engine"; return 0; }
+  if (n == 0) return 1;
+  std::vector<uint2> pairs(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    if (dst[i] >= e->nslots || src[i] >= e->nslots) { g_err = "nrx_copy_slots: slot out of range"; return 0; }
+    pairs[i] = make_uint2(dst[i], src[i]);
+  }
+  CK(cudaSetDevice(e->device));
+  if (!refresh_views(e)) return 0;
+  uint2 *d_pairs;
+  if (!upload(e, pairs.data(), pairs.size(), &d_pairs)) return 0;
+  cudaEvent_t ev0, ev1;
+  prof_begin(e, &ev0, &ev1);
+  unsigned long long bytes = 0;
+  for (const Part &p : e->parts) bytes += 2ull * n * (p.clv_entries * sizeof(double) + (size_t)p.d.patterns * sizeof(uint32_t));
+  unsigned long long launches = 0;
+  for (const ShapeClass &c : e->classes) {
+    if (c.max_patterns == 0) continue;
+    const uint32_t z = (uint32_t)c.parts.size();
+    const uint64_t units = (uint64_t)c.max_patterns * c.cats * ((c.states + 3) & ~3u) / 4;
+    dim3 grid(tiles_for(units, BLOCK * 4, n * z), n, z);
+    k_copy_slots<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs);
+    e->launches++; launches++;
+    CK(cudaGetLastError());
+  }
+  prof_end(e, ev0, ev1, launches, n, bytes, NRX_PROF_COPY);
+  return 1;
+}
+
 /* validation + algorithmic-byte accounting of a batch of CLV updates */
 static int check_ops(nrx_engine *e, const nrx_op *ops, uint32_t nops, unsigned long long *updates, unsigned long long *bytes) {
   for (uint32_t i = 0; i < nops; ++i) {
@@ -658,7 +689,8 @@ static int check_ops(nrx_engine *e, const nrx_op *ops, uint32_t nops, unsigned l
 }
 
 /* K2 launches (one per partition shape class) for `nops` device-resident ops; `with_tips`: some op has a tip operand */
-static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, bool with_tips, bool fused = false) {
+static bool has_aa_dmma(const nrx_engine *e);
+static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, bool with_tips, bool fused = false, uint32_t ntt = 0) {
   for (const ShapeClass &c : e->classes) {
     if (c.max_patterns == 0) continue;
     const uint32_t z = (uint32_t)c.parts.size();
@@ -681,13 +713,26 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
         else { g_err = "NRX_K2: unknown register-kernel variant"; return 0; }
       }
     } else if (c.states == 20 && c.cats == 4 && !e->aa_generic && class_tip_codes(e, c) <= (uint32_t)AA_LUT_CODES) {
-      // protein: FP64 tensor cores (DMMA); 3 resident blocks of 4+1 warps per SM, 8-pattern tiles
+      // protein.  The first `ntt` ops are tip-tip: a table product, written by a plain streaming kernel
+      if (ntt) {
+        const uint32_t want = std::max<uint32_t>(1, (148u * 8 + ntt * z - 1) / (ntt * z));
+        uint32_t chunk = (c.max_patterns + want - 1) / want;
+        chunk = std::max<uint32_t>(64, (chunk + 31) & ~31u);
+        dim3 grid((c.max_patterns + chunk - 1) / chunk, ntt, z);
+        k_clv_aa20_tiptip<<<grid, BLOCK, (size_t)2 * class_tip_codes(e, c) * 80 * sizeof(double), e->stream>>>(c.d_views, d_ops, chunk);
+        if (ntt == nops) { e->launches++; CK(cudaGetLastError()); continue; }
+        e->launches++;
+      }
+      // the rest on the FP64 tensor cores (DMMA): 3 resident blocks of 4+1 warps per SM, 8-pattern tiles
+      const uint32_t rest = nops - ntt;
       const uint32_t ntiles = (c.max_patterns + AA_TP - 1) / AA_TP;
-      uint32_t groups = std::max<uint32_t>(1, (e->aa_blocks + nops * z - 1) / (nops * z));
+      uint32_t groups = std::max<uint32_t>(1, (e->aa_blocks + rest * z - 1) / (rest * z));
       groups = std::min(groups, std::max<uint32_t>(1, ntiles / 8));
-      dim3 grid(nops * groups, 1, z);
-      const size_t smem = sizeof(AaSmem) + (with_tips ? 2 * AA_LUT_CODES * 80 * sizeof(double) : 0);
-      k_aa20_dmma<AA_CLV><<<grid, AA_THREADS, smem, e->stream>>>(c.d_views, d_ops, nops, groups, with_tips ? 1 : 0, nullptr, 0, 0.0);
+      dim3 grid(rest * groups, 1, z);
+      // tip-tip ops went to the table kernel above unless that path is disabled: then two tables are needed
+      const int luts = !with_tips ? 0 : (has_aa_dmma(e) ? 1 : 2);
+      const size_t smem = sizeof(AaSmem) + (size_t)luts * class_tip_codes(e, c) * 80 * sizeof(double);
+      k_aa20_dmma<AA_CLV><<<grid, AA_THREADS, smem, e->stream>>>(c.d_views, d_ops + ntt, rest, groups, luts, nullptr, 0, 0.0);
     } else {
       dim3 grid(tiles_for(c.max_patterns, BLOCK, nops * z), nops, z);
       k_clv_generic<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops, nullptr);
@@ -696,6 +741,18 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
     CK(cudaGetLastError());
   }
   return 1;
+}
+
+/* engines with a 20-state tensor-core class order each batch tip-tip first (ops of a batch are independent) */
+static bool has_aa_dmma(const nrx_engine *e) {
+  for (const ShapeClass &c : e->classes)
+    if (c.states == 20 && c.cats == 4 && !e->aa_generic && class_tip_codes(e, c) <= (uint32_t)AA_LUT_CODES && !std::getenv("NRX_AA_NO_TT")) return true;
+  return false;
+}
+static uint32_t order_tiptip_first(const nrx_engine *e, std::vector<nrx_op> &ops) {
+  if (!has_aa_dmma(e)) return 0;
+  auto mid = std::stable_partition(ops.begin(), ops.end(), [](const nrx_op &o) { return o.left_kind == NRX_TIP && o.right_kind == NRX_TIP; });
+  return (uint32_t)(mid - ops.begin());
 }
 
 static bool any_tip(const nrx_op *ops, uint32_t nops) {
@@ -710,11 +767,13 @@ int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops) {
   unsigned long long updates = 0, bytes = 0;
   if (!check_ops(e, ops, nops, &updates, &bytes)) return 0;
   if (!refresh_views(e)) return 0;
+  std::vector<nrx_op> ordered(ops, ops + nops);
+  const uint32_t ntt = order_tiptip_first(e, ordered);
   nrx_op *d_ops;
-  if (!upload(e, ops, nops, &d_ops)) return 0;
+  if (!upload(e, ordered.data(), nops, &d_ops)) return 0;
   cudaEvent_t ev0, ev1;
   prof_begin(e, &ev0, &ev1);
-  if (!launch_clv_batch(e, d_ops, nops, any_tip(ops, nops))) return 0;
+  if (!launch_clv_batch(e, d_ops, nops, any_tip(ops, nops), false, ntt)) return 0;
   prof_end(e, ev0, ev1, e->classes.size(), updates, bytes);
   return 1;
 }
@@ -725,14 +784,19 @@ int nrx_plan_create(nrx_engine *e, const nrx_op *ops, const uint32_t *batch_size
   CK(cudaSetDevice(e->device));
   EnginePlan pl;
   size_t total = 0;
+  std::vector<nrx_op> ordered;
   for (uint32_t b = 0; b < nbatches; ++b) {
     if (batch_sizes[b] == 0) { g_err = "nrx_plan_create: empty batch"; return 0; }
     if (!check_ops(e, ops + total, batch_sizes[b], &pl.updates, &pl.bytes)) return 0;
     pl.offsets.push_back(total);
     pl.sizes.push_back(batch_sizes[b]);
     pl.tips.push_back(any_tip(ops + total, batch_sizes[b]));
+    std::vector<nrx_op> batch(ops + total, ops + total + batch_sizes[b]);
+    pl.ntt.push_back(order_tiptip_first(e, batch));
+    ordered.insert(ordered.end(), batch.begin(), batch.end());
     total += batch_sizes[b];
   }
+  ops = ordered.data();
   if (total) {
     CK(cudaMalloc((void **)&pl.d_ops, total * sizeof(nrx_op)));
     CK(cudaStreamSynchronize(e->stream));
@@ -770,7 +834,7 @@ int nrx_plan_run(nrx_engine *e, uint32_t plan_id) {
     const unsigned long long l0 = e->launches;
     CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
     int ok = 1;
-    for (size_t b = 0; b < pl.sizes.size() && ok; ++b) ok = launch_clv_batch(e, pl.d_ops + pl.offsets[b], pl.sizes[b], pl.tips[b], pl.lnl_items != 0);
+    for (size_t b = 0; b < pl.sizes.size() && ok; ++b) ok = launch_clv_batch(e, pl.d_ops + pl.offsets[b], pl.sizes[b], pl.tips[b], pl.lnl_items != 0, pl.ntt[b]);
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
     e->launches = l0;
@@ -784,7 +848,7 @@ int nrx_plan_run(nrx_engine *e, uint32_t plan_id) {
     e->launches += per_run;
   } else {
     for (size_t b = 0; b < pl.sizes.size(); ++b)
-      if (!launch_clv_batch(e, pl.d_ops + pl.offsets[b], pl.sizes[b], pl.tips[b], pl.lnl_items != 0)) return 0;
+      if (!launch_clv_batch(e, pl.d_ops + pl.offsets[b], pl.sizes[b], pl.tips[b], pl.lnl_items != 0, pl.ntt[b])) return 0;
   }
   prof_end(e, ev0, ev1, per_run, pl.updates, pl.bytes);
   return 1;
@@ -808,9 +872,18 @@ int nrx_plan_destroy(nrx_engine *e, uint32_t plan_id) {
   return 1;
 }
 
+static bool pow2_cats(const ShapeClass &c) { return c.cats <= 32 && (c.cats & (c.cats - 1)) == 0 && !std::getenv("NRX_NO_PC"); }
+
 /* blocks along x for the reduction kernels (one value per call: the partial-sum layout uses gridDim.x as its stride) */
 static uint32_t reduce_blocks(const nrx_engine *e, uint32_t items) {
-  const uint64_t full = std::max<uint64_t>(1, ((uint64_t)e->max_patterns + BLOCK - 1) / BLOCK);
+  // work items per (tree / pair): patterns for the thread-per-pattern kernels, patterns x categories where the class
+  // runs thread-per-(pattern, category) or, for the 20-state tensor-core kernels, tile groups
+  uint64_t work = 0;
+  for (const ShapeClass &c : e->classes) {
+    const bool dna4 = c.states == 4 && c.cats == 4;
+    work = std::max<uint64_t>(work, (uint64_t)c.max_patterns * ((!dna4 && pow2_cats(c)) ? c.cats : 1));
+  }
+  const uint64_t full = std::max<uint64_t>(1, (work + BLOCK - 1) / BLOCK);
   const uint64_t want = std::max<uint64_t>(1, (148ull * 32) / std::max<uint32_t>(1, items));  // ~32 blocks per SM in total
   return (uint32_t)std::min<uint64_t>(full, want);
 }
@@ -856,6 +929,8 @@ int nrx_tree_lnl(nrx_engine *e, const uint32_t *slots, uint32_t n, double *out, 
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
     if (c.states == 4 && c.cats == 4) k_tree_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
+    else if (pow2_cats(c) && c.states == 20) k_tree_lnl_pc<20><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
+    else if (pow2_cats(c)) k_tree_lnl_pc<0><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
     else k_tree_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
     e->launches++;
     CK(cudaGetLastError());
@@ -950,7 +1025,7 @@ int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n
       const std::vector<nrx_op> ops = pairs_to_ops(pairs, n, edge, false, &tips);
       nrx_op *d_ops;
       if (!upload(e, ops.data(), ops.size(), &d_ops)) return 0;
-      const size_t smem = sizeof(AaSmem) + (tips ? 2 * AA_LUT_CODES * 80 * sizeof(double) : 0);
+      const size_t smem = sizeof(AaSmem) + (tips ? (size_t)class_tip_codes(e, c) * 80 * sizeof(double) : 0);   // pairs are never tip-tip: one table
       k_aa20_dmma<AA_EDGE><<<dim3(n * nblk, 1, (uint32_t)c.parts.size()), AA_THREADS, smem, e->stream>>>(c.d_views, d_ops, n, nblk, tips ? 1 : 0, e->d_partial, P, log_thresh);
     }
     else k_edge_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh);
@@ -985,7 +1060,7 @@ int nrx_sumtables(nrx_engine *e, const nrx_pair *pairs, uint32_t n) {
       const uint32_t ntiles = (c.max_patterns + AA_TP - 1) / AA_TP;
       uint32_t groups = std::max<uint32_t>(1, (e->aa_blocks + n * z - 1) / (n * z));
       groups = std::min(groups, std::max<uint32_t>(1, ntiles / 8));
-      const size_t smem = sizeof(AaSmem) + (tips ? 2 * AA_LUT_CODES * 80 * sizeof(double) : 0);
+      const size_t smem = sizeof(AaSmem) + (tips ? (size_t)class_tip_codes(e, c) * 80 * sizeof(double) : 0);
       k_aa20_dmma<AA_SUM><<<dim3(n * groups, 1, z), AA_THREADS, smem, e->stream>>>(c.d_views, d_ops, n, groups, tips ? 1 : 0, nullptr, 0, 0.0);
     } else {
       dim3 grid(tiles_for((uint64_t)c.max_patterns * c.cats, BLOCK, n * z), n, z);
@@ -1032,6 +1107,8 @@ int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen, double *out)
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
     if (c.states == 4 && c.cats == 4) k_derivatives_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P);
+    else if (pow2_cats(c) && c.states == 20) k_derivatives_pc<20><<<grid, BLOCK, ((size_t)c.cats * c.states * 4 + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P);
+    else if (pow2_cats(c)) k_derivatives_pc<0><<<grid, BLOCK, ((size_t)c.cats * c.states * 4 + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P);
     else k_derivatives<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P);
     e->launches++;
     CK(cudaGetLastError());

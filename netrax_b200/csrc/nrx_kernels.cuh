@@ -461,6 +461,36 @@ __global__ void k_tip_lut20(PartView pv, double *lut_out, const uint32_t *edge_i
   }
 }
 
+/* K2, protein, tip-tip ops: the parent CLV is a pure table product lutL[code_l] * lutR[code_r] (the reference's
+ * tip-tip case, LIBPLL/core_partials.c:371-470: scaler := 0, no scaling test), i.e. a 640 B/pattern WRITE stream.
+ * Both edge tables (K1b) sit in shared memory; thread = one double2 of the output, a warp writes 512 contiguous bytes. */
+__global__ void __launch_bounds__(BLOCK) k_clv_aa20_tiptip(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops, uint32_t chunk) {
+  extern __shared__ __align__(16) double tt_lut[];
+  const PartView &pv = parts[blockIdx.z];
+  const nrx_op op = ops[blockIdx.y];
+  const uint64_t p_lo = (uint64_t)blockIdx.x * chunk;
+  if (p_lo >= pv.patterns) return;
+  const uint64_t p_hi = (p_lo + chunk < pv.patterns) ? p_lo + chunk : pv.patterns;
+  const uint32_t n_lut = pv.tip_codes * 80;
+  double *lutL = tt_lut, *lutR = tt_lut + n_lut;
+  const double *gl = pv.tiplut + (size_t)op.left_edge * AA_LUT_CODES * 80, *gr = pv.tiplut + (size_t)op.right_edge * AA_LUT_CODES * 80;
+  for (uint32_t i = threadIdx.x; i < n_lut; i += BLOCK) { lutL[i] = gl[i]; lutR[i] = gr[i]; }
+  __syncthreads();
+  const uint8_t *tipL = pv.tipchars + (size_t)op.left_idx * pv.tip_pitch, *tipR = pv.tipchars + (size_t)op.right_idx * pv.tip_pitch;
+  double2 *par = reinterpret_cast<double2 *>(pv.clv[op.parent_slot]);
+  uint32_t *psc = pv.scaler[op.parent_slot];
+  const double2 *l2 = reinterpret_cast<const double2 *>(lutL), *r2 = reinterpret_cast<const double2 *>(lutR);
+  for (uint64_t f = p_lo * 40 + threadIdx.x; f < p_hi * 40; f += BLOCK) {
+    const uint64_t pat = f / 40;
+    const uint32_t r = (uint32_t)(f - pat * 40);
+    const double2 a = l2[(uint32_t)tipL[pat] * 40 + r], b = r2[(uint32_t)tipR[pat] * 40 + r];
+    double2 v;
+    v.x = __dmul_rn(a.x, b.x); v.y = __dmul_rn(a.y, b.y);
+    par[f] = v;
+    if (r == 0) psc[pat] = 0u;
+  }
+}
+
 /* The same pipeline serves all three 20-state contractions (MODE):
  *   AA_CLV  (K2): parent = (P_l . left) * (P_r . right), scaled, stored as a CLV slot.
  *   AA_SUM  (K5): sumtable = (A_L . left) * (A_R . right) with the category-independent eigen matrices of PartView::summat
@@ -477,9 +507,11 @@ __global__ void __launch_bounds__(AA_THREADS, 3) k_aa20_dmma(const PartView *__r
                                                               double *__restrict__ partial, uint32_t nparts_total, double log_thresh) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   AaSmem &sm = *reinterpret_cast<AaSmem *>(smem_raw);
-  double *lutL = reinterpret_cast<double *>(smem_raw + sizeof(AaSmem));
-  double *lutR = lutL + AA_LUT_CODES * 80;
+  // with_lut: 0 = no tip operand in this launch, 1 = every op has at most ONE tip operand (both tables alias one
+  // buffer of tip_codes x 640 B: 3 resident blocks per SM), 2 = tip-tip ops present (two tables)
   const PartView &pv = parts[blockIdx.z];
+  double *lutL = reinterpret_cast<double *>(smem_raw + sizeof(AaSmem));
+  double *lutR = (with_lut == 2) ? lutL + pv.tip_codes * 80 : lutL;
   const nrx_op op = ops[blockIdx.x % nops];
   const uint32_t grp = blockIdx.x / nops;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -943,6 +975,140 @@ __global__ void __launch_bounds__(BLOCK) k_derivatives(const PartView *__restric
     acc[0] += pw * log(lk0);
     acc[1] += pw * d1;
     acc[2] += pw * d2;
+  }
+  block_sum<3>(acc, red);
+  if (threadIdx.x == 0) {
+    double *p = partial + ((size_t)blockIdx.y * nparts_total + pv.part_index) * 3 * gridDim.x;
+    p[0 * gridDim.x + blockIdx.x] = acc[0];
+    p[1 * gridDim.x + blockIdx.x] = acc[1];
+    p[2 * gridDim.x + blockIdx.x] = acc[2];
+  }
+}
+
+/* Slot copies of the virtual re-rooting save/restore (the reference copy-assigns NodeDisplayedTreeData, i.e. memcpy's
+ * every CLV of a node on the host, LH/VirtualRerooting.cpp:211-220,234-238): all (dst, src) pairs x partitions in ONE
+ * launch instead of two cudaMemcpyAsync per slot and partition.  grid = (chunks, pairs, partitions of this shape). */
+__global__ void __launch_bounds__(BLOCK) k_copy_slots(const PartView *__restrict__ parts, const uint2 *__restrict__ dst_src) {
+  const PartView &pv = parts[blockIdx.z];
+  const uint2 ds = dst_src[blockIdx.y];
+  const uint64_t n4 = (uint64_t)pv.patterns * pv.cats * pv.sp / 4;   // sp is a multiple of 4: 32-byte units
+  const double *src = pv.clv[ds.y];
+  double *dst = pv.clv[ds.x];
+  for (uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * BLOCK) stg256(dst + i * 4, ldg256(src + i * 4));
+  const uint32_t *ssrc = pv.scaler[ds.y];
+  uint32_t *sdst = pv.scaler[ds.x];
+  for (uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; i < pv.patterns; i += (uint64_t)gridDim.x * BLOCK) sdst[i] = ssrc[i];
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K3 / K6 for any state count when the category count is a power of two (the 20-state case): thread = one
+ * (pattern, category) item = `sp` contiguous doubles read as 256-bit loads (a warp covers 32 consecutive items =
+ * one contiguous span), the per-category results of a pattern are gathered IN CATEGORY ORDER from the adjacent
+ * lanes (same summation order as the thread-per-pattern kernels above and as the reference), constants in shared
+ * memory.  4x the threads and 1/4 of the load instructions of the thread-per-pattern version.
+ * ---------------------------------------------------------------------------------------------- */
+template <int SC /* compile-time state count (loops unroll, all loads issue up front); 0 = run time */>
+__global__ void __launch_bounds__(BLOCK) k_tree_lnl_pc(const PartView *__restrict__ parts, const uint32_t *__restrict__ slots,
+                                                        double *__restrict__ partial, uint32_t nparts_total, double log_thresh,
+                                                        double *__restrict__ persite, size_t persite_stride) {
+  __shared__ double red[BLOCK / 32];
+  __shared__ double sfreq[32], swt[32];
+  const PartView &pv = parts[blockIdx.z];
+  const uint32_t S = SC ? (uint32_t)SC : pv.states, SP = SC ? (uint32_t)((SC + 3) & ~3) : pv.sp, C = pv.cats;
+  const uint32_t slot = slots[blockIdx.y];
+  const double *clv = pv.clv[slot];
+  const uint32_t *sc = pv.scaler[slot];
+  if (threadIdx.x < S) sfreq[threadIdx.x] = pv.freqs[threadIdx.x];
+  if (threadIdx.x < C) swt[threadIdx.x] = pv.rate_weights[threadIdx.x];
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, c = threadIdx.x & (C - 1);
+  const uint64_t n_items = (uint64_t)pv.patterns * C;
+  const uint64_t span = ((n_items + BLOCK - 1) / BLOCK) * BLOCK;  // whole warps stay in the loop for the shuffles
+  double acc[1] = {0.0};
+  for (uint64_t g = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; g < span; g += (uint64_t)gridDim.x * BLOCK) {
+    double t = 0.0;
+    if (g < n_items) {
+      const double *v = clv + g * SP;
+      double term_r = 0.0;
+#pragma unroll
+      for (uint32_t k = 0; k < SP; k += 4) {
+        const D4 q = ldg256(v + k);
+        term_r = __dadd_rn(term_r, __dmul_rn(q.x, sfreq[k]));
+        if (k + 1 < S) term_r = __dadd_rn(term_r, __dmul_rn(q.y, sfreq[k + 1]));
+        if (k + 2 < S) term_r = __dadd_rn(term_r, __dmul_rn(q.z, sfreq[k + 2]));
+        if (k + 3 < S) term_r = __dadd_rn(term_r, __dmul_rn(q.w, sfreq[k + 3]));
+      }
+      t = __dmul_rn(term_r, swt[c]);
+    }
+    double term = 0.0;
+    for (uint32_t i = 0; i < C; ++i) term = __dadd_rn(term, __shfl_sync(0xffffffffu, t, (lane & ~(C - 1)) + i));
+    if (c == 0 && g < n_items) {
+      const uint64_t n = g / C;
+      double lk = log(term);
+      const uint32_t s = sc[n];
+      if (s) lk = __dadd_rn(lk, __dmul_rn((double)s, log_thresh));
+      lk = __dmul_rn(lk, (double)pv.weights[n]);
+      if (persite) persite[((size_t)blockIdx.y * nparts_total + pv.part_index) * persite_stride + n] = lk;
+      acc[0] += lk;
+    }
+  }
+  block_sum<1>(acc, red);
+  if (threadIdx.x == 0) partial[((size_t)blockIdx.y * nparts_total + pv.part_index) * gridDim.x + blockIdx.x] = acc[0];
+}
+
+template <int SC>
+__global__ void __launch_bounds__(BLOCK) k_derivatives_pc(const PartView *__restrict__ parts, double *__restrict__ partial,
+                                                           uint32_t nparts_total) {
+  __shared__ double red[3 * (BLOCK / 32)];
+  extern __shared__ double sdiag[];  // [cats][states][4] + [cats] rate weights
+  const PartView &pv = parts[blockIdx.z];
+  const uint32_t S = SC ? (uint32_t)SC : pv.states, SP = SC ? (uint32_t)((SC + 3) & ~3) : pv.sp, C = pv.cats;
+  double *swt = sdiag + (size_t)C * S * 4;
+  for (uint32_t i = threadIdx.x; i < C * S * 4; i += BLOCK) sdiag[i] = pv.diagp[i];
+  if (threadIdx.x < C) swt[threadIdx.x] = pv.rate_weights[threadIdx.x];
+  __syncthreads();
+  const double *st = pv.sumtable[blockIdx.y];
+  const uint32_t lane = threadIdx.x & 31, c = threadIdx.x & (C - 1);
+  const double *dg = sdiag + (size_t)c * S * 4;
+  const uint64_t n_items = (uint64_t)pv.patterns * C;
+  const uint64_t span = ((n_items + BLOCK - 1) / BLOCK) * BLOCK;
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (uint64_t g = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; g < span; g += (uint64_t)gridDim.x * BLOCK) {
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    if (g < n_items) {
+      const double *v = st + g * SP;
+      double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+#pragma unroll
+      for (uint32_t k = 0; k < SP; k += 4) {
+        const D4 q = ldg256(v + k);
+        const double e[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (uint32_t h = 0; h < 4; ++h)
+          if (k + h < S) {
+            const double2 d01 = *reinterpret_cast<const double2 *>(dg + (k + h) * 4);
+            c0 = __dadd_rn(c0, __dmul_rn(e[h], d01.x));
+            c1 = __dadd_rn(c1, __dmul_rn(e[h], d01.y));
+            c2 = __dadd_rn(c2, __dmul_rn(e[h], dg[(k + h) * 4 + 2]));
+          }
+      }
+      const double w = swt[c];
+      t0 = __dmul_rn(c0, w); t1 = __dmul_rn(c1, w); t2 = __dmul_rn(c2, w);
+    }
+    double lk0 = 0.0, lk1 = 0.0, lk2 = 0.0;
+    for (uint32_t i = 0; i < C; ++i) {
+      const int src = (int)((lane & ~(C - 1)) + i);
+      lk0 = __dadd_rn(lk0, __shfl_sync(0xffffffffu, t0, src));
+      lk1 = __dadd_rn(lk1, __shfl_sync(0xffffffffu, t1, src));
+      lk2 = __dadd_rn(lk2, __shfl_sync(0xffffffffu, t2, src));
+    }
+    if (c == 0 && g < n_items) {
+      const double pw = (double)pv.weights[g / C];
+      const double d1 = -lk1 / lk0;
+      const double d2 = d1 * d1 - lk2 / lk0;
+      acc[0] += pw * log(lk0);
+      acc[1] += pw * d1;
+      acc[2] += pw * d2;
+    }
   }
   block_sum<3>(acc, red);
   if (threadIdx.x == 0) {

@@ -398,6 +398,28 @@ def test_mixed_dna_and_protein_partitions():
     g.close()
 
 
+@pytest.mark.parametrize("cats", [1, 2, 3, 8])
+def test_other_category_counts_use_generic_kernels(cats):
+    """GTR + Gamma with 1, 2, 3 or 8 rate categories: the 4x4 specialisations do not apply, so K2-K6 go through the
+    generic kernels (power-of-two category counts: thread per (pattern, category); 3: thread per pattern)."""
+    from oracle import oracle
+    net = random_network(11, 2, seed=40 + cats)
+    m, w = simulate_alignment(net, 333, seed=40 + cats)
+    rates = oracle.api("port").gamma_rates(0.7, cats) if cats > 1 else np.ones(1)
+    part = Partition(4, cats, m, DNA_FREQS, GTR_RATES, rates, pattern_weights=w)
+    g, o = _gpu(net, [part]), _oracle(net, [part])
+    _inject_eigen(g, o)
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
+    for e in (0, int(net.ret_first_edge[0]), net.num_edges - 1):
+        assert g.brlen_prepare(e) == pytest.approx(o.brlen_prepare(e), rel=LNL_RTOL)
+        assert g.computeLoglikelihoodBrlenOpt(e) == pytest.approx(o.computeLoglikelihoodBrlenOpt(e), rel=LNL_RTOL)
+        assert g.computePartitionSumtables(e) == o.computePartitionSumtables(e)
+        dg, do = g.computeLoglikelihoodDerivatives(e), o.computeLoglikelihoodDerivatives(e)
+        np.testing.assert_allclose(dg[4], do[4], rtol=DERIV_RTOL, atol=1e-9)
+        assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL)
+    g.close()
+
+
 def test_empty_partition_slice_is_skipped():
     """A site shard may own NO pattern of a partition (reference: partitions[p] == NULL, 'skip remote partitions',
     LH/ImprovedLoglikelihood.cpp:128-131): the engine must accept patterns = 0 and contribute exactly 0 to that partition."""

@@ -359,7 +359,8 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
     if (!cuda_ok(cudaFuncSetAttribute(k_aa20_dmma<AA_CLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa_smem), "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(k_aa20_dmma<AA_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa_smem), "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(k_aa20_dmma<AA_EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa_smem), "cudaFuncSetAttribute")) { delete e; return nullptr; }
-    if (!cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClvPipeSmem)), "cudaFuncSetAttribute")) { delete e; return nullptr; }
+    if (!cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClvPipeSmem)), "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClvPipeSmem)), "cudaFuncSetAttribute")) { delete e; return nullptr; }
   }
   for (uint32_t i = 0; i < nparts; ++i) {
     Part &p = e->parts[i];
@@ -695,14 +696,18 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
     if (c.max_patterns == 0) continue;
     const uint32_t z = (uint32_t)c.parts.size();
     if (c.states == 4 && c.cats == 4) {
-      if (e->k2_variant == 0) {
+      if (e->k2_variant == 0 || e->k2_variant == 1) {
         // bulk-async pipeline: 2 resident blocks per SM; block b = (op b % nops, tile group b / nops)
         const uint32_t ntiles = (c.max_patterns + TP - 1) / TP;
         uint32_t groups = std::max<uint32_t>(1, (e->k2_blocks + nops * z - 1) / (nops * z));
         groups = std::min(groups, std::max<uint32_t>(1, ntiles / 4));  // >= 4 tiles per block: amortise the pipeline fill
         dim3 grid(nops * groups, 1, z);
-        k_clv_dna4_pipe<<<grid, BLOCK, sizeof(ClvPipeSmem), e->stream>>>(c.d_views, d_ops, nops, groups, fused ? e->d_fused : nullptr,
-                                                                         (size_t)e->max_patterns, (uint32_t)e->parts.size());
+        if (e->k2_variant == 0)
+          k_clv_dna4_pipe2<<<grid, BLOCK, sizeof(ClvPipeSmem), e->stream>>>(c.d_views, d_ops, nops, groups, fused ? e->d_fused : nullptr,
+                                                                            (size_t)e->max_patterns, (uint32_t)e->parts.size());
+        else
+          k_clv_dna4_pipe<<<grid, BLOCK, sizeof(ClvPipeSmem), e->stream>>>(c.d_views, d_ops, nops, groups, fused ? e->d_fused : nullptr,
+                                                                           (size_t)e->max_patterns, (uint32_t)e->parts.size());
       } else {
         const uint32_t U = e->k2_variant / 10, MB = e->k2_variant % 10;
         dim3 grid(tiles_for((uint64_t)c.max_patterns * 4, BLOCK * U, nops * z), nops, z);
@@ -855,7 +860,7 @@ int nrx_plan_run(nrx_engine *e, uint32_t plan_id) {
 }
 
 int nrx_supports_fused_lnl(nrx_engine *e) {
-  if (!e || e->k2_variant != 0 || std::getenv("NRX_NO_FUSED_LNL")) return 0;
+  if (!e || (e->k2_variant != 0 && e->k2_variant != 1) || std::getenv("NRX_NO_FUSED_LNL")) return 0;
   for (const ShapeClass &c : e->classes) if (!(c.states == 4 && c.cats == 4)) return 0;
   return 1;
 }

@@ -48,6 +48,9 @@ int nrxh_init(void *h);
 int nrxh_comm_get_unique_id(uint8_t *id128);
 int nrxh_comm_init(void *h, const uint8_t *id128, int rank, int nranks);
 int nrxh_compute_loglikelihood(void *h, int incremental, int update_pmatrices, double *out);
+/* batched scoring of n networks (n handles, one engine / CUDA stream each): all evaluations are enqueued, then collected;
+ * out[i] == nrxh_compute_loglikelihood(handles[i], ...) (reference: the sequential candidate loop of src/search/Filtering.cpp:210-260) */
+int nrxh_compute_loglikelihood_batch(void **handles, unsigned n, int incremental, int update_pmatrices, double *out);
 unsigned nrxh_num_partitions(void *h);
 unsigned nrxh_root(void *h);
 unsigned nrxh_num_nodes(void *h);

@@ -118,6 +118,12 @@ int nrx_plan_destroy(nrx_engine *e, uint32_t plan_id);
  * persite (optional): [n] pointers-free layout out_persite[(i * nparts + p) * max_patterns + site]. */
 int nrx_tree_lnl(nrx_engine *e, const uint32_t *slots, uint32_t n, double *out, double *persite,
                  size_t persite_stride);
+/* Asynchronous forms for batched scoring of several networks (one engine = one stream each): the launches, the
+ * cross-rank all-reduce and the device->host copy are enqueued and the call returns; nrx_result_wait blocks on THIS
+ * engine's stream and hands out the `count` = n * nparts doubles.  One result may be pending per engine. */
+int nrx_tree_lnl_async(nrx_engine *e, const uint32_t *slots, uint32_t n);
+int nrx_tree_lnl_fused_async(nrx_engine *e, uint32_t plan_id, const uint32_t *slots, uint32_t n);
+int nrx_result_wait(nrx_engine *e, double *out, uint32_t count);
 /* K4: edge lnL for n operand pairs over P-matrix `edge`, out[n][nparts]. */
 int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n, double *out);
 /* K5: sumtables for n pairs into sumtable slots [0, n) (pool grows on demand). */

@@ -150,6 +150,15 @@ int nrxh_compute_loglikelihood(void *hv, int incremental, int update_pmatrices, 
   return guarded([&] { *out = computeLoglikelihood(H(hv)->ann, incremental, update_pmatrices); });
 }
 
+int nrxh_compute_loglikelihood_batch(void **handles, unsigned n, int incremental, int update_pmatrices, double *out) {
+  return guarded([&] {
+    std::vector<AnnotatedNetwork *> anns;
+    for (unsigned i = 0; i < n; ++i) anns.push_back(&H(handles[i])->ann);
+    const std::vector<double> r = computeLoglikelihoodBatch(anns, incremental, update_pmatrices);
+    for (unsigned i = 0; i < n; ++i) out[i] = r[i];
+  });
+}
+
 unsigned nrxh_num_partitions(void *hv) { return H(hv)->ann.fake_treeinfo->partition_count; }
 unsigned nrxh_root(void *hv) { return (unsigned)H(hv)->ann.network.root->clv_index; }
 unsigned nrxh_num_nodes(void *hv) { return (unsigned)H(hv)->ann.network.num_nodes(); }

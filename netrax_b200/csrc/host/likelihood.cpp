@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <exception>
 
 #include "host_internal.hpp"
 
@@ -495,10 +496,11 @@ void processNodeImproved(AnnotatedNetwork &ann, int incremental, Node *node, std
   validateSingleClv(ann, v);
 }
 
-/* computeDisplayedTreeLoglikelihood (:410-486) for ALL root trees: one K3 launch, one reduction */
-static void computeDisplayedTreeLoglikelihoods(AnnotatedNetwork &ann, Node *actRoot, bool replayed, std::vector<uint32_t> *slots_out) {
+/* computeDisplayedTreeLoglikelihood (:410-486) for ALL root trees: one K3 launch, one reduction.  Split in two so that
+ * several networks can be in flight at once (computeLoglikelihoodBatch): Begin selects the trees and enqueues the device
+ * work without blocking, End collects the [trees][partitions] sums. */
+static void treeLoglikelihoodsBegin(AnnotatedNetwork &ann, Node *actRoot, bool replayed, std::vector<uint32_t> *slots_out) {
   NodeDisplayedTreeData &rd = ann.pernode_displayed_tree_data[actRoot->clv_index];
-  const unsigned P = ann.fake_treeinfo->partition_count;
   std::vector<uint32_t> slots;
   std::vector<size_t> which;
   for (size_t i = 0; i < rd.num_active_displayed_trees; ++i) {
@@ -520,15 +522,27 @@ static void computeDisplayedTreeLoglikelihoods(AnnotatedNetwork &ann, Node *actR
     which.push_back(i);
   }
   flushPendingOps(ann);
-  std::vector<double> out(slots.size() * P, 0.0);
   if (slots_out) *slots_out = slots;
   if (!slots.empty()) {
     // after a plan replay whose ops carried lnl marks for exactly these trees, K2 has already written the per-site lnLs
     if (replayed && ann.plan->fused && ann.plan->on_device && slots == ann.plan->lnl_slots)
-      engineCheck(nrx_tree_lnl_fused(ann.engine, ann.plan->engine_plan, slots.data(), (uint32_t)slots.size(), out.data()), "nrx_tree_lnl_fused");
+      engineCheck(nrx_tree_lnl_fused_async(ann.engine, ann.plan->engine_plan, slots.data(), (uint32_t)slots.size()), "nrx_tree_lnl_fused");
     else
-      engineCheck(nrx_tree_lnl(ann.engine, slots.data(), (uint32_t)slots.size(), out.data(), nullptr, 0), "nrx_tree_lnl");
+      engineCheck(nrx_tree_lnl_async(ann.engine, slots.data(), (uint32_t)slots.size()), "nrx_tree_lnl");
   }
+  ann.pending_root = actRoot->clv_index;
+  ann.pending_trees = which;
+  ann.pending_eval = true;
+}
+
+static void treeLoglikelihoodsEnd(AnnotatedNetwork &ann) {
+  if (!ann.pending_eval) return;
+  ann.pending_eval = false;
+  NodeDisplayedTreeData &rd = ann.pernode_displayed_tree_data[ann.pending_root];
+  const unsigned P = ann.fake_treeinfo->partition_count;
+  const std::vector<size_t> &which = ann.pending_trees;
+  std::vector<double> out(which.size() * P, 0.0);
+  if (!which.empty()) engineCheck(nrx_result_wait(ann.engine, out.data(), (uint32_t)out.size()), "nrx_result_wait");
   reduceSum(ann, out.data(), out.size());  // C2: one reduction for all trees (reference: one per tree)
   for (size_t k = 0; k < which.size(); ++k) {
     TreeLoglData &t = rd.displayed_trees[which[k]].treeLoglData;
@@ -624,14 +638,15 @@ static void processPartitionsImproved(AnnotatedNetwork &ann, int incremental) { 
       pc.recording = false;
       snapshotPlan(ann);
       std::vector<uint32_t> root_slots;
-      computeDisplayedTreeLoglikelihoods(ann, ann.network.root, false, &root_slots);
+      treeLoglikelihoodsBegin(ann, ann.network.root, false, &root_slots);
+      treeLoglikelihoodsEnd(ann);   // creating the engine plan synchronises anyway (first evaluation of a topology)
       createEnginePlan(ann, root_slots);
       return;
     }
-    computeDisplayedTreeLoglikelihoods(ann, ann.network.root, false, nullptr);
+    treeLoglikelihoodsBegin(ann, ann.network.root, false, nullptr);
     return;
   }
-  computeDisplayedTreeLoglikelihoods(ann, ann.network.root, true, nullptr);
+  treeLoglikelihoodsBegin(ann, ann.network.root, true, nullptr);
 }
 
 double evaluateTreesPartition(AnnotatedNetwork &ann, size_t p, std::vector<TreeLoglData> &trees) {  // :521-604
@@ -684,17 +699,62 @@ static bool reuseOldDisplayedTreesCheck(AnnotatedNetwork &ann, int incremental, 
   return true;
 }
 
-double computeLoglikelihoodImproved(AnnotatedNetwork &ann, int incremental, int update_pmatrices) {  // :646-671
+/* computeLoglikelihoodImproved (:646-671) in two halves: Begin enqueues P-matrices, CLV updates, per-tree root lnLs,
+ * the cross-rank reduction and the result copy on the network's own stream and returns; End waits for that stream and
+ * mixes the trees.  computeLoglikelihoodImproved = Begin + End. */
+static void computeLoglikelihoodImprovedBegin(AnnotatedNetwork &ann, int incremental, int update_pmatrices) {
+  if (ann.pending_eval) throw std::runtime_error("computeLoglikelihoodBegin: an evaluation of this network is already in flight");
+  ann.begin_returns_cached = false;
   if (!incremental) invalidateAllCLVs(ann);
   const bool reuse = reuseOldDisplayedTreesCheck(ann, incremental, ann.network.root->clv_index);
   if (reuse) {
-    if (ann.cached_logl_valid) return ann.cached_logl;
-  } else {
-    if (update_pmatrices) pllmod_treeinfo_update_prob_matrices(ann, !incremental);
-    processPartitionsImproved(ann, incremental);
+    if (ann.cached_logl_valid) ann.begin_returns_cached = true;
+    return;
+  }
+  if (update_pmatrices) pllmod_treeinfo_update_prob_matrices(ann, !incremental);
+  ann.begin_ran_traversal = true;
+  processPartitionsImproved(ann, incremental);
+}
+
+static double computeLoglikelihoodImprovedEnd(AnnotatedNetwork &ann) {
+  if (ann.begin_returns_cached) { ann.begin_returns_cached = false; return ann.cached_logl; }
+  treeLoglikelihoodsEnd(ann);
+  if (ann.begin_ran_traversal) {
+    ann.begin_ran_traversal = false;
     if (!clvValidCheck(ann, ann.network.root->clv_index)) throw std::runtime_error("Invalid displayed trees after loglikelihood computation");
   }
   return evaluateTrees(ann, ann.network.root);
+}
+
+double computeLoglikelihoodImproved(AnnotatedNetwork &ann, int incremental, int update_pmatrices) {  // :646-671
+  computeLoglikelihoodImprovedBegin(ann, incremental, update_pmatrices);
+  return computeLoglikelihoodImprovedEnd(ann);
+}
+
+/* Batched scoring: the reference scores candidate networks one after the other
+ * (src/search/Filtering.cpp:210-260: performMove -> optimise -> scoreNetwork -> undoMove); here every candidate is its
+ * own AnnotatedNetwork = its own engine and CUDA stream, all evaluations are enqueued first and collected afterwards,
+ * so the small kernels of different candidates overlap on the GPU and the host never idles on one stream at a time.
+ * Result i is exactly computeLoglikelihood(*anns[i], incremental, update_pmatrices). */
+std::vector<double> computeLoglikelihoodBatch(const std::vector<AnnotatedNetwork *> &anns, int incremental, int update_pmatrices) {
+  for (AnnotatedNetwork *a : anns)
+    if (a->options.likelihood_variant == LikelihoodVariant::SARAH_PSEUDO)
+      throw std::runtime_error("SARAH_PSEUDO is not implemented by this engine (disabled in the reference CLI, src/main.cpp:115-116)");
+  std::vector<double> out(anns.size(), 0.0);
+  size_t begun = 0;
+  try {
+    for (; begun < anns.size(); ++begun) computeLoglikelihoodImprovedBegin(*anns[begun], incremental, update_pmatrices);
+  } catch (...) {
+    for (size_t i = 0; i < begun; ++i) { try { computeLoglikelihoodImprovedEnd(*anns[i]); } catch (...) {} }
+    throw;
+  }
+  std::exception_ptr first;
+  for (size_t i = 0; i < anns.size(); ++i) {
+    try { out[i] = computeLoglikelihoodImprovedEnd(*anns[i]); }
+    catch (...) { if (!first) first = std::current_exception(); anns[i]->pending_eval = false; }
+  }
+  if (first) std::rethrow_exception(first);
+  return out;
 }
 
 double computeLoglikelihood(AnnotatedNetwork &ann, int incremental, int update_pmatrices) {  // LikelihoodComputation.cpp:18-33

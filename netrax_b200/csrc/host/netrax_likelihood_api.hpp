@@ -209,6 +209,10 @@ struct AnnotatedNetwork {  // src/graph/AnnotatedNetwork.hpp:42-89
   PlanCache *plan = nullptr;
   bool use_plan_cache = true;
   uint64_t clv_site_updates = 0;              // Σ trees × local patterns actually launched
+  bool pending_eval = false;                  // root-tree lnLs enqueued on the engine stream, not yet collected (batched scoring)
+  bool begin_returns_cached = false, begin_ran_traversal = false;
+  size_t pending_root = 0;
+  std::vector<size_t> pending_trees;
   ~AnnotatedNetwork();
   AnnotatedNetwork() = default;
   AnnotatedNetwork(const AnnotatedNetwork &) = delete;
@@ -227,6 +231,8 @@ void topology_changed(AnnotatedNetwork &ann);  // callers that edit the topology
 /* ---- the likelihood API --------------------------------------------------------------------------------- */
 double computeLoglikelihood(AnnotatedNetwork &ann_network, int incremental = 1, int update_pmatrices = 1);
 double computeLoglikelihoodImproved(AnnotatedNetwork &ann_network, int incremental, int update_pmatrices);
+/* batched scoring of candidate networks (one engine / stream each): result[i] == computeLoglikelihood(*anns[i], ...) */
+std::vector<double> computeLoglikelihoodBatch(const std::vector<AnnotatedNetwork *> &anns, int incremental = 1, int update_pmatrices = 1);
 void processNodeImproved(AnnotatedNetwork &ann_network, int incremental, Node *node, std::vector<Node *> &children,
                          const ReticulationConfigSet &extraRestrictions, bool append = false);
 double evaluateTreesPartition(AnnotatedNetwork &ann_network, size_t partition_idx, std::vector<TreeLoglData> &treeLoglData);

@@ -129,6 +129,7 @@ struct nrx_engine {
   double *d_persite = nullptr;
   size_t persite_cap = 0;
   unsigned long long launches = 0;
+  uint32_t pending_result = 0;  // doubles of an enqueued, not yet collected result (nrx_*_async / nrx_result_wait)
   int k2_variant = 0;       // 0: k_clv_dna4_pipe (production); UM: k_clv_dna4<U, MINB> (A/B experiments, env NRX_K2=UM)
   bool aa_generic = false;  // env NRX_AA=generic: force the scalar kernel for 20-state partitions (A/B)
   uint32_t aa_blocks = 148 * 3 * 4;  // block-count target of the DMMA kernel
@@ -893,7 +894,8 @@ static uint32_t reduce_blocks(const nrx_engine *e, uint32_t items) {
   return (uint32_t)std::min<uint64_t>(full, want);
 }
 
-static int finish_reduction(nrx_engine *e, uint32_t total, uint32_t nblk, double *out) {
+/* second stage + cross-rank sum + device->host copy, all stream-ordered; the host blocks only in wait_result */
+static int enqueue_reduction(nrx_engine *e, uint32_t total, uint32_t nblk) {
   cudaEvent_t ev0, ev1;
   prof_begin(e, &ev0, &ev1);
   k_reduce_partials<<<(total + 3) / 4, 128, 0, e->stream>>>(e->d_partial, e->d_result, nblk, total);
@@ -905,12 +907,20 @@ static int finish_reduction(nrx_engine *e, uint32_t total, uint32_t nblk, double
     if (rc != 0) { g_err = std::string("ncclAllReduce: ") + nccl().GetErrorString(rc); return 0; }
   }
   CK(cudaMemcpyAsync(e->h_result, e->d_result, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
-  if (out) std::memcpy(out, e->h_result, (size_t)total * sizeof(double));
+  e->pending_result = total;
   return 1;
 }
+static int wait_result(nrx_engine *e, uint32_t total, double *out) {
+  CK(cudaStreamSynchronize(e->stream));
+  if (out) std::memcpy(out, e->h_result, (size_t)total * sizeof(double));
+  e->pending_result = 0;
+  return 1;
+}
+static int finish_reduction(nrx_engine *e, uint32_t total, uint32_t nblk, double *out) {
+  return enqueue_reduction(e, total, nblk) && wait_result(e, total, out);
+}
 
-int nrx_tree_lnl(nrx_engine *e, const uint32_t *slots, uint32_t n, double *out, double *persite, size_t persite_stride) {
+static int tree_lnl_impl(nrx_engine *e, const uint32_t *slots, uint32_t n, double *out, double *persite, size_t persite_stride, bool async) {
   if (!e) { g_err = "null engine"; return 0; }
   if (n == 0) return 1;
   CK(cudaSetDevice(e->device));
@@ -941,12 +951,23 @@ int nrx_tree_lnl(nrx_engine *e, const uint32_t *slots, uint32_t n, double *out, 
     CK(cudaGetLastError());
   }
   { unsigned long long u = 0; const unsigned long long b = stream_bytes(e, n, 1, persite ? 16 : 8, &u); prof_end(e, ev0, ev1, e->classes.size(), u, b, NRX_PROF_K3); }
+  if (async) return enqueue_reduction(e, n * P, nblk);
   if (!finish_reduction(e, n * P, nblk, out)) return 0;
   if (persite) CK(cudaMemcpy(persite, e->d_persite, (size_t)n * P * persite_stride * sizeof(double), cudaMemcpyDeviceToHost));
   return 1;
 }
+int nrx_tree_lnl(nrx_engine *e, const uint32_t *slots, uint32_t n, double *out, double *persite, size_t persite_stride) {
+  return tree_lnl_impl(e, slots, n, out, persite, persite_stride, false);
+}
+int nrx_tree_lnl_async(nrx_engine *e, const uint32_t *slots, uint32_t n) { return tree_lnl_impl(e, slots, n, nullptr, nullptr, 0, true); }
+int nrx_result_wait(nrx_engine *e, double *out, uint32_t count) {
+  if (!e) { g_err = "null engine"; return 0; }
+  if (count != e->pending_result) { g_err = "nrx_result_wait: no pending result of that size"; return 0; }
+  CK(cudaSetDevice(e->device));
+  return wait_result(e, count, out);
+}
 
-int nrx_tree_lnl_fused(nrx_engine *e, uint32_t plan_id, const uint32_t *slots, uint32_t n, double *out) {
+static int tree_lnl_fused_impl(nrx_engine *e, uint32_t plan_id, const uint32_t *slots, uint32_t n, double *out, bool async) {
   if (!e || plan_id >= e->plans.size() || !e->plans[plan_id].alive) { g_err = "nrx_tree_lnl_fused: no such plan"; return 0; }
   if (n == 0) return 1;
   if (n > e->plans[plan_id].lnl_items || !e->d_fused) { g_err = "nrx_tree_lnl_fused: the plan carries fewer lnl marks"; return 0; }
@@ -967,7 +988,13 @@ int nrx_tree_lnl_fused(nrx_engine *e, uint32_t plan_id, const uint32_t *slots, u
     CK(cudaGetLastError());
   }
   { unsigned long long u = 0; const unsigned long long b = stream_bytes(e, n, 0, 16, &u); prof_end(e, ev0, ev1, e->classes.size(), u, b, NRX_PROF_K3F); }
-  return finish_reduction(e, n * P, nblk, out);
+  return async ? enqueue_reduction(e, n * P, nblk) : finish_reduction(e, n * P, nblk, out);
+}
+int nrx_tree_lnl_fused(nrx_engine *e, uint32_t plan_id, const uint32_t *slots, uint32_t n, double *out) {
+  return tree_lnl_fused_impl(e, plan_id, slots, n, out, false);
+}
+int nrx_tree_lnl_fused_async(nrx_engine *e, uint32_t plan_id, const uint32_t *slots, uint32_t n) {
+  return tree_lnl_fused_impl(e, plan_id, slots, n, nullptr, true);
 }
 
 static int check_pairs(nrx_engine *e, const nrx_pair *pairs, uint32_t n, const char *who) {

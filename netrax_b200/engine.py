@@ -53,6 +53,9 @@ def load() -> FlatAPI:
         lib.nrxh_engine.argtypes = [C.c_void_p]
         lib.nrxh_upload_alignment_u8.restype = C.c_int
         lib.nrxh_upload_alignment_u8.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p]
+        lib.nrxh_compute_loglikelihood_batch.restype = C.c_int
+        lib.nrxh_compute_loglikelihood_batch.argtypes = [C.POINTER(C.c_void_p), C.c_uint, C.c_int, C.c_int,
+                                                         np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")]
         lib.nrxh_timer_start.restype = C.c_int
         lib.nrxh_timer_start.argtypes = [C.c_void_p]
         lib.nrxh_timer_stop.restype = C.c_int
@@ -73,6 +76,16 @@ def device_count() -> int:
     lib = C.CDLL(ENGINE_SO, mode=C.RTLD_GLOBAL)
     lib.nrx_device_count.restype = C.c_int
     return lib.nrx_device_count()
+
+
+def compute_loglikelihood_batch(engines: Sequence["NetraxB200"], incremental: int = 1, update_pmatrices: int = 1) -> np.ndarray:
+    """Batched scoring of candidate networks: every engine = its own CUDA stream; all evaluations are
+    enqueued before the first result is collected.  out[i] == engines[i].computeLoglikelihood(incremental, update_pmatrices)."""
+    api = load()
+    hs = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    out = np.zeros(len(engines))
+    api.check(api.lib.nrxh_compute_loglikelihood_batch(hs, len(engines), incremental, update_pmatrices, out))
+    return out
 
 
 class NetraxB200(LikelihoodEngine):

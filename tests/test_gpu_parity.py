@@ -420,6 +420,35 @@ def test_other_category_counts_use_generic_kernels(cats):
     g.close()
 
 
+def test_batched_scoring_equals_sequential():
+    """computeLoglikelihoodBatch over candidate networks (different topologies / branch lengths over one alignment, one
+    engine and stream each): every result equals the single evaluation and the oracle's; full (plan replay, fused K3),
+    incremental after branch-length changes, and cached re-evaluation."""
+    from netrax_b200.engine import compute_loglikelihood_batch
+    base = random_network(14, 2, seed=77)
+    m, w = simulate_alignment(base, 700, seed=77)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    nets = [base] + [random_network(14, r, seed=80 + r) for r in (0, 1, 3)]
+    gs = [_gpu(n, [part]) for n in nets]
+    os_ = [_oracle(n, [part]) for n in nets]
+    for g, o in zip(gs, os_):
+        _inject_eigen(g, o)
+    want = np.array([o.computeLoglikelihood(0, 1) for o in os_])
+    got = compute_loglikelihood_batch(gs, 0, 1)          # first evaluation: records the plans
+    np.testing.assert_allclose(got, want, rtol=LNL_RTOL)
+    got2 = compute_loglikelihood_batch(gs, 0, 1)         # plan replay + fused K3, all four in flight
+    np.testing.assert_array_equal(got2, np.array([g.computeLoglikelihood(0, 1) for g in gs]))
+    np.testing.assert_allclose(got2, want, rtol=LNL_RTOL)
+    for k, (g, o) in enumerate(zip(gs, os_)):            # candidates diverge: one branch each, incremental re-evaluation
+        for eng in (g, o):
+            eng.set_branch_length(k + 1, 0.05 * (k + 1))
+    want3 = np.array([o.computeLoglikelihood(1, 1) for o in os_])
+    np.testing.assert_allclose(compute_loglikelihood_batch(gs, 1, 1), want3, rtol=LNL_RTOL)
+    np.testing.assert_allclose(compute_loglikelihood_batch(gs, 1, 1), want3, rtol=LNL_RTOL)   # cached
+    for g in gs:
+        g.close()
+
+
 def test_empty_partition_slice_is_skipped():
     """A site shard may own NO pattern of a partition (reference: partitions[p] == NULL, 'skip remote partitions',
     LH/ImprovedLoglikelihood.cpp:128-131): the engine must accept patterns = 0 and contribute exactly 0 to that partition."""

@@ -81,6 +81,12 @@ int nrxh_optimize_branch(void *h, unsigned edge, int method, unsigned max_iters,
 int nrxh_optimize_branches(void *h, int max_iters, int max_iters_outside, int radius, int method, double *final_logl);
 int nrxh_optimize_reticulation(void *h, unsigned r, double *final_logl);
 int nrxh_optimize_reticulations(void *h, int max_iters, double *final_logl);
+/* model-parameter loop: Gamma shape of partition p (treeinfo_set_alpha, PLLMOD/algorithm/pllmod_algorithm.c:566-587)
+ * and the ALPHA step of optimize_params (src/optimization/ModelOptimization.cpp:56-65 = pllmod_algo_opt_onedim_treeinfo):
+ * Brent over the alphas of all partitions that carry one, one full device re-evaluation per iterate. */
+int nrxh_set_alpha(void *h, unsigned p, double alpha);
+int nrxh_get_alpha(void *h, unsigned p, double *alpha);
+int nrxh_optimize_alpha(void *h, double min_alpha, double max_alpha, double tolerance, double *final_logl);
 int nrxh_get_branch_lengths(void *h, int partition /* -1: linked */, double *out /* [edges] */);
 int nrxh_get_reticulation_probs(void *h, double *out /* [reticulations] */);
 unsigned long long nrxh_clv_update_count(void *h);

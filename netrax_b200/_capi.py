@@ -72,6 +72,9 @@ class FlatAPI:
         g("optimize_branches", C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double))
         g("optimize_reticulation", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
         g("optimize_reticulations", C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double))
+        g("set_alpha", C.c_int, C.c_void_p, C.c_uint, C.c_double)
+        g("get_alpha", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
+        g("optimize_alpha", C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double))
         g("get_branch_lengths", C.c_int, C.c_void_p, C.c_int, _f64p)
         g("get_reticulation_probs", C.c_int, C.c_void_p, _f64p)
         g("clv_update_count", C.c_ulonglong, C.c_void_p)
@@ -284,6 +287,21 @@ class LikelihoodEngine:
     def optimize_reticulation(self, r: int) -> float:
         out = C.c_double()
         self.api.check(self.api._optimize_reticulation(self.h, r, C.byref(out)))
+        return out.value
+
+    def set_alpha(self, p: int, alpha: float):
+        """treeinfo_set_alpha: Gamma shape -> discrete rates of partition p (mean mode)."""
+        self.api.check(self.api._set_alpha(self.h, p, alpha))
+
+    def get_alpha(self, p: int) -> float:
+        out = C.c_double()
+        self.api.check(self.api._get_alpha(self.h, p, C.byref(out)))
+        return out.value
+
+    def optimize_alpha(self, min_alpha: float = 0.0201, max_alpha: float = 100.0, tolerance: float = 0.001) -> float:
+        """The ALPHA step of optimize_params (ModelOptimization.cpp:56-65): Brent over all partitions' Gamma shapes."""
+        out = C.c_double()
+        self.api.check(self.api._optimize_alpha(self.h, min_alpha, max_alpha, tolerance, C.byref(out)))
         return out.value
 
     def optimize_reticulations(self, max_iters: int = 10) -> float:

@@ -222,15 +222,7 @@ int nrxh_set_reticulation_prob(void *hv, unsigned r, double prob) {
   return guarded([&] { setReticulationProb(H(hv)->ann, r, prob); });
 }
 
-static void pushModel(AnnotatedNetwork &ann, unsigned p) {
-  PartitionModel &m = ann.fake_treeinfo->partitions.at(p);
-  if (!m.eigen_decomp_valid) update_eigen(m);
-  std::vector<double> freqs(m.states_padded, 0.0);
-  std::copy(m.frequencies.begin(), m.frequencies.begin() + m.states, freqs.begin());
-  detail::engineCheck(nrx_set_model(ann.engine, p, freqs.data(), m.eigenvecs.data(), m.inv_eigenvecs.data(), m.eigenvals.data(), m.rates.data(), m.rate_weights.data(), 0.0), "nrx_set_model");
-  for (auto &v : ann.fake_treeinfo->pmatrix_valid[p]) v = 0;
-  invalidateAllCLVs(ann);
-}
+static void pushModel(AnnotatedNetwork &ann, unsigned p) { pushPartitionModel(ann, p); }
 
 int nrxh_set_model(void *hv, unsigned p, const double *freqs, const double *subst, const double *rates, const double *rw) {
   return guarded([&] {
@@ -368,6 +360,18 @@ int nrxh_optimize_reticulation(void *hv, unsigned r, double *final_logl) {
   });
 }
 
+int nrxh_set_alpha(void *hv, unsigned p, double alpha) {
+  return guarded([&] { setAlpha(H(hv)->ann, p, alpha); });
+}
+int nrxh_get_alpha(void *hv, unsigned p, double *alpha) {
+  return guarded([&] { *alpha = H(hv)->ann.fake_treeinfo->partitions.at(p).alpha; });
+}
+int nrxh_optimize_alpha(void *hv, double min_alpha, double max_alpha, double tolerance, double *final_logl) {
+  return guarded([&] {
+    const double l = optimize_alpha(H(hv)->ann, min_alpha, max_alpha, tolerance);
+    if (final_logl) *final_logl = l;
+  });
+}
 int nrxh_optimize_reticulations(void *hv, int max_iters, double *final_logl) {
   return guarded([&] {
     const double l = optimize_reticulations(H(hv)->ann, max_iters);

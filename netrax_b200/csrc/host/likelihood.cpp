@@ -270,6 +270,12 @@ static void uploadModel(AnnotatedNetwork &ann, unsigned p) {
                             m.rates.data(), m.rate_weights.data(), 0.0), "nrx_set_model");
 }
 
+void pushPartitionModel(AnnotatedNetwork &ann, unsigned p) {
+  uploadModel(ann, p);
+  for (auto &v : ann.fake_treeinfo->pmatrix_valid.at(p)) v = 0;
+  invalidateAllCLVs(ann);
+}
+
 void init_annotated_network(AnnotatedNetwork &ann, const std::vector<PartitionInput> &parts, int device) {
   Network &nw = ann.network;
   FakeTreeinfo &ti = *ann.fake_treeinfo;

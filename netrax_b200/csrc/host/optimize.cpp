@@ -309,4 +309,78 @@ double optimize_reticulations(AnnotatedNetwork &ann, int max_iters) {  // :102-1
   return act_logl;
 }
 
+/* ---- model-parameter loop: the ALPHA step of optimize_params (src/optimization/ModelOptimization.cpp:56-65)
+ * = pllmod_algo_opt_onedim_treeinfo(PLLMOD_OPT_PARAM_ALPHA) (PLLMOD/algorithm/pllmod_algorithm.c:743-866): Brent for the
+ * alphas of ALL partitions at once (brent_opt_alt, opt_algorithms.c:1043-1254, through BrentState above), each iterate =
+ * new Gamma rates per unconverged partition (treeinfo_set_alpha, :566-587) + ONE full re-evaluation
+ * (target_func_onedim_treeinfo, algo_callback.c:295-363) whose per-partition lnLs drive the per-partition Brent states.
+ * On the device an iterate is: a < 1 KB model upload per partition, P-matrices of every edge (K1), the cached plan
+ * replayed as one CUDA graph (K2 + fused K3) — no eigendecomposition, the rate matrix has not changed. */
+void setAlpha(AnnotatedNetwork &ann, unsigned p, double alpha) {
+  PartitionModel &m = ann.fake_treeinfo->partitions.at(p);
+  std::vector<double> rates(m.rate_cats);
+  if (!compute_gamma_cats(alpha, m.rate_cats, rates.data(), m.gamma_mode)) throw std::runtime_error("Invalid alpha value / GAMMA discretization mode");
+  m.alpha = alpha;
+  m.rates = rates;
+  pushPartitionModel(ann, p);
+}
+
+double optimize_alpha(AnnotatedNetwork &ann, double min_alpha, double max_alpha, double tolerance) {
+  FakeTreeinfo &ti = *ann.fake_treeinfo;
+  std::vector<unsigned> parts;   // params_to_optimize & PLLMOD_OPT_PARAM_ALPHA
+  for (unsigned p = 0; p < ti.partition_count; ++p) if (ti.partitions[p].alpha > 0.0) parts.push_back(p);
+  const size_t n = parts.size();
+  if (n) {
+    std::vector<double> xguess(n), ax(n), cx(n), lmin(n, min_alpha), lmax(n, max_alpha);
+    for (size_t j = 0; j < n; ++j) xguess[j] = ti.partitions[parts[j]].alpha;
+    std::vector<char> converged(n, 0);
+    bool all_converged = false;
+    // target_func_onedim_treeinfo: set the unconverged partitions' alphas, one full evaluation, per-partition scores
+    auto target = [&](const std::vector<double> &x, bool with_flags) {
+      double unconverged = 0.0;
+      for (size_t j = 0; j < n; ++j) {
+        if (with_flags && converged[j]) continue;
+        unconverged = 1.0;
+        setAlpha(ann, parts[j], x[j]);
+      }
+      computeLoglikelihood(ann, 0, 1);
+      std::vector<double> fx(n);
+      for (size_t j = 0; j < n; ++j) fx[j] = -1 * ti.partition_loglh[parts[j]];
+      if (with_flags) {
+        if (ti.parallel_reduce_cb) ti.parallel_reduce_cb(ti.parallel_context, &unconverged, 1, PLLMOD_COMMON_REDUCE_SUM);
+        all_converged = !(unconverged > 0.0);
+      }
+      return fx;
+    };
+    for (size_t j = 0; j < n; ++j) {
+      xguess[j] = std::max(std::min(xguess[j], lmax[j]), lmin[j]);
+      const double eps = xguess[j] > 0 ? xguess[j] * tolerance * 50.0 : 2. * tolerance;  // bracketing heuristic (:1138-1148)
+      ax[j] = std::max(xguess[j] - eps, lmin[j]);
+      cx[j] = std::min(xguess[j] + eps, lmax[j]);
+    }
+    std::vector<double> fa = target(ax, false);
+    const std::vector<double> fb = target(xguess, false);
+    std::vector<double> fc = target(cx, false);
+    const std::vector<double> fmin = target(lmin, false), fmax = target(lmax, false);
+    std::vector<BrentState> st(n);
+    for (size_t j = 0; j < n; ++j) {
+      if (fa[j] < fb[j] || fc[j] < fb[j]) { fa[j] = fmin[j]; fc[j] = fmax[j]; ax[j] = lmin[j]; cx[j] = lmax[j]; }
+      if (!st[j].init(ax[j], xguess[j], cx[j], tolerance, fa[j], fb[j], fc[j])) converged[j] = 1;
+    }
+    std::vector<double> u(n);
+    for (int iter = 0; iter <= BrentState::kItmax; ++iter) {
+      for (size_t j = 0; j < n; ++j) u[j] = st[j].u;
+      const std::vector<double> fu = target(u, true);   // with every partition converged this sets no alpha but still evaluates, as the reference does
+      const bool iterate = !all_converged;
+      for (size_t j = 0; j < n; ++j)
+        if (!converged[j]) converged[j] = !st[j].absorb(fu[j]);
+      if (!iterate) break;
+    }
+    std::vector<double> xopt(n);
+    for (size_t j = 0; j < n; ++j) xopt[j] = (st[j].fx > st[j].fstartx) ? st[j].startx : st[j].x;  // if the new score is worse, return the initial value
+    target(xopt, false);
+  }
+  return computeLoglikelihood(ann, 0, 1);
+}
+
 }  // namespace netrax

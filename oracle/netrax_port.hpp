@@ -132,6 +132,8 @@ struct Backend {
                         const double *weights) = 0;  // recomputes eigen
   virtual void getEigen(unsigned p, double *eigenvecs, double *inv_eigenvecs, double *eigenvals) const = 0;
   virtual void getRates(unsigned p, double *rates, double *weights, double *freqs) const = 0;
+  virtual void setCategoryRates(unsigned p, const double *rates) = 0;                       // pll_set_category_rates
+  virtual bool gammaRates(double alpha, unsigned cats, double *out, int mode) const = 0;   // pll_compute_gamma_cats
   virtual void updatePmatrix(unsigned p, unsigned edge, double brlen) = 0;
   virtual const double *pmatrix(unsigned p, unsigned edge) const = 0;
   virtual void updatePartials(unsigned p, double *parent_clv, unsigned *parent_scaler,
@@ -215,6 +217,7 @@ struct AnnotatedNetwork {  // SRC/graph/AnnotatedNetwork.hpp:42-89 (fields the p
   std::vector<std::vector<double>> branch_lengths;  // [partition][edge+1] (fake_treeinfo->branch_lengths)
   std::vector<double> linked_branch_lengths;        // [edge+1]
   std::vector<double> partition_loglh;
+  std::vector<double> alphas;  // fake_treeinfo->alphas (0 = no Gamma shape attached to the partition's rates)
   double cached_logl = 0;
   bool cached_logl_valid = false;
   // statistics for the benchmark metric (Σ trees(node) × patterns)
@@ -257,5 +260,7 @@ double optimize_branch(AnnotatedNetwork &ann, size_t pmatrix_index, int method, 
 double optimize_branches(AnnotatedNetwork &ann, int max_iters, int max_iters_outside, int radius, int method, bool restricted_total_iters = false);
 double optimize_reticulation(AnnotatedNetwork &ann, size_t reticulation_index);
 double optimize_reticulations(AnnotatedNetwork &ann, int max_iters);
+void setAlpha(AnnotatedNetwork &ann, unsigned partition, double alpha);   // treeinfo_set_alpha (PLLMOD/algorithm/pllmod_algorithm.c:566-587)
+double optimize_alpha(AnnotatedNetwork &ann, double min_alpha, double max_alpha, double tolerance);  // pllmod_algo_opt_onedim_treeinfo(ALPHA)
 
 }  // namespace orc

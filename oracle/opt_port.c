@@ -5,6 +5,7 @@
  * (PLLMOD = /root/reference/libs/raxml-ng/libs/pll-modules/src):
  *   orcopt_newton_multi  <- pllmod_opt_minimize_newton_multi   PLLMOD/optimize/opt_algorithms.c:133-261
  *   orcopt_brent         <- pllmod_opt_minimize_brent          PLLMOD/optimize/opt_algorithms.c:1404-1429
+ *   orcopt_brent_multi   <- pllmod_opt_minimize_brent_multi    PLLMOD/optimize/opt_algorithms.c:1448-1468 -> brent_opt_alt (any xnum)
  *                           -> brent_opt_alt (xnum = 1, global range) :1043-1254, brent_opt_init :859-939,
  *                              brent_opt_post_loop :941-1027
  * Same signatures as the originals so that the `_ref` build can bind the REAL functions instead
@@ -138,4 +139,74 @@ double orcopt_brent(double xmin, double xguess, double xmax, double xtol, double
   fb = target_funk(params, xopt);
   if (fx) *fx = fb;
   return xopt;
+}
+
+/* Brent for xnum variables at once (one per partition), the target evaluating all of them in one call and reporting
+ * per-variable scores: brent_opt_alt as pllmod_opt_minimize_brent_multi runs it (opt_algorithms.c:1043-1254).  The
+ * target receives converged[] (xnum + 1 entries, the last one = "all converged", set by the target itself). */
+int orcopt_brent_multi(unsigned int xnum, int *opt_mask, double *xmin, double *xguess, double *xmax, double xtol, double *xopt,
+                       double *fx, double *f2x, void *params, double (*target_funk)(void *, double *, double *, int *), int global_range) {
+  brent_state *st = calloc(xnum, sizeof(brent_state));
+  double *ax = calloc(xnum, sizeof(double)), *cx = calloc(xnum, sizeof(double)), *fa = calloc(xnum, sizeof(double));
+  double *fb = calloc(xnum, sizeof(double)), *fc = calloc(xnum, sizeof(double)), *fxmin = calloc(xnum, sizeof(double));
+  double *fxmax = calloc(xnum, sizeof(double)), *lmin = calloc(xnum, sizeof(double)), *lmax = calloc(xnum, sizeof(double));
+  double *u = calloc(xnum, sizeof(double)), *fu = calloc(xnum, sizeof(double));
+  int *converged = calloc(xnum + 1, sizeof(int));
+  unsigned int i;
+  int iterate = 1, iter_num = 0;
+  (void)f2x;
+  for (i = 0; i < xnum; ++i) { lmin[i] = global_range ? *xmin : xmin[i]; lmax[i] = global_range ? *xmax : xmax[i]; }
+  for (i = 0; i < xnum; ++i) {
+    double eps;
+    if (opt_mask && !opt_mask[i]) continue;
+    if (xguess[i] < lmin[i]) xguess[i] = lmin[i];
+    if (xguess[i] > lmax[i]) xguess[i] = lmax[i];
+    eps = xguess[i] > 0 ? xguess[i] * xtol * 50.0 : 2. * xtol;
+    ax[i] = xguess[i] - eps; if (ax[i] < lmin[i]) ax[i] = lmin[i];
+    cx[i] = xguess[i] + eps; if (cx[i] > lmax[i]) cx[i] = lmax[i];
+  }
+  target_funk(params, ax, fa, NULL);
+  target_funk(params, xguess, fb, NULL);
+  target_funk(params, cx, fc, NULL);
+  target_funk(params, lmin, fxmin, NULL);
+  target_funk(params, lmax, fxmax, NULL);
+  for (i = 0; i < xnum; ++i) {
+    brent_state *s = &st[i];
+    if (opt_mask && !opt_mask[i]) continue;
+    if ((fa[i] < fb[i]) || (fc[i] < fb[i])) { fa[i] = fxmin[i]; fc[i] = fxmax[i]; ax[i] = lmin[i]; cx[i] = lmax[i]; }
+    s->tol = xtol;
+    s->a = ax[i] < cx[i] ? ax[i] : cx[i];
+    s->b = ax[i] > cx[i] ? ax[i] : cx[i];
+    s->startx = s->x = xguess[i];
+    s->fstartx = s->fx = fb[i];
+    if (fa[i] < fc[i]) { s->w = ax[i]; s->fw = fa[i]; s->v = cx[i]; s->fv = fc[i]; } else { s->w = cx[i]; s->fw = fc[i]; s->v = ax[i]; s->fv = fa[i]; }
+    if (!brent_next(s)) converged[i] = 1;
+  }
+  while (iterate) {
+    for (i = 0; i < xnum; ++i) u[i] = st[i].u;
+    target_funk(params, u, fu, converged);
+    iterate = !converged[xnum];
+    for (i = 0; i < xnum; ++i) {
+      brent_state *s = &st[i];
+      if (opt_mask && !opt_mask[i]) continue;
+      if (converged[i]) continue;
+      s->fu = fu[i];
+      if (s->fu <= s->fx) {
+        if (s->u >= s->x) s->a = s->x; else s->b = s->x;
+        s->v = s->w; s->w = s->x; s->x = s->u;
+        s->fv = s->fw; s->fw = s->fx; s->fx = s->fu;
+      } else {
+        if (s->u < s->x) s->a = s->u; else s->b = s->u;
+        if (s->fu <= s->fw || s->w == s->x) { s->v = s->w; s->w = s->u; s->fv = s->fw; s->fw = s->fu; }
+        else if (s->fu <= s->fv || s->v == s->x || s->v == s->w) { s->v = s->u; s->fv = s->fu; }
+      }
+      converged[i] = !brent_next(s);
+    }
+    iter_num++;
+    iterate &= (iter_num <= BRENT_ITMAX);
+  }
+  for (i = 0; i < xnum; ++i) xopt[i] = (st[i].fx > st[i].fstartx) ? st[i].startx : st[i].x;
+  target_funk(params, xopt, fx, NULL);
+  free(st); free(ax); free(cx); free(fa); free(fb); free(fc); free(fxmin); free(fxmax); free(lmin); free(lmax); free(u); free(fu); free(converged);
+  return 1;
 }

@@ -4,11 +4,17 @@
  * Restatement of the immediate callers of the likelihood path (SRC = /root/reference/src):
  *   optimize_branch / optimize_branches      SRC/optimization/BranchLengthOptimization.cpp:63-156,165-241,285-476,567-576
  *   optimize_reticulation(s)                 SRC/optimization/ReticulationOptimization.cpp:40-46,68-117
+ *   optimize_alpha                           the ALPHA step of optimize_params (SRC/optimization/ModelOptimization.cpp:56-65) =
+ *                                            pllmod_algo_opt_onedim_treeinfo (PLLMOD/algorithm/pllmod_algorithm.c:743-866) with
+ *                                            target_func_onedim_treeinfo (algo_callback.c:295-363) and treeinfo_set_alpha (:566-587)
  * written the way the reference writes them: parameter structs + C callbacks handed to pll-modules' minimisers.
  * In the `_ref` build (ORC_HAVE_REF) the minimisers ARE the reference's pllmod_opt_minimize_newton_multi /
  * pllmod_opt_minimize_brent (opt_algorithms.c compiled where it lies); in the port build they are opt_port.c.
  */
 #include <cmath>
+#include <limits>
+#include <stdexcept>
+#include <vector>
 #include <unordered_set>
 
 #include "netrax_port.hpp"
@@ -19,15 +25,21 @@ int pllmod_opt_minimize_newton_multi(unsigned int xnum, double xmin, double *xgu
                                      int *converged, void *params, void(deriv_func)(void *, double *, double *, double *));
 double pllmod_opt_minimize_brent(double xmin, double xguess, double xmax, double xtol, double *fx, double *f2x, void *params,
                                  double (*target_funk)(void *, double));
+int pllmod_opt_minimize_brent_multi(unsigned int xnum, int *opt_mask, double *xmin, double *xguess, double *xmax, double xtol, double *xopt,
+                                    double *fx, double *f2x, void *params, double (*target_funk)(void *, double *, double *, int *), int global_range);
 #define MIN_NEWTON pllmod_opt_minimize_newton_multi
 #define MIN_BRENT pllmod_opt_minimize_brent
+#define MIN_BRENT_MULTI pllmod_opt_minimize_brent_multi
 #else
 int orcopt_newton_multi(unsigned int xnum, double xmin, double *xguess, double xmax, double tolerance, unsigned int max_iters, int *converged,
                         void *params, void (*deriv_func)(void *, double *, double *, double *));
 double orcopt_brent(double xmin, double xguess, double xmax, double xtol, double *fx, double *f2x, void *params,
                     double (*target_funk)(void *, double));
+int orcopt_brent_multi(unsigned int xnum, int *opt_mask, double *xmin, double *xguess, double *xmax, double xtol, double *xopt,
+                       double *fx, double *f2x, void *params, double (*target_funk)(void *, double *, double *, int *), int global_range);
 #define MIN_NEWTON orcopt_newton_multi
 #define MIN_BRENT orcopt_brent
+#define MIN_BRENT_MULTI orcopt_brent_multi
 #endif
 }
 
@@ -182,6 +194,54 @@ double optimize_reticulations(AnnotatedNetwork &ann, int max_iters) {  // :102-1
     act_logl = loop_logl;
   }
   return act_logl;
+}
+
+/* treeinfo_set_alpha: alpha -> discrete Gamma rates (mean mode, the raxml-ng default) -> partition rates; every P-matrix
+ * and CLV of the partition is stale afterwards (the optimiser re-evaluates with incremental = 0 anyway) */
+void setAlpha(AnnotatedNetwork &ann, unsigned p, double alpha) {
+  if (ann.alphas.size() < ann.partitionCount()) ann.alphas.resize(ann.partitionCount(), 0.0);
+  std::vector<double> rates(ann.backend->rateCats(p));
+  if (!ann.backend->gammaRates(alpha, (unsigned)rates.size(), rates.data(), 0)) throw std::runtime_error("Invalid alpha value / GAMMA discretization mode");
+  ann.alphas[p] = alpha;
+  ann.backend->setCategoryRates(p, rates.data());
+  for (auto &v : ann.pmatrix_valid[p]) v = 0;
+  invalidateAllCLVs(ann);
+}
+
+namespace {
+struct AlphaOptParams { AnnotatedNetwork *ann; std::vector<unsigned> parts; };
+
+double target_func_onedim_alpha(void *p, double *x, double *fx, int *converged) {  // algo_callback.c:295-363
+  AlphaOptParams *q = static_cast<AlphaOptParams *>(p);
+  AnnotatedNetwork &ann = *q->ann;
+  double score = -std::numeric_limits<double>::infinity(), unconverged_flag = 0.;
+  for (size_t j = 0; j < q->parts.size(); ++j) {
+    if (converged && converged[j]) continue;
+    unconverged_flag = 1.;
+    if (x) setAlpha(ann, q->parts[j], x[j]);
+  }
+  if (x) score = -1 * computeLoglikelihood(ann, 0, 1);   // pllmod_treeinfo_compute_loglh(treeinfo, 0)
+  if (fx) for (size_t j = 0; j < q->parts.size(); ++j) fx[j] = -1 * ann.partition_loglh[q->parts[j]];
+  if (converged) {
+    if (ann.parallel_reduce_cb) ann.parallel_reduce_cb(ann.parallel_context, &unconverged_flag, 1, 0);
+    converged[q->parts.size()] = unconverged_flag > 0. ? 0 : 1;
+  }
+  return score;
+}
+}  // namespace
+
+double optimize_alpha(AnnotatedNetwork &ann, double min_alpha, double max_alpha, double tolerance) {  // pllmod_algorithm.c:743-818
+  AlphaOptParams q{&ann, {}};
+  if (ann.alphas.size() < ann.partitionCount()) ann.alphas.resize(ann.partitionCount(), 0.0);
+  for (unsigned p = 0; p < ann.partitionCount(); ++p) if (ann.alphas[p] > 0.0) q.parts.push_back(p);  // params_to_optimize & ALPHA
+  if (!q.parts.empty()) {
+    std::vector<double> vals;
+    for (unsigned p : q.parts) vals.push_back(ann.alphas[p]);
+    std::vector<int> mask(q.parts.size(), 1);
+    MIN_BRENT_MULTI((unsigned)q.parts.size(), mask.data(), &min_alpha, vals.data(), &max_alpha, tolerance, vals.data(), nullptr, nullptr, &q,
+                    &target_func_onedim_alpha, 1);
+  }
+  return computeLoglikelihood(ann, 0, 1);
 }
 
 }  // namespace orc

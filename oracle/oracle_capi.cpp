@@ -333,6 +333,18 @@ int orc_optimize_reticulation(void *hv, unsigned r, double *final_logl) {
   Handle *h = static_cast<Handle *>(hv);
   return guarded([&] { double l = optimize_reticulation(h->ann, r); if (final_logl) *final_logl = l; });
 }
+int orc_set_alpha(void *hv, unsigned p, double alpha) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] { setAlpha(h->ann, p, alpha); });
+}
+int orc_get_alpha(void *hv, unsigned p, double *alpha) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] { *alpha = p < h->ann.alphas.size() ? h->ann.alphas[p] : 0.0; });
+}
+int orc_optimize_alpha(void *hv, double min_alpha, double max_alpha, double tolerance, double *final_logl) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] { double l = optimize_alpha(h->ann, min_alpha, max_alpha, tolerance); if (final_logl) *final_logl = l; });
+}
 int orc_optimize_reticulations(void *hv, int max_iters, double *final_logl) {
   Handle *h = static_cast<Handle *>(hv);
   return guarded([&] { double l = optimize_reticulations(h->ann, max_iters); if (final_logl) *final_logl = l; });

@@ -41,7 +41,13 @@ def optimisation_round(eng):
     l0 = eng.computeLoglikelihood(0, 1)
     t = time.perf_counter(); l1 = eng.optimize_branches(); tb = time.perf_counter() - t
     t = time.perf_counter(); l2 = eng.optimize_reticulations(); tr = time.perf_counter() - t
-    return {"brlen_round_s": tb, "retprob_round_s": tr, "lnl_start": l0, "lnl_after_brlen": l1, "lnl_after_retprob": l2}
+    out = {"brlen_round_s": tb, "retprob_round_s": tr, "lnl_start": l0, "lnl_after_brlen": l1, "lnl_after_retprob": l2}
+    if hasattr(eng, "optimize_alpha"):  # the ALPHA step of optimize_params: start from a wrong shape (2.0)
+        for p in range(len(eng.partitions)):
+            eng.set_alpha(p, 2.0)
+        t = time.perf_counter(); l3 = eng.optimize_alpha(); ta = time.perf_counter() - t
+        out.update({"alpha_opt_s": ta, "lnl_after_alpha": l3, "alpha": eng.get_alpha(0)})
+    return out
 
 
 def _cpu_worker(args):
@@ -73,6 +79,7 @@ def cpu_arm(cfg, cores, patterns_per_core, reps, sweep):
         out["sweep_s_on_sample"] = max(r["sweep"][0] for r in res)
         out["brlen_round_s_on_sample"] = max(r["opt"]["brlen_round_s"] for r in res)
         out["retprob_round_s_on_sample"] = max(r["opt"]["retprob_round_s"] for r in res)
+        out["alpha_opt_s_on_sample"] = max(r["opt"].get("alpha_opt_s", 0.0) for r in res)
     return out
 
 
@@ -138,6 +145,9 @@ def main():
             if sweep:
                 cpu["sweep_s_full_config_est"] = cpu["sweep_s_on_sample"] * scale
                 cpu["brlen_round_s_full_config_est"] = cpu["brlen_round_s_on_sample"] * scale
+                cpu["alpha_opt_s_full_config_est"] = cpu["alpha_opt_s_on_sample"] * scale
+                if r["gpu"]["optimisation_round"].get("alpha_opt_s"):
+                    r["speedup_alpha_opt"] = cpu["alpha_opt_s_full_config_est"] / r["gpu"]["optimisation_round"]["alpha_opt_s"]
                 r["speedup_brlen_round"] = cpu["brlen_round_s_full_config_est"] / r["gpu"]["optimisation_round"]["brlen_round_s"]
                 r["speedup_derivative_sweep"] = cpu["sweep_s_full_config_est"] / (r["gpu"]["ms_per_derivative_sweep"] / 1e3)
         results[f"config{c}"] = r

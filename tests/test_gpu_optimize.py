@@ -86,3 +86,30 @@ def test_brent_reroot_raises_the_reference_error():
         g.optimize_branch(0, method=BRENT_REROOT)
     # the engine stays usable: a full re-evaluation recovers
     assert np.isfinite(g.computeLoglikelihood(0, 1))
+
+
+@pytest.mark.parametrize("variant", [AVERAGE, BEST])
+def test_optimize_alpha_matches_oracle(variant):
+    """Model-parameter loop: the ALPHA step of optimize_params on the device — every Brent iterate is a
+    new set of Gamma rates + one full re-evaluation (plan replay) — against pll-modules' real minimiser over libpll."""
+    net = random_network(12, 2, seed=3)
+    parts = []
+    for k in range(2):
+        m, w = simulate_alignment(net, 600, seed=30 + k)
+        parts.append(Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w))
+    g, o = _pair(net, parts, variant=variant)
+    for eng in (g, o):
+        eng.set_alpha(0, 2.0)
+        eng.set_alpha(1, 0.1)
+    l0g, l0o = g.computeLoglikelihood(0, 1), o.computeLoglikelihood(0, 1)
+    assert l0g == pytest.approx(l0o, rel=1e-10)
+    lg, lo = g.optimize_alpha(), o.optimize_alpha()
+    assert lg >= l0g - 1e-6
+    assert lg == pytest.approx(lo, rel=1e-9)
+    for p in range(2):
+        assert g.get_alpha(p) == pytest.approx(o.get_alpha(p), rel=1e-5)
+    assert g.computeLoglikelihood(1, 1) == pytest.approx(lg, rel=1e-13)
+    # the loop around it (optimizeAllNonTopology's order: model, reticulation probabilities, branch lengths)
+    rg, ro = g.optimize_reticulations(), o.optimize_reticulations()
+    assert rg == pytest.approx(ro, rel=1e-9) and rg >= lg - 1e-3
+    g.close()

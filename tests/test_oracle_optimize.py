@@ -155,3 +155,45 @@ def test_unlinked_newton_uses_partition_zero_derivative():
     l1 = e.optimize_branch(2)
     assert l1 >= l0 - 1e-9
     assert l1 == pytest.approx(e.computeLoglikelihood(0, 1), rel=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------- model loop: alpha
+@pytest.mark.parametrize("variant", [AVERAGE, BEST])
+def test_optimize_alpha_port_equals_reference_minimiser(variant):
+    """The ALPHA step of optimize_params (ModelOptimization.cpp:56-65): the restated Brent-multi driver (opt_port.c)
+    against pll-modules' real pllmod_opt_minimize_brent_multi + libpll's Gamma rates (_ref), two partitions that start
+    from different wrong shapes; the data were simulated with alpha = 0.5."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    net = random_network(12, 2, seed=3)
+    parts = []
+    for k in range(2):
+        m, w = simulate_alignment(net, 600, seed=30 + k)
+        parts.append(Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w))
+    res = {}
+    for kind in ("port", "ref"):
+        e = oracle.make_engine(kind, net, parts, variant=variant)
+        e.set_alpha(0, 2.0)
+        e.set_alpha(1, 0.1)
+        l0 = e.computeLoglikelihood(0, 1)
+        l1 = e.optimize_alpha()
+        assert l1 >= l0 - 1e-6
+        res[kind] = (l0, l1, e.get_alpha(0), e.get_alpha(1), e.computeLoglikelihood(0, 1))
+        assert res[kind][4] == pytest.approx(l1, rel=1e-12)
+    assert res["port"][0] == pytest.approx(res["ref"][0], rel=1e-10)
+    assert res["port"][1] == pytest.approx(res["ref"][1], rel=1e-9)
+    assert res["port"][2] == pytest.approx(res["ref"][2], rel=1e-5)
+    assert res["port"][3] == pytest.approx(res["ref"][3], rel=1e-5)
+    for a in res["ref"][2:4]:
+        assert 0.3 < a < 0.8   # the generating shape is 0.5
+
+
+def test_optimize_alpha_skips_partitions_without_shape():
+    """Partitions whose rates were given directly (alpha = 0: not in params_to_optimize) are left alone."""
+    net = random_network(8, 1, seed=4)
+    m, w = simulate_alignment(net, 300, seed=4)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    e = oracle.make_engine("port", net, [part])
+    l0 = e.computeLoglikelihood(0, 1)
+    assert e.optimize_alpha() == pytest.approx(l0, rel=1e-13)
+    assert e.get_alpha(0) == 0.0

@@ -130,6 +130,7 @@ struct nrx_engine {
   size_t persite_cap = 0;
   unsigned long long launches = 0;
   uint32_t pending_result = 0;  // doubles of an enqueued, not yet collected result (nrx_*_async / nrx_result_wait)
+  uint32_t k2_nt = 2;       // env NRX_K2_NT: 64-pattern sub-tiles per ring stage of k_clv_dna4_pipe2 (1 or 2; 2 measured 1-2 % faster)
   int k2_variant = 0;       // 0: k_clv_dna4_pipe (production); UM: k_clv_dna4<U, MINB> (A/B experiments, env NRX_K2=UM)
   bool aa_generic = false;  // env NRX_AA=generic: force the scalar kernel for 20-state partitions (A/B)
   uint32_t aa_blocks = 148 * 3 * 4;  // block-count target of the DMMA kernel
@@ -349,6 +350,7 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
   e->parts.resize(nparts);
   if (const char *v = std::getenv("NRX_K2")) e->k2_variant = std::atoi(v);
   if (const char *v = std::getenv("NRX_GRAPH")) e->use_graphs = std::atoi(v) != 0;
+  if (const char *v = std::getenv("NRX_K2_NT")) e->k2_nt = std::atoi(v) == 1 ? 1u : 2u;
   if (const char *v = std::getenv("NRX_AA")) e->aa_generic = std::string(v) == "generic";
   if (const char *v = std::getenv("NRX_AA_BLOCKS")) e->aa_blocks = (uint32_t)std::max(1, std::atoi(v));
   if (const char *v = std::getenv("NRX_K2_BLOCKS")) e->k2_blocks = (uint32_t)std::max(1, std::atoi(v));
@@ -361,14 +363,15 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
         !cuda_ok(cudaFuncSetAttribute(k_aa20_dmma<AA_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa_smem), "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(k_aa20_dmma<AA_EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa_smem), "cudaFuncSetAttribute")) { delete e; return nullptr; }
     if (!cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClvPipeSmem)), "cudaFuncSetAttribute") ||
-        !cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClvPipeSmem)), "cudaFuncSetAttribute")) { delete e; return nullptr; }
+        !cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem<1>)), "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem<2>)), "cudaFuncSetAttribute")) { delete e; return nullptr; }
   }
   for (uint32_t i = 0; i < nparts; ++i) {
     Part &p = e->parts[i];
     p.d = descs[i];
     if (p.d.states < 2 || p.d.states > 32 || p.d.rate_cats < 1 || p.d.rate_cats > 16) { g_err = "unsupported states / rate_cats"; nrx_engine_destroy(e); return nullptr; }
     p.sp = (p.d.states + 3) & ~3u;
-    p.pat_pad = (p.d.patterns + TP - 1) / TP * TP;
+    p.pat_pad = (p.d.patterns + 2 * TP - 1) / (2 * TP) * (2 * TP);   // whole 128-pattern tiles: bulk copies always move full tiles
     p.clv_entries = (size_t)p.d.patterns * p.d.rate_cats * p.sp;
     p.pmat_entries = (size_t)p.d.rate_cats * p.d.states * p.sp;
     e->max_patterns = std::max(e->max_patterns, p.d.patterns);
@@ -699,16 +702,18 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
     if (c.states == 4 && c.cats == 4) {
       if (e->k2_variant == 0 || e->k2_variant == 1) {
         // bulk-async pipeline: 2 resident blocks per SM; block b = (op b % nops, tile group b / nops)
-        const uint32_t ntiles = (c.max_patterns + TP - 1) / TP;
+        const uint32_t nt = (e->k2_variant == 0) ? e->k2_nt : 1;   // 64-pattern sub-tiles per ring stage
+        const uint32_t ntiles = (c.max_patterns + nt * TP - 1) / (nt * TP);
         uint32_t groups = std::max<uint32_t>(1, (e->k2_blocks + nops * z - 1) / (nops * z));
         groups = std::min(groups, std::max<uint32_t>(1, ntiles / 4));  // >= 4 tiles per block: amortise the pipeline fill
         dim3 grid(nops * groups, 1, z);
-        if (e->k2_variant == 0)
-          k_clv_dna4_pipe2<<<grid, BLOCK, sizeof(ClvPipeSmem), e->stream>>>(c.d_views, d_ops, nops, groups, fused ? e->d_fused : nullptr,
-                                                                            (size_t)e->max_patterns, (uint32_t)e->parts.size());
+        double *fused_ptr = fused ? e->d_fused : nullptr;
+        if (e->k2_variant == 0 && nt == 2)
+          k_clv_dna4_pipe2<2><<<grid, BLOCK, sizeof(PipeSmem<2>), e->stream>>>(c.d_views, d_ops, nops, groups, fused_ptr, (size_t)e->max_patterns, (uint32_t)e->parts.size());
+        else if (e->k2_variant == 0)
+          k_clv_dna4_pipe2<1><<<grid, BLOCK, sizeof(PipeSmem<1>), e->stream>>>(c.d_views, d_ops, nops, groups, fused_ptr, (size_t)e->max_patterns, (uint32_t)e->parts.size());
         else
-          k_clv_dna4_pipe<<<grid, BLOCK, sizeof(ClvPipeSmem), e->stream>>>(c.d_views, d_ops, nops, groups, fused ? e->d_fused : nullptr,
-                                                                           (size_t)e->max_patterns, (uint32_t)e->parts.size());
+          k_clv_dna4_pipe<<<grid, BLOCK, sizeof(ClvPipeSmem), e->stream>>>(c.d_views, d_ops, nops, groups, fused_ptr, (size_t)e->max_patterns, (uint32_t)e->parts.size());
       } else {
         const uint32_t U = e->k2_variant / 10, MB = e->k2_variant % 10;
         dim3 grid(tiles_for((uint64_t)c.max_patterns * 4, BLOCK * U, nops * z), nops, z);

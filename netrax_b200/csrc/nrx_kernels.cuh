@@ -416,90 +416,121 @@ struct PipeCtx {
   uint32_t grp, groups, count, patterns;
 };
 
-template <int LK, int RK>
-__device__ __forceinline__ void pipe_issue(ClvPipeSmem &sm, const PipeCtx &c, uint32_t k, uint32_t stage) {
-  ClvStage &st = sm.st[stage];
+/* NT = 64-pattern sub-tiles per ring stage (1: 6 stages x 64 patterns, the geometry of k_clv_dna4_pipe; 2: 3 stages x 128
+ * patterns — the same bytes in flight, half as many mbarrier waits / block barriers / refills per byte, two independent
+ * items per thread between barriers). */
+template <int NT>
+struct __align__(128) PipeStage {
+  double l[NT * TP * 16];
+  double r[NT * TP * 16];
+  uint32_t scl[NT * TP];
+  uint32_t scr[NT * TP];
+  uint8_t tl[NT * TP];
+  uint8_t tr[NT * TP];
+};
+template <int NT>
+struct __align__(128) PipeSmem {
+  static constexpr int NST = NSTAGE / NT;
+  PipeStage<NT> st[NST];
+  double lutL[256];
+  double lutR[256];
+  unsigned long long full[NST];
+};
+
+template <int LK, int RK, int NT>
+__device__ __forceinline__ void pipe_issue(PipeSmem<NT> &sm, const PipeCtx &c, uint32_t k, uint32_t stage) {
+  constexpr uint32_t TPX = NT * TP;
+  PipeStage<NT> &st = sm.st[stage];
   unsigned long long *bar = &sm.full[stage];
-  const size_t p0 = ((size_t)c.grp + (size_t)k * c.groups) * TP;
-  constexpr uint32_t tx = ((LK == NRX_CLV) ? TP * 128u + TP * 4u : (LK == NRX_TIP ? (uint32_t)TP : 0u)) +
-                          ((RK == NRX_CLV) ? TP * 128u + TP * 4u : (RK == NRX_TIP ? (uint32_t)TP : 0u));
+  const size_t p0 = ((size_t)c.grp + (size_t)k * c.groups) * TPX;
+  constexpr uint32_t tx = ((LK == NRX_CLV) ? TPX * 128u + TPX * 4u : (LK == NRX_TIP ? TPX : 0u)) +
+                          ((RK == NRX_CLV) ? TPX * 128u + TPX * 4u : (RK == NRX_TIP ? TPX : 0u));
   mbar_expect_tx(bar, tx);
-  if (LK == NRX_CLV) { bulk_g2s(st.l, c.clvL + p0 * 16, TP * 128u, bar); bulk_g2s(st.scl, c.scL + p0, TP * 4u, bar); }
-  else if (LK == NRX_TIP) bulk_g2s(st.tl, c.tipL + p0, TP, bar);
-  if (RK == NRX_CLV) { bulk_g2s(st.r, c.clvR + p0 * 16, TP * 128u, bar); bulk_g2s(st.scr, c.scR + p0, TP * 4u, bar); }
-  else if (RK == NRX_TIP) bulk_g2s(st.tr, c.tipR + p0, TP, bar);
+  if (LK == NRX_CLV) { bulk_g2s(st.l, c.clvL + p0 * 16, TPX * 128u, bar); bulk_g2s(st.scl, c.scL + p0, TPX * 4u, bar); }
+  else if (LK == NRX_TIP) bulk_g2s(st.tl, c.tipL + p0, TPX, bar);
+  if (RK == NRX_CLV) { bulk_g2s(st.r, c.clvR + p0 * 16, TPX * 128u, bar); bulk_g2s(st.scr, c.scR + p0, TPX * 4u, bar); }
+  else if (RK == NRX_TIP) bulk_g2s(st.tr, c.tipR + p0, TPX, bar);
 }
 
-template <int LK, int RK, bool EMIT>
-__device__ __forceinline__ void pipe_loop(ClvPipeSmem &sm, const PipeCtx &c, const double (&PL)[16], const double (&PR)[16],
+template <int LK, int RK, bool EMIT, int NT>
+__device__ __forceinline__ void pipe_loop(PipeSmem<NT> &sm, const PipeCtx &c, const double (&PL)[16], const double (&PR)[16],
                                           double f0, double f1, double f2, double f3, double wcat) {
+  constexpr uint32_t TPX = NT * TP;
+  constexpr uint32_t NST = PipeSmem<NT>::NST;
   const int tid = threadIdx.x, cat = tid & 3, lane = tid & 31, pl = tid >> 2;
   constexpr bool tiptip = (LK == NRX_TIP && RK == NRX_TIP);
   const unsigned quad = 0xFu << (lane & ~3);
   if (tid == 0) {
-    const uint32_t pre = c.count < (uint32_t)NSTAGE ? c.count : (uint32_t)NSTAGE;
-    for (uint32_t k = 0; k < pre; ++k) pipe_issue<LK, RK>(sm, c, k, k);
+    const uint32_t pre = c.count < NST ? c.count : NST;
+    for (uint32_t k = 0; k < pre; ++k) pipe_issue<LK, RK, NT>(sm, c, k, k);
   }
-  uint32_t site = c.grp * TP + pl;                       // patterns < 2^32
-  const uint32_t site_step = c.groups * TP;
-  double *out = c.par + ((size_t)site * 4 + cat) * 4;
+  uint32_t site0 = c.grp * TPX + pl;                       // patterns < 2^32
+  const uint32_t site_step = c.groups * TPX;
+  double *out0 = c.par + ((size_t)site0 * 4 + cat) * 4;
   const size_t out_step = (size_t)site_step * 16;
   uint32_t stage = 0, phase = 0;
   for (uint32_t k = 0; k < c.count; ++k) {
-    const ClvStage &st = sm.st[stage];
+    const PipeStage<NT> &st = sm.st[stage];
     mbar_wait(&sm.full[stage], phase);
-    const bool act = site < c.patterns;
-    D4 x, y, p;
-    if (LK == NRX_CLV) x = matvec4_reg(PL, *reinterpret_cast<const D4 *>(st.l + tid * 4));
-    else if (LK == NRX_TIP) x = *reinterpret_cast<const D4 *>(sm.lutL + ((st.tl[pl] & 15) * 4 + cat) * 4);
-    if (RK == NRX_CLV) y = matvec4_reg(PR, *reinterpret_cast<const D4 *>(st.r + tid * 4));
-    else if (RK == NRX_TIP) y = *reinterpret_cast<const D4 *>(sm.lutR + ((st.tr[pl] & 15) * 4 + cat) * 4);
-    if (RK == NRX_NONE) p = x;
-    else if (LK == NRX_NONE) p = y;
-    else { p.x = __dmul_rn(x.x, y.x); p.y = __dmul_rn(x.y, y.y); p.z = __dmul_rn(x.z, y.z); p.w = __dmul_rn(x.w, y.w); }
-    uint32_t s = 0;
-    if (!tiptip) {
-      const bool small = act & (p.x < SCALE_THRESHOLD) & (p.y < SCALE_THRESHOLD) & (p.z < SCALE_THRESHOLD) & (p.w < SCALE_THRESHOLD);
-      const unsigned b = __ballot_sync(0xffffffffu, small);
-      const bool scale = (b & quad) == quad;
-      if (LK == NRX_CLV) s += st.scl[pl];
-      if (RK == NRX_CLV) s += st.scr[pl];
-      s += scale ? 1u : 0u;
-      if (scale) { p.x = __dmul_rn(p.x, SCALE_FACTOR); p.y = __dmul_rn(p.y, SCALE_FACTOR); p.z = __dmul_rn(p.z, SCALE_FACTOR); p.w = __dmul_rn(p.w, SCALE_FACTOR); }
-    }
-    if (act) {
-      stg256(out, p);
-      if (cat == 0) c.psc[site] = s;
-    }
-    if (EMIT) {
-      double t = 0.0;
-      if (act) t = __dmul_rn(tree4(__dmul_rn(f0, p.x), __dmul_rn(f1, p.y), __dmul_rn(f2, p.z), __dmul_rn(f3, p.w)), wcat);
-      const double t1 = __shfl_down_sync(0xffffffffu, t, 1), t2 = __shfl_down_sync(0xffffffffu, t, 2), t3 = __shfl_down_sync(0xffffffffu, t, 3);
-      if (act && cat == 0) c.ps_out[site] = __dadd_rn(__dadd_rn(__dadd_rn(t, t1), t2), t3);
+#pragma unroll
+    for (int u = 0; u < NT; ++u) {
+      const uint32_t site = site0 + u * TP;
+      const int plu = pl + u * TP, tu = tid + u * BLOCK;
+      double *out = out0 + (size_t)u * TP * 16;
+      const bool act = site < c.patterns;
+      D4 x, y, p;
+      if (LK == NRX_CLV) x = matvec4_reg(PL, *reinterpret_cast<const D4 *>(st.l + tu * 4));
+      else if (LK == NRX_TIP) x = *reinterpret_cast<const D4 *>(sm.lutL + ((st.tl[plu] & 15) * 4 + cat) * 4);
+      if (RK == NRX_CLV) y = matvec4_reg(PR, *reinterpret_cast<const D4 *>(st.r + tu * 4));
+      else if (RK == NRX_TIP) y = *reinterpret_cast<const D4 *>(sm.lutR + ((st.tr[plu] & 15) * 4 + cat) * 4);
+      if (RK == NRX_NONE) p = x;
+      else if (LK == NRX_NONE) p = y;
+      else { p.x = __dmul_rn(x.x, y.x); p.y = __dmul_rn(x.y, y.y); p.z = __dmul_rn(x.z, y.z); p.w = __dmul_rn(x.w, y.w); }
+      uint32_t s = 0;
+      if (!tiptip) {
+        const bool small = act & (p.x < SCALE_THRESHOLD) & (p.y < SCALE_THRESHOLD) & (p.z < SCALE_THRESHOLD) & (p.w < SCALE_THRESHOLD);
+        const unsigned b = __ballot_sync(0xffffffffu, small);
+        const bool scale = (b & quad) == quad;
+        if (LK == NRX_CLV) s += st.scl[plu];
+        if (RK == NRX_CLV) s += st.scr[plu];
+        s += scale ? 1u : 0u;
+        if (scale) { p.x = __dmul_rn(p.x, SCALE_FACTOR); p.y = __dmul_rn(p.y, SCALE_FACTOR); p.z = __dmul_rn(p.z, SCALE_FACTOR); p.w = __dmul_rn(p.w, SCALE_FACTOR); }
+      }
+      if (act) {
+        stg256(out, p);
+        if (cat == 0) c.psc[site] = s;
+      }
+      if (EMIT) {
+        double t = 0.0;
+        if (act) t = __dmul_rn(tree4(__dmul_rn(f0, p.x), __dmul_rn(f1, p.y), __dmul_rn(f2, p.z), __dmul_rn(f3, p.w)), wcat);
+        const double t1 = __shfl_down_sync(0xffffffffu, t, 1), t2 = __shfl_down_sync(0xffffffffu, t, 2), t3 = __shfl_down_sync(0xffffffffu, t, 3);
+        if (act && cat == 0) c.ps_out[site] = __dadd_rn(__dadd_rn(__dadd_rn(t, t1), t2), t3);
+      }
     }
     __syncthreads();   // lock-step refill (see k_clv_dna4_pipe: per-warp release measured 18 % slower)
-    if (tid == 0 && k + NSTAGE < c.count) pipe_issue<LK, RK>(sm, c, k + NSTAGE, stage);
-    site += site_step;
-    out += out_step;
-    if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+    if (tid == 0 && k + NST < c.count) pipe_issue<LK, RK, NT>(sm, c, k + NST, stage);
+    site0 += site_step;
+    out0 += out_step;
+    if (++stage == NST) { stage = 0; phase ^= 1u; }
   }
 }
 
+template <int NT>
 __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe2(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops,
                                                               uint32_t nops, uint32_t groups, double *__restrict__ persite,
                                                               size_t persite_stride, uint32_t nparts_total) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  ClvPipeSmem &sm = *reinterpret_cast<ClvPipeSmem *>(smem_raw);
+  PipeSmem<NT> &sm = *reinterpret_cast<PipeSmem<NT> *>(smem_raw);
   const PartView &pv = parts[blockIdx.z];
   const nrx_op op = ops[blockIdx.x % nops];
   const uint32_t grp = blockIdx.x / nops;
   const int tid = threadIdx.x, cat = tid & 3;
-  const uint32_t ntiles = (pv.patterns + TP - 1) / TP;
+  const uint32_t ntiles = (pv.patterns + NT * TP - 1) / (NT * TP);
   if (grp >= ntiles) return;
   const int lk = op.left_kind, rk = op.right_kind;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) mbar_init(&sm.full[s], 1);
+    for (int s = 0; s < PipeSmem<NT>::NST; ++s) mbar_init(&sm.full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (lk == NRX_TIP) build_tip_lut4(sm.lutL, pv.pmat + (size_t)op.left_edge * 64, tid);
@@ -534,10 +565,10 @@ __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe2(const PartView *__r
     f0 = pv.freqs[0]; f1 = pv.freqs[1]; f2 = pv.freqs[2]; f3 = pv.freqs[3]; wcat = pv.rate_weights[cat];
     c.ps_out = persite + ((size_t)(op.lnl_item - 1) * nparts_total + pv.part_index) * persite_stride;
   }
-#define NRX_PIPE_CASE(L, R)                                                              \
-  case (L) * 3 + (R):                                                                    \
-    if (emit) pipe_loop<L, R, true>(sm, c, PL, PR, f0, f1, f2, f3, wcat);                \
-    else pipe_loop<L, R, false>(sm, c, PL, PR, f0, f1, f2, f3, wcat);                    \
+#define NRX_PIPE_CASE(L, R)                                                                  \
+  case (L) * 3 + (R):                                                                        \
+    if (emit) pipe_loop<L, R, true, NT>(sm, c, PL, PR, f0, f1, f2, f3, wcat);                \
+    else pipe_loop<L, R, false, NT>(sm, c, PL, PR, f0, f1, f2, f3, wcat);                    \
     break;
   switch (lk * 3 + rk) {
     NRX_PIPE_CASE(NRX_CLV, NRX_CLV)

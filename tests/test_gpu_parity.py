@@ -449,6 +449,47 @@ def test_batched_scoring_equals_sequential():
         g.close()
 
 
+def _fuzz_cases():
+    rng = np.random.default_rng(2026)
+    sizes = [1, 2, 63, 64, 65, 127, 128, 129, 191, 255, 256, 257, 383, 500]   # around the 64 / 128-pattern tile edges
+    cases = []
+    for k, pat in enumerate(sizes):
+        cases.append((int(rng.integers(4, 28)), int(rng.integers(0, 5)), pat, 100 + k, bool(k % 3 == 0), AVERAGE if k % 2 else BEST))
+    return cases
+
+
+@pytest.mark.parametrize("n,r,pat,seed,random_cells,variant", _fuzz_cases())
+def test_randomised_networks_bitexact(n, r, pat, seed, random_cells, variant):
+    """Seeded random networks / alignment sizes around the kernel tile edges (ragged last tiles, a single pattern),
+    uniform-random cells every third case (the worst case for scaling), random reticulation probabilities: CLVs and
+    scalers bit-identical to the reference's libpll, lnL / derivatives within tolerance, re-rooting on two random edges."""
+    rng = np.random.default_rng(seed)
+    r = min(r, max(0, n - 3))
+    net = random_network(n, r, seed=seed)
+    m, w = simulate_alignment(net, pat, seed=seed, random_cells=random_cells)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    g, o = _gpu(net, [part], variant=variant), _oracle(net, [part], variant=variant)
+    _inject_eigen(g, o)
+    for i in range(net.num_reticulations):
+        pr = float(rng.uniform(0.05, 0.95))
+        g.set_reticulation_prob(i, pr); o.set_reticulation_prob(i, pr)
+    lo, lg = o.computeLoglikelihood(0, 1), g.computeLoglikelihood(0, 1)
+    assert lg == pytest.approx(lo, rel=LNL_RTOL)
+    same_p = all(np.array_equal(g.get_pmatrix(e), o.get_pmatrix(e)) for e in range(net.num_edges + 1))
+    _compare_all_clvs(g, o, exact=same_p)
+    assert g.computeLoglikelihood(0, 1) == lg     # plan replay + fused K3
+    for e in sorted({int(x) for x in rng.integers(0, net.num_edges, 2)}):
+        assert g.brlen_prepare(e) == pytest.approx(o.brlen_prepare(e), rel=LNL_RTOL)
+        assert g.computeLoglikelihoodBrlenOpt(e) == pytest.approx(o.computeLoglikelihoodBrlenOpt(e), rel=LNL_RTOL)
+        ng = g.computePartitionSumtables(e)
+        assert ng == o.computePartitionSumtables(e)
+        if ng:
+            dg, do = g.computeLoglikelihoodDerivatives(e), o.computeLoglikelihoodDerivatives(e)
+            np.testing.assert_allclose(dg[4], do[4], rtol=DERIV_RTOL, atol=1e-9)
+        assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL)
+    g.close()
+
+
 def test_empty_partition_slice_is_skipped():
     """A site shard may own NO pattern of a partition (reference: partitions[p] == NULL, 'skip remote partitions',
     LH/ImprovedLoglikelihood.cpp:128-131): the engine must accept patterns = 0 and contribute exactly 0 to that partition."""

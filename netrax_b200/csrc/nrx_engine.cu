@@ -1046,7 +1046,13 @@ int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n
   if (!check_pairs(e, pairs, n, "nrx_edge_lnl")) return 0;
   for (const Part &p : e->parts) if (edge >= p.d.edges) { g_err = "nrx_edge_lnl: edge out of range"; return 0; }
   const uint32_t P = (uint32_t)e->parts.size();
-  const uint32_t nblk = reduce_blocks(e, n * P);
+  uint32_t nblk = reduce_blocks(e, n * P);
+  {  // engines whose partitions all run the tensor-core kernel: nblk = tile groups per pair; keep >= ~50 tiles per block so
+     // that the per-block set-up (B fragments, tip table) is amortised (4736 blocks of 21 tiles ran at 7 % tensor pipe)
+    bool only_aa = !e->classes.empty();
+    for (const ShapeClass &c : e->classes) only_aa = only_aa && aa_dmma_class(e, c);
+    if (only_aa) nblk = std::max<uint32_t>(1, std::min<uint32_t>(nblk, e->aa_blocks / std::max<uint32_t>(1, n * P)));
+  }
   if (!ensure_result(e, (size_t)n * P, (size_t)n * P * nblk) || !refresh_views(e)) return 0;
   nrx_pair *d_pairs;
   if (!upload(e, pairs, n, &d_pairs)) return 0;

@@ -1191,7 +1191,9 @@ __global__ void __launch_bounds__(BLOCK) k_copy_slots(const PartView *__restrict
  * (pattern, category) item = `sp` contiguous doubles read as 256-bit loads (a warp covers 32 consecutive items =
  * one contiguous span), the per-category results of a pattern are gathered IN CATEGORY ORDER from the adjacent
  * lanes (same summation order as the thread-per-pattern kernels above and as the reference), constants in shared
- * memory.  4x the threads and 1/4 of the load instructions of the thread-per-pattern version.
+ * memory.  4x the threads and 1/4 of the load instructions of the thread-per-pattern version.  (A warp-per-pattern
+ * variant of K6 with fully contiguous 640-byte warp loads and 20 active lanes was measured SLOWER: 0.22 vs 0.34 of the
+ * HBM roofline at 200 k protein patterns — one load in flight per lane and a 27-shuffle chain per pattern.)
  * ---------------------------------------------------------------------------------------------- */
 template <int SC /* compile-time state count (loops unroll, all loads issue up front); 0 = run time */>
 __global__ void __launch_bounds__(BLOCK) k_tree_lnl_pc(const PartView *__restrict__ parts, const uint32_t *__restrict__ slots,

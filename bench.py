@@ -15,7 +15,7 @@ metric  = CLV site-updates/s (sum over nodes of displayed trees(node) x patterns
 value   = inputs resident in HBM, timed with CUDA events on the engine's stream, max over ranks.
 e2e     = the same step through the host C-ABI with HOST buffers: every step re-uploads the rank's alignment
           slice (tipchars + pattern weights, pinned host memory) and reads the lnL back.
-roofline= K2 (k_clv_dna4) only: algorithmic bytes / CUDA-event time of the K2 launches.
+roofline= K2 (k_clv_dna4_pipe2) only: algorithmic bytes / CUDA-event time of the K2 launches.
 cpu_baseline / --impl reference = the restated NetRAX layer over the REAL forked libpll (oracle/_ref, kind
           "reference"; the scalar port if _ref is absent), site-sharded over all host cores, bounded sample.
 """
@@ -293,7 +293,7 @@ def main():
                         "ms_per_step": ms_e2e / args.steps, "lnl_evals_per_sec": 1e3 / (ms_e2e / args.steps)},
                 "gpu_launches": int(launches),
                 "clocks": clocks,
-                "roofline": {"kernel": "k_clv_dna4 (K2, CLV update)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "roofline": {"kernel": "k_clv_dna4_pipe2 (K2, CLV update)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
                              "dram_frac": (traffic / (prof["clv_ms"] / max(1, prof["clv_launches"]) / 1e3) / 1e9 / peak) if traffic and peak and prof["clv_ms"] > 0 else None,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",

@@ -84,6 +84,16 @@ int nrxh_optimize_reticulations(void *h, int max_iters, double *final_logl);
 /* model-parameter loop: Gamma shape of partition p (treeinfo_set_alpha, PLLMOD/algorithm/pllmod_algorithm.c:566-587)
  * and the ALPHA step of optimize_params (src/optimization/ModelOptimization.cpp:56-65 = pllmod_algo_opt_onedim_treeinfo):
  * Brent over the alphas of all partitions that carry one, one full device re-evaluation per iterate. */
+/* src/likelihood/ComplexityScoring.hpp: BIC of the network (what the search compares) */
+int nrxh_score_network(void *h, double *bic_score);
+int nrxh_set_scoring_sizes(void *h, unsigned long long total_num_model_parameters, unsigned long long total_num_sites /* 0: keep */);
+/* src/optimization/Optimization.hpp:23-25: model (alpha or the caller's optimize_params), reticulation probabilities and
+ * branch lengths in rounds until the BIC stops improving; type 0 QUICK, 1 NORMAL, 2 SLOW */
+int nrxh_optimize_all_non_topology(void *h, int type, double *bic_score);
+/* The slot pll-modules' optimisers re-enter through: same signature as pllmod_treeinfo_t::likelihood_target_function
+ * (PLLMOD/tree/pll_tree.h:267-271) / network_logl_wrapper (src/RaxmlWrapper.cpp:21-26); params from nrxh_network_params(h). */
+double nrxh_likelihood_target_function(void *network_params, int incremental, int update_pmatrices, double **persite_lnl);
+void *nrxh_network_params(void *h);
 int nrxh_set_alpha(void *h, unsigned p, double alpha);
 int nrxh_get_alpha(void *h, unsigned p, double *alpha);
 int nrxh_optimize_alpha(void *h, double min_alpha, double max_alpha, double tolerance, double *final_logl);

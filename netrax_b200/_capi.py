@@ -72,6 +72,9 @@ class FlatAPI:
         g("optimize_branches", C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double))
         g("optimize_reticulation", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
         g("optimize_reticulations", C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double))
+        g("score_network", C.c_int, C.c_void_p, C.POINTER(C.c_double))
+        g("set_scoring_sizes", C.c_int, C.c_void_p, C.c_ulonglong, C.c_ulonglong)
+        g("optimize_all_non_topology", C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double))
         g("set_alpha", C.c_int, C.c_void_p, C.c_uint, C.c_double)
         g("get_alpha", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
         g("optimize_alpha", C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double))
@@ -287,6 +290,21 @@ class LikelihoodEngine:
     def optimize_reticulation(self, r: int) -> float:
         out = C.c_double()
         self.api.check(self.api._optimize_reticulation(self.h, r, C.byref(out)))
+        return out.value
+
+    def scoreNetwork(self) -> float:
+        """BIC of the network (src/likelihood/ComplexityScoring.cpp:57-67); smaller is better."""
+        out = C.c_double()
+        self.api.check(self.api._score_network(self.h, C.byref(out)))
+        return out.value
+
+    def set_scoring_sizes(self, total_num_model_parameters: int, total_num_sites: int = 0):
+        self.api.check(self.api._set_scoring_sizes(self.h, total_num_model_parameters, total_num_sites))
+
+    def optimizeAllNonTopology(self, type: int = 1) -> float:
+        """src/optimization/Optimization.cpp:118-214 (0 QUICK, 1 NORMAL, 2 SLOW); returns the final BIC."""
+        out = C.c_double()
+        self.api.check(self.api._optimize_all_non_topology(self.h, type, C.byref(out)))
         return out.value
 
     def set_alpha(self, p: int, alpha: float):

@@ -22,6 +22,7 @@ struct Handle {
   bool net_set = false, inited = false;
   std::vector<DisplayedTreeData> oldTrees;
   std::vector<std::vector<SumtableInfo>> sumtables;
+  NetworkParams params{nullptr};
 };
 
 template <class F> int guarded(F &&f) {
@@ -360,6 +361,29 @@ int nrxh_optimize_reticulation(void *hv, unsigned r, double *final_logl) {
   });
 }
 
+int nrxh_score_network(void *hv, double *bic_score) {
+  return guarded([&] { *bic_score = scoreNetwork(H(hv)->ann); });
+}
+int nrxh_set_scoring_sizes(void *hv, unsigned long long total_num_model_parameters, unsigned long long total_num_sites) {
+  return guarded([&] {
+    H(hv)->ann.total_num_model_parameters = (size_t)total_num_model_parameters;
+    if (total_num_sites) H(hv)->ann.total_num_sites = (size_t)total_num_sites;
+  });
+}
+int nrxh_optimize_all_non_topology(void *hv, int type, double *bic_score) {
+  return guarded([&] {
+    optimizeAllNonTopology(H(hv)->ann, (OptimizeAllNonTopologyType)type);
+    if (bic_score) *bic_score = scoreNetwork(H(hv)->ann);
+  });
+}
+double nrxh_likelihood_target_function(void *network_params, int incremental, int update_pmatrices, double **persite_lnl) {
+  try { return network_logl_wrapper(network_params, incremental, update_pmatrices, persite_lnl); }
+  catch (const std::exception &e) { g_err = e.what(); return -std::numeric_limits<double>::infinity(); }
+}
+void *nrxh_network_params(void *hv) {  // the likelihood_computation_params pointer for the handle's network
+  H(hv)->params.ann_network = &H(hv)->ann;
+  return &H(hv)->params;
+}
 int nrxh_set_alpha(void *hv, unsigned p, double alpha) {
   return guarded([&] { setAlpha(H(hv)->ann, p, alpha); });
 }

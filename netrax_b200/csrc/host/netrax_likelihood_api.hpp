@@ -201,6 +201,11 @@ struct AnnotatedNetwork {  // src/graph/AnnotatedNetwork.hpp:42-89
   std::vector<Node *> travbuffer;
   double cached_logl = 0.0;
   bool cached_logl_valid = false;
+  size_t total_num_model_parameters = 0;  // parted_msa->total_free_model_params() (src/RaxmlWrapper.cpp:682-684); caller-set
+  size_t total_num_sites = 0;             // parted_msa->total_sites(); default: sum of this process's pattern weights
+  /* optimize_params (src/optimization/ModelOptimization.cpp:25-97): pll-modules' model optimisers in a NetRAX build; when
+   * unset, optimizeModel runs the one step this repo implements itself, optimize_alpha */
+  double (*optimize_params_cb)(AnnotatedNetwork &) = nullptr;
 
   /* device side */
   nrx_engine *engine = nullptr;
@@ -267,6 +272,29 @@ void pushPartitionModel(AnnotatedNetwork &ann_network, unsigned partition);
 void setAlpha(AnnotatedNetwork &ann_network, unsigned partition, double alpha);
 /* the ALPHA step of optimize_params (src/optimization/ModelOptimization.cpp:56-65); defaults = PLLMOD_OPT_MIN/MAX_ALPHA, RAXML_PARAM_EPSILON */
 double optimize_alpha(AnnotatedNetwork &ann_network, double min_alpha = 0.0201, double max_alpha = 100.0, double tolerance = 0.001);
+
+/* ---- src/likelihood/ComplexityScoring.hpp:7-13 (what the search calls a network's score) ------------------------- */
+size_t get_param_count(AnnotatedNetwork &ann_network);
+size_t get_sample_size(AnnotatedNetwork &ann_network);
+double aic(AnnotatedNetwork &ann_network, double logl);
+double aicc(AnnotatedNetwork &ann_network, double logl);
+double bic(AnnotatedNetwork &ann_network, double logl);
+double scoreNetwork(AnnotatedNetwork &ann_network);
+
+/* ---- src/optimization/Optimization.hpp:12-25: the non-topology optimisation rounds around the path ---------------- */
+enum class OptimizeAllNonTopologyType { QUICK = 0, NORMAL = 1, SLOW = 2 };
+void optimizeBranches(AnnotatedNetwork &ann_network, double brlen_smooth_factor = 1.0, bool silent = true, bool restricted_total_iters = false);
+void optimizeModel(AnnotatedNetwork &ann_network, bool silent = true);
+void optimizeReticulationProbs(AnnotatedNetwork &ann_network, bool silent = true);
+void optimizeAllNonTopology(AnnotatedNetwork &ann_network, OptimizeAllNonTopologyType type, bool silent = true);
+
+/* the slot pll-modules' optimisers re-enter through (src/RaxmlWrapper.cpp:21-26, src/RaxmlWrapper.hpp:20-24):
+ * pllmod_treeinfo_t::likelihood_target_function = network_logl_wrapper, likelihood_computation_params = NetworkParams* */
+struct NetworkParams {
+  AnnotatedNetwork *ann_network;
+  explicit NetworkParams(AnnotatedNetwork *a) : ann_network(a) {}
+};
+double network_logl_wrapper(void *network_params, int incremental, int update_pmatrices, double **persite_lnl);
 
 /* ---- src/helper/InvalidationHelper.cpp -------------------------------------------------------------------- */
 void invalidateSingleClv(AnnotatedNetwork &ann_network, unsigned int clv_index);

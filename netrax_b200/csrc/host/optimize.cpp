@@ -383,4 +383,95 @@ double optimize_alpha(AnnotatedNetwork &ann, double min_alpha, double max_alpha,
   return computeLoglikelihood(ann, 0, 1);
 }
 
+/* ---- src/likelihood/ComplexityScoring.cpp:7-67 --------------------------------------------------------------------- */
+static double aic_(double logl, double k) { return -2 * logl + 2 * k; }
+static double aicc_(double logl, double k, double n) { return aic_(logl, k) + (2 * k * k + 2 * k) / (n - k - 1); }
+static double bic_(double logl, double k, double n) { return -2 * logl + k * std::log(n); }
+
+size_t get_param_count(AnnotatedNetwork &ann) {  // :13-34
+  size_t param_count = ann.total_num_model_parameters;
+  param_count += ann.network.num_reticulations();  // reticulation probs as free parameters
+  if (ann.fake_treeinfo->brlen_linkage == PLLMOD_COMMON_BRLEN_UNLINKED) param_count += ann.fake_treeinfo->partition_count * ann.network.num_branches();
+  else {
+    param_count += ann.network.num_branches();
+    if (ann.fake_treeinfo->brlen_linkage == PLLMOD_COMMON_BRLEN_SCALED) param_count += ann.fake_treeinfo->partition_count - 1;
+  }
+  return param_count;
+}
+size_t get_sample_size(AnnotatedNetwork &ann) { return ann.total_num_sites * ann.network.num_tips(); }  // :36-38
+double aic(AnnotatedNetwork &ann, double logl) { return aic_(logl, (double)get_param_count(ann)); }
+double aicc(AnnotatedNetwork &ann, double logl) { return aicc_(logl, (double)get_param_count(ann), (double)get_sample_size(ann)); }
+double bic(AnnotatedNetwork &ann, double logl) { return bic_(logl, (double)get_param_count(ann), (double)get_sample_size(ann)); }
+
+double scoreNetwork(AnnotatedNetwork &ann) {  // :57-67
+  const double logl = computeLoglikelihood(ann, 1, 1);
+  const double bic_score = bic(ann, logl);
+  if (bic_score == std::numeric_limits<double>::infinity()) throw std::runtime_error("Invalid BIC score");
+  return bic_score;
+}
+
+double network_logl_wrapper(void *network_params, int incremental, int update_pmatrices, double **) {  // RaxmlWrapper.cpp:21-26
+  return computeLoglikelihood(*static_cast<NetworkParams *>(network_params)->ann_network, incremental, update_pmatrices);
+}
+
+/* ---- src/optimization/Optimization.cpp:17-216 ------------------------------------------------------------------------ */
+void optimizeBranches(AnnotatedNetwork &ann, double brlen_smooth_factor, bool, bool restricted_total_iters) {  // :17-38
+  const double old_score = scoreNetwork(ann);
+  const int max_iters = (int)(brlen_smooth_factor * 32);  // RAXML_BRLEN_SMOOTHINGS
+  optimize_branches(ann, max_iters, max_iters, -1 /* PLLMOD_OPT_BRLEN_OPTIMIZE_ALL */, restricted_total_iters);
+  const double new_score = scoreNetwork(ann);
+  if (new_score - old_score > 1E-3) throw std::runtime_error("Complete brlenopt made BIC worse");
+  // optimize_scalers (:37): only for scaled branch-length linkage, which this engine rejects
+}
+
+void optimizeModel(AnnotatedNetwork &ann, bool) {  // :72-84
+  scoreNetwork(ann);
+  if (ann.optimize_params_cb) ann.optimize_params_cb(ann);
+  else optimize_alpha(ann);
+  scoreNetwork(ann);
+}
+
+void optimizeReticulationProbs(AnnotatedNetwork &ann, bool) {  // :91-108
+  if (ann.network.num_reticulations() == 0) return;
+  const double old_score = scoreNetwork(ann);
+  optimize_reticulations(ann, 10);
+  const double new_score = scoreNetwork(ann);
+  if (new_score - old_score > 1E-3) throw std::runtime_error("BIC got worse after optimizing reticulation probs");
+}
+
+void optimizeAllNonTopology(AnnotatedNetwork &ann, OptimizeAllNonTopologyType type, bool silent) {  // :118-214
+  const int max_rounds_slow = 2;
+  int act_rounds_slow = 0;
+  bool gotBetterSlow = true;
+  while (gotBetterSlow) {
+    gotBetterSlow = false;
+    bool doBrlenOpt = true, doReticulationOpt = true, doModelOpt = true;
+    const double score_epsilon = 0.01;
+    bool gotBetter = true;
+    while (gotBetter) {
+      gotBetter = false;
+      const double score_before = scoreNetwork(ann);
+      if (doModelOpt) {
+        const double before = scoreNetwork(ann);
+        optimizeModel(ann, silent);
+        if (before - scoreNetwork(ann) > score_epsilon) doModelOpt = false;   // as written in the reference (:161-164)
+      }
+      if (doReticulationOpt) {
+        const double before = scoreNetwork(ann);
+        optimizeReticulationProbs(ann, silent);
+        if (before - scoreNetwork(ann) > score_epsilon) doReticulationOpt = false;
+      }
+      if (doBrlenOpt) {
+        const double before = scoreNetwork(ann);
+        optimizeBranches(ann, 1.0, silent);
+        if (before - scoreNetwork(ann) > score_epsilon) doBrlenOpt = false;
+      }
+      const double overall_improv = score_before - scoreNetwork(ann);
+      if (overall_improv > score_epsilon && type != OptimizeAllNonTopologyType::QUICK && (doBrlenOpt || doReticulationOpt || doModelOpt)) gotBetter = true;
+      if (overall_improv > score_epsilon && type == OptimizeAllNonTopologyType::SLOW) gotBetterSlow = true;
+    }
+    if (++act_rounds_slow >= max_rounds_slow) break;
+  }
+}
+
 }  // namespace netrax

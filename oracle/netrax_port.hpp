@@ -217,6 +217,7 @@ struct AnnotatedNetwork {  // SRC/graph/AnnotatedNetwork.hpp:42-89 (fields the p
   std::vector<std::vector<double>> branch_lengths;  // [partition][edge+1] (fake_treeinfo->branch_lengths)
   std::vector<double> linked_branch_lengths;        // [edge+1]
   std::vector<double> partition_loglh;
+  size_t total_num_model_parameters = 0, total_num_sites = 0;  // SRC/graph/AnnotatedNetwork.hpp:47-48
   std::vector<double> alphas;  // fake_treeinfo->alphas (0 = no Gamma shape attached to the partition's rates)
   double cached_logl = 0;
   bool cached_logl_valid = false;
@@ -260,6 +261,8 @@ double optimize_branch(AnnotatedNetwork &ann, size_t pmatrix_index, int method, 
 double optimize_branches(AnnotatedNetwork &ann, int max_iters, int max_iters_outside, int radius, int method, bool restricted_total_iters = false);
 double optimize_reticulation(AnnotatedNetwork &ann, size_t reticulation_index);
 double optimize_reticulations(AnnotatedNetwork &ann, int max_iters);
+double scoreNetwork(AnnotatedNetwork &ann);                               // LH/ComplexityScoring.cpp:57-67 (BIC)
+void optimizeAllNonTopology(AnnotatedNetwork &ann, int type /* 0 QUICK, 1 NORMAL, 2 SLOW */);  // SRC/optimization/Optimization.cpp:118-214
 void setAlpha(AnnotatedNetwork &ann, unsigned partition, double alpha);   // treeinfo_set_alpha (PLLMOD/algorithm/pllmod_algorithm.c:566-587)
 double optimize_alpha(AnnotatedNetwork &ann, double min_alpha, double max_alpha, double tolerance);  // pllmod_algo_opt_onedim_treeinfo(ALPHA)
 

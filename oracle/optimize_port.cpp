@@ -244,4 +244,78 @@ double optimize_alpha(AnnotatedNetwork &ann, double min_alpha, double max_alpha,
   return computeLoglikelihood(ann, 0, 1);
 }
 
+/* ---- LH/ComplexityScoring.cpp:7-67 and SRC/optimization/Optimization.cpp:17-214, with optimize_params reduced to its ALPHA
+ * step (the only model step restated; the product's default optimize_params hook does the same) ---------------------- */
+double scoreNetwork(AnnotatedNetwork &ann) {
+  const double logl = computeLoglikelihood(ann, 1, 1);
+  size_t k = ann.total_num_model_parameters + ann.network.num_reticulations();
+  if (ann.options.brlen_linkage == BRLEN_UNLINKED) k += ann.partitionCount() * ann.network.num_branches();
+  else {
+    k += ann.network.num_branches();
+    if (ann.options.brlen_linkage == BRLEN_SCALED) k += ann.partitionCount() - 1;
+  }
+  const double n = (double)(ann.total_num_sites * ann.network.num_tips);
+  const double bic = -2 * logl + (double)k * std::log(n);
+  if (bic == std::numeric_limits<double>::infinity()) throw std::runtime_error("Invalid BIC score");
+  return bic;
+}
+
+namespace {
+void optimizeBranches(AnnotatedNetwork &ann, double brlen_smooth_factor) {  // Optimization.cpp:17-38
+  const double old_score = scoreNetwork(ann);
+  const int max_iters = (int)(brlen_smooth_factor * 32);
+  optimize_branches(ann, max_iters, max_iters, -1, OPT_NEWTON_RAPHSON, false);
+  if (scoreNetwork(ann) - old_score > 1E-3) throw std::runtime_error("Complete brlenopt made BIC worse");
+}
+void optimizeModel(AnnotatedNetwork &ann) {  // :72-84
+  scoreNetwork(ann);
+  optimize_alpha(ann, 0.0201, 100., 0.001);  // PLLMOD_OPT_MIN_ALPHA, PLLMOD_OPT_MAX_ALPHA, RAXML_PARAM_EPSILON
+  scoreNetwork(ann);
+}
+void optimizeReticulationProbs(AnnotatedNetwork &ann) {  // :91-108
+  if (ann.network.num_reticulations() == 0) return;
+  const double old_score = scoreNetwork(ann);
+  optimize_reticulations(ann, 10);
+  if (scoreNetwork(ann) - old_score > 1E-3) throw std::runtime_error("BIC got worse after optimizing reticulation probs");
+}
+}  // namespace
+
+void optimizeAllNonTopology(AnnotatedNetwork &ann, int type) {  // :118-214
+  int max_rounds_slow = 2, act_rounds_slow = 0;
+  bool gotBetterSlow = true;
+  while (gotBetterSlow) {
+    gotBetterSlow = false;
+    bool doBrlenOpt = true, doReticulationOpt = true, doModelOpt = true;
+    double score_epsilon = 0.01;
+    bool gotBetter = true;
+    while (gotBetter) {
+      gotBetter = false;
+      double score_before = scoreNetwork(ann);
+      if (doModelOpt) {
+        double score_before_model = scoreNetwork(ann);
+        optimizeModel(ann);
+        double score_after_model = scoreNetwork(ann);
+        if (score_before_model - score_after_model > score_epsilon) doModelOpt = false;
+      }
+      if (doReticulationOpt) {
+        double score_before_probs = scoreNetwork(ann);
+        optimizeReticulationProbs(ann);
+        double score_after_probs = scoreNetwork(ann);
+        if (score_before_probs - score_after_probs > score_epsilon) doReticulationOpt = false;
+      }
+      if (doBrlenOpt) {
+        double score_before_branches = scoreNetwork(ann);
+        optimizeBranches(ann, 1.0);
+        double score_after_branches = scoreNetwork(ann);
+        if (score_before_branches - score_after_branches > score_epsilon) doBrlenOpt = false;
+      }
+      double overall_improv = score_before - scoreNetwork(ann);
+      if (overall_improv > score_epsilon && type != 0 && (doBrlenOpt || doReticulationOpt || doModelOpt)) gotBetter = true;
+      if (overall_improv > score_epsilon && type == 2) gotBetterSlow = true;
+    }
+    act_rounds_slow++;
+    if (act_rounds_slow >= max_rounds_slow) break;
+  }
+}
+
 }  // namespace orc

@@ -84,6 +84,7 @@ int orc_add_partition(void *hv, unsigned states, unsigned rate_cats, unsigned si
     d.rate_weights.assign(rate_weights, rate_weights + rate_cats);
     if (weights) d.pattern_weights.assign(weights, weights + sites);
     else d.pattern_weights.assign(sites, 1);
+    for (unsigned w : d.pattern_weights) h->ann.total_num_sites += w;
     unsigned tips = h->ann.network.num_tips;
     d.tip_masks.resize(tips);
     for (unsigned t = 0; t < tips; ++t) d.tip_masks[t].assign(tip_masks + (size_t)t * sites, tip_masks + (size_t)(t + 1) * sites);
@@ -332,6 +333,20 @@ int orc_optimize_branches(void *hv, int max_iters, int max_iters_outside, int ra
 int orc_optimize_reticulation(void *hv, unsigned r, double *final_logl) {
   Handle *h = static_cast<Handle *>(hv);
   return guarded([&] { double l = optimize_reticulation(h->ann, r); if (final_logl) *final_logl = l; });
+}
+int orc_score_network(void *hv, double *bic_score) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] { *bic_score = scoreNetwork(h->ann); });
+}
+int orc_set_scoring_sizes(void *hv, unsigned long long total_num_model_parameters, unsigned long long total_num_sites) {
+  Handle *h = static_cast<Handle *>(hv);
+  h->ann.total_num_model_parameters = (size_t)total_num_model_parameters;
+  if (total_num_sites) h->ann.total_num_sites = (size_t)total_num_sites;
+  return 1;
+}
+int orc_optimize_all_non_topology(void *hv, int type, double *bic_score) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] { optimizeAllNonTopology(h->ann, type); if (bic_score) *bic_score = scoreNetwork(h->ann); });
 }
 int orc_set_alpha(void *hv, unsigned p, double alpha) {
   Handle *h = static_cast<Handle *>(hv);

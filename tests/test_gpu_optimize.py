@@ -113,3 +113,24 @@ def test_optimize_alpha_matches_oracle(variant):
     rg, ro = g.optimize_reticulations(), o.optimize_reticulations()
     assert rg == pytest.approx(ro, rel=1e-9) and rg >= lg - 1e-3
     g.close()
+
+
+@pytest.mark.parametrize("variant", [AVERAGE, BEST])
+def test_optimize_all_non_topology_matches_oracle(variant):
+    """The whole non-topology optimisation round (model = alpha, reticulation probabilities, branch lengths, scored by
+    BIC; src/optimization/Optimization.cpp:118-214) on the device against the oracle."""
+    net = random_network(10, 2, seed=9)
+    m, w = simulate_alignment(net, 400, seed=9)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    g, o = _pair(net, [part], variant=variant)
+    for eng in (g, o):
+        eng.set_alpha(0, 1.5)
+        eng.set_scoring_sizes(9)
+    b0g, b0o = g.scoreNetwork(), o.scoreNetwork()
+    assert b0g == pytest.approx(b0o, rel=1e-10)
+    bg, bo = g.optimizeAllNonTopology(1), o.optimizeAllNonTopology(1)
+    assert bg <= b0g + 1e-3
+    assert bg == pytest.approx(bo, rel=1e-8)
+    assert g.get_alpha(0) == pytest.approx(o.get_alpha(0), rel=1e-4)
+    np.testing.assert_allclose(g.branch_lengths(), o.branch_lengths(), rtol=1e-4, atol=2e-6)
+    g.close()

@@ -197,3 +197,26 @@ def test_optimize_alpha_skips_partitions_without_shape():
     l0 = e.computeLoglikelihood(0, 1)
     assert e.optimize_alpha() == pytest.approx(l0, rel=1e-13)
     assert e.get_alpha(0) == 0.0
+
+
+def test_optimize_all_non_topology_improves_bic_and_flavours_agree():
+    """scoreNetwork (BIC, ComplexityScoring.cpp:57-67) + optimizeAllNonTopology (Optimization.cpp:118-214) over the scalar
+    port and over real libpll + real pll-modules minimisers: same trajectory end point; the BIC never gets worse."""
+    net = random_network(10, 2, seed=9)
+    m, w = simulate_alignment(net, 400, seed=9)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    res = {}
+    for kind in (["port", "ref"] if oracle.have_ref() else ["port"]):
+        e = oracle.make_engine(kind, net, [part])
+        e.set_alpha(0, 1.5)
+        e.set_scoring_sizes(9)   # GTR (5) + frequencies (3) + alpha (1)
+        b0 = e.scoreNetwork()
+        l0 = e.computeLoglikelihood(1, 1)
+        k = 9 + net.num_reticulations + net.num_edges
+        assert b0 == pytest.approx(-2 * l0 + k * math.log(float(w.sum()) * net.num_tips), rel=1e-13)
+        b1 = e.optimizeAllNonTopology(1)
+        assert b1 <= b0 + 1e-3
+        res[kind] = (b1, e.get_alpha(0))
+    if "ref" in res:
+        assert res["port"][0] == pytest.approx(res["ref"][0], rel=1e-9)
+        assert res["port"][1] == pytest.approx(res["ref"][1], rel=1e-5)

@@ -133,7 +133,7 @@ struct nrx_engine {
   uint32_t k2_nt = 2;       // env NRX_K2_NT: 64-pattern sub-tiles per ring stage of k_clv_dna4_pipe2 (1 or 2; 2 measured 1-2 % faster)
   int k2_variant = 0;       // 0: k_clv_dna4_pipe (production); UM: k_clv_dna4<U, MINB> (A/B experiments, env NRX_K2=UM)
   bool aa_generic = false;  // env NRX_AA=generic: force the scalar kernel for 20-state partitions (A/B)
-  uint32_t aa_blocks = 148 * 3 * 4;  // block-count target of the DMMA kernel
+  uint32_t aa_blocks = 148 * 3 * 2;  // block-count target of the DMMA kernels: two waves of 3 resident blocks per SM (A/B: profiles/r1e_all_configs.md)
   uint32_t k2_blocks = 2368; // block-count target of the pipelined kernel: 8 waves of 2 resident blocks per SM (measured best, profiles/)
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   bool views_dirty = true;

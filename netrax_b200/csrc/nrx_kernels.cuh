@@ -452,6 +452,15 @@ __device__ __forceinline__ void pipe_issue(PipeSmem<NT> &sm, const PipeCtx &c, u
   else if (RK == NRX_TIP) bulk_g2s(st.tr, c.tipR + p0, TPX, bar);
 }
 
+/* first ring fill, by one thread, BEFORE the block loads its P-matrices / builds its tip tables: the copies fly while the
+ * prologue runs (small alignments are latency-bound: ~1 us per launch) */
+template <int LK, int RK, int NT>
+__device__ __forceinline__ void pipe_prefetch(PipeSmem<NT> &sm, const PipeCtx &c) {
+  constexpr uint32_t NST = PipeSmem<NT>::NST;
+  const uint32_t pre = c.count < NST ? c.count : NST;
+  for (uint32_t k = 0; k < pre; ++k) pipe_issue<LK, RK, NT>(sm, c, k, k);
+}
+
 template <int LK, int RK, bool EMIT, int NT>
 __device__ __forceinline__ void pipe_loop(PipeSmem<NT> &sm, const PipeCtx &c, const double (&PL)[16], const double (&PR)[16],
                                           double f0, double f1, double f2, double f3, double wcat) {
@@ -460,11 +469,7 @@ __device__ __forceinline__ void pipe_loop(PipeSmem<NT> &sm, const PipeCtx &c, co
   const int tid = threadIdx.x, cat = tid & 3, lane = tid & 31, pl = tid >> 2;
   constexpr bool tiptip = (LK == NRX_TIP && RK == NRX_TIP);
   const unsigned quad = 0xFu << (lane & ~3);
-  if (tid == 0) {
-    const uint32_t pre = c.count < NST ? c.count : NST;
-    for (uint32_t k = 0; k < pre; ++k) pipe_issue<LK, RK, NT>(sm, c, k, k);
-  }
-  uint32_t site0 = c.grp * TPX + pl;                       // patterns < 2^32
+  uint32_t site0 = c.grp * TPX + pl;                       // patterns < 2^32 (the first NST stages were issued by pipe_prefetch)
   const uint32_t site_step = c.groups * TPX;
   double *out0 = c.par + ((size_t)site0 * 4 + cat) * 4;
   const size_t out_step = (size_t)site_step * 16;
@@ -528,10 +533,30 @@ __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe2(const PartView *__r
   const uint32_t ntiles = (pv.patterns + NT * TP - 1) / (NT * TP);
   if (grp >= ntiles) return;
   const int lk = op.left_kind, rk = op.right_kind;
+  PipeCtx c;
+  c.clvL = (lk == NRX_CLV) ? pv.clv[op.left_idx] : nullptr;
+  c.clvR = (rk == NRX_CLV) ? pv.clv[op.right_idx] : nullptr;
+  c.scL = (lk == NRX_CLV) ? pv.scaler[op.left_idx] : nullptr;
+  c.scR = (rk == NRX_CLV) ? pv.scaler[op.right_idx] : nullptr;
+  c.tipL = (lk == NRX_TIP) ? pv.tipchars + (size_t)op.left_idx * pv.tip_pitch : nullptr;
+  c.tipR = (rk == NRX_TIP) ? pv.tipchars + (size_t)op.right_idx * pv.tip_pitch : nullptr;
+  c.par = pv.clv[op.parent_slot];
+  c.psc = pv.scaler[op.parent_slot];
+  c.grp = grp; c.groups = groups; c.patterns = pv.patterns;
+  c.count = (ntiles - grp + groups - 1) / groups;
+  c.ps_out = nullptr;
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < PipeSmem<NT>::NST; ++s) mbar_init(&sm.full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#define NRX_PIPE_PRE(L, R) case (L) * 3 + (R): pipe_prefetch<L, R, NT>(sm, c); break;
+    switch (lk * 3 + rk) {
+      NRX_PIPE_PRE(NRX_CLV, NRX_CLV) NRX_PIPE_PRE(NRX_CLV, NRX_TIP) NRX_PIPE_PRE(NRX_CLV, NRX_NONE)
+      NRX_PIPE_PRE(NRX_TIP, NRX_CLV) NRX_PIPE_PRE(NRX_TIP, NRX_TIP) NRX_PIPE_PRE(NRX_TIP, NRX_NONE)
+      NRX_PIPE_PRE(NRX_NONE, NRX_CLV) NRX_PIPE_PRE(NRX_NONE, NRX_TIP)
+      default: break;
+    }
+#undef NRX_PIPE_PRE
   }
   if (lk == NRX_TIP) build_tip_lut4(sm.lutL, pv.pmat + (size_t)op.left_edge * 64, tid);
   if (rk == NRX_TIP) build_tip_lut4(sm.lutR, pv.pmat + (size_t)op.right_edge * 64, tid);
@@ -547,20 +572,8 @@ __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe2(const PartView *__r
     for (int i = 0; i < 16; ++i) PR[i] = src[i];
   }
   __syncthreads();
-  PipeCtx c;
-  c.clvL = (lk == NRX_CLV) ? pv.clv[op.left_idx] : nullptr;
-  c.clvR = (rk == NRX_CLV) ? pv.clv[op.right_idx] : nullptr;
-  c.scL = (lk == NRX_CLV) ? pv.scaler[op.left_idx] : nullptr;
-  c.scR = (rk == NRX_CLV) ? pv.scaler[op.right_idx] : nullptr;
-  c.tipL = (lk == NRX_TIP) ? pv.tipchars + (size_t)op.left_idx * pv.tip_pitch : nullptr;
-  c.tipR = (rk == NRX_TIP) ? pv.tipchars + (size_t)op.right_idx * pv.tip_pitch : nullptr;
-  c.par = pv.clv[op.parent_slot];
-  c.psc = pv.scaler[op.parent_slot];
-  c.grp = grp; c.groups = groups; c.patterns = pv.patterns;
-  c.count = (ntiles - grp + groups - 1) / groups;
   const bool emit = op.lnl_item != 0 && persite != nullptr;
   double f0 = 0, f1 = 0, f2 = 0, f3 = 0, wcat = 0;
-  c.ps_out = nullptr;
   if (emit) {
     f0 = pv.freqs[0]; f1 = pv.freqs[1]; f2 = pv.freqs[2]; f3 = pv.freqs[3]; wcat = pv.rate_weights[cat];
     c.ps_out = persite + ((size_t)(op.lnl_item - 1) * nparts_total + pv.part_index) * persite_stride;

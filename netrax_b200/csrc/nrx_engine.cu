@@ -129,6 +129,7 @@ struct nrx_engine {
   double *d_persite = nullptr;
   size_t persite_cap = 0;
   unsigned long long launches = 0;
+  int sm_count = 148;
   uint32_t pending_result = 0;  // doubles of an enqueued, not yet collected result (nrx_*_async / nrx_result_wait)
   uint32_t k2_nt = 2;       // env NRX_K2_NT: 64-pattern sub-tiles per ring stage of k_clv_dna4_pipe2 (1 or 2; 2 measured 1-2 % faster)
   int k2_variant = 0;       // 0: k_clv_dna4_pipe (production); UM: k_clv_dna4<U, MINB> (A/B experiments, env NRX_K2=UM)
@@ -357,6 +358,7 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
   {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    e->sm_count = sms;
     if (!std::getenv("NRX_K2_BLOCKS")) e->k2_blocks = 16u * (uint32_t)sms;
     const int aa_smem = (int)(sizeof(AaSmem) + 2 * AA_LUT_CODES * 80 * sizeof(double));
     if (!cuda_ok(cudaFuncSetAttribute(k_aa20_dmma<AA_CLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa_smem), "cudaFuncSetAttribute") ||
@@ -705,7 +707,10 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
         const uint32_t nt = (e->k2_variant == 0) ? e->k2_nt : 1;   // 64-pattern sub-tiles per ring stage
         const uint32_t ntiles = (c.max_patterns + nt * TP - 1) / (nt * TP);
         uint32_t groups = std::max<uint32_t>(1, (e->k2_blocks + nops * z - 1) / (nops * z));
-        groups = std::min(groups, std::max<uint32_t>(1, ntiles / 4));  // >= 4 tiles per block: amortise the pipeline fill
+        // >= 4 tiles per block amortise the pipeline fill — unless the whole launch fits the 2 x SMs resident blocks anyway:
+        // then one tile per block (small alignments: 38 blocks walking 4 tiles each left 110 SMs idle)
+        const uint32_t one_wave = (2u * (uint32_t)e->sm_count) / std::max<uint32_t>(1, nops * z);
+        groups = std::min(groups, std::max<uint32_t>(std::max<uint32_t>(1, ntiles / 4), std::min(ntiles, one_wave)));
         dim3 grid(nops * groups, 1, z);
         double *fused_ptr = fused ? e->d_fused : nullptr;
         if (e->k2_variant == 0 && nt == 2)

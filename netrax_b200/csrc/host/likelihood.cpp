@@ -750,6 +750,11 @@ std::vector<double> computeLoglikelihoodBatch(const std::vector<AnnotatedNetwork
     if (a->options.likelihood_variant == LikelihoodVariant::SARAH_PSEUDO)
       throw std::runtime_error("SARAH_PSEUDO is not implemented by this engine (disabled in the reference CLI, src/main.cpp:115-116)");
   std::vector<double> out(anns.size(), 0.0);
+  struct ModeGuard {  // throughput launch geometry while several networks are in flight
+    const std::vector<AnnotatedNetwork *> &a;
+    explicit ModeGuard(const std::vector<AnnotatedNetwork *> &a_) : a(a_) { if (a.size() > 1) for (AnnotatedNetwork *n : a) nrx_set_throughput_mode(n->engine, 1); }
+    ~ModeGuard() { for (AnnotatedNetwork *n : a) nrx_set_throughput_mode(n->engine, 0); }
+  } guard(anns);
   size_t begun = 0;
   try {
     for (; begun < anns.size(); ++begun) computeLoglikelihoodImprovedBegin(*anns[begun], incremental, update_pmatrices);

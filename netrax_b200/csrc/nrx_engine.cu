@@ -100,7 +100,7 @@ struct EnginePlan {
   std::vector<uint32_t> sizes;
   std::vector<char> tips;
   std::vector<uint32_t> ntt;   // leading tip-tip ops of each batch (20-state engines order them first)
-  cudaGraphExec_t exec = nullptr;
+  cudaGraphExec_t exec[2] = {nullptr, nullptr};   // [0] latency geometry, [1] throughput geometry (nrx_set_throughput_mode)
   unsigned long long updates = 0, bytes = 0;
   uint32_t lnl_items = 0;    // number of ops carrying an lnl_item mark (fused K3)
 };
@@ -130,6 +130,7 @@ struct nrx_engine {
   size_t persite_cap = 0;
   unsigned long long launches = 0;
   int sm_count = 148;
+  bool throughput_mode = false;  // several engines share the GPU (batched scoring): fewer, longer-running blocks per launch
   uint32_t pending_result = 0;  // doubles of an enqueued, not yet collected result (nrx_*_async / nrx_result_wait)
   uint32_t k2_nt = 2;       // env NRX_K2_NT: 64-pattern sub-tiles per ring stage of k_clv_dna4_pipe2 (1 or 2; 2 measured 1-2 % faster)
   int k2_variant = 0;       // 0: k_clv_dna4_pipe (production); UM: k_clv_dna4<U, MINB> (A/B experiments, env NRX_K2=UM)
@@ -409,7 +410,7 @@ void nrx_engine_destroy(nrx_engine *e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->comm && nccl().ok) nccl().CommDestroy(e->comm);
-  for (EnginePlan &pl : e->plans) { if (pl.exec) cudaGraphExecDestroy(pl.exec); cudaFree(pl.d_ops); }
+  for (EnginePlan &pl : e->plans) { for (cudaGraphExec_t &x : pl.exec) if (x) cudaGraphExecDestroy(x); cudaFree(pl.d_ops); }
   for (Part &p : e->parts) {
     cudaFree(p.pmat); cudaFree(p.tiplut); cudaFree(p.summat); cudaFree(p.sumlut); cudaFree(p.tipchars); cudaFree(p.tipmap); cudaFree(p.weights); cudaFree(p.model);
     for (void *m : p.slot_mem) cudaFree(m);
@@ -709,7 +710,7 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
         uint32_t groups = std::max<uint32_t>(1, (e->k2_blocks + nops * z - 1) / (nops * z));
         // >= 4 tiles per block amortise the pipeline fill — unless the whole launch fits the 2 x SMs resident blocks anyway:
         // then one tile per block (small alignments: 38 blocks walking 4 tiles each left 110 SMs idle)
-        const uint32_t one_wave = (2u * (uint32_t)e->sm_count) / std::max<uint32_t>(1, nops * z);
+        const uint32_t one_wave = e->throughput_mode ? 0u : (2u * (uint32_t)e->sm_count) / std::max<uint32_t>(1, nops * z);
         groups = std::min(groups, std::max<uint32_t>(std::max<uint32_t>(1, ntiles / 4), std::min(ntiles, one_wave)));
         dim3 grid(nops * groups, 1, z);
         double *fused_ptr = fused ? e->d_fused : nullptr;
@@ -828,7 +829,7 @@ int nrx_plan_create(nrx_engine *e, const nrx_op *ops, const uint32_t *batch_size
       e->d_fused = nullptr; e->fused_cap = 0;
       CK(cudaMalloc((void **)&e->d_fused, need * sizeof(double)));
       e->fused_cap = need;
-      for (EnginePlan &o : e->plans) if (o.exec) { cudaGraphExecDestroy(o.exec); o.exec = nullptr; }
+      for (EnginePlan &o : e->plans) for (cudaGraphExec_t &x : o.exec) if (x) { cudaGraphExecDestroy(x); x = nullptr; }
     }
   }
   pl.alive = true;
@@ -846,7 +847,8 @@ int nrx_plan_run(nrx_engine *e, uint32_t plan_id) {
   cudaEvent_t ev0, ev1;
   prof_begin(e, &ev0, &ev1);
   const unsigned long long per_run = pl.sizes.size() * e->classes.size();
-  if (e->use_graphs && !pl.exec) {  // capture the launches once; kernel arguments (views, resident ops, geometry) never change
+  cudaGraphExec_t &gexec = pl.exec[e->throughput_mode ? 1 : 0];
+  if (e->use_graphs && !gexec) {  // capture the launches once per geometry; kernel arguments (views, resident ops) never change
     const unsigned long long l0 = e->launches;
     CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
     int ok = 1;
@@ -855,18 +857,24 @@ int nrx_plan_run(nrx_engine *e, uint32_t plan_id) {
     const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
     e->launches = l0;
     if (!ok || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); if (ok) cuda_ok(ce, "cudaStreamEndCapture"); cudaGetLastError(); return 0; }
-    const cudaError_t ie = cudaGraphInstantiate(&pl.exec, graph, 0);
+    const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
     cudaGraphDestroy(graph);
     if (!cuda_ok(ie, "cudaGraphInstantiate")) return 0;
   }
-  if (pl.exec) {
-    CK(cudaGraphLaunch(pl.exec, e->stream));
+  if (gexec) {
+    CK(cudaGraphLaunch(gexec, e->stream));
     e->launches += per_run;
   } else {
     for (size_t b = 0; b < pl.sizes.size(); ++b)
       if (!launch_clv_batch(e, pl.d_ops + pl.offsets[b], pl.sizes[b], pl.tips[b], pl.lnl_items != 0, pl.ntt[b])) return 0;
   }
   prof_end(e, ev0, ev1, per_run, pl.updates, pl.bytes);
+  return 1;
+}
+
+int nrx_set_throughput_mode(nrx_engine *e, int on) {
+  if (!e) { g_err = "null engine"; return 0; }
+  e->throughput_mode = on != 0;
   return 1;
 }
 
@@ -882,7 +890,7 @@ int nrx_plan_destroy(nrx_engine *e, uint32_t plan_id) {
   EnginePlan &pl = e->plans[plan_id];
   if (!pl.alive) return 1;
   CK(cudaStreamSynchronize(e->stream));
-  if (pl.exec) cudaGraphExecDestroy(pl.exec);
+  for (cudaGraphExec_t &x : pl.exec) if (x) cudaGraphExecDestroy(x);
   cudaFree(pl.d_ops);
   pl = EnginePlan();
   return 1;

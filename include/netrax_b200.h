@@ -38,7 +38,7 @@ int nrxh_set_network(void *h, unsigned num_tips, unsigned num_nodes, unsigned ro
 int nrxh_add_partition(void *h, unsigned states, unsigned rate_cats, unsigned sites, const uint32_t *tip_masks,
                        const unsigned *pattern_weights, const double *freqs, const double *subst_params, const double *rates,
                        const double *rate_weights);
-int nrxh_set_options(void *h, int likelihood_variant /* 0 AVERAGE, 1 BEST */, int brlen_linkage /* 0 linked, 2 unlinked */);
+int nrxh_set_options(void *h, int likelihood_variant /* 0 AVERAGE, 1 BEST, 2 SARAH_PSEUDO */, int brlen_linkage /* 0 linked, 2 unlinked */);
 int nrxh_set_partition_brlens(void *h, unsigned p, const double *brlens);
 int nrxh_set_reduce_callback(void *h, nrxh_reduce_cb cb, void *context);
 int nrxh_init(void *h);
@@ -84,6 +84,11 @@ int nrxh_optimize_reticulations(void *h, int max_iters, double *final_logl);
 /* model-parameter loop: Gamma shape of partition p (treeinfo_set_alpha, PLLMOD/algorithm/pllmod_algorithm.c:566-587)
  * and the ALPHA step of optimize_params (src/optimization/ModelOptimization.cpp:56-65 = pllmod_algo_opt_onedim_treeinfo):
  * Brent over the alphas of all partitions that carry one, one full device re-evaluation per iterate. */
+/* src/likelihood/PseudoLoglikelihood.hpp: the pseudo-likelihood (also what nrxh_compute_loglikelihood returns when the
+ * likelihood variant is 2 = SARAH_PSEUDO, src/likelihood/LikelihoodComputation.cpp:23-27) + test hooks for its per-node CLVs */
+int nrxh_compute_pseudo_loglikelihood(void *h, int incremental, int update_pmatrices, double *out);
+int nrxh_read_pseudo_clv(void *h, unsigned node, unsigned p, double *out);
+int nrxh_read_pseudo_scaler(void *h, unsigned node, unsigned p, unsigned *out);
 /* src/likelihood/ComplexityScoring.hpp: BIC of the network (what the search compares) */
 int nrxh_score_network(void *h, double *bic_score);
 int nrxh_set_scoring_sizes(void *h, unsigned long long total_num_model_parameters, unsigned long long total_num_sites /* 0: keep */);

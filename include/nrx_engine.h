@@ -62,6 +62,18 @@ typedef struct nrx_op {
                       * per-site likelihood term (first half of K3 fused into K2's epilogue; see nrx_plan_create / nrx_tree_lnl_fused) */
 } nrx_op;
 
+/* One pseudo-likelihood CLV update (src/likelihood/PseudoLoglikelihood.cpp:57-190): the node's CLV is the weighted blend
+ * w[0] * update(left, right) + w[1] * update(left, fake) + w[2] * update(fake, right) + w[3] * 1 of up to three libpll
+ * updates (each with its own per-site scaling test) — the reference runs them into scratch CLVs and merges on the host
+ * (merge_clvs, :8-55).  The parent scaler is that of the LAST executed update, as in the reference. */
+typedef struct nrx_pseudo_op {
+  uint32_t parent_slot;
+  uint32_t left_kind, left_idx, left_edge;
+  uint32_t right_kind, right_idx, right_edge;
+  uint32_t pad_;
+  double w[4];
+} nrx_pseudo_op;
+
 /* An (a, b) operand pair on one edge: (source-tree, target-tree) of computeLoglikelihoodBrlenOpt /
  * computePartitionSumtables (src/likelihood/VirtualRerooting.cpp:403-439, LikelihoodDerivatives.cpp:312-341). */
 typedef struct nrx_pair {
@@ -99,6 +111,10 @@ int nrx_copy_slots(nrx_engine *e, const uint32_t *dst, const uint32_t *src, uint
 /* K2: ONE launch per same-shape partition group updating `nops` CLVs (all displayed trees of a node —
  * or of several independent nodes — x patterns x rate categories).  The ops must be mutually independent. */
 int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops);
+
+/* K2p: `nops` mutually independent pseudo-likelihood updates in ONE launch per partition shape: reads each child once and
+ * writes the merged CLV once (the reference: three kernel calls + a merge pass over three scratch CLVs). */
+int nrx_update_pseudo_clvs(nrx_engine *e, const nrx_pseudo_op *ops, uint32_t nops);
 
 /* Evaluation plan: the K2 batches of one whole traversal (the enumeration of displayed trees depends only on the
  * topology).  The ops stay resident on the device and nrx_plan_run replays all batches as ONE

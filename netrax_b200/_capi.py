@@ -15,7 +15,7 @@ import numpy as np
 
 from .network_io import NetworkDesc
 
-AVERAGE, BEST = 0, 1                 # LikelihoodVariant (src/likelihood/LikelihoodVariant.hpp)
+AVERAGE, BEST, SARAH_PSEUDO = 0, 1, 2  # LikelihoodVariant (src/likelihood/LikelihoodVariant.hpp)
 BRENT_NORMAL, BRENT_REROOT, NEWTON_RAPHSON = 0, 1, 2   # BrlenOptMethod (src/NetraxOptions.hpp:17-21)
 LINKED, SCALED, UNLINKED = 0, 1, 2   # PLLMOD_COMMON_BRLEN_*
 
@@ -72,6 +72,9 @@ class FlatAPI:
         g("optimize_branches", C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double))
         g("optimize_reticulation", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
         g("optimize_reticulations", C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double))
+        g("compute_pseudo_loglikelihood", C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double))
+        g("read_pseudo_clv", C.c_int, C.c_void_p, C.c_uint, C.c_uint, _f64p)
+        g("read_pseudo_scaler", C.c_int, C.c_void_p, C.c_uint, C.c_uint, np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS"))
         g("score_network", C.c_int, C.c_void_p, C.POINTER(C.c_double))
         g("set_scoring_sizes", C.c_int, C.c_void_p, C.c_ulonglong, C.c_ulonglong)
         g("optimize_all_non_topology", C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double))
@@ -291,6 +294,23 @@ class LikelihoodEngine:
         out = C.c_double()
         self.api.check(self.api._optimize_reticulation(self.h, r, C.byref(out)))
         return out.value
+
+    def computePseudoLoglikelihood(self, incremental: int = 1, update_pmatrices: int = 1) -> float:
+        """src/likelihood/PseudoLoglikelihood.cpp:57-226: one merged CLV per node, weights = reticulation probabilities."""
+        out = C.c_double()
+        self.api.check(self.api._compute_pseudo_loglikelihood(self.h, incremental, update_pmatrices, C.byref(out)))
+        return out.value
+
+    def read_pseudo_clv(self, node: int, p: int = 0) -> np.ndarray:
+        part = self.partitions[p]
+        out = np.zeros(part.sites * part.rate_cats * ((part.states + 3) & ~3))
+        self.api.check(self.api._read_pseudo_clv(self.h, node, p, out))
+        return out
+
+    def read_pseudo_scaler(self, node: int, p: int = 0) -> np.ndarray:
+        out = np.zeros(self.partitions[p].sites, dtype=np.uint32)
+        self.api.check(self.api._read_pseudo_scaler(self.h, node, p, out))
+        return out
 
     def scoreNetwork(self) -> float:
         """BIC of the network (src/likelihood/ComplexityScoring.cpp:57-67); smaller is better."""

@@ -87,7 +87,7 @@ int nrxh_add_partition(void *hv, unsigned states, unsigned rate_cats, unsigned s
 }
 
 int nrxh_set_options(void *hv, int variant, int linkage) {
-  H(hv)->ann.options.likelihood_variant = variant ? LikelihoodVariant::BEST_DISPLAYED_TREE : LikelihoodVariant::AVERAGE_DISPLAYED_TREES;
+  H(hv)->ann.options.likelihood_variant = variant == 2 ? LikelihoodVariant::SARAH_PSEUDO : (variant ? LikelihoodVariant::BEST_DISPLAYED_TREE : LikelihoodVariant::AVERAGE_DISPLAYED_TREES);
   H(hv)->ann.options.brlen_linkage = linkage;
   return 1;
 }
@@ -361,6 +361,23 @@ int nrxh_optimize_reticulation(void *hv, unsigned r, double *final_logl) {
   });
 }
 
+int nrxh_compute_pseudo_loglikelihood(void *hv, int incremental, int update_pmatrices, double *out) {
+  return guarded([&] { *out = computePseudoLoglikelihood(H(hv)->ann, incremental, update_pmatrices); });
+}
+int nrxh_read_pseudo_clv(void *hv, unsigned node, unsigned p, double *out) {
+  return guarded([&] {
+    AnnotatedNetwork &ann = H(hv)->ann;
+    if (node >= ann.pseudo_slot.size() || ann.pseudo_slot[node] == UINT32_MAX) throw std::runtime_error("no pseudo CLV at that node");
+    detail::engineCheck(nrx_read_clv(ann.engine, p, ann.pseudo_slot[node], out), "nrx_read_clv");
+  });
+}
+int nrxh_read_pseudo_scaler(void *hv, unsigned node, unsigned p, unsigned *out) {
+  return guarded([&] {
+    AnnotatedNetwork &ann = H(hv)->ann;
+    if (node >= ann.pseudo_slot.size() || ann.pseudo_slot[node] == UINT32_MAX) throw std::runtime_error("no pseudo CLV at that node");
+    detail::engineCheck(nrx_read_scaler(ann.engine, p, ann.pseudo_slot[node], out), "nrx_read_scaler");
+  });
+}
 int nrxh_score_network(void *hv, double *bic_score) {
   return guarded([&] { *bic_score = scoreNetwork(H(hv)->ann); });
 }

@@ -177,6 +177,7 @@ void invalidateSingleClv(AnnotatedNetwork &ann, unsigned int clv_index) {  // :8
     nd.displayed_trees[i].treeLoglData.tree_logl_valid = false;
   }
   nd.num_active_displayed_trees = 0;
+  if (clv_index < ann.pseudo_clv_valid.size()) ann.pseudo_clv_valid[clv_index] = 0;  // :37
   ann.cached_logl_valid = false;
 }
 
@@ -249,6 +250,8 @@ void setReticulationProb(AnnotatedNetwork &ann, size_t r, double prob) {  // src
   ann.second_parent_logprobs[r] = std::log(1.0 - prob);
   ann.cached_logl_valid = false;
   invalidateTreeLogprobs(ann);
+  if (ann.options.likelihood_variant == LikelihoodVariant::SARAH_PSEUDO)  // InvalidationHelper.cpp:296-301: the blend weights changed
+    invalidateHigher(ann, ann.network.reticulations[r].node, false);
 }
 
 static void dropEnginePlan(AnnotatedNetwork &ann) {
@@ -747,8 +750,7 @@ double computeLoglikelihoodImproved(AnnotatedNetwork &ann, int incremental, int 
  * Result i is exactly computeLoglikelihood(*anns[i], incremental, update_pmatrices). */
 std::vector<double> computeLoglikelihoodBatch(const std::vector<AnnotatedNetwork *> &anns, int incremental, int update_pmatrices) {
   for (AnnotatedNetwork *a : anns)
-    if (a->options.likelihood_variant == LikelihoodVariant::SARAH_PSEUDO)
-      throw std::runtime_error("SARAH_PSEUDO is not implemented by this engine (disabled in the reference CLI, src/main.cpp:115-116)");
+    if (a->options.likelihood_variant == LikelihoodVariant::SARAH_PSEUDO) throw std::runtime_error("computeLoglikelihoodBatch: the pseudo-likelihood variant is evaluated one network at a time");
   std::vector<double> out(anns.size(), 0.0);
   struct ModeGuard {  // throughput launch geometry while several networks are in flight
     const std::vector<AnnotatedNetwork *> &a;
@@ -771,9 +773,76 @@ std::vector<double> computeLoglikelihoodBatch(const std::vector<AnnotatedNetwork
   return out;
 }
 
+/* ---- src/likelihood/PseudoLoglikelihood.cpp:57-226 ------------------------------------------------------------------
+ * One CLV per node.  The reference runs up to three libpll updates per node and partition into scratch CLVs and merges
+ * them on the host; here a node is ONE nrx_pseudo_op (the kernel does the three updates and the merge in registers), and
+ * nodes whose children are final share a launch, like the displayed-tree ops of the exact evaluation. */
+double computePseudoLoglikelihood(AnnotatedNetwork &ann, int incremental, int update_pmatrices) {
+  Network &nw = ann.network;
+  const unsigned P = ann.fake_treeinfo->partition_count;
+  flushPendingOps(ann);
+  if (ann.pseudo_clv_valid.size() != nw.num_nodes()) {  // src/graph/AnnotatedNetwork.cpp:160-184
+    ann.pseudo_clv_valid.assign(nw.num_nodes(), 0);
+    for (size_t i = 0; i < nw.num_tips(); ++i) ann.pseudo_clv_valid[i] = 1;
+    ann.pseudo_slot.assign(nw.num_nodes(), UINT32_MAX);
+  }
+  if (update_pmatrices) pllmod_treeinfo_update_prob_matrices(ann, !incremental);
+  auto parentProb = [&](long child, size_t parent) {  // :95-118
+    if (child < 0 || nw.nodes[child].type != NodeType::RETICULATION_NODE) return 1.0;
+    const size_t r = nw.nodes[child].reticulation_index;
+    return parent == nw.reticulations[r].first_parent ? ann.reticulation_probs[r] : 1.0 - ann.reticulation_probs[r];
+  };
+  auto operand = [&](long child, size_t parent, uint32_t &kind, uint32_t &idx, uint32_t &edge) {
+    if (child < 0) { kind = NRX_NONE; idx = 0; edge = (uint32_t)nw.num_branches(); return; }   // fake clv behind the fake pmatrix
+    edge = (uint32_t)edgeBetween(nw, (size_t)child, parent);
+    if ((size_t)child < nw.num_tips()) { kind = NRX_TIP; idx = (uint32_t)child; }
+    else { kind = NRX_CLV; idx = ann.pseudo_slot[child]; }
+  };
+  std::vector<nrx_pseudo_op> batch;
+  std::vector<char> in_batch(nw.num_nodes(), 0);
+  uint64_t local_sites = 0;
+  for (const PartitionModel &m : ann.fake_treeinfo->partitions) local_sites += m.sites;
+  auto flush = [&] {
+    if (batch.empty()) return;
+    engineCheck(nrx_update_pseudo_clvs(ann.engine, batch.data(), (uint32_t)batch.size()), "nrx_update_pseudo_clvs");
+    ann.clv_site_updates += local_sites * batch.size();
+    batch.clear();
+    std::fill(in_batch.begin(), in_batch.end(), 0);
+  };
+  for (Node *node : ann.travbuffer) {
+    const size_t v = node->clv_index;
+    if (v < nw.num_tips()) continue;
+    if (incremental && ann.pseudo_clv_valid[v]) continue;
+    const std::vector<size_t> &children = node->children;   // getChildren: all children, whatever the active parents are
+    if (children.empty() || children.size() > 2) throw std::runtime_error("computePseudoLoglikelihood: node with 0 or more than 2 children");
+    const long left = (long)children[0], right = children.size() == 1 ? -1 : (long)children[1];
+    if (in_batch[left] || (right >= 0 && in_batch[right])) flush();   // a launch holds mutually independent nodes only
+    if (ann.pseudo_slot[v] == UINT32_MAX) ann.pseudo_slot[v] = allocSlot(ann);
+    const double p_left = parentProb(left, v), p_right = parentProb(right, v);
+    nrx_pseudo_op op{};
+    op.parent_slot = ann.pseudo_slot[v];
+    operand(left, v, op.left_kind, op.left_idx, op.left_edge);
+    operand(right, v, op.right_kind, op.right_idx, op.right_edge);
+    op.w[0] = p_left * p_right;
+    op.w[1] = p_left * (1.0 - p_right);
+    op.w[2] = (1.0 - p_left) * p_right;
+    op.w[3] = (1.0 - p_left) * (1.0 - p_right);
+    batch.push_back(op);
+    in_batch[v] = 1;
+    ann.pseudo_clv_valid[v] = 1;
+  }
+  flush();
+  std::vector<double> partition_pseudo_logl(P, 0.0);
+  const uint32_t root_slot = ann.pseudo_slot[nw.root->clv_index];
+  engineCheck(nrx_tree_lnl(ann.engine, &root_slot, 1, partition_pseudo_logl.data(), nullptr, 0), "nrx_tree_lnl");
+  reduceSum(ann, partition_pseudo_logl.data(), P);
+  double pseudo_logl = 0.0;
+  for (unsigned p = 0; p < P; ++p) { pseudo_logl += partition_pseudo_logl[p]; ann.fake_treeinfo->partition_loglh[p] = partition_pseudo_logl[p]; }
+  return pseudo_logl;
+}
+
 double computeLoglikelihood(AnnotatedNetwork &ann, int incremental, int update_pmatrices) {  // LikelihoodComputation.cpp:18-33
-  if (ann.options.likelihood_variant == LikelihoodVariant::SARAH_PSEUDO)
-    throw std::runtime_error("SARAH_PSEUDO is not implemented by this engine (disabled in the reference CLI, src/main.cpp:115-116)");
+  if (ann.options.likelihood_variant == LikelihoodVariant::SARAH_PSEUDO) return computePseudoLoglikelihood(ann, incremental, update_pmatrices);
   return computeLoglikelihoodImproved(ann, incremental, update_pmatrices);
 }
 

@@ -216,6 +216,8 @@ struct AnnotatedNetwork {  // src/graph/AnnotatedNetwork.hpp:42-89
   PlanCache *plan = nullptr;
   bool use_plan_cache = true;
   uint64_t clv_site_updates = 0;              // Σ trees × local patterns actually launched
+  std::vector<char> pseudo_clv_valid;         // [node]  (src/graph/AnnotatedNetwork.hpp:64; tips: valid)
+  std::vector<uint32_t> pseudo_slot;          // [node]  device slot of the node's pseudo-likelihood CLV (UINT32_MAX: none yet)
   bool pending_eval = false;                  // root-tree lnLs enqueued on the engine stream, not yet collected (batched scoring)
   bool begin_returns_cached = false, begin_ran_traversal = false;
   size_t pending_root = 0;
@@ -238,6 +240,8 @@ void topology_changed(AnnotatedNetwork &ann);  // callers that edit the topology
 /* ---- the likelihood API --------------------------------------------------------------------------------- */
 double computeLoglikelihood(AnnotatedNetwork &ann_network, int incremental = 1, int update_pmatrices = 1);
 double computeLoglikelihoodImproved(AnnotatedNetwork &ann_network, int incremental, int update_pmatrices);
+double computePseudoLoglikelihood(AnnotatedNetwork &ann_network, int incremental = 1, int update_pmatrices = 1);  // src/likelihood/PseudoLoglikelihood.hpp
+double scoreNetworkPseudo(AnnotatedNetwork &ann_network);  // src/likelihood/ComplexityScoring.cpp:69-79
 /* batched scoring of candidate networks (one engine / stream each): result[i] == computeLoglikelihood(*anns[i], ...) */
 std::vector<double> computeLoglikelihoodBatch(const std::vector<AnnotatedNetwork *> &anns, int incremental = 1, int update_pmatrices = 1);
 void processNodeImproved(AnnotatedNetwork &ann_network, int incremental, Node *node, std::vector<Node *> &children,

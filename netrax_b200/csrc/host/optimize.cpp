@@ -410,6 +410,13 @@ double scoreNetwork(AnnotatedNetwork &ann) {  // :57-67
   return bic_score;
 }
 
+double scoreNetworkPseudo(AnnotatedNetwork &ann) {  // :69-79
+  const double logl = computePseudoLoglikelihood(ann, 1, 1);
+  const double bic_score = bic(ann, logl);
+  if (bic_score == std::numeric_limits<double>::infinity()) throw std::runtime_error("Invalid BIC score");
+  return bic_score;
+}
+
 double network_logl_wrapper(void *network_params, int incremental, int update_pmatrices, double **) {  // RaxmlWrapper.cpp:21-26
   return computeLoglikelihood(*static_cast<NetworkParams *>(network_params)->ann_network, incremental, update_pmatrices);
 }

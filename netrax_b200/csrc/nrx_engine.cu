@@ -795,6 +795,43 @@ int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops) {
   return 1;
 }
 
+int nrx_update_pseudo_clvs(nrx_engine *e, const nrx_pseudo_op *ops, uint32_t nops) {
+  if (!e) { g_err = "null engine"; return 0; }
+  if (nops == 0) return 1;
+  CK(cudaSetDevice(e->device));
+  unsigned long long updates = 0, bytes = 0;
+  for (uint32_t i = 0; i < nops; ++i) {   // same operand rules as nrx_update_clvs, except that both operands may be absent
+    const nrx_pseudo_op &o = ops[i];
+    nrx_op chk{};
+    chk.parent_slot = o.parent_slot;
+    chk.left_kind = o.left_kind; chk.left_idx = o.left_idx; chk.left_edge = o.left_edge;
+    chk.right_kind = o.right_kind; chk.right_idx = o.right_idx; chk.right_edge = o.right_edge;
+    if (chk.left_kind == NRX_NONE && chk.right_kind == NRX_NONE) { chk.left_kind = NRX_TIP; chk.left_idx = 0; chk.left_edge = 0; }
+    if (!check_ops(e, &chk, 1, &updates, &bytes)) return 0;
+    for (int k = 0; k < 4; ++k) if (!(o.w[k] >= 0.0 && o.w[k] <= 1.0)) { g_err = "nrx_update_pseudo_clvs: weight outside [0, 1]"; return 0; }
+  }
+  if (!refresh_views(e)) return 0;
+  nrx_pseudo_op *d_ops;
+  if (!upload(e, ops, nops, &d_ops)) return 0;
+  cudaEvent_t ev0, ev1;
+  prof_begin(e, &ev0, &ev1);
+  for (const ShapeClass &c : e->classes) {
+    if (c.max_patterns == 0) continue;
+    const uint32_t z = (uint32_t)c.parts.size();
+    if (c.states == 4 && c.cats == 4) {
+      dim3 grid(tiles_for((uint64_t)c.max_patterns * 4, BLOCK, nops * z), nops, z);
+      k_clv_pseudo_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops);
+    } else {
+      dim3 grid(tiles_for(c.max_patterns, BLOCK, nops * z), nops, z);
+      k_clv_pseudo_generic<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops);
+    }
+    e->launches++;
+    CK(cudaGetLastError());
+  }
+  prof_end(e, ev0, ev1, e->classes.size(), updates, bytes);
+  return 1;
+}
+
 /* ---- evaluation plans: the K2 launches of a whole traversal, ops resident on the device, replayed as ONE CUDA graph ---- */
 int nrx_plan_create(nrx_engine *e, const nrx_op *ops, const uint32_t *batch_sizes, uint32_t nbatches, uint32_t *plan_id) {
   if (!e) { g_err = "null engine"; return 0; }

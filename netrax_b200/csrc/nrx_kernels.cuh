@@ -993,6 +993,134 @@ __global__ void __launch_bounds__(BLOCK) k_clv_generic(const PartView *__restric
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * K2p  pseudo-likelihood CLV update (src/likelihood/PseudoLoglikelihood.cpp:57-190), fused: x = P_l . left and
+ * y = P_r . right are computed ONCE; the three updates the reference runs (both / left only / right only, each with the
+ * per-site scaling test of LIBPLL/core_partials*.c) and merge_clvs (:8-55, same term order, separate multiply and add)
+ * happen in registers.  An absent operand is the fake all-ones CLV behind the identity matrix.  Scaler = that of the last
+ * executed update (the reference's three calls share one scale buffer).
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(BLOCK) k_clv_pseudo_dna4(const PartView *__restrict__ parts, const nrx_pseudo_op *__restrict__ ops) {
+  const PartView &pv = parts[blockIdx.z];
+  const nrx_pseudo_op op = ops[blockIdx.y];
+  const int tid = threadIdx.x, cat = tid & 3, lane = tid & 31;
+  const uint64_t n_items = (uint64_t)pv.patterns * 4;
+  __shared__ __align__(32) double lutL[256];
+  __shared__ __align__(32) double lutR[256];
+  __shared__ __align__(16) double sPL[4 * PCAT];
+  __shared__ __align__(16) double sPR[4 * PCAT];
+  const int lk = op.left_kind, rk = op.right_kind;
+  if (lk == NRX_CLV) { if (tid < 64) sPL[(tid >> 4) * PCAT + (tid & 15)] = pv.pmat[(size_t)op.left_edge * 64 + tid]; }
+  else if (lk == NRX_TIP) build_tip_lut4(lutL, pv.pmat + (size_t)op.left_edge * 64, tid);
+  if (rk == NRX_CLV) { if (tid >= 64 && tid < 128) sPR[((tid - 64) >> 4) * PCAT + (tid & 15)] = pv.pmat[(size_t)op.right_edge * 64 + tid - 64]; }
+  else if (rk == NRX_TIP) build_tip_lut4(lutR, pv.pmat + (size_t)op.right_edge * 64, tid);
+  __syncthreads();
+  const double *PL = sPL + cat * PCAT, *PR = sPR + cat * PCAT;
+  const double *clvL = (lk == NRX_CLV) ? pv.clv[op.left_idx] : nullptr;
+  const double *clvR = (rk == NRX_CLV) ? pv.clv[op.right_idx] : nullptr;
+  const uint32_t *scL = (lk == NRX_CLV) ? pv.scaler[op.left_idx] : nullptr;
+  const uint32_t *scR = (rk == NRX_CLV) ? pv.scaler[op.right_idx] : nullptr;
+  const uint8_t *tipL = (lk == NRX_TIP) ? pv.tipchars + (size_t)op.left_idx * pv.tip_pitch : nullptr;
+  const uint8_t *tipR = (rk == NRX_TIP) ? pv.tipchars + (size_t)op.right_idx * pv.tip_pitch : nullptr;
+  double *par = pv.clv[op.parent_slot];
+  uint32_t *psc = pv.scaler[op.parent_slot];
+  const double w1 = op.w[0], w2 = op.w[1], w3 = op.w[2], w4 = op.w[3];
+  const unsigned quad = 0xFu << (lane & ~3);
+  const D4 ones{1.0, 1.0, 1.0, 1.0};
+  const uint64_t span = ((n_items + BLOCK - 1) / BLOCK) * BLOCK;   // whole warps stay in the loop for the ballots
+  for (uint64_t g = (uint64_t)blockIdx.x * BLOCK + tid; g < span; g += (uint64_t)gridDim.x * BLOCK) {
+    const bool act = g < n_items;
+    const uint64_t site = g >> 2;
+    D4 x = ones, y = ones;
+    uint32_t sl = 0, sr = 0;
+    if (act) {
+      if (lk == NRX_CLV) { x = matvec4(PL, ldg256(clvL + g * 4)); sl = scL[site]; }
+      else if (lk == NRX_TIP) x = *reinterpret_cast<const D4 *>(lutL + ((tipL[site] & 15) * 4 + cat) * 4);
+      if (rk == NRX_CLV) { y = matvec4(PR, ldg256(clvR + g * 4)); sr = scR[site]; }
+      else if (rk == NRX_TIP) y = *reinterpret_cast<const D4 *>(lutR + ((tipR[site] & 15) * 4 + cat) * 4);
+    }
+    D4 m{0.0, 0.0, 0.0, 0.0};
+    uint32_t s_out = 0;
+    // one libpll update: value c (operands present: pl, pr), its scaling test unless both operands are tips, blend
+    auto blend = [&](D4 c, bool tiptip, uint32_t s_in, double w) {
+      const bool small = act & (c.x < SCALE_THRESHOLD) & (c.y < SCALE_THRESHOLD) & (c.z < SCALE_THRESHOLD) & (c.w < SCALE_THRESHOLD);
+      const unsigned b = __ballot_sync(0xffffffffu, small);
+      const bool scale = !tiptip && ((b & quad) == quad);
+      if (scale) { c.x = __dmul_rn(c.x, SCALE_FACTOR); c.y = __dmul_rn(c.y, SCALE_FACTOR); c.z = __dmul_rn(c.z, SCALE_FACTOR); c.w = __dmul_rn(c.w, SCALE_FACTOR); }
+      m.x = __dadd_rn(m.x, __dmul_rn(w, c.x)); m.y = __dadd_rn(m.y, __dmul_rn(w, c.y));
+      m.z = __dadd_rn(m.z, __dmul_rn(w, c.z)); m.w = __dadd_rn(m.w, __dmul_rn(w, c.w));
+      s_out = tiptip ? 0u : s_in + (scale ? 1u : 0u);
+    };
+    if (w1 > 0.0) {   // case 1: take both
+      D4 c;
+      if (rk == NRX_NONE) c = x; else if (lk == NRX_NONE) c = y;
+      else { c.x = __dmul_rn(x.x, y.x); c.y = __dmul_rn(x.y, y.y); c.z = __dmul_rn(x.z, y.z); c.w = __dmul_rn(x.w, y.w); }
+      blend(c, lk == NRX_TIP && rk == NRX_TIP, sl + sr, w1);
+    }
+    if (w2 > 0.0) blend(x, false, sl, w2);   // case 2: left child only (right = fake inner CLV)
+    if (w3 > 0.0) blend(y, false, sr, w3);   // case 3: right child only
+    if (w4 > 0.0) { m.x = __dadd_rn(m.x, w4); m.y = __dadd_rn(m.y, w4); m.z = __dadd_rn(m.z, w4); m.w = __dadd_rn(m.w, w4); }
+    if (act) {
+      stg256(par + g * 4, m);
+      if (cat == 0 && (w1 > 0.0 || w2 > 0.0 || w3 > 0.0)) psc[site] = s_out;
+    }
+  }
+}
+
+/* any state / category count: one thread per pattern, two passes (scaling decisions of the three updates, then blend) */
+__global__ void __launch_bounds__(BLOCK) k_clv_pseudo_generic(const PartView *__restrict__ parts, const nrx_pseudo_op *__restrict__ ops) {
+  const PartView &pv = parts[blockIdx.z];
+  const nrx_pseudo_op op = ops[blockIdx.y];
+  const uint32_t S = pv.states, SP = pv.sp, C = pv.cats;
+  const int lk = op.left_kind, rk = op.right_kind;
+  const double *pmL = pv.pmat + (size_t)op.left_edge * C * S * SP;
+  const double *pmR = pv.pmat + (size_t)op.right_edge * C * S * SP;
+  double *par = pv.clv[op.parent_slot];
+  uint32_t *psc = pv.scaler[op.parent_slot];
+  const double w1 = op.w[0], w2 = op.w[1], w3 = op.w[2], w4 = op.w[3];
+  const bool tiptip = (lk == NRX_TIP && rk == NRX_TIP);
+  for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
+    const uint32_t mL = (lk == NRX_TIP) ? pv.tipmap[pv.tipchars[(size_t)op.left_idx * pv.tip_pitch + n]] : 0;
+    const uint32_t mR = (rk == NRX_TIP) ? pv.tipmap[pv.tipchars[(size_t)op.right_idx * pv.tip_pitch + n]] : 0;
+    const double *cl = (lk == NRX_CLV) ? pv.clv[op.left_idx] + n * C * SP : nullptr;
+    const double *cr = (rk == NRX_CLV) ? pv.clv[op.right_idx] + n * C * SP : nullptr;
+    double *out = par + n * C * SP;
+    auto xy = [&](uint32_t c, uint32_t i, double &x, double &y) {
+      const double *lrow = pmL + ((size_t)c * S + i) * SP, *rrow = pmR + ((size_t)c * S + i) * SP;
+      x = 1.0; y = 1.0;
+      if (lk == NRX_CLV) x = row_dot(lrow, cl + c * SP, S); else if (lk == NRX_TIP) x = masked_rowsum(lrow, S, mL);
+      if (rk == NRX_CLV) y = row_dot(rrow, cr + c * SP, S); else if (rk == NRX_TIP) y = masked_rowsum(rrow, S, mR);
+    };
+    bool small1 = true, small2 = true, small3 = true;
+    for (uint32_t c = 0; c < C; ++c)
+      for (uint32_t i = 0; i < S; ++i) {
+        double x, y;
+        xy(c, i, x, y);
+        small1 &= (__dmul_rn(x, y) < SCALE_THRESHOLD);
+        small2 &= (x < SCALE_THRESHOLD);
+        small3 &= (y < SCALE_THRESHOLD);
+      }
+    const bool sc1 = !tiptip && small1, sc2 = small2, sc3 = small3;
+    for (uint32_t c = 0; c < C; ++c) {
+      for (uint32_t i = 0; i < S; ++i) {
+        double x, y;
+        xy(c, i, x, y);
+        double m = 0.0;
+        if (w1 > 0.0) { double v = __dmul_rn(x, y); if (sc1) v = __dmul_rn(v, SCALE_FACTOR); m = __dadd_rn(m, __dmul_rn(w1, v)); }
+        if (w2 > 0.0) { double v = x; if (sc2) v = __dmul_rn(v, SCALE_FACTOR); m = __dadd_rn(m, __dmul_rn(w2, v)); }
+        if (w3 > 0.0) { double v = y; if (sc3) v = __dmul_rn(v, SCALE_FACTOR); m = __dadd_rn(m, __dmul_rn(w3, v)); }
+        if (w4 > 0.0) m = __dadd_rn(m, w4);
+        out[c * SP + i] = m;
+      }
+      for (uint32_t i = S; i < SP; ++i) out[c * SP + i] = (w4 > 0.0) ? w4 : 0.0;   // padding of the scratch CLVs is 0, of the fake CLV 1
+    }
+    const uint32_t sl = (lk == NRX_CLV) ? pv.scaler[op.left_idx][n] : 0u, sr = (rk == NRX_CLV) ? pv.scaler[op.right_idx][n] : 0u;
+    if (w3 > 0.0) psc[n] = sr + (sc3 ? 1u : 0u);
+    else if (w2 > 0.0) psc[n] = sl + (sc2 ? 1u : 0u);
+    else if (w1 > 0.0) psc[n] = tiptip ? 0u : sl + sr + (sc1 ? 1u : 0u);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * Block-level deterministic sum of up to 3 values; result valid in thread 0.
  * ---------------------------------------------------------------------------------------------- */
 template <int N>

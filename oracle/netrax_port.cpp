@@ -445,6 +445,7 @@ void invalidateSingleClv(AnnotatedNetwork &ann, unsigned clv_index) {  // :8-39
     nd.displayed_trees[i].treeLoglData.tree_logl_valid = false;
   }
   nd.num_active_displayed_trees = 0;
+  if (clv_index < ann.pseudo_clv_valid.size()) ann.pseudo_clv_valid[clv_index] = 0;  // InvalidationHelper.cpp:37
   ann.cached_logl_valid = false;
 }
 
@@ -519,6 +520,8 @@ void setReticulationProb(AnnotatedNetwork &ann, size_t r, double prob) {  // SRC
   ann.second_parent_logprobs[r] = std::log(1.0 - prob);
   ann.cached_logl_valid = false;
   invalidateTreeLogprobs(ann);
+  if (ann.options.likelihood_variant == LikelihoodVariant::SARAH_PSEUDO)  // InvalidationHelper.cpp:296-301
+    invalidateHigherCLVs(ann, ann.network.rets[r].node, false);
 }
 
 void setBranchLength(AnnotatedNetwork &ann, int partition, size_t pmatrix_index, double value) {
@@ -824,6 +827,7 @@ static double evaluateTrees(AnnotatedNetwork &ann, unsigned virtual_root) {  // 
 }
 
 double computeLoglikelihood(AnnotatedNetwork &ann, int incremental, int update_pmatrices) {  // :646-671 + LikelihoodComputation.cpp:18-33
+  if (ann.options.likelihood_variant == LikelihoodVariant::SARAH_PSEUDO) return computePseudoLoglikelihood(ann, incremental, update_pmatrices);
   if (!incremental) invalidateAllCLVs(ann);
   bool reuse = reuseOldDisplayedTreesCheck(ann, incremental, ann.network.root);
   if (reuse) {
@@ -841,6 +845,83 @@ double computeLoglikelihood(AnnotatedNetwork &ann, int incremental, int update_p
  * trees is evaluated on its own by plain pruning over the active, alive part of the network; no
  * config sets, no CLV sharing.  Mixing as in the reference's naive path (:86-113).
  * ---------------------------------------------------------------------------------------- */
+/* ---- LH/PseudoLoglikelihood.cpp ------------------------------------------------------------------------------------
+ * One CLV per node: up to three libpll updates (both children / left only / right only) into scratch CLVs that SHARE the
+ * node's scaler (the last executed update's scaler wins — kept as the reference has it), merged with the reticulation
+ * probabilities of the children as weights; the fourth term is the all-ones fake CLV. */
+static void merge_clvs(AnnotatedNetwork &ann, unsigned node, double w1, double w2, double w3, double w4) {  // :8-55
+  for (unsigned p = 0; p < ann.partitionCount(); ++p) {
+    double *clv = ann.pseudo_clv[node][p].p;
+    const double *t1 = ann.tmp_clv_1[p].p, *t2 = ann.tmp_clv_2[p].p, *t3 = ann.tmp_clv_3[p].p;
+    const size_t n = ann.backend->clvEntries(p);
+    for (size_t i = 0; i < n; ++i) {
+      double merged_entry = 0.0;
+      if (w1 > 0.0) merged_entry += w1 * t1[i];
+      if (w2 > 0.0) merged_entry += w2 * t2[i];
+      if (w3 > 0.0) merged_entry += w3 * t3[i];
+      if (w4 > 0.0) merged_entry += w4 * 1.0;   // partition->clv[fake_clv_index][i]
+      clv[i] = merged_entry;
+    }
+  }
+}
+
+double computePseudoLoglikelihood(AnnotatedNetwork &ann, int incremental, int update_pmatrices) {  // :57-226
+  Network &nw = ann.network;
+  const unsigned P = ann.partitionCount();
+  if (ann.pseudo_clv_valid.size() != nw.nodes.size()) {  // SRC/graph/AnnotatedNetwork.cpp:160-184
+    ann.pseudo_clv_valid.assign(nw.nodes.size(), 0);
+    for (unsigned i = 0; i < nw.num_tips; ++i) ann.pseudo_clv_valid[i] = 1;
+    ann.pseudo_clv.clear(); ann.pseudo_scaler.clear();
+    ann.pseudo_clv.resize(nw.nodes.size()); ann.pseudo_scaler.resize(nw.nodes.size());
+    for (unsigned v = nw.num_tips; v < nw.nodes.size(); ++v) {
+      ann.pseudo_clv[v].resize(P); ann.pseudo_scaler[v].resize(P);
+      for (unsigned p = 0; p < P; ++p) { ann.pseudo_clv[v][p].alloc(ann.backend->clvEntries(p)); ann.pseudo_scaler[v][p].alloc(ann.backend->sites(p)); }
+    }
+    ann.tmp_clv_1.clear(); ann.tmp_clv_2.clear(); ann.tmp_clv_3.clear();
+    ann.tmp_clv_1.resize(P); ann.tmp_clv_2.resize(P); ann.tmp_clv_3.resize(P);
+    for (unsigned p = 0; p < P; ++p) { ann.tmp_clv_1[p].alloc(ann.backend->clvEntries(p)); ann.tmp_clv_2[p].alloc(ann.backend->clvEntries(p)); ann.tmp_clv_3[p].alloc(ann.backend->clvEntries(p)); }
+  }
+  if (update_pmatrices) updateProbMatrices(ann, !incremental);
+  auto operandOf = [&](int child, unsigned p, unsigned parent) {
+    Operand o;
+    if (child < 0) { o.kind = 2; o.edge = ann.fakePmatrixIndex(); return o; }
+    o.edge = nw.edgeBetween((unsigned)child, parent);
+    if ((unsigned)child < nw.num_tips) { o.kind = 1; o.tip = (unsigned)child; }
+    else { o.kind = 0; o.clv = ann.pseudo_clv[child][p].p; o.scaler = ann.pseudo_scaler[child][p].p; }
+    return o;
+  };
+  auto parentProb = [&](int child, unsigned parent) {  // :95-118
+    if (child < 0 || !nw.nodes[child].is_ret) return 1.0;
+    const Network::Ret &R = nw.rets[nw.nodes[child].ret_index];
+    return parent == R.first_parent ? ann.reticulation_probs[nw.nodes[child].ret_index] : 1.0 - ann.reticulation_probs[nw.nodes[child].ret_index];
+  };
+  for (unsigned node : ann.travbuffer) {
+    if (node < nw.num_tips) continue;
+    if (incremental && ann.pseudo_clv_valid[node]) continue;
+    const std::vector<unsigned> &children = nw.nodes[node].children;
+    if (children.empty() || children.size() > 2) throw std::runtime_error("computePseudoLoglikelihood: node with 0 or > 2 children");
+    const int left = (int)children[0], right = children.size() == 1 ? -1 : (int)children[1];
+    const double p_left = parentProb(left, node), p_right = parentProb(right, node);
+    const double w1 = p_left * p_right, w2 = p_left * (1.0 - p_right), w3 = (1.0 - p_left) * p_right, w4 = (1.0 - p_left) * (1.0 - p_right);
+    for (unsigned p = 0; p < P; ++p) {
+      const Operand l = operandOf(left, p, node), r = operandOf(right, p, node), fake = operandOf(-1, p, node);
+      unsigned *parent_scaler = ann.pseudo_scaler[node][p].p;
+      if (w1 > 0.0) ann.backend->updatePartials(p, ann.tmp_clv_1[p].p, parent_scaler, l, r);      // case 1: take both
+      if (w2 > 0.0) ann.backend->updatePartials(p, ann.tmp_clv_2[p].p, parent_scaler, l, fake);   // case 2: take left only
+      if (w3 > 0.0) ann.backend->updatePartials(p, ann.tmp_clv_3[p].p, parent_scaler, fake, r);   // case 3: take right only
+    }
+    merge_clvs(ann, node, w1, w2, w3, w4);
+    ann.pseudo_clv_valid[node] = 1;
+  }
+  std::vector<double> partition_pseudo_logl(P, 0.0);
+  for (unsigned p = 0; p < P; ++p)
+    partition_pseudo_logl[p] = ann.backend->rootLogl(p, ann.pseudo_clv[nw.root][p].p, ann.pseudo_scaler[nw.root][p].p, nullptr);
+  if (ann.parallel_reduce_cb) ann.parallel_reduce_cb(ann.parallel_context, partition_pseudo_logl.data(), P, 0);
+  double pseudo_logl = 0.0;
+  for (unsigned p = 0; p < P; ++p) { pseudo_logl += partition_pseudo_logl[p]; ann.partition_loglh[p] = partition_pseudo_logl[p]; }
+  return pseudo_logl;
+}
+
 namespace {
 struct NaiveCtx {
   AnnotatedNetwork &ann;

@@ -175,7 +175,7 @@ struct NodeDisplayedTreeData {
   size_t num_active_displayed_trees = 0;
 };
 
-enum class LikelihoodVariant { AVERAGE_DISPLAYED_TREES = 0, BEST_DISPLAYED_TREE = 1 };
+enum class LikelihoodVariant { AVERAGE_DISPLAYED_TREES = 0, BEST_DISPLAYED_TREE = 1, SARAH_PSEUDO = 2 };
 enum { BRLEN_LINKED = 0, BRLEN_SCALED = 1, BRLEN_UNLINKED = 2 };  // PLLMOD_COMMON_BRLEN_*
 
 struct Options {  // SRC/NetraxOptions.hpp
@@ -217,6 +217,12 @@ struct AnnotatedNetwork {  // SRC/graph/AnnotatedNetwork.hpp:42-89 (fields the p
   std::vector<std::vector<double>> branch_lengths;  // [partition][edge+1] (fake_treeinfo->branch_lengths)
   std::vector<double> linked_branch_lengths;        // [edge+1]
   std::vector<double> partition_loglh;
+  // pseudo-likelihood state (SRC/graph/AnnotatedNetwork.hpp:64-68): one CLV + scaler per node and partition (the
+  // reference keeps them in partition->clv[node] / scale_buffer[node]) and the three scratch CLVs
+  std::vector<char> pseudo_clv_valid;                       // [node]
+  std::vector<std::vector<ABuf<double>>> pseudo_clv;        // [node][partition]
+  std::vector<std::vector<ABuf<unsigned>>> pseudo_scaler;   // [node][partition]
+  std::vector<ABuf<double>> tmp_clv_1, tmp_clv_2, tmp_clv_3; // [partition]
   size_t total_num_model_parameters = 0, total_num_sites = 0;  // SRC/graph/AnnotatedNetwork.hpp:47-48
   std::vector<double> alphas;  // fake_treeinfo->alphas (0 = no Gamma shape attached to the partition's rates)
   double cached_logl = 0;
@@ -234,6 +240,7 @@ void init_annotated_network(AnnotatedNetwork &ann);  // SRC/graph/AnnotatedNetwo
 
 /* upper seam, same names/arguments as the reference */
 double computeLoglikelihood(AnnotatedNetwork &ann, int incremental = 1, int update_pmatrices = 1);
+double computePseudoLoglikelihood(AnnotatedNetwork &ann, int incremental = 1, int update_pmatrices = 1);  // LH/PseudoLoglikelihood.cpp:57-226
 double computeLoglikelihoodNaive(AnnotatedNetwork &ann, std::vector<double> *tree_logl, std::vector<double> *tree_logprob);
 void invalidateSingleClv(AnnotatedNetwork &ann, unsigned clv_index);
 void invalidateHigherCLVs(AnnotatedNetwork &ann, unsigned node, bool invalidate_myself);

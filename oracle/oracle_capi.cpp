@@ -94,7 +94,7 @@ int orc_add_partition(void *hv, unsigned states, unsigned rate_cats, unsigned si
 
 int orc_set_options(void *hv, int likelihood_variant, int brlen_linkage) {
   Handle *h = static_cast<Handle *>(hv);
-  h->ann.options.likelihood_variant = likelihood_variant ? LikelihoodVariant::BEST_DISPLAYED_TREE : LikelihoodVariant::AVERAGE_DISPLAYED_TREES;
+  h->ann.options.likelihood_variant = likelihood_variant == 2 ? LikelihoodVariant::SARAH_PSEUDO : (likelihood_variant ? LikelihoodVariant::BEST_DISPLAYED_TREE : LikelihoodVariant::AVERAGE_DISPLAYED_TREES);
   h->ann.options.brlen_linkage = brlen_linkage;
   return 1;
 }
@@ -333,6 +333,24 @@ int orc_optimize_branches(void *hv, int max_iters, int max_iters_outside, int ra
 int orc_optimize_reticulation(void *hv, unsigned r, double *final_logl) {
   Handle *h = static_cast<Handle *>(hv);
   return guarded([&] { double l = optimize_reticulation(h->ann, r); if (final_logl) *final_logl = l; });
+}
+int orc_compute_pseudo_loglikelihood(void *hv, int incremental, int update_pmatrices, double *out) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] { *out = computePseudoLoglikelihood(h->ann, incremental, update_pmatrices); });
+}
+int orc_read_pseudo_clv(void *hv, unsigned node, unsigned p, double *out) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] {
+    if (node >= h->ann.pseudo_clv.size() || p >= h->ann.pseudo_clv[node].size()) throw std::runtime_error("no pseudo CLV at that node");
+    std::memcpy(out, h->ann.pseudo_clv[node][p].p, sizeof(double) * h->ann.backend->clvEntries(p));
+  });
+}
+int orc_read_pseudo_scaler(void *hv, unsigned node, unsigned p, unsigned *out) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] {
+    if (node >= h->ann.pseudo_scaler.size() || p >= h->ann.pseudo_scaler[node].size()) throw std::runtime_error("no pseudo CLV at that node");
+    std::memcpy(out, h->ann.pseudo_scaler[node][p].p, sizeof(unsigned) * h->ann.backend->sites(p));
+  });
 }
 int orc_score_network(void *hv, double *bic_score) {
   Handle *h = static_cast<Handle *>(hv);

@@ -490,6 +490,70 @@ def test_randomised_networks_bitexact(n, r, pat, seed, random_cells, variant):
     g.close()
 
 
+# ---------------------------------------------------------------------------------------------- pseudo-likelihood
+@pytest.mark.parametrize("cfg", [(10, 2, 257, 2), (14, 3, 128, 3), (9, 4, 65, 4), (12, 0, 300, 5), (25, 5, 1, 6)])
+def test_pseudo_loglikelihood_bitexact(cfg):
+    """computePseudoLoglikelihood (src/likelihood/PseudoLoglikelihood.cpp:57-226) as ONE fused kernel per node batch
+    (three libpll updates + merge_clvs in registers) against the reference's libpll under the restated driver: every node's
+    merged CLV and scaler bit-identical (DNA), incremental == full, variant SARAH_PSEUDO dispatches to it."""
+    from netrax_b200._capi import SARAH_PSEUDO
+    n, r, pat, seed = cfg
+    net = random_network(n, r, seed=seed)
+    m, w = simulate_alignment(net, pat, seed=seed)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    g, o = _gpu(net, [part], variant=SARAH_PSEUDO), _oracle(net, [part], variant=SARAH_PSEUDO)
+    _inject_eigen(g, o)
+    lg, lo = g.computeLoglikelihood(0, 1), o.computeLoglikelihood(0, 1)     # dispatch (LikelihoodComputation.cpp:23-27)
+    assert lg == pytest.approx(lo, rel=LNL_RTOL)
+    same_p = all(np.array_equal(g.get_pmatrix(e), o.get_pmatrix(e)) for e in range(net.num_edges + 1))
+    for v in range(net.num_tips, net.num_nodes):
+        assert np.array_equal(g.read_pseudo_scaler(v), o.read_pseudo_scaler(v)), v
+        a, b = g.read_pseudo_clv(v), o.read_pseudo_clv(v)
+        if same_p:
+            assert np.array_equal(a, b), (v, np.abs(a - b).max())
+        else:
+            np.testing.assert_allclose(a, b, rtol=1e-12, atol=0)
+    if r == 0:
+        e2 = _gpu(net, [part])
+        assert lg == pytest.approx(e2.computeLoglikelihood(0, 1), rel=1e-12)   # a tree: pseudo == exact
+        e2.close()
+    for eng in (g, o):
+        eng.set_branch_length(1, 0.37)
+        if r:
+            eng.set_reticulation_prob(0, 0.8)
+    inc_g, inc_o = g.computeLoglikelihood(1, 1), o.computeLoglikelihood(1, 1)
+    assert inc_g == pytest.approx(inc_o, rel=LNL_RTOL)
+    assert inc_g == pytest.approx(g.computePseudoLoglikelihood(0, 1), rel=1e-13)
+    g.close()
+
+
+def test_pseudo_loglikelihood_scaler_stress_and_protein():
+    """Deep caterpillar with one reticulation (scaler counts >= 2 in the blended CLVs: the three updates scale separately and
+    the last one's scaler wins, as in the reference) and a 20-state partition through the generic kernel."""
+    from netrax_b200._capi import SARAH_PSEUDO
+    net = caterpillar_network(400)
+    m, w = simulate_alignment(net, 300, seed=11, random_cells=True)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    g, o = _gpu(net, [part], variant=SARAH_PSEUDO), _oracle(net, [part], variant=SARAH_PSEUDO)
+    _inject_eigen(g, o)
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
+    mx = 0
+    for v in range(net.num_tips, net.num_nodes):
+        sg = g.read_pseudo_scaler(v)
+        assert np.array_equal(sg, o.read_pseudo_scaler(v)), v
+        mx = max(mx, int(sg.max()))
+    assert mx >= 2
+    g.close()
+    net2, aa = _protein_case(10, 2, 97, 8)
+    g, o = _gpu(net2, [aa], variant=SARAH_PSEUDO), _oracle(net2, [aa], variant=SARAH_PSEUDO)
+    _inject_eigen(g, o)
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
+    for v in range(net2.num_tips, net2.num_nodes):
+        assert np.array_equal(g.read_pseudo_scaler(v), o.read_pseudo_scaler(v))
+        np.testing.assert_allclose(g.read_pseudo_clv(v), o.read_pseudo_clv(v), rtol=1e-11, atol=1e-300)
+    g.close()
+
+
 def test_empty_partition_slice_is_skipped():
     """A site shard may own NO pattern of a partition (reference: partitions[p] == NULL, 'skip remote partitions',
     LH/ImprovedLoglikelihood.cpp:128-131): the engine must accept patterns = 0 and contribute exactly 0 to that partition."""

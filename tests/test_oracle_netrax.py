@@ -229,3 +229,42 @@ def test_protein_port_equals_reference():
         eng.brlen_prepare(e); eng.computePartitionSumtables(e)
     da, db = a.computeLoglikelihoodDerivatives(e), b.computeLoglikelihoodDerivatives(e)
     assert da[0] == pytest.approx(db[0], rel=1e-9) and da[1] == pytest.approx(db[1], rel=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------- pseudo-likelihood
+@pytest.mark.parametrize("kind", KINDS)
+def test_pseudo_loglikelihood_equals_exact_on_a_tree(kind):
+    """Without reticulations every weight is (1, 0, 0, 0): computePseudoLoglikelihood (LH/PseudoLoglikelihood.cpp:57-226)
+    is the ordinary tree likelihood."""
+    net = random_network(12, 0, seed=5)
+    m, w = simulate_alignment(net, 300, seed=5)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    e = oracle.make_engine(kind, net, [part])
+    assert e.computePseudoLoglikelihood(0, 1) == pytest.approx(e.computeLoglikelihood(0, 1), rel=1e-13)
+
+
+def test_pseudo_loglikelihood_port_equals_reference_and_dispatch():
+    """Scalar port vs real libpll under the same restated driver: CLVs and scalers of every node bit-identical (DNA);
+    incremental == full after a branch-length and a reticulation-probability change; variant SARAH_PSEUDO routes
+    computeLoglikelihood to it (LH/LikelihoodComputation.cpp:23-27)."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from netrax_b200._capi import SARAH_PSEUDO
+    for n, r, seed in ((10, 2, 2), (14, 3, 3), (9, 4, 4)):
+        net = random_network(n, r, seed=seed)
+        m, w = simulate_alignment(net, 257, seed=seed)
+        part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+        a, b = oracle.make_engine("port", net, [part], variant=SARAH_PSEUDO), oracle.make_engine("ref", net, [part], variant=SARAH_PSEUDO)
+        la, lb = a.computePseudoLoglikelihood(0, 1), b.computePseudoLoglikelihood(0, 1)
+        assert la == pytest.approx(lb, rel=1e-12)
+        for v in range(net.num_tips, net.num_nodes):
+            assert np.array_equal(a.read_pseudo_scaler(v), b.read_pseudo_scaler(v))
+            np.testing.assert_allclose(a.read_pseudo_clv(v), b.read_pseudo_clv(v), rtol=1e-13, atol=0)
+        for eng in (a, b):
+            eng.set_branch_length(1, 0.37)
+            eng.set_reticulation_prob(0, 0.8)
+        inc = a.computePseudoLoglikelihood(1, 1)
+        assert inc == pytest.approx(b.computePseudoLoglikelihood(1, 1), rel=1e-12)
+        assert inc == pytest.approx(a.computePseudoLoglikelihood(0, 1), rel=1e-13) and inc != la
+        c = oracle.make_engine("ref", net, [part], variant=SARAH_PSEUDO)
+        assert c.computeLoglikelihood(0, 1) == pytest.approx(lb, rel=1e-13)

@@ -520,10 +520,14 @@ __device__ __forceinline__ void pipe_loop(PipeSmem<NT> &sm, const PipeCtx &c, co
   }
 }
 
+/* pdl != 0: the launch carries the programmatic-stream-serialization attribute (plan graphs): the block may start while the
+ * previous K2 launch still runs, does everything that does not depend on it (mbarrier init, P-matrices, tip tables),
+ * lets ITS successor start (griddepcontrol.launch_dependents) and only then waits for the predecessor's CLVs
+ * (griddepcontrol.wait) before the first ring fill.  Small alignments: ~2 us of prologue per launch off the critical path. */
 template <int NT>
 __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe2(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops,
                                                               uint32_t nops, uint32_t groups, double *__restrict__ persite,
-                                                              size_t persite_stride, uint32_t nparts_total) {
+                                                              size_t persite_stride, uint32_t nparts_total, int pdl) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PipeSmem<NT> &sm = *reinterpret_cast<PipeSmem<NT> *>(smem_raw);
   const PartView &pv = parts[blockIdx.z];
@@ -545,18 +549,19 @@ __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe2(const PartView *__r
   c.grp = grp; c.groups = groups; c.patterns = pv.patterns;
   c.count = (ntiles - grp + groups - 1) / groups;
   c.ps_out = nullptr;
+#define NRX_PIPE_PRE(L, R) case (L) * 3 + (R): pipe_prefetch<L, R, NT>(sm, c); break;
+#define NRX_PIPE_PREFETCH()                                                                                     \
+  switch (lk * 3 + rk) {                                                                                        \
+    NRX_PIPE_PRE(NRX_CLV, NRX_CLV) NRX_PIPE_PRE(NRX_CLV, NRX_TIP) NRX_PIPE_PRE(NRX_CLV, NRX_NONE)               \
+    NRX_PIPE_PRE(NRX_TIP, NRX_CLV) NRX_PIPE_PRE(NRX_TIP, NRX_TIP) NRX_PIPE_PRE(NRX_TIP, NRX_NONE)               \
+    NRX_PIPE_PRE(NRX_NONE, NRX_CLV) NRX_PIPE_PRE(NRX_NONE, NRX_TIP)                                             \
+    default: break;                                                                                             \
+  }
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < PipeSmem<NT>::NST; ++s) mbar_init(&sm.full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#define NRX_PIPE_PRE(L, R) case (L) * 3 + (R): pipe_prefetch<L, R, NT>(sm, c); break;
-    switch (lk * 3 + rk) {
-      NRX_PIPE_PRE(NRX_CLV, NRX_CLV) NRX_PIPE_PRE(NRX_CLV, NRX_TIP) NRX_PIPE_PRE(NRX_CLV, NRX_NONE)
-      NRX_PIPE_PRE(NRX_TIP, NRX_CLV) NRX_PIPE_PRE(NRX_TIP, NRX_TIP) NRX_PIPE_PRE(NRX_TIP, NRX_NONE)
-      NRX_PIPE_PRE(NRX_NONE, NRX_CLV) NRX_PIPE_PRE(NRX_NONE, NRX_TIP)
-      default: break;
-    }
-#undef NRX_PIPE_PRE
+    if (!pdl) { NRX_PIPE_PREFETCH() }   // stream-ordered launch: the children are final, fill the ring before the prologue
   }
   if (lk == NRX_TIP) build_tip_lut4(sm.lutL, pv.pmat + (size_t)op.left_edge * 64, tid);
   if (rk == NRX_TIP) build_tip_lut4(sm.lutR, pv.pmat + (size_t)op.right_edge * 64, tid);
@@ -571,6 +576,13 @@ __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe2(const PartView *__r
 #pragma unroll
     for (int i = 0; i < 16; ++i) PR[i] = src[i];
   }
+  if (pdl) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // every thread: the predecessor's CLVs / scalers are complete and visible
+    if (tid == 0) { NRX_PIPE_PREFETCH() }
+  }
+#undef NRX_PIPE_PREFETCH
+#undef NRX_PIPE_PRE
   __syncthreads();
   const bool emit = op.lnl_item != 0 && persite != nullptr;
   double f0 = 0, f1 = 0, f2 = 0, f3 = 0, wcat = 0;

@@ -645,7 +645,7 @@ struct __align__(128) AaSmem {
   unsigned long long full[NSTAGE_AA];
   unsigned long long empty[NSTAGE_AA];
   unsigned long long lutbar;
-  uint32_t flags[2][4][AA_TP];
+  uint32_t flags[8][4][AA_TP];
   double exch[2][4][AA_TP];   // AA_EDGE: per (category, pattern) weighted site-likelihood terms
   // followed by double lutL[AA_LUT_CODES*80], lutR[AA_LUT_CODES*80] when the launch has tip operands
 };
@@ -910,14 +910,26 @@ __global__ void __launch_bounds__(AA_THREADS, 3) k_aa20_dmma(const PartView *__r
       }
       continue;
     }
-    // all 20 states of (pattern, cat): AND over the quad; all 4 cats: shared flags + named barrier over the 4 consumer warps
+    // all 20 states of (pattern, cat): AND over the quad; all 4 cats: flags in shared memory + a SPLIT named barrier.  A
+    // pattern is scaled only if all four categories are small, so a warp none of whose eight items is small in ITS category
+    // knows the answer (no scaling) without the others: it publishes its flags and only ARRIVES (non-blocking); a warp that
+    // does need the other categories' flags SYNCs on the same barrier.  Underflow is rare, so the common path never waits
+    // (the blocking 4-warp barrier per tile cost 10 % of the kernel).  Barrier ids / flag slots cycle over 8 tiles: warps of a
+    // block cannot drift further apart than the NSTAGE_AA = 4 ring stages.
     unsigned b = __ballot_sync(0xffffffffu, small);
     const bool cat_small = ((b >> (lane & ~3)) & 0xFu) == 0xFu;
     bool scale = false;
     if (!tiptip) {
-      if (q == 0) sm.flags[k & 1][cat][item] = cat_small ? 1u : 0u;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      scale = (sm.flags[k & 1][0][item] & sm.flags[k & 1][1][item] & sm.flags[k & 1][2][item] & sm.flags[k & 1][3][item]) != 0u;
+      const bool need = __any_sync(0xffffffffu, cat_small);
+      if (q == 0) sm.flags[k & 7][cat][item] = cat_small ? 1u : 0u;
+      const uint32_t bar_id = 1u + (k & 7u);
+      if (!need) {
+        __syncwarp();
+        asm volatile("bar.arrive %0, 128;" ::"r"(bar_id) : "memory");
+      } else {
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        scale = (sm.flags[k & 7][0][item] & sm.flags[k & 7][1][item] & sm.flags[k & 7][2][item] & sm.flags[k & 7][3][item]) != 0u;
+      }
     }
     if (act) {
       double *dst = par + site * 80 + cat * 20;

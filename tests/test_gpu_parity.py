@@ -578,3 +578,107 @@ def test_empty_partition_slice_is_skipped():
     with pytest.raises(LikelihoodError, match="bad partition logl"):
         g.computeLoglikelihoodBrlenOpt(e)
     g.close()
+
+
+# ---------------------------------------------------------------------------------------------- BASELINE full sizes
+def test_headline_topology_matches_oracle():
+    """BASELINE config 5's network (100 taxa, 8 reticulations: 776 displayed-tree CLVs, 192 root trees) at a pattern count
+    the oracle finishes in seconds: lnL, every per-tree lnL, scalers and CLVs of the root against libpll."""
+    import bench
+    cfg = dict(bench.CONFIGS[5])
+    net, parts, _ = bench.make_inputs(cfg, 700, 0)
+    g, o = _gpu(net, parts), _oracle(net, parts)
+    _inject_eigen(g, o)
+    lg, lo = g.computeLoglikelihood(0, 1), o.computeLoglikelihood(0, 1)
+    assert lg == pytest.approx(lo, rel=LNL_RTOL)
+    assert sum(g.num_trees(v) for v in range(net.num_tips, net.num_nodes)) == 776
+    root = net.root
+    assert g.num_trees(root) == o.num_trees(root) == 192
+    for t in range(g.num_trees(root)):
+        assert g.tree_config(root, t) == o.tree_config(root, t)
+        assert g.tree_info(root, t)[1] == pytest.approx(o.tree_info(root, t)[1], rel=LNL_RTOL)
+        assert np.array_equal(g.read_scaler(root, t), o.read_scaler(root, t))
+    assert g.computeLoglikelihood(0, 1) == lg   # plan replay (CUDA graph, PDL, fused K3)
+    e = int(net.ret_first_edge[3])
+    assert g.brlen_prepare(e) == pytest.approx(o.brlen_prepare(e), rel=LNL_RTOL)
+    assert g.computeLoglikelihoodBrlenOpt(e) == pytest.approx(o.computeLoglikelihoodBrlenOpt(e), rel=LNL_RTOL)
+    assert g.computePartitionSumtables(e) == o.computePartitionSumtables(e)
+    dg, do = g.computeLoglikelihoodDerivatives(e), o.computeLoglikelihoodDerivatives(e)
+    assert dg[0] == pytest.approx(do[0], rel=DERIV_RTOL, abs=1e-7)
+    assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL)
+    g.close()
+
+
+def test_full_size_config5_size_independent_properties():
+    """BASELINE config 5 at its FULL size (1 M patterns, 102 GB of CLVs on one B200) through properties that need no
+    oracle run: replay determinism, per-site terms sum to the tree lnL, additivity over pattern slices (what site sharding
+    relies on), re-rooting preserves the network lnL, incremental == full.  NRX_TEST_FULL_PATTERNS overrides the size."""
+    import os
+
+    import bench
+    import torch
+    patterns = int(os.environ.get("NRX_TEST_FULL_PATTERNS", "1000000"))
+    free, _total = torch.cuda.mem_get_info(0)
+    need = 776 * patterns * 132 * 1.08
+    if free < need:
+        pytest.skip(f"needs {need / 1e9:.0f} GB of free device memory, have {free / 1e9:.0f} GB")
+    cfg = dict(bench.CONFIGS[5])
+    net, parts, _ = bench.make_inputs(cfg, patterns, 0)
+    g = _gpu(net, parts)
+    l0 = g.computeLoglikelihood(0, 1)
+    assert g.computeLoglikelihood(0, 1) == l0                      # replay: bit-identical
+    root = net.root
+    trees = [g.tree_info(root, t)[1][0] for t in range(g.num_trees(root))]
+    for t in (0, g.num_trees(root) - 1):
+        ps = g.persite_lnl(t)[0]
+        assert float(ps[:patterns].sum()) == pytest.approx(trees[t], rel=1e-11)
+    e = int(net.ret_first_edge[0])
+    g.brlen_prepare(e)
+    assert g.computeLoglikelihoodBrlenOpt(e) == pytest.approx(l0, rel=1e-11)   # re-rooting preserves lnL (BrlenOptTest.cpp:297-367)
+    assert g.brlen_finish(e) == pytest.approx(l0, rel=1e-12)
+    g.set_branch_length(5, 0.123)
+    inc = g.computeLoglikelihood(1, 1)
+    assert inc == pytest.approx(g.computeLoglikelihood(0, 1), rel=1e-13) and inc != l0
+    g.close()
+    del g
+    # additivity over pattern slices: per-tree lnLs of the two halves add up to the whole (the cross-rank SUM of §8e)
+    half = patterns // 2
+    acc = np.zeros(len(trees))
+    for lo, hi in ((0, half), (half, patterns)):
+        s = _gpu(net, [parts[0].slice(lo, hi)])
+        s.computeLoglikelihood(0, 1)
+        acc += np.array([s.tree_info(root, t)[1][0] for t in range(s.num_trees(root))])
+        s.close()
+        del s
+    np.testing.assert_allclose(acc, np.array(trees), rtol=1e-11)
+
+
+@pytest.mark.parametrize("config", [1, 2, 3, 4])
+def test_baseline_configs_full_size_match_oracle(config):
+    """BASELINE configs 1-4 at their FULL sizes, directly against the reference's libpll under the restated driver (the
+    oracle needs seconds for these): network lnL, per-partition lnL, every root tree's lnL, root scalers; config 2
+    additionally the branch-length derivative on one reticulation edge (the sweep of bench_configs.py edge by edge)."""
+    import bench
+    cfg = dict(bench.CONFIGS[config])
+    net, parts, brl = bench.make_inputs(cfg, cfg["patterns"], 0)
+    kw = dict(variant=cfg["variant"], linkage=cfg["linkage"], partition_brlens=brl)
+    g, o = _gpu(net, parts, **kw), _oracle(net, parts, **kw)
+    _inject_eigen(g, o)
+    lg, lo = g.computeLoglikelihood(0, 1), o.computeLoglikelihood(0, 1)
+    assert lg == pytest.approx(lo, rel=LNL_RTOL)
+    np.testing.assert_allclose(g.partition_loglh(), o.partition_loglh(), rtol=LNL_RTOL)
+    root = net.root
+    for t in range(g.num_trees(root)):
+        np.testing.assert_allclose(g.tree_info(root, t)[1], o.tree_info(root, t)[1], rtol=LNL_RTOL)
+        assert np.array_equal(g.read_scaler(root, t), o.read_scaler(root, t))
+    assert g.computeLoglikelihood(0, 1) == lg
+    if config == 2:
+        e = int(net.ret_first_edge[1])
+        assert g.brlen_prepare(e) == pytest.approx(o.brlen_prepare(e), rel=LNL_RTOL)
+        assert g.computeLoglikelihoodBrlenOpt(e) == pytest.approx(o.computeLoglikelihoodBrlenOpt(e), rel=LNL_RTOL)
+        assert g.computePartitionSumtables(e) == o.computePartitionSumtables(e)
+        dg, do = g.computeLoglikelihoodDerivatives(e), o.computeLoglikelihoodDerivatives(e)
+        np.testing.assert_allclose(dg[4], do[4], rtol=DERIV_RTOL, atol=1e-9)
+        assert dg[0] == pytest.approx(do[0], rel=DERIV_RTOL, abs=1e-7)
+        assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL)
+    g.close()

@@ -77,6 +77,41 @@ def main():
         assert float(t[0]) == lnl and float(-t[1]) == lnl, "ranks disagree on the network lnL"
         g.close()
         report["cases"].append(case)
+    # ---- the callers under sharding: alpha optimisation (every Brent iterate all-reduces per-partition lnLs; the
+    # "all converged" flag travels through the same reduction), pseudo-likelihood, batched scoring of two networks
+    from netrax_b200._capi import SARAH_PSEUDO
+    from netrax_b200.engine import compute_loglikelihood_batch
+    net = random_network(16, 2, seed=91)
+    m, w = simulate_alignment(net, 2001, seed=91)
+    full = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    shard = full.slice(rank * full.sites // world, (rank + 1) * full.sites // world)
+    g = NetraxB200(net, [shard], device=lr, comm=(fresh_uid(), rank, world))
+    g.set_alpha(0, 2.0)
+    la = g.optimize_alpha()
+    alpha = g.get_alpha(0)
+    gp = NetraxB200(net, [shard], variant=SARAH_PSEUDO, device=lr, comm=(fresh_uid(), rank, world))
+    lp = gp.computeLoglikelihood(0, 1)
+    net2 = random_network(16, 3, seed=92)
+    g2 = NetraxB200(net2, [shard], device=lr, comm=(fresh_uid(), rank, world))
+    lb2 = compute_loglikelihood_batch([g, g2], 0, 1)
+    case = {"variant": "callers", "alpha": alpha}
+    if rank == 0:
+        s = NetraxB200(net, [full], device=lr)
+        s.set_alpha(0, 2.0)
+        la1 = s.optimize_alpha()
+        assert abs(la - la1) <= 1e-9 * abs(la1) and abs(alpha - s.get_alpha(0)) <= 1e-5 * alpha, (la, la1, alpha, s.get_alpha(0))
+        sp = NetraxB200(net, [full], variant=SARAH_PSEUDO, device=lr)
+        lp1 = sp.computeLoglikelihood(0, 1)
+        assert abs(lp - lp1) <= 1e-12 * abs(lp1), (lp, lp1)
+        s2 = NetraxB200(net2, [full], device=lr)
+        want = [s.computeLoglikelihood(0, 1), s2.computeLoglikelihood(0, 1)]
+        np.testing.assert_allclose(lb2, want, rtol=1e-12)
+        case.update({"lnl": la, "lnl_single_gpu": la1, "rel_diff": abs(la - la1) / abs(la1), "pseudo": lp, "batched": [float(x) for x in lb2]})
+        for x in (s, sp, s2):
+            x.close()
+    for x in (g, gp, g2):
+        x.close()
+    report["cases"].append(case)
     if rank == 0:
         report["ok"] = True
         print(json.dumps(report))

@@ -22,4 +22,5 @@ def test_two_gpu_sharded_equals_single_gpu():
     rep = json.loads(line)
     assert rep["ok"] and rep["world"] == 2
     for c in rep["cases"]:
-        assert c["rel_diff"] <= 1e-12
+        assert c["rel_diff"] <= (1e-9 if c["variant"] == "callers" else 1e-12)   # "callers": lnL after a Brent optimisation of alpha
+    assert rep["cases"][-1]["variant"] == "callers"

@@ -48,6 +48,36 @@ def parse_libpll_golden():
     return len(blocks)
 
 
+def parse_libpll_alpha_cats():
+    """libpll test/out/alpha-cats.out: discrete-Gamma rates (MEAN and MEDIAN) and an edge lnL for 9 alphas x 5 category counts."""
+    lines = open(LIBPLL_TEST + "/out/alpha-cats.out").read().splitlines()
+    blocks, i = [], 0
+    while i < len(lines):
+        m = re.match(r"\s*TEST alpha\(ncats\) =\s*([\d.]+)\(\s*(\d+)\), mode = (\w+)", lines[i])
+        if m:
+            j = i + 1
+            while not lines[j].strip():
+                j += 1
+            # the block header prints MODENAME(m) with m the LOOP INDEX over modes[] = {MEDIAN, MEAN} (test/src/alpha-cats.c:38-39,135-136),
+            # so its label is swapped; the summary lines at the end use MODENAME(modes[m]) and are right
+            mode = "MEDIAN" if m.group(3) == "MEAN" else "MEAN"
+            blocks.append({"alpha": float(m.group(1)), "ncats": int(m.group(2)), "mode": mode, "rates": [float(x) for x in lines[j].split()]})
+            i = j
+        i += 1
+    logl = {}
+    for l in lines:
+        m = re.match(r"ti/tv:alpha\(ncats\) =\s*([\d.]+)\(\s*(\d+)\), mode =\s*(\w+)\((\d)\)\s+logL:\s+(\S+)", l)
+        if m:
+            logl[(float(m.group(1)), int(m.group(2)), m.group(3))] = float(m.group(5))
+    for b in blocks:
+        b["logl"] = logl[(b["alpha"], b["ncats"], b["mode"])]
+    json.dump({"source": "libpll test/out/alpha-cats.out (test/src/alpha-cats.c: 5 taxa x 20 sites, HKY titv 2.5, pi=(.3,.4,.1,.2), branch lengths m0=0.1 m1=0.2; per (alpha, categories, mode): discrete Gamma rates (6 decimals) and the edge lnL between clv6 and clv7 (6 decimals))",
+               "tips": ["WAACTCGCTA--ATTCTAAT", "CACCATGCTA--ATTGTCTT", "AG-C-TGCAG--CTTCTACT", "CGTCTTGCAA--AT-C-AAG", "CGACTTGCCA--AT-T-AAG"],
+               "freqs": [0.3, 0.4, 0.1, 0.2], "subst": [1, 2.5, 1, 1, 2.5, 1], "branch_lengths": [0.1, 0.2], "blocks": blocks},
+              open(os.path.join(HERE, "libpll_alpha_cats_golden.json"), "w"), indent=0)
+    return len(blocks)
+
+
 def netrax_golden():
     out = {}
     for name, (nw, aln) in FIXTURE_PAIRS.items():
@@ -64,4 +94,5 @@ def netrax_golden():
 if __name__ == "__main__":
     copy_fixtures()
     print("libpll golden blocks:", parse_libpll_golden())
+    print("libpll alpha-cats blocks:", parse_libpll_alpha_cats())
     print("netrax golden cases:", netrax_golden())

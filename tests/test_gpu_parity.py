@@ -682,3 +682,60 @@ def test_baseline_configs_full_size_match_oracle(config):
         assert dg[0] == pytest.approx(do[0], rel=DERIV_RTOL, abs=1e-7)
         assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL)
     g.close()
+
+
+# ---------------------------------------------------------------------------------------------- libpll's own golden vectors
+def _golden_five_taxon(G, t, tip_edge, ncats, rates):
+    from netrax_b200.network_io import encode_dna, parse_extended_newick
+    b0, b1 = G["branch_lengths"]
+    h = t / 2
+    if not tip_edge:
+        nw = f"(((T0:{b1},T1:{b1}):{b0},T2:{b1})X6:{h},(T3:{b1},T4:{b1})X7:{h});"
+    else:
+        nw = f"(T4:{h},(((T0:{b1},T1:{b1}):{b0},T2:{b1}):{b0},T3:{b0})X7:{h});"
+    net = parse_extended_newick(nw)
+    order = [int(l[1:]) for l in net.tip_labels]
+    masks = np.stack([encode_dna(G["tips"][i]) for i in order])
+    return net, Partition(4, ncats, masks, G["freqs"], G["subst"], rates)
+
+
+def test_libpll_golden_alpha_cats_on_gpu():
+    """The PRODUCT against libpll's regression output test/out/alpha-cats.out (tests/golden/libpll_alpha_cats_golden.json):
+    the edge lnL of the 5-taxon data set for 9 alphas x {1, 2, 4, 8, 16} categories x {MEAN, MEDIAN} with the product's own
+    Gamma rates, eigendecomposition, P-matrices and kernels (4 categories: the pipelined 4x4 kernels; others: generic)."""
+    from helpers import load_golden
+    from netrax_b200.engine import load
+    GA = load_golden("libpll_alpha_cats_golden.json")
+    api = load()
+    for b in GA["blocks"]:
+        rates = api.gamma_rates(b["alpha"], b["ncats"], {"MEAN": 0, "MEDIAN": 1}[b["mode"]]) if b["ncats"] > 1 else np.ones(1)
+        net, part = _golden_five_taxon(GA, GA["branch_lengths"][0], False, b["ncats"], rates)
+        g = _gpu(net, [part])
+        assert abs(g.computeLoglikelihood(0, 1) - b["logl"]) < 2e-6, (b["alpha"], b["ncats"], b["mode"])
+        g.close()
+
+
+@pytest.mark.parametrize("tip_edge", [False, True])
+def test_libpll_golden_derivatives_on_gpu(tip_edge):
+    """The PRODUCT against libpll's test/out/derivatives.out (tests/golden/libpll_derivatives_golden.json): edge lnL (6
+    decimals) and first / second derivative (5 significant digits) on an inner and on a tip edge, for every (alpha,
+    categories) block at three branch lengths — K1, K2, K4, K5, K6 and the host mixing pinned to the reference's own vectors."""
+    from helpers import load_golden
+    from netrax_b200.engine import load
+    G = load_golden("libpll_derivatives_golden.json")
+    api = load()
+    for block in G["blocks"]:
+        rates = api.gamma_rates(block["alpha"], block["ncats"]) if block["ncats"] > 1 else np.ones(1)
+        for t, f, d1, d2 in block["tip" if tip_edge else "inner"][:6:2]:
+            net, part = _golden_five_taxon(G, t, tip_edge, block["ncats"], rates)
+            g = _gpu(net, [part])
+            lnl = g.computeLoglikelihood(0, 1)
+            assert abs(lnl - f) < 2e-6, (block["alpha"], block["ncats"], t, lnl, f)
+            edge = [e for e in range(net.num_edges) if net.edge_source[e] == net.root][0]
+            g.brlen_prepare(edge)
+            assert abs(g.computeLoglikelihoodBrlenOpt(edge) - lnl) < 1e-9
+            assert g.computePartitionSumtables(edge) == 1
+            g1, g2, *_ = g.computeLoglikelihoodDerivatives(edge)
+            assert g1 == pytest.approx(d1, rel=2e-4, abs=1e-9), (t, g1, d1)
+            assert g2 == pytest.approx(d2, rel=2e-4, abs=1e-9), (t, g2, d2)
+            g.close()

@@ -52,3 +52,49 @@ def test_libpll_golden_edge_lnl_and_derivatives(kind, bi, tip_edge):
         assert g2 == pytest.approx(d2, rel=2e-4, abs=1e-9), (t, g2, d2)
         assert abs(eng.brlen_finish(edge) - lnl) < 1e-9
         eng.close()
+
+
+# ---- second golden set: libpll test/out/alpha-cats.out (Gamma rates, both discretisation modes, and an edge lnL) ----------
+GA = load_golden("libpll_alpha_cats_golden.json")
+MODE = {"MEAN": 0, "MEDIAN": 1}   # PLL_GAMMA_RATES_MEAN / _MEDIAN (LIBPLL/pll.h)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_libpll_golden_gamma_rates_oracle(kind):
+    """pll_compute_gamma_cats for alpha in 0.1..100, 1..16 categories, MEAN and MEDIAN: the golden prints 6 decimals."""
+    api = oracle.api(kind)
+    for b in GA["blocks"]:
+        want = np.array(b["rates"])
+        got = api.gamma_rates(b["alpha"], b["ncats"], MODE[b["mode"]]) if b["ncats"] > 1 else np.ones(1)
+        np.testing.assert_allclose(got, want, rtol=0, atol=5.1e-7, err_msg=str((b["alpha"], b["ncats"], b["mode"])))
+
+
+def test_libpll_golden_gamma_rates_product_host():
+    """The PRODUCT's own Gamma discretisation (host/model.cpp compute_gamma_cats, what setAlpha / optimize_alpha use)
+    against the same golden vectors — host code, no device needed."""
+    from netrax_b200 import engine
+    api = engine.load()
+    for b in GA["blocks"]:
+        if b["ncats"] == 1:
+            continue
+        got = api.gamma_rates(b["alpha"], b["ncats"], MODE[b["mode"]])
+        np.testing.assert_allclose(got, np.array(b["rates"]), rtol=0, atol=5.1e-7, err_msg=str((b["alpha"], b["ncats"], b["mode"])))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_libpll_golden_alpha_cats_edge_lnl(kind):
+    """The golden edge lnL between clv6 = ((t0,t1),t2) and clv7 = (t3,t4) for every (alpha, categories, mode): same tree
+    rooted on that edge (0.1 split in two halves), rates = the oracle's own Gamma rates for that mode."""
+    b0, b1 = GA["branch_lengths"]
+    h = b0 / 2
+    nw = f"(((T0:{b1},T1:{b1}):{b0},T2:{b1})X6:{h},(T3:{b1},T4:{b1})X7:{h});"
+    net = parse_extended_newick(nw)
+    order = [int(l[1:]) for l in net.tip_labels]
+    masks = np.stack([encode_dna(GA["tips"][i]) for i in order])
+    api = oracle.api(kind)
+    for b in GA["blocks"]:
+        rates = api.gamma_rates(b["alpha"], b["ncats"], MODE[b["mode"]]) if b["ncats"] > 1 else np.ones(1)
+        part = Partition(4, b["ncats"], masks, GA["freqs"], GA["subst"], rates)
+        eng = oracle.make_engine(kind, net, [part])
+        assert abs(eng.computeLoglikelihood(0, 1) - b["logl"]) < 2e-6, (b["alpha"], b["ncats"], b["mode"])
+        eng.close()

@@ -76,7 +76,7 @@ int nrxh_add_partition(void *hv, unsigned states, unsigned rate_cats, unsigned s
     if (!h->net_set) throw std::runtime_error("set the network first");
     PartitionInput in;
     in.model.states = states; in.model.rate_cats = rate_cats; in.model.sites = sites;
-    in.model.frequencies.assign(freqs, freqs + states);
+    set_frequencies(in.model, freqs);
     in.model.subst_params.assign(subst, subst + states * (states - 1) / 2);
     in.model.rates.assign(rates, rates + rate_cats);
     in.model.rate_weights.assign(rate_weights, rate_weights + rate_cats);
@@ -229,7 +229,7 @@ int nrxh_set_model(void *hv, unsigned p, const double *freqs, const double *subs
   return guarded([&] {
     AnnotatedNetwork &ann = H(hv)->ann;
     PartitionModel &m = ann.fake_treeinfo->partitions.at(p);
-    m.frequencies.assign(freqs, freqs + m.states);
+    set_frequencies(m, freqs);
     m.subst_params.assign(subst, subst + m.states * (m.states - 1) / 2);
     m.rates.assign(rates, rates + m.rate_cats);
     m.rate_weights.assign(rw, rw + m.rate_cats);

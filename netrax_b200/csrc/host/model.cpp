@@ -16,6 +16,18 @@
 
 namespace netrax {
 
+/* pll_set_frequencies (LIBPLL/models.c:445-467): copy, and make sure the frequencies sum up to 1 — libpll's own empirical
+ * amino-acid tables (pll_aa_freqs_*) sum to 1 + 1e-6, so this is not a corner case: without it every protein lnL is off by
+ * ~1e-7 relative (found by pinning against test/out/protein-models.out). */
+void set_frequencies(PartitionModel &m, const double *frequencies) {
+  m.frequencies.assign(frequencies, frequencies + m.states);
+  double sum = 0.;
+  for (unsigned i = 0; i < m.states; ++i) sum += m.frequencies[i];
+  if (std::fabs(sum - 1.0) > 1e-8 /* PLL_MISC_EPSILON */)
+    for (unsigned i = 0; i < m.states; ++i) m.frequencies[i] /= sum;
+  m.eigen_decomp_valid = false;
+}
+
 void update_eigen(PartitionModel &m) {
   const unsigned n = m.states, sp = m.states_padded;
   const unsigned nparams = n * (n - 1) / 2;

@@ -134,6 +134,7 @@ struct PartitionModel {
   std::vector<double> eigenvecs, inv_eigenvecs, eigenvals;  // filled by update_eigen (own Jacobi solver) or set explicitly
   bool eigen_decomp_valid = false;
 };
+void set_frequencies(PartitionModel &m, const double *frequencies);                    // pll_set_frequencies (LIBPLL/models.c:445-467): renormalises when |sum - 1| > 1e-8
 void update_eigen(PartitionModel &m);                                                 // role of pll_update_eigen
 bool compute_gamma_cats(double alpha, unsigned cats, double *out_rates, int mode);    // role of pll_compute_gamma_cats
 

@@ -26,12 +26,12 @@ GAMMA4_ALPHA05 = np.array([0.03338775337571123, 0.25191592470299234, 0.820268478
 
 def lg_model():
     """(rates[190], freqs[20]) of the LG amino-acid model (netrax_b200/lg_model.json, extracted from the reference's
-    libpll constants by tests/golden/make_lg_model.py); frequencies renormalised to sum to 1."""
+    libpll constants by tests/golden/make_lg_model.py).  The table sums to 1 + 1e-6 exactly as libpll ships it; the engine
+    renormalises it the way pll_set_frequencies does."""
     import json
     import os
     d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "lg_model.json")))
-    f = np.asarray(d["freqs"], float)
-    return np.asarray(d["rates"], float), f / f.sum()
+    return np.asarray(d["rates"], float), np.asarray(d["freqs"], float)
 
 
 def random_network(n_taxa: int, n_ret: int, seed: int = 42, mean_brlen: float = 0.1) -> NetworkDesc:

@@ -5,6 +5,8 @@
 #include "netrax_port.hpp"
 #include "pll_port.h"
 
+#include <cmath>
+
 #include <map>
 
 namespace orc {
@@ -21,7 +23,9 @@ struct PortBackend : Backend {
   unsigned states(unsigned p) const override { return parts[p]->states; }
   void setModel(unsigned p, const double *freqs, const double *subst, const double *rates, const double *weights) override {
     port_partition *pp = parts[p];
-    for (unsigned i = 0; i < pp->states; ++i) pp->freqs[i] = freqs[i];
+    double sum = 0.;   // pll_set_frequencies (LIBPLL/models.c:445-467): renormalise when |sum - 1| > PLL_MISC_EPSILON
+    for (unsigned i = 0; i < pp->states; ++i) { pp->freqs[i] = freqs[i]; sum += freqs[i]; }
+    if (std::fabs(sum - 1.0) > 1e-8) for (unsigned i = 0; i < pp->states; ++i) pp->freqs[i] /= sum;
     for (unsigned i = 0; i < pp->states * (pp->states - 1) / 2; ++i) pp->subst_params[i] = subst[i];
     for (unsigned i = 0; i < pp->rate_cats; ++i) { pp->rates[i] = rates[i]; pp->rate_weights[i] = weights[i]; }
     port_update_eigen(pp);

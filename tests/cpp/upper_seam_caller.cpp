@@ -33,6 +33,7 @@ int main(int argc, char **argv) {
     part.model.states = 4; part.model.rate_cats = 4; part.model.sites = (unsigned)sites;
     part.model.frequencies.resize(4); part.model.subst_params.resize(6); part.model.rates.resize(4);
     for (double &v : part.model.frequencies) in >> v;
+    set_frequencies(part.model, std::vector<double>(part.model.frequencies).data());   // pll_set_frequencies
     for (double &v : part.model.subst_params) in >> v;
     for (double &v : part.model.rates) in >> v;
     if (!in) throw std::runtime_error("short input file");

@@ -78,6 +78,31 @@ def parse_libpll_alpha_cats():
     return len(blocks)
 
 
+def parse_libpll_protein_models():
+    """libpll test/out/protein-models.out: edge lnL under 20 empirical amino-acid models; the model DATA tables come from the
+    reference's compiled libpll (oracle/_ref/libpll_ref.so symbols pll_aa_rates_* / pll_aa_freqs_*, LIBPLL/pll.h:553-600)."""
+    import ctypes as C
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libpll_ref.so"))
+    names = ["Dayhoff", "LG", "DCMut", "JTT", "MtREV", "WAG", "RtREV", "CpREV", "VT", "Blosum62", "MtMam", "MtArt", "MtZoa", "PMB", "HIVb",
+             "HIVw", "JTT-DCMut", "FLU", "StmtREV", "DEN"]
+    logl = {}
+    for l in open(LIBPLL_TEST + "/out/protein-models.out"):
+        m = re.match(r"Log-L \((\S+)\): (\S+)", l)
+        if m:
+            logl[m.group(1)] = float(m.group(2))
+    src = open(LIBPLL_TEST + "/src/protein-models.c").read()
+    seqs = re.findall(r'pll_set_tip_states \(partition, \d, pll_map_aa,\s*"([^"]+)"\);', src)
+    models = {}
+    for n in names:
+        s = {"JTT-DCMut": "jttdcmut"}.get(n, n.lower())
+        models[n] = {"rates": list((C.c_double * 190).in_dll(lib, "pll_aa_rates_" + s)), "freqs": list((C.c_double * 20).in_dll(lib, "pll_aa_freqs_" + s)),
+                     "logl": logl[n]}
+    json.dump({"source": "libpll test/out/protein-models.out (test/src/protein-models.c: 5 taxa x 113 amino-acid sites, Gamma alpha = 1 with 4 MEAN categories, branch lengths m0=0.1 m1=0.2, edge lnL between clv6=((t0,t1),t2) and clv7=(t3,t4) over matrix 0, 6 decimals); exchangeabilities / frequencies = the model DATA tables pll_aa_rates_* / pll_aa_freqs_* of the reference's compiled libpll",
+               "alpha": 1.0, "ncats": 4, "branch_lengths": [0.1, 0.2], "tips": seqs, "aa_order": "ARNDCQEGHILKMFPSTWYV", "models": models},
+              open(os.path.join(HERE, "libpll_protein_models_golden.json"), "w"))
+    return len(models)
+
+
 def netrax_golden():
     out = {}
     for name, (nw, aln) in FIXTURE_PAIRS.items():
@@ -95,4 +120,5 @@ if __name__ == "__main__":
     copy_fixtures()
     print("libpll golden blocks:", parse_libpll_golden())
     print("libpll alpha-cats blocks:", parse_libpll_alpha_cats())
+    print("libpll protein models:", parse_libpll_protein_models())
     print("netrax golden cases:", netrax_golden())

@@ -58,3 +58,39 @@ def fixture_summary(eng):
 
 def load_golden(name):
     return json.load(open(os.path.join(GOLDEN, name)))
+
+
+AA_ORDER = "ARNDCQEGHILKMFPSTWYV"   # pll_map_aa (LIBPLL/maps.c:66-100)
+_AA_AMBIG = {"B": "ND", "Z": "QE", "J": "IL"}
+
+
+def encode_aa(seq: str):
+    """Amino-acid characters -> 20-bit state masks exactly as pll_map_aa: gaps / X / ? / * are fully ambiguous."""
+    import numpy as np
+    out = np.zeros(len(seq), dtype=np.uint32)
+    for i, ch in enumerate(seq.upper()):
+        if ch in AA_ORDER:
+            out[i] = 1 << AA_ORDER.index(ch)
+        elif ch in _AA_AMBIG:
+            out[i] = sum(1 << AA_ORDER.index(c) for c in _AA_AMBIG[ch])
+        elif ch in "-X?*":
+            out[i] = (1 << 20) - 1
+        else:
+            raise ValueError(f"illegal amino-acid character {ch!r}")
+    return out
+
+
+def protein_golden_case(GP, model):
+    """5-taxon tree of libpll's test/src/protein-models.c rooted on the edge the golden lnL is computed on."""
+    import numpy as np
+    from netrax_b200._capi import Partition
+    from netrax_b200.network_io import parse_extended_newick
+    from oracle import oracle
+    b0, b1 = GP["branch_lengths"]
+    h = b0 / 2
+    net = parse_extended_newick(f"(((T0:{b1},T1:{b1}):{b0},T2:{b1})X6:{h},(T3:{b1},T4:{b1})X7:{h});")
+    order = [int(l[1:]) for l in net.tip_labels]
+    masks = np.stack([encode_aa(GP["tips"][i]) for i in order])
+    rates = oracle.api("port").gamma_rates(GP["alpha"], GP["ncats"])
+    m = GP["models"][model]
+    return net, Partition(20, GP["ncats"], masks, m["freqs"], m["rates"], rates)

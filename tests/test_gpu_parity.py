@@ -739,3 +739,27 @@ def test_libpll_golden_derivatives_on_gpu(tip_edge):
             assert g1 == pytest.approx(d1, rel=2e-4, abs=1e-9), (t, g1, d1)
             assert g2 == pytest.approx(d2, rel=2e-4, abs=1e-9), (t, g2, d2)
             g.close()
+
+
+def test_libpll_golden_protein_models_on_gpu():
+    """The PRODUCT's 20-state path (own Jacobi eigendecomposition, K1 + tip tables, tensor-core K2, K3) against libpll's
+    test/out/protein-models.out for all 20 empirical amino-acid models; LG additionally through the tensor-core edge-lnL
+    (K4) and sumtable / derivative kernels against the oracle."""
+    from helpers import load_golden, protein_golden_case
+    GP = load_golden("libpll_protein_models_golden.json")
+    for model, m in GP["models"].items():
+        net, part = protein_golden_case(GP, model)
+        g = _gpu(net, [part])
+        lnl = g.computeLoglikelihood(0, 1)
+        assert abs(lnl - m["logl"]) < 2e-6, (model, lnl, m["logl"])
+        if model == "LG":
+            o = _oracle(net, [part])
+            o.computeLoglikelihood(0, 1)
+            edge = [e for e in range(net.num_edges) if net.edge_source[e] == net.root][0]
+            assert g.brlen_prepare(edge) == pytest.approx(o.brlen_prepare(edge), rel=1e-9)
+            assert abs(g.computeLoglikelihoodBrlenOpt(edge) - m["logl"]) < 2e-6     # K4 against the golden value
+            assert g.computePartitionSumtables(edge) == o.computePartitionSumtables(edge)
+            dg, do = g.computeLoglikelihoodDerivatives(edge), o.computeLoglikelihoodDerivatives(edge)
+            assert dg[0] == pytest.approx(do[0], rel=1e-7, abs=1e-7)
+            assert dg[1] == pytest.approx(do[1], rel=1e-7, abs=1e-7)
+        g.close()

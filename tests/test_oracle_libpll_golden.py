@@ -98,3 +98,27 @@ def test_libpll_golden_alpha_cats_edge_lnl(kind):
         eng = oracle.make_engine(kind, net, [part])
         assert abs(eng.computeLoglikelihood(0, 1) - b["logl"]) < 2e-6, (b["alpha"], b["ncats"], b["mode"])
         eng.close()
+
+
+# ---- third golden set: libpll test/out/protein-models.out (20 empirical amino-acid models, 20-state kernels) -------------
+GP = load_golden("libpll_protein_models_golden.json")
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("model", list(GP["models"]))
+def test_libpll_golden_protein_models(kind, model):
+    """Edge lnL of a 5-taxon, 113-site amino-acid alignment under each of libpll's 20 empirical models (Gamma alpha = 1,
+    4 categories): the 20-state arithmetic of both oracle flavours against the reference's regression output (6 decimals)."""
+    from helpers import protein_golden_case
+    net, part = protein_golden_case(GP, model)
+    eng = oracle.make_engine(kind, net, [part])
+    assert abs(eng.computeLoglikelihood(0, 1) - GP["models"][model]["logl"]) < 2e-6
+    eng.close()
+
+
+def test_shipped_lg_model_is_the_reference_table():
+    """netrax_b200/lg_model.json (the model data bench config 4 uses) == the LG table the golden file was produced with."""
+    from netrax_b200.synth import lg_model
+    rates, freqs = lg_model()
+    np.testing.assert_array_equal(np.asarray(rates), np.asarray(GP["models"]["LG"]["rates"]))
+    np.testing.assert_array_equal(np.asarray(freqs), np.asarray(GP["models"]["LG"]["freqs"]))

@@ -29,9 +29,9 @@ def copy_fixtures():
         shutil.copy(os.path.join(src, f), os.path.join(HERE, "fixtures", f))
 
 
-def parse_libpll_golden():
+def _parse_derivative_blocks(path):
     blocks, cur = [], None
-    for line in open(LIBPLL_TEST + "/out/derivatives.out"):
+    for line in open(path):
         m = re.match(r"\s*TEST alpha\(ncats\) =\s*([\d.]+)\(\s*(\d+)\) ; pinv = ([\d.]+)", line)
         if m:
             cur = {"alpha": float(m.group(1)), "ncats": int(m.group(2)), "pinv": float(m.group(3)), "inner": [], "tip": []}
@@ -40,11 +40,29 @@ def parse_libpll_golden():
         m = re.match(r"Branch(\(Tip\))?\s+([\d.]+) :\s+(\S+)\s+(\S+)\s+(\S+)", line)
         if m and cur is not None:
             cur["tip" if m.group(1) else "inner"].append([float(m.group(2)), float(m.group(3)), float(m.group(4)), float(m.group(5))])
-    blocks = [b for b in blocks if b["pinv"] == 0.0]
+    return [b for b in blocks if b["pinv"] == 0.0]
+
+
+def parse_libpll_golden():
+    blocks = _parse_derivative_blocks(LIBPLL_TEST + "/out/derivatives.out")
     json.dump({"source": "libpll test/out/derivatives.out (pinv=0 blocks); columns: branch, edge lnL, d(-lnL)/dt, d2(-lnL)/dt2",
                "tips": ["WAACTCGCTA--ATTCTAAT", "CACCATGCTA--ATTGTCTT", "AG-C-TGCAG--CTTCTACT", "CGTCTTGCAA--AT-C-AAG", "CGACTTGCCA--AT-T-AAG"],
                "freqs": [0.3, 0.4, 0.1, 0.2], "subst": [1, 2.5, 1, 1, 2.5, 1], "branch_lengths": [0.1, 0.2],
                "blocks": blocks}, open(os.path.join(HERE, "libpll_derivatives_golden.json"), "w"), indent=1)
+    return len(blocks)
+
+
+def parse_libpll_oddstates():
+    """libpll test/out/derivatives-oddstates.out: the same experiment with FIVE states (states_padded = 8), inline data of
+    test/src/derivatives-oddstates.c:100-145; characters through odd5_map (test/src/common.c:8-19: A..D = states 0..3,
+    E = C|D, gap = all five)."""
+    blocks = _parse_derivative_blocks(LIBPLL_TEST + "/out/derivatives-oddstates.out")
+    json.dump({"source": "libpll test/out/derivatives-oddstates.out (pinv=0 blocks); 5 states; columns: branch, edge lnL, d(-lnL)/dt, d2(-lnL)/dt2",
+               "states": 5, "char_masks": {"A": 1, "B": 2, "C": 4, "D": 8, "E": 12, "-": 31},
+               "tips": ["DAACBCECBA--ABBCBAAB", "CACCABECBA--ABBEBCBB", "AE-C-BECAE--CBBCBACB", "CEBCBBECAA--AB-C-AAE", "CEACBBECCA--AB-B-AAE"],
+               "freqs": [0.3, 0.25, 0.1, 0.2, 0.15],
+               "subst": [1.452176, 0.937951, 0.462880, 0.617729, 1.745312, 0.937951, 0.462880, 0.617729, 1.745312, 1.000000],
+               "branch_lengths": [0.1, 0.2], "blocks": blocks}, open(os.path.join(HERE, "libpll_derivatives_oddstates_golden.json"), "w"), indent=1)
     return len(blocks)
 
 
@@ -119,6 +137,7 @@ def netrax_golden():
 if __name__ == "__main__":
     copy_fixtures()
     print("libpll golden blocks:", parse_libpll_golden())
+    print("libpll odd-states blocks:", parse_libpll_oddstates())
     print("libpll alpha-cats blocks:", parse_libpll_alpha_cats())
     print("libpll protein models:", parse_libpll_protein_models())
     print("netrax golden cases:", netrax_golden())

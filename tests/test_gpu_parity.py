@@ -763,3 +763,29 @@ def test_libpll_golden_protein_models_on_gpu():
             assert dg[0] == pytest.approx(do[0], rel=1e-7, abs=1e-7)
             assert dg[1] == pytest.approx(do[1], rel=1e-7, abs=1e-7)
         g.close()
+
+
+@pytest.mark.parametrize("tip_edge", [False, True])
+def test_libpll_golden_oddstates_on_gpu(tip_edge):
+    """The PRODUCT's generic kernels (5 states in 8-double rows: states != states_padded nowhere else in the suite) against
+    libpll's test/out/derivatives-oddstates.out: edge lnL, first and second derivative on an inner and a tip edge."""
+    from test_oracle_libpll_golden import GO, oddstates_case
+    from netrax_b200.engine import load
+    api = load()
+    for block in GO["blocks"]:
+        rates = api.gamma_rates(block["alpha"], block["ncats"]) if block["ncats"] > 1 else np.ones(1)
+        for t, f, d1, d2 in block["tip" if tip_edge else "inner"]:
+            if t > 10:
+                continue
+            net, part = oddstates_case(t, tip_edge, block["ncats"], rates)
+            g = _gpu(net, [part])
+            lnl = g.computeLoglikelihood(0, 1)
+            assert abs(lnl - f) < 2e-6, (block["alpha"], block["ncats"], t, lnl, f)
+            edge = [e for e in range(net.num_edges) if net.edge_source[e] == net.root][0]
+            g.brlen_prepare(edge)
+            assert abs(g.computeLoglikelihoodBrlenOpt(edge) - lnl) < 1e-9
+            assert g.computePartitionSumtables(edge) == 1
+            g1, g2, *_ = g.computeLoglikelihoodDerivatives(edge)
+            assert g1 == pytest.approx(d1, rel=2e-4, abs=1e-9), (t, g1, d1)
+            assert g2 == pytest.approx(d2, rel=2e-4, abs=1e-9), (t, g2, d2)
+            g.close()

@@ -122,3 +122,43 @@ def test_shipped_lg_model_is_the_reference_table():
     rates, freqs = lg_model()
     np.testing.assert_array_equal(np.asarray(rates), np.asarray(GP["models"]["LG"]["rates"]))
     np.testing.assert_array_equal(np.asarray(freqs), np.asarray(GP["models"]["LG"]["freqs"]))
+
+
+# ---- fourth golden set: libpll test/out/derivatives-oddstates.out (5 states, states_padded = 8) --------------------------
+GO = load_golden("libpll_derivatives_oddstates_golden.json")
+
+
+def oddstates_case(t, tip_edge, ncats, rates):
+    b0, b1 = GO["branch_lengths"]
+    h = t / 2
+    if not tip_edge:
+        nw = f"(((T0:{b1},T1:{b1}):{b0},T2:{b1})X6:{h},(T3:{b1},T4:{b1})X7:{h});"
+    else:
+        nw = f"(T4:{h},(((T0:{b1},T1:{b1}):{b0},T2:{b1}):{b0},T3:{b0})X7:{h});"
+    net = parse_extended_newick(nw)
+    order = [int(l[1:]) for l in net.tip_labels]
+    masks = np.stack([np.array([GO["char_masks"][c] for c in GO["tips"][i]], dtype=np.uint32) for i in order])
+    return net, Partition(GO["states"], ncats, masks, GO["freqs"], GO["subst"], rates)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("tip_edge", [False, True])
+def test_libpll_golden_oddstates(kind, tip_edge):
+    """Five states (padded to eight: the only golden set where states != states_padded): edge lnL and derivatives."""
+    for block in GO["blocks"]:
+        rates = oracle.api("port").gamma_rates(block["alpha"], block["ncats"]) if block["ncats"] > 1 else np.ones(1)
+        for t, f, d1, d2 in block["tip" if tip_edge else "inner"]:
+            if t > 10:
+                continue
+            net, part = oddstates_case(t, tip_edge, block["ncats"], rates)
+            eng = oracle.make_engine(kind, net, [part])
+            lnl = eng.computeLoglikelihood(0, 1)
+            assert abs(lnl - f) < 2e-6, (block["alpha"], block["ncats"], t, lnl, f)
+            edge = [e for e in range(net.num_edges) if net.edge_source[e] == net.root][0]
+            eng.brlen_prepare(edge)
+            assert abs(eng.computeLoglikelihoodBrlenOpt(edge) - lnl) < 1e-9
+            assert eng.computePartitionSumtables(edge) == 1
+            g1, g2, *_ = eng.computeLoglikelihoodDerivatives(edge)
+            assert g1 == pytest.approx(d1, rel=2e-4, abs=1e-9), (t, g1, d1)
+            assert g2 == pytest.approx(d2, rel=2e-4, abs=1e-9), (t, g2, d2)
+            eng.close()

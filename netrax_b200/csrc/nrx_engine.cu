@@ -135,7 +135,7 @@ struct nrx_engine {
   bool throughput_mode = false;  // several engines share the GPU (batched scoring): fewer, longer-running blocks per launch
   uint32_t pending_result = 0;  // doubles of an enqueued, not yet collected result (nrx_*_async / nrx_result_wait)
   uint32_t k2_nt = 2;       // env NRX_K2_NT: 64-pattern sub-tiles per ring stage of k_clv_dna4_pipe2 (1 or 2; 2 measured 1-2 % faster)
-  int k2_variant = 0;       // 0: k_clv_dna4_pipe (production); UM: k_clv_dna4<U, MINB> (A/B experiments, env NRX_K2=UM)
+  int k2_variant = 0;       // 0: k_clv_dna4_pipe2 (production); 1: k_clv_dna4_pipe (A/B baseline, env NRX_K2=1)
   bool aa_generic = false;  // env NRX_AA=generic: force the scalar kernel for 20-state partitions (A/B)
   uint32_t aa_blocks = 148 * 3 * 2;  // block-count target of the DMMA kernels: two waves of 3 resident blocks per SM (A/B: profiles/r1e_all_configs.md)
   uint32_t k2_blocks = 2368; // block-count target of the pipelined kernel: 8 waves of 2 resident blocks per SM (measured best, profiles/)
@@ -736,15 +736,7 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
           e->pdl_prev_is_k2 = true;
         } else
           k_clv_dna4_pipe<<<grid, BLOCK, sizeof(ClvPipeSmem), e->stream>>>(c.d_views, d_ops, nops, groups, fused_ptr, (size_t)e->max_patterns, (uint32_t)e->parts.size());
-      } else {
-        const uint32_t U = e->k2_variant / 10, MB = e->k2_variant % 10;
-        dim3 grid(tiles_for((uint64_t)c.max_patterns * 4, BLOCK * U, nops * z), nops, z);
-        if (U == 2 && MB == 2) k_clv_dna4<2, 2><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops);
-        else if (U == 2 && MB == 4) k_clv_dna4<2, 4><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops);
-        else if (U == 1 && MB == 5) k_clv_dna4<1, 5><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops);
-        else if (U == 4 && MB == 2) k_clv_dna4<4, 2><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops);
-        else { g_err = "NRX_K2: unknown register-kernel variant"; return 0; }
-      }
+      } else { g_err = "NRX_K2: unknown K2 variant (0 = k_clv_dna4_pipe2, 1 = k_clv_dna4_pipe)"; return 0; }
     } else if (c.states == 20 && c.cats == 4 && !e->aa_generic && class_tip_codes(e, c) <= (uint32_t)AA_LUT_CODES) {
       // protein.  The first `ntt` ops are tip-tip: a table product, written by a plain streaming kernel
       if (ntt) {

@@ -129,93 +129,10 @@ __device__ __forceinline__ D4 matvec4(const double *__restrict__ P /* smem, this
   return r;
 }
 
-template <int UNROLL, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) k_clv_dna4(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops) {
-  const PartView &pv = parts[blockIdx.z];
-  const nrx_op op = ops[blockIdx.y];
-  const int tid = threadIdx.x, cat = tid & 3, lane = tid & 31;
-  const uint64_t n_items = (uint64_t)pv.patterns * 4;
-  if ((uint64_t)blockIdx.x * BLOCK * UNROLL >= n_items) return;
-
-  __shared__ __align__(32) double lutL[256];
-  __shared__ __align__(32) double lutR[256];
-  __shared__ __align__(16) double sPL[4 * PCAT];
-  __shared__ __align__(16) double sPR[4 * PCAT];
-  const int lk = op.left_kind, rk = op.right_kind;
-  if (lk == NRX_CLV) {
-    if (tid < 64) sPL[(tid >> 4) * PCAT + (tid & 15)] = pv.pmat[(size_t)op.left_edge * 64 + tid];
-  } else if (lk == NRX_TIP) {
-    build_tip_lut4(lutL, pv.pmat + (size_t)op.left_edge * 64, tid);
-  }
-  if (rk == NRX_CLV) {
-    if (tid >= 64 && tid < 128) sPR[((tid - 64) >> 4) * PCAT + (tid & 15)] = pv.pmat[(size_t)op.right_edge * 64 + tid - 64];
-  } else if (rk == NRX_TIP) {
-    build_tip_lut4(lutR, pv.pmat + (size_t)op.right_edge * 64, tid);
-  }
-  __syncthreads();
-  const double *PL = sPL + cat * PCAT, *PR = sPR + cat * PCAT;
-
-  const double *clvL = (lk == NRX_CLV) ? pv.clv[op.left_idx] : nullptr;
-  const double *clvR = (rk == NRX_CLV) ? pv.clv[op.right_idx] : nullptr;
-  const uint32_t *scL = (lk == NRX_CLV) ? pv.scaler[op.left_idx] : nullptr;
-  const uint32_t *scR = (rk == NRX_CLV) ? pv.scaler[op.right_idx] : nullptr;
-  const uint8_t *tipL = (lk == NRX_TIP) ? pv.tipchars + (size_t)op.left_idx * pv.tip_pitch : nullptr;
-  const uint8_t *tipR = (rk == NRX_TIP) ? pv.tipchars + (size_t)op.right_idx * pv.tip_pitch : nullptr;
-  double *par = pv.clv[op.parent_slot];
-  uint32_t *psc = pv.scaler[op.parent_slot];
-  const bool tiptip = (lk == NRX_TIP && rk == NRX_TIP);  // scaler := 0, no scaling test (core_partials_avx.c:1003-1009)
-  const unsigned quad = 0xFu << (lane & ~3);
-
-  for (uint64_t base = (uint64_t)blockIdx.x * BLOCK * UNROLL; base < n_items; base += (uint64_t)gridDim.x * BLOCK * UNROLL) {
-    D4 l[UNROLL], r[UNROLL];
-    bool act[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {  // issue all loads first (memory-level parallelism)
-      const uint64_t g = base + (uint64_t)u * BLOCK + tid;
-      act[u] = g < n_items;
-      if (act[u]) {
-        if (lk == NRX_CLV) l[u] = ldg256(clvL + g * 4);
-        if (rk == NRX_CLV) r[u] = ldg256(clvR + g * 4);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const uint64_t g = base + (uint64_t)u * BLOCK + tid;
-      const uint64_t site = g >> 2;
-      D4 x, y, p;
-      bool small = false;
-      if (act[u]) {
-        if (lk == NRX_CLV) x = matvec4(PL, l[u]);
-        else if (lk == NRX_TIP) x = *reinterpret_cast<const D4 *>(lutL + ((tipL[site] & 15) * 4 + cat) * 4);
-        if (rk == NRX_CLV) y = matvec4(PR, r[u]);
-        else if (rk == NRX_TIP) y = *reinterpret_cast<const D4 *>(lutR + ((tipR[site] & 15) * 4 + cat) * 4);
-        if (rk == NRX_NONE) p = x;        // x * 1.0 (fake all-ones CLV through identity P) is x, exactly
-        else if (lk == NRX_NONE) p = y;
-        else { p.x = __dmul_rn(x.x, y.x); p.y = __dmul_rn(x.y, y.y); p.z = __dmul_rn(x.z, y.z); p.w = __dmul_rn(x.w, y.w); }
-        small = (p.x < SCALE_THRESHOLD) & (p.y < SCALE_THRESHOLD) & (p.z < SCALE_THRESHOLD) & (p.w < SCALE_THRESHOLD);
-      }
-      // per-site scaling: all 16 entries of the site below 2^-256 (core_partials_avx.c:531-563)
-      const unsigned b = __ballot_sync(0xffffffffu, small);
-      const bool scale = !tiptip && ((b & quad) == quad);
-      if (act[u]) {
-        if (scale) { p.x = __dmul_rn(p.x, SCALE_FACTOR); p.y = __dmul_rn(p.y, SCALE_FACTOR); p.z = __dmul_rn(p.z, SCALE_FACTOR); p.w = __dmul_rn(p.w, SCALE_FACTOR); }
-        stg256(par + g * 4, p);
-        if (cat == 0) {
-          uint32_t s = 0;
-          if (!tiptip) {
-            if (scL) s += scL[site];
-            if (scR) s += scR[site];
-            s += scale ? 1u : 0u;
-          }
-          psc[site] = s;
-        }
-      }
-    }
-  }
-}
-
 /* ------------------------------------------------------------------------------------------------
- * K2, DNA 4x4, bulk-async pipelined version (the production kernel).
+ * K2, DNA 4x4, bulk-async pipelined version (round-1b production kernel; kept as the A/B baseline of k_clv_dna4_pipe2,
+ * env NRX_K2=1.  Its predecessor, a register-streaming kernel — loads held in registers, 98 registers -> 16 warps/SM,
+ * 0.68 of the copy peak, profiles/r1a_* — was removed).
  *
  * HBM-bound streaming needs many bytes in flight per SM; holding them in registers caps occupancy.  Here a
  * block owns one op and walks pattern tiles (TP patterns = 8 KB per CLV operand); one elected thread keeps

@@ -789,3 +789,53 @@ def test_libpll_golden_oddstates_on_gpu(tip_edge):
             assert g1 == pytest.approx(d1, rel=2e-4, abs=1e-9), (t, g1, d1)
             assert g2 == pytest.approx(d2, rel=2e-4, abs=1e-9), (t, g2, d2)
             g.close()
+
+
+def test_engines_driven_from_concurrent_host_threads():
+    """One engine per host thread on the same GPU (the reference runs one AnnotatedNetwork per worker thread,
+    RAXML/ParallelContext.cpp): handles are independent — own stream, own staging ring, thread-local error state — so
+    concurrent evaluations, re-rootings and optimisations give exactly the sequential results."""
+    import threading
+    nets = [random_network(12 + k, 2, seed=300 + k) for k in range(4)]
+    parts = []
+    for k, n in enumerate(nets):
+        m, w = simulate_alignment(n, 900 + 37 * k, seed=300 + k)
+        parts.append(Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w))
+
+    def work(eng, net):
+        out = [eng.computeLoglikelihood(0, 1)]
+        for _ in range(20):
+            out.append(eng.computeLoglikelihood(0, 1))
+        e = int(net.ret_first_edge[0])
+        eng.brlen_prepare(e)
+        out.append(eng.computeLoglikelihoodBrlenOpt(e))
+        eng.computePartitionSumtables(e)
+        out.extend(eng.computeLoglikelihoodDerivatives(e)[:2])
+        out.append(eng.brlen_finish(e))
+        out.append(eng.optimize_branches())
+        return out
+
+    want = []
+    for n, p in zip(nets, parts):
+        g = _gpu(n, [p])
+        want.append(work(g, n))
+        g.close()
+    engines = [_gpu(n, [p]) for n, p in zip(nets, parts)]
+    got, errors = [None] * 4, []
+
+    def run(i):
+        try:
+            got[i] = work(engines[i], nets[i])
+        except Exception as ex:  # noqa: BLE001
+            errors.append(ex)
+
+    threads = [threading.Thread(target=run, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for a, b in zip(got, want):
+        assert a == b
+    for g in engines:
+        g.close()

@@ -99,6 +99,8 @@ int nrxh_optimize_all_non_topology(void *h, int type, double *bic_score);
  * (PLLMOD/tree/pll_tree.h:267-271) / network_logl_wrapper (src/RaxmlWrapper.cpp:21-26); params from nrxh_network_params(h). */
 double nrxh_likelihood_target_function(void *network_params, int incremental, int update_pmatrices, double **persite_lnl);
 void *nrxh_network_params(void *h);
+/* +I: proportion of invariant sites of partition p (pll_update_invariant_sites_proportion, LIBPLL/models.c:495-543) */
+int nrxh_set_pinv(void *h, unsigned p, double prop_invar);
 int nrxh_set_alpha(void *h, unsigned p, double alpha);
 int nrxh_get_alpha(void *h, unsigned p, double *alpha);
 int nrxh_optimize_alpha(void *h, double min_alpha, double max_alpha, double tolerance, double *final_logl);

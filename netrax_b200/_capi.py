@@ -78,6 +78,7 @@ class FlatAPI:
         g("score_network", C.c_int, C.c_void_p, C.POINTER(C.c_double))
         g("set_scoring_sizes", C.c_int, C.c_void_p, C.c_ulonglong, C.c_ulonglong)
         g("optimize_all_non_topology", C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double))
+        g("set_pinv", C.c_int, C.c_void_p, C.c_uint, C.c_double)
         g("set_alpha", C.c_int, C.c_void_p, C.c_uint, C.c_double)
         g("get_alpha", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
         g("optimize_alpha", C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double))
@@ -326,6 +327,10 @@ class LikelihoodEngine:
         out = C.c_double()
         self.api.check(self.api._optimize_all_non_topology(self.h, type, C.byref(out)))
         return out.value
+
+    def set_pinv(self, p: int, prop_invar: float):
+        """+I: proportion of invariant sites (pll_update_invariant_sites_proportion)."""
+        self.api.check(self.api._set_pinv(self.h, p, prop_invar))
 
     def set_alpha(self, p: int, alpha: float):
         """treeinfo_set_alpha: Gamma shape -> discrete rates of partition p (mean mode)."""

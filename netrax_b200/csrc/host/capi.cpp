@@ -401,6 +401,9 @@ void *nrxh_network_params(void *hv) {  // the likelihood_computation_params poin
   H(hv)->params.ann_network = &H(hv)->ann;
   return &H(hv)->params;
 }
+int nrxh_set_pinv(void *hv, unsigned p, double prop_invar) {
+  return guarded([&] { setPinv(H(hv)->ann, p, prop_invar); });
+}
 int nrxh_set_alpha(void *hv, unsigned p, double alpha) {
   return guarded([&] { setAlpha(H(hv)->ann, p, alpha); });
 }

@@ -270,7 +270,7 @@ static void uploadModel(AnnotatedNetwork &ann, unsigned p) {
   std::vector<double> freqs(m.states_padded, 0.0);
   std::copy(m.frequencies.begin(), m.frequencies.begin() + m.states, freqs.begin());
   engineCheck(nrx_set_model(ann.engine, p, freqs.data(), m.eigenvecs.data(), m.inv_eigenvecs.data(), m.eigenvals.data(),
-                            m.rates.data(), m.rate_weights.data(), 0.0), "nrx_set_model");
+                            m.rates.data(), m.rate_weights.data(), m.prop_invar), "nrx_set_model");
 }
 
 void pushPartitionModel(AnnotatedNetwork &ann, unsigned p) {
@@ -537,7 +537,7 @@ static void treeLoglikelihoodsBegin(AnnotatedNetwork &ann, Node *actRoot, bool r
   if (slots_out) *slots_out = slots;
   if (!slots.empty()) {
     // after a plan replay whose ops carried lnl marks for exactly these trees, K2 has already written the per-site lnLs
-    if (replayed && ann.plan->fused && ann.plan->on_device && slots == ann.plan->lnl_slots)
+    if (replayed && ann.plan->fused && ann.plan->on_device && slots == ann.plan->lnl_slots && nrx_supports_fused_lnl(ann.engine))
       engineCheck(nrx_tree_lnl_fused_async(ann.engine, ann.plan->engine_plan, slots.data(), (uint32_t)slots.size()), "nrx_tree_lnl_fused");
     else
       engineCheck(nrx_tree_lnl_async(ann.engine, slots.data(), (uint32_t)slots.size()), "nrx_tree_lnl");

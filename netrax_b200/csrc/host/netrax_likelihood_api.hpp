@@ -129,6 +129,7 @@ struct NetraxOptions {
 struct PartitionModel {
   unsigned states = 4, states_padded = 4, rate_cats = 4, sites = 0;
   std::vector<double> frequencies, subst_params, rates, rate_weights;
+  double prop_invar = 0.0;  // pll_partition_t::prop_invar[0] (+I); the invariant-site indices are derived from the tips by the engine
   double alpha = 0.0;   // pllmod_treeinfo_t::alphas[p]; > 0: `rates` are the discrete-Gamma rates of this shape and optimize_alpha may change it
   int gamma_mode = 0;   // PLL_GAMMA_RATES_MEAN (raxml-ng default)
   std::vector<double> eigenvecs, inv_eigenvecs, eigenvals;  // filled by update_eigen (own Jacobi solver) or set explicitly
@@ -275,6 +276,7 @@ double optimize_reticulations(AnnotatedNetwork &ann_network, int max_iters);
 /* model-parameter loop: the model of partition p changed on the host -> upload it, invalidate its P-matrices and all CLVs */
 void pushPartitionModel(AnnotatedNetwork &ann_network, unsigned partition);
 void setAlpha(AnnotatedNetwork &ann_network, unsigned partition, double alpha);
+void setPinv(AnnotatedNetwork &ann_network, unsigned partition, double prop_invar);   // pll_update_invariant_sites_proportion (LIBPLL/models.c:495-543)
 /* the ALPHA step of optimize_params (src/optimization/ModelOptimization.cpp:56-65); defaults = PLLMOD_OPT_MIN/MAX_ALPHA, RAXML_PARAM_EPSILON */
 double optimize_alpha(AnnotatedNetwork &ann_network, double min_alpha = 0.0201, double max_alpha = 100.0, double tolerance = 0.001);
 

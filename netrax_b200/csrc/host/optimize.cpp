@@ -325,6 +325,12 @@ void setAlpha(AnnotatedNetwork &ann, unsigned p, double alpha) {
   pushPartitionModel(ann, p);
 }
 
+void setPinv(AnnotatedNetwork &ann, unsigned p, double prop_invar) {
+  if (!(prop_invar >= 0.0 && prop_invar < 1.0)) throw std::runtime_error("Invalid proportion of invariant sites (" + std::to_string(prop_invar) + ")");
+  ann.fake_treeinfo->partitions.at(p).prop_invar = prop_invar;
+  pushPartitionModel(ann, p);   // P-matrices depend on rates / (1 - pinv): everything of the partition is stale
+}
+
 double optimize_alpha(AnnotatedNetwork &ann, double min_alpha, double max_alpha, double tolerance) {
   FakeTreeinfo &ti = *ann.fake_treeinfo;
   std::vector<unsigned> parts;   // params_to_optimize & PLLMOD_OPT_PARAM_ALPHA

@@ -33,6 +33,9 @@ struct Part {
   size_t clv_entries = 0, pmat_entries = 0;
   double *pmat = nullptr;
   double *tiplut = nullptr;  // 20-state partitions only
+  bool invariant_stale = false;  // tips were replaced through nrx_set_tipchars_u8 while pinv == 0: recompute before +I is switched on
+  double pinv = 0.0;        // proportion of invariant sites (+I)
+  int *invariant = nullptr; // device [pat_pad]: pll_update_invariant_sites
   double *summat = nullptr, *sumlut = nullptr;  // 20-state partitions only: K5 operand matrices / tip table (PartView)
   std::vector<uint32_t> h_tipmap;               // code -> state mask, host copy
   std::vector<double> h_freqs, h_inv_eigenvecs, h_eigenvecs;
@@ -241,6 +244,7 @@ PartView make_view(const Part &p, uint32_t index) {
   v.rates = p.rates; v.rate_weights = p.rate_weights;
   v.clv = p.d_clv; v.scaler = p.d_scaler; v.sumtable = p.d_sumtable; v.diagp = p.diagp; v.tiplut = p.tiplut;
   v.summat = p.summat; v.sumlut = p.sumlut;
+  v.pinv = p.pinv; v.invariant = p.invariant;
   return v;
 }
 
@@ -279,6 +283,22 @@ int refresh_tiplut(nrx_engine *e, uint32_t pi, const uint32_t *edges, uint32_t n
   CK(cudaGetLastError());
   return 1;
 }
+/* pll_update_invariant_sites (LIBPLL/models.c:651-760): AND of all tips' state masks per pattern; exactly one state left ->
+ * its index, otherwise -1.  masks[t * patterns + i] = state mask of tip t at pattern i. */
+template <class T> int upload_invariant(nrx_engine *e, Part &p, const T *masks, const uint32_t *tipmap) {
+  const size_t n = p.d.patterns;
+  std::vector<int> inv(std::max<size_t>(1, n), -1);
+  const uint32_t gap = (p.d.states >= 32) ? 0xffffffffu : ((1u << p.d.states) - 1);
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t st = gap;
+    for (uint32_t t = 0; t < p.d.tips; ++t) st &= tipmap ? tipmap[masks[(size_t)t * n + i]] : (uint32_t)masks[(size_t)t * n + i];
+    inv[i] = (st == 0 || __builtin_popcount(st) > 1) ? -1 : __builtin_ctz(st);
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  if (n) CK(cudaMemcpy(p.invariant, inv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+  return 1;
+}
+
 /* K5 operands of a 20-state partition: A_L[j][k] = pi_k Vinv[k][j], A_R[j][k] = V[j][k] and the tip table
  * sum_{k in code} pi_k Vinv[k][j] (serial k order as the reference's tip-inner sumtable loop, LIBPLL/core_derivatives.c:473-641) */
 int refresh_summat(nrx_engine *e, uint32_t pi) {
@@ -387,7 +407,8 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
               cuda_ok(cudaMalloc((void **)&p.tipchars, std::max<size_t>(1, (size_t)p.d.tips * p.pat_pad)), "cudaMalloc tipchars") &&
               cuda_ok(cudaMalloc((void **)&p.tipmap, 256 * sizeof(uint32_t)), "cudaMalloc tipmap") &&
               cuda_ok(cudaMalloc((void **)&p.weights, std::max<size_t>(1, p.pat_pad) * sizeof(uint32_t)), "cudaMalloc weights") &&
-              cuda_ok(cudaMalloc((void **)&p.model, model_doubles * sizeof(double)), "cudaMalloc model");
+              cuda_ok(cudaMalloc((void **)&p.model, model_doubles * sizeof(double)), "cudaMalloc model") &&
+              cuda_ok(cudaMalloc((void **)&p.invariant, std::max<size_t>(1, p.pat_pad) * sizeof(int)), "cudaMalloc invariant");
     if (ok && p.d.states == 20 && p.d.rate_cats == 4)
       ok = cuda_ok(cudaMalloc((void **)&p.tiplut, (size_t)p.d.edges * AA_LUT_CODES * 80 * sizeof(double)), "cudaMalloc tiplut") &&
            cuda_ok(cudaMalloc((void **)&p.summat, 800 * sizeof(double)), "cudaMalloc summat") &&
@@ -415,7 +436,7 @@ void nrx_engine_destroy(nrx_engine *e) {
   if (e->comm && nccl().ok) nccl().CommDestroy(e->comm);
   for (EnginePlan &pl : e->plans) { for (cudaGraphExec_t &x : pl.exec) if (x) cudaGraphExecDestroy(x); cudaFree(pl.d_ops); }
   for (Part &p : e->parts) {
-    cudaFree(p.pmat); cudaFree(p.tiplut); cudaFree(p.summat); cudaFree(p.sumlut); cudaFree(p.tipchars); cudaFree(p.tipmap); cudaFree(p.weights); cudaFree(p.model);
+    cudaFree(p.invariant); cudaFree(p.pmat); cudaFree(p.tiplut); cudaFree(p.summat); cudaFree(p.sumlut); cudaFree(p.tipchars); cudaFree(p.tipmap); cudaFree(p.weights); cudaFree(p.model);
     for (void *m : p.slot_mem) cudaFree(m);
     for (double *m : p.h_sumtable) cudaFree(m);
     cudaFree(p.d_clv); cudaFree(p.d_scaler); cudaFree(p.d_sumtable);
@@ -466,6 +487,7 @@ int nrx_set_tips(nrx_engine *e, uint32_t pi, const uint32_t *tip_masks) {
   for (uint32_t i = 0; i < 256; ++i) if (tipmap[i]) p.tip_codes = i + 1;
   p.tips_set = true;
   p.h_tipmap = tipmap;
+  if (!upload_invariant(e, p, codes.data(), tipmap.data())) return 0;
   e->views_dirty = true;
   if (p.model_set && (!refresh_tiplut(e, pi, nullptr, 0) || !refresh_summat(e, pi))) return 0;  // the code -> state-set map may have changed
   return 1;
@@ -483,6 +505,8 @@ int nrx_set_tipchars_u8(nrx_engine *e, uint32_t pi, const uint8_t *codes) {
   CK(cudaMemcpyAsync(p.tipmap, tipmap.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   p.tips_set = true;
+  if (p.pinv > 0.0 && !upload_invariant(e, p, codes, (const uint32_t *)nullptr)) return 0;   // only +I partitions read it
+  p.invariant_stale = !(p.pinv > 0.0);
   if (p.tip_codes != 16) { p.tip_codes = 16; e->views_dirty = true; }
   return 1;
 }
@@ -499,9 +523,11 @@ int nrx_set_pattern_weights(nrx_engine *e, uint32_t pi, const uint32_t *w) {
 int nrx_set_model(nrx_engine *e, uint32_t pi, const double *freqs, const double *eigenvecs, const double *inv_eigenvecs,
                   const double *eigenvals, const double *rates, const double *rate_weights, double prop_invar) {
   if (!check_part(e, pi)) return 0;
-  if (prop_invar != 0.0) { g_err = "proportion of invariant sites (+I) is not supported by this engine"; return 0; }
+  if (!(prop_invar >= 0.0 && prop_invar < 1.0)) { g_err = "Invalid proportion of invariant sites"; return 0; }   // pll_update_invariant_sites_proportion
   CK(cudaSetDevice(e->device));
   Part &p = e->parts[pi];
+  if (prop_invar > 0.0 && p.invariant_stale) { g_err = "nrx_set_model: +I after nrx_set_tipchars_u8: call nrx_set_tips (or upload the tips again) first"; return 0; }
+  if (p.pinv != prop_invar) { p.pinv = prop_invar; e->views_dirty = true; }
   const size_t S = p.d.states, SP = p.sp, C = p.d.rate_cats;
   std::vector<double> h(SP + 2 * S * SP + SP + 2 * C, 0.0);
   double *q = h.data();
@@ -930,6 +956,7 @@ int nrx_set_throughput_mode(nrx_engine *e, int on) {
 int nrx_supports_fused_lnl(nrx_engine *e) {
   if (!e || (e->k2_variant != 0 && e->k2_variant != 1) || std::getenv("NRX_NO_FUSED_LNL")) return 0;
   for (const ShapeClass &c : e->classes) if (!(c.states == 4 && c.cats == 4)) return 0;
+  for (const Part &p : e->parts) if (p.pinv > 0.0) return 0;   // the K2 epilogue does not carry the invariant-site term
   return 1;
 }
 
@@ -1193,7 +1220,7 @@ int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen, double *out)
     std::vector<double> diag((size_t)C * S * 4);
     double *dp = diag.data();
     for (uint32_t i = 0; i < C; ++i) {
-      const double ki = p.h_rates[i] / (1.0 - 0.0);
+      const double ki = p.h_rates[i] / (1.0 - p.pinv);   // LIBPLL/core_derivatives.c:716
       for (uint32_t j = 0; j < S; ++j) {
         dp[0] = std::exp(p.h_eigenvals[j] * ki * brlen[pi]);
         dp[1] = p.h_eigenvals[j] * ki * dp[0];

@@ -40,6 +40,8 @@ struct PartView {
   const double *diagp;       // [cats][states][4] for the current derivative call
   const double *tiplut;      // 20-state partitions: [edges][AA_LUT_CODES][cats*20] sums of P rows over each tip code's states (K1b)
   const double *summat;      // 20-state partitions: K5 operand matrices [2][20][20]: A_L[j][k] = pi_k Vinv[k][j], A_R[j][k] = V[j][k]
+  double pinv;               // proportion of invariant sites (+I, pll_partition_t::prop_invar); 0 = none
+  const int *invariant;      // [patterns] state index of an invariant pattern (pll_update_invariant_sites, LIBPLL/models.c:651-760), else -1
   const double *sumlut;      // 20-state partitions: K5 tip table [AA_LUT_CODES][cats*20]: sum_{k in code} pi_k Vinv[k][j], replicated per category
 };
 
@@ -48,6 +50,45 @@ __device__ __forceinline__ double tree4(double a, double b, double c, double d) 
 }
 
 struct D4 { double x, y, z, w; };
+
+/* +I (proportion of invariant sites), the three places libpll accounts for it (formulas identical in the generic, AVX and AVX2
+ * kernels): root lnL per category  w (t (1 - pinv) + pi_inv pinv)            LIBPLL/core_likelihood.c:176-188
+ *           edge lnL               terma += w t (1 - pinv); terminv += w pi_inv pinv, the site scaling undone on terma only
+ *                                                                             LIBPLL/core_likelihood.c:523-560
+ *           derivatives per category  (c0 (1 - pinv) + pi_inv pinv, c1 (1 - pinv), c2 (1 - pinv))   core_derivatives.c:676-686
+ * invf = frequency of the pattern's invariant state, 0 if the pattern is variable. */
+__device__ __forceinline__ double root_cat_term(double term_r, double w, double pinv, double invf) {
+  if (pinv > 0.0) return __dmul_rn(w, __dadd_rn(__dmul_rn(term_r, __dsub_rn(1.0, pinv)), __dmul_rn(invf, pinv)));
+  return __dmul_rn(term_r, w);
+}
+__device__ __forceinline__ void edge_cat_accum(double terma_r, double w, double pinv, double invf, bool has_inv, double &terma, double &terminv) {
+  if (pinv > 0.0) {
+    terma = __dadd_rn(terma, __dmul_rn(__dmul_rn(w, terma_r), __dsub_rn(1.0, pinv)));
+    if (has_inv) terminv = __dadd_rn(terminv, __dmul_rn(__dmul_rn(w, invf), pinv));
+  } else {
+    terma = __dadd_rn(terma, __dmul_rn(terma_r, w));
+  }
+}
+__device__ __forceinline__ double edge_site_lnl(double terma, double terminv, uint32_t s, double log_thresh) {
+  if (s) {
+    if (terminv > 0.0) {   // undo the scaling of the non-invariant term only, capped at PLL_SCALE_RATE_MAXDIFF = 4 steps
+      double f = SCALE_THRESHOLD;
+      const uint32_t capped = s < 4u ? s : 4u;
+      for (uint32_t i = 1; i < capped; ++i) f = __dmul_rn(f, SCALE_THRESHOLD);
+      return log(__dadd_rn(__dmul_rn(terma, f), terminv));
+    }
+    return __dadd_rn(log(terma), __dmul_rn((double)s, log_thresh));
+  }
+  return log(__dadd_rn(terma, terminv));
+}
+__device__ __forceinline__ void deriv_cat_pinv(double &c0, double &c1, double &c2, double pinv, double invf) {
+  if (pinv > 0.0) {
+    const double q = __dsub_rn(1.0, pinv);
+    c0 = __dadd_rn(__dmul_rn(c0, q), __dmul_rn(invf, pinv));
+    c1 = __dmul_rn(c1, q);
+    c2 = __dmul_rn(c2, q);
+  }
+}
 
 __device__ __forceinline__ D4 ldg256(const double *p) {
   D4 v;
@@ -70,8 +111,10 @@ __global__ void k_pmatrix(PartView pv, double *pmat_out, const uint32_t *edge_id
   double *out = pmat_out + (size_t)edge * C * S * SP;
   for (uint32_t i = threadIdx.x; i < C * S; i += blockDim.x) {
     const uint32_t c = i / S, m = i % S;
-    // (eval*rate)*t exactly as core_pmatrix_avx.c:104-108 (pinv == 0)
-    expd[i] = expm1(__dmul_rn(__dmul_rn(pv.eigenvals[m], pv.rates[c]), t));
+    // (eval*rate)*t exactly as core_pmatrix_avx.c:104-108, divided by (1 - pinv) for +I partitions (:113-117, core_pmatrix.c:196-200)
+    double a = __dmul_rn(__dmul_rn(pv.eigenvals[m], pv.rates[c]), t);
+    if (pv.pinv > 1e-8 /* PLL_MISC_EPSILON */) a = __ddiv_rn(a, __dsub_rn(1.0, pv.pinv));
+    expd[i] = expm1(a);
   }
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < C * S * SP; i += blockDim.x) {
@@ -806,12 +849,22 @@ __global__ void __launch_bounds__(AA_THREADS, 3) k_aa20_dmma(const PartView *__r
       for (int i = 0; i < 6; ++i) t = __dadd_rn(t, pz[i]);   // padding states carry pi = 0
       t = __dadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 1));
       t = __dadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 2));
-      if (q == 0) sm.exch[k & 1][cat][item] = __dmul_rn(t, wcat);
+      if (q == 0) sm.exch[k & 1][cat][item] = (pv.pinv > 0.0) ? t : __dmul_rn(t, wcat);   // +I: the raw category term, weighted below
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (cat == 0 && q == 0 && act) {
-        const double term = __dadd_rn(__dadd_rn(__dadd_rn(sm.exch[k & 1][0][item], sm.exch[k & 1][1][item]), sm.exch[k & 1][2][item]), sm.exch[k & 1][3][item]);
-        double lkv = log(term);
-        if (sc) lkv = __dadd_rn(lkv, __dmul_rn((double)sc, log_thresh));
+        double lkv;
+        if (pv.pinv > 0.0) {
+          const int iv = pv.invariant[site];
+          const double invf = iv < 0 ? 0.0 : pv.freqs[iv];
+          double terma = 0.0, terminv = 0.0;
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) edge_cat_accum(sm.exch[k & 1][c4][item], pv.rate_weights[c4], pv.pinv, invf, iv >= 0, terma, terminv);
+          lkv = edge_site_lnl(terma, terminv, sc, log_thresh);
+        } else {
+          const double term = __dadd_rn(__dadd_rn(__dadd_rn(sm.exch[k & 1][0][item], sm.exch[k & 1][1][item]), sm.exch[k & 1][2][item]), sm.exch[k & 1][3][item]);
+          lkv = log(term);
+          if (sc) lkv = __dadd_rn(lkv, __dmul_rn((double)sc, log_thresh));
+        }
         acc += __dmul_rn(lkv, (double)pv.weights[site]);
       }
       continue;
@@ -1115,7 +1168,9 @@ __global__ void __launch_bounds__(BLOCK) k_tree_lnl(const PartView *__restrict__
   double acc[1] = {0.0};
   for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
     const double *c = clv + n * C * SP;
-    double term = 0.0;
+    double term = 0.0, invf = 0.0;
+    const double pinv = pv.pinv;
+    if (pinv > 0.0) { const int iv = pv.invariant[n]; invf = iv < 0 ? 0.0 : pv.freqs[iv]; }
     for (uint32_t j = 0; j < C; ++j) {
       double term_r;
       if (S == 4) {
@@ -1125,7 +1180,7 @@ __global__ void __launch_bounds__(BLOCK) k_tree_lnl(const PartView *__restrict__
         term_r = 0.0;
         for (uint32_t k = 0; k < S; ++k) term_r = __dadd_rn(term_r, __dmul_rn(c[j * SP + k], pv.freqs[k]));
       }
-      term = __dadd_rn(term, __dmul_rn(term_r, pv.rate_weights[j]));
+      term = __dadd_rn(term, root_cat_term(term_r, pv.rate_weights[j], pinv, invf));
     }
     double lk = log(term);
     const uint32_t s = sc[n];
@@ -1156,7 +1211,10 @@ __global__ void __launch_bounds__(BLOCK) k_edge_lnl(const PartView *__restrict__
   double acc[1] = {0.0};
   for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
     const uint32_t mask = tip ? pv.tipmap[tip[n]] : 0;
-    double terma = 0.0;
+    double terma = 0.0, terminv = 0.0, invf = 0.0;
+    const double pinv = pv.pinv;
+    int iv = -1;
+    if (pinv > 0.0) { iv = pv.invariant[n]; invf = iv < 0 ? 0.0 : pv.freqs[iv]; }
     for (uint32_t i = 0; i < C; ++i) {
       const double *cp = clvp + (n * C + i) * SP;
       const double *cc = clvc ? clvc + (n * C + i) * SP : nullptr;
@@ -1166,11 +1224,12 @@ __global__ void __launch_bounds__(BLOCK) k_edge_lnl(const PartView *__restrict__
         const double termb = tip ? masked_rowsum(row, S, mask) : row_dot(row, cc, S);
         terma_r = __dadd_rn(terma_r, __dmul_rn(__dmul_rn(cp[j], pv.freqs[j]), termb));
       }
-      terma = __dadd_rn(terma, __dmul_rn(terma_r, pv.rate_weights[i]));
+      edge_cat_accum(terma_r, pv.rate_weights[i], pinv, invf, iv >= 0, terma, terminv);
     }
-    double lk = log(terma);
     const uint32_t s = scp[n] + (scc ? scc[n] : 0u);
-    if (s) lk = __dadd_rn(lk, __dmul_rn((double)s, log_thresh));
+    double lk;
+    if (pinv > 0.0) lk = edge_site_lnl(terma, terminv, s, log_thresh);
+    else { lk = log(terma); if (s) lk = __dadd_rn(lk, __dmul_rn((double)s, log_thresh)); }
     acc[0] += __dmul_rn(lk, (double)pv.weights[n]);
   }
   block_sum<1>(acc, red);
@@ -1222,7 +1281,9 @@ __global__ void __launch_bounds__(BLOCK) k_derivatives(const PartView *__restric
   double acc[3] = {0.0, 0.0, 0.0};
   for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
     const double *sum = st + n * C * SP;
-    double lk0 = 0.0, lk1 = 0.0, lk2 = 0.0;
+    double lk0 = 0.0, lk1 = 0.0, lk2 = 0.0, invf = 0.0;
+    const double pinv = pv.pinv;
+    if (pinv > 0.0) { const int iv = pv.invariant[n]; invf = iv < 0 ? 0.0 : pv.freqs[iv]; }
     for (uint32_t i = 0; i < C; ++i) {
       double c0 = 0.0, c1 = 0.0, c2 = 0.0;
       const double *dg = pv.diagp + (size_t)i * S * 4;
@@ -1233,6 +1294,7 @@ __global__ void __launch_bounds__(BLOCK) k_derivatives(const PartView *__restric
         c2 = __dadd_rn(c2, __dmul_rn(v, dg[j * 4 + 2]));
       }
       const double w = pv.rate_weights[i];
+      deriv_cat_pinv(c0, c1, c2, pinv, invf);
       lk0 = __dadd_rn(lk0, __dmul_rn(c0, w));
       lk1 = __dadd_rn(lk1, __dmul_rn(c1, w));
       lk2 = __dadd_rn(lk2, __dmul_rn(c2, w));
@@ -1294,6 +1356,7 @@ __global__ void __launch_bounds__(BLOCK) k_tree_lnl_pc(const PartView *__restric
   const uint32_t lane = threadIdx.x & 31, c = threadIdx.x & (C - 1);
   const uint64_t n_items = (uint64_t)pv.patterns * C;
   const uint64_t span = ((n_items + BLOCK - 1) / BLOCK) * BLOCK;  // whole warps stay in the loop for the shuffles
+  const double pinv = pv.pinv;
   double acc[1] = {0.0};
   for (uint64_t g = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; g < span; g += (uint64_t)gridDim.x * BLOCK) {
     double t = 0.0;
@@ -1308,7 +1371,9 @@ __global__ void __launch_bounds__(BLOCK) k_tree_lnl_pc(const PartView *__restric
         if (k + 2 < S) term_r = __dadd_rn(term_r, __dmul_rn(q.z, sfreq[k + 2]));
         if (k + 3 < S) term_r = __dadd_rn(term_r, __dmul_rn(q.w, sfreq[k + 3]));
       }
-      t = __dmul_rn(term_r, swt[c]);
+      double invf = 0.0;
+      if (pinv > 0.0) { const int iv = pv.invariant[g / C]; invf = iv < 0 ? 0.0 : sfreq[iv]; }
+      t = root_cat_term(term_r, swt[c], pinv, invf);
     }
     double term = 0.0;
     for (uint32_t i = 0; i < C; ++i) term = __dadd_rn(term, __shfl_sync(0xffffffffu, t, (lane & ~(C - 1)) + i));
@@ -1342,6 +1407,7 @@ __global__ void __launch_bounds__(BLOCK) k_derivatives_pc(const PartView *__rest
   const double *dg = sdiag + (size_t)c * S * 4;
   const uint64_t n_items = (uint64_t)pv.patterns * C;
   const uint64_t span = ((n_items + BLOCK - 1) / BLOCK) * BLOCK;
+  const double pinv = pv.pinv;
   double acc[3] = {0.0, 0.0, 0.0};
   for (uint64_t g = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; g < span; g += (uint64_t)gridDim.x * BLOCK) {
     double t0 = 0.0, t1 = 0.0, t2 = 0.0;
@@ -1362,6 +1428,7 @@ __global__ void __launch_bounds__(BLOCK) k_derivatives_pc(const PartView *__rest
           }
       }
       const double w = swt[c];
+      if (pinv > 0.0) { const int iv = pv.invariant[g / C]; deriv_cat_pinv(c0, c1, c2, pinv, iv < 0 ? 0.0 : pv.freqs[iv]); }
       t0 = __dmul_rn(c0, w); t1 = __dmul_rn(c1, w); t2 = __dmul_rn(c2, w);
     }
     double lk0 = 0.0, lk1 = 0.0, lk2 = 0.0;
@@ -1411,16 +1478,19 @@ __global__ void __launch_bounds__(BLOCK) k_tree_lnl_dna4(const PartView *__restr
   const uint32_t *sc = pv.scaler[slot];
   const double f0 = pv.freqs[0], f1 = pv.freqs[1], f2 = pv.freqs[2], f3 = pv.freqs[3];
   const double w0 = pv.rate_weights[0], w1 = pv.rate_weights[1], w2 = pv.rate_weights[2], w3 = pv.rate_weights[3];
+  const double pinv = pv.pinv;
   double acc[1] = {0.0};
   for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
     const double *c = clv + n * 16;
     const D4 v0 = ldg256(c), v1 = ldg256(c + 4), v2 = ldg256(c + 8), v3 = ldg256(c + 12);
     const uint32_t s = sc[n];
     const double pw = (double)pv.weights[n];
-    double term = __dmul_rn(tree4(__dmul_rn(f0, v0.x), __dmul_rn(f1, v0.y), __dmul_rn(f2, v0.z), __dmul_rn(f3, v0.w)), w0);
-    term = __dadd_rn(term, __dmul_rn(tree4(__dmul_rn(f0, v1.x), __dmul_rn(f1, v1.y), __dmul_rn(f2, v1.z), __dmul_rn(f3, v1.w)), w1));
-    term = __dadd_rn(term, __dmul_rn(tree4(__dmul_rn(f0, v2.x), __dmul_rn(f1, v2.y), __dmul_rn(f2, v2.z), __dmul_rn(f3, v2.w)), w2));
-    term = __dadd_rn(term, __dmul_rn(tree4(__dmul_rn(f0, v3.x), __dmul_rn(f1, v3.y), __dmul_rn(f2, v3.z), __dmul_rn(f3, v3.w)), w3));
+    double invf = 0.0;
+    if (pinv > 0.0) { const int iv = pv.invariant[n]; invf = iv < 0 ? 0.0 : pv.freqs[iv]; }
+    double term = root_cat_term(tree4(__dmul_rn(f0, v0.x), __dmul_rn(f1, v0.y), __dmul_rn(f2, v0.z), __dmul_rn(f3, v0.w)), w0, pinv, invf);
+    term = __dadd_rn(term, root_cat_term(tree4(__dmul_rn(f0, v1.x), __dmul_rn(f1, v1.y), __dmul_rn(f2, v1.z), __dmul_rn(f3, v1.w)), w1, pinv, invf));
+    term = __dadd_rn(term, root_cat_term(tree4(__dmul_rn(f0, v2.x), __dmul_rn(f1, v2.y), __dmul_rn(f2, v2.z), __dmul_rn(f3, v2.w)), w2, pinv, invf));
+    term = __dadd_rn(term, root_cat_term(tree4(__dmul_rn(f0, v3.x), __dmul_rn(f1, v3.y), __dmul_rn(f2, v3.z), __dmul_rn(f3, v3.w)), w3, pinv, invf));
     double lk = log(term);
     if (s) lk = __dadd_rn(lk, __dmul_rn((double)s, log_thresh));
     lk = __dmul_rn(lk, pw);
@@ -1479,6 +1549,7 @@ __global__ void __launch_bounds__(BLOCK) k_edge_lnl_dna4(const PartView *__restr
   const uint8_t *tip = tipc ? pv.tipchars + (size_t)pr.b_idx * pv.tip_pitch : nullptr;
   const double f0 = pv.freqs[0], f1 = pv.freqs[1], f2 = pv.freqs[2], f3 = pv.freqs[3];
   const double w0 = pv.rate_weights[0], w1 = pv.rate_weights[1], w2 = pv.rate_weights[2], w3 = pv.rate_weights[3];
+  const double pinv = pv.pinv;
   double acc[1] = {0.0};
   for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
     const double *cp = clvp + n * 16;
@@ -1496,12 +1567,24 @@ __global__ void __launch_bounds__(BLOCK) k_edge_lnl_dna4(const PartView *__restr
       y0 = matvec4(sP, b0); y1 = matvec4(sP + 16, b1); y2 = matvec4(sP + 32, b2); y3 = matvec4(sP + 48, b3);
     }
     const double pw = (double)pv.weights[n];
-    double term = __dmul_rn(edge_cat_term(a0, y0, f0, f1, f2, f3), w0);
-    term = __dadd_rn(term, __dmul_rn(edge_cat_term(a1, y1, f0, f1, f2, f3), w1));
-    term = __dadd_rn(term, __dmul_rn(edge_cat_term(a2, y2, f0, f1, f2, f3), w2));
-    term = __dadd_rn(term, __dmul_rn(edge_cat_term(a3, y3, f0, f1, f2, f3), w3));
-    double lk = log(term);
-    if (s) lk = __dadd_rn(lk, __dmul_rn((double)s, log_thresh));
+    double lk;
+    if (pinv > 0.0) {
+      const int iv = pv.invariant[n];
+      const double invf = iv < 0 ? 0.0 : pv.freqs[iv];
+      double terma = 0.0, terminv = 0.0;
+      edge_cat_accum(edge_cat_term(a0, y0, f0, f1, f2, f3), w0, pinv, invf, iv >= 0, terma, terminv);
+      edge_cat_accum(edge_cat_term(a1, y1, f0, f1, f2, f3), w1, pinv, invf, iv >= 0, terma, terminv);
+      edge_cat_accum(edge_cat_term(a2, y2, f0, f1, f2, f3), w2, pinv, invf, iv >= 0, terma, terminv);
+      edge_cat_accum(edge_cat_term(a3, y3, f0, f1, f2, f3), w3, pinv, invf, iv >= 0, terma, terminv);
+      lk = edge_site_lnl(terma, terminv, s, log_thresh);
+    } else {
+      double term = __dmul_rn(edge_cat_term(a0, y0, f0, f1, f2, f3), w0);
+      term = __dadd_rn(term, __dmul_rn(edge_cat_term(a1, y1, f0, f1, f2, f3), w1));
+      term = __dadd_rn(term, __dmul_rn(edge_cat_term(a2, y2, f0, f1, f2, f3), w2));
+      term = __dadd_rn(term, __dmul_rn(edge_cat_term(a3, y3, f0, f1, f2, f3), w3));
+      lk = log(term);
+      if (s) lk = __dadd_rn(lk, __dmul_rn((double)s, log_thresh));
+    }
     acc[0] += __dmul_rn(lk, pw);
   }
   block_sum<1>(acc, red);
@@ -1557,7 +1640,8 @@ __global__ void __launch_bounds__(BLOCK) k_sumtable_dna4(const PartView *__restr
   }
 }
 
-__device__ __forceinline__ void deriv_cat(const D4 &v, const double *dg, double w, double &lk0, double &lk1, double &lk2, bool first) {
+__device__ __forceinline__ void deriv_cat(const D4 &v, const double *dg, double w, double &lk0, double &lk1, double &lk2, bool first,
+                                          double pinv = 0.0, double invf = 0.0) {
   const double sv[4] = {v.x, v.y, v.z, v.w};
   double c0 = 0.0, c1 = 0.0, c2 = 0.0;
 #pragma unroll
@@ -1566,6 +1650,7 @@ __device__ __forceinline__ void deriv_cat(const D4 &v, const double *dg, double 
     c1 = __dadd_rn(c1, __dmul_rn(sv[j], dg[j * 4 + 1]));
     c2 = __dadd_rn(c2, __dmul_rn(sv[j], dg[j * 4 + 2]));
   }
+  deriv_cat_pinv(c0, c1, c2, pinv, invf);
   if (first) { lk0 = __dmul_rn(c0, w); lk1 = __dmul_rn(c1, w); lk2 = __dmul_rn(c2, w); }
   else { lk0 = __dadd_rn(lk0, __dmul_rn(c0, w)); lk1 = __dadd_rn(lk1, __dmul_rn(c1, w)); lk2 = __dadd_rn(lk2, __dmul_rn(c2, w)); }
 }
@@ -1580,16 +1665,18 @@ __global__ void __launch_bounds__(BLOCK) k_derivatives_dna4(const PartView *__re
   __syncthreads();
   const double *st = pv.sumtable[blockIdx.y];
   const double w0 = pv.rate_weights[0], w1 = pv.rate_weights[1], w2 = pv.rate_weights[2], w3 = pv.rate_weights[3];
+  const double pinv = pv.pinv;
   double acc[3] = {0.0, 0.0, 0.0};
   for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
     const double *c = st + n * 16;
     const D4 v0 = ldg256(c), v1 = ldg256(c + 4), v2 = ldg256(c + 8), v3 = ldg256(c + 12);
     const double pw = (double)pv.weights[n];
-    double lk0, lk1, lk2;
-    deriv_cat(v0, sD, w0, lk0, lk1, lk2, true);
-    deriv_cat(v1, sD + 16, w1, lk0, lk1, lk2, false);
-    deriv_cat(v2, sD + 32, w2, lk0, lk1, lk2, false);
-    deriv_cat(v3, sD + 48, w3, lk0, lk1, lk2, false);
+    double lk0, lk1, lk2, invf = 0.0;
+    if (pinv > 0.0) { const int iv = pv.invariant[n]; invf = iv < 0 ? 0.0 : pv.freqs[iv]; }
+    deriv_cat(v0, sD, w0, lk0, lk1, lk2, true, pinv, invf);
+    deriv_cat(v1, sD + 16, w1, lk0, lk1, lk2, false, pinv, invf);
+    deriv_cat(v2, sD + 32, w2, lk0, lk1, lk2, false, pinv, invf);
+    deriv_cat(v3, sD + 48, w3, lk0, lk1, lk2, false, pinv, invf);
     const double d1 = -lk1 / lk0;
     const double d2 = d1 * d1 - lk2 / lk0;
     acc[0] += pw * log(lk0);

@@ -42,6 +42,9 @@ struct PortBackend : Backend {
     std::memcpy(weights, pp->rate_weights, sizeof(double) * pp->rate_cats);
     std::memcpy(freqs, pp->freqs, sizeof(double) * pp->states_padded);
   }
+  void setPinv(unsigned, double pinv) override {
+    if (pinv != 0.0) throw std::runtime_error("+I is restated only through the reference backend (oracle kind \"ref\"): the scalar port has no invariant-site terms");
+  }
   void setCategoryRates(unsigned p, const double *rates) override { for (unsigned i = 0; i < parts[p]->rate_cats; ++i) parts[p]->rates[i] = rates[i]; }
   bool gammaRates(double alpha, unsigned cats, double *out, int mode) const override { return port_compute_gamma_cats(alpha, cats, out, mode) != 0; }
   void updatePmatrix(unsigned p, unsigned edge, double brlen) override { port_update_pmatrix(parts[p], edge, brlen); }

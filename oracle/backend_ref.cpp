@@ -50,6 +50,9 @@ struct RefBackend : Backend {
     std::memcpy(weights, pp->rate_weights, sizeof(double) * pp->rate_cats);
     std::memcpy(freqs, pp->frequencies[0], sizeof(double) * pp->states_padded);
   }
+  void setPinv(unsigned p, double pinv) override {
+    if (!pll_update_invariant_sites_proportion(parts[p], 0, pinv)) throw std::runtime_error(pll_errmsg);
+  }
   void setCategoryRates(unsigned p, const double *rates) override { pll_set_category_rates(parts[p], rates); }
   bool gammaRates(double alpha, unsigned cats, double *out, int mode) const override { return pll_compute_gamma_cats(alpha, cats, out, mode) != 0; }
   void updatePmatrix(unsigned p, unsigned edge, double brlen) override {

@@ -132,6 +132,7 @@ struct Backend {
                         const double *weights) = 0;  // recomputes eigen
   virtual void getEigen(unsigned p, double *eigenvecs, double *inv_eigenvecs, double *eigenvals) const = 0;
   virtual void getRates(unsigned p, double *rates, double *weights, double *freqs) const = 0;
+  virtual void setPinv(unsigned p, double prop_invar) = 0;                                 // pll_update_invariant_sites_proportion
   virtual void setCategoryRates(unsigned p, const double *rates) = 0;                       // pll_set_category_rates
   virtual bool gammaRates(double alpha, unsigned cats, double *out, int mode) const = 0;   // pll_compute_gamma_cats
   virtual void updatePmatrix(unsigned p, unsigned edge, double brlen) = 0;
@@ -270,6 +271,7 @@ double optimize_reticulation(AnnotatedNetwork &ann, size_t reticulation_index);
 double optimize_reticulations(AnnotatedNetwork &ann, int max_iters);
 double scoreNetwork(AnnotatedNetwork &ann);                               // LH/ComplexityScoring.cpp:57-67 (BIC)
 void optimizeAllNonTopology(AnnotatedNetwork &ann, int type /* 0 QUICK, 1 NORMAL, 2 SLOW */);  // SRC/optimization/Optimization.cpp:118-214
+void setPinv(AnnotatedNetwork &ann, unsigned partition, double prop_invar);
 void setAlpha(AnnotatedNetwork &ann, unsigned partition, double alpha);   // treeinfo_set_alpha (PLLMOD/algorithm/pllmod_algorithm.c:566-587)
 double optimize_alpha(AnnotatedNetwork &ann, double min_alpha, double max_alpha, double tolerance);  // pllmod_algo_opt_onedim_treeinfo(ALPHA)
 

@@ -196,6 +196,12 @@ double optimize_reticulations(AnnotatedNetwork &ann, int max_iters) {  // :102-1
   return act_logl;
 }
 
+void setPinv(AnnotatedNetwork &ann, unsigned p, double prop_invar) {
+  ann.backend->setPinv(p, prop_invar);
+  for (auto &v : ann.pmatrix_valid[p]) v = 0;
+  invalidateAllCLVs(ann);
+}
+
 /* treeinfo_set_alpha: alpha -> discrete Gamma rates (mean mode, the raxml-ng default) -> partition rates; every P-matrix
  * and CLV of the partition is stale afterwards (the optimiser re-evaluates with incremental = 0 anyway) */
 void setAlpha(AnnotatedNetwork &ann, unsigned p, double alpha) {

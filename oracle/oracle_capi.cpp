@@ -366,6 +366,10 @@ int orc_optimize_all_non_topology(void *hv, int type, double *bic_score) {
   Handle *h = static_cast<Handle *>(hv);
   return guarded([&] { optimizeAllNonTopology(h->ann, type); if (bic_score) *bic_score = scoreNetwork(h->ann); });
 }
+int orc_set_pinv(void *hv, unsigned p, double prop_invar) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] { setPinv(h->ann, p, prop_invar); });
+}
 int orc_set_alpha(void *hv, unsigned p, double alpha) {
   Handle *h = static_cast<Handle *>(hv);
   return guarded([&] { setAlpha(h->ann, p, alpha); });

@@ -29,7 +29,7 @@ def copy_fixtures():
         shutil.copy(os.path.join(src, f), os.path.join(HERE, "fixtures", f))
 
 
-def _parse_derivative_blocks(path):
+def _parse_derivative_blocks(path, pinv=False):
     blocks, cur = [], None
     for line in open(path):
         m = re.match(r"\s*TEST alpha\(ncats\) =\s*([\d.]+)\(\s*(\d+)\) ; pinv = ([\d.]+)", line)
@@ -40,7 +40,18 @@ def _parse_derivative_blocks(path):
         m = re.match(r"Branch(\(Tip\))?\s+([\d.]+) :\s+(\S+)\s+(\S+)\s+(\S+)", line)
         if m and cur is not None:
             cur["tip" if m.group(1) else "inner"].append([float(m.group(2)), float(m.group(3)), float(m.group(4)), float(m.group(5))])
-    return [b for b in blocks if b["pinv"] == 0.0]
+    return [b for b in blocks if (b["pinv"] > 0.0) == pinv]
+
+
+def parse_libpll_pinv():
+    """The pinv = 0.3 / 0.6 / 0.9 blocks of derivatives.out and derivatives-oddstates.out (+I: proportion of invariant sites)."""
+    for src, ref, dst in (("derivatives.out", "libpll_derivatives_golden.json", "libpll_derivatives_pinv_golden.json"),
+                          ("derivatives-oddstates.out", "libpll_derivatives_oddstates_golden.json", "libpll_derivatives_oddstates_pinv_golden.json")):
+        base = json.load(open(os.path.join(HERE, ref)))
+        base["blocks"] = _parse_derivative_blocks(LIBPLL_TEST + "/out/" + src, pinv=True)
+        base["source"] = base["source"].replace("pinv=0 blocks", "pinv > 0 blocks")
+        json.dump(base, open(os.path.join(HERE, dst), "w"), indent=1)
+    return len(base["blocks"])
 
 
 def parse_libpll_golden():
@@ -138,6 +149,7 @@ if __name__ == "__main__":
     copy_fixtures()
     print("libpll golden blocks:", parse_libpll_golden())
     print("libpll odd-states blocks:", parse_libpll_oddstates())
+    print("libpll +I blocks:", parse_libpll_pinv())
     print("libpll alpha-cats blocks:", parse_libpll_alpha_cats())
     print("libpll protein models:", parse_libpll_protein_models())
     print("netrax golden cases:", netrax_golden())

@@ -839,3 +839,48 @@ def test_engines_driven_from_concurrent_host_threads():
         assert a == b
     for g in engines:
         g.close()
+
+
+@pytest.mark.parametrize("which", ["dna", "oddstates"])
+@pytest.mark.parametrize("tip_edge", [False, True])
+def test_libpll_golden_pinv_on_gpu(which, tip_edge):
+    """+I (proportion of invariant sites) in the PRODUCT — K1 rate scaling, the invariant-site terms of K3 / K4 / K6, the
+    invariant-pattern detection from the tips — against libpll's golden blocks with pinv in {0.3, 0.6, 0.9}: 4 states with
+    1 / 2 / 4 categories (the 4x4 kernels and the generic ones) and 5 states (generic kernels, padded rows)."""
+    from test_oracle_libpll_golden import GI, GOI, check_pinv_golden
+    from netrax_b200.engine import load
+    check_pinv_golden(lambda net, part: _gpu(net, [part]), GI if which == "dna" else GOI, tip_edge, load().gamma_rates)
+
+
+def test_pinv_on_networks_matches_reference_oracle():
+    """+I on networks: DNA (4x4 kernels; fused K3 switched off), protein (tensor-core edge lnL) and a deep caterpillar whose
+    scaled sites exercise libpll's 'undo the scaling on the non-invariant term only' branch, against real libpll."""
+    from oracle import oracle
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    cases = []
+    net = random_network(14, 3, seed=61)
+    m, w = simulate_alignment(net, 500, seed=61)
+    cases.append((net, Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w), 0.25))
+    cases.append(_protein_case(10, 2, 150, 62) + (0.4,))
+    cat = caterpillar_network(300)
+    m, w = simulate_alignment(cat, 200, seed=63, gap_frac=0.0)
+    m[:, :60] = m[0, :60]          # 60 invariant columns on a tree deep enough to scale
+    cases.append((cat, Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w), 0.3))
+    for net, part, pinv in cases:
+        g, o = _gpu(net, [part]), oracle.make_engine("ref", net, [part])
+        _inject_eigen(g, o)
+        g.set_pinv(0, pinv); o.set_pinv(0, pinv)
+        lg, lo = g.computeLoglikelihood(0, 1), o.computeLoglikelihood(0, 1)
+        assert lg == pytest.approx(lo, rel=LNL_RTOL), (part.states, pinv)
+        assert g.computeLoglikelihood(0, 1) == lg
+        for e in (0, net.num_edges - 1) + ((int(net.ret_first_edge[0]),) if net.num_reticulations else ()):
+            assert g.brlen_prepare(e) == pytest.approx(o.brlen_prepare(e), rel=LNL_RTOL)
+            assert g.computeLoglikelihoodBrlenOpt(e) == pytest.approx(o.computeLoglikelihoodBrlenOpt(e), rel=LNL_RTOL), (part.states, e)
+            assert g.computePartitionSumtables(e) == o.computePartitionSumtables(e)
+            dg, do = g.computeLoglikelihoodDerivatives(e), o.computeLoglikelihoodDerivatives(e)
+            np.testing.assert_allclose(dg[4], do[4], rtol=DERIV_RTOL, atol=1e-9)
+            assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL)
+        g.set_pinv(0, 0.0); o.set_pinv(0, 0.0)
+        assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
+        g.close()

@@ -162,3 +162,59 @@ def test_libpll_golden_oddstates(kind, tip_edge):
             assert g1 == pytest.approx(d1, rel=2e-4, abs=1e-9), (t, g1, d1)
             assert g2 == pytest.approx(d2, rel=2e-4, abs=1e-9), (t, g2, d2)
             eng.close()
+
+
+# ---- +I: the pinv = 0.3 / 0.6 / 0.9 blocks of derivatives.out and derivatives-oddstates.out ------------------------------
+GI = load_golden("libpll_derivatives_pinv_golden.json")
+GOI = load_golden("libpll_derivatives_oddstates_pinv_golden.json")
+
+
+def pinv_case(G, t, tip_edge, ncats, rates):
+    """Same 5-taxon tree; works for the 4-state and the 5-state data set."""
+    if "char_masks" in G:
+        return oddstates_case(t, tip_edge, ncats, rates)
+    b0, b1 = G["branch_lengths"]
+    h = t / 2
+    if not tip_edge:
+        nw = f"(((T0:{b1},T1:{b1}):{b0},T2:{b1})X6:{h},(T3:{b1},T4:{b1})X7:{h});"
+    else:
+        nw = f"(T4:{h},(((T0:{b1},T1:{b1}):{b0},T2:{b1}):{b0},T3:{b0})X7:{h});"
+    net = parse_extended_newick(nw)
+    order = [int(l[1:]) for l in net.tip_labels]
+    masks = np.stack([encode_dna(G["tips"][i]) for i in order])
+    return net, Partition(4, ncats, masks, G["freqs"], G["subst"], rates)
+
+
+def check_pinv_golden(make_engine, G, tip_edge, gamma):
+    for block in G["blocks"]:
+        rates = gamma(block["alpha"], block["ncats"]) if block["ncats"] > 1 else np.ones(1)
+        for t, f, d1, d2 in block["tip" if tip_edge else "inner"]:
+            if t > 10:
+                continue
+            net, part = pinv_case(G, t, tip_edge, block["ncats"], rates)
+            eng = make_engine(net, part)
+            eng.set_pinv(0, block["pinv"])
+            lnl = eng.computeLoglikelihood(0, 1)
+            assert abs(lnl - f) < 2e-6, (block["alpha"], block["ncats"], block["pinv"], t, lnl, f)
+            edge = [e for e in range(net.num_edges) if net.edge_source[e] == net.root][0]
+            eng.brlen_prepare(edge)
+            assert abs(eng.computeLoglikelihoodBrlenOpt(edge) - lnl) < 1e-8
+            assert eng.computePartitionSumtables(edge) == 1
+            g1, g2, *_ = eng.computeLoglikelihoodDerivatives(edge)
+            assert g1 == pytest.approx(d1, rel=2e-4, abs=1e-9), (block["pinv"], t, g1, d1)
+            assert g2 == pytest.approx(d2, rel=2e-4, abs=1e-9), (block["pinv"], t, g2, d2)
+            eng.close()
+
+
+@pytest.mark.parametrize("which", ["dna", "oddstates"])
+@pytest.mark.parametrize("tip_edge", [False, True])
+def test_libpll_golden_pinv_reference_oracle(which, tip_edge):
+    """+I through the reference backend (real libpll): the golden edge lnL / derivatives with pinv in {0.3, 0.6, 0.9}.  (The
+    scalar port has no invariant-site terms and says so.)"""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    G = GI if which == "dna" else GOI
+    check_pinv_golden(lambda net, part: oracle.make_engine("ref", net, [part]), G, tip_edge, oracle.api("ref").gamma_rates)
+    net, part = pinv_case(G, 0.1, False, 1, np.ones(1))
+    with pytest.raises(Exception, match="reference backend"):
+        oracle.make_engine("port", net, [part]).set_pinv(0, 0.3)

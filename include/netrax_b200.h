@@ -109,6 +109,11 @@ int nrxh_get_reticulation_probs(void *h, double *out /* [reticulations] */);
 unsigned long long nrxh_clv_update_count(void *h);
 void nrxh_reset_counters(void *h);
 int nrxh_gamma_rates(double alpha, unsigned cats, int mode, double *out);
+/* device-free: the host's eigendecomposition (role of pll_update_eigen, LIBPLL/models.c:293-410) of the reversible model
+ * (freqs[states], subst[states (states - 1) / 2]): eigenvecs / inv_eigenvecs [states][states_padded], eigenvals [states_padded]
+ * — exactly what the host hands to nrx_set_model */
+int nrxh_eigen_decompose(unsigned states, const double *freqs, const double *subst, double *eigenvecs, double *inv_eigenvecs,
+                         double *eigenvals);
 /* bench / profiling hooks */
 unsigned long long nrxh_launch_count(void *h);
 unsigned nrxh_num_slots(void *h);

@@ -92,7 +92,8 @@ int nrx_set_tips(nrx_engine *e, uint32_t p, const uint32_t *tip_masks);
 int nrx_set_tipchars_u8(nrx_engine *e, uint32_t p, const uint8_t *codes);
 int nrx_set_pattern_weights(nrx_engine *e, uint32_t p, const uint32_t *weights);
 /* eigenvecs / inv_eigenvecs: [states][states_padded]; eigenvals, freqs: [states_padded] (padding ignored);
- * prop_invar must be 0 (+I partitions are rejected). */
+ * prop_invar in [0, 1): proportion of invariant sites (+I; pll_update_invariant_sites_proportion, LIBPLL/models.c:495-543).
+ * The invariant-pattern table (pll_update_invariant_sites, LIBPLL/models.c:651-760) is derived from the tips on upload. */
 int nrx_set_model(nrx_engine *e, uint32_t p, const double *freqs, const double *eigenvecs,
                   const double *inv_eigenvecs, const double *eigenvals, const double *rates,
                   const double *rate_weights, double prop_invar);

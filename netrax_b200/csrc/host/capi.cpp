@@ -444,6 +444,21 @@ int nrxh_gamma_rates(double alpha, unsigned cats, int mode, double *out) {
   if (!compute_gamma_cats(alpha, cats, out, mode)) { g_err = "Invalid alpha value / GAMMA discretization mode"; return 0; }
   return 1;
 }
+/* device-free: the host's own eigendecomposition of (frequencies, exchangeabilities) — what nrx_set_model receives */
+int nrxh_eigen_decompose(unsigned states, const double *freqs, const double *subst, double *ev, double *iev, double *evals) {
+  return guarded([&] {
+    if (states < 2 || states > 32) throw std::runtime_error("nrxh_eigen_decompose: states must be in 2..32");
+    PartitionModel m;
+    m.states = states;
+    m.states_padded = (states + 3) & ~3u;
+    set_frequencies(m, freqs);
+    m.subst_params.assign(subst, subst + states * (states - 1) / 2);
+    update_eigen(m);
+    std::copy(m.eigenvecs.begin(), m.eigenvecs.end(), ev);
+    std::copy(m.inv_eigenvecs.begin(), m.inv_eigenvecs.end(), iev);
+    std::copy(m.eigenvals.begin(), m.eigenvals.end(), evals);
+  });
+}
 unsigned long long nrxh_launch_count(void *hv) { return nrx_launch_count(H(hv)->ann.engine); }
 unsigned nrxh_num_slots(void *hv) { return H(hv)->ann.next_slot; }
 int nrxh_profile_enable(void *hv, int on) { return nrx_profile_enable(H(hv)->ann.engine, on); }

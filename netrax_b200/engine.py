@@ -33,6 +33,8 @@ def load() -> FlatAPI:
         a = FlatAPI(lib, "nrxh_")
         lib.nrxh_set_eigen.restype = C.c_int
         lib.nrxh_set_eigen.argtypes = [C.c_void_p, C.c_uint] + [np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")] * 3
+        lib.nrxh_eigen_decompose.restype = C.c_int
+        lib.nrxh_eigen_decompose.argtypes = [C.c_uint] + [np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")] * 5
         lib.nrxh_comm_get_unique_id.restype = C.c_int
         lib.nrxh_comm_get_unique_id.argtypes = [C.c_char_p]
         lib.nrxh_comm_init.restype = C.c_int
@@ -62,6 +64,16 @@ def load() -> FlatAPI:
         lib.nrxh_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         _api = a
     return _api
+
+
+def eigen_decompose(states: int, freqs, subst):
+    """The host library's own eigendecomposition (no device needed): (eigenvecs [S][SP], inv_eigenvecs [S][SP], eigenvals [SP])."""
+    api = load()
+    sp = (states + 3) & ~3
+    ev, iev, evals = np.zeros(states * sp), np.zeros(states * sp), np.zeros(sp)
+    api.check(api.lib.nrxh_eigen_decompose(states, np.ascontiguousarray(freqs, np.float64), np.ascontiguousarray(subst, np.float64),
+                                           ev, iev, evals))
+    return ev.reshape(states, sp), iev.reshape(states, sp), evals
 
 
 def comm_unique_id() -> bytes:

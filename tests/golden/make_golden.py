@@ -132,6 +132,89 @@ def parse_libpll_protein_models():
     return len(models)
 
 
+def _parse_matrix_block(lines, i, states, cats):
+    """pll_show_pmatrix (LIBPLL/output.c): per category `states` rows of `states` numbers, then a blank line."""
+    out = np.zeros((cats, states, states))
+    for c in range(cats):
+        for r in range(states):
+            out[c, r] = [float(x) for x in lines[i].split()]
+            i += 1
+        i += 1
+    return out, i
+
+
+def parse_libpll_pmatrix():
+    """libpll test/out/pmatrix.out (test/src/pmatrix.c): P-matrices printed with 9 decimals for DNA (4), PROT (20) and ODD (5)
+    states x 3 frequency vectors (equal / skewed / extreme) x 3 exchangeability vectors (equal / skewed / extreme: 1e-3 .. 1e3)
+    x 5 branch lengths (1e-6 .. 100) x 4 category rates (1e-31, 1e-6, 1, 100).  The frequency and rate vectors are printed
+    with 6 decimals only, so the tests rebuild them from the formulas of init_freqs / init_rates (:112-170) and use the
+    printed ones as a check."""
+    lines = open(LIBPLL_TEST + "/out/pmatrix.out").read().splitlines()
+    states_of = {"DNA": 4, "PROT": 20, "ODD": 5}
+    out, i, n = {}, 0, 0
+    while i < len(lines):
+        m = re.match(r"datatype = (\w+)", lines[i])
+        if not m:
+            i += 1
+            continue
+        dt = m.group(1)
+        S = states_of[dt]
+        freqs = [float(x) for x in lines[i + 1].split("[")[1].split("]")[0].split()]
+        subst = [float(x) for x in lines[i + 2].split("[")[1].split("]")[0].split()]
+        i += 3
+        mats, brlens = [], []
+        for b in range(5):
+            mm = re.match(r"P-matrix: (\d+), brlen = ([\d.]+)", lines[i])
+            assert mm and int(mm.group(1)) == b, lines[i]
+            brlens.append(float(mm.group(2)))
+            mat, i = _parse_matrix_block(lines, i + 1, S, 4)
+            mats.append(mat)
+        k = sum(1 for key in out if key.startswith(dt + "_P_"))
+        out[f"{dt}_P_{k}"] = np.stack(mats)                 # [5 branches][4 cats][S][S]
+        out[f"{dt}_freqs_{k}"] = np.array(freqs)
+        out[f"{dt}_subst_{k}"] = np.array(subst)
+        n += 1
+    out["branch_lengths"] = np.array([1e-6, 1e-2, 0.2, 1.0, 100.0])
+    out["cat_rates"] = np.array([1e-31, 1e-6, 1.0, 100.0])
+    np.savez_compressed(os.path.join(HERE, "libpll_pmatrix_golden.npz"), **out)
+    return n
+
+
+def parse_libpll_hky():
+    """libpll test/out/hky.out (test/src/hky.c): the 5-taxon / 20-site data set of derivatives.c under HKY with 10 ti/tv
+    ratios, pi = (.3,.4,.1,.2), Gamma alpha = 1 (4 MEAN categories), branch lengths m0 = 0.1, m1 = 0.2: per ratio the
+    P-matrices (4 decimals), the inner CLVs 5 = (t0,t1), 6 = (clv5,t2), 7 = (t3,t4) (5 decimals) and the edge lnL between
+    clv6 and clv7 over matrix 0 (4 decimals)."""
+    lines = open(LIBPLL_TEST + "/out/hky.out").read().splitlines()
+    titv, P, clvs, logl = [], [], [], []
+    i = 0
+    while i < len(lines):
+        m = re.match(r"\s*TEST ti/tv = ([\d.]+)", lines[i])
+        if m:
+            titv.append(float(m.group(1)))
+            P.append([])
+            clvs.append({})
+        m = re.match(r"\[(\d+)\] P-matrix for branch length ([\d.]+)", lines[i])
+        if m:
+            mat, i = _parse_matrix_block(lines, i + 1, 4, 4)
+            P[-1].append(mat)
+            continue
+        m = re.match(r"\[(\d+)\] CLV (\d): \[(.*)\]", lines[i])
+        if m:
+            nums = [float(x) for x in re.findall(r"[-+]?\d+\.\d+", m.group(3))]
+            clvs[-1][int(m.group(2))] = np.array(nums).reshape(20, 4, 4)
+        m = re.match(r"ti/tv:\s+([\d.]+)\s+logL:\s+(\S+)", lines[i])
+        if m:
+            logl.append(float(m.group(2)))
+        i += 1
+    assert len(titv) == len(logl) == 10
+    np.savez_compressed(os.path.join(HERE, "libpll_hky_golden.npz"),
+                        titv=np.array([0.175, 1, 1.5, 2.25, 2.725, 4, 7.125, 8.19283745, 9.73647382, 10]),   # hky.c:28-30 (printed with 4 decimals)
+                        titv_printed=np.array(titv), P=np.array(P), logl=np.array(logl),
+                        clv5=np.stack([c[5] for c in clvs]), clv6=np.stack([c[6] for c in clvs]), clv7=np.stack([c[7] for c in clvs]))
+    return len(titv)
+
+
 def netrax_golden():
     out = {}
     for name, (nw, aln) in FIXTURE_PAIRS.items():
@@ -152,4 +235,6 @@ if __name__ == "__main__":
     print("libpll +I blocks:", parse_libpll_pinv())
     print("libpll alpha-cats blocks:", parse_libpll_alpha_cats())
     print("libpll protein models:", parse_libpll_protein_models())
+    print("libpll pmatrix evaluations:", parse_libpll_pmatrix())
+    print("libpll hky ratios:", parse_libpll_hky())
     print("netrax golden cases:", netrax_golden())

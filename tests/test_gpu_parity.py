@@ -884,3 +884,24 @@ def test_pinv_on_networks_matches_reference_oracle():
         g.set_pinv(0, 0.0); o.set_pinv(0, 0.0)
         assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
         g.close()
+
+
+# ---- libpll's pmatrix.out / hky.out directly against the product (K1 incl. the host eigendecomposition; K2 CLVs; K4 lnL) ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("datatype", ["DNA", "PROT", "ODD"])
+def test_libpll_golden_pmatrix_on_gpu(datatype):
+    """K1 (k_pmatrix) + the host's Jacobi eigendecomposition: every entry of the 135 golden P-matrices per datatype (4 / 20 / 5
+    states; equal / skewed / extreme frequencies and exchangeabilities; t = 1e-6 .. 100; rates 1e-31 .. 100) to 9 decimals."""
+    import os
+    from helpers import GOLDEN, check_pmatrix_golden
+    G = np.load(os.path.join(GOLDEN, "libpll_pmatrix_golden.npz"))
+    worst = check_pmatrix_golden(lambda net, part: _gpu(net, [part]), G, datatype)
+    assert worst < 6e-10
+
+
+@pytest.mark.gpu
+def test_libpll_golden_hky_on_gpu():
+    """hky.out: P-matrices, the three inner CLVs (K2 tip-tip, tip-inner) and the edge lnL for 10 ti/tv ratios."""
+    import os
+    from helpers import GOLDEN, check_hky_golden
+    check_hky_golden(lambda net, part: _gpu(net, [part]), np.load(os.path.join(GOLDEN, "libpll_hky_golden.npz")))

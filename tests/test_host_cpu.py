@@ -48,3 +48,26 @@ def test_no_cpu_fallback():
     m, w = simulate_alignment(net, 50, seed=1)
     with pytest.raises(LikelihoodError, match="no usable CUDA device"):
         eng.NetraxB200(net, [Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)])
+
+
+@pytest.mark.parametrize("datatype", ["DNA", "PROT", "ODD"])
+def test_product_eigendecomposition_reproduces_libpll_golden_pmatrices(datatype):
+    """The PRODUCT's host eigendecomposition (host/model.cpp: cyclic Jacobi, not libpll's Householder + QL) against libpll's
+    test/out/pmatrix.out: P(t) = I + V^-1 diag(expm1(lambda r t)) V assembled here in numpy from the host's eigen output —
+    the formula K1 evaluates on the device (LIBPLL/core_pmatrix.c:24-244) — for 4 / 20 / 5 states, equal / skewed / extreme
+    frequencies and exchangeabilities, branch lengths 1e-6 .. 100, category rates 1e-31 .. 100; 9 printed decimals."""
+    import os
+    from helpers import GOLDEN, pmatrix_golden_inputs
+    from netrax_b200 import engine
+    G = np.load(os.path.join(GOLDEN, "libpll_pmatrix_golden.npz"))
+    S = {"DNA": 4, "PROT": 20, "ODD": 5}[datatype]
+    freqs, substs = pmatrix_golden_inputs(S)
+    for j in range(3):
+        for k in range(3):
+            ev, iev, evals = engine.eigen_decompose(S, freqs[j], substs[k])
+            V, Vinv, lam = ev[:, :S], iev[:, :S], evals[:S]
+            for b, t in enumerate(G["branch_lengths"]):
+                for c, r in enumerate(G["cat_rates"]):
+                    P = np.eye(S) + Vinv @ np.diag(np.expm1(lam * r * t)) @ V
+                    np.testing.assert_allclose(P, G[f"{datatype}_P_{j * 3 + k}"][b][c], atol=6e-10, rtol=0,
+                                               err_msg=str((datatype, j, k, t, r)))

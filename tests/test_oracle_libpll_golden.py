@@ -218,3 +218,26 @@ def test_libpll_golden_pinv_reference_oracle(which, tip_edge):
     net, part = pinv_case(G, 0.1, False, 1, np.ones(1))
     with pytest.raises(Exception, match="reference backend"):
         oracle.make_engine("port", net, [part]).set_pinv(0, 0.3)
+
+
+# ---- fifth / sixth golden set: libpll test/out/pmatrix.out (K1 + eigendecomposition, 9 decimals) and hky.out ---------------
+def _npz(name):
+    import os
+    from helpers import GOLDEN
+    return np.load(os.path.join(GOLDEN, name))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("datatype", ["DNA", "PROT", "ODD"])
+def test_libpll_golden_pmatrix(kind, datatype):
+    """P(t) for 4 / 20 / 5 states x equal / skewed / extreme frequencies and exchangeabilities x branch lengths 1e-6 .. 100 x
+    category rates 1e-31 .. 100: eigendecomposition + pll_core_update_pmatrix against libpll's regression output."""
+    from helpers import check_pmatrix_golden
+    check_pmatrix_golden(lambda net, part: oracle.make_engine(kind, net, [part]), _npz("libpll_pmatrix_golden.npz"), datatype)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_libpll_golden_hky(kind):
+    """HKY with 10 ti/tv ratios: P-matrices, the inner CLVs and the edge lnL of libpll's test/out/hky.out."""
+    from helpers import check_hky_golden
+    check_hky_golden(lambda net, part: oracle.make_engine(kind, net, [part]), _npz("libpll_hky_golden.npz"))

@@ -63,6 +63,10 @@ int nrxh_partition_loglh(void *h, double *out);
 int nrxh_set_branch_length(void *h, int partition, unsigned edge, double value);
 int nrxh_set_reticulation_prob(void *h, unsigned r, double prob);
 int nrxh_set_model(void *h, unsigned p, const double *freqs, const double *subst_params, const double *rates, const double *rate_weights);
+/* Mixture with one rate matrix per rate category (LG4M / LG4X): what raxml-ng's Model::ratecat_submodels() is to NetRAX
+ * (src/RaxmlWrapper.cpp:199-203 -> pllmod param_indices -> every libpll call).  n rate matrices, freqs [n][states],
+ * subst [n][states (states - 1) / 2], category c uses matrix ratecat_submodels[c]; n == 1 goes back to a single matrix. */
+int nrxh_set_submodels(void *h, unsigned p, unsigned n, const unsigned *ratecat_submodels, const double *freqs, const double *subst);
 int nrxh_get_eigen(void *h, unsigned p, double *eigenvecs, double *inv_eigenvecs, double *eigenvals);
 int nrxh_set_eigen(void *h, unsigned p, const double *eigenvecs, const double *inv_eigenvecs, const double *eigenvals);
 int nrxh_get_pmatrix(void *h, unsigned p, unsigned edge, double *out);

@@ -97,6 +97,14 @@ int nrx_set_pattern_weights(nrx_engine *e, uint32_t p, const uint32_t *weights);
 int nrx_set_model(nrx_engine *e, uint32_t p, const double *freqs, const double *eigenvecs,
                   const double *inv_eigenvecs, const double *eigenvals, const double *rates,
                   const double *rate_weights, double prop_invar);
+/* The same for mixtures with one rate matrix per category (LG4M / LG4X; raxml-ng's ratecat_submodels forwarded by NetRAX as
+ * libpll's params_indices, src/RaxmlWrapper.cpp:199-203, LIBPLL/core_pmatrix.c:182-185): category c uses matrix cat_model[c] <
+ * nmodels <= 16; freqs / eigenvals are [nmodels][states_padded], eigenvecs / inv_eigenvecs [nmodels][states][states_padded].
+ * nmodels == 1 (cat_model may be NULL) is nrx_set_model.  K1 and the generic K3-K6 kernels index the model by category;
+ * K2 reads only P-matrices and keeps its fast paths. */
+int nrx_set_model_mixture(nrx_engine *e, uint32_t p, uint32_t nmodels, const uint32_t *cat_model, const double *freqs,
+                          const double *eigenvecs, const double *inv_eigenvecs, const double *eigenvals, const double *rates,
+                          const double *rate_weights, double prop_invar);
 /* K1: P(t) for n edges of partition p in one launch. */
 int nrx_update_pmatrices(nrx_engine *e, uint32_t p, uint32_t n, const uint32_t *edge_idx, const double *brlen);
 int nrx_get_pmatrix(nrx_engine *e, uint32_t p, uint32_t edge, double *out);

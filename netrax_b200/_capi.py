@@ -79,6 +79,7 @@ class FlatAPI:
         g("set_scoring_sizes", C.c_int, C.c_void_p, C.c_ulonglong, C.c_ulonglong)
         g("optimize_all_non_topology", C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double))
         g("set_pinv", C.c_int, C.c_void_p, C.c_uint, C.c_double)
+        g("set_submodels", C.c_int, C.c_void_p, C.c_uint, C.c_uint, _u32p, _f64p, _f64p)
         g("set_alpha", C.c_int, C.c_void_p, C.c_uint, C.c_double)
         g("get_alpha", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
         g("optimize_alpha", C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double))
@@ -331,6 +332,12 @@ class LikelihoodEngine:
     def set_pinv(self, p: int, prop_invar: float):
         """+I: proportion of invariant sites (pll_update_invariant_sites_proportion)."""
         self.api.check(self.api._set_pinv(self.h, p, prop_invar))
+
+    def set_submodels(self, p: int, ratecat_submodels, freqs, subst):
+        """One rate matrix per rate category (LG4M / LG4X; raxml-ng Model::ratecat_submodels -> libpll params_indices):
+        freqs [n][states], subst [n][states (states - 1) / 2], category c uses matrix ratecat_submodels[c]."""
+        freqs, subst = _as(np.atleast_2d(freqs), np.float64), _as(np.atleast_2d(subst), np.float64)
+        self.api.check(self.api._set_submodels(self.h, p, freqs.shape[0], _as(ratecat_submodels, np.uint32), freqs, subst))
 
     def set_alpha(self, p: int, alpha: float):
         """treeinfo_set_alpha: Gamma shape -> discrete rates of partition p (mean mode)."""

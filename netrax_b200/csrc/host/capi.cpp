@@ -238,6 +238,14 @@ int nrxh_set_model(void *hv, unsigned p, const double *freqs, const double *subs
   });
 }
 
+int nrxh_set_submodels(void *hv, unsigned p, unsigned n, const unsigned *ratecat_submodels, const double *freqs, const double *subst) {
+  return guarded([&] {
+    AnnotatedNetwork &ann = H(hv)->ann;
+    set_submodels(ann.fake_treeinfo->partitions.at(p), n, ratecat_submodels, freqs, subst);
+    pushModel(ann, p);
+  });
+}
+
 int nrxh_get_eigen(void *hv, unsigned p, double *ev, double *iev, double *evals) {
   return guarded([&] {
     const PartitionModel &m = H(hv)->ann.fake_treeinfo->partitions.at(p);

@@ -267,10 +267,28 @@ void topology_changed(AnnotatedNetwork &ann) {
 static void uploadModel(AnnotatedNetwork &ann, unsigned p) {
   PartitionModel &m = ann.fake_treeinfo->partitions[p];
   if (!m.eigen_decomp_valid) update_eigen(m);
-  std::vector<double> freqs(m.states_padded, 0.0);
-  std::copy(m.frequencies.begin(), m.frequencies.begin() + m.states, freqs.begin());
-  engineCheck(nrx_set_model(ann.engine, p, freqs.data(), m.eigenvecs.data(), m.inv_eigenvecs.data(), m.eigenvals.data(),
-                            m.rates.data(), m.rate_weights.data(), m.prop_invar), "nrx_set_model");
+  const size_t S = m.states, SP = m.states_padded, M = 1 + m.submodels.size();
+  std::vector<double> freqs(M * SP, 0.0);
+  std::copy(m.frequencies.begin(), m.frequencies.begin() + S, freqs.begin());
+  if (M == 1) {
+    engineCheck(nrx_set_model(ann.engine, p, freqs.data(), m.eigenvecs.data(), m.inv_eigenvecs.data(), m.eigenvals.data(),
+                              m.rates.data(), m.rate_weights.data(), m.prop_invar), "nrx_set_model");
+    return;
+  }
+  // one rate matrix per category (LG4M / LG4X): the matrices back to back, category -> matrix map = pllmod's param_indices
+  std::vector<double> ev(m.eigenvecs), iev(m.inv_eigenvecs), evals(m.eigenvals);
+  evals.resize(SP, 0.0);
+  for (size_t i = 0; i + 1 < M; ++i) {
+    const PartitionModel::SubModel &sm = m.submodels[i];
+    std::copy(sm.frequencies.begin(), sm.frequencies.begin() + S, freqs.begin() + (i + 1) * SP);
+    ev.insert(ev.end(), sm.eigenvecs.begin(), sm.eigenvecs.end());
+    iev.insert(iev.end(), sm.inv_eigenvecs.begin(), sm.inv_eigenvecs.end());
+    evals.insert(evals.end(), sm.eigenvals.begin(), sm.eigenvals.end());
+    evals.resize((i + 2) * SP, 0.0);
+  }
+  std::vector<uint32_t> cm(m.ratecat_submodels.begin(), m.ratecat_submodels.end());
+  engineCheck(nrx_set_model_mixture(ann.engine, p, (uint32_t)M, cm.data(), freqs.data(), ev.data(), iev.data(), evals.data(),
+                                    m.rates.data(), m.rate_weights.data(), m.prop_invar), "nrx_set_model_mixture");
 }
 
 void pushPartitionModel(AnnotatedNetwork &ann, unsigned p) {

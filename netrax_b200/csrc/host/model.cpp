@@ -91,6 +91,27 @@ void update_eigen(PartitionModel &m) {
   m.eigen_decomp_valid = true;
 }
 
+void set_submodels(PartitionModel &m, unsigned n, const unsigned *ratecat_submodels, const double *freqs, const double *subst) {
+  const unsigned S = m.states, NR = S * (S - 1) / 2;
+  if (n < 1 || n > 16) throw std::runtime_error("set_submodels: 1..16 rate matrices");
+  for (unsigned c = 0; n > 1 && c < m.rate_cats; ++c)
+    if (ratecat_submodels[c] >= n) throw std::runtime_error("set_submodels: rate-matrix index of a category out of range");
+  set_frequencies(m, freqs);
+  m.subst_params.assign(subst, subst + NR);
+  m.submodels.clear();
+  m.ratecat_submodels.clear();
+  for (unsigned i = 1; i < n; ++i) {
+    PartitionModel tmp;   // pll_set_frequencies / pll_set_subst_params / pll_update_eigen with params_index i
+    tmp.states = S; tmp.states_padded = m.states_padded;
+    set_frequencies(tmp, freqs + (size_t)i * S);
+    tmp.subst_params.assign(subst + (size_t)i * NR, subst + (size_t)(i + 1) * NR);
+    update_eigen(tmp);
+    m.submodels.push_back({tmp.frequencies, tmp.subst_params, tmp.eigenvecs, tmp.inv_eigenvecs, tmp.eigenvals});
+  }
+  if (n > 1) m.ratecat_submodels.assign(ratecat_submodels, ratecat_submodels + m.rate_cats);
+  m.eigen_decomp_valid = false;
+}
+
 namespace {
 double lnGamma(double a) {  // Algorithm 291
   double x = a, f = 0.0;

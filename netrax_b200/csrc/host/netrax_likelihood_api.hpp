@@ -134,7 +134,19 @@ struct PartitionModel {
   int gamma_mode = 0;   // PLL_GAMMA_RATES_MEAN (raxml-ng default)
   std::vector<double> eigenvecs, inv_eigenvecs, eigenvals;  // filled by update_eigen (own Jacobi solver) or set explicitly
   bool eigen_decomp_valid = false;
+  /* Mixtures with one rate matrix per rate category (LG4M / LG4X): raxml-ng's Model::ratecat_submodels(), which NetRAX hands
+   * to pll-modules as param_indices and from there to every libpll call (src/RaxmlWrapper.cpp:199-203,
+   * LH/ImprovedLoglikelihood.cpp:452).  Rate matrix 0 is (frequencies, subst_params) above; matrices 1.. are `submodels`;
+   * category c uses matrix ratecat_submodels[c] (empty = all 0, the single-matrix case of every BASELINE config). */
+  struct SubModel {
+    std::vector<double> frequencies, subst_params, eigenvecs, inv_eigenvecs, eigenvals;
+  };
+  std::vector<SubModel> submodels;
+  std::vector<unsigned> ratecat_submodels;
 };
+/* installs rate matrices 1..n-1 (matrix 0 = freqs[0] / subst[0] too) and the category -> matrix map; n == 1 removes the mixture */
+void set_submodels(PartitionModel &m, unsigned n, const unsigned *ratecat_submodels, const double *freqs /*[n][states]*/,
+                   const double *subst /*[n][states (states - 1) / 2]*/);
 void set_frequencies(PartitionModel &m, const double *frequencies);                    // pll_set_frequencies (LIBPLL/models.c:445-467): renormalises when |sum - 1| > 1e-8
 void update_eigen(PartitionModel &m);                                                 // role of pll_update_eigen
 bool compute_gamma_cats(double alpha, unsigned cats, double *out_rates, int mode);    // role of pll_compute_gamma_cats

@@ -43,7 +43,9 @@ struct Part {
   uint32_t *tipmap = nullptr, *weights = nullptr;
   double *model = nullptr;  // freqs | eigenvecs | inv_eigenvecs | eigenvals | rates | rate_weights | diagp
   double *freqs = nullptr, *eigenvecs = nullptr, *inv_eigenvecs = nullptr, *eigenvals = nullptr, *rates = nullptr, *rate_weights = nullptr, *diagp = nullptr;
-  std::vector<double> h_eigenvals, h_rates;
+  std::vector<double> h_eigenvals, h_rates;   // h_eigenvals: [nmodels][states]
+  uint32_t nmodels = 1, model_cap = 1;        // rate matrices in use / the model buffer has room for (PartView::nmodels)
+  uint8_t cat_model[16] = {};                 // rate category -> rate matrix (libpll's params_indices)
   std::vector<void *> slot_mem;       // one allocation per slot: [clv | scaler]
   std::vector<double *> h_clv;
   std::vector<uint32_t *> h_scaler;
@@ -245,6 +247,8 @@ PartView make_view(const Part &p, uint32_t index) {
   v.clv = p.d_clv; v.scaler = p.d_scaler; v.sumtable = p.d_sumtable; v.diagp = p.diagp; v.tiplut = p.tiplut;
   v.summat = p.summat; v.sumlut = p.sumlut;
   v.pinv = p.pinv; v.invariant = p.invariant;
+  v.nmodels = p.nmodels;
+  std::memcpy(v.cat_model, p.cat_model, sizeof(v.cat_model));
   return v;
 }
 
@@ -520,32 +524,61 @@ int nrx_set_pattern_weights(nrx_engine *e, uint32_t pi, const uint32_t *w) {
   return 1;
 }
 
-int nrx_set_model(nrx_engine *e, uint32_t pi, const double *freqs, const double *eigenvecs, const double *inv_eigenvecs,
-                  const double *eigenvals, const double *rates, const double *rate_weights, double prop_invar) {
+/* Model of partition pi with `nmodels` rate matrices: category c uses matrix cat_model[c] (libpll's params_indices; LG4M / LG4X).
+ * freqs / eigenvals: [nmodels][states_padded]; eigenvecs / inv_eigenvecs: [nmodels][states][states_padded]. */
+int nrx_set_model_mixture(nrx_engine *e, uint32_t pi, uint32_t nmodels, const uint32_t *cat_model, const double *freqs,
+                          const double *eigenvecs, const double *inv_eigenvecs, const double *eigenvals, const double *rates,
+                          const double *rate_weights, double prop_invar) {
   if (!check_part(e, pi)) return 0;
   if (!(prop_invar >= 0.0 && prop_invar < 1.0)) { g_err = "Invalid proportion of invariant sites"; return 0; }   // pll_update_invariant_sites_proportion
   CK(cudaSetDevice(e->device));
   Part &p = e->parts[pi];
+  const size_t S = p.d.states, SP = p.sp, C = p.d.rate_cats, M = nmodels;
+  if (M < 1 || M > 16) { g_err = "nrx_set_model_mixture: 1..16 rate matrices"; return 0; }
+  for (size_t c = 0; M > 1 && c < C; ++c)
+    if (!cat_model || cat_model[c] >= M) { g_err = "nrx_set_model_mixture: rate-matrix index of a category out of range"; return 0; }
   if (prop_invar > 0.0 && p.invariant_stale) { g_err = "nrx_set_model: +I after nrx_set_tipchars_u8: call nrx_set_tips (or upload the tips again) first"; return 0; }
-  if (p.pinv != prop_invar) { p.pinv = prop_invar; e->views_dirty = true; }
-  const size_t S = p.d.states, SP = p.sp, C = p.d.rate_cats;
-  std::vector<double> h(SP + 2 * S * SP + SP + 2 * C, 0.0);
-  double *q = h.data();
-  std::memcpy(q, freqs, S * sizeof(double)); q += SP;
-  std::memcpy(q, eigenvecs, S * SP * sizeof(double)); q += S * SP;
-  std::memcpy(q, inv_eigenvecs, S * SP * sizeof(double)); q += S * SP;
-  std::memcpy(q, eigenvals, S * sizeof(double)); q += SP;
-  std::memcpy(q, rates, C * sizeof(double)); q += C;
-  std::memcpy(q, rate_weights, C * sizeof(double));
   CK(cudaStreamSynchronize(e->stream));
+  if (M > p.model_cap) {   // grow the model buffer: freqs | eigenvecs | inv_eigenvecs | eigenvals (M blocks each) | rates | rate_weights | diagp
+    double *nm = nullptr;
+    CK(cudaMalloc((void **)&nm, (M * (2 * SP + 2 * S * SP) + 2 * C + C * S * 4) * sizeof(double)));
+    cudaFree(p.model);
+    p.model = nm;
+    p.model_cap = (uint32_t)M;
+    e->views_dirty = true;
+  }
+  const size_t Mc = p.model_cap;
+  p.freqs = p.model; p.eigenvecs = p.freqs + Mc * SP; p.inv_eigenvecs = p.eigenvecs + Mc * S * SP; p.eigenvals = p.inv_eigenvecs + Mc * S * SP;
+  p.rates = p.eigenvals + Mc * SP; p.rate_weights = p.rates + C; p.diagp = p.rate_weights + C;
+  uint8_t cm[16] = {};
+  for (size_t c = 0; M > 1 && c < C; ++c) cm[c] = (uint8_t)cat_model[c];
+  if (p.pinv != prop_invar || p.nmodels != M || std::memcmp(cm, p.cat_model, sizeof(cm)) != 0) e->views_dirty = true;
+  p.pinv = prop_invar;
+  p.nmodels = (uint32_t)M;
+  std::memcpy(p.cat_model, cm, sizeof(cm));
+  std::vector<double> h((size_t)(p.rate_weights + C - p.model), 0.0);
+  for (size_t m = 0; m < M; ++m) {
+    std::memcpy(h.data() + m * SP, freqs + m * SP, S * sizeof(double));
+    std::memcpy(h.data() + (p.eigenvecs - p.model) + m * S * SP, eigenvecs + m * S * SP, S * SP * sizeof(double));
+    std::memcpy(h.data() + (p.inv_eigenvecs - p.model) + m * S * SP, inv_eigenvecs + m * S * SP, S * SP * sizeof(double));
+    std::memcpy(h.data() + (p.eigenvals - p.model) + m * SP, eigenvals + m * SP, S * sizeof(double));
+  }
+  std::memcpy(h.data() + (p.rates - p.model), rates, C * sizeof(double));
+  std::memcpy(h.data() + (p.rate_weights - p.model), rate_weights, C * sizeof(double));
   CK(cudaMemcpy(p.model, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
-  p.h_eigenvals.assign(eigenvals, eigenvals + S);
+  p.h_eigenvals.assign(M * S, 0.0);
+  for (size_t m = 0; m < M; ++m) std::memcpy(p.h_eigenvals.data() + m * S, eigenvals + m * SP, S * sizeof(double));
   p.h_rates.assign(rates, rates + C);
-  p.h_freqs.assign(freqs, freqs + S);
+  p.h_freqs.assign(freqs, freqs + S);   // matrix 0: the single-matrix tables of the 20-state tensor-core K5 (unused by mixtures)
   p.h_eigenvecs.assign(eigenvecs, eigenvecs + S * SP);
   p.h_inv_eigenvecs.assign(inv_eigenvecs, inv_eigenvecs + S * SP);
   p.model_set = true;
   return refresh_summat(e, pi);
+}
+
+int nrx_set_model(nrx_engine *e, uint32_t pi, const double *freqs, const double *eigenvecs, const double *inv_eigenvecs,
+                  const double *eigenvals, const double *rates, const double *rate_weights, double prop_invar) {
+  return nrx_set_model_mixture(e, pi, 1, nullptr, freqs, eigenvecs, inv_eigenvecs, eigenvals, rates, rate_weights, prop_invar);
 }
 
 int nrx_update_pmatrices(nrx_engine *e, uint32_t pi, uint32_t n, const uint32_t *edge_idx, const double *brlen) {
@@ -956,7 +989,7 @@ int nrx_set_throughput_mode(nrx_engine *e, int on) {
 int nrx_supports_fused_lnl(nrx_engine *e) {
   if (!e || (e->k2_variant != 0 && e->k2_variant != 1) || std::getenv("NRX_NO_FUSED_LNL")) return 0;
   for (const ShapeClass &c : e->classes) if (!(c.states == 4 && c.cats == 4)) return 0;
-  for (const Part &p : e->parts) if (p.pinv > 0.0) return 0;   // the K2 epilogue does not carry the invariant-site term
+  for (const Part &p : e->parts) if (p.pinv > 0.0 || p.nmodels > 1) return 0;   // the K2 epilogue carries neither the invariant-site term nor per-category frequencies
   return 1;
 }
 
@@ -972,6 +1005,12 @@ int nrx_plan_destroy(nrx_engine *e, uint32_t plan_id) {
   return 1;
 }
 
+/* a partition of this class mixes several rate matrices over its categories (LG4M / LG4X): K3-K6 take the generic kernels,
+ * which index the model by category; every fast kernel assumes one matrix */
+static bool class_mixture(const nrx_engine *e, const ShapeClass &c) {
+  for (uint32_t pi : c.parts) if (e->parts[pi].nmodels > 1) return true;
+  return false;
+}
 static bool pow2_cats(const ShapeClass &c) { return c.cats <= 32 && (c.cats & (c.cats - 1)) == 0 && !std::getenv("NRX_NO_PC"); }
 
 /* blocks along x for the reduction kernels (one value per call: the partial-sum layout uses gridDim.x as its stride) */
@@ -1037,9 +1076,10 @@ static int tree_lnl_impl(nrx_engine *e, const uint32_t *slots, uint32_t n, doubl
   prof_begin(e, &ev0, &ev1);
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
-    if (c.states == 4 && c.cats == 4) k_tree_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
-    else if (pow2_cats(c) && c.states == 20) k_tree_lnl_pc<20><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
-    else if (pow2_cats(c)) k_tree_lnl_pc<0><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
+    const bool mix = class_mixture(e, c);
+    if (!mix && c.states == 4 && c.cats == 4) k_tree_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
+    else if (!mix && pow2_cats(c) && c.states == 20) k_tree_lnl_pc<20><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
+    else if (!mix && pow2_cats(c)) k_tree_lnl_pc<0><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
     else k_tree_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
     e->launches++;
     CK(cudaGetLastError());
@@ -1111,6 +1151,9 @@ static int check_pairs(nrx_engine *e, const nrx_pair *pairs, uint32_t n, const c
 static bool aa_dmma_class(const nrx_engine *e, const ShapeClass &c) {
   return c.states == 20 && c.cats == 4 && !e->aa_generic && class_tip_codes(e, c) <= (uint32_t)AA_LUT_CODES;
 }
+/* K4 / K5 on the tensor cores use category-independent frequency / eigen-matrix operands: single-matrix partitions only
+ * (K2's AA_CLV mode reads only P-matrices and keeps running for mixtures) */
+static bool aa_dmma_pairs_class(const nrx_engine *e, const ShapeClass &c) { return aa_dmma_class(e, c) && !class_mixture(e, c); }
 static std::vector<nrx_op> pairs_to_ops(const nrx_pair *pairs, uint32_t n, uint32_t edge, bool tip_left, bool *any_tip_out) {
   std::vector<nrx_op> ops(n);
   *any_tip_out = false;
@@ -1139,7 +1182,7 @@ int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n
   {  // engines whose partitions all run the tensor-core kernel: nblk = tile groups per pair; keep >= ~50 tiles per block so
      // that the per-block set-up (B fragments, tip table) is amortised (4736 blocks of 21 tiles ran at 7 % tensor pipe)
     bool only_aa = !e->classes.empty();
-    for (const ShapeClass &c : e->classes) only_aa = only_aa && aa_dmma_class(e, c);
+    for (const ShapeClass &c : e->classes) only_aa = only_aa && aa_dmma_pairs_class(e, c);
     if (only_aa) nblk = std::max<uint32_t>(1, std::min<uint32_t>(nblk, e->aa_blocks / std::max<uint32_t>(1, n * P)));
   }
   if (!ensure_result(e, (size_t)n * P, (size_t)n * P * nblk) || !refresh_views(e)) return 0;
@@ -1151,8 +1194,8 @@ int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n
   prof_begin(e, &ev0, &ev1);
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
-    if (c.states == 4 && c.cats == 4) k_edge_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh);
-    else if (aa_dmma_class(e, c)) {  // FP64 tensor cores: block b = (pair b % n, tile group b / n), one partial per (pair, group)
+    if (c.states == 4 && c.cats == 4 && !class_mixture(e, c)) k_edge_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh);
+    else if (aa_dmma_pairs_class(e, c)) {  // FP64 tensor cores: block b = (pair b % n, tile group b / n), one partial per (pair, group)
       bool tips;
       const std::vector<nrx_op> ops = pairs_to_ops(pairs, n, edge, false, &tips);
       nrx_op *d_ops;
@@ -1181,10 +1224,10 @@ int nrx_sumtables(nrx_engine *e, const nrx_pair *pairs, uint32_t n) {
   for (const ShapeClass &c : e->classes) {
     if (c.max_patterns == 0) continue;
     const uint32_t z = (uint32_t)c.parts.size();
-    if (c.states == 4 && c.cats == 4) {
+    if (c.states == 4 && c.cats == 4 && !class_mixture(e, c)) {
       dim3 grid(tiles_for((uint64_t)c.max_patterns * 4, BLOCK * RU, n * z), n, z);
       k_sumtable_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs);
-    } else if (aa_dmma_class(e, c)) {
+    } else if (aa_dmma_pairs_class(e, c)) {
       bool tips;
       const std::vector<nrx_op> ops = pairs_to_ops(pairs, n, 0, true, &tips);
       nrx_op *d_ops;
@@ -1221,10 +1264,11 @@ int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen, double *out)
     double *dp = diag.data();
     for (uint32_t i = 0; i < C; ++i) {
       const double ki = p.h_rates[i] / (1.0 - p.pinv);   // LIBPLL/core_derivatives.c:716
+      const double *ev = p.h_eigenvals.data() + (size_t)(p.nmodels > 1 ? p.cat_model[i] : 0) * S;   // eigenvals[params_indices[i]] (:712)
       for (uint32_t j = 0; j < S; ++j) {
-        dp[0] = std::exp(p.h_eigenvals[j] * ki * brlen[pi]);
-        dp[1] = p.h_eigenvals[j] * ki * dp[0];
-        dp[2] = p.h_eigenvals[j] * ki * p.h_eigenvals[j] * ki * dp[0];
+        dp[0] = std::exp(ev[j] * ki * brlen[pi]);
+        dp[1] = ev[j] * ki * dp[0];
+        dp[2] = ev[j] * ki * ev[j] * ki * dp[0];
         dp[3] = 0;
         dp += 4;
       }
@@ -1238,9 +1282,10 @@ int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen, double *out)
   prof_begin(e, &ev0, &ev1);
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
-    if (c.states == 4 && c.cats == 4) k_derivatives_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P);
-    else if (pow2_cats(c) && c.states == 20) k_derivatives_pc<20><<<grid, BLOCK, ((size_t)c.cats * c.states * 4 + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P);
-    else if (pow2_cats(c)) k_derivatives_pc<0><<<grid, BLOCK, ((size_t)c.cats * c.states * 4 + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P);
+    const bool mix = class_mixture(e, c);   // (only the +I term of K6 reads frequencies; the generic kernel is the one that indexes them by category)
+    if (!mix && c.states == 4 && c.cats == 4) k_derivatives_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P);
+    else if (!mix && pow2_cats(c) && c.states == 20) k_derivatives_pc<20><<<grid, BLOCK, ((size_t)c.cats * c.states * 4 + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P);
+    else if (!mix && pow2_cats(c)) k_derivatives_pc<0><<<grid, BLOCK, ((size_t)c.cats * c.states * 4 + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P);
     else k_derivatives<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P);
     e->launches++;
     CK(cudaGetLastError());

@@ -43,7 +43,16 @@ struct PartView {
   double pinv;               // proportion of invariant sites (+I, pll_partition_t::prop_invar); 0 = none
   const int *invariant;      // [patterns] state index of an invariant pattern (pll_update_invariant_sites, LIBPLL/models.c:651-760), else -1
   const double *sumlut;      // 20-state partitions: K5 tip table [AA_LUT_CODES][cats*20]: sum_{k in code} pi_k Vinv[k][j], replicated per category
+  /* Mixtures with one rate matrix per category (LG4M / LG4X: raxml-ng's ratecat_submodels = libpll's params_indices[c],
+   * src/RaxmlWrapper.cpp:199-203): freqs / eigenvecs / inv_eigenvecs / eigenvals hold `nmodels` blocks back to back (strides sp,
+   * states*sp, states*sp, sp) and category c uses block cat_model[c].  nmodels == 1: the single-matrix layout every fast kernel
+   * assumes; partitions with nmodels > 1 run K1 and the generic K3-K6 kernels (K2 only reads P-matrices, which are per category
+   * already). */
+  uint32_t nmodels;
+  uint8_t cat_model[16];
 };
+
+__device__ __forceinline__ uint32_t cat_model_of(const PartView &pv, uint32_t c) { return pv.nmodels > 1 ? pv.cat_model[c] : 0u; }
 
 __device__ __forceinline__ double tree4(double a, double b, double c, double d) {
   return __dadd_rn(__dadd_rn(a, b), __dadd_rn(c, d));
@@ -112,7 +121,7 @@ __global__ void k_pmatrix(PartView pv, double *pmat_out, const uint32_t *edge_id
   for (uint32_t i = threadIdx.x; i < C * S; i += blockDim.x) {
     const uint32_t c = i / S, m = i % S;
     // (eval*rate)*t exactly as core_pmatrix_avx.c:104-108, divided by (1 - pinv) for +I partitions (:113-117, core_pmatrix.c:196-200)
-    double a = __dmul_rn(__dmul_rn(pv.eigenvals[m], pv.rates[c]), t);
+    double a = __dmul_rn(__dmul_rn(pv.eigenvals[cat_model_of(pv, c) * SP + m], pv.rates[c]), t);
     if (pv.pinv > 1e-8 /* PLL_MISC_EPSILON */) a = __ddiv_rn(a, __dsub_rn(1.0, pv.pinv));
     expd[i] = expm1(a);
   }
@@ -123,16 +132,18 @@ __global__ void k_pmatrix(PartView pv, double *pmat_out, const uint32_t *edge_id
     if (k < S) {
       if (t > 0.0) {
         const double *ex = expd + c * S;
+        const size_t mo = (size_t)cat_model_of(pv, c) * S * SP;   // this category's rate matrix (params_indices[c], core_pmatrix.c:160-166)
+        const double *iev = pv.inv_eigenvecs + mo, *ev = pv.eigenvecs + mo;
         if (S == 4) {  // tree sum, identity added last (core_pmatrix_avx.c:127-258)
-          double p0 = __dmul_rn(__dmul_rn(pv.inv_eigenvecs[j * SP + 0], ex[0]), pv.eigenvecs[0 * SP + k]);
-          double p1 = __dmul_rn(__dmul_rn(pv.inv_eigenvecs[j * SP + 1], ex[1]), pv.eigenvecs[1 * SP + k]);
-          double p2 = __dmul_rn(__dmul_rn(pv.inv_eigenvecs[j * SP + 2], ex[2]), pv.eigenvecs[2 * SP + k]);
-          double p3 = __dmul_rn(__dmul_rn(pv.inv_eigenvecs[j * SP + 3], ex[3]), pv.eigenvecs[3 * SP + k]);
+          double p0 = __dmul_rn(__dmul_rn(iev[j * SP + 0], ex[0]), ev[0 * SP + k]);
+          double p1 = __dmul_rn(__dmul_rn(iev[j * SP + 1], ex[1]), ev[1 * SP + k]);
+          double p2 = __dmul_rn(__dmul_rn(iev[j * SP + 2], ex[2]), ev[2 * SP + k]);
+          double p3 = __dmul_rn(__dmul_rn(iev[j * SP + 3], ex[3]), ev[3 * SP + k]);
           v = __dadd_rn(tree4(p0, p1, p2, p3), (j == k) ? 1.0 : 0.0);
         } else {       // identity first, serial accumulation (core_pmatrix.c:205-217)
           v = (j == k) ? 1.0 : 0.0;
           for (uint32_t m = 0; m < S; ++m)
-            v = __dadd_rn(v, __dmul_rn(__dmul_rn(pv.inv_eigenvecs[j * SP + m], ex[m]), pv.eigenvecs[m * SP + k]));
+            v = __dadd_rn(v, __dmul_rn(__dmul_rn(iev[j * SP + m], ex[m]), ev[m * SP + k]));
         }
       } else {
         v = (j == k) ? 1.0 : 0.0;  // zero branch length: identity (core_pmatrix.c:220-226)
@@ -1168,19 +1179,20 @@ __global__ void __launch_bounds__(BLOCK) k_tree_lnl(const PartView *__restrict__
   double acc[1] = {0.0};
   for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
     const double *c = clv + n * C * SP;
-    double term = 0.0, invf = 0.0;
+    double term = 0.0;
     const double pinv = pv.pinv;
-    if (pinv > 0.0) { const int iv = pv.invariant[n]; invf = iv < 0 ? 0.0 : pv.freqs[iv]; }
+    const int iv = pinv > 0.0 ? pv.invariant[n] : -1;
     for (uint32_t j = 0; j < C; ++j) {
+      const double *fr = pv.freqs + cat_model_of(pv, j) * SP;   // freqs_indices[j] (core_likelihood.c:150-160)
       double term_r;
       if (S == 4) {
         const D4 v = ldg256(c + j * 4);
-        term_r = tree4(__dmul_rn(pv.freqs[0], v.x), __dmul_rn(pv.freqs[1], v.y), __dmul_rn(pv.freqs[2], v.z), __dmul_rn(pv.freqs[3], v.w));
+        term_r = tree4(__dmul_rn(fr[0], v.x), __dmul_rn(fr[1], v.y), __dmul_rn(fr[2], v.z), __dmul_rn(fr[3], v.w));
       } else {
         term_r = 0.0;
-        for (uint32_t k = 0; k < S; ++k) term_r = __dadd_rn(term_r, __dmul_rn(c[j * SP + k], pv.freqs[k]));
+        for (uint32_t k = 0; k < S; ++k) term_r = __dadd_rn(term_r, __dmul_rn(c[j * SP + k], fr[k]));
       }
-      term = __dadd_rn(term, root_cat_term(term_r, pv.rate_weights[j], pinv, invf));
+      term = __dadd_rn(term, root_cat_term(term_r, pv.rate_weights[j], pinv, iv < 0 ? 0.0 : fr[iv]));
     }
     double lk = log(term);
     const uint32_t s = sc[n];
@@ -1211,20 +1223,20 @@ __global__ void __launch_bounds__(BLOCK) k_edge_lnl(const PartView *__restrict__
   double acc[1] = {0.0};
   for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
     const uint32_t mask = tip ? pv.tipmap[tip[n]] : 0;
-    double terma = 0.0, terminv = 0.0, invf = 0.0;
+    double terma = 0.0, terminv = 0.0;
     const double pinv = pv.pinv;
-    int iv = -1;
-    if (pinv > 0.0) { iv = pv.invariant[n]; invf = iv < 0 ? 0.0 : pv.freqs[iv]; }
+    const int iv = pinv > 0.0 ? pv.invariant[n] : -1;
     for (uint32_t i = 0; i < C; ++i) {
+      const double *fr = pv.freqs + cat_model_of(pv, i) * SP;   // freqs_indices[i] (core_likelihood.c:1236-1240)
       const double *cp = clvp + (n * C + i) * SP;
       const double *cc = clvc ? clvc + (n * C + i) * SP : nullptr;
       double terma_r = 0.0;
       for (uint32_t j = 0; j < S; ++j) {
         const double *row = pm + ((size_t)i * S + j) * SP;
         const double termb = tip ? masked_rowsum(row, S, mask) : row_dot(row, cc, S);
-        terma_r = __dadd_rn(terma_r, __dmul_rn(__dmul_rn(cp[j], pv.freqs[j]), termb));
+        terma_r = __dadd_rn(terma_r, __dmul_rn(__dmul_rn(cp[j], fr[j]), termb));
       }
-      edge_cat_accum(terma_r, pv.rate_weights[i], pinv, invf, iv >= 0, terma, terminv);
+      edge_cat_accum(terma_r, pv.rate_weights[i], pinv, iv < 0 ? 0.0 : fr[iv], iv >= 0, terma, terminv);
     }
     const uint32_t s = scp[n] + (scc ? scc[n] : 0u);
     double lk;
@@ -1252,6 +1264,8 @@ __global__ void __launch_bounds__(BLOCK) k_sumtable(const PartView *__restrict__
   const uint64_t n_items = (uint64_t)pv.patterns * C;
   for (uint64_t g = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; g < n_items; g += (uint64_t)gridDim.x * BLOCK) {
     const uint64_t n = g / C;
+    const uint32_t cm = cat_model_of(pv, (uint32_t)(g % C));   // params_indices[i] (core_derivatives.c:362-366)
+    const double *fr = pv.freqs + cm * SP, *iev = pv.inv_eigenvecs + (size_t)cm * S * SP, *ev = pv.eigenvecs + (size_t)cm * S * SP;
     const double *cr = clvr + g * SP;
     const double *cl = clvl ? clvl + g * SP : nullptr;
     const uint32_t mask = tip ? pv.tipmap[tip[n]] : 0;
@@ -1259,8 +1273,8 @@ __global__ void __launch_bounds__(BLOCK) k_sumtable(const PartView *__restrict__
       double lefterm = 0.0, righterm = 0.0;
       for (uint32_t k = 0; k < S; ++k) {
         const double lv = tip ? (double)((mask >> k) & 1u) : cl[k];
-        lefterm = __dadd_rn(lefterm, __dmul_rn(__dmul_rn(lv, pv.freqs[k]), pv.inv_eigenvecs[k * SP + j]));
-        righterm = __dadd_rn(righterm, __dmul_rn(pv.eigenvecs[j * SP + k], cr[k]));
+        lefterm = __dadd_rn(lefterm, __dmul_rn(__dmul_rn(lv, fr[k]), iev[k * SP + j]));
+        righterm = __dadd_rn(righterm, __dmul_rn(ev[j * SP + k], cr[k]));
       }
       out[g * SP + j] = __dmul_rn(lefterm, righterm);
     }
@@ -1281,10 +1295,11 @@ __global__ void __launch_bounds__(BLOCK) k_derivatives(const PartView *__restric
   double acc[3] = {0.0, 0.0, 0.0};
   for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
     const double *sum = st + n * C * SP;
-    double lk0 = 0.0, lk1 = 0.0, lk2 = 0.0, invf = 0.0;
+    double lk0 = 0.0, lk1 = 0.0, lk2 = 0.0;
     const double pinv = pv.pinv;
-    if (pinv > 0.0) { const int iv = pv.invariant[n]; invf = iv < 0 ? 0.0 : pv.freqs[iv]; }
+    const int iv = pinv > 0.0 ? pv.invariant[n] : -1;
     for (uint32_t i = 0; i < C; ++i) {
+      const double invf = iv < 0 ? 0.0 : pv.freqs[cat_model_of(pv, i) * SP + iv];   // freqs[params_indices[i]] (core_derivatives.c:676-686)
       double c0 = 0.0, c1 = 0.0, c2 = 0.0;
       const double *dg = pv.diagp + (size_t)i * S * 4;
       for (uint32_t j = 0; j < S; ++j) {

@@ -42,6 +42,9 @@ struct PortBackend : Backend {
     std::memcpy(weights, pp->rate_weights, sizeof(double) * pp->rate_cats);
     std::memcpy(freqs, pp->freqs, sizeof(double) * pp->states_padded);
   }
+  void setSubmodels(unsigned, unsigned n, const unsigned *, const double *, const double *) override {
+    if (n > 1) throw std::runtime_error("per-category rate matrices are restated only through the reference backend (oracle kind \"ref\"): the scalar port has one rate matrix per partition");
+  }
   void setPinv(unsigned, double pinv) override {
     if (pinv != 0.0) throw std::runtime_error("+I is restated only through the reference backend (oracle kind \"ref\"): the scalar port has no invariant-site terms");
   }

@@ -22,7 +22,8 @@ namespace {
 struct RefBackend : Backend {
   std::vector<pll_partition_t *> parts;
   unsigned tips = 0, fake_clv = 0;
-  std::vector<unsigned> params_indices;  // all zero
+  std::vector<std::vector<unsigned>> pidx;   // per partition: params_indices (all zero unless setSubmodels installed a mixture)
+  std::vector<unsigned> nmat;                // rate matrices in use per partition
   ~RefBackend() override { for (auto *p : parts) pll_partition_destroy(p); }
   const char *kind() const override { return "reference"; }
   unsigned partitionCount() const override { return (unsigned)parts.size(); }
@@ -50,13 +51,27 @@ struct RefBackend : Backend {
     std::memcpy(weights, pp->rate_weights, sizeof(double) * pp->rate_cats);
     std::memcpy(freqs, pp->frequencies[0], sizeof(double) * pp->states_padded);
   }
-  void setPinv(unsigned p, double pinv) override {
-    if (!pll_update_invariant_sites_proportion(parts[p], 0, pinv)) throw std::runtime_error(pll_errmsg);
+  void setSubmodels(unsigned p, unsigned n, const unsigned *cat_model, const double *freqs, const double *subst) override {
+    pll_partition_t *pp = parts[p];
+    if (n < 1 || n > pp->rate_matrices) throw std::runtime_error("setSubmodels: number of rate matrices out of range");
+    const unsigned nr = pp->states * (pp->states - 1) / 2;
+    for (unsigned i = 0; i < n; ++i) {
+      pll_set_frequencies(pp, i, freqs + (size_t)i * pp->states);
+      pll_set_subst_params(pp, i, subst + (size_t)i * nr);
+      pll_update_eigen(pp, i);
+      if (i > 0 && !pll_update_invariant_sites_proportion(pp, i, pp->prop_invar[0])) throw std::runtime_error(pll_errmsg);
+    }
+    for (unsigned c = 0; c < pp->rate_cats; ++c) pidx[p][c] = n > 1 ? cat_model[c] : 0;
+    nmat[p] = n;
+  }
+  void setPinv(unsigned p, double pinv) override {   // raxml-ng applies one pinv to every submodel (Model.cpp assign())
+    for (unsigned i = 0; i < nmat[p]; ++i)
+      if (!pll_update_invariant_sites_proportion(parts[p], i, pinv)) throw std::runtime_error(pll_errmsg);
   }
   void setCategoryRates(unsigned p, const double *rates) override { pll_set_category_rates(parts[p], rates); }
   bool gammaRates(double alpha, unsigned cats, double *out, int mode) const override { return pll_compute_gamma_cats(alpha, cats, out, mode) != 0; }
   void updatePmatrix(unsigned p, unsigned edge, double brlen) override {
-    if (!pll_update_prob_matrices(parts[p], params_indices.data(), &edge, &brlen, 1)) throw std::runtime_error(pll_errmsg);
+    if (!pll_update_prob_matrices(parts[p], pidx[p].data(), &edge, &brlen, 1)) throw std::runtime_error(pll_errmsg);
   }
   const double *pmatrix(unsigned p, unsigned edge) const override { return parts[p]->pmatrix[edge]; }
   unsigned clvIndex(const Operand &o) const { return o.kind == 1 ? o.tip : (o.kind == 0 ? tips + 1 : fake_clv); }
@@ -74,26 +89,26 @@ struct RefBackend : Backend {
                                r.kind == 0 ? const_cast<unsigned *>(r.scaler) : nullptr);
   }
   double rootLogl(unsigned p, const double *clv, const unsigned *scaler, double *persite) override {
-    return pll_compute_root_loglikelihood(parts[p], tips + 1, const_cast<double *>(clv), const_cast<unsigned *>(scaler), params_indices.data(), persite);
+    return pll_compute_root_loglikelihood(parts[p], tips + 1, const_cast<double *>(clv), const_cast<unsigned *>(scaler), pidx[p].data(), persite);
   }
   double edgeLogl(unsigned p, const Operand &a, const Operand &b, unsigned edge, double *persite) override {
     return pll_compute_edge_loglikelihood(parts[p], clvIndex(a), clvPtr(p, a), a.kind == 0 ? const_cast<unsigned *>(a.scaler) : nullptr,
                                           clvIndex(b), clvPtr(p, b), b.kind == 0 ? const_cast<unsigned *>(b.scaler) : nullptr,
-                                          edge, params_indices.data(), persite);
+                                          edge, pidx[p].data(), persite);
   }
   void sumtable(unsigned p, const Operand &a, const Operand &b, double *out) override {
     if (!pll_update_sumtable(parts[p], clvIndex(a), clvPtr(p, a), clvIndex(b), clvPtr(p, b),
                              a.kind == 0 ? const_cast<unsigned *>(a.scaler) : nullptr,
-                             b.kind == 0 ? const_cast<unsigned *>(b.scaler) : nullptr, params_indices.data(), out))
+                             b.kind == 0 ? const_cast<unsigned *>(b.scaler) : nullptr, pidx[p].data(), out))
       throw std::runtime_error(pll_errmsg);
   }
   void derivatives(unsigned p, const double *st, double brlen, bool want_f, double *f, double *d1, double *d2) override {
     // LH/LikelihoodDerivatives.cpp:75-88,98-106,146-170
     double **eigenvals = nullptr, *prop_invar = nullptr;
-    pll_compute_eigenvals_and_prop_invar(parts[p], params_indices.data(), &eigenvals, &prop_invar);
+    pll_compute_eigenvals_and_prop_invar(parts[p], pidx[p].data(), &eigenvals, &prop_invar);
     double *diag = pll_compute_diagptable(parts[p]->states, parts[p]->rate_cats, brlen, prop_invar, parts[p]->rates, eigenvals);
     free(eigenvals);
-    pll_compute_loglikelihood_derivatives(parts[p], 0, nullptr, 0, nullptr, brlen, params_indices.data(), st,
+    pll_compute_loglikelihood_derivatives(parts[p], 0, nullptr, 0, nullptr, brlen, pidx[p].data(), st,
                                           want_f ? f : nullptr, d1, d2, diag, prop_invar);
     pll_aligned_free(diag);
     free(prop_invar);
@@ -105,16 +120,20 @@ Backend *makeRefBackend(unsigned tips, unsigned edges_plus_fake, const std::vect
   RefBackend *b = new RefBackend();
   b->tips = tips;
   b->fake_clv = tips;  // clv_buffers: [0] = fake all-ones CLV, [1] = placeholder "inner" index
-  b->params_indices.assign(64, 0);
   for (const PartitionDesc &d : descs) {
     unsigned attrs = PLL_ATTRIB_ARCH_AVX2 | PLL_ATTRIB_PATTERN_TIP;  // RAXML/TreeInfo.cpp:646-676, SURVEY F4
-    pll_partition_t *pp = pll_partition_create(tips, 2, d.states, d.sites, 1, edges_plus_fake, d.rate_cats, 1, attrs);
+    pll_partition_t *pp = pll_partition_create(tips, 2, d.states, d.sites, d.rate_cats /* room for one rate matrix per category */, edges_plus_fake, d.rate_cats, 1, attrs);
     if (!pp) throw std::runtime_error(std::string("pll_partition_create failed: ") + pll_errmsg);
     if (!d.pattern_weights.empty()) pll_set_pattern_weights(pp, d.pattern_weights.data());
     // tip states: synthetic char map code -> state mask (role of pll_map_nt / pll_map_aa)
     std::map<uint32_t, unsigned> code;
     std::vector<pll_state_t> map(256, 0);
     std::vector<std::string> seqs(tips, std::string(d.sites, '\0'));
+    if (d.states == 4)   // a COMPLETE 16-entry map, as pll_map_nt is: with PATTERN_TIP + ARCH_AVX2 libpll sizes ttlookup from the largest
+      for (uint32_t m = 1; m < 16; ++m) {   // mask in the map (LIBPLL/pll.c:352-396 tests ARCH_AVX only) while the 4x4 AVX lookup kernel it
+        code.emplace(m, m);                 // dispatches to always writes all 16 x 16 entries (core_partials_avx.c:255-395): a map built from
+        map[m] = m;                         // an alignment without T / gaps overflowed the heap (found with ASAN on 1-site partitions)
+      }
     for (unsigned t = 0; t < tips; ++t)
       for (unsigned s = 0; s < d.sites; ++s) {
         uint32_t m = d.tip_masks[t][s];
@@ -137,6 +156,8 @@ Backend *makeRefBackend(unsigned tips, unsigned edges_plus_fake, const std::vect
         clv += pp->states_padded;
       }
     b->parts.push_back(pp);
+    b->pidx.emplace_back(64, 0u);
+    b->nmat.push_back(1);
     b->setModel((unsigned)b->parts.size() - 1, d.freqs.data(), d.subst_params.data(), d.rates.data(), d.rate_weights.data());
   }
   return b;

@@ -132,6 +132,9 @@ struct Backend {
                         const double *weights) = 0;  // recomputes eigen
   virtual void getEigen(unsigned p, double *eigenvecs, double *inv_eigenvecs, double *eigenvals) const = 0;
   virtual void getRates(unsigned p, double *rates, double *weights, double *freqs) const = 0;
+  /* n rate matrices, category c uses matrix cat_model[c] (libpll params_indices; LG4M / LG4X): pll_set_frequencies /
+   * pll_set_subst_params / pll_update_eigen per matrix index */
+  virtual void setSubmodels(unsigned p, unsigned n, const unsigned *cat_model, const double *freqs, const double *subst) = 0;
   virtual void setPinv(unsigned p, double prop_invar) = 0;                                 // pll_update_invariant_sites_proportion
   virtual void setCategoryRates(unsigned p, const double *rates) = 0;                       // pll_set_category_rates
   virtual bool gammaRates(double alpha, unsigned cats, double *out, int mode) const = 0;   // pll_compute_gamma_cats
@@ -272,6 +275,7 @@ double optimize_reticulations(AnnotatedNetwork &ann, int max_iters);
 double scoreNetwork(AnnotatedNetwork &ann);                               // LH/ComplexityScoring.cpp:57-67 (BIC)
 void optimizeAllNonTopology(AnnotatedNetwork &ann, int type /* 0 QUICK, 1 NORMAL, 2 SLOW */);  // SRC/optimization/Optimization.cpp:118-214
 void setPinv(AnnotatedNetwork &ann, unsigned partition, double prop_invar);
+void setSubmodels(AnnotatedNetwork &ann, unsigned partition, unsigned n, const unsigned *cat_model, const double *freqs, const double *subst);
 void setAlpha(AnnotatedNetwork &ann, unsigned partition, double alpha);   // treeinfo_set_alpha (PLLMOD/algorithm/pllmod_algorithm.c:566-587)
 double optimize_alpha(AnnotatedNetwork &ann, double min_alpha, double max_alpha, double tolerance);  // pllmod_algo_opt_onedim_treeinfo(ALPHA)
 

@@ -202,6 +202,12 @@ void setPinv(AnnotatedNetwork &ann, unsigned p, double prop_invar) {
   invalidateAllCLVs(ann);
 }
 
+void setSubmodels(AnnotatedNetwork &ann, unsigned p, unsigned n, const unsigned *cat_model, const double *freqs, const double *subst) {
+  ann.backend->setSubmodels(p, n, cat_model, freqs, subst);
+  for (auto &v : ann.pmatrix_valid[p]) v = 0;
+  invalidateAllCLVs(ann);
+}
+
 /* treeinfo_set_alpha: alpha -> discrete Gamma rates (mean mode, the raxml-ng default) -> partition rates; every P-matrix
  * and CLV of the partition is stale afterwards (the optimiser re-evaluates with incremental = 0 anyway) */
 void setAlpha(AnnotatedNetwork &ann, unsigned p, double alpha) {

@@ -196,3 +196,38 @@ def check_hky_golden(make_engine, H):
         for e, b in ((e01, 0), (e02, 1)):
             np.testing.assert_allclose(eng.get_pmatrix(e, 0).reshape(4, 4, 4), H["P"][i][b], atol=5.1e-5, rtol=0)
         eng.close()
+
+
+# ---- mixtures with one rate matrix per rate category (LG4M / LG4X shape) ---------------------------------------------------
+def mixture_models(states, n, seed):
+    """n reversible models of `states` states: seeded log-normal perturbations of a base model (GTR test model / LG)."""
+    from netrax_b200.synth import lg_model
+    rng = np.random.default_rng(seed)
+    if states == 20:
+        r0, f0 = lg_model()
+    else:
+        nr = states * (states - 1) // 2
+        r0 = np.asarray(GTR_RATES, float) if states == 4 else np.linspace(0.5, 2.0, nr)
+        f0 = np.asarray(DNA_FREQS, float) if states == 4 else np.full(states, 1.0 / states)
+    subst = np.stack([r0 * np.exp(rng.normal(0, 0.5, r0.shape)) for _ in range(n)])
+    subst /= subst[:, -1:]
+    freqs = np.stack([f0 * np.exp(rng.normal(0, 0.3, f0.shape)) for _ in range(n)])
+    freqs /= freqs.sum(axis=1, keepdims=True)
+    return freqs, subst
+
+
+def mixture_lnl_by_categories(make_engine, net, part, cat_model, freqs, subst):
+    """The mixture lnL assembled from SINGLE-matrix, single-category, single-pattern evaluations only:
+    lnL = sum_sites w_site log sum_c weight_c L_c(site), L_c = site likelihood under matrix cat_model[c] at rate rates[c]."""
+    total = 0.0
+    pw = part.pattern_weights if part.pattern_weights is not None else np.ones(part.sites, dtype=np.uint32)
+    for s in range(part.sites):
+        lk = 0.0
+        for c in range(part.rate_cats):
+            m = int(cat_model[c])
+            one = Partition(part.states, 1, part.tip_masks[:, s:s + 1], freqs[m], subst[m], [part.rates[c]], rate_weights=[1.0])
+            eng = make_engine(net, one)
+            lk += part.rate_weights[c] * np.exp(eng.computeLoglikelihood(0, 1))
+            eng.close()
+        total += float(pw[s]) * np.log(lk)
+    return total

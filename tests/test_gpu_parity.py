@@ -905,3 +905,103 @@ def test_libpll_golden_hky_on_gpu():
     import os
     from helpers import GOLDEN, check_hky_golden
     check_hky_golden(lambda net, part: _gpu(net, [part]), np.load(os.path.join(GOLDEN, "libpll_hky_golden.npz")))
+
+
+# ---- one rate matrix per rate category (LG4M / LG4X: raxml-ng ratecat_submodels -> libpll params_indices) ------------------
+def _mixture_case(states, seed):
+    from helpers import mixture_models
+    if states == 20:
+        net, part = _protein_case(11, 2, 260, seed)
+    else:
+        net = random_network(13, 3, seed=seed)
+        m, w = simulate_alignment(net, 400, seed=seed)
+        part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    part.rates = np.array([0.15, 0.6, 1.2, 2.9])            # LG4X: free rates and weights
+    part.rate_weights = np.array([0.35, 0.3, 0.25, 0.1])
+    freqs, subst = mixture_models(states, 4, seed)
+    return net, part, [2, 0, 3, 1], freqs, subst
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("states", [4, 20])
+@pytest.mark.parametrize("variant", [AVERAGE, BEST])
+def test_submodels_match_reference_oracle(states, variant):
+    """Per-category rate matrices against the reference's libpll called with the same params_indices: network lnL, per-tree
+    lnLs, scalers (bit-exact), then on every edge the edge-rooted lnL, the sumtables and the derivatives; with and without +I.
+    K2 keeps its fast kernels (pipelined DNA / tensor-core protein), K1 and K3-K6 run the per-category generic kernels."""
+    from oracle import oracle
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    net, part, cat_model, freqs, subst = _mixture_case(states, 71 + states)
+    g, o = _gpu(net, [part], variant=variant), oracle.make_engine("ref", net, [part], variant=variant)
+    l_single = g.computeLoglikelihood(0, 1)
+    assert l_single == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
+    for eng in (g, o):
+        eng.set_submodels(0, cat_model, freqs, subst)
+    for pinv in (0.0, 0.2):
+        for eng in (g, o):
+            eng.set_pinv(0, pinv)
+        lg, lo = g.computeLoglikelihood(0, 1), o.computeLoglikelihood(0, 1)
+        assert lg == pytest.approx(lo, rel=LNL_RTOL), (states, pinv)
+        assert abs(lg - l_single) > 1e-3
+        root = net.root
+        assert g.num_trees(root) == o.num_trees(root)
+        for t in range(g.num_trees(root)):
+            np.testing.assert_allclose(g.tree_info(root, t)[1], o.tree_info(root, t)[1], rtol=LNL_RTOL)
+            assert np.array_equal(g.read_scaler(root, t), o.read_scaler(root, t))
+        for e in range(0, net.num_edges, 3 if pinv else 1):
+            assert g.brlen_prepare(e) == pytest.approx(o.brlen_prepare(e), rel=LNL_RTOL)
+            lb = g.computeLoglikelihoodBrlenOpt(e)
+            assert lb == pytest.approx(lg, rel=1e-11), e
+            assert lb == pytest.approx(o.computeLoglikelihoodBrlenOpt(e), rel=LNL_RTOL)
+            ng = g.computePartitionSumtables(e)
+            assert ng == o.computePartitionSumtables(e)
+            for i in range(ng):
+                # sumtable rows live in the eigenbasis: the host's Jacobi solver and libpll's QL order the eigenvectors of
+                # matrices 1.. differently (only matrix 0 can be injected), signs cancel in the product -> compare sorted rows
+                sp = (states + 3) & ~3
+                sg, so = (np.sort(x.read_sumtable(0, i)[0].reshape(-1, sp), axis=1) for x in (g, o))
+                np.testing.assert_allclose(sg, so, rtol=1e-8, atol=1e-12 * np.abs(so).max())
+            if ng:
+                t0 = float(net.edge_length[e])
+                for t in (t0, 0.04, 0.8):
+                    for eng in (g, o):
+                        eng.brlen_set_length(e, t)
+                    dg, do = g.computeLoglikelihoodDerivatives(e), o.computeLoglikelihoodDerivatives(e)
+                    np.testing.assert_allclose(dg[4], do[4], rtol=DERIV_RTOL, atol=1e-9)
+                    assert dg[0] == pytest.approx(do[0], rel=DERIV_RTOL, abs=1e-7)
+                    assert dg[1] == pytest.approx(do[1], rel=DERIV_RTOL, abs=1e-7)
+                for eng in (g, o):
+                    eng.brlen_set_length(e, t0)
+            assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL)
+    # branch-length optimisation runs on top of it; and the mixture can be taken away again
+    e = int(net.ret_first_edge[0])
+    assert g.optimize_branch(e) == pytest.approx(o.optimize_branch(e), rel=1e-9)
+    for eng in (g, o):
+        eng.set_pinv(0, 0.0)
+        eng.set_submodels(0, [0, 0, 0, 0], freqs[:1], subst[:1])
+        eng.set_model(0, part.freqs, part.subst, part.rates, part.rate_weights)
+        eng.set_branch_length(e, float(net.edge_length[e]))
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(l_single, rel=1e-13)
+    g.close(); o.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("states", [4, 20])
+def test_submodels_equal_the_sum_over_single_matrix_categories(states):
+    """Independent of any oracle: the product's mixture lnL on a tree equals the value assembled from the product's own
+    SINGLE-matrix, single-category, single-pattern evaluations (lnL = sum_sites log sum_c w_c L_c(site))."""
+    from helpers import mixture_lnl_by_categories, mixture_models
+    from netrax_b200.network_io import parse_extended_newick
+    net = parse_extended_newick("(((T0:0.1,T1:0.2):0.05,T2:0.3):0.1,(T3:0.15,T4:0.25):0.2);")
+    rng = np.random.default_rng(3)
+    masks = (1 << rng.integers(0, states, size=(5, 7))).astype(np.uint32)
+    masks[2, 4] = (1 << states) - 1
+    freqs, subst = mixture_models(states, 4, seed=11)
+    part = Partition(states, 4, masks, freqs[0], subst[0], [0.2, 0.7, 1.3, 2.4], rate_weights=[0.4, 0.3, 0.2, 0.1])
+    g = _gpu(net, [part])
+    cat_model = [2, 0, 3, 1]
+    g.set_submodels(0, cat_model, freqs, subst)
+    want = mixture_lnl_by_categories(lambda net, part: _gpu(net, [part]), net, part, cat_model, freqs, subst)
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(want, rel=1e-12)
+    g.close()

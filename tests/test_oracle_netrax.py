@@ -268,3 +268,40 @@ def test_pseudo_loglikelihood_port_equals_reference_and_dispatch():
         assert inc == pytest.approx(a.computePseudoLoglikelihood(0, 1), rel=1e-13) and inc != la
         c = oracle.make_engine("ref", net, [part], variant=SARAH_PSEUDO)
         assert c.computeLoglikelihood(0, 1) == pytest.approx(lb, rel=1e-13)
+
+
+# ---- one rate matrix per rate category (LG4M / LG4X: raxml-ng ratecat_submodels -> libpll params_indices) ------------------
+@pytest.mark.parametrize("states", [4, 20])
+def test_submodels_reference_oracle_semantics(states):
+    """The reference backend (real libpll with params_indices): (i) a mixture of identical matrices is the single-matrix
+    model, bit for bit; (ii) a real mixture equals the lnL assembled from single-matrix, single-category, single-site
+    evaluations; (iii) the scalar port says that it has no mixtures."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from helpers import encode_aa, mixture_lnl_by_categories, mixture_models
+    from netrax_b200.network_io import parse_extended_newick
+    net = parse_extended_newick("(((T0:0.1,T1:0.2):0.05,T2:0.3):0.1,(T3:0.15,T4:0.25):0.2);")   # a tree: one displayed tree, AVERAGE = plain lnL
+    rng = np.random.default_rng(3)
+    masks = (1 << rng.integers(0, states, size=(5, 9))).astype(np.uint32)
+    masks[2, 4] = (1 << states) - 1   # a gap
+    freqs, subst = mixture_models(states, 4, seed=11)
+    rates, weights = np.array([0.2, 0.7, 1.3, 2.4]), np.array([0.4, 0.3, 0.2, 0.1])   # LG4X: free rates and weights
+    part = Partition(states, 4, masks, freqs[0], subst[0], rates, rate_weights=weights)
+    make = lambda net, part: oracle.make_engine("ref", net, [part])
+    e = make(net, part)
+    l_single = e.computeLoglikelihood(0, 1)
+    e.set_submodels(0, [0, 1, 2, 3], np.stack([freqs[0]] * 4), np.stack([subst[0]] * 4))
+    assert e.computeLoglikelihood(0, 1) == l_single
+    cat_model = [2, 0, 3, 1]
+    e.set_submodels(0, cat_model, freqs, subst)
+    l_mix = e.computeLoglikelihood(0, 1)
+    assert abs(l_mix - l_single) > 1e-3
+    want = mixture_lnl_by_categories(make, net, part, cat_model, freqs, subst)
+    assert l_mix == pytest.approx(want, rel=1e-12)
+    e.set_submodels(0, [0, 0, 0, 0], freqs[:1], subst[:1])   # back to one matrix
+    assert e.computeLoglikelihood(0, 1) == l_single
+    e.close()
+    p = oracle.make_engine("port", net, [part])
+    with pytest.raises(Exception, match="reference backend"):
+        p.set_submodels(0, cat_model, freqs, subst)
+    p.close()

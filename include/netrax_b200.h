@@ -63,6 +63,9 @@ int nrxh_partition_loglh(void *h, double *out);
 int nrxh_set_branch_length(void *h, int partition, unsigned edge, double value);
 int nrxh_set_reticulation_prob(void *h, unsigned r, double prob);
 int nrxh_set_model(void *h, unsigned p, const double *freqs, const double *subst_params, const double *rates, const double *rate_weights);
+/* Scaled branch-length linkage (brlen_linkage = 1): pllmod_treeinfo_t::brlen_scalers[p]; the P-matrices of partition p use
+ * scaler x the linked branch length (PLLMOD/tree/treeinfo.c:862-864).  Fails unless the linkage is scaled. */
+int nrxh_set_brlen_scaler(void *h, unsigned p, double scaler);
 /* Mixture with one rate matrix per rate category (LG4M / LG4X): what raxml-ng's Model::ratecat_submodels() is to NetRAX
  * (src/RaxmlWrapper.cpp:199-203 -> pllmod param_indices -> every libpll call).  n rate matrices, freqs [n][states],
  * subst [n][states (states - 1) / 2], category c uses matrix ratecat_submodels[c]; n == 1 goes back to a single matrix. */

@@ -79,6 +79,7 @@ class FlatAPI:
         g("set_scoring_sizes", C.c_int, C.c_void_p, C.c_ulonglong, C.c_ulonglong)
         g("optimize_all_non_topology", C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double))
         g("set_pinv", C.c_int, C.c_void_p, C.c_uint, C.c_double)
+        g("set_brlen_scaler", C.c_int, C.c_void_p, C.c_uint, C.c_double)
         g("set_submodels", C.c_int, C.c_void_p, C.c_uint, C.c_uint, _u32p, _f64p, _f64p)
         g("set_alpha", C.c_int, C.c_void_p, C.c_uint, C.c_double)
         g("get_alpha", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
@@ -332,6 +333,10 @@ class LikelihoodEngine:
     def set_pinv(self, p: int, prop_invar: float):
         """+I: proportion of invariant sites (pll_update_invariant_sites_proportion)."""
         self.api.check(self.api._set_pinv(self.h, p, prop_invar))
+
+    def set_brlen_scaler(self, p: int, scaler: float):
+        """pllmod_treeinfo_t::brlen_scalers[p] under scaled branch-length linkage (linkage = SCALED)."""
+        self.api.check(self.api._set_brlen_scaler(self.h, p, scaler))
 
     def set_submodels(self, p: int, ratecat_submodels, freqs, subst):
         """One rate matrix per rate category (LG4M / LG4X; raxml-ng Model::ratecat_submodels -> libpll params_indices):

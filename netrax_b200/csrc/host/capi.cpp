@@ -238,6 +238,10 @@ int nrxh_set_model(void *hv, unsigned p, const double *freqs, const double *subs
   });
 }
 
+int nrxh_set_brlen_scaler(void *hv, unsigned p, double scaler) {
+  return guarded([&] { set_brlen_scaler(H(hv)->ann, p, scaler); });
+}
+
 int nrxh_set_submodels(void *hv, unsigned p, unsigned n, const unsigned *ratecat_submodels, const double *freqs, const double *subst) {
   return guarded([&] {
     AnnotatedNetwork &ann = H(hv)->ann;

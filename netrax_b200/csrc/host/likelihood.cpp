@@ -291,6 +291,15 @@ static void uploadModel(AnnotatedNetwork &ann, unsigned p) {
                                     m.rates.data(), m.rate_weights.data(), m.prop_invar), "nrx_set_model_mixture");
 }
 
+void set_brlen_scaler(AnnotatedNetwork &ann, unsigned p, double scaler) {
+  FakeTreeinfo &ti = *ann.fake_treeinfo;
+  if (ti.brlen_linkage != PLLMOD_COMMON_BRLEN_SCALED) throw std::runtime_error("Branch length scalers exist only in scaled branch length mode.");
+  if (ti.brlen_scalers.size() < ti.partition_count) ti.brlen_scalers.resize(ti.partition_count, 1.0);
+  ti.brlen_scalers.at(p) = scaler;
+  for (auto &v : ti.pmatrix_valid.at(p)) v = 0;
+  invalidateAllCLVs(ann);
+}
+
 void pushPartitionModel(AnnotatedNetwork &ann, unsigned p) {
   uploadModel(ann, p);
   for (auto &v : ann.fake_treeinfo->pmatrix_valid.at(p)) v = 0;
@@ -364,7 +373,9 @@ int pllmod_treeinfo_update_prob_matrices(AnnotatedNetwork &ann, int update_all) 
     for (size_t m = 0; m < ti.pmatrix_valid[p].size(); ++m) {
       if (ti.pmatrix_valid[p][m] && !update_all) continue;
       idx.push_back((uint32_t)m);
-      len.push_back(ti.branch_lengths[p][m]);
+      double p_brlen = ti.branch_lengths[p][m];
+      if (ti.brlen_linkage == PLLMOD_COMMON_BRLEN_SCALED && p < ti.brlen_scalers.size()) p_brlen *= ti.brlen_scalers[p];  // :862-864
+      len.push_back(p_brlen);
       ti.pmatrix_valid[p][m] = 1;
     }
     if (!idx.empty()) engineCheck(nrx_update_pmatrices(ann.engine, p, (uint32_t)idx.size(), idx.data(), len.data()), "nrx_update_pmatrices");

@@ -145,6 +145,12 @@ struct PartitionModel {
   std::vector<unsigned> ratecat_submodels;
 };
 /* installs rate matrices 1..n-1 (matrix 0 = freqs[0] / subst[0] too) and the category -> matrix map; n == 1 removes the mixture */
+struct AnnotatedNetwork;
+/* fake_treeinfo->brlen_scalers[p] = scaler (scaled linkage): the P-matrices of partition p use scaler x linked branch length
+ * (pllmod_treeinfo_update_prob_matrices, PLLMOD/tree/treeinfo.c:862-864); what pll-modules' scaler optimiser
+ * (pllmod_algo_opt_brlen_scalers_treeinfo, called by optimize_scalers, src/optimization/BranchLengthOptimization.cpp:581-599)
+ * changes before it re-enters through likelihood_target_function */
+void set_brlen_scaler(AnnotatedNetwork &ann, unsigned partition, double scaler);
 void set_submodels(PartitionModel &m, unsigned n, const unsigned *ratecat_submodels, const double *freqs /*[n][states]*/,
                    const double *subst /*[n][states (states - 1) / 2]*/);
 void set_frequencies(PartitionModel &m, const double *frequencies);                    // pll_set_frequencies (LIBPLL/models.c:445-467): renormalises when |sum - 1| > 1e-8
@@ -157,6 +163,7 @@ struct FakeTreeinfo {
   std::vector<PartitionModel> partitions;
   std::vector<std::vector<double>> branch_lengths;   // [partition][edge + 1 fake]
   std::vector<double> linked_branch_lengths;         // [edge + 1 fake]
+  std::vector<double> brlen_scalers;                 // [partition], PLLMOD_COMMON_BRLEN_SCALED only (PLLMOD/tree/pll_tree.h:236); empty = all 1
   int brlen_linkage = PLLMOD_COMMON_BRLEN_LINKED;
   std::vector<double> partition_loglh;
   std::vector<std::vector<char>> clv_valid;          // [partition][node]

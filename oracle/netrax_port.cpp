@@ -537,7 +537,9 @@ void updateProbMatrices(AnnotatedNetwork &ann, int update_all) {  // PLLMOD/tree
   for (unsigned p = 0; p < ann.partitionCount(); ++p)
     for (size_t m = 0; m < ann.network.edges.size() + 1; ++m) {
       if (ann.pmatrix_valid[p][m] && !update_all) continue;
-      ann.backend->updatePmatrix(p, (unsigned)m, ann.branch_lengths[p][m]);
+      double p_brlen = ann.branch_lengths[p][m];
+      if (ann.options.brlen_linkage == BRLEN_SCALED && p < ann.brlen_scalers.size()) p_brlen *= ann.brlen_scalers[p];  // :862-864
+      ann.backend->updatePmatrix(p, (unsigned)m, p_brlen);
       ann.pmatrix_valid[p][m] = 1;
     }
 }

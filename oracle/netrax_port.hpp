@@ -220,6 +220,7 @@ struct AnnotatedNetwork {  // SRC/graph/AnnotatedNetwork.hpp:42-89 (fields the p
   std::vector<std::vector<char>> pmatrix_valid;   // [partition][edge]
   std::vector<std::vector<double>> branch_lengths;  // [partition][edge+1] (fake_treeinfo->branch_lengths)
   std::vector<double> linked_branch_lengths;        // [edge+1]
+  std::vector<double> brlen_scalers;                // [partition] pllmod_treeinfo_t::brlen_scalers (BRLEN_SCALED only; empty = all 1)
   std::vector<double> partition_loglh;
   // pseudo-likelihood state (SRC/graph/AnnotatedNetwork.hpp:64-68): one CLV + scaler per node and partition (the
   // reference keeps them in partition->clv[node] / scale_buffer[node]) and the three scratch CLVs
@@ -275,6 +276,7 @@ double optimize_reticulations(AnnotatedNetwork &ann, int max_iters);
 double scoreNetwork(AnnotatedNetwork &ann);                               // LH/ComplexityScoring.cpp:57-67 (BIC)
 void optimizeAllNonTopology(AnnotatedNetwork &ann, int type /* 0 QUICK, 1 NORMAL, 2 SLOW */);  // SRC/optimization/Optimization.cpp:118-214
 void setPinv(AnnotatedNetwork &ann, unsigned partition, double prop_invar);
+void setBrlenScaler(AnnotatedNetwork &ann, unsigned partition, double scaler);
 void setSubmodels(AnnotatedNetwork &ann, unsigned partition, unsigned n, const unsigned *cat_model, const double *freqs, const double *subst);
 void setAlpha(AnnotatedNetwork &ann, unsigned partition, double alpha);   // treeinfo_set_alpha (PLLMOD/algorithm/pllmod_algorithm.c:566-587)
 double optimize_alpha(AnnotatedNetwork &ann, double min_alpha, double max_alpha, double tolerance);  // pllmod_algo_opt_onedim_treeinfo(ALPHA)

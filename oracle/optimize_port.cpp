@@ -202,6 +202,15 @@ void setPinv(AnnotatedNetwork &ann, unsigned p, double prop_invar) {
   invalidateAllCLVs(ann);
 }
 
+/* pllmod_treeinfo_t::brlen_scalers[p] (scaled branch-length linkage): P-matrices of partition p use scaler x linked length */
+void setBrlenScaler(AnnotatedNetwork &ann, unsigned p, double scaler) {
+  if (ann.options.brlen_linkage != BRLEN_SCALED) throw std::runtime_error("Branch length scalers exist only in scaled branch length mode.");
+  if (ann.brlen_scalers.size() < ann.partitionCount()) ann.brlen_scalers.resize(ann.partitionCount(), 1.0);
+  ann.brlen_scalers.at(p) = scaler;
+  for (auto &v : ann.pmatrix_valid[p]) v = 0;
+  invalidateAllCLVs(ann);
+}
+
 void setSubmodels(AnnotatedNetwork &ann, unsigned p, unsigned n, const unsigned *cat_model, const double *freqs, const double *subst) {
   ann.backend->setSubmodels(p, n, cat_model, freqs, subst);
   for (auto &v : ann.pmatrix_valid[p]) v = 0;

@@ -370,6 +370,10 @@ int orc_set_pinv(void *hv, unsigned p, double prop_invar) {
   Handle *h = static_cast<Handle *>(hv);
   return guarded([&] { setPinv(h->ann, p, prop_invar); });
 }
+int orc_set_brlen_scaler(void *hv, unsigned p, double scaler) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] { setBrlenScaler(h->ann, p, scaler); });
+}
 int orc_set_submodels(void *hv, unsigned p, unsigned n, const unsigned *cat_model, const double *freqs, const double *subst) {
   Handle *h = static_cast<Handle *>(hv);
   return guarded([&] { setSubmodels(h->ann, p, n, cat_model, freqs, subst); });

@@ -1005,3 +1005,31 @@ def test_submodels_equal_the_sum_over_single_matrix_categories(states):
     want = mixture_lnl_by_categories(lambda net, part: _gpu(net, [part]), net, part, cat_model, freqs, subst)
     assert g.computeLoglikelihood(0, 1) == pytest.approx(want, rel=1e-12)
     g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [AVERAGE, BEST])
+def test_scaled_branch_length_linkage_on_gpu(variant):
+    """Scaled linkage: P-matrices of partition p from brlen_scalers[p] x linked length — equal to the oracle, and bit-identical
+    to the product's own unlinked evaluation at the scaled lengths (same kernels, same inputs)."""
+    from netrax_b200._capi import SCALED
+    from test_oracle_netrax import scaled_linkage_case
+    net, parts, scalers = scaled_linkage_case()
+    g, o = _gpu(net, parts, variant=variant, linkage=SCALED), _oracle(net, parts, variant=variant, linkage=SCALED)
+    _inject_eigen(g, o)
+    for p, s in enumerate(scalers):
+        g.set_brlen_scaler(p, s); o.set_brlen_scaler(p, s)
+    lg = g.computeLoglikelihood(1, 1)
+    assert lg == pytest.approx(o.computeLoglikelihood(1, 1), rel=LNL_RTOL)
+    np.testing.assert_allclose(g.partition_loglh(), o.partition_loglh(), rtol=LNL_RTOL)
+    un = _gpu(net, parts, variant=variant, linkage=UNLINKED, partition_brlens=[net.edge_length * s for s in scalers])
+    _inject_eigen(un, o)
+    assert un.computeLoglikelihood(0, 1) == lg
+    e = int(net.ret_first_edge[0])
+    g.set_branch_length(e, 0.33); o.set_branch_length(e, 0.33)
+    assert g.computeLoglikelihood(1, 1) == pytest.approx(o.computeLoglikelihood(1, 1), rel=LNL_RTOL)
+    g.brlen_prepare(e)
+    g.computePartitionSumtables(e)
+    with pytest.raises(Exception, match="scaled branch lengths"):
+        g.computeLoglikelihoodDerivatives(e)
+    g.close(); un.close(); o.close()

@@ -305,3 +305,44 @@ def test_submodels_reference_oracle_semantics(states):
     with pytest.raises(Exception, match="reference backend"):
         p.set_submodels(0, cat_model, freqs, subst)
     p.close()
+
+
+def scaled_linkage_case(seed=5):
+    net = random_network(9, 2, seed=seed)
+    parts = []
+    for i in range(3):
+        m, w = simulate_alignment(net, 150 + 40 * i, seed=seed + i)
+        parts.append(Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w))
+    return net, parts, [0.5, 1.0, 1.7]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_scaled_branch_length_linkage(kind):
+    """PLLMOD_COMMON_BRLEN_SCALED: the P-matrices of partition p use brlen_scalers[p] x the linked length
+    (PLLMOD/tree/treeinfo.c:862-864) — identical to an unlinked analysis whose per-partition lengths are the scaled ones;
+    scalers of 1 give the linked result; derivatives refuse, as the reference does (LH/LikelihoodDerivatives.cpp:42-46)."""
+    from netrax_b200._capi import SCALED
+    net, parts, scalers = scaled_linkage_case()
+    lin = oracle.make_engine(kind, net, parts, linkage=LINKED)
+    sc = oracle.make_engine(kind, net, parts, linkage=SCALED)
+    assert sc.computeLoglikelihood(0, 1) == lin.computeLoglikelihood(0, 1)
+    for p, s in enumerate(scalers):
+        sc.set_brlen_scaler(p, s)
+    un = oracle.make_engine(kind, net, parts, linkage=UNLINKED, partition_brlens=[net.edge_length * s for s in scalers])
+    l_sc = sc.computeLoglikelihood(1, 1)
+    assert l_sc == un.computeLoglikelihood(0, 1)
+    np.testing.assert_array_equal(sc.partition_loglh(), un.partition_loglh())
+    assert abs(l_sc - lin.computeLoglikelihood(0, 1)) > 1e-3
+    e = int(net.ret_first_edge[0])
+    sc.set_branch_length(e, 0.33); un_len = 0.33
+    for p, s in enumerate(scalers):
+        un.set_branch_length(e, un_len * s, partition=p)
+    assert sc.computeLoglikelihood(1, 1) == un.computeLoglikelihood(1, 1)
+    sc.brlen_prepare(e)
+    sc.computePartitionSumtables(e)
+    with pytest.raises(Exception, match="scaled branch lengths"):
+        sc.computeLoglikelihoodDerivatives(e)
+    with pytest.raises(Exception, match="scaled branch length mode"):
+        lin.set_brlen_scaler(0, 2.0)
+    for x in (lin, sc, un):
+        x.close()

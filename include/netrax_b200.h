@@ -66,6 +66,13 @@ int nrxh_set_model(void *h, unsigned p, const double *freqs, const double *subst
 /* Scaled branch-length linkage (brlen_linkage = 1): pllmod_treeinfo_t::brlen_scalers[p]; the P-matrices of partition p use
  * scaler x the linked branch length (PLLMOD/tree/treeinfo.c:862-864).  Fails unless the linkage is scaled. */
 int nrxh_set_brlen_scaler(void *h, unsigned p, double scaler);
+int nrxh_get_brlen_scalers(void *h, double *out /* [partitions] */);
+/* optimize_scalers (src/optimization/BranchLengthOptimization.cpp:581-599) = pllmod_algo_opt_brlen_scalers_treeinfo with raxml-ng's
+ * bounds: Brent over all partitions' scalers at once, scalers normalised to a site-weighted mean of 1; returns the BIC */
+int nrxh_optimize_scalers(void *h, double *bic_score);
+/* the PINV step of optimize_params (src/optimization/ModelOptimization.cpp:67-76) over the partitions with +I */
+int nrxh_optimize_pinv(void *h, double min_pinv, double max_pinv, double tolerance, double *final_logl);
+int nrxh_get_pinv(void *h, unsigned p, double *prop_invar);
 /* Mixture with one rate matrix per rate category (LG4M / LG4X): what raxml-ng's Model::ratecat_submodels() is to NetRAX
  * (src/RaxmlWrapper.cpp:199-203 -> pllmod param_indices -> every libpll call).  n rate matrices, freqs [n][states],
  * subst [n][states (states - 1) / 2], category c uses matrix ratecat_submodels[c]; n == 1 goes back to a single matrix. */

@@ -84,6 +84,10 @@ class FlatAPI:
         g("set_alpha", C.c_int, C.c_void_p, C.c_uint, C.c_double)
         g("get_alpha", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
         g("optimize_alpha", C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double))
+        g("optimize_pinv", C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double))
+        g("get_pinv", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
+        g("optimize_scalers", C.c_int, C.c_void_p, C.POINTER(C.c_double))
+        g("get_brlen_scalers", C.c_int, C.c_void_p, _f64p)
         g("get_branch_lengths", C.c_int, C.c_void_p, C.c_int, _f64p)
         g("get_reticulation_probs", C.c_int, C.c_void_p, _f64p)
         g("clv_update_count", C.c_ulonglong, C.c_void_p)
@@ -358,6 +362,29 @@ class LikelihoodEngine:
         out = C.c_double()
         self.api.check(self.api._optimize_alpha(self.h, min_alpha, max_alpha, tolerance, C.byref(out)))
         return out.value
+
+    def optimize_pinv(self, min_pinv: float = 0.0, max_pinv: float = 0.99, tolerance: float = 0.001) -> float:
+        """The PINV step of optimize_params (ModelOptimization.cpp:67-76): Brent over the +I partitions' proportions."""
+        out = C.c_double()
+        self.api.check(self.api._optimize_pinv(self.h, min_pinv, max_pinv, tolerance, C.byref(out)))
+        return out.value
+
+    def get_pinv(self, p: int) -> float:
+        out = C.c_double()
+        self.api.check(self.api._get_pinv(self.h, p, C.byref(out)))
+        return out.value
+
+    def optimize_scalers(self) -> float:
+        """optimize_scalers (BranchLengthOptimization.cpp:581-599): pllmod_algo_opt_brlen_scalers_treeinfo under scaled
+        linkage with several partitions, otherwise a no-op; returns the BIC."""
+        out = C.c_double()
+        self.api.check(self.api._optimize_scalers(self.h, C.byref(out)))
+        return out.value
+
+    def brlen_scalers(self) -> np.ndarray:
+        out = np.zeros(self.P)
+        self.api.check(self.api._get_brlen_scalers(self.h, out))
+        return out
 
     def optimize_reticulations(self, max_iters: int = 10) -> float:
         out = C.c_double()

@@ -238,6 +238,21 @@ int nrxh_set_model(void *hv, unsigned p, const double *freqs, const double *subs
   });
 }
 
+int nrxh_optimize_pinv(void *hv, double min_pinv, double max_pinv, double tolerance, double *final_logl) {
+  return guarded([&] { const double l = optimize_pinv(H(hv)->ann, min_pinv, max_pinv, tolerance); if (final_logl) *final_logl = l; });
+}
+int nrxh_optimize_scalers(void *hv, double *bic_score) {
+  return guarded([&] { const double b = optimize_scalers(H(hv)->ann, true); if (bic_score) *bic_score = b; });
+}
+int nrxh_get_brlen_scalers(void *hv, double *out) {
+  return guarded([&] {
+    const FakeTreeinfo &ti = *H(hv)->ann.fake_treeinfo;
+    for (unsigned p = 0; p < ti.partition_count; ++p) out[p] = p < ti.brlen_scalers.size() ? ti.brlen_scalers[p] : 1.0;
+  });
+}
+int nrxh_get_pinv(void *hv, unsigned p, double *out) {
+  return guarded([&] { *out = H(hv)->ann.fake_treeinfo->partitions.at(p).prop_invar; });
+}
 int nrxh_set_brlen_scaler(void *hv, unsigned p, double scaler) {
   return guarded([&] { set_brlen_scaler(H(hv)->ann, p, scaler); });
 }

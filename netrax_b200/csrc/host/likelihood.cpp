@@ -322,9 +322,11 @@ void init_annotated_network(AnnotatedNetwork &ann, const std::vector<PartitionIn
     ti.partitions.push_back(m);
     descs[p] = nrx_partition_desc{m.states, m.rate_cats, m.sites, (uint32_t)nw.num_tips(), (uint32_t)nw.num_branches() + 1};
   }
+  ann.pattern_weight_sums.assign(P, 0.0);   // pll_partition_t::pattern_weight_sum of this shard
+  for (unsigned p = 0; p < P; ++p)
+    for (unsigned i = 0; i < parts[p].model.sites; ++i) ann.pattern_weight_sums[p] += parts[p].pattern_weights ? parts[p].pattern_weights[i] : 1;
   if (ann.total_num_sites == 0)
-    for (unsigned p = 0; p < P; ++p)
-      for (unsigned i = 0; i < parts[p].model.sites; ++i) ann.total_num_sites += parts[p].pattern_weights ? parts[p].pattern_weights[i] : 1;
+    for (unsigned p = 0; p < P; ++p) ann.total_num_sites += (size_t)ann.pattern_weight_sums[p];
   ann.engine = nrx_engine_create(descs.data(), P, device);
   if (!ann.engine) throw std::runtime_error(std::string("nrx_engine_create: ") + nrx_last_error());
   for (unsigned p = 0; p < P; ++p) {

@@ -224,8 +224,10 @@ struct AnnotatedNetwork {  // src/graph/AnnotatedNetwork.hpp:42-89
   bool cached_logl_valid = false;
   size_t total_num_model_parameters = 0;  // parted_msa->total_free_model_params() (src/RaxmlWrapper.cpp:682-684); caller-set
   size_t total_num_sites = 0;             // parted_msa->total_sites(); default: sum of this process's pattern weights
+  std::vector<double> pattern_weight_sums;   // [partition] pll_partition_t::pattern_weight_sum of this site shard
+  double pattern_weight_sum(unsigned p) const { return pattern_weight_sums.at(p); }
   /* optimize_params (src/optimization/ModelOptimization.cpp:25-97): pll-modules' model optimisers in a NetRAX build; when
-   * unset, optimizeModel runs the one step this repo implements itself, optimize_alpha */
+   * unset, optimizeModel runs the steps this repo implements itself: optimize_alpha, then optimize_pinv */
   double (*optimize_params_cb)(AnnotatedNetwork &) = nullptr;
 
   /* device side */
@@ -298,6 +300,12 @@ void setAlpha(AnnotatedNetwork &ann_network, unsigned partition, double alpha);
 void setPinv(AnnotatedNetwork &ann_network, unsigned partition, double prop_invar);   // pll_update_invariant_sites_proportion (LIBPLL/models.c:495-543)
 /* the ALPHA step of optimize_params (src/optimization/ModelOptimization.cpp:56-65); defaults = PLLMOD_OPT_MIN/MAX_ALPHA, RAXML_PARAM_EPSILON */
 double optimize_alpha(AnnotatedNetwork &ann_network, double min_alpha = 0.0201, double max_alpha = 100.0, double tolerance = 0.001);
+/* the PINV step of optimize_params (src/optimization/ModelOptimization.cpp:67-76): pllmod_algo_opt_onedim_treeinfo(PLLMOD_OPT_PARAM_PINV)
+ * over the partitions with +I (PLLMOD_OPT_MIN_PINV / MAX_PINV / RAXML_PARAM_EPSILON) */
+double optimize_pinv(AnnotatedNetwork &ann_network, double min_pinv = 0.0, double max_pinv = 0.99, double tolerance = 0.001);
+/* pllmod_algo_opt_brlen_scalers_treeinfo (PLLMOD/algorithm/pllmod_algorithm.c:869-960); returns the log-likelihood */
+double optimize_brlen_scalers(AnnotatedNetwork &ann_network, double min_scaler, double max_scaler, double min_brlen, double max_brlen, double lh_epsilon);
+double optimize_scalers(AnnotatedNetwork &ann_network, bool silent = true);   // src/optimization/BranchLengthOptimization.cpp:581-599; returns the BIC
 
 /* ---- src/likelihood/ComplexityScoring.hpp:7-13 (what the search calls a network's score) ------------------------- */
 size_t get_param_count(AnnotatedNetwork &ann_network);

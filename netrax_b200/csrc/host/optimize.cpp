@@ -331,23 +331,38 @@ void setPinv(AnnotatedNetwork &ann, unsigned p, double prop_invar) {
   pushPartitionModel(ann, p);   // P-matrices depend on rates / (1 - pinv): everything of the partition is stale
 }
 
-double optimize_alpha(AnnotatedNetwork &ann, double min_alpha, double max_alpha, double tolerance) {
+/* pllmod_algo_opt_onedim_treeinfo (PLLMOD/algorithm/pllmod_algorithm.c:743-866): ONE Brent search per partition, all of them
+ * advanced together, for the parameter kinds pll-modules supports there: ALPHA (treeinfo_set_alpha :566-587), PINV
+ * (treeinfo_set_pinv :601-622) and BRANCH_LEN_SCALER (treeinfo_set_brlen_scaler :636-647). */
+enum OnedimParam { ONEDIM_ALPHA, ONEDIM_PINV, ONEDIM_BRLEN_SCALER };
+
+static double optimize_onedim(AnnotatedNetwork &ann, OnedimParam param, double min_value, double max_value, double tolerance) {
   FakeTreeinfo &ti = *ann.fake_treeinfo;
-  std::vector<unsigned> parts;   // params_to_optimize & PLLMOD_OPT_PARAM_ALPHA
-  for (unsigned p = 0; p < ti.partition_count; ++p) if (ti.partitions[p].alpha > 0.0) parts.push_back(p);
+  std::vector<unsigned> parts;   // params_to_optimize[p] & param
+  for (unsigned p = 0; p < ti.partition_count; ++p) {
+    const PartitionModel &m = ti.partitions[p];
+    if (param == ONEDIM_ALPHA ? m.alpha > 0.0 : param == ONEDIM_PINV ? m.prop_invar > 0.0 : true) parts.push_back(p);
+  }
+  if (param == ONEDIM_BRLEN_SCALER && ti.brlen_scalers.size() < ti.partition_count) ti.brlen_scalers.resize(ti.partition_count, 1.0);
+  auto get = [&](unsigned p) { return param == ONEDIM_ALPHA ? ti.partitions[p].alpha : param == ONEDIM_PINV ? ti.partitions[p].prop_invar : ti.brlen_scalers[p]; };
+  auto set = [&](unsigned p, double x) {
+    if (param == ONEDIM_ALPHA) setAlpha(ann, p, x);
+    else if (param == ONEDIM_PINV) setPinv(ann, p, x);
+    else set_brlen_scaler(ann, p, x);
+  };
   const size_t n = parts.size();
   if (n) {
-    std::vector<double> xguess(n), ax(n), cx(n), lmin(n, min_alpha), lmax(n, max_alpha);
-    for (size_t j = 0; j < n; ++j) xguess[j] = ti.partitions[parts[j]].alpha;
+    std::vector<double> xguess(n), ax(n), cx(n), lmin(n, min_value), lmax(n, max_value);
+    for (size_t j = 0; j < n; ++j) xguess[j] = get(parts[j]);
     std::vector<char> converged(n, 0);
     bool all_converged = false;
-    // target_func_onedim_treeinfo: set the unconverged partitions' alphas, one full evaluation, per-partition scores
+    // target_func_onedim_treeinfo: set the unconverged partitions' parameters, one full evaluation, per-partition scores
     auto target = [&](const std::vector<double> &x, bool with_flags) {
       double unconverged = 0.0;
       for (size_t j = 0; j < n; ++j) {
         if (with_flags && converged[j]) continue;
         unconverged = 1.0;
-        setAlpha(ann, parts[j], x[j]);
+        set(parts[j], x[j]);
       }
       computeLoglikelihood(ann, 0, 1);
       std::vector<double> fx(n);
@@ -376,7 +391,7 @@ double optimize_alpha(AnnotatedNetwork &ann, double min_alpha, double max_alpha,
     std::vector<double> u(n);
     for (int iter = 0; iter <= BrentState::kItmax; ++iter) {
       for (size_t j = 0; j < n; ++j) u[j] = st[j].u;
-      const std::vector<double> fu = target(u, true);   // with every partition converged this sets no alpha but still evaluates, as the reference does
+      const std::vector<double> fu = target(u, true);   // with every partition converged this sets nothing but still evaluates, as the reference does
       const bool iterate = !all_converged;
       for (size_t j = 0; j < n; ++j)
         if (!converged[j]) converged[j] = !st[j].absorb(fu[j]);
@@ -387,6 +402,83 @@ double optimize_alpha(AnnotatedNetwork &ann, double min_alpha, double max_alpha,
     target(xopt, false);
   }
   return computeLoglikelihood(ann, 0, 1);
+}
+
+double optimize_alpha(AnnotatedNetwork &ann, double min_alpha, double max_alpha, double tolerance) {
+  return optimize_onedim(ann, ONEDIM_ALPHA, min_alpha, max_alpha, tolerance);
+}
+
+/* the PINV step of optimize_params (src/optimization/ModelOptimization.cpp:67-76): partitions with +I */
+double optimize_pinv(AnnotatedNetwork &ann, double min_pinv, double max_pinv, double tolerance) {
+  return optimize_onedim(ann, ONEDIM_PINV, min_pinv, max_pinv, tolerance);
+}
+
+/* pllmod_algo_opt_brlen_scalers_treeinfo (PLLMOD/algorithm/pllmod_algorithm.c:869-960) on the fake treeinfo (no subnodes: the
+ * `else` branches that work on branch_lengths[0]).  Returns the log-likelihood. */
+double optimize_brlen_scalers(AnnotatedNetwork &ann, double min_scaler, double max_scaler, double min_brlen, double max_brlen, double lh_epsilon) {
+  FakeTreeinfo &ti = *ann.fake_treeinfo;
+  if (ti.brlen_linkage != PLLMOD_COMMON_BRLEN_SCALED) throw std::runtime_error("Branch length scaler optimization works only in scaled branch length mode.");
+  const unsigned P = ti.partition_count;
+  const size_t E = ann.network.num_branches();
+  if (ti.brlen_scalers.size() < P) ti.brlen_scalers.resize(P, 1.0);
+  const double old_loglh = computeLoglikelihood(ann, 0, 1);
+  const std::vector<double> old_scalers = ti.brlen_scalers, old_brlen = ti.linked_branch_lengths;
+  auto scale_branches_all = [&](double f) {   // pllmod_treeinfo_scale_branches_all (PLLMOD/tree/treeinfo.c:1132-1155): no invalidation
+    for (size_t e = 0; e < E; ++e) { ti.linked_branch_lengths[e] *= f; for (auto &b : ti.branch_lengths) b[e] = ti.linked_branch_lengths[e]; }
+  };
+  {  // fix_brlen_scalers (:649-706): force the scalers into [min, max], branches scaled by the inverse
+    double lo = ti.brlen_scalers[0], hi = ti.brlen_scalers[0];
+    for (unsigned p = 0; p < P; ++p) { lo = std::min(lo, ti.brlen_scalers[p]); hi = std::max(hi, ti.brlen_scalers[p]); }
+    if (lo < min_scaler || hi > max_scaler) {
+      const double g = lo < min_scaler ? min_scaler / lo : max_scaler / hi;
+      for (unsigned p = 0; p < P; ++p) ti.brlen_scalers[p] *= g;
+      scale_branches_all(1.0 / g);
+    }
+  }
+  double loglh = optimize_onedim(ann, ONEDIM_BRLEN_SCALER, min_scaler, max_scaler, lh_epsilon);
+  {  // pllmod_treeinfo_normalize_brlen_scalers (PLLMOD/tree/treeinfo.c:1186-1227): site-weighted mean scaler = 1
+    double sum_scalers = 0., sum_sites = 0.;
+    for (unsigned p = 0; p < P; ++p) {
+      const double pat_sites = ann.pattern_weight_sum(p);   // this shard's pattern_weight_sum
+      sum_sites += pat_sites;
+      sum_scalers += ti.brlen_scalers[p] * pat_sites;
+    }
+    if (ti.parallel_reduce_cb) {
+      ti.parallel_reduce_cb(ti.parallel_context, &sum_scalers, 1, PLLMOD_COMMON_REDUCE_SUM);
+      ti.parallel_reduce_cb(ti.parallel_context, &sum_sites, 1, PLLMOD_COMMON_REDUCE_SUM);
+    }
+    const double mean_rate = sum_scalers / sum_sites;
+    scale_branches_all(mean_rate);
+    for (unsigned p = 0; p < P; ++p) ti.brlen_scalers[p] /= mean_rate;
+  }
+  bool brlen_fixed = false;   // fix_brlen_minmax (:708-740)
+  for (size_t e = 0; e < E; ++e) {
+    double &b = ti.linked_branch_lengths[e];
+    if (b < min_brlen) { b = min_brlen; brlen_fixed = true; }
+    else if (b > max_brlen) { b = max_brlen; brlen_fixed = true; }
+    for (auto &pb : ti.branch_lengths) pb[e] = b;
+  }
+  if (brlen_fixed) {
+    loglh = computeLoglikelihood(ann, 0, 1);
+    if (loglh < old_loglh) {   // revert optimization and restore old values
+      ti.brlen_scalers = old_scalers;
+      ti.linked_branch_lengths = old_brlen;
+      for (auto &pb : ti.branch_lengths) pb = old_brlen;
+      loglh = computeLoglikelihood(ann, 0, 1);
+    }
+  }
+  return loglh;
+}
+
+/* optimize_scalers (src/optimization/BranchLengthOptimization.cpp:581-599) */
+double optimize_scalers(AnnotatedNetwork &ann, bool) {
+  const double old_score = scoreNetwork(ann);
+  if (ann.options.brlen_linkage == PLLMOD_COMMON_BRLEN_SCALED && ann.fake_treeinfo->partition_count > 1) {
+    optimize_brlen_scalers(ann, 0.01 /* RAXML_BRLEN_SCALER_MIN */, 100. /* RAXML_BRLEN_SCALER_MAX */, ann.options.brlen_min, ann.options.brlen_max,
+                           0.001 /* RAXML_PARAM_EPSILON */);
+    return scoreNetwork(ann);
+  }
+  return old_score;
 }
 
 /* ---- src/likelihood/ComplexityScoring.cpp:7-67 --------------------------------------------------------------------- */
@@ -434,13 +526,13 @@ void optimizeBranches(AnnotatedNetwork &ann, double brlen_smooth_factor, bool, b
   optimize_branches(ann, max_iters, max_iters, -1 /* PLLMOD_OPT_BRLEN_OPTIMIZE_ALL */, restricted_total_iters);
   const double new_score = scoreNetwork(ann);
   if (new_score - old_score > 1E-3) throw std::runtime_error("Complete brlenopt made BIC worse");
-  // optimize_scalers (:37): only for scaled branch-length linkage, which this engine rejects
+  optimize_scalers(ann, true);  // :37 (a no-op unless the linkage is scaled and there are several partitions)
 }
 
 void optimizeModel(AnnotatedNetwork &ann, bool) {  // :72-84
   scoreNetwork(ann);
   if (ann.optimize_params_cb) ann.optimize_params_cb(ann);
-  else optimize_alpha(ann);
+  else { optimize_alpha(ann); optimize_pinv(ann); }   // the ALPHA and PINV steps of optimize_params, in its order
   scoreNetwork(ann);
 }
 

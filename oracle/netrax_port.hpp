@@ -229,6 +229,8 @@ struct AnnotatedNetwork {  // SRC/graph/AnnotatedNetwork.hpp:42-89 (fields the p
   std::vector<std::vector<ABuf<unsigned>>> pseudo_scaler;   // [node][partition]
   std::vector<ABuf<double>> tmp_clv_1, tmp_clv_2, tmp_clv_3; // [partition]
   size_t total_num_model_parameters = 0, total_num_sites = 0;  // SRC/graph/AnnotatedNetwork.hpp:47-48
+  std::vector<double> pinvs;   // partition->prop_invar[param_indices[p][0]] as last set (0 = no +I)
+  std::vector<double> pattern_weight_sums;  // [partition] pll_partition_t::pattern_weight_sum
   std::vector<double> alphas;  // fake_treeinfo->alphas (0 = no Gamma shape attached to the partition's rates)
   double cached_logl = 0;
   bool cached_logl_valid = false;
@@ -280,5 +282,8 @@ void setBrlenScaler(AnnotatedNetwork &ann, unsigned partition, double scaler);
 void setSubmodels(AnnotatedNetwork &ann, unsigned partition, unsigned n, const unsigned *cat_model, const double *freqs, const double *subst);
 void setAlpha(AnnotatedNetwork &ann, unsigned partition, double alpha);   // treeinfo_set_alpha (PLLMOD/algorithm/pllmod_algorithm.c:566-587)
 double optimize_alpha(AnnotatedNetwork &ann, double min_alpha, double max_alpha, double tolerance);  // pllmod_algo_opt_onedim_treeinfo(ALPHA)
+double optimize_pinv(AnnotatedNetwork &ann, double min_pinv, double max_pinv, double tolerance);     // pllmod_algo_opt_onedim_treeinfo(PINV)
+double optimize_brlen_scalers(AnnotatedNetwork &ann, double min_scaler, double max_scaler, double min_brlen, double max_brlen, double lh_epsilon);
+double optimize_scalers(AnnotatedNetwork &ann);  // SRC/optimization/BranchLengthOptimization.cpp:581-599; returns the BIC
 
 }  // namespace orc

@@ -4,6 +4,9 @@
  * Restatement of the immediate callers of the likelihood path (SRC = /root/reference/src):
  *   optimize_branch / optimize_branches      SRC/optimization/BranchLengthOptimization.cpp:63-156,165-241,285-476,567-576
  *   optimize_reticulation(s)                 SRC/optimization/ReticulationOptimization.cpp:40-46,68-117
+ *   optimize_pinv / optimize_scalers         the PINV step (SRC/optimization/ModelOptimization.cpp:67-76) and
+ *                                            pllmod_algo_opt_brlen_scalers_treeinfo (pllmod_algorithm.c:869-960) behind
+ *                                            SRC/optimization/BranchLengthOptimization.cpp:581-599
  *   optimize_alpha                           the ALPHA step of optimize_params (SRC/optimization/ModelOptimization.cpp:56-65) =
  *                                            pllmod_algo_opt_onedim_treeinfo (PLLMOD/algorithm/pllmod_algorithm.c:743-866) with
  *                                            target_func_onedim_treeinfo (algo_callback.c:295-363) and treeinfo_set_alpha (:566-587)
@@ -197,6 +200,8 @@ double optimize_reticulations(AnnotatedNetwork &ann, int max_iters) {  // :102-1
 }
 
 void setPinv(AnnotatedNetwork &ann, unsigned p, double prop_invar) {
+  if (ann.pinvs.size() < ann.partitionCount()) ann.pinvs.resize(ann.partitionCount(), 0.0);
+  ann.pinvs[p] = prop_invar;
   ann.backend->setPinv(p, prop_invar);
   for (auto &v : ann.pmatrix_valid[p]) v = 0;
   invalidateAllCLVs(ann);
@@ -230,16 +235,25 @@ void setAlpha(AnnotatedNetwork &ann, unsigned p, double alpha) {
 }
 
 namespace {
-struct AlphaOptParams { AnnotatedNetwork *ann; std::vector<unsigned> parts; };
+/* the three parameter kinds pllmod_algo_opt_onedim_treeinfo accepts (pllmod_algorithm.c:830-855) with their setters:
+ * treeinfo_set_alpha (:566-587), treeinfo_set_pinv (:601-622), treeinfo_set_brlen_scaler (:636-647) */
+enum OnedimParam { ONEDIM_ALPHA, ONEDIM_PINV, ONEDIM_BRLEN_SCALER };
+struct OnedimOptParams { AnnotatedNetwork *ann; OnedimParam param; std::vector<unsigned> parts; };
 
-double target_func_onedim_alpha(void *p, double *x, double *fx, int *converged) {  // algo_callback.c:295-363
-  AlphaOptParams *q = static_cast<AlphaOptParams *>(p);
+void onedimSet(AnnotatedNetwork &ann, OnedimParam param, unsigned p, double x) {
+  if (param == ONEDIM_ALPHA) setAlpha(ann, p, x);
+  else if (param == ONEDIM_PINV) setPinv(ann, p, x);
+  else ann.brlen_scalers.at(p) = x;   // no invalidation: the evaluation below runs with incremental = 0, which refreshes every P-matrix
+}
+
+double target_func_onedim(void *p, double *x, double *fx, int *converged) {  // algo_callback.c:295-363
+  OnedimOptParams *q = static_cast<OnedimOptParams *>(p);
   AnnotatedNetwork &ann = *q->ann;
   double score = -std::numeric_limits<double>::infinity(), unconverged_flag = 0.;
   for (size_t j = 0; j < q->parts.size(); ++j) {
     if (converged && converged[j]) continue;
     unconverged_flag = 1.;
-    if (x) setAlpha(ann, q->parts[j], x[j]);
+    if (x) onedimSet(ann, q->param, q->parts[j], x[j]);
   }
   if (x) score = -1 * computeLoglikelihood(ann, 0, 1);   // pllmod_treeinfo_compute_loglh(treeinfo, 0)
   if (fx) for (size_t j = 0; j < q->parts.size(); ++j) fx[j] = -1 * ann.partition_loglh[q->parts[j]];
@@ -249,24 +263,94 @@ double target_func_onedim_alpha(void *p, double *x, double *fx, int *converged) 
   }
   return score;
 }
-}  // namespace
 
-double optimize_alpha(AnnotatedNetwork &ann, double min_alpha, double max_alpha, double tolerance) {  // pllmod_algorithm.c:743-818
-  AlphaOptParams q{&ann, {}};
-  if (ann.alphas.size() < ann.partitionCount()) ann.alphas.resize(ann.partitionCount(), 0.0);
-  for (unsigned p = 0; p < ann.partitionCount(); ++p) if (ann.alphas[p] > 0.0) q.parts.push_back(p);  // params_to_optimize & ALPHA
+double optimize_onedim(AnnotatedNetwork &ann, OnedimParam param, double min_value, double max_value, double tolerance) {  // pllmod_algorithm.c:743-818
+  OnedimOptParams q{&ann, param, {}};
+  const unsigned P = ann.partitionCount();
+  if (ann.alphas.size() < P) ann.alphas.resize(P, 0.0);
+  if (ann.pinvs.size() < P) ann.pinvs.resize(P, 0.0);
+  if (param == ONEDIM_BRLEN_SCALER && ann.brlen_scalers.size() < P) ann.brlen_scalers.resize(P, 1.0);
+  for (unsigned p = 0; p < P; ++p)   // params_to_optimize[p] & param: raxml-ng sets ALPHA for +G, PINV for +I, the scaler bit under scaled linkage
+    if (param == ONEDIM_ALPHA ? ann.alphas[p] > 0.0 : param == ONEDIM_PINV ? ann.pinvs[p] > 0.0 : true) q.parts.push_back(p);
   if (!q.parts.empty()) {
     std::vector<double> vals;
-    for (unsigned p : q.parts) vals.push_back(ann.alphas[p]);
+    for (unsigned p : q.parts) vals.push_back(param == ONEDIM_ALPHA ? ann.alphas[p] : param == ONEDIM_PINV ? ann.pinvs[p] : ann.brlen_scalers[p]);
     std::vector<int> mask(q.parts.size(), 1);
-    MIN_BRENT_MULTI((unsigned)q.parts.size(), mask.data(), &min_alpha, vals.data(), &max_alpha, tolerance, vals.data(), nullptr, nullptr, &q,
-                    &target_func_onedim_alpha, 1);
+    MIN_BRENT_MULTI((unsigned)q.parts.size(), mask.data(), &min_value, vals.data(), &max_value, tolerance, vals.data(), nullptr, nullptr, &q,
+                    &target_func_onedim, 1);
   }
   return computeLoglikelihood(ann, 0, 1);
 }
+}  // namespace
+
+double optimize_alpha(AnnotatedNetwork &ann, double min_alpha, double max_alpha, double tolerance) {
+  return optimize_onedim(ann, ONEDIM_ALPHA, min_alpha, max_alpha, tolerance);
+}
+
+double optimize_pinv(AnnotatedNetwork &ann, double min_pinv, double max_pinv, double tolerance) {  // SRC/optimization/ModelOptimization.cpp:67-76
+  return optimize_onedim(ann, ONEDIM_PINV, min_pinv, max_pinv, tolerance);
+}
+
+/* pllmod_algo_opt_brlen_scalers_treeinfo (PLLMOD/algorithm/pllmod_algorithm.c:869-960) as it runs on NetRAX's fake treeinfo
+ * (subnode_count == 0: the branches live in branch_lengths[0]) */
+double optimize_brlen_scalers(AnnotatedNetwork &ann, double min_scaler, double max_scaler, double min_brlen, double max_brlen, double lh_epsilon) {
+  if (ann.options.brlen_linkage != BRLEN_SCALED) throw std::runtime_error("Branch length scaler optimization works only in scaled branch length mode.");
+  const unsigned P = ann.partitionCount();
+  const size_t E = ann.network.edges.size();
+  if (ann.brlen_scalers.size() < P) ann.brlen_scalers.resize(P, 1.0);
+  const double old_loglh = computeLoglikelihood(ann, 0, 1);
+  const std::vector<double> old_scalers = ann.brlen_scalers, old_brlen = ann.linked_branch_lengths;
+  auto setLinked = [&](size_t e, double v) {   // branch_lengths[0][e] of the reference: the one array every partition reads; no invalidation
+    ann.linked_branch_lengths[e] = v;
+    for (auto &b : ann.branch_lengths) b[e] = v;
+  };
+  auto scaleBranchesAll = [&](double f) {   // pllmod_treeinfo_scale_branches_all (PLLMOD/tree/treeinfo.c:1132-1155)
+    for (size_t e = 0; e < E; ++e) setLinked(e, ann.linked_branch_lengths[e] * f);
+  };
+  {  // fix_brlen_scalers (:649-706)
+    double lowest = ann.brlen_scalers[0], highest = ann.brlen_scalers[0];
+    for (double s : ann.brlen_scalers) { if (s < lowest) lowest = s; if (s > highest) highest = s; }
+    if (lowest < min_scaler || highest > max_scaler) {
+      const double global_scaler = lowest < min_scaler ? min_scaler / lowest : max_scaler / highest;
+      for (double &s : ann.brlen_scalers) s *= global_scaler;
+      scaleBranchesAll(1.0 / global_scaler);
+    }
+  }
+  double loglh = optimize_onedim(ann, ONEDIM_BRLEN_SCALER, min_scaler, max_scaler, lh_epsilon);
+  {  // pllmod_treeinfo_normalize_brlen_scalers (PLLMOD/tree/treeinfo.c:1186-1227)
+    double sum_scalers = 0., sum_sites = 0.;
+    for (unsigned p = 0; p < P; ++p) {
+      const double pat_sites = ann.pattern_weight_sums.at(p);
+      sum_sites += pat_sites;
+      sum_scalers += ann.brlen_scalers[p] * pat_sites;
+    }
+    if (ann.parallel_reduce_cb) {
+      ann.parallel_reduce_cb(ann.parallel_context, &sum_scalers, 1, 0);
+      ann.parallel_reduce_cb(ann.parallel_context, &sum_sites, 1, 0);
+    }
+    const double mean_rate = sum_scalers / sum_sites;
+    scaleBranchesAll(mean_rate);
+    for (double &s : ann.brlen_scalers) s /= mean_rate;
+  }
+  bool brlen_fixed = false;   // fix_brlen_minmax (:708-740)
+  for (size_t e = 0; e < E; ++e) {
+    const double b = ann.linked_branch_lengths[e];
+    if (b < min_brlen) { setLinked(e, min_brlen); brlen_fixed = true; }
+    else if (b > max_brlen) { setLinked(e, max_brlen); brlen_fixed = true; }
+  }
+  if (brlen_fixed) {
+    loglh = computeLoglikelihood(ann, 0, 1);
+    if (loglh < old_loglh) {
+      ann.brlen_scalers = old_scalers;
+      for (size_t e = 0; e < E; ++e) setLinked(e, old_brlen[e]);
+      loglh = computeLoglikelihood(ann, 0, 1);
+    }
+  }
+  return loglh;
+}
 
 /* ---- LH/ComplexityScoring.cpp:7-67 and SRC/optimization/Optimization.cpp:17-214, with optimize_params reduced to its ALPHA
- * step (the only model step restated; the product's default optimize_params hook does the same) ---------------------- */
+ * and PINV steps (the model steps restated; the product's default optimize_params hook does the same) ---------------------- */
 double scoreNetwork(AnnotatedNetwork &ann) {
   const double logl = computeLoglikelihood(ann, 1, 1);
   size_t k = ann.total_num_model_parameters + ann.network.num_reticulations();
@@ -281,16 +365,27 @@ double scoreNetwork(AnnotatedNetwork &ann) {
   return bic;
 }
 
+double optimize_scalers(AnnotatedNetwork &ann) {  // SRC/optimization/BranchLengthOptimization.cpp:581-599
+  const double old_score = scoreNetwork(ann);
+  if (ann.options.brlen_linkage == BRLEN_SCALED && ann.partitionCount() > 1) {
+    optimize_brlen_scalers(ann, 0.01 /* RAXML_BRLEN_SCALER_MIN */, 100. /* RAXML_BRLEN_SCALER_MAX */, ann.opt.brlen_min, ann.opt.brlen_max, 0.001 /* RAXML_PARAM_EPSILON */);
+    return scoreNetwork(ann);
+  }
+  return old_score;
+}
+
 namespace {
 void optimizeBranches(AnnotatedNetwork &ann, double brlen_smooth_factor) {  // Optimization.cpp:17-38
   const double old_score = scoreNetwork(ann);
   const int max_iters = (int)(brlen_smooth_factor * 32);
   optimize_branches(ann, max_iters, max_iters, -1, OPT_NEWTON_RAPHSON, false);
   if (scoreNetwork(ann) - old_score > 1E-3) throw std::runtime_error("Complete brlenopt made BIC worse");
+  optimize_scalers(ann);  // :37
 }
 void optimizeModel(AnnotatedNetwork &ann) {  // :72-84
   scoreNetwork(ann);
   optimize_alpha(ann, 0.0201, 100., 0.001);  // PLLMOD_OPT_MIN_ALPHA, PLLMOD_OPT_MAX_ALPHA, RAXML_PARAM_EPSILON
+  optimize_pinv(ann, 0.0, 0.99, 0.001);      // PLLMOD_OPT_MIN_PINV, PLLMOD_OPT_MAX_PINV
   scoreNetwork(ann);
 }
 void optimizeReticulationProbs(AnnotatedNetwork &ann) {  // :91-108

@@ -85,6 +85,7 @@ int orc_add_partition(void *hv, unsigned states, unsigned rate_cats, unsigned si
     if (weights) d.pattern_weights.assign(weights, weights + sites);
     else d.pattern_weights.assign(sites, 1);
     for (unsigned w : d.pattern_weights) h->ann.total_num_sites += w;
+    { double sum = 0; for (unsigned w : d.pattern_weights) sum += w; h->ann.pattern_weight_sums.push_back(sum); }
     unsigned tips = h->ann.network.num_tips;
     d.tip_masks.resize(tips);
     for (unsigned t = 0; t < tips; ++t) d.tip_masks[t].assign(tip_masks + (size_t)t * sites, tip_masks + (size_t)(t + 1) * sites);
@@ -389,6 +390,22 @@ int orc_get_alpha(void *hv, unsigned p, double *alpha) {
 int orc_optimize_alpha(void *hv, double min_alpha, double max_alpha, double tolerance, double *final_logl) {
   Handle *h = static_cast<Handle *>(hv);
   return guarded([&] { double l = optimize_alpha(h->ann, min_alpha, max_alpha, tolerance); if (final_logl) *final_logl = l; });
+}
+int orc_optimize_pinv(void *hv, double min_pinv, double max_pinv, double tolerance, double *final_logl) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] { double l = optimize_pinv(h->ann, min_pinv, max_pinv, tolerance); if (final_logl) *final_logl = l; });
+}
+int orc_optimize_scalers(void *hv, double *bic_score) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] { double b = optimize_scalers(h->ann); if (bic_score) *bic_score = b; });
+}
+int orc_get_brlen_scalers(void *hv, double *out) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] { for (unsigned p = 0; p < h->ann.partitionCount(); ++p) out[p] = p < h->ann.brlen_scalers.size() ? h->ann.brlen_scalers[p] : 1.0; });
+}
+int orc_get_pinv(void *hv, unsigned p, double *out) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] { *out = p < h->ann.pinvs.size() ? h->ann.pinvs[p] : 0.0; });
 }
 int orc_optimize_reticulations(void *hv, int max_iters, double *final_logl) {
   Handle *h = static_cast<Handle *>(hv);

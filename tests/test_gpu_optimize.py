@@ -134,3 +134,63 @@ def test_optimize_all_non_topology_matches_oracle(variant):
     assert g.get_alpha(0) == pytest.approx(o.get_alpha(0), rel=1e-4)
     np.testing.assert_allclose(g.branch_lengths(), o.branch_lengths(), rtol=1e-4, atol=2e-6)
     g.close()
+
+
+def test_optimize_pinv_matches_oracle():
+    """The PINV step of optimize_params (ModelOptimization.cpp:67-76) on the device — every Brent iterate rescales the
+    rates by 1 / (1 - pinv) and re-evaluates with the invariant-site terms — against pll-modules' real minimiser over
+    libpll's +I kernels."""
+    from oracle import oracle
+    if not oracle.have_ref():
+        pytest.skip("+I is restated only through the reference backend")
+    from test_oracle_optimize import _pinv_case
+    net, parts = _pinv_case()
+    g, o = _pair(net, parts)
+    for eng in (g, o):
+        eng.set_pinv(0, 0.05)
+    l0g, l0o = g.computeLoglikelihood(0, 1), o.computeLoglikelihood(0, 1)
+    assert l0g == pytest.approx(l0o, rel=1e-10)
+    lg, lo = g.optimize_pinv(), o.optimize_pinv()
+    assert lg >= l0g - 1e-6
+    assert lg == pytest.approx(lo, rel=1e-9)
+    assert g.get_pinv(0) == pytest.approx(o.get_pinv(0), rel=1e-4)
+    assert g.get_pinv(1) == 0.0
+    assert g.computeLoglikelihood(1, 1) == pytest.approx(lg, rel=1e-13)
+    g.close()
+
+
+@pytest.mark.parametrize("variant", [AVERAGE, BEST])
+def test_optimize_scalers_matches_oracle(variant):
+    """optimize_scalers (BranchLengthOptimization.cpp:581-599 -> pllmod_algo_opt_brlen_scalers_treeinfo): scalers forced
+    into range, one Brent search per partition (each iterate refreshes that partition's P-matrices from scaler x linked
+    length and replays the evaluation plan), normalisation to a site-weighted mean of 1."""
+    from netrax_b200._capi import SCALED
+    from test_oracle_netrax import scaled_linkage_case
+    net, parts, _ = scaled_linkage_case()
+    g, o = _pair(net, parts, variant=variant, linkage=SCALED)
+    for eng in (g, o):
+        for p, s in enumerate([3.0, 0.3, 150.0]):
+            eng.set_brlen_scaler(p, s)
+        eng.set_scoring_sizes(9)
+    b0g, b0o = g.scoreNetwork(), o.scoreNetwork()
+    assert b0g == pytest.approx(b0o, rel=1e-10)
+    bg, bo = g.optimize_scalers(), o.optimize_scalers()
+    assert bg <= b0g
+    assert bg == pytest.approx(bo, rel=1e-9)
+    np.testing.assert_allclose(g.brlen_scalers(), o.brlen_scalers(), rtol=1e-4)
+    np.testing.assert_allclose(g.branch_lengths(), o.branch_lengths(), rtol=1e-4)
+    wsum = np.array([float(p.pattern_weights.sum()) for p in parts])
+    assert float((g.brlen_scalers() * wsum).sum() / wsum.sum()) == pytest.approx(1.0, rel=1e-12)
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=1e-10)
+    g.close()
+
+
+def test_optimize_scalers_is_a_noop_without_scaled_linkage():
+    net = random_network(8, 1, seed=4)
+    m, w = simulate_alignment(net, 300, seed=4)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    g = _gpu(net, [part, part])
+    b0 = g.scoreNetwork()
+    assert g.optimize_scalers() == b0
+    np.testing.assert_array_equal(g.brlen_scalers(), [1.0, 1.0])
+    g.close()

@@ -220,3 +220,81 @@ def test_optimize_all_non_topology_improves_bic_and_flavours_agree():
     if "ref" in res:
         assert res["port"][0] == pytest.approx(res["ref"][0], rel=1e-9)
         assert res["port"][1] == pytest.approx(res["ref"][1], rel=1e-5)
+
+
+# ------------------------------------------------------------------------- model loop: +I and the branch-length scalers
+def _pinv_case():
+    net = random_network(10, 2, seed=6)
+    parts = []
+    for k in range(2):
+        m, w = simulate_alignment(net, 500, seed=60 + k)
+        w = w.copy()
+        if k == 0:   # pile weight on the constant columns so that +I has something to find
+            const = np.all(m == m[0:1], axis=0) & (np.bitwise_count(m[0]) == 1)
+            w[const] *= 6
+        parts.append(Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w))
+    return net, parts
+
+
+def test_optimize_pinv_reference_backend():
+    """The PINV step of optimize_params (ModelOptimization.cpp:67-76): pllmod_algo_opt_onedim_treeinfo(PINV) driven over
+    libpll's real +I kernels by pll-modules' real Brent-multi (_ref; the scalar port has no invariant-site terms, and its
+    Brent-multi restatement is pinned by the alpha test above).  Partitions without +I (pinv = 0) are not in
+    params_to_optimize and stay untouched; the end point is a maximum of the lnL in the proportion."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    net, parts = _pinv_case()
+    e = oracle.make_engine("ref", net, parts)
+    e.set_pinv(0, 0.05)
+    l0 = e.computeLoglikelihood(0, 1)
+    l1 = e.optimize_pinv()
+    assert l1 >= l0 - 1e-6
+    assert e.get_pinv(1) == 0.0
+    x = e.get_pinv(0)
+    assert 0.1 < x < 0.99   # the inflated constant columns pull the proportion up from 0.05
+    assert e.computeLoglikelihood(0, 1) == pytest.approx(l1, rel=1e-12)
+    for d in (-0.02, 0.02):
+        e.set_pinv(0, x + d)
+        assert e.computeLoglikelihood(0, 1) < l1
+    e.close()
+
+
+def test_optimize_scalers_port_equals_reference_minimiser():
+    """optimize_scalers (BranchLengthOptimization.cpp:581-599) = pllmod_algo_opt_brlen_scalers_treeinfo (pllmod_algorithm.c:
+    869-960): out-of-range scalers forced into [0.01, 100] with the branches scaled by the inverse, one Brent search per
+    partition, scalers normalised to a site-weighted mean of 1 with the branches scaled by the mean — the product
+    scaler x length, and with it the lnL, survives the normalisation."""
+    from netrax_b200._capi import SCALED
+    from test_oracle_netrax import scaled_linkage_case
+    net, parts, _ = scaled_linkage_case()
+    res = {}
+    for kind in (["port", "ref"] if oracle.have_ref() else ["port"]):
+        e = oracle.make_engine(kind, net, parts, linkage=SCALED)
+        for p, s in enumerate([3.0, 0.3, 150.0]):   # 150 > RAXML_BRLEN_SCALER_MAX: fix_brlen_scalers rescales all three
+            e.set_brlen_scaler(p, s)
+        e.set_scoring_sizes(9)
+        b0, l0 = e.scoreNetwork(), e.computeLoglikelihood(1, 1)
+        b1 = e.optimize_scalers()
+        l1 = e.computeLoglikelihood(1, 1)
+        sc, bl = e.brlen_scalers(), e.branch_lengths()
+        assert b1 <= b0 and l1 >= l0
+        wsum = np.array([float(p.pattern_weights.sum()) for p in parts])
+        assert float((sc * wsum).sum() / wsum.sum()) == pytest.approx(1.0, rel=1e-12)
+        assert e.computeLoglikelihood(0, 1) == pytest.approx(l1, rel=1e-10)   # cached value vs a full re-evaluation of the normalised state
+        res[kind] = (b1, sc, bl)
+        e.close()
+    if "ref" in res:
+        assert res["port"][0] == pytest.approx(res["ref"][0], rel=1e-9)
+        np.testing.assert_allclose(res["port"][1], res["ref"][1], rtol=1e-4)
+        np.testing.assert_allclose(res["port"][2], res["ref"][2], rtol=1e-4)
+
+
+def test_optimize_scalers_is_a_noop_without_scaled_linkage():
+    net = random_network(8, 1, seed=4)
+    m, w = simulate_alignment(net, 300, seed=4)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    e = oracle.make_engine("port", net, [part, part])
+    b0 = e.scoreNetwork()
+    assert e.optimize_scalers() == b0
+    np.testing.assert_array_equal(e.brlen_scalers(), [1.0, 1.0])
+    e.close()

@@ -23,6 +23,7 @@ uint32_t allocSlot(AnnotatedNetwork &ann);
 void releaseSlot(AnnotatedNetwork &ann, uint32_t slot);
 nrx_pair makePair(const DisplayedTreeData &a, const DisplayedTreeData &b);
 void reduceSum(AnnotatedNetwork &ann, double *data, size_t count);
+void reduceHostSum(AnnotatedNetwork &ann, double *data, size_t count);
 /* log(sum_t exp(a_t)) and friends without leaving double range (stands in for mpfr::mpreal) */
 double logSumExp(const std::vector<double> &a);
 }  // namespace detail

@@ -74,6 +74,14 @@ void reduceSum(AnnotatedNetwork &ann, double *data, size_t count) {
     ann.fake_treeinfo->parallel_reduce_cb(ann.fake_treeinfo->parallel_context, data, count, PLLMOD_COMMON_REDUCE_SUM);
 }
 
+/* SUM over site shards of values that live on the HOST (the Brent drivers' convergence flag, the scaler normalisation's
+ * weight sums): through the engine's NCCL communicator when one is attached, else through parallel_reduce_cb */
+void reduceHostSum(AnnotatedNetwork &ann, double *data, size_t count) {
+  if (ann.engine && nrx_comm_size(ann.engine) > 1) engineCheck(nrx_comm_allreduce_sum(ann.engine, data, count), "nrx_comm_allreduce_sum");
+  else if (ann.fake_treeinfo->parallel_reduce_cb)
+    ann.fake_treeinfo->parallel_reduce_cb(ann.fake_treeinfo->parallel_context, data, count, PLLMOD_COMMON_REDUCE_SUM);
+}
+
 double logSumExp(const std::vector<double> &a) {
   double m = -std::numeric_limits<double>::infinity();
   for (double x : a) m = std::max(m, x);

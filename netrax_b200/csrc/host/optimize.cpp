@@ -368,6 +368,8 @@ static double optimize_onedim(AnnotatedNetwork &ann, OnedimParam param, double m
       std::vector<double> fx(n);
       for (size_t j = 0; j < n; ++j) fx[j] = -1 * ti.partition_loglh[parts[j]];
       if (with_flags) {
+        // every shard holds a slice of EVERY partition and the reduced per-partition lnLs, so the flags already agree under an
+        // NCCL communicator; the callback is honoured because the reference calls it here
         if (ti.parallel_reduce_cb) ti.parallel_reduce_cb(ti.parallel_context, &unconverged, 1, PLLMOD_COMMON_REDUCE_SUM);
         all_converged = !(unconverged > 0.0);
       }
@@ -443,10 +445,9 @@ double optimize_brlen_scalers(AnnotatedNetwork &ann, double min_scaler, double m
       sum_sites += pat_sites;
       sum_scalers += ti.brlen_scalers[p] * pat_sites;
     }
-    if (ti.parallel_reduce_cb) {
-      ti.parallel_reduce_cb(ti.parallel_context, &sum_scalers, 1, PLLMOD_COMMON_REDUCE_SUM);
-      ti.parallel_reduce_cb(ti.parallel_context, &sum_sites, 1, PLLMOD_COMMON_REDUCE_SUM);
-    }
+    double sums[2] = {sum_scalers, sum_sites};   // the reference reduces them one after the other; one message here
+    reduceHostSum(ann, sums, 2);
+    sum_scalers = sums[0]; sum_sites = sums[1];
     const double mean_rate = sum_scalers / sum_sites;
     scale_branches_all(mean_rate);
     for (unsigned p = 0; p < P; ++p) ti.brlen_scalers[p] /= mean_rate;

@@ -111,6 +111,34 @@ def main():
             x.close()
     for x in (g, gp, g2):
         x.close()
+    # optimize_scalers under sharding: the normalisation sums scaler x pattern_weight_sum over the shards (host values,
+    # all-reduced through the engine's communicator)
+    from netrax_b200._capi import SCALED
+    net = random_network(9, 2, seed=5)
+    fulls = []
+    for i in range(3):
+        m, w = simulate_alignment(net, 150 + 40 * i, seed=5 + i)
+        fulls.append(Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w))
+    total_sites = int(sum(int(p.pattern_weights.sum()) for p in fulls))
+
+    def run_scalers(eng):
+        for p, sc in enumerate([3.0, 0.3, 150.0]):
+            eng.set_brlen_scaler(p, sc)
+        eng.set_scoring_sizes(9, total_sites)
+        return eng.optimize_scalers(), eng.brlen_scalers(), eng.branch_lengths()
+
+    gs = NetraxB200(net, [p.slice(rank * p.sites // world, (rank + 1) * p.sites // world) for p in fulls], linkage=SCALED, device=lr,
+                    comm=(fresh_uid(), rank, world))
+    bic, scal, brl = run_scalers(gs)
+    if rank == 0:
+        s = NetraxB200(net, fulls, linkage=SCALED, device=lr)
+        bic1, scal1, brl1 = run_scalers(s)
+        assert abs(bic - bic1) <= 1e-9 * abs(bic1), (bic, bic1)
+        np.testing.assert_allclose(scal, scal1, rtol=1e-5)
+        np.testing.assert_allclose(brl, brl1, rtol=1e-5)
+        case.update({"scalers": [float(x) for x in scal], "scalers_single_gpu": [float(x) for x in scal1], "bic": bic, "bic_single_gpu": bic1})
+        s.close()
+    gs.close()
     report["cases"].append(case)
     if rank == 0:
         report["ok"] = True

@@ -38,6 +38,30 @@ def _evaluate(eng, net):
     return np.concatenate([[lnl, lb, lf, d[0], d[1]], eng.partition_loglh(), np.ravel(d[2]), np.ravel(d[3])])
 
 
+def _scalers_case():
+    from netrax_b200._capi import Partition
+    from netrax_b200.synth import DNA_FREQS, GAMMA4_ALPHA05, GTR_RATES, random_network, simulate_alignment
+    net = random_network(9, 2, seed=5)
+    parts = []
+    for i in range(3):
+        m, w = simulate_alignment(net, 150 + 40 * i, seed=5 + i)
+        parts.append(Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w))
+    return net, parts
+
+
+def _optimize_scalers(eng, parts_full):
+    """optimize_scalers + the alpha step under scaled linkage: the callers whose site-sharded form needs more than the lnL
+    all-reduce (pllmod_treeinfo_normalize_brlen_scalers sums scaler x pattern_weight_sum over the shards; the Brent
+    drivers all-reduce their convergence flag)."""
+    for p, s in enumerate([3.0, 0.3, 150.0]):
+        eng.set_brlen_scaler(p, s)
+    eng.set_alpha(1, 1.3)
+    eng.set_scoring_sizes(9, int(sum(int(p.pattern_weights.sum()) for p in parts_full)))
+    bic = eng.optimize_scalers()
+    la = eng.optimize_alpha()
+    return np.concatenate([[bic, la, eng.get_alpha(1)], eng.brlen_scalers(), eng.branch_lengths()])
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     import torch
@@ -57,6 +81,13 @@ def _worker(rank, world, port, q):
         eng.set_reduce(reduce)
         out[name] = _evaluate(eng, net)
         eng.close()
+    from netrax_b200._capi import SCALED
+    net, parts = _scalers_case()
+    shard = [p.slice(rank * p.sites // world, (rank + 1) * p.sites // world) for p in parts]
+    eng = oracle.make_engine("port", net, shard, linkage=SCALED)
+    eng.set_reduce(reduce)
+    out["scalers"] = _optimize_scalers(eng, parts)
+    eng.close()
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -82,6 +113,13 @@ def test_world_size_2_gloo_sharded_equals_unsharded():
         assert np.array_equal(res[0][name], res[1][name])             # all ranks hold identical global values
         np.testing.assert_allclose(res[0][name][:3 + 2 + nparts], want[:3 + 2 + nparts], rtol=1e-12)   # lnLs: sum order only
         np.testing.assert_allclose(res[0][name], want, rtol=1e-8, atol=1e-8)                         # derivatives
+    from netrax_b200._capi import SCALED
+    net, parts = _scalers_case()
+    eng = oracle.make_engine("port", net, parts, linkage=SCALED)
+    want = _optimize_scalers(eng, parts)
+    assert np.array_equal(res[0]["scalers"], res[1]["scalers"])
+    np.testing.assert_allclose(res[0]["scalers"][:2], want[:2], rtol=1e-9)      # BIC, lnL after the alpha step
+    np.testing.assert_allclose(res[0]["scalers"][2:], want[2:], rtol=1e-5)      # alpha, scalers (mean 1 over ALL sites), branch lengths
 
 
 def test_partition_slice_covers_every_pattern_once():

@@ -128,6 +128,13 @@ int nrxh_gamma_rates(double alpha, unsigned cats, int mode, double *out);
  * — exactly what the host hands to nrx_set_model */
 int nrxh_eigen_decompose(unsigned states, const double *freqs, const double *subst, double *eigenvecs, double *inv_eigenvecs,
                          double *eigenvals);
+/* device-free: the host library's restatements of pll-modules' single-variable minimisers — pllmod_opt_minimize_newton_multi
+ * with xnum = 1 (PLLMOD/optimize/opt_algorithms.c:133-261; deriv(ctx, x, f', f'') as its deriv_func; *converged = PLL_SUCCESS /
+ * PLL_FAILURE, x holds the last iterate either way) and pllmod_opt_minimize_brent (:1404-1429; stops at convergence instead of
+ * re-evaluating the unchanged proposal up to iteration 101).  optimize_branch / optimize_reticulation run these. */
+int nrxh_minimize_newton(double xmin, double *x, double xmax, double tolerance, unsigned max_iters,
+                         void (*deriv)(void *ctx, double *x, double *f, double *df), void *ctx, int *converged);
+int nrxh_minimize_brent(double xmin, double xguess, double xmax, double xtol, double (*target)(void *ctx, double x), void *ctx, double *xopt);
 /* bench / profiling hooks */
 unsigned long long nrxh_launch_count(void *h);
 unsigned nrxh_num_slots(void *h);

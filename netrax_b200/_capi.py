@@ -401,6 +401,12 @@ class LikelihoodEngine:
         self.api.check(self.api._get_reticulation_probs(self.h, out))
         return out[: self.net.num_reticulations]
 
+    def toExtendedNewick(self, precision: Optional[int] = None) -> str:
+        """toExtendedNewick(AnnotatedNetwork&) (src/io/NetworkIO.cpp:517-523): updateNetwork (:493-508) copies the linked
+        branch lengths and the reticulation probabilities of the current (optimised) state into the network, then writes it."""
+        from .network_io import to_extended_newick
+        return to_extended_newick(self.net, self.branch_lengths(), self.reticulation_probs(), precision)
+
     def clv_update_count(self) -> int:
         return int(self.api._clv_update_count(self.h))
 

@@ -486,6 +486,14 @@ int nrxh_eigen_decompose(unsigned states, const double *freqs, const double *sub
     std::copy(m.eigenvals.begin(), m.eigenvals.end(), evals);
   });
 }
+/* device-free: the host's restatements of pll-modules' 1-D minimisers, the ones optimize_branch / optimize_reticulation run */
+int nrxh_minimize_newton(double xmin, double *x, double xmax, double tolerance, unsigned max_iters,
+                         void (*deriv)(void *, double *, double *, double *), void *ctx, int *converged) {
+  return guarded([&] { const bool ok = netrax::detail::minimizeNewton(xmin, x, xmax, tolerance, max_iters, deriv, ctx); if (converged) *converged = ok ? 1 : 0; });
+}
+int nrxh_minimize_brent(double xmin, double xguess, double xmax, double xtol, double (*target)(void *, double), void *ctx, double *xopt) {
+  return guarded([&] { *xopt = netrax::detail::minimizeBrent(xmin, xguess, xmax, xtol, target, ctx); });
+}
 unsigned long long nrxh_launch_count(void *hv) { return nrx_launch_count(H(hv)->ann.engine); }
 unsigned nrxh_num_slots(void *hv) { return H(hv)->ann.next_slot; }
 int nrxh_profile_enable(void *hv, int on) { return nrx_profile_enable(H(hv)->ann.engine, on); }

@@ -29,13 +29,19 @@ using namespace detail;
 
 namespace {
 
+/* libpll's PLL_MIN / PLL_MAX (LIBPLL/pll.h:67-68) with their operand order: they differ from std::min / std::max when an
+ * operand is NaN (PLL_MIN(NaN, b) = b, std::min(NaN, b) = NaN), and the Newton step below does produce NaN — f = df = 0 on a
+ * saturated branch gives dx = -0/0 — which the reference turns into a step of +dxmax instead of a NaN branch length. */
+inline double pllMin(double a, double b) { return a < b ? a : b; }
+inline double pllMax(double a, double b) { return a > b ? a : b; }
+
 /* ---- pllmod_opt_minimize_newton_multi for xnum functions (opt_algorithms.c:133-261) ---------------------------- */
 bool newtonMulti(unsigned xnum, double xmin, double *x, double xmax, double tolerance, unsigned max_iters,
                  const std::function<void(double *x, double *f, double *df)> &deriv) {
   const double dxmax = xmax / max_iters;
   std::vector<double> lo(xnum, xmin), hi(xnum, xmax), f(xnum, 0.0), df(xnum, 0.0);
   std::vector<char> done(xnum, 0);
-  for (unsigned i = 0; i < xnum; ++i) x[i] = std::max(std::min(x[i], xmax), xmin);
+  for (unsigned i = 0; i < xnum; ++i) x[i] = pllMax(pllMin(x[i], xmax), xmin);
   unsigned iter = 0;
   bool all = false;
   while (!all) {
@@ -53,12 +59,12 @@ bool newtonMulti(unsigned xnum, double xmin, double *x, double xmax, double tole
       } else {
         dx = -1 * f[i] / std::fabs(df[i]);
       }
-      dx = std::max(std::min(dx, dxmax), -dxmax);
+      dx = pllMax(pllMin(dx, dxmax), -dxmax);
       if (x[i] + dx < lo[i]) dx = lo[i] - x[i];
       if (x[i] + dx > hi[i]) dx = hi[i] - x[i];
       if (std::fabs(dx) < tolerance) { done[i] = 1; continue; }
       x[i] += dx;
-      x[i] = std::max(std::min(x[i], xmax), xmin);
+      x[i] = pllMax(pllMin(x[i], xmax), xmin);
       all = all && done[i];
     }
   }
@@ -221,6 +227,16 @@ double optimizeBranchPartition(AnnotatedNetwork &ann, std::vector<DisplayedTreeD
 }
 
 }  // namespace
+
+/* the two single-variable minimisers above behind plain callbacks (device-free; nrxh_minimize_newton / nrxh_minimize_brent) */
+namespace detail {
+bool minimizeNewton(double xmin, double *x, double xmax, double tolerance, unsigned max_iters, void (*deriv)(void *, double *, double *, double *), void *ctx) {
+  return newtonMulti(1, xmin, x, xmax, tolerance, max_iters, [&](double *xx, double *f, double *df) { deriv(ctx, xx, f, df); });
+}
+double minimizeBrent(double xmin, double xguess, double xmax, double xtol, double (*target)(void *, double), void *ctx) {
+  return brentSingle(xmin, xguess, xmax, xtol, [&](double x) { return target(ctx, x); });
+}
+}  // namespace detail
 
 /* optimize_branch (BranchLengthOptimization.cpp:345-421) */
 double optimize_branch(AnnotatedNetwork &ann, size_t pmatrix_index, BrlenOptMethod method, unsigned int max_iters) {

@@ -218,3 +218,50 @@ def compress_patterns(masks: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     order = np.argsort(first, kind="stable")
     weights = np.bincount(inverse.ravel(), minlength=cols.shape[0]).astype(np.uint32)
     return np.ascontiguousarray(cols[order].T.astype(np.uint32)), weights[order]
+
+
+def to_extended_newick(net: NetworkDesc, branch_lengths: Optional[Sequence[float]] = None,
+                       reticulation_probs: Optional[Sequence[float]] = None, precision: Optional[int] = None) -> str:
+    """The writer side of the reference's network format (toExtendedNewick / printNodeNewick / newickNodeName,
+    src/io/NetworkIO.cpp:384-452,510-523): children in parentheses, tips by label, a reticulation node printed under
+    BOTH parents as ``#H<reticulation index>:length::prob`` (support left empty; first parent carries prob, second
+    1 - prob) with its subtree expanded only at the first visit.  ``branch_lengths`` [E] / ``reticulation_probs`` [R]
+    override the description's values, which is what updateNetwork (:493-508) does with the optimised state before
+    writing.  ``precision`` = significant digits (the reference streams doubles with the default 6); None writes the
+    shortest representation that reads back to the same double."""
+    length = np.asarray(net.edge_length if branch_lengths is None else branch_lengths, float)
+    if length.shape[0] < net.num_edges:
+        raise ValueError("branch_lengths must cover every edge")
+    first_prob = {int(net.ret_node[i]): (float(net.edge_prob[int(net.ret_first_edge[i])]) if reticulation_probs is None
+                                         else float(reticulation_probs[i])) for i in range(net.num_reticulations)}
+    ret_index = {int(v): i for i, v in enumerate(net.ret_node)}
+    second_edges = set(int(e) for e in net.ret_second_edge)
+    kids: Dict[int, List[int]] = {}
+    for e in range(net.num_edges):
+        kids.setdefault(int(net.edge_source[e]), []).append(e)
+
+    def num(x: float) -> str:
+        return repr(float(x)) if precision is None else f"{float(x):.{precision}g}"
+
+    visited = set()
+
+    def emit(node: int, via_edge: Optional[int]) -> str:
+        out = ""
+        is_ret = node in ret_index
+        ch = kids.get(node, [])
+        if is_ret and not ch:
+            raise ValueError("Encountered a reticulation node that has no children")
+        if ch and node not in visited:
+            out += "(" + ",".join(emit(int(net.edge_target[e]), e) for e in ch) + ")"
+            if is_ret:
+                visited.add(node)
+        if node < net.num_tips and net.tip_labels:
+            out += net.tip_labels[node]
+        if is_ret:
+            p = first_prob[node]
+            out += f"#H{ret_index[node]}:{num(length[via_edge])}::{num(1.0 - p if via_edge in second_edges else p)}"
+        elif via_edge is not None:
+            out += ":" + num(length[via_edge])
+        return out
+
+    return emit(int(net.root), None) + ";"

@@ -23,7 +23,9 @@
 #define BRENT_ZEPS 1.0e-7
 
 static double with_sign(double a, double b) { return b >= 0.0 ? fabs(a) : -fabs(a); }
-static double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+/* PLL_MAX(PLL_MIN(v, hi), lo) with libpll's macros (LIBPLL/pll.h:67-68), operand order included: a NaN v (the Newton step
+ * -0/0 when f = df = 0) comes out as hi, as in the reference */
+static double clampd(double v, double lo, double hi) { const double m = v < hi ? v : hi; return m > lo ? m : lo; }
 
 int orcopt_newton_multi(unsigned int xnum, double xmin, double *xguess, double xmax, double tolerance, unsigned int max_iters,
                         int *converged, void *params, void (*deriv_func)(void *, double *, double *, double *)) {

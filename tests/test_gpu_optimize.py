@@ -194,3 +194,25 @@ def test_optimize_scalers_is_a_noop_without_scaled_linkage():
     assert g.optimize_scalers() == b0
     np.testing.assert_array_equal(g.brlen_scalers(), [1.0, 1.0])
     g.close()
+
+
+def test_score_only_from_files_matches_oracle():
+    """netrax --score_only (src/main.cpp:287-326) from the reference's fixture files: network file + FASTA + model string ->
+    partitions -> optimizeModel -> BIC / lnL -> optimizeAllNonTopology(SLOW) -> BIC / lnL / AIC / AICc + the written network,
+    the whole flow on the device against the same flow over the oracle."""
+    import os
+    from helpers import FIX
+    from netrax_b200.score import score_only
+    from oracle import oracle
+    nw, aln = FIXTURE_PAIRS["small"]
+    net_text, msa_text = open(os.path.join(FIX, nw)).read(), open(os.path.join(FIX, aln)).read()
+    model = "GTR{1/2.5/0.8/1.2/3.0/1}+FC+G"
+    rg = score_only(lambda net, parts, **kw: _gpu(net, parts, **kw), net_text, msa_text, model, log=None)
+    ro = score_only(lambda net, parts, **kw: oracle.make_engine("ref" if oracle.have_ref() else "port", net, parts, **kw),
+                    net_text, msa_text, model, log=None)
+    for key in ("start_bic", "start_logl"):
+        assert rg[key] == pytest.approx(ro[key], rel=1e-9)
+    for key in ("bic", "logl", "aic", "aicc"):
+        assert rg[key] == pytest.approx(ro[key], rel=1e-7)
+    assert rg["alphas"][0] == pytest.approx(ro["alphas"][0], rel=1e-3)
+    assert rg["bic"] <= rg["start_bic"] + 1e-3

@@ -71,3 +71,76 @@ def test_product_eigendecomposition_reproduces_libpll_golden_pmatrices(datatype)
                     P = np.eye(S) + Vinv @ np.diag(np.expm1(lam * r * t)) @ V
                     np.testing.assert_allclose(P, G[f"{datatype}_P_{j * 3 + k}"][b][c], atol=6e-10, rtol=0,
                                                err_msg=str((datatype, j, k, t, r)))
+
+
+def _product_minimisers():
+    import ctypes as C
+    from netrax_b200 import engine
+    lib = engine.load().lib
+    TARGET_T = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_double)
+    DERIV_T = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double))
+    lib.nrxh_minimize_brent.restype = C.c_int
+    lib.nrxh_minimize_brent.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, TARGET_T, C.c_void_p, C.POINTER(C.c_double)]
+    lib.nrxh_minimize_newton.restype = C.c_int
+    lib.nrxh_minimize_newton.argtypes = [C.c_double, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_uint, DERIV_T, C.c_void_p, C.POINTER(C.c_int)]
+    return lib, TARGET_T, DERIV_T
+
+
+def test_product_newton_equals_the_reference_minimiser_call_for_call():
+    """The host library's Newton-Raphson (optimize.cpp newtonMulti) against pll-modules' real pllmod_opt_minimize_newton_multi
+    (oracle/_ref) on the cases of test_oracle_optimize.py, incl. the f = df = 0 ones where the step is NaN and libpll's
+    PLL_MIN / PLL_MAX operand order decides the next iterate: same iterates, same final x, same status."""
+    import ctypes as C
+    from oracle import oracle
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from test_oracle_optimize import NEWTON_CASES, _minimisers
+    ref = _minimisers("ref")
+    lib, _, DERIV_T = _product_minimisers()
+    for f, lo, guess, hi, tol, iters in NEWTON_CASES:
+        res = []
+        for which in ("ref", "product"):
+            calls = []
+
+            def deriv(_, x, d1, d2):
+                calls.append(x[0])
+                d1[0], d2[0] = f(x[0])
+            x, st = C.c_double(guess), C.c_int()
+            if which == "ref":
+                assert ref.orc_test_newton(1, lo, C.byref(x), hi, tol, iters, DERIV_T(deriv), C.byref(st))
+            else:
+                assert lib.nrxh_minimize_newton(lo, C.byref(x), hi, tol, iters, DERIV_T(deriv), None, C.byref(st))
+            res.append((x.value, st.value, calls))
+        assert res[0] == res[1]
+
+
+def test_product_brent_equals_the_reference_minimiser_up_to_convergence():
+    """brentSingle against pllmod_opt_minimize_brent: the same optimum and the same evaluation sequence — the product's is the
+    reference's with the post-convergence repeats of the last proposal cut (deviation D1), then the final target(xopt)."""
+    import ctypes as C
+    from oracle import oracle
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from test_oracle_optimize import BRENT_CASES, TARGET_T as ORC_TARGET_T, _minimisers
+    ref = _minimisers("ref")
+    lib, TARGET_T, _ = _product_minimisers()
+    for f, lo, guess, hi, tol in BRENT_CASES:
+        seqs = []
+        for which in ("ref", "product"):
+            calls = []
+
+            def target(_, x):
+                calls.append(x)
+                return f(x)
+            out = C.c_double()
+            if which == "ref":
+                assert ref.orc_test_brent(1, lo, guess, hi, tol, ORC_TARGET_T(target), C.byref(out))
+            else:
+                assert lib.nrxh_minimize_brent(lo, guess, hi, tol, TARGET_T(target), None, C.byref(out))
+            seqs.append((out.value, calls))
+        (xr, cr), (xp, cp) = seqs
+        assert xp == xr
+        assert cp[-1] == xr and cr[-1] == xr                     # both finish with target(xopt)
+        body = cp[:-1]
+        assert body == cr[:len(body)]                            # identical bracketing + iterates
+        assert all(c == cr[len(body) - 1] for c in cr[len(body):-1]) or len(body) == len(cr) - 1   # what was cut: repeats of the last proposal

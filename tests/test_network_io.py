@@ -61,3 +61,46 @@ def test_reference_fixture_networks_parse(name):
     nw, _ = FIXTURE_PAIRS[name]
     net = parse_extended_newick(open(os.path.join(FIX, nw)).read())
     sanity_checks(net)
+
+
+def _canonical(net):
+    """Numbering-free description: per edge (tips below the child, tips below the parent, length, prob), sorted."""
+    below = {}
+
+    def tips_below(v):
+        if v not in below:
+            ch = [int(net.edge_target[e]) for e in range(net.num_edges) if int(net.edge_source[e]) == v]
+            below[v] = frozenset([net.tip_labels[v]]) if not ch else frozenset().union(*(tips_below(c) for c in ch))
+        return below[v]
+
+    rows = []
+    for e in range(net.num_edges):
+        rows.append((sorted(tips_below(int(net.edge_target[e]))), sorted(tips_below(int(net.edge_source[e]))),
+                     float(net.edge_length[e]), float(net.edge_prob[e])))
+    return sorted(rows)
+
+
+@pytest.mark.parametrize("name", sorted(n for n in os.listdir(FIX) if n.endswith(".nw")))
+def test_extended_newick_writer_round_trips_reference_fixtures(name):
+    """toExtendedNewick (src/io/NetworkIO.cpp:384-452,510-523): what we write parses back to the same network — same
+    clusters under every edge, same lengths and inheritance probabilities, same displayed-tree count."""
+    from netrax_b200.network_io import to_extended_newick
+    net = parse_extended_newick(open(os.path.join(FIX, name)).read())
+    text = to_extended_newick(net)
+    back = parse_extended_newick(text)
+    assert (back.num_tips, back.num_nodes, back.num_edges, back.num_reticulations) == (net.num_tips, net.num_nodes, net.num_edges, net.num_reticulations)
+    assert sorted(back.tip_labels) == sorted(net.tip_labels)
+    assert _canonical(back) == _canonical(net)
+    assert text.count("#H") == 2 * net.num_reticulations and text.endswith(";")
+
+
+def test_extended_newick_writer_takes_the_optimised_state_and_the_reference_precision():
+    from netrax_b200.network_io import to_extended_newick
+    net = parse_extended_newick("((A:0.1,(B:0.2)X#H1:0.3::0.4)P:0.5,(X#H1:0.6::0.6,C:0.7)Q:0.8)R;")
+    brl = net.edge_length * 2.0
+    text = to_extended_newick(net, branch_lengths=brl, reticulation_probs=[0.25], precision=6)
+    back = parse_extended_newick(text)
+    np.testing.assert_allclose(sorted(back.edge_length), sorted(brl), rtol=1e-6)
+    e = int(back.ret_first_edge[0])
+    assert back.edge_prob[e] == pytest.approx(0.25) and back.edge_prob[int(back.ret_second_edge[0])] == pytest.approx(0.75)
+    assert "#H0:0.6::0.25" in text and "#H0:1.2::0.75" in text   # newickNodeName: "#H" + reticulation index, empty support field

@@ -67,6 +67,10 @@ NEWTON_CASES = [
     (lambda x: (-1.0 / x + 0.5, 1.0 / (x * x)), 1e-6, 0.1, 100.0, 1e-7, 32),
     (lambda x: (1.0, -1.0), 1e-6, 0.5, 100.0, 1e-7, 8),     # negative curvature: marches to the lower bound
     (lambda x: (math.sin(5 * x), 5 * math.cos(5 * x)), 1e-6, 1.0, 100.0, 1e-7, 4),   # hits the iteration limit
+    # f = df = 0 (a saturated branch): dx = -0/0 = NaN, which PLL_MAX(PLL_MIN(dx, dxmax), -dxmax) turns into +dxmax
+    (lambda x: (0.0, 0.0) if x < 30 else (x - 40.0, 1.0), 1e-6, 5.0, 100.0, 1e-7, 32),
+    (lambda x: (0.0, 0.0), 1e-6, 99.0, 100.0, 1e-7, 32),
+    (lambda x: (1.0, 0.0), 1e-6, 50.0, 100.0, 1e-7, 8),     # df = 0, f != 0: dx = -inf, clamped to -dxmax
 ]
 
 

@@ -135,6 +135,12 @@ int nrxh_eigen_decompose(unsigned states, const double *freqs, const double *sub
 int nrxh_minimize_newton(double xmin, double *x, double xmax, double tolerance, unsigned max_iters,
                          void (*deriv)(void *ctx, double *x, double *f, double *df), void *ctx, int *converged);
 int nrxh_minimize_brent(double xmin, double xguess, double xmax, double xtol, double (*target)(void *ctx, double x), void *ctx, double *xopt);
+/* pllmod_opt_minimize_brent_multi(xnum = n, opt_mask all set, global_range = 1) (:1431-1459 -> brent_opt_alt :1040-1254), the
+ * driver under optimize_alpha / optimize_pinv / optimize_scalers: target(ctx, x, fx, converged) with pll-modules' contract
+ * (converged NULL on plain calls; otherwise skip converged[j] != 0 and write the "all converged" flag to converged[n]).
+ * x: in = the guesses, out = the optima. */
+int nrxh_minimize_brent_multi(unsigned n, double xmin, double *x, double xmax, double xtol,
+                              double (*target)(void *ctx, double *x, double *fx, int *converged), void *ctx);
 /* bench / profiling hooks */
 unsigned long long nrxh_launch_count(void *h);
 unsigned nrxh_num_slots(void *h);

@@ -494,6 +494,10 @@ int nrxh_minimize_newton(double xmin, double *x, double xmax, double tolerance, 
 int nrxh_minimize_brent(double xmin, double xguess, double xmax, double xtol, double (*target)(void *, double), void *ctx, double *xopt) {
   return guarded([&] { *xopt = netrax::detail::minimizeBrent(xmin, xguess, xmax, xtol, target, ctx); });
 }
+int nrxh_minimize_brent_multi(unsigned n, double xmin, double *x, double xmax, double xtol,
+                              double (*target)(void *, double *, double *, int *), void *ctx) {
+  return guarded([&] { netrax::detail::minimizeBrentMulti(n, xmin, x, xmax, xtol, target, ctx); });
+}
 unsigned long long nrxh_launch_count(void *hv) { return nrx_launch_count(H(hv)->ann.engine); }
 unsigned nrxh_num_slots(void *hv) { return H(hv)->ann.next_slot; }
 int nrxh_profile_enable(void *hv, int on) { return nrx_profile_enable(H(hv)->ann.engine, on); }

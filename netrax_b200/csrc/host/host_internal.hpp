@@ -26,6 +26,7 @@ void reduceSum(AnnotatedNetwork &ann, double *data, size_t count);
 void reduceHostSum(AnnotatedNetwork &ann, double *data, size_t count);
 bool minimizeNewton(double xmin, double *x, double xmax, double tolerance, unsigned max_iters, void (*deriv)(void *, double *, double *, double *), void *ctx);
 double minimizeBrent(double xmin, double xguess, double xmax, double xtol, double (*target)(void *, double), void *ctx);
+void minimizeBrentMulti(unsigned n, double xmin, double *x, double xmax, double xtol, double (*target)(void *, double *, double *, int *), void *ctx);
 /* log(sum_t exp(a_t)) and friends without leaving double range (stands in for mpfr::mpreal) */
 double logSumExp(const std::vector<double> &a);
 }  // namespace detail

@@ -153,6 +153,47 @@ double brentSingle(double xmin, double xguess, double xmax, double xtol, const s
   return xopt;
 }
 
+/* pllmod_opt_minimize_brent_multi with global_range = 1 and every variable in the mask -> brent_opt_alt (opt_algorithms.c:
+ * 1040-1254): one Brent search per variable, all of them advanced together, one target call per step for ALL variables.
+ * target(x, converged, all_converged): converged == nullptr is the reference's target_funk(..., NULL) (bracketing and the final
+ * call); otherwise the callee skips converged variables and reports through *all_converged what the reference reads from
+ * converged[xnum].  x: in = the guesses, out = xopt (the start value where the search ended worse than it began). */
+using BrentMultiTarget = std::function<std::vector<double>(const std::vector<double> &x, const std::vector<char> *converged, bool *all_converged)>;
+void brentMulti(size_t n, double min_value, double max_value, double tolerance, std::vector<double> &x, const BrentMultiTarget &target) {
+  std::vector<double> xguess = x, ax(n), cx(n), lmin(n, min_value), lmax(n, max_value);
+  std::vector<char> converged(n, 0);
+  bool all_converged = false;
+  for (size_t j = 0; j < n; ++j) {
+    if (xguess[j] < lmin[j]) xguess[j] = lmin[j];
+    if (xguess[j] > lmax[j]) xguess[j] = lmax[j];
+    const double eps = xguess[j] > 0 ? xguess[j] * tolerance * 50.0 : 2. * tolerance;  // bracketing heuristic (:1138-1148)
+    ax[j] = xguess[j] - eps;
+    if (ax[j] < lmin[j]) ax[j] = lmin[j];
+    cx[j] = xguess[j] + eps;
+    if (cx[j] > lmax[j]) cx[j] = lmax[j];
+  }
+  std::vector<double> fa = target(ax, nullptr, nullptr);
+  const std::vector<double> fb = target(xguess, nullptr, nullptr);
+  std::vector<double> fc = target(cx, nullptr, nullptr);
+  const std::vector<double> fmin = target(lmin, nullptr, nullptr), fmax = target(lmax, nullptr, nullptr);
+  std::vector<BrentState> st(n);
+  for (size_t j = 0; j < n; ++j) {
+    if (fa[j] < fb[j] || fc[j] < fb[j]) { fa[j] = fmin[j]; fc[j] = fmax[j]; ax[j] = lmin[j]; cx[j] = lmax[j]; }
+    if (!st[j].init(ax[j], xguess[j], cx[j], tolerance, fa[j], fb[j], fc[j])) converged[j] = 1;
+  }
+  std::vector<double> u(n);
+  for (int iter = 0; iter <= BrentState::kItmax; ++iter) {
+    for (size_t j = 0; j < n; ++j) u[j] = st[j].u;
+    const std::vector<double> fu = target(u, &converged, &all_converged);   // with every variable converged the callee sets nothing but still evaluates, as the reference does
+    const bool iterate = !all_converged;
+    for (size_t j = 0; j < n; ++j)
+      if (!converged[j]) converged[j] = !st[j].absorb(fu[j]);
+    if (!iterate) break;
+  }
+  for (size_t j = 0; j < n; ++j) x[j] = (st[j].fx > st[j].fstartx) ? st[j].startx : st[j].x;  // if the new score is worse, return the initial value
+  target(x, nullptr, nullptr);
+}
+
 double &brlenRef(AnnotatedNetwork &ann, size_t partition_index, size_t pmatrix_index) {
   FakeTreeinfo &ti = *ann.fake_treeinfo;
   return ti.brlen_linkage == PLLMOD_COMMON_BRLEN_UNLINKED ? ti.branch_lengths[partition_index][pmatrix_index]
@@ -235,6 +276,21 @@ bool minimizeNewton(double xmin, double *x, double xmax, double tolerance, unsig
 }
 double minimizeBrent(double xmin, double xguess, double xmax, double xtol, double (*target)(void *, double), void *ctx) {
   return brentSingle(xmin, xguess, xmax, xtol, [&](double x) { return target(ctx, x); });
+}
+/* target: pll-modules' callback contract (algo_callback.c:295-363) — target(ctx, x, fx, converged) with converged == NULL for the
+ * plain calls and converged[n] = "all converged" written by the callee otherwise */
+void minimizeBrentMulti(unsigned n, double xmin, double *x, double xmax, double xtol, double (*target)(void *, double *, double *, int *), void *ctx) {
+  std::vector<double> v(x, x + n);
+  brentMulti(n, xmin, xmax, xtol, v, [&](const std::vector<double> &xs, const std::vector<char> *converged, bool *all_converged) {
+    std::vector<double> in(xs), fx(n, 0.0);
+    if (!converged) { target(ctx, in.data(), fx.data(), nullptr); return fx; }
+    std::vector<int> flags(n + 1, 0);
+    for (unsigned j = 0; j < n; ++j) flags[j] = (*converged)[j];
+    target(ctx, in.data(), fx.data(), flags.data());
+    *all_converged = flags[n] != 0;
+    return fx;
+  });
+  std::copy(v.begin(), v.end(), x);
 }
 }  // namespace detail
 
@@ -368,56 +424,28 @@ static double optimize_onedim(AnnotatedNetwork &ann, OnedimParam param, double m
   };
   const size_t n = parts.size();
   if (n) {
-    std::vector<double> xguess(n), ax(n), cx(n), lmin(n, min_value), lmax(n, max_value);
-    for (size_t j = 0; j < n; ++j) xguess[j] = get(parts[j]);
-    std::vector<char> converged(n, 0);
-    bool all_converged = false;
-    // target_func_onedim_treeinfo: set the unconverged partitions' parameters, one full evaluation, per-partition scores
-    auto target = [&](const std::vector<double> &x, bool with_flags) {
+    std::vector<double> x(n);
+    for (size_t j = 0; j < n; ++j) x[j] = get(parts[j]);
+    // target_func_onedim_treeinfo (algo_callback.c:295-363): set the unconverged partitions' parameters, one full evaluation,
+    // per-partition scores
+    brentMulti(n, min_value, max_value, tolerance, x, [&](const std::vector<double> &v, const std::vector<char> *converged, bool *all_converged) {
       double unconverged = 0.0;
       for (size_t j = 0; j < n; ++j) {
-        if (with_flags && converged[j]) continue;
+        if (converged && (*converged)[j]) continue;
         unconverged = 1.0;
-        set(parts[j], x[j]);
+        set(parts[j], v[j]);
       }
       computeLoglikelihood(ann, 0, 1);
       std::vector<double> fx(n);
       for (size_t j = 0; j < n; ++j) fx[j] = -1 * ti.partition_loglh[parts[j]];
-      if (with_flags) {
+      if (converged) {
         // every shard holds a slice of EVERY partition and the reduced per-partition lnLs, so the flags already agree under an
         // NCCL communicator; the callback is honoured because the reference calls it here
         if (ti.parallel_reduce_cb) ti.parallel_reduce_cb(ti.parallel_context, &unconverged, 1, PLLMOD_COMMON_REDUCE_SUM);
-        all_converged = !(unconverged > 0.0);
+        *all_converged = !(unconverged > 0.0);
       }
       return fx;
-    };
-    for (size_t j = 0; j < n; ++j) {
-      xguess[j] = std::max(std::min(xguess[j], lmax[j]), lmin[j]);
-      const double eps = xguess[j] > 0 ? xguess[j] * tolerance * 50.0 : 2. * tolerance;  // bracketing heuristic (:1138-1148)
-      ax[j] = std::max(xguess[j] - eps, lmin[j]);
-      cx[j] = std::min(xguess[j] + eps, lmax[j]);
-    }
-    std::vector<double> fa = target(ax, false);
-    const std::vector<double> fb = target(xguess, false);
-    std::vector<double> fc = target(cx, false);
-    const std::vector<double> fmin = target(lmin, false), fmax = target(lmax, false);
-    std::vector<BrentState> st(n);
-    for (size_t j = 0; j < n; ++j) {
-      if (fa[j] < fb[j] || fc[j] < fb[j]) { fa[j] = fmin[j]; fc[j] = fmax[j]; ax[j] = lmin[j]; cx[j] = lmax[j]; }
-      if (!st[j].init(ax[j], xguess[j], cx[j], tolerance, fa[j], fb[j], fc[j])) converged[j] = 1;
-    }
-    std::vector<double> u(n);
-    for (int iter = 0; iter <= BrentState::kItmax; ++iter) {
-      for (size_t j = 0; j < n; ++j) u[j] = st[j].u;
-      const std::vector<double> fu = target(u, true);   // with every partition converged this sets nothing but still evaluates, as the reference does
-      const bool iterate = !all_converged;
-      for (size_t j = 0; j < n; ++j)
-        if (!converged[j]) converged[j] = !st[j].absorb(fu[j]);
-      if (!iterate) break;
-    }
-    std::vector<double> xopt(n);
-    for (size_t j = 0; j < n; ++j) xopt[j] = (st[j].fx > st[j].fstartx) ? st[j].startx : st[j].x;  // if the new score is worse, return the initial value
-    target(xopt, false);
+    });
   }
   return computeLoglikelihood(ann, 0, 1);
 }

@@ -428,7 +428,11 @@ extern "C" {
 #ifdef ORC_HAVE_REF
 int pllmod_opt_minimize_newton_multi(unsigned int, double, double *, double, double, unsigned int, int *, void *, void(deriv_func)(void *, double *, double *, double *));
 double pllmod_opt_minimize_brent(double, double, double, double, double *, double *, void *, double (*)(void *, double));
+int pllmod_opt_minimize_brent_multi(unsigned int, int *, double *, double *, double *, double, double *, double *, double *, void *,
+                                    double (*)(void *, double *, double *, int *), int);
 #endif
+int orcopt_brent_multi(unsigned int, int *, double *, double *, double *, double, double *, double *, double *, void *,
+                       double (*)(void *, double *, double *, int *), int);
 int orcopt_newton_multi(unsigned int, double, double *, double, double, unsigned int, int *, void *, void (*)(void *, double *, double *, double *));
 double orcopt_brent(double, double, double, double, double *, double *, void *, double (*)(void *, double));
 }
@@ -440,6 +444,14 @@ int orc_test_brent(int use_ref, double xmin, double xguess, double xmax, double 
   if (use_ref) return 0;
   *xopt = orcopt_brent(xmin, xguess, xmax, xtol, &fx, &f2x, nullptr, target);
   return 1;
+}
+int orc_test_brent_multi(int use_ref, unsigned n, double xmin, double *x, double xmax, double xtol, double (*target)(void *, double *, double *, int *)) {
+  std::vector<int> mask(n, 1);
+#ifdef ORC_HAVE_REF
+  if (use_ref) return pllmod_opt_minimize_brent_multi(n, mask.data(), &xmin, x, &xmax, xtol, x, nullptr, nullptr, nullptr, target, 1);
+#endif
+  if (use_ref) return 0;
+  return orcopt_brent_multi(n, mask.data(), &xmin, x, &xmax, xtol, x, nullptr, nullptr, nullptr, target, 1);
 }
 int orc_test_newton(int use_ref, double xmin, double *x, double xmax, double tol, unsigned max_iters, void (*deriv)(void *, double *, double *, double *), int *status) {
 #ifdef ORC_HAVE_REF

@@ -144,3 +144,54 @@ def test_product_brent_equals_the_reference_minimiser_up_to_convergence():
         body = cp[:-1]
         assert body == cr[:len(body)]                            # identical bracketing + iterates
         assert all(c == cr[len(body) - 1] for c in cr[len(body):-1]) or len(body) == len(cr) - 1   # what was cut: repeats of the last proposal
+
+
+def test_product_brent_multi_equals_the_reference_minimiser_call_for_call():
+    """brentMulti (the driver under optimize_alpha / optimize_pinv / optimize_scalers) against pll-modules' real
+    pllmod_opt_minimize_brent_multi and its restatement in the oracle port, three variables with different curvature that
+    converge at different iterations: identical x vectors call after call (converged variables keep being passed, the callee
+    skips them), identical optima."""
+    import ctypes as C
+    import math
+    from oracle import oracle
+    lib = _product_minimisers()[0]
+    MT = C.CFUNCTYPE(C.c_double, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int))
+    lib.nrxh_minimize_brent_multi.restype = C.c_int
+    lib.nrxh_minimize_brent_multi.argtypes = [C.c_uint, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_double, MT, C.c_void_p]
+    funcs = [lambda x: (x - 0.5) ** 2, lambda x: math.cosh(2 * (x - 3.0)) + 0.05 * x, lambda x: -math.log(0.2 * x + 0.1) + 0.3 * x, lambda x: 1.0]
+    cases = [([2.0, 0.1, 1.0, 1.0], 0.0201, 100.0, 0.001), ([0.05, 0.3, 0.0, 0.5], 0.0, 0.99, 0.001), ([3.0, 0.3, 150.0, 1.0], 0.01, 100.0, 0.001)]
+    for guess, lo, hi, tol in cases:
+        n = len(guess)
+        runs = {}
+        kinds = ["product", "port"] + (["ref"] if oracle.have_ref() else [])
+        for which in kinds:
+            calls = []
+
+            def target(_, x, fx, conv):
+                xs = [x[j] for j in range(n)]
+                flags = None if not conv else [conv[j] for j in range(n)]
+                calls.append((xs, flags))
+                unconverged = 0
+                for j in range(n):
+                    if conv and conv[j]:
+                        continue
+                    unconverged = 1
+                if fx:
+                    for j in range(n):
+                        fx[j] = funcs[j](x[j])
+                if conv:
+                    conv[n] = 0 if unconverged else 1
+                return 0.0
+            x = (C.c_double * n)(*guess)
+            if which == "product":
+                assert lib.nrxh_minimize_brent_multi(n, lo, x, hi, tol, MT(target), None)
+            else:
+                olib = oracle.api("ref" if which == "ref" else "port").lib
+                olib.orc_test_brent_multi.restype = C.c_int
+                olib.orc_test_brent_multi.argtypes = [C.c_int, C.c_uint, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_double, MT]
+                assert olib.orc_test_brent_multi(1 if which == "ref" else 0, n, lo, x, hi, tol, MT(target))
+            runs[which] = (list(x), calls)
+        for which in kinds[1:]:
+            assert runs["product"][0] == runs[which][0], which
+            assert runs["product"][1] == runs[which][1], which
+        assert 5 + 2 < len(runs["product"][1]) <= 5 + 101 + 1

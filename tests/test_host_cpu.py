@@ -195,3 +195,68 @@ def test_product_brent_multi_equals_the_reference_minimiser_call_for_call():
             assert runs["product"][0] == runs[which][0], which
             assert runs["product"][1] == runs[which][1], which
         assert 5 + 2 < len(runs["product"][1]) <= 5 + 101 + 1
+
+
+def test_product_minimisers_fuzzed_against_the_reference():
+    """300 seeded random targets — quadratics, exponentials, flat and step functions, oscillations, zones returning NaN or inf —
+    with random bounds, guesses (also out of range) and tolerances: the product's Newton and Brent produce the reference's
+    iterates and results bit for bit (NaN-aware comparison through repr)."""
+    import ctypes as C
+    import math
+    import random
+    from oracle import oracle
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from test_oracle_optimize import TARGET_T as ORC_TARGET_T, _minimisers
+    ref = _minimisers("ref")
+    lib, TARGET_T, DERIV_T = _product_minimisers()
+    rnd = random.Random(1)
+
+    def make():
+        kind = rnd.choice(["quad", "exp", "flat", "step", "nanzone", "inf", "osc", "lin"])
+        a, b, c = rnd.uniform(0, 5), rnd.uniform(0.1, 10), rnd.uniform(-3, 3)
+        ex = lambda x: math.exp(min(50, b * (x - a)))
+        f = {"quad": lambda x: b * (x - a) ** 2 + c, "exp": lambda x: ex(x) - c * x, "flat": lambda x: c,
+             "step": lambda x: c if x < a else c + b, "nanzone": lambda x: float("nan") if a < x < a + b else (x - a) ** 2,
+             "inf": lambda x: float("inf") if x > a + b else (x - a) ** 2, "osc": lambda x: math.sin(b * x) + 0.01 * x,
+             "lin": lambda x: b * x + c}[kind]
+        d = {"quad": lambda x: (2 * b * (x - a), 2 * b), "exp": lambda x: (b * ex(x) - c, b * b * ex(x)), "flat": lambda x: (0.0, 0.0),
+             "step": lambda x: (0.0, 0.0) if x < a else (1.0, 0.0), "nanzone": lambda x: (float("nan"), 1.0) if a < x < a + b else (2 * (x - a), 2.0),
+             "inf": lambda x: (float("inf"), 1.0) if x > a + b else (2 * (x - a), 2.0),
+             "osc": lambda x: (b * math.cos(b * x) + 0.01, -b * b * math.sin(b * x)), "lin": lambda x: (b, 0.0)}[kind]
+        return f, d
+
+    for _ in range(300):
+        f, d = make()
+        lo, hi = rnd.choice([(1e-6, 100.0), (1e-6, 1 - 1e-6), (0.0, 0.99), (0.01, 100.0)])
+        guess = rnd.uniform(lo, hi) if rnd.random() < 0.8 else rnd.choice([lo, hi, hi * 2, -1.0])
+        tol, iters = rnd.choice([0.1, 1e-3, 1e-4, 1e-7]), rnd.choice([4, 8, 32])
+        res = []
+        for which in (0, 1):
+            calls = []
+
+            def deriv(_, x, d1, d2):
+                calls.append(repr(x[0]))
+                d1[0], d2[0] = d(x[0])
+            x, st = C.c_double(guess), C.c_int()
+            if which == 0:
+                ref.orc_test_newton(1, lo, C.byref(x), hi, tol, iters, DERIV_T(deriv), C.byref(st))
+            else:
+                lib.nrxh_minimize_newton(lo, C.byref(x), hi, tol, iters, DERIV_T(deriv), None, C.byref(st))
+            res.append((repr(x.value), st.value, calls))
+        assert res[0] == res[1]
+        seqs = []
+        for which in (0, 1):
+            calls = []
+
+            def target(_, x):
+                calls.append(repr(x))
+                return f(x)
+            out = C.c_double()
+            if which == 0:
+                ref.orc_test_brent(1, lo, guess, hi, tol, ORC_TARGET_T(target), C.byref(out))
+            else:
+                lib.nrxh_minimize_brent(lo, guess, hi, tol, TARGET_T(target), None, C.byref(out))
+            seqs.append((repr(out.value), calls))
+        (xr, cr), (xp, cp) = seqs
+        assert xr == xp and cp[:-1] == cr[:len(cp) - 1]

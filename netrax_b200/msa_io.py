@@ -15,7 +15,8 @@ evaluates, following raxml-ng (RAXML = /root/reference/libs/raxml-ng/src) and pl
                         src/RaxmlWrapper.cpp:682-684)
 
 Not covered (a ValueError names the option): FreeRate (+R), ascertainment bias (+ASC), custom character maps (+M), mixture
-and multistate models, protein matrices other than LG (the one matrix this repo ships, ``lg_model.json``), PAML files.
+multistate models, LG4X (FreeRate mixture), PROTGTR, PAML files.  The 20 empirical protein matrices and the LG4M components
+come from ``aa_models.json`` (libpll's tables, extracted by tests/golden/make_aa_models.py).
 Nothing here touches the GPU; the Partition objects it returns are what ``NetraxB200`` takes.
 """
 from __future__ import annotations
@@ -49,9 +50,24 @@ _AA_ORDER = "ARNDCQEGHILKMFPSTWYV"
 _AA_AMBIG = {"B": "ND", "Z": "QE", "J": "IL"}
 
 
-def _lg() -> Tuple[np.ndarray, np.ndarray]:
-    d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "lg_model.json")))
-    return np.asarray(d["rates"], float), np.asarray(d["freqs"], float)
+_AA_MODELS: Dict[str, Dict[str, List[float]]] = {}
+
+
+def aa_model(name: str) -> Tuple[np.ndarray, np.ndarray]:
+    """(190 exchangeabilities, 20 frequencies) of one of libpll's empirical protein matrices, by pll-modules' name
+    (PLLMOD/util/models_aa.c:28-59; data file written by tests/golden/make_aa_models.py from the compiled reference library)."""
+    if not _AA_MODELS:
+        d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "aa_models.json")))
+        _AA_MODELS.update({k.upper(): v for k, v in d["models"].items()})
+    m = _AA_MODELS.get(name.upper())
+    if m is None:
+        raise ValueError(f"Invalid model name: {name}")
+    return np.asarray(m["rates"], float), np.asarray(m["freqs"], float)
+
+
+def aa_model_names() -> List[str]:
+    aa_model("LG")
+    return sorted(_AA_MODELS)
 
 
 @dataclass
@@ -73,6 +89,9 @@ class ModelSpec:
     pinv_mode: str = "undefined"        # undefined (no +I) | ML | empirical | user
     brlen_scaler: float = 1.0
     brlen_scaler_mode: str = "undefined"
+    # mixture with one matrix per rate category (LG4M): [(rates, freqs)] and the matrix of each category
+    submodels: Optional[List[Tuple[np.ndarray, np.ndarray]]] = None
+    ratecat_submodels: Optional[List[int]] = None
 
     @property
     def num_uniq_rates(self) -> int:
@@ -110,7 +129,7 @@ def _floats(text: str) -> List[float]:
 def parse_model(spec: str) -> ModelSpec:
     """``GTR+G4{0.7}+I``, ``HKY{1/2.5}+FC``, ``LG+G+F`` ... -> ModelSpec (RAXML/Model.cpp:206-296, 378-870)."""
     spec = spec.strip()
-    m = re.match(r"[A-Za-z0-9]+", spec)
+    m = re.match(r"[A-Za-z0-9]+(?:-[A-Za-z]+)?", spec)   # "JTT-DCMUT" carries a dash
     if not m:
         raise ValueError(f"Invalid model name: {spec!r}")
     name = m.group(0)
@@ -126,11 +145,17 @@ def parse_model(spec: str) -> ModelSpec:
         ms.freqs = np.full(4, 0.25)
         ms.rate_mode = "model" if max(sym) == 0 else "ML"
         ms.subst_rates = np.ones(6)
-    elif up in ("LG", "PROT", "PROTGTR"):
-        if up != "LG":
-            raise ValueError(f"protein model {name}: only the LG matrix is available in this repository")
-        r, f = _lg()
-        ms = ModelSpec("LG", "AA", 20, freq_mode="model", rate_mode="model", subst_rates=r, freqs=f)
+    elif up == "LG4M":   # M_LG4M (PLLMOD/util/models_aa.c:103-105): four LG4M matrices, one per GAMMA category
+        comps = [aa_model(f"LG4M{k + 1}") for k in range(4)]
+        ms = ModelSpec("LG4M", "AA", 20, freq_mode="model", rate_mode="model", subst_rates=comps[0][0], freqs=comps[0][1],
+                       rate_cats=4, alpha_mode="ML", submodels=comps, ratecat_submodels=[0, 1, 2, 3])
+    elif up == "LG4X":
+        raise ValueError("LG4X is a FreeRate mixture (PLLMOD_UTIL_MIXTYPE_FREE): free rates / weights are not supported by this input layer")
+    elif up in ("PROTGTR", "PROT"):
+        raise ValueError(f"protein model {name}: a 189-parameter GTR needs pll-modules' BFGS optimiser (optimize_params_cb)")
+    elif up in [n for n in aa_model_names() if not n.startswith("LG4")]:
+        r, f = aa_model(up)
+        ms = ModelSpec(up, "AA", 20, freq_mode="model", rate_mode="model", subst_rates=r, freqs=f)
     else:
         raise ValueError(f"Invalid model name: {name}")
     user, i = _read_braces(spec, i)
@@ -150,11 +175,15 @@ def parse_model(spec: str) -> ModelSpec:
             raise ValueError("Invalid model options: trailing '+'")
         opt = spec[i].upper()
         i += 1
+        if ms.submodels is not None and opt in ("F", "R"):
+            raise ValueError(f"{ms.name}: +{opt} is not defined for a mixture with one matrix per category")
         if opt == "G":
             mm = re.match(r"\d+", spec[i:])
             if mm:
                 ms.rate_cats = int(mm.group(0))
                 i += mm.end()
+                if ms.submodels is not None and ms.rate_cats != len(ms.submodels):
+                    raise ValueError(f"{ms.name} has {len(ms.submodels)} matrices: the number of rate categories must match")
             elif ms.rate_cats == 1:
                 ms.rate_cats = 4
             if i < len(spec) and spec[i] in "aA":
@@ -422,6 +451,8 @@ def apply_model_state(eng, specs: Sequence[ModelSpec]) -> int:
             eng.set_pinv(p, ms.pinv)
         if ms.brlen_scaler_mode == "user":
             eng.set_brlen_scaler(p, ms.brlen_scaler)
+        if ms.submodels is not None:   # raxml-ng's ratecat_submodels -> libpll params_indices (src/RaxmlWrapper.cpp:199-203)
+            eng.set_submodels(p, ms.ratecat_submodels, np.stack([f for _, f in ms.submodels]), np.stack([r for r, _ in ms.submodels]))
     k = sum(ms.free_params() for ms in specs)
     eng.set_scoring_sizes(k)
     return k

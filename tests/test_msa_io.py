@@ -37,7 +37,7 @@ def test_model_names_symmetries_and_free_parameter_counts():
     assert (m.states, m.rate_cats, m.freq_mode, m.rate_mode, m.free_params()) == (20, 4, "empirical", "model", 19 + 1)
     assert parse_model("LG").free_params() == 0
     for bad, msg in (("FOO", "Invalid model name"), ("GTR+R4", r"\+R"), ("GTR+ASC_LEWIS", "ascertainment"), ("GTR{1/2}", "expected 6"),
-                     ("GTR+FU{0.5/0.5}", "user frequencies"), ("GTR+X", "Invalid model options"), ("WAG", "Invalid model name")):
+                     ("GTR+FU{0.5/0.5}", "user frequencies"), ("GTR+X", "Invalid model options"), ("LG4X", "FreeRate"), ("PROTGTR", "BFGS")):
         with pytest.raises(ValueError, match=msg):
             parse_model(bad)
 
@@ -179,3 +179,57 @@ def test_score_only_flow_over_the_oracle_engine():
     back = parse_extended_newick(res["network"])
     assert back.num_reticulations == res["reticulations"] and np.all(back.edge_length >= 1e-6)
     assert any(l.startswith("BIC Score: ") for l in lines) and any(l.startswith("Number of reticulations: 1") for l in lines)
+
+
+GP = load_golden("libpll_protein_models_golden.json")
+
+
+@pytest.mark.parametrize("model", list(GP["models"]))
+def test_protein_model_names_reproduce_libpll_golden_lnl(model):
+    """FASTA text + ``<NAME>+G4{1.0}`` for each of libpll's 20 empirical protein matrices -> partitions -> lnL equal to libpll's
+    own regression output (test/out/protein-models.out, 6 decimals): pins aa_models.json, the name lookup (case-insensitive,
+    ``JTT-DCMut`` with its dash) and the amino-acid encoding of the input layer."""
+    from oracle import oracle
+    b0, b1 = GP["branch_lengths"]
+    net = parse_extended_newick(f"(((T0:{b1},T1:{b1}):{b0},T2:{b1})X6:{b0 / 2},(T3:{b1},T4:{b1})X7:{b0 / 2});")
+    fasta = "".join(f">T{i}\n{s}\n" for i, s in enumerate(GP["tips"]))
+    parts, specs = build_partitions(read_msa(fasta), net.tip_labels, f"{model}+G{GP['ncats']}{{{GP['alpha']}}}", compress=False)
+    assert specs[0].name == model.upper() and specs[0].free_params() == 0
+    np.testing.assert_array_equal(parts[0].subst, np.asarray(GP["models"][model]["rates"]))
+    eng = oracle.make_engine("port", net, parts)
+    assert abs(eng.computeLoglikelihood(0, 1) - GP["models"][model]["logl"]) < 2e-6
+    eng.close()
+    parts_c, _ = build_partitions(read_msa(fasta), net.tip_labels, f"{model}+G{GP['ncats']}{{{GP['alpha']}}}")   # compressed: same lnL
+    eng = oracle.make_engine("port", net, parts_c)
+    assert abs(eng.computeLoglikelihood(0, 1) - GP["models"][model]["logl"]) < 2e-6
+    eng.close()
+
+
+def test_lg4m_is_a_per_category_mixture_through_set_submodels():
+    """``LG4M`` (PLLMOD/util/models_aa.c:103-105): four matrices, category c uses matrix c; apply_model_state hands them to
+    set_submodels (raxml-ng's ratecat_submodels -> libpll params_indices).  Checked against the sum over categories of
+    single-matrix, single-rate evaluations through real libpll."""
+    from oracle import oracle
+    if not oracle.have_ref():
+        pytest.skip("per-category matrices are restated only through the reference backend")
+    from netrax_b200._capi import Partition
+    b0, b1 = GP["branch_lengths"]
+    net = parse_extended_newick(f"(((T0:{b1},T1:{b1}):{b0},T2:{b1})X6:{b0 / 2},(T3:{b1},T4:{b1})X7:{b0 / 2});")
+    fasta = "".join(f">T{i}\n{s}\n" for i, s in enumerate(GP["tips"]))
+    parts, specs = build_partitions(read_msa(fasta), net.tip_labels, "LG4M+G4{0.8}", compress=False)
+    ms = specs[0]
+    assert ms.ratecat_submodels == [0, 1, 2, 3] and len(ms.submodels) == 4 and ms.free_params() == 0
+    eng = oracle.make_engine("ref", net, parts)
+    apply_model_state(eng, specs)
+    lnl = eng.computeLoglikelihood(0, 1)
+    from helpers import mixture_lnl_by_categories
+    short = Partition(20, 4, parts[0].tip_masks[:, :12], parts[0].freqs, parts[0].subst, parts[0].rates)   # 12 sites: 48 tiny engines
+    e = oracle.make_engine("ref", net, [short])
+    apply_model_state(e, specs)
+    want = mixture_lnl_by_categories(lambda n, p: oracle.make_engine("ref", n, [p]), net, short, ms.ratecat_submodels,
+                                     [f for _, f in ms.submodels], [r for r, _ in ms.submodels])
+    assert e.computeLoglikelihood(0, 1) == pytest.approx(want, rel=1e-10)
+    e.close()
+    single = oracle.make_engine("ref", net, parts)
+    assert abs(single.computeLoglikelihood(0, 1) - lnl) > 1e-3   # without the mixture: matrix 0 for every category
+    eng.close(); single.close()

@@ -1,8 +1,8 @@
-"""Flat network description + a minimal extended-Newick / FASTA reader.
+"""Flat network description + extended-Newick reader / writer + FASTA reader (data formats).
 
-File formats are OUT OF SCOPE of the hot path; this module exists only so that
-tests and the bench can feed the reference's own fixtures (test/sample_networks/*.nw, *_alignment.txt)
-and synthetic networks through the likelihood API.  Numbering follows the reference's
+File formats are not part of the hot path; this module feeds the reference's own fixtures
+(test/sample_networks/*.nw, *_alignment.txt), user files (scripts/score_network.py) and synthetic networks through
+the likelihood API and writes the optimised network back (to_extended_newick).  Numbering follows the reference's
 ``convertNetworkToplevel`` (src/io/NetworkIO.cpp:59-330): tips 0..n-1 in order of appearance, then
 inner tree nodes with the root last, then reticulation nodes; the pmatrix index of a non-reticulation
 node's parent edge equals its clv index; reticulation i owns edges base+2i (first parent) and

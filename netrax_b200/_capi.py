@@ -139,6 +139,7 @@ class LikelihoodEngine:
     def __init__(self, api: FlatAPI, net: NetworkDesc, partitions: Sequence[Partition], variant: int = AVERAGE,
                  linkage: int = LINKED, backend: str = "", partition_brlens: Optional[Sequence[np.ndarray]] = None):
         self.api, self.net, self.partitions = api, net, list(partitions)
+        self.variant, self.linkage = variant, linkage
         self.h = api._new(backend.encode())
         if not self.h:
             raise LikelihoodError(api._last_error().decode())
@@ -401,11 +402,18 @@ class LikelihoodEngine:
         self.api.check(self.api._get_reticulation_probs(self.h, out))
         return out[: self.net.num_reticulations]
 
-    def toExtendedNewick(self, precision: Optional[int] = None) -> str:
+    def toExtendedNewick(self, precision: Optional[int] = None, average_unlinked: bool = True) -> str:
         """toExtendedNewick(AnnotatedNetwork&) (src/io/NetworkIO.cpp:517-523): updateNetwork (:493-508) copies the linked
-        branch lengths and the reticulation probabilities of the current (optimised) state into the network, then writes it."""
+        branch lengths and the reticulation probabilities of the current (optimised) state into the network, then writes it.
+        With unlinked branch lengths the search first replaces the linked lengths by the partitions' average weighted with
+        their share of the alignment (collect_average_branches, :455-491, called from src/search/ScoreImprovement.cpp:38);
+        ``average_unlinked`` does the same here."""
         from .network_io import to_extended_newick
-        return to_extended_newick(self.net, self.branch_lengths(), self.reticulation_probs(), precision)
+        lengths = self.branch_lengths()
+        if self.linkage == UNLINKED and average_unlinked:
+            w = np.array([float(p.pattern_weights.sum()) if p.pattern_weights is not None else float(p.sites) for p in self.partitions])
+            lengths = sum(self.branch_lengths(p) * (w[p] / w.sum()) for p in range(self.P))
+        return to_extended_newick(self.net, lengths, self.reticulation_probs(), precision)
 
     def clv_update_count(self) -> int:
         return int(self.api._clv_update_count(self.h))

@@ -104,3 +104,25 @@ def test_extended_newick_writer_takes_the_optimised_state_and_the_reference_prec
     e = int(back.ret_first_edge[0])
     assert back.edge_prob[e] == pytest.approx(0.25) and back.edge_prob[int(back.ret_second_edge[0])] == pytest.approx(0.75)
     assert "#H0:0.6::0.25" in text and "#H0:1.2::0.75" in text   # newickNodeName: "#H" + reticulation index, empty support field
+
+
+def test_engine_newick_writes_the_current_state_and_averages_unlinked_lengths():
+    """toExtendedNewick(ann_network) = updateNetwork + write (src/io/NetworkIO.cpp:493-523); unlinked analyses write the
+    partition-weighted average (collect_average_branches, :455-491).  Driven over the oracle engine (the wrapper is shared)."""
+    from netrax_b200._capi import UNLINKED, Partition
+    from netrax_b200.synth import DNA_FREQS, GAMMA4_ALPHA05, GTR_RATES, random_network, simulate_alignment
+    from oracle import oracle
+    net = random_network(6, 1, seed=2)
+    parts = []
+    for k, n in enumerate((100, 300)):
+        m, w = simulate_alignment(net, n, seed=20 + k)
+        parts.append(Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w))
+    brl = [net.edge_length * 1.0, net.edge_length * 3.0]
+    e = oracle.make_engine("port", net, parts, linkage=UNLINKED, partition_brlens=brl)
+    e.set_reticulation_prob(0, 0.3)
+    back = parse_extended_newick(e.toExtendedNewick())
+    w = np.array([float(p.pattern_weights.sum()) for p in parts])
+    want = (brl[0] * w[0] + brl[1] * w[1]) / w.sum()
+    np.testing.assert_allclose(sorted(back.edge_length), sorted(want), rtol=1e-12)
+    assert back.edge_prob[int(back.ret_first_edge[0])] in (pytest.approx(0.3), pytest.approx(0.7))
+    e.close()

@@ -5,6 +5,19 @@
  * Every function returns 1 on success, 0 on failure (message in nrxh_last_error(), the text of the
  * std::runtime_error the reference would have thrown).
  *
+ *   nrxh_new / nrxh_set_network  <- the Network inside an AnnotatedNetwork (src/graph/Network.hpp:20-80, numbering of
+ *                                   convertNetworkToplevel, src/io/NetworkIO.cpp:59-330) + build_annotated_network
+ *                                   (src/graph/AnnotatedNetwork.cpp:199-213)
+ *   nrxh_add_partition           <- create_pll_partition's inputs (src/RaxmlWrapper.cpp:135-205): states, rate categories,
+ *                                   tip states, pattern weights, frequencies, exchangeabilities, category rates / weights
+ *   nrxh_set_options             <- NetraxOptions::likelihood_variant / brlen_linkage (src/NetraxOptions.hpp:99-125)
+ *   nrxh_set_partition_brlens    <- fake_treeinfo->branch_lengths[p] (createNetworkPllTreeinfoInternal, src/RaxmlWrapper.cpp:539-669)
+ *   nrxh_init                    <- init_annotated_network (src/graph/AnnotatedNetwork.cpp:80-185) + createNetworkPllTreeinfo (:671)
+ *   nrxh_read_clv / _scaler, nrxh_tree_info / _config, nrxh_num_trees
+ *                                <- pernode_displayed_tree_data[node].displayed_trees[t]: clv_vector, scale_buffer,
+ *                                   treeLoglData (src/graph/DisplayedTreeData.hpp:18-60, TreeLoglData.hpp) — what the tests compare
+ *   nrxh_partition_loglh         <- fake_treeinfo->partition_loglh (src/likelihood/LikelihoodComputation.cpp: evaluateTrees)
+ *   nrxh_persite_lnl             <- the persite_lnl output of pll_compute_root_loglikelihood (LIBPLL/likelihood.c:30-120)
  *   nrxh_compute_loglikelihood   <- netrax::computeLoglikelihood            src/likelihood/LikelihoodComputation.hpp:17
  *   nrxh_brlen_prepare           <- extractOldTrees + getRestrictionsActiveAliveBranch + updateCLVsVirtualRerootTrees
  *                                   (optimize_branch step 1, src/optimization/BranchLengthOptimization.cpp:355-373)
@@ -38,7 +51,7 @@ int nrxh_set_network(void *h, unsigned num_tips, unsigned num_nodes, unsigned ro
 int nrxh_add_partition(void *h, unsigned states, unsigned rate_cats, unsigned sites, const uint32_t *tip_masks,
                        const unsigned *pattern_weights, const double *freqs, const double *subst_params, const double *rates,
                        const double *rate_weights);
-int nrxh_set_options(void *h, int likelihood_variant /* 0 AVERAGE, 1 BEST, 2 SARAH_PSEUDO */, int brlen_linkage /* 0 linked, 2 unlinked */);
+int nrxh_set_options(void *h, int likelihood_variant /* 0 AVERAGE, 1 BEST, 2 SARAH_PSEUDO */, int brlen_linkage /* PLLMOD_COMMON_BRLEN_*: 0 linked, 1 scaled, 2 unlinked */);
 int nrxh_set_partition_brlens(void *h, unsigned p, const double *brlens);
 int nrxh_set_reduce_callback(void *h, nrxh_reduce_cb cb, void *context);
 int nrxh_init(void *h);

@@ -5,17 +5,17 @@
  * Every function returns 1 on success, 0 on failure (message in nrxh_last_error(), the text of the
  * std::runtime_error the reference would have thrown).
  *
- *   nrxh_new / nrxh_set_network  <- the Network inside an AnnotatedNetwork (src/graph/Network.hpp:20-80, numbering of
+ *   nrxh_new / nrxh_set_network  <- the Network inside an AnnotatedNetwork (src/graph/Network.hpp:20-84, numbering of
  *                                   convertNetworkToplevel, src/io/NetworkIO.cpp:59-330) + build_annotated_network
  *                                   (src/graph/AnnotatedNetwork.cpp:199-213)
- *   nrxh_add_partition           <- create_pll_partition's inputs (src/RaxmlWrapper.cpp:135-205): states, rate categories,
+ *   nrxh_add_partition           <- create_pll_partition's inputs (libs/raxml-ng/src/TreeInfo.cpp:629-707, called at src/RaxmlWrapper.cpp:195,252): states, rate categories,
  *                                   tip states, pattern weights, frequencies, exchangeabilities, category rates / weights
- *   nrxh_set_options             <- NetraxOptions::likelihood_variant / brlen_linkage (src/NetraxOptions.hpp:99-125)
+ *   nrxh_set_options             <- NetraxOptions::likelihood_variant / brlen_linkage (src/NetraxOptions.hpp:36,98)
  *   nrxh_set_partition_brlens    <- fake_treeinfo->branch_lengths[p] (createNetworkPllTreeinfoInternal, src/RaxmlWrapper.cpp:539-669)
  *   nrxh_init                    <- init_annotated_network (src/graph/AnnotatedNetwork.cpp:80-185) + createNetworkPllTreeinfo (:671)
  *   nrxh_read_clv / _scaler, nrxh_tree_info / _config, nrxh_num_trees
  *                                <- pernode_displayed_tree_data[node].displayed_trees[t]: clv_vector, scale_buffer,
- *                                   treeLoglData (src/graph/DisplayedTreeData.hpp:18-60, TreeLoglData.hpp) — what the tests compare
+ *                                   treeLoglData (src/graph/DisplayedTreeData.hpp:18-44, TreeLoglData.hpp) — what the tests compare
  *   nrxh_partition_loglh         <- fake_treeinfo->partition_loglh (src/likelihood/LikelihoodComputation.cpp: evaluateTrees)
  *   nrxh_persite_lnl             <- the persite_lnl output of pll_compute_root_loglikelihood (LIBPLL/likelihood.c:30-120)
  *   nrxh_compute_loglikelihood   <- netrax::computeLoglikelihood            src/likelihood/LikelihoodComputation.hpp:17

@@ -45,8 +45,8 @@ struct PortBackend : Backend {
   void setSubmodels(unsigned, unsigned n, const unsigned *, const double *, const double *) override {
     if (n > 1) throw std::runtime_error("per-category rate matrices are restated only through the reference backend (oracle kind \"ref\"): the scalar port has one rate matrix per partition");
   }
-  void setPinv(unsigned, double pinv) override {
-    if (pinv != 0.0) throw std::runtime_error("+I is restated only through the reference backend (oracle kind \"ref\"): the scalar port has no invariant-site terms");
+  void setPinv(unsigned p, double pinv) override {   // pll_update_invariant_sites_proportion (LIBPLL/models.c:495-543)
+    if (!port_set_prop_invar(parts[p], pinv)) throw std::runtime_error("Invalid proportion of invariant sites");
   }
   void setCategoryRates(unsigned p, const double *rates) override { for (unsigned i = 0; i < parts[p]->rate_cats; ++i) parts[p]->rates[i] = rates[i]; }
   bool gammaRates(double alpha, unsigned cats, double *out, int mode) const override { return port_compute_gamma_cats(alpha, cats, out, mode) != 0; }

@@ -58,6 +58,7 @@ port_partition *port_partition_create(unsigned states, unsigned rate_cats, unsig
 }
 
 void port_partition_destroy(port_partition *p) {
+  if (p) free(p->invariant);
   unsigned i;
   if (!p) return;
   for (i = 0; i < p->tips; ++i) free(p->tipchars[i]);
@@ -75,6 +76,28 @@ void port_partition_destroy(port_partition *p) {
  * 1975, chi-square quantile).  Their truncation constants (1e-8, .5e-6) are part of the result
  * at the 1e-7 level, so the same published constants are used here.
  * ---------------------------------------------------------------------------------------- */
+int port_update_invariant_sites(port_partition *p) { /* LIBPLL/models.c:651-750, PATTERN_TIP branch */
+  unsigned i, j;
+  uint32_t gap_state = 0, *inv;
+  for (i = 0; i < p->states; ++i) gap_state = (gap_state << 1) | 1;
+  if (!p->invariant) p->invariant = (int *)xcalloc(p->sites, sizeof(int));
+  inv = (uint32_t *)xcalloc(p->sites, sizeof(uint32_t));
+  for (j = 0; j < p->sites; ++j) inv[j] = gap_state;
+  for (i = 0; i < p->tips; ++i)
+    for (j = 0; j < p->sites; ++j) inv[j] &= p->tipmap[p->tipchars[i][j]];
+  for (j = 0; j < p->sites; ++j)
+    p->invariant[j] = (inv[j] == 0 || __builtin_popcount(inv[j]) > 1) ? -1 : __builtin_ctz(inv[j]);
+  free(inv);
+  return 1;
+}
+
+int port_set_prop_invar(port_partition *p, double prop_invar) { /* LIBPLL/models.c:495-543 */
+  if (prop_invar < 0 || prop_invar >= 1) return 0; /* "Invalid proportion of invariant sites" */
+  if (prop_invar > 0 && !p->invariant) port_update_invariant_sites(p);
+  p->prop_invar = prop_invar;
+  return 1;
+}
+
 static double ln_gamma_pike_hill(double alpha) { /* gamma.c:92-118 */
   double x = alpha, f = 0.0, z;
   if (x < 7.0) {
@@ -528,7 +551,11 @@ double port_root_loglikelihood(const port_partition *p, const double *clv, const
         term_r = 0;
         for (k = 0; k < states; ++k) term_r += c[k] * p->freqs[k];
       }
-      term += term_r * p->rate_weights[j];
+      if (p->prop_invar > 0) { /* core_likelihood.c:174-186 (the AVX / AVX2 kernels have the same lines) */
+        const double inv_site_lk = (p->invariant[n] == -1) ? 0 : p->freqs[p->invariant[n]];
+        term += p->rate_weights[j] * (term_r * (1 - p->prop_invar) + inv_site_lk * p->prop_invar);
+      } else
+        term += term_r * p->rate_weights[j];
     }
     term = log(term);
     if (scaler && scaler[n]) term += scaler[n] * log(PORT_SCALE_THRESHOLD);
@@ -549,7 +576,7 @@ double port_edge_loglikelihood(const port_partition *p, const port_operand *pare
   if (parent->kind == 1) { in = child; ot = parent; }
   if (in->kind != 0) return -INFINITY; /* tip-tip: invalid */
   for (n = 0; n < p->sites; ++n) {
-    double terma = 0, site_lk;
+    double terma = 0, terminv = 0, site_lk;
     unsigned site_scalings = 0;
     if (in->scaler) site_scalings += in->scaler[n];
     if (ot->kind == 0 && ot->scaler) site_scalings += ot->scaler[n];
@@ -563,10 +590,25 @@ double port_edge_loglikelihood(const port_partition *p, const port_operand *pare
                            : row_dot(pm + j * sp, ot->clv + ((size_t)n * cats + i) * sp, states);
         terma_r += clvp[j] * p->freqs[j] * termb; /* core_likelihood.c:1433 */
       }
-      terma += terma_r * p->rate_weights[i];
+      if (p->prop_invar > 0) { /* core_likelihood_avx.c:471-486, core_likelihood_avx2.c:391-406 */
+        terma += p->rate_weights[i] * terma_r * (1. - p->prop_invar);
+        if (p->invariant[n] != -1) terminv += p->rate_weights[i] * p->freqs[p->invariant[n]] * p->prop_invar;
+      } else
+        terma += terma_r * p->rate_weights[i];
     }
-    site_lk = log(terma);
-    if (site_scalings) site_lk += site_scalings * log(PORT_SCALE_THRESHOLD);
+    if (site_scalings) {
+      if (terminv > 0.) { /* "undoing the scaling for non-variant likelihood term only" (core_likelihood_avx.c:493-501) */
+        const unsigned capped = site_scalings < 4 ? site_scalings : 4; /* PLL_SCALE_RATE_MAXDIFF */
+        double scale_factor = 1.0;
+        unsigned s_;
+        for (s_ = 0; s_ < capped; ++s_) scale_factor *= PORT_SCALE_THRESHOLD; /* scale_minlh[capped - 1] (:323-333) */
+        site_lk = log(terma * scale_factor + terminv);
+      } else {
+        site_lk = log(terma);
+        site_lk += site_scalings * log(PORT_SCALE_THRESHOLD);
+      }
+    } else
+      site_lk = log(terma + terminv);
     site_lk *= p->pattern_weights[n];
     if (persite_lnl) persite_lnl[n] = site_lk;
     logl += site_lk;
@@ -645,6 +687,10 @@ int port_loglikelihood_derivatives(const port_partition *p, const double *sumtab
         c1 += sum[j] * diagp[1];
         c2 += sum[j] * diagp[2];
         diagp += 4;
+      }
+      if (p->prop_invar > 0) { /* core_derivatives_avx2.c:1736-1749 (generic: core_derivatives.c:672-684) */
+        c0 *= 1. - p->prop_invar; c1 *= 1. - p->prop_invar; c2 *= 1. - p->prop_invar;
+        if (p->invariant && p->invariant[n] != -1) c0 += p->freqs[p->invariant[n]] * p->prop_invar;
       }
       lk[0] += c0 * p->rate_weights[i];
       lk[1] += c1 * p->rate_weights[i];

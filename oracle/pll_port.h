@@ -45,7 +45,8 @@ typedef struct port_partition {
   double *eigenvals;      /* [states_padded] */
   double *rates;          /* [rate_cats] */
   double *rate_weights;   /* [rate_cats] */
-  double prop_invar;      /* must stay 0: +I is rejected (SURVEY §8a "not in first scope") */
+  double prop_invar;      /* +I: pll_partition_t::prop_invar[0] (one rate matrix) */
+  int *invariant;         /* [sites] frequency index of an invariant pattern, -1 otherwise; NULL until +I is first used */
   unsigned *pattern_weights; /* [sites] */
   unsigned char **tipchars;  /* [tips][sites]: code into tipmap (DNA: the 4-bit state mask itself) */
   uint32_t tipmap[256];      /* code -> state bit mask */
@@ -57,6 +58,9 @@ port_partition *port_partition_create(unsigned states, unsigned rate_cats, unsig
                                       unsigned tips, unsigned edges);
 void port_partition_destroy(port_partition *p);
 
+/* LIBPLL/models.c:651-750 pll_update_invariant_sites (PATTERN_TIP branch) and :495-543 pll_update_invariant_sites_proportion */
+int port_update_invariant_sites(port_partition *p);
+int port_set_prop_invar(port_partition *p, double prop_invar);
 /* LIBPLL/gamma.c:267-330 pll_compute_gamma_cats, PLL_GAMMA_RATES_MEAN (mode 0) / MEDIAN (1) */
 int port_compute_gamma_cats(double alpha, unsigned categories, double *out_rates, int mode);
 /* LIBPLL/models.c:293-410 pll_update_eigen (Householder tridiagonalisation + QL, :24-180) */

@@ -140,9 +140,6 @@ def test_optimize_pinv_matches_oracle():
     """The PINV step of optimize_params (ModelOptimization.cpp:67-76) on the device — every Brent iterate rescales the
     rates by 1 / (1 - pinv) and re-evaluates with the invariant-site terms — against pll-modules' real minimiser over
     libpll's +I kernels."""
-    from oracle import oracle
-    if not oracle.have_ref():
-        pytest.skip("+I is restated only through the reference backend")
     from test_oracle_optimize import _pinv_case
     net, parts = _pinv_case()
     g, o = _pair(net, parts)

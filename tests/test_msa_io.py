@@ -146,8 +146,8 @@ def test_partition_file_ranges_models_and_starting_values():
     np.testing.assert_allclose(parts[0].rates, oracle.make_engine("port", net, parts[:1]).api.gamma_rates(1.0, 4), rtol=1e-12)
     k = sum(s.free_params() for s in specs)
     assert k == (3 + 5 + 1) + (3 + 1 + 1) + 0
-    if oracle.have_ref():   # +I needs the reference backend
-        e = oracle.make_engine("ref", net, parts)
+    for kind in ["port"] + (["ref"] if oracle.have_ref() else []):
+        e = oracle.make_engine(kind, net, parts)
         assert apply_model_state(e, specs) == k
         assert e.get_alpha(0) == 1.0 and e.get_pinv(1) == pytest.approx(inv / 2) and e.get_pinv(0) == 0.0
         lnl = e.computeLoglikelihood(0, 1)

@@ -206,18 +206,19 @@ def check_pinv_golden(make_engine, G, tip_edge, gamma):
             eng.close()
 
 
+@pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("which", ["dna", "oddstates"])
 @pytest.mark.parametrize("tip_edge", [False, True])
-def test_libpll_golden_pinv_reference_oracle(which, tip_edge):
-    """+I through the reference backend (real libpll): the golden edge lnL / derivatives with pinv in {0.3, 0.6, 0.9}.  (The
-    scalar port has no invariant-site terms and says so.)"""
-    if not oracle.have_ref():
-        pytest.skip("oracle/_ref not built")
+def test_libpll_golden_pinv(kind, which, tip_edge):
+    """+I through both oracle flavours — the scalar port's invariant-site terms (pll_port.c: root / edge lnL, derivatives,
+    invariant-pattern detection) and real libpll: the golden edge lnL / derivatives with pinv in {0.3, 0.6, 0.9}."""
     G = GI if which == "dna" else GOI
-    check_pinv_golden(lambda net, part: oracle.make_engine("ref", net, [part]), G, tip_edge, oracle.api("ref").gamma_rates)
+    check_pinv_golden(lambda net, part: oracle.make_engine(kind, net, [part]), G, tip_edge, oracle.api(kind).gamma_rates)
     net, part = pinv_case(G, 0.1, False, 1, np.ones(1))
-    with pytest.raises(Exception, match="reference backend"):
-        oracle.make_engine("port", net, [part]).set_pinv(0, 0.3)
+    e = oracle.make_engine(kind, net, [part])
+    with pytest.raises(Exception, match="[Ii]nvalid proportion|invariant"):
+        e.set_pinv(0, 1.0)
+    e.close()
 
 
 # ---- fifth / sixth golden set: libpll test/out/pmatrix.out (K1 + eigendecomposition, 9 decimals) and hky.out ---------------

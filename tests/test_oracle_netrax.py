@@ -346,3 +346,41 @@ def test_scaled_branch_length_linkage(kind):
         lin.set_brlen_scaler(0, 2.0)
     for x in (lin, sc, un):
         x.close()
+
+
+def test_pinv_port_equals_real_libpll_on_networks():
+    """+I in the scalar port against the reference's real libpll under the same restated driver: a DNA network, a protein
+    network and a 300-taxon caterpillar with invariant columns whose scaled sites take libpll's "undo the scaling on the
+    non-invariant term only" branch of the edge lnL (core_likelihood_avx.c:493-501) — lnL, re-rooted edge lnL, sumtables and
+    derivatives on a tip edge, an inner edge and a reticulation edge."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from netrax_b200.synth import caterpillar_network, lg_model
+    cases = []
+    net = random_network(14, 3, seed=61)
+    m, w = simulate_alignment(net, 500, seed=61)
+    cases.append((net, Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w), 0.25))
+    netp = random_network(10, 2, seed=62)
+    lr, lf = lg_model()
+    mp, wp = simulate_alignment(netp, 150, seed=62, states=20, rates=np.asarray(lr), freqs=np.asarray(lf))
+    cases.append((netp, Partition(20, 4, mp, lf, lr, GAMMA4_ALPHA05, pattern_weights=wp), 0.4))
+    cat = caterpillar_network(300)
+    m, w = simulate_alignment(cat, 200, seed=63, gap_frac=0.0)
+    m[:, :60] = m[0, :60]
+    cases.append((cat, Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w), 0.3))
+    for net, part, pinv in cases:
+        a, b = oracle.make_engine("port", net, [part]), oracle.make_engine("ref", net, [part])
+        a.set_eigen(0, *b.get_eigen(0)) if hasattr(a, "set_eigen") else None
+        a.set_pinv(0, pinv); b.set_pinv(0, pinv)
+        la, lb = a.computeLoglikelihood(0, 1), b.computeLoglikelihood(0, 1)
+        assert la == pytest.approx(lb, rel=1e-11), (part.states, pinv)
+        for e in (0, net.num_edges - 1) + ((int(net.ret_first_edge[0]),) if net.num_reticulations else ()):
+            assert a.brlen_prepare(e) == pytest.approx(b.brlen_prepare(e), rel=1e-11)
+            assert a.computeLoglikelihoodBrlenOpt(e) == pytest.approx(b.computeLoglikelihoodBrlenOpt(e), rel=1e-11), (part.states, e)
+            assert a.computePartitionSumtables(e) == b.computePartitionSumtables(e)
+            da, db = a.computeLoglikelihoodDerivatives(e), b.computeLoglikelihoodDerivatives(e)
+            np.testing.assert_allclose(da[4], db[4], rtol=1e-9, atol=1e-10)
+            assert a.brlen_finish(e) == pytest.approx(b.brlen_finish(e), rel=1e-11)
+        a.set_pinv(0, 0.0); b.set_pinv(0, 0.0)
+        assert a.computeLoglikelihood(0, 1) == pytest.approx(b.computeLoglikelihood(0, 1), rel=1e-11)
+        a.close(); b.close()

@@ -240,27 +240,32 @@ def _pinv_case():
     return net, parts
 
 
-def test_optimize_pinv_reference_backend():
-    """The PINV step of optimize_params (ModelOptimization.cpp:67-76): pllmod_algo_opt_onedim_treeinfo(PINV) driven over
-    libpll's real +I kernels by pll-modules' real Brent-multi (_ref; the scalar port has no invariant-site terms, and its
-    Brent-multi restatement is pinned by the alpha test above).  Partitions without +I (pinv = 0) are not in
-    params_to_optimize and stay untouched; the end point is a maximum of the lnL in the proportion."""
-    if not oracle.have_ref():
-        pytest.skip("oracle/_ref not built")
+def test_optimize_pinv_port_equals_reference_minimiser():
+    """The PINV step of optimize_params (ModelOptimization.cpp:67-76): pllmod_algo_opt_onedim_treeinfo(PINV) restated over the
+    scalar port (its own +I terms and Brent-multi) against pll-modules' real Brent-multi over libpll's +I kernels (_ref).
+    Partitions without +I (pinv = 0) are not in params_to_optimize and stay untouched; the end point is a maximum of the lnL
+    in the proportion."""
     net, parts = _pinv_case()
-    e = oracle.make_engine("ref", net, parts)
-    e.set_pinv(0, 0.05)
-    l0 = e.computeLoglikelihood(0, 1)
-    l1 = e.optimize_pinv()
-    assert l1 >= l0 - 1e-6
-    assert e.get_pinv(1) == 0.0
-    x = e.get_pinv(0)
-    assert 0.1 < x < 0.99   # the inflated constant columns pull the proportion up from 0.05
-    assert e.computeLoglikelihood(0, 1) == pytest.approx(l1, rel=1e-12)
-    for d in (-0.02, 0.02):
-        e.set_pinv(0, x + d)
-        assert e.computeLoglikelihood(0, 1) < l1
-    e.close()
+    res = {}
+    for kind in (["port", "ref"] if oracle.have_ref() else ["port"]):
+        e = oracle.make_engine(kind, net, parts)
+        e.set_pinv(0, 0.05)
+        l0 = e.computeLoglikelihood(0, 1)
+        l1 = e.optimize_pinv()
+        assert l1 >= l0 - 1e-6
+        assert e.get_pinv(1) == 0.0
+        x = e.get_pinv(0)
+        assert 0.1 < x < 0.99   # the inflated constant columns pull the proportion up from 0.05
+        assert e.computeLoglikelihood(0, 1) == pytest.approx(l1, rel=1e-12)
+        for d in (-0.02, 0.02):
+            e.set_pinv(0, x + d)
+            assert e.computeLoglikelihood(0, 1) < l1
+        res[kind] = (l0, l1, x)
+        e.close()
+    if "ref" in res:
+        assert res["port"][0] == pytest.approx(res["ref"][0], rel=1e-10)
+        assert res["port"][1] == pytest.approx(res["ref"][1], rel=1e-9)
+        assert res["port"][2] == pytest.approx(res["ref"][2], rel=1e-4)
 
 
 def test_optimize_scalers_port_equals_reference_minimiser():

@@ -867,6 +867,12 @@ def test_pinv_on_networks_matches_reference_oracle():
     m, w = simulate_alignment(cat, 200, seed=63, gap_frac=0.0)
     m[:, :60] = m[0, :60]          # 60 invariant columns on a tree deep enough to scale
     cases.append((cat, Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w), 0.3))
+    # with Gamma categories the slowest category keeps invariant columns above the scaling threshold; ONE category on saturated
+    # branches scales them too (scaler 2 on every column): the case that really takes the "non-invariant term only" branch
+    sat = caterpillar_network(300, brlen=4.0)
+    m1, w1 = simulate_alignment(sat, 200, seed=63, gap_frac=0.0)
+    m1[:, :60] = m1[0, :60]
+    cases.append((sat, Partition(4, 1, m1, DNA_FREQS, GTR_RATES, np.ones(1), pattern_weights=w1), 0.3))
     for net, part, pinv in cases:
         g, o = _gpu(net, [part]), oracle.make_engine("ref", net, [part])
         _inject_eigen(g, o)

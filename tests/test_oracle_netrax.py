@@ -368,12 +368,22 @@ def test_pinv_port_equals_real_libpll_on_networks():
     m, w = simulate_alignment(cat, 200, seed=63, gap_frac=0.0)
     m[:, :60] = m[0, :60]
     cases.append((cat, Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w), 0.3))
+    # with Gamma categories the slowest category keeps invariant columns above the scaling threshold; ONE category on saturated
+    # branches scales them too (scaler 2 on every column): the case that really takes the "non-invariant term only" branch
+    sat = caterpillar_network(300, brlen=4.0)
+    m1, w1 = simulate_alignment(sat, 200, seed=63, gap_frac=0.0)
+    m1[:, :60] = m1[0, :60]
+    cases.append((sat, Partition(4, 1, m1, DNA_FREQS, GTR_RATES, np.ones(1), pattern_weights=w1), 0.3))
     for net, part, pinv in cases:
         a, b = oracle.make_engine("port", net, [part]), oracle.make_engine("ref", net, [part])
         a.set_eigen(0, *b.get_eigen(0)) if hasattr(a, "set_eigen") else None
         a.set_pinv(0, pinv); b.set_pinv(0, pinv)
         la, lb = a.computeLoglikelihood(0, 1), b.computeLoglikelihood(0, 1)
         assert la == pytest.approx(lb, rel=1e-11), (part.states, pinv)
+        if net is sat:   # the invariant columns (the first 60) are scaled here, and only here
+            assert np.all(a.read_scaler(net.root, 0)[:60] > 0) and np.array_equal(a.read_scaler(net.root, 0), b.read_scaler(net.root, 0))
+        elif net is cat:
+            assert np.all(a.read_scaler(net.root, 0)[:60] == 0) and np.any(a.read_scaler(net.root, 0) > 0)
         for e in (0, net.num_edges - 1) + ((int(net.ret_first_edge[0]),) if net.num_reticulations else ()):
             assert a.brlen_prepare(e) == pytest.approx(b.brlen_prepare(e), rel=1e-11)
             assert a.computeLoglikelihoodBrlenOpt(e) == pytest.approx(b.computeLoglikelihoodBrlenOpt(e), rel=1e-11), (part.states, e)

@@ -42,8 +42,8 @@ struct PortBackend : Backend {
     std::memcpy(weights, pp->rate_weights, sizeof(double) * pp->rate_cats);
     std::memcpy(freqs, pp->freqs, sizeof(double) * pp->states_padded);
   }
-  void setSubmodels(unsigned, unsigned n, const unsigned *, const double *, const double *) override {
-    if (n > 1) throw std::runtime_error("per-category rate matrices are restated only through the reference backend (oracle kind \"ref\"): the scalar port has one rate matrix per partition");
+  void setSubmodels(unsigned p, unsigned n, const unsigned *cat_model, const double *freqs, const double *subst) override {
+    if (!port_set_submodels(parts[p], n, cat_model, freqs, subst)) throw std::runtime_error("set_submodels: 1..16 rate matrices, every category's index below the matrix count");
   }
   void setPinv(unsigned p, double pinv) override {   // pll_update_invariant_sites_proportion (LIBPLL/models.c:495-543)
     if (!port_set_prop_invar(parts[p], pinv)) throw std::runtime_error("Invalid proportion of invariant sites");

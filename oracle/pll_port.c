@@ -43,6 +43,10 @@ port_partition *port_partition_create(unsigned states, unsigned rate_cats, unsig
     p->rates[i] = 1.0;
     p->rate_weights[i] = 1.0 / rate_cats;
   }
+  p->nmodels = 1;
+  p->cat_model = (unsigned *)xcalloc(rate_cats, sizeof(unsigned));
+  p->m_freqs[0] = p->freqs; p->m_subst[0] = p->subst_params; p->m_eigenvecs[0] = p->eigenvecs;
+  p->m_inv_eigenvecs[0] = p->inv_eigenvecs; p->m_eigenvals[0] = p->eigenvals;
   p->pattern_weights = (unsigned *)xcalloc(sites, sizeof(unsigned));
   for (i = 0; i < sites; ++i) p->pattern_weights[i] = 1;
   p->tipchars = (unsigned char **)xcalloc(tips, sizeof(unsigned char *));
@@ -63,6 +67,10 @@ void port_partition_destroy(port_partition *p) {
   if (!p) return;
   for (i = 0; i < p->tips; ++i) free(p->tipchars[i]);
   for (i = 0; i < p->edges; ++i) free(p->pmatrix[i]);
+  for (i = 1; i < PORT_MAX_MODELS; ++i) {
+    free(p->m_freqs[i]); free(p->m_subst[i]); free(p->m_eigenvecs[i]); free(p->m_inv_eigenvecs[i]); free(p->m_eigenvals[i]);
+  }
+  free(p->cat_model);
   free(p->tipchars); free(p->pmatrix); free(p->pattern_weights);
   free(p->freqs); free(p->subst_params); free(p->eigenvecs); free(p->inv_eigenvecs);
   free(p->eigenvals); free(p->rates); free(p->rate_weights);
@@ -76,6 +84,38 @@ void port_partition_destroy(port_partition *p) {
  * 1975, chi-square quantile).  Their truncation constants (1e-8, .5e-6) are part of the result
  * at the 1e-7 level, so the same published constants are used here.
  * ---------------------------------------------------------------------------------------- */
+int port_set_submodels(port_partition *p, unsigned n, const unsigned *cat_model, const double *freqs, const double *subst) {
+  const unsigned states = p->states, sp = p->states_padded, nrates = states * (states - 1) / 2;
+  unsigned m, i;
+  if (n < 1 || n > PORT_MAX_MODELS) return 0;
+  for (i = 0; i < p->rate_cats; ++i)
+    if (cat_model[i] >= n) return 0;
+  for (m = 0; m < n; ++m) {
+    double sum = 0., *sf, *ss, *sev, *siv, *sva;
+    if (!p->m_freqs[m]) {
+      p->m_freqs[m] = (double *)xcalloc(sp, sizeof(double));
+      p->m_subst[m] = (double *)xcalloc(nrates, sizeof(double));
+      p->m_eigenvecs[m] = (double *)xcalloc((size_t)states * sp, sizeof(double));
+      p->m_inv_eigenvecs[m] = (double *)xcalloc((size_t)states * sp, sizeof(double));
+      p->m_eigenvals[m] = (double *)xcalloc(sp, sizeof(double));
+    }
+    /* pll_set_frequencies (LIBPLL/models.c:445-467): renormalise when |sum - 1| > PLL_MISC_EPSILON */
+    for (i = 0; i < states; ++i) { p->m_freqs[m][i] = freqs[(size_t)m * states + i]; sum += p->m_freqs[m][i]; }
+    if (fabs(sum - 1.0) > PORT_MISC_EPSILON)
+      for (i = 0; i < states; ++i) p->m_freqs[m][i] /= sum;
+    memcpy(p->m_subst[m], subst + (size_t)m * nrates, nrates * sizeof(double));
+    /* pll_update_eigen(partition, m): the single-matrix routine run on matrix m's arrays */
+    sf = p->freqs; ss = p->subst_params; sev = p->eigenvecs; siv = p->inv_eigenvecs; sva = p->eigenvals;
+    p->freqs = p->m_freqs[m]; p->subst_params = p->m_subst[m]; p->eigenvecs = p->m_eigenvecs[m];
+    p->inv_eigenvecs = p->m_inv_eigenvecs[m]; p->eigenvals = p->m_eigenvals[m];
+    port_update_eigen(p);
+    p->freqs = sf; p->subst_params = ss; p->eigenvecs = sev; p->inv_eigenvecs = siv; p->eigenvals = sva;
+  }
+  p->nmodels = n;
+  for (i = 0; i < p->rate_cats; ++i) p->cat_model[i] = cat_model[i];
+  return 1;
+}
+
 int port_update_invariant_sites(port_partition *p) { /* LIBPLL/models.c:651-750, PATTERN_TIP branch */
   unsigned i, j;
   uint32_t gap_state = 0, *inv;
@@ -435,27 +475,30 @@ int port_update_pmatrix(port_partition *p, unsigned edge, double t) {
   if (t < 0) { free(expd); free(temp); return 0; }
   for (n = 0; n < p->rate_cats; ++n) {
     double *pmat = p->pmatrix[edge] + (size_t)n * states * sp;
+    /* core_pmatrix.c:182-185: the category's matrix through params_indices */
+    const double *eigenvals = p->m_eigenvals[p->cat_model[n]], *eigenvecs = p->m_eigenvecs[p->cat_model[n]],
+                 *inv_eigenvecs = p->m_inv_eigenvecs[p->cat_model[n]];
     if (t > 0.) {
       /* core_pmatrix_avx.c:97-125: (eval*rate)*t, divided by (1-pinv) only if pinv > eps */
       for (j = 0; j < states; ++j) {
-        double x = (p->eigenvals[j] * p->rates[n]) * t;
+        double x = (eigenvals[j] * p->rates[n]) * t;
         if (p->prop_invar > PORT_MISC_EPSILON) x = x / (1.0 - p->prop_invar);
         expd[j] = expm1(x);
       }
       for (j = 0; j < states; ++j)
-        for (k = 0; k < states; ++k) temp[j * states + k] = p->inv_eigenvecs[j * sp + k] * expd[k];
+        for (k = 0; k < states; ++k) temp[j * states + k] = inv_eigenvecs[j * sp + k] * expd[k];
       if (states == 4) { /* core_pmatrix_avx.c:127-258: tree sum, identity added last */
         for (j = 0; j < 4; ++j)
           for (k = 0; k < 4; ++k) {
-            double s = tree4(temp[j * 4 + 0] * p->eigenvecs[0 * sp + k], temp[j * 4 + 1] * p->eigenvecs[1 * sp + k],
-                             temp[j * 4 + 2] * p->eigenvecs[2 * sp + k], temp[j * 4 + 3] * p->eigenvecs[3 * sp + k]);
+            double s = tree4(temp[j * 4 + 0] * eigenvecs[0 * sp + k], temp[j * 4 + 1] * eigenvecs[1 * sp + k],
+                             temp[j * 4 + 2] * eigenvecs[2 * sp + k], temp[j * 4 + 3] * eigenvecs[3 * sp + k]);
             pmat[j * sp + k] = s + ((j == k) ? 1.0 : 0.0);
           }
       } else { /* core_pmatrix.c:205-217: identity first, then serial accumulation */
         for (j = 0; j < states; ++j)
           for (k = 0; k < states; ++k) {
             double s = (j == k) ? 1.0 : 0;
-            for (m = 0; m < states; ++m) s += temp[j * states + m] * p->eigenvecs[m * sp + k];
+            for (m = 0; m < states; ++m) s += temp[j * states + m] * eigenvecs[m * sp + k];
             pmat[j * sp + k] = s;
           }
       }
@@ -544,15 +587,16 @@ double port_root_loglikelihood(const port_partition *p, const double *clv, const
     double term = 0;
     for (j = 0; j < cats; ++j) {
       const double *c = clv + ((size_t)n * cats + j) * sp;
+      const double *freqs = p->m_freqs[p->cat_model[j]]; /* frequencies[freqs_indices[j]] */
       double term_r;
       if (states == 4) /* core_likelihood_avx.c:232-245: mul, hadd, [0]+[2] */
-        term_r = tree4(p->freqs[0] * c[0], p->freqs[1] * c[1], p->freqs[2] * c[2], p->freqs[3] * c[3]);
+        term_r = tree4(freqs[0] * c[0], freqs[1] * c[1], freqs[2] * c[2], freqs[3] * c[3]);
       else { /* core_likelihood.c:163-171 */
         term_r = 0;
-        for (k = 0; k < states; ++k) term_r += c[k] * p->freqs[k];
+        for (k = 0; k < states; ++k) term_r += c[k] * freqs[k];
       }
       if (p->prop_invar > 0) { /* core_likelihood.c:174-186 (the AVX / AVX2 kernels have the same lines) */
-        const double inv_site_lk = (p->invariant[n] == -1) ? 0 : p->freqs[p->invariant[n]];
+        const double inv_site_lk = (p->invariant[n] == -1) ? 0 : freqs[p->invariant[n]];
         term += p->rate_weights[j] * (term_r * (1 - p->prop_invar) + inv_site_lk * p->prop_invar);
       } else
         term += term_r * p->rate_weights[j];
@@ -583,16 +627,17 @@ double port_edge_loglikelihood(const port_partition *p, const port_operand *pare
     for (i = 0; i < cats; ++i) {
       const double *clvp = in->clv + ((size_t)n * cats + i) * sp;
       const double *pm = p->pmatrix[edge] + (size_t)i * states * sp;
+      const double *freqs = p->m_freqs[p->cat_model[i]];
       double terma_r = 0;
       for (j = 0; j < states; ++j) {
         double termb = (ot->kind == 1)
                            ? masked_rowsum(pm + j * sp, states, p->tipmap[p->tipchars[ot->tip][n]])
                            : row_dot(pm + j * sp, ot->clv + ((size_t)n * cats + i) * sp, states);
-        terma_r += clvp[j] * p->freqs[j] * termb; /* core_likelihood.c:1433 */
+        terma_r += clvp[j] * freqs[j] * termb; /* core_likelihood.c:1433 */
       }
       if (p->prop_invar > 0) { /* core_likelihood_avx.c:471-486, core_likelihood_avx2.c:391-406 */
         terma += p->rate_weights[i] * terma_r * (1. - p->prop_invar);
-        if (p->invariant[n] != -1) terminv += p->rate_weights[i] * p->freqs[p->invariant[n]] * p->prop_invar;
+        if (p->invariant[n] != -1) terminv += p->rate_weights[i] * freqs[p->invariant[n]] * p->prop_invar;
       } else
         terma += terma_r * p->rate_weights[i];
     }
@@ -629,20 +674,23 @@ int port_update_sumtable(const port_partition *p, const port_operand *parent,
     for (i = 0; i < cats; ++i) {
       const double *cr = r->clv + ((size_t)n * cats + i) * sp;
       double *sum = sumtable + ((size_t)n * cats + i) * sp;
+      /* core_derivatives.c:362-366: eigenvectors / frequencies of the category's matrix */
+      const double *freqs = p->m_freqs[p->cat_model[i]], *eigenvecs = p->m_eigenvecs[p->cat_model[i]],
+                   *inv_eigenvecs = p->m_inv_eigenvecs[p->cat_model[i]];
       for (j = 0; j < states; ++j) {
         double lefterm = 0, righterm = 0;
         if (l->kind == 1) { /* core_derivatives.c:616-627 */
           uint32_t ts = p->tipmap[p->tipchars[l->tip][n]];
           for (k = 0; k < states; ++k) {
-            lefterm += (double)(ts & 1) * p->freqs[k] * p->inv_eigenvecs[k * sp + j];
-            righterm += p->eigenvecs[j * sp + k] * cr[k];
+            lefterm += (double)(ts & 1) * freqs[k] * inv_eigenvecs[k * sp + j];
+            righterm += eigenvecs[j * sp + k] * cr[k];
             ts >>= 1;
           }
         } else { /* core_derivatives.c:447-456 */
           const double *cl = l->clv + ((size_t)n * cats + i) * sp;
           for (k = 0; k < states; ++k) {
-            lefterm += cl[k] * p->freqs[k] * p->inv_eigenvecs[k * sp + j];
-            righterm += p->eigenvecs[j * sp + k] * cr[k];
+            lefterm += cl[k] * freqs[k] * inv_eigenvecs[k * sp + j];
+            righterm += eigenvecs[j * sp + k] * cr[k];
           }
         }
         sum[j] = lefterm * righterm;
@@ -658,10 +706,11 @@ void port_compute_diagptable(const port_partition *p, double t, double *diagp) {
   unsigned i, j;
   for (i = 0; i < p->rate_cats; ++i) {
     double ki = p->rates[i] / (1.0 - p->prop_invar);
+    const double *eigenvals = p->m_eigenvals[p->cat_model[i]]; /* core_derivatives.c:712 */
     for (j = 0; j < p->states; ++j) {
-      diagp[0] = exp(p->eigenvals[j] * ki * t);
-      diagp[1] = p->eigenvals[j] * ki * diagp[0];
-      diagp[2] = p->eigenvals[j] * ki * p->eigenvals[j] * ki * diagp[0];
+      diagp[0] = exp(eigenvals[j] * ki * t);
+      diagp[1] = eigenvals[j] * ki * diagp[0];
+      diagp[2] = eigenvals[j] * ki * eigenvals[j] * ki * diagp[0];
       diagp[3] = 0;
       diagp += 4;
     }
@@ -690,7 +739,7 @@ int port_loglikelihood_derivatives(const port_partition *p, const double *sumtab
       }
       if (p->prop_invar > 0) { /* core_derivatives_avx2.c:1736-1749 (generic: core_derivatives.c:672-684) */
         c0 *= 1. - p->prop_invar; c1 *= 1. - p->prop_invar; c2 *= 1. - p->prop_invar;
-        if (p->invariant && p->invariant[n] != -1) c0 += p->freqs[p->invariant[n]] * p->prop_invar;
+        if (p->invariant && p->invariant[n] != -1) c0 += p->m_freqs[p->cat_model[i]][p->invariant[n]] * p->prop_invar;
       }
       lk[0] += c0 * p->rate_weights[i];
       lk[1] += c1 * p->rate_weights[i];

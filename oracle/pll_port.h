@@ -31,6 +31,8 @@ extern "C" {
 
 /* One partition's model + data, the subset of pll_partition_t (LIBPLL/pll.h:230-277) the path reads.
  * Single rate matrix per partition (params_indices == 0 everywhere, as in every BASELINE config). */
+#define PORT_MAX_MODELS 16
+
 typedef struct port_partition {
   unsigned states;         /* 4 or 20 */
   unsigned states_padded;  /* (states+3)&~3, LIBPLL/pll.c:482-483 (AVX/AVX2) */
@@ -47,6 +49,12 @@ typedef struct port_partition {
   double *rate_weights;   /* [rate_cats] */
   double prop_invar;      /* +I: pll_partition_t::prop_invar[0] (one rate matrix) */
   int *invariant;         /* [sites] frequency index of an invariant pattern, -1 otherwise; NULL until +I is first used */
+  /* several rate matrices, one per rate category (libpll rate_matrices + params_indices; LG4M / LG4X): matrix 0 is the set of
+   * arrays above, matrices 1.. are allocated by port_set_submodels; cat_model[c] names the matrix of category c */
+  unsigned nmodels;
+  unsigned *cat_model;       /* [rate_cats] */
+  double *m_freqs[PORT_MAX_MODELS], *m_subst[PORT_MAX_MODELS], *m_eigenvecs[PORT_MAX_MODELS], *m_inv_eigenvecs[PORT_MAX_MODELS],
+      *m_eigenvals[PORT_MAX_MODELS];
   unsigned *pattern_weights; /* [sites] */
   unsigned char **tipchars;  /* [tips][sites]: code into tipmap (DNA: the 4-bit state mask itself) */
   uint32_t tipmap[256];      /* code -> state bit mask */
@@ -59,6 +67,9 @@ port_partition *port_partition_create(unsigned states, unsigned rate_cats, unsig
 void port_partition_destroy(port_partition *p);
 
 /* LIBPLL/models.c:651-750 pll_update_invariant_sites (PATTERN_TIP branch) and :495-543 pll_update_invariant_sites_proportion */
+/* pll_set_frequencies / pll_set_subst_params / pll_update_eigen per matrix index + the params_indices every libpll call takes
+ * (LIBPLL/models.c:445-493, core_pmatrix.c:182-185, core_likelihood.c:166, core_derivatives.c:362-366,712) */
+int port_set_submodels(port_partition *p, unsigned n, const unsigned *cat_model, const double *freqs, const double *subst);
 int port_update_invariant_sites(port_partition *p);
 int port_set_prop_invar(port_partition *p, double prop_invar);
 /* LIBPLL/gamma.c:267-330 pll_compute_gamma_cats, PLL_GAMMA_RATES_MEAN (mode 0) / MEDIAN (1) */

@@ -208,28 +208,27 @@ def test_protein_model_names_reproduce_libpll_golden_lnl(model):
 def test_lg4m_is_a_per_category_mixture_through_set_submodels():
     """``LG4M`` (PLLMOD/util/models_aa.c:103-105): four matrices, category c uses matrix c; apply_model_state hands them to
     set_submodels (raxml-ng's ratecat_submodels -> libpll params_indices).  Checked against the sum over categories of
-    single-matrix, single-rate evaluations through real libpll."""
+    single-matrix, single-rate evaluations."""
     from oracle import oracle
-    if not oracle.have_ref():
-        pytest.skip("per-category matrices are restated only through the reference backend")
     from netrax_b200._capi import Partition
+    kind = "ref" if oracle.have_ref() else "port"
     b0, b1 = GP["branch_lengths"]
     net = parse_extended_newick(f"(((T0:{b1},T1:{b1}):{b0},T2:{b1})X6:{b0 / 2},(T3:{b1},T4:{b1})X7:{b0 / 2});")
     fasta = "".join(f">T{i}\n{s}\n" for i, s in enumerate(GP["tips"]))
     parts, specs = build_partitions(read_msa(fasta), net.tip_labels, "LG4M+G4{0.8}", compress=False)
     ms = specs[0]
     assert ms.ratecat_submodels == [0, 1, 2, 3] and len(ms.submodels) == 4 and ms.free_params() == 0
-    eng = oracle.make_engine("ref", net, parts)
+    eng = oracle.make_engine(kind, net, parts)
     apply_model_state(eng, specs)
     lnl = eng.computeLoglikelihood(0, 1)
     from helpers import mixture_lnl_by_categories
     short = Partition(20, 4, parts[0].tip_masks[:, :12], parts[0].freqs, parts[0].subst, parts[0].rates)   # 12 sites: 48 tiny engines
-    e = oracle.make_engine("ref", net, [short])
+    e = oracle.make_engine(kind, net, [short])
     apply_model_state(e, specs)
-    want = mixture_lnl_by_categories(lambda n, p: oracle.make_engine("ref", n, [p]), net, short, ms.ratecat_submodels,
+    want = mixture_lnl_by_categories(lambda n, p: oracle.make_engine(kind, n, [p]), net, short, ms.ratecat_submodels,
                                      [f for _, f in ms.submodels], [r for r, _ in ms.submodels])
     assert e.computeLoglikelihood(0, 1) == pytest.approx(want, rel=1e-10)
     e.close()
-    single = oracle.make_engine("ref", net, parts)
+    single = oracle.make_engine(kind, net, parts)
     assert abs(single.computeLoglikelihood(0, 1) - lnl) > 1e-3   # without the mixture: matrix 0 for every category
     eng.close(); single.close()

@@ -271,13 +271,12 @@ def test_pseudo_loglikelihood_port_equals_reference_and_dispatch():
 
 
 # ---- one rate matrix per rate category (LG4M / LG4X: raxml-ng ratecat_submodels -> libpll params_indices) ------------------
+@pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("states", [4, 20])
-def test_submodels_reference_oracle_semantics(states):
-    """The reference backend (real libpll with params_indices): (i) a mixture of identical matrices is the single-matrix
-    model, bit for bit; (ii) a real mixture equals the lnL assembled from single-matrix, single-category, single-site
-    evaluations; (iii) the scalar port says that it has no mixtures."""
-    if not oracle.have_ref():
-        pytest.skip("oracle/_ref not built")
+def test_submodels_oracle_semantics(kind, states):
+    """Both oracle flavours (the scalar port's per-category matrices, pll_port.c port_set_submodels; real libpll with
+    params_indices): (i) a mixture of identical matrices is the single-matrix model, bit for bit; (ii) a real mixture equals
+    the lnL assembled from single-matrix, single-category, single-site evaluations; (iii) back to one matrix."""
     from helpers import encode_aa, mixture_lnl_by_categories, mixture_models
     from netrax_b200.network_io import parse_extended_newick
     net = parse_extended_newick("(((T0:0.1,T1:0.2):0.05,T2:0.3):0.1,(T3:0.15,T4:0.25):0.2);")   # a tree: one displayed tree, AVERAGE = plain lnL
@@ -287,7 +286,7 @@ def test_submodels_reference_oracle_semantics(states):
     freqs, subst = mixture_models(states, 4, seed=11)
     rates, weights = np.array([0.2, 0.7, 1.3, 2.4]), np.array([0.4, 0.3, 0.2, 0.1])   # LG4X: free rates and weights
     part = Partition(states, 4, masks, freqs[0], subst[0], rates, rate_weights=weights)
-    make = lambda net, part: oracle.make_engine("ref", net, [part])
+    make = lambda net, part: oracle.make_engine(kind, net, [part])
     e = make(net, part)
     l_single = e.computeLoglikelihood(0, 1)
     e.set_submodels(0, [0, 1, 2, 3], np.stack([freqs[0]] * 4), np.stack([subst[0]] * 4))
@@ -300,11 +299,41 @@ def test_submodels_reference_oracle_semantics(states):
     assert l_mix == pytest.approx(want, rel=1e-12)
     e.set_submodels(0, [0, 0, 0, 0], freqs[:1], subst[:1])   # back to one matrix
     assert e.computeLoglikelihood(0, 1) == l_single
+    if kind == "port":
+        with pytest.raises(Exception, match="matri"):
+            e.set_submodels(0, [0, 1, 2, 4], freqs, subst)   # category 3 names a matrix that does not exist
     e.close()
-    p = oracle.make_engine("port", net, [part])
-    with pytest.raises(Exception, match="reference backend"):
-        p.set_submodels(0, cat_model, freqs, subst)
-    p.close()
+
+
+@pytest.mark.parametrize("states", [4, 20])
+def test_submodels_port_equals_real_libpll_on_networks(states):
+    """Per-category matrices in the scalar port against real libpll with the same params_indices on a network with two
+    reticulations, with and without +I: lnL, the re-rooted edge lnL, every sumtable entry and the derivatives."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from helpers import mixture_models
+    net = random_network(9, 2, seed=71)
+    freqs, subst = mixture_models(states, 4, seed=12)
+    m, w = simulate_alignment(net, 120, seed=71, states=states, rates=subst[0], freqs=freqs[0] / freqs[0].sum())
+    part = Partition(states, 4, m, freqs[0], subst[0], GAMMA4_ALPHA05, pattern_weights=w)
+    for pinv in (0.0, 0.2):
+        a, b = oracle.make_engine("port", net, [part]), oracle.make_engine("ref", net, [part])
+        for eng in (a, b):
+            eng.set_submodels(0, [3, 1, 0, 2], freqs, subst)
+            eng.set_pinv(0, pinv)
+        assert a.computeLoglikelihood(0, 1) == pytest.approx(b.computeLoglikelihood(0, 1), rel=1e-11)
+        for e in (0, net.num_edges - 1, int(net.ret_first_edge[0])):
+            assert a.brlen_prepare(e) == pytest.approx(b.brlen_prepare(e), rel=1e-11)
+            assert a.computeLoglikelihoodBrlenOpt(e) == pytest.approx(b.computeLoglikelihoodBrlenOpt(e), rel=1e-11)
+            n_tables = a.computePartitionSumtables(e)
+            assert n_tables == b.computePartitionSumtables(e)
+            for k in range(n_tables):
+                sb = b.read_sumtable(0, k)[0]   # entries are lefterm x righterm, each a cancelling sum: tolerance against the table's scale
+                np.testing.assert_allclose(a.read_sumtable(0, k)[0], sb, rtol=1e-9, atol=1e-12 * np.abs(sb).max())
+            da, db = a.computeLoglikelihoodDerivatives(e), b.computeLoglikelihoodDerivatives(e)
+            np.testing.assert_allclose(da[4], db[4], rtol=1e-9, atol=1e-10)
+            assert a.brlen_finish(e) == pytest.approx(b.brlen_finish(e), rel=1e-11)
+        a.close(); b.close()
 
 
 def scaled_linkage_case(seed=5):

@@ -232,3 +232,20 @@ def test_lg4m_is_a_per_category_mixture_through_set_submodels():
     single = oracle.make_engine(kind, net, parts)
     assert abs(single.computeLoglikelihood(0, 1) - lnl) > 1e-3   # without the mixture: matrix 0 for every category
     eng.close(); single.close()
+
+
+def test_score_network_cli_refuses_to_run_without_a_gpu():
+    """scripts/score_network.py drives the CUDA engine only: on a box without a device it stops with the engine's message
+    (no CPU fallback, nothing under oracle/ is imported)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "score_network.py"), "--msa", os.path.join(FIX, "small_fake_alignment.txt"),
+                        "--start_network", os.path.join(FIX, "small.nw"), "--model", "GTR+G"], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+    for rel in (("scripts", "score_network.py"), ("netrax_b200", "score.py"), ("netrax_b200", "msa_io.py"), ("netrax_b200", "network_io.py")):
+        src = open(os.path.join(root, *rel)).read()
+        assert "from oracle" not in src and "import oracle" not in src, rel

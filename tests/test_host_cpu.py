@@ -260,3 +260,57 @@ def test_product_minimisers_fuzzed_against_the_reference():
             seqs.append((repr(out.value), calls))
         (xr, cr), (xp, cp) = seqs
         assert xr == xp and cp[:-1] == cr[:len(cp) - 1]
+
+
+def test_product_brent_multi_fuzzed_against_the_reference():
+    """150 seeded cases, 1-5 variables with random targets (incl. NaN zones, steps, flat functions), random bounds / guesses /
+    tolerances: the product's Brent-multi driver and pll-modules' pllmod_opt_minimize_brent_multi issue identical calls
+    (x vectors and convergence flags) and return identical optima."""
+    import ctypes as C
+    import math
+    import random
+    from oracle import oracle
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    lib = _product_minimisers()[0]
+    MT = C.CFUNCTYPE(C.c_double, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int))
+    lib.nrxh_minimize_brent_multi.restype = C.c_int
+    lib.nrxh_minimize_brent_multi.argtypes = [C.c_uint, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_double, MT, C.c_void_p]
+    olib = oracle.api("ref").lib
+    olib.orc_test_brent_multi.restype = C.c_int
+    olib.orc_test_brent_multi.argtypes = [C.c_int, C.c_uint, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_double, MT]
+    rnd = random.Random(7)
+
+    def make():
+        kind = rnd.choice(["quad", "cosh", "flat", "step", "nanzone", "lin", "osc"])
+        a, b, c = rnd.uniform(0, 5), rnd.uniform(0.1, 10), rnd.uniform(-3, 3)
+        return {"quad": lambda x: b * (x - a) ** 2 + c, "cosh": lambda x: math.cosh(min(30, b * (x - a))) + c * x, "flat": lambda x: c,
+                "step": lambda x: c if x < a else c + b, "nanzone": lambda x: float("nan") if a < x < a + 0.3 * b else (x - a) ** 2,
+                "lin": lambda x: b * x + c, "osc": lambda x: math.sin(b * x) + 0.01 * x}[kind]
+
+    for _ in range(150):
+        n = rnd.choice([1, 2, 3, 5])
+        funcs = [make() for _ in range(n)]
+        lo, hi = rnd.choice([(0.0201, 100.0), (0.0, 0.99), (0.01, 100.0), (1e-6, 1 - 1e-6)])
+        guess = [rnd.uniform(lo, hi) if rnd.random() < 0.85 else rnd.choice([lo, hi, 2 * hi, 0.0]) for _ in range(n)]
+        tol = rnd.choice([0.1, 1e-3, 1e-4])
+        runs = []
+        for which in (0, 1):
+            calls = []
+
+            def target(_, x, fx, conv):
+                calls.append(([repr(x[j]) for j in range(n)], None if not conv else [conv[j] for j in range(n)]))
+                unconverged = 0 if conv and all(conv[j] for j in range(n)) else 1
+                if fx:
+                    for j in range(n):
+                        fx[j] = funcs[j](x[j])
+                if conv:
+                    conv[n] = 0 if unconverged else 1
+                return 0.0
+            x = (C.c_double * n)(*guess)
+            if which == 0:
+                assert lib.nrxh_minimize_brent_multi(n, lo, x, hi, tol, MT(target), None)
+            else:
+                assert olib.orc_test_brent_multi(1, n, lo, x, hi, tol, MT(target))
+            runs.append(([repr(v) for v in x], calls))
+        assert runs[0] == runs[1]

@@ -126,3 +126,18 @@ def test_engine_newick_writes_the_current_state_and_averages_unlinked_lengths():
     np.testing.assert_allclose(sorted(back.edge_length), sorted(want), rtol=1e-12)
     assert back.edge_prob[int(back.ret_first_edge[0])] in (pytest.approx(0.3), pytest.approx(0.7))
     e.close()
+
+
+@pytest.mark.parametrize("taxa,rets,seed", [(8, 1, 1), (20, 4, 2), (50, 8, 3), (100, 8, 47)])
+def test_extended_newick_writer_round_trips_synthetic_networks(taxa, rets, seed):
+    """The bench's synthetic networks (up to the headline 100 taxa / 8 reticulations) survive write -> read: same clusters,
+    lengths and inheritance probabilities on every edge, and the same number of displayed trees at the root."""
+    from netrax_b200.network_io import to_extended_newick
+    from netrax_b200.synth import random_network
+    net = random_network(taxa, rets, seed=seed)
+    back = parse_extended_newick(to_extended_newick(net))
+    assert (back.num_tips, back.num_edges, back.num_reticulations) == (net.num_tips, net.num_edges, net.num_reticulations)
+    got, want = _canonical(back), _canonical(net)
+    assert [(r[0], r[1]) for r in got] == [(r[0], r[1]) for r in want]
+    np.testing.assert_allclose([r[2] for r in got], [r[2] for r in want], rtol=0, atol=0)
+    np.testing.assert_allclose([r[3] for r in got], [r[3] for r in want], rtol=1e-15)

@@ -50,7 +50,7 @@ def _scalers_case():
 
 
 def _optimize_scalers(eng, parts_full):
-    """optimize_scalers + the alpha step under scaled linkage: the callers whose site-sharded form needs more than the lnL
+    """optimize_scalers + the alpha and pinv steps under scaled linkage: the callers whose site-sharded form needs more than the lnL
     all-reduce (pllmod_treeinfo_normalize_brlen_scalers sums scaler x pattern_weight_sum over the shards; the Brent
     drivers all-reduce their convergence flag)."""
     for p, s in enumerate([3.0, 0.3, 150.0]):
@@ -59,7 +59,9 @@ def _optimize_scalers(eng, parts_full):
     eng.set_scoring_sizes(9, int(sum(int(p.pattern_weights.sum()) for p in parts_full)))
     bic = eng.optimize_scalers()
     la = eng.optimize_alpha()
-    return np.concatenate([[bic, la, eng.get_alpha(1)], eng.brlen_scalers(), eng.branch_lengths()])
+    eng.set_pinv(2, 0.1)    # +I: every shard finds the invariant patterns of its own slice
+    lp = eng.optimize_pinv()
+    return np.concatenate([[bic, la, lp, eng.get_alpha(1), eng.get_pinv(2)], eng.brlen_scalers(), eng.branch_lengths()])
 
 
 def _worker(rank, world, port, q):
@@ -118,8 +120,8 @@ def test_world_size_2_gloo_sharded_equals_unsharded():
     eng = oracle.make_engine("port", net, parts, linkage=SCALED)
     want = _optimize_scalers(eng, parts)
     assert np.array_equal(res[0]["scalers"], res[1]["scalers"])
-    np.testing.assert_allclose(res[0]["scalers"][:2], want[:2], rtol=1e-9)      # BIC, lnL after the alpha step
-    np.testing.assert_allclose(res[0]["scalers"][2:], want[2:], rtol=1e-5)      # alpha, scalers (mean 1 over ALL sites), branch lengths
+    np.testing.assert_allclose(res[0]["scalers"][:3], want[:3], rtol=1e-9)      # BIC, lnL after the alpha step, lnL after the pinv step
+    np.testing.assert_allclose(res[0]["scalers"][3:], want[3:], rtol=1e-4, atol=1e-6)   # alpha, pinv, scalers (mean 1 over ALL sites), branch lengths
 
 
 def test_partition_slice_covers_every_pattern_once():

@@ -423,3 +423,18 @@ def test_pinv_port_equals_real_libpll_on_networks():
         a.set_pinv(0, 0.0); b.set_pinv(0, 0.0)
         assert a.computeLoglikelihood(0, 1) == pytest.approx(b.computeLoglikelihood(0, 1), rel=1e-11)
         a.close(); b.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_empty_shard_of_a_partition_contributes_nothing(kind):
+    """Site sharding may leave a rank without any pattern of a small partition (the reference's partitions[p] == NULL,
+    "skip remote partitions", LH/ImprovedLoglikelihood.cpp:128-131): a zero-pattern shard evaluates to lnL 0 and leaves the
+    other partitions alone, so the all-reduced sums are those of the ranks that own patterns."""
+    net = random_network(8, 1, seed=4)
+    m, w = simulate_alignment(net, 50, seed=4)
+    full = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    alone = oracle.make_engine(kind, net, [full])
+    both = oracle.make_engine(kind, net, [full, full.slice(0, 0)])
+    assert both.computeLoglikelihood(0, 1) == alone.computeLoglikelihood(0, 1)
+    np.testing.assert_array_equal(both.partition_loglh(), [alone.partition_loglh()[0], 0.0])
+    alone.close(); both.close()

@@ -5,19 +5,27 @@ A "step" = ONE full network lnL evaluation, computeLoglikelihood(ann, incrementa
 P-matrices for every edge + every CLV of every displayed tree at every node + per-tree root lnL + the
 cross-rank reduction + AVERAGE/BEST mixing (BASELINE.md §4 "What is timed").
 
-Workload (default): BASELINE.json configs[4], the configuration the metric is quoted on — DNA GTR+G4, 100 taxa,
-8 reticulations, 1M site patterns sharded across 1/2/4/8 B200 (STRONG scaling: the 1M patterns are split evenly
-over the ranks; at N=1 all 776 CLV slots x 1M patterns = 102 GB live on one GPU).  `--config 2` (50 taxa /
-4 reticulations / 100 k patterns) etc. select the others; `--patterns N` overrides the global pattern count.
+Workload (headline): BASELINE.json configs[4], the configuration the metric is quoted on — DNA GTR+G4, 100 taxa,
+8 reticulations, 1M site patterns sharded across 1/2/4/8 B200 (STRONG scaling: ONE seeded global alignment, generated
+in fixed chunks that do not depend on the world size; rank r owns the contiguous slice [r*G/N, (r+1)*G/N) of it, so the
+printed lnL is the same number at every N up to summation order).  `--config 2` etc. select another headline.
 
 metric  = CLV site-updates/s (sum over nodes of displayed trees(node) x patterns, per second, whole job);
           lnl_evals_per_sec is reported beside it.
 value   = inputs resident in HBM, timed with CUDA events on the engine's stream, max over ranks.
 e2e     = the same step through the host C-ABI with HOST buffers: every step re-uploads the rank's alignment
           slice (tipchars + pattern weights, pinned host memory) and reads the lnL back.
-roofline= K2 (k_clv_dna4_pipe2) only: algorithmic bytes / CUDA-event time of the K2 launches.
+roofline= K2 (k_clv_dna4_pipe2) only: COMPULSORY bytes per launch (every distinct child CLV / tip row of the launch read
+          once + every parent written once; the ops of a node share children through the L2) / CUDA-event time of the K2
+          launches, against MEASURED_PEAKS.json:hbm_gbs.  The SURVEY §8d per-op ("algorithmic") figure is printed beside it.
+configs = (N = 1 only) the other four BASELINE configs + config 2's branch-length derivative sweep, each with ms per
+          evaluation, site-updates/s, launches, per-kernel-family compulsory-byte roofline fractions, a parity check
+          against the oracle on a pattern prefix and the CPU arm on the same inputs.
+parity  = lnL / per-tree lnL / scalers of the CUDA path against oracle/_ref (real libpll) on a 700-pattern prefix of
+          the SAME global alignment — the checker, outside every timed region.
 cpu_baseline / --impl reference = the restated NetRAX layer over the REAL forked libpll (oracle/_ref, kind
-          "reference"; the scalar port if _ref is absent), site-sharded over all host cores, bounded sample.
+          "reference"; the scalar port if _ref is absent), site-sharded over all host cores, bounded sample
+          (a prefix of the same global alignment, one contiguous slice per worker).
 """
 from __future__ import annotations
 
@@ -45,55 +53,103 @@ CONFIGS = {
     4: dict(name="config4: Protein LG+G4, 30 taxa, 2 reticulations, 20k patterns, AVERAGE", taxa=30, ret=2, patterns=20_000, parts=1, variant=AVERAGE, linkage=LINKED, states=20),
     5: dict(name="config5: DNA GTR+G4, 100 taxa, 8 reticulations, 1M site patterns sharded across the GPUs", taxa=100, ret=8, patterns=1_000_000, parts=1, variant=AVERAGE, linkage=LINKED),
 }
+CHUNK = 31_250   # the global alignment is the concatenation of independently seeded chunks of this many patterns
 
 
-def make_inputs(cfg, patterns_local, rank):
-    """Seeded synthetic inputs of the named shape; every rank simulates only its own slice (different seed per
-    rank = different columns, same network and model)."""
+def _global_columns(cfg, net, p, lo, hi):
+    """Columns [lo, hi) of partition p of THE global alignment of this config: chunk c (patterns [c*CHUNK, (c+1)*CHUNK)) is
+    simulated with seed 1000 * (c + 1) + p, whatever the world size / worker count, and trimmed to the requested range."""
+    states = cfg.get("states", 4)
+    cols = []
+    for c in range(lo // CHUNK, max(lo // CHUNK + 1, -(-hi // CHUNK))):
+        c_lo, c_hi = c * CHUNK, min((c + 1) * CHUNK, cfg["patterns"])
+        if c_hi <= lo or c_lo >= hi:
+            continue
+        if states == 20:
+            rates, freqs = lg_model()
+            m, _ = simulate_alignment(net, c_hi - c_lo, seed=1000 * (c + 1) + p, dedup=False, states=20, rates=rates, freqs=freqs)
+        else:
+            m, _ = simulate_alignment(net, c_hi - c_lo, seed=1000 * (c + 1) + p, dedup=False)
+        cols.append(m[:, max(lo, c_lo) - c_lo: min(hi, c_hi) - c_lo])
+    if not cols:
+        return np.zeros((net.num_tips, 0), np.uint32)
+    return np.ascontiguousarray(np.concatenate(cols, axis=1))
+
+
+def make_inputs(cfg, lo, hi=None):
+    """Network, model and the pattern slice [lo, hi) of every partition of the config's global alignment.
+    make_inputs(cfg, n) == the prefix [0, n) (tests use this form)."""
+    if hi is None:
+        lo, hi = 0, lo
     net = random_network(cfg["taxa"], cfg["ret"], seed=42 + cfg["taxa"])
     parts, brl = [], []
     rng = np.random.default_rng(5)
     for p in range(cfg["parts"]):
+        m = _global_columns(cfg, net, p, lo, hi)
+        w = np.ones(m.shape[1], np.uint32)
         if cfg.get("states", 4) == 20:
             rates, freqs = lg_model()
-            m, w = simulate_alignment(net, patterns_local, seed=1000 * (rank + 1) + p, dedup=False, states=20, rates=rates, freqs=freqs)
             parts.append(Partition(20, 4, m, freqs, rates, GAMMA4_ALPHA05, pattern_weights=w))
-            continue
-        m, w = simulate_alignment(net, patterns_local, seed=1000 * (rank + 1) + p, dedup=False)
-        parts.append(Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w))
+        else:
+            parts.append(Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w))
         brl.append(net.edge_length * rng.uniform(0.5, 2.0, net.num_edges))
     return net, parts, (brl if cfg["linkage"] == UNLINKED else None)
 
 
+def derivative_sweep(eng, net, iters=3):
+    """For EVERY edge: virtual re-rooting, edge-rooted lnL, sumtables, `iters` Newton-iterate derivative evaluations, restore —
+    the loop of optimize_branch (src/optimization/BranchLengthOptimization.cpp:345-420) with a fixed iterate count."""
+    for e in range(net.num_edges):
+        t0 = float(net.edge_length[e])
+        eng.brlen_prepare(e)
+        eng.computeLoglikelihoodBrlenOpt(e)
+        if eng.computePartitionSumtables(e):
+            for k in range(iters):
+                eng.brlen_set_length(e, t0 * (1.0 + 0.1 * (k + 1)))
+                eng.computeLoglikelihoodDerivatives(e)
+            eng.brlen_set_length(e, t0)
+        eng.brlen_finish(e)
+
+
 # ---------------------------------------------------------------------------------------------- CPU reference arm
 def _cpu_worker(args):
-    kind, cfg, patterns, widx, reps = args
+    kind, cfg, patterns, widx, reps, sweep = args
     from oracle import oracle
-    net, parts, brl = make_inputs(cfg, patterns, 100 + widx)
+    net, parts, brl = make_inputs(cfg, widx * patterns, (widx + 1) * patterns)   # worker widx: its slice of the global prefix
     eng = oracle.make_engine(kind, net, parts, variant=cfg["variant"], linkage=cfg["linkage"], partition_brlens=brl)
-    eng.computeLoglikelihood(0, 1)  # warm-up
+    lnl = eng.computeLoglikelihood(0, 1)  # warm-up
     eng.reset_counters()
     times = []
     for _ in range(reps):
         t = time.perf_counter()
         eng.computeLoglikelihood(0, 1)
         times.append(time.perf_counter() - t)
-    return times, eng.clv_update_count() // reps
+    updates = eng.clv_update_count() // max(1, reps)
+    ts = None
+    if sweep:
+        t = time.perf_counter()
+        derivative_sweep(eng, net)
+        ts = time.perf_counter() - t
+    return times, updates, ts, lnl
 
 
-def cpu_reference(cfg, cores, patterns_per_core, reps):
+def cpu_reference(cfg, cores, patterns_per_core, reps, sweep=False):
     """All host cores, one worker per core, each owning a slice of every partition (the reference's MPI site
     parallelism, RAXML/ParallelContext.cpp:354-487); per-step time = max over workers."""
     from oracle import oracle
     kind = "ref" if oracle.have_ref() else "port"
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(kind, cfg, patterns_per_core, i, reps) for i in range(cores)])
+        res = pool.map(_cpu_worker, [(kind, cfg, patterns_per_core, i, reps, sweep) for i in range(cores)])
     step_times = [max(r[0][k] for r in res) for k in range(reps)]
     updates = sum(r[1] for r in res)
-    return {"kind": "reference" if kind == "ref" else "port", "step_times": step_times, "site_updates_per_step": updates,
-            "sample": f"{cores} workers x {patterns_per_core} patterns of the same network/model, {reps} full evaluations each "
-                      f"(libpll AVX2 kernels under the restated NetRAX driver, not the netrax binary)"}
+    out = {"kind": "reference" if kind == "ref" else "port", "step_times": step_times, "site_updates_per_step": updates,
+           "sample": f"prefix of {cores * patterns_per_core} of the config's {cfg['patterns']} global patterns (per partition): {cores} workers x "
+                     f"{patterns_per_core} patterns, {reps} full evaluations each (libpll AVX2 kernels under the restated NetRAX driver, "
+                     f"not the netrax binary; the arm is memory-bound on the host: 16 -> 32 cores gave 1.3x in round 1)"}
+    if sweep:
+        out["sweep_s"] = max(r[2] for r in res)
+    return out
 
 
 def host_cores():
@@ -134,6 +190,99 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+# ---------------------------------------------------------------------------------------------- helpers of our arm
+def family_table(prof, reps, total_ms, peak):
+    """per kernel family: ms, launches, compulsory-byte GB/s and its fraction of the measured HBM peak"""
+    rows = {}
+    for k, v in prof.items():
+        if v["launches"] == 0 or v["ms"] <= 0:
+            continue
+        gbs = v["compulsory_bytes"] / (v["ms"] / 1e3) / 1e9
+        rows[k] = {"ms": v["ms"] / reps, "launches": v["launches"] / reps, "share": v["ms"] / reps / total_ms if total_ms else None,
+                   "compulsory_GBps": gbs, "frac_of_hbm_peak": gbs / peak,
+                   "algorithmic_over_compulsory": v["bytes"] / v["compulsory_bytes"] if v["compulsory_bytes"] else None}
+    return rows
+
+
+def parity_check(cfg, n_patterns, device):
+    """The CUDA path against the oracle (real libpll when oracle/_ref is present) on the first n_patterns columns of the
+    config's global alignment: network lnL, every per-tree partition lnL, every root scaler array.  Checker only."""
+    from netrax_b200.engine import NetraxB200
+    from oracle import oracle
+    net, parts, brl = make_inputs(cfg, min(n_patterns, cfg["patterns"]))
+    kind = "ref" if oracle.have_ref() else "port"
+    g = NetraxB200(net, parts, variant=cfg["variant"], linkage=cfg["linkage"], device=device, partition_brlens=brl)
+    o = oracle.make_engine(kind, net, parts, variant=cfg["variant"], linkage=cfg["linkage"], partition_brlens=brl)
+    for p in range(g.P):
+        g.set_eigen(p, *o.get_eigen(p))
+    lg, lo = g.computeLoglikelihood(0, 1), o.computeLoglikelihood(0, 1)
+    root = net.root
+    worst, scalers_equal, best_equal = 0.0, True, None
+    for t in range(g.num_trees(root)):
+        a, b = g.tree_info(root, t)[1], o.tree_info(root, t)[1]
+        worst = max(worst, float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))))
+        scalers_equal = scalers_equal and all(np.array_equal(g.read_scaler(root, t, p), o.read_scaler(root, t, p)) for p in range(g.P))
+    out = {"oracle": "reference libpll (oracle/_ref)" if kind == "ref" else "scalar port", "patterns": int(parts[0].sites), "lnl": lg, "oracle_lnl": lo,
+           "lnl_rel_diff": abs(lg - lo) / abs(lo), "root_trees": g.num_trees(root), "per_tree_lnl_max_rel_diff": worst,
+           "root_scalers_bit_equal": bool(scalers_equal), "trees_per_node_equal": all(g.num_trees(v) == o.num_trees(v) for v in range(net.num_tips, net.num_nodes))}
+    out["pass"] = bool(out["lnl_rel_diff"] <= 1e-10 and worst <= 1e-10 and scalers_equal and out["trees_per_node_equal"])
+    g.close(); o.close()
+    return out
+
+
+def measure_config(c, device, peak, reps, with_cpu, cores):
+    """One BASELINE config on one GPU: full evaluations (+ config 2: the derivative sweep) with per-family rooflines."""
+    from netrax_b200.engine import NetraxB200
+    cfg = dict(CONFIGS[c])
+    net, parts, brl = make_inputs(cfg, cfg["patterns"])
+    eng = NetraxB200(net, parts, variant=cfg["variant"], linkage=cfg["linkage"], device=device, partition_brlens=brl)
+    for _ in range(3):
+        lnl = eng.computeLoglikelihood(0, 1)
+    slots = sum(eng.num_trees(v) for v in range(net.num_tips, net.num_nodes))
+    updates = slots * sum(p.sites for p in parts)
+    eng.profile_enable(True)
+    l0 = eng.launch_count()
+    t = time.perf_counter()
+    eng.timer_start()
+    for _ in range(reps):
+        eng.computeLoglikelihood(0, 1)
+    ms = eng.timer_stop() / reps
+    wall = 1e3 * (time.perf_counter() - t) / reps
+    launches = (eng.launch_count() - l0) / reps
+    fam = family_table(eng.profile_read_all(), reps, ms, peak)
+    eng.profile_enable(False)
+    r = {"workload": cfg["name"], "patterns": cfg["patterns"], "partitions": cfg["parts"], "sum_trees_per_node": slots, "root_trees": eng.num_trees(net.root),
+         "lnl": lnl, "ms_per_eval": ms, "wall_ms_per_eval": wall, "lnl_evals_per_sec": 1e3 / ms, "site_updates_per_sec": updates / (ms / 1e3),
+         "launches_per_eval": launches, "kernel_families": fam}
+    if c == 2:
+        derivative_sweep(eng, net)  # warm-up (allocates re-rooting slots and sumtables)
+        eng.profile_enable(True)
+        l0 = eng.launch_count()
+        t = time.perf_counter()
+        eng.timer_start()
+        derivative_sweep(eng, net)
+        ms_s = eng.timer_stop()
+        wall_s = 1e3 * (time.perf_counter() - t)
+        r["derivative_sweep"] = {"what": "every edge: re-rooting + edge lnL + sumtables + 3 Newton-iterate derivative evaluations + restore",
+                                 "edges": int(net.num_edges), "ms": ms_s, "wall_ms": wall_s, "launches": eng.launch_count() - l0,
+                                 "edges_per_sec": net.num_edges / (wall_s / 1e3), "kernel_families": family_table(eng.profile_read_all(), 1, ms_s, peak)}
+        eng.profile_enable(False)
+    eng.close()
+    r["parity"] = parity_check(cfg, 500, device)
+    if with_cpu:
+        ppc = min(4000 if c == 2 else 16000, max(64, -(-cfg["patterns"] // cores)))
+        cpu = cpu_reference(cfg, cores, ppc, 3, sweep=(c == 2))
+        t_eval = float(np.median(cpu["step_times"]))
+        scale = cfg["patterns"] / (ppc * cores)   # the sample covers ppc*cores of the config's patterns
+        r["cpu"] = {"kind": cpu["kind"], "cores": cores, "sample": cpu["sample"], "site_updates_per_sec": cpu["site_updates_per_step"] / t_eval,
+                    "ms_per_eval_on_sample": 1e3 * t_eval, "sample_fraction_of_config": 1.0 / scale}
+        r["speedup_site_updates_vs_cpu"] = r["site_updates_per_sec"] / r["cpu"]["site_updates_per_sec"]
+        if c == 2:
+            r["cpu"]["sweep_ms_on_sample"] = 1e3 * cpu["sweep_s"]
+            r["derivative_sweep"]["speedup_vs_cpu_scaled_to_config"] = (1e3 * cpu["sweep_s"] * scale) / r["derivative_sweep"]["wall_ms"]
+    return r
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -144,6 +293,8 @@ def main():
     ap.add_argument("--patterns", type=int, default=0, help="global pattern count per partition (default: the config's)")
     ap.add_argument("--cpu-patterns-per-core", type=int, default=0, help="0: the arm's global pattern count / host cores, capped at 16000")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (BASELINE configs 1-4 + sweep, N = 1 only)")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -157,7 +308,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     # strong scaling: rank r owns the contiguous slice [r*G/N, (r+1)*G/N) of every partition (reference: C1 site sharding)
     G = cfg["patterns"]
-    local_patterns = (rank + 1) * G // world - rank * G // world
+    lo, hi = rank * G // world, (rank + 1) * G // world
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -165,6 +316,7 @@ def main():
         pass
     config = {"workload": cfg["name"], "global_patterns": cfg["patterns"], "patterns_per_gpu": -(-cfg["patterns"] // world), "partitions": cfg["parts"],
               "lh_model": "AVERAGE" if cfg["variant"] == AVERAGE else "BEST", "parallelism": f"site-sharding x{world}",
+              "alignment": f"one seeded global alignment (chunks of {CHUNK} patterns, seed = 1000 * (chunk + 1) + partition), sliced contiguously by rank",
               "l2": "per-step working set (all CLV slots) is GBs >> 126 MB L2: inputs larger than L2, no flush needed"}
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
@@ -180,6 +332,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "lnl_evals_per_sec_on_sample": 1e3 / ms,
+                "note": "ms_per_step is the time of one evaluation of the SAMPLE (see cpu_baseline.sample), not of the whole config; compare site-updates/s",
                 "cpu_baseline": {"value": v, "unit": "site-updates/s", "cores": cores, "kind": r["kind"], "sample": r["sample"]},
                 "e2e": {"value": v, "unit": "site-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -194,7 +347,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from netrax_b200.engine import NetraxB200
 
-    net, parts, brl = make_inputs(cfg, local_patterns, rank)
+    net, parts, brl = make_inputs(cfg, lo, hi)
     comm = None
     if world > 1:
         # the reference's parallel_reduce_cb (MPI_Allreduce SUM) -> ONE ncclAllReduce inside the engine per evaluation;
@@ -216,7 +369,7 @@ def main():
         torch.cuda.synchronize()
 
     # pinned host copies of this rank's alignment slice for the e2e leg
-    tip_u8 = [torch.from_numpy(p.tip_masks.astype(np.uint8)).pin_memory() for p in parts]
+    tip_u8 = [torch.from_numpy(p.tip_masks.astype(np.uint8)).pin_memory() for p in parts] if all(p.states == 4 for p in parts) else None
     w_u32 = [torch.from_numpy((p.pattern_weights if p.pattern_weights is not None else np.ones(p.sites, np.uint32)).astype(np.int32)).pin_memory() for p in parts]
 
     # clocks are sampled from the warm-up to the end of the e2e region (every part of it is the same step under load)
@@ -240,25 +393,28 @@ def main():
     barrier()
     ms_wall = 1e3 * (time.perf_counter() - t_wall)
     launches = eng.launch_count() - l0
-    prof = eng.profile_read()
+    prof_all = eng.profile_read_all()
+    prof = prof_all["K2_clv_update"]
     eng.profile_enable(False)
 
     # ---- timed region 2: end to end with host buffers ----
-    barrier()
-    eng.timer_start()
-    for _ in range(args.steps):
-        for p in range(len(parts)):
-            eng.upload_alignment_u8(p, tip_u8[p].data_ptr(), w_u32[p].data_ptr())
-        lnl_e2e = eng.computeLoglikelihood(0, 1)
-    ms_e2e = eng.timer_stop()
-    barrier()
+    ms_e2e, lnl_e2e = None, None
+    if tip_u8 is not None:
+        barrier()
+        eng.timer_start()
+        for _ in range(args.steps):
+            for p in range(len(parts)):
+                eng.upload_alignment_u8(p, tip_u8[p].data_ptr(), w_u32[p].data_ptr())
+            lnl_e2e = eng.computeLoglikelihood(0, 1)
+        ms_e2e = eng.timer_stop()
+        barrier()
+        assert abs(lnl_e2e - lnl) <= 1e-9 * abs(lnl)
     clocks = sampler.stop()
-    assert abs(lnl_e2e - lnl) <= 1e-9 * abs(lnl)
-    h2d = sum(int(t.numel()) for t in tip_u8) + sum(4 * int(t.numel()) for t in w_u32) + 8 * (net.num_edges + 1) * len(parts)
+    h2d = (sum(int(t.numel()) for t in tip_u8) if tip_u8 else 0) + sum(4 * int(t.numel()) for t in w_u32) + 8 * (net.num_edges + 1) * len(parts)
     d2h = 8 * eng.num_trees(net.root) * len(parts) + 8
 
     if dist is not None:
-        t = torch.tensor([ms_dev, ms_e2e, ms_wall], dtype=torch.float64, device=f"cuda:{local_rank}")
+        t = torch.tensor([ms_dev, ms_e2e or 0.0, ms_wall], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_dev, ms_e2e, ms_wall = (float(x) for x in t.cpu())
         u = torch.tensor([float(updates_per_step_local)], dtype=torch.float64, device=f"cuda:{local_rank}")
@@ -270,18 +426,20 @@ def main():
     if rank == 0:
         ms_step = ms_dev / args.steps
         value = updates_per_step / (ms_step / 1e3)
-        e2e_value = updates_per_step / (ms_e2e / args.steps / 1e3)
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = prof["clv_bytes"] / (prof["clv_ms"] / 1e3) / 1e9 if prof["clv_ms"] > 0 else 0.0
-        # DRAM traffic of K2 from the committed ncu --set full capture (profiles/k2_traffic.json): the ratio measured
-        # traffic / algorithmic bytes of one evaluation step is a property of the plan (which ops share children),
-        # independent of the pattern count, so it scales the per-launch algorithmic bytes of THIS run.
+        nl = max(1, prof["launches"])
+        avg_launch_s = prof["ms"] / nl / 1e3 if prof["ms"] > 0 else float("inf")
+        achieved = prof["compulsory_bytes"] / nl / avg_launch_s / 1e9
+        algorithmic = prof["bytes"] / nl / avg_launch_s / 1e9
+        # DRAM traffic of K2: dram__bytes_read.sum + dram__bytes_write.sum per launch from an ncu pass over one evaluation
+        # step of THIS workload at N = 1 (profiles/k2_traffic.json, which names the command); at N > 1 each GPU holds 1/N of
+        # the patterns and the per-launch traffic scales with them (flagged "scaled")
         traffic, traffic_src = None, None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "k2_traffic.json")))
-            if args.config == 5:
-                traffic = tr["traffic_over_algorithmic"] * prof["clv_bytes"] / max(1, prof["clv_launches"])
-                traffic_src = tr["source"]
+            if args.config == tr.get("config", 5) and cfg["patterns"] == tr.get("global_patterns"):
+                traffic = tr["dram_bytes_per_launch"] / world
+                traffic_src = tr["source"] + ("" if world == 1 else f" (scaled by 1/{world}: patterns per GPU)")
         except Exception:
             pass
         line = {"metric": "clv_site_updates_per_sec", "value": value, "unit": "site-updates/s", "n_gpus": world, "steps": args.steps,
@@ -289,24 +447,46 @@ def main():
                 "dtype": "f64", "data": "synthetic", "config": config,
                 "lnl_evals_per_sec": 1e3 / ms_step, "lnl": lnl, "sum_trees_per_node": slots_sum, "root_trees": eng.num_trees(net.root),
                 "wall_ms_per_step": ms_wall / args.steps,
-                "e2e": {"value": e2e_value, "unit": "site-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / args.steps, "lnl_evals_per_sec": 1e3 / (ms_e2e / args.steps)},
                 "gpu_launches": int(launches),
                 "clocks": clocks,
-                "roofline": {"kernel": "k_clv_dna4_pipe2 (K2, CLV update)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "roofline": {"kernel": "k_clv_dna4_pipe2 (K2, CLV update)" if cfg.get("states", 4) == 4 else "k_aa20_dmma<AA_CLV> (K2, CLV update)",
+                             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
-                             "dram_frac": (traffic / (prof["clv_ms"] / max(1, prof["clv_launches"]) / 1e3) / 1e9 / peak) if traffic and peak and prof["clv_ms"] > 0 else None,
+                             "numerator": "compulsory bytes per launch: every distinct child CLV + scaler / tip row read once, every parent CLV + scaler written once",
+                             "compulsory_bytes_per_launch": prof["compulsory_bytes"] / nl,
+                             "traffic_over_compulsory": (traffic / (prof["compulsory_bytes"] / nl)) if traffic else None,
+                             "dram_frac": (traffic / avg_launch_s / 1e9 / peak) if traffic and peak else None,
+                             "algorithmic_per_op": {"what": "SURVEY §8d per-op bytes (every op charged both children); re-reads of shared children are L2 hits, so this is NOT a fraction of the HBM peak",
+                                                    "bytes_per_launch": prof["bytes"] / nl, "GBps": algorithmic},
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                             "launches": int(prof["clv_launches"]), "avg_launch_ms": prof["clv_ms"] / max(1, prof["clv_launches"]),
-                             "algorithmic_bytes_per_launch": prof["clv_bytes"] / max(1, prof["clv_launches"]),
-                             "site_updates_per_sec_in_kernel": prof["clv_site_updates"] / (prof["clv_ms"] / 1e3) if prof["clv_ms"] > 0 else None,
-                             "share_of_step": prof["clv_ms"] / ms_dev if ms_dev > 0 else None}}
+                             "launches": int(prof["launches"]), "avg_launch_ms": prof["ms"] / nl,
+                             "site_updates_per_sec_in_kernel": prof["units"] / (prof["ms"] / 1e3) if prof["ms"] > 0 else None,
+                             "share_of_step": prof["ms"] / ms_dev if ms_dev > 0 else None},
+                "kernel_families": family_table(prof_all, args.steps, ms_step, peak)}
+        if ms_e2e:
+            e2e_value = updates_per_step / (ms_e2e / args.steps / 1e3)
+            line["e2e"] = {"value": e2e_value, "unit": "site-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                           "ms_per_step": ms_e2e / args.steps, "lnl_evals_per_sec": 1e3 / (ms_e2e / args.steps)}
+    eng.close()
+    del eng
+    if rank == 0:
+        if not args.no_parity:
+            line["parity"] = parity_check(cfg, 700, local_rank)
+        cores = host_cores()
         if world == 1 and not args.no_cpu_baseline:
-            cores = host_cores()
             r = cpu_reference(cfg, cores, args.cpu_patterns_per_core, 1 + 5)
             st = r["step_times"][1:]
             v = r["site_updates_per_step"] / float(np.median(st))
             line["cpu_baseline"] = {"value": v, "unit": "site-updates/s", "cores": cores, "kind": r["kind"], "sample": r["sample"]}
+        if world == 1 and not args.no_configs:
+            line["configs"] = {}
+            for c in (1, 2, 3, 4):
+                if c == args.config:
+                    continue
+                try:
+                    line["configs"][str(c)] = measure_config(c, local_rank, float(peaks.get("hbm_gbs", 6650.0)), 20, not args.no_cpu_baseline, cores)
+                except Exception as ex:   # a failing side measurement must not take the headline line with it
+                    line["configs"][str(c)] = {"error": f"{type(ex).__name__}: {ex}"}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -160,7 +160,8 @@ unsigned nrxh_num_slots(void *h);
 int nrxh_profile_enable(void *h, int on);
 int nrxh_profile_read(void *h, double *clv_ms, unsigned long long *launches, unsigned long long *site_updates, unsigned long long *bytes);
 /* per kernel family (kind = NRX_PROF_* of nrx_engine.h): device ms, launches, units of work, algorithmic bytes */
-int nrxh_profile_read_kind(void *h, int kind, double *ms, unsigned long long *launches, unsigned long long *units, unsigned long long *bytes);
+int nrxh_profile_read_kind(void *h, int kind, double *ms, unsigned long long *launches, unsigned long long *units, unsigned long long *bytes,
+                           unsigned long long *compulsory_bytes);
 int nrxh_persite_lnl(void *h, unsigned tree, double *out /* [nparts][max_sites] */, unsigned stride);
 void *nrxh_engine(void *h); /* the underlying nrx_engine* */
 /* re-upload one partition's alignment slice from HOST buffers (tipchars: 1 byte per cell, DNA) + pattern weights */

@@ -194,8 +194,10 @@ int nrx_profile_enable(nrx_engine *e, int on);
 int nrx_profile_read(nrx_engine *e, double *clv_ms, unsigned long long *clv_launches, unsigned long long *clv_site_updates,
                      unsigned long long *clv_bytes);
 /* the same per kernel family: device ms (CUDA events around the family's launches), launches, units of work
- * (edges for K1, site-updates for K2, (item, pattern) pairs for K3-K6, outputs for the reduction) and
- * ALGORITHMIC bytes (§8d table) — the per-kernel roofline table of scripts/kernel_rooflines.py */
+ * (edges for K1, site-updates for K2, (item, pattern) pairs for K3-K6, outputs for the reduction),
+ * ALGORITHMIC bytes (§8d table: every op / pair charged all of its operands) and COMPULSORY bytes (per launch, every
+ * distinct operand CLV / tip row read once + every output written once: what has to cross the HBM pins when the ops of a
+ * launch share operands through the L2 — the numerator of the roofline fraction) */
 enum {
   NRX_PROF_K2 = 0,      /* CLV update (k_clv_*) */
   NRX_PROF_K1 = 1,      /* P-matrices (+ protein tip tables) */
@@ -209,7 +211,7 @@ enum {
   NRX_PROF_KINDS = 9
 };
 int nrx_profile_read_kind(nrx_engine *e, int kind, double *ms, unsigned long long *launches, unsigned long long *units,
-                          unsigned long long *bytes);
+                          unsigned long long *bytes, unsigned long long *compulsory_bytes);
 
 #ifdef __cplusplus
 }

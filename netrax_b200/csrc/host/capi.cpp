@@ -505,8 +505,8 @@ int nrxh_profile_read(void *hv, double *ms, unsigned long long *l, unsigned long
   if (!nrx_profile_read(H(hv)->ann.engine, ms, l, u, b)) { g_err = nrx_last_error(); return 0; }
   return 1;
 }
-int nrxh_profile_read_kind(void *hv, int kind, double *ms, unsigned long long *l, unsigned long long *u, unsigned long long *b) {
-  if (!nrx_profile_read_kind(H(hv)->ann.engine, kind, ms, l, u, b)) { g_err = nrx_last_error(); return 0; }
+int nrxh_profile_read_kind(void *hv, int kind, double *ms, unsigned long long *l, unsigned long long *u, unsigned long long *b, unsigned long long *cb) {
+  if (!nrx_profile_read_kind(H(hv)->ann.engine, kind, ms, l, u, b, cb)) { g_err = nrx_last_error(); return 0; }
   return 1;
 }
 int nrxh_persite_lnl(void *hv, unsigned tree, double *out, unsigned stride) {

@@ -106,7 +106,7 @@ struct EnginePlan {
   std::vector<char> tips;
   std::vector<uint32_t> ntt;   // leading tip-tip ops of each batch (20-state engines order them first)
   cudaGraphExec_t exec[2] = {nullptr, nullptr};   // [0] latency geometry, [1] throughput geometry (nrx_set_throughput_mode)
-  unsigned long long updates = 0, bytes = 0;
+  unsigned long long updates = 0, bytes = 0, cbytes = 0;
   uint32_t lnl_items = 0;    // number of ops carrying an lnl_item mark (fused K3)
 };
 
@@ -142,7 +142,9 @@ struct nrx_engine {
   uint32_t k2_nt = 2;       // env NRX_K2_NT: 64-pattern sub-tiles per ring stage of k_clv_dna4_pipe2 (1 or 2; 2 measured 1-2 % faster)
   int k2_variant = 0;       // 0: k_clv_dna4_pipe2 (production); 1: k_clv_dna4_pipe (A/B baseline, env NRX_K2=1)
   bool aa_generic = false;  // env NRX_AA=generic: force the scalar kernel for 20-state partitions (A/B)
-  uint32_t aa_blocks = 148 * 3 * 2;  // block-count target of the DMMA kernels: two waves of 3 resident blocks per SM (A/B: profiles/r1e_all_configs.md)
+  bool aa_v1 = true;        // K2 / K5 on the round-1 kernel k_aa20_dmma; env NRX_AA=v2: the warp-specialised k_aa20_mma (A/B)
+  uint32_t aa_blocks = 148 * 3 * 2;  // block-count target of k_aa20_dmma: two waves of 3 resident blocks per SM (A/B: profiles/r1e_all_configs.md)
+  uint32_t aa2_blocks = 148 * 2 * 2; // block-count target of k_aa20_mma: two waves of 2 resident blocks per SM (env NRX_AA2_BLOCKS)
   uint32_t k2_blocks = 2368; // block-count target of the pipelined kernel: 8 waves of 2 resident blocks per SM (measured best, profiles/)
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   bool views_dirty = true;
@@ -151,7 +153,7 @@ struct nrx_engine {
   struct ProfKind {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
     double ms = 0;
-    unsigned long long launches = 0, units = 0, bytes = 0;
+    unsigned long long launches = 0, units = 0, bytes = 0, cbytes = 0;   // bytes: algorithmic (SURVEY §8d per op); cbytes: compulsory (each distinct operand once per launch)
   };
   ProfKind profk[NRX_PROF_KINDS];  // per kernel family (nrx_engine.h: NRX_PROF_K2 ...), CUDA events on the engine stream
 };
@@ -218,7 +220,7 @@ static void prof_begin(nrx_engine *e, cudaEvent_t *ev0, cudaEvent_t *ev1) {
   if (e->prof) { cudaEventCreate(ev0); cudaEventCreate(ev1); cudaEventRecord(*ev0, e->stream); }
 }
 static void prof_end(nrx_engine *e, cudaEvent_t ev0, cudaEvent_t ev1, unsigned long long launches, unsigned long long updates, unsigned long long bytes,
-                     int kind = NRX_PROF_K2) {
+                     int kind = NRX_PROF_K2, unsigned long long cbytes = ~0ull /* default: nothing shared, compulsory == algorithmic */) {
   if (!e->prof) return;
   cudaEventRecord(ev1, e->stream);
   nrx_engine::ProfKind &k = e->profk[kind];
@@ -226,6 +228,7 @@ static void prof_end(nrx_engine *e, cudaEvent_t ev0, cudaEvent_t ev1, unsigned l
   k.launches += launches;
   k.units += updates;
   k.bytes += bytes;
+  k.cbytes += (cbytes == ~0ull) ? bytes : cbytes;
 }
 /* algorithmic bytes of the pattern-streaming kernels K3-K6: per (item, pattern) `clvs` CLV-sized streams + `extra` bytes */
 static unsigned long long stream_bytes(const nrx_engine *e, unsigned long long items, unsigned clvs, unsigned extra, unsigned long long *units) {
@@ -380,7 +383,8 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
   if (const char *v = std::getenv("NRX_GRAPH")) e->use_graphs = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_PDL")) e->use_pdl = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_K2_NT")) e->k2_nt = std::atoi(v) == 1 ? 1u : 2u;
-  if (const char *v = std::getenv("NRX_AA")) e->aa_generic = std::string(v) == "generic";
+  if (const char *v = std::getenv("NRX_AA")) { e->aa_generic = std::string(v) == "generic"; if (std::string(v) == "v2") e->aa_v1 = false; if (std::string(v) == "v1") e->aa_v1 = true; }
+  if (const char *v = std::getenv("NRX_AA2_BLOCKS")) e->aa2_blocks = (uint32_t)std::max(1, std::atoi(v));
   if (const char *v = std::getenv("NRX_AA_BLOCKS")) e->aa_blocks = (uint32_t)std::max(1, std::atoi(v));
   if (const char *v = std::getenv("NRX_K2_BLOCKS")) e->k2_blocks = (uint32_t)std::max(1, std::atoi(v));
   {
@@ -392,6 +396,9 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
     if (!cuda_ok(cudaFuncSetAttribute(k_aa20_dmma<AA_CLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa_smem), "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(k_aa20_dmma<AA_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa_smem), "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(k_aa20_dmma<AA_EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa_smem), "cudaFuncSetAttribute")) { delete e; return nullptr; }
+    const int aa2_smem = (int)(sizeof(AaSmem2) + 2 * AA_LUT_CODES * 80 * sizeof(double));
+    if (!cuda_ok(cudaFuncSetAttribute(k_aa20_mma<AA_CLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa2_smem), "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(k_aa20_mma<AA_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa2_smem), "cudaFuncSetAttribute")) { delete e; return nullptr; }
     if (!cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClvPipeSmem)), "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem<1>)), "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem<2>)), "cudaFuncSetAttribute")) { delete e; return nullptr; }
@@ -731,8 +738,15 @@ int nrx_copy_slots(nrx_engine *e, const uint32_t *dst, const uint32_t *src, uint
   return 1;
 }
 
-/* validation + algorithmic-byte accounting of a batch of CLV updates */
-static int check_ops(nrx_engine *e, const nrx_op *ops, uint32_t nops, unsigned long long *updates, unsigned long long *bytes) {
+/* validation + byte accounting of ONE batch (= one launch per shape class) of CLV updates.
+ *   *bytes  : ALGORITHMIC bytes, SURVEY §8d's per-op figures (every op charged both of its operands);
+ *   *cbytes : COMPULSORY bytes of the launch — every distinct child CLV (+ scaler) / tip row read once, every parent CLV
+ *             (+ scaler) written once.  The ops of a node share children (12 x 8 compatible pairs share 20 children), the
+ *             re-reads hit the 126 MB L2, so this — not the algorithmic figure — is what must cross the HBM pins and is the
+ *             numerator of the roofline fraction (the algorithmic numerator gave 1.38 "of peak"). */
+static int check_ops(nrx_engine *e, const nrx_op *ops, uint32_t nops, unsigned long long *updates, unsigned long long *bytes,
+                     unsigned long long *cbytes = nullptr) {
+  std::vector<uint64_t> operands;   // (kind << 32 | idx) of every CLV / tip operand of the batch
   for (uint32_t i = 0; i < nops; ++i) {
     const nrx_op &o = ops[i];
     if (o.parent_slot >= e->nslots) { g_err = "nrx_update_clvs: parent slot out of range"; return 0; }
@@ -744,6 +758,7 @@ static int check_ops(nrx_engine *e, const nrx_op *ops, uint32_t nops, unsigned l
         if (kinds[s] == NRX_TIP && idx[s] >= p.d.tips) { g_err = "nrx_update_clvs: tip index out of range"; return 0; }
         if (kinds[s] != NRX_NONE && edges[s] >= p.d.edges) { g_err = "nrx_update_clvs: edge index out of range"; return 0; }
       }
+      if (kinds[s] != NRX_NONE) operands.push_back(((uint64_t)kinds[s] << 32) | idx[s]);
     }
     if (o.left_kind == NRX_NONE && o.right_kind == NRX_NONE) { g_err = "nrx_update_clvs: both operands absent"; return 0; }
     for (const Part &p : e->parts) {
@@ -755,7 +770,35 @@ static int check_ops(nrx_engine *e, const nrx_op *ops, uint32_t nops, unsigned l
       *updates += p.d.patterns;
     }
   }
+  if (cbytes) {
+    std::sort(operands.begin(), operands.end());
+    operands.erase(std::unique(operands.begin(), operands.end()), operands.end());
+    unsigned long long clvs = 0, tips = 0;
+    for (uint64_t o : operands) ((o >> 32) == NRX_CLV ? clvs : tips)++;
+    for (const Part &p : e->parts) {
+      const unsigned long long Cb = (unsigned long long)p.d.rate_cats * p.sp * 8;
+      *cbytes += (clvs * (Cb + 4) + tips + (unsigned long long)nops * (Cb + 4)) * p.d.patterns;
+    }
+  }
   return 1;
+}
+/* compulsory bytes of a K4 / K5 launch over `n` operand pairs: every distinct CLV operand (+ its scaler when the kernel reads
+ * it) / tip row once, plus `out_clvs` CLV-sized outputs per pair and `extra` bytes per (pair, pattern) */
+static unsigned long long pair_cbytes(const nrx_engine *e, const nrx_pair *pairs, uint32_t n, bool scalers, unsigned out_clvs, unsigned extra) {
+  std::vector<uint64_t> operands;
+  for (uint32_t i = 0; i < n; ++i) {
+    operands.push_back(((uint64_t)pairs[i].a_kind << 32) | pairs[i].a_idx);
+    operands.push_back(((uint64_t)pairs[i].b_kind << 32) | pairs[i].b_idx);
+  }
+  std::sort(operands.begin(), operands.end());
+  operands.erase(std::unique(operands.begin(), operands.end()), operands.end());
+  unsigned long long clvs = 0, tips = 0, b = 0;
+  for (uint64_t o : operands) ((o >> 32) == NRX_CLV ? clvs : tips)++;
+  for (const Part &p : e->parts) {
+    const unsigned long long Cb = (unsigned long long)p.d.rate_cats * p.sp * 8;
+    b += (clvs * (Cb + (scalers ? 4 : 0)) + tips + (unsigned long long)n * (out_clvs * Cb + extra)) * p.d.patterns;
+  }
+  return b;
 }
 
 /* K2 launches (one per partition shape class) for `nops` device-resident ops; `with_tips`: some op has a tip operand */
@@ -810,13 +853,15 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
       // the rest on the FP64 tensor cores (DMMA): 3 resident blocks of 4+1 warps per SM, 8-pattern tiles
       const uint32_t rest = nops - ntt;
       const uint32_t ntiles = (c.max_patterns + AA_TP - 1) / AA_TP;
-      uint32_t groups = std::max<uint32_t>(1, (e->aa_blocks + rest * z - 1) / (rest * z));
+      const uint32_t target = e->aa_v1 ? e->aa_blocks : e->aa2_blocks;
+      uint32_t groups = std::max<uint32_t>(1, (target + rest * z - 1) / (rest * z));
       groups = std::min(groups, std::max<uint32_t>(1, ntiles / 8));
       dim3 grid(rest * groups, 1, z);
       // tip-tip ops went to the table kernel above unless that path is disabled: then two tables are needed
       const int luts = !with_tips ? 0 : (has_aa_dmma(e) ? 1 : 2);
-      const size_t smem = sizeof(AaSmem) + (size_t)luts * class_tip_codes(e, c) * 80 * sizeof(double);
-      k_aa20_dmma<AA_CLV><<<grid, AA_THREADS, smem, e->stream>>>(c.d_views, d_ops + ntt, rest, groups, luts, nullptr, 0, 0.0);
+      const size_t lut_bytes = (size_t)luts * class_tip_codes(e, c) * 80 * sizeof(double);
+      if (e->aa_v1) k_aa20_dmma<AA_CLV><<<grid, AA_THREADS, sizeof(AaSmem) + lut_bytes, e->stream>>>(c.d_views, d_ops + ntt, rest, groups, luts, nullptr, 0, 0.0);
+      else k_aa20_mma<AA_CLV><<<grid, AA2_THREADS, sizeof(AaSmem2) + lut_bytes, e->stream>>>(c.d_views, d_ops + ntt, rest, groups, luts);
     } else {
       dim3 grid(tiles_for(c.max_patterns, BLOCK, nops * z), nops, z);
       k_clv_generic<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops, nullptr);
@@ -848,8 +893,8 @@ int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops) {
   if (!e) { g_err = "null engine"; return 0; }
   if (nops == 0) return 1;
   CK(cudaSetDevice(e->device));
-  unsigned long long updates = 0, bytes = 0;
-  if (!check_ops(e, ops, nops, &updates, &bytes)) return 0;
+  unsigned long long updates = 0, bytes = 0, cbytes = 0;
+  if (!check_ops(e, ops, nops, &updates, &bytes, &cbytes)) return 0;
   if (!refresh_views(e)) return 0;
   std::vector<nrx_op> ordered(ops, ops + nops);
   const uint32_t ntt = order_tiptip_first(e, ordered);
@@ -858,7 +903,7 @@ int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops) {
   cudaEvent_t ev0, ev1;
   prof_begin(e, &ev0, &ev1);
   if (!launch_clv_batch(e, d_ops, nops, any_tip(ops, nops), false, ntt)) return 0;
-  prof_end(e, ev0, ev1, e->classes.size(), updates, bytes);
+  prof_end(e, ev0, ev1, e->classes.size(), updates, bytes, NRX_PROF_K2, cbytes);
   return 1;
 }
 
@@ -908,7 +953,7 @@ int nrx_plan_create(nrx_engine *e, const nrx_op *ops, const uint32_t *batch_size
   std::vector<nrx_op> ordered;
   for (uint32_t b = 0; b < nbatches; ++b) {
     if (batch_sizes[b] == 0) { g_err = "nrx_plan_create: empty batch"; return 0; }
-    if (!check_ops(e, ops + total, batch_sizes[b], &pl.updates, &pl.bytes)) return 0;
+    if (!check_ops(e, ops + total, batch_sizes[b], &pl.updates, &pl.bytes, &pl.cbytes)) return 0;
     pl.offsets.push_back(total);
     pl.sizes.push_back(batch_sizes[b]);
     pl.tips.push_back(any_tip(ops + total, batch_sizes[b]));
@@ -976,7 +1021,7 @@ int nrx_plan_run(nrx_engine *e, uint32_t plan_id) {
     for (size_t b = 0; b < pl.sizes.size(); ++b)
       if (!launch_clv_batch(e, pl.d_ops + pl.offsets[b], pl.sizes[b], pl.tips[b], pl.lnl_items != 0, pl.ntt[b])) return 0;
   }
-  prof_end(e, ev0, ev1, per_run, pl.updates, pl.bytes);
+  prof_end(e, ev0, ev1, per_run, pl.updates, pl.bytes, NRX_PROF_K2, pl.cbytes);
   return 1;
 }
 
@@ -1207,7 +1252,7 @@ int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n
     e->launches++;
     CK(cudaGetLastError());
   }
-  { unsigned long long u = 0; const unsigned long long b = stream_bytes(e, n, 2, 12, &u); prof_end(e, ev0, ev1, e->classes.size(), u, b, NRX_PROF_K4); }
+  { unsigned long long u = 0; const unsigned long long b = stream_bytes(e, n, 2, 12, &u); prof_end(e, ev0, ev1, e->classes.size(), u, b, NRX_PROF_K4, pair_cbytes(e, pairs, n, true, 0, 4)); }
   return finish_reduction(e, n * P, nblk, out);
 }
 
@@ -1233,10 +1278,11 @@ int nrx_sumtables(nrx_engine *e, const nrx_pair *pairs, uint32_t n) {
       nrx_op *d_ops;
       if (!upload(e, ops.data(), ops.size(), &d_ops)) return 0;
       const uint32_t ntiles = (c.max_patterns + AA_TP - 1) / AA_TP;
-      uint32_t groups = std::max<uint32_t>(1, (e->aa_blocks + n * z - 1) / (n * z));
+      uint32_t groups = std::max<uint32_t>(1, ((e->aa_v1 ? e->aa_blocks : e->aa2_blocks) + n * z - 1) / (n * z));
       groups = std::min(groups, std::max<uint32_t>(1, ntiles / 8));
-      const size_t smem = sizeof(AaSmem) + (tips ? (size_t)class_tip_codes(e, c) * 80 * sizeof(double) : 0);
-      k_aa20_dmma<AA_SUM><<<dim3(n * groups, 1, z), AA_THREADS, smem, e->stream>>>(c.d_views, d_ops, n, groups, tips ? 1 : 0, nullptr, 0, 0.0);
+      const size_t lut_bytes = tips ? (size_t)class_tip_codes(e, c) * 80 * sizeof(double) : 0;
+      if (e->aa_v1) k_aa20_dmma<AA_SUM><<<dim3(n * groups, 1, z), AA_THREADS, sizeof(AaSmem) + lut_bytes, e->stream>>>(c.d_views, d_ops, n, groups, tips ? 1 : 0, nullptr, 0, 0.0);
+      else k_aa20_mma<AA_SUM><<<dim3(n * groups, 1, z), AA2_THREADS, sizeof(AaSmem2) + lut_bytes, e->stream>>>(c.d_views, d_ops, n, groups, tips ? 1 : 0);
     } else {
       dim3 grid(tiles_for((uint64_t)c.max_patterns * c.cats, BLOCK, n * z), n, z);
       k_sumtable<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs);
@@ -1244,7 +1290,7 @@ int nrx_sumtables(nrx_engine *e, const nrx_pair *pairs, uint32_t n) {
     e->launches++;
     CK(cudaGetLastError());
   }
-  { unsigned long long u = 0; const unsigned long long b = stream_bytes(e, n, 3, 0, &u); prof_end(e, ev0, ev1, e->classes.size(), u, b, NRX_PROF_K5); }
+  { unsigned long long u = 0; const unsigned long long b = stream_bytes(e, n, 3, 0, &u); prof_end(e, ev0, ev1, e->classes.size(), u, b, NRX_PROF_K5, pair_cbytes(e, pairs, n, false, 1, 0)); }
   return 1;
 }
 
@@ -1284,8 +1330,8 @@ int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen, double *out)
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
     const bool mix = class_mixture(e, c);   // (only the +I term of K6 reads frequencies; the generic kernel is the one that indexes them by category)
     if (!mix && c.states == 4 && c.cats == 4) k_derivatives_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P);
-    else if (!mix && pow2_cats(c) && c.states == 20) k_derivatives_pc<20><<<grid, BLOCK, ((size_t)c.cats * c.states * 4 + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P);
-    else if (!mix && pow2_cats(c)) k_derivatives_pc<0><<<grid, BLOCK, ((size_t)c.cats * c.states * 4 + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P);
+    else if (!mix && pow2_cats(c) && c.states == 20) k_derivatives_pc<20, 2><<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P);
+    else if (!mix && pow2_cats(c)) k_derivatives_pc<0, 2><<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P);
     else k_derivatives<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P);
     e->launches++;
     CK(cudaGetLastError());
@@ -1405,7 +1451,8 @@ int nrx_profile_enable(nrx_engine *e, int on) {
   return 1;
 }
 
-int nrx_profile_read_kind(nrx_engine *e, int kind, double *ms, unsigned long long *launches, unsigned long long *units, unsigned long long *bytes) {
+int nrx_profile_read_kind(nrx_engine *e, int kind, double *ms, unsigned long long *launches, unsigned long long *units, unsigned long long *bytes,
+                          unsigned long long *compulsory_bytes) {
   if (!e) { g_err = "null engine"; return 0; }
   if (kind < 0 || kind >= NRX_PROF_KINDS) { g_err = "nrx_profile_read_kind: bad kind"; return 0; }
   CK(cudaSetDevice(e->device));
@@ -1422,11 +1469,12 @@ int nrx_profile_read_kind(nrx_engine *e, int kind, double *ms, unsigned long lon
   if (launches) *launches = k.launches;
   if (units) *units = k.units;
   if (bytes) *bytes = k.bytes;
+  if (compulsory_bytes) *compulsory_bytes = k.cbytes;
   return 1;
 }
 
 int nrx_profile_read(nrx_engine *e, double *clv_ms, unsigned long long *clv_launches, unsigned long long *clv_site_updates, unsigned long long *clv_bytes) {
-  return nrx_profile_read_kind(e, NRX_PROF_K2, clv_ms, clv_launches, clv_site_updates, clv_bytes);
+  return nrx_profile_read_kind(e, NRX_PROF_K2, clv_ms, clv_launches, clv_site_updates, clv_bytes, nullptr);
 }
 
 }  // extern "C"

@@ -934,6 +934,261 @@ __global__ void __launch_bounds__(AA_THREADS, 3) k_aa20_dmma(const PartView *__r
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * K2 / K5, protein, round-2 kernel: k_aa20_mma<MODE> (MODE = AA_CLV or AA_SUM; AA_EDGE stays on k_aa20_dmma).
+ *
+ * What ncu said about k_aa20_dmma<AA_CLV> (profiles/r2a_aa20_dmma_stalls.md): the kernel is bound by the FP64 pipe — one
+ * DMMA.8x8x4 holds an SM sub-partition's FP64 tensor path for 16 cycles (128 flop/clk/SM, the same peak as the DFMA pipe, and
+ * DMUL competes for it) — yet that pipe was only 56-60 % busy: ~300 issued instructions per 30 DMMAs (address arithmetic,
+ * predication on the operand kinds, the product / scaling-test / FSEL / partial-sector store epilogue, flags + named barrier)
+ * executed in order by 3 warps per sub-partition.  Here the roles are split three ways so that the warps that own the
+ * tensor pipe do almost nothing else:
+ *   warp 4  LOADER   per-row cp.async.bulk copies of 8-pattern tiles of both children into an NIN-deep ring (as before);
+ *   warps 0-3  MMA   (warp = rate category, both edges' B fragments in registers): 10 LDS of A fragments, 30 DMMAs, 6 DMUL,
+ *                    the "< 2^-256" test (6 DSETP + ballot), then the UNSCALED products go to a shared-memory output tile
+ *                    [8 patterns][88] (3 conflict-free 128-bit STS per lane) + one flag per (category, pattern);
+ *   warp 5  STORER   waits for the four category warps of a tile, ANDs the flags (scaling needs all 80 entries of a pattern,
+ *                    LIBPLL/core_partials.c:727-757; rows that do scale — rare — are multiplied in shared memory), writes
+ *                    the scalers and issues ONE 640-byte cp.async.bulk store per pattern row: full-line, fully coalesced
+ *                    HBM writes by the TMA engine instead of 16-byte partial-sector stores from 96 lanes.
+ * All hand-offs are mbarriers (full_in / empty_in / full_out / empty_out); generic-proxy writes to the output tile are made
+ * visible to the async proxy with fence.proxy.async before the storer is signalled.  Arithmetic (DMMA k-step order, products,
+ * exact power-of-two scaling) is identical to k_aa20_dmma, so results are bit-identical to it.
+ * ---------------------------------------------------------------------------------------------- */
+constexpr int NIN_AA = 6;            // input ring stages (8 patterns x 2 operands x 672 B each)
+constexpr int NOUT_AA = 3;           // output tiles in flight
+constexpr int AA_OPITCH = 88;        // doubles per output row: 128-bit stores of a quarter-warp (2 patterns x 4 lanes) hit disjoint banks
+constexpr int AA2_THREADS = 192;     // 4 MMA warps + loader + storer
+
+struct __align__(128) AaOut {
+  double v[AA_TP * AA_OPITCH];
+  uint32_t sc[AA_TP];              // sum of the children's scalers (written by the category-0 warp)
+  uint32_t flag[4][AA_TP];         // 1: all 20 entries of (category, pattern) are below the scaling threshold
+};
+struct __align__(128) AaSmem2 {
+  AaStage in[NIN_AA];
+  AaOut out[NOUT_AA];
+  unsigned long long full_in[NIN_AA], empty_in[NIN_AA], full_out[NOUT_AA], empty_out[NOUT_AA];
+  unsigned long long lutbar;
+  // followed by double lutL[tip_codes*80] (and lutR when with_lut == 2)
+};
+
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(AA2_THREADS, 2) k_aa20_mma(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops,
+                                                              uint32_t nops, uint32_t groups, int with_lut) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  AaSmem2 &sm = *reinterpret_cast<AaSmem2 *>(smem_raw);
+  const PartView &pv = parts[blockIdx.z];
+  double *lutL = reinterpret_cast<double *>(smem_raw + sizeof(AaSmem2));
+  double *lutR = (with_lut == 2) ? lutL + pv.tip_codes * 80 : lutL;
+  const nrx_op op = ops[blockIdx.x % nops];
+  const uint32_t grp = blockIdx.x / nops;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t ntiles = (pv.patterns + AA_TP - 1) / AA_TP;
+  if (grp >= ntiles) return;
+  const uint32_t count = (ntiles - grp + groups - 1) / groups;
+  const int lk = op.left_kind, rk = op.right_kind;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NIN_AA; ++s) { mbar_init(&sm.full_in[s], 1); mbar_init(&sm.empty_in[s], 4); }
+#pragma unroll
+    for (int s = 0; s < NOUT_AA; ++s) { mbar_init(&sm.full_out[s], 4); mbar_init(&sm.empty_out[s], 1); }
+    mbar_init(&sm.lutbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (with_lut && tid == 0) {
+    const uint32_t bytes = pv.tip_codes * 640u;
+    const uint32_t tx = (lk == NRX_TIP ? bytes : 0u) + (rk == NRX_TIP ? bytes : 0u);
+    if (tx) {
+      mbar_expect_tx(&sm.lutbar, tx);
+      if (lk == NRX_TIP) bulk_g2s(lutL, MODE == AA_SUM ? pv.sumlut : pv.tiplut + (size_t)op.left_edge * AA_LUT_CODES * 80, bytes, &sm.lutbar);
+      if (rk == NRX_TIP) bulk_g2s(lutR, pv.tiplut + (size_t)op.right_edge * AA_LUT_CODES * 80, bytes, &sm.lutbar);
+    }
+  }
+  const bool wait_lut = with_lut && (lk == NRX_TIP || rk == NRX_TIP);
+
+  if (warp == 4) {
+    /* ---------------- loader ---------------- */
+    const double *clvL = (lk == NRX_CLV) ? pv.clv[op.left_idx] : nullptr;
+    const double *clvR = (rk == NRX_CLV) ? pv.clv[op.right_idx] : nullptr;
+    const uint32_t *scL = (lk == NRX_CLV) ? pv.scaler[op.left_idx] : nullptr;
+    const uint32_t *scR = (rk == NRX_CLV) ? pv.scaler[op.right_idx] : nullptr;
+    const uint8_t *tipL = (lk == NRX_TIP) ? pv.tipchars + (size_t)op.left_idx * pv.tip_pitch : nullptr;
+    const uint8_t *tipR = (rk == NRX_TIP) ? pv.tipchars + (size_t)op.right_idx * pv.tip_pitch : nullptr;
+    const uint32_t sc_bytes = (MODE == AA_SUM) ? 0u : AA_TP * 4u;
+    const uint32_t tx_bytes = ((lk == NRX_CLV) ? AA_TP * 640u + sc_bytes : (lk == NRX_TIP ? 16u : 0u)) +
+                              ((rk == NRX_CLV) ? AA_TP * 640u + sc_bytes : (rk == NRX_TIP ? 16u : 0u));
+    uint32_t s = 0, ph = 0;
+    for (uint32_t k = 0; k < count; ++k) {
+      if (k >= (uint32_t)NIN_AA) mbar_wait(&sm.empty_in[s], ph ^ 1u);
+      AaStage &st = sm.in[s];
+      unsigned long long *bar = &sm.full_in[s];
+      const size_t p0 = (size_t)(grp + (size_t)k * groups) * AA_TP;
+      if (lane == 0) mbar_expect_tx(bar, tx_bytes);
+      __syncwarp();
+      if (lane < AA_TP) {
+        if (lk == NRX_CLV) bulk_g2s(st.l + lane * AA_PITCH, clvL + (p0 + lane) * 80, 640u, bar);
+      } else if (lane < 2 * AA_TP) {
+        if (rk == NRX_CLV) bulk_g2s(st.r + (lane - AA_TP) * AA_PITCH, clvR + (p0 + lane - AA_TP) * 80, 640u, bar);
+      } else if (lane == 16) {
+        if (lk == NRX_CLV) { if (MODE != AA_SUM) bulk_g2s(st.scl, scL + p0, AA_TP * 4u, bar); }
+        else if (lk == NRX_TIP) bulk_g2s(st.tl, tipL + (p0 & ~(size_t)15), 16u, bar);
+      } else if (lane == 17) {
+        if (rk == NRX_CLV) { if (MODE != AA_SUM) bulk_g2s(st.scr, scR + p0, AA_TP * 4u, bar); }
+        else if (rk == NRX_TIP) bulk_g2s(st.tr, tipR + (p0 & ~(size_t)15), 16u, bar);
+      }
+      if (++s == NIN_AA) { s = 0; ph ^= 1u; }
+    }
+    return;
+  }
+
+  if (warp == 5) {
+    /* ---------------- storer ---------------- */
+    double *par = (MODE == AA_SUM) ? pv.sumtable[op.parent_slot] : pv.clv[op.parent_slot];
+    uint32_t *psc = (MODE == AA_CLV) ? pv.scaler[op.parent_slot] : nullptr;
+    const bool tiptip = (lk == NRX_TIP && rk == NRX_TIP);
+    uint32_t o = 0, ph = 0, prev = 0;
+    for (uint32_t k = 0; k < count; ++k) {
+      AaOut &ot = sm.out[o];
+      mbar_wait(&sm.full_out[o], ph);
+      const size_t p0 = (size_t)(grp + (size_t)k * groups) * AA_TP;
+      if (MODE == AA_CLV) {
+        // lanes 0..7 = the tile's patterns: a pattern is scaled only if all four categories flagged it
+        uint32_t f = 0, scv = 0;
+        if (lane < AA_TP) {
+          f = tiptip ? 0u : (ot.flag[0][lane] & ot.flag[1][lane] & ot.flag[2][lane] & ot.flag[3][lane]);
+          scv = tiptip ? 0u : ot.sc[lane] + f;
+          if (p0 + lane < pv.patterns) psc[p0 + lane] = scv;
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, f != 0u);
+        if (any) {   // rare: multiply the flagged rows by 2^256 in shared memory (exact), then hand them to the async proxy
+          for (int r = 0; r < AA_TP; ++r)
+            if ((any >> r) & 1u)
+              for (int i = lane; i < 80; i += 32) ot.v[r * AA_OPITCH + i] = __dmul_rn(ot.v[r * AA_OPITCH + i], SCALE_FACTOR);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+        }
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < AA_TP; ++r)
+          if (p0 + r < pv.patterns) bulk_s2g(par + (p0 + r) * 80, ot.v + r * AA_OPITCH, 640u);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // all but the newest group have been READ out of shared memory: the previous tile's buffer can be rewritten
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (k > 0) mbar_arrive(&sm.empty_out[prev]);
+      }
+      prev = o;
+      if (++o == NOUT_AA) { o = 0; ph ^= 1u; }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the stores must have landed before the block's shared memory goes away
+    return;
+  }
+
+  /* ---------------- MMA warps: warp = rate category ---------------- */
+  const int cat = warp, item = lane >> 2, q = lane & 3;
+  double BL[15], BR[15];   // B fragments: [ntile * 5 + kstep] = M[8*ntile + lane/4][4*kstep + lane%4]
+  {
+    const int i_base = lane >> 2, j_base = lane & 3;
+#pragma unroll
+    for (int n = 0; n < 3; ++n)
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int i = 8 * n + i_base, j = 4 * k + j_base;
+        if (MODE == AA_SUM) {
+          BL[n * 5 + k] = (lk == NRX_CLV && i < 20) ? pv.summat[i * 20 + j] : 0.0;
+          BR[n * 5 + k] = (rk == NRX_CLV && i < 20) ? pv.summat[400 + i * 20 + j] : 0.0;
+        } else {
+          BL[n * 5 + k] = (lk == NRX_CLV && i < 20) ? pv.pmat[(size_t)op.left_edge * 1600 + (cat * 20 + i) * 20 + j] : 0.0;
+          BR[n * 5 + k] = (rk == NRX_CLV && i < 20) ? pv.pmat[(size_t)op.right_edge * 1600 + (cat * 20 + i) * 20 + j] : 0.0;
+        }
+      }
+  }
+  if (wait_lut) mbar_wait(&sm.lutbar, 0);
+  uint32_t s = 0, ph = 0, o = 0, pho = 0;
+  for (uint32_t k = 0; k < count; ++k) {
+    const AaStage &st = sm.in[s];
+    mbar_wait(&sm.full_in[s], ph);
+    const uint32_t p0lo = (uint32_t)(((size_t)(grp + (size_t)k * groups) * AA_TP) & 15u);
+    double aL[5], aR[5];
+    uint32_t codeL = 0, codeR = 0, sc = 0;
+    if (lk == NRX_CLV) {
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) aL[kk] = st.l[item * AA_PITCH + cat * 20 + 4 * kk + q];
+      if (MODE == AA_CLV) sc += st.scl[item];
+    } else if (lk == NRX_TIP) codeL = st.tl[p0lo + item];
+    if (rk == NRX_CLV) {
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) aR[kk] = st.r[item * AA_PITCH + cat * 20 + 4 * kk + q];
+      if (MODE == AA_CLV) sc += st.scr[item];
+    } else if (rk == NRX_TIP) codeR = st.tr[p0lo + item];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty_in[s]);
+
+    double x[6], y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { x[i] = 0.0; y[i] = 0.0; }
+    if (lk == NRX_CLV) {
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk)
+#pragma unroll
+        for (int n = 0; n < 3; ++n) dmma884(x[2 * n], x[2 * n + 1], aL[kk], BL[n * 5 + kk]);
+    }
+    if (rk == NRX_CLV) {
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk)
+#pragma unroll
+        for (int n = 0; n < 3; ++n) dmma884(y[2 * n], y[2 * n + 1], aR[kk], BR[n * 5 + kk]);
+    }
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+      const int i0 = 8 * n + 2 * q;
+      if (lk == NRX_TIP && i0 < 20) { const double2 v = *reinterpret_cast<const double2 *>(lutL + (codeL * 4 + cat) * 20 + i0); x[2 * n] = v.x; x[2 * n + 1] = v.y; }
+      if (rk == NRX_TIP && i0 < 20) { const double2 v = *reinterpret_cast<const double2 *>(lutR + (codeR * 4 + cat) * 20 + i0); y[2 * n] = v.x; y[2 * n + 1] = v.y; }
+    }
+    double pz[6];
+    bool small = true;
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+      const int i0 = 8 * n + 2 * q;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double v;
+        if (rk == NRX_NONE) v = x[2 * n + h];
+        else if (lk == NRX_NONE) v = y[2 * n + h];
+        else v = __dmul_rn(x[2 * n + h], y[2 * n + h]);
+        pz[2 * n + h] = v;
+        if (MODE == AA_CLV && i0 < 20) small &= (v < SCALE_THRESHOLD);
+      }
+    }
+    AaOut &ot = sm.out[o];
+    mbar_wait(&sm.empty_out[o], pho ^ 1u);   // the bulk stores of the tile that used this buffer NOUT_AA tiles ago have read it
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+      const int i0 = 8 * n + 2 * q;
+      if (i0 < 20) *reinterpret_cast<double2 *>(ot.v + item * AA_OPITCH + cat * 20 + i0) = make_double2(pz[2 * n], pz[2 * n + 1]);
+    }
+    if (MODE == AA_CLV) {
+      const unsigned b = __ballot_sync(0xffffffffu, small);
+      if (q == 0) {
+        ot.flag[cat][item] = (((b >> (lane & ~3)) & 0xFu) == 0xFu) ? 1u : 0u;
+        if (cat == 0) ot.sc[item] = sc;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the storer's bulk copies
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.full_out[o]);
+    if (++s == NIN_AA) { s = 0; ph ^= 1u; }
+    if (++o == NOUT_AA) { o = 0; pho ^= 1u; }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * K2 generic (any states <= 32, any cats): one thread per (pattern, category), P rows from L1/L2.
  * Used for protein data until the DMMA kernel takes over, and for unusual category counts.
  * ---------------------------------------------------------------------------------------------- */
@@ -1406,60 +1661,88 @@ __global__ void __launch_bounds__(BLOCK) k_tree_lnl_pc(const PartView *__restric
   if (threadIdx.x == 0) partial[((size_t)blockIdx.y * nparts_total + pv.part_index) * gridDim.x + blockIdx.x] = acc[0];
 }
 
-template <int SC>
+/* K6, thread = (pattern, category), NP patterns per thread.  ncu on the first version (profiles/r2a_k6_protein_200k.md): 54 % of the
+ * warp stalls on the shared-memory scoreboard + 17 % MIO throttle, 36 M excessive shared wavefronts per launch — the diag table
+ * rows of the four categories of a warp lay 640 B apart, i.e. in the SAME banks (4-way conflict on each of the 40 LDS per item),
+ * and one item per thread kept only 5 x 32 B of HBM loads in flight.  Now: the per-category stride of the table is padded to
+ * = 2 (mod 16) doubles so the four (broadcast) double2 reads of a warp fall into disjoint bank groups, and every diag entry read
+ * from shared memory is applied to NP patterns (NP x 5 independent 256-bit loads in flight per thread).  Per-(pattern,
+ * category) arithmetic and summation order are unchanged. */
+__host__ __device__ constexpr uint32_t diag_stride(uint32_t S) { return ((S * 4 + 13) / 16) * 16 + 2; }
+
+template <int SC, int NP>
 __global__ void __launch_bounds__(BLOCK) k_derivatives_pc(const PartView *__restrict__ parts, double *__restrict__ partial,
                                                            uint32_t nparts_total) {
   __shared__ double red[3 * (BLOCK / 32)];
-  extern __shared__ double sdiag[];  // [cats][states][4] + [cats] rate weights
+  extern __shared__ __align__(16) double sdiag[];  // [cats][diag_stride(states)] (entries [state][4]) + [cats] rate weights
   const PartView &pv = parts[blockIdx.z];
   const uint32_t S = SC ? (uint32_t)SC : pv.states, SP = SC ? (uint32_t)((SC + 3) & ~3) : pv.sp, C = pv.cats;
-  double *swt = sdiag + (size_t)C * S * 4;
-  for (uint32_t i = threadIdx.x; i < C * S * 4; i += BLOCK) sdiag[i] = pv.diagp[i];
+  const uint32_t DS = diag_stride(S);
+  double *swt = sdiag + (size_t)C * DS;
+  for (uint32_t i = threadIdx.x; i < C * S * 4; i += BLOCK) sdiag[(i / (S * 4)) * DS + i % (S * 4)] = pv.diagp[i];
   if (threadIdx.x < C) swt[threadIdx.x] = pv.rate_weights[threadIdx.x];
   __syncthreads();
   const double *st = pv.sumtable[blockIdx.y];
   const uint32_t lane = threadIdx.x & 31, c = threadIdx.x & (C - 1);
-  const double *dg = sdiag + (size_t)c * S * 4;
+  const double *dg = sdiag + (size_t)c * DS;
   const uint64_t n_items = (uint64_t)pv.patterns * C;
-  const uint64_t span = ((n_items + BLOCK - 1) / BLOCK) * BLOCK;
+  const uint64_t span = ((n_items + (uint64_t)BLOCK * NP - 1) / ((uint64_t)BLOCK * NP)) * ((uint64_t)BLOCK * NP);   // whole warps stay in the loop for the shuffles
   const double pinv = pv.pinv;
+  const double w = swt[c];
   double acc[3] = {0.0, 0.0, 0.0};
-  for (uint64_t g = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; g < span; g += (uint64_t)gridDim.x * BLOCK) {
-    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-    if (g < n_items) {
-      const double *v = st + g * SP;
-      double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+  for (uint64_t base = (uint64_t)blockIdx.x * BLOCK * NP; base < span; base += (uint64_t)gridDim.x * BLOCK * NP) {
+    double c0[NP], c1[NP], c2[NP];
+    const double *v[NP];
+    bool on[NP];
 #pragma unroll
-      for (uint32_t k = 0; k < SP; k += 4) {
-        const D4 q = ldg256(v + k);
-        const double e[4] = {q.x, q.y, q.z, q.w};
+    for (int u = 0; u < NP; ++u) {
+      const uint64_t g = base + (uint64_t)u * BLOCK + threadIdx.x;   // BLOCK is a multiple of C: the category is the same for every u
+      on[u] = g < n_items;
+      v[u] = st + (on[u] ? g : 0) * SP;
+      c0[u] = c1[u] = c2[u] = 0.0;
+    }
 #pragma unroll
-        for (uint32_t h = 0; h < 4; ++h)
-          if (k + h < S) {
-            const double2 d01 = *reinterpret_cast<const double2 *>(dg + (k + h) * 4);
-            c0 = __dadd_rn(c0, __dmul_rn(e[h], d01.x));
-            c1 = __dadd_rn(c1, __dmul_rn(e[h], d01.y));
-            c2 = __dadd_rn(c2, __dmul_rn(e[h], dg[(k + h) * 4 + 2]));
+    for (uint32_t k = 0; k < SP; k += 4) {
+      D4 q[NP];
+#pragma unroll
+      for (int u = 0; u < NP; ++u) q[u] = ldg256(v[u] + k);
+#pragma unroll
+      for (uint32_t h = 0; h < 4; ++h)
+        if (k + h < S) {
+          const double2 d01 = *reinterpret_cast<const double2 *>(dg + (k + h) * 4);
+          const double d2 = dg[(k + h) * 4 + 2];
+#pragma unroll
+          for (int u = 0; u < NP; ++u) {
+            const double e = h == 0 ? q[u].x : (h == 1 ? q[u].y : (h == 2 ? q[u].z : q[u].w));
+            c0[u] = __dadd_rn(c0[u], __dmul_rn(e, d01.x));
+            c1[u] = __dadd_rn(c1[u], __dmul_rn(e, d01.y));
+            c2[u] = __dadd_rn(c2[u], __dmul_rn(e, d2));
           }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NP; ++u) {
+      const uint64_t g = base + (uint64_t)u * BLOCK + threadIdx.x;
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+      if (on[u]) {
+        if (pinv > 0.0) { const int iv = pv.invariant[g / C]; deriv_cat_pinv(c0[u], c1[u], c2[u], pinv, iv < 0 ? 0.0 : pv.freqs[iv]); }
+        t0 = __dmul_rn(c0[u], w); t1 = __dmul_rn(c1[u], w); t2 = __dmul_rn(c2[u], w);
       }
-      const double w = swt[c];
-      if (pinv > 0.0) { const int iv = pv.invariant[g / C]; deriv_cat_pinv(c0, c1, c2, pinv, iv < 0 ? 0.0 : pv.freqs[iv]); }
-      t0 = __dmul_rn(c0, w); t1 = __dmul_rn(c1, w); t2 = __dmul_rn(c2, w);
-    }
-    double lk0 = 0.0, lk1 = 0.0, lk2 = 0.0;
-    for (uint32_t i = 0; i < C; ++i) {
-      const int src = (int)((lane & ~(C - 1)) + i);
-      lk0 = __dadd_rn(lk0, __shfl_sync(0xffffffffu, t0, src));
-      lk1 = __dadd_rn(lk1, __shfl_sync(0xffffffffu, t1, src));
-      lk2 = __dadd_rn(lk2, __shfl_sync(0xffffffffu, t2, src));
-    }
-    if (c == 0 && g < n_items) {
-      const double pw = (double)pv.weights[g / C];
-      const double d1 = -lk1 / lk0;
-      const double d2 = d1 * d1 - lk2 / lk0;
-      acc[0] += pw * log(lk0);
-      acc[1] += pw * d1;
-      acc[2] += pw * d2;
+      double lk0 = 0.0, lk1 = 0.0, lk2 = 0.0;
+      for (uint32_t i = 0; i < C; ++i) {
+        const int src = (int)((lane & ~(C - 1)) + i);
+        lk0 = __dadd_rn(lk0, __shfl_sync(0xffffffffu, t0, src));
+        lk1 = __dadd_rn(lk1, __shfl_sync(0xffffffffu, t1, src));
+        lk2 = __dadd_rn(lk2, __shfl_sync(0xffffffffu, t2, src));
+      }
+      if (c == 0 && on[u]) {
+        const double pw = (double)pv.weights[g / C];
+        const double d1 = -lk1 / lk0;
+        const double d2 = d1 * d1 - lk2 / lk0;
+        acc[0] += pw * log(lk0);
+        acc[1] += pw * d1;
+        acc[2] += pw * d2;
+      }
     }
   }
   block_sum<3>(acc, red);

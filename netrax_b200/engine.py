@@ -48,7 +48,7 @@ def load() -> FlatAPI:
         lib.nrxh_profile_read.restype = C.c_int
         lib.nrxh_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double)] + [C.POINTER(C.c_ulonglong)] * 3
         lib.nrxh_profile_read_kind.restype = C.c_int
-        lib.nrxh_profile_read_kind.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)] + [C.POINTER(C.c_ulonglong)] * 3
+        lib.nrxh_profile_read_kind.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)] + [C.POINTER(C.c_ulonglong)] * 4
         lib.nrxh_persite_lnl.restype = C.c_int
         lib.nrxh_persite_lnl.argtypes = [C.c_void_p, C.c_uint, np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), C.c_uint]
         lib.nrxh_engine.restype = C.c_void_p
@@ -143,13 +143,14 @@ class NetraxB200(LikelihoodEngine):
                   "reduce_partials", "slot_copy")  # NRX_PROF_* of include/nrx_engine.h
 
     def profile_read_all(self):
-        """{kernel family: {ms, launches, units, bytes}} since profile_enable(True) (CUDA events on the engine stream)."""
+        """{kernel family: {ms, launches, units, bytes, compulsory_bytes}} since profile_enable(True) (CUDA events on the engine
+        stream).  bytes = algorithmic (SURVEY §8d per op), compulsory_bytes = each distinct operand once per launch."""
         out = {}
         for kind, name in enumerate(self.PROF_KINDS):
             ms = C.c_double()
-            l, u, b = C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong()
-            self.api.check(self.api.lib.nrxh_profile_read_kind(self.h, kind, C.byref(ms), C.byref(l), C.byref(u), C.byref(b)))
-            out[name] = {"ms": ms.value, "launches": l.value, "units": u.value, "bytes": b.value}
+            l, u, b, cb = C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong()
+            self.api.check(self.api.lib.nrxh_profile_read_kind(self.h, kind, C.byref(ms), C.byref(l), C.byref(u), C.byref(b), C.byref(cb)))
+            out[name] = {"ms": ms.value, "launches": l.value, "units": u.value, "bytes": b.value, "compulsory_bytes": cb.value}
         return out
 
     def persite_lnl(self, tree: int) -> np.ndarray:

@@ -785,6 +785,18 @@ static void computeDisplayedTreeLoglikelihood(AnnotatedNetwork &ann, DisplayedTr
   treeAtRoot.treeLoglData.tree_logl_valid = true;
 }
 
+/* Per-site lnL of root displayed tree `tree` in partition p: the `persite_lnl` array the reference hands to
+ * pll_compute_root_loglikelihood and then discards (LH/ImprovedLoglikelihood.cpp:448-453; filled per pattern, pattern weight
+ * applied, LIBPLL/core_likelihood.c:190-200).  Returns the partition sum. */
+double persiteLoglikelihood(AnnotatedNetwork &ann, size_t tree, unsigned p, double *persite) {
+  NodeDisplayedTreeData &rd = ann.pernode_displayed_tree_data[ann.network.root];
+  if (tree >= rd.num_active_displayed_trees) throw std::runtime_error("persiteLoglikelihood: no such root displayed tree");
+  DisplayedTreeData &treeAtRoot = rd.displayed_trees[tree];
+  unsigned dtr = findFirstNodeWithTwoActiveChildren(ann, treeAtRoot.treeLoglData.reticulationChoices, ann.network.root);
+  DisplayedTreeData &t = findMatchingDisplayedTree(ann, treeAtRoot.treeLoglData.reticulationChoices, ann.pernode_displayed_tree_data[dtr]);
+  return ann.backend->rootLogl(p, t.clv_vector[p].p, t.scale_buffer[p].p, persite);
+}
+
 static void processPartitionsImproved(AnnotatedNetwork &ann, int incremental) {  // :488-519
   for (size_t i = 0; i < ann.travbuffer.size(); ++i) {
     unsigned n = ann.travbuffer[i];

@@ -248,6 +248,7 @@ void init_annotated_network(AnnotatedNetwork &ann);  // SRC/graph/AnnotatedNetwo
 /* upper seam, same names/arguments as the reference */
 double computeLoglikelihood(AnnotatedNetwork &ann, int incremental = 1, int update_pmatrices = 1);
 double computePseudoLoglikelihood(AnnotatedNetwork &ann, int incremental = 1, int update_pmatrices = 1);  // LH/PseudoLoglikelihood.cpp:57-226
+double persiteLoglikelihood(AnnotatedNetwork &ann, size_t tree, unsigned p, double *persite);
 double computeLoglikelihoodNaive(AnnotatedNetwork &ann, std::vector<double> *tree_logl, std::vector<double> *tree_logprob);
 void invalidateSingleClv(AnnotatedNetwork &ann, unsigned clv_index);
 void invalidateHigherCLVs(AnnotatedNetwork &ann, unsigned node, bool invalidate_myself);

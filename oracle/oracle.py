@@ -67,3 +67,15 @@ def naive_loglikelihood(eng: LikelihoodEngine):
     out = C.c_double()
     eng.api.check(eng.api.lib.orc_naive_loglikelihood(eng.h, C.byref(out), tl.ctypes.data_as(C.c_void_p), lp.ctypes.data_as(C.c_void_p)))
     return out.value, tl.reshape(T, eng.P), lp
+
+
+def persite_lnl(eng: LikelihoodEngine, tree: int) -> np.ndarray:
+    """Per-site lnL of root displayed tree `tree`, [P, max sites] — what pll_compute_root_loglikelihood writes into the
+    `persite_lnl` array of LH/ImprovedLoglikelihood.cpp:448-453 (pattern weight applied)."""
+    fn = eng.api.lib.orc_persite_lnl
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_uint, np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), C.c_uint]
+    stride = max(p.sites for p in eng.partitions)
+    out = np.zeros((eng.P, stride))
+    eng.api.check(fn(eng.h, tree, out.reshape(-1), stride))
+    return out

@@ -158,6 +158,17 @@ int orc_naive_loglikelihood(void *hv, double *out, double *tree_logl, double *tr
   });
 }
 
+/* per-site lnL of root displayed tree `tree`: out[p * stride + site] (same shape as the product's nrxh_persite_lnl) */
+int orc_persite_lnl(void *hv, unsigned tree, double *out, unsigned stride) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] {
+    for (unsigned p = 0; p < h->ann.partitionCount(); ++p) {
+      if (h->ann.backend->sites(p) > stride) throw std::runtime_error("orc_persite_lnl: stride smaller than the partition");
+      persiteLoglikelihood(h->ann, tree, p, out + (size_t)p * stride);
+    }
+  });
+}
+
 unsigned orc_num_partitions(void *hv) { return static_cast<Handle *>(hv)->ann.partitionCount(); }
 unsigned orc_root(void *hv) { return static_cast<Handle *>(hv)->ann.network.root; }
 unsigned orc_num_nodes(void *hv) { return (unsigned)static_cast<Handle *>(hv)->ann.network.num_nodes(); }

@@ -23,7 +23,7 @@ def main():
     args = ap.parse_args()
     from netrax_b200.engine import NetraxB200, compute_loglikelihood_batch
     cfg = dict(bench.CONFIGS[args.config])
-    _, parts, brl = bench.make_inputs(cfg, cfg["patterns"], 0)
+    _, parts, brl = bench.make_inputs(cfg, cfg["patterns"])
     engs = []
     for k in range(args.candidates):
         net = random_network(cfg["taxa"], cfg["ret"], seed=500 + k)

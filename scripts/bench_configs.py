@@ -21,17 +21,7 @@ import bench  # noqa: E402
 from netrax_b200._capi import UNLINKED  # noqa: E402
 
 
-def derivative_sweep(eng, net, iters=3):
-    for e in range(net.num_edges):
-        t0 = float(net.edge_length[e])
-        eng.brlen_prepare(e)
-        eng.computeLoglikelihoodBrlenOpt(e)
-        if eng.computePartitionSumtables(e):
-            for k in range(iters):
-                eng.brlen_set_length(e, t0 * (1.0 + 0.1 * (k + 1)))
-                eng.computeLoglikelihoodDerivatives(e)
-            eng.brlen_set_length(e, t0)
-        eng.brlen_finish(e)
+from bench import derivative_sweep  # noqa: E402,F401  (the sweep definition lives with the driver-run bench)
 
 
 def optimisation_round(eng):
@@ -53,7 +43,7 @@ def optimisation_round(eng):
 def _cpu_worker(args):
     kind, cfg, patterns, widx, reps, sweep = args
     from oracle import oracle
-    net, parts, brl = bench.make_inputs(cfg, patterns, 100 + widx)
+    net, parts, brl = bench.make_inputs(cfg, widx * patterns, (widx + 1) * patterns)
     eng = oracle.make_engine(kind, net, parts, variant=cfg["variant"], linkage=cfg["linkage"], partition_brlens=brl)
     eng.computeLoglikelihood(0, 1)
     out = {"lnl": [], "sweep": []}
@@ -98,7 +88,7 @@ def main():
         if args.patterns:
             cfg["patterns"] = args.patterns
             cfg["name"] += f" [patterns overridden: {args.patterns}]"
-        net, parts, brl = bench.make_inputs(cfg, cfg["patterns"], 0)
+        net, parts, brl = bench.make_inputs(cfg, cfg["patterns"])
         eng = NetraxB200(net, parts, variant=cfg["variant"], linkage=cfg["linkage"], partition_brlens=brl)
         for _ in range(3):
             eng.computeLoglikelihood(0, 1)

@@ -25,7 +25,7 @@ def main():
     args = ap.parse_args()
     from netrax_b200.engine import NetraxB200
     cfg = dict(bench.CONFIGS[args.config])
-    net, parts, brl = bench.make_inputs(cfg, cfg["patterns"], 0)
+    net, parts, brl = bench.make_inputs(cfg, cfg["patterns"])
     out = {"workload": cfg["name"], "variants": {}}
     for name in ("default", "probs_0.5", "random_cells"):
         ps = parts

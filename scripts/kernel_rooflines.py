@@ -13,7 +13,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
-from scripts.bench_configs import derivative_sweep  # noqa: E402
+from bench import derivative_sweep  # noqa: E402
 
 
 def peak_gbs():
@@ -37,10 +37,10 @@ def measure(eng, fn, reps):
     for k, v in prof.items():
         if v["launches"] == 0:
             continue
-        gbs = v["bytes"] / (v["ms"] / 1e3) / 1e9 if v["ms"] > 0 else 0.0
+        gbs = v["compulsory_bytes"] / (v["ms"] / 1e3) / 1e9 if v["ms"] > 0 else 0.0
         rows[k] = {"ms_per_pass": v["ms"] / reps, "launches_per_pass": v["launches"] / reps, "units_per_pass": v["units"] / reps,
-                   "algorithmic_GB_per_pass": v["bytes"] / reps / 1e9, "GBps": gbs, "frac_of_peak": gbs / peak_gbs(),
-                   "share_of_pass": v["ms"] / reps / ms}
+                   "compulsory_GB_per_pass": v["compulsory_bytes"] / reps / 1e9, "algorithmic_GB_per_pass": v["bytes"] / reps / 1e9,
+                   "GBps": gbs, "frac_of_peak": gbs / peak_gbs(), "share_of_pass": v["ms"] / reps / ms}
     return {"device_ms": ms, "wall_ms": wall, "launches": (eng.launch_count() - l0) / reps, "kernels": rows}
 
 
@@ -57,7 +57,7 @@ def main():
         cfg = dict(bench.CONFIGS[c])
         if args.patterns:
             cfg["patterns"] = args.patterns
-        net, parts, brl = bench.make_inputs(cfg, cfg["patterns"], 0)
+        net, parts, brl = bench.make_inputs(cfg, cfg["patterns"])
         eng = NetraxB200(net, parts, variant=cfg["variant"], linkage=cfg["linkage"], partition_brlens=brl)
         eng.computeLoglikelihood(0, 1)
         r = {"workload": cfg["name"], "patterns": cfg["patterns"]}
@@ -72,7 +72,7 @@ def main():
     if args.md:
         with open(args.md, "w") as f:
             f.write(f"# Per-kernel rooflines (scripts/kernel_rooflines.py; CUDA events on the engine stream; peak = {peak_gbs():.0f} GB/s measured copy bandwidth)\n\n")
-            f.write("Algorithmic bytes are SURVEY §8d's per-unit figures x units; fractions above 1 mean the 126 MB L2 served re-reads.\n")
+            f.write("GB/s and the fraction use COMPULSORY bytes (per launch: every distinct operand CLV / tip row once + every output once); the SURVEY §8d per-op figure is the `algorithmic GB` column.\n")
             for c, r in res.items():
                 if not c.startswith("config"):
                     continue
@@ -81,9 +81,9 @@ def main():
                         continue
                     m = r[phase]
                     f.write(f"\n## {r['workload']} — {phase.replace('_', ' ')}: {m['device_ms']:.3f} ms device, {m['wall_ms']:.3f} ms wall, {m['launches']:.0f} launches\n\n")
-                    f.write("| kernel family | launches | ms | share | algorithmic GB | GB/s | frac of peak |\n|---|---|---|---|---|---|---|\n")
+                    f.write("| kernel family | launches | ms | share | compulsory GB | algorithmic GB | GB/s | frac of peak |\n|---|---|---|---|---|---|---|---|\n")
                     for k, v in sorted(m["kernels"].items(), key=lambda kv: -kv[1]["ms_per_pass"]):
-                        f.write(f"| {k} | {v['launches_per_pass']:.0f} | {v['ms_per_pass']:.3f} | {100 * v['share_of_pass']:.1f} % | {v['algorithmic_GB_per_pass']:.3f} | {v['GBps']:.0f} | {v['frac_of_peak']:.2f} |\n")
+                        f.write(f"| {k} | {v['launches_per_pass']:.0f} | {v['ms_per_pass']:.3f} | {100 * v['share_of_pass']:.1f} % | {v['compulsory_GB_per_pass']:.3f} | {v['algorithmic_GB_per_pass']:.3f} | {v['GBps']:.0f} | {v['frac_of_peak']:.2f} |\n")
 
 
 if __name__ == "__main__":

@@ -12,7 +12,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
-from scripts.bench_configs import derivative_sweep  # noqa: E402
+from bench import derivative_sweep  # noqa: E402
 
 
 def main():
@@ -27,7 +27,7 @@ def main():
     cfg = dict(bench.CONFIGS[args.config])
     if args.patterns:
         cfg["patterns"] = args.patterns
-    net, parts, brl = bench.make_inputs(cfg, cfg["patterns"], 0)
+    net, parts, brl = bench.make_inputs(cfg, cfg["patterns"])
     eng = NetraxB200(net, parts, variant=cfg["variant"], linkage=cfg["linkage"], partition_brlens=brl)
     for _ in range(3):
         eng.computeLoglikelihood(0, 1)

@@ -19,7 +19,7 @@ def main():
     args = ap.parse_args()
     from netrax_b200.engine import NetraxB200
     cfg = dict(bench.CONFIGS[args.config])
-    net, parts, brl = bench.make_inputs(cfg, cfg["patterns"], 0)
+    net, parts, brl = bench.make_inputs(cfg, cfg["patterns"])
     eng = NetraxB200(net, parts, variant=cfg["variant"], linkage=cfg["linkage"], partition_brlens=brl)
     eng.computeLoglikelihood(0, 1)
     acc = collections.OrderedDict()

@@ -101,18 +101,67 @@ def test_full_evaluation_bitexact_clvs(cfg, variant):
     g.close()
 
 
-def test_persite_lnl_matches_oracle():
+def _persite_cases():
+    """(name, net, partition, pinv): one case per K3 kernel variant and per branch inside it."""
     from oracle import oracle
+    from netrax_b200.synth import lg_model
+    cases = []
     net = random_network(10, 1, seed=9)
     m, w = simulate_alignment(net, 300, seed=9)
-    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
-    g = _gpu(net, [part])
-    o = _oracle(net, [part])
+    cases.append(("dna4 k_tree_lnl_dna4", net, Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w), 0.0))
+    cases.append(("dna4 +I", net, Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w), 0.3))
+    cat = caterpillar_network(300)
+    m, w = simulate_alignment(cat, 257, seed=63, gap_frac=0.0)
+    cases.append(("dna4 scaled sites", cat, Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w), 0.0))
+    cases.append(("protein k_tree_lnl_pc<20>",) + _protein_case(12, 2, 301, 11) + (0.0,))
+    cases.append(("protein +I",) + _protein_case(9, 1, 130, 12) + (0.4,))
+    pcat = caterpillar_network(120)
+    rates, freqs = lg_model()
+    m, w = simulate_alignment(pcat, 90, seed=13, states=20, rates=rates, freqs=freqs, gap_frac=0.0)
+    cases.append(("protein scaled sites", pcat, Partition(20, 4, m, freqs, rates, GAMMA4_ALPHA05, pattern_weights=w), 0.0))
+    net = random_network(11, 2, seed=43)
+    m, w = simulate_alignment(net, 333, seed=43)
+    for cats in (1, 3, 8):   # 3 categories: thread-per-pattern generic kernel; 1 / 8: k_tree_lnl_pc<0>
+        r = oracle.api("port").gamma_rates(0.7, cats) if cats > 1 else np.ones(1)
+        cases.append((f"dna {cats} categories", net, Partition(4, cats, m, DNA_FREQS, GTR_RATES, r, pattern_weights=w), 0.0))
+    return cases
+
+
+def test_persite_lnl_matches_oracle():
+    """north_star: PER-SITE lnL within 1e-10 relative.  Every site of every root displayed tree against the `persite_lnl` array
+    the reference's pll_compute_root_loglikelihood fills (LH/ImprovedLoglikelihood.cpp:448-453, LIBPLL/likelihood.c:122-184,
+    core_likelihood.c:190-200), for every K3 kernel variant, with and without site scaling and +I."""
+    from oracle import oracle
+    for name, net, part, pinv in _persite_cases():
+        g, o = _gpu(net, [part]), _oracle(net, [part])
+        _inject_eigen(g, o)
+        if pinv:
+            g.set_pinv(0, pinv); o.set_pinv(0, pinv)
+        assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL), name
+        assert g.num_trees(net.root) == o.num_trees(net.root)
+        scaled = 0
+        for t in range(g.num_trees(net.root)):
+            ps, po = g.persite_lnl(t)[0], oracle.persite_lnl(o, t)[0]
+            assert np.all(po < 0) and np.all(np.isfinite(po)), name
+            np.testing.assert_allclose(ps, po, rtol=LNL_RTOL, atol=0, err_msg=f"{name}, root tree {t}")
+            assert ps.sum() == pytest.approx(o.tree_info(net.root, t)[1][0], rel=LNL_RTOL)
+            scaled += int(o.read_scaler(net.root, t).sum()) if "scaled" in name else 0
+        if "scaled" in name:
+            assert scaled > 0, name   # the case really exercises the scaler term
+        g.close()
+
+
+def test_persite_lnl_headline_topology():
+    """The same element-wise comparison on BASELINE config 5's network (192 root displayed trees), 700 patterns."""
+    import bench
+    from oracle import oracle
+    net, parts, _ = bench.make_inputs(dict(bench.CONFIGS[5]), 700)
+    g, o = _gpu(net, parts), _oracle(net, parts)
+    _inject_eigen(g, o)
     g.computeLoglikelihood(0, 1); o.computeLoglikelihood(0, 1)
     for t in range(g.num_trees(net.root)):
-        ps = g.persite_lnl(t)[0]
-        assert ps.sum() == pytest.approx(o.tree_info(net.root, t)[1][0], rel=LNL_RTOL)
-        assert np.all(ps < 0)
+        np.testing.assert_allclose(g.persite_lnl(t)[0], oracle.persite_lnl(o, t)[0], rtol=LNL_RTOL, atol=0, err_msg=f"root tree {t}")
+    g.close()
 
 
 def test_incremental_and_cached_semantics():
@@ -586,7 +635,7 @@ def test_headline_topology_matches_oracle():
     the oracle finishes in seconds: lnL, every per-tree lnL, scalers and CLVs of the root against libpll."""
     import bench
     cfg = dict(bench.CONFIGS[5])
-    net, parts, _ = bench.make_inputs(cfg, 700, 0)
+    net, parts, _ = bench.make_inputs(cfg, 700)
     g, o = _gpu(net, parts), _oracle(net, parts)
     _inject_eigen(g, o)
     lg, lo = g.computeLoglikelihood(0, 1), o.computeLoglikelihood(0, 1)
@@ -623,7 +672,7 @@ def test_full_size_config5_size_independent_properties():
     if free < need:
         pytest.skip(f"needs {need / 1e9:.0f} GB of free device memory, have {free / 1e9:.0f} GB")
     cfg = dict(bench.CONFIGS[5])
-    net, parts, _ = bench.make_inputs(cfg, patterns, 0)
+    net, parts, _ = bench.make_inputs(cfg, patterns)
     g = _gpu(net, parts)
     l0 = g.computeLoglikelihood(0, 1)
     assert g.computeLoglikelihood(0, 1) == l0                      # replay: bit-identical
@@ -660,7 +709,7 @@ def test_baseline_configs_full_size_match_oracle(config):
     additionally the branch-length derivative on one reticulation edge (the sweep of bench_configs.py edge by edge)."""
     import bench
     cfg = dict(bench.CONFIGS[config])
-    net, parts, brl = bench.make_inputs(cfg, cfg["patterns"], 0)
+    net, parts, brl = bench.make_inputs(cfg, cfg["patterns"])
     kw = dict(variant=cfg["variant"], linkage=cfg["linkage"], partition_brlens=brl)
     g, o = _gpu(net, parts, **kw), _oracle(net, parts, **kw)
     _inject_eigen(g, o)

@@ -438,3 +438,44 @@ def test_empty_shard_of_a_partition_contributes_nothing(kind):
     assert both.computeLoglikelihood(0, 1) == alone.computeLoglikelihood(0, 1)
     np.testing.assert_array_equal(both.partition_loglh(), [alone.partition_loglh()[0], 0.0])
     alone.close(); both.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_persite_lnl_sums_to_the_tree_lnl(kind):
+    """orc_persite_lnl: the per-site array of pll_compute_root_loglikelihood (LH/ImprovedLoglikelihood.cpp:448-453) sums to the
+    per-tree partition lnL, pattern weights applied, scaled sites included."""
+    for net, seed in ((random_network(12, 2, seed=5), 5), (caterpillar_network(300), 63)):
+        m, w = simulate_alignment(net, 200, seed=seed)
+        part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+        eng = oracle.make_engine(kind, net, [part])
+        eng.computeLoglikelihood(0, 1)
+        for t in range(eng.num_trees(net.root)):
+            ps = oracle.persite_lnl(eng, t)[0]
+            assert ps.shape == (200,) and np.all(ps < 0)
+            assert ps.sum() == pytest.approx(eng.tree_info(net.root, t)[1][0], rel=1e-12)
+        eng.close()
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+def test_persite_lnl_port_equals_real_libpll():
+    """element-wise: the restated root-lnL kernel against libpll's own persite_lnl output (DNA, scaled sites, +I, protein)"""
+    from netrax_b200.synth import lg_model
+    rates, freqs = lg_model()
+    cases = []
+    net = random_network(12, 2, seed=5)
+    m, w = simulate_alignment(net, 200, seed=5)
+    cases.append((net, Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w), 0.0))
+    cases.append((net, Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w), 0.25))
+    cat = caterpillar_network(300)
+    m, w = simulate_alignment(cat, 150, seed=63, gap_frac=0.0)
+    cases.append((cat, Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w), 0.0))
+    m, w = simulate_alignment(net, 120, seed=6, states=20, rates=rates, freqs=freqs)
+    cases.append((net, Partition(20, 4, m, freqs, rates, GAMMA4_ALPHA05, pattern_weights=w), 0.0))
+    for net, part, pinv in cases:
+        a, b = oracle.make_engine("port", net, [part]), oracle.make_engine("ref", net, [part])
+        if pinv:
+            a.set_pinv(0, pinv); b.set_pinv(0, pinv)
+        a.computeLoglikelihood(0, 1); b.computeLoglikelihood(0, 1)
+        for t in range(a.num_trees(net.root)):
+            np.testing.assert_allclose(oracle.persite_lnl(a, t)[0], oracle.persite_lnl(b, t)[0], rtol=1e-12, atol=0)
+        a.close(); b.close()

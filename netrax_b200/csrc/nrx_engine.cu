@@ -131,6 +131,8 @@ struct nrx_engine {
   size_t partial_cap = 0;
   double *d_result = nullptr, *h_result = nullptr;
   size_t result_cap = 0;
+  uint32_t *d_tickets = nullptr;   // one self-resetting ticket counter per reduction output (item, partition): fused second stage
+  bool fuse_reduce = true;         // env NRX_FUSE_REDUCE=0: separate k_reduce_partials launch (A/B)
   double *d_persite = nullptr;
   size_t persite_cap = 0;
   unsigned long long launches = 0;
@@ -142,9 +144,10 @@ struct nrx_engine {
   uint32_t k2_nt = 2;       // env NRX_K2_NT: 64-pattern sub-tiles per ring stage of k_clv_dna4_pipe2 (1 or 2; 2 measured 1-2 % faster)
   int k2_variant = 0;       // 0: k_clv_dna4_pipe2 (production); 1: k_clv_dna4_pipe (A/B baseline, env NRX_K2=1)
   bool aa_generic = false;  // env NRX_AA=generic: force the scalar kernel for 20-state partitions (A/B)
-  bool aa_v1 = true;        // K2 / K5 on the round-1 kernel k_aa20_dmma; env NRX_AA=v2: the warp-specialised k_aa20_mma (A/B)
+  bool aa_pipe = true;      // software-pipelined MMA loop for the CLV update (env NRX_AA_PIPE=0: straight loop, A/B; the sumtable always pipelines)
+  bool aa_v1 = false;       // env NRX_AA=v1: K2 / K5 on the round-1 kernel k_aa20_dmma instead of the warp-specialised k_aa20_mma (A/B)
   uint32_t aa_blocks = 148 * 3 * 2;  // block-count target of k_aa20_dmma: two waves of 3 resident blocks per SM (A/B: profiles/r1e_all_configs.md)
-  uint32_t aa2_blocks = 148 * 2 * 2; // block-count target of k_aa20_mma: two waves of 2 resident blocks per SM (env NRX_AA2_BLOCKS)
+  uint32_t aa2_blocks = 0;           // block-count target of k_aa20_mma; 0 = by launch size: 2 waves of 2 resident blocks per SM for small launches, 4 for big ones (env NRX_AA2_BLOCKS) (env NRX_AA2_BLOCKS)
   uint32_t k2_blocks = 2368; // block-count target of the pipelined kernel: 8 waves of 2 resident blocks per SM (measured best, profiles/)
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   bool views_dirty = true;
@@ -189,11 +192,15 @@ int stage_alloc(nrx_engine *e, size_t bytes, void **hptr, void **dptr) {
 
 int ensure_result(nrx_engine *e, size_t n_doubles, size_t n_partial) {
   if (n_doubles > e->result_cap) {
+    CK(cudaStreamSynchronize(e->stream));
     if (e->d_result) cudaFree(e->d_result);
     if (e->h_result) cudaFreeHost(e->h_result);
     size_t cap = std::max<size_t>(n_doubles, 4096);
     CK(cudaMalloc((void **)&e->d_result, cap * sizeof(double)));
     CK(cudaMallocHost((void **)&e->h_result, cap * sizeof(double)));
+    if (e->d_tickets) cudaFree(e->d_tickets);
+    CK(cudaMalloc((void **)&e->d_tickets, cap * sizeof(uint32_t)));
+    CK(cudaMemset(e->d_tickets, 0, cap * sizeof(uint32_t)));
     e->result_cap = cap;
   }
   if (n_partial > e->partial_cap) {
@@ -382,8 +389,10 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
   if (const char *v = std::getenv("NRX_K2")) e->k2_variant = std::atoi(v);
   if (const char *v = std::getenv("NRX_GRAPH")) e->use_graphs = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_PDL")) e->use_pdl = std::atoi(v) != 0;
+  if (const char *v = std::getenv("NRX_FUSE_REDUCE")) e->fuse_reduce = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_K2_NT")) e->k2_nt = std::atoi(v) == 1 ? 1u : 2u;
   if (const char *v = std::getenv("NRX_AA")) { e->aa_generic = std::string(v) == "generic"; if (std::string(v) == "v2") e->aa_v1 = false; if (std::string(v) == "v1") e->aa_v1 = true; }
+  if (const char *v = std::getenv("NRX_AA_PIPE")) e->aa_pipe = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_AA2_BLOCKS")) e->aa2_blocks = (uint32_t)std::max(1, std::atoi(v));
   if (const char *v = std::getenv("NRX_AA_BLOCKS")) e->aa_blocks = (uint32_t)std::max(1, std::atoi(v));
   if (const char *v = std::getenv("NRX_K2_BLOCKS")) e->k2_blocks = (uint32_t)std::max(1, std::atoi(v));
@@ -397,8 +406,9 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
         !cuda_ok(cudaFuncSetAttribute(k_aa20_dmma<AA_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa_smem), "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(k_aa20_dmma<AA_EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa_smem), "cudaFuncSetAttribute")) { delete e; return nullptr; }
     const int aa2_smem = (int)(sizeof(AaSmem2) + 2 * AA_LUT_CODES * 80 * sizeof(double));
-    if (!cuda_ok(cudaFuncSetAttribute(k_aa20_mma<AA_CLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa2_smem), "cudaFuncSetAttribute") ||
-        !cuda_ok(cudaFuncSetAttribute(k_aa20_mma<AA_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa2_smem), "cudaFuncSetAttribute")) { delete e; return nullptr; }
+    if (!cuda_ok(cudaFuncSetAttribute(k_aa20_mma<AA_CLV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa2_smem), "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(k_aa20_mma<AA_CLV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa2_smem), "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(k_aa20_mma<AA_SUM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa2_smem), "cudaFuncSetAttribute")) { delete e; return nullptr; }
     if (!cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClvPipeSmem)), "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem<1>)), "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem<2>)), "cudaFuncSetAttribute")) { delete e; return nullptr; }
@@ -456,7 +466,7 @@ void nrx_engine_destroy(nrx_engine *e) {
   for (nrx_engine::ProfKind &k : e->profk) for (auto &ev : k.events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (e->h_stage) cudaFreeHost(e->h_stage);
   cudaFree(e->d_fused);
-  cudaFree(e->d_stage); cudaFree(e->d_partial); cudaFree(e->d_result); cudaFree(e->d_persite);
+  cudaFree(e->d_stage); cudaFree(e->d_partial); cudaFree(e->d_result); cudaFree(e->d_persite); cudaFree(e->d_tickets);
   if (e->h_result) cudaFreeHost(e->h_result);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -853,7 +863,10 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
       // the rest on the FP64 tensor cores (DMMA): 3 resident blocks of 4+1 warps per SM, 8-pattern tiles
       const uint32_t rest = nops - ntt;
       const uint32_t ntiles = (c.max_patterns + AA_TP - 1) / AA_TP;
-      const uint32_t target = e->aa_v1 ? e->aa_blocks : e->aa2_blocks;
+      // k_aa20_mma: >= ~48 tiles per block amortise the set-up (config 4 at 20 k patterns: 592 blocks 0.348 ms, 1184 blocks 0.374 ms;
+      // at 200 k patterns 2.75 vs 2.67 ms the other way round)
+      const uint32_t by_size = (uint32_t)std::min<uint64_t>(8ull * e->sm_count, std::max<uint64_t>(4ull * e->sm_count, (uint64_t)rest * z * ntiles / 48));
+      const uint32_t target = e->aa_v1 ? e->aa_blocks : (e->aa2_blocks ? e->aa2_blocks : by_size);
       uint32_t groups = std::max<uint32_t>(1, (target + rest * z - 1) / (rest * z));
       groups = std::min(groups, std::max<uint32_t>(1, ntiles / 8));
       dim3 grid(rest * groups, 1, z);
@@ -861,7 +874,8 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
       const int luts = !with_tips ? 0 : (has_aa_dmma(e) ? 1 : 2);
       const size_t lut_bytes = (size_t)luts * class_tip_codes(e, c) * 80 * sizeof(double);
       if (e->aa_v1) k_aa20_dmma<AA_CLV><<<grid, AA_THREADS, sizeof(AaSmem) + lut_bytes, e->stream>>>(c.d_views, d_ops + ntt, rest, groups, luts, nullptr, 0, 0.0);
-      else k_aa20_mma<AA_CLV><<<grid, AA2_THREADS, sizeof(AaSmem2) + lut_bytes, e->stream>>>(c.d_views, d_ops + ntt, rest, groups, luts);
+      else if (e->aa_pipe) k_aa20_mma<AA_CLV, true><<<grid, AA2_THREADS, sizeof(AaSmem2) + lut_bytes, e->stream>>>(c.d_views, d_ops + ntt, rest, groups, luts);
+      else k_aa20_mma<AA_CLV, false><<<grid, AA2_THREADS, sizeof(AaSmem2) + lut_bytes, e->stream>>>(c.d_views, d_ops + ntt, rest, groups, luts);
     } else {
       dim3 grid(tiles_for(c.max_patterns, BLOCK, nops * z), nops, z);
       k_clv_generic<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops, nullptr);
@@ -1073,13 +1087,15 @@ static uint32_t reduce_blocks(const nrx_engine *e, uint32_t items) {
 }
 
 /* second stage + cross-rank sum + device->host copy, all stream-ordered; the host blocks only in wait_result */
-static int enqueue_reduction(nrx_engine *e, uint32_t total, uint32_t nblk) {
-  cudaEvent_t ev0, ev1;
-  prof_begin(e, &ev0, &ev1);
-  k_reduce_partials<<<(total + 3) / 4, 128, 0, e->stream>>>(e->d_partial, e->d_result, nblk, total);
-  e->launches++;
-  CK(cudaGetLastError());
-  prof_end(e, ev0, ev1, 1, total, (unsigned long long)total * nblk * 8, NRX_PROF_REDUCE);
+static int enqueue_reduction(nrx_engine *e, uint32_t total, uint32_t nblk, bool fused = false) {
+  if (!fused) {   // the second stage was not done by the last block of the reducing kernel itself
+    cudaEvent_t ev0, ev1;
+    prof_begin(e, &ev0, &ev1);
+    k_reduce_partials<<<(total + 3) / 4, 128, 0, e->stream>>>(e->d_partial, e->d_result, nblk, total);
+    e->launches++;
+    CK(cudaGetLastError());
+    prof_end(e, ev0, ev1, 1, total, (unsigned long long)total * nblk * 8, NRX_PROF_REDUCE);
+  }
   if (e->comm) {  // C2-C4: one all-reduce over NVLink for all trees / pairs x partitions
     const int rc = nccl().AllReduce(e->d_result, e->d_result, total, NCCL_FLOAT64, NCCL_SUM, e->comm, e->stream);
     if (rc != 0) { g_err = std::string("ncclAllReduce: ") + nccl().GetErrorString(rc); return 0; }
@@ -1094,8 +1110,8 @@ static int wait_result(nrx_engine *e, uint32_t total, double *out) {
   e->pending_result = 0;
   return 1;
 }
-static int finish_reduction(nrx_engine *e, uint32_t total, uint32_t nblk, double *out) {
-  return enqueue_reduction(e, total, nblk) && wait_result(e, total, out);
+static int finish_reduction(nrx_engine *e, uint32_t total, uint32_t nblk, double *out, bool fused = false) {
+  return enqueue_reduction(e, total, nblk, fused) && wait_result(e, total, out);
 }
 
 static int tree_lnl_impl(nrx_engine *e, const uint32_t *slots, uint32_t n, double *out, double *persite, size_t persite_stride, bool async) {
@@ -1115,23 +1131,24 @@ static int tree_lnl_impl(nrx_engine *e, const uint32_t *slots, uint32_t n, doubl
     CK(cudaMemsetAsync(e->d_persite, 0, need * sizeof(double), e->stream));
     d_ps = e->d_persite;
   }
-  CK(cudaMemsetAsync(e->d_partial, 0, (size_t)n * P * nblk * sizeof(double), e->stream));
+  // every block of the launches below writes its partial sum (blocks without patterns write 0): no memset needed
   const double log_thresh = std::log(SCALE_THRESHOLD);
+  uint32_t *tk = e->fuse_reduce ? e->d_tickets : nullptr;
   cudaEvent_t ev0, ev1;
   prof_begin(e, &ev0, &ev1);
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
     const bool mix = class_mixture(e, c);
-    if (!mix && c.states == 4 && c.cats == 4) k_tree_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
-    else if (!mix && pow2_cats(c) && c.states == 20) k_tree_lnl_pc<20><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
-    else if (!mix && pow2_cats(c)) k_tree_lnl_pc<0><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
-    else k_tree_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride);
+    if (!mix && c.states == 4 && c.cats == 4) k_tree_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
+    else if (!mix && pow2_cats(c) && c.states == 20) k_tree_lnl_pc<20><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
+    else if (!mix && pow2_cats(c)) k_tree_lnl_pc<0><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
+    else k_tree_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
     e->launches++;
     CK(cudaGetLastError());
   }
   { unsigned long long u = 0; const unsigned long long b = stream_bytes(e, n, 1, persite ? 16 : 8, &u); prof_end(e, ev0, ev1, e->classes.size(), u, b, NRX_PROF_K3); }
-  if (async) return enqueue_reduction(e, n * P, nblk);
-  if (!finish_reduction(e, n * P, nblk, out)) return 0;
+  if (async) return enqueue_reduction(e, n * P, nblk, tk != nullptr);
+  if (!finish_reduction(e, n * P, nblk, out, tk != nullptr)) return 0;
   if (persite) CK(cudaMemcpy(persite, e->d_persite, (size_t)n * P * persite_stride * sizeof(double), cudaMemcpyDeviceToHost));
   return 1;
 }
@@ -1157,17 +1174,17 @@ static int tree_lnl_fused_impl(nrx_engine *e, uint32_t plan_id, const uint32_t *
   for (uint32_t i = 0; i < n; ++i) if (slots[i] >= e->nslots) { g_err = "nrx_tree_lnl_fused: slot out of range"; return 0; }
   uint32_t *d_slots;
   if (!upload(e, slots, n, &d_slots)) return 0;
-  CK(cudaMemsetAsync(e->d_partial, 0, (size_t)n * P * nblk * sizeof(double), e->stream));
+  uint32_t *tk = e->fuse_reduce ? e->d_tickets : nullptr;
   cudaEvent_t ev0, ev1;
   prof_begin(e, &ev0, &ev1);
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
-    k_term_lnl_sum<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_fused, (size_t)e->max_patterns, e->d_partial, P, std::log(SCALE_THRESHOLD));
+    k_term_lnl_sum<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_fused, (size_t)e->max_patterns, e->d_partial, P, std::log(SCALE_THRESHOLD), e->d_result, tk);
     e->launches++;
     CK(cudaGetLastError());
   }
   { unsigned long long u = 0; const unsigned long long b = stream_bytes(e, n, 0, 16, &u); prof_end(e, ev0, ev1, e->classes.size(), u, b, NRX_PROF_K3F); }
-  return async ? enqueue_reduction(e, n * P, nblk) : finish_reduction(e, n * P, nblk, out);
+  return async ? enqueue_reduction(e, n * P, nblk, tk != nullptr) : finish_reduction(e, n * P, nblk, out, tk != nullptr);
 }
 int nrx_tree_lnl_fused(nrx_engine *e, uint32_t plan_id, const uint32_t *slots, uint32_t n, double *out) {
   return tree_lnl_fused_impl(e, plan_id, slots, n, out, false);
@@ -1233,13 +1250,18 @@ int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n
   if (!ensure_result(e, (size_t)n * P, (size_t)n * P * nblk) || !refresh_views(e)) return 0;
   nrx_pair *d_pairs;
   if (!upload(e, pairs, n, &d_pairs)) return 0;
-  CK(cudaMemsetAsync(e->d_partial, 0, (size_t)n * P * nblk * sizeof(double), e->stream));
+  // the tensor-core edge kernel lets surplus blocks exit before they write a partial sum: that path keeps the memset and
+  // the separate second stage; every other kernel writes all partials and finishes the reduction in its last block
+  bool any_aa = false;
+  for (const ShapeClass &c : e->classes) any_aa = any_aa || aa_dmma_pairs_class(e, c);
+  uint32_t *tk = (e->fuse_reduce && !any_aa) ? e->d_tickets : nullptr;
+  if (any_aa) CK(cudaMemsetAsync(e->d_partial, 0, (size_t)n * P * nblk * sizeof(double), e->stream));
   const double log_thresh = std::log(SCALE_THRESHOLD);
   cudaEvent_t ev0, ev1;
   prof_begin(e, &ev0, &ev1);
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
-    if (c.states == 4 && c.cats == 4 && !class_mixture(e, c)) k_edge_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh);
+    if (c.states == 4 && c.cats == 4 && !class_mixture(e, c)) k_edge_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh, e->d_result, tk);
     else if (aa_dmma_pairs_class(e, c)) {  // FP64 tensor cores: block b = (pair b % n, tile group b / n), one partial per (pair, group)
       bool tips;
       const std::vector<nrx_op> ops = pairs_to_ops(pairs, n, edge, false, &tips);
@@ -1248,12 +1270,12 @@ int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n
       const size_t smem = sizeof(AaSmem) + (tips ? (size_t)class_tip_codes(e, c) * 80 * sizeof(double) : 0);   // pairs are never tip-tip: one table
       k_aa20_dmma<AA_EDGE><<<dim3(n * nblk, 1, (uint32_t)c.parts.size()), AA_THREADS, smem, e->stream>>>(c.d_views, d_ops, n, nblk, tips ? 1 : 0, e->d_partial, P, log_thresh);
     }
-    else k_edge_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh);
+    else k_edge_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh, e->d_result, tk);
     e->launches++;
     CK(cudaGetLastError());
   }
   { unsigned long long u = 0; const unsigned long long b = stream_bytes(e, n, 2, 12, &u); prof_end(e, ev0, ev1, e->classes.size(), u, b, NRX_PROF_K4, pair_cbytes(e, pairs, n, true, 0, 4)); }
-  return finish_reduction(e, n * P, nblk, out);
+  return finish_reduction(e, n * P, nblk, out, tk != nullptr);
 }
 
 int nrx_sumtables(nrx_engine *e, const nrx_pair *pairs, uint32_t n) {
@@ -1278,11 +1300,12 @@ int nrx_sumtables(nrx_engine *e, const nrx_pair *pairs, uint32_t n) {
       nrx_op *d_ops;
       if (!upload(e, ops.data(), ops.size(), &d_ops)) return 0;
       const uint32_t ntiles = (c.max_patterns + AA_TP - 1) / AA_TP;
-      uint32_t groups = std::max<uint32_t>(1, ((e->aa_v1 ? e->aa_blocks : e->aa2_blocks) + n * z - 1) / (n * z));
+      const uint32_t by_size = (uint32_t)std::min<uint64_t>(8ull * e->sm_count, std::max<uint64_t>(4ull * e->sm_count, (uint64_t)n * z * ntiles / 48));
+      uint32_t groups = std::max<uint32_t>(1, ((e->aa_v1 ? e->aa_blocks : (e->aa2_blocks ? e->aa2_blocks : by_size)) + n * z - 1) / (n * z));
       groups = std::min(groups, std::max<uint32_t>(1, ntiles / 8));
       const size_t lut_bytes = tips ? (size_t)class_tip_codes(e, c) * 80 * sizeof(double) : 0;
       if (e->aa_v1) k_aa20_dmma<AA_SUM><<<dim3(n * groups, 1, z), AA_THREADS, sizeof(AaSmem) + lut_bytes, e->stream>>>(c.d_views, d_ops, n, groups, tips ? 1 : 0, nullptr, 0, 0.0);
-      else k_aa20_mma<AA_SUM><<<dim3(n * groups, 1, z), AA2_THREADS, sizeof(AaSmem2) + lut_bytes, e->stream>>>(c.d_views, d_ops, n, groups, tips ? 1 : 0);
+      else k_aa20_mma<AA_SUM, true><<<dim3(n * groups, 1, z), AA2_THREADS, sizeof(AaSmem2) + lut_bytes, e->stream>>>(c.d_views, d_ops, n, groups, tips ? 1 : 0);
     } else {
       dim3 grid(tiles_for((uint64_t)c.max_patterns * c.cats, BLOCK, n * z), n, z);
       k_sumtable<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs);
@@ -1323,21 +1346,21 @@ int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen, double *out)
     if (!upload(e, diag.data(), diag.size(), &d_tmp)) return 0;
     CK(cudaMemcpyAsync(p.diagp, d_tmp, diag.size() * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
   }
-  CK(cudaMemsetAsync(e->d_partial, 0, (size_t)n * P * 3 * nblk * sizeof(double), e->stream));
+  uint32_t *tk = e->fuse_reduce ? e->d_tickets : nullptr;
   cudaEvent_t ev0, ev1;
   prof_begin(e, &ev0, &ev1);
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
     const bool mix = class_mixture(e, c);   // (only the +I term of K6 reads frequencies; the generic kernel is the one that indexes them by category)
-    if (!mix && c.states == 4 && c.cats == 4) k_derivatives_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P);
-    else if (!mix && pow2_cats(c) && c.states == 20) k_derivatives_pc<20, 2><<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P);
-    else if (!mix && pow2_cats(c)) k_derivatives_pc<0, 2><<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P);
-    else k_derivatives<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P);
+    if (!mix && c.states == 4 && c.cats == 4) k_derivatives_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
+    else if (!mix && pow2_cats(c) && c.states == 20) k_derivatives_pc<20, 2><<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
+    else if (!mix && pow2_cats(c)) k_derivatives_pc<0, 2><<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
+    else k_derivatives<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
     e->launches++;
     CK(cudaGetLastError());
   }
   { unsigned long long u = 0; const unsigned long long b = stream_bytes(e, n, 1, 4, &u); prof_end(e, ev0, ev1, e->classes.size(), u, b, NRX_PROF_K6); }
-  return finish_reduction(e, n * P * 3, nblk, out);
+  return finish_reduction(e, n * P * 3, nblk, out, tk != nullptr);
 }
 
 int nrx_read_clv(nrx_engine *e, uint32_t pi, uint32_t slot, double *out) {

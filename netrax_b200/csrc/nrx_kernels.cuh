@@ -942,22 +942,23 @@ __global__ void __launch_bounds__(AA_THREADS, 3) k_aa20_dmma(const PartView *__r
  * predication on the operand kinds, the product / scaling-test / FSEL / partial-sector store epilogue, flags + named barrier)
  * executed in order by 3 warps per sub-partition.  Here the roles are split three ways so that the warps that own the
  * tensor pipe do almost nothing else:
- *   warp 4  LOADER   per-row cp.async.bulk copies of 8-pattern tiles of both children into an NIN-deep ring (as before);
+ *   warps 4, 6  LOADERS  8-pattern tiles of the left / right child into an NIN-deep ring with 16-byte cp.async (see below);
  *   warps 0-3  MMA   (warp = rate category, both edges' B fragments in registers): 10 LDS of A fragments, 30 DMMAs, 6 DMUL,
  *                    the "< 2^-256" test (6 DSETP + ballot), then the UNSCALED products go to a shared-memory output tile
- *                    [8 patterns][88] (3 conflict-free 128-bit STS per lane) + one flag per (category, pattern);
+ *                    [8 patterns][80] (3 128-bit STS per lane) + one flag per (category, pattern);
  *   warp 5  STORER   waits for the four category warps of a tile, ANDs the flags (scaling needs all 80 entries of a pattern,
  *                    LIBPLL/core_partials.c:727-757; rows that do scale — rare — are multiplied in shared memory), writes
- *                    the scalers and issues ONE 640-byte cp.async.bulk store per pattern row: full-line, fully coalesced
- *                    HBM writes by the TMA engine instead of 16-byte partial-sector stores from 96 lanes.
+ *                    the scalers and issues ONE 5120-byte cp.async.bulk store per tile (8 consecutive patterns are contiguous in
+ *                    the CLV): full-line, fully coalesced HBM writes by the TMA engine instead of 16-byte partial-sector stores.
  * All hand-offs are mbarriers (full_in / empty_in / full_out / empty_out); generic-proxy writes to the output tile are made
  * visible to the async proxy with fence.proxy.async before the storer is signalled.  Arithmetic (DMMA k-step order, products,
  * exact power-of-two scaling) is identical to k_aa20_dmma, so results are bit-identical to it.
  * ---------------------------------------------------------------------------------------------- */
 constexpr int NIN_AA = 6;            // input ring stages (8 patterns x 2 operands x 672 B each)
 constexpr int NOUT_AA = 3;           // output tiles in flight
-constexpr int AA_OPITCH = 88;        // doubles per output row: 128-bit stores of a quarter-warp (2 patterns x 4 lanes) hit disjoint banks
-constexpr int AA2_THREADS = 192;     // 4 MMA warps + loader + storer
+constexpr int AA_OPITCH = 80;        // output rows dense (2-way conflict on 3 STS per lane and tile is noise): the tile leaves as ONE 5120-byte bulk store
+constexpr int AA2_THREADS = 256;     // warpgroup 0: 4 MMA warps; warpgroup 1: left loader, storer, right loader, 1 idle warp (register donor)
+constexpr int AA2_REGS_MMA = 200, AA2_REGS_AUX = 56;   // setmaxnreg budgets: 128 x 200 + 128 x 56 = 256 x 128 = the launch allocation
 
 struct __align__(128) AaOut {
   double v[AA_TP * AA_OPITCH];
@@ -976,7 +977,138 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
 }
 
-template <int MODE>
+/* The MMA warps' loop, specialised on the operand kinds and software-pipelined: ncu on the straight version showed an MMA
+ * warp only 38 % of its time in the DMMA region (24 % before it: barrier wait, A-fragment loads; 38 % after it: waiting for the
+ * last DMMA, product, threshold test, stores, proxy fence), so two such warps kept a sub-partition's FP64 pipe ~50 % busy.
+ * Here tile k+1's A-fragment loads and its 15-30 DMMAs are issued BEFORE tile k's epilogue, in one basic block (both barrier
+ * waits first), with two accumulator sets: the epilogue's ~100 ALU / LSU instructions fill the issue slots under the 16-cycle
+ * DMMAs instead of following them. */
+struct AaFrag { double aL[5], aR[5]; uint32_t codeL, codeR, sc; };
+
+template <int MODE, int LK, int RK, bool PIPE>
+__device__ __forceinline__ void aa_mma_loop(AaSmem2 &sm, const PartView &pv, const nrx_op &op, const double *__restrict__ lutL,
+                                            const double *__restrict__ lutR, uint32_t grp, uint32_t groups, uint32_t count, int cat, int lane) {
+  const int item = lane >> 2, q = lane & 3;
+  double BL[15], BR[15];   // B fragments: [ntile * 5 + kstep] = M[8*ntile + lane/4][4*kstep + lane%4]
+#pragma unroll
+  for (int n = 0; n < 3; ++n)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int i = 8 * n + item, j = 4 * k + q;
+      if (MODE == AA_SUM) {
+        BL[n * 5 + k] = (LK == NRX_CLV && i < 20) ? pv.summat[i * 20 + j] : 0.0;
+        BR[n * 5 + k] = (RK == NRX_CLV && i < 20) ? pv.summat[400 + i * 20 + j] : 0.0;
+      } else {
+        BL[n * 5 + k] = (LK == NRX_CLV && i < 20) ? pv.pmat[(size_t)op.left_edge * 1600 + (cat * 20 + i) * 20 + j] : 0.0;
+        BR[n * 5 + k] = (RK == NRX_CLV && i < 20) ? pv.pmat[(size_t)op.right_edge * 1600 + (cat * 20 + i) * 20 + j] : 0.0;
+      }
+    }
+  const uint32_t a_off = item * AA_PITCH + cat * 20 + q, o_off = item * AA_OPITCH + cat * 20 + 2 * q;
+
+  // pull tile k's operands out of its input stage (the stage's full barrier has been waited for) and release the stage
+  auto pull = [&](uint32_t k, AaFrag &f) {
+    const uint32_t s = k % NIN_AA;
+    const AaStage &st = sm.in[s];
+    const uint32_t p0lo = (uint32_t)(((size_t)(grp + (size_t)k * groups) * AA_TP) & 15u);
+    f.sc = 0; f.codeL = 0; f.codeR = 0;
+    if (LK == NRX_CLV) {
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) f.aL[kk] = st.l[a_off + 4 * kk];
+      if (MODE == AA_CLV) f.sc += st.scl[item];
+    } else if (LK == NRX_TIP) f.codeL = st.tl[p0lo + item];
+    if (RK == NRX_CLV) {
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) f.aR[kk] = st.r[a_off + 4 * kk];
+      if (MODE == AA_CLV) f.sc += st.scr[item];
+    } else if (RK == NRX_TIP) f.codeR = st.tr[p0lo + item];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty_in[s]);
+  };
+  auto mma = [&](const AaFrag &f, double (&x)[6], double (&y)[6]) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { x[i] = 0.0; y[i] = 0.0; }
+#pragma unroll
+    for (int kk = 0; kk < 5; ++kk)
+#pragma unroll
+      for (int n = 0; n < 3; ++n) {
+        if (LK == NRX_CLV) dmma884(x[2 * n], x[2 * n + 1], f.aL[kk], BL[n * 5 + kk]);
+        if (RK == NRX_CLV) dmma884(y[2 * n], y[2 * n + 1], f.aR[kk], BR[n * 5 + kk]);
+      }
+  };
+  // products, threshold test, output tile (its empty barrier has been waited for), flags, hand-over to the storer
+  auto finish = [&](uint32_t k, const AaFrag &f, double (&x)[6], double (&y)[6]) {
+    AaOut &ot = sm.out[k % NOUT_AA];
+    bool small = true;
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+      const int i0 = 8 * n + 2 * q;
+      if (LK == NRX_TIP && i0 < 20) { const double2 v = *reinterpret_cast<const double2 *>(lutL + (f.codeL * 4 + cat) * 20 + i0); x[2 * n] = v.x; x[2 * n + 1] = v.y; }
+      if (RK == NRX_TIP && i0 < 20) { const double2 v = *reinterpret_cast<const double2 *>(lutR + (f.codeR * 4 + cat) * 20 + i0); y[2 * n] = v.x; y[2 * n + 1] = v.y; }
+      double v0, v1;
+      if (RK == NRX_NONE) { v0 = x[2 * n]; v1 = x[2 * n + 1]; }
+      else if (LK == NRX_NONE) { v0 = y[2 * n]; v1 = y[2 * n + 1]; }
+      else { v0 = __dmul_rn(x[2 * n], y[2 * n]); v1 = __dmul_rn(x[2 * n + 1], y[2 * n + 1]); }
+      if (i0 < 20) {
+        if (MODE == AA_CLV) small &= (v0 < SCALE_THRESHOLD) & (v1 < SCALE_THRESHOLD);
+        *reinterpret_cast<double2 *>(ot.v + o_off + 8 * n) = make_double2(v0, v1);
+      }
+    }
+    if (MODE == AA_CLV) {
+      const unsigned b = __ballot_sync(0xffffffffu, small);
+      if (q == 0) {
+        ot.flag[cat][item] = (((b >> (lane & ~3)) & 0xFu) == 0xFu) ? 1u : 0u;
+        if (cat == 0) ot.sc[item] = f.sc;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the storer's bulk copy
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.full_out[k % NOUT_AA]);
+  };
+  auto wait_in = [&](uint32_t k) { mbar_wait(&sm.full_in[k % NIN_AA], (k / NIN_AA) & 1u); };
+  auto wait_out = [&](uint32_t k) { mbar_wait(&sm.empty_out[k % NOUT_AA], ((k / NOUT_AA) & 1u) ^ 1u); };
+
+  AaFrag f0, f1;
+  double x0[6], y0[6], x1[6], y1[6];
+  if (!PIPE) {   // straight order (measured: the CLV update is no faster pipelined — 3.27 vs 3.46 ms on config 4 at 200 k patterns —
+                 // while the sumtable, which has no threshold test / flags in its epilogue, gains 17 %)
+    for (uint32_t k = 0; k < count; ++k) {
+      wait_in(k);
+      pull(k, f0);
+      mma(f0, x0, y0);
+      wait_out(k);
+      finish(k, f0, x0, y0);
+    }
+    return;
+  }
+  wait_in(0);
+  pull(0, f0);
+  mma(f0, x0, y0);
+  for (uint32_t k = 0; k < count; k += 2) {
+    if (k + 1 < count) {   // tile k+1's DMMAs are issued first, tile k's epilogue fills the issue slots under them
+      wait_in(k + 1);
+      wait_out(k);
+      pull(k + 1, f1);
+      mma(f1, x1, y1);
+      finish(k, f0, x0, y0);
+    } else {
+      wait_out(k);
+      finish(k, f0, x0, y0);
+      break;
+    }
+    if (k + 2 < count) {
+      wait_in(k + 2);
+      wait_out(k + 1);
+      pull(k + 2, f0);
+      mma(f0, x0, y0);
+      finish(k + 1, f1, x1, y1);
+    } else {
+      wait_out(k + 1);
+      finish(k + 1, f1, x1, y1);
+    }
+  }
+}
+
+template <int MODE, bool PIPE>
 __global__ void __launch_bounds__(AA2_THREADS, 2) k_aa20_mma(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops,
                                                               uint32_t nops, uint32_t groups, int with_lut) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -994,7 +1126,7 @@ __global__ void __launch_bounds__(AA2_THREADS, 2) k_aa20_mma(const PartView *__r
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < NIN_AA; ++s) { mbar_init(&sm.full_in[s], 1); mbar_init(&sm.empty_in[s], 4); }
+    for (int s = 0; s < NIN_AA; ++s) { mbar_init(&sm.full_in[s], 64); mbar_init(&sm.empty_in[s], 4); }
 #pragma unroll
     for (int s = 0; s < NOUT_AA; ++s) { mbar_init(&sm.full_out[s], 4); mbar_init(&sm.empty_out[s], 1); }
     mbar_init(&sm.lutbar, 1);
@@ -1012,38 +1144,58 @@ __global__ void __launch_bounds__(AA2_THREADS, 2) k_aa20_mma(const PartView *__r
   }
   const bool wait_lut = with_lut && (lk == NRX_TIP || rk == NRX_TIP);
 
-  if (warp == 4) {
-    /* ---------------- loader ---------------- */
-    const double *clvL = (lk == NRX_CLV) ? pv.clv[op.left_idx] : nullptr;
-    const double *clvR = (rk == NRX_CLV) ? pv.clv[op.right_idx] : nullptr;
-    const uint32_t *scL = (lk == NRX_CLV) ? pv.scaler[op.left_idx] : nullptr;
-    const uint32_t *scR = (rk == NRX_CLV) ? pv.scaler[op.right_idx] : nullptr;
-    const uint8_t *tipL = (lk == NRX_TIP) ? pv.tipchars + (size_t)op.left_idx * pv.tip_pitch : nullptr;
-    const uint8_t *tipR = (rk == NRX_TIP) ? pv.tipchars + (size_t)op.right_idx * pv.tip_pitch : nullptr;
-    const uint32_t sc_bytes = (MODE == AA_SUM) ? 0u : AA_TP * 4u;
-    const uint32_t tx_bytes = ((lk == NRX_CLV) ? AA_TP * 640u + sc_bytes : (lk == NRX_TIP ? 16u : 0u)) +
-                              ((rk == NRX_CLV) ? AA_TP * 640u + sc_bytes : (rk == NRX_TIP ? 16u : 0u));
+  /* Register re-allocation between the roles (setmaxnreg, sm_90+): two resident blocks of 8 warps leave 128 registers per thread
+   * at launch; the loader / storer warpgroup gives back down to 56 and the MMA warpgroup grows to 200 — room for both edges' B
+   * fragments (60), TWO accumulator sets (48) and two tiles' A fragments (40) of the software-pipelined loop.  (Three blocks
+   * of 4 MMA warps at 120 registers were measured too: no faster, the straight loop was the limit, not the warp count.) */
+  if (warp >= 4) {   // (the role branches never re-join: ptxas budgets each side by its own setmaxnreg)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AA2_REGS_AUX));
+    if (warp == 7) return;
+  }
+
+  if (warp == 4 || warp == 6) {
+    /* ---------------- loaders: warp 4 streams the left operand, warp 6 the right one ----------------
+     * ncu on the first cut (and on k_aa20_dmma, same producer): ONE warp issuing 18 per-row cp.async.bulk copies per 8-pattern
+     * tile was the bottleneck — the uniform datapath issues them one lane at a time (ELECT / R2UR / UBLKCP / BRA.U.ANY loop, ~600
+     * cycles per tile) while the MMA warps waited on full_in and the tensor pipe idled at 45 %.  The rows must land at a padded
+     * pitch (672 B: the A-fragment reads of 8 rows then hit disjoint banks), which a single bulk copy cannot do; 16-byte cp.async
+     * (LDGSTS) can: 10 fully coalesced 512-byte warp copies per operand and tile, completion counted on the stage's mbarrier
+     * (cp.async.mbarrier.arrive.noinc, one arrival per lane of both loader warps = 64).  Keeping this loop free of register
+     * spills mattered as much: at 40 registers it spilled its chunk offsets and K2 ran at 3.4 instead of 2.8 ms. */
+    const bool left = warp == 4;
+    const int kind = left ? lk : rk;
+    const uint32_t idx = left ? op.left_idx : op.right_idx;
+    const double *clv = (kind == NRX_CLV) ? pv.clv[idx] : nullptr;
+    const uint32_t *sc = (kind == NRX_CLV && MODE != AA_SUM) ? pv.scaler[idx] : nullptr;
+    const uint8_t *tip = (kind == NRX_TIP) ? pv.tipchars + (size_t)idx * pv.tip_pitch : nullptr;
+    // chunk c = i * 32 + lane of a tile (320 chunks of 16 B): row c / 40, 16-byte column c % 40
+    uint32_t soff[10], goff[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const uint32_t c = (uint32_t)i * 32u + (uint32_t)lane;
+      soff[i] = ((c / 40u) * AA_PITCH + (c % 40u) * 2u) * 8u;
+      goff[i] = (c / 40u) * 80u + (c % 40u) * 2u;
+    }
     uint32_t s = 0, ph = 0;
     for (uint32_t k = 0; k < count; ++k) {
       if (k >= (uint32_t)NIN_AA) mbar_wait(&sm.empty_in[s], ph ^ 1u);
       AaStage &st = sm.in[s];
-      unsigned long long *bar = &sm.full_in[s];
       const size_t p0 = (size_t)(grp + (size_t)k * groups) * AA_TP;
-      if (lane == 0) mbar_expect_tx(bar, tx_bytes);
-      __syncwarp();
-      if (lane < AA_TP) {
-        if (lk == NRX_CLV) bulk_g2s(st.l + lane * AA_PITCH, clvL + (p0 + lane) * 80, 640u, bar);
-      } else if (lane < 2 * AA_TP) {
-        if (rk == NRX_CLV) bulk_g2s(st.r + (lane - AA_TP) * AA_PITCH, clvR + (p0 + lane - AA_TP) * 80, 640u, bar);
-      } else if (lane == 16) {
-        if (lk == NRX_CLV) { if (MODE != AA_SUM) bulk_g2s(st.scl, scL + p0, AA_TP * 4u, bar); }
-        else if (lk == NRX_TIP) bulk_g2s(st.tl, tipL + (p0 & ~(size_t)15), 16u, bar);
-      } else if (lane == 17) {
-        if (rk == NRX_CLV) { if (MODE != AA_SUM) bulk_g2s(st.scr, scR + p0, AA_TP * 4u, bar); }
-        else if (rk == NRX_TIP) bulk_g2s(st.tr, tipR + (p0 & ~(size_t)15), 16u, bar);
+      if (clv) {
+        const double *g = clv + p0 * 80;
+        const uint32_t d = smem_u32(left ? st.l : st.r);
+#pragma unroll
+        for (int i = 0; i < 10; ++i)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + soff[i]), "l"(g + goff[i]) : "memory");
+        if (sc && lane < AA_TP)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32((left ? st.scl : st.scr) + lane)), "l"(sc + p0 + lane) : "memory");
+      } else if (tip && lane == 0) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(left ? st.tl : st.tr)), "l"(tip + (p0 & ~(size_t)15)) : "memory");
       }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&sm.full_in[s])) : "memory");
       if (++s == NIN_AA) { s = 0; ph ^= 1u; }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     return;
   }
 
@@ -1075,9 +1227,8 @@ __global__ void __launch_bounds__(AA2_THREADS, 2) k_aa20_mma(const PartView *__r
         }
       }
       if (lane == 0) {
-#pragma unroll
-        for (int r = 0; r < AA_TP; ++r)
-          if (p0 + r < pv.patterns) bulk_s2g(par + (p0 + r) * 80, ot.v + r * AA_OPITCH, 640u);
+        const uint32_t rows = (p0 + AA_TP <= pv.patterns) ? (uint32_t)AA_TP : (uint32_t)(pv.patterns - p0);   // consecutive patterns: one contiguous span
+        bulk_s2g(par + p0 * 80, ot.v, rows * 640u);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         // all but the newest group have been READ out of shared memory: the previous tile's buffer can be rewritten
         asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -1091,101 +1242,17 @@ __global__ void __launch_bounds__(AA2_THREADS, 2) k_aa20_mma(const PartView *__r
   }
 
   /* ---------------- MMA warps: warp = rate category ---------------- */
-  const int cat = warp, item = lane >> 2, q = lane & 3;
-  double BL[15], BR[15];   // B fragments: [ntile * 5 + kstep] = M[8*ntile + lane/4][4*kstep + lane%4]
-  {
-    const int i_base = lane >> 2, j_base = lane & 3;
-#pragma unroll
-    for (int n = 0; n < 3; ++n)
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const int i = 8 * n + i_base, j = 4 * k + j_base;
-        if (MODE == AA_SUM) {
-          BL[n * 5 + k] = (lk == NRX_CLV && i < 20) ? pv.summat[i * 20 + j] : 0.0;
-          BR[n * 5 + k] = (rk == NRX_CLV && i < 20) ? pv.summat[400 + i * 20 + j] : 0.0;
-        } else {
-          BL[n * 5 + k] = (lk == NRX_CLV && i < 20) ? pv.pmat[(size_t)op.left_edge * 1600 + (cat * 20 + i) * 20 + j] : 0.0;
-          BR[n * 5 + k] = (rk == NRX_CLV && i < 20) ? pv.pmat[(size_t)op.right_edge * 1600 + (cat * 20 + i) * 20 + j] : 0.0;
-        }
-      }
-  }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(AA2_REGS_MMA));
   if (wait_lut) mbar_wait(&sm.lutbar, 0);
-  uint32_t s = 0, ph = 0, o = 0, pho = 0;
-  for (uint32_t k = 0; k < count; ++k) {
-    const AaStage &st = sm.in[s];
-    mbar_wait(&sm.full_in[s], ph);
-    const uint32_t p0lo = (uint32_t)(((size_t)(grp + (size_t)k * groups) * AA_TP) & 15u);
-    double aL[5], aR[5];
-    uint32_t codeL = 0, codeR = 0, sc = 0;
-    if (lk == NRX_CLV) {
-#pragma unroll
-      for (int kk = 0; kk < 5; ++kk) aL[kk] = st.l[item * AA_PITCH + cat * 20 + 4 * kk + q];
-      if (MODE == AA_CLV) sc += st.scl[item];
-    } else if (lk == NRX_TIP) codeL = st.tl[p0lo + item];
-    if (rk == NRX_CLV) {
-#pragma unroll
-      for (int kk = 0; kk < 5; ++kk) aR[kk] = st.r[item * AA_PITCH + cat * 20 + 4 * kk + q];
-      if (MODE == AA_CLV) sc += st.scr[item];
-    } else if (rk == NRX_TIP) codeR = st.tr[p0lo + item];
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.empty_in[s]);
-
-    double x[6], y[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { x[i] = 0.0; y[i] = 0.0; }
-    if (lk == NRX_CLV) {
-#pragma unroll
-      for (int kk = 0; kk < 5; ++kk)
-#pragma unroll
-        for (int n = 0; n < 3; ++n) dmma884(x[2 * n], x[2 * n + 1], aL[kk], BL[n * 5 + kk]);
-    }
-    if (rk == NRX_CLV) {
-#pragma unroll
-      for (int kk = 0; kk < 5; ++kk)
-#pragma unroll
-        for (int n = 0; n < 3; ++n) dmma884(y[2 * n], y[2 * n + 1], aR[kk], BR[n * 5 + kk]);
-    }
-#pragma unroll
-    for (int n = 0; n < 3; ++n) {
-      const int i0 = 8 * n + 2 * q;
-      if (lk == NRX_TIP && i0 < 20) { const double2 v = *reinterpret_cast<const double2 *>(lutL + (codeL * 4 + cat) * 20 + i0); x[2 * n] = v.x; x[2 * n + 1] = v.y; }
-      if (rk == NRX_TIP && i0 < 20) { const double2 v = *reinterpret_cast<const double2 *>(lutR + (codeR * 4 + cat) * 20 + i0); y[2 * n] = v.x; y[2 * n + 1] = v.y; }
-    }
-    double pz[6];
-    bool small = true;
-#pragma unroll
-    for (int n = 0; n < 3; ++n) {
-      const int i0 = 8 * n + 2 * q;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        double v;
-        if (rk == NRX_NONE) v = x[2 * n + h];
-        else if (lk == NRX_NONE) v = y[2 * n + h];
-        else v = __dmul_rn(x[2 * n + h], y[2 * n + h]);
-        pz[2 * n + h] = v;
-        if (MODE == AA_CLV && i0 < 20) small &= (v < SCALE_THRESHOLD);
-      }
-    }
-    AaOut &ot = sm.out[o];
-    mbar_wait(&sm.empty_out[o], pho ^ 1u);   // the bulk stores of the tile that used this buffer NOUT_AA tiles ago have read it
-#pragma unroll
-    for (int n = 0; n < 3; ++n) {
-      const int i0 = 8 * n + 2 * q;
-      if (i0 < 20) *reinterpret_cast<double2 *>(ot.v + item * AA_OPITCH + cat * 20 + i0) = make_double2(pz[2 * n], pz[2 * n + 1]);
-    }
-    if (MODE == AA_CLV) {
-      const unsigned b = __ballot_sync(0xffffffffu, small);
-      if (q == 0) {
-        ot.flag[cat][item] = (((b >> (lane & ~3)) & 0xFu) == 0xFu) ? 1u : 0u;
-        if (cat == 0) ot.sc[item] = sc;
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the storer's bulk copies
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.full_out[o]);
-    if (++s == NIN_AA) { s = 0; ph ^= 1u; }
-    if (++o == NOUT_AA) { o = 0; pho ^= 1u; }
+  // the operand kinds are fixed per block: one specialised, software-pipelined loop per combination (no predication inside)
+#define NRX_AA_CASE(L, R) case (L) * 3 + (R): aa_mma_loop<MODE, L, R, PIPE>(sm, pv, op, lutL, lutR, grp, groups, count, warp, lane); break;
+  switch (lk * 3 + rk) {
+    NRX_AA_CASE(NRX_CLV, NRX_CLV) NRX_AA_CASE(NRX_CLV, NRX_TIP) NRX_AA_CASE(NRX_TIP, NRX_CLV)
+    NRX_AA_CASE(NRX_CLV, NRX_NONE) NRX_AA_CASE(NRX_NONE, NRX_CLV) NRX_AA_CASE(NRX_TIP, NRX_NONE) NRX_AA_CASE(NRX_NONE, NRX_TIP)
+    NRX_AA_CASE(NRX_TIP, NRX_TIP)
+    default: break;
   }
+#undef NRX_AA_CASE
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -1416,6 +1483,34 @@ __global__ void __launch_bounds__(128) k_reduce_partials(const double *__restric
   if (lane == 0) out[i] = s;
 }
 
+/* The same second stage FUSED into the reducing kernels (round 2: the derivative sweep spent 550 of its 3089 launches in
+ * k_reduce_partials): a block that has written its partial sums takes a ticket for its (item, partition) output; the block that
+ * draws the last ticket sums all nblk partials — same lane-strided order + shuffle tree as k_reduce_partials, so the result is
+ * bit-identical to the two-launch form and independent of WHICH block finishes last — writes out[] and re-arms the counter.
+ * `partial` = this output's [N][nblk] block of partial sums, `out` = its N results.  counter == nullptr: two-launch form. */
+template <int N>
+__device__ __forceinline__ void finish_partials(const double *partial, double *out, uint32_t *counter, uint32_t nblk) {
+  if (counter == nullptr) return;
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(counter, 1u) == nblk - 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < (uint32_t)N) {
+    const double *p = partial + (size_t)warp * nblk;
+    double s = 0.0;
+    for (uint32_t b = lane; b < nblk; b += 32) s += __ldcg(p + b);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+    if (lane == 0) out[warp] = s;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * K3  root lnL (LIBPLL/core_likelihood.c:25-209, 4x4: core_likelihood_avx.c:206-282).
  * K4  edge lnL (LIBPLL/core_likelihood.c:1191-1496 ii, :351-922 ti).
@@ -1424,7 +1519,8 @@ __global__ void __launch_bounds__(128) k_reduce_partials(const double *__restric
  * ---------------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(BLOCK) k_tree_lnl(const PartView *__restrict__ parts, const uint32_t *__restrict__ slots,
                                                      double *__restrict__ partial, uint32_t nparts_total, double log_thresh,
-                                                     double *__restrict__ persite, size_t persite_stride) {
+                                                     double *__restrict__ persite, size_t persite_stride,
+                                                     double *__restrict__ out, uint32_t *__restrict__ counters) {
   __shared__ double red[BLOCK / 32];
   const PartView &pv = parts[blockIdx.z];
   const uint32_t S = pv.states, SP = pv.sp, C = pv.cats;
@@ -1457,12 +1553,14 @@ __global__ void __launch_bounds__(BLOCK) k_tree_lnl(const PartView *__restrict__
     acc[0] += lk;
   }
   block_sum<1>(acc, red);
-  if (threadIdx.x == 0) partial[((size_t)blockIdx.y * nparts_total + pv.part_index) * gridDim.x + blockIdx.x] = acc[0];
+  const size_t oi = (size_t)blockIdx.y * nparts_total + pv.part_index;
+  if (threadIdx.x == 0) partial[oi * gridDim.x + blockIdx.x] = acc[0];
+  finish_partials<1>(partial + oi * gridDim.x, out + oi, counters ? counters + oi : nullptr, gridDim.x);
 }
 
 __global__ void __launch_bounds__(BLOCK) k_edge_lnl(const PartView *__restrict__ parts, const nrx_pair *__restrict__ pairs,
                                                      uint32_t edge, double *__restrict__ partial, uint32_t nparts_total,
-                                                     double log_thresh) {
+                                                     double log_thresh, double *__restrict__ out, uint32_t *__restrict__ counters) {
   __shared__ double red[BLOCK / 32];
   const PartView &pv = parts[blockIdx.z];
   const uint32_t S = pv.states, SP = pv.sp, C = pv.cats;
@@ -1500,7 +1598,9 @@ __global__ void __launch_bounds__(BLOCK) k_edge_lnl(const PartView *__restrict__
     acc[0] += __dmul_rn(lk, (double)pv.weights[n]);
   }
   block_sum<1>(acc, red);
-  if (threadIdx.x == 0) partial[((size_t)blockIdx.y * nparts_total + pv.part_index) * gridDim.x + blockIdx.x] = acc[0];
+  const size_t oi = (size_t)blockIdx.y * nparts_total + pv.part_index;
+  if (threadIdx.x == 0) partial[oi * gridDim.x + blockIdx.x] = acc[0];
+  finish_partials<1>(partial + oi * gridDim.x, out + oi, counters ? counters + oi : nullptr, gridDim.x);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -1542,7 +1642,7 @@ __global__ void __launch_bounds__(BLOCK) k_sumtable(const PartView *__restrict__
  * f as in core_derivatives_avx2.c:1788-1874: no scaler term).  thread per pattern.
  * ---------------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(BLOCK) k_derivatives(const PartView *__restrict__ parts, double *__restrict__ partial,
-                                                        uint32_t nparts_total) {
+                                                        uint32_t nparts_total, double *__restrict__ out, uint32_t *__restrict__ counters) {
   __shared__ double red[3 * (BLOCK / 32)];
   const PartView &pv = parts[blockIdx.z];
   const uint32_t S = pv.states, SP = pv.sp, C = pv.cats;
@@ -1577,12 +1677,14 @@ __global__ void __launch_bounds__(BLOCK) k_derivatives(const PartView *__restric
     acc[2] += pw * d2;
   }
   block_sum<3>(acc, red);
+  const size_t oi = (size_t)blockIdx.y * nparts_total + pv.part_index;
+  double *p = partial + oi * 3 * gridDim.x;
   if (threadIdx.x == 0) {
-    double *p = partial + ((size_t)blockIdx.y * nparts_total + pv.part_index) * 3 * gridDim.x;
     p[0 * gridDim.x + blockIdx.x] = acc[0];
     p[1 * gridDim.x + blockIdx.x] = acc[1];
     p[2 * gridDim.x + blockIdx.x] = acc[2];
   }
+  finish_partials<3>(p, out + oi * 3, counters ? counters + oi : nullptr, gridDim.x);
 }
 
 /* Slot copies of the virtual re-rooting save/restore (the reference copy-assigns NodeDisplayedTreeData, i.e. memcpy's
@@ -1612,7 +1714,8 @@ __global__ void __launch_bounds__(BLOCK) k_copy_slots(const PartView *__restrict
 template <int SC /* compile-time state count (loops unroll, all loads issue up front); 0 = run time */>
 __global__ void __launch_bounds__(BLOCK) k_tree_lnl_pc(const PartView *__restrict__ parts, const uint32_t *__restrict__ slots,
                                                         double *__restrict__ partial, uint32_t nparts_total, double log_thresh,
-                                                        double *__restrict__ persite, size_t persite_stride) {
+                                                        double *__restrict__ persite, size_t persite_stride,
+                                                        double *__restrict__ out, uint32_t *__restrict__ counters) {
   __shared__ double red[BLOCK / 32];
   __shared__ double sfreq[32], swt[32];
   const PartView &pv = parts[blockIdx.z];
@@ -1658,7 +1761,9 @@ __global__ void __launch_bounds__(BLOCK) k_tree_lnl_pc(const PartView *__restric
     }
   }
   block_sum<1>(acc, red);
-  if (threadIdx.x == 0) partial[((size_t)blockIdx.y * nparts_total + pv.part_index) * gridDim.x + blockIdx.x] = acc[0];
+  const size_t oi = (size_t)blockIdx.y * nparts_total + pv.part_index;
+  if (threadIdx.x == 0) partial[oi * gridDim.x + blockIdx.x] = acc[0];
+  finish_partials<1>(partial + oi * gridDim.x, out + oi, counters ? counters + oi : nullptr, gridDim.x);
 }
 
 /* K6, thread = (pattern, category), NP patterns per thread.  ncu on the first version (profiles/r2a_k6_protein_200k.md): 54 % of the
@@ -1672,7 +1777,7 @@ __host__ __device__ constexpr uint32_t diag_stride(uint32_t S) { return ((S * 4 
 
 template <int SC, int NP>
 __global__ void __launch_bounds__(BLOCK) k_derivatives_pc(const PartView *__restrict__ parts, double *__restrict__ partial,
-                                                           uint32_t nparts_total) {
+                                                           uint32_t nparts_total, double *__restrict__ out, uint32_t *__restrict__ counters) {
   __shared__ double red[3 * (BLOCK / 32)];
   extern __shared__ __align__(16) double sdiag[];  // [cats][diag_stride(states)] (entries [state][4]) + [cats] rate weights
   const PartView &pv = parts[blockIdx.z];
@@ -1746,12 +1851,14 @@ __global__ void __launch_bounds__(BLOCK) k_derivatives_pc(const PartView *__rest
     }
   }
   block_sum<3>(acc, red);
+  const size_t oi = (size_t)blockIdx.y * nparts_total + pv.part_index;
+  double *p = partial + oi * 3 * gridDim.x;
   if (threadIdx.x == 0) {
-    double *p = partial + ((size_t)blockIdx.y * nparts_total + pv.part_index) * 3 * gridDim.x;
     p[0 * gridDim.x + blockIdx.x] = acc[0];
     p[1 * gridDim.x + blockIdx.x] = acc[1];
     p[2 * gridDim.x + blockIdx.x] = acc[2];
   }
+  finish_partials<3>(p, out + oi * 3, counters ? counters + oi : nullptr, gridDim.x);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -1768,7 +1875,8 @@ constexpr int RU = 4;  // k_sumtable_dna4: independent 256-bit loads in flight p
  * loads (every 32-byte sector fetched is fully used). */
 __global__ void __launch_bounds__(BLOCK) k_tree_lnl_dna4(const PartView *__restrict__ parts, const uint32_t *__restrict__ slots,
                                                           double *__restrict__ partial, uint32_t nparts_total, double log_thresh,
-                                                          double *__restrict__ persite, size_t persite_stride) {
+                                                          double *__restrict__ persite, size_t persite_stride,
+                                                          double *__restrict__ out, uint32_t *__restrict__ counters) {
   __shared__ double red[BLOCK / 32];
   const PartView &pv = parts[blockIdx.z];
   const uint32_t slot = slots[blockIdx.y];
@@ -1796,14 +1904,17 @@ __global__ void __launch_bounds__(BLOCK) k_tree_lnl_dna4(const PartView *__restr
     acc[0] += lk;
   }
   block_sum<1>(acc, red);
-  if (threadIdx.x == 0) partial[((size_t)blockIdx.y * nparts_total + pv.part_index) * gridDim.x + blockIdx.x] = acc[0];
+  const size_t oi = (size_t)blockIdx.y * nparts_total + pv.part_index;
+  if (threadIdx.x == 0) partial[oi * gridDim.x + blockIdx.x] = acc[0];
+  finish_partials<1>(partial + oi * gridDim.x, out + oi, counters ? counters + oi : nullptr, gridDim.x);
 }
 
 /* second half of the fused K3: log, scaler term and pattern weight on the per-site terms K2 wrote — same traversal and
  * accumulation order as k_tree_lnl_dna4, hence bit-identical partial sums */
 __global__ void __launch_bounds__(BLOCK) k_term_lnl_sum(const PartView *__restrict__ parts, const uint32_t *__restrict__ slots,
                                                          const double *__restrict__ terms, size_t persite_stride,
-                                                         double *__restrict__ partial, uint32_t nparts_total, double log_thresh) {
+                                                         double *__restrict__ partial, uint32_t nparts_total, double log_thresh,
+                                                         double *__restrict__ out, uint32_t *__restrict__ counters) {
   __shared__ double red[BLOCK / 32];
   const PartView &pv = parts[blockIdx.z];
   const double *ps = terms + ((size_t)blockIdx.y * nparts_total + pv.part_index) * persite_stride;
@@ -1816,7 +1927,9 @@ __global__ void __launch_bounds__(BLOCK) k_term_lnl_sum(const PartView *__restri
     acc[0] += __dmul_rn(lk, (double)pv.weights[n]);
   }
   block_sum<1>(acc, red);
-  if (threadIdx.x == 0) partial[((size_t)blockIdx.y * nparts_total + pv.part_index) * gridDim.x + blockIdx.x] = acc[0];
+  const size_t oi = (size_t)blockIdx.y * nparts_total + pv.part_index;
+  if (threadIdx.x == 0) partial[oi * gridDim.x + blockIdx.x] = acc[0];
+  finish_partials<1>(partial + oi * gridDim.x, out + oi, counters ? counters + oi : nullptr, gridDim.x);
 }
 
 __device__ __forceinline__ double edge_cat_term(const D4 &a, const D4 &y, double f0, double f1, double f2, double f3) {
@@ -1828,7 +1941,7 @@ __device__ __forceinline__ double edge_cat_term(const D4 &a, const D4 &y, double
 
 __global__ void __launch_bounds__(BLOCK) k_edge_lnl_dna4(const PartView *__restrict__ parts, const nrx_pair *__restrict__ pairs,
                                                           uint32_t edge, double *__restrict__ partial, uint32_t nparts_total,
-                                                          double log_thresh) {
+                                                          double log_thresh, double *__restrict__ out, uint32_t *__restrict__ counters) {
   __shared__ double red[BLOCK / 32];
   __shared__ __align__(32) double lut[256];
   __shared__ __align__(16) double sP[64];
@@ -1886,7 +1999,9 @@ __global__ void __launch_bounds__(BLOCK) k_edge_lnl_dna4(const PartView *__restr
     acc[0] += __dmul_rn(lk, pw);
   }
   block_sum<1>(acc, red);
-  if (threadIdx.x == 0) partial[((size_t)blockIdx.y * nparts_total + pv.part_index) * gridDim.x + blockIdx.x] = acc[0];
+  const size_t oi = (size_t)blockIdx.y * nparts_total + pv.part_index;
+  if (threadIdx.x == 0) partial[oi * gridDim.x + blockIdx.x] = acc[0];
+  finish_partials<1>(partial + oi * gridDim.x, out + oi, counters ? counters + oi : nullptr, gridDim.x);
 }
 
 __global__ void __launch_bounds__(BLOCK) k_sumtable_dna4(const PartView *__restrict__ parts, const nrx_pair *__restrict__ pairs) {
@@ -1954,7 +2069,7 @@ __device__ __forceinline__ void deriv_cat(const D4 &v, const double *dg, double 
 }
 
 __global__ void __launch_bounds__(BLOCK) k_derivatives_dna4(const PartView *__restrict__ parts, double *__restrict__ partial,
-                                                             uint32_t nparts_total) {
+                                                             uint32_t nparts_total, double *__restrict__ out, uint32_t *__restrict__ counters) {
   __shared__ double red[3 * (BLOCK / 32)];
   __shared__ double sD[64];   // diag table [cat][state][4]: every lane reads the same entry (broadcast)
   const PartView &pv = parts[blockIdx.z];
@@ -1982,12 +2097,14 @@ __global__ void __launch_bounds__(BLOCK) k_derivatives_dna4(const PartView *__re
     acc[2] += pw * d2;
   }
   block_sum<3>(acc, red);
+  const size_t oi = (size_t)blockIdx.y * nparts_total + pv.part_index;
+  double *p = partial + oi * 3 * gridDim.x;
   if (threadIdx.x == 0) {
-    double *p = partial + ((size_t)blockIdx.y * nparts_total + pv.part_index) * 3 * gridDim.x;
     p[0 * gridDim.x + blockIdx.x] = acc[0];
     p[1 * gridDim.x + blockIdx.x] = acc[1];
     p[2 * gridDim.x + blockIdx.x] = acc[2];
   }
+  finish_partials<3>(p, out + oi * 3, counters ? counters + oi : nullptr, gridDim.x);
 }
 
 }  // namespace nrx

@@ -15,6 +15,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
+BRPROB_MIN, BRPROB_MAX = 1e-6, 1.0 - 1e-6   # NetraxOptions::brprob_min / brprob_max (src/NetraxOptions.hpp)
 BRLEN_MIN = 1e-6   # raxml-ng RAXML_BRLEN_MIN (libs/raxml-ng/src/constants.hpp:14)
 BRLEN_MAX = 100.0  # RAXML_BRLEN_MAX (:15)
 
@@ -154,10 +155,12 @@ def parse_extended_newick(newick: str) -> NetworkDesc:
     rf, rs = [], []
     for i, n in enumerate(retn):
         p0, p1 = n.probs
-        if p0 == 0 and p1 == 0:       # RootedNetworkParser.cpp:317-324
+        if p0 == 0 and p1 == 0:       # RootedNetworkParser.cpp:317-324: probabilities not given -> 0.5 / 0.5
             p0 = p1 = 0.5
-        elif p0 == 0:
-            p0 = 1.0 - p1
+        else:                         # :325-345: clamp each to [brprob_min, brprob_max], then the two must sum to 1
+            p0, p1 = min(max(p0, BRPROB_MIN), BRPROB_MAX), min(max(p1, BRPROB_MIN), BRPROB_MAX)
+            if abs(1.0 - (p0 + p1)) >= 1e-3:
+                raise ValueError(f"Reticulation probs do not sum up to 1 (reticulation {n.ret_name}: {p0} + {p1})")
         for k in (0, 1):
             e = base + 2 * i + k
             src[e], tgt[e], length[e] = n.parents[k].index, n.index, n.lengths[k]

@@ -244,8 +244,24 @@ def test_score_network_cli_refuses_to_run_without_a_gpu():
         pytest.skip("a CUDA device is present")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "scripts", "score_network.py"), "--msa", os.path.join(FIX, "small_fake_alignment.txt"),
-                        "--start_network", os.path.join(FIX, "small.nw"), "--model", "GTR+G"], capture_output=True, text=True, timeout=300)
+                        "--start_network", os.path.join(FIX, "small.nw"), "--model", "GTR{1/2.5/0.8/1.2/3.0/1}+FC+G"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
     for rel in (("scripts", "score_network.py"), ("netrax_b200", "score.py"), ("netrax_b200", "msa_io.py"), ("netrax_b200", "network_io.py")):
         src = open(os.path.join(root, *rel)).read()
         assert "from oracle" not in src and "import oracle" not in src, rel
+
+
+def test_score_only_refuses_ml_estimated_rates_and_frequencies():
+    """The reference's optimizeModel fits ML rates / frequencies with L-BFGS-B (out of scope): plain GTR+G must not be scored
+    silently at its start values."""
+    from netrax_b200.score import UnoptimisedModelError, score_only
+    from oracle import oracle
+    nw, aln = FIXTURE_PAIRS["small"]
+    net_text, msa_text = open(os.path.join(FIX, nw)).read(), open(os.path.join(FIX, aln)).read()
+    factory = lambda net, parts, **kw: oracle.make_engine("port", net, parts, **kw)   # noqa: E731
+    with pytest.raises(UnoptimisedModelError, match="substitution rates"):
+        score_only(factory, net_text, msa_text, "GTR+G", log=None)
+    lines = []
+    res = score_only(factory, net_text, msa_text, "GTR+G", log=lines.append, optimize=False, allow_unoptimised_ml_params=True)
+    assert res["unoptimised_ml_params"] and any(l.startswith("WARNING: model parameters") for l in lines)
+    assert score_only(factory, net_text, msa_text, "GTR{1/2.5/0.8/1.2/3.0/1}+FC+G", log=None, optimize=False)["unoptimised_ml_params"] == []

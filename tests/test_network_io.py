@@ -51,7 +51,7 @@ def test_network_io_format_variants(name, text, tips, rets, prob):
     assert net.num_tips == tips and net.num_reticulations == rets
     sanity_checks(net)
     if prob is not None:
-        assert float(net.edge_prob[int(net.ret_first_edge[0])]) == pytest.approx(prob)
+        assert float(net.edge_prob[int(net.ret_first_edge[0])]) == pytest.approx(min(max(prob, 1e-6), 1.0 - 1e-6), rel=1e-12)   # clamped to [brprob_min, brprob_max]
     elif rets:
         assert float(net.edge_prob[int(net.ret_first_edge[0])]) == pytest.approx(0.5)   # unspecified: 0.5 / 0.5
 
@@ -141,3 +141,19 @@ def test_extended_newick_writer_round_trips_synthetic_networks(taxa, rets, seed)
     assert [(r[0], r[1]) for r in got] == [(r[0], r[1]) for r in want]
     np.testing.assert_allclose([r[2] for r in got], [r[2] for r in want], rtol=0, atol=0)
     np.testing.assert_allclose([r[3] for r in got], [r[3] for r in want], rtol=1e-15)
+
+
+def test_reticulation_probabilities_are_clamped_and_checked_like_the_reference():
+    """RootedNetworkParser.cpp:317-345: probabilities not given -> 0.5 / 0.5; otherwise each is clamped to [1e-6, 1 - 1e-6] and
+    the pair must sum to 1 within 1e-3 (the reference throws)."""
+    from netrax_b200.network_io import parse_extended_newick
+    nw = "((A:1,(B:1)X#H1:1::{p0}):1,(X#H1:1::{p1},C:1):1);"
+    net = parse_extended_newick(nw.format(p0="0.4", p1="0.6"))
+    assert net.edge_prob[net.ret_first_edge[0]] == pytest.approx(0.4) and net.edge_prob[net.ret_second_edge[0]] == pytest.approx(0.6)
+    net = parse_extended_newick(nw.format(p0="1e-10", p1="1.0"))        # clamped, and 1e-6 + (1 - 1e-6) still sums to 1
+    assert net.edge_prob[net.ret_first_edge[0]] == 1e-6 and np.log(net.edge_prob).min() > -14
+    for bad in (("0.4", "0.4"), ("0.3", "0"), ("0.7", "0.7")):      # inconsistent, or one probability missing
+        with pytest.raises(ValueError, match="do not sum up to 1"):
+            parse_extended_newick(nw.format(p0=bad[0], p1=bad[1]))
+    net = parse_extended_newick("((A:1,(B:1)X#H1:1):1,(X#H1:1,C:1):1);")   # not given at all
+    assert net.edge_prob[net.ret_first_edge[0]] == 0.5

@@ -408,7 +408,8 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
     const int aa2_smem = (int)(sizeof(AaSmem2) + 2 * AA_LUT_CODES * 80 * sizeof(double));
     if (!cuda_ok(cudaFuncSetAttribute(k_aa20_mma<AA_CLV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa2_smem), "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(k_aa20_mma<AA_CLV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa2_smem), "cudaFuncSetAttribute") ||
-        !cuda_ok(cudaFuncSetAttribute(k_aa20_mma<AA_SUM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa2_smem), "cudaFuncSetAttribute")) { delete e; return nullptr; }
+        !cuda_ok(cudaFuncSetAttribute(k_aa20_mma<AA_SUM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa2_smem), "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(k_aa20_mma<AA_EDGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa2_smem), "cudaFuncSetAttribute")) { delete e; return nullptr; }
     if (!cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClvPipeSmem)), "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem<1>)), "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem<2>)), "cudaFuncSetAttribute")) { delete e; return nullptr; }
@@ -874,8 +875,8 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
       const int luts = !with_tips ? 0 : (has_aa_dmma(e) ? 1 : 2);
       const size_t lut_bytes = (size_t)luts * class_tip_codes(e, c) * 80 * sizeof(double);
       if (e->aa_v1) k_aa20_dmma<AA_CLV><<<grid, AA_THREADS, sizeof(AaSmem) + lut_bytes, e->stream>>>(c.d_views, d_ops + ntt, rest, groups, luts, nullptr, 0, 0.0);
-      else if (e->aa_pipe) k_aa20_mma<AA_CLV, true><<<grid, AA2_THREADS, sizeof(AaSmem2) + lut_bytes, e->stream>>>(c.d_views, d_ops + ntt, rest, groups, luts);
-      else k_aa20_mma<AA_CLV, false><<<grid, AA2_THREADS, sizeof(AaSmem2) + lut_bytes, e->stream>>>(c.d_views, d_ops + ntt, rest, groups, luts);
+      else if (e->aa_pipe) k_aa20_mma<AA_CLV, true><<<grid, AA2_THREADS, sizeof(AaSmem2) + lut_bytes, e->stream>>>(c.d_views, d_ops + ntt, rest, groups, luts, nullptr, 0, 0.0, nullptr, nullptr);
+      else k_aa20_mma<AA_CLV, false><<<grid, AA2_THREADS, sizeof(AaSmem2) + lut_bytes, e->stream>>>(c.d_views, d_ops + ntt, rest, groups, luts, nullptr, 0, 0.0, nullptr, nullptr);
     } else {
       dim3 grid(tiles_for(c.max_patterns, BLOCK, nops * z), nops, z);
       k_clv_generic<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops, nullptr);
@@ -1245,7 +1246,12 @@ int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n
      // that the per-block set-up (B fragments, tip table) is amortised (4736 blocks of 21 tiles ran at 7 % tensor pipe)
     bool only_aa = !e->classes.empty();
     for (const ShapeClass &c : e->classes) only_aa = only_aa && aa_dmma_pairs_class(e, c);
-    if (only_aa) nblk = std::max<uint32_t>(1, std::min<uint32_t>(nblk, e->aa_blocks / std::max<uint32_t>(1, n * P)));
+    if (only_aa && e->aa_v1) nblk = std::max<uint32_t>(1, std::min<uint32_t>(nblk, e->aa_blocks / std::max<uint32_t>(1, n * P)));
+    else if (only_aa) {   // k_aa20_mma: 2 resident blocks per SM; 2 or 4 whole waves depending on the launch size (as for K2)
+      const uint64_t ntiles = (e->max_patterns + AA_TP - 1) / AA_TP;
+      const uint64_t blocks = e->aa2_blocks ? e->aa2_blocks : std::min<uint64_t>(8ull * e->sm_count, std::max<uint64_t>(4ull * e->sm_count, (uint64_t)n * P * ntiles / 48));
+      nblk = (uint32_t)std::max<uint64_t>(1, blocks / std::max<uint32_t>(1, n * P));
+    }
   }
   if (!ensure_result(e, (size_t)n * P, (size_t)n * P * nblk) || !refresh_views(e)) return 0;
   nrx_pair *d_pairs;
@@ -1254,8 +1260,11 @@ int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n
   // the separate second stage; every other kernel writes all partials and finishes the reduction in its last block
   bool any_aa = false;
   for (const ShapeClass &c : e->classes) any_aa = any_aa || aa_dmma_pairs_class(e, c);
-  uint32_t *tk = (e->fuse_reduce && !any_aa) ? e->d_tickets : nullptr;
-  if (any_aa) CK(cudaMemsetAsync(e->d_partial, 0, (size_t)n * P * nblk * sizeof(double), e->stream));
+  if (any_aa)   // the tensor-core kernels hand tiles to blocks: never more blocks per pair than tiles (every block writes its partial)
+    for (const ShapeClass &c : e->classes) if (c.max_patterns) nblk = std::min<uint32_t>(nblk, (c.max_patterns + AA_TP - 1) / AA_TP);
+  const bool aa_old = any_aa && e->aa_v1;   // k_aa20_dmma<AA_EDGE> lets surplus blocks exit early: memset + separate second stage
+  uint32_t *tk = (e->fuse_reduce && !aa_old) ? e->d_tickets : nullptr;
+  if (aa_old) CK(cudaMemsetAsync(e->d_partial, 0, (size_t)n * P * nblk * sizeof(double), e->stream));
   const double log_thresh = std::log(SCALE_THRESHOLD);
   cudaEvent_t ev0, ev1;
   prof_begin(e, &ev0, &ev1);
@@ -1268,7 +1277,9 @@ int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n
       nrx_op *d_ops;
       if (!upload(e, ops.data(), ops.size(), &d_ops)) return 0;
       const size_t smem = sizeof(AaSmem) + (tips ? (size_t)class_tip_codes(e, c) * 80 * sizeof(double) : 0);   // pairs are never tip-tip: one table
-      k_aa20_dmma<AA_EDGE><<<dim3(n * nblk, 1, (uint32_t)c.parts.size()), AA_THREADS, smem, e->stream>>>(c.d_views, d_ops, n, nblk, tips ? 1 : 0, e->d_partial, P, log_thresh);
+      if (e->aa_v1) k_aa20_dmma<AA_EDGE><<<dim3(n * nblk, 1, (uint32_t)c.parts.size()), AA_THREADS, smem, e->stream>>>(c.d_views, d_ops, n, nblk, tips ? 1 : 0, e->d_partial, P, log_thresh);
+      else k_aa20_mma<AA_EDGE, true><<<dim3(n * nblk, 1, (uint32_t)c.parts.size()), AA2_THREADS, sizeof(AaSmem2) + (tips ? (size_t)class_tip_codes(e, c) * 80 * sizeof(double) : 0), e->stream>>>(
+            c.d_views, d_ops, n, nblk, tips ? 1 : 0, e->d_partial, P, log_thresh, e->d_result, tk);
     }
     else k_edge_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh, e->d_result, tk);
     e->launches++;
@@ -1305,7 +1316,7 @@ int nrx_sumtables(nrx_engine *e, const nrx_pair *pairs, uint32_t n) {
       groups = std::min(groups, std::max<uint32_t>(1, ntiles / 8));
       const size_t lut_bytes = tips ? (size_t)class_tip_codes(e, c) * 80 * sizeof(double) : 0;
       if (e->aa_v1) k_aa20_dmma<AA_SUM><<<dim3(n * groups, 1, z), AA_THREADS, sizeof(AaSmem) + lut_bytes, e->stream>>>(c.d_views, d_ops, n, groups, tips ? 1 : 0, nullptr, 0, 0.0);
-      else k_aa20_mma<AA_SUM, true><<<dim3(n * groups, 1, z), AA2_THREADS, sizeof(AaSmem2) + lut_bytes, e->stream>>>(c.d_views, d_ops, n, groups, tips ? 1 : 0);
+      else k_aa20_mma<AA_SUM, true><<<dim3(n * groups, 1, z), AA2_THREADS, sizeof(AaSmem2) + lut_bytes, e->stream>>>(c.d_views, d_ops, n, groups, tips ? 1 : 0, nullptr, 0, 0.0, nullptr, nullptr);
     } else {
       dim3 grid(tiles_for((uint64_t)c.max_patterns * c.cats, BLOCK, n * z), n, z);
       k_sumtable<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs);

@@ -964,6 +964,7 @@ struct __align__(128) AaOut {
   double v[AA_TP * AA_OPITCH];
   uint32_t sc[AA_TP];              // sum of the children's scalers (written by the category-0 warp)
   uint32_t flag[4][AA_TP];         // 1: all 20 entries of (category, pattern) are below the scaling threshold
+  double term[4][AA_TP];           // AA_EDGE: per (category, pattern) site-likelihood term sum_i pi_i parent_i (P child)_i
 };
 struct __align__(128) AaSmem2 {
   AaStage in[NIN_AA];
@@ -999,19 +1000,37 @@ __device__ __forceinline__ void aa_mma_loop(AaSmem2 &sm, const PartView &pv, con
         BL[n * 5 + k] = (LK == NRX_CLV && i < 20) ? pv.summat[i * 20 + j] : 0.0;
         BR[n * 5 + k] = (RK == NRX_CLV && i < 20) ? pv.summat[400 + i * 20 + j] : 0.0;
       } else {
-        BL[n * 5 + k] = (LK == NRX_CLV && i < 20) ? pv.pmat[(size_t)op.left_edge * 1600 + (cat * 20 + i) * 20 + j] : 0.0;
+        BL[n * 5 + k] = (MODE == AA_CLV && LK == NRX_CLV && i < 20) ? pv.pmat[(size_t)op.left_edge * 1600 + (cat * 20 + i) * 20 + j] : 0.0;
         BR[n * 5 + k] = (RK == NRX_CLV && i < 20) ? pv.pmat[(size_t)op.right_edge * 1600 + (cat * 20 + i) * 20 + j] : 0.0;
       }
     }
   const uint32_t a_off = item * AA_PITCH + cat * 20 + q, o_off = item * AA_OPITCH + cat * 20 + 2 * q;
+  double fr[6], wcat = 0.0;   // AA_EDGE: pi of this lane's six output states, rate weight of its category
+  if (MODE == AA_EDGE) {
+    wcat = pv.rate_weights[cat];
+#pragma unroll
+    for (int n = 0; n < 3; ++n)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) { const int i = 8 * n + 2 * q + h; fr[2 * n + h] = (i < 20) ? pv.freqs[i] : 0.0; }
+  }
 
   // pull tile k's operands out of its input stage (the stage's full barrier has been waited for) and release the stage
-  auto pull = [&](uint32_t k, AaFrag &f) {
+  double e_xl[2][6];   // AA_EDGE: pi-weighted parent entries of the two tiles in flight
+  auto pull = [&](uint32_t k, AaFrag &f, int which) {
     const uint32_t s = k % NIN_AA;
     const AaStage &st = sm.in[s];
     const uint32_t p0lo = (uint32_t)(((size_t)(grp + (size_t)k * groups) * AA_TP) & 15u);
     f.sc = 0; f.codeL = 0; f.codeR = 0;
-    if (LK == NRX_CLV) {
+    if (MODE == AA_EDGE) {   // the parent CLV enters as it lies: this lane's six output states, times pi, parked in aL[0..2] / aR is the child
+#pragma unroll
+      for (int n = 0; n < 3; ++n) {
+        const int i0 = 8 * n + 2 * q;
+        double2 v = make_double2(0.0, 0.0);
+        if (i0 < 20) v = *reinterpret_cast<const double2 *>(st.l + item * AA_PITCH + cat * 20 + i0);
+        e_xl[which][2 * n] = __dmul_rn(v.x, fr[2 * n]); e_xl[which][2 * n + 1] = __dmul_rn(v.y, fr[2 * n + 1]);
+      }
+      f.sc += st.scl[item];
+    } else if (LK == NRX_CLV) {
 #pragma unroll
       for (int kk = 0; kk < 5; ++kk) f.aL[kk] = st.l[a_off + 4 * kk];
       if (MODE == AA_CLV) f.sc += st.scl[item];
@@ -1019,7 +1038,7 @@ __device__ __forceinline__ void aa_mma_loop(AaSmem2 &sm, const PartView &pv, con
     if (RK == NRX_CLV) {
 #pragma unroll
       for (int kk = 0; kk < 5; ++kk) f.aR[kk] = st.r[a_off + 4 * kk];
-      if (MODE == AA_CLV) f.sc += st.scr[item];
+      if (MODE != AA_SUM) f.sc += st.scr[item];
     } else if (RK == NRX_TIP) f.codeR = st.tr[p0lo + item];
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty_in[s]);
@@ -1031,13 +1050,33 @@ __device__ __forceinline__ void aa_mma_loop(AaSmem2 &sm, const PartView &pv, con
     for (int kk = 0; kk < 5; ++kk)
 #pragma unroll
       for (int n = 0; n < 3; ++n) {
-        if (LK == NRX_CLV) dmma884(x[2 * n], x[2 * n + 1], f.aL[kk], BL[n * 5 + kk]);
+        if (MODE != AA_EDGE && LK == NRX_CLV) dmma884(x[2 * n], x[2 * n + 1], f.aL[kk], BL[n * 5 + kk]);
         if (RK == NRX_CLV) dmma884(y[2 * n], y[2 * n + 1], f.aR[kk], BR[n * 5 + kk]);
       }
   };
   // products, threshold test, output tile (its empty barrier has been waited for), flags, hand-over to the storer
-  auto finish = [&](uint32_t k, const AaFrag &f, double (&x)[6], double (&y)[6]) {
+  auto finish = [&](uint32_t k, const AaFrag &f, double (&x)[6], double (&y)[6], int which) {
     AaOut &ot = sm.out[k % NOUT_AA];
+    if (MODE == AA_EDGE) {
+      // sum over this (pattern, category)'s 20 states: six per lane in state order, then the quad (as k_aa20_dmma<AA_EDGE>)
+      double t = 0.0;
+#pragma unroll
+      for (int n = 0; n < 3; ++n) {
+        const int i0 = 8 * n + 2 * q;
+        if (RK == NRX_TIP && i0 < 20) { const double2 v = *reinterpret_cast<const double2 *>(lutR + (f.codeR * 4 + cat) * 20 + i0); y[2 * n] = v.x; y[2 * n + 1] = v.y; }
+        t = __dadd_rn(t, __dmul_rn(e_xl[which][2 * n], y[2 * n]));
+        t = __dadd_rn(t, __dmul_rn(e_xl[which][2 * n + 1], y[2 * n + 1]));   // padding states carry pi = 0
+      }
+      t = __dadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 1));
+      t = __dadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 2));
+      if (q == 0) {
+        ot.term[cat][item] = (pv.pinv > 0.0) ? t : __dmul_rn(t, wcat);   // +I: the raw category term, weighted by the storer
+        if (cat == 0) ot.sc[item] = f.sc;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.full_out[k % NOUT_AA]);
+      return;
+    }
     bool small = true;
 #pragma unroll
     for (int n = 0; n < 3; ++n) {
@@ -1073,44 +1112,46 @@ __device__ __forceinline__ void aa_mma_loop(AaSmem2 &sm, const PartView &pv, con
                  // while the sumtable, which has no threshold test / flags in its epilogue, gains 17 %)
     for (uint32_t k = 0; k < count; ++k) {
       wait_in(k);
-      pull(k, f0);
+      pull(k, f0, 0);
       mma(f0, x0, y0);
       wait_out(k);
-      finish(k, f0, x0, y0);
+      finish(k, f0, x0, y0, 0);
     }
     return;
   }
   wait_in(0);
-  pull(0, f0);
+  pull(0, f0, 0);
   mma(f0, x0, y0);
   for (uint32_t k = 0; k < count; k += 2) {
     if (k + 1 < count) {   // tile k+1's DMMAs are issued first, tile k's epilogue fills the issue slots under them
       wait_in(k + 1);
       wait_out(k);
-      pull(k + 1, f1);
+      pull(k + 1, f1, 1);
       mma(f1, x1, y1);
-      finish(k, f0, x0, y0);
+      finish(k, f0, x0, y0, 0);
     } else {
       wait_out(k);
-      finish(k, f0, x0, y0);
+      finish(k, f0, x0, y0, 0);
       break;
     }
     if (k + 2 < count) {
       wait_in(k + 2);
       wait_out(k + 1);
-      pull(k + 2, f0);
+      pull(k + 2, f0, 0);
       mma(f0, x0, y0);
-      finish(k + 1, f1, x1, y1);
+      finish(k + 1, f1, x1, y1, 1);
     } else {
       wait_out(k + 1);
-      finish(k + 1, f1, x1, y1);
+      finish(k + 1, f1, x1, y1, 1);
     }
   }
 }
 
 template <int MODE, bool PIPE>
 __global__ void __launch_bounds__(AA2_THREADS, 2) k_aa20_mma(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops,
-                                                              uint32_t nops, uint32_t groups, int with_lut) {
+                                                              uint32_t nops, uint32_t groups, int with_lut,
+                                                              double *__restrict__ partial, uint32_t nparts_total, double log_thresh,
+                                                              double *__restrict__ red_out, uint32_t *__restrict__ counters) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   AaSmem2 &sm = *reinterpret_cast<AaSmem2 *>(smem_raw);
   const PartView &pv = parts[blockIdx.z];
@@ -1201,9 +1242,11 @@ __global__ void __launch_bounds__(AA2_THREADS, 2) k_aa20_mma(const PartView *__r
 
   if (warp == 5) {
     /* ---------------- storer ---------------- */
-    double *par = (MODE == AA_SUM) ? pv.sumtable[op.parent_slot] : pv.clv[op.parent_slot];
+    double *par = (MODE == AA_SUM) ? pv.sumtable[op.parent_slot] : (MODE == AA_CLV ? pv.clv[op.parent_slot] : nullptr);
     uint32_t *psc = (MODE == AA_CLV) ? pv.scaler[op.parent_slot] : nullptr;
     const bool tiptip = (lk == NRX_TIP && rk == NRX_TIP);
+    double edge_acc = 0.0, pend_t = 0.0, pend_w = 0.0;   // AA_EDGE: block sum; the pattern this lane finishes at the next flush
+    uint32_t pend_s = 0;
     uint32_t o = 0, ph = 0, prev = 0;
     for (uint32_t k = 0; k < count; ++k) {
       AaOut &ot = sm.out[o];
@@ -1226,7 +1269,43 @@ __global__ void __launch_bounds__(AA2_THREADS, 2) k_aa20_mma(const PartView *__r
           __syncwarp();
         }
       }
-      if (lane == 0) {
+      if (MODE == AA_EDGE) {
+        // K4: category sum (order 0..3) per pattern on lanes 0..7; the log / scaler term / pattern weight — ~150 dependent FP64
+        // instructions — are batched over FOUR tiles so that all 32 lanes do them at once (one lane per pattern): done per tile on
+        // 8 lanes, this warp was the slowest stage of the pipeline (K4 ran at 0.28 of the HBM peak, below k_aa20_dmma's 0.34)
+        const uint32_t slot = k & 3u;
+        double t = 0.0, w = 0.0;
+        uint32_t scv = 0;
+        if (lane < AA_TP && p0 + lane < pv.patterns) {
+          const size_t site = p0 + lane;
+          scv = ot.sc[lane];
+          w = (double)pv.weights[site];
+          if (pv.pinv > 0.0) {   // +I: finished here, per tile (terma / terminv do not batch as one number)
+            const int iv = pv.invariant[site];
+            const double invf = iv < 0 ? 0.0 : pv.freqs[iv];
+            double terma = 0.0, terminv = 0.0;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) edge_cat_accum(ot.term[c4][lane], pv.rate_weights[c4], pv.pinv, invf, iv >= 0, terma, terminv);
+            edge_acc += __dmul_rn(edge_site_lnl(terma, terminv, scv, log_thresh), w);
+            w = 0.0;
+          } else {
+            t = __dadd_rn(__dadd_rn(__dadd_rn(ot.term[0][lane], ot.term[1][lane]), ot.term[2][lane]), ot.term[3][lane]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty_out[o]);   // nothing asynchronous reads the tile: free at once
+        const double tt = __shfl_sync(0xffffffffu, t, lane & 7), ww = __shfl_sync(0xffffffffu, w, lane & 7);
+        const uint32_t ss = __shfl_sync(0xffffffffu, scv, lane & 7);
+        if ((uint32_t)(lane >> 3) == slot) { pend_t = tt; pend_w = ww; pend_s = ss; }
+        if (slot == 3u || k + 1 == count) {
+          if (pend_w != 0.0) {
+            double lkv = log(pend_t);
+            if (pend_s) lkv = __dadd_rn(lkv, __dmul_rn((double)pend_s, log_thresh));
+            edge_acc += __dmul_rn(lkv, pend_w);
+          }
+          pend_w = 0.0;
+        }
+      } else if (lane == 0) {
         const uint32_t rows = (p0 + AA_TP <= pv.patterns) ? (uint32_t)AA_TP : (uint32_t)(pv.patterns - p0);   // consecutive patterns: one contiguous span
         bulk_s2g(par + p0 * 80, ot.v, rows * 640u);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -1237,6 +1316,28 @@ __global__ void __launch_bounds__(AA2_THREADS, 2) k_aa20_mma(const PartView *__r
       prev = o;
       if (++o == NOUT_AA) { o = 0; ph ^= 1u; }
     }
+    if (MODE == AA_EDGE) {
+      // block partial, then the fused second stage: the block drawing the last ticket of its (pair,
+      // partition) sums all partials in the fixed lane-strided order (see finish_partials; one warp here, no block barrier)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) edge_acc += __shfl_down_sync(0xffffffffu, edge_acc, off);
+      const size_t oi = (size_t)(blockIdx.x % nops) * nparts_total + pv.part_index;
+      int last = 0;
+      if (lane == 0) {
+        partial[oi * groups + grp] = edge_acc;
+        if (counters) { __threadfence(); last = (atomicAdd(counters + oi, 1u) == groups - 1u) ? 1 : 0; }
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        __threadfence();
+        double sum = 0.0;
+        for (uint32_t b = lane; b < groups; b += 32) sum += __ldcg(partial + oi * groups + b);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off);
+        if (lane == 0) { red_out[oi] = sum; counters[oi] = 0u; }
+      }
+      return;
+    }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the stores must have landed before the block's shared memory goes away
     return;
   }
@@ -1246,6 +1347,13 @@ __global__ void __launch_bounds__(AA2_THREADS, 2) k_aa20_mma(const PartView *__r
   if (wait_lut) mbar_wait(&sm.lutbar, 0);
   // the operand kinds are fixed per block: one specialised, software-pipelined loop per combination (no predication inside)
 #define NRX_AA_CASE(L, R) case (L) * 3 + (R): aa_mma_loop<MODE, L, R, PIPE>(sm, pv, op, lutL, lutR, grp, groups, count, warp, lane); break;
+  if (MODE == AA_EDGE) {   // pairs: the parent is always a CLV, the child a CLV or a tip
+    switch (lk * 3 + rk) {
+      NRX_AA_CASE(NRX_CLV, NRX_CLV) NRX_AA_CASE(NRX_CLV, NRX_TIP)
+      default: break;
+    }
+    return;
+  }
   switch (lk * 3 + rk) {
     NRX_AA_CASE(NRX_CLV, NRX_CLV) NRX_AA_CASE(NRX_CLV, NRX_TIP) NRX_AA_CASE(NRX_TIP, NRX_CLV)
     NRX_AA_CASE(NRX_CLV, NRX_NONE) NRX_AA_CASE(NRX_NONE, NRX_CLV) NRX_AA_CASE(NRX_TIP, NRX_NONE) NRX_AA_CASE(NRX_NONE, NRX_TIP)

@@ -137,6 +137,13 @@ int nrx_supports_fused_lnl(nrx_engine *e);
  * pattern weight and the sum over the per-site likelihood terms the K2 epilogue wrote (16 B per site read instead of
  * the whole CLV) -> out[n][nparts], bit-identical to nrx_tree_lnl on the same slots. */
 int nrx_tree_lnl_fused(nrx_engine *e, uint32_t plan_id, const uint32_t *slots, uint32_t n, double *out);
+/* nrx_plan_run + nrx_tree_lnl_fused_async in one call: the whole evaluation of a plan (all CLVs of the traversal + the n marked
+ * trees' root lnLs; result collected with nrx_result_wait).  Small alignments are launch-latency-bound (one launch per
+ * dependency level), so when the plan has a "tile-walk" form — every partition on the 4-state x 4-category kernels, the live
+ * CLVs of a depth-first walk fit one block's shared memory — this is ONE launch: a block owns a tile of patterns and walks the
+ * whole plan for it, children from shared memory, every CLV still written to its HBM slot (k_walk_dna4).  env NRX_WALK=0 / 1 / 2:
+ * never / whenever possible / when possible and at most NRX_WALK_TILES tiles (default). */
+int nrx_plan_evaluate_async(nrx_engine *e, uint32_t plan_id, const uint32_t *slots, uint32_t n);
 int nrx_plan_destroy(nrx_engine *e, uint32_t plan_id);
 
 /* K3: per-tree per-partition root lnL, out[n][nparts] (LOCAL sums: the caller all-reduces across ranks).

@@ -30,6 +30,7 @@ struct PlanCache {
   // fused K3: the root displayed trees' slots at recording time; their producing ops carry lnl_item = index + 1
   bool fused = false;
   std::vector<uint32_t> lnl_slots;
+  bool run_pending = false;   // a replay whose device launches are issued together with the root lnLs (nrx_plan_evaluate_async)
 };
 
 AnnotatedNetwork::~AnnotatedNetwork() {
@@ -576,11 +577,18 @@ static void treeLoglikelihoodsBegin(AnnotatedNetwork &ann, Node *actRoot, bool r
   if (slots_out) *slots_out = slots;
   if (!slots.empty()) {
     // after a plan replay whose ops carried lnl marks for exactly these trees, K2 has already written the per-site lnLs
-    if (replayed && ann.plan->fused && ann.plan->on_device && slots == ann.plan->lnl_slots && nrx_supports_fused_lnl(ann.engine))
-      engineCheck(nrx_tree_lnl_fused_async(ann.engine, ann.plan->engine_plan, slots.data(), (uint32_t)slots.size()), "nrx_tree_lnl_fused");
-    else
+    if (replayed && ann.plan->fused && ann.plan->on_device && slots == ann.plan->lnl_slots && nrx_supports_fused_lnl(ann.engine)) {
+      if (ann.plan->run_pending) {   // CLVs + root lnLs of the replayed plan in one engine call (one launch when the plan tile-walks)
+        ann.plan->run_pending = false;
+        engineCheck(nrx_plan_evaluate_async(ann.engine, ann.plan->engine_plan, slots.data(), (uint32_t)slots.size()), "nrx_plan_evaluate");
+      } else
+        engineCheck(nrx_tree_lnl_fused_async(ann.engine, ann.plan->engine_plan, slots.data(), (uint32_t)slots.size()), "nrx_tree_lnl_fused");
+    } else {
+      if (ann.plan && ann.plan->run_pending) { ann.plan->run_pending = false; engineCheck(nrx_plan_run(ann.engine, ann.plan->engine_plan), "nrx_plan_run"); }
       engineCheck(nrx_tree_lnl_async(ann.engine, slots.data(), (uint32_t)slots.size()), "nrx_tree_lnl");
+    }
   }
+  if (ann.plan && ann.plan->run_pending) { ann.plan->run_pending = false; engineCheck(nrx_plan_run(ann.engine, ann.plan->engine_plan), "nrx_plan_run"); }
   ann.pending_root = actRoot->clv_index;
   ann.pending_trees = which;
   ann.pending_eval = true;
@@ -665,7 +673,10 @@ static void replayPlan(AnnotatedNetwork &ann) {
   }
   uint64_t local_sites = 0;
   for (const PartitionModel &m : ann.fake_treeinfo->partitions) local_sites += m.sites;
-  if (pc.on_device) engineCheck(nrx_plan_run(ann.engine, pc.engine_plan), "nrx_plan_run");
+  if (pc.on_device) {
+    if (pc.fused) pc.run_pending = true;   // treeLoglikelihoodsBegin, called next, issues it together with the root lnLs
+    else engineCheck(nrx_plan_run(ann.engine, pc.engine_plan), "nrx_plan_run");
+  }
   for (const std::vector<nrx_op> &b : pc.batches) {
     if (!pc.on_device) engineCheck(nrx_update_clvs(ann.engine, b.data(), (uint32_t)b.size()), "nrx_update_clvs");
     ann.clv_site_updates += local_sites * b.size();

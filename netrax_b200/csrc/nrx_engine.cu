@@ -32,6 +32,7 @@ struct Part {
   uint32_t sp = 0, pat_pad = 0;  // pat_pad: patterns rounded up to a whole K2 tile (bulk copies always move full tiles)
   size_t clv_entries = 0, pmat_entries = 0;
   double *pmat = nullptr;
+  double *pmat_pad = nullptr;   // DNA 4x4 partitions: P-matrices at k_walk_dna4's shared-memory pitch (written by K1 alongside pmat)
   double *tiplut = nullptr;  // 20-state partitions only
   bool invariant_stale = false;  // tips were replaced through nrx_set_tipchars_u8 while pinv == 0: recompute before +I is switched on
   double pinv = 0.0;        // proportion of invariant sites (+I)
@@ -55,6 +56,9 @@ struct Part {
   double **d_sumtable = nullptr;
   uint32_t table_cap = 0, st_cap = 0;
   bool model_set = false, tips_set = false;
+  std::vector<double> h_len;        // current branch length per edge (-1: never set) — the tile walk recomputes P-matrices from these
+  std::vector<char> pend;           // edges whose P-matrix update is deferred (see nrx_update_pmatrices)
+  uint32_t npend = 0;
   uint32_t tip_codes = 0;  // distinct tip codes in use
 };
 
@@ -108,6 +112,11 @@ struct EnginePlan {
   cudaGraphExec_t exec[2] = {nullptr, nullptr};   // [0] latency geometry, [1] throughput geometry (nrx_set_throughput_mode)
   unsigned long long updates = 0, bytes = 0, cbytes = 0;
   uint32_t lnl_items = 0;    // number of ops carrying an lnl_item mark (fused K3)
+  // tile-walk form of the plan (k_walk_dna4): the ops in a depth-first order with shared-memory buffer assignments
+  nrx_walk_op *d_walk = nullptr;
+  uint32_t walk_nops = 0, walk_nbuf = 0;
+  size_t walk_smem = 0;
+  unsigned long long walk_cbytes = 0;   // compulsory HBM bytes of one walk: every parent CLV + scaler written, every tip row read
 };
 
 struct nrx_engine {
@@ -133,6 +142,9 @@ struct nrx_engine {
   size_t result_cap = 0;
   uint32_t *d_tickets = nullptr;   // one self-resetting ticket counter per reduction output (item, partition): fused second stage
   bool fuse_reduce = true;         // env NRX_FUSE_REDUCE=0: separate k_reduce_partials launch (A/B)
+  bool defer_pmat = false;         // P-matrix updates are deferred until a launch needs them: the tile walk computes them itself (one launch per evaluation)
+  int walk_mode = 2;               // env NRX_WALK: 0 never, 1 whenever the plan has a tile-walk form, 2 (default) when it has one and the launch is small enough
+  uint32_t walk_max_tiles = 0;     // mode 2: use the walk up to this many tiles per partition (env NRX_WALK_TILES; default set in nrx_engine_create)
   double *d_persite = nullptr;
   size_t persite_cap = 0;
   unsigned long long launches = 0;
@@ -251,7 +263,7 @@ PartView make_view(const Part &p, uint32_t index) {
   PartView v{};
   v.states = p.d.states; v.sp = p.sp; v.cats = p.d.rate_cats; v.patterns = p.d.patterns; v.tips = p.d.tips; v.edges = p.d.edges;
   v.part_index = index; v.tip_pitch = p.pat_pad; v.tip_codes = p.tip_codes;
-  v.pmat = p.pmat; v.tipchars = p.tipchars; v.tipmap = p.tipmap; v.weights = p.weights;
+  v.pmat = p.pmat; v.pmat_pad = p.pmat_pad; v.tipchars = p.tipchars; v.tipmap = p.tipmap; v.weights = p.weights;
   v.freqs = p.freqs; v.eigenvecs = p.eigenvecs; v.inv_eigenvecs = p.inv_eigenvecs; v.eigenvals = p.eigenvals;
   v.rates = p.rates; v.rate_weights = p.rate_weights;
   v.clv = p.d_clv; v.scaler = p.d_scaler; v.sumtable = p.d_sumtable; v.diagp = p.diagp; v.tiplut = p.tiplut;
@@ -364,6 +376,8 @@ uint32_t class_tip_codes(const nrx_engine *e, const ShapeClass &c) {
 
 extern "C" {
 
+static int flush_pmatrices(nrx_engine *e);
+
 const char *nrx_last_error(void) { return g_err.c_str(); }
 
 int nrx_device_count(void) {
@@ -390,6 +404,8 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
   if (const char *v = std::getenv("NRX_GRAPH")) e->use_graphs = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_PDL")) e->use_pdl = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_FUSE_REDUCE")) e->fuse_reduce = std::atoi(v) != 0;
+  if (const char *v = std::getenv("NRX_WALK")) e->walk_mode = std::atoi(v);
+  if (const char *v = std::getenv("NRX_WALK_TILES")) e->walk_max_tiles = (uint32_t)std::max(0, std::atoi(v));
   if (const char *v = std::getenv("NRX_K2_NT")) e->k2_nt = std::atoi(v) == 1 ? 1u : 2u;
   if (const char *v = std::getenv("NRX_AA")) { e->aa_generic = std::string(v) == "generic"; if (std::string(v) == "v2") e->aa_v1 = false; if (std::string(v) == "v1") e->aa_v1 = true; }
   if (const char *v = std::getenv("NRX_AA_PIPE")) e->aa_pipe = std::atoi(v) != 0;
@@ -401,6 +417,10 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     e->sm_count = sms;
     if (!std::getenv("NRX_K2_BLOCKS")) e->k2_blocks = 16u * (uint32_t)sms;
+    // measured (profiles/r2r_tile_walk.md): 10 k patterns (313 tiles) 73 vs 89 us per evaluation; at 100 k patterns the walk's serial
+    // op chain per block loses 3x to the bandwidth-bound level-by-level kernels -> only while the launch is latency-bound
+    if (!std::getenv("NRX_WALK_TILES")) e->walk_max_tiles = 4u * (uint32_t)sms;
+    if (!cuda_ok(cudaFuncSetAttribute(k_walk_dna4, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024), "cudaFuncSetAttribute")) { delete e; return nullptr; }
     const int aa_smem = (int)(sizeof(AaSmem) + 2 * AA_LUT_CODES * 80 * sizeof(double));
     if (!cuda_ok(cudaFuncSetAttribute(k_aa20_dmma<AA_CLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa_smem), "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(k_aa20_dmma<AA_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa_smem), "cudaFuncSetAttribute") ||
@@ -431,6 +451,9 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
               cuda_ok(cudaMalloc((void **)&p.weights, std::max<size_t>(1, p.pat_pad) * sizeof(uint32_t)), "cudaMalloc weights") &&
               cuda_ok(cudaMalloc((void **)&p.model, model_doubles * sizeof(double)), "cudaMalloc model") &&
               cuda_ok(cudaMalloc((void **)&p.invariant, std::max<size_t>(1, p.pat_pad) * sizeof(int)), "cudaMalloc invariant");
+    if (ok && p.d.states == 4 && p.d.rate_cats == 4)
+      ok = cuda_ok(cudaMalloc((void **)&p.pmat_pad, std::max<size_t>(1, (size_t)p.d.edges * WALK_PE) * sizeof(double)), "cudaMalloc pmat_pad") &&
+           cuda_ok(cudaMemset(p.pmat_pad, 0, std::max<size_t>(1, (size_t)p.d.edges * WALK_PE) * sizeof(double)), "cudaMemset pmat_pad");
     if (ok && p.d.states == 20 && p.d.rate_cats == 4)
       ok = cuda_ok(cudaMalloc((void **)&p.tiplut, (size_t)p.d.edges * AA_LUT_CODES * 80 * sizeof(double)), "cudaMalloc tiplut") &&
            cuda_ok(cudaMalloc((void **)&p.summat, 800 * sizeof(double)), "cudaMalloc summat") &&
@@ -448,6 +471,8 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
       if (c.states == p.d.states && c.cats == p.d.rate_cats) { c.parts.push_back(i); c.max_patterns = std::max(c.max_patterns, p.d.patterns); found = true; }
     if (!found) { ShapeClass c; c.states = p.d.states; c.cats = p.d.rate_cats; c.parts = {i}; c.max_patterns = p.d.patterns; e->classes.push_back(c); }
   }
+  e->defer_pmat = e->walk_mode != 0 && e->classes.size() == 1 && e->classes[0].states == 4 && e->classes[0].cats == 4 && !std::getenv("NRX_NO_DEFER_PMAT");
+  for (Part &p : e->parts) { p.h_len.assign(p.d.edges, -1.0); p.pend.assign(p.d.edges, 0); }
   return e;
 }
 
@@ -456,9 +481,9 @@ void nrx_engine_destroy(nrx_engine *e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->comm && nccl().ok) nccl().CommDestroy(e->comm);
-  for (EnginePlan &pl : e->plans) { for (cudaGraphExec_t &x : pl.exec) if (x) cudaGraphExecDestroy(x); cudaFree(pl.d_ops); }
+  for (EnginePlan &pl : e->plans) { for (cudaGraphExec_t &x : pl.exec) if (x) cudaGraphExecDestroy(x); cudaFree(pl.d_ops); cudaFree(pl.d_walk); }
   for (Part &p : e->parts) {
-    cudaFree(p.invariant); cudaFree(p.pmat); cudaFree(p.tiplut); cudaFree(p.summat); cudaFree(p.sumlut); cudaFree(p.tipchars); cudaFree(p.tipmap); cudaFree(p.weights); cudaFree(p.model);
+    cudaFree(p.invariant); cudaFree(p.pmat); cudaFree(p.pmat_pad); cudaFree(p.tiplut); cudaFree(p.summat); cudaFree(p.sumlut); cudaFree(p.tipchars); cudaFree(p.tipmap); cudaFree(p.weights); cudaFree(p.model);
     for (void *m : p.slot_mem) cudaFree(m);
     for (double *m : p.h_sumtable) cudaFree(m);
     cudaFree(p.d_clv); cudaFree(p.d_scaler); cudaFree(p.d_sumtable);
@@ -550,6 +575,7 @@ int nrx_set_model_mixture(nrx_engine *e, uint32_t pi, uint32_t nmodels, const ui
   if (!check_part(e, pi)) return 0;
   if (!(prop_invar >= 0.0 && prop_invar < 1.0)) { g_err = "Invalid proportion of invariant sites"; return 0; }   // pll_update_invariant_sites_proportion
   CK(cudaSetDevice(e->device));
+  if (!flush_pmatrices(e)) return 0;
   Part &p = e->parts[pi];
   const size_t S = p.d.states, SP = p.sp, C = p.d.rate_cats, M = nmodels;
   if (M < 1 || M > 16) { g_err = "nrx_set_model_mixture: 1..16 rate matrices"; return 0; }
@@ -599,16 +625,9 @@ int nrx_set_model(nrx_engine *e, uint32_t pi, const double *freqs, const double 
   return nrx_set_model_mixture(e, pi, 1, nullptr, freqs, eigenvecs, inv_eigenvecs, eigenvals, rates, rate_weights, prop_invar);
 }
 
-int nrx_update_pmatrices(nrx_engine *e, uint32_t pi, uint32_t n, const uint32_t *edge_idx, const double *brlen) {
-  if (!check_part(e, pi)) return 0;
-  if (n == 0) return 1;
-  CK(cudaSetDevice(e->device));
+/* K1 launch for n edges of partition pi (inputs through the staging ring) */
+static int launch_pmatrices(nrx_engine *e, uint32_t pi, uint32_t n, const uint32_t *edge_idx, const double *brlen) {
   Part &p = e->parts[pi];
-  if (!p.model_set) { g_err = "nrx_update_pmatrices: model not set"; return 0; }
-  for (uint32_t i = 0; i < n; ++i) {
-    if (edge_idx[i] >= p.d.edges) { g_err = "nrx_update_pmatrices: edge index out of range"; return 0; }
-    if (!(brlen[i] >= 0.0)) { g_err = "nrx_update_pmatrices: negative branch length"; return 0; }
-  }
   uint32_t *d_idx; double *d_len;
   if (!upload(e, edge_idx, n, &d_idx) || !upload(e, brlen, n, &d_len)) return 0;
   PartView v = make_view(p, pi);
@@ -621,10 +640,48 @@ int nrx_update_pmatrices(nrx_engine *e, uint32_t pi, uint32_t n, const uint32_t 
   prof_end(e, ev0, ev1, 1, n, (unsigned long long)n * p.pmat_entries * 8, NRX_PROF_K1);
   return 1;
 }
+/* issue the deferred P-matrix updates (every entry point that reads P-matrices calls this first) */
+static int flush_pmatrices(nrx_engine *e) {
+  for (uint32_t pi = 0; pi < e->parts.size(); ++pi) {
+    Part &p = e->parts[pi];
+    if (!p.npend) continue;
+    std::vector<uint32_t> idx;
+    std::vector<double> len;
+    for (uint32_t m = 0; m < p.d.edges; ++m) if (p.pend[m]) { idx.push_back(m); len.push_back(p.h_len[m]); p.pend[m] = 0; }
+    p.npend = 0;
+    if (!launch_pmatrices(e, pi, (uint32_t)idx.size(), idx.data(), len.data())) return 0;
+  }
+  return 1;
+}
+
+int nrx_update_pmatrices(nrx_engine *e, uint32_t pi, uint32_t n, const uint32_t *edge_idx, const double *brlen) {
+  if (!check_part(e, pi)) return 0;
+  if (n == 0) return 1;
+  CK(cudaSetDevice(e->device));
+  Part &p = e->parts[pi];
+  if (!p.model_set) { g_err = "nrx_update_pmatrices: model not set"; return 0; }
+  for (uint32_t i = 0; i < n; ++i) {
+    if (edge_idx[i] >= p.d.edges) { g_err = "nrx_update_pmatrices: edge index out of range"; return 0; }
+    if (!(brlen[i] >= 0.0)) { g_err = "nrx_update_pmatrices: negative branch length"; return 0; }
+  }
+  for (uint32_t i = 0; i < n; ++i) p.h_len[edge_idx[i]] = brlen[i];
+  if (e->defer_pmat && p.pinv == 0.0 && p.nmodels == 1) {
+    // deferred: a full evaluation that tile-walks computes the P-matrices inside its one launch (nrx_plan_evaluate_async);
+    // anything else that reads P-matrices flushes the pending edges through K1 first
+    for (uint32_t i = 0; i < n; ++i) if (!p.pend[edge_idx[i]]) { p.pend[edge_idx[i]] = 1; p.npend++; }
+    return 1;
+  }
+  if (p.npend) {   // keep the order of updates: an edge that is pending and updated again here must end with the newer length
+    for (uint32_t i = 0; i < n; ++i) if (p.pend[edge_idx[i]]) { p.pend[edge_idx[i]] = 0; p.npend--; }
+    if (!flush_pmatrices(e)) return 0;
+  }
+  return launch_pmatrices(e, pi, n, edge_idx, brlen);
+}
 
 int nrx_get_pmatrix(nrx_engine *e, uint32_t pi, uint32_t edge, double *out) {
   if (!check_part(e, pi)) return 0;
   CK(cudaSetDevice(e->device));
+  if (!flush_pmatrices(e)) return 0;
   Part &p = e->parts[pi];
   if (edge >= p.d.edges) { g_err = "edge index out of range"; return 0; }
   CK(cudaStreamSynchronize(e->stream));
@@ -635,10 +692,13 @@ int nrx_get_pmatrix(nrx_engine *e, uint32_t pi, uint32_t edge, double *out) {
 int nrx_set_pmatrix(nrx_engine *e, uint32_t pi, uint32_t edge, const double *in) {
   if (!check_part(e, pi)) return 0;
   CK(cudaSetDevice(e->device));
+  if (!flush_pmatrices(e)) return 0;
   Part &p = e->parts[pi];
   if (edge >= p.d.edges) { g_err = "edge index out of range"; return 0; }
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaMemcpy(p.pmat + (size_t)edge * p.pmat_entries, in, p.pmat_entries * sizeof(double), cudaMemcpyHostToDevice));
+  if (p.pmat_pad)   // keep the tile-walk copy in step (test hook: one 2-D copy, 4 category blocks of 16 doubles at pitch PCAT)
+    CK(cudaMemcpy2D(p.pmat_pad + (size_t)edge * WALK_PE, PCAT * sizeof(double), in, 16 * sizeof(double), 16 * sizeof(double), 4, cudaMemcpyHostToDevice));
   return refresh_tiplut(e, pi, &edge, 1);
 }
 
@@ -908,6 +968,7 @@ int nrx_update_clvs(nrx_engine *e, const nrx_op *ops, uint32_t nops) {
   if (!e) { g_err = "null engine"; return 0; }
   if (nops == 0) return 1;
   CK(cudaSetDevice(e->device));
+  if (!flush_pmatrices(e)) return 0;
   unsigned long long updates = 0, bytes = 0, cbytes = 0;
   if (!check_ops(e, ops, nops, &updates, &bytes, &cbytes)) return 0;
   if (!refresh_views(e)) return 0;
@@ -926,6 +987,7 @@ int nrx_update_pseudo_clvs(nrx_engine *e, const nrx_pseudo_op *ops, uint32_t nop
   if (!e) { g_err = "null engine"; return 0; }
   if (nops == 0) return 1;
   CK(cudaSetDevice(e->device));
+  if (!flush_pmatrices(e)) return 0;
   unsigned long long updates = 0, bytes = 0;
   for (uint32_t i = 0; i < nops; ++i) {   // same operand rules as nrx_update_clvs, except that both operands may be absent
     const nrx_pseudo_op &o = ops[i];
@@ -956,6 +1018,85 @@ int nrx_update_pseudo_clvs(nrx_engine *e, const nrx_pseudo_op *ops, uint32_t nop
     CK(cudaGetLastError());
   }
   prof_end(e, ev0, ev1, e->classes.size(), updates, bytes);
+  return 1;
+}
+
+/* Tile-walk form of a plan (k_walk_dna4): (1) order the ops depth-first from the CLVs nobody consumes (the root displayed trees),
+ * children before parents, so that a CLV is consumed soon after it is produced; (2) run a linear-scan allocation of
+ * shared-memory buffers over that order — a CLV needs a buffer from its op until its last consumer; (3) accept the form if
+ * P-matrices + buffers + program + tip codes fit one block's shared memory.  Leaves pl.d_walk == nullptr when the plan has no
+ * such form (other partition shapes, +I, a CLV produced twice or not at all, too many live CLVs): the level-by-level graph runs. */
+static int build_walk_program(nrx_engine *e, EnginePlan &pl, const nrx_op *ops, size_t total) {
+  if (e->classes.size() != 1 || e->classes[0].states != 4 || e->classes[0].cats != 4 || !nrx_supports_fused_lnl(e) || total == 0 || total > 60000) return 1;
+  std::map<uint32_t, uint32_t> producer;   // slot -> op
+  for (size_t i = 0; i < total; ++i) if (!producer.emplace(ops[i].parent_slot, (uint32_t)i).second) return 1;
+  std::vector<uint32_t> uses(total, 0);
+  for (size_t i = 0; i < total; ++i) {
+    const uint32_t kinds[2] = {ops[i].left_kind, ops[i].right_kind}, idx[2] = {ops[i].left_idx, ops[i].right_idx};
+    for (int c = 0; c < 2; ++c)
+      if (kinds[c] == NRX_CLV) {
+        auto it = producer.find(idx[c]);
+        if (it == producer.end() || it->second >= i) return 1;   // child not produced by this traversal (or not before its consumer)
+        uses[it->second]++;
+      }
+  }
+  // depth-first emission (explicit stack), roots in plan order
+  std::vector<uint32_t> order;
+  std::vector<char> done(total, 0);
+  for (size_t r = 0; r < total; ++r) {
+    if (uses[r] != 0 || done[r]) continue;
+    std::vector<std::pair<uint32_t, int>> stack{{(uint32_t)r, 0}};
+    while (!stack.empty()) {
+      auto &[op, stage] = stack.back();
+      const uint32_t kinds[2] = {ops[op].left_kind, ops[op].right_kind}, idx[2] = {ops[op].left_idx, ops[op].right_idx};
+      if (stage < 2) {
+        const int c = stage++;
+        if (kinds[c] == NRX_CLV) { const uint32_t q = producer[idx[c]]; if (!done[q]) { done[q] = 1; stack.push_back({q, 0}); } }
+      } else {
+        order.push_back(op);
+        stack.pop_back();
+      }
+    }
+    done[r] = 1;
+  }
+  if (order.size() != total) return 1;
+  // linear-scan buffer allocation
+  std::vector<uint16_t> buf(total, (uint16_t)WALK_NOBUF);
+  std::vector<uint32_t> left(uses);
+  std::vector<uint16_t> free_list;
+  uint32_t nbuf = 0;
+  std::vector<nrx_walk_op> prog(total);
+  std::vector<char> tip_used;
+  for (size_t k = 0; k < total; ++k) {
+    const nrx_op &o = ops[order[k]];
+    nrx_walk_op w{};
+    w.parent_slot = o.parent_slot;
+    w.kinds = (uint16_t)(o.left_kind | (o.right_kind << 2));
+    w.left_idx = o.left_idx; w.right_idx = o.right_idx; w.left_edge = o.left_edge; w.right_edge = o.right_edge;
+    w.lnl_item = o.lnl_item;
+    w.lbuf = w.rbuf = (uint16_t)WALK_NOBUF;
+    if (o.left_kind == NRX_CLV) w.lbuf = buf[producer[o.left_idx]];
+    if (o.right_kind == NRX_CLV) w.rbuf = buf[producer[o.right_idx]];
+    if (uses[order[k]] > 0) {   // the parent gets its buffer BEFORE the children's are released: no aliasing within an op
+      if (free_list.empty()) { if (nbuf >= 4096) return 1; free_list.push_back((uint16_t)nbuf++); }
+      std::sort(free_list.begin(), free_list.end(), std::greater<uint16_t>());
+      buf[order[k]] = free_list.back(); free_list.pop_back();
+    }
+    w.pbuf = buf[order[k]];
+    const uint32_t kinds[2] = {o.left_kind, o.right_kind}, idx[2] = {o.left_idx, o.right_idx};
+    for (int c = 0; c < 2; ++c)
+      if (kinds[c] == NRX_CLV) { const uint32_t q = producer[idx[c]]; if (--left[q] == 0) free_list.push_back(buf[q]); }
+    prog[k] = w;
+  }
+  const Part &p0 = e->parts[e->classes[0].parts[0]];
+  for (const Part &p : e->parts) if (p.d.edges != p0.d.edges || p.d.tips != p0.d.tips) return 1;
+  const size_t smem = (size_t)p0.d.edges * WALK_PE * 8 + (size_t)nbuf * (WALK_TP * 128 + WALK_TP * 4) + (size_t)pl.lnl_items * (WALK_THREADS / 32) * 8 +
+                      total * (sizeof(nrx_walk_op) + 16) + (size_t)p0.d.tips * WALK_TP;
+  if (smem > 226 * 1024) return 1;
+  CK(cudaMalloc((void **)&pl.d_walk, total * sizeof(nrx_walk_op)));
+  CK(cudaMemcpy(pl.d_walk, prog.data(), total * sizeof(nrx_walk_op), cudaMemcpyHostToDevice));
+  pl.walk_nops = (uint32_t)total; pl.walk_nbuf = nbuf; pl.walk_smem = (smem + 127) & ~(size_t)127;
+  for (const Part &p : e->parts) pl.walk_cbytes += (unsigned long long)p.d.patterns * (total * 132ull + p.d.tips);
   return 1;
 }
 
@@ -996,6 +1137,7 @@ int nrx_plan_create(nrx_engine *e, const nrx_op *ops, const uint32_t *batch_size
       for (EnginePlan &o : e->plans) for (cudaGraphExec_t &x : o.exec) if (x) { cudaGraphExecDestroy(x); x = nullptr; }
     }
   }
+  if (pl.lnl_items && e->walk_mode != 0 && !build_walk_program(e, pl, ops, total)) return 0;
   pl.alive = true;
   e->plans.push_back(pl);
   *plan_id = (uint32_t)e->plans.size() - 1;
@@ -1005,6 +1147,7 @@ int nrx_plan_create(nrx_engine *e, const nrx_op *ops, const uint32_t *batch_size
 int nrx_plan_run(nrx_engine *e, uint32_t plan_id) {
   if (!e || plan_id >= e->plans.size() || !e->plans[plan_id].alive) { g_err = "nrx_plan_run: no such plan"; return 0; }
   CK(cudaSetDevice(e->device));
+  if (!flush_pmatrices(e)) return 0;
   EnginePlan &pl = e->plans[plan_id];
   if (pl.sizes.empty()) return 1;
   if (!refresh_views(e)) return 0;
@@ -1061,6 +1204,7 @@ int nrx_plan_destroy(nrx_engine *e, uint32_t plan_id) {
   CK(cudaStreamSynchronize(e->stream));
   for (cudaGraphExec_t &x : pl.exec) if (x) cudaGraphExecDestroy(x);
   cudaFree(pl.d_ops);
+  cudaFree(pl.d_walk);
   pl = EnginePlan();
   return 1;
 }
@@ -1194,6 +1338,44 @@ int nrx_tree_lnl_fused_async(nrx_engine *e, uint32_t plan_id, const uint32_t *sl
   return tree_lnl_fused_impl(e, plan_id, slots, n, nullptr, true);
 }
 
+/* Full evaluation of a plan whose root trees carry lnl marks: every CLV of the traversal + the n per-tree root lnLs, result
+ * enqueued like nrx_tree_lnl_fused_async.  One k_walk_dna4 launch when the plan has a tile-walk form and the launch is small
+ * enough to be latency-bound (or NRX_WALK=1), otherwise nrx_plan_run + nrx_tree_lnl_fused_async. */
+int nrx_plan_evaluate_async(nrx_engine *e, uint32_t plan_id, const uint32_t *slots, uint32_t n) {
+  if (!e || plan_id >= e->plans.size() || !e->plans[plan_id].alive) { g_err = "nrx_plan_evaluate: no such plan"; return 0; }
+  EnginePlan &pl = e->plans[plan_id];
+  const uint32_t ntiles = (e->max_patterns + WALK_TP - 1) / WALK_TP;
+  const bool walk = pl.d_walk && n == pl.lnl_items && n > 0 && !e->throughput_mode && e->fuse_reduce &&
+                    (e->walk_mode == 1 || (e->walk_mode == 2 && (uint64_t)ntiles * e->parts.size() <= e->walk_max_tiles));
+  if (!walk) return nrx_plan_run(e, plan_id) && nrx_tree_lnl_fused_async(e, plan_id, slots, n);
+  CK(cudaSetDevice(e->device));
+  const uint32_t P = (uint32_t)e->parts.size();
+  if (!ensure_result(e, (size_t)n * P, (size_t)n * P * ntiles) || !refresh_views(e)) return 0;
+  for (uint32_t i = 0; i < n; ++i) if (slots[i] >= e->nslots) { g_err = "nrx_plan_evaluate: slot out of range"; return 0; }
+  const ShapeClass &c = e->classes[0];
+  // deferred P-matrix updates: the walk computes ALL P-matrices itself from the current branch lengths (K1 fused into the launch)
+  int compute_p = 0;
+  double *d_len = nullptr;
+  {
+    bool pending = false, complete = true;
+    for (const Part &p : e->parts) { pending = pending || p.npend; for (double t : p.h_len) complete = complete && t >= 0.0; }
+    if (pending && complete && (size_t)pl.walk_nbuf * WALK_TP * 16 >= (size_t)e->parts[0].d.edges * 16) {
+      std::vector<double> lens;
+      for (Part &p : e->parts) { lens.insert(lens.end(), p.h_len.begin(), p.h_len.end()); std::fill(p.pend.begin(), p.pend.end(), 0); p.npend = 0; }
+      if (!upload(e, lens.data(), lens.size(), &d_len)) return 0;
+      compute_p = 1;
+    } else if (pending && !flush_pmatrices(e)) return 0;
+  }
+  cudaEvent_t ev0, ev1;
+  prof_begin(e, &ev0, &ev1);
+  k_walk_dna4<<<dim3(ntiles, 1, (uint32_t)c.parts.size()), WALK_THREADS, pl.walk_smem, e->stream>>>(
+      c.d_views, pl.d_walk, pl.walk_nops, pl.walk_nbuf, n, std::log(SCALE_THRESHOLD), e->d_partial, P, e->d_result, e->d_tickets, compute_p, d_len);
+  e->launches++;
+  CK(cudaGetLastError());
+  prof_end(e, ev0, ev1, 1, pl.updates, pl.bytes, NRX_PROF_K2, pl.walk_cbytes);
+  return enqueue_reduction(e, n * P, ntiles, true);
+}
+
 static int check_pairs(nrx_engine *e, const nrx_pair *pairs, uint32_t n, const char *who) {
   for (uint32_t i = 0; i < n; ++i) {
     const nrx_pair &q = pairs[i];
@@ -1238,6 +1420,7 @@ int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n
   if (!e) { g_err = "null engine"; return 0; }
   if (n == 0) return 1;
   CK(cudaSetDevice(e->device));
+  if (!flush_pmatrices(e)) return 0;
   if (!check_pairs(e, pairs, n, "nrx_edge_lnl")) return 0;
   for (const Part &p : e->parts) if (edge >= p.d.edges) { g_err = "nrx_edge_lnl: edge out of range"; return 0; }
   const uint32_t P = (uint32_t)e->parts.size();
@@ -1407,6 +1590,7 @@ int nrx_read_sumtable(nrx_engine *e, uint32_t pi, uint32_t st, double *out) {
 int nrx_sync(nrx_engine *e) {
   if (!e) { g_err = "null engine"; return 0; }
   CK(cudaSetDevice(e->device));
+  if (!flush_pmatrices(e)) return 0;
   CK(cudaStreamSynchronize(e->stream));
   return 1;
 }

@@ -42,6 +42,7 @@ struct PartView {
   const double *summat;      // 20-state partitions: K5 operand matrices [2][20][20]: A_L[j][k] = pi_k Vinv[k][j], A_R[j][k] = V[j][k]
   double pinv;               // proportion of invariant sites (+I, pll_partition_t::prop_invar); 0 = none
   const int *invariant;      // [patterns] state index of an invariant pattern (pll_update_invariant_sites, LIBPLL/models.c:651-760), else -1
+  double *pmat_pad;          // 4-state x 4-category partitions: the same P-matrices at the bank-conflict-free pitch of k_walk_dna4's shared-memory table, [edges][4][PCAT]
   const double *sumlut;      // 20-state partitions: K5 tip table [AA_LUT_CODES][cats*20]: sum_{k in code} pi_k Vinv[k][j], replicated per category
   /* Mixtures with one rate matrix per category (LG4M / LG4X: raxml-ng's ratecat_submodels = libpll's params_indices[c],
    * src/RaxmlWrapper.cpp:199-203): freqs / eigenvecs / inv_eigenvecs / eigenvals hold `nmodels` blocks back to back (strides sp,
@@ -150,6 +151,7 @@ __global__ void k_pmatrix(PartView pv, double *pmat_out, const uint32_t *edge_id
       }
     }
     out[i] = v;
+    if (pv.pmat_pad && S == 4 && C == 4) pv.pmat_pad[(size_t)edge * 72 + c * 18 + j * 4 + k] = v;   // 72 = 4 * PCAT (k_walk_dna4)
   }
 }
 
@@ -578,6 +580,237 @@ __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe2(const PartView *__r
     default: break;
   }
 #undef NRX_PIPE_CASE
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole-evaluation "tile walk" (round 2), DNA 4x4: ONE launch computes every CLV of a traversal plan AND the per-tree root
+ * lnLs.  The post-order dependencies of a likelihood traversal are per PATTERN: a block that owns a tile of WALK_TP patterns can
+ * run the whole plan for it from the tips to the root without ever synchronising with another block.  So, instead of one
+ * launch per dependency level (config 1: 12 dependent launches of ~3 us each = launch-latency-bound at 90-107 us per evaluation,
+ * profiles/r2b_*), each block walks the op list in a depth-first order chosen by the host (nrx_plan_create) such that the CLVs
+ * still needed later stay in a small set of shared-memory buffers:
+ *   - children are read from SHARED MEMORY (the parent written a few ops earlier by the same block), never from HBM;
+ *   - every CLV + scaler is still streamed out to its HBM slot (incremental updates, branch-length optimisation and the
+ *     parity read-back use the slots exactly as before) — HBM traffic of an evaluation drops from (children read + parents
+ *     written) to (parents written + tips read);
+ *   - the P-matrices of all edges sit in shared memory (bulk-copied from the array K1 wrote), tip codes of the tile too;
+ *   - ops marked as root displayed trees finish their per-site lnL in place (log, scaler term, pattern weight) and the block
+ *     keeps one partial sum per tree; the last block (ticket) adds the partials of all tiles in a fixed order.
+ * Arithmetic per (pattern, category) is the same instruction sequence as k_clv_dna4_pipe2 (P rows in registers per op, pairwise
+ * sums, separate multiply / add), so CLVs and scalers stay bit-identical to libpll; per-tree lnLs are summed in a different
+ * (fixed) order than k_tree_lnl_dna4's and agree with it to rounding.
+ * grid = (tiles, 1, partitions of the class); block = WALK_TP x 4 threads: thread = (pattern, rate category).
+ * ---------------------------------------------------------------------------------------------- */
+constexpr int WALK_TP = 32;                 // patterns per tile
+constexpr int WALK_THREADS = WALK_TP * 4;   // thread = (pattern, rate category): 4 CLV entries per op.  (One entry per thread —
+                                            // 512 threads — was measured: 2.7x the instructions, the op decode is paid per warp, 57 vs 40 us.)
+constexpr uint32_t WALK_NOBUF = 0xffffu;
+constexpr int WALK_PE = 4 * PCAT;           // doubles per edge in the shared-memory P table (4 categories x (16 + 2 padding))
+
+struct nrx_walk_op {   // 32 bytes; buffers index the block's shared-memory CLV buffers
+  uint32_t parent_slot;
+  uint16_t lbuf, rbuf, pbuf, kinds;   // kinds = left_kind | right_kind << 2; pbuf == WALK_NOBUF: nobody reads this CLV again
+  uint32_t left_idx, right_idx;       // tip number for NRX_TIP
+  uint32_t left_edge, right_edge;
+  uint32_t lnl_item;
+};
+
+__device__ __forceinline__ D4 walk_tip_vec(const double *__restrict__ P /* this category's 4x4 block in shared memory, 16-byte aligned */, uint32_t m) {
+  // masked row sums, same expression as build_tip_lut4 (core_partials_avx.c:1372-1400)
+  const double2 *q = reinterpret_cast<const double2 *>(P);
+  const bool m0 = m & 1, m1 = m & 2, m2 = m & 4, m3 = m & 8;
+  D4 r;
+  double2 a, b;
+  a = q[0]; b = q[1]; r.x = tree4(m0 ? a.x : 0.0, m1 ? a.y : 0.0, m2 ? b.x : 0.0, m3 ? b.y : 0.0);
+  a = q[2]; b = q[3]; r.y = tree4(m0 ? a.x : 0.0, m1 ? a.y : 0.0, m2 ? b.x : 0.0, m3 ? b.y : 0.0);
+  a = q[4]; b = q[5]; r.z = tree4(m0 ? a.x : 0.0, m1 ? a.y : 0.0, m2 ? b.x : 0.0, m3 ? b.y : 0.0);
+  a = q[6]; b = q[7]; r.w = tree4(m0 ? a.x : 0.0, m1 ? a.y : 0.0, m2 ? b.x : 0.0, m3 ? b.y : 0.0);
+  return r;
+}
+
+struct WalkCtx {
+  const double *sP; double *sClv; uint32_t *sSc; const uint8_t *sTip;
+  int tid, pl, cat; bool act; unsigned quad;
+};
+
+/* one op, specialised on the operand kinds (no predication on them inside): the thread's category block of the parent CLV
+ * (scaled if the pattern scales) and the pattern's scaler.  Expressions as in k_clv_dna4_pipe2 / build_tip_lut4. */
+template <int LK, int RK>
+__device__ __forceinline__ D4 walk_op(const WalkCtx &c, const nrx_walk_op &op, uint32_t &s_out) {
+  D4 x, y, p;
+  uint32_t s = 0;
+  if (LK == NRX_CLV) { x = matvec4(c.sP + op.left_edge * WALK_PE + c.cat * PCAT, *reinterpret_cast<const D4 *>(c.sClv + ((size_t)op.lbuf * WALK_TP * 4 + c.tid) * 4)); s += c.sSc[op.lbuf * WALK_TP + c.pl]; }
+  else if (LK == NRX_TIP) x = walk_tip_vec(c.sP + op.left_edge * WALK_PE + c.cat * PCAT, c.sTip[op.left_idx * WALK_TP + c.pl] & 15u);
+  if (RK == NRX_CLV) { y = matvec4(c.sP + op.right_edge * WALK_PE + c.cat * PCAT, *reinterpret_cast<const D4 *>(c.sClv + ((size_t)op.rbuf * WALK_TP * 4 + c.tid) * 4)); s += c.sSc[op.rbuf * WALK_TP + c.pl]; }
+  else if (RK == NRX_TIP) y = walk_tip_vec(c.sP + op.right_edge * WALK_PE + c.cat * PCAT, c.sTip[op.right_idx * WALK_TP + c.pl] & 15u);
+  if (RK == NRX_NONE) p = x;
+  else if (LK == NRX_NONE) p = y;
+  else { p.x = __dmul_rn(x.x, y.x); p.y = __dmul_rn(x.y, y.y); p.z = __dmul_rn(x.z, y.z); p.w = __dmul_rn(x.w, y.w); }
+  if (LK == NRX_TIP && RK == NRX_TIP) { s_out = 0; return p; }   // no scaling test in the tip-tip case (core_partials.c:371-470)
+  const bool small = c.act & (p.x < SCALE_THRESHOLD) & (p.y < SCALE_THRESHOLD) & (p.z < SCALE_THRESHOLD) & (p.w < SCALE_THRESHOLD);
+  const unsigned b = __ballot_sync(0xffffffffu, small);
+  const bool scale = (b & c.quad) == c.quad;
+  s_out = s + (scale ? 1u : 0u);
+  if (scale) { p.x = __dmul_rn(p.x, SCALE_FACTOR); p.y = __dmul_rn(p.y, SCALE_FACTOR); p.z = __dmul_rn(p.z, SCALE_FACTOR); p.w = __dmul_rn(p.w, SCALE_FACTOR); }
+  return p;
+}
+
+/* compute_p != 0: the branch lengths changed since K1 last ran — the block computes ALL P-matrices itself from `brlen`
+ * ([partition][edges], same arithmetic as k_pmatrix, so bit-identical) instead of copying K1's table, and the blocks of tile 0
+ * write them back to the partition's pmat / pmat_pad arrays for the kernels that run later (K4, incremental K2). */
+__global__ void __launch_bounds__(WALK_THREADS) k_walk_dna4(const PartView *__restrict__ parts, const nrx_walk_op *__restrict__ prog,
+                                                            uint32_t nops, uint32_t nbuf, uint32_t nitems, double log_thresh,
+                                                            double *__restrict__ partial /* [item][part][tiles] */, uint32_t nparts_total,
+                                                            double *__restrict__ out /* [item][part] */, uint32_t *__restrict__ counter,
+                                                            int compute_p, const double *__restrict__ brlen) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const PartView &pv = parts[blockIdx.z];
+  const uint32_t ntiles = gridDim.x;
+  const uint32_t tile = blockIdx.x;
+  const int tid = threadIdx.x, pl = tid >> 2, cat = tid & 3, lane = tid & 31, warp = tid >> 5;
+  const uint32_t edges = pv.edges, tips = pv.tips, patterns = pv.patterns;
+  // shared-memory carve-up: P-matrices | CLV buffers | scaler buffers | per-tree block sums | program | output pointers | tip codes
+  double *sP = reinterpret_cast<double *>(smem_raw);                                  // [edges][4][PCAT]: category blocks 18 doubles apart (disjoint banks)
+  double *sClv = sP + (size_t)edges * WALK_PE;                                        // [nbuf][WALK_TP * 16]
+  uint32_t *sSc = reinterpret_cast<uint32_t *>(sClv + (size_t)nbuf * WALK_TP * 16);  // [nbuf][WALK_TP]
+  double *sAcc = reinterpret_cast<double *>(sSc + (size_t)nbuf * WALK_TP);            // [nitems][WALK_THREADS / 32]
+  nrx_walk_op *sProg = reinterpret_cast<nrx_walk_op *>(sAcc + (size_t)nitems * (WALK_THREADS / 32));   // [nops]
+  double **sPar = reinterpret_cast<double **>(sProg + nops);                          // [nops] this partition's parent CLV pointers
+  uint32_t **sPsc = reinterpret_cast<uint32_t **>(sPar + nops);                       // [nops] ... and scaler pointers
+  uint8_t *sTip = reinterpret_cast<uint8_t *>(sPsc + nops);                           // [tips][WALK_TP]
+  __shared__ unsigned long long bar;
+  __shared__ double sModel[16 + 16 + 4 + 4];   // inv_eigenvecs | eigenvecs | eigenvals | rates (compute_p)
+  __shared__ int s_last;
+  const size_t site0 = (size_t)tile * WALK_TP;
+  const bool tile_live = site0 < patterns;   // partitions of a class may differ in length: surplus tiles only take their ticket
+
+  if (tile_live) {
+    if (tid == 0) {
+      mbar_init(&bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      // the program and (unless this launch computes them) all P-matrices at the pitch K1 writes for this kernel: bulk copies
+      const uint32_t pbytes = compute_p ? 0u : edges * (uint32_t)(WALK_PE * 8), gbytes = nops * (uint32_t)sizeof(nrx_walk_op);
+      mbar_expect_tx(&bar, pbytes + gbytes);
+      if (!compute_p) bulk_g2s(sP, pv.pmat_pad, pbytes, &bar);
+      bulk_g2s(sProg, prog, gbytes, &bar);
+    }
+    // tip codes of this tile (rows are padded to whole 128-pattern tiles: always in bounds)
+    for (uint32_t i = tid; i < tips * (WALK_TP / 4); i += WALK_THREADS) {
+      const uint32_t t = i / (WALK_TP / 4), w = i % (WALK_TP / 4);
+      reinterpret_cast<uint32_t *>(sTip)[i] = *reinterpret_cast<const uint32_t *>(pv.tipchars + (size_t)t * pv.tip_pitch + site0 + 4 * w);
+    }
+    for (uint32_t i = tid; i < nitems * (WALK_THREADS / 32); i += WALK_THREADS) sAcc[i] = 0.0;
+    {   // the output pointers of every op, fetched up front (two dependent global loads in front of every store otherwise)
+      double *const *clv_tab = pv.clv;
+      uint32_t *const *sc_tab = pv.scaler;
+      for (uint32_t i = tid; i < nops; i += WALK_THREADS) { const uint32_t slot = prog[i].parent_slot; sPar[i] = clv_tab[slot]; sPsc[i] = sc_tab[slot]; }
+    }
+    if (compute_p) {
+      /* K1 in the block (k_pmatrix's arithmetic, 4 states: (eval * rate) * t, expm1, pairwise sum of iev[j][m] ex[m] ev[m][k],
+       * identity added last; t == 0 -> identity).  The expm1 values of an edge go through the padding doubles' neighbours:
+       * stage 1 writes ex[c][m] into sP[edge][c][m] (entries 0..3), stage 2 reads them into registers before overwriting. */
+      if (tid < 16) { sModel[tid] = pv.inv_eigenvecs[tid]; sModel[16 + tid] = pv.eigenvecs[tid]; }
+      if (tid < 4) { sModel[32 + tid] = pv.eigenvals[tid]; sModel[36 + tid] = pv.rates[tid]; }
+      __syncthreads();
+      const double *bl = brlen + (size_t)pv.part_index * edges;
+      double *sEx = sClv;   // scratch: [edges][16] expm1 values (the CLV buffers are not in use yet); nbuf * 512 >= edges * 16 is checked by the host
+      for (uint32_t i = tid; i < edges * 16u; i += WALK_THREADS) {
+        const uint32_t e = i >> 4, c = (i >> 2) & 3u, m = i & 3u;
+        sEx[i] = expm1(__dmul_rn(__dmul_rn(sModel[32 + m], sModel[36 + c]), bl[e]));
+      }
+      __syncthreads();
+      for (uint32_t i = tid; i < edges * 64u; i += WALK_THREADS) {
+        const uint32_t e = i >> 6, c = (i >> 4) & 3u, j = (i >> 2) & 3u, k = i & 3u;
+        const double *ex = sEx + e * 16 + c * 4, *iev = sModel, *ev = sModel + 16;
+        double v;
+        if (bl[e] > 0.0) {
+          const double p0 = __dmul_rn(__dmul_rn(iev[j * 4 + 0], ex[0]), ev[0 * 4 + k]);
+          const double p1 = __dmul_rn(__dmul_rn(iev[j * 4 + 1], ex[1]), ev[1 * 4 + k]);
+          const double p2 = __dmul_rn(__dmul_rn(iev[j * 4 + 2], ex[2]), ev[2 * 4 + k]);
+          const double p3 = __dmul_rn(__dmul_rn(iev[j * 4 + 3], ex[3]), ev[3 * 4 + k]);
+          v = __dadd_rn(tree4(p0, p1, p2, p3), (j == k) ? 1.0 : 0.0);
+        } else {
+          v = (j == k) ? 1.0 : 0.0;
+        }
+        sP[e * WALK_PE + c * PCAT + j * 4 + k] = v;
+        if (tile == 0) { pv.pmat_pad[(size_t)e * WALK_PE + c * PCAT + j * 4 + k] = v; const_cast<double *>(pv.pmat)[i] = v; }
+      }
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+
+    WalkCtx c;
+    c.sP = sP; c.sClv = sClv; c.sSc = sSc; c.sTip = sTip;
+    c.tid = tid; c.pl = pl; c.cat = cat;
+    const size_t site = site0 + pl;
+    c.act = site < patterns;
+    c.quad = 0xFu << (lane & ~3);
+    const double f0 = pv.freqs[0], f1 = pv.freqs[1], f2 = pv.freqs[2], f3 = pv.freqs[3], wcat = pv.rate_weights[cat];
+    const double pw = c.act ? (double)pv.weights[site] : 0.0;
+    const size_t out_off = (site * 4 + cat) * 4;
+    for (uint32_t i = 0; i < nops; ++i) {
+      const nrx_walk_op op = sProg[i];
+      uint32_t s = 0;
+      D4 p;
+#define NRX_WALK_CASE(L, R) case (L) | ((R) << 2): p = walk_op<L, R>(c, op, s); break;
+      switch (op.kinds) {
+        NRX_WALK_CASE(NRX_CLV, NRX_CLV) NRX_WALK_CASE(NRX_CLV, NRX_TIP) NRX_WALK_CASE(NRX_TIP, NRX_CLV) NRX_WALK_CASE(NRX_TIP, NRX_TIP)
+        NRX_WALK_CASE(NRX_CLV, NRX_NONE) NRX_WALK_CASE(NRX_NONE, NRX_CLV) NRX_WALK_CASE(NRX_TIP, NRX_NONE) NRX_WALK_CASE(NRX_NONE, NRX_TIP)
+        default: p.x = p.y = p.z = p.w = 0.0; break;
+      }
+#undef NRX_WALK_CASE
+      if (op.pbuf != WALK_NOBUF) {
+        *reinterpret_cast<D4 *>(sClv + ((size_t)op.pbuf * WALK_TP * 4 + tid) * 4) = p;
+        if (cat == 0) sSc[op.pbuf * WALK_TP + pl] = s;
+      }
+      if (c.act) {
+        stg256(sPar[i] + out_off, p);
+        if (cat == 0) sPsc[i][site] = s;
+      }
+      if (op.lnl_item) {   // root displayed tree: per-site lnL right here (same per-site arithmetic and order as k_tree_lnl_dna4)
+        double t = 0.0;
+        if (c.act) t = __dmul_rn(tree4(__dmul_rn(f0, p.x), __dmul_rn(f1, p.y), __dmul_rn(f2, p.z), __dmul_rn(f3, p.w)), wcat);
+        const double t1 = __shfl_down_sync(0xffffffffu, t, 1), t2 = __shfl_down_sync(0xffffffffu, t, 2), t3 = __shfl_down_sync(0xffffffffu, t, 3);
+        double lkv = 0.0;
+        if (c.act && cat == 0) {
+          lkv = log(__dadd_rn(__dadd_rn(__dadd_rn(t, t1), t2), t3));
+          if (s) lkv = __dadd_rn(lkv, __dmul_rn((double)s, log_thresh));
+          lkv = __dmul_rn(lkv, pw);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) lkv += __shfl_down_sync(0xffffffffu, lkv, off);
+        if (lane == 0) sAcc[(op.lnl_item - 1) * (WALK_THREADS / 32) + warp] = lkv;
+      }
+      __syncthreads();   // the parent buffer is complete before any later op reads it (and before a freed buffer is rewritten)
+    }
+    // block sums of the marked trees, warps in order
+    for (uint32_t it = tid; it < nitems; it += WALK_THREADS) {
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < WALK_THREADS / 32; ++w) sum += sAcc[it * (WALK_THREADS / 32) + w];
+      partial[((size_t)it * nparts_total + pv.part_index) * ntiles + tile] = sum;
+    }
+  } else {
+    for (uint32_t it = tid; it < nitems; it += WALK_THREADS) partial[((size_t)it * nparts_total + pv.part_index) * ntiles + tile] = 0.0;
+  }
+  // second stage, fused: the block that draws the last ticket of this partition adds the tiles' partial sums in a fixed order
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(counter + pv.part_index, 1u) == ntiles - 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (uint32_t it = warp; it < nitems; it += WALK_THREADS / 32) {
+    const double *pp = partial + ((size_t)it * nparts_total + pv.part_index) * ntiles;
+    double sum = 0.0;
+    for (uint32_t b = lane; b < ntiles; b += 32) sum += __ldcg(pp + b);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off);
+    if (lane == 0) out[(size_t)it * nparts_total + pv.part_index] = sum;
+  }
+  if (tid == 0) counter[pv.part_index] = 0u;
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -369,7 +369,16 @@ def main():
         torch.cuda.synchronize()
 
     # pinned host copies of this rank's alignment slice for the e2e leg
-    tip_u8 = [torch.from_numpy(p.tip_masks.astype(np.uint8)).pin_memory() for p in parts] if all(p.states == 4 for p in parts) else None
+    # (4 states: the mask is the code; other alphabets: 1-byte codes + the code -> state-set map)
+    tipmaps = [None] * len(parts)
+    tip_u8 = []
+    for i, p in enumerate(parts):
+        if p.states == 4:
+            tip_u8.append(torch.from_numpy(p.tip_masks.astype(np.uint8)).pin_memory())
+        else:
+            tm, inv = np.unique(p.tip_masks, return_inverse=True)
+            tipmaps[i] = tm.astype(np.uint32)
+            tip_u8.append(torch.from_numpy(inv.reshape(p.tip_masks.shape).astype(np.uint8)).pin_memory())
     w_u32 = [torch.from_numpy((p.pattern_weights if p.pattern_weights is not None else np.ones(p.sites, np.uint32)).astype(np.int32)).pin_memory() for p in parts]
 
     # clocks are sampled from the warm-up to the end of the e2e region (every part of it is the same step under load)
@@ -404,7 +413,10 @@ def main():
         eng.timer_start()
         for _ in range(args.steps):
             for p in range(len(parts)):
-                eng.upload_alignment_u8(p, tip_u8[p].data_ptr(), w_u32[p].data_ptr())
+                if tipmaps[p] is None:
+                    eng.upload_alignment_u8(p, tip_u8[p].data_ptr(), w_u32[p].data_ptr())
+                else:
+                    eng.upload_alignment_codes(p, tip_u8[p].data_ptr(), tipmaps[p], w_u32[p].data_ptr())
             lnl_e2e = eng.computeLoglikelihood(0, 1)
         ms_e2e = eng.timer_stop()
         barrier()

@@ -75,6 +75,9 @@ int nrxh_read_scaler(void *h, unsigned node, unsigned tree, unsigned p, unsigned
 int nrxh_partition_loglh(void *h, double *out);
 int nrxh_set_branch_length(void *h, int partition, unsigned edge, double value);
 int nrxh_set_reticulation_prob(void *h, unsigned r, double prob);
+/* pllmod_treeinfo_t::params_to_optimize[p] for the one-dimensional model optimisers: bit 0 alpha, bit 1 pinv (so that a +I partition
+ * whose proportion is 0 stays a free parameter); -1 = derive from the current values */
+int nrxh_set_params_to_optimize(void *h, unsigned p, int mask);
 int nrxh_set_model(void *h, unsigned p, const double *freqs, const double *subst_params, const double *rates, const double *rate_weights);
 /* Scaled branch-length linkage (brlen_linkage = 1): pllmod_treeinfo_t::brlen_scalers[p]; the P-matrices of partition p use
  * scaler x the linked branch length (PLLMOD/tree/treeinfo.c:862-864).  Fails unless the linkage is scaled. */
@@ -166,6 +169,8 @@ int nrxh_persite_lnl(void *h, unsigned tree, double *out /* [nparts][max_sites] 
 void *nrxh_engine(void *h); /* the underlying nrx_engine* */
 /* re-upload one partition's alignment slice from HOST buffers (tipchars: 1 byte per cell, DNA) + pattern weights */
 int nrxh_upload_alignment_u8(void *h, unsigned p, const uint8_t *tipchars, const unsigned *pattern_weights);
+/* the same for any alphabet (e.g. 20 states): 1-byte codes + the code -> state-set map; asynchronous like the call above */
+int nrxh_upload_alignment_codes(void *h, unsigned p, const uint8_t *codes, const uint32_t *tipmap, unsigned ncodes, const unsigned *pattern_weights);
 int nrxh_timer_start(void *h);
 int nrxh_timer_stop(void *h, double *elapsed_ms);
 

@@ -88,8 +88,15 @@ void nrx_engine_destroy(nrx_engine *e);
 
 /* tip_masks: [tips][patterns] state bit masks (bit k = state k; DNA 1..15).  Re-coded to uint8 on upload. */
 int nrx_set_tips(nrx_engine *e, uint32_t p, const uint32_t *tip_masks);
-/* Same, for callers that already hold libpll-style tipchars (1 byte per cell; DNA: the 4-bit mask itself). */
+/* Same, for callers that already hold libpll-style tipchars (1 byte per cell; DNA: the 4-bit mask itself), ASYNCHRONOUS: the
+ * copy into the padded device rows and a device-side check — every code must denote a non-empty state set, as
+ * pll_set_tip_states requires (LIBPLL/pll.c:875-957); the invariant-site table of +I is rebuilt too — are enqueued on the engine's
+ * stream and the call returns.  `codes` is borrowed until the engine next synchronises (nrx_result_wait, nrx_sync, any
+ * read-back); an illegal code makes THAT call fail with "Illegal state code in tip". */
 int nrx_set_tipchars_u8(nrx_engine *e, uint32_t p, const uint8_t *codes);
+/* the same for any alphabet: code c stands for the state set tipmap[c] (c < ncodes <= 256), the role of pll_map_aa & co. */
+int nrx_set_tipcodes_u8(nrx_engine *e, uint32_t p, const uint8_t *codes, const uint32_t *tipmap, uint32_t ncodes);
+int nrx_set_pattern_weights_async(nrx_engine *e, uint32_t p, const uint32_t *weights); /* borrowed like `codes` above */
 int nrx_set_pattern_weights(nrx_engine *e, uint32_t p, const uint32_t *weights);
 /* eigenvecs / inv_eigenvecs: [states][states_padded]; eigenvals, freqs: [states_padded] (padding ignored);
  * prop_invar in [0, 1): proportion of invariant sites (+I; pll_update_invariant_sites_proportion, LIBPLL/models.c:495-543).

@@ -80,6 +80,7 @@ class FlatAPI:
         g("optimize_all_non_topology", C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double))
         g("set_pinv", C.c_int, C.c_void_p, C.c_uint, C.c_double)
         g("set_brlen_scaler", C.c_int, C.c_void_p, C.c_uint, C.c_double)
+        g("set_params_to_optimize", C.c_int, C.c_void_p, C.c_uint, C.c_int)
         g("set_submodels", C.c_int, C.c_void_p, C.c_uint, C.c_uint, _u32p, _f64p, _f64p)
         g("set_alpha", C.c_int, C.c_void_p, C.c_uint, C.c_double)
         g("get_alpha", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
@@ -338,6 +339,10 @@ class LikelihoodEngine:
     def set_pinv(self, p: int, prop_invar: float):
         """+I: proportion of invariant sites (pll_update_invariant_sites_proportion)."""
         self.api.check(self.api._set_pinv(self.h, p, prop_invar))
+
+    def set_params_to_optimize(self, p: int, alpha: bool, pinv: bool):
+        """pllmod_treeinfo_t::params_to_optimize of partition p for optimize_alpha / optimize_pinv (instead of "the value is > 0")."""
+        self.api.check(self.api._set_params_to_optimize(self.h, p, (1 if alpha else 0) | (2 if pinv else 0)))
 
     def set_brlen_scaler(self, p: int, scaler: float):
         """pllmod_treeinfo_t::brlen_scalers[p] under scaled branch-length linkage (linkage = SCALED)."""

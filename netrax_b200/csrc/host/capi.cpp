@@ -163,10 +163,17 @@ int nrxh_compute_loglikelihood_batch(void **handles, unsigned n, int incremental
 unsigned nrxh_num_partitions(void *hv) { return H(hv)->ann.fake_treeinfo->partition_count; }
 unsigned nrxh_root(void *hv) { return (unsigned)H(hv)->ann.network.root->clv_index; }
 unsigned nrxh_num_nodes(void *hv) { return (unsigned)H(hv)->ann.network.num_nodes(); }
-int nrxh_num_trees(void *hv, unsigned node) { return (int)H(hv)->ann.pernode_displayed_tree_data[node].num_active_displayed_trees; }
+static void checkNode(AnnotatedNetwork &ann, unsigned node) {
+  if (node >= ann.pernode_displayed_tree_data.size()) throw std::runtime_error("node index " + std::to_string(node) + " out of range");
+}
+int nrxh_num_trees(void *hv, unsigned node) {
+  if (node >= H(hv)->ann.pernode_displayed_tree_data.size()) { g_err = "node index " + std::to_string(node) + " out of range"; return -1; }
+  return (int)H(hv)->ann.pernode_displayed_tree_data[node].num_active_displayed_trees;
+}
 
 int nrxh_tree_config(void *hv, unsigned node, unsigned tree, char *buf, unsigned buflen) {
   return guarded([&] {
+    checkNode(H(hv)->ann, node);
     std::string s = toString(H(hv)->ann.pernode_displayed_tree_data[node].displayed_trees.at(tree).treeLoglData.reticulationChoices, H(hv)->ann.network.num_reticulations());
     std::snprintf(buf, buflen, "%s", s.c_str());
   });
@@ -174,6 +181,7 @@ int nrxh_tree_config(void *hv, unsigned node, unsigned tree, char *buf, unsigned
 
 int nrxh_tree_info(void *hv, unsigned node, unsigned tree, double *logprob, double *partition_logl, int *flags) {
   return guarded([&] {
+    checkNode(H(hv)->ann, node);
     const DisplayedTreeData &d = H(hv)->ann.pernode_displayed_tree_data[node].displayed_trees.at(tree);
     if (logprob) *logprob = d.treeLoglData.tree_logprob;
     if (partition_logl) std::copy(d.treeLoglData.tree_partition_logl.begin(), d.treeLoglData.tree_partition_logl.end(), partition_logl);
@@ -207,6 +215,11 @@ int nrxh_partition_loglh(void *hv, double *out) {
 
 static void setBranchLength(AnnotatedNetwork &ann, int partition, unsigned edge, double value) {
   FakeTreeinfo &ti = *ann.fake_treeinfo;
+  if (edge >= ann.network.num_branches()) throw std::runtime_error("branch index " + std::to_string(edge) + " out of range (the network has " + std::to_string(ann.network.num_branches()) + " branches)");
+  if (!(value >= 0.0)) throw std::runtime_error("negative or NaN branch length");
+  if (partition >= 0 && ti.brlen_linkage != PLLMOD_COMMON_BRLEN_UNLINKED)   // writing one partition's copy would desynchronise a linked length
+    throw std::runtime_error("per-partition branch lengths exist only under unlinked branch-length linkage");
+  if (partition >= (int)ti.partition_count) throw std::runtime_error("partition index out of range");
   if (partition < 0) {
     ti.linked_branch_lengths[edge] = value;
     for (auto &b : ti.branch_lengths) b[edge] = value;
@@ -220,7 +233,16 @@ int nrxh_set_branch_length(void *hv, int partition, unsigned edge, double value)
 }
 
 int nrxh_set_reticulation_prob(void *hv, unsigned r, double prob) {
-  return guarded([&] { setReticulationProb(H(hv)->ann, r, prob); });
+  return guarded([&] {
+    AnnotatedNetwork &ann = H(hv)->ann;
+    if (r >= ann.network.num_reticulations()) throw std::runtime_error("reticulation index " + std::to_string(r) + " out of range");
+    if (!(prob >= ann.options.brprob_min && prob <= ann.options.brprob_max))   // NetraxOptions::brprob_min / brprob_max: log(0) otherwise
+      throw std::runtime_error("reticulation probability outside [brprob_min, brprob_max]");
+    setReticulationProb(ann, r, prob);
+  });
+}
+int nrxh_set_params_to_optimize(void *hv, unsigned p, int mask) {
+  return guarded([&] { H(hv)->ann.fake_treeinfo->partitions.at(p).params_to_optimize = mask; });
 }
 
 static void pushModel(AnnotatedNetwork &ann, unsigned p) { pushPartitionModel(ann, p); }
@@ -529,10 +551,18 @@ int nrxh_persite_lnl(void *hv, unsigned tree, double *out, unsigned stride) {
 }
 void *nrxh_engine(void *hv) { return H(hv)->ann.engine; }
 int nrxh_upload_alignment_u8(void *hv, unsigned p, const uint8_t *tipchars, const unsigned *pw) {
-  return guarded([&] {
+  return guarded([&] {   // asynchronous: the buffers are borrowed until the next evaluation has been collected
     AnnotatedNetwork &ann = H(hv)->ann;
     detail::engineCheck(nrx_set_tipchars_u8(ann.engine, p, tipchars), "nrx_set_tipchars_u8");
-    if (pw) detail::engineCheck(nrx_set_pattern_weights(ann.engine, p, pw), "nrx_set_pattern_weights");
+    if (pw) detail::engineCheck(nrx_set_pattern_weights_async(ann.engine, p, pw), "nrx_set_pattern_weights");
+    invalidateAllCLVs(ann);
+  });
+}
+int nrxh_upload_alignment_codes(void *hv, unsigned p, const uint8_t *codes, const uint32_t *tipmap, unsigned ncodes, const unsigned *pw) {
+  return guarded([&] {   // any alphabet: code c = state set tipmap[c]
+    AnnotatedNetwork &ann = H(hv)->ann;
+    detail::engineCheck(nrx_set_tipcodes_u8(ann.engine, p, codes, tipmap, ncodes), "nrx_set_tipcodes_u8");
+    if (pw) detail::engineCheck(nrx_set_pattern_weights_async(ann.engine, p, pw), "nrx_set_pattern_weights");
     invalidateAllCLVs(ann);
   });
 }

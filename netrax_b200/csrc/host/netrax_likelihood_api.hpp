@@ -132,6 +132,10 @@ struct PartitionModel {
   double prop_invar = 0.0;  // pll_partition_t::prop_invar[0] (+I); the invariant-site indices are derived from the tips by the engine
   double alpha = 0.0;   // pllmod_treeinfo_t::alphas[p]; > 0: `rates` are the discrete-Gamma rates of this shape and optimize_alpha may change it
   int gamma_mode = 0;   // PLL_GAMMA_RATES_MEAN (raxml-ng default)
+  /* pllmod_treeinfo_t::params_to_optimize[p] for the 1-D optimisers (bit 0: alpha, bit 1: pinv); -1 = not set: derived from the
+   * current values (alpha > 0 / prop_invar > 0) as before.  Set from the model spec so that a +I partition whose proportion
+   * is (or was optimised to) 0 stays a free parameter. */
+  int params_to_optimize = -1;
   std::vector<double> eigenvecs, inv_eigenvecs, eigenvals;  // filled by update_eigen (own Jacobi solver) or set explicitly
   bool eigen_decomp_valid = false;
   /* Mixtures with one rate matrix per rate category (LG4M / LG4X): raxml-ng's Model::ratecat_submodels(), which NetRAX hands

@@ -413,7 +413,10 @@ static double optimize_onedim(AnnotatedNetwork &ann, OnedimParam param, double m
   std::vector<unsigned> parts;   // params_to_optimize[p] & param
   for (unsigned p = 0; p < ti.partition_count; ++p) {
     const PartitionModel &m = ti.partitions[p];
-    if (param == ONEDIM_ALPHA ? m.alpha > 0.0 : param == ONEDIM_PINV ? m.prop_invar > 0.0 : true) parts.push_back(p);
+    bool on = true;   // params_to_optimize[p] & param (PLLMOD/algorithm/pllmod_algorithm.c:765-772)
+    if (param == ONEDIM_ALPHA) on = m.params_to_optimize >= 0 ? (m.params_to_optimize & 1) != 0 && m.alpha > 0.0 : m.alpha > 0.0;
+    else if (param == ONEDIM_PINV) on = m.params_to_optimize >= 0 ? (m.params_to_optimize & 2) != 0 : m.prop_invar > 0.0;
+    if (on) parts.push_back(p);
   }
   if (param == ONEDIM_BRLEN_SCALER && ti.brlen_scalers.size() < ti.partition_count) ti.brlen_scalers.resize(ti.partition_count, 1.0);
   auto get = [&](unsigned p) { return param == ONEDIM_ALPHA ? ti.partitions[p].alpha : param == ONEDIM_PINV ? ti.partitions[p].prop_invar : ti.brlen_scalers[p]; };

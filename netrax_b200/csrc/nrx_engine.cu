@@ -140,6 +140,7 @@ struct nrx_engine {
   size_t partial_cap = 0;
   double *d_result = nullptr, *h_result = nullptr;
   size_t result_cap = 0;
+  int *h_err = nullptr;            // mapped pinned flag raised by k_check_tipchars (illegal tip code in an asynchronous upload)
   uint32_t *d_tickets = nullptr;   // one self-resetting ticket counter per reduction output (item, partition): fused second stage
   bool fuse_reduce = true;         // env NRX_FUSE_REDUCE=0: separate k_reduce_partials launch (A/B)
   bool defer_pmat = false;         // P-matrix updates are deferred until a launch needs them: the tile walk computes them itself (one launch per evaluation)
@@ -399,6 +400,8 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
   nrx_engine *e = new nrx_engine();
   e->device = device;
   if (!cuda_ok(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete e; return nullptr; }
+  if (!cuda_ok(cudaHostAlloc((void **)&e->h_err, sizeof(int), cudaHostAllocMapped), "cudaHostAlloc")) { delete e; return nullptr; }
+  *e->h_err = 0;
   e->parts.resize(nparts);
   if (const char *v = std::getenv("NRX_K2")) e->k2_variant = std::atoi(v);
   if (const char *v = std::getenv("NRX_GRAPH")) e->use_graphs = std::atoi(v) != 0;
@@ -494,6 +497,7 @@ void nrx_engine_destroy(nrx_engine *e) {
   cudaFree(e->d_fused);
   cudaFree(e->d_stage); cudaFree(e->d_partial); cudaFree(e->d_result); cudaFree(e->d_persite); cudaFree(e->d_tickets);
   if (e->h_result) cudaFreeHost(e->h_result);
+  if (e->h_err) cudaFreeHost(e->h_err);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -540,21 +544,65 @@ int nrx_set_tips(nrx_engine *e, uint32_t pi, const uint32_t *tip_masks) {
   return 1;
 }
 
+/* Asynchronous tip upload: codes [tips][patterns] (1 byte per cell) + the code -> state-set map.  Everything is enqueued on the
+ * engine stream — the 2-D copy into the padded rows, the map, and k_check_tipchars, which validates every code and rebuilds the
+ * invariant-site table on the device — and the call returns; `codes` is borrowed until the engine next synchronises
+ * (nrx_result_wait / nrx_sync; pageable memory is staged by the driver before the call returns).  An illegal code surfaces as
+ * a failure of that synchronising call. */
+static int set_tipcodes_async(nrx_engine *e, uint32_t pi, const uint8_t *codes, const uint32_t *tipmap256, uint32_t ncodes) {
+  Part &p = e->parts[pi];
+  const size_t n = (size_t)p.d.tips * p.d.patterns;
+  const uint32_t full = (p.d.states >= 32) ? 0xffffffffu : ((1u << p.d.states) - 1);
+  std::vector<uint32_t> tipmap(tipmap256, tipmap256 + 256);
+  const bool map_changed = !p.tips_set || tipmap != p.h_tipmap;
+  if (n) CK(cudaMemcpy2DAsync(p.tipchars, p.pat_pad, codes, p.d.patterns, p.d.patterns, p.d.tips, cudaMemcpyHostToDevice, e->stream));
+  if (map_changed) {
+    uint32_t *d_map;
+    if (!upload(e, tipmap.data(), 256, &d_map)) return 0;
+    CK(cudaMemcpyAsync(p.tipmap, d_map, 256 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
+    p.h_tipmap = tipmap;
+    if (p.tip_codes != ncodes) { p.tip_codes = ncodes; e->views_dirty = true; }
+  }
+  if (p.d.patterns) {
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>(((uint64_t)p.d.patterns + BLOCK - 1) / BLOCK, 8ull * e->sm_count);
+    k_check_tipchars<<<blocks, BLOCK, 0, e->stream>>>(p.tipchars, p.d.tips, p.d.patterns, p.pat_pad, p.tipmap, full, p.invariant, e->h_err);
+    e->launches++;
+    CK(cudaGetLastError());
+  }
+  p.tips_set = true;
+  p.invariant_stale = false;
+  if (map_changed && p.model_set && (!refresh_tiplut(e, pi, nullptr, 0) || !refresh_summat(e, pi))) return 0;   // 20 states: the tables are per code
+  return 1;
+}
+
 int nrx_set_tipchars_u8(nrx_engine *e, uint32_t pi, const uint8_t *codes) {
   if (!check_part(e, pi)) return 0;
   CK(cudaSetDevice(e->device));
+  if (e->parts[pi].d.states != 4) { g_err = "nrx_set_tipchars_u8: only 4-state partitions store the mask as the code (use nrx_set_tipcodes_u8)"; return 0; }
+  uint32_t tipmap[256] = {};
+  for (uint32_t i = 1; i < 16; ++i) tipmap[i] = i;   // code == state mask; 0 and everything above 15 is illegal
+  return set_tipcodes_async(e, pi, codes, tipmap, 16);
+}
+
+int nrx_set_tipcodes_u8(nrx_engine *e, uint32_t pi, const uint8_t *codes, const uint32_t *tipmap, uint32_t ncodes) {
+  if (!check_part(e, pi)) return 0;
+  CK(cudaSetDevice(e->device));
   Part &p = e->parts[pi];
-  if (p.d.states != 4) { g_err = "nrx_set_tipchars_u8: only 4-state partitions store the mask as the code"; return 0; }
-  const size_t n = (size_t)p.d.tips * p.d.patterns;
-  std::vector<uint32_t> tipmap(256, 0);
-  for (uint32_t i = 0; i < 16; ++i) tipmap[i] = i;
-  if (n) CK(cudaMemcpy2DAsync(p.tipchars, p.pat_pad, codes, p.d.patterns, p.d.patterns, p.d.tips, cudaMemcpyHostToDevice, e->stream));
-  CK(cudaMemcpyAsync(p.tipmap, tipmap.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
-  p.tips_set = true;
-  if (p.pinv > 0.0 && !upload_invariant(e, p, codes, (const uint32_t *)nullptr)) return 0;   // only +I partitions read it
-  p.invariant_stale = !(p.pinv > 0.0);
-  if (p.tip_codes != 16) { p.tip_codes = 16; e->views_dirty = true; }
+  if (ncodes == 0 || ncodes > 256) { g_err = "nrx_set_tipcodes_u8: 1..256 codes"; return 0; }
+  const uint32_t full = (p.d.states >= 32) ? 0xffffffffu : ((1u << p.d.states) - 1);
+  uint32_t map[256] = {};
+  for (uint32_t i = 0; i < ncodes; ++i) {
+    if (tipmap[i] == 0 || (tipmap[i] & ~full)) { g_err = "Illegal state code in tip"; return 0; }
+    map[i] = tipmap[i];
+  }
+  return set_tipcodes_async(e, pi, codes, map, ncodes);
+}
+
+int nrx_set_pattern_weights_async(nrx_engine *e, uint32_t pi, const uint32_t *w) {
+  if (!check_part(e, pi)) return 0;
+  CK(cudaSetDevice(e->device));
+  Part &p = e->parts[pi];
+  if (p.d.patterns) CK(cudaMemcpyAsync(p.weights, w, (size_t)p.d.patterns * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
   return 1;
 }
 
@@ -581,7 +629,6 @@ int nrx_set_model_mixture(nrx_engine *e, uint32_t pi, uint32_t nmodels, const ui
   if (M < 1 || M > 16) { g_err = "nrx_set_model_mixture: 1..16 rate matrices"; return 0; }
   for (size_t c = 0; M > 1 && c < C; ++c)
     if (!cat_model || cat_model[c] >= M) { g_err = "nrx_set_model_mixture: rate-matrix index of a category out of range"; return 0; }
-  if (prop_invar > 0.0 && p.invariant_stale) { g_err = "nrx_set_model: +I after nrx_set_tipchars_u8: call nrx_set_tips (or upload the tips again) first"; return 0; }
   CK(cudaStreamSynchronize(e->stream));
   if (M > p.model_cap) {   // grow the model buffer: freqs | eigenvecs | inv_eigenvecs | eigenvals (M blocks each) | rates | rate_weights | diagp
     double *nm = nullptr;
@@ -1249,8 +1296,13 @@ static int enqueue_reduction(nrx_engine *e, uint32_t total, uint32_t nblk, bool 
   e->pending_result = total;
   return 1;
 }
+static int check_async_error(nrx_engine *e) {
+  if (e->h_err && *e->h_err) { *e->h_err = 0; g_err = "Illegal state code in tip (asynchronous tip upload)"; return 0; }
+  return 1;
+}
 static int wait_result(nrx_engine *e, uint32_t total, double *out) {
   CK(cudaStreamSynchronize(e->stream));
+  if (!check_async_error(e)) { e->pending_result = 0; return 0; }
   if (out) std::memcpy(out, e->h_result, (size_t)total * sizeof(double));
   e->pending_result = 0;
   return 1;
@@ -1592,7 +1644,7 @@ int nrx_sync(nrx_engine *e) {
   CK(cudaSetDevice(e->device));
   if (!flush_pmatrices(e)) return 0;
   CK(cudaStreamSynchronize(e->stream));
-  return 1;
+  return check_async_error(e);
 }
 
 int nrx_comm_get_unique_id(uint8_t *id128) {

@@ -155,6 +155,30 @@ __global__ void k_pmatrix(PartView pv, double *pmat_out, const uint32_t *edge_id
   }
 }
 
+/* Tip-code upload check, on the device (round 2: nrx_set_tipchars_u8 used to trust its input and left the invariant-site table
+ * stale): every code must map to a non-empty state set (pll_set_tip_states rejects unknown characters, LIBPLL/pll.c:875-957) —
+ * otherwise *err is raised (mapped host memory, read by the host at its next synchronisation) — and the invariant-site table
+ * is rebuilt as pll_update_invariant_sites does (LIBPLL/models.c:651-760): AND of all tips' state sets per pattern; exactly one
+ * state left -> its index, else -1.  thread = pattern: tip rows are read coalesced. */
+__global__ void __launch_bounds__(BLOCK) k_check_tipchars(const uint8_t *__restrict__ tipchars, uint32_t tips, uint32_t patterns, uint32_t pitch,
+                                                           const uint32_t *__restrict__ tipmap, uint32_t full_mask, int *__restrict__ invariant,
+                                                           volatile int *err) {
+  __shared__ uint32_t smap[256];
+  for (int i = threadIdx.x; i < 256; i += BLOCK) smap[i] = tipmap[i];
+  __syncthreads();
+  for (uint32_t n = blockIdx.x * BLOCK + threadIdx.x; n < patterns; n += gridDim.x * BLOCK) {
+    uint32_t st = full_mask;
+    bool bad = false;
+    for (uint32_t t = 0; t < tips; ++t) {
+      const uint32_t m = smap[tipchars[(size_t)t * pitch + n]];
+      bad |= (m == 0u);
+      st &= m;
+    }
+    if (bad) *err = 1;
+    invariant[n] = (st == 0u || __popc(st) > 1) ? -1 : (__ffs(st) - 1);
+  }
+}
+
 /* ------------------------------------------------------------------------------------------------
  * K2  CLV update, DNA (4 states) x 4 rate categories fast path.
  * grid = (pattern tiles, ops, partitions of this shape); thread = one (pattern, category).

@@ -55,6 +55,8 @@ def load() -> FlatAPI:
         lib.nrxh_engine.argtypes = [C.c_void_p]
         lib.nrxh_upload_alignment_u8.restype = C.c_int
         lib.nrxh_upload_alignment_u8.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p]
+        lib.nrxh_upload_alignment_codes.restype = C.c_int
+        lib.nrxh_upload_alignment_codes.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS"), C.c_uint, C.c_void_p]
         lib.nrxh_compute_loglikelihood_batch.restype = C.c_int
         lib.nrxh_compute_loglikelihood_batch.argtypes = [C.POINTER(C.c_void_p), C.c_uint, C.c_int, C.c_int,
                                                          np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")]
@@ -162,6 +164,12 @@ class NetraxB200(LikelihoodEngine):
     def upload_alignment_u8(self, p: int, tipchars_ptr: int, weights_ptr: int = 0):
         """Host -> device re-upload of one partition's alignment slice (pointers to pinned or pageable host memory)."""
         self.api.check(self.api.lib.nrxh_upload_alignment_u8(self.h, p, C.c_void_p(tipchars_ptr), C.c_void_p(weights_ptr) if weights_ptr else None))
+
+    def upload_alignment_codes(self, p: int, codes_ptr: int, tipmap: np.ndarray, weights_ptr: int = 0):
+        """Any alphabet: 1-byte codes [tips][patterns] (pointer to host memory) + tipmap[code] = state-set mask.  Asynchronous: the
+        buffers must stay alive until the next evaluation has returned; an illegal code fails that evaluation."""
+        tm = np.ascontiguousarray(tipmap, np.uint32)
+        self.api.check(self.api.lib.nrxh_upload_alignment_codes(self.h, p, C.c_void_p(codes_ptr), tm, len(tm), C.c_void_p(weights_ptr) if weights_ptr else None))
 
     def timer_start(self):
         self.api.check(self.api.lib.nrxh_timer_start(self.h))

@@ -449,6 +449,9 @@ def apply_model_state(eng, specs: Sequence[ModelSpec]) -> int:
             eng.set_alpha(p, ms.alpha)
         if ms.pinv_mode != "undefined" and ms.pinv > 0.0:
             eng.set_pinv(p, ms.pinv)
+        # which of the two are FREE parameters comes from the model spec, not from the current value: a +I partition whose
+        # empirical (or optimised) proportion is 0 must stay in optimize_pinv (pll-modules' params_to_optimize)
+        eng.set_params_to_optimize(p, alpha=(ms.rate_cats > 1 and ms.alpha_mode == "ML"), pinv=(ms.pinv_mode == "ML"))
         if ms.brlen_scaler_mode == "user":
             eng.set_brlen_scaler(p, ms.brlen_scaler)
         if ms.submodels is not None:   # raxml-ng's ratecat_submodels -> libpll params_indices (src/RaxmlWrapper.cpp:199-203)

@@ -231,6 +231,7 @@ struct AnnotatedNetwork {  // SRC/graph/AnnotatedNetwork.hpp:42-89 (fields the p
   size_t total_num_model_parameters = 0, total_num_sites = 0;  // SRC/graph/AnnotatedNetwork.hpp:47-48
   std::vector<double> pinvs;   // partition->prop_invar[param_indices[p][0]] as last set (0 = no +I)
   std::vector<double> pattern_weight_sums;  // [partition] pll_partition_t::pattern_weight_sum
+  std::vector<int> params_to_optimize;   // pllmod_treeinfo_t::params_to_optimize per partition (bit 0 alpha, bit 1 pinv); empty / -1 = derive from the values
   std::vector<double> alphas;  // fake_treeinfo->alphas (0 = no Gamma shape attached to the partition's rates)
   double cached_logl = 0;
   bool cached_logl_valid = false;

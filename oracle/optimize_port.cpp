@@ -270,8 +270,13 @@ double optimize_onedim(AnnotatedNetwork &ann, OnedimParam param, double min_valu
   if (ann.alphas.size() < P) ann.alphas.resize(P, 0.0);
   if (ann.pinvs.size() < P) ann.pinvs.resize(P, 0.0);
   if (param == ONEDIM_BRLEN_SCALER && ann.brlen_scalers.size() < P) ann.brlen_scalers.resize(P, 1.0);
-  for (unsigned p = 0; p < P; ++p)   // params_to_optimize[p] & param: raxml-ng sets ALPHA for +G, PINV for +I, the scaler bit under scaled linkage
-    if (param == ONEDIM_ALPHA ? ann.alphas[p] > 0.0 : param == ONEDIM_PINV ? ann.pinvs[p] > 0.0 : true) q.parts.push_back(p);
+  for (unsigned p = 0; p < P; ++p) {   // params_to_optimize[p] & param: raxml-ng sets ALPHA for +G, PINV for +I, the scaler bit under scaled linkage
+    const int pto = p < ann.params_to_optimize.size() ? ann.params_to_optimize[p] : -1;   // (pllmod_algorithm.c:765-772)
+    bool on = true;
+    if (param == ONEDIM_ALPHA) on = pto >= 0 ? (pto & 1) != 0 && ann.alphas[p] > 0.0 : ann.alphas[p] > 0.0;
+    else if (param == ONEDIM_PINV) on = pto >= 0 ? (pto & 2) != 0 : ann.pinvs[p] > 0.0;
+    if (on) q.parts.push_back(p);
+  }
   if (!q.parts.empty()) {
     std::vector<double> vals;
     for (unsigned p : q.parts) vals.push_back(param == ONEDIM_ALPHA ? ann.alphas[p] : param == ONEDIM_PINV ? ann.pinvs[p] : ann.brlen_scalers[p]);

@@ -382,6 +382,14 @@ int orc_set_pinv(void *hv, unsigned p, double prop_invar) {
   Handle *h = static_cast<Handle *>(hv);
   return guarded([&] { setPinv(h->ann, p, prop_invar); });
 }
+int orc_set_params_to_optimize(void *hv, unsigned p, int mask) {
+  Handle *h = static_cast<Handle *>(hv);
+  return guarded([&] {
+    if (p >= h->ann.partitionCount()) throw std::runtime_error("partition index out of range");
+    if (h->ann.params_to_optimize.size() <= p) h->ann.params_to_optimize.resize(h->ann.partitionCount(), -1);
+    h->ann.params_to_optimize[p] = mask;
+  });
+}
 int orc_set_brlen_scaler(void *hv, unsigned p, double scaler) {
   Handle *h = static_cast<Handle *>(hv);
   return guarded([&] { setBrlenScaler(h->ann, p, scaler); });

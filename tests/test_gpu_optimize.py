@@ -213,3 +213,40 @@ def test_score_only_from_files_matches_oracle():
         assert rg[key] == pytest.approx(ro[key], rel=1e-7)
     assert rg["alphas"][0] == pytest.approx(ro["alphas"][0], rel=1e-3)
     assert rg["bic"] <= rg["start_bic"] + 1e-3
+
+
+def test_params_to_optimize_flags_and_capi_range_checks():
+    """(1) which partitions optimize_pinv treats as free comes from pll-modules' params_to_optimize flags, not from
+    "the value is > 0": a +I partition that starts at proportion 0 is optimised once flagged, and a flagged-off partition is left
+    alone; (2) the flat C-ABI rejects out-of-range edge / reticulation / node indices and probabilities outside
+    [brprob_min, brprob_max] instead of writing out of bounds."""
+    from netrax_b200._capi import LikelihoodError
+    from test_oracle_optimize import _pinv_case
+    net, parts = _pinv_case()
+    g, o = _pair(net, parts)
+    for eng in (g, o):
+        eng.set_params_to_optimize(0, alpha=False, pinv=True)    # +I, starting at 0
+        eng.set_params_to_optimize(1, alpha=False, pinv=False)
+    assert g.get_pinv(0) == 0.0
+    lg, lo = g.optimize_pinv(), o.optimize_pinv()
+    assert lg == pytest.approx(lo, rel=1e-9)
+    assert g.get_pinv(0) == pytest.approx(o.get_pinv(0), rel=1e-4) and g.get_pinv(0) > 0.01
+    assert g.get_pinv(1) == 0.0
+    # range checks
+    with pytest.raises(LikelihoodError, match="out of range"):
+        g.set_branch_length(net.num_edges + 5, 0.1)
+    with pytest.raises(LikelihoodError, match="unlinked"):
+        g.set_branch_length(0, 0.1, partition=0)                 # linked linkage: no per-partition lengths
+    with pytest.raises(LikelihoodError, match="negative"):
+        g.set_branch_length(0, -1.0)
+    if net.num_reticulations:
+        with pytest.raises(LikelihoodError, match="out of range"):
+            g.set_reticulation_prob(net.num_reticulations, 0.5)
+        for bad in (0.0, 1.0, -0.1, float("nan")):
+            with pytest.raises(LikelihoodError, match="brprob"):
+                g.set_reticulation_prob(0, bad)
+    assert g.num_trees(net.num_nodes + 3) == -1
+    with pytest.raises(LikelihoodError, match="out of range"):
+        g.tree_config(net.num_nodes + 3, 0)
+    assert g.computeLoglikelihood(1, 1) == pytest.approx(lg, rel=1e-12)   # nothing was corrupted
+    g.close()

@@ -1143,3 +1143,51 @@ def test_tile_walk_evaluation_equals_level_by_level_launches(monkeypatch):
         for a, b in zip(res["0"][1], res["1"][1]):
             np.testing.assert_allclose(a, b, rtol=REPLAY_RTOL, atol=0)
         assert res["1"][2] < res["0"][2]
+
+
+def test_async_tip_upload_is_validated_on_the_device_and_serves_any_alphabet():
+    """Round 2 (ADVICE): nrx_set_tipchars_u8 / nrx_set_tipcodes_u8 enqueue the copy and return; a device kernel checks
+    every code (an illegal one fails the next synchronising call with pll_set_tip_states' message) and rebuilds the invariant-site
+    table, so +I may be switched on after such an upload; 20-state partitions take 1-byte codes + the code -> state-set map."""
+    from netrax_b200._capi import LikelihoodError
+    net = random_network(12, 2, seed=21)
+    m, w = simulate_alignment(net, 700, seed=21)
+    m[:, :90] = m[0, :90]                           # some invariant columns for +I
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    g, o = _gpu(net, [part]), _oracle(net, [part])
+    _inject_eigen(g, o)
+    l0 = g.computeLoglikelihood(0, 1)
+    assert l0 == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
+    codes = np.ascontiguousarray(m.astype(np.uint8))
+    w32 = np.ascontiguousarray(w.astype(np.uint32))
+    bad = codes.copy(); bad[3, 17] = 0              # no state at all
+    g.upload_alignment_u8(0, bad.ctypes.data, w32.ctypes.data)
+    with pytest.raises(LikelihoodError, match="Illegal state code in tip"):
+        g.computeLoglikelihood(0, 1)
+    bad[3, 17] = 200                                # not a DNA code
+    g.upload_alignment_u8(0, bad.ctypes.data, w32.ctypes.data)
+    with pytest.raises(LikelihoodError, match="Illegal state code in tip"):
+        g.computeLoglikelihood(0, 1)
+    g.upload_alignment_u8(0, codes.ctypes.data, w32.ctypes.data)
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(l0, rel=REPLAY_RTOL)
+    g.set_pinv(0, 0.3); o.set_pinv(0, 0.3)          # +I after an asynchronous upload: the invariant table is current
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
+    g.close()
+    # protein: codes + map
+    net, part = _protein_case(10, 1, 257, 22)
+    g, o = _gpu(net, [part]), _oracle(net, [part])
+    _inject_eigen(g, o)
+    lo = o.computeLoglikelihood(0, 1)
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(lo, rel=LNL_RTOL)
+    tipmap, inv = np.unique(part.tip_masks, return_inverse=True)
+    codes = np.ascontiguousarray(inv.reshape(part.tip_masks.shape).astype(np.uint8))
+    perm = np.arange(len(tipmap))[::-1].copy()      # a different code assignment than the engine derived itself
+    codes_p = np.ascontiguousarray(perm[codes].astype(np.uint8)); tipmap_p = np.zeros(len(tipmap), np.uint32); tipmap_p[perm] = tipmap
+    w32 = np.ascontiguousarray(part.pattern_weights.astype(np.uint32))
+    g.upload_alignment_codes(0, codes_p.ctypes.data, tipmap_p, w32.ctypes.data)
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(lo, rel=LNL_RTOL)
+    e = net.num_edges - 1
+    assert g.brlen_prepare(e) == pytest.approx(o.brlen_prepare(e), rel=LNL_RTOL)
+    assert g.computeLoglikelihoodBrlenOpt(e) == pytest.approx(o.computeLoglikelihoodBrlenOpt(e), rel=LNL_RTOL)
+    assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL)
+    g.close()

@@ -307,3 +307,18 @@ def test_optimize_scalers_is_a_noop_without_scaled_linkage():
     assert e.optimize_scalers() == b0
     np.testing.assert_array_equal(e.brlen_scalers(), [1.0, 1.0])
     e.close()
+
+
+@pytest.mark.parametrize("kind", ["port"] + (["ref"] if oracle.have_ref() else []))
+def test_params_to_optimize_flags_select_the_free_pinv_partitions(kind):
+    """pllmod_algo_opt_onedim_treeinfo selects partitions by params_to_optimize[p] & param (PLLMOD/algorithm/pllmod_algorithm.c:765-772),
+    not by the parameter's current value: a +I partition starting at proportion 0 is optimised, an unflagged one is not."""
+    net, parts = _pinv_case()
+    e = oracle.make_engine(kind, net, parts)
+    l0 = e.computeLoglikelihood(0, 1)
+    assert e.optimize_pinv() == pytest.approx(l0, rel=1e-13) and e.get_pinv(0) == 0.0     # by value: nothing to optimise
+    e.set_params_to_optimize(0, alpha=False, pinv=True)
+    e.set_params_to_optimize(1, alpha=False, pinv=False)
+    l1 = e.optimize_pinv()
+    assert l1 > l0 + 1e-3 and e.get_pinv(0) > 0.01 and e.get_pinv(1) == 0.0
+    e.close()

@@ -260,6 +260,9 @@ static unsigned long long stream_bytes(const nrx_engine *e, unsigned long long i
   return b;
 }
 
+/* partition shapes served by the pipelined 4-state kernel k_clv_dna4_pipe2<NT, CATS> */
+static bool dna_pipe_cats(uint32_t states, uint32_t cats) { return states == 4 && (cats == 1 || cats == 2 || cats == 4 || cats == 8 || cats == 16); }
+
 PartView make_view(const Part &p, uint32_t index) {
   PartView v{};
   v.states = p.d.states; v.sp = p.sp; v.cats = p.d.rate_cats; v.patterns = p.d.patterns; v.tips = p.d.tips; v.edges = p.d.edges;
@@ -434,15 +437,19 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
         !cuda_ok(cudaFuncSetAttribute(k_aa20_mma<AA_SUM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa2_smem), "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(k_aa20_mma<AA_EDGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa2_smem), "cudaFuncSetAttribute")) { delete e; return nullptr; }
     if (!cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClvPipeSmem)), "cudaFuncSetAttribute") ||
-        !cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem<1>)), "cudaFuncSetAttribute") ||
-        !cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem<2>)), "cudaFuncSetAttribute")) { delete e; return nullptr; }
+        !cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem<1, 4>)), "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem<2, 4>)), "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe2<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem<2, 1>)), "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe2<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem<2, 2>)), "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe2<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem<2, 8>)), "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(k_clv_dna4_pipe2<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem<2, 16>)), "cudaFuncSetAttribute")) { delete e; return nullptr; }
   }
   for (uint32_t i = 0; i < nparts; ++i) {
     Part &p = e->parts[i];
     p.d = descs[i];
     if (p.d.states < 2 || p.d.states > 32 || p.d.rate_cats < 1 || p.d.rate_cats > 16) { g_err = "unsupported states / rate_cats"; nrx_engine_destroy(e); return nullptr; }
     p.sp = (p.d.states + 3) & ~3u;
-    p.pat_pad = (p.d.patterns + 2 * TP - 1) / (2 * TP) * (2 * TP);   // whole 128-pattern tiles: bulk copies always move full tiles
+    p.pat_pad = (p.d.patterns + 511) / 512 * 512;   // whole tiles of every kernel (k_clv_dna4_pipe2 with one rate category: 512 patterns per stage): bulk copies always move full tiles
     p.clv_entries = (size_t)p.d.patterns * p.d.rate_cats * p.sp;
     p.pmat_entries = (size_t)p.d.rate_cats * p.d.states * p.sp;
     e->max_patterns = std::max(e->max_patterns, p.d.patterns);
@@ -925,11 +932,12 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
   for (const ShapeClass &c : e->classes) {
     if (c.max_patterns == 0) continue;
     const uint32_t z = (uint32_t)c.parts.size();
-    if (c.states == 4 && c.cats == 4) {
+    if (dna_pipe_cats(c.states, c.cats) && (c.cats == 4 || e->k2_variant == 0)) {
       if (e->k2_variant == 0 || e->k2_variant == 1) {
         // bulk-async pipeline: 2 resident blocks per SM; block b = (op b % nops, tile group b / nops)
-        const uint32_t nt = (e->k2_variant == 0) ? e->k2_nt : 1;   // 64-pattern sub-tiles per ring stage
-        const uint32_t ntiles = (c.max_patterns + nt * TP - 1) / (nt * TP);
+        const uint32_t nt = (e->k2_variant == 0 && c.cats == 4) ? e->k2_nt : (e->k2_variant == 0 ? 2u : 1u);   // 256-item sub-tiles per ring stage
+        const uint32_t tpx = nt * (BLOCK / c.cats);   // patterns per stage (4 categories: 64 per sub-tile)
+        const uint32_t ntiles = (c.max_patterns + tpx - 1) / tpx;
         uint32_t groups = std::max<uint32_t>(1, (e->k2_blocks + nops * z - 1) / (nops * z));
         // >= 4 tiles per block amortise the pipeline fill — unless the whole launch fits the 2 x SMs resident blocks anyway:
         // then one tile per block (small alignments: 38 blocks walking 4 tiles each left 110 SMs idle)
@@ -941,7 +949,6 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
           // inside a plan capture the launch is programmatically serialised behind the previous K2 launch (PDL)
           cudaLaunchConfig_t cfg{};
           cfg.gridDim = grid; cfg.blockDim = dim3(BLOCK); cfg.stream = e->stream;
-          cfg.dynamicSmemBytes = nt == 2 ? sizeof(PipeSmem<2>) : sizeof(PipeSmem<1>);
           cudaLaunchAttribute attr[1];
           attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
           attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -951,8 +958,17 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
           cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
           const size_t stride = (size_t)e->max_patterns;
           const uint32_t np = (uint32_t)e->parts.size();
-          if (nt == 2) CK(cudaLaunchKernelEx(&cfg, k_clv_dna4_pipe2<2>, (const PartView *)c.d_views, d_ops, nops, groups, fused_ptr, stride, np, pdl));
-          else CK(cudaLaunchKernelEx(&cfg, k_clv_dna4_pipe2<1>, (const PartView *)c.d_views, d_ops, nops, groups, fused_ptr, stride, np, pdl));
+#define NRX_K2_LAUNCH(NT_, CATS_)                                                                                                    \
+  do {                                                                                                                               \
+    cfg.dynamicSmemBytes = sizeof(PipeSmem<NT_, CATS_>);                                                                             \
+    CK(cudaLaunchKernelEx(&cfg, k_clv_dna4_pipe2<NT_, CATS_>, (const PartView *)c.d_views, d_ops, nops, groups, fused_ptr, stride, np, pdl)); \
+  } while (0)
+          if (c.cats == 4) { if (nt == 2) NRX_K2_LAUNCH(2, 4); else NRX_K2_LAUNCH(1, 4); }
+          else if (c.cats == 1) NRX_K2_LAUNCH(2, 1);
+          else if (c.cats == 2) NRX_K2_LAUNCH(2, 2);
+          else if (c.cats == 8) NRX_K2_LAUNCH(2, 8);
+          else NRX_K2_LAUNCH(2, 16);
+#undef NRX_K2_LAUNCH
           e->pdl_prev_is_k2 = true;
         } else
           k_clv_dna4_pipe<<<grid, BLOCK, sizeof(ClvPipeSmem), e->stream>>>(c.d_views, d_ops, nops, groups, fused_ptr, (size_t)e->max_patterns, (uint32_t)e->parts.size());
@@ -1206,7 +1222,7 @@ int nrx_plan_run(nrx_engine *e, uint32_t plan_id) {
     const unsigned long long l0 = e->launches;
     CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
     // PDL only where every launch of the plan is the pipelined 4-state kernel (one shape class): the chain K2 -> K2 -> ...
-    e->capturing_pdl = e->use_pdl && e->classes.size() == 1 && e->classes[0].states == 4 && e->classes[0].cats == 4 && e->k2_variant == 0;
+    e->capturing_pdl = e->use_pdl && e->classes.size() == 1 && dna_pipe_cats(e->classes[0].states, e->classes[0].cats) && e->k2_variant == 0;
     e->pdl_prev_is_k2 = false;
     int ok = 1;
     for (size_t b = 0; b < pl.sizes.size() && ok; ++b) ok = launch_clv_batch(e, pl.d_ops + pl.offsets[b], pl.sizes[b], pl.tips[b], pl.lnl_items != 0, pl.ntt[b]);
@@ -1238,7 +1254,7 @@ int nrx_set_throughput_mode(nrx_engine *e, int on) {
 
 int nrx_supports_fused_lnl(nrx_engine *e) {
   if (!e || (e->k2_variant != 0 && e->k2_variant != 1) || std::getenv("NRX_NO_FUSED_LNL")) return 0;
-  for (const ShapeClass &c : e->classes) if (!(c.states == 4 && c.cats == 4)) return 0;
+  for (const ShapeClass &c : e->classes) if (!(dna_pipe_cats(c.states, c.cats) && (c.cats == 4 || e->k2_variant == 0))) return 0;
   for (const Part &p : e->parts) if (p.pinv > 0.0 || p.nmodels > 1) return 0;   // the K2 epilogue carries neither the invariant-site term nor per-category frequencies
   return 1;
 }

@@ -416,75 +416,92 @@ struct PipeCtx {
 /* NT = 64-pattern sub-tiles per ring stage (1: 6 stages x 64 patterns, the geometry of k_clv_dna4_pipe; 2: 3 stages x 128
  * patterns — the same bytes in flight, half as many mbarrier waits / block barriers / refills per byte, two independent
  * items per thread between barriers). */
-template <int NT>
+/* CATS = rate categories (1, 2, 4, 8 or 16; round 2: every power-of-two category count runs this kernel — a sub-tile is always 256
+ * (pattern, category) items = 8 KB per CLV operand, i.e. 256 / CATS patterns; the reference's AVX kernels loop over rate_cats at
+ * full SIMD speed too, LIBPLL/core_partials_avx.c:402-565). */
+template <int NT, int CATS>
 struct __align__(128) PipeStage {
-  double l[NT * TP * 16];
-  double r[NT * TP * 16];
-  uint32_t scl[NT * TP];
-  uint32_t scr[NT * TP];
-  uint8_t tl[NT * TP];
-  uint8_t tr[NT * TP];
+  static constexpr int TPC = BLOCK / CATS;   // patterns per sub-tile
+  double l[NT * BLOCK * 4];
+  double r[NT * BLOCK * 4];
+  uint32_t scl[NT * TPC];
+  uint32_t scr[NT * TPC];
+  uint8_t tl[NT * TPC < 16 ? 16 : NT * TPC];
+  uint8_t tr[NT * TPC < 16 ? 16 : NT * TPC];
 };
-template <int NT>
+template <int NT, int CATS>
 struct __align__(128) PipeSmem {
   static constexpr int NST = NSTAGE / NT;
-  PipeStage<NT> st[NST];
-  double lutL[256];
-  double lutR[256];
+  PipeStage<NT, CATS> st[NST];
+  double lutL[16 * CATS * 4];
+  double lutR[16 * CATS * 4];
   unsigned long long full[NST];
 };
 
-template <int LK, int RK, int NT>
-__device__ __forceinline__ void pipe_issue(PipeSmem<NT> &sm, const PipeCtx &c, uint32_t k, uint32_t stage) {
-  constexpr uint32_t TPX = NT * TP;
-  PipeStage<NT> &st = sm.st[stage];
+template <int CATS>
+__device__ __forceinline__ void build_tip_lut(double *lut /*[16][CATS][4]*/, const double *pm /*[CATS][4][4] of the edge*/, int tid) {
+  for (int idx = tid; idx < 16 * CATS * 4; idx += BLOCK) {
+    const int mask = idx / (CATS * 4), c = (idx >> 2) % CATS, i = idx & 3;
+    const double *row = pm + (c * 4 + i) * 4;
+    lut[idx] = tree4((mask & 1) ? row[0] : 0.0, (mask & 2) ? row[1] : 0.0, (mask & 4) ? row[2] : 0.0, (mask & 8) ? row[3] : 0.0);
+  }
+}
+
+template <int LK, int RK, int NT, int CATS>
+__device__ __forceinline__ void pipe_issue(PipeSmem<NT, CATS> &sm, const PipeCtx &c, uint32_t k, uint32_t stage) {
+  constexpr uint32_t TPX = NT * (BLOCK / CATS);   // patterns per stage
+  constexpr uint32_t CB = CATS * 32u;             // CLV bytes per pattern
+  constexpr uint32_t TIPB = TPX < 16u ? 16u : TPX;   // bulk copies move multiples of 16 bytes (rows are padded)
+  PipeStage<NT, CATS> &st = sm.st[stage];
   unsigned long long *bar = &sm.full[stage];
   const size_t p0 = ((size_t)c.grp + (size_t)k * c.groups) * TPX;
-  constexpr uint32_t tx = ((LK == NRX_CLV) ? TPX * 128u + TPX * 4u : (LK == NRX_TIP ? TPX : 0u)) +
-                          ((RK == NRX_CLV) ? TPX * 128u + TPX * 4u : (RK == NRX_TIP ? TPX : 0u));
+  constexpr uint32_t tx = ((LK == NRX_CLV) ? TPX * CB + TPX * 4u : (LK == NRX_TIP ? TIPB : 0u)) +
+                          ((RK == NRX_CLV) ? TPX * CB + TPX * 4u : (RK == NRX_TIP ? TIPB : 0u));
   mbar_expect_tx(bar, tx);
-  if (LK == NRX_CLV) { bulk_g2s(st.l, c.clvL + p0 * 16, TPX * 128u, bar); bulk_g2s(st.scl, c.scL + p0, TPX * 4u, bar); }
-  else if (LK == NRX_TIP) bulk_g2s(st.tl, c.tipL + p0, TPX, bar);
-  if (RK == NRX_CLV) { bulk_g2s(st.r, c.clvR + p0 * 16, TPX * 128u, bar); bulk_g2s(st.scr, c.scR + p0, TPX * 4u, bar); }
-  else if (RK == NRX_TIP) bulk_g2s(st.tr, c.tipR + p0, TPX, bar);
+  if (LK == NRX_CLV) { bulk_g2s(st.l, c.clvL + p0 * (CATS * 4), TPX * CB, bar); bulk_g2s(st.scl, c.scL + p0, TPX * 4u, bar); }
+  else if (LK == NRX_TIP) bulk_g2s(st.tl, c.tipL + p0, TIPB, bar);
+  if (RK == NRX_CLV) { bulk_g2s(st.r, c.clvR + p0 * (CATS * 4), TPX * CB, bar); bulk_g2s(st.scr, c.scR + p0, TPX * 4u, bar); }
+  else if (RK == NRX_TIP) bulk_g2s(st.tr, c.tipR + p0, TIPB, bar);
 }
 
 /* first ring fill, by one thread, BEFORE the block loads its P-matrices / builds its tip tables: the copies fly while the
  * prologue runs (small alignments are latency-bound: ~1 us per launch) */
-template <int LK, int RK, int NT>
-__device__ __forceinline__ void pipe_prefetch(PipeSmem<NT> &sm, const PipeCtx &c) {
-  constexpr uint32_t NST = PipeSmem<NT>::NST;
+template <int LK, int RK, int NT, int CATS>
+__device__ __forceinline__ void pipe_prefetch(PipeSmem<NT, CATS> &sm, const PipeCtx &c) {
+  constexpr uint32_t NST = PipeSmem<NT, CATS>::NST;
   const uint32_t pre = c.count < NST ? c.count : NST;
-  for (uint32_t k = 0; k < pre; ++k) pipe_issue<LK, RK, NT>(sm, c, k, k);
+  for (uint32_t k = 0; k < pre; ++k) pipe_issue<LK, RK, NT, CATS>(sm, c, k, k);
 }
 
-template <int LK, int RK, bool EMIT, int NT>
-__device__ __forceinline__ void pipe_loop(PipeSmem<NT> &sm, const PipeCtx &c, const double (&PL)[16], const double (&PR)[16],
+template <int LK, int RK, bool EMIT, int NT, int CATS>
+__device__ __forceinline__ void pipe_loop(PipeSmem<NT, CATS> &sm, const PipeCtx &c, const double (&PL)[16], const double (&PR)[16],
                                           double f0, double f1, double f2, double f3, double wcat) {
-  constexpr uint32_t TPX = NT * TP;
-  constexpr uint32_t NST = PipeSmem<NT>::NST;
-  const int tid = threadIdx.x, cat = tid & 3, lane = tid & 31, pl = tid >> 2;
+  constexpr uint32_t TPC = BLOCK / CATS;   // patterns per sub-tile
+  constexpr uint32_t TPX = NT * TPC;
+  constexpr uint32_t NST = PipeSmem<NT, CATS>::NST;
+  const int tid = threadIdx.x, cat = tid & (CATS - 1), lane = tid & 31, pl = tid / CATS;
   constexpr bool tiptip = (LK == NRX_TIP && RK == NRX_TIP);
-  const unsigned quad = 0xFu << (lane & ~3);
+  // the lanes holding the categories of this thread's pattern (CATS <= 16: a group never straddles a warp)
+  const unsigned quad = (CATS >= 32 ? 0xffffffffu : ((1u << CATS) - 1u)) << (lane & ~(CATS - 1));
   uint32_t site0 = c.grp * TPX + pl;                       // patterns < 2^32 (the first NST stages were issued by pipe_prefetch)
   const uint32_t site_step = c.groups * TPX;
-  double *out0 = c.par + ((size_t)site0 * 4 + cat) * 4;
-  const size_t out_step = (size_t)site_step * 16;
+  double *out0 = c.par + ((size_t)site0 * CATS + cat) * 4;
+  const size_t out_step = (size_t)site_step * (CATS * 4);
   uint32_t stage = 0, phase = 0;
   for (uint32_t k = 0; k < c.count; ++k) {
-    const PipeStage<NT> &st = sm.st[stage];
+    const PipeStage<NT, CATS> &st = sm.st[stage];
     mbar_wait(&sm.full[stage], phase);
 #pragma unroll
     for (int u = 0; u < NT; ++u) {
-      const uint32_t site = site0 + u * TP;
-      const int plu = pl + u * TP, tu = tid + u * BLOCK;
-      double *out = out0 + (size_t)u * TP * 16;
+      const uint32_t site = site0 + u * TPC;
+      const int plu = pl + u * TPC, tu = tid + u * BLOCK;
+      double *out = out0 + (size_t)u * BLOCK * 4;
       const bool act = site < c.patterns;
       D4 x, y, p;
       if (LK == NRX_CLV) x = matvec4_reg(PL, *reinterpret_cast<const D4 *>(st.l + tu * 4));
-      else if (LK == NRX_TIP) x = *reinterpret_cast<const D4 *>(sm.lutL + ((st.tl[plu] & 15) * 4 + cat) * 4);
+      else if (LK == NRX_TIP) x = *reinterpret_cast<const D4 *>(sm.lutL + ((st.tl[plu] & 15) * CATS + cat) * 4);
       if (RK == NRX_CLV) y = matvec4_reg(PR, *reinterpret_cast<const D4 *>(st.r + tu * 4));
-      else if (RK == NRX_TIP) y = *reinterpret_cast<const D4 *>(sm.lutR + ((st.tr[plu] & 15) * 4 + cat) * 4);
+      else if (RK == NRX_TIP) y = *reinterpret_cast<const D4 *>(sm.lutR + ((st.tr[plu] & 15) * CATS + cat) * 4);
       if (RK == NRX_NONE) p = x;
       else if (LK == NRX_NONE) p = y;
       else { p.x = __dmul_rn(x.x, y.x); p.y = __dmul_rn(x.y, y.y); p.z = __dmul_rn(x.z, y.z); p.w = __dmul_rn(x.w, y.w); }
@@ -505,12 +522,14 @@ __device__ __forceinline__ void pipe_loop(PipeSmem<NT> &sm, const PipeCtx &c, co
       if (EMIT) {
         double t = 0.0;
         if (act) t = __dmul_rn(tree4(__dmul_rn(f0, p.x), __dmul_rn(f1, p.y), __dmul_rn(f2, p.z), __dmul_rn(f3, p.w)), wcat);
-        const double t1 = __shfl_down_sync(0xffffffffu, t, 1), t2 = __shfl_down_sync(0xffffffffu, t, 2), t3 = __shfl_down_sync(0xffffffffu, t, 3);
-        if (act && cat == 0) c.ps_out[site] = __dadd_rn(__dadd_rn(__dadd_rn(t, t1), t2), t3);
+        double acc = t;   // categories in order: ((t0 + t1) + t2) + ...
+#pragma unroll
+        for (int i = 1; i < CATS; ++i) acc = __dadd_rn(acc, __shfl_down_sync(0xffffffffu, t, i));
+        if (act && cat == 0) c.ps_out[site] = acc;
       }
     }
     __syncthreads();   // lock-step refill (see k_clv_dna4_pipe: per-warp release measured 18 % slower)
-    if (tid == 0 && k + NST < c.count) pipe_issue<LK, RK, NT>(sm, c, k + NST, stage);
+    if (tid == 0 && k + NST < c.count) pipe_issue<LK, RK, NT, CATS>(sm, c, k + NST, stage);
     site0 += site_step;
     out0 += out_step;
     if (++stage == NST) { stage = 0; phase ^= 1u; }
@@ -521,17 +540,18 @@ __device__ __forceinline__ void pipe_loop(PipeSmem<NT> &sm, const PipeCtx &c, co
  * previous K2 launch still runs, does everything that does not depend on it (mbarrier init, P-matrices, tip tables),
  * lets ITS successor start (griddepcontrol.launch_dependents) and only then waits for the predecessor's CLVs
  * (griddepcontrol.wait) before the first ring fill.  Small alignments: ~2 us of prologue per launch off the critical path. */
-template <int NT>
+template <int NT, int CATS = 4>
 __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe2(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops,
                                                               uint32_t nops, uint32_t groups, double *__restrict__ persite,
                                                               size_t persite_stride, uint32_t nparts_total, int pdl) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  PipeSmem<NT> &sm = *reinterpret_cast<PipeSmem<NT> *>(smem_raw);
+  PipeSmem<NT, CATS> &sm = *reinterpret_cast<PipeSmem<NT, CATS> *>(smem_raw);
   const PartView &pv = parts[blockIdx.z];
   const nrx_op op = ops[blockIdx.x % nops];
   const uint32_t grp = blockIdx.x / nops;
-  const int tid = threadIdx.x, cat = tid & 3;
-  const uint32_t ntiles = (pv.patterns + NT * TP - 1) / (NT * TP);
+  const int tid = threadIdx.x, cat = tid & (CATS - 1);
+  constexpr uint32_t TPX = NT * (BLOCK / CATS);
+  const uint32_t ntiles = (pv.patterns + TPX - 1) / TPX;
   if (grp >= ntiles) return;
   const int lk = op.left_kind, rk = op.right_kind;
   PipeCtx c;
@@ -546,7 +566,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe2(const PartView *__r
   c.grp = grp; c.groups = groups; c.patterns = pv.patterns;
   c.count = (ntiles - grp + groups - 1) / groups;
   c.ps_out = nullptr;
-#define NRX_PIPE_PRE(L, R) case (L) * 3 + (R): pipe_prefetch<L, R, NT>(sm, c); break;
+#define NRX_PIPE_PRE(L, R) case (L) * 3 + (R): pipe_prefetch<L, R, NT, CATS>(sm, c); break;
 #define NRX_PIPE_PREFETCH()                                                                                     \
   switch (lk * 3 + rk) {                                                                                        \
     NRX_PIPE_PRE(NRX_CLV, NRX_CLV) NRX_PIPE_PRE(NRX_CLV, NRX_TIP) NRX_PIPE_PRE(NRX_CLV, NRX_NONE)               \
@@ -556,20 +576,20 @@ __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe2(const PartView *__r
   }
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < PipeSmem<NT>::NST; ++s) mbar_init(&sm.full[s], 1);
+    for (int s = 0; s < PipeSmem<NT, CATS>::NST; ++s) mbar_init(&sm.full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (!pdl) { NRX_PIPE_PREFETCH() }   // stream-ordered launch: the children are final, fill the ring before the prologue
   }
-  if (lk == NRX_TIP) build_tip_lut4(sm.lutL, pv.pmat + (size_t)op.left_edge * 64, tid);
-  if (rk == NRX_TIP) build_tip_lut4(sm.lutR, pv.pmat + (size_t)op.right_edge * 64, tid);
+  if (lk == NRX_TIP) build_tip_lut<CATS>(sm.lutL, pv.pmat + (size_t)op.left_edge * (CATS * 16), tid);
+  if (rk == NRX_TIP) build_tip_lut<CATS>(sm.lutR, pv.pmat + (size_t)op.right_edge * (CATS * 16), tid);
   double PL[16], PR[16];
   if (lk == NRX_CLV) {
-    const double *src = pv.pmat + (size_t)op.left_edge * 64 + cat * 16;
+    const double *src = pv.pmat + (size_t)op.left_edge * (CATS * 16) + cat * 16;
 #pragma unroll
     for (int i = 0; i < 16; ++i) PL[i] = src[i];
   }
   if (rk == NRX_CLV) {
-    const double *src = pv.pmat + (size_t)op.right_edge * 64 + cat * 16;
+    const double *src = pv.pmat + (size_t)op.right_edge * (CATS * 16) + cat * 16;
 #pragma unroll
     for (int i = 0; i < 16; ++i) PR[i] = src[i];
   }
@@ -589,8 +609,8 @@ __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe2(const PartView *__r
   }
 #define NRX_PIPE_CASE(L, R)                                                                  \
   case (L) * 3 + (R):                                                                        \
-    if (emit) pipe_loop<L, R, true, NT>(sm, c, PL, PR, f0, f1, f2, f3, wcat);                \
-    else pipe_loop<L, R, false, NT>(sm, c, PL, PR, f0, f1, f2, f3, wcat);                    \
+    if (emit) pipe_loop<L, R, true, NT, CATS>(sm, c, PL, PR, f0, f1, f2, f3, wcat);          \
+    else pipe_loop<L, R, false, NT, CATS>(sm, c, PL, PR, f0, f1, f2, f3, wcat);              \
     break;
   switch (lk * 3 + rk) {
     NRX_PIPE_CASE(NRX_CLV, NRX_CLV)

@@ -451,18 +451,26 @@ def test_mixed_dna_and_protein_partitions():
     g.close()
 
 
-@pytest.mark.parametrize("cats", [1, 2, 3, 8])
-def test_other_category_counts_use_generic_kernels(cats):
-    """GTR + Gamma with 1, 2, 3 or 8 rate categories: the 4x4 specialisations do not apply, so K2-K6 go through the
-    generic kernels (power-of-two category counts: thread per (pattern, category); 3: thread per pattern)."""
+@pytest.mark.parametrize("cats", [1, 2, 3, 8, 16])
+def test_other_category_counts(cats):
+    """GTR + Gamma with 1, 2, 8 or 16 rate categories runs the pipelined K2 kernel templated on the category count (round 2; the
+    reference's AVX kernels loop over rate_cats at full speed, LIBPLL/core_partials_avx.c:402-565): CLVs and scalers bit-identical
+    to libpll as for 4 categories, incl. plan replay with the fused K3.  3 categories: the generic thread-per-pattern kernels.
+    K3-K6: thread per (pattern, category) for power-of-two counts."""
     from oracle import oracle
     net = random_network(11, 2, seed=40 + cats)
-    m, w = simulate_alignment(net, 333, seed=40 + cats)
+    m, w = simulate_alignment(net, 1333, seed=40 + cats)
     rates = oracle.api("port").gamma_rates(0.7, cats) if cats > 1 else np.ones(1)
     part = Partition(4, cats, m, DNA_FREQS, GTR_RATES, rates, pattern_weights=w)
     g, o = _gpu(net, [part]), _oracle(net, [part])
     _inject_eigen(g, o)
-    assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
+    lo = o.computeLoglikelihood(0, 1)
+    lg = g.computeLoglikelihood(0, 1)
+    assert lg == pytest.approx(lo, rel=LNL_RTOL)
+    same_p = all(np.array_equal(g.get_pmatrix(e), o.get_pmatrix(e)) for e in range(net.num_edges + 1))
+    _compare_all_clvs(g, o, exact=same_p and cats != 3)
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(lg, rel=REPLAY_RTOL)     # plan replay (graph + fused K3 for 1 / 2 / 8 / 16)
+    _compare_all_clvs(g, o, exact=same_p and cats != 3)
     for e in (0, int(net.ret_first_edge[0]), net.num_edges - 1):
         assert g.brlen_prepare(e) == pytest.approx(o.brlen_prepare(e), rel=LNL_RTOL)
         assert g.computeLoglikelihoodBrlenOpt(e) == pytest.approx(o.computeLoglikelihoodBrlenOpt(e), rel=LNL_RTOL)
@@ -471,6 +479,26 @@ def test_other_category_counts_use_generic_kernels(cats):
         np.testing.assert_allclose(dg[4], do[4], rtol=DERIV_RTOL, atol=1e-9)
         assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL)
     g.close()
+
+
+def test_category_counts_scaler_stress():
+    """the per-pattern scaling vote over a 1-, 2-, 8- or 16-lane group: deep caterpillar, scaler counts bit-exact"""
+    from oracle import oracle
+    net = caterpillar_network(300)
+    m, w = simulate_alignment(net, 300, seed=77, random_cells=True)
+    for cats in (1, 2, 8, 16):
+        rates = oracle.api("port").gamma_rates(0.5, cats) if cats > 1 else np.ones(1)
+        part = Partition(4, cats, m, DNA_FREQS, GTR_RATES, rates, pattern_weights=w)
+        g, o = _gpu(net, [part]), _oracle(net, [part])
+        _inject_eigen(g, o)
+        assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
+        mx = 0
+        for t in range(g.num_trees(net.root)):
+            sg, so = g.read_scaler(net.root, t), o.read_scaler(net.root, t)
+            assert np.array_equal(sg, so)
+            mx = max(mx, int(so.max()))
+        assert mx >= 1, cats
+        g.close()
 
 
 def test_batched_scoring_equals_sequential():

@@ -112,6 +112,11 @@ struct EnginePlan {
   cudaGraphExec_t exec[2] = {nullptr, nullptr};   // [0] latency geometry, [1] throughput geometry (nrx_set_throughput_mode)
   unsigned long long updates = 0, bytes = 0, cbytes = 0;
   uint32_t lnl_items = 0;    // number of ops carrying an lnl_item mark (fused K3)
+  // node-centric K2 (k_clv_node_dna4): per batch, the groups of ops that share children; the batch's remaining ops stay in d_ops
+  nrx_node_group *d_ngroups = nullptr;
+  nrx_node_op *d_nops = nullptr;
+  nrx_node_block *d_nblocks = nullptr;
+  std::vector<uint32_t> node_block_off, node_block_cnt, node_ncmax;   // per batch: range in d_nblocks (count 0: no node launch), largest group (children)
   // tile-walk form of the plan (k_walk_dna4): the ops in a depth-first order with shared-memory buffer assignments
   nrx_walk_op *d_walk = nullptr;
   uint32_t walk_nops = 0, walk_nbuf = 0;
@@ -144,6 +149,8 @@ struct nrx_engine {
   uint32_t *d_tickets = nullptr;   // one self-resetting ticket counter per reduction output (item, partition): fused second stage
   bool fuse_reduce = true;         // env NRX_FUSE_REDUCE=0: separate k_reduce_partials launch (A/B)
   bool defer_pmat = false;         // P-matrix updates are deferred until a launch needs them: the tile walk computes them itself (one launch per evaluation)
+  uint32_t node_maxc = NODE_MAXC, node_blocks = 0;   // env NRX_NODE_MAXC (children per group, <= 16), NRX_NODE_BLOCKS (block target per launch; 0 = 24 x SMs)
+  int node_mode = 0;               // env NRX_NODE=1: ops of a node that share children run on k_clv_node_dna4 (A/B; measured 10 % slower than the per-op kernel, profiles/r3a_node_centric_ab.md)
   int walk_mode = 2;               // env NRX_WALK: 0 never, 1 whenever the plan has a tile-walk form, 2 (default) when it has one and the launch is small enough
   uint32_t walk_max_tiles = 0;     // mode 2: use the walk up to this many tiles per partition (env NRX_WALK_TILES; default set in nrx_engine_create)
   double *d_persite = nullptr;
@@ -410,6 +417,9 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
   if (const char *v = std::getenv("NRX_GRAPH")) e->use_graphs = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_PDL")) e->use_pdl = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_FUSE_REDUCE")) e->fuse_reduce = std::atoi(v) != 0;
+  if (const char *v = std::getenv("NRX_NODE")) e->node_mode = std::atoi(v);
+  if (const char *v = std::getenv("NRX_NODE_MAXC")) e->node_maxc = (uint32_t)std::min(NODE_MAXC, std::max(2, std::atoi(v)));
+  if (const char *v = std::getenv("NRX_NODE_BLOCKS")) e->node_blocks = (uint32_t)std::max(0, std::atoi(v));
   if (const char *v = std::getenv("NRX_WALK")) e->walk_mode = std::atoi(v);
   if (const char *v = std::getenv("NRX_WALK_TILES")) e->walk_max_tiles = (uint32_t)std::max(0, std::atoi(v));
   if (const char *v = std::getenv("NRX_K2_NT")) e->k2_nt = std::atoi(v) == 1 ? 1u : 2u;
@@ -426,7 +436,9 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
     // measured (profiles/r2r_tile_walk.md): 10 k patterns (313 tiles) 73 vs 89 us per evaluation; at 100 k patterns the walk's serial
     // op chain per block loses 3x to the bandwidth-bound level-by-level kernels -> only while the launch is latency-bound
     if (!std::getenv("NRX_WALK_TILES")) e->walk_max_tiles = 4u * (uint32_t)sms;
-    if (!cuda_ok(cudaFuncSetAttribute(k_walk_dna4, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024), "cudaFuncSetAttribute")) { delete e; return nullptr; }
+    if (!cuda_ok(cudaFuncSetAttribute(k_walk_dna4, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024), "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(k_clv_node_dna4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)node_smem_bytes(NODE_MAXC)), "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(k_clv_node_dna4, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute")) { delete e; return nullptr; }
     const int aa_smem = (int)(sizeof(AaSmem) + 2 * AA_LUT_CODES * 80 * sizeof(double));
     if (!cuda_ok(cudaFuncSetAttribute(k_aa20_dmma<AA_CLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa_smem), "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(k_aa20_dmma<AA_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, aa_smem), "cudaFuncSetAttribute") ||
@@ -491,7 +503,7 @@ void nrx_engine_destroy(nrx_engine *e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->comm && nccl().ok) nccl().CommDestroy(e->comm);
-  for (EnginePlan &pl : e->plans) { for (cudaGraphExec_t &x : pl.exec) if (x) cudaGraphExecDestroy(x); cudaFree(pl.d_ops); cudaFree(pl.d_walk); }
+  for (EnginePlan &pl : e->plans) { for (cudaGraphExec_t &x : pl.exec) if (x) cudaGraphExecDestroy(x); cudaFree(pl.d_ops); cudaFree(pl.d_walk); cudaFree(pl.d_ngroups); cudaFree(pl.d_nops); cudaFree(pl.d_nblocks); }
   for (Part &p : e->parts) {
     cudaFree(p.invariant); cudaFree(p.pmat); cudaFree(p.pmat_pad); cudaFree(p.tiplut); cudaFree(p.summat); cudaFree(p.sumlut); cudaFree(p.tipchars); cudaFree(p.tipmap); cudaFree(p.weights); cudaFree(p.model);
     for (void *m : p.slot_mem) cudaFree(m);
@@ -1084,6 +1096,83 @@ int nrx_update_pseudo_clvs(nrx_engine *e, const nrx_pseudo_op *ops, uint32_t nop
   return 1;
 }
 
+/* Node-centric grouping of ONE batch (k_clv_node_dna4).  Candidates are the inner x inner ops; ops with the same (left edge,
+ * right edge) belong to one network node; their (left slot, right slot) pairs form a bipartite graph whose connected components
+ * are (in practice complete) bipartite blocks — displayed trees that agree on the shared reticulations.  A component with
+ * <= NODE_MAXC children becomes one group; a larger one is cut along its larger side (the smaller side whole when it has
+ * <= NODE_MAXC / 2 children, else both sides in chunks of NODE_MAXC / 2).  A group is kept if it saves reads: 2 ops > children.
+ * Returns the ops that stay on the per-op kernel in `rest`; appends groups / group ops. */
+static void group_batch_for_node_kernel(const std::vector<nrx_op> &batch, std::vector<nrx_op> &rest, std::vector<nrx_node_group> &groups,
+                                        std::vector<nrx_node_op> &gops, std::vector<uint32_t> &batch_groups, const size_t MAXC) {
+  std::map<std::pair<uint32_t, uint32_t>, std::vector<uint32_t>> by_node;
+  for (uint32_t i = 0; i < batch.size(); ++i) {
+    const nrx_op &o = batch[i];
+    if (o.left_kind == NRX_CLV && o.right_kind == NRX_CLV) by_node[{o.left_edge, o.right_edge}].push_back(i);
+    else rest.push_back(o);
+  }
+  for (auto &kv : by_node) {
+    const std::vector<uint32_t> &idx = kv.second;
+    // connected components over (left slot, right slot)
+    std::map<uint32_t, uint32_t> lcomp, rcomp;
+    std::vector<uint32_t> comp(idx.size());
+    uint32_t ncomp = 0;
+    std::vector<uint32_t> parent;
+    auto find = [&](uint32_t x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+    for (size_t k = 0; k < idx.size(); ++k) {
+      const nrx_op &o = batch[idx[k]];
+      auto li = lcomp.find(o.left_idx), ri = rcomp.find(o.right_idx);
+      uint32_t c;
+      if (li == lcomp.end() && ri == rcomp.end()) { c = ncomp++; parent.push_back(c); }
+      else if (li != lcomp.end() && ri != rcomp.end()) { const uint32_t a = find(li->second), b = find(ri->second); parent[b] = a; c = a; }
+      else c = find(li != lcomp.end() ? li->second : ri->second);
+      lcomp[o.left_idx] = c; rcomp[o.right_idx] = c; comp[k] = c;
+    }
+    std::map<uint32_t, std::vector<uint32_t>> comps;
+    for (size_t k = 0; k < idx.size(); ++k) comps[find(comp[k])].push_back(idx[k]);
+    for (auto &cv : comps) {
+      std::vector<uint32_t> L, R;
+      for (uint32_t i : cv.second) {
+        if (std::find(L.begin(), L.end(), batch[i].left_idx) == L.end()) L.push_back(batch[i].left_idx);
+        if (std::find(R.begin(), R.end(), batch[i].right_idx) == R.end()) R.push_back(batch[i].right_idx);
+      }
+      // chunk sizes per side
+      size_t cl = L.size(), cr = R.size();
+      if (L.size() + R.size() > MAXC) {
+        if (L.size() <= MAXC / 2) cr = MAXC - L.size();
+        else if (R.size() <= MAXC / 2) cl = MAXC - R.size();
+        else cl = cr = MAXC / 2;
+      }
+      for (size_t l0 = 0; l0 < L.size(); l0 += cl)
+        for (size_t r0 = 0; r0 < R.size(); r0 += cr) {
+          const size_t l1 = std::min(L.size(), l0 + cl), r1 = std::min(R.size(), r0 + cr);
+          std::vector<nrx_node_op> ops;
+          std::vector<uint32_t> members;
+          for (uint32_t i : cv.second) {
+            const auto li = std::find(L.begin() + l0, L.begin() + l1, batch[i].left_idx), ri = std::find(R.begin() + r0, R.begin() + r1, batch[i].right_idx);
+            if (li == L.begin() + l1 || ri == R.begin() + r1) continue;
+            nrx_node_op no{};
+            no.li = (uint16_t)(li - (L.begin() + l0)); no.rj = (uint16_t)(ri - (R.begin() + r0));
+            no.parent_slot = batch[i].parent_slot; no.lnl_item = batch[i].lnl_item;
+            ops.push_back(no);
+            members.push_back(i);
+          }
+          if (ops.empty()) continue;
+          // children actually referenced by this chunk's ops (a sparse component may leave some unused)
+          const size_t children = (l1 - l0) + (r1 - r0);
+          if (2 * ops.size() <= children + 1 || ops.size() > (size_t)NODE_MAXOPS) { for (uint32_t i : members) rest.push_back(batch[i]); continue; }
+          nrx_node_group g{};
+          g.nl = (uint32_t)(l1 - l0); g.nr = (uint32_t)(r1 - r0); g.nops = (uint32_t)ops.size();
+          g.left_edge = kv.first.first; g.right_edge = kv.first.second; g.op_first = (uint32_t)gops.size();
+          for (size_t a = l0; a < l1; ++a) g.child_slot[a - l0] = L[a];
+          for (size_t a = r0; a < r1; ++a) g.child_slot[g.nl + (a - r0)] = R[a];
+          batch_groups.push_back((uint32_t)groups.size());
+          groups.push_back(g);
+          gops.insert(gops.end(), ops.begin(), ops.end());
+        }
+    }
+  }
+}
+
 /* Tile-walk form of a plan (k_walk_dna4): (1) order the ops depth-first from the CLVs nobody consumes (the root displayed trees),
  * children before parents, so that a CLV is consumed soon after it is produced; (2) run a linear-scan allocation of
  * shared-memory buffers over that order — a CLV needs a buffer from its op until its last consumer; (3) accept the form if
@@ -1170,16 +1259,60 @@ int nrx_plan_create(nrx_engine *e, const nrx_op *ops, const uint32_t *batch_size
   EnginePlan pl;
   size_t total = 0;
   std::vector<nrx_op> ordered;
+  // node-centric K2 for the ops of a node that share children: single-class 4-state x 4-category engines
+  const bool node_ok = e->node_mode != 0 && e->classes.size() == 1 && e->classes[0].states == 4 && e->classes[0].cats == 4 && e->k2_variant == 0;
+  std::vector<nrx_node_group> ngroups;
+  std::vector<nrx_node_op> ngops;
+  std::vector<nrx_node_block> nblocks;
+  std::vector<nrx_op> all_ops(ops, ops + [&] { size_t t = 0; for (uint32_t b = 0; b < nbatches; ++b) t += batch_sizes[b]; return t; }());   // original order (tile walk)
+  size_t in_off = 0;
   for (uint32_t b = 0; b < nbatches; ++b) {
     if (batch_sizes[b] == 0) { g_err = "nrx_plan_create: empty batch"; return 0; }
-    if (!check_ops(e, ops + total, batch_sizes[b], &pl.updates, &pl.bytes, &pl.cbytes)) return 0;
+    if (!check_ops(e, ops + in_off, batch_sizes[b], &pl.updates, &pl.bytes, &pl.cbytes)) return 0;
+    std::vector<nrx_op> batch(ops + in_off, ops + in_off + batch_sizes[b]);
+    in_off += batch_sizes[b];
+    std::vector<uint32_t> bgroups;
+    if (node_ok) {
+      std::vector<nrx_op> rest;
+      group_batch_for_node_kernel(batch, rest, ngroups, ngops, bgroups, e->node_maxc);
+      batch.swap(rest);
+    }
+    // blocks of the node launch: ~8 waves of 3 resident blocks per SM in total, shared out by the groups' op counts, >= 4 tiles per block
+    pl.node_block_off.push_back((uint32_t)nblocks.size());
+    if (!bgroups.empty()) {
+      const uint32_t ntiles = (e->max_patterns + NODE_TP - 1) / NODE_TP;
+      uint64_t wsum = 0;
+      for (uint32_t g : bgroups) wsum += ngroups[g].nops + ngroups[g].nl + ngroups[g].nr;
+      const uint32_t target = e->node_blocks ? e->node_blocks : 24u * (uint32_t)e->sm_count;
+      for (uint32_t g : bgroups) {
+        const uint64_t w = ngroups[g].nops + ngroups[g].nl + ngroups[g].nr;
+        uint32_t nb = (uint32_t)std::max<uint64_t>(1, (uint64_t)target * w / std::max<uint64_t>(1, wsum));
+        nb = std::min(nb, std::max<uint32_t>(1, ntiles / 4));
+        for (uint32_t k = 0; k < nb; ++k) nblocks.push_back(nrx_node_block{g, k, nb, 0});
+      }
+    }
+    pl.node_block_cnt.push_back((uint32_t)nblocks.size() - pl.node_block_off.back());
+    { uint32_t m = 0; for (uint32_t g : bgroups) m = std::max(m, ngroups[g].nl + ngroups[g].nr); pl.node_ncmax.push_back(m); }
     pl.offsets.push_back(total);
-    pl.sizes.push_back(batch_sizes[b]);
-    pl.tips.push_back(any_tip(ops + total, batch_sizes[b]));
-    std::vector<nrx_op> batch(ops + total, ops + total + batch_sizes[b]);
+    pl.sizes.push_back((uint32_t)batch.size());
+    pl.tips.push_back(any_tip(batch.data(), (uint32_t)batch.size()));
     pl.ntt.push_back(order_tiptip_first(e, batch));
     ordered.insert(ordered.end(), batch.begin(), batch.end());
-    total += batch_sizes[b];
+    total += batch.size();
+  }
+  if (!ngroups.empty()) {
+    // interleave the blocks of a batch's groups (group-fastest), so that the big and the small groups of a launch finish together
+    for (size_t b = 0; b < pl.node_block_cnt.size(); ++b) {
+      auto first = nblocks.begin() + pl.node_block_off[b], last = first + pl.node_block_cnt[b];
+      std::stable_sort(first, last, [](const nrx_node_block &x, const nrx_node_block &y) { return x.tile0 < y.tile0; });
+    }
+    CK(cudaMalloc((void **)&pl.d_ngroups, ngroups.size() * sizeof(nrx_node_group)));
+    CK(cudaMalloc((void **)&pl.d_nops, ngops.size() * sizeof(nrx_node_op)));
+    CK(cudaMalloc((void **)&pl.d_nblocks, nblocks.size() * sizeof(nrx_node_block)));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(pl.d_ngroups, ngroups.data(), ngroups.size() * sizeof(nrx_node_group), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pl.d_nops, ngops.data(), ngops.size() * sizeof(nrx_node_op), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pl.d_nblocks, nblocks.data(), nblocks.size() * sizeof(nrx_node_block), cudaMemcpyHostToDevice));
   }
   ops = ordered.data();
   if (total) {
@@ -1187,7 +1320,7 @@ int nrx_plan_create(nrx_engine *e, const nrx_op *ops, const uint32_t *batch_size
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaMemcpy(pl.d_ops, ops, total * sizeof(nrx_op), cudaMemcpyHostToDevice));
   }
-  for (size_t i = 0; i < total; ++i) pl.lnl_items = std::max(pl.lnl_items, ops[i].lnl_item);
+  for (const nrx_op &o : all_ops) pl.lnl_items = std::max(pl.lnl_items, o.lnl_item);
   if (pl.lnl_items) {
     if (!nrx_supports_fused_lnl(e)) { cudaFree(pl.d_ops); g_err = "nrx_plan_create: lnl_item marks need every partition on the pipelined 4-state kernel"; return 0; }
     const size_t need = (size_t)pl.lnl_items * e->parts.size() * std::max<uint32_t>(1, e->max_patterns);
@@ -1200,10 +1333,24 @@ int nrx_plan_create(nrx_engine *e, const nrx_op *ops, const uint32_t *batch_size
       for (EnginePlan &o : e->plans) for (cudaGraphExec_t &x : o.exec) if (x) { cudaGraphExecDestroy(x); x = nullptr; }
     }
   }
-  if (pl.lnl_items && e->walk_mode != 0 && !build_walk_program(e, pl, ops, total)) return 0;
+  if (pl.lnl_items && e->walk_mode != 0 && !build_walk_program(e, pl, all_ops.data(), all_ops.size())) return 0;
   pl.alive = true;
   e->plans.push_back(pl);
   *plan_id = (uint32_t)e->plans.size() - 1;
+  return 1;
+}
+
+/* one batch of a plan: the ops that share children on the node-centric kernel, the rest on the per-op kernels */
+static int launch_plan_batch(nrx_engine *e, EnginePlan &pl, size_t b) {
+  if (pl.sizes[b] && !launch_clv_batch(e, pl.d_ops + pl.offsets[b], pl.sizes[b], pl.tips[b], pl.lnl_items != 0, pl.ntt[b])) return 0;
+  if (pl.node_block_cnt[b]) {
+    const ShapeClass &c = e->classes[0];
+    k_clv_node_dna4<<<dim3(pl.node_block_cnt[b], 1, (uint32_t)c.parts.size()), NODE_THREADS, node_smem_bytes(pl.node_ncmax[b]), e->stream>>>(
+        c.d_views, pl.d_ngroups, pl.d_nops, pl.d_nblocks + pl.node_block_off[b], pl.lnl_items ? e->d_fused : nullptr, (size_t)e->max_patterns, (uint32_t)e->parts.size(), pl.node_ncmax[b]);
+    e->launches++;
+    e->pdl_prev_is_k2 = false;   // the next pipelined launch must not be programmatically serialised behind this one
+    CK(cudaGetLastError());
+  }
   return 1;
 }
 
@@ -1216,7 +1363,8 @@ int nrx_plan_run(nrx_engine *e, uint32_t plan_id) {
   if (!refresh_views(e)) return 0;
   cudaEvent_t ev0, ev1;
   prof_begin(e, &ev0, &ev1);
-  const unsigned long long per_run = pl.sizes.size() * e->classes.size();
+  unsigned long long per_run = 0;
+  for (size_t b = 0; b < pl.sizes.size(); ++b) per_run += (pl.sizes[b] ? e->classes.size() : 0) + (pl.node_block_cnt[b] ? 1 : 0);
   cudaGraphExec_t &gexec = pl.exec[e->throughput_mode ? 1 : 0];
   if (e->use_graphs && !gexec) {  // capture the launches once per geometry; kernel arguments (views, resident ops) never change
     const unsigned long long l0 = e->launches;
@@ -1225,7 +1373,7 @@ int nrx_plan_run(nrx_engine *e, uint32_t plan_id) {
     e->capturing_pdl = e->use_pdl && e->classes.size() == 1 && dna_pipe_cats(e->classes[0].states, e->classes[0].cats) && e->k2_variant == 0;
     e->pdl_prev_is_k2 = false;
     int ok = 1;
-    for (size_t b = 0; b < pl.sizes.size() && ok; ++b) ok = launch_clv_batch(e, pl.d_ops + pl.offsets[b], pl.sizes[b], pl.tips[b], pl.lnl_items != 0, pl.ntt[b]);
+    for (size_t b = 0; b < pl.sizes.size() && ok; ++b) ok = launch_plan_batch(e, pl, b);
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
     e->capturing_pdl = false;
@@ -1240,7 +1388,7 @@ int nrx_plan_run(nrx_engine *e, uint32_t plan_id) {
     e->launches += per_run;
   } else {
     for (size_t b = 0; b < pl.sizes.size(); ++b)
-      if (!launch_clv_batch(e, pl.d_ops + pl.offsets[b], pl.sizes[b], pl.tips[b], pl.lnl_items != 0, pl.ntt[b])) return 0;
+      if (!launch_plan_batch(e, pl, b)) return 0;
   }
   prof_end(e, ev0, ev1, per_run, pl.updates, pl.bytes, NRX_PROF_K2, pl.cbytes);
   return 1;
@@ -1268,6 +1416,7 @@ int nrx_plan_destroy(nrx_engine *e, uint32_t plan_id) {
   for (cudaGraphExec_t &x : pl.exec) if (x) cudaGraphExecDestroy(x);
   cudaFree(pl.d_ops);
   cudaFree(pl.d_walk);
+  cudaFree(pl.d_ngroups); cudaFree(pl.d_nops); cudaFree(pl.d_nblocks);
   pl = EnginePlan();
   return 1;
 }

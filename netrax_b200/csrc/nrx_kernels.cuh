@@ -627,6 +627,134 @@ __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe2(const PartView *__r
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * K2, DNA 4x4, NODE-CENTRIC variant (round 2): for the ops of a network node that share children.
+ *
+ * k_clv_dna4_pipe2 gives every op (= displayed tree) its own block, so an op re-reads both of its children and recomputes
+ * P_edge . child although the 96 displayed trees of a big node are the 12 x 8 compatible pairs of only 20 children; the re-reads are
+ * served by the L2 most of the time, but at 1 M patterns 13 % more than the compulsory bytes cross the HBM pins (profiles/
+ * r2b_k2_traffic_1M.md: 22.5 GB per step, 15.5 of them in the root node's launch).  The compatible (left tree, right tree) pairs of a
+ * node form complete bipartite blocks (trees that agree on the shared reticulations); the host cuts the ops of a plan batch into such
+ * GROUPS of <= NODE_MAXC distinct children (nrx_plan_create).  Here block = (group, tile of NODE_TP patterns):
+ *   1. every distinct child tile (+ scalers) is bulk-copied into shared memory ONCE;
+ *   2. x_i = P_left . left_i and y_j = P_right . right_j are computed ONCE per distinct child, in place (thread = (pattern, category)
+ *      only ever touches its own 32 bytes of a tile, so no barrier is needed between the steps);
+ *   3. every op (i, j) is a product x_i * y_j, the per-pattern scaling vote, and a streamed 256-bit store — ~30 instructions per item
+ *      instead of ~95, HBM traffic = compulsory.
+ * Arithmetic is the same instruction sequence per value as the pipelined kernel (matvec4_reg, separate multiply / add), so CLVs and
+ * scalers stay bit-identical.  Three blocks per SM interleave one block's load phase with the others' store phases.
+ * ---------------------------------------------------------------------------------------------- */
+constexpr int NODE_TP = 32;          // patterns per tile: a child tile is 4 KB
+constexpr int NODE_THREADS = NODE_TP * 4;
+constexpr int NODE_MAXC = 16;        // distinct children per group (left + right)
+constexpr int NODE_MAXOPS = 128;     // ops per group
+
+struct nrx_node_op { uint16_t li, rj; uint32_t parent_slot; uint32_t lnl_item; uint32_t pad_; };   // 16 bytes; li / rj index the group's left / right children
+struct nrx_node_group {             // 16-byte multiple: bulk-copied into shared memory together with its ops
+  uint32_t nl, nr, nops, left_edge, right_edge, op_first, pad0_, pad1_;
+  uint32_t child_slot[NODE_MAXC];   // nl left slots, then nr right slots
+};
+struct nrx_node_block { uint32_t group, tile0, stride, pad_; };   // block b works on tiles tile0, tile0 + stride, ... of its group
+
+struct __align__(128) NodeSmemFixed {   // followed by double tile[ncmax][NODE_TP * 16] and uint32_t sc[ncmax][NODE_TP] (ncmax = the launch's largest group)
+  nrx_node_group grp;
+  nrx_node_op ops[NODE_MAXOPS];
+  double *par[NODE_MAXOPS];
+  uint32_t *psc[NODE_MAXOPS];
+  const double *cclv[NODE_MAXC];
+  const uint32_t *csc[NODE_MAXC];
+  unsigned long long bar, bar_desc;
+};
+__host__ __device__ constexpr size_t node_smem_bytes(uint32_t ncmax) { return sizeof(NodeSmemFixed) + (size_t)ncmax * (NODE_TP * 128 + NODE_TP * 4); }
+
+__global__ void __launch_bounds__(NODE_THREADS, 4) k_clv_node_dna4(const PartView *__restrict__ parts, const nrx_node_group *__restrict__ groups,
+                                                                    const nrx_node_op *__restrict__ gops, const nrx_node_block *__restrict__ blocks,
+                                                                    double *__restrict__ persite, size_t persite_stride, uint32_t nparts_total, uint32_t ncmax) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  NodeSmemFixed &sm = *reinterpret_cast<NodeSmemFixed *>(smem_raw);
+  double *s_tile = reinterpret_cast<double *>(smem_raw + sizeof(NodeSmemFixed));          // [ncmax][NODE_TP * 16]
+  uint32_t *s_sc = reinterpret_cast<uint32_t *>(s_tile + (size_t)ncmax * NODE_TP * 16);    // [ncmax][NODE_TP]
+  const PartView &pv = parts[blockIdx.z];
+  const nrx_node_block blk = blocks[blockIdx.x];
+  const int tid = threadIdx.x, cat = tid & 3, pl = tid >> 2, lane = tid & 31;
+  const uint32_t ntiles = (pv.patterns + NODE_TP - 1) / NODE_TP;
+  if (blk.tile0 >= ntiles) return;
+  if (tid == 0) {
+    mbar_init(&sm.bar, 1);
+    mbar_init(&sm.bar_desc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const nrx_node_group *g = groups + blk.group;
+    const uint32_t nops = g->nops;   // (one global read; the copy below brings the rest)
+    mbar_expect_tx(&sm.bar_desc, (uint32_t)sizeof(nrx_node_group) + nops * (uint32_t)sizeof(nrx_node_op));
+    bulk_g2s(&sm.grp, g, (uint32_t)sizeof(nrx_node_group), &sm.bar_desc);
+    bulk_g2s(sm.ops, gops + g->op_first, nops * (uint32_t)sizeof(nrx_node_op), &sm.bar_desc);
+  }
+  __syncthreads();
+  mbar_wait(&sm.bar_desc, 0);
+  const uint32_t nl = sm.grp.nl, nc = sm.grp.nl + sm.grp.nr, nops = sm.grp.nops;
+  {   // input / output pointers of the group for this partition, fetched once (slot tables live in global memory)
+    double *const *clv_tab = pv.clv;
+    uint32_t *const *sc_tab = pv.scaler;
+    for (uint32_t i = tid; i < nops; i += NODE_THREADS) { sm.par[i] = clv_tab[sm.ops[i].parent_slot]; sm.psc[i] = sc_tab[sm.ops[i].parent_slot]; }
+    if ((uint32_t)tid < nc) { sm.cclv[tid] = clv_tab[sm.grp.child_slot[tid]]; sm.csc[tid] = sc_tab[sm.grp.child_slot[tid]]; }
+  }
+  double PL[16], PR[16];
+  {
+    const double *a = pv.pmat + (size_t)sm.grp.left_edge * 64 + cat * 16, *b = pv.pmat + (size_t)sm.grp.right_edge * 64 + cat * 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { PL[i] = a[i]; PR[i] = b[i]; }
+  }
+  const bool emit_any = persite != nullptr;
+  double f0 = 0, f1 = 0, f2 = 0, f3 = 0, wcat = 0;
+  if (emit_any) { f0 = pv.freqs[0]; f1 = pv.freqs[1]; f2 = pv.freqs[2]; f3 = pv.freqs[3]; wcat = pv.rate_weights[cat]; }
+  const unsigned quad = 0xFu << (lane & ~3);
+  __syncthreads();
+  uint32_t phase = 0;
+  for (uint32_t t = blk.tile0; t < ntiles; t += blk.stride) {
+    const size_t p0 = (size_t)t * NODE_TP;
+    if (tid == 0) {
+      mbar_expect_tx(&sm.bar, nc * (uint32_t)(NODE_TP * 128 + NODE_TP * 4));
+      for (uint32_t c = 0; c < nc; ++c) {
+        bulk_g2s(s_tile + (size_t)c * NODE_TP * 16, sm.cclv[c] + p0 * 16, NODE_TP * 128u, &sm.bar);
+        bulk_g2s(s_sc + c * NODE_TP, sm.csc[c] + p0, NODE_TP * 4u, &sm.bar);
+      }
+    }
+    mbar_wait(&sm.bar, phase);
+    phase ^= 1u;
+    // step 2: P . child once per distinct child, in place (own 32 bytes)
+    for (uint32_t c = 0; c < nc; ++c) {
+      D4 *v = reinterpret_cast<D4 *>(s_tile + (size_t)c * NODE_TP * 16 + tid * 4);
+      *v = (c < nl) ? matvec4_reg(PL, *v) : matvec4_reg(PR, *v);
+    }
+    // step 3: the ops
+    const size_t site = p0 + pl;
+    const bool act = site < pv.patterns;
+    const size_t out_off = (site * 4 + cat) * 4;
+    for (uint32_t i = 0; i < nops; ++i) {
+      const nrx_node_op op = sm.ops[i];
+      const D4 x = *reinterpret_cast<const D4 *>(s_tile + (size_t)op.li * NODE_TP * 16 + tid * 4), y = *reinterpret_cast<const D4 *>(s_tile + (size_t)(nl + op.rj) * NODE_TP * 16 + tid * 4);
+      D4 p;
+      p.x = __dmul_rn(x.x, y.x); p.y = __dmul_rn(x.y, y.y); p.z = __dmul_rn(x.z, y.z); p.w = __dmul_rn(x.w, y.w);
+      const bool small = act & (p.x < SCALE_THRESHOLD) & (p.y < SCALE_THRESHOLD) & (p.z < SCALE_THRESHOLD) & (p.w < SCALE_THRESHOLD);
+      const unsigned b = __ballot_sync(0xffffffffu, small);
+      const bool scale = (b & quad) == quad;
+      const uint32_t s = s_sc[op.li * NODE_TP + pl] + s_sc[(nl + op.rj) * NODE_TP + pl] + (scale ? 1u : 0u);
+      if (scale) { p.x = __dmul_rn(p.x, SCALE_FACTOR); p.y = __dmul_rn(p.y, SCALE_FACTOR); p.z = __dmul_rn(p.z, SCALE_FACTOR); p.w = __dmul_rn(p.w, SCALE_FACTOR); }
+      if (act) {
+        stg256(sm.par[i] + out_off, p);
+        if (cat == 0) sm.psc[i][site] = s;
+      }
+      if (emit_any && op.lnl_item) {   // fused K3, first half (as k_clv_dna4_pipe2)
+        double tt = 0.0;
+        if (act) tt = __dmul_rn(tree4(__dmul_rn(f0, p.x), __dmul_rn(f1, p.y), __dmul_rn(f2, p.z), __dmul_rn(f3, p.w)), wcat);
+        const double t1 = __shfl_down_sync(0xffffffffu, tt, 1), t2 = __shfl_down_sync(0xffffffffu, tt, 2), t3 = __shfl_down_sync(0xffffffffu, tt, 3);
+        if (act && cat == 0) persite[((size_t)(op.lnl_item - 1) * nparts_total + pv.part_index) * persite_stride + site] = __dadd_rn(__dadd_rn(__dadd_rn(tt, t1), t2), t3);
+      }
+    }
+    __syncthreads();   // everyone is done with the tiles before the next load overwrites them
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * Whole-evaluation "tile walk" (round 2), DNA 4x4: ONE launch computes every CLV of a traversal plan AND the per-tree root
  * lnLs.  The post-order dependencies of a likelihood traversal are per PATTERN: a block that owns a tile of WALK_TP patterns can
  * run the whole plan for it from the tips to the root without ever synchronising with another block.  So, instead of one

@@ -96,19 +96,30 @@ def make_inputs(cfg, lo, hi=None):
     return net, parts, (brl if cfg["linkage"] == UNLINKED else None)
 
 
-def derivative_sweep(eng, net, iters=3):
+def derivative_sweep(eng, net, iters=3, accept=False):
     """For EVERY edge: virtual re-rooting, edge-rooted lnL, sumtables, `iters` Newton-iterate derivative evaluations, restore —
-    the loop of optimize_branch (src/optimization/BranchLengthOptimization.cpp:345-420) with a fixed iterate count."""
-    for e in range(net.num_edges):
-        t0 = float(net.edge_length[e])
+    the loop of optimize_branch (src/optimization/BranchLengthOptimization.cpp:345-420) with a fixed iterate count.  The reference
+    visits the candidates in unordered_set order (:423-476), i.e. any order is the reference's; the product proposes the pre-order
+    in which consecutive branches share their re-rooting paths (nrxh_brlen_sweep_order), the checker walks the same list.
+    accept=False restores the old length (a converged optimisation round); accept=True keeps the last proposal, as an
+    optimisation that moves every branch does — the nodes above the edge are then recomputed, as in the reference."""
+    order = eng.brlen_sweep_order() if hasattr(eng.api, "_brlen_sweep_order") else range(net.num_edges)
+    lengths = eng.branch_lengths()
+    for e in order:
+        e = int(e)
+        t0 = float(lengths[e])
         eng.brlen_prepare(e)
         eng.computeLoglikelihoodBrlenOpt(e)
         if eng.computePartitionSumtables(e):
             for k in range(iters):
                 eng.brlen_set_length(e, t0 * (1.0 + 0.1 * (k + 1)))
                 eng.computeLoglikelihoodDerivatives(e)
-            eng.brlen_set_length(e, t0)
+            if not accept:
+                eng.brlen_set_length(e, t0)
         eng.brlen_finish(e)
+    if accept:   # put the lengths back so that the next sweep starts from the same state
+        for e in range(net.num_edges):
+            eng.set_branch_length(e, float(lengths[e]))
 
 
 # ---------------------------------------------------------------------------------------------- CPU reference arm
@@ -255,18 +266,25 @@ def measure_config(c, device, peak, reps, with_cpu, cores):
          "lnl": lnl, "ms_per_eval": ms, "wall_ms_per_eval": wall, "lnl_evals_per_sec": 1e3 / ms, "site_updates_per_sec": updates / (ms / 1e3),
          "launches_per_eval": launches, "kernel_families": fam}
     if c == 2:
-        derivative_sweep(eng, net)  # warm-up (allocates re-rooting slots and sumtables)
-        eng.profile_enable(True)
-        l0 = eng.launch_count()
-        t = time.perf_counter()
-        eng.timer_start()
-        derivative_sweep(eng, net)
-        ms_s = eng.timer_stop()
-        wall_s = 1e3 * (time.perf_counter() - t)
-        r["derivative_sweep"] = {"what": "every edge: re-rooting + edge lnL + sumtables + 3 Newton-iterate derivative evaluations + restore",
-                                 "edges": int(net.num_edges), "ms": ms_s, "wall_ms": wall_s, "launches": eng.launch_count() - l0,
-                                 "edges_per_sec": net.num_edges / (wall_s / 1e3), "kernel_families": family_table(eng.profile_read_all(), 1, ms_s, peak)}
-        eng.profile_enable(False)
+        for key, accept in (("derivative_sweep", False), ("derivative_sweep_accept", True)):
+            derivative_sweep(eng, net, accept=accept)  # warm-up (allocates re-rooting slots and sumtables)
+            eng.computeLoglikelihood(1, 1)
+            st0 = eng.reroot_stats()
+            eng.profile_enable(True)
+            l0 = eng.launch_count()
+            t = time.perf_counter()
+            eng.timer_start()
+            derivative_sweep(eng, net, accept=accept)
+            ms_s = eng.timer_stop()
+            wall_s = 1e3 * (time.perf_counter() - t)
+            st1 = eng.reroot_stats()
+            r[key] = {"what": "every edge in pre-order: re-rooting + edge lnL + sumtables + 3 Newton-iterate derivative evaluations + "
+                              + ("last proposal kept (nodes above the edge recomputed)" if accept else "old length restored"),
+                      "edges": int(net.num_edges), "ms": ms_s, "wall_ms": wall_s, "launches": eng.launch_count() - l0,
+                      "edges_per_sec": net.num_edges / (wall_s / 1e3),
+                      "reroot_memo": {"hits": st1["hits"] - st0["hits"], "misses": st1["misses"] - st0["misses"], "cached_slots": st1["cached_slots"]},
+                      "kernel_families": family_table(eng.profile_read_all(), 1, ms_s, peak)}
+            eng.profile_enable(False)
     eng.close()
     r["parity"] = parity_check(cfg, 500, device)
     if with_cpu:

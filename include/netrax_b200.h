@@ -25,7 +25,8 @@
  *   nrxh_brlen_sumtables         <- netrax::computePartitionSumtables       src/likelihood/LikelihoodDerivatives.hpp:86
  *   nrxh_brlen_set_length        <- network_derivative_func_multi's proposal step (BranchLengthOptimization.cpp:176-187)
  *   nrxh_brlen_derivatives       <- netrax::computeLoglikelihoodDerivatives src/likelihood/LikelihoodDerivatives.hpp:82
- *   nrxh_brlen_finish            <- invalidatePmatrixIndex + computeLoglikelihood (BranchLengthOptimization.cpp:413-419)
+ *   nrxh_brlen_finish            <- invalidatePmatrixIndex + computeLoglikelihood (BranchLengthOptimization.cpp:413-419); the invalidation
+ *                                   happens only when the branch length differs from the one nrxh_brlen_prepare found (nothing was overwritten)
  *   nrxh_set_branch_length / nrxh_set_reticulation_prob / nrxh_set_model
  *                                <- what optimize_branch / setReticulationProb / pll_set_* + invalidate do to the state
  *   nrxh_set_reduce_callback     <- fake_treeinfo->parallel_reduce_cb        src/RaxmlWrapper.cpp:717-718
@@ -103,6 +104,15 @@ int nrxh_brlen_read_sumtable(void *h, unsigned p, unsigned idx, double *out, dou
 int nrxh_brlen_set_length(void *h, int partition, unsigned edge, double value);
 int nrxh_brlen_derivatives(void *h, unsigned edge, double *d1, double *d2, double *part_d1, double *part_d2, double *raw);
 int nrxh_brlen_finish(void *h, unsigned edge, double *final_logl);
+/* Virtual re-rooting on the device never overwrites a root-directed CLV (the reference re-roots in place and recomputes,
+ * src/likelihood/VirtualRerooting.cpp:192-252) and memoises the re-rooted trees of the path nodes between calls:
+ *   nrxh_brlen_sweep_order       <- the candidate order of optimize_branches_internal (BranchLengthOptimization.cpp:423-476 visits an
+ *                                   unordered_set): all branches in depth-first pre-order, edges_out[num_branches]
+ *   nrxh_reroot_stats            <- memo hits / misses (processNodeImproved calls of re-rooting paths), live entries and the CLV slots they hold
+ *   nrxh_set_reroot_cache_slots  <- slot budget of the memo (-1: default, 0: nothing survives a session) */
+int nrxh_brlen_sweep_order(void *h, unsigned *edges_out);
+int nrxh_reroot_stats(void *h, unsigned long long *hits, unsigned long long *misses, unsigned *entries, unsigned *cached_slots);
+int nrxh_set_reroot_cache_slots(void *h, long long max_slots);
 /* The immediate callers of the path, same control flow as the reference:
  *   nrxh_optimize_branch(es)      <- netrax::optimize_branch / optimize_branches  src/optimization/BranchLengthOptimization.cpp:345-421,423-476,567-576
  *   nrxh_optimize_reticulation(s) <- netrax::optimize_reticulation(s)             src/optimization/ReticulationOptimization.cpp:68-117

@@ -68,6 +68,10 @@ class FlatAPI:
         g("brlen_derivatives", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double), C.POINTER(C.c_double),
           C.c_void_p, C.c_void_p, C.c_void_p)
         g("brlen_finish", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
+        if self.has("brlen_sweep_order"):   # product only: the checker re-roots in place, as the reference does
+            g("brlen_sweep_order", C.c_int, C.c_void_p, C.c_void_p)
+            g("reroot_stats", C.c_int, C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint), C.POINTER(C.c_uint))
+            g("set_reroot_cache_slots", C.c_int, C.c_void_p, C.c_longlong)
         g("optimize_branch", C.c_int, C.c_void_p, C.c_uint, C.c_int, C.c_uint, C.POINTER(C.c_double))
         g("optimize_branches", C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double))
         g("optimize_reticulation", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
@@ -285,6 +289,20 @@ class LikelihoodEngine:
         out = C.c_double()
         self.api.check(self.api._brlen_finish(self.h, edge, C.byref(out)))
         return out.value
+
+    def brlen_sweep_order(self) -> np.ndarray:
+        """All branches in depth-first pre-order: consecutive branches share their re-rooting paths (memoised on the device)."""
+        out = np.zeros(self.net.num_edges, dtype=np.uint32)
+        self.api.check(self.api._brlen_sweep_order(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def reroot_stats(self) -> dict:
+        h, m, n, s = C.c_ulonglong(), C.c_ulonglong(), C.c_uint(), C.c_uint()
+        self.api.check(self.api._reroot_stats(self.h, C.byref(h), C.byref(m), C.byref(n), C.byref(s)))
+        return {"hits": h.value, "misses": m.value, "entries": n.value, "cached_slots": s.value}
+
+    def set_reroot_cache_slots(self, max_slots: int = -1):
+        self.api.check(self.api._set_reroot_cache_slots(self.h, max_slots))
 
     # ---- the immediate callers (src/optimization/BranchLengthOptimization.cpp, ReticulationOptimization.cpp) ----
     def optimize_branch(self, edge: int, method: int = NEWTON_RAPHSON, max_iters: int = 32) -> float:

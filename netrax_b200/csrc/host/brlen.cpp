@@ -7,6 +7,7 @@
  */
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <queue>
 #include <unordered_set>
 
@@ -125,79 +126,306 @@ NodeSaveInformation computeNodeSaveInformation(const std::vector<PathToVirtualRo
   return info;
 }
 
-/* deep copy of a node's displayed trees into temporary device slots / back (the reference copy-assigns
- * NodeDisplayedTreeData, i.e. memcpy's CLVs on the host: VirtualRerooting.cpp:211-220,234-238) */
-struct SavedNode { std::vector<DisplayedTreeData> trees; size_t num_active = 0; };
+}  // namespace
 
-struct SlotCopies {  // (dst, src) pairs of one save / restore step, issued as ONE device launch
-  std::vector<uint32_t> dst, src;
-  void add(uint32_t d, uint32_t s) { dst.push_back(d); src.push_back(s); }
-  void run(AnnotatedNetwork &ann) {
-    if (!dst.empty()) engineCheck(nrx_copy_slots(ann.engine, dst.data(), src.data(), (uint32_t)dst.size()), "nrx_copy_slots");
-    dst.clear(); src.clear();
-  }
+/* ---- shadow re-rooting + memoised re-rooted node data ---------------------------------------------------------------------------
+ * The reference re-roots IN PLACE: processNodeImproved overwrites the displayed trees of every node on the root -> new-root paths,
+ * nodes a later path still needs in their original form are deep-copied first and copied back (VirtualRerooting.cpp:131-190,
+ * 211-220,234-238), and after the branch is optimised `invalidatePmatrixIndex` throws everything above the edge away so that the
+ * next computeLoglikelihood recomputes it (BranchLengthOptimization.cpp:417-420).  On the device that is two HBM passes per path
+ * node and edge that buy nothing, so here:
+ *  (1) a re-rooting SESSION never overwrites a root-directed CLV: the node's NodeDisplayedTreeData is moved into a stash, the
+ *      re-rooted trees go to fresh slots, "restoring" a node for a later path is a metadata copy, and finishVirtualReroot moves the
+ *      stash back.  If the branch length is what it was, nothing is invalid afterwards;
+ *  (2) what processNodeImproved produced for (node, ordered children, the children's data identity, the lengths of the edges to
+ *      them, the path's restriction set) is MEMOISED: the same call in a later session — the neighbouring edge's path shares all
+ *      but its last node — installs the cached trees instead of launching K2 again.  Identity of a child's data = the id of the
+ *      cache entry installed there, or the node's version counter for root-directed data (bumped by every recomputation), so a
+ *      changed branch length or CLV anywhere below simply misses; reticulation probabilities, models, tips and the topology
+ *      bump `clv_epoch`, which empties the cache.  A sweep that visits the edges in pre-order therefore costs ~1 node update
+ *      per edge instead of the whole path down and up again.  The enumeration (which trees, which configs, which op per tree) is
+ *      the reference's, call for call: hits return exactly what the miss computed. */
+struct RerootCache {
+  struct Entry {
+    uint64_t id = 0, last_use = 0, pinned_session = 0;
+    size_t node = 0;
+    std::vector<size_t> children;
+    std::vector<uint64_t> child_stamp;
+    std::vector<double> lengths;          // [child][partition]
+    std::vector<ReticulationConfig> extra;
+    size_t extra_max = 0;
+    NodeDisplayedTreeData data;           // owns the slots of data.displayed_trees
+  };
+  std::vector<Entry> entries;
+  uint64_t next_id = 1, tick = 0, session = 0, epoch = 0;
+  size_t cached_slots = 0;
+  // the open session
+  bool active = false;
+  size_t edge = 0;
+  std::vector<double> start_lengths;                 // [partition]
+  std::vector<char> stashed;                         // [node]
+  std::vector<NodeDisplayedTreeData> orig;           // [node] root-directed data while stashed
+  std::vector<std::vector<char>> orig_valid;         // [node][partition]
+  std::vector<size_t> alias_n;                       // [node] leading trees of the CURRENT data whose slots belong to the stash or to an entry
+  std::vector<uint64_t> installed;                   // [node] id of the entry whose trees are installed (state SHOWS_ENTRY)
+  enum State : char { UNTOUCHED = 0, OWN, SHOWS_ENTRY, SHOWS_ORIGINAL, MIXED };
+  std::vector<char> state;                           // [node] what the node's current data is
+  std::vector<size_t> touched;
 };
 
-SavedNode saveNode(AnnotatedNetwork &ann, size_t v, SlotCopies &copies) {
-  SavedNode s;
-  NodeDisplayedTreeData &nd = ann.pernode_displayed_tree_data[v];
-  s.num_active = nd.num_active_displayed_trees;
-  for (size_t i = 0; i < nd.num_active_displayed_trees; ++i) {
-    DisplayedTreeData d = nd.displayed_trees[i];
-    if (!d.isTip) {
-      d.slot = allocSlot(ann);
-      copies.add(d.slot, nd.displayed_trees[i].slot);
-    }
-    s.trees.push_back(d);
+namespace {
+constexpr uint64_t STAMP_ENTRY = 1ull << 63;
+
+RerootCache &rerootState(AnnotatedNetwork &ann) {
+  if (!ann.reroot) ann.reroot = new RerootCache();
+  RerootCache &rc = *ann.reroot;
+  const size_t n = ann.network.num_nodes();
+  if (rc.stashed.size() != n) {
+    rc.stashed.assign(n, 0); rc.orig.assign(n, NodeDisplayedTreeData()); rc.orig_valid.assign(n, {}); rc.alias_n.assign(n, 0); rc.installed.assign(n, 0);
+    rc.state.assign(n, RerootCache::UNTOUCHED);
   }
-  return s;
+  if (ann.node_version.size() != n) ann.node_version.assign(n, 0);
+  return rc;
 }
 
-void restoreNode(AnnotatedNetwork &ann, size_t v, const SavedNode &s, SlotCopies &copies) {
+size_t rerootBudget(AnnotatedNetwork &ann) {
+  if (ann.reroot_cache_max_slots != SIZE_MAX) return ann.reroot_cache_max_slots;
+  if (const char *v = std::getenv("NRX_REROOT_CACHE_SLOTS")) return (size_t)std::max(0l, std::atol(v));
+  // default: as many slots as the network itself uses, but no more than 24 GB of CLVs + scalers
+  double slot_bytes = 0;
+  for (const PartitionModel &m : ann.fake_treeinfo->partitions) slot_bytes += (double)m.sites * (m.rate_cats * m.states_padded * 8.0 + 4.0);
+  const size_t by_mem = (size_t)(24e9 / std::max(1.0, slot_bytes));
+  return std::min<size_t>(std::max<size_t>(ann.next_slot, 32), by_mem);
+}
+
+void releaseEntry(AnnotatedNetwork &ann, RerootCache &rc, RerootCache::Entry &e) {
+  for (const DisplayedTreeData &d : e.data.displayed_trees)
+    if (!d.isTip && d.slot != UINT32_MAX) { releaseSlot(ann, d.slot); rc.cached_slots--; }
+  e.data = NodeDisplayedTreeData();
+}
+
+/* the node's current (re-rooted) data goes away: slots it owns itself are released, aliased ones stay with their owner */
+void dropCurrent(AnnotatedNetwork &ann, RerootCache &rc, size_t v) {
   NodeDisplayedTreeData &nd = ann.pernode_displayed_tree_data[v];
-  if (v < ann.network.num_tips()) return;  // tips are immutable
-  for (size_t i = 0; i < s.trees.size(); ++i) {
-    if (i >= nd.displayed_trees.size()) {
-      DisplayedTreeData d;
-      d.slot = allocSlot(ann);
-      nd.displayed_trees.push_back(d);
-    }
-    const uint32_t own = nd.displayed_trees[i].slot;
-    nd.displayed_trees[i] = s.trees[i];
-    nd.displayed_trees[i].slot = own;  // entries keep their own slot; only the contents come back
-    copies.add(own, s.trees[i].slot);
+  for (size_t i = rc.alias_n[v]; i < nd.displayed_trees.size(); ++i)
+    if (!nd.displayed_trees[i].isTip && nd.displayed_trees[i].slot != UINT32_MAX) releaseSlot(ann, nd.displayed_trees[i].slot);
+  nd = NodeDisplayedTreeData();
+  rc.alias_n[v] = 0;
+  rc.installed[v] = 0;
+  rc.state[v] = RerootCache::OWN;
+}
+
+void stashNode(AnnotatedNetwork &ann, RerootCache &rc, size_t v) {
+  if (rc.stashed[v]) return;
+  rc.orig[v] = std::move(ann.pernode_displayed_tree_data[v]);
+  ann.pernode_displayed_tree_data[v] = NodeDisplayedTreeData();
+  rc.orig_valid[v].resize(ann.fake_treeinfo->partition_count);
+  for (unsigned p = 0; p < ann.fake_treeinfo->partition_count; ++p) rc.orig_valid[v][p] = ann.fake_treeinfo->clv_valid[p][v];
+  rc.stashed[v] = 1;
+  rc.alias_n[v] = 0;
+  rc.installed[v] = 0;
+  rc.state[v] = RerootCache::OWN;
+  rc.touched.push_back(v);
+}
+
+/* restoreNode of the reference (VirtualRerooting.cpp:234-238): the node shows its root-directed trees again — a metadata copy */
+void showOriginal(AnnotatedNetwork &ann, RerootCache &rc, size_t v) {
+  if (v < ann.network.num_tips() || !rc.stashed[v]) return;   // tips are immutable; an un-stashed node still holds its original
+  dropCurrent(ann, rc, v);
+  NodeDisplayedTreeData &nd = ann.pernode_displayed_tree_data[v];
+  nd = rc.orig[v];
+  nd.displayed_trees.resize(nd.num_active_displayed_trees);   // trees appended later must take slots of their own
+  rc.alias_n[v] = nd.displayed_trees.size();
+  rc.state[v] = RerootCache::SHOWS_ORIGINAL;
+  for (unsigned p = 0; p < ann.fake_treeinfo->partition_count; ++p) ann.fake_treeinfo->clv_valid[p][v] = rc.orig_valid[v][p];
+}
+
+uint64_t childStamp(AnnotatedNetwork &ann, RerootCache &rc, size_t c) {
+  if (c < ann.network.num_tips()) return 0;
+  switch (rc.stashed[c] ? rc.state[c] : RerootCache::UNTOUCHED) {
+    case RerootCache::UNTOUCHED: case RerootCache::SHOWS_ORIGINAL: return ann.node_version[c];
+    case RerootCache::SHOWS_ENTRY: return STAMP_ENTRY | rc.installed[c];
+    default: return STAMP_ENTRY | rc.next_id++;   // own or mixed data (append mode): never matches
   }
-  nd.num_active_displayed_trees = s.num_active;
+}
+
+/* processNodeImproved(ann, 0, node, children, extra, false) of a re-rooting path, through the memo */
+void processPathNode(AnnotatedNetwork &ann, RerootCache &rc, size_t v, std::vector<Node *> &children, const ReticulationConfigSet &extra) {
+  if (v < ann.network.num_tips()) return;
+  const unsigned P = ann.fake_treeinfo->partition_count;
+  std::vector<size_t> ch;
+  std::vector<uint64_t> stamps;
+  std::vector<double> lengths;
+  for (Node *c : children) {
+    ch.push_back(c->clv_index);
+    stamps.push_back(childStamp(ann, rc, c->clv_index));
+    const size_t e = edgeBetween(ann.network, c->clv_index, v);
+    for (unsigned p = 0; p < P; ++p) {
+      double len = ann.fake_treeinfo->branch_lengths[p][e];
+      if (ann.fake_treeinfo->brlen_linkage != PLLMOD_COMMON_BRLEN_UNLINKED) len = ann.fake_treeinfo->linked_branch_lengths[e];
+      lengths.push_back(len);
+    }
+  }
+  stashNode(ann, rc, v);
+  const size_t budget = rerootBudget(ann);
+  if (budget > 0)
+    for (RerootCache::Entry &e : rc.entries)
+      if (e.node == v && e.children == ch && e.child_stamp == stamps && e.lengths == lengths && e.extra_max == extra.max_reticulations && e.extra == extra.configs) {
+        dropCurrent(ann, rc, v);
+        ann.pernode_displayed_tree_data[v] = e.data;
+        rc.alias_n[v] = e.data.displayed_trees.size();
+        rc.installed[v] = e.id;
+        rc.state[v] = RerootCache::SHOWS_ENTRY;
+        e.last_use = ++rc.tick;
+        e.pinned_session = rc.session;
+        for (unsigned p = 0; p < P; ++p) ann.fake_treeinfo->clv_valid[p][v] = 1;
+        ann.reroot_hits++;
+        return;
+      }
+  ann.reroot_misses++;
+  dropCurrent(ann, rc, v);
+  processNodeImproved(ann, 0, &ann.network.nodes[v], children, extra, false);
+  // the fresh trees become an entry (which owns their slots from now on); the node keeps showing them
+  RerootCache::Entry e;
+  e.id = rc.next_id++;
+  e.last_use = ++rc.tick;
+  e.pinned_session = rc.session;
+  e.node = v; e.children = ch; e.child_stamp = stamps; e.lengths = lengths; e.extra = extra.configs; e.extra_max = extra.max_reticulations;
+  e.data = ann.pernode_displayed_tree_data[v];
+  for (const DisplayedTreeData &d : e.data.displayed_trees) if (!d.isTip && d.slot != UINT32_MAX) rc.cached_slots++;
+  rc.alias_n[v] = e.data.displayed_trees.size();
+  rc.installed[v] = e.id;
+  rc.state[v] = RerootCache::SHOWS_ENTRY;
+  rc.entries.push_back(std::move(e));
+}
+
+void evictRerootEntries(AnnotatedNetwork &ann, RerootCache &rc, size_t budget) {
+  // superseded entries first (same node + children + restrictions as a younger entry: their stamps can never match again once the
+  // data they were computed from has been recomputed), then least recently used
+  while (rc.cached_slots > budget) {
+    size_t victim = SIZE_MAX;
+    for (size_t i = 0; i < rc.entries.size(); ++i) {
+      if (rc.active && rc.entries[i].pinned_session == rc.session) continue;
+      if (victim == SIZE_MAX || rc.entries[i].last_use < rc.entries[victim].last_use) victim = i;
+    }
+    if (victim == SIZE_MAX) break;
+    releaseEntry(ann, rc, rc.entries[victim]);
+    rc.entries.erase(rc.entries.begin() + victim);
+  }
 }
 }  // namespace
+
+void dropRerootCache(AnnotatedNetwork &ann) {
+  if (!ann.reroot) return;
+  RerootCache &rc = *ann.reroot;
+  std::vector<RerootCache::Entry> keep;
+  for (RerootCache::Entry &e : rc.entries) {
+    if (rc.active && e.pinned_session == rc.session) { keep.push_back(std::move(e)); continue; }
+    releaseEntry(ann, rc, e);
+  }
+  rc.entries.swap(keep);
+}
+
+namespace detail {
+void destroyRerootCache(AnnotatedNetwork &ann) { delete ann.reroot; ann.reroot = nullptr; }
+bool rerootSessionOpen(const AnnotatedNetwork &ann) { return ann.reroot && ann.reroot->active; }
+void rerootCacheSize(const AnnotatedNetwork &ann, size_t *entries, size_t *slots) {
+  *entries = ann.reroot ? ann.reroot->entries.size() : 0;
+  *slots = ann.reroot ? ann.reroot->cached_slots : 0;
+}
+/* the branches in depth-first pre-order from the root: consecutive branches share all but the last node of their re-rooting
+ * paths, so a sweep in this order finds the path's re-rooted trees memoised (the reference visits an unordered_set, i.e. in no
+ * particular order: src/optimization/BranchLengthOptimization.cpp:423-476) */
+std::vector<size_t> branchesInPreorder(const AnnotatedNetwork &ann) {
+  const Network &nw = ann.network;
+  std::vector<size_t> order, stack{nw.root->clv_index};
+  std::vector<char> seen(nw.num_nodes(), 0), emitted(nw.num_branches(), 0);
+  seen[nw.root->clv_index] = 1;
+  // iterative DFS that emits (v -> c) right before descending into c
+  std::vector<std::pair<size_t, size_t>> frames{{nw.root->clv_index, 0}};
+  while (!frames.empty()) {
+    const size_t v = frames.back().first, k = frames.back().second;
+    if (k >= nw.nodes[v].children.size()) { frames.pop_back(); continue; }
+    frames.back().second++;
+    const size_t c = nw.nodes[v].children[k];
+    const size_t e = edgeBetween(nw, c, v);
+    if (e < emitted.size() && !emitted[e]) { emitted[e] = 1; order.push_back(e); }
+    if (!seen[c]) { seen[c] = 1; frames.push_back({c, 0}); }
+  }
+  for (size_t e = 0; e < emitted.size(); ++e) if (!emitted[e]) order.push_back(e);
+  return order;
+}
+}  // namespace detail
+
+void finishVirtualReroot(AnnotatedNetwork &ann) {
+  if (!ann.reroot || !ann.reroot->active) return;
+  RerootCache &rc = *ann.reroot;
+  flushPendingOps(ann);
+  for (size_t v : rc.touched) {
+    dropCurrent(ann, rc, v);
+    ann.pernode_displayed_tree_data[v] = std::move(rc.orig[v]);
+    rc.orig[v] = NodeDisplayedTreeData();
+    for (unsigned p = 0; p < ann.fake_treeinfo->partition_count; ++p) ann.fake_treeinfo->clv_valid[p][v] = rc.orig_valid[v][p];
+    rc.stashed[v] = 0;
+    rc.state[v] = RerootCache::UNTOUCHED;
+  }
+  rc.touched.clear();
+  rc.active = false;
+  const size_t budget = rerootBudget(ann);
+  if (budget == 0 || rc.epoch != ann.clv_epoch) dropRerootCache(ann);
+  else evictRerootEntries(ann, rc, budget);
+  FakeTreeinfo &ti = *ann.fake_treeinfo;
+  bool changed = false;
+  for (unsigned p = 0; p < ti.partition_count; ++p)
+    changed |= ((ti.brlen_linkage == PLLMOD_COMMON_BRLEN_UNLINKED ? ti.branch_lengths[p][rc.edge] : ti.linked_branch_lengths[rc.edge]) != rc.start_lengths[p]);
+  ann.cached_logl_valid = false;   // the cached value is the edge-rooted one; evaluateTrees re-mixes the root trees on the host
+  if (changed) invalidatePmatrixIndex(ann, rc.edge);
+  else pllmod_treeinfo_update_prob_matrices(ann, 0);   // lengths tried in between left the edge's P-matrix flagged invalid: refresh it now,
+                                                       // because an evaluation that finds every CLV valid returns before its P-matrix update
+}
 
 void updateCLVsVirtualRerootTrees(AnnotatedNetwork &ann, Node *old_virtual_root, Node *new_virtual_root,
                                   Node *new_virtual_root_back, ReticulationConfigSet &restrictions) {  // :192-252
   const size_t old_vr = old_virtual_root->clv_index, new_vr = new_virtual_root->clv_index, back = new_virtual_root_back->clv_index;
   if (ann.pernode_displayed_tree_data[old_vr].num_active_displayed_trees == 0) throw std::runtime_error("no displayed trees at the old virtual root");
   flushPendingOps(ann);
+  finishVirtualReroot(ann);   // a session left open by the caller
+  RerootCache &rc = rerootState(ann);
+  if (rc.epoch != ann.clv_epoch) { dropRerootCache(ann); rc.epoch = ann.clv_epoch; }
   const std::vector<PathToVirtualRoot> paths = getPathsToVirtualRoot(ann, old_vr, new_vr, back);
   const NodeSaveInformation info = computeNodeSaveInformation(paths);
-  std::vector<SavedNode> buffered(ann.network.num_nodes());
-  SlotCopies copies;
-  for (size_t n : info.nodesInDanger) buffered[n] = saveNode(ann, n, copies);
-  copies.run(ann);
-  for (size_t p = 0; p < paths.size(); ++p) {
-    if (!reticulationConfigsCompatible(paths[p].reticulationChoices, restrictions)) continue;
-    if (!info.pathNodesToRestore[p].empty()) flushPendingOps(ann);
-    for (size_t n : info.pathNodesToRestore[p]) restoreNode(ann, n, buffered[n], copies);
-    copies.run(ann);
-    for (size_t i = 0; i < paths[p].path.size(); ++i) {
-      const bool appendMode = (p > 0) && (paths[p].path[i] == new_vr);
-      std::vector<Node *> children;
-      for (size_t c : paths[p].children[i]) children.push_back(&ann.network.nodes[c]);
-      processNodeImproved(ann, 0, &ann.network.nodes[paths[p].path[i]], children, paths[p].reticulationChoices, appendMode);
+  rc.active = true;
+  rc.session++;
+  rc.edge = edgeBetween(ann.network, new_vr, back);
+  rc.start_lengths.clear();
+  for (unsigned p = 0; p < ann.fake_treeinfo->partition_count; ++p)
+    rc.start_lengths.push_back(ann.fake_treeinfo->brlen_linkage == PLLMOD_COMMON_BRLEN_UNLINKED ? ann.fake_treeinfo->branch_lengths[p][rc.edge]
+                                                                                                  : ann.fake_treeinfo->linked_branch_lengths[rc.edge]);
+  try {
+    for (size_t p = 0; p < paths.size(); ++p) {
+      if (!reticulationConfigsCompatible(paths[p].reticulationChoices, restrictions)) continue;
+      for (size_t n : info.pathNodesToRestore[p]) showOriginal(ann, rc, n);
+      for (size_t i = 0; i < paths[p].path.size(); ++i) {
+        const size_t v = paths[p].path[i];
+        const bool appendMode = (p > 0) && (v == new_vr);
+        std::vector<Node *> children;
+        for (size_t c : paths[p].children[i]) children.push_back(&ann.network.nodes[c]);
+        if (!appendMode) { processPathNode(ann, rc, v, children, paths[p].reticulationChoices); continue; }
+        // further paths APPEND their trees to the new virtual root: the trees already there stay aliased, the new ones get own slots
+        if (v >= ann.network.num_tips()) {
+          if (!rc.stashed[v]) { stashNode(ann, rc, v); showOriginal(ann, rc, v); }   // no earlier path reached it: the reference appends to the root-directed trees
+          rc.state[v] = RerootCache::MIXED;
+        }
+        processNodeImproved(ann, 0, &ann.network.nodes[v], children, paths[p].reticulationChoices, true);
+      }
     }
+    flushPendingOps(ann);
+  } catch (...) {
+    ann.pending_ops.clear();
+    std::fill(ann.pending_parent.begin(), ann.pending_parent.end(), 0);
+    finishVirtualReroot(ann);
+    throw;
   }
-  flushPendingOps(ann);
-  for (size_t n : info.nodesInDanger)
-    for (const DisplayedTreeData &d : buffered[n].trees)
-      if (!d.isTip) releaseSlot(ann, d.slot);
   if (ann.pernode_displayed_tree_data[new_vr].num_active_displayed_trees == 0) throw std::runtime_error("no displayed trees at the new virtual root");
 }
 

@@ -380,9 +380,37 @@ int nrxh_brlen_finish(void *hv, unsigned edge, double *final_logl) {
     Handle *h = H(hv);
     h->sumtables.clear();
     h->oldTrees.clear();
-    invalidatePmatrixIndex(h->ann, edge);
+    (void)edge;
+    finishVirtualReroot(h->ann);   // restores the root-directed trees; invalidates above the edge only if its length changed
     const double l = computeLoglikelihood(h->ann, 1, 1);
     if (final_logl) *final_logl = l;
+  });
+}
+
+int nrxh_brlen_sweep_order(void *hv, unsigned *edges_out) {
+  return guarded([&] {
+    const std::vector<size_t> order = detail::branchesInPreorder(H(hv)->ann);
+    for (size_t i = 0; i < order.size(); ++i) edges_out[i] = (unsigned)order[i];
+  });
+}
+
+int nrxh_reroot_stats(void *hv, unsigned long long *hits, unsigned long long *misses, unsigned *entries, unsigned *cached_slots) {
+  return guarded([&] {
+    const AnnotatedNetwork &ann = H(hv)->ann;
+    size_t n = 0, s = 0;
+    detail::rerootCacheSize(ann, &n, &s);
+    if (hits) *hits = ann.reroot_hits;
+    if (misses) *misses = ann.reroot_misses;
+    if (entries) *entries = (unsigned)n;
+    if (cached_slots) *cached_slots = (unsigned)s;
+  });
+}
+
+int nrxh_set_reroot_cache_slots(void *hv, long long max_slots) {
+  return guarded([&] {
+    AnnotatedNetwork &ann = H(hv)->ann;
+    ann.reroot_cache_max_slots = max_slots < 0 ? SIZE_MAX : (size_t)max_slots;
+    if (max_slots == 0) dropRerootCache(ann);
   });
 }
 

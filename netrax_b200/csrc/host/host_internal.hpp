@@ -29,5 +29,9 @@ double minimizeBrent(double xmin, double xguess, double xmax, double xtol, doubl
 void minimizeBrentMulti(unsigned n, double xmin, double *x, double xmax, double xtol, double (*target)(void *, double *, double *, int *), void *ctx);
 /* log(sum_t exp(a_t)) and friends without leaving double range (stands in for mpfr::mpreal) */
 double logSumExp(const std::vector<double> &a);
+void destroyRerootCache(AnnotatedNetwork &ann);          // host/brlen.cpp
+void rerootCacheSize(const AnnotatedNetwork &ann, size_t *entries, size_t *slots);
+std::vector<size_t> branchesInPreorder(const AnnotatedNetwork &ann);
+bool rerootSessionOpen(const AnnotatedNetwork &ann);    // between updateCLVsVirtualRerootTrees and finishVirtualReroot
 }  // namespace detail
 }  // namespace netrax

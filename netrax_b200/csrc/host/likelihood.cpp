@@ -36,6 +36,7 @@ struct PlanCache {
 AnnotatedNetwork::~AnnotatedNetwork() {
   if (plan && plan->on_device && engine) nrx_plan_destroy(engine, plan->engine_plan);
   delete plan;
+  detail::destroyRerootCache(*this);
   if (engine) nrx_engine_destroy(engine);
 }
 
@@ -237,6 +238,7 @@ bool allClvsValid(AnnotatedNetwork &ann, size_t clv_index) {  // :194-237
 }
 
 void invalidateAllCLVs(AnnotatedNetwork &ann) {  // :255-260
+  ann.clv_epoch++;
   for (size_t i = ann.network.num_tips(); i < ann.network.num_nodes(); ++i) invalidateSingleClv(ann, (unsigned)i);
 }
 
@@ -258,6 +260,7 @@ void setReticulationProb(AnnotatedNetwork &ann, size_t r, double prob) {  // src
   ann.first_parent_logprobs[r] = std::log(prob);
   ann.second_parent_logprobs[r] = std::log(1.0 - prob);
   ann.cached_logl_valid = false;
+  ann.clv_epoch++;   // memoised re-rooted trees carry their tree_logprob
   invalidateTreeLogprobs(ann);
   if (ann.options.likelihood_variant == LikelihoodVariant::SARAH_PSEUDO)  // InvalidationHelper.cpp:296-301: the blend weights changed
     invalidateHigher(ann, ann.network.reticulations[r].node, false);
@@ -269,6 +272,8 @@ static void dropEnginePlan(AnnotatedNetwork &ann) {
 
 void topology_changed(AnnotatedNetwork &ann) {
   if (ann.plan) { ann.plan->valid = false; dropEnginePlan(ann); }
+  ann.clv_epoch++;
+  ann.node_version.clear();
   ann.travbuffer = reversed_topological_sort(ann.network);
 }
 
@@ -543,6 +548,7 @@ void processNodeImproved(AnnotatedNetwork &ann, int incremental, Node *node, std
   else if (children.size() == 2) processNodeImprovedTwoChildren(ann, node, children[0], children[1], extra);
   else throw std::runtime_error("Node has too many children");
   ann.pending_parent[v] = 1;
+  if (!rerootSessionOpen(ann) && v < ann.node_version.size()) ann.node_version[v]++;   // root-directed data recomputed: memoised re-rooted trees built on it miss from now on
   if (ann.pernode_displayed_tree_data[v].num_active_displayed_trees > ((size_t)1 << ann.network.num_reticulations()))
     throw std::runtime_error("Too many displayed trees stored at node " + std::to_string(v));
   validateSingleClv(ann, v);
@@ -670,6 +676,7 @@ static void replayPlan(AnnotatedNetwork &ann) {
     }
     nd.num_active_displayed_trees = sn.configs.size();
     validateSingleClv(ann, v);
+    if (v < ann.node_version.size()) ann.node_version[v]++;
   }
   uint64_t local_sites = 0;
   for (const PartitionModel &m : ann.fake_treeinfo->partitions) local_sites += m.sites;
@@ -766,6 +773,7 @@ static bool reuseOldDisplayedTreesCheck(AnnotatedNetwork &ann, int incremental, 
  * mixes the trees.  computeLoglikelihoodImproved = Begin + End. */
 static void computeLoglikelihoodImprovedBegin(AnnotatedNetwork &ann, int incremental, int update_pmatrices) {
   if (ann.pending_eval) throw std::runtime_error("computeLoglikelihoodBegin: an evaluation of this network is already in flight");
+  finishVirtualReroot(ann);   // a re-rooting session the caller left open: the root-directed trees come back first
   ann.begin_returns_cached = false;
   if (!incremental) invalidateAllCLVs(ann);
   const bool reuse = reuseOldDisplayedTreesCheck(ann, incremental, ann.network.root->clv_index);
@@ -831,6 +839,7 @@ double computePseudoLoglikelihood(AnnotatedNetwork &ann, int incremental, int up
   Network &nw = ann.network;
   const unsigned P = ann.fake_treeinfo->partition_count;
   flushPendingOps(ann);
+  finishVirtualReroot(ann);
   if (ann.pseudo_clv_valid.size() != nw.num_nodes()) {  // src/graph/AnnotatedNetwork.cpp:160-184
     ann.pseudo_clv_valid.assign(nw.num_nodes(), 0);
     for (size_t i = 0; i < nw.num_tips(); ++i) ann.pseudo_clv_valid[i] = 1;

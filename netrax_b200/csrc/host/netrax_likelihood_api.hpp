@@ -215,6 +215,7 @@ struct LoglDerivatives {
 };
 
 struct PlanCache;  // cached evaluation plan (ops per launch) for unchanged topology
+struct RerootCache;  // virtual re-rooting session + memoised re-rooted node data (host/brlen.cpp)
 
 struct AnnotatedNetwork {  // src/graph/AnnotatedNetwork.hpp:42-89
   NetraxOptions options;
@@ -242,6 +243,12 @@ struct AnnotatedNetwork {  // src/graph/AnnotatedNetwork.hpp:42-89
   std::vector<char> pending_parent;           // [node] 1 if the node's trees are outputs of pending_ops
   PlanCache *plan = nullptr;
   bool use_plan_cache = true;
+  /* virtual re-rooting writes into shadow slots (the root-directed CLVs stay intact) and memoises the re-rooted node data */
+  RerootCache *reroot = nullptr;
+  std::vector<uint64_t> node_version;         // [node] bumped whenever the node's root-directed displayed trees are recomputed
+  uint64_t clv_epoch = 0;                     // bumped by invalidateAllCLVs / setReticulationProb / topology_changed: drops the memoised data
+  size_t reroot_cache_max_slots = SIZE_MAX;   // SIZE_MAX: default budget (env NRX_REROOT_CACHE_SLOTS); 0: nothing survives a re-rooting session
+  uint64_t reroot_hits = 0, reroot_misses = 0;
   uint64_t clv_site_updates = 0;              // Σ trees × local patterns actually launched
   std::vector<char> pseudo_clv_valid;         // [node]  (src/graph/AnnotatedNetwork.hpp:64; tips: valid)
   std::vector<uint32_t> pseudo_slot;          // [node]  device slot of the node's pseudo-likelihood CLV (UINT32_MAX: none yet)
@@ -280,6 +287,12 @@ std::vector<DisplayedTreeData> extractOldTrees(AnnotatedNetwork &ann_network, No
 ReticulationConfigSet getRestrictionsActiveAliveBranch(AnnotatedNetwork &ann_network, size_t pmatrix_index);
 void updateCLVsVirtualRerootTrees(AnnotatedNetwork &ann_network, Node *old_virtual_root, Node *new_virtual_root,
                                   Node *new_virtual_root_back, ReticulationConfigSet &restrictions);
+/* ends the re-rooting session updateCLVsVirtualRerootTrees opened: the root-directed displayed trees come back (they were never
+ * overwritten), and — only if the branch length of the session's edge differs from the one it started with — the edge's P-matrix
+ * and the CLVs above it are invalidated (the reference's unconditional `invalidatePmatrixIndex` "restore the network root",
+ * src/optimization/BranchLengthOptimization.cpp:417-419, recomputes what it had overwritten).  No-op without an open session. */
+void finishVirtualReroot(AnnotatedNetwork &ann_network);
+void dropRerootCache(AnnotatedNetwork &ann_network);   // releases every memoised slot (keeps an open session's own data)
 double computeLoglikelihoodBrlenOpt(AnnotatedNetwork &ann_network, const std::vector<DisplayedTreeData> &oldTrees,
                                     unsigned int pmatrix_index, int update_pmatrices = 1, bool print_extra_debug_info = false);
 std::vector<std::vector<SumtableInfo>> computePartitionSumtables(AnnotatedNetwork &ann_network, unsigned int pmatrix_index);

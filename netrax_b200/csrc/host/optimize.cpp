@@ -318,7 +318,7 @@ double optimize_branch(AnnotatedNetwork &ann, size_t pmatrix_index, BrlenOptMeth
   } else {
     optimizeBranchPartition(ann, oldTrees, sumtables, pmatrix_index, 0, method, max_iters);
   }
-  if (method != BrlenOptMethod::BRENT_NORMAL) invalidatePmatrixIndex(ann, pmatrix_index);  // restore the network root
+  if (method != BrlenOptMethod::BRENT_NORMAL) finishVirtualReroot(ann);  // restore the network root: invalidatePmatrixIndex only if the length changed
   return computeLoglikelihood(ann);
 }
 

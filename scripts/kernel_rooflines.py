@@ -63,7 +63,11 @@ def main():
         r = {"workload": cfg["name"], "patterns": cfg["patterns"]}
         r["full_evaluation"] = measure(eng, lambda: eng.computeLoglikelihood(0, 1), 10)
         if cfg["patterns"] * cfg["parts"] <= 200_000:
+            derivative_sweep(eng, net)   # warm-up: re-rooting slots, sumtables, the re-root memo
             r["derivative_sweep"] = measure(eng, lambda: derivative_sweep(eng, net), 1)
+            derivative_sweep(eng, net, accept=True)
+            r["derivative_sweep_accept"] = measure(eng, lambda: derivative_sweep(eng, net, accept=True), 1)
+            r["reroot_memo"] = eng.reroot_stats()
         eng.close()
         res[f"config{c}"] = r
         print(json.dumps({f"config{c}": r}), flush=True)
@@ -76,7 +80,7 @@ def main():
             for c, r in res.items():
                 if not c.startswith("config"):
                     continue
-                for phase in ("full_evaluation", "derivative_sweep"):
+                for phase in ("full_evaluation", "derivative_sweep", "derivative_sweep_accept"):
                     if phase not in r:
                         continue
                     m = r[phase]

@@ -150,6 +150,8 @@ struct nrx_engine {
   bool fuse_reduce = true;         // env NRX_FUSE_REDUCE=0: separate k_reduce_partials launch (A/B)
   bool defer_pmat = false;         // P-matrix updates are deferred until a launch needs them: the tile walk computes them itself (one launch per evaluation)
   uint32_t node_maxc = NODE_MAXC, node_blocks = 0;   // env NRX_NODE_MAXC (children per group, <= 16), NRX_NODE_BLOCKS (block target per launch; 0 = 24 x SMs)
+  uint32_t quad_total = 0;         // env NRX_QUAD_BLOCKS: blocks per launch of the quad kernels (0: 2 per SM)
+  bool quad = true;                // env NRX_QUAD=0: thread-per-pattern k_tree_lnl_dna4 / k_edge_lnl_dna4 / k_derivatives_dna4 instead of the coalesced quad kernels (A/B)
   int node_mode = 0;               // env NRX_NODE=1: ops of a node that share children run on k_clv_node_dna4 (A/B; measured 10 % slower than the per-op kernel, profiles/r3a_node_centric_ab.md)
   int walk_mode = 2;               // env NRX_WALK: 0 never, 1 whenever the plan has a tile-walk form, 2 (default) when it has one and the launch is small enough
   uint32_t walk_max_tiles = 0;     // mode 2: use the walk up to this many tiles per partition (env NRX_WALK_TILES; default set in nrx_engine_create)
@@ -417,6 +419,8 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
   if (const char *v = std::getenv("NRX_GRAPH")) e->use_graphs = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_PDL")) e->use_pdl = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_FUSE_REDUCE")) e->fuse_reduce = std::atoi(v) != 0;
+  if (const char *v = std::getenv("NRX_QUAD")) e->quad = std::atoi(v) != 0;
+  if (const char *v = std::getenv("NRX_QUAD_BLOCKS")) e->quad_total = (uint32_t)std::max(0, std::atoi(v));
   if (const char *v = std::getenv("NRX_NODE")) e->node_mode = std::atoi(v);
   if (const char *v = std::getenv("NRX_NODE_MAXC")) e->node_maxc = (uint32_t)std::min(NODE_MAXC, std::max(2, std::atoi(v)));
   if (const char *v = std::getenv("NRX_NODE_BLOCKS")) e->node_blocks = (uint32_t)std::max(0, std::atoi(v));
@@ -1439,8 +1443,16 @@ static uint32_t reduce_blocks(const nrx_engine *e, uint32_t items) {
     work = std::max<uint64_t>(work, (uint64_t)c.max_patterns * ((!dna4 && pow2_cats(c)) ? c.cats : 1));
   }
   const uint64_t full = std::max<uint64_t>(1, (work + BLOCK - 1) / BLOCK);
-  const uint64_t want = std::max<uint64_t>(1, (148ull * 32) / std::max<uint32_t>(1, items));  // ~32 blocks per SM in total
-  return (uint32_t)std::min<uint64_t>(full, want);
+  // the quad kernels (DNA 4x4) prefetch their next pass: few long-lived blocks (quad_total, default 2 per SM = one resident wave; measured 296 / 592 / 1184 / 2368 blocks: K6 0.76 / 0.71 / 0.62 / 0.54 of the HBM peak); everything else
+  // one pass per block where possible, ~32 blocks per SM in total
+  bool all_quad = e->quad && !e->classes.empty();
+  for (const ShapeClass &c : e->classes) all_quad = all_quad && c.states == 4 && c.cats == 4 && !class_mixture(e, c);
+  const uint64_t total = all_quad ? (e->quad_total ? e->quad_total : 2ull * e->sm_count) : 148ull * 32;
+  const uint64_t want = std::max<uint64_t>(1, total / std::max<uint32_t>(1, items));
+  if (full <= want) return (uint32_t)full;
+  const uint64_t passes = (full + want - 1) / want;       // every block makes the same number of passes (the last one maybe one less):
+  return (uint32_t)((full + passes - 1) / passes);        // 391 chunks over 315 blocks would leave 239 blocks idle during the second pass
+
 }
 
 /* second stage + cross-rank sum + device->host copy, all stream-ordered; the host blocks only in wait_result */
@@ -1501,7 +1513,8 @@ static int tree_lnl_impl(nrx_engine *e, const uint32_t *slots, uint32_t n, doubl
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
     const bool mix = class_mixture(e, c);
-    if (!mix && c.states == 4 && c.cats == 4) k_tree_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
+    if (!mix && c.states == 4 && c.cats == 4 && e->quad) k_tree_lnl_dna4q<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
+    else if (!mix && c.states == 4 && c.cats == 4) k_tree_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
     else if (!mix && pow2_cats(c) && c.states == 20) k_tree_lnl_pc<20><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
     else if (!mix && pow2_cats(c)) k_tree_lnl_pc<0><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
     else k_tree_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
@@ -1670,7 +1683,8 @@ int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n
   prof_begin(e, &ev0, &ev1);
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
-    if (c.states == 4 && c.cats == 4 && !class_mixture(e, c)) k_edge_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh, e->d_result, tk);
+    if (c.states == 4 && c.cats == 4 && !class_mixture(e, c) && e->quad) k_edge_lnl_dna4q<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh, e->d_result, tk);
+    else if (c.states == 4 && c.cats == 4 && !class_mixture(e, c)) k_edge_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh, e->d_result, tk);
     else if (aa_dmma_pairs_class(e, c)) {  // FP64 tensor cores: block b = (pair b % n, tile group b / n), one partial per (pair, group)
       bool tips;
       const std::vector<nrx_op> ops = pairs_to_ops(pairs, n, edge, false, &tips);
@@ -1763,7 +1777,8 @@ int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen, double *out)
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
     const bool mix = class_mixture(e, c);   // (only the +I term of K6 reads frequencies; the generic kernel is the one that indexes them by category)
-    if (!mix && c.states == 4 && c.cats == 4) k_derivatives_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
+    if (!mix && c.states == 4 && c.cats == 4 && e->quad) k_derivatives_dna4q<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
+    else if (!mix && c.states == 4 && c.cats == 4) k_derivatives_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
     else if (!mix && pow2_cats(c) && c.states == 20) k_derivatives_pc<20, 2><<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
     else if (!mix && pow2_cats(c)) k_derivatives_pc<0, 2><<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
     else k_derivatives<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);

@@ -2620,4 +2620,242 @@ __global__ void __launch_bounds__(BLOCK) k_derivatives_dna4(const PartView *__re
   finish_partials<3>(p, out + oi * 3, counters ? counters + oi : nullptr, gridDim.x);
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * K3 / K4 / K6, DNA 4x4, "quad" versions (round 2).  The thread-per-pattern kernels above read 32 bytes per lane at a 128-byte
+ * stride: every sector is used, but a warp-wide load touches 32 different lines, and the L1 tag stage (one line per clock) then
+ * tops out at about the HBM rate — measured 0.35-0.54 of the copy peak inside the derivative sweep
+ * (profiles/r3b_sweep_shadow_reroot_memo_config2.md) against 0.78 for k_sumtable_dna4, which loads thread = (pattern, category).
+ * Here every load is thread = (pattern, category) (a warp reads 1 KB contiguous = 8 lines), four independent 256-bit loads per
+ * operand and thread are in flight, the per-category constants (P-matrix block, diag-table rows, weight) sit in registers because
+ * a thread's category never changes, and the four categories of a pattern are brought together by a 3-shuffle transposing
+ * reduction inside the quad that leaves lane q of the quad with the sum of the thread's q-th item — so all 32 lanes still take
+ * one log / division each.  Category sum order is the fixed tree (c0 + c2) + (c1 + c3).
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ double quad_gather_sum(double x0, double x1, double x2, double x3, int q) {
+  const bool hi = (q & 2) != 0;
+  double keepA = hi ? x2 : x0, keepB = hi ? x3 : x1;
+  const double sendA = hi ? x0 : x2, sendB = hi ? x1 : x3;
+  keepA = __dadd_rn(keepA, __shfl_xor_sync(0xffffffffu, sendA, 2));
+  keepB = __dadd_rn(keepB, __shfl_xor_sync(0xffffffffu, sendB, 2));
+  const bool odd = (q & 1) != 0;
+  const double keep = odd ? keepB : keepA, send = odd ? keepA : keepB;
+  return __dadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+}
+
+constexpr int QU = 4;   // items per thread and pass = lanes of a quad
+
+/* one pass of a block = BLOCK * QU consecutive (pattern, category) items = 256 patterns; the next pass's loads are issued before
+ * the current pass is consumed (register double buffer), blocks are few and long-lived (about two resident blocks per SM in total,
+ * nrx_engine.cu:quad_blocks): ncu showed the one-pass-per-block form latency-bound — 36 % issue slots, 30 % FP64 pipe, 3.3 TB/s —
+ * because a block's loads, its log / division tail and its block reduction ran strictly one after the other. */
+__device__ __forceinline__ void quad_load(D4 (&v)[QU], const double *__restrict__ src, uint64_t base, uint64_t n_items, int tid) {
+#pragma unroll
+  for (int u = 0; u < QU; ++u) {
+    const uint64_t g = base + (uint64_t)u * BLOCK + tid;
+    if (g < n_items) v[u] = ldg256(src + g * 4);
+    else { v[u].x = v[u].y = v[u].z = v[u].w = 0.0; }
+  }
+}
+
+__global__ void __launch_bounds__(BLOCK, 2) k_derivatives_dna4q(const PartView *__restrict__ parts, double *__restrict__ partial,
+                                                                 uint32_t nparts_total, double *__restrict__ out, uint32_t *__restrict__ counters) {
+  __shared__ double red[3 * (BLOCK / 32)];
+  const PartView &pv = parts[blockIdx.z];
+  const int tid = threadIdx.x, q = tid & 3;
+  double dg[12];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dg[j * 3 + k] = pv.diagp[q * 16 + j * 4 + k];
+  const double w = pv.rate_weights[q], pinv = pv.pinv;
+  const double *st = pv.sumtable[blockIdx.y];
+  const uint64_t n_items = (uint64_t)pv.patterns * 4, stride = (uint64_t)gridDim.x * BLOCK * QU;
+  double acc[3] = {0.0, 0.0, 0.0};
+  uint64_t base = (uint64_t)blockIdx.x * BLOCK * QU;
+  D4 nxt[QU];
+  quad_load(nxt, st, base, n_items, tid);
+  for (; base < n_items; base += stride) {
+    D4 v[QU];
+#pragma unroll
+    for (int u = 0; u < QU; ++u) v[u] = nxt[u];
+    if (base + stride < n_items) quad_load(nxt, st, base + stride, n_items, tid);
+    double l0[QU], l1[QU], l2[QU];
+#pragma unroll
+    for (int u = 0; u < QU; ++u) {
+      const double sv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        c0 = __dadd_rn(c0, __dmul_rn(sv[j], dg[j * 3 + 0]));
+        c1 = __dadd_rn(c1, __dmul_rn(sv[j], dg[j * 3 + 1]));
+        c2 = __dadd_rn(c2, __dmul_rn(sv[j], dg[j * 3 + 2]));
+      }
+      if (pinv > 0.0) {
+        const uint64_t g = base + (uint64_t)u * BLOCK + tid;
+        double invf = 0.0;
+        if (g < n_items) { const int iv = pv.invariant[g >> 2]; invf = iv < 0 ? 0.0 : pv.freqs[iv]; }
+        deriv_cat_pinv(c0, c1, c2, pinv, invf);
+      }
+      l0[u] = __dmul_rn(c0, w); l1[u] = __dmul_rn(c1, w); l2[u] = __dmul_rn(c2, w);
+    }
+    const double lk0 = quad_gather_sum(l0[0], l0[1], l0[2], l0[3], q);
+    const double lk1 = quad_gather_sum(l1[0], l1[1], l1[2], l1[3], q);
+    const double lk2 = quad_gather_sum(l2[0], l2[1], l2[2], l2[3], q);
+    const uint64_t n = (base >> 2) + (uint64_t)q * (BLOCK / 4) + (tid >> 2);   // the pattern of this thread's q-th item
+    if (n < pv.patterns) {
+      const double pw = (double)pv.weights[n];
+      const double d1 = -lk1 / lk0;
+      const double d2 = d1 * d1 - lk2 / lk0;
+      acc[0] += pw * log(lk0);
+      acc[1] += pw * d1;
+      acc[2] += pw * d2;
+    }
+  }
+  block_sum<3>(acc, red);
+  const size_t oi = (size_t)blockIdx.y * nparts_total + pv.part_index;
+  double *p = partial + oi * 3 * gridDim.x;
+  if (threadIdx.x == 0) {
+    p[0 * gridDim.x + blockIdx.x] = acc[0];
+    p[1 * gridDim.x + blockIdx.x] = acc[1];
+    p[2 * gridDim.x + blockIdx.x] = acc[2];
+  }
+  finish_partials<3>(p, out + oi * 3, counters ? counters + oi : nullptr, gridDim.x);
+}
+
+__global__ void __launch_bounds__(BLOCK, 2) k_tree_lnl_dna4q(const PartView *__restrict__ parts, const uint32_t *__restrict__ slots,
+                                                              double *__restrict__ partial, uint32_t nparts_total, double log_thresh,
+                                                              double *__restrict__ persite, size_t persite_stride,
+                                                              double *__restrict__ out, uint32_t *__restrict__ counters) {
+  __shared__ double red[BLOCK / 32];
+  const PartView &pv = parts[blockIdx.z];
+  const int tid = threadIdx.x, q = tid & 3;
+  const uint32_t slot = slots[blockIdx.y];
+  const double *clv = pv.clv[slot];
+  const uint32_t *sc = pv.scaler[slot];
+  const double f0 = pv.freqs[0], f1 = pv.freqs[1], f2 = pv.freqs[2], f3 = pv.freqs[3];
+  const double w = pv.rate_weights[q], pinv = pv.pinv;
+  const uint64_t n_items = (uint64_t)pv.patterns * 4, stride = (uint64_t)gridDim.x * BLOCK * QU;
+  double acc[1] = {0.0};
+  uint64_t base = (uint64_t)blockIdx.x * BLOCK * QU;
+  D4 nxt[QU];
+  quad_load(nxt, clv, base, n_items, tid);
+  for (; base < n_items; base += stride) {
+    D4 v[QU];
+#pragma unroll
+    for (int u = 0; u < QU; ++u) v[u] = nxt[u];
+    if (base + stride < n_items) quad_load(nxt, clv, base + stride, n_items, tid);
+    double t[QU];
+#pragma unroll
+    for (int u = 0; u < QU; ++u) {
+      double invf = 0.0;
+      if (pinv > 0.0) {
+        const uint64_t g = base + (uint64_t)u * BLOCK + tid;
+        if (g < n_items) { const int iv = pv.invariant[g >> 2]; invf = iv < 0 ? 0.0 : pv.freqs[iv]; }
+      }
+      t[u] = root_cat_term(tree4(__dmul_rn(f0, v[u].x), __dmul_rn(f1, v[u].y), __dmul_rn(f2, v[u].z), __dmul_rn(f3, v[u].w)), w, pinv, invf);
+    }
+    const double term = quad_gather_sum(t[0], t[1], t[2], t[3], q);
+    const uint64_t n = (base >> 2) + (uint64_t)q * (BLOCK / 4) + (tid >> 2);
+    if (n < pv.patterns) {
+      const uint32_t s = sc[n];
+      double lk = log(term);
+      if (s) lk = __dadd_rn(lk, __dmul_rn((double)s, log_thresh));
+      lk = __dmul_rn(lk, (double)pv.weights[n]);
+      if (persite) persite[((size_t)blockIdx.y * nparts_total + pv.part_index) * persite_stride + n] = lk;
+      acc[0] += lk;
+    }
+  }
+  block_sum<1>(acc, red);
+  const size_t oi = (size_t)blockIdx.y * nparts_total + pv.part_index;
+  if (threadIdx.x == 0) partial[oi * gridDim.x + blockIdx.x] = acc[0];
+  finish_partials<1>(partial + oi * gridDim.x, out + oi, counters ? counters + oi : nullptr, gridDim.x);
+}
+
+/* K4: two items per thread and half-pass (a quad still collects four items before it transposes), P(edge) block of the thread's
+ * category in shared memory at the padded pitch — the double buffer of both operands would not fit 128 registers otherwise */
+constexpr int QH = 2;
+__device__ __forceinline__ void quad_load_half(D4 (&a)[QH], D4 (&b)[QH], const double *__restrict__ clvp, const double *__restrict__ clvc,
+                                               const uint8_t *__restrict__ tip, const double *__restrict__ lut, uint64_t base, uint64_t n_items, int tid, int q) {
+#pragma unroll
+  for (int u = 0; u < QH; ++u) {
+    const uint64_t g = base + (uint64_t)u * BLOCK + tid;
+    if (g < n_items) {
+      a[u] = ldg256(clvp + g * 4);
+      if (clvc) b[u] = ldg256(clvc + g * 4);
+      else b[u] = *reinterpret_cast<const D4 *>(lut + (tip[g >> 2] & 15) * 16 + q * 4);
+    } else { a[u].x = a[u].y = a[u].z = a[u].w = 0.0; b[u] = a[u]; }
+  }
+}
+
+__global__ void __launch_bounds__(BLOCK, 2) k_edge_lnl_dna4q(const PartView *__restrict__ parts, const nrx_pair *__restrict__ pairs,
+                                                              uint32_t edge, double *__restrict__ partial, uint32_t nparts_total,
+                                                              double log_thresh, double *__restrict__ out, uint32_t *__restrict__ counters) {
+  __shared__ double red[BLOCK / 32];
+  __shared__ __align__(32) double lut[256];
+  __shared__ __align__(16) double sP[4 * PCAT];
+  const PartView &pv = parts[blockIdx.z];
+  nrx_pair pr = pairs[blockIdx.y];
+  if (pr.a_kind == NRX_TIP) { nrx_pair t = pr; pr.a_kind = t.b_kind; pr.a_idx = t.b_idx; pr.b_kind = t.a_kind; pr.b_idx = t.a_idx; }
+  const int tid = threadIdx.x, q = tid & 3;
+  const bool tipc = pr.b_kind == NRX_TIP;
+  if (tipc) build_tip_lut4(lut, pv.pmat + (size_t)edge * 64, tid);
+  else if (tid < 64) sP[(tid >> 4) * PCAT + (tid & 15)] = pv.pmat[(size_t)edge * 64 + tid];
+  __syncthreads();
+  const double *Pq = sP + q * PCAT;
+  const double *clvp = pv.clv[pr.a_idx];
+  const uint32_t *scp = pv.scaler[pr.a_idx];
+  const double *clvc = tipc ? nullptr : pv.clv[pr.b_idx];
+  const uint32_t *scc = tipc ? nullptr : pv.scaler[pr.b_idx];
+  const uint8_t *tip = tipc ? pv.tipchars + (size_t)pr.b_idx * pv.tip_pitch : nullptr;
+  const double f0 = pv.freqs[0], f1 = pv.freqs[1], f2 = pv.freqs[2], f3 = pv.freqs[3];
+  const double w = pv.rate_weights[q], pinv = pv.pinv;
+  const uint64_t n_items = (uint64_t)pv.patterns * 4, stride = (uint64_t)gridDim.x * BLOCK * QU;
+  double acc[1] = {0.0};
+  uint64_t base = (uint64_t)blockIdx.x * BLOCK * QU;
+  D4 na[QH], nb[QH];
+  quad_load_half(na, nb, clvp, clvc, tip, lut, base, n_items, tid, q);
+  for (; base < n_items; base += stride) {
+    double ta[QU], ti[QU];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      D4 a[QH], b[QH];
+#pragma unroll
+      for (int u = 0; u < QH; ++u) { a[u] = na[u]; b[u] = nb[u]; }
+      // next half-pass: the second half of this pass, or the first half of the block's next pass
+      const uint64_t nbase = h == 0 ? base + (uint64_t)QH * BLOCK : base + stride;
+      if (h == 0 || nbase < n_items) quad_load_half(na, nb, clvp, clvc, tip, lut, nbase, n_items, tid, q);
+#pragma unroll
+      for (int u = 0; u < QH; ++u) {
+        const D4 y = tipc ? b[u] : matvec4(Pq, b[u]);
+        const double tr = edge_cat_term(a[u], y, f0, f1, f2, f3);
+        const int k = h * QH + u;
+        if (pinv > 0.0) {
+          const uint64_t g = base + (uint64_t)k * BLOCK + tid;
+          int iv = -1;
+          if (g < n_items) iv = pv.invariant[g >> 2];
+          const double invf = iv < 0 ? 0.0 : pv.freqs[iv];
+          ta[k] = 0.0; ti[k] = 0.0;
+          edge_cat_accum(tr, w, pinv, invf, iv >= 0, ta[k], ti[k]);
+        } else { ta[k] = __dmul_rn(tr, w); ti[k] = 0.0; }
+      }
+    }
+    const double terma = quad_gather_sum(ta[0], ta[1], ta[2], ta[3], q);
+    double terminv = 0.0;
+    if (pinv > 0.0) terminv = quad_gather_sum(ti[0], ti[1], ti[2], ti[3], q);
+    const uint64_t n = (base >> 2) + (uint64_t)q * (BLOCK / 4) + (tid >> 2);
+    if (n < pv.patterns) {
+      uint32_t s = scp[n];
+      if (!tipc) s += scc[n];
+      double lk;
+      if (pinv > 0.0) lk = edge_site_lnl(terma, terminv, s, log_thresh);
+      else { lk = log(terma); if (s) lk = __dadd_rn(lk, __dmul_rn((double)s, log_thresh)); }
+      acc[0] += __dmul_rn(lk, (double)pv.weights[n]);
+    }
+  }
+  block_sum<1>(acc, red);
+  const size_t oi = (size_t)blockIdx.y * nparts_total + pv.part_index;
+  if (threadIdx.x == 0) partial[oi * gridDim.x + blockIdx.x] = acc[0];
+  finish_partials<1>(partial + oi * gridDim.x, out + oi, counters ? counters + oi : nullptr, gridDim.x);
+}
+
 }  // namespace nrx

@@ -31,7 +31,7 @@ std::vector<DisplayedTreeData> extractOldTrees(AnnotatedNetwork &ann, Node *virt
   return old;
 }
 
-ReticulationConfigSet getRestrictionsActiveAliveBranch(AnnotatedNetwork &ann, size_t pmatrix_index) {  // ReticulationConfigHelper.cpp:319-331
+static ReticulationConfigSet computeRestrictionsActiveAliveBranch(AnnotatedNetwork &ann, size_t pmatrix_index) {  // ReticulationConfigHelper.cpp:319-331
   ReticulationConfigSet res;  // max_reticulations stays 0 as in the reference: simplify only removes duplicates
   for (size_t t = 0; t < ((size_t)1 << ann.network.num_reticulations()); ++t) {
     const ReticulationConfigSet tc = getTreeConfig(ann, t);
@@ -157,6 +157,12 @@ struct RerootCache {
     NodeDisplayedTreeData data;           // owns the slots of data.displayed_trees
   };
   std::vector<Entry> entries;
+  /* the host algebra of one re-rooting (paths, their children and restriction sets, the restore sets) depends on the topology only:
+   * kept per (old root, new root, node behind it) until topology_changed() */
+  struct Plan { size_t old_vr, new_vr, back; std::vector<PathToVirtualRoot> paths; NodeSaveInformation info; };
+  std::vector<Plan> plans;
+  std::vector<std::pair<size_t, ReticulationConfigSet>> edge_restrictions;   // getRestrictionsActiveAliveBranch per branch
+  uint64_t topology_epoch = 0;
   uint64_t next_id = 1, tick = 0, session = 0, epoch = 0;
   size_t cached_slots = 0;
   // the open session
@@ -315,6 +321,14 @@ void evictRerootEntries(AnnotatedNetwork &ann, RerootCache &rc, size_t budget) {
 }
 }  // namespace
 
+ReticulationConfigSet getRestrictionsActiveAliveBranch(AnnotatedNetwork &ann, size_t pmatrix_index) {  // ReticulationConfigHelper.cpp:319-331, per topology
+  RerootCache &rc = rerootState(ann);
+  if (rc.topology_epoch != ann.topology_epoch) { rc.plans.clear(); rc.edge_restrictions.clear(); rc.topology_epoch = ann.topology_epoch; }
+  for (const auto &kv : rc.edge_restrictions) if (kv.first == pmatrix_index) return kv.second;
+  rc.edge_restrictions.emplace_back(pmatrix_index, computeRestrictionsActiveAliveBranch(ann, pmatrix_index));
+  return rc.edge_restrictions.back().second;
+}
+
 void dropRerootCache(AnnotatedNetwork &ann) {
   if (!ann.reroot) return;
   RerootCache &rc = *ann.reroot;
@@ -392,8 +406,17 @@ void updateCLVsVirtualRerootTrees(AnnotatedNetwork &ann, Node *old_virtual_root,
   finishVirtualReroot(ann);   // a session left open by the caller
   RerootCache &rc = rerootState(ann);
   if (rc.epoch != ann.clv_epoch) { dropRerootCache(ann); rc.epoch = ann.clv_epoch; }
-  const std::vector<PathToVirtualRoot> paths = getPathsToVirtualRoot(ann, old_vr, new_vr, back);
-  const NodeSaveInformation info = computeNodeSaveInformation(paths);
+  if (rc.topology_epoch != ann.topology_epoch) { rc.plans.clear(); rc.edge_restrictions.clear(); rc.topology_epoch = ann.topology_epoch; }
+  const RerootCache::Plan *plan = nullptr;
+  for (const RerootCache::Plan &pl : rc.plans) if (pl.old_vr == old_vr && pl.new_vr == new_vr && pl.back == back) { plan = &pl; break; }
+  if (!plan) {
+    RerootCache::Plan pl{old_vr, new_vr, back, getPathsToVirtualRoot(ann, old_vr, new_vr, back), {}};
+    pl.info = computeNodeSaveInformation(pl.paths);
+    rc.plans.push_back(std::move(pl));
+    plan = &rc.plans.back();
+  }
+  const std::vector<PathToVirtualRoot> &paths = plan->paths;
+  const NodeSaveInformation &info = plan->info;
   rc.active = true;
   rc.session++;
   rc.edge = edgeBetween(ann.network, new_vr, back);

@@ -273,6 +273,7 @@ static void dropEnginePlan(AnnotatedNetwork &ann) {
 void topology_changed(AnnotatedNetwork &ann) {
   if (ann.plan) { ann.plan->valid = false; dropEnginePlan(ann); }
   ann.clv_epoch++;
+  ann.topology_epoch++;
   ann.node_version.clear();
   ann.travbuffer = reversed_topological_sort(ann.network);
 }

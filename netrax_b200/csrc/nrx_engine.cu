@@ -1434,7 +1434,7 @@ static bool class_mixture(const nrx_engine *e, const ShapeClass &c) {
 static bool pow2_cats(const ShapeClass &c) { return c.cats <= 32 && (c.cats & (c.cats - 1)) == 0 && !std::getenv("NRX_NO_PC"); }
 
 /* blocks along x for the reduction kernels (one value per call: the partial-sum layout uses gridDim.x as its stride) */
-static uint32_t reduce_blocks(const nrx_engine *e, uint32_t items) {
+static uint32_t reduce_blocks(const nrx_engine *e, uint32_t items, bool quad_kernels = true) {
   // work items per (tree / pair): patterns for the thread-per-pattern kernels, patterns x categories where the class
   // runs thread-per-(pattern, category) or, for the 20-state tensor-core kernels, tile groups
   uint64_t work = 0;
@@ -1445,7 +1445,7 @@ static uint32_t reduce_blocks(const nrx_engine *e, uint32_t items) {
   const uint64_t full = std::max<uint64_t>(1, (work + BLOCK - 1) / BLOCK);
   // the quad kernels (DNA 4x4) prefetch their next pass: few long-lived blocks (quad_total, default 2 per SM = one resident wave; measured 296 / 592 / 1184 / 2368 blocks: K6 0.76 / 0.71 / 0.62 / 0.54 of the HBM peak); everything else
   // one pass per block where possible, ~32 blocks per SM in total
-  bool all_quad = e->quad && !e->classes.empty();
+  bool all_quad = quad_kernels && e->quad && !e->classes.empty();
   for (const ShapeClass &c : e->classes) all_quad = all_quad && c.states == 4 && c.cats == 4 && !class_mixture(e, c);
   const uint64_t total = all_quad ? (e->quad_total ? e->quad_total : 2ull * e->sm_count) : 148ull * 32;
   const uint64_t want = std::max<uint64_t>(1, total / std::max<uint32_t>(1, items));
@@ -1544,7 +1544,7 @@ static int tree_lnl_fused_impl(nrx_engine *e, uint32_t plan_id, const uint32_t *
   if (n > e->plans[plan_id].lnl_items || !e->d_fused) { g_err = "nrx_tree_lnl_fused: the plan carries fewer lnl marks"; return 0; }
   CK(cudaSetDevice(e->device));
   const uint32_t P = (uint32_t)e->parts.size();
-  const uint32_t nblk = reduce_blocks(e, n * P);   // same geometry as nrx_tree_lnl on n trees -> bit-identical sums
+  const uint32_t nblk = reduce_blocks(e, n * P, false);   // k_term_lnl_sum makes one pass per block: the one-pass geometry
   if (!ensure_result(e, (size_t)n * P, (size_t)n * P * nblk) || !refresh_views(e)) return 0;
   for (uint32_t i = 0; i < n; ++i) if (slots[i] >= e->nslots) { g_err = "nrx_tree_lnl_fused: slot out of range"; return 0; }
   uint32_t *d_slots;

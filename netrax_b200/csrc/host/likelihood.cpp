@@ -51,7 +51,16 @@ uint32_t allocSlot(AnnotatedNetwork &ann) {
   const uint32_t s = ann.next_slot++;
   if (s >= nrx_num_slots(ann.engine)) {
     const uint32_t want = std::max<uint32_t>(s + 1, nrx_num_slots(ann.engine) + std::max<uint32_t>(16, nrx_num_slots(ann.engine) / 2));
-    if (!nrx_reserve_slots(ann.engine, want)) engineCheck(nrx_reserve_slots(ann.engine, s + 1), "nrx_reserve_slots");
+    if (!nrx_reserve_slots(ann.engine, want) && !nrx_reserve_slots(ann.engine, s + 1)) {
+      // out of device memory: the memoised re-rooted trees are only a cache — give their slots back and take one of those
+      const std::string err = nrx_last_error();
+      ann.next_slot--;
+      dropRerootCache(ann);
+      if (ann.free_slots.empty()) throw std::runtime_error("nrx_reserve_slots: " + err);
+      const uint32_t r = ann.free_slots.back();
+      ann.free_slots.pop_back();
+      return r;
+    }
   }
   return s;
 }

@@ -944,6 +944,7 @@ static unsigned long long pair_cbytes(const nrx_engine *e, const nrx_pair *pairs
 
 /* K2 launches (one per partition shape class) for `nops` device-resident ops; `with_tips`: some op has a tip operand */
 static bool has_aa_dmma(const nrx_engine *e);
+static bool aa_dmma_class(const nrx_engine *e, const ShapeClass &c);
 static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, bool with_tips, bool fused = false, uint32_t ntt = 0) {
   for (const ShapeClass &c : e->classes) {
     if (c.max_patterns == 0) continue;
@@ -1014,8 +1015,21 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
       const int luts = !with_tips ? 0 : (has_aa_dmma(e) ? 1 : 2);
       const size_t lut_bytes = (size_t)luts * class_tip_codes(e, c) * 80 * sizeof(double);
       if (e->aa_v1) k_aa20_dmma<AA_CLV><<<grid, AA_THREADS, sizeof(AaSmem) + lut_bytes, e->stream>>>(c.d_views, d_ops + ntt, rest, groups, luts, nullptr, 0, 0.0);
-      else if (e->aa_pipe) k_aa20_mma<AA_CLV, true><<<grid, AA2_THREADS, sizeof(AaSmem2) + lut_bytes, e->stream>>>(c.d_views, d_ops + ntt, rest, groups, luts, nullptr, 0, 0.0, nullptr, nullptr);
-      else k_aa20_mma<AA_CLV, false><<<grid, AA2_THREADS, sizeof(AaSmem2) + lut_bytes, e->stream>>>(c.d_views, d_ops + ntt, rest, groups, luts, nullptr, 0, 0.0, nullptr, nullptr);
+      else {
+        // inside a plan capture the launch is programmatically serialised behind the previous K2 launch (PDL): its blocks take the
+        // SM slots the draining predecessor frees and run their prologue there; the loader warps wait for the predecessor's CLVs
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid; cfg.blockDim = dim3(AA2_THREADS); cfg.stream = e->stream; cfg.dynamicSmemBytes = sizeof(AaSmem2) + lut_bytes;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        const int pdl = (e->capturing_pdl && e->pdl_prev_is_k2) ? 1 : 0;
+        cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+        const nrx_op *ops_rest = d_ops + ntt;
+        if (e->aa_pipe) CK(cudaLaunchKernelEx(&cfg, k_aa20_mma<AA_CLV, true>, (const PartView *)c.d_views, ops_rest, rest, groups, luts, (double *)nullptr, 0u, 0.0, (double *)nullptr, (uint32_t *)nullptr, pdl));
+        else CK(cudaLaunchKernelEx(&cfg, k_aa20_mma<AA_CLV, false>, (const PartView *)c.d_views, ops_rest, rest, groups, luts, (double *)nullptr, 0u, 0.0, (double *)nullptr, (uint32_t *)nullptr, pdl));
+        e->pdl_prev_is_k2 = true;
+      }
     } else {
       dim3 grid(tiles_for(c.max_patterns, BLOCK, nops * z), nops, z);
       k_clv_generic<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_ops, nullptr);
@@ -1374,7 +1388,8 @@ int nrx_plan_run(nrx_engine *e, uint32_t plan_id) {
     const unsigned long long l0 = e->launches;
     CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
     // PDL only where every launch of the plan is the pipelined 4-state kernel (one shape class): the chain K2 -> K2 -> ...
-    e->capturing_pdl = e->use_pdl && e->classes.size() == 1 && dna_pipe_cats(e->classes[0].states, e->classes[0].cats) && e->k2_variant == 0;
+    e->capturing_pdl = e->use_pdl && e->classes.size() == 1 &&
+                       ((dna_pipe_cats(e->classes[0].states, e->classes[0].cats) && e->k2_variant == 0) || (aa_dmma_class(e, e->classes[0]) && !e->aa_v1));
     e->pdl_prev_is_k2 = false;
     int ok = 1;
     for (size_t b = 0; b < pl.sizes.size() && ok; ++b) ok = launch_plan_batch(e, pl, b);
@@ -1693,7 +1708,7 @@ int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n
       const size_t smem = sizeof(AaSmem) + (tips ? (size_t)class_tip_codes(e, c) * 80 * sizeof(double) : 0);   // pairs are never tip-tip: one table
       if (e->aa_v1) k_aa20_dmma<AA_EDGE><<<dim3(n * nblk, 1, (uint32_t)c.parts.size()), AA_THREADS, smem, e->stream>>>(c.d_views, d_ops, n, nblk, tips ? 1 : 0, e->d_partial, P, log_thresh);
       else k_aa20_mma<AA_EDGE, true><<<dim3(n * nblk, 1, (uint32_t)c.parts.size()), AA2_THREADS, sizeof(AaSmem2) + (tips ? (size_t)class_tip_codes(e, c) * 80 * sizeof(double) : 0), e->stream>>>(
-            c.d_views, d_ops, n, nblk, tips ? 1 : 0, e->d_partial, P, log_thresh, e->d_result, tk);
+            c.d_views, d_ops, n, nblk, tips ? 1 : 0, e->d_partial, P, log_thresh, e->d_result, tk, 0);
     }
     else k_edge_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh, e->d_result, tk);
     e->launches++;
@@ -1730,7 +1745,7 @@ int nrx_sumtables(nrx_engine *e, const nrx_pair *pairs, uint32_t n) {
       groups = std::min(groups, std::max<uint32_t>(1, ntiles / 8));
       const size_t lut_bytes = tips ? (size_t)class_tip_codes(e, c) * 80 * sizeof(double) : 0;
       if (e->aa_v1) k_aa20_dmma<AA_SUM><<<dim3(n * groups, 1, z), AA_THREADS, sizeof(AaSmem) + lut_bytes, e->stream>>>(c.d_views, d_ops, n, groups, tips ? 1 : 0, nullptr, 0, 0.0);
-      else k_aa20_mma<AA_SUM, true><<<dim3(n * groups, 1, z), AA2_THREADS, sizeof(AaSmem2) + lut_bytes, e->stream>>>(c.d_views, d_ops, n, groups, tips ? 1 : 0, nullptr, 0, 0.0, nullptr, nullptr);
+      else k_aa20_mma<AA_SUM, true><<<dim3(n * groups, 1, z), AA2_THREADS, sizeof(AaSmem2) + lut_bytes, e->stream>>>(c.d_views, d_ops, n, groups, tips ? 1 : 0, nullptr, 0, 0.0, nullptr, nullptr, 0);
     } else {
       dim3 grid(tiles_for((uint64_t)c.max_patterns * c.cats, BLOCK, n * z), n, z);
       k_sumtable<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs);
@@ -1767,9 +1782,10 @@ int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen, double *out)
         dp += 4;
       }
     }
-    double *d_tmp;
-    if (!upload(e, diag.data(), diag.size(), &d_tmp)) return 0;
-    CK(cudaMemcpyAsync(p.diagp, d_tmp, diag.size() * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+    void *h_stage, *d_unused;   // pinned staging -> the partition's table in ONE copy (330 calls per derivative sweep)
+    if (!stage_alloc(e, diag.size() * sizeof(double), &h_stage, &d_unused)) return 0;
+    std::memcpy(h_stage, diag.data(), diag.size() * sizeof(double));
+    CK(cudaMemcpyAsync(p.diagp, h_stage, diag.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   }
   uint32_t *tk = e->fuse_reduce ? e->d_tickets : nullptr;
   cudaEvent_t ev0, ev1;

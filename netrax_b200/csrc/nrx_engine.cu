@@ -1461,7 +1461,7 @@ static uint32_t reduce_blocks(const nrx_engine *e, uint32_t items, bool quad_ker
   // the quad kernels (DNA 4x4) prefetch their next pass: few long-lived blocks (quad_total, default 2 per SM = one resident wave; measured 296 / 592 / 1184 / 2368 blocks: K6 0.76 / 0.71 / 0.62 / 0.54 of the HBM peak); everything else
   // one pass per block where possible, ~32 blocks per SM in total
   bool all_quad = quad_kernels && e->quad && !e->classes.empty();
-  for (const ShapeClass &c : e->classes) all_quad = all_quad && c.states == 4 && c.cats == 4 && !class_mixture(e, c);
+  for (const ShapeClass &c : e->classes) all_quad = all_quad && ((c.states == 4 && c.cats == 4) || (c.states == 20 && c.cats == 4 && pow2_cats(c))) && !class_mixture(e, c);
   const uint64_t total = all_quad ? (e->quad_total ? e->quad_total : 2ull * e->sm_count) : 148ull * 32;
   const uint64_t want = std::max<uint64_t>(1, total / std::max<uint32_t>(1, items));
   if (full <= want) return (uint32_t)full;
@@ -1530,6 +1530,7 @@ static int tree_lnl_impl(nrx_engine *e, const uint32_t *slots, uint32_t n, doubl
     const bool mix = class_mixture(e, c);
     if (!mix && c.states == 4 && c.cats == 4 && e->quad) k_tree_lnl_dna4q<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
     else if (!mix && c.states == 4 && c.cats == 4) k_tree_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
+    else if (!mix && pow2_cats(c) && c.states == 20 && c.cats == 4 && e->quad) k_tree_lnl_aa20p<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
     else if (!mix && pow2_cats(c) && c.states == 20) k_tree_lnl_pc<20><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
     else if (!mix && pow2_cats(c)) k_tree_lnl_pc<0><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
     else k_tree_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
@@ -1795,6 +1796,7 @@ int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen, double *out)
     const bool mix = class_mixture(e, c);   // (only the +I term of K6 reads frequencies; the generic kernel is the one that indexes them by category)
     if (!mix && c.states == 4 && c.cats == 4 && e->quad) k_derivatives_dna4q<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
     else if (!mix && c.states == 4 && c.cats == 4) k_derivatives_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
+    else if (!mix && pow2_cats(c) && c.states == 20 && c.cats == 4 && e->quad) k_derivatives_aa20p<<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
     else if (!mix && pow2_cats(c) && c.states == 20) k_derivatives_pc<20, 2><<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
     else if (!mix && pow2_cats(c)) k_derivatives_pc<0, 2><<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
     else k_derivatives<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);

@@ -2383,6 +2383,156 @@ __global__ void __launch_bounds__(BLOCK) k_derivatives_pc(const PartView *__rest
   finish_partials<3>(p, out + oi * 3, counters ? counters + oi : nullptr, gridDim.x);
 }
 
+/* K3 / K6 for 20 states x 4 categories, pipelined (round 2): same thread = (pattern, category) mapping, arithmetic and category
+ * gather as k_tree_lnl_pc<20> / k_derivatives_pc<20, NP>, but few long-lived blocks (reduce_blocks' quad geometry) that load the
+ * NEXT pass's five 256-bit chunks into registers before the current pass is consumed — the restructuring that took the DNA K6
+ * from 0.49 to 0.76 of the HBM peak (profiles/r3d_k4_k5_k6_dna_sweep_ncu.md: one pass per block = load, log / division tail and
+ * block reduction strictly one after the other). */
+constexpr int AA_CH = 5;   // 256-bit chunks per (pattern, category) item: 20 states
+
+__device__ __forceinline__ void aa_item_load(D4 (&v)[AA_CH], const double *__restrict__ src, uint64_t g, uint64_t n_items) {
+  if (g < n_items) {
+#pragma unroll
+    for (int k = 0; k < AA_CH; ++k) v[k] = ldg256(src + g * 20 + k * 4);
+  } else {
+#pragma unroll
+    for (int k = 0; k < AA_CH; ++k) { v[k].x = v[k].y = v[k].z = v[k].w = 0.0; }
+  }
+}
+
+__global__ void __launch_bounds__(BLOCK, 2) k_derivatives_aa20p(const PartView *__restrict__ parts, double *__restrict__ partial,
+                                                                 uint32_t nparts_total, double *__restrict__ out, uint32_t *__restrict__ counters) {
+  __shared__ double red[3 * (BLOCK / 32)];
+  extern __shared__ __align__(16) double sdiag[];  // [4][diag_stride(20)] (entries [state][4]) + [4] rate weights
+  const PartView &pv = parts[blockIdx.z];
+  constexpr uint32_t S = 20, C = 4;
+  const uint32_t DS = diag_stride(S);
+  double *swt = sdiag + (size_t)C * DS;
+  for (uint32_t i = threadIdx.x; i < C * S * 4; i += BLOCK) sdiag[(i / (S * 4)) * DS + i % (S * 4)] = pv.diagp[i];
+  if (threadIdx.x < C) swt[threadIdx.x] = pv.rate_weights[threadIdx.x];
+  __syncthreads();
+  const double *st = pv.sumtable[blockIdx.y];
+  const uint32_t lane = threadIdx.x & 31, c = threadIdx.x & (C - 1);
+  const double *dg = sdiag + (size_t)c * DS;
+  const uint64_t n_items = (uint64_t)pv.patterns * C, stride = (uint64_t)gridDim.x * BLOCK;
+  const double pinv = pv.pinv, w = swt[c];
+  double acc[3] = {0.0, 0.0, 0.0};
+  uint64_t base = (uint64_t)blockIdx.x * BLOCK;
+  D4 nxt[AA_CH];
+  aa_item_load(nxt, st, base + threadIdx.x, n_items);
+  for (; base < n_items; base += stride) {
+    D4 q[AA_CH];
+#pragma unroll
+    for (int k = 0; k < AA_CH; ++k) q[k] = nxt[k];
+    const uint64_t g = base + threadIdx.x;
+    if (base + stride < n_items) aa_item_load(nxt, st, g + stride, n_items);
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < AA_CH; ++k) {
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const double2 d01 = *reinterpret_cast<const double2 *>(dg + (k * 4 + h) * 4);
+        const double d2 = dg[(k * 4 + h) * 4 + 2];
+        const double e = h == 0 ? q[k].x : (h == 1 ? q[k].y : (h == 2 ? q[k].z : q[k].w));
+        c0 = __dadd_rn(c0, __dmul_rn(e, d01.x));
+        c1 = __dadd_rn(c1, __dmul_rn(e, d01.y));
+        c2 = __dadd_rn(c2, __dmul_rn(e, d2));
+      }
+    }
+    const bool on = g < n_items;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    if (on) {
+      if (pinv > 0.0) { const int iv = pv.invariant[g / C]; deriv_cat_pinv(c0, c1, c2, pinv, iv < 0 ? 0.0 : pv.freqs[iv]); }
+      t0 = __dmul_rn(c0, w); t1 = __dmul_rn(c1, w); t2 = __dmul_rn(c2, w);
+    }
+    double lk0 = 0.0, lk1 = 0.0, lk2 = 0.0;
+#pragma unroll
+    for (uint32_t i = 0; i < C; ++i) {
+      const int src = (int)((lane & ~(C - 1)) + i);
+      lk0 = __dadd_rn(lk0, __shfl_sync(0xffffffffu, t0, src));
+      lk1 = __dadd_rn(lk1, __shfl_sync(0xffffffffu, t1, src));
+      lk2 = __dadd_rn(lk2, __shfl_sync(0xffffffffu, t2, src));
+    }
+    if (c == 0 && on) {
+      const double pw = (double)pv.weights[g / C];
+      const double d1 = -lk1 / lk0;
+      const double d2 = d1 * d1 - lk2 / lk0;
+      acc[0] += pw * log(lk0);
+      acc[1] += pw * d1;
+      acc[2] += pw * d2;
+    }
+  }
+  block_sum<3>(acc, red);
+  const size_t oi = (size_t)blockIdx.y * nparts_total + pv.part_index;
+  double *p = partial + oi * 3 * gridDim.x;
+  if (threadIdx.x == 0) {
+    p[0 * gridDim.x + blockIdx.x] = acc[0];
+    p[1 * gridDim.x + blockIdx.x] = acc[1];
+    p[2 * gridDim.x + blockIdx.x] = acc[2];
+  }
+  finish_partials<3>(p, out + oi * 3, counters ? counters + oi : nullptr, gridDim.x);
+}
+
+__global__ void __launch_bounds__(BLOCK, 2) k_tree_lnl_aa20p(const PartView *__restrict__ parts, const uint32_t *__restrict__ slots,
+                                                              double *__restrict__ partial, uint32_t nparts_total, double log_thresh,
+                                                              double *__restrict__ persite, size_t persite_stride,
+                                                              double *__restrict__ out, uint32_t *__restrict__ counters) {
+  __shared__ double red[BLOCK / 32];
+  __shared__ double sfreq[32], swt[32];
+  const PartView &pv = parts[blockIdx.z];
+  constexpr uint32_t S = 20, C = 4;
+  const uint32_t slot = slots[blockIdx.y];
+  const double *clv = pv.clv[slot];
+  const uint32_t *sc = pv.scaler[slot];
+  if (threadIdx.x < S) sfreq[threadIdx.x] = pv.freqs[threadIdx.x];
+  if (threadIdx.x < C) swt[threadIdx.x] = pv.rate_weights[threadIdx.x];
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, c = threadIdx.x & (C - 1);
+  const uint64_t n_items = (uint64_t)pv.patterns * C, stride = (uint64_t)gridDim.x * BLOCK;
+  const double pinv = pv.pinv;
+  double acc[1] = {0.0};
+  uint64_t base = (uint64_t)blockIdx.x * BLOCK;
+  D4 nxt[AA_CH];
+  aa_item_load(nxt, clv, base + threadIdx.x, n_items);
+  for (; base < n_items; base += stride) {
+    D4 q[AA_CH];
+#pragma unroll
+    for (int k = 0; k < AA_CH; ++k) q[k] = nxt[k];
+    const uint64_t g = base + threadIdx.x;
+    if (base + stride < n_items) aa_item_load(nxt, clv, g + stride, n_items);
+    double t = 0.0;
+    if (g < n_items) {
+      double term_r = 0.0;
+#pragma unroll
+      for (int k = 0; k < AA_CH; ++k) {
+        term_r = __dadd_rn(term_r, __dmul_rn(q[k].x, sfreq[k * 4]));
+        term_r = __dadd_rn(term_r, __dmul_rn(q[k].y, sfreq[k * 4 + 1]));
+        term_r = __dadd_rn(term_r, __dmul_rn(q[k].z, sfreq[k * 4 + 2]));
+        term_r = __dadd_rn(term_r, __dmul_rn(q[k].w, sfreq[k * 4 + 3]));
+      }
+      double invf = 0.0;
+      if (pinv > 0.0) { const int iv = pv.invariant[g / C]; invf = iv < 0 ? 0.0 : sfreq[iv]; }
+      t = root_cat_term(term_r, swt[c], pinv, invf);
+    }
+    double term = 0.0;
+#pragma unroll
+    for (uint32_t i = 0; i < C; ++i) term = __dadd_rn(term, __shfl_sync(0xffffffffu, t, (lane & ~(C - 1)) + i));
+    if (c == 0 && g < n_items) {
+      const uint64_t n = g / C;
+      double lk = log(term);
+      const uint32_t s = sc[n];
+      if (s) lk = __dadd_rn(lk, __dmul_rn((double)s, log_thresh));
+      lk = __dmul_rn(lk, (double)pv.weights[n]);
+      if (persite) persite[((size_t)blockIdx.y * nparts_total + pv.part_index) * persite_stride + n] = lk;
+      acc[0] += lk;
+    }
+  }
+  block_sum<1>(acc, red);
+  const size_t oi = (size_t)blockIdx.y * nparts_total + pv.part_index;
+  if (threadIdx.x == 0) partial[oi * gridDim.x + blockIdx.x] = acc[0];
+  finish_partials<1>(partial + oi * gridDim.x, out + oi, counters ? counters + oi : nullptr, gridDim.x);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * K3-K6, DNA 4x4 specialisations.  Same arithmetic as the generic kernels above (same summation order), but
  * thread = (pattern, rate category) like K2: a warp reads 1 KB of contiguous CLV per 256-bit load, UNROLL

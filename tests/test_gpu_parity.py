@@ -1352,3 +1352,41 @@ def test_shadow_rerooting_restored_length_leaves_nothing_invalid():
     assert g.clv_update_count() > u0
     _compare_all_clvs(g, o, exact=False)
     g.close()
+
+
+@pytest.mark.parametrize("kind", ["unlinked_best", "protein"])
+def test_shadow_rerooting_memo_other_shapes(kind):
+    """The memo keys on the branch lengths of EVERY partition and is independent of the kernels underneath: unlinked branch lengths
+    over ragged partitions with the BEST variant, and a protein partition (tensor-core K2 / K4 / K5), swept in pre-order with the
+    last proposal kept — memo on == memo off bit for bit, both equal to the in-place checker."""
+    from netrax_b200.synth import lg_model
+    if kind == "protein":
+        net = random_network(12, 2, seed=31)
+        rates, freqs = lg_model()
+        m, w = simulate_alignment(net, 160, seed=31, states=20, rates=rates, freqs=freqs)
+        parts, kw = [Partition(20, 4, m, freqs, rates, GAMMA4_ALPHA05, pattern_weights=w)], {}
+    else:
+        net = random_network(16, 3, seed=32)
+        rng = np.random.default_rng(3)
+        parts, brl = [], []
+        for p, pat in enumerate((300, 97, 211)):
+            m, w = simulate_alignment(net, pat, seed=40 + p)
+            parts.append(Partition(4, 4, m, DNA_FREQS, GTR_RATES * (1 + 0.1 * p), GAMMA4_ALPHA05, pattern_weights=w))
+            brl.append(net.edge_length * rng.uniform(0.5, 2, net.num_edges))
+        kw = dict(variant=BEST, linkage=UNLINKED, partition_brlens=brl)
+    g, g0, o = _gpu(net, parts, **kw), _gpu(net, parts, **kw), _oracle(net, parts, **kw)
+    _inject_eigen(g, o)
+    _inject_eigen(g0, o)
+    g0.set_reroot_cache_slots(0)
+    for eng in (g, g0, o):
+        eng.computeLoglikelihood(0, 1)
+    order = g.brlen_sweep_order()
+    rg, rg0, ro = (_sweep_records(eng, net, order, True) for eng in (g, g0, o))
+    for e, a, b, c in zip(order, rg, rg0, ro):
+        assert np.array_equal(a, b), int(e)
+        np.testing.assert_allclose(a[:2], c[:2], rtol=LNL_RTOL)
+        np.testing.assert_allclose(a[-1], c[-1], rtol=LNL_RTOL)
+        np.testing.assert_allclose(a[2:-1], c[2:-1], rtol=DERIV_RTOL, atol=1e-7)
+    assert g.reroot_stats()["hits"] > 0
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
+    g.close(); g0.close()

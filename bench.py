@@ -311,6 +311,7 @@ def main():
     ap.add_argument("--patterns", type=int, default=0, help="global pattern count per partition (default: the config's)")
     ap.add_argument("--cpu-patterns-per-core", type=int, default=0, help="0: the arm's global pattern count / host cores, capped at 16000")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-score-only", action="store_true", help="skip the score-only region (root displayed trees' CLVs not stored)")
     ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (BASELINE configs 1-4 + sweep, N = 1 only)")
     ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
@@ -439,14 +440,29 @@ def main():
         ms_e2e = eng.timer_stop()
         barrier()
         assert abs(lnl_e2e - lnl) <= 1e-9 * abs(lnl)
+    # ---- region 3 (reported beside the headline, never instead of it): score-only evaluations — candidate scoring reads nothing but
+    # the lnL, so the replayed plan does not store the CLVs of the root displayed trees (nrxh_set_score_only) ----
+    ms_so, lnl_so = None, None
+    if hasattr(eng.api, "_set_score_only") and not args.no_score_only:
+        eng.set_score_only(True)
+        for _ in range(2):
+            eng.computeLoglikelihood(0, 1)
+        barrier()
+        eng.timer_start()
+        for _ in range(args.steps):
+            lnl_so = eng.computeLoglikelihood(0, 1)
+        ms_so = eng.timer_stop()
+        barrier()
+        eng.set_score_only(False)
+        assert lnl_so == lnl, (lnl_so, lnl)   # same kernels, same per-site terms: the same number
     clocks = sampler.stop()
     h2d = (sum(int(t.numel()) for t in tip_u8) if tip_u8 else 0) + sum(4 * int(t.numel()) for t in w_u32) + 8 * (net.num_edges + 1) * len(parts)
     d2h = 8 * eng.num_trees(net.root) * len(parts) + 8
 
     if dist is not None:
-        t = torch.tensor([ms_dev, ms_e2e or 0.0, ms_wall], dtype=torch.float64, device=f"cuda:{local_rank}")
+        t = torch.tensor([ms_dev, ms_e2e or 0.0, ms_wall, ms_so or 0.0], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, ms_e2e, ms_wall = (float(x) for x in t.cpu())
+        ms_dev, ms_e2e, ms_wall, ms_so = (float(x) for x in t.cpu())
         u = torch.tensor([float(updates_per_step_local)], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(u)
         updates_per_step = float(u.cpu()[0])
@@ -497,6 +513,10 @@ def main():
             e2e_value = updates_per_step / (ms_e2e / args.steps / 1e3)
             line["e2e"] = {"value": e2e_value, "unit": "site-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                            "ms_per_step": ms_e2e / args.steps, "lnl_evals_per_sec": 1e3 / (ms_e2e / args.steps)}
+        if ms_so:
+            line["score_only"] = {"what": "the same full evaluation with nrxh_set_score_only: the CLVs of the root displayed trees (root_trees of sum_trees_per_node "
+                                          "slots) are computed and reduced to their per-site lnL but not stored; NOT the headline — batched candidate scoring (SURVEY §8f f3)",
+                                  "ms_per_step": ms_so / args.steps, "value": updates_per_step / (ms_so / args.steps / 1e3), "unit": "site-updates/s", "lnl": lnl_so}
     eng.close()
     del eng
     if rank == 0:

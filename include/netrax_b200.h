@@ -110,6 +110,10 @@ int nrxh_brlen_finish(void *h, unsigned edge, double *final_logl);
  *                                   unordered_set): all branches in depth-first pre-order, edges_out[num_branches]
  *   nrxh_reroot_stats            <- memo hits / misses (processNodeImproved calls of re-rooting paths), live entries and the CLV slots they hold
  *   nrxh_set_reroot_cache_slots  <- slot budget of the memo (-1: default, 0: nothing survives a session) */
+/* nrxh_set_score_only: full evaluations (incremental = 0) that replay the cached plan do not store the CLVs of the root displayed trees
+ * — candidate scoring (src/search/Filtering.cpp:210-260: performMove, score, undoMove) reads nothing but the lnL.  The next incremental
+ * evaluation, re-rooting or CLV read-back first re-evaluates with the stores on. */
+int nrxh_set_score_only(void *h, int on);
 int nrxh_brlen_sweep_order(void *h, unsigned *edges_out);
 int nrxh_reroot_stats(void *h, unsigned long long *hits, unsigned long long *misses, unsigned *entries, unsigned *cached_slots);
 int nrxh_set_reroot_cache_slots(void *h, long long max_slots);

@@ -166,6 +166,11 @@ int nrx_result_wait(nrx_engine *e, double *out, uint32_t count);
 /* Launch geometry of K2: latency (default: a small launch spreads over all SMs, one tile per block) or throughput (several
  * engines share the GPU: fewer, longer-running blocks; measured +40 % evaluations/s with 32 networks in flight). */
 int nrx_set_throughput_mode(nrx_engine *e, int on);
+/* Score-only replays (candidate scoring, src/search/Filtering.cpp:210-260 reads nothing but the lnL): while on, the ops of a plan that
+ * carry an lnl mark — the root displayed trees, whose per-site lnL K2 emits itself — do NOT store their CLV (25 % of the write
+ * stream of BASELINE config 5); scalers and per-site terms are written as always.  The slots of those trees then hold stale CLVs:
+ * the caller must re-evaluate without the flag before anything reads them (the host layer does, AnnotatedNetwork::score_only). */
+int nrx_set_score_only(nrx_engine *e, int on);
 /* K4: edge lnL for n operand pairs over P-matrix `edge`, out[n][nparts]. */
 int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n, double *out);
 /* K5: sumtables for n pairs into sumtable slots [0, n) (pool grows on demand). */

@@ -72,6 +72,7 @@ class FlatAPI:
             g("brlen_sweep_order", C.c_int, C.c_void_p, C.c_void_p)
             g("reroot_stats", C.c_int, C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint), C.POINTER(C.c_uint))
             g("set_reroot_cache_slots", C.c_int, C.c_void_p, C.c_longlong)
+            g("set_score_only", C.c_int, C.c_void_p, C.c_int)
         g("optimize_branch", C.c_int, C.c_void_p, C.c_uint, C.c_int, C.c_uint, C.POINTER(C.c_double))
         g("optimize_branches", C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double))
         g("optimize_reticulation", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
@@ -300,6 +301,10 @@ class LikelihoodEngine:
         h, m, n, s = C.c_ulonglong(), C.c_ulonglong(), C.c_uint(), C.c_uint()
         self.api.check(self.api._reroot_stats(self.h, C.byref(h), C.byref(m), C.byref(n), C.byref(s)))
         return {"hits": h.value, "misses": m.value, "entries": n.value, "cached_slots": s.value}
+
+    def set_score_only(self, on: bool = True):
+        """Full evaluations replaying the cached plan skip the CLV stores of the root displayed trees (candidate scoring)."""
+        self.api.check(self.api._set_score_only(self.h, 1 if on else 0))
 
     def set_reroot_cache_slots(self, max_slots: int = -1):
         self.api.check(self.api._set_reroot_cache_slots(self.h, max_slots))

@@ -189,9 +189,14 @@ int nrxh_tree_info(void *hv, unsigned node, unsigned tree, double *logprob, doub
   });
 }
 
+int nrxh_set_score_only(void *hv, int on) {
+  return guarded([&] { H(hv)->ann.score_only = on != 0; });
+}
+
 int nrxh_read_clv(void *hv, unsigned node, unsigned tree, unsigned p, double *out) {
   return guarded([&] {
     detail::flushPendingOps(H(hv)->ann);
+    if (H(hv)->ann.root_clvs_stale) computeLoglikelihood(H(hv)->ann, 1, 1);   // a score-only evaluation did not store the root trees' CLVs
     const DisplayedTreeData &d = H(hv)->ann.pernode_displayed_tree_data[node].displayed_trees.at(tree);
     if (d.isTip) throw std::runtime_error("tips have no CLV (PATTERN_TIP)");
     detail::engineCheck(nrx_read_clv(H(hv)->ann.engine, p, d.slot, out), "nrx_read_clv");

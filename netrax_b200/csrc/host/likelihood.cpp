@@ -691,6 +691,7 @@ static void replayPlan(AnnotatedNetwork &ann) {
   uint64_t local_sites = 0;
   for (const PartitionModel &m : ann.fake_treeinfo->partitions) local_sites += m.sites;
   if (pc.on_device) {
+    if (pc.fused && ann.score_only_now) ann.root_clvs_stale = true;   // this replay leaves the root displayed trees' CLVs unwritten
     if (pc.fused) pc.run_pending = true;   // treeLoglikelihoodsBegin, called next, issues it together with the root lnLs
     else engineCheck(nrx_plan_run(ann.engine, pc.engine_plan), "nrx_plan_run");
   }
@@ -784,6 +785,14 @@ static bool reuseOldDisplayedTreesCheck(AnnotatedNetwork &ann, int incremental, 
 static void computeLoglikelihoodImprovedBegin(AnnotatedNetwork &ann, int incremental, int update_pmatrices) {
   if (ann.pending_eval) throw std::runtime_error("computeLoglikelihoodBegin: an evaluation of this network is already in flight");
   finishVirtualReroot(ann);   // a re-rooting session the caller left open: the root-directed trees come back first
+  if (ann.root_clvs_stale && (incremental || !ann.score_only)) {   // a score-only evaluation left the root trees' CLVs unwritten
+    incremental = 0;
+    ann.root_clvs_stale = false;
+    ann.score_only_now = false;
+  } else {
+    ann.score_only_now = !incremental && ann.score_only;
+  }
+  if (!incremental) engineCheck(nrx_set_score_only(ann.engine, ann.score_only_now ? 1 : 0), "nrx_set_score_only");
   ann.begin_returns_cached = false;
   if (!incremental) invalidateAllCLVs(ann);
   const bool reuse = reuseOldDisplayedTreesCheck(ann, incremental, ann.network.root->clv_index);

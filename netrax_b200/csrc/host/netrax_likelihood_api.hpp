@@ -243,6 +243,10 @@ struct AnnotatedNetwork {  // src/graph/AnnotatedNetwork.hpp:42-89
   std::vector<char> pending_parent;           // [node] 1 if the node's trees are outputs of pending_ops
   PlanCache *plan = nullptr;
   bool use_plan_cache = true;
+  /* score-only evaluation (candidate scoring reads nothing but the lnL): a full evaluation that replays a fused-K3 plan does not
+   * store the CLVs of the root displayed trees.  They are then stale (`root_clvs_stale`): the next incremental evaluation, re-rooting
+   * or CLV read-back first runs a full evaluation with the stores on. */
+  bool score_only = false, root_clvs_stale = false, score_only_now = false;
   /* virtual re-rooting writes into shadow slots (the root-directed CLVs stay intact) and memoises the re-rooted node data */
   RerootCache *reroot = nullptr;
   std::vector<uint64_t> node_version;         // [node] bumped whenever the node's root-directed displayed trees are recomputed

@@ -109,7 +109,7 @@ struct EnginePlan {
   std::vector<uint32_t> sizes;
   std::vector<char> tips;
   std::vector<uint32_t> ntt;   // leading tip-tip ops of each batch (20-state engines order them first)
-  cudaGraphExec_t exec[2] = {nullptr, nullptr};   // [0] latency geometry, [1] throughput geometry (nrx_set_throughput_mode)
+  cudaGraphExec_t exec[4] = {nullptr, nullptr, nullptr, nullptr};   // [0] latency geometry, [1] throughput geometry (nrx_set_throughput_mode); +2: score-only (nrx_set_score_only)
   unsigned long long updates = 0, bytes = 0, cbytes = 0;
   uint32_t lnl_items = 0;    // number of ops carrying an lnl_item mark (fused K3)
   // node-centric K2 (k_clv_node_dna4): per batch, the groups of ops that share children; the batch's remaining ops stay in d_ops
@@ -150,6 +150,7 @@ struct nrx_engine {
   bool fuse_reduce = true;         // env NRX_FUSE_REDUCE=0: separate k_reduce_partials launch (A/B)
   bool defer_pmat = false;         // P-matrix updates are deferred until a launch needs them: the tile walk computes them itself (one launch per evaluation)
   uint32_t node_maxc = NODE_MAXC, node_blocks = 0;   // env NRX_NODE_MAXC (children per group, <= 16), NRX_NODE_BLOCKS (block target per launch; 0 = 24 x SMs)
+  bool score_only = false;         // nrx_set_score_only: replays of a fused-K3 plan do not store the root displayed trees' CLVs (scalers and per-site terms only)
   uint32_t quad_total = 0;         // env NRX_QUAD_BLOCKS: blocks per launch of the quad kernels (0: 2 per SM)
   bool quad = true;                // env NRX_QUAD=0: thread-per-pattern k_tree_lnl_dna4 / k_edge_lnl_dna4 / k_derivatives_dna4 instead of the coalesced quad kernels (A/B)
   int node_mode = 0;               // env NRX_NODE=1: ops of a node that share children run on k_clv_node_dna4 (A/B; measured 10 % slower than the per-op kernel, profiles/r3a_node_centric_ab.md)
@@ -978,7 +979,7 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
 #define NRX_K2_LAUNCH(NT_, CATS_)                                                                                                    \
   do {                                                                                                                               \
     cfg.dynamicSmemBytes = sizeof(PipeSmem<NT_, CATS_>);                                                                             \
-    CK(cudaLaunchKernelEx(&cfg, k_clv_dna4_pipe2<NT_, CATS_>, (const PartView *)c.d_views, d_ops, nops, groups, fused_ptr, stride, np, pdl)); \
+    CK(cudaLaunchKernelEx(&cfg, k_clv_dna4_pipe2<NT_, CATS_>, (const PartView *)c.d_views, d_ops, nops, groups, fused_ptr, stride, np, pdl | ((fused && e->score_only) ? 2 : 0))); \
   } while (0)
           if (c.cats == 4) { if (nt == 2) NRX_K2_LAUNCH(2, 4); else NRX_K2_LAUNCH(1, 4); }
           else if (c.cats == 1) NRX_K2_LAUNCH(2, 1);
@@ -1383,7 +1384,7 @@ int nrx_plan_run(nrx_engine *e, uint32_t plan_id) {
   prof_begin(e, &ev0, &ev1);
   unsigned long long per_run = 0;
   for (size_t b = 0; b < pl.sizes.size(); ++b) per_run += (pl.sizes[b] ? e->classes.size() : 0) + (pl.node_block_cnt[b] ? 1 : 0);
-  cudaGraphExec_t &gexec = pl.exec[e->throughput_mode ? 1 : 0];
+  cudaGraphExec_t &gexec = pl.exec[(e->throughput_mode ? 1 : 0) + (e->score_only ? 2 : 0)];
   if (e->use_graphs && !gexec) {  // capture the launches once per geometry; kernel arguments (views, resident ops) never change
     const unsigned long long l0 = e->launches;
     CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
@@ -1416,6 +1417,12 @@ int nrx_plan_run(nrx_engine *e, uint32_t plan_id) {
 int nrx_set_throughput_mode(nrx_engine *e, int on) {
   if (!e) { g_err = "null engine"; return 0; }
   e->throughput_mode = on != 0;
+  return 1;
+}
+
+int nrx_set_score_only(nrx_engine *e, int on) {
+  if (!e) { g_err = "null engine"; return 0; }
+  e->score_only = on != 0;
   return 1;
 }
 

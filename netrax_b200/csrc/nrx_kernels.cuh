@@ -411,6 +411,7 @@ struct PipeCtx {
   uint32_t *psc;
   double *ps_out;   // fused K3 output row of this op (or nullptr)
   uint32_t grp, groups, count, patterns;
+  bool skip_clv;    // score-only evaluation: the CLV of a root displayed tree (EMIT) is not stored, only its per-site term and scaler
 };
 
 /* NT = 64-pattern sub-tiles per ring stage (1: 6 stages x 64 patterns, the geometry of k_clv_dna4_pipe; 2: 3 stages x 128
@@ -516,7 +517,7 @@ __device__ __forceinline__ void pipe_loop(PipeSmem<NT, CATS> &sm, const PipeCtx 
         if (scale) { p.x = __dmul_rn(p.x, SCALE_FACTOR); p.y = __dmul_rn(p.y, SCALE_FACTOR); p.z = __dmul_rn(p.z, SCALE_FACTOR); p.w = __dmul_rn(p.w, SCALE_FACTOR); }
       }
       if (act) {
-        stg256(out, p);
+        if (!(EMIT && c.skip_clv)) stg256(out, p);
         if (cat == 0) c.psc[site] = s;
       }
       if (EMIT) {
@@ -543,7 +544,8 @@ __device__ __forceinline__ void pipe_loop(PipeSmem<NT, CATS> &sm, const PipeCtx 
 template <int NT, int CATS = 4>
 __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe2(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops,
                                                               uint32_t nops, uint32_t groups, double *__restrict__ persite,
-                                                              size_t persite_stride, uint32_t nparts_total, int pdl) {
+                                                              size_t persite_stride, uint32_t nparts_total, int flags /* bit 0: PDL launch, bit 1: score-only (root CLVs not stored) */) {
+  const int pdl = flags & 1;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PipeSmem<NT, CATS> &sm = *reinterpret_cast<PipeSmem<NT, CATS> *>(smem_raw);
   const PartView &pv = parts[blockIdx.z];
@@ -566,6 +568,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe2(const PartView *__r
   c.grp = grp; c.groups = groups; c.patterns = pv.patterns;
   c.count = (ntiles - grp + groups - 1) / groups;
   c.ps_out = nullptr;
+  c.skip_clv = false;
 #define NRX_PIPE_PRE(L, R) case (L) * 3 + (R): pipe_prefetch<L, R, NT, CATS>(sm, c); break;
 #define NRX_PIPE_PREFETCH()                                                                                     \
   switch (lk * 3 + rk) {                                                                                        \
@@ -606,6 +609,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_clv_dna4_pipe2(const PartView *__r
   if (emit) {
     f0 = pv.freqs[0]; f1 = pv.freqs[1]; f2 = pv.freqs[2]; f3 = pv.freqs[3]; wcat = pv.rate_weights[cat];
     c.ps_out = persite + ((size_t)(op.lnl_item - 1) * nparts_total + pv.part_index) * persite_stride;
+    c.skip_clv = (flags & 2) != 0;
   }
 #define NRX_PIPE_CASE(L, R)                                                                  \
   case (L) * 3 + (R):                                                                        \

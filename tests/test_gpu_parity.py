@@ -1390,3 +1390,44 @@ def test_shadow_rerooting_memo_other_shapes(kind):
     assert g.reroot_stats()["hits"] > 0
     assert g.computeLoglikelihood(0, 1) == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL)
     g.close(); g0.close()
+
+
+def test_score_only_evaluation_skips_root_clv_stores_and_heals():
+    """VERDICT r1 item 7 (second part): with score_only on, a full evaluation that replays the fused-K3 plan does not store the CLVs of
+    the root displayed trees — the lnL is the same to the last bit (same kernels, same per-site terms), the root slots are stale, and
+    the next incremental evaluation / CLV read-back re-evaluates with the stores on before anything reads them."""
+    net = random_network(40, 4, seed=9)
+    m, w = simulate_alignment(net, 6000, seed=9)     # large enough that the level-by-level plan (not the tile walk) runs
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    g, o = _gpu(net, [part]), _oracle(net, [part])
+    _inject_eigen(g, o)
+    lo = o.computeLoglikelihood(0, 1)
+    g.computeLoglikelihood(0, 1)
+    l_full = g.computeLoglikelihood(0, 1)            # replayed plan, stores on
+    root = net.root
+    before = [g.read_clv(root, t).copy() for t in range(g.num_trees(root))]
+    # poison one branch so that stale root CLVs would be visible, then score-only
+    e = 0
+    t0 = float(net.edge_length[e])
+    g.set_branch_length(e, 3.0 * t0)
+    o.set_branch_length(e, 3.0 * t0)
+    g.set_score_only(True)
+    l_so = g.computeLoglikelihood(0, 1)
+    assert l_so == pytest.approx(o.computeLoglikelihood(0, 1), rel=LNL_RTOL) and l_so != l_full
+    g.set_score_only(False)
+    l_ref = g.computeLoglikelihood(0, 1)
+    assert l_so == l_ref                             # bit-identical lnL with and without the stores
+    g.set_score_only(True)
+    assert g.computeLoglikelihood(0, 1) == l_ref
+    # read-back heals: the CLVs handed out are the ones of the current branch lengths, equal to the checker's
+    _compare_all_clvs(g, o, exact=False)
+    after = [g.read_clv(root, t) for t in range(g.num_trees(root))]
+    assert any(not np.array_equal(a, b) for a, b in zip(before, after))
+    # incremental evaluation after a score-only one
+    assert g.computeLoglikelihood(0, 1) == l_ref     # score-only again (stale)
+    assert g.computeLoglikelihood(1, 1) == pytest.approx(l_ref, rel=REPLAY_RTOL)
+    for eng in (g, o):
+        eng.brlen_prepare(e)
+    assert g.computeLoglikelihoodBrlenOpt(e) == pytest.approx(o.computeLoglikelihoodBrlenOpt(e), rel=LNL_RTOL)
+    assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL)
+    g.close()

@@ -266,7 +266,8 @@ def measure_config(c, device, peak, reps, with_cpu, cores):
          "lnl": lnl, "ms_per_eval": ms, "wall_ms_per_eval": wall, "lnl_evals_per_sec": 1e3 / ms, "site_updates_per_sec": updates / (ms / 1e3),
          "launches_per_eval": launches, "kernel_families": fam}
     if c == 2:
-        for key, accept in (("derivative_sweep", False), ("derivative_sweep_accept", True)):
+        for key, accept, lazy in (("derivative_sweep", False, False), ("derivative_sweep_accept", True, False), ("derivative_sweep_accept_lazy", True, True)):
+            eng.set_lazy_rerooting(lazy)
             derivative_sweep(eng, net, accept=accept)  # warm-up (allocates re-rooting slots and sumtables)
             eng.computeLoglikelihood(1, 1)
             st0 = eng.reroot_stats()
@@ -279,12 +280,14 @@ def measure_config(c, device, peak, reps, with_cpu, cores):
             wall_s = 1e3 * (time.perf_counter() - t)
             st1 = eng.reroot_stats()
             r[key] = {"what": "every edge in pre-order: re-rooting + edge lnL + sumtables + 3 Newton-iterate derivative evaluations + "
-                              + ("last proposal kept (nodes above the edge recomputed)" if accept else "old length restored"),
+                              + ("last proposal kept (nodes above the edge recomputed)" if accept else "old length restored")
+                              + (" — lazy re-rooting: no evaluation from the root around each branch, stale root-directed CLVs recomputed when a later re-rooting reads them" if lazy else ""),
                       "edges": int(net.num_edges), "ms": ms_s, "wall_ms": wall_s, "launches": eng.launch_count() - l0,
                       "edges_per_sec": net.num_edges / (wall_s / 1e3),
                       "reroot_memo": {"hits": st1["hits"] - st0["hits"], "misses": st1["misses"] - st0["misses"], "cached_slots": st1["cached_slots"]},
                       "kernel_families": family_table(eng.profile_read_all(), 1, ms_s, peak)}
             eng.profile_enable(False)
+        eng.set_lazy_rerooting(False)
     eng.close()
     r["parity"] = parity_check(cfg, 500, device)
     if with_cpu:

@@ -114,6 +114,13 @@ int nrxh_brlen_finish(void *h, unsigned edge, double *final_logl);
  * — candidate scoring (src/search/Filtering.cpp:210-260: performMove, score, undoMove) reads nothing but the lnL.  The next incremental
  * evaluation, re-rooting or CLV read-back first re-evaluates with the stores on. */
 int nrxh_set_score_only(void *h, int on);
+/* nrxh_set_lazy_rerooting: optimize_branch / nrxh_brlen_prepare + _finish skip the evaluation from the network root before a re-rooting
+ * and after the branch is done (src/optimization/BranchLengthOptimization.cpp:352,420) when the branch is active and alive in every
+ * displayed tree and its re-rooting plan is known: only the root-directed CLVs the re-rooting reads are brought up to date, the lnL
+ * returned is the edge-rooted one (computeLoglikelihoodBrlenOpt; equal to the root's to rounding), nrxh_brlen_prepare hands out the
+ * lnL of the previous step.  Stale CLVs are recomputed when read, at the latest by the next nrxh_compute_loglikelihood. */
+int nrxh_set_lazy_rerooting(void *h, int on);
+int nrxh_lazy_reroot_stats(void *h, unsigned long long *sessions, unsigned long long *fallbacks);   /* lazily prepared re-rootings / of those, redone from an evaluated root */
 int nrxh_brlen_sweep_order(void *h, unsigned *edges_out);
 int nrxh_reroot_stats(void *h, unsigned long long *hits, unsigned long long *misses, unsigned *entries, unsigned *cached_slots);
 int nrxh_set_reroot_cache_slots(void *h, long long max_slots);

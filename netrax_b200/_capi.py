@@ -73,6 +73,8 @@ class FlatAPI:
             g("reroot_stats", C.c_int, C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint), C.POINTER(C.c_uint))
             g("set_reroot_cache_slots", C.c_int, C.c_void_p, C.c_longlong)
             g("set_score_only", C.c_int, C.c_void_p, C.c_int)
+            g("set_lazy_rerooting", C.c_int, C.c_void_p, C.c_int)
+            g("lazy_reroot_stats", C.c_int, C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong))
         g("optimize_branch", C.c_int, C.c_void_p, C.c_uint, C.c_int, C.c_uint, C.POINTER(C.c_double))
         g("optimize_branches", C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double))
         g("optimize_reticulation", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double))
@@ -305,6 +307,15 @@ class LikelihoodEngine:
     def set_score_only(self, on: bool = True):
         """Full evaluations replaying the cached plan skip the CLV stores of the root displayed trees (candidate scoring)."""
         self.api.check(self.api._set_score_only(self.h, 1 if on else 0))
+
+    def set_lazy_rerooting(self, on: bool = True):
+        """brlen_prepare / brlen_finish / optimize_branch without the evaluations from the network root around every branch."""
+        self.api.check(self.api._set_lazy_rerooting(self.h, 1 if on else 0))
+
+    def lazy_reroot_stats(self) -> dict:
+        a, b = C.c_ulonglong(), C.c_ulonglong()
+        self.api.check(self.api._lazy_reroot_stats(self.h, C.byref(a), C.byref(b)))
+        return {"sessions": a.value, "fallbacks": b.value}
 
     def set_reroot_cache_slots(self, max_slots: int = -1):
         self.api.check(self.api._set_reroot_cache_slots(self.h, max_slots))

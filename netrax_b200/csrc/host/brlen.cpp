@@ -31,12 +31,13 @@ std::vector<DisplayedTreeData> extractOldTrees(AnnotatedNetwork &ann, Node *virt
   return old;
 }
 
-static ReticulationConfigSet computeRestrictionsActiveAliveBranch(AnnotatedNetwork &ann, size_t pmatrix_index) {  // ReticulationConfigHelper.cpp:319-331
+static ReticulationConfigSet computeRestrictionsActiveAliveBranch(AnnotatedNetwork &ann, size_t pmatrix_index, bool *all_trees = nullptr) {  // ReticulationConfigHelper.cpp:319-331
   ReticulationConfigSet res;  // max_reticulations stays 0 as in the reference: simplify only removes duplicates
   for (size_t t = 0; t < ((size_t)1 << ann.network.num_reticulations()); ++t) {
     const ReticulationConfigSet tc = getTreeConfig(ann, t);
     if (isActiveAliveBranch(ann, tc, pmatrix_index)) res.configs.push_back(tc.configs[0]);
   }
+  if (all_trees) *all_trees = res.configs.size() == ((size_t)1 << ann.network.num_reticulations());
   simplifyReticulationChoices(res);
   return res;
 }
@@ -162,6 +163,8 @@ struct RerootCache {
   struct Plan { size_t old_vr, new_vr, back; std::vector<PathToVirtualRoot> paths; NodeSaveInformation info; };
   std::vector<Plan> plans;
   std::vector<std::pair<size_t, ReticulationConfigSet>> edge_restrictions;   // getRestrictionsActiveAliveBranch per branch
+  std::vector<std::pair<size_t, bool>> edge_all_trees;                        // ... and whether the branch is active and alive in ALL displayed trees
+  bool lazy_session = false;                         // the open session was prepared without evaluating the network from its root first
   uint64_t topology_epoch = 0;
   uint64_t next_id = 1, tick = 0, session = 0, epoch = 0;
   size_t cached_slots = 0;
@@ -323,11 +326,68 @@ void evictRerootEntries(AnnotatedNetwork &ann, RerootCache &rc, size_t budget) {
 
 ReticulationConfigSet getRestrictionsActiveAliveBranch(AnnotatedNetwork &ann, size_t pmatrix_index) {  // ReticulationConfigHelper.cpp:319-331, per topology
   RerootCache &rc = rerootState(ann);
-  if (rc.topology_epoch != ann.topology_epoch) { rc.plans.clear(); rc.edge_restrictions.clear(); rc.topology_epoch = ann.topology_epoch; }
+  if (rc.topology_epoch != ann.topology_epoch) { rc.plans.clear(); rc.edge_restrictions.clear(); rc.edge_all_trees.clear(); rc.topology_epoch = ann.topology_epoch; }
   for (const auto &kv : rc.edge_restrictions) if (kv.first == pmatrix_index) return kv.second;
-  rc.edge_restrictions.emplace_back(pmatrix_index, computeRestrictionsActiveAliveBranch(ann, pmatrix_index));
+  bool all = false;
+  rc.edge_restrictions.emplace_back(pmatrix_index, computeRestrictionsActiveAliveBranch(ann, pmatrix_index, &all));
+  rc.edge_all_trees.emplace_back(pmatrix_index, all);
   return rc.edge_restrictions.back().second;
 }
+
+/* ---- lazy re-rooting (AnnotatedNetwork::lazy_reroot) --------------------------------------------------------------------------------
+ * optimize_branch evaluates the network from its root before it re-roots and again after the branch is done
+ * (src/optimization/BranchLengthOptimization.cpp:352,420): once a length has changed, that is the whole path from the branch up to
+ * the root, per branch.  None of it is needed to optimise the NEXT branch when (a) the branch is active and alive in every displayed
+ * tree — then computeLoglikelihoodBrlenOpt never falls back on the per-tree lnLs of the old root (VirtualRerooting.cpp:455-544 only
+ * does for trees in which the branch is inactive or dead) — and (b) the re-rooting plan of the branch is known (it depends on the
+ * topology only).  What a re-rooting does read are the root-directed trees of the nodes hanging off its paths; only those (and
+ * whatever is invalid below them) are brought up to date here.  A pre-order sweep therefore recomputes a node's root-directed CLV
+ * once, when the sweep leaves its subtree, instead of after every branch below it. */
+namespace detail {
+bool lazyRerootPossible(AnnotatedNetwork &ann, size_t pmatrix_index) {
+  if (!ann.lazy_reroot || !ann.reroot) return false;
+  RerootCache &rc = rerootState(ann);
+  if (rc.topology_epoch != ann.topology_epoch) return false;
+  bool all = false, known = false;
+  for (const auto &kv : rc.edge_all_trees) if (kv.first == pmatrix_index) { all = kv.second; known = true; }
+  if (!known || !all) return false;
+  const size_t old_vr = ann.network.root->clv_index, new_vr = ann.network.edges[pmatrix_index].source, back = ann.network.edges[pmatrix_index].target;
+  for (const RerootCache::Plan &pl : rc.plans) if (pl.old_vr == old_vr && pl.new_vr == new_vr && pl.back == back) return true;
+  return false;
+}
+
+/* the root-directed displayed trees a re-rooting towards `pmatrix_index` reads — the children of its path nodes that are not on
+ * the path themselves — and everything invalid below them, in post-order (incremental processNodeImproved: valid nodes return) */
+void validateRerootInputs(AnnotatedNetwork &ann, size_t pmatrix_index) {
+  RerootCache &rc = rerootState(ann);
+  const size_t old_vr = ann.network.root->clv_index, new_vr = ann.network.edges[pmatrix_index].source, back = ann.network.edges[pmatrix_index].target;
+  const RerootCache::Plan *plan = nullptr;
+  for (const RerootCache::Plan &pl : rc.plans) if (pl.old_vr == old_vr && pl.new_vr == new_vr && pl.back == back) { plan = &pl; break; }
+  if (!plan) throw std::runtime_error("validateRerootInputs: no re-rooting plan for this branch");
+  finishVirtualReroot(ann);
+  std::vector<char> need(ann.network.num_nodes(), 0);
+  std::vector<size_t> stack;
+  for (const PathToVirtualRoot &p : plan->paths)
+    for (size_t i = 0; i < p.path.size(); ++i)
+      for (size_t c : p.children[i])
+        if (std::find(p.path.begin(), p.path.end(), c) == p.path.end() && !need[c]) { need[c] = 1; stack.push_back(c); }
+  while (!stack.empty()) {
+    const size_t v = stack.back(); stack.pop_back();
+    for (size_t c : ann.network.nodes[v].children) if (!need[c]) { need[c] = 1; stack.push_back(c); }
+  }
+  pllmod_treeinfo_update_prob_matrices(ann, 0);
+  for (Node *n : ann.travbuffer) {
+    if (!need[n->clv_index]) continue;
+    std::vector<Node *> children;
+    for (size_t c : n->children) children.push_back(&ann.network.nodes[c]);
+    processNodeImproved(ann, 1, n, children, ReticulationConfigSet());
+  }
+  flushPendingOps(ann);
+  rc.lazy_session = true;   // picked up (and reset) by the updateCLVsVirtualRerootTrees call that follows
+  ann.lazy_sessions++;
+}
+bool rerootSessionIsLazy(const AnnotatedNetwork &ann) { return ann.reroot && ann.reroot->active && ann.reroot->lazy_session; }
+}  // namespace detail
 
 void dropRerootCache(AnnotatedNetwork &ann) {
   if (!ann.reroot) return;
@@ -372,7 +432,8 @@ std::vector<size_t> branchesInPreorder(const AnnotatedNetwork &ann) {
 }  // namespace detail
 
 void finishVirtualReroot(AnnotatedNetwork &ann) {
-  if (!ann.reroot || !ann.reroot->active) return;
+  if (!ann.reroot) return;
+  if (!ann.reroot->active) { ann.reroot->lazy_session = false; return; }
   RerootCache &rc = *ann.reroot;
   flushPendingOps(ann);
   for (size_t v : rc.touched) {
@@ -385,6 +446,7 @@ void finishVirtualReroot(AnnotatedNetwork &ann) {
   }
   rc.touched.clear();
   rc.active = false;
+  rc.lazy_session = false;
   const size_t budget = rerootBudget(ann);
   if (budget == 0 || rc.epoch != ann.clv_epoch) dropRerootCache(ann);
   else evictRerootEntries(ann, rc, budget);
@@ -401,15 +463,18 @@ void finishVirtualReroot(AnnotatedNetwork &ann) {
 void updateCLVsVirtualRerootTrees(AnnotatedNetwork &ann, Node *old_virtual_root, Node *new_virtual_root,
                                   Node *new_virtual_root_back, ReticulationConfigSet &restrictions) {  // :192-252
   const size_t old_vr = old_virtual_root->clv_index, new_vr = new_virtual_root->clv_index, back = new_virtual_root_back->clv_index;
-  if (ann.pernode_displayed_tree_data[old_vr].num_active_displayed_trees == 0) throw std::runtime_error("no displayed trees at the old virtual root");
+  const bool lazy = ann.reroot && !ann.reroot->active && ann.reroot->lazy_session;   // validateRerootInputs ran for this branch: the root itself may be stale
+  if (!lazy && ann.pernode_displayed_tree_data[old_vr].num_active_displayed_trees == 0) throw std::runtime_error("no displayed trees at the old virtual root");
   flushPendingOps(ann);
   finishVirtualReroot(ann);   // a session left open by the caller
   RerootCache &rc = rerootState(ann);
+  rc.lazy_session = lazy;
   if (rc.epoch != ann.clv_epoch) { dropRerootCache(ann); rc.epoch = ann.clv_epoch; }
-  if (rc.topology_epoch != ann.topology_epoch) { rc.plans.clear(); rc.edge_restrictions.clear(); rc.topology_epoch = ann.topology_epoch; }
+  if (rc.topology_epoch != ann.topology_epoch) { rc.plans.clear(); rc.edge_restrictions.clear(); rc.edge_all_trees.clear(); rc.topology_epoch = ann.topology_epoch; }
   const RerootCache::Plan *plan = nullptr;
   for (const RerootCache::Plan &pl : rc.plans) if (pl.old_vr == old_vr && pl.new_vr == new_vr && pl.back == back) { plan = &pl; break; }
   if (!plan) {
+    if (lazy) throw std::runtime_error("lazy re-rooting without a plan");
     RerootCache::Plan pl{old_vr, new_vr, back, getPathsToVirtualRoot(ann, old_vr, new_vr, back), {}};
     pl.info = computeNodeSaveInformation(pl.paths);
     rc.plans.push_back(std::move(pl));
@@ -452,15 +517,29 @@ void updateCLVsVirtualRerootTrees(AnnotatedNetwork &ann, Node *old_virtual_root,
   if (ann.pernode_displayed_tree_data[new_vr].num_active_displayed_trees == 0) throw std::runtime_error("no displayed trees at the new virtual root");
 }
 
+void redoRerootFromRoot(AnnotatedNetwork &ann, unsigned int pmatrix_index, std::vector<DisplayedTreeData> &oldTrees) {
+  RerootCache &rc = rerootState(ann);
+  finishVirtualReroot(ann);
+  for (auto &kv : rc.edge_all_trees) if (kv.first == pmatrix_index) kv.second = false;   // this branch is not a lazy one after all
+  ann.lazy_fallbacks++;
+  ann.lazy_last_logl = computeLoglikelihood(ann, 1, 1);
+  oldTrees = extractOldTrees(ann, ann.network.root);
+  ReticulationConfigSet restrictions = getRestrictionsActiveAliveBranch(ann, pmatrix_index);
+  updateCLVsVirtualRerootTrees(ann, ann.network.root, &ann.network.nodes[ann.network.edges[pmatrix_index].source],
+                               &ann.network.nodes[ann.network.edges[pmatrix_index].target], restrictions);
+  ann.cached_logl_valid = false;
+}
+
 namespace {
-const TreeLoglData &getMatchingTreeData(const std::vector<DisplayedTreeData> &trees, const ReticulationConfigSet &query) {  // ReticulationConfigHelper.cpp:290-302
+const TreeLoglData &getMatchingTreeData(const std::vector<DisplayedTreeData> &trees, const ReticulationConfigSet &query, bool lazy = false) {  // ReticulationConfigHelper.cpp:290-302
+  if (lazy && trees.empty()) throw LazyRerootNeedsRoot();
   for (const DisplayedTreeData &t : trees)
     if (reticulationConfigsCompatible(query, t.treeLoglData.reticulationChoices)) return t.treeLoglData;
   throw std::runtime_error("No compatible old tree data found");
 }
 
 void updateTreeData(AnnotatedNetwork &ann, const std::vector<DisplayedTreeData> &oldTrees, TreeLoglData &td) {  // VirtualRerooting.cpp:254-277
-  const TreeLoglData &old = getMatchingTreeData(oldTrees, td.reticulationChoices);
+  const TreeLoglData &old = getMatchingTreeData(oldTrees, td.reticulationChoices, rerootSessionIsLazy(ann));
   td.tree_partition_logl = old.tree_partition_logl;
   td.tree_logprob = computeReticulationConfigLogProb(td.reticulationChoices, ann.first_parent_logprobs, ann.second_parent_logprobs);
   td.tree_logprob_valid = true;
@@ -476,7 +555,7 @@ double computeLoglikelihoodBrlenOpt(AnnotatedNetwork &ann, const std::vector<Dis
   NodeDisplayedTreeData &td = ann.pernode_displayed_tree_data[target];
   const size_t ns = sd.num_active_displayed_trees, nt = td.num_active_displayed_trees;
   const unsigned P = ann.fake_treeinfo->partition_count;
-  if (!clvValidCheck(ann, ann.network.root->clv_index, false))
+  if (!rerootSessionIsLazy(ann) && !clvValidCheck(ann, ann.network.root->clv_index, false))
     throw std::runtime_error("Cannot reuse old displayed trees. For some reason, they are invalidated at the root node " + std::to_string(ann.network.root->clv_index));
   if (update_pmatrices) pllmod_treeinfo_update_prob_matrices(ann, 0);
   std::vector<TreeLoglData> combined;

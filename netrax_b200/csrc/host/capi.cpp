@@ -189,6 +189,10 @@ int nrxh_tree_info(void *hv, unsigned node, unsigned tree, double *logprob, doub
   });
 }
 
+int nrxh_set_lazy_rerooting(void *hv, int on) {
+  return guarded([&] { H(hv)->ann.lazy_reroot = on != 0; });
+}
+
 int nrxh_set_score_only(void *hv, int on) {
   return guarded([&] { H(hv)->ann.score_only = on != 0; });
 }
@@ -321,7 +325,21 @@ int nrxh_brlen_prepare(void *hv, unsigned edge, double *old_logl) {
   return guarded([&] {
     Handle *h = H(hv);
     AnnotatedNetwork &ann = h->ann;
+    if (edge >= ann.network.num_branches()) throw std::runtime_error("nrxh_brlen_prepare: edge out of range");
+    if (detail::lazyRerootPossible(ann, edge) && !ann.root_clvs_stale) {
+      // lazy re-rooting: no evaluation from the root, only the root-directed trees this re-rooting reads are brought up to date;
+      // the old lnL handed out is the one the previous step returned
+      if (old_logl) *old_logl = ann.lazy_last_logl;
+      h->oldTrees.clear();
+      ReticulationConfigSet restrictions = getRestrictionsActiveAliveBranch(ann, edge);
+      detail::validateRerootInputs(ann, edge);
+      updateCLVsVirtualRerootTrees(ann, ann.network.root, &ann.network.nodes[ann.network.edges[edge].source],
+                                   &ann.network.nodes[ann.network.edges[edge].target], restrictions);
+      ann.cached_logl_valid = false;
+      return;
+    }
     const double l = computeLoglikelihood(ann, 1, 1);
+    ann.lazy_last_logl = l;
     if (old_logl) *old_logl = l;
     h->oldTrees = extractOldTrees(ann, ann.network.root);
     ReticulationConfigSet restrictions = getRestrictionsActiveAliveBranch(ann, edge);
@@ -334,7 +352,11 @@ int nrxh_brlen_prepare(void *hv, unsigned edge, double *old_logl) {
 int nrxh_brlen_logl(void *hv, unsigned edge, double *out) {
   return guarded([&] {
     H(hv)->ann.cached_logl_valid = false;
-    *out = computeLoglikelihoodBrlenOpt(H(hv)->ann, H(hv)->oldTrees, edge, 1);
+    try { *out = computeLoglikelihoodBrlenOpt(H(hv)->ann, H(hv)->oldTrees, edge, 1); }
+    catch (const LazyRerootNeedsRoot &) {
+      redoRerootFromRoot(H(hv)->ann, edge, H(hv)->oldTrees);
+      *out = computeLoglikelihoodBrlenOpt(H(hv)->ann, H(hv)->oldTrees, edge, 1);
+    }
   });
 }
 
@@ -384,10 +406,21 @@ int nrxh_brlen_finish(void *hv, unsigned edge, double *final_logl) {
   return guarded([&] {
     Handle *h = H(hv);
     h->sumtables.clear();
+    if (detail::rerootSessionIsLazy(h->ann)) {   // the edge-rooted lnL at the final length; whatever became invalid stays so until it is read
+      h->ann.cached_logl_valid = false;
+      double l;
+      try { l = computeLoglikelihoodBrlenOpt(h->ann, h->oldTrees, edge, 1); }
+      catch (const LazyRerootNeedsRoot &) { redoRerootFromRoot(h->ann, edge, h->oldTrees); l = computeLoglikelihoodBrlenOpt(h->ann, h->oldTrees, edge, 1); }
+      h->sumtables.clear();
+      finishVirtualReroot(h->ann);
+      h->ann.lazy_last_logl = l;
+      if (final_logl) *final_logl = l;
+      return;
+    }
     h->oldTrees.clear();
-    (void)edge;
     finishVirtualReroot(h->ann);   // restores the root-directed trees; invalidates above the edge only if its length changed
     const double l = computeLoglikelihood(h->ann, 1, 1);
+    h->ann.lazy_last_logl = l;
     if (final_logl) *final_logl = l;
   });
 }
@@ -408,6 +441,13 @@ int nrxh_reroot_stats(void *hv, unsigned long long *hits, unsigned long long *mi
     if (misses) *misses = ann.reroot_misses;
     if (entries) *entries = (unsigned)n;
     if (cached_slots) *cached_slots = (unsigned)s;
+  });
+}
+
+int nrxh_lazy_reroot_stats(void *hv, unsigned long long *sessions, unsigned long long *fallbacks) {
+  return guarded([&] {
+    if (sessions) *sessions = H(hv)->ann.lazy_sessions;
+    if (fallbacks) *fallbacks = H(hv)->ann.lazy_fallbacks;
   });
 }
 

@@ -32,6 +32,9 @@ double logSumExp(const std::vector<double> &a);
 void destroyRerootCache(AnnotatedNetwork &ann);          // host/brlen.cpp
 void rerootCacheSize(const AnnotatedNetwork &ann, size_t *entries, size_t *slots);
 std::vector<size_t> branchesInPreorder(const AnnotatedNetwork &ann);
-bool rerootSessionOpen(const AnnotatedNetwork &ann);    // between updateCLVsVirtualRerootTrees and finishVirtualReroot
+bool rerootSessionOpen(const AnnotatedNetwork &ann);
+bool rerootSessionIsLazy(const AnnotatedNetwork &ann);
+bool lazyRerootPossible(AnnotatedNetwork &ann, size_t pmatrix_index);   // lazy_reroot on, branch active + alive in all trees, plan known
+void validateRerootInputs(AnnotatedNetwork &ann, size_t pmatrix_index);  // brings the side children of the branch's re-rooting paths up to date    // between updateCLVsVirtualRerootTrees and finishVirtualReroot
 }  // namespace detail
 }  // namespace netrax

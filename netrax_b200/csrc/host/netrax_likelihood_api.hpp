@@ -254,6 +254,13 @@ struct AnnotatedNetwork {  // src/graph/AnnotatedNetwork.hpp:42-89
   uint64_t clv_epoch = 0;                     // bumped by invalidateAllCLVs / setReticulationProb / topology_changed: drops the memoised data
   size_t reroot_cache_max_slots = SIZE_MAX;   // SIZE_MAX: default budget (env NRX_REROOT_CACHE_SLOTS); 0: nothing survives a re-rooting session
   uint64_t reroot_hits = 0, reroot_misses = 0;
+  /* lazy re-rooting (opt-in): optimize_branch / the brlen_* flow neither evaluate the network from its root before a re-rooting nor
+   * after the branch is done, when the branch is active and alive in every displayed tree; the lnL they return is then the edge-rooted
+   * one (equal to the root's to rounding), and stale root-directed CLVs are recomputed when a later re-rooting reads them or by the
+   * next computeLoglikelihood (host/brlen.cpp: lazyRerootPossible) */
+  bool lazy_reroot = false;
+  uint64_t lazy_sessions = 0, lazy_fallbacks = 0;   // re-rootings prepared lazily / of those, redone from the root because old per-tree lnLs were needed after all
+  double lazy_last_logl = -std::numeric_limits<double>::infinity();
   uint64_t clv_site_updates = 0;              // Σ trees × local patterns actually launched
   std::vector<char> pseudo_clv_valid;         // [node]  (src/graph/AnnotatedNetwork.hpp:64; tips: valid)
   std::vector<uint32_t> pseudo_slot;          // [node]  device slot of the node's pseudo-likelihood CLV (UINT32_MAX: none yet)
@@ -297,6 +304,10 @@ void updateCLVsVirtualRerootTrees(AnnotatedNetwork &ann_network, Node *old_virtu
  * and the CLVs above it are invalidated (the reference's unconditional `invalidatePmatrixIndex` "restore the network root",
  * src/optimization/BranchLengthOptimization.cpp:417-419, recomputes what it had overwritten).  No-op without an open session. */
 void finishVirtualReroot(AnnotatedNetwork &ann_network);
+/* thrown by computeLoglikelihoodBrlenOpt inside a LAZY re-rooting session when a displayed tree turns out to need the per-tree lnL of
+ * the old root (a source / target tree without a compatible partner): the caller redoes the re-rooting from an evaluated root */
+struct LazyRerootNeedsRoot : std::runtime_error { LazyRerootNeedsRoot() : std::runtime_error("lazy re-rooting: the old root's per-tree lnLs are needed") {} };
+void redoRerootFromRoot(AnnotatedNetwork &ann_network, unsigned int pmatrix_index, std::vector<DisplayedTreeData> &oldTrees);
 void dropRerootCache(AnnotatedNetwork &ann_network);   // releases every memoised slot (keeps an open session's own data)
 double computeLoglikelihoodBrlenOpt(AnnotatedNetwork &ann_network, const std::vector<DisplayedTreeData> &oldTrees,
                                     unsigned int pmatrix_index, int update_pmatrices = 1, bool print_extra_debug_info = false);

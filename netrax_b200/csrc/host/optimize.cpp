@@ -297,17 +297,27 @@ void minimizeBrentMulti(unsigned n, double xmin, double *x, double xmax, double 
 /* optimize_branch (BranchLengthOptimization.cpp:345-421) */
 double optimize_branch(AnnotatedNetwork &ann, size_t pmatrix_index, BrlenOptMethod method, unsigned int max_iters) {
   if (pmatrix_index >= ann.network.num_branches()) throw std::runtime_error("optimize_branch: pmatrix index out of range");
-  const double old_logl = computeLoglikelihood(ann);
+  // lazy re-rooting (opt-in, host/brlen.cpp): no evaluation from the root before and after a branch that is active and alive in every tree
+  bool lazy = method != BrlenOptMethod::BRENT_NORMAL && !ann.root_clvs_stale && detail::lazyRerootPossible(ann, pmatrix_index);
+  // (lazy: the reference's re-rooting sanity check below compares against the lnL from the root, which is not evaluated — skipped)
+  const double old_logl = lazy ? -std::numeric_limits<double>::infinity() : computeLoglikelihood(ann);
   std::vector<DisplayedTreeData> oldTrees;
   std::vector<std::vector<SumtableInfo>> sumtables;
   if (method != BrlenOptMethod::BRENT_NORMAL) {  // step 1: the virtual re-rooting
-    oldTrees = extractOldTrees(ann, ann.network.root);
+    if (lazy) detail::validateRerootInputs(ann, pmatrix_index);
+    else oldTrees = extractOldTrees(ann, ann.network.root);
     Node *new_virtual_root = &ann.network.nodes[ann.network.edges[pmatrix_index].source];
     Node *new_virtual_root_back = &ann.network.nodes[ann.network.edges[pmatrix_index].target];
     ReticulationConfigSet restrictions = getRestrictionsActiveAliveBranch(ann, pmatrix_index);
     updateCLVsVirtualRerootTrees(ann, ann.network.root, new_virtual_root, new_virtual_root_back, restrictions);
     ann.cached_logl_valid = false;
-    const double brlenopt_logl = computeLoglikelihoodBrlenOpt(ann, oldTrees, (unsigned)pmatrix_index);
+    double brlenopt_logl;
+    try { brlenopt_logl = computeLoglikelihoodBrlenOpt(ann, oldTrees, (unsigned)pmatrix_index); }
+    catch (const LazyRerootNeedsRoot &) {   // a displayed tree needs the old root's per-tree lnL after all: redo this branch from an evaluated root
+      redoRerootFromRoot(ann, (unsigned)pmatrix_index, oldTrees);
+      lazy = false;
+      brlenopt_logl = computeLoglikelihoodBrlenOpt(ann, oldTrees, (unsigned)pmatrix_index);
+    }
     if (old_logl - brlenopt_logl >= 1E-3)  // the reference's `fabs(old_logl - brlenopt_logl >= 1E-3)` (:377): one-sided
       throw std::runtime_error("Something went wrong when rerooting CLVs during brlen optimization");
     if (method == BrlenOptMethod::NEWTON_RAPHSON) sumtables = computePartitionSumtables(ann, (unsigned)pmatrix_index);
@@ -318,8 +328,14 @@ double optimize_branch(AnnotatedNetwork &ann, size_t pmatrix_index, BrlenOptMeth
   } else {
     optimizeBranchPartition(ann, oldTrees, sumtables, pmatrix_index, 0, method, max_iters);
   }
+  if (lazy) {
+    ann.cached_logl_valid = false;
+    const double l = computeLoglikelihoodBrlenOpt(ann, oldTrees, (unsigned)pmatrix_index, 1);
+    finishVirtualReroot(ann);
+    return ann.lazy_last_logl = l;
+  }
   if (method != BrlenOptMethod::BRENT_NORMAL) finishVirtualReroot(ann);  // restore the network root: invalidatePmatrixIndex only if the length changed
-  return computeLoglikelihood(ann);
+  return ann.lazy_last_logl = computeLoglikelihood(ann);
 }
 
 /* optimize_branches_internal (:423-476); `radius` is unused there as well (the neighbour re-queueing is commented out).

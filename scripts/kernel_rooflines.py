@@ -67,6 +67,10 @@ def main():
             r["derivative_sweep"] = measure(eng, lambda: derivative_sweep(eng, net), 1)
             derivative_sweep(eng, net, accept=True)
             r["derivative_sweep_accept"] = measure(eng, lambda: derivative_sweep(eng, net, accept=True), 1)
+            eng.set_lazy_rerooting(True)
+            derivative_sweep(eng, net, accept=True)
+            r["derivative_sweep_accept_lazy"] = measure(eng, lambda: derivative_sweep(eng, net, accept=True), 1)
+            eng.set_lazy_rerooting(False)
             r["reroot_memo"] = eng.reroot_stats()
         eng.close()
         res[f"config{c}"] = r
@@ -80,7 +84,7 @@ def main():
             for c, r in res.items():
                 if not c.startswith("config"):
                     continue
-                for phase in ("full_evaluation", "derivative_sweep", "derivative_sweep_accept"):
+                for phase in ("full_evaluation", "derivative_sweep", "derivative_sweep_accept", "derivative_sweep_accept_lazy"):
                     if phase not in r:
                         continue
                     m = r[phase]

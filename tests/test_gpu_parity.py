@@ -1431,3 +1431,67 @@ def test_score_only_evaluation_skips_root_clv_stores_and_heals():
     assert g.computeLoglikelihoodBrlenOpt(e) == pytest.approx(o.computeLoglikelihoodBrlenOpt(e), rel=LNL_RTOL)
     assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL)
     g.close()
+
+
+@pytest.mark.parametrize("cfg", [(30, 3, 300, 5), (24, 5, 200, 6), (40, 0, 150, 7)])
+def test_lazy_rerooting_sweep_matches_reference_flow(cfg):
+    """Lazy re-rooting: a pre-order sweep that KEEPS every proposal, without the evaluations from the root around each branch.  Per
+    edge the edge-rooted lnL and every derivative equal the checker's (which evaluates from the root before and after every branch,
+    as the reference does); the lnL a lazy finish returns is the edge-rooted one = the checker's root lnL to rounding; after the
+    sweep a plain incremental evaluation settles everything and agrees with the checker, CLV for CLV."""
+    n, r, pat, seed = cfg
+    net = random_network(n, r, seed=seed)
+    m, w = simulate_alignment(net, pat, seed=seed)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    g, o = _gpu(net, [part]), _oracle(net, [part])
+    _inject_eigen(g, o)
+    for eng in (g, o):
+        eng.computeLoglikelihood(0, 1)
+    order = g.brlen_sweep_order()
+    _sweep_records(g, net, order, False)          # first pass: every branch's re-rooting plan becomes known (topology-only)
+    g.set_lazy_rerooting(True)
+    u0, l0 = g.clv_update_count(), g.launch_count()
+    rg = _sweep_records(g, net, order, True)
+    lazy_updates, lazy_launches = g.clv_update_count() - u0, g.launch_count() - l0
+    st = g.lazy_reroot_stats()
+    assert st["sessions"] > net.num_edges // 3 and st["fallbacks"] < st["sessions"], st
+    ro = _sweep_records(o, net, order, True)
+    for e, a, c in zip(order, rg, ro):
+        np.testing.assert_allclose(a[1], c[1], rtol=LNL_RTOL, err_msg=str(int(e)))           # edge-rooted lnL
+        np.testing.assert_allclose(a[-1], c[-1], rtol=LNL_RTOL, err_msg=str(int(e)))         # final lnL
+        np.testing.assert_allclose(a[2:-1], c[2:-1], rtol=DERIV_RTOL, atol=1e-7)
+    g.set_lazy_rerooting(False)
+    lg, lo = g.computeLoglikelihood(1, 1), o.computeLoglikelihood(1, 1)
+    assert lg == pytest.approx(lo, rel=LNL_RTOL)
+    _compare_all_clvs(g, o, exact=False)
+    # the same sweep without the lazy mode recomputes the path above every branch
+    g2 = _gpu(net, [part])
+    _inject_eigen(g2, o)
+    g2.computeLoglikelihood(0, 1)
+    _sweep_records(g2, net, order, False)
+    u0, l0 = g2.clv_update_count(), g2.launch_count()
+    _sweep_records(g2, net, order, True)
+    assert lazy_updates < g2.clv_update_count() - u0 and lazy_launches < g2.launch_count() - l0
+    g.close(); g2.close()
+
+
+def test_lazy_optimize_branch_matches_reference_flow():
+    """optimize_branch (Newton-Raphson) over all branches in pre-order with lazy re-rooting: same final lengths and lnL as the checker's
+    reference flow."""
+    net = random_network(25, 2, seed=13)
+    m, w = simulate_alignment(net, 400, seed=13)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    g, o = _gpu(net, [part]), _oracle(net, [part])
+    _inject_eigen(g, o)
+    for eng in (g, o):
+        eng.computeLoglikelihood(0, 1)
+    order = [int(e) for e in g.brlen_sweep_order()]
+    _sweep_records(g, net, order, False)
+    g.set_lazy_rerooting(True)
+    for e in order:
+        lg, lo = g.optimize_branch(e), o.optimize_branch(e)
+        assert lg == pytest.approx(lo, rel=1e-9), e
+    np.testing.assert_allclose(g.branch_lengths(), o.branch_lengths(), rtol=1e-6, atol=1e-9)
+    g.set_lazy_rerooting(False)
+    assert g.computeLoglikelihood(1, 1) == pytest.approx(o.computeLoglikelihood(1, 1), rel=1e-9)
+    g.close()

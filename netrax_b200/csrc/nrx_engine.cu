@@ -1567,7 +1567,13 @@ static int tree_lnl_fused_impl(nrx_engine *e, uint32_t plan_id, const uint32_t *
   if (n > e->plans[plan_id].lnl_items || !e->d_fused) { g_err = "nrx_tree_lnl_fused: the plan carries fewer lnl marks"; return 0; }
   CK(cudaSetDevice(e->device));
   const uint32_t P = (uint32_t)e->parts.size();
-  const uint32_t nblk = reduce_blocks(e, n * P, false);   // k_term_lnl_sum makes one pass per block: the one-pass geometry
+  uint32_t nblk;
+  {  // k_term_lnl_sum: a pass = 4 x BLOCK patterns, ~8 blocks per SM in total, every block the same number of passes
+    const uint64_t chunks = std::max<uint64_t>(1, ((uint64_t)e->max_patterns + 4ull * BLOCK - 1) / (4ull * BLOCK));
+    const uint64_t want = std::max<uint64_t>(1, (8ull * e->sm_count) / std::max<uint32_t>(1, n * P));
+    const uint64_t passes = (chunks + want - 1) / want;
+    nblk = (uint32_t)((chunks + passes - 1) / passes);
+  }
   if (!ensure_result(e, (size_t)n * P, (size_t)n * P * nblk) || !refresh_views(e)) return 0;
   for (uint32_t i = 0; i < n; ++i) if (slots[i] >= e->nslots) { g_err = "nrx_tree_lnl_fused: slot out of range"; return 0; }
   uint32_t *d_slots;
@@ -1621,7 +1627,7 @@ int nrx_plan_evaluate_async(nrx_engine *e, uint32_t plan_id, const uint32_t *slo
   }
   cudaEvent_t ev0, ev1;
   prof_begin(e, &ev0, &ev1);
-  k_walk_dna4<<<dim3(ntiles, 1, (uint32_t)c.parts.size()), WALK_THREADS, pl.walk_smem, e->stream>>>(
+  k_walk_dna4<<<dim3(ntiles, 1, (uint32_t)c.parts.size()), WALK_BLOCK, pl.walk_smem, e->stream>>>(
       c.d_views, pl.d_walk, pl.walk_nops, pl.walk_nbuf, n, std::log(SCALE_THRESHOLD), e->d_partial, P, e->d_result, e->d_tickets, compute_p, d_len);
   e->launches++;
   CK(cudaGetLastError());

@@ -780,6 +780,10 @@ __global__ void __launch_bounds__(NODE_THREADS, 4) k_clv_node_dna4(const PartVie
 constexpr int WALK_TP = 32;                 // patterns per tile
 constexpr int WALK_THREADS = WALK_TP * 4;   // thread = (pattern, rate category): 4 CLV entries per op.  (One entry per thread —
                                             // 512 threads — was measured: 2.7x the instructions, the op decode is paid per warp, 57 vs 40 us.)
+constexpr int WALK_HELPERS = 128;           // extra threads that share the prologue (P-matrices of all edges, tip codes, pointers) and then exit:
+                                            // a third of the kernel was that prologue at five expm1 per thread (ncu, gpurun_out/r3i_walk.ncu-rep)
+constexpr int WALK_BLOCK = WALK_THREADS + WALK_HELPERS;
+__device__ __forceinline__ void walk_bar() { asm volatile("bar.sync 1, %0;" ::"n"(WALK_THREADS) : "memory"); }   // the 128 walking threads only
 constexpr uint32_t WALK_NOBUF = 0xffffu;
 constexpr int WALK_PE = 4 * PCAT;           // doubles per edge in the shared-memory P table (4 categories x (16 + 2 padding))
 
@@ -834,7 +838,7 @@ __device__ __forceinline__ D4 walk_op(const WalkCtx &c, const nrx_walk_op &op, u
 /* compute_p != 0: the branch lengths changed since K1 last ran — the block computes ALL P-matrices itself from `brlen`
  * ([partition][edges], same arithmetic as k_pmatrix, so bit-identical) instead of copying K1's table, and the blocks of tile 0
  * write them back to the partition's pmat / pmat_pad arrays for the kernels that run later (K4, incremental K2). */
-__global__ void __launch_bounds__(WALK_THREADS) k_walk_dna4(const PartView *__restrict__ parts, const nrx_walk_op *__restrict__ prog,
+__global__ void __launch_bounds__(WALK_BLOCK) k_walk_dna4(const PartView *__restrict__ parts, const nrx_walk_op *__restrict__ prog,
                                                             uint32_t nops, uint32_t nbuf, uint32_t nitems, double log_thresh,
                                                             double *__restrict__ partial /* [item][part][tiles] */, uint32_t nparts_total,
                                                             double *__restrict__ out /* [item][part] */, uint32_t *__restrict__ counter,
@@ -871,31 +875,33 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk_dna4(const PartView *__re
       bulk_g2s(sProg, prog, gbytes, &bar);
     }
     // tip codes of this tile (rows are padded to whole 128-pattern tiles: always in bounds)
-    for (uint32_t i = tid; i < tips * (WALK_TP / 4); i += WALK_THREADS) {
+    if (compute_p) {   // model constants first: their latency hides under the other prologue loads
+      if (tid < 16) { sModel[tid] = pv.inv_eigenvecs[tid]; sModel[16 + tid] = pv.eigenvecs[tid]; }
+      if (tid < 4) { sModel[32 + tid] = pv.eigenvals[tid]; sModel[36 + tid] = pv.rates[tid]; }
+    }
+    for (uint32_t i = tid; i < tips * (WALK_TP / 4); i += WALK_BLOCK) {
       const uint32_t t = i / (WALK_TP / 4), w = i % (WALK_TP / 4);
       reinterpret_cast<uint32_t *>(sTip)[i] = *reinterpret_cast<const uint32_t *>(pv.tipchars + (size_t)t * pv.tip_pitch + site0 + 4 * w);
     }
-    for (uint32_t i = tid; i < nitems * (WALK_THREADS / 32); i += WALK_THREADS) sAcc[i] = 0.0;
+    for (uint32_t i = tid; i < nitems * (WALK_THREADS / 32); i += WALK_BLOCK) sAcc[i] = 0.0;
     {   // the output pointers of every op, fetched up front (two dependent global loads in front of every store otherwise)
       double *const *clv_tab = pv.clv;
       uint32_t *const *sc_tab = pv.scaler;
-      for (uint32_t i = tid; i < nops; i += WALK_THREADS) { const uint32_t slot = prog[i].parent_slot; sPar[i] = clv_tab[slot]; sPsc[i] = sc_tab[slot]; }
+      for (uint32_t i = tid; i < nops; i += WALK_BLOCK) { const uint32_t slot = prog[i].parent_slot; sPar[i] = clv_tab[slot]; sPsc[i] = sc_tab[slot]; }
     }
     if (compute_p) {
       /* K1 in the block (k_pmatrix's arithmetic, 4 states: (eval * rate) * t, expm1, pairwise sum of iev[j][m] ex[m] ev[m][k],
        * identity added last; t == 0 -> identity).  The expm1 values of an edge go through the padding doubles' neighbours:
        * stage 1 writes ex[c][m] into sP[edge][c][m] (entries 0..3), stage 2 reads them into registers before overwriting. */
-      if (tid < 16) { sModel[tid] = pv.inv_eigenvecs[tid]; sModel[16 + tid] = pv.eigenvecs[tid]; }
-      if (tid < 4) { sModel[32 + tid] = pv.eigenvals[tid]; sModel[36 + tid] = pv.rates[tid]; }
       __syncthreads();
       const double *bl = brlen + (size_t)pv.part_index * edges;
       double *sEx = sClv;   // scratch: [edges][16] expm1 values (the CLV buffers are not in use yet); nbuf * 512 >= edges * 16 is checked by the host
-      for (uint32_t i = tid; i < edges * 16u; i += WALK_THREADS) {
+      for (uint32_t i = tid; i < edges * 16u; i += WALK_BLOCK) {
         const uint32_t e = i >> 4, c = (i >> 2) & 3u, m = i & 3u;
         sEx[i] = expm1(__dmul_rn(__dmul_rn(sModel[32 + m], sModel[36 + c]), bl[e]));
       }
       __syncthreads();
-      for (uint32_t i = tid; i < edges * 64u; i += WALK_THREADS) {
+      for (uint32_t i = tid; i < edges * 64u; i += WALK_BLOCK) {
         const uint32_t e = i >> 6, c = (i >> 4) & 3u, j = (i >> 2) & 3u, k = i & 3u;
         const double *ex = sEx + e * 16 + c * 4, *iev = sModel, *ev = sModel + 16;
         double v;
@@ -913,6 +919,7 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk_dna4(const PartView *__re
       }
     }
     __syncthreads();
+    if (tid >= WALK_THREADS) return;   // the helpers are done; from here on only walk_bar() (128 threads) synchronises
     mbar_wait(&bar, 0);
 
     WalkCtx c;
@@ -962,7 +969,7 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk_dna4(const PartView *__re
       // the four warps of a tile wait for each other 32 times per evaluation (ncu: 15 % of the samples on the barrier)
       __syncwarp();
     }
-    __syncthreads();
+    walk_bar();
     // block sums of the marked trees, warps in order
     for (uint32_t it = tid; it < nitems; it += WALK_THREADS) {
       double sum = 0.0;
@@ -971,15 +978,16 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk_dna4(const PartView *__re
       partial[((size_t)it * nparts_total + pv.part_index) * ntiles + tile] = sum;
     }
   } else {
+    if (tid >= WALK_THREADS) return;
     for (uint32_t it = tid; it < nitems; it += WALK_THREADS) partial[((size_t)it * nparts_total + pv.part_index) * ntiles + tile] = 0.0;
   }
   // second stage, fused: the block that draws the last ticket of this partition adds the tiles' partial sums in a fixed order
-  __syncthreads();
+  walk_bar();
   if (tid == 0) {
     __threadfence();
     s_last = (atomicAdd(counter + pv.part_index, 1u) == ntiles - 1u) ? 1 : 0;
   }
-  __syncthreads();
+  walk_bar();
   if (!s_last) return;
   __threadfence();
   for (uint32_t it = warp; it < nitems; it += WALK_THREADS / 32) {
@@ -2587,6 +2595,18 @@ __global__ void __launch_bounds__(BLOCK) k_tree_lnl_dna4(const PartView *__restr
 
 /* second half of the fused K3: log, scaler term and pattern weight on the per-site terms K2 wrote — same traversal and
  * accumulation order as k_tree_lnl_dna4, hence bit-identical partial sums */
+constexpr int TU = 4;   // k_term_lnl_sum: patterns per thread and pass
+__device__ __forceinline__ void term_load(double (&t)[TU], uint32_t (&s)[TU], uint32_t (&w)[TU], const double *__restrict__ ps,
+                                          const uint32_t *__restrict__ sc, const uint32_t *__restrict__ wt, uint64_t base, uint64_t n_pat, int tid) {
+#pragma unroll
+  for (int u = 0; u < TU; ++u) {
+    const uint64_t n = base + (uint64_t)u * BLOCK + tid;
+    if (n < n_pat) { t[u] = ps[n]; s[u] = sc[n]; w[u] = wt[n]; }
+    else { t[u] = 1.0; s[u] = 0u; w[u] = 0u; }   // log(1) * 0: contributes nothing
+  }
+}
+/* four independent logs per thread and pass, the next pass's 16 bytes per pattern loaded before the current ones are consumed
+ * (the one-pattern-per-thread form ran at 0.16-0.25 of the HBM peak: a log is ~40 dependent FP64 instructions) */
 __global__ void __launch_bounds__(BLOCK) k_term_lnl_sum(const PartView *__restrict__ parts, const uint32_t *__restrict__ slots,
                                                          const double *__restrict__ terms, size_t persite_stride,
                                                          double *__restrict__ partial, uint32_t nparts_total, double log_thresh,
@@ -2595,12 +2615,24 @@ __global__ void __launch_bounds__(BLOCK) k_term_lnl_sum(const PartView *__restri
   const PartView &pv = parts[blockIdx.z];
   const double *ps = terms + ((size_t)blockIdx.y * nparts_total + pv.part_index) * persite_stride;
   const uint32_t *sc = pv.scaler[slots[blockIdx.y]];
+  const uint32_t *wt = pv.weights;
+  const uint64_t n_pat = pv.patterns, stride = (uint64_t)gridDim.x * BLOCK * TU;
+  const int tid = threadIdx.x;
   double acc[1] = {0.0};
-  for (uint64_t n = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; n < pv.patterns; n += (uint64_t)gridDim.x * BLOCK) {
-    double lk = log(ps[n]);
-    const uint32_t s = sc[n];
-    if (s) lk = __dadd_rn(lk, __dmul_rn((double)s, log_thresh));
-    acc[0] += __dmul_rn(lk, (double)pv.weights[n]);
+  uint64_t base = (uint64_t)blockIdx.x * BLOCK * TU;
+  double tn[TU]; uint32_t sn[TU], wn[TU];
+  term_load(tn, sn, wn, ps, sc, wt, base, n_pat, tid);
+  for (; base < n_pat; base += stride) {
+    double t[TU]; uint32_t s[TU], w[TU];
+#pragma unroll
+    for (int u = 0; u < TU; ++u) { t[u] = tn[u]; s[u] = sn[u]; w[u] = wn[u]; }
+    if (base + stride < n_pat) term_load(tn, sn, wn, ps, sc, wt, base + stride, n_pat, tid);
+#pragma unroll
+    for (int u = 0; u < TU; ++u) {
+      double lk = log(t[u]);
+      if (s[u]) lk = __dadd_rn(lk, __dmul_rn((double)s[u], log_thresh));
+      acc[0] += __dmul_rn(lk, (double)w[u]);
+    }
   }
   block_sum<1>(acc, red);
   const size_t oi = (size_t)blockIdx.y * nparts_total + pv.part_index;

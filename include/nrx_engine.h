@@ -199,7 +199,8 @@ int nrx_comm_size(nrx_engine *e); /* 1 when no communicator is attached */
 int nrx_comm_allreduce_sum(nrx_engine *e, double *host_inout, size_t n);
 
 /* device-side access for callers that keep data on the GPU (NCCL all-reduce of the [n][nparts] results):
- * the last nrx_tree_lnl / nrx_edge_lnl / nrx_derivatives result also stays in this device buffer. */
+ * with a communicator attached (or NRX_ZEROCOPY=0) the last nrx_tree_lnl / nrx_edge_lnl / nrx_derivatives result also stays in this
+ * device buffer; otherwise the reducing kernels write it straight into the engine's mapped host buffer and this one is not touched. */
 void *nrx_result_device_ptr(nrx_engine *e);
 void *nrx_stream(nrx_engine *e); /* cudaStream_t */
 /* CUDA-event stopwatch on the engine's own stream (torch.cuda.Event cannot see this stream). */

@@ -150,6 +150,8 @@ struct nrx_engine {
   bool fuse_reduce = true;         // env NRX_FUSE_REDUCE=0: separate k_reduce_partials launch (A/B)
   bool defer_pmat = false;         // P-matrix updates are deferred until a launch needs them: the tile walk computes them itself (one launch per evaluation)
   uint32_t node_maxc = NODE_MAXC, node_blocks = 0;   // env NRX_NODE_MAXC (children per group, <= 16), NRX_NODE_BLOCKS (block target per launch; 0 = 24 x SMs)
+  double *d_result_map = nullptr;  // device address of h_result (pinned, mapped): reducing kernels write their result there (result_out)
+  bool zero_copy = true;           // env NRX_ZEROCOPY=0: results go to d_result and are copied
   bool score_only = false;         // nrx_set_score_only: replays of a fused-K3 plan do not store the root displayed trees' CLVs (scalers and per-site terms only)
   uint32_t quad_total = 0;         // env NRX_QUAD_BLOCKS: blocks per launch of the quad kernels (0: 2 per SM)
   bool quad = true;                // env NRX_QUAD=0: thread-per-pattern k_tree_lnl_dna4 / k_edge_lnl_dna4 / k_derivatives_dna4 instead of the coalesced quad kernels (A/B)
@@ -221,6 +223,8 @@ int ensure_result(nrx_engine *e, size_t n_doubles, size_t n_partial) {
     size_t cap = std::max<size_t>(n_doubles, 4096);
     CK(cudaMalloc((void **)&e->d_result, cap * sizeof(double)));
     CK(cudaMallocHost((void **)&e->h_result, cap * sizeof(double)));
+    e->d_result_map = nullptr;
+    { void *dp = nullptr; if (cudaHostGetDevicePointer(&dp, e->h_result, 0) == cudaSuccess) e->d_result_map = (double *)dp; else cudaGetLastError(); }
     if (e->d_tickets) cudaFree(e->d_tickets);
     CK(cudaMalloc((void **)&e->d_tickets, cap * sizeof(uint32_t)));
     CK(cudaMemset(e->d_tickets, 0, cap * sizeof(uint32_t)));
@@ -420,6 +424,7 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
   if (const char *v = std::getenv("NRX_GRAPH")) e->use_graphs = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_PDL")) e->use_pdl = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_FUSE_REDUCE")) e->fuse_reduce = std::atoi(v) != 0;
+  if (const char *v = std::getenv("NRX_ZEROCOPY")) e->zero_copy = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_QUAD")) e->quad = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_QUAD_BLOCKS")) e->quad_total = (uint32_t)std::max(0, std::atoi(v));
   if (const char *v = std::getenv("NRX_NODE")) e->node_mode = std::atoi(v);
@@ -1477,8 +1482,16 @@ static uint32_t reduce_blocks(const nrx_engine *e, uint32_t items, bool quad_ker
 
 }
 
+/* Where the last block of a reducing kernel writes the reduced values.  Without a communicator and with the fused second stage that is
+ * the pinned host buffer itself (mapped into the device's address space): the result needs no device->host copy, one stream operation
+ * and ~3 us less per synchronous call — the derivative sweep makes 440 of them on config 2.  Env NRX_ZEROCOPY=0: device buffer + copy. */
+static double *result_out(nrx_engine *e, const uint32_t *tk) {
+  return (tk && e->zero_copy && !e->comm && e->d_result_map) ? e->d_result_map : e->d_result;
+}
+
 /* second stage + cross-rank sum + device->host copy, all stream-ordered; the host blocks only in wait_result */
 static int enqueue_reduction(nrx_engine *e, uint32_t total, uint32_t nblk, bool fused = false) {
+  if (fused && result_out(e, e->d_tickets) != e->d_result) { e->pending_result = total; return 1; }   // the kernel wrote h_result directly
   if (!fused) {   // the second stage was not done by the last block of the reducing kernel itself
     cudaEvent_t ev0, ev1;
     prof_begin(e, &ev0, &ev1);
@@ -1535,12 +1548,12 @@ static int tree_lnl_impl(nrx_engine *e, const uint32_t *slots, uint32_t n, doubl
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
     const bool mix = class_mixture(e, c);
-    if (!mix && c.states == 4 && c.cats == 4 && e->quad) k_tree_lnl_dna4q<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
-    else if (!mix && c.states == 4 && c.cats == 4) k_tree_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
-    else if (!mix && pow2_cats(c) && c.states == 20 && c.cats == 4 && e->quad) k_tree_lnl_aa20p<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
-    else if (!mix && pow2_cats(c) && c.states == 20) k_tree_lnl_pc<20><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
-    else if (!mix && pow2_cats(c)) k_tree_lnl_pc<0><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
-    else k_tree_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, e->d_result, tk);
+    if (!mix && c.states == 4 && c.cats == 4 && e->quad) k_tree_lnl_dna4q<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, result_out(e, tk), tk);
+    else if (!mix && c.states == 4 && c.cats == 4) k_tree_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, result_out(e, tk), tk);
+    else if (!mix && pow2_cats(c) && c.states == 20 && c.cats == 4 && e->quad) k_tree_lnl_aa20p<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, result_out(e, tk), tk);
+    else if (!mix && pow2_cats(c) && c.states == 20) k_tree_lnl_pc<20><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, result_out(e, tk), tk);
+    else if (!mix && pow2_cats(c)) k_tree_lnl_pc<0><<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, result_out(e, tk), tk);
+    else k_tree_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_partial, P, log_thresh, d_ps, persite_stride, result_out(e, tk), tk);
     e->launches++;
     CK(cudaGetLastError());
   }
@@ -1583,7 +1596,7 @@ static int tree_lnl_fused_impl(nrx_engine *e, uint32_t plan_id, const uint32_t *
   prof_begin(e, &ev0, &ev1);
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
-    k_term_lnl_sum<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_fused, (size_t)e->max_patterns, e->d_partial, P, std::log(SCALE_THRESHOLD), e->d_result, tk);
+    k_term_lnl_sum<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_slots, e->d_fused, (size_t)e->max_patterns, e->d_partial, P, std::log(SCALE_THRESHOLD), result_out(e, tk), tk);
     e->launches++;
     CK(cudaGetLastError());
   }
@@ -1628,7 +1641,7 @@ int nrx_plan_evaluate_async(nrx_engine *e, uint32_t plan_id, const uint32_t *slo
   cudaEvent_t ev0, ev1;
   prof_begin(e, &ev0, &ev1);
   k_walk_dna4<<<dim3(ntiles, 1, (uint32_t)c.parts.size()), WALK_BLOCK, pl.walk_smem, e->stream>>>(
-      c.d_views, pl.d_walk, pl.walk_nops, pl.walk_nbuf, n, std::log(SCALE_THRESHOLD), e->d_partial, P, e->d_result, e->d_tickets, compute_p, d_len);
+      c.d_views, pl.d_walk, pl.walk_nops, pl.walk_nbuf, n, std::log(SCALE_THRESHOLD), e->d_partial, P, result_out(e, e->d_tickets), e->d_tickets, compute_p, d_len);
   e->launches++;
   CK(cudaGetLastError());
   prof_end(e, ev0, ev1, 1, pl.updates, pl.bytes, NRX_PROF_K2, pl.walk_cbytes);
@@ -1712,8 +1725,8 @@ int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n
   prof_begin(e, &ev0, &ev1);
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
-    if (c.states == 4 && c.cats == 4 && !class_mixture(e, c) && e->quad) k_edge_lnl_dna4q<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh, e->d_result, tk);
-    else if (c.states == 4 && c.cats == 4 && !class_mixture(e, c)) k_edge_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh, e->d_result, tk);
+    if (c.states == 4 && c.cats == 4 && !class_mixture(e, c) && e->quad) k_edge_lnl_dna4q<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh, result_out(e, tk), tk);
+    else if (c.states == 4 && c.cats == 4 && !class_mixture(e, c)) k_edge_lnl_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh, result_out(e, tk), tk);
     else if (aa_dmma_pairs_class(e, c)) {  // FP64 tensor cores: block b = (pair b % n, tile group b / n), one partial per (pair, group)
       bool tips;
       const std::vector<nrx_op> ops = pairs_to_ops(pairs, n, edge, false, &tips);
@@ -1722,9 +1735,9 @@ int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n
       const size_t smem = sizeof(AaSmem) + (tips ? (size_t)class_tip_codes(e, c) * 80 * sizeof(double) : 0);   // pairs are never tip-tip: one table
       if (e->aa_v1) k_aa20_dmma<AA_EDGE><<<dim3(n * nblk, 1, (uint32_t)c.parts.size()), AA_THREADS, smem, e->stream>>>(c.d_views, d_ops, n, nblk, tips ? 1 : 0, e->d_partial, P, log_thresh);
       else k_aa20_mma<AA_EDGE, true><<<dim3(n * nblk, 1, (uint32_t)c.parts.size()), AA2_THREADS, sizeof(AaSmem2) + (tips ? (size_t)class_tip_codes(e, c) * 80 * sizeof(double) : 0), e->stream>>>(
-            c.d_views, d_ops, n, nblk, tips ? 1 : 0, e->d_partial, P, log_thresh, e->d_result, tk, 0);
+            c.d_views, d_ops, n, nblk, tips ? 1 : 0, e->d_partial, P, log_thresh, result_out(e, tk), tk, 0);
     }
-    else k_edge_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh, e->d_result, tk);
+    else k_edge_lnl<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, edge, e->d_partial, P, log_thresh, result_out(e, tk), tk);
     e->launches++;
     CK(cudaGetLastError());
   }
@@ -1807,12 +1820,12 @@ int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen, double *out)
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
     const bool mix = class_mixture(e, c);   // (only the +I term of K6 reads frequencies; the generic kernel is the one that indexes them by category)
-    if (!mix && c.states == 4 && c.cats == 4 && e->quad) k_derivatives_dna4q<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
-    else if (!mix && c.states == 4 && c.cats == 4) k_derivatives_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
-    else if (!mix && pow2_cats(c) && c.states == 20 && c.cats == 4 && e->quad) k_derivatives_aa20p<<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
-    else if (!mix && pow2_cats(c) && c.states == 20) k_derivatives_pc<20, 2><<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
-    else if (!mix && pow2_cats(c)) k_derivatives_pc<0, 2><<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
-    else k_derivatives<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P, e->d_result, tk);
+    if (!mix && c.states == 4 && c.cats == 4 && e->quad) k_derivatives_dna4q<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P, result_out(e, tk), tk);
+    else if (!mix && c.states == 4 && c.cats == 4) k_derivatives_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P, result_out(e, tk), tk);
+    else if (!mix && pow2_cats(c) && c.states == 20 && c.cats == 4 && e->quad) k_derivatives_aa20p<<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P, result_out(e, tk), tk);
+    else if (!mix && pow2_cats(c) && c.states == 20) k_derivatives_pc<20, 2><<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P, result_out(e, tk), tk);
+    else if (!mix && pow2_cats(c)) k_derivatives_pc<0, 2><<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P, result_out(e, tk), tk);
+    else k_derivatives<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P, result_out(e, tk), tk);
     e->launches++;
     CK(cudaGetLastError());
   }

@@ -105,12 +105,17 @@ def derivative_sweep(eng, net, iters=3, accept=False):
     optimisation that moves every branch does — the nodes above the edge are then recomputed, as in the reference."""
     order = eng.brlen_sweep_order() if hasattr(eng.api, "_brlen_sweep_order") else range(net.num_edges)
     lengths = eng.branch_lengths()
+    fused_call = hasattr(eng.api, "_brlen_logl_sumtables") and not os.environ.get("NRX_BENCH_SEPARATE_K4_K5")
     for e in order:
         e = int(e)
         t0 = float(lengths[e])
         eng.brlen_prepare(e)
-        eng.computeLoglikelihoodBrlenOpt(e)
-        if eng.computePartitionSumtables(e):
+        if fused_call:   # product: the edge-rooted lnL and the sumtables come out of one pass over the pairs' CLVs
+            n_tables = eng.computeLoglikelihoodBrlenOptAndSumtables(e)[1]
+        else:
+            eng.computeLoglikelihoodBrlenOpt(e)
+            n_tables = eng.computePartitionSumtables(e)
+        if n_tables:
             for k in range(iters):
                 eng.brlen_set_length(e, t0 * (1.0 + 0.1 * (k + 1)))
                 eng.computeLoglikelihoodDerivatives(e)

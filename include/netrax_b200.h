@@ -100,6 +100,9 @@ int nrxh_get_pmatrix(void *h, unsigned p, unsigned edge, double *out);
 int nrxh_brlen_prepare(void *h, unsigned edge, double *old_logl);
 int nrxh_brlen_logl(void *h, unsigned edge, double *out);
 int nrxh_brlen_sumtables(void *h, unsigned edge, unsigned *count);
+/* nrxh_brlen_logl + nrxh_brlen_sumtables of the same branch in one pass over the displayed-tree pairs' CLVs
+ * (netrax::computeLoglikelihoodBrlenOptAndSumtables; the reference makes the two calls back to back, BranchLengthOptimization.cpp:374-381) */
+int nrxh_brlen_logl_sumtables(void *h, unsigned edge, double *out, unsigned *count);
 int nrxh_brlen_read_sumtable(void *h, unsigned p, unsigned idx, double *out, double *tree_prob, unsigned *left_tree, unsigned *right_tree);
 int nrxh_brlen_set_length(void *h, int partition, unsigned edge, double value);
 int nrxh_brlen_derivatives(void *h, unsigned edge, double *d1, double *d2, double *part_d1, double *part_d2, double *raw);

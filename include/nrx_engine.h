@@ -175,6 +175,10 @@ int nrx_set_score_only(nrx_engine *e, int on);
 int nrx_edge_lnl(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n, double *out);
 /* K5: sumtables for n pairs into sumtable slots [0, n) (pool grows on demand). */
 int nrx_sumtables(nrx_engine *e, const nrx_pair *pairs, uint32_t n);
+/* K4 + K5 of one branch in ONE pass over the pairs' CLVs: sumtable slot i for pairs[i], and for the pairs with lnl_index[i] >= 0 the edge
+ * lnL as nrx_edge_lnl gives it, out[lnl_index[i]][nparts] (n_lnl outputs; the reference calls pll_compute_edge_loglikelihood and
+ * pll_update_sumtable on the same CLVs back to back: src/likelihood/VirtualRerooting.cpp:279-346, LikelihoodDerivatives.cpp:291-344). */
+int nrx_edge_lnl_sumtables(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n, const int32_t *lnl_index, uint32_t n_lnl, double *out);
 /* K6: for sumtable slots [0, n): out[n][nparts][3] = (f, d(-lnL)/dt, d2(-lnL)/dt2) at brlen[p]
  * (f = sum w log lk0 without scaler term, the reference's AVX2 behaviour). */
 int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen_per_partition, double *out);
@@ -228,7 +232,8 @@ enum {
   NRX_PROF_K6 = 6,      /* derivatives per sumtable and Newton iterate */
   NRX_PROF_REDUCE = 7,  /* second-stage reduction of the per-block partial sums */
   NRX_PROF_COPY = 8,    /* slot copies of the virtual re-rooting save/restore */
-  NRX_PROF_KINDS = 9
+  NRX_PROF_K45 = 9,     /* edge lnL + sumtables of the same pairs in one pass (k_edge_sum_dna4q) */
+  NRX_PROF_KINDS = 10
 };
 int nrx_profile_read_kind(nrx_engine *e, int kind, double *ms, unsigned long long *launches, unsigned long long *units,
                           unsigned long long *bytes, unsigned long long *compulsory_bytes);

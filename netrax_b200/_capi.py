@@ -73,6 +73,7 @@ class FlatAPI:
             g("reroot_stats", C.c_int, C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint), C.POINTER(C.c_uint))
             g("set_reroot_cache_slots", C.c_int, C.c_void_p, C.c_longlong)
             g("set_score_only", C.c_int, C.c_void_p, C.c_int)
+            g("brlen_logl_sumtables", C.c_int, C.c_void_p, C.c_uint, C.POINTER(C.c_double), C.POINTER(C.c_uint))
             g("set_lazy_rerooting", C.c_int, C.c_void_p, C.c_int)
             g("lazy_reroot_stats", C.c_int, C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong))
         g("optimize_branch", C.c_int, C.c_void_p, C.c_uint, C.c_int, C.c_uint, C.POINTER(C.c_double))
@@ -270,6 +271,13 @@ class LikelihoodEngine:
         self.api.check(self.api._brlen_sumtables(self.h, edge, C.byref(n)))
         self._n_sumtables = n.value
         return n.value
+
+    def computeLoglikelihoodBrlenOptAndSumtables(self, edge: int):
+        """(edge-rooted lnL, number of sumtables): both from ONE pass over the displayed-tree pairs' CLVs."""
+        out, n = C.c_double(), C.c_uint()
+        self.api.check(self.api._brlen_logl_sumtables(self.h, edge, C.byref(out), C.byref(n)))
+        self._n_sumtables = n.value
+        return out.value, n.value
 
     def read_sumtable(self, p: int, idx: int):
         out = np.zeros(self.clv_entries(p))

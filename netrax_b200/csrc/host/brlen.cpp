@@ -547,9 +547,12 @@ void updateTreeData(AnnotatedNetwork &ann, const std::vector<DisplayedTreeData> 
 }
 }  // namespace
 
-double computeLoglikelihoodBrlenOpt(AnnotatedNetwork &ann, const std::vector<DisplayedTreeData> &oldTrees, unsigned int pmatrix_index,
-                                    int update_pmatrices, bool) {  // :348-585
-  if (ann.cached_logl_valid) return ann.cached_logl;
+static std::vector<std::vector<SumtableInfo>> buildSumtablePairs(AnnotatedNetwork &ann, unsigned int pmatrix_index, std::vector<nrx_pair> &pairs);
+
+/* sumtables_out != nullptr: the sumtables of the branch are made in the same pass over the pairs' CLVs (nrx_edge_lnl_sumtables) */
+static double brlenOptImpl(AnnotatedNetwork &ann, const std::vector<DisplayedTreeData> &oldTrees, unsigned int pmatrix_index,
+                           int update_pmatrices, std::vector<std::vector<SumtableInfo>> *sumtables_out) {  // :348-585
+  if (ann.cached_logl_valid && !sumtables_out) return ann.cached_logl;
   const size_t source = ann.network.edges[pmatrix_index].source, target = ann.network.edges[pmatrix_index].target;
   NodeDisplayedTreeData &sd = ann.pernode_displayed_tree_data[source];
   NodeDisplayedTreeData &td = ann.pernode_displayed_tree_data[target];
@@ -580,7 +583,26 @@ double computeLoglikelihoodBrlenOpt(AnnotatedNetwork &ann, const std::vector<Dis
     }
   flushPendingOps(ann);
   std::vector<double> out(pairs.size() * P, 0.0);
-  if (!pairs.empty()) engineCheck(nrx_edge_lnl(ann.engine, pmatrix_index, pairs.data(), (uint32_t)pairs.size(), out.data()), "nrx_edge_lnl");
+  bool fused_done = false;
+  if (sumtables_out) {
+    std::vector<nrx_pair> pairs5;
+    *sumtables_out = buildSumtablePairs(ann, pmatrix_index, pairs5);
+    // every edge-lnL pair (compatible, active AND alive, interesting) is also a sumtable pair (compatible, active, interesting)
+    std::vector<int32_t> lnl_index(pairs5.size(), -1);
+    size_t found = 0;
+    for (size_t k = 0; k < pairs.size(); ++k)
+      for (size_t q = 0; q < pairs5.size(); ++q)
+        if (lnl_index[q] < 0 && pairs5[q].a_kind == pairs[k].a_kind && pairs5[q].a_idx == pairs[k].a_idx && pairs5[q].b_kind == pairs[k].b_kind && pairs5[q].b_idx == pairs[k].b_idx) {
+          lnl_index[q] = (int32_t)k; ++found; break;
+        }
+    if (found == pairs.size() && !pairs5.empty()) {
+      engineCheck(nrx_edge_lnl_sumtables(ann.engine, pmatrix_index, pairs5.data(), (uint32_t)pairs5.size(), lnl_index.data(), (uint32_t)pairs.size(), out.data()), "nrx_edge_lnl_sumtables");
+      fused_done = true;
+    } else if (!pairs5.empty()) {
+      engineCheck(nrx_sumtables(ann.engine, pairs5.data(), (uint32_t)pairs5.size()), "nrx_sumtables");
+    }
+  }
+  if (!fused_done && !pairs.empty()) engineCheck(nrx_edge_lnl(ann.engine, pmatrix_index, pairs.data(), (uint32_t)pairs.size(), out.data()), "nrx_edge_lnl");
   reduceSum(ann, out.data(), out.size());  // C3
   for (size_t k = 0; k < pairs.size(); ++k) {
     TreeLoglData &c = combined[pair_owner[k]];
@@ -632,13 +654,23 @@ double computeLoglikelihoodBrlenOpt(AnnotatedNetwork &ann, const std::vector<Dis
   return network_logl;
 }
 
-std::vector<std::vector<SumtableInfo>> computePartitionSumtables(AnnotatedNetwork &ann, unsigned int pmatrix_index) {  // LikelihoodDerivatives.cpp:291-344
+double computeLoglikelihoodBrlenOpt(AnnotatedNetwork &ann, const std::vector<DisplayedTreeData> &oldTrees, unsigned int pmatrix_index,
+                                    int update_pmatrices, bool) {
+  return brlenOptImpl(ann, oldTrees, pmatrix_index, update_pmatrices, nullptr);
+}
+
+double computeLoglikelihoodBrlenOptAndSumtables(AnnotatedNetwork &ann, const std::vector<DisplayedTreeData> &oldTrees, unsigned int pmatrix_index,
+                                                std::vector<std::vector<SumtableInfo>> &sumtables, int update_pmatrices) {
+  return brlenOptImpl(ann, oldTrees, pmatrix_index, update_pmatrices, &sumtables);
+}
+
+/* the displayed-tree pairs computePartitionSumtables makes a sumtable for, in its order (LikelihoodDerivatives.cpp:291-344) */
+static std::vector<std::vector<SumtableInfo>> buildSumtablePairs(AnnotatedNetwork &ann, unsigned int pmatrix_index, std::vector<nrx_pair> &pairs) {
   const unsigned P = ann.fake_treeinfo->partition_count;
   std::vector<std::vector<SumtableInfo>> res(P);
   const size_t source = ann.network.edges[pmatrix_index].source, target = ann.network.edges[pmatrix_index].target;
   NodeDisplayedTreeData &sd = ann.pernode_displayed_tree_data[source];
   NodeDisplayedTreeData &td = ann.pernode_displayed_tree_data[target];
-  std::vector<nrx_pair> pairs;
   for (size_t i = 0; i < sd.num_active_displayed_trees; ++i)
     for (size_t j = 0; j < td.num_active_displayed_trees; ++j) {
       const ReticulationConfigSet &a = sd.displayed_trees[i].treeLoglData.reticulationChoices, &b = td.displayed_trees[j].treeLoglData.reticulationChoices;
@@ -653,6 +685,12 @@ std::vector<std::vector<SumtableInfo>> computePartitionSumtables(AnnotatedNetwor
       pairs.push_back(makePair(sd.displayed_trees[i], td.displayed_trees[j]));
       for (unsigned p = 0; p < P; ++p) res[p].push_back(si);
     }
+  return res;
+}
+
+std::vector<std::vector<SumtableInfo>> computePartitionSumtables(AnnotatedNetwork &ann, unsigned int pmatrix_index) {  // LikelihoodDerivatives.cpp:291-344
+  std::vector<nrx_pair> pairs;
+  std::vector<std::vector<SumtableInfo>> res = buildSumtablePairs(ann, pmatrix_index, pairs);
   flushPendingOps(ann);
   if (!pairs.empty()) engineCheck(nrx_sumtables(ann.engine, pairs.data(), (uint32_t)pairs.size()), "nrx_sumtables");
   return res;

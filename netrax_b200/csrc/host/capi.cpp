@@ -360,6 +360,19 @@ int nrxh_brlen_logl(void *hv, unsigned edge, double *out) {
   });
 }
 
+int nrxh_brlen_logl_sumtables(void *hv, unsigned edge, double *out, unsigned *count) {
+  return guarded([&] {
+    Handle *h = H(hv);
+    h->ann.cached_logl_valid = false;
+    try { *out = computeLoglikelihoodBrlenOptAndSumtables(h->ann, h->oldTrees, edge, h->sumtables, 1); }
+    catch (const LazyRerootNeedsRoot &) {
+      redoRerootFromRoot(h->ann, edge, h->oldTrees);
+      *out = computeLoglikelihoodBrlenOptAndSumtables(h->ann, h->oldTrees, edge, h->sumtables, 1);
+    }
+    if (count) *count = h->sumtables.empty() ? 0 : (unsigned)h->sumtables[0].size();
+  });
+}
+
 int nrxh_brlen_sumtables(void *hv, unsigned edge, unsigned *count) {
   return guarded([&] {
     H(hv)->sumtables = computePartitionSumtables(H(hv)->ann, edge);

@@ -312,6 +312,11 @@ void dropRerootCache(AnnotatedNetwork &ann_network);   // releases every memoise
 double computeLoglikelihoodBrlenOpt(AnnotatedNetwork &ann_network, const std::vector<DisplayedTreeData> &oldTrees,
                                     unsigned int pmatrix_index, int update_pmatrices = 1, bool print_extra_debug_info = false);
 std::vector<std::vector<SumtableInfo>> computePartitionSumtables(AnnotatedNetwork &ann_network, unsigned int pmatrix_index);
+/* computeLoglikelihoodBrlenOpt + computePartitionSumtables of the same branch in ONE pass over the displayed-tree pairs' CLVs (what
+ * optimize_branch asks for back to back, src/optimization/BranchLengthOptimization.cpp:374-381): returns the edge-rooted lnL and
+ * fills `sumtables`.  Same results as the two calls; partitions the fused kernel does not cover take the two engine calls. */
+double computeLoglikelihoodBrlenOptAndSumtables(AnnotatedNetwork &ann_network, const std::vector<DisplayedTreeData> &oldTrees, unsigned int pmatrix_index,
+                                                std::vector<std::vector<SumtableInfo>> &sumtables, int update_pmatrices = 1);
 LoglDerivatives computeLoglikelihoodDerivatives(AnnotatedNetwork &ann_network,
                                                 const std::vector<std::vector<SumtableInfo>> &sumtables,
                                                 unsigned int pmatrix_index);

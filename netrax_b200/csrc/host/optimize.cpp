@@ -311,16 +311,21 @@ double optimize_branch(AnnotatedNetwork &ann, size_t pmatrix_index, BrlenOptMeth
     ReticulationConfigSet restrictions = getRestrictionsActiveAliveBranch(ann, pmatrix_index);
     updateCLVsVirtualRerootTrees(ann, ann.network.root, new_virtual_root, new_virtual_root_back, restrictions);
     ann.cached_logl_valid = false;
+    // Newton-Raphson: the sumtables are made in the same pass over the pairs' CLVs as the edge-rooted lnL (the reference calls
+    // computeLoglikelihoodBrlenOpt and computePartitionSumtables back to back, :374-381)
+    const bool nr = method == BrlenOptMethod::NEWTON_RAPHSON;
+    auto edge_logl = [&] { return nr ? computeLoglikelihoodBrlenOptAndSumtables(ann, oldTrees, (unsigned)pmatrix_index, sumtables)
+                                     : computeLoglikelihoodBrlenOpt(ann, oldTrees, (unsigned)pmatrix_index); };
     double brlenopt_logl;
-    try { brlenopt_logl = computeLoglikelihoodBrlenOpt(ann, oldTrees, (unsigned)pmatrix_index); }
+    try { brlenopt_logl = edge_logl(); }
     catch (const LazyRerootNeedsRoot &) {   // a displayed tree needs the old root's per-tree lnL after all: redo this branch from an evaluated root
       redoRerootFromRoot(ann, (unsigned)pmatrix_index, oldTrees);
       lazy = false;
-      brlenopt_logl = computeLoglikelihoodBrlenOpt(ann, oldTrees, (unsigned)pmatrix_index);
+      brlenopt_logl = edge_logl();
     }
     if (old_logl - brlenopt_logl >= 1E-3)  // the reference's `fabs(old_logl - brlenopt_logl >= 1E-3)` (:377): one-sided
       throw std::runtime_error("Something went wrong when rerooting CLVs during brlen optimization");
-    if (method == BrlenOptMethod::NEWTON_RAPHSON) sumtables = computePartitionSumtables(ann, (unsigned)pmatrix_index);
+    // (sumtables: made above together with brlenopt_logl)
   }
   if (ann.fake_treeinfo->brlen_linkage == PLLMOD_COMMON_BRLEN_UNLINKED) {
     for (size_t p = 0; p < ann.fake_treeinfo->partition_count; ++p)

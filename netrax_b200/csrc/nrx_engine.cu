@@ -1784,6 +1784,48 @@ int nrx_sumtables(nrx_engine *e, const nrx_pair *pairs, uint32_t n) {
   return 1;
 }
 
+/* K4 + K5 in one pass over the pairs' CLVs (k_edge_sum_dna4q); engines / pairs the fused kernel does not cover take the two calls */
+int nrx_edge_lnl_sumtables(nrx_engine *e, uint32_t edge, const nrx_pair *pairs, uint32_t n, const int32_t *lnl_index, uint32_t n_lnl, double *out) {
+  if (!e) { g_err = "null engine"; return 0; }
+  if (n == 0) return 1;
+  for (uint32_t i = 0; i < n; ++i) if (lnl_index[i] >= (int32_t)n_lnl) { g_err = "nrx_edge_lnl_sumtables: lnl index out of range"; return 0; }
+  bool fusable = e->quad && !std::getenv("NRX_NO_EDGE_SUM");
+  for (const ShapeClass &c : e->classes) fusable = fusable && c.states == 4 && c.cats == 4 && !class_mixture(e, c);
+  for (uint32_t i = 0; i < n; ++i) fusable = fusable && pairs[i].a_kind == NRX_CLV;
+  if (!fusable) {
+    if (!nrx_sumtables(e, pairs, n)) return 0;
+    if (n_lnl == 0) return 1;
+    std::vector<nrx_pair> sub(n_lnl);
+    for (uint32_t i = 0; i < n; ++i) if (lnl_index[i] >= 0) sub[lnl_index[i]] = pairs[i];
+    return nrx_edge_lnl(e, edge, sub.data(), n_lnl, out);
+  }
+  CK(cudaSetDevice(e->device));
+  if (!flush_pmatrices(e)) return 0;
+  if (!check_pairs(e, pairs, n, "nrx_edge_lnl_sumtables")) return 0;
+  for (const Part &p : e->parts) if (edge >= p.d.edges) { g_err = "nrx_edge_lnl_sumtables: edge out of range"; return 0; }
+  const uint32_t P = (uint32_t)e->parts.size();
+  const uint32_t nblk = reduce_blocks(e, n * P);
+  if (!reserve_sumtables(e, n)) return 0;
+  if (!ensure_result(e, (size_t)std::max<uint32_t>(1, n_lnl) * P, (size_t)std::max<uint32_t>(1, n_lnl) * P * nblk) || !refresh_views(e)) return 0;
+  nrx_pair *d_pairs;
+  int32_t *d_idx;
+  if (!upload(e, pairs, n, &d_pairs) || !upload(e, lnl_index, n, &d_idx)) return 0;
+  uint32_t *tk = e->fuse_reduce ? e->d_tickets : nullptr;
+  const double log_thresh = std::log(SCALE_THRESHOLD);
+  cudaEvent_t ev0, ev1;
+  prof_begin(e, &ev0, &ev1);
+  for (const ShapeClass &c : e->classes) {
+    if (c.max_patterns == 0) continue;
+    dim3 grid(nblk, n, (uint32_t)c.parts.size());
+    k_edge_sum_dna4q<<<grid, BLOCK, 0, e->stream>>>(c.d_views, d_pairs, d_idx, edge, e->d_partial, P, log_thresh, result_out(e, tk), tk);
+    e->launches++;
+    CK(cudaGetLastError());
+  }
+  { unsigned long long u = 0; const unsigned long long b = stream_bytes(e, n, 3, 12, &u); prof_end(e, ev0, ev1, e->classes.size(), u, b, NRX_PROF_K45, pair_cbytes(e, pairs, n, true, 1, 4)); }
+  if (n_lnl == 0) return 1;
+  return finish_reduction(e, n_lnl * P, nblk, out, tk != nullptr);
+}
+
 int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen, double *out) {
   if (!e) { g_err = "null engine"; return 0; }
   if (n == 0) return 1;

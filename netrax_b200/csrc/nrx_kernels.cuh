@@ -3053,4 +3053,127 @@ __global__ void __launch_bounds__(BLOCK, 2) k_edge_lnl_dna4q(const PartView *__r
   finish_partials<1>(partial + oi * gridDim.x, out + oi, counters ? counters + oi : nullptr, gridDim.x);
 }
 
+/* K4 + K5 in one pass (round 2): the edge lnL of a displayed-tree pair and its sumtable read the same two CLVs.  optimize_branch
+ * asks for both back to back (computeLoglikelihoodBrlenOpt, then computePartitionSumtables; BranchLengthOptimization.cpp:374-381), so
+ * the host may issue them together (nrx_edge_lnl_sumtables): 2C read + C written per pair and pattern instead of (2C) + (2C + C).
+ * Pair i writes sumtable slot i; lnl_index[i] >= 0: it is also edge-lnL output lnl_index[i] (the sumtable list is a superset of the
+ * edge-lnL list: active vs. active-and-alive branch).  a must be a CLV (the source side of a branch always is), b a CLV or a tip.
+ * Arithmetic per output as in k_edge_lnl_dna4q and k_sumtable_dna4. */
+__device__ __forceinline__ void es_load_half(D4 (&a)[QH], D4 (&b)[QH], uint32_t (&code)[QH], const double *__restrict__ clva, const double *__restrict__ clvb,
+                                             const uint8_t *__restrict__ tip, uint64_t base, uint64_t n_items, int tid) {
+#pragma unroll
+  for (int u = 0; u < QH; ++u) {
+    const uint64_t g = base + (uint64_t)u * BLOCK + tid;
+    code[u] = 0u;
+    if (g < n_items) {
+      a[u] = ldg256(clva + g * 4);
+      if (clvb) b[u] = ldg256(clvb + g * 4);
+      else { code[u] = tip[g >> 2] & 15u; b[u].x = b[u].y = b[u].z = b[u].w = 0.0; }
+    } else { a[u].x = a[u].y = a[u].z = a[u].w = 0.0; b[u] = a[u]; }
+  }
+}
+
+__global__ void __launch_bounds__(BLOCK, 2) k_edge_sum_dna4q(const PartView *__restrict__ parts, const nrx_pair *__restrict__ pairs,
+                                                              const int32_t *__restrict__ lnl_index, uint32_t edge,
+                                                              double *__restrict__ partial, uint32_t nparts_total, double log_thresh,
+                                                              double *__restrict__ out, uint32_t *__restrict__ counters) {
+  __shared__ double red[BLOCK / 32];
+  __shared__ __align__(32) double lut[256];
+  __shared__ __align__(16) double sP[4 * PCAT];
+  __shared__ double sV[16], sIV[16], sF[4];
+  const PartView &pv = parts[blockIdx.z];
+  const nrx_pair pr = pairs[blockIdx.y];
+  const int li = lnl_index[blockIdx.y];
+  const int tid = threadIdx.x, q = tid & 3;
+  const bool tipb = pr.b_kind == NRX_TIP;
+  if (tipb) build_tip_lut4(lut, pv.pmat + (size_t)edge * 64, tid);
+  else if (tid < 64) sP[(tid >> 4) * PCAT + (tid & 15)] = pv.pmat[(size_t)edge * 64 + tid];
+  if (tid < 16) { sV[tid] = pv.eigenvecs[tid]; sIV[tid] = pv.inv_eigenvecs[tid]; }
+  if (tid < 4) sF[tid] = pv.freqs[tid];
+  __syncthreads();
+  const double *Pq = sP + q * PCAT;
+  const double *clva = pv.clv[pr.a_idx];
+  const uint32_t *sca = pv.scaler[pr.a_idx];
+  const double *clvb = tipb ? nullptr : pv.clv[pr.b_idx];
+  const uint32_t *scb = tipb ? nullptr : pv.scaler[pr.b_idx];
+  const uint8_t *tip = tipb ? pv.tipchars + (size_t)pr.b_idx * pv.tip_pitch : nullptr;
+  double *st = pv.sumtable[blockIdx.y];
+  const double f0 = sF[0], f1 = sF[1], f2 = sF[2], f3 = sF[3];
+  const double w = pv.rate_weights[q], pinv = pv.pinv;
+  const uint64_t n_items = (uint64_t)pv.patterns * 4, stride = (uint64_t)gridDim.x * BLOCK * QU;
+  double acc[1] = {0.0};
+  uint64_t base = (uint64_t)blockIdx.x * BLOCK * QU;
+  D4 na[QH], nb[QH];
+  uint32_t nc[QH];
+  es_load_half(na, nb, nc, clva, clvb, tip, base, n_items, tid);
+  for (; base < n_items; base += stride) {
+    double ta[QU], ti[QU];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      D4 a[QH], b[QH];
+      uint32_t code[QH];
+#pragma unroll
+      for (int u = 0; u < QH; ++u) { a[u] = na[u]; b[u] = nb[u]; code[u] = nc[u]; }
+      const uint64_t nbase = h == 0 ? base + (uint64_t)QH * BLOCK : base + stride;
+      if (h == 0 || nbase < n_items) es_load_half(na, nb, nc, clva, clvb, tip, nbase, n_items, tid);
+#pragma unroll
+      for (int u = 0; u < QH; ++u) {
+        const int k = h * QH + u;
+        const uint64_t g = base + (uint64_t)k * BLOCK + tid;
+        // ---- K5: sumtable entry (k_sumtable_dna4: the tip, if any, is the left operand) ----
+        D4 left = a[u], right = b[u];
+        if (tipb) {
+          right = a[u];
+          left.x = (double)(code[u] & 1u); left.y = (double)((code[u] >> 1) & 1u); left.z = (double)((code[u] >> 2) & 1u); left.w = (double)((code[u] >> 3) & 1u);
+        }
+        const double lf[4] = {__dmul_rn(left.x, f0), __dmul_rn(left.y, f1), __dmul_rn(left.z, f2), __dmul_rn(left.w, f3)};
+        const double rv[4] = {right.x, right.y, right.z, right.w};
+        double o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          double le = 0.0, ri = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            le = __dadd_rn(le, __dmul_rn(lf[kk], sIV[kk * 4 + j]));
+            ri = __dadd_rn(ri, __dmul_rn(sV[j * 4 + kk], rv[kk]));
+          }
+          o[j] = __dmul_rn(le, ri);
+        }
+        if (g < n_items) { D4 ov; ov.x = o[0]; ov.y = o[1]; ov.z = o[2]; ov.w = o[3]; stg256(st + g * 4, ov); }
+        // ---- K4: edge lnL term (k_edge_lnl_dna4q: a is the parent, b goes through P(edge)) ----
+        ta[k] = 0.0; ti[k] = 0.0;
+        if (li >= 0) {
+          const D4 y = tipb ? *reinterpret_cast<const D4 *>(lut + code[u] * 16 + q * 4) : matvec4(Pq, b[u]);
+          const double tr = edge_cat_term(a[u], y, f0, f1, f2, f3);
+          if (pinv > 0.0) {
+            int iv = -1;
+            if (g < n_items) iv = pv.invariant[g >> 2];
+            const double invf = iv < 0 ? 0.0 : pv.freqs[iv];
+            edge_cat_accum(tr, w, pinv, invf, iv >= 0, ta[k], ti[k]);
+          } else ta[k] = __dmul_rn(tr, w);
+        }
+      }
+    }
+    if (li >= 0) {
+      const double terma = quad_gather_sum(ta[0], ta[1], ta[2], ta[3], q);
+      double terminv = 0.0;
+      if (pinv > 0.0) terminv = quad_gather_sum(ti[0], ti[1], ti[2], ti[3], q);
+      const uint64_t n = (base >> 2) + (uint64_t)q * (BLOCK / 4) + (tid >> 2);
+      if (n < pv.patterns) {
+        uint32_t s = sca[n];
+        if (!tipb) s += scb[n];
+        double lk;
+        if (pinv > 0.0) lk = edge_site_lnl(terma, terminv, s, log_thresh);
+        else { lk = log(terma); if (s) lk = __dadd_rn(lk, __dmul_rn((double)s, log_thresh)); }
+        acc[0] += __dmul_rn(lk, (double)pv.weights[n]);
+      }
+    }
+  }
+  if (li < 0) return;   // block-uniform: this pair has no edge-lnL output
+  block_sum<1>(acc, red);
+  const size_t oi = (size_t)li * nparts_total + pv.part_index;
+  if (threadIdx.x == 0) partial[oi * gridDim.x + blockIdx.x] = acc[0];
+  finish_partials<1>(partial + oi * gridDim.x, out + oi, counters ? counters + oi : nullptr, gridDim.x);
+}
+
 }  // namespace nrx

@@ -142,7 +142,7 @@ class NetraxB200(LikelihoodEngine):
         return {"clv_ms": ms.value, "clv_launches": l.value, "clv_site_updates": u.value, "clv_bytes": b.value}
 
     PROF_KINDS = ("K2_clv_update", "K1_pmatrix", "K3_tree_lnl", "K3F_term_lnl_sum", "K4_edge_lnl", "K5_sumtable", "K6_derivatives",
-                  "reduce_partials", "slot_copy")  # NRX_PROF_* of include/nrx_engine.h
+                  "reduce_partials", "slot_copy", "K45_edge_lnl_sumtable")  # NRX_PROF_* of include/nrx_engine.h
 
     def profile_read_all(self):
         """{kernel family: {ms, launches, units, bytes, compulsory_bytes}} since profile_enable(True) (CUDA events on the engine

@@ -19,8 +19,12 @@ for patterns in (100000, 64):
     for e in order:
         e = int(e); t0 = float(lengths[e])
         timed("prepare", eng.brlen_prepare, e)
-        timed("brlen_logl", eng.computeLoglikelihoodBrlenOpt, e)
-        if timed("sumtables", eng.computePartitionSumtables, e):
+        if os.environ.get("NRX_BENCH_SEPARATE_K4_K5"):
+            timed("brlen_logl", eng.computeLoglikelihoodBrlenOpt, e)
+            n_tables = timed("sumtables", eng.computePartitionSumtables, e)
+        else:
+            n_tables = timed("brlen_logl+sumtables", eng.computeLoglikelihoodBrlenOptAndSumtables, e)[1]
+        if n_tables:
             for k in range(3):
                 timed("set_length", eng.brlen_set_length, e, t0 * (1.0 + 0.1 * (k + 1)))
                 timed("derivatives", eng.computeLoglikelihoodDerivatives, e)

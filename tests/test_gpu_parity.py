@@ -1497,3 +1497,83 @@ def test_lazy_optimize_branch_matches_reference_flow():
     g.set_lazy_rerooting(False)
     assert g.computeLoglikelihood(1, 1) == pytest.approx(o.computeLoglikelihood(1, 1), rel=1e-9)
     g.close()
+
+
+@pytest.mark.parametrize("name", ["small", "two_reticulations", "three_reticulations", "reticulation_in_reticulation", "tree"])
+@pytest.mark.parametrize("variant", [AVERAGE, BEST])
+def test_edge_lnl_and_sumtables_in_one_pass(name, variant):
+    """computeLoglikelihoodBrlenOptAndSumtables (k_edge_sum_dna4q: the edge lnL and the sumtable of a displayed-tree pair from ONE read
+    of its two CLVs) on every edge of the reference's fixtures: the lnL equals the separate call's and the checker's, every sumtable
+    entry equals the separate K5's bit for bit and the checker's to rounding, the derivatives taken from them too."""
+    net, part = load_fixture(*FIXTURE_PAIRS[name])
+    g, g2, o = _gpu(net, [part], variant=variant), _gpu(net, [part], variant=variant), _oracle(net, [part], variant=variant)
+    _inject_eigen(g, o)
+    _inject_eigen(g2, o)
+    for eng in (g, g2, o):
+        eng.computeLoglikelihood(0, 1)
+    for e in range(net.num_edges):
+        for eng in (g, g2, o):
+            eng.brlen_prepare(e)
+        lf, nf = g.computeLoglikelihoodBrlenOptAndSumtables(e)
+        ls, ns = g2.computeLoglikelihoodBrlenOpt(e), g2.computePartitionSumtables(e)
+        lo, no = o.computeLoglikelihoodBrlenOpt(e), o.computePartitionSumtables(e)
+        assert nf == ns == no
+        assert lf == pytest.approx(ls, rel=1e-13) and lf == pytest.approx(lo, rel=LNL_RTOL)
+        for i in range(nf):
+            sf, pf, lf_, rf = g.read_sumtable(0, i)
+            ss, ps, ls_, rs = g2.read_sumtable(0, i)
+            so, po, lo_, ro = o.read_sumtable(0, i)
+            assert (lf_, rf) == (ls_, rs) == (lo_, ro) and pf == ps
+            assert np.array_equal(sf, ss), (e, i)
+            np.testing.assert_allclose(sf, so, rtol=1e-10, atol=1e-14 * np.abs(so).max())
+        if nf:
+            for eng in (g, g2, o):
+                eng.brlen_set_length(e, 0.13)
+            df, ds, do = g.computeLoglikelihoodDerivatives(e), g2.computeLoglikelihoodDerivatives(e), o.computeLoglikelihoodDerivatives(e)
+            assert df[0] == ds[0] and df[1] == ds[1]
+            assert df[0] == pytest.approx(do[0], rel=DERIV_RTOL, abs=1e-7) and df[1] == pytest.approx(do[1], rel=DERIV_RTOL, abs=1e-7)
+            for eng in (g, g2, o):
+                eng.brlen_set_length(e, float(net.edge_length[e]))
+        for eng in (g, g2, o):
+            eng.brlen_finish(e)
+    g.close(); g2.close()
+
+
+def test_edge_lnl_and_sumtables_in_one_pass_pinv_and_other_shapes():
+    """+I (terma / terminv through the quad reduction), unlinked ragged partitions, and a protein partition (not covered by the fused
+    kernel: the call falls back to the two engine calls) — same numbers as the separate calls and as the checker."""
+    from netrax_b200.synth import lg_model
+    cases = []
+    net = random_network(18, 3, seed=51)
+    m, w = simulate_alignment(net, 257, seed=51)
+    cases.append((net, [Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)], {}, 0.3))
+    rng = np.random.default_rng(5)
+    parts, brl = [], []
+    for p, pat in enumerate((130, 61)):
+        m, w = simulate_alignment(net, pat, seed=60 + p)
+        parts.append(Partition(4, 4, m, DNA_FREQS, GTR_RATES * (1 + 0.2 * p), GAMMA4_ALPHA05, pattern_weights=w))
+        brl.append(net.edge_length * rng.uniform(0.5, 2, net.num_edges))
+    cases.append((net, parts, dict(linkage=UNLINKED, partition_brlens=brl), 0.0))
+    pnet = random_network(9, 1, seed=52)
+    rates, freqs = lg_model()
+    pm, pw = simulate_alignment(pnet, 90, seed=52, states=20, rates=rates, freqs=freqs)
+    cases.append((pnet, [Partition(20, 4, pm, freqs, rates, GAMMA4_ALPHA05, pattern_weights=pw)], {}, 0.0))
+    for net, parts, kw, pinv in cases:
+        g, o = _gpu(net, parts, **kw), _oracle(net, parts, **kw)
+        _inject_eigen(g, o)
+        if pinv:
+            for eng in (g, o):
+                eng.set_pinv(0, pinv)
+        for eng in (g, o):
+            eng.computeLoglikelihood(0, 1)
+        for e in range(0, net.num_edges, 2):
+            for eng in (g, o):
+                eng.brlen_prepare(e)
+            lf, nf = g.computeLoglikelihoodBrlenOptAndSumtables(e)
+            lo, no = o.computeLoglikelihoodBrlenOpt(e), o.computePartitionSumtables(e)
+            assert nf == no and lf == pytest.approx(lo, rel=LNL_RTOL)
+            if nf:
+                dg, do = g.computeLoglikelihoodDerivatives(e), o.computeLoglikelihoodDerivatives(e)
+                np.testing.assert_allclose(dg[4], do[4], rtol=DERIV_RTOL, atol=1e-7)
+            assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL)
+        g.close()

@@ -319,6 +319,7 @@ def main():
     ap.add_argument("--patterns", type=int, default=0, help="global pattern count per partition (default: the config's)")
     ap.add_argument("--cpu-patterns-per-core", type=int, default=0, help="0: the arm's global pattern count / host cores, capped at 16000")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-pipelined", action="store_true", help="e2e region: double-buffered uploads (step k + 1's copy overlaps step k's kernels) — measured SLOWER on config 5, see DESIGN.md §6")
     ap.add_argument("--no-score-only", action="store_true", help="skip the score-only region (root displayed trees' CLVs not stored)")
     ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (BASELINE configs 1-4 + sweep, N = 1 only)")
     ap.add_argument("--no-parity", action="store_true")
@@ -435,15 +436,30 @@ def main():
 
     # ---- timed region 2: end to end with host buffers ----
     ms_e2e, lnl_e2e = None, None
+    # every step uploads its alignment slice from pinned host memory and reads its lnL back: the upload sits in front of its own
+    # evaluation on the engine stream.  --e2e-pipelined (4-state partitions): double-buffered instead — the copy of step k + 1 runs on the
+    # engine's copy stream while step k computes (stage / commit).  Measured on config 5: 42.9 instead of 34.8 ms per step — K2 keeps the
+    # HBM at 98 % of its pin bandwidth and the DMA writes of the overlapped copy crawl, so the copy becomes the critical path.
+    pipelined = all(t is None for t in tipmaps) and args.e2e_pipelined
     if tip_u8 is not None:
+        def stage():
+            for p in range(len(parts)):
+                eng.stage_alignment_u8(p, tip_u8[p].data_ptr(), w_u32[p].data_ptr())
         barrier()
         eng.timer_start()
-        for _ in range(args.steps):
-            for p in range(len(parts)):
-                if tipmaps[p] is None:
-                    eng.upload_alignment_u8(p, tip_u8[p].data_ptr(), w_u32[p].data_ptr())
-                else:
-                    eng.upload_alignment_codes(p, tip_u8[p].data_ptr(), tipmaps[p], w_u32[p].data_ptr())
+        if pipelined:
+            stage()
+        for k in range(args.steps):
+            if pipelined:
+                eng.commit_staged_alignment()
+                if k + 1 < args.steps:
+                    stage()
+            else:
+                for p in range(len(parts)):
+                    if tipmaps[p] is None:
+                        eng.upload_alignment_u8(p, tip_u8[p].data_ptr(), w_u32[p].data_ptr())
+                    else:
+                        eng.upload_alignment_codes(p, tip_u8[p].data_ptr(), tipmaps[p], w_u32[p].data_ptr())
             lnl_e2e = eng.computeLoglikelihood(0, 1)
         ms_e2e = eng.timer_stop()
         barrier()
@@ -520,7 +536,9 @@ def main():
         if ms_e2e:
             e2e_value = updates_per_step / (ms_e2e / args.steps / 1e3)
             line["e2e"] = {"value": e2e_value, "unit": "site-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                           "ms_per_step": ms_e2e / args.steps, "lnl_evals_per_sec": 1e3 / (ms_e2e / args.steps)}
+                           "ms_per_step": ms_e2e / args.steps, "lnl_evals_per_sec": 1e3 / (ms_e2e / args.steps),
+                           "uploads": ("double-buffered: step k + 1's host->device copy overlaps step k's kernels (nrxh_stage_alignment_u8 / nrxh_commit_staged_alignment); "
+                                       "one upload per step, all inside the timed region") if pipelined else "in front of each evaluation on the engine stream"}
         if ms_so:
             line["score_only"] = {"what": "the same full evaluation with nrxh_set_score_only: the CLVs of the root displayed trees (root_trees of sum_trees_per_node "
                                           "slots) are computed and reduced to their per-site lnL but not stored; NOT the headline — batched candidate scoring (SURVEY §8f f3)",

@@ -194,6 +194,11 @@ void *nrxh_engine(void *h); /* the underlying nrx_engine* */
 /* re-upload one partition's alignment slice from HOST buffers (tipchars: 1 byte per cell, DNA) + pattern weights */
 int nrxh_upload_alignment_u8(void *h, unsigned p, const uint8_t *tipchars, const unsigned *pattern_weights);
 /* the same for any alphabet (e.g. 20 states): 1-byte codes + the code -> state-set map; asynchronous like the call above */
+/* double-buffered upload (4-state partitions): stage the NEXT alignment while the current one is being evaluated, commit before the
+ * evaluation that should see it (nrx_stage_alignment_u8 / nrx_commit_staged_alignment; the role of re-reading the MSA slices between
+ * analyses, src/main.cpp:715-736, without stalling the device) */
+int nrxh_stage_alignment_u8(void *h, unsigned partition, const uint8_t *tipchars, const unsigned *pattern_weights);
+int nrxh_commit_staged_alignment(void *h);
 int nrxh_upload_alignment_codes(void *h, unsigned p, const uint8_t *codes, const uint32_t *tipmap, unsigned ncodes, const unsigned *pattern_weights);
 int nrxh_timer_start(void *h);
 int nrxh_timer_stop(void *h, double *elapsed_ms);

@@ -97,6 +97,13 @@ int nrx_set_tipchars_u8(nrx_engine *e, uint32_t p, const uint8_t *codes);
 /* the same for any alphabet: code c stands for the state set tipmap[c] (c < ncodes <= 256), the role of pll_map_aa & co. */
 int nrx_set_tipcodes_u8(nrx_engine *e, uint32_t p, const uint8_t *codes, const uint32_t *tipmap, uint32_t ncodes);
 int nrx_set_pattern_weights_async(nrx_engine *e, uint32_t p, const uint32_t *weights); /* borrowed like `codes` above */
+/* Double-buffered form of the asynchronous upload (4-state partitions): stage copies the NEXT alignment (tips [tips][patterns] as state
+ * masks and / or pattern weights; either may be NULL) into shadow buffers on a separate copy stream — it overlaps with every kernel
+ * enqueued after this call, i.e. with the evaluation of the current alignment; commit makes the staged buffers the live ones
+ * (the engine stream waits for the copies), validates the codes and rebuilds the invariant-site table.  Host buffers are borrowed until
+ * the commit's evaluation has been collected. */
+int nrx_stage_alignment_u8(nrx_engine *e, uint32_t partition, const uint8_t *codes, const uint32_t *weights);
+int nrx_commit_staged_alignment(nrx_engine *e);
 int nrx_set_pattern_weights(nrx_engine *e, uint32_t p, const uint32_t *weights);
 /* eigenvecs / inv_eigenvecs: [states][states_padded]; eigenvals, freqs: [states_padded] (padding ignored);
  * prop_invar in [0, 1): proportion of invariant sites (+I; pll_update_invariant_sites_proportion, LIBPLL/models.c:495-543).

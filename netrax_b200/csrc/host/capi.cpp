@@ -644,6 +644,17 @@ int nrxh_upload_alignment_u8(void *hv, unsigned p, const uint8_t *tipchars, cons
     invalidateAllCLVs(ann);
   });
 }
+int nrxh_stage_alignment_u8(void *hv, unsigned p, const uint8_t *tipchars, const unsigned *pw) {
+  return guarded([&] { detail::engineCheck(nrx_stage_alignment_u8(H(hv)->ann.engine, p, tipchars, pw), "nrx_stage_alignment_u8"); });
+}
+int nrxh_commit_staged_alignment(void *hv) {
+  return guarded([&] {
+    AnnotatedNetwork &ann = H(hv)->ann;
+    finishVirtualReroot(ann);
+    detail::engineCheck(nrx_commit_staged_alignment(ann.engine), "nrx_commit_staged_alignment");
+    invalidateAllCLVs(ann);
+  });
+}
 int nrxh_upload_alignment_codes(void *hv, unsigned p, const uint8_t *codes, const uint32_t *tipmap, unsigned ncodes, const unsigned *pw) {
   return guarded([&] {   // any alphabet: code c = state set tipmap[c]
     AnnotatedNetwork &ann = H(hv)->ann;

@@ -42,6 +42,11 @@ struct Part {
   std::vector<double> h_freqs, h_inv_eigenvecs, h_eigenvecs;
   uint8_t *tipchars = nullptr;
   uint32_t *tipmap = nullptr, *weights = nullptr;
+  // double buffer of the alignment (nrx_stage_alignment_u8 / nrx_commit_staged_alignment): the next step's tips and weights are copied on
+  // the engine's copy stream while the current step computes; commit swaps the pointers
+  uint8_t *tipchars_next = nullptr;
+  uint32_t *weights_next = nullptr;
+  bool staged_tips = false, staged_weights = false;
   double *model = nullptr;  // freqs | eigenvecs | inv_eigenvecs | eigenvals | rates | rate_weights | diagp
   double *freqs = nullptr, *eigenvecs = nullptr, *inv_eigenvecs = nullptr, *eigenvals = nullptr, *rates = nullptr, *rate_weights = nullptr, *diagp = nullptr;
   std::vector<double> h_eigenvals, h_rates;   // h_eigenvals: [nmodels][states]
@@ -150,6 +155,8 @@ struct nrx_engine {
   bool fuse_reduce = true;         // env NRX_FUSE_REDUCE=0: separate k_reduce_partials launch (A/B)
   bool defer_pmat = false;         // P-matrix updates are deferred until a launch needs them: the tile walk computes them itself (one launch per evaluation)
   uint32_t node_maxc = NODE_MAXC, node_blocks = 0;   // env NRX_NODE_MAXC (children per group, <= 16), NRX_NODE_BLOCKS (block target per launch; 0 = 24 x SMs)
+  cudaStream_t copy_stream = nullptr;   // host -> device copies of staged alignments (overlap with the kernels on `stream`)
+  cudaEvent_t ev_main = nullptr, ev_copy = nullptr;
   double *d_result_map = nullptr;  // device address of h_result (pinned, mapped): reducing kernels write their result there (result_out)
   bool zero_copy = true;           // env NRX_ZEROCOPY=0: results go to d_result and are copied
   bool score_only = false;         // nrx_set_score_only: replays of a fused-K3 plan do not store the root displayed trees' CLVs (scalers and per-site terms only)
@@ -512,10 +519,12 @@ void nrx_engine_destroy(nrx_engine *e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); cudaEventDestroy(e->ev_main); cudaEventDestroy(e->ev_copy); }
   if (e->comm && nccl().ok) nccl().CommDestroy(e->comm);
   for (EnginePlan &pl : e->plans) { for (cudaGraphExec_t &x : pl.exec) if (x) cudaGraphExecDestroy(x); cudaFree(pl.d_ops); cudaFree(pl.d_walk); cudaFree(pl.d_ngroups); cudaFree(pl.d_nops); cudaFree(pl.d_nblocks); }
   for (Part &p : e->parts) {
     cudaFree(p.invariant); cudaFree(p.pmat); cudaFree(p.pmat_pad); cudaFree(p.tiplut); cudaFree(p.summat); cudaFree(p.sumlut); cudaFree(p.tipchars); cudaFree(p.tipmap); cudaFree(p.weights); cudaFree(p.model);
+    cudaFree(p.tipchars_next); cudaFree(p.weights_next);
     for (void *m : p.slot_mem) cudaFree(m);
     for (double *m : p.h_sumtable) cudaFree(m);
     cudaFree(p.d_clv); cudaFree(p.d_scaler); cudaFree(p.d_sumtable);
@@ -632,6 +641,76 @@ int nrx_set_pattern_weights_async(nrx_engine *e, uint32_t pi, const uint32_t *w)
   CK(cudaSetDevice(e->device));
   Part &p = e->parts[pi];
   if (p.d.patterns) CK(cudaMemcpyAsync(p.weights, w, (size_t)p.d.patterns * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+  return 1;
+}
+
+/* Double-buffered alignment upload (4-state partitions, code == state mask).  stage: the copies go to the shadow buffers on the copy
+ * stream, ordered after everything already enqueued on the engine stream (the shadow buffers were the live ones of the previous
+ * step) — so they overlap with whatever the engine stream is given AFTER this call.  commit: the engine stream waits for the copies,
+ * the buffers swap, the codes are validated and the invariant-site table rebuilt as in nrx_set_tipchars_u8. */
+int nrx_stage_alignment_u8(nrx_engine *e, uint32_t pi, const uint8_t *codes, const uint32_t *weights) {
+  if (!check_part(e, pi)) return 0;
+  CK(cudaSetDevice(e->device));
+  Part &p = e->parts[pi];
+  if (p.d.states != 4) { g_err = "nrx_stage_alignment_u8: only 4-state partitions store the mask as the code"; return 0; }
+  if (!e->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->ev_main, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming));
+  }
+  if (codes && !p.tipchars_next) {
+    CK(cudaMalloc((void **)&p.tipchars_next, std::max<size_t>(1, (size_t)p.d.tips * p.pat_pad)));
+    CK(cudaMemset(p.tipchars_next, 0, std::max<size_t>(1, (size_t)p.d.tips * p.pat_pad)));
+  }
+  if (weights && !p.weights_next) {
+    std::vector<uint32_t> ones(std::max<uint32_t>(1, p.pat_pad), 1);
+    CK(cudaMalloc((void **)&p.weights_next, ones.size() * sizeof(uint32_t)));
+    CK(cudaMemcpy(p.weights_next, ones.data(), ones.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
+  CK(cudaEventRecord(e->ev_main, e->stream));
+  CK(cudaStreamWaitEvent(e->copy_stream, e->ev_main, 0));
+  const size_t n = (size_t)p.d.tips * p.d.patterns;
+  if (codes && n) CK(cudaMemcpy2DAsync(p.tipchars_next, p.pat_pad, codes, p.d.patterns, p.d.patterns, p.d.tips, cudaMemcpyHostToDevice, e->copy_stream));
+  if (weights && p.d.patterns) CK(cudaMemcpyAsync(p.weights_next, weights, (size_t)p.d.patterns * sizeof(uint32_t), cudaMemcpyHostToDevice, e->copy_stream));
+  p.staged_tips = p.staged_tips || codes != nullptr;
+  p.staged_weights = p.staged_weights || weights != nullptr;
+  return 1;
+}
+
+int nrx_commit_staged_alignment(nrx_engine *e) {
+  if (!e) { g_err = "null engine"; return 0; }
+  CK(cudaSetDevice(e->device));
+  bool any = false;
+  for (const Part &p : e->parts) any = any || p.staged_tips || p.staged_weights;
+  if (!any) return 1;
+  CK(cudaEventRecord(e->ev_copy, e->copy_stream));
+  CK(cudaStreamWaitEvent(e->stream, e->ev_copy, 0));
+  for (uint32_t pi = 0; pi < e->parts.size(); ++pi) {
+    Part &p = e->parts[pi];
+    if (p.staged_weights) { std::swap(p.weights, p.weights_next); p.staged_weights = false; e->views_dirty = true; }
+    if (!p.staged_tips) continue;
+    std::swap(p.tipchars, p.tipchars_next);
+    p.staged_tips = false;
+    e->views_dirty = true;
+    uint32_t tipmap[256] = {};
+    for (uint32_t i = 1; i < 16; ++i) tipmap[i] = i;
+    std::vector<uint32_t> tm(tipmap, tipmap + 256);
+    if (!p.tips_set || tm != p.h_tipmap) {
+      uint32_t *d_map;
+      if (!upload(e, tm.data(), 256, &d_map)) return 0;
+      CK(cudaMemcpyAsync(p.tipmap, d_map, 256 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
+      p.h_tipmap = tm;
+      if (p.tip_codes != 16) { p.tip_codes = 16; }
+    }
+    if (p.d.patterns) {
+      const uint32_t blocks = (uint32_t)std::min<uint64_t>(((uint64_t)p.d.patterns + BLOCK - 1) / BLOCK, 8ull * e->sm_count);
+      k_check_tipchars<<<blocks, BLOCK, 0, e->stream>>>(p.tipchars, p.d.tips, p.d.patterns, p.pat_pad, p.tipmap, 15u, p.invariant, e->h_err);
+      e->launches++;
+      CK(cudaGetLastError());
+    }
+    p.tips_set = true;
+    p.invariant_stale = false;
+  }
   return 1;
 }
 

@@ -55,6 +55,10 @@ def load() -> FlatAPI:
         lib.nrxh_engine.argtypes = [C.c_void_p]
         lib.nrxh_upload_alignment_u8.restype = C.c_int
         lib.nrxh_upload_alignment_u8.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p]
+        lib.nrxh_stage_alignment_u8.restype = C.c_int
+        lib.nrxh_stage_alignment_u8.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p]
+        lib.nrxh_commit_staged_alignment.restype = C.c_int
+        lib.nrxh_commit_staged_alignment.argtypes = [C.c_void_p]
         lib.nrxh_upload_alignment_codes.restype = C.c_int
         lib.nrxh_upload_alignment_codes.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS"), C.c_uint, C.c_void_p]
         lib.nrxh_compute_loglikelihood_batch.restype = C.c_int
@@ -164,6 +168,14 @@ class NetraxB200(LikelihoodEngine):
     def upload_alignment_u8(self, p: int, tipchars_ptr: int, weights_ptr: int = 0):
         """Host -> device re-upload of one partition's alignment slice (pointers to pinned or pageable host memory)."""
         self.api.check(self.api.lib.nrxh_upload_alignment_u8(self.h, p, C.c_void_p(tipchars_ptr), C.c_void_p(weights_ptr) if weights_ptr else None))
+
+    def stage_alignment_u8(self, p: int, tipchars_ptr: int, weights_ptr: int = 0):
+        """Double-buffered upload (4-state partitions): the copy runs on a separate stream and overlaps with every evaluation enqueued
+        after this call; commit_staged_alignment() makes it the live alignment."""
+        self.api.check(self.api.lib.nrxh_stage_alignment_u8(self.h, p, C.c_void_p(tipchars_ptr) if tipchars_ptr else None, C.c_void_p(weights_ptr) if weights_ptr else None))
+
+    def commit_staged_alignment(self):
+        self.api.check(self.api.lib.nrxh_commit_staged_alignment(self.h))
 
     def upload_alignment_codes(self, p: int, codes_ptr: int, tipmap: np.ndarray, weights_ptr: int = 0):
         """Any alphabet: 1-byte codes [tips][patterns] (pointer to host memory) + tipmap[code] = state-set mask.  Asynchronous: the

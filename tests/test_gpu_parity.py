@@ -1577,3 +1577,41 @@ def test_edge_lnl_and_sumtables_in_one_pass_pinv_and_other_shapes():
                 np.testing.assert_allclose(dg[4], do[4], rtol=DERIV_RTOL, atol=1e-7)
             assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL)
         g.close()
+
+
+def test_staged_alignment_upload_double_buffer():
+    """nrxh_stage_alignment_u8 / nrxh_commit_staged_alignment: the next alignment is copied on the engine's copy stream while the
+    current one is evaluated; only the commit makes it live.  Two different alignments alternate: every evaluation sees exactly the
+    alignment committed before it (lnL of the checker for that alignment), also with +I (the invariant-site table is rebuilt at
+    commit), and an illegal staged code fails the evaluation after its commit."""
+    from netrax_b200._capi import LikelihoodError
+    net = random_network(14, 2, seed=23)
+    ma, wa = simulate_alignment(net, 900, seed=23)
+    mb, wb = simulate_alignment(net, 900, seed=24)
+    ma[:, :70] = ma[0, :70]
+    parts = {k: Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w) for k, (m, w) in (("a", (ma, wa)), ("b", (mb, wb)))}
+    oa, ob = _oracle(net, [parts["a"]]), _oracle(net, [parts["b"]])
+    g = _gpu(net, [parts["a"]])
+    _inject_eigen(g, oa)   # both checkers hold the same model, hence the same decomposition
+    la, lb = oa.computeLoglikelihood(0, 1), ob.computeLoglikelihood(0, 1)
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(la, rel=LNL_RTOL)
+    bufs = {k: (np.ascontiguousarray(m.astype(np.uint8)), np.ascontiguousarray(w.astype(np.uint32))) for k, (m, w) in (("a", (ma, wa)), ("b", (mb, wb)))}
+    want = {"a": la, "b": lb}
+    g.stage_alignment_u8(0, bufs["b"][0].ctypes.data, bufs["b"][1].ctypes.data)
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(la, rel=LNL_RTOL)          # staged, not committed: still alignment a
+    seq = ["b", "a", "b", "b", "a"]
+    for k, name in enumerate(seq):
+        g.commit_staged_alignment()
+        if k + 1 < len(seq):
+            nxt = seq[k + 1]
+            g.stage_alignment_u8(0, bufs[nxt][0].ctypes.data, bufs[nxt][1].ctypes.data)   # overlaps with the evaluation below
+        assert g.computeLoglikelihood(0, 1) == pytest.approx(want[name], rel=LNL_RTOL), (k, name)
+    for eng in (g, oa):
+        eng.set_pinv(0, 0.25)
+    assert g.computeLoglikelihood(0, 1) == pytest.approx(oa.computeLoglikelihood(0, 1), rel=LNL_RTOL)   # last committed: a
+    bad = bufs["b"][0].copy(); bad[2, 5] = 0
+    g.stage_alignment_u8(0, bad.ctypes.data, 0)
+    g.commit_staged_alignment()
+    with pytest.raises(LikelihoodError, match="Illegal state code in tip"):
+        g.computeLoglikelihood(0, 1)
+    g.close()

@@ -402,6 +402,7 @@ uint32_t class_tip_codes(const nrx_engine *e, const ShapeClass &c) {
 extern "C" {
 
 static int flush_pmatrices(nrx_engine *e);
+static bool aa_dmma_class(const nrx_engine *e, const ShapeClass &c);
 
 const char *nrx_last_error(void) { return g_err.c_str(); }
 
@@ -797,6 +798,33 @@ static int launch_pmatrices(nrx_engine *e, uint32_t pi, uint32_t n, const uint32
 }
 /* issue the deferred P-matrix updates (every entry point that reads P-matrices calls this first) */
 static int flush_pmatrices(nrx_engine *e) {
+  // several partitions of one shape class with pending edges (unlinked branch lengths): ONE launch for the class
+  for (const ShapeClass &c : e->classes) {
+    if (aa_dmma_class(e, c) || std::getenv("NRX_NO_K1_MULTI")) continue;   // 20-state classes refresh their tip tables per partition (K1b)
+    uint32_t pending_parts = 0;
+    for (uint32_t pi : c.parts) pending_parts += e->parts[pi].npend ? 1 : 0;
+    if (pending_parts < 2) continue;
+    std::vector<uint32_t> idx, off(1, 0);
+    std::vector<double> len;
+    uint32_t most = 0, smem_doubles = 0;
+    for (uint32_t pi : c.parts) {
+      Part &p = e->parts[pi];
+      for (uint32_t m = 0; m < p.d.edges; ++m) if (p.pend[m]) { idx.push_back(m); len.push_back(p.h_len[m]); p.pend[m] = 0; }
+      p.npend = 0;
+      most = std::max<uint32_t>(most, (uint32_t)idx.size() - off.back());
+      off.push_back((uint32_t)idx.size());
+      smem_doubles = std::max<uint32_t>(smem_doubles, p.d.rate_cats * p.d.states);
+    }
+    if (!refresh_views(e)) return 0;
+    uint32_t *d_idx, *d_off; double *d_len;
+    if (!upload(e, idx.data(), idx.size(), &d_idx) || !upload(e, len.data(), len.size(), &d_len) || !upload(e, off.data(), off.size(), &d_off)) return 0;
+    cudaEvent_t ev0, ev1;
+    prof_begin(e, &ev0, &ev1);
+    k_pmatrix_multi<<<dim3(most, (uint32_t)c.parts.size()), 128, smem_doubles * sizeof(double), e->stream>>>(c.d_views, d_idx, d_len, d_off);
+    e->launches++;
+    CK(cudaGetLastError());
+    prof_end(e, ev0, ev1, 1, idx.size(), (unsigned long long)idx.size() * e->parts[c.parts[0]].pmat_entries * 8, NRX_PROF_K1);
+  }
   for (uint32_t pi = 0; pi < e->parts.size(); ++pi) {
     Part &p = e->parts[pi];
     if (!p.npend) continue;

@@ -113,11 +113,8 @@ __device__ __forceinline__ void stg256(double *p, const D4 &v) {
  * K1  P(t) = I + V^-1 diag(expm1(lambda r_c t)) V      (LIBPLL/core_pmatrix.c:24-244, core_pmatrix_avx.c:42)
  * grid.x = edges to update, block = 128 threads looping over the cats*states*states outputs.
  * ---------------------------------------------------------------------------------------------- */
-__global__ void k_pmatrix(PartView pv, double *pmat_out, const uint32_t *edge_idx, const double *brlen) {
-  extern __shared__ double expd[];  // [cats][states]
+__device__ __forceinline__ void pmatrix_body(const PartView &pv, double *pmat_out, uint32_t edge, double t, double *expd /* shared [cats][states] */) {
   const uint32_t S = pv.states, SP = pv.sp, C = pv.cats;
-  const uint32_t edge = edge_idx[blockIdx.x];
-  const double t = brlen[blockIdx.x];
   double *out = pmat_out + (size_t)edge * C * S * SP;
   for (uint32_t i = threadIdx.x; i < C * S; i += blockDim.x) {
     const uint32_t c = i / S, m = i % S;
@@ -153,6 +150,23 @@ __global__ void k_pmatrix(PartView pv, double *pmat_out, const uint32_t *edge_id
     out[i] = v;
     if (pv.pmat_pad && S == 4 && C == 4) pv.pmat_pad[(size_t)edge * 72 + c * 18 + j * 4 + k] = v;   // 72 = 4 * PCAT (k_walk_dna4)
   }
+}
+
+__global__ void k_pmatrix(PartView pv, double *pmat_out, const uint32_t *edge_idx, const double *brlen) {
+  extern __shared__ double expd[];  // [cats][states]
+  pmatrix_body(pv, pmat_out, edge_idx[blockIdx.x], brlen[blockIdx.x], expd);
+}
+
+/* the same for several partitions of one shape class in ONE launch (unlinked branch lengths: BASELINE config 3 updates the 10
+ * partitions' P-matrices before every evaluation — ten launches with two small uploads each were 2.6 % of its step):
+ * grid = (most edges of a partition, partitions); partition y updates edge_idx / brlen [offset[y], offset[y + 1]) */
+__global__ void k_pmatrix_multi(const PartView *__restrict__ views, const uint32_t *__restrict__ edge_idx, const double *__restrict__ brlen,
+                                const uint32_t *__restrict__ offset) {
+  extern __shared__ double expd[];
+  const uint32_t o0 = offset[blockIdx.y], n = offset[blockIdx.y + 1] - o0;
+  if (blockIdx.x >= n) return;
+  const PartView &pv = views[blockIdx.y];
+  pmatrix_body(pv, const_cast<double *>(pv.pmat), edge_idx[o0 + blockIdx.x], brlen[o0 + blockIdx.x], expd);
 }
 
 /* Tip-code upload check, on the device (round 2: nrx_set_tipchars_u8 used to trust its input and left the invariant-site table

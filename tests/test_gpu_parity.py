@@ -1615,3 +1615,42 @@ def test_staged_alignment_upload_double_buffer():
     with pytest.raises(LikelihoodError, match="Illegal state code in tip"):
         g.computeLoglikelihood(0, 1)
     g.close()
+
+
+def test_config2_full_size_sweep_slice_matches_oracle():
+    """BASELINE config 2 at its FULL size (100 k patterns): the bench's derivative sweep on a slice of the pre-order — eight consecutive
+    branches (their re-rooting paths share memoised nodes), proposals kept, edge lnL and sumtables made in one pass, then again with lazy
+    re-rooting — against the reference's libpll under the restated in-place driver, edge by edge."""
+    import bench
+    cfg = dict(bench.CONFIGS[2])
+    net, parts, brl = bench.make_inputs(cfg, cfg["patterns"])
+    kw = dict(variant=cfg["variant"], linkage=cfg["linkage"], partition_brlens=brl)
+    g, o = _gpu(net, parts, **kw), _oracle(net, parts, **kw)
+    _inject_eigen(g, o)
+    for eng in (g, o):
+        eng.computeLoglikelihood(0, 1)
+    order = [int(e) for e in g.brlen_sweep_order()]
+    for lazy, chunk in ((False, order[20:28]), (True, order[28:36])):
+        if lazy:
+            _sweep_records(g, net, chunk, False)      # the branches' re-rooting plans become known
+            g.set_lazy_rerooting(True)
+        for e in chunk:
+            t0 = float(g.branch_lengths()[e])
+            assert o.branch_lengths()[e] == t0
+            for eng in (g, o):
+                eng.brlen_prepare(e)
+            lg, ng = g.computeLoglikelihoodBrlenOptAndSumtables(e)
+            lo, no = o.computeLoglikelihoodBrlenOpt(e), o.computePartitionSumtables(e)
+            assert ng == no and lg == pytest.approx(lo, rel=LNL_RTOL), e
+            if ng:
+                for k in range(2):
+                    for eng in (g, o):
+                        eng.brlen_set_length(e, t0 * (1.15 + 0.2 * k))
+                    dg, do = g.computeLoglikelihoodDerivatives(e), o.computeLoglikelihoodDerivatives(e)
+                    np.testing.assert_allclose(dg[4], do[4], rtol=DERIV_RTOL, atol=1e-7)
+                    assert dg[0] == pytest.approx(do[0], rel=DERIV_RTOL, abs=1e-6) and dg[1] == pytest.approx(do[1], rel=DERIV_RTOL, abs=1e-6)
+            assert g.brlen_finish(e) == pytest.approx(o.brlen_finish(e), rel=LNL_RTOL), e
+    g.set_lazy_rerooting(False)
+    assert g.computeLoglikelihood(1, 1) == pytest.approx(o.computeLoglikelihood(1, 1), rel=LNL_RTOL)
+    assert g.reroot_stats()["hits"] > 0 and g.lazy_reroot_stats()["sessions"] > 0
+    g.close()

@@ -158,6 +158,7 @@ struct nrx_engine {
   cudaStream_t copy_stream = nullptr;   // host -> device copies of staged alignments (overlap with the kernels on `stream`)
   cudaEvent_t ev_main = nullptr, ev_copy = nullptr;
   double *d_result_map = nullptr;  // device address of h_result (pinned, mapped): reducing kernels write their result there (result_out)
+  bool k6_ring = false;            // env NRX_K6_RING=1: K6 streams the sumtable through a cp.async.bulk ring (k_derivatives_dna4r) instead of registers — measured SLOWER (0.62 vs 0.69 of the HBM peak in the config-2 sweep, gpurun_out/r4c_*), kept for the A/B
   bool zero_copy = true;           // env NRX_ZEROCOPY=0: results go to d_result and are copied
   bool score_only = false;         // nrx_set_score_only: replays of a fused-K3 plan do not store the root displayed trees' CLVs (scalers and per-site terms only)
   uint32_t quad_total = 0;         // env NRX_QUAD_BLOCKS: blocks per launch of the quad kernels (0: 2 per SM)
@@ -433,6 +434,7 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
   if (const char *v = std::getenv("NRX_PDL")) e->use_pdl = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_FUSE_REDUCE")) e->fuse_reduce = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_ZEROCOPY")) e->zero_copy = std::atoi(v) != 0;
+  if (const char *v = std::getenv("NRX_K6_RING")) e->k6_ring = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_QUAD")) e->quad = std::atoi(v) != 0;
   if (const char *v = std::getenv("NRX_QUAD_BLOCKS")) e->quad_total = (uint32_t)std::max(0, std::atoi(v));
   if (const char *v = std::getenv("NRX_NODE")) e->node_mode = std::atoi(v);
@@ -455,6 +457,7 @@ nrx_engine *nrx_engine_create(const nrx_partition_desc *descs, uint32_t nparts, 
     // op chain per block loses 3x to the bandwidth-bound level-by-level kernels -> only while the launch is latency-bound
     if (!std::getenv("NRX_WALK_TILES")) e->walk_max_tiles = 4u * (uint32_t)sms;
     if (!cuda_ok(cudaFuncSetAttribute(k_walk_dna4, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024), "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(k_derivatives_dna4r, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K6RingSmem)), "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(k_clv_node_dna4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)node_smem_bytes(NODE_MAXC)), "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(k_clv_node_dna4, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute")) { delete e; return nullptr; }
     const int aa_smem = (int)(sizeof(AaSmem) + 2 * AA_LUT_CODES * 80 * sizeof(double));
@@ -1969,7 +1972,8 @@ int nrx_derivatives(nrx_engine *e, uint32_t n, const double *brlen, double *out)
   for (const ShapeClass &c : e->classes) {
     dim3 grid(nblk, n, (uint32_t)c.parts.size());
     const bool mix = class_mixture(e, c);   // (only the +I term of K6 reads frequencies; the generic kernel is the one that indexes them by category)
-    if (!mix && c.states == 4 && c.cats == 4 && e->quad) k_derivatives_dna4q<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P, result_out(e, tk), tk);
+    if (!mix && c.states == 4 && c.cats == 4 && e->quad && e->k6_ring) k_derivatives_dna4r<<<grid, BLOCK, sizeof(K6RingSmem), e->stream>>>(c.d_views, e->d_partial, P, result_out(e, tk), tk);
+    else if (!mix && c.states == 4 && c.cats == 4 && e->quad) k_derivatives_dna4q<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P, result_out(e, tk), tk);
     else if (!mix && c.states == 4 && c.cats == 4) k_derivatives_dna4<<<grid, BLOCK, 0, e->stream>>>(c.d_views, e->d_partial, P, result_out(e, tk), tk);
     else if (!mix && pow2_cats(c) && c.states == 20 && c.cats == 4 && e->quad) k_derivatives_aa20p<<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P, result_out(e, tk), tk);
     else if (!mix && pow2_cats(c) && c.states == 20) k_derivatives_pc<20, 2><<<grid, BLOCK, ((size_t)c.cats * diag_stride(c.states) + c.cats) * sizeof(double), e->stream>>>(c.d_views, e->d_partial, P, result_out(e, tk), tk);

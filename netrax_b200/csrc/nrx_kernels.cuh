@@ -3067,6 +3067,104 @@ __global__ void __launch_bounds__(BLOCK, 2) k_edge_lnl_dna4q(const PartView *__r
   finish_partials<1>(partial + oi * gridDim.x, out + oi, counters ? counters + oi : nullptr, gridDim.x);
 }
 
+/* K6 with the sumtable streamed through a cp.async.bulk ring in shared memory (K2's recipe) instead of through registers: ncu on
+ * k_derivatives_dna4q (profiles/r4b_sweep_kernels_after_ncu.md) showed 64 KB of loads in flight per SM — all 118 registers allow —
+ * and a third of the samples waiting on memory at 4.75 TB/s.  Here one elected thread keeps K6R_STAGES tiles of 256 patterns
+ * (32 KB each) in flight per block, 2 blocks per SM = 192 KB; the consumers read their items from shared memory (thread = (pattern,
+ * category), conflict-free 256-bit reads) and finish exactly as the register version does (same arithmetic, same quad reduction).
+ * MEASURED SLOWER and therefore opt-in (NRX_K6_RING=1): 16.5 vs 14.9 ms for the 330 K6 launches of the config-2 sweep (0.62 vs 0.69
+ * of the HBM peak) — a 45-us launch of 18 blocks per pair does not amortise the ring's fill and its lock-step refill barrier. */
+constexpr int K6R_TP = 256;       // patterns per tile
+constexpr int K6R_STAGES = 3;
+struct __align__(128) K6RingSmem {
+  double st[K6R_STAGES][K6R_TP * 16];
+  unsigned long long full[K6R_STAGES];
+};
+
+__global__ void __launch_bounds__(BLOCK, 2) k_derivatives_dna4r(const PartView *__restrict__ parts, double *__restrict__ partial,
+                                                                 uint32_t nparts_total, double *__restrict__ out, uint32_t *__restrict__ counters) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  K6RingSmem &sm = *reinterpret_cast<K6RingSmem *>(smem_raw);
+  __shared__ double red[3 * (BLOCK / 32)];
+  const PartView &pv = parts[blockIdx.z];
+  const int tid = threadIdx.x, q = tid & 3;
+  double dg[12];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dg[j * 3 + k] = pv.diagp[q * 16 + j * 4 + k];
+  const double w = pv.rate_weights[q], pinv = pv.pinv;
+  const double *st = pv.sumtable[blockIdx.y];
+  const uint32_t patterns = pv.patterns;
+  const uint32_t ntiles = (patterns + K6R_TP - 1) / K6R_TP, first = blockIdx.x, step = gridDim.x;
+  const uint32_t count = first < ntiles ? (ntiles - first + step - 1) / step : 0u;
+  auto issue = [&](uint32_t k, uint32_t stage) {
+    const uint32_t p0 = (first + k * step) * K6R_TP;
+    const uint32_t rows = patterns - p0 < (uint32_t)K6R_TP ? patterns - p0 : (uint32_t)K6R_TP;
+    mbar_expect_tx(&sm.full[stage], rows * 128u);
+    bulk_g2s(sm.st[stage], st + (size_t)p0 * 16, rows * 128u, &sm.full[stage]);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < K6R_STAGES; ++s) mbar_init(&sm.full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (uint32_t s = 0; s < (uint32_t)K6R_STAGES && s < count; ++s) issue(s, s);
+  }
+  __syncthreads();
+  double acc[3] = {0.0, 0.0, 0.0};
+  uint32_t stage = 0, phase = 0;
+  for (uint32_t k = 0; k < count; ++k) {
+    mbar_wait(&sm.full[stage], phase);
+    const uint32_t p0 = (first + k * step) * K6R_TP;
+    const double *tile = sm.st[stage];
+    double l0[QU], l1[QU], l2[QU];
+#pragma unroll
+    for (int u = 0; u < QU; ++u) {
+      const uint32_t it = (uint32_t)u * BLOCK + tid;   // item of the tile: pattern it / 4, category q
+      const D4 v = *reinterpret_cast<const D4 *>(tile + (size_t)it * 4);
+      const double sv[4] = {v.x, v.y, v.z, v.w};
+      double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        c0 = __dadd_rn(c0, __dmul_rn(sv[j], dg[j * 3 + 0]));
+        c1 = __dadd_rn(c1, __dmul_rn(sv[j], dg[j * 3 + 1]));
+        c2 = __dadd_rn(c2, __dmul_rn(sv[j], dg[j * 3 + 2]));
+      }
+      if (pinv > 0.0) {
+        const uint32_t n = p0 + (it >> 2);
+        double invf = 0.0;
+        if (n < patterns) { const int iv = pv.invariant[n]; invf = iv < 0 ? 0.0 : pv.freqs[iv]; }
+        deriv_cat_pinv(c0, c1, c2, pinv, invf);
+      }
+      l0[u] = __dmul_rn(c0, w); l1[u] = __dmul_rn(c1, w); l2[u] = __dmul_rn(c2, w);
+    }
+    const double lk0 = quad_gather_sum(l0[0], l0[1], l0[2], l0[3], q);
+    const double lk1 = quad_gather_sum(l1[0], l1[1], l1[2], l1[3], q);
+    const double lk2 = quad_gather_sum(l2[0], l2[1], l2[2], l2[3], q);
+    const uint32_t n = p0 + (uint32_t)q * (BLOCK / 4) + (tid >> 2);   // the pattern of this thread's q-th item (rows past the end of a ragged
+    if (n < patterns) {                                               //  last tile hold stale data and are never owned)
+      const double pw = (double)pv.weights[n];
+      const double d1 = -lk1 / lk0;
+      const double d2 = d1 * d1 - lk2 / lk0;
+      acc[0] += pw * log(lk0);
+      acc[1] += pw * d1;
+      acc[2] += pw * d2;
+    }
+    __syncthreads();   // every thread has read the stage: refill it
+    if (tid == 0 && k + K6R_STAGES < count) issue(k + K6R_STAGES, stage);
+    if (++stage == (uint32_t)K6R_STAGES) { stage = 0; phase ^= 1u; }
+  }
+  block_sum<3>(acc, red);
+  const size_t oi = (size_t)blockIdx.y * nparts_total + pv.part_index;
+  double *p = partial + oi * 3 * gridDim.x;
+  if (threadIdx.x == 0) {
+    p[0 * gridDim.x + blockIdx.x] = acc[0];
+    p[1 * gridDim.x + blockIdx.x] = acc[1];
+    p[2 * gridDim.x + blockIdx.x] = acc[2];
+  }
+  finish_partials<3>(p, out + oi * 3, counters ? counters + oi : nullptr, gridDim.x);
+}
+
 /* K4 + K5 in one pass (round 2): the edge lnL of a displayed-tree pair and its sumtable read the same two CLVs.  optimize_branch
  * asks for both back to back (computeLoglikelihoodBrlenOpt, then computePartitionSumtables; BranchLengthOptimization.cpp:374-381), so
  * the host may issue them together (nrx_edge_lnl_sumtables): 2C read + C written per pair and pattern instead of (2C) + (2C + C).

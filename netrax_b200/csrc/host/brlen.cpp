@@ -164,6 +164,7 @@ struct RerootCache {
   std::vector<Plan> plans;
   std::vector<std::pair<size_t, ReticulationConfigSet>> edge_restrictions;   // getRestrictionsActiveAliveBranch per branch
   std::vector<std::pair<size_t, bool>> edge_all_trees;                        // ... and whether the branch is active and alive in ALL displayed trees
+  size_t base_slots = 0;                             // slots the network itself used when the first session opened (the memo's default budget)
   bool lazy_session = false;                         // the open session was prepared without evaluating the network from its root first
   uint64_t topology_epoch = 0;
   uint64_t next_id = 1, tick = 0, session = 0, epoch = 0;
@@ -194,6 +195,7 @@ RerootCache &rerootState(AnnotatedNetwork &ann) {
     rc.state.assign(n, RerootCache::UNTOUCHED);
   }
   if (ann.node_version.size() != n) ann.node_version.assign(n, 0);
+  if (!rc.base_slots) rc.base_slots = ann.next_slot - ann.free_slots.size();
   return rc;
 }
 
@@ -204,7 +206,9 @@ size_t rerootBudget(AnnotatedNetwork &ann) {
   double slot_bytes = 0;
   for (const PartitionModel &m : ann.fake_treeinfo->partitions) slot_bytes += (double)m.sites * (m.rate_cats * m.states_padded * 8.0 + 4.0);
   const size_t by_mem = (size_t)(24e9 / std::max(1.0, slot_bytes));
-  return std::min<size_t>(std::max<size_t>(ann.next_slot, 32), by_mem);
+  // (next_slot counts the memo's and the sessions' own slots too: the network's own ones are what was allocated before the first session)
+  const size_t own = ann.reroot && ann.reroot->base_slots ? ann.reroot->base_slots : ann.next_slot;
+  return std::min<size_t>(std::max<size_t>(own, 32), by_mem);
 }
 
 void releaseEntry(AnnotatedNetwork &ann, RerootCache &rc, RerootCache::Entry &e) {

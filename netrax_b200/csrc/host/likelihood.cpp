@@ -663,7 +663,11 @@ static void createEnginePlan(AnnotatedNetwork &ann, const std::vector<uint32_t> 
     for (nrx_op &op : flat)
       for (size_t k = 0; k < root_slots.size(); ++k)
         if (op.parent_slot == root_slots[k]) { op.lnl_item = (uint32_t)k + 1; ++marked; }
-    if (marked != root_slots.size()) {  // a root tree's CLV is not produced by this traversal (cannot happen for a full one)
+    bool aa = false;
+    for (const PartitionModel &m : ann.fake_treeinfo->partitions) aa = aa || m.states != 4;
+    bool tiptip_marked = false;   // 20 states: tip x tip updates are a table kernel without the per-site epilogue
+    for (const nrx_op &op : flat) tiptip_marked = tiptip_marked || (aa && op.lnl_item && op.left_kind == NRX_TIP && op.right_kind == NRX_TIP);
+    if (marked != root_slots.size() || tiptip_marked) {  // a root tree's CLV is not produced by this traversal (cannot happen for a full one)
       for (nrx_op &op : flat) op.lnl_item = 0;
       pc.fused = false;
     }

@@ -1142,8 +1142,11 @@ static int launch_clv_batch(nrx_engine *e, const nrx_op *d_ops, uint32_t nops, b
         const int pdl = (e->capturing_pdl && e->pdl_prev_is_k2) ? 1 : 0;
         cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
         const nrx_op *ops_rest = d_ops + ntt;
-        if (e->aa_pipe) CK(cudaLaunchKernelEx(&cfg, k_aa20_mma<AA_CLV, true>, (const PartView *)c.d_views, ops_rest, rest, groups, luts, (double *)nullptr, 0u, 0.0, (double *)nullptr, (uint32_t *)nullptr, pdl));
-        else CK(cudaLaunchKernelEx(&cfg, k_aa20_mma<AA_CLV, false>, (const PartView *)c.d_views, ops_rest, rest, groups, luts, (double *)nullptr, 0u, 0.0, (double *)nullptr, (uint32_t *)nullptr, pdl));
+        double *ps = fused ? e->d_fused : nullptr;   // fused K3: the ops marked as root displayed trees also emit their per-site terms
+        const uint32_t np = (uint32_t)e->parts.size();
+        const size_t ps_stride = (size_t)e->max_patterns;
+        if (e->aa_pipe) CK(cudaLaunchKernelEx(&cfg, k_aa20_mma<AA_CLV, true>, (const PartView *)c.d_views, ops_rest, rest, groups, luts, (double *)nullptr, np, 0.0, (double *)nullptr, (uint32_t *)nullptr, pdl, ps, ps_stride));
+        else CK(cudaLaunchKernelEx(&cfg, k_aa20_mma<AA_CLV, false>, (const PartView *)c.d_views, ops_rest, rest, groups, luts, (double *)nullptr, np, 0.0, (double *)nullptr, (uint32_t *)nullptr, pdl, ps, ps_stride));
         e->pdl_prev_is_k2 = true;
       }
     } else {
@@ -1543,7 +1546,9 @@ int nrx_set_score_only(nrx_engine *e, int on) {
 
 int nrx_supports_fused_lnl(nrx_engine *e) {
   if (!e || (e->k2_variant != 0 && e->k2_variant != 1) || std::getenv("NRX_NO_FUSED_LNL")) return 0;
-  for (const ShapeClass &c : e->classes) if (!(dna_pipe_cats(c.states, c.cats) && (c.cats == 4 || e->k2_variant == 0))) return 0;
+  for (const ShapeClass &c : e->classes)
+    if (!(dna_pipe_cats(c.states, c.cats) && (c.cats == 4 || e->k2_variant == 0)) && !(aa_dmma_class(e, c) && !e->aa_v1 && std::getenv("NRX_AA_FUSED_LNL"))) return 0;   // 20 states: built, opt-in — the storer warp's extra 20 x 4
+                                                                                           // multiply-adds per pattern cost K2 what the saved K3 pass gains (0.421 vs 0.422 ms at 20 k patterns, 2.813 vs 2.802 ms at 200 k; gpurun_out/r4e_*)
   for (const Part &p : e->parts) if (p.pinv > 0.0 || p.nmodels > 1) return 0;   // the K2 epilogue carries neither the invariant-site term nor per-category frequencies
   return 1;
 }

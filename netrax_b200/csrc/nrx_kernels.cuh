@@ -1586,7 +1586,8 @@ template <int MODE, bool PIPE>
 __global__ void __launch_bounds__(AA2_THREADS, 2) k_aa20_mma(const PartView *__restrict__ parts, const nrx_op *__restrict__ ops,
                                                               uint32_t nops, uint32_t groups, int with_lut,
                                                               double *__restrict__ partial, uint32_t nparts_total, double log_thresh,
-                                                              double *__restrict__ red_out, uint32_t *__restrict__ counters, int pdl) {
+                                                              double *__restrict__ red_out, uint32_t *__restrict__ counters, int pdl,
+                                                              double *__restrict__ persite = nullptr, size_t persite_stride = 0) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   AaSmem2 &sm = *reinterpret_cast<AaSmem2 *>(smem_raw);
   // pdl: launched programmatically serialised behind the previous K2 launch of a plan graph — the successor may start its own
@@ -1685,6 +1686,7 @@ __global__ void __launch_bounds__(AA2_THREADS, 2) k_aa20_mma(const PartView *__r
     double *par = (MODE == AA_SUM) ? pv.sumtable[op.parent_slot] : (MODE == AA_CLV ? pv.clv[op.parent_slot] : nullptr);
     uint32_t *psc = (MODE == AA_CLV) ? pv.scaler[op.parent_slot] : nullptr;
     const bool tiptip = (lk == NRX_TIP && rk == NRX_TIP);
+    double *ps_out = (MODE == AA_CLV && persite && op.lnl_item) ? persite + ((size_t)(op.lnl_item - 1) * nparts_total + pv.part_index) * persite_stride : nullptr;
     double edge_acc = 0.0, pend_t = 0.0, pend_w = 0.0;   // AA_EDGE: block sum; the pattern this lane finishes at the next flush
     uint32_t pend_s = 0;
     uint32_t o = 0, ph = 0, prev = 0;
@@ -1708,6 +1710,21 @@ __global__ void __launch_bounds__(AA2_THREADS, 2) k_aa20_mma(const PartView *__r
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
         }
+      }
+      if (MODE == AA_CLV && ps_out) {
+        // fused K3 (root displayed trees of a replayed plan, as the DNA kernel's epilogue does): the per-site likelihood term of the
+        // tile as it leaves — lane = (pattern, category), pi-weighted sum over the 20 states in state order, category weight, categories
+        // 0..3 in order (k_tree_lnl_aa20p's arithmetic); k_term_lnl_sum then takes log / scaler / weight from 16 B per site
+        const int pp = lane >> 2, cc = lane & 3;
+        const double *row = ot.v + pp * AA_OPITCH + cc * 20;
+        double tr = 0.0;
+#pragma unroll
+        for (int i = 0; i < 20; ++i) tr = __dadd_rn(tr, __dmul_rn(row[i], __ldg(pv.freqs + i)));
+        const double tw = __dmul_rn(tr, __ldg(pv.rate_weights + cc));
+        double term = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) term = __dadd_rn(term, __shfl_sync(0xffffffffu, tw, (lane & ~3) + i));
+        if (cc == 0 && p0 + pp < pv.patterns) ps_out[p0 + pp] = term;
       }
       if (MODE == AA_EDGE) {
         // K4: category sum (order 0..3) per pattern on lanes 0..7; the log / scaler term / pattern weight — ~150 dependent FP64

@@ -270,8 +270,9 @@ def measure_config(c, device, peak, reps, with_cpu, cores):
     r = {"workload": cfg["name"], "patterns": cfg["patterns"], "partitions": cfg["parts"], "sum_trees_per_node": slots, "root_trees": eng.num_trees(net.root),
          "lnl": lnl, "ms_per_eval": ms, "wall_ms_per_eval": wall, "lnl_evals_per_sec": 1e3 / ms, "site_updates_per_sec": updates / (ms / 1e3),
          "launches_per_eval": launches, "kernel_families": fam}
-    if c == 2:
-        for key, accept, lazy in (("derivative_sweep", False, False), ("derivative_sweep_accept", True, False), ("derivative_sweep_accept_lazy", True, True)):
+    if c in (2, 4):   # config 4: the old-length-restored flavour only (the protein K4 / K5 / K6 fractions under the driver's clock)
+        for key, accept, lazy in ((("derivative_sweep", False, False), ("derivative_sweep_accept", True, False), ("derivative_sweep_accept_lazy", True, True)) if c == 2
+                                  else (("derivative_sweep", False, False),)):
             eng.set_lazy_rerooting(lazy)
             derivative_sweep(eng, net, accept=accept)  # warm-up (allocates re-rooting slots and sumtables)
             eng.computeLoglikelihood(1, 1)

@@ -1654,3 +1654,29 @@ def test_config2_full_size_sweep_slice_matches_oracle():
     assert g.computeLoglikelihood(1, 1) == pytest.approx(o.computeLoglikelihood(1, 1), rel=LNL_RTOL)
     assert g.reroot_stats()["hits"] > 0 and g.lazy_reroot_stats()["sessions"] > 0
     g.close()
+
+
+def test_batched_scoring_with_score_only():
+    """Candidate scoring as the search would use it: several networks in flight (computeLoglikelihoodBatch), score-only replays (root
+    CLVs not stored) — same lnLs as the plain sequential evaluations, and an incremental batch afterwards heals the stale roots."""
+    from netrax_b200.engine import compute_loglikelihood_batch
+    base = random_network(30, 3, seed=91)
+    m, w = simulate_alignment(base, 5000, seed=91)
+    part = Partition(4, 4, m, DNA_FREQS, GTR_RATES, GAMMA4_ALPHA05, pattern_weights=w)
+    nets = [base] + [random_network(30, r, seed=92 + r) for r in (1, 2, 4)]
+    gs = [_gpu(n, [part]) for n in nets]
+    want = np.array([g.computeLoglikelihood(0, 1) for g in gs])
+    compute_loglikelihood_batch(gs, 0, 1)                                  # plans recorded
+    for g in gs:
+        g.set_score_only(True)
+    got = compute_loglikelihood_batch(gs, 0, 1)
+    np.testing.assert_allclose(got, want, rtol=REPLAY_RTOL)
+    np.testing.assert_array_equal(got, compute_loglikelihood_batch(gs, 0, 1))
+    for k, g in enumerate(gs):
+        g.set_branch_length(k + 2, 0.07 * (k + 1))
+    inc = compute_loglikelihood_batch(gs, 1, 1)                            # incremental after score-only: full re-evaluation with the stores on
+    for g in gs:
+        g.set_score_only(False)
+    np.testing.assert_allclose(inc, np.array([g.computeLoglikelihood(0, 1) for g in gs]), rtol=REPLAY_RTOL)
+    for g in gs:
+        g.close()

@@ -31,6 +31,14 @@ struct PlanCache {
   bool fused = false;
   std::vector<uint32_t> lnl_slots;
   bool run_pending = false;   // a replay whose device launches are issued together with the root lnLs (nrx_plan_evaluate_async)
+  // which root displayed trees are evaluated and where their CLVs live (findFirstNodeWithTwoActiveChildren + findMatchingDisplayedTree
+  // per tree: O(trees x (nodes + trees)) of host algebra, 192 trees on BASELINE config 5) — a function of the topology and, through
+  // the min_interesting_tree_logprob filter, of the reticulation probabilities: kept per plan while `prob_epoch` stands, so that a
+  // replay issues its launches at once instead of leaving the GPU idle behind that loop
+  bool root_cached = false;
+  uint64_t root_prob_epoch = 0;
+  std::vector<uint32_t> root_slots;
+  std::vector<size_t> root_which;
 };
 
 AnnotatedNetwork::~AnnotatedNetwork() {
@@ -269,6 +277,7 @@ void setReticulationProb(AnnotatedNetwork &ann, size_t r, double prob) {  // src
   ann.first_parent_logprobs[r] = std::log(prob);
   ann.second_parent_logprobs[r] = std::log(1.0 - prob);
   ann.cached_logl_valid = false;
+  ann.prob_epoch++;  // which root trees are interesting (min_interesting_tree_logprob) may change
   ann.clv_epoch++;   // memoised re-rooted trees carry their tree_logprob
   invalidateTreeLogprobs(ann);
   if (ann.options.likelihood_variant == LikelihoodVariant::SARAH_PSEUDO)  // InvalidationHelper.cpp:296-301: the blend weights changed
@@ -280,7 +289,7 @@ static void dropEnginePlan(AnnotatedNetwork &ann) {
 }
 
 void topology_changed(AnnotatedNetwork &ann) {
-  if (ann.plan) { ann.plan->valid = false; dropEnginePlan(ann); }
+  if (ann.plan) { ann.plan->valid = false; ann.plan->root_cached = false; dropEnginePlan(ann); }
   ann.clv_epoch++;
   ann.topology_epoch++;
   ann.node_version.clear();
@@ -571,7 +580,10 @@ static void treeLoglikelihoodsBegin(AnnotatedNetwork &ann, Node *actRoot, bool r
   NodeDisplayedTreeData &rd = ann.pernode_displayed_tree_data[actRoot->clv_index];
   std::vector<uint32_t> slots;
   std::vector<size_t> which;
-  for (size_t i = 0; i < rd.num_active_displayed_trees; ++i) {
+  PlanCache *pcr = (replayed && ann.plan && ann.plan->valid && actRoot == ann.network.root) ? ann.plan : nullptr;
+  const bool use_cached = pcr && pcr->root_cached && pcr->root_prob_epoch == ann.prob_epoch;
+  if (use_cached) { slots = pcr->root_slots; which = pcr->root_which; }
+  for (size_t i = 0; !use_cached && i < rd.num_active_displayed_trees; ++i) {
     DisplayedTreeData &t = rd.displayed_trees[i];
     refreshLogprob(ann, t.treeLoglData);
     if (t.treeLoglData.tree_logprob < ann.options.min_interesting_tree_logprob) continue;
@@ -589,6 +601,7 @@ static void treeLoglikelihoodsBegin(AnnotatedNetwork &ann, Node *actRoot, bool r
     slots.push_back(match->slot);
     which.push_back(i);
   }
+  if (pcr && !use_cached) { pcr->root_slots = slots; pcr->root_which = which; pcr->root_prob_epoch = ann.prob_epoch; pcr->root_cached = true; }
   flushPendingOps(ann);
   if (slots_out) *slots_out = slots;
   if (!slots.empty()) {
@@ -711,7 +724,7 @@ static void processPartitionsImproved(AnnotatedNetwork &ann, int incremental) { 
     replayPlan(ann);
   } else {
     const bool record = !incremental && ann.use_plan_cache;
-    if (record) { pc.batches.clear(); pc.site_updates = 0; pc.recording = true; pc.valid = false; dropEnginePlan(ann); }
+    if (record) { pc.batches.clear(); pc.site_updates = 0; pc.recording = true; pc.valid = false; pc.root_cached = false; dropEnginePlan(ann); }
     for (Node *n : ann.travbuffer) {
       std::vector<Node *> children;
       for (size_t c : n->children) children.push_back(&ann.network.nodes[c]);

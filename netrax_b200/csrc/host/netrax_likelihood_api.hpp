@@ -250,6 +250,7 @@ struct AnnotatedNetwork {  // src/graph/AnnotatedNetwork.hpp:42-89
   /* virtual re-rooting writes into shadow slots (the root-directed CLVs stay intact) and memoises the re-rooted node data */
   RerootCache *reroot = nullptr;
   std::vector<uint64_t> node_version;         // [node] bumped whenever the node's root-directed displayed trees are recomputed
+  uint64_t prob_epoch = 1;                    // bumped by setReticulationProb: drops the plan's cached list of root trees to evaluate
   uint64_t topology_epoch = 1;                // bumped by topology_changed(): drops the per-branch re-rooting plans (paths, restriction sets)
   uint64_t clv_epoch = 0;                     // bumped by invalidateAllCLVs / setReticulationProb / topology_changed: drops the memoised data
   size_t reroot_cache_max_slots = SIZE_MAX;   // SIZE_MAX: default budget (env NRX_REROOT_CACHE_SLOTS); 0: nothing survives a re-rooting session

@@ -746,20 +746,35 @@ static void processPartitionsImproved(AnnotatedNetwork &ann, int incremental) { 
   treeLoglikelihoodsBegin(ann, ann.network.root, true, nullptr);
 }
 
-double evaluateTreesPartition(AnnotatedNetwork &ann, size_t p, std::vector<TreeLoglData> &trees) {  // :521-604
-  if (trees.empty()) throw std::runtime_error("evaluateTreesPartition: no trees");
+/* the mixing itself, over any sequence of trees (evaluateTrees used to deep-copy every root tree's TreeLoglData first: 192 x two
+ * vectors per evaluation of BASELINE config 5, 20 us of host time behind which the GPU sat idle) */
+template <class Get>
+static double mixTreesPartition(AnnotatedNetwork &ann, size_t p, size_t n, Get get) {
+  if (n == 0) throw std::runtime_error("evaluateTreesPartition: no trees");
   double pl;
   if (ann.options.likelihood_variant == LikelihoodVariant::AVERAGE_DISPLAYED_TREES) {
-    std::vector<double> terms;  // log(exp(tree_logprob) * exp(tree_partition_logl)), summed as the reference does but in log space
-    for (TreeLoglData &t : trees) {
+    // log(sum_t exp(tree_logprob_t + tree_partition_logl_t)): summed as the reference does, in log space (logSumExp's max-shift)
+    double m = -std::numeric_limits<double>::infinity();
+    for (size_t i = 0; i < n; ++i) {
+      TreeLoglData &t = get(i);
       if (t.tree_logprob < ann.options.min_interesting_tree_logprob) continue;
       if (!t.tree_logl_valid) throw std::runtime_error("invalid tree logl");
-      terms.push_back(t.tree_logprob + t.tree_partition_logl[p]);
+      m = std::max(m, t.tree_logprob + t.tree_partition_logl[p]);
     }
-    pl = logSumExp(terms);
+    if (m == -std::numeric_limits<double>::infinity()) pl = m;
+    else {
+      double sum = 0.0;
+      for (size_t i = 0; i < n; ++i) {
+        TreeLoglData &t = get(i);
+        if (t.tree_logprob < ann.options.min_interesting_tree_logprob) continue;
+        sum += std::exp(t.tree_logprob + t.tree_partition_logl[p] - m);
+      }
+      pl = m + std::log(sum);
+    }
   } else {
     pl = -std::numeric_limits<double>::infinity();
-    for (TreeLoglData &t : trees) {
+    for (size_t i = 0; i < n; ++i) {
+      TreeLoglData &t = get(i);
       if (t.tree_logprob < ann.options.min_interesting_tree_logprob) continue;
       if (!t.tree_logl_valid) throw std::runtime_error("invalid tree logl");
       pl = std::max(pl, t.tree_logprob + t.tree_partition_logl[p]);
@@ -769,15 +784,16 @@ double evaluateTreesPartition(AnnotatedNetwork &ann, size_t p, std::vector<TreeL
   return pl;
 }
 
+double evaluateTreesPartition(AnnotatedNetwork &ann, size_t p, std::vector<TreeLoglData> &trees) {  // :521-604
+  return mixTreesPartition(ann, p, trees.size(), [&](size_t i) -> TreeLoglData & { return trees[i]; });
+}
+
 static double evaluateTrees(AnnotatedNetwork &ann, Node *virtual_root) {  // :606-644
   NodeDisplayedTreeData &nd = ann.pernode_displayed_tree_data[virtual_root->clv_index];
-  std::vector<TreeLoglData> tl;
-  for (size_t i = 0; i < nd.num_active_displayed_trees; ++i) {
-    refreshLogprob(ann, nd.displayed_trees[i].treeLoglData);
-    tl.push_back(nd.displayed_trees[i].treeLoglData);
-  }
+  for (size_t i = 0; i < nd.num_active_displayed_trees; ++i) refreshLogprob(ann, nd.displayed_trees[i].treeLoglData);
   double network_logl = 0.0;
-  for (unsigned p = 0; p < ann.fake_treeinfo->partition_count; ++p) network_logl += evaluateTreesPartition(ann, p, tl);
+  for (unsigned p = 0; p < ann.fake_treeinfo->partition_count; ++p)
+    network_logl += mixTreesPartition(ann, p, nd.num_active_displayed_trees, [&](size_t i) -> TreeLoglData & { return nd.displayed_trees[i].treeLoglData; });
   if (network_logl == -std::numeric_limits<double>::infinity()) throw std::runtime_error("Invalid network likelihood: negative infinity \n");
   ann.cached_logl = network_logl;
   ann.cached_logl_valid = true;
